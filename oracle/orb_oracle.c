@@ -1,0 +1,999 @@
+/* orb_oracle.c - CPU oracle (TEST INFRASTRUCTURE, not product code).  See orb_oracle.h.
+ *
+ * Parity status: the reference holds no golden vectors for this path,
+ * and its own sources cannot be compiled here (they need OpenCV/Eigen/ROS headers).  The
+ * OpenCV primitives restated below are pinned against cv2 4.13.0 (the reference's third-party
+ * dependency, whose version the reference leaves open) by tests/test_oracle_pin_cv2.py and
+ * by the fixtures under tests/golden/ (made by oracle/gen_golden.py).
+ *
+ * Build with -ffp-contract=off: the reference is built without -march=native
+ * (R/../CMakeLists.txt:15-19), so x86-64 emits separate mul/add and no FMA.
+ *
+ * R/ = /root/reference/src/orb_slam3_ros/orb_slam3/
+ */
+#include "orb_oracle.h"
+#include <float.h>
+#include <limits.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+static const int32_t kPattern[1024] = {
+#include "../multi_orbslam3_b200/csrc/orb_pattern.inc"
+};
+
+#define PATCH_SIZE 31
+#define HALF_PATCH_SIZE 15
+#define EDGE_THRESHOLD 19
+#define TH_HIGH 100
+#define TH_LOW 50
+#define HISTO_LENGTH 30
+#define GRID_COLS 64
+#define GRID_ROWS 48
+
+/* ------------------------------------------------------------------------------------------
+ * OpenCV primitives
+ * ---------------------------------------------------------------------------------------- */
+
+/* cvRound(float): SSE cvtss2si, round-half-to-even in the default rounding mode. */
+int orc_cv_round_f(float v) { return (int)lrintf(v); }
+static int cv_round_d(double v) { return (int)lrint(v); }
+
+/* cv::resize(u8, INTER_LINEAR) fixed-point path (OpenCV imgproc resize.cpp: HResizeLinear /
+ * VResizeLinear with INTER_RESIZE_COEF_BITS = 11); call site R/src/ORBextractor.cc:1165. */
+void orc_resize_linear_u8(const uint8_t* src, int sw, int sh, int sstride,
+                          uint8_t* dst, int dw, int dh, int dstride)
+{
+    double inv_scale_x = (double)dw / sw, inv_scale_y = (double)dh / sh;
+    double scale_x = 1. / inv_scale_x, scale_y = 1. / inv_scale_y;
+    int* xofs = (int*)malloc(sizeof(int) * dw * 2);
+    short* ialpha = (short*)malloc(sizeof(short) * dw * 2);
+    int* rows[2];
+    rows[0] = (int*)malloc(sizeof(int) * dw);
+    rows[1] = (int*)malloc(sizeof(int) * dw);
+    for (int dx = 0; dx < dw; dx++) {
+        float fx = (float)((dx + 0.5) * scale_x - 0.5);
+        int sx = (int)floorf(fx);
+        fx -= sx;
+        if (sx < 0) { fx = 0; sx = 0; }
+        if (sx >= sw - 1) { fx = 0; sx = sw - 1; }
+        xofs[dx * 2] = sx;
+        xofs[dx * 2 + 1] = sx + 1 < sw ? sx + 1 : sw - 1;
+        ialpha[dx * 2] = (short)orc_cv_round_f((1.f - fx) * 2048.f);
+        ialpha[dx * 2 + 1] = (short)orc_cv_round_f(fx * 2048.f);
+    }
+    for (int dy = 0; dy < dh; dy++) {
+        float fy = (float)((dy + 0.5) * scale_y - 0.5);
+        int sy = (int)floorf(fy);
+        fy -= sy;
+        short b0 = (short)orc_cv_round_f((1.f - fy) * 2048.f);
+        short b1 = (short)orc_cv_round_f(fy * 2048.f);
+        int sy0 = sy < 0 ? 0 : (sy > sh - 1 ? sh - 1 : sy);
+        int sy1 = sy + 1 < 0 ? 0 : (sy + 1 > sh - 1 ? sh - 1 : sy + 1);
+        const uint8_t* S0 = src + (size_t)sy0 * sstride;
+        const uint8_t* S1 = src + (size_t)sy1 * sstride;
+        for (int dx = 0; dx < dw; dx++) {
+            int x0 = xofs[dx * 2], x1 = xofs[dx * 2 + 1];
+            int a0 = ialpha[dx * 2], a1 = ialpha[dx * 2 + 1];
+            rows[0][dx] = S0[x0] * a0 + S0[x1] * a1;
+            rows[1][dx] = S1[x0] * a0 + S1[x1] * a1;
+        }
+        uint8_t* D = dst + (size_t)dy * dstride;
+        for (int dx = 0; dx < dw; dx++) {
+            int v = (((b0 * (rows[0][dx] >> 4)) >> 16) + ((b1 * (rows[1][dx] >> 4)) >> 16) + 2) >> 2;
+            D[dx] = (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+        }
+    }
+    free(xofs); free(ialpha); free(rows[0]); free(rows[1]);
+}
+
+static int reflect101(int p, int n)
+{
+    if (n == 1) return 0;
+    while (p < 0 || p >= n) {
+        if (p < 0) p = -p;
+        else p = 2 * (n - 1) - p;
+    }
+    return p;
+}
+
+/* cv::GaussianBlur(u8, Size(7,7), 2, 2, BORDER_REFLECT_101), OpenCV >= 3.4.1 fixed-point path
+ * (smooth.simd.hpp, ufixedpoint16 kernel); call site R/src/ORBextractor.cc:1115. */
+void orc_gaussian_blur7(const uint8_t* src, int w, int h, int sstride, uint8_t* dst, int dstride)
+{
+    static const int K[7] = {18, 34, 48, 56, 48, 34, 18};
+    uint16_t* H = (uint16_t*)malloc(sizeof(uint16_t) * (size_t)w * h);
+    for (int y = 0; y < h; y++) {
+        const uint8_t* S = src + (size_t)y * sstride;
+        for (int x = 0; x < w; x++) {
+            int acc = 0;
+            if (x >= 3 && x < w - 3) {
+                for (int i = 0; i < 7; i++) acc += K[i] * S[x + i - 3];
+            } else {
+                for (int i = 0; i < 7; i++) acc += K[i] * S[reflect101(x + i - 3, w)];
+            }
+            H[(size_t)y * w + x] = (uint16_t)acc;
+        }
+    }
+    for (int y = 0; y < h; y++) {
+        const uint16_t* R[7];
+        for (int i = 0; i < 7; i++) R[i] = H + (size_t)reflect101(y + i - 3, h) * w;
+        uint8_t* D = dst + (size_t)y * dstride;
+        for (int x = 0; x < w; x++) {
+            uint32_t acc = 0;
+            for (int i = 0; i < 7; i++) acc += (uint32_t)K[i] * R[i][x];
+            D[x] = (uint8_t)((acc + 32768u) >> 16);
+        }
+    }
+    free(H);
+}
+
+/* FAST-9/16 ring, (dx,dy) in OpenCV's order (features2d fast_score.cpp makeOffsets, patternSize 16) */
+static const int kRing[16][2] = {
+    {0, 3}, {1, 3}, {2, 2}, {3, 1}, {3, 0}, {3, -1}, {2, -2}, {1, -3},
+    {0, -3}, {-1, -3}, {-2, -2}, {-3, -1}, {-3, 0}, {-3, 1}, {-2, 2}, {-1, 3}};
+
+/* m = max over the 16 arcs of 9 contiguous ring pixels of max(min d, min -d); corner <=> m > t;
+ * cornerScore<16>() returns max(t, m) - 1 (OpenCV fast_score.cpp).  Sliding min/max by doubling. */
+static int fast_arc_measure(const uint8_t* p, const int* off)
+{
+    int d[25], lo2[24], hi2[24], lo4[22], hi4[22];
+    int v = p[0];
+    for (int k = 0; k < 16; k++) d[k] = v - p[off[k]];
+    for (int k = 16; k < 25; k++) d[k] = d[k - 16];
+    for (int k = 0; k < 24; k++) { lo2[k] = d[k] < d[k + 1] ? d[k] : d[k + 1]; hi2[k] = d[k] > d[k + 1] ? d[k] : d[k + 1]; }
+    for (int k = 0; k < 22; k++) { lo4[k] = lo2[k] < lo2[k + 2] ? lo2[k] : lo2[k + 2]; hi4[k] = hi2[k] > hi2[k + 2] ? hi2[k] : hi2[k + 2]; }
+    int best = -256;
+    for (int s = 0; s < 16; s++) {
+        int mn = lo4[s] < lo4[s + 4] ? lo4[s] : lo4[s + 4];
+        int mx = hi4[s] > hi4[s + 4] ? hi4[s] : hi4[s + 4];
+        if (d[s + 8] < mn) mn = d[s + 8];
+        if (d[s + 8] > mx) mx = d[s + 8];
+        if (mn > best) best = mn;
+        if (-mx > best) best = -mx;
+    }
+    return best;
+}
+
+/* OpenCV's high-speed pre-test: every arc of 9 holds one pixel of each opposite pair (k, k+8), so a
+ * pixel whose pairs do not all have a member darker than v-t (or all a member brighter than v+t)
+ * cannot be a corner at threshold t. */
+static int fast_maybe_corner(const uint8_t* p, const int* off, int t)
+{
+    const int lo = p[0] - t, hi = p[0] + t;
+#define CLS(k) ((p[off[k]] < lo ? 1 : 0) | (p[off[k]] > hi ? 2 : 0))
+    int d = CLS(0) | CLS(8);
+    if (!d) return 0;
+    d &= CLS(2) | CLS(10); d &= CLS(4) | CLS(12); d &= CLS(6) | CLS(14);
+    if (!d) return 0;
+    d &= CLS(1) | CLS(9); d &= CLS(3) | CLS(11); d &= CLS(5) | CLS(13); d &= CLS(7) | CLS(15);
+#undef CLS
+    return d;
+}
+
+/* cv::FAST(img, keypoints, threshold, nonmaxSuppression=true) (features2d fast.cpp FAST_t<16>);
+ * call sites R/src/ORBextractor.cc:808, :827.  Output order: row-major. */
+int orc_fast9_16(const uint8_t* img, int w, int h, int stride, int threshold, int nms,
+                 int32_t* out, int cap)
+{
+    int n = 0;
+    if (threshold < 0) threshold = 0;
+    if (threshold > 255) threshold = 255;
+    if (w < 7 || h < 7) return 0;
+    int off[16];
+    for (int k = 0; k < 16; k++) off[k] = kRing[k][1] * stride + kRing[k][0];
+    /* score = 0 for non-corners (OpenCV zeroes its row buffers); corner flag kept apart because a
+     * corner with m == 1 (only possible at threshold 0) scores 0 */
+    int* score = (int*)calloc((size_t)w * h, sizeof(int));
+    uint8_t* corner = (uint8_t*)calloc((size_t)w * h, 1);
+    for (int y = 3; y < h - 3; y++)
+        for (int x = 3; x < w - 3; x++) {
+            const uint8_t* p = img + (size_t)y * stride + x;
+            if (!fast_maybe_corner(p, off, threshold)) continue;
+            int m = fast_arc_measure(p, off);
+            if (m > threshold) { corner[(size_t)y * w + x] = 1; score[(size_t)y * w + x] = m - 1; }
+        }
+    for (int y = 3; y < h - 3; y++)
+        for (int x = 3; x < w - 3; x++) {
+            if (!corner[(size_t)y * w + x]) continue;
+            int s = score[(size_t)y * w + x];
+            if (nms) {
+                const int* c = score + (size_t)y * w + x;
+                if (!(s > c[-1] && s > c[1] && s > c[-w - 1] && s > c[-w] && s > c[-w + 1] &&
+                      s > c[w - 1] && s > c[w] && s > c[w + 1]))
+                    continue;
+            }
+            if (n < cap) { out[n * 3] = x; out[n * 3 + 1] = y; out[n * 3 + 2] = s; }
+            n++;
+        }
+    free(score); free(corner);
+    return n;
+}
+
+/* cv::fastAtan2 (core mathfuncs_core.simd.hpp atan_f32), OpenCV 3.x/4.x constants; call site
+ * R/src/ORBextractor.cc:101.  All ops fp32, no FMA. */
+float orc_fast_atan2(float y, float x)
+{
+    const float scale = (float)(180.0 / 3.141592653589793238462643383279502884);
+    const float p1 = 0.9997878412794807f * scale;
+    const float p3 = -0.3258083974640975f * scale;
+    const float p5 = 0.1555786518463281f * scale;
+    const float p7 = -0.04432655554792128f * scale;
+    float ax = fabsf(x), ay = fabsf(y);
+    float a, c, c2;
+    if (ax >= ay) {
+        c = ay / (ax + (float)DBL_EPSILON);
+        c2 = c * c;
+        a = (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
+    } else {
+        c = ax / (ay + (float)DBL_EPSILON);
+        c2 = c * c;
+        a = 90.f - (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
+    }
+    if (x < 0) a = 180.f - a;
+    if (y < 0) a = 360.f - a;
+    return a;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Extractor
+ * ---------------------------------------------------------------------------------------- */
+typedef struct { float x, y, r; } Cand;
+
+struct OrcExtractor {
+    int nfeatures; double scaleFactor; int nlevels, iniTh, minTh;
+    float *scale, *invScale, *sigma2, *invSigma2;
+    int* featuresPerLevel;
+    int umax[HALF_PATCH_SIZE + 1];
+    /* per-call state */
+    uint8_t** level; uint8_t** blurred; int *lw, *lh;
+    Cand** cand; int *ncand, *capcand;
+    OrcKeyPoint** lkp; int* nlkp;
+};
+
+/* ORBextractor::ORBextractor, R/src/ORBextractor.cc:408-468 */
+OrcExtractor* orc_extractor_create(int nfeatures, float scale_factor, int nlevels, int ini_th, int min_th)
+{
+    OrcExtractor* e = (OrcExtractor*)calloc(1, sizeof(OrcExtractor));
+    e->nfeatures = nfeatures; e->scaleFactor = (double)scale_factor; e->nlevels = nlevels;
+    e->iniTh = ini_th; e->minTh = min_th;
+    e->scale = (float*)calloc(nlevels, sizeof(float));
+    e->invScale = (float*)calloc(nlevels, sizeof(float));
+    e->sigma2 = (float*)calloc(nlevels, sizeof(float));
+    e->invSigma2 = (float*)calloc(nlevels, sizeof(float));
+    e->featuresPerLevel = (int*)calloc(nlevels, sizeof(int));
+    e->scale[0] = 1.0f; e->sigma2[0] = 1.0f;
+    for (int i = 1; i < nlevels; i++) {
+        e->scale[i] = (float)(e->scale[i - 1] * e->scaleFactor);      /* float*double -> float, :419 */
+        e->sigma2[i] = e->scale[i] * e->scale[i];
+    }
+    for (int i = 0; i < nlevels; i++) {
+        e->invScale[i] = 1.0f / e->scale[i];
+        e->invSigma2[i] = 1.0f / e->sigma2[i];
+    }
+    float factor = (float)(1.0f / e->scaleFactor);                     /* :434 */
+    float nDesired = nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)nlevels));
+    int sum = 0;
+    for (int l = 0; l < nlevels - 1; l++) {
+        e->featuresPerLevel[l] = orc_cv_round_f(nDesired);
+        sum += e->featuresPerLevel[l];
+        nDesired *= factor;
+    }
+    e->featuresPerLevel[nlevels - 1] = nfeatures - sum > 0 ? nfeatures - sum : 0;
+
+    /* umax, :452-467 */
+    int v, v0, vmax = (int)floor(HALF_PATCH_SIZE * sqrtf(2.f) / 2 + 1);
+    int vmin = (int)ceil(HALF_PATCH_SIZE * sqrtf(2.f) / 2);
+    const double hp2 = HALF_PATCH_SIZE * HALF_PATCH_SIZE;
+    for (v = 0; v <= vmax; ++v) e->umax[v] = cv_round_d(sqrt(hp2 - v * v));
+    for (v = HALF_PATCH_SIZE, v0 = 0; v >= vmin; --v) {
+        while (e->umax[v0] == e->umax[v0 + 1]) ++v0;
+        e->umax[v] = v0;
+        ++v0;
+    }
+    e->level = (uint8_t**)calloc(nlevels, sizeof(uint8_t*));
+    e->blurred = (uint8_t**)calloc(nlevels, sizeof(uint8_t*));
+    e->lw = (int*)calloc(nlevels, sizeof(int));
+    e->lh = (int*)calloc(nlevels, sizeof(int));
+    e->cand = (Cand**)calloc(nlevels, sizeof(Cand*));
+    e->ncand = (int*)calloc(nlevels, sizeof(int));
+    e->capcand = (int*)calloc(nlevels, sizeof(int));
+    e->lkp = (OrcKeyPoint**)calloc(nlevels, sizeof(OrcKeyPoint*));
+    e->nlkp = (int*)calloc(nlevels, sizeof(int));
+    return e;
+}
+
+static void extractor_clear(OrcExtractor* e)
+{
+    for (int l = 0; l < e->nlevels; l++) {
+        free(e->level[l]); e->level[l] = NULL;
+        free(e->blurred[l]); e->blurred[l] = NULL;
+        free(e->cand[l]); e->cand[l] = NULL; e->ncand[l] = 0; e->capcand[l] = 0;
+        free(e->lkp[l]); e->lkp[l] = NULL; e->nlkp[l] = 0;
+    }
+}
+
+void orc_extractor_destroy(OrcExtractor* e)
+{
+    if (!e) return;
+    extractor_clear(e);
+    free(e->scale); free(e->invScale); free(e->sigma2); free(e->invSigma2); free(e->featuresPerLevel);
+    free(e->level); free(e->blurred); free(e->lw); free(e->lh);
+    free(e->cand); free(e->ncand); free(e->capcand); free(e->lkp); free(e->nlkp);
+    free(e);
+}
+
+void orc_extractor_tables(const OrcExtractor* e, float* scale, float* inv_scale, float* sigma2,
+                          float* inv_sigma2, int32_t* fpl, int32_t* umax16)
+{
+    for (int i = 0; i < e->nlevels; i++) {
+        if (scale) scale[i] = e->scale[i];
+        if (inv_scale) inv_scale[i] = e->invScale[i];
+        if (sigma2) sigma2[i] = e->sigma2[i];
+        if (inv_sigma2) inv_sigma2[i] = e->invSigma2[i];
+        if (fpl) fpl[i] = e->featuresPerLevel[i];
+    }
+    if (umax16) for (int i = 0; i <= HALF_PATCH_SIZE; i++) umax16[i] = e->umax[i];
+}
+
+/* ---- DistributeOctTree, R/src/ORBextractor.cc:479-761 ---- */
+typedef struct ONode {
+    int x0, y0, x1, y1;          /* UL=(x0,y0) UR=(x1,y0) BL=(x0,y1) BR=(x1,y1) */
+    int* keys; int nkeys;
+    int noMore;
+    long seq;                    /* creation sequence = canonical stand-in for the heap address (:682) */
+    struct ONode *prev, *next;
+} ONode;
+
+typedef struct { ONode *head, *tail; int size; long nextSeq; } OList;
+
+static ONode* onode_new(OList* L, int x0, int y0, int x1, int y1, int cap)
+{
+    ONode* n = (ONode*)calloc(1, sizeof(ONode));
+    n->x0 = x0; n->y0 = y0; n->x1 = x1; n->y1 = y1;
+    n->keys = (int*)malloc(sizeof(int) * (cap > 0 ? cap : 1));
+    n->seq = L->nextSeq++;
+    return n;
+}
+static void olist_push_front(OList* L, ONode* n)
+{
+    n->prev = NULL; n->next = L->head;
+    if (L->head) L->head->prev = n; else L->tail = n;
+    L->head = n; L->size++;
+}
+static void olist_push_back(OList* L, ONode* n)
+{
+    n->next = NULL; n->prev = L->tail;
+    if (L->tail) L->tail->next = n; else L->head = n;
+    L->tail = n; L->size++;
+}
+static ONode* olist_erase(OList* L, ONode* n)
+{
+    ONode* nx = n->next;
+    if (n->prev) n->prev->next = n->next; else L->head = n->next;
+    if (n->next) n->next->prev = n->prev; else L->tail = n->prev;
+    L->size--;
+    free(n->keys); free(n);
+    return nx;
+}
+
+/* ExtractorNode::DivideNode, :479-535 */
+static void divide_node(OList* L, const ONode* p, const Cand* pts, ONode* c[4])
+{
+    const int halfX = (int)ceilf((float)(p->x1 - p->x0) / 2);
+    const int halfY = (int)ceilf((float)(p->y1 - p->y0) / 2);
+    const int mx = p->x0 + halfX, my = p->y0 + halfY;
+    c[0] = onode_new(L, p->x0, p->y0, mx, my, p->nkeys);
+    c[1] = onode_new(L, mx, p->y0, p->x1, my, p->nkeys);
+    c[2] = onode_new(L, p->x0, my, mx, p->y1, p->nkeys);
+    c[3] = onode_new(L, mx, my, p->x1, p->y1, p->nkeys);
+    for (int i = 0; i < p->nkeys; i++) {
+        const Cand* kp = &pts[p->keys[i]];
+        ONode* d;
+        if (kp->x < (float)mx) d = (kp->y < (float)my) ? c[0] : c[2];
+        else d = (kp->y < (float)my) ? c[1] : c[3];
+        d->keys[d->nkeys++] = p->keys[i];
+    }
+    for (int k = 0; k < 4; k++) if (c[k]->nkeys == 1) c[k]->noMore = 1;
+}
+
+typedef struct { int size; long seq; ONode* node; } SizeNode;
+static int cmp_sizenode(const void* a, const void* b)
+{
+    const SizeNode* A = (const SizeNode*)a; const SizeNode* B = (const SizeNode*)b;
+    if (A->size != B->size) return A->size < B->size ? -1 : 1;
+    return A->seq < B->seq ? -1 : (A->seq > B->seq ? 1 : 0);
+}
+
+/* push the non-empty children to the front (n1..n4), record the multi-point ones; returns how many recorded */
+static int push_children(OList* L, ONode* c[4], SizeNode* vec, int* nvec)
+{
+    int expand = 0;
+    for (int k = 0; k < 4; k++) {
+        if (c[k]->nkeys > 0) {
+            olist_push_front(L, c[k]);
+            if (c[k]->nkeys > 1) {
+                expand++;
+                vec[*nvec].size = c[k]->nkeys; vec[*nvec].seq = c[k]->seq; vec[*nvec].node = c[k];
+                (*nvec)++;
+            }
+        } else {
+            free(c[k]->keys); free(c[k]);
+        }
+    }
+    return expand;
+}
+
+static int distribute_octree(const Cand* pts, int n, int minX, int maxX, int minY, int maxY, int N,
+                             Cand* out, int cap)
+{
+    OList L; memset(&L, 0, sizeof(L));
+    int nIni = (int)roundf((float)(maxX - minX) / (maxY - minY));
+    if (nIni < 1) nIni = 1;     /* the reference would divide by zero; images this tall are out of scope */
+    const float hX = (float)(maxX - minX) / nIni;
+    ONode** ini = (ONode**)malloc(sizeof(ONode*) * nIni);
+    for (int i = 0; i < nIni; i++) {
+        ONode* r = onode_new(&L, (int)(hX * (float)i), 0, (int)(hX * (float)(i + 1)), maxY - minY, n);
+        olist_push_back(&L, r);
+        ini[i] = r;
+    }
+    for (int i = 0; i < n; i++) {
+        int r = (int)(pts[i].x / hX);
+        if (r >= nIni) r = nIni - 1;      /* cannot happen for x < maxX-minX; guard only */
+        ini[r]->keys[ini[r]->nkeys++] = i;
+    }
+    free(ini);
+    for (ONode* it = L.head; it;) {
+        if (it->nkeys == 1) { it->noMore = 1; it = it->next; }
+        else if (it->nkeys == 0) it = olist_erase(&L, it);
+        else it = it->next;
+    }
+    int finish = 0;
+    int vcap = 4 * (n + 8) + 16;
+    SizeNode* vec = (SizeNode*)malloc(sizeof(SizeNode) * vcap);
+    SizeNode* prevVec = (SizeNode*)malloc(sizeof(SizeNode) * vcap);
+    int nvec = 0;
+    while (!finish) {
+        int prevSize = L.size;
+        int nToExpand = 0;
+        nvec = 0;
+        for (ONode* it = L.head; it;) {
+            if (it->noMore) { it = it->next; continue; }
+            ONode* c[4];
+            divide_node(&L, it, pts, c);
+            nToExpand += push_children(&L, c, vec, &nvec);
+            it = olist_erase(&L, it);
+        }
+        if (L.size >= N || L.size == prevSize) {
+            finish = 1;
+        } else if (L.size + nToExpand * 3 > N) {
+            while (!finish) {
+                prevSize = L.size;
+                int nprev = nvec;
+                memcpy(prevVec, vec, sizeof(SizeNode) * nvec);
+                nvec = 0;
+                qsort(prevVec, nprev, sizeof(SizeNode), cmp_sizenode);
+                for (int j = nprev - 1; j >= 0; j--) {
+                    ONode* c[4];
+                    divide_node(&L, prevVec[j].node, pts, c);
+                    push_children(&L, c, vec, &nvec);
+                    olist_erase(&L, prevVec[j].node);
+                    if (L.size >= N) break;
+                }
+                if (L.size >= N || L.size == prevSize) finish = 1;
+            }
+        }
+    }
+    free(vec); free(prevVec);
+    int nout = 0;
+    for (ONode* it = L.head; it; it = it->next) {
+        int best = it->keys[0];
+        float maxr = pts[best].r;
+        for (int k = 1; k < it->nkeys; k++)
+            if (pts[it->keys[k]].r > maxr) { best = it->keys[k]; maxr = pts[best].r; }
+        if (nout < cap) out[nout] = pts[best];
+        nout++;
+    }
+    while (L.head) olist_erase(&L, L.head);
+    return nout;
+}
+
+int orc_distribute_octree(const float* xyr, int n, int minX, int maxX, int minY, int maxY, int N,
+                          float* out_xyr, int cap)
+{
+    return distribute_octree((const Cand*)xyr, n, minX, maxX, minY, maxY, N, (Cand*)out_xyr, cap);
+}
+
+/* IC_Angle, R/src/ORBextractor.cc:75-102 */
+static float ic_angle(const uint8_t* img, int step, float px, float py, const int* umax)
+{
+    int m_01 = 0, m_10 = 0;
+    const uint8_t* center = img + (size_t)orc_cv_round_f(py) * step + orc_cv_round_f(px);
+    for (int u = -HALF_PATCH_SIZE; u <= HALF_PATCH_SIZE; ++u) m_10 += u * center[u];
+    for (int v = 1; v <= HALF_PATCH_SIZE; ++v) {
+        int v_sum = 0;
+        int d = umax[v];
+        for (int u = -d; u <= d; ++u) {
+            int val_plus = center[u + v * step], val_minus = center[u - v * step];
+            v_sum += (val_plus - val_minus);
+            m_10 += u * (val_plus + val_minus);
+        }
+        m_01 += v * v_sum;
+    }
+    return orc_fast_atan2((float)m_01, (float)m_10);
+}
+
+/* computeOrbDescriptor, R/src/ORBextractor.cc:105-145.  `cos(angle)` on a float under
+ * `using namespace std` (:65) resolves to the float overload, i.e. cosf/sinf. */
+static void orb_descriptor(const OrcKeyPoint* kpt, const uint8_t* img, int step, uint8_t* desc)
+{
+    const float factorPI = (float)(3.1415926535897932384626433832795 / 180.f);
+    float angle = (float)kpt->angle * factorPI;
+    float a = cosf(angle), b = sinf(angle);
+    const uint8_t* center = img + (size_t)orc_cv_round_f(kpt->y) * step + orc_cv_round_f(kpt->x);
+    const int32_t* pat = kPattern;
+#define GET_VALUE(idx) \
+    center[orc_cv_round_f(pat[2 * (idx)] * b + pat[2 * (idx) + 1] * a) * step + \
+           orc_cv_round_f(pat[2 * (idx)] * a - pat[2 * (idx) + 1] * b)]
+    for (int i = 0; i < 32; ++i, pat += 32) {
+        int val = 0;
+        for (int k = 0; k < 8; k++) {
+            int t0 = GET_VALUE(2 * k), t1 = GET_VALUE(2 * k + 1);
+            val |= (t0 < t1) << k;
+        }
+        desc[i] = (uint8_t)val;
+    }
+#undef GET_VALUE
+}
+
+static void cand_push(OrcExtractor* e, int l, float x, float y, float r)
+{
+    if (e->ncand[l] == e->capcand[l]) {
+        e->capcand[l] = e->capcand[l] ? e->capcand[l] * 2 : 4096;
+        e->cand[l] = (Cand*)realloc(e->cand[l], sizeof(Cand) * e->capcand[l]);
+    }
+    Cand* c = &e->cand[l][e->ncand[l]++];
+    c->x = x; c->y = y; c->r = r;
+}
+
+/* ComputePyramid, R/src/ORBextractor.cc:1152-1177.  The 19-px reflected border the reference
+ * materialises is never read by anything downstream (all keypoints are >= 19 px inside) and is omitted. */
+static void compute_pyramid(OrcExtractor* e, const uint8_t* img, int w, int h, int stride)
+{
+    for (int l = 0; l < e->nlevels; l++) {
+        float scale = e->invScale[l];
+        int sw = orc_cv_round_f((float)w * scale), sh = orc_cv_round_f((float)h * scale);
+        e->lw[l] = sw; e->lh[l] = sh;
+        e->level[l] = (uint8_t*)malloc((size_t)(sw > 0 ? sw : 1) * (sh > 0 ? sh : 1));
+        if (l == 0) {
+            for (int y = 0; y < h; y++) memcpy(e->level[0] + (size_t)y * w, img + (size_t)y * stride, w);
+        } else {
+            orc_resize_linear_u8(e->level[l - 1], e->lw[l - 1], e->lh[l - 1], e->lw[l - 1],
+                                 e->level[l], sw, sh, sw);
+        }
+    }
+}
+
+/* ComputeKeyPointsOctTree, R/src/ORBextractor.cc:763-878 */
+static void compute_keypoints_octree(OrcExtractor* e)
+{
+    const float W = 30;
+    int32_t* cell = (int32_t*)malloc(sizeof(int32_t) * 3 * 8192);
+    for (int level = 0; level < e->nlevels; ++level) {
+        const int minBorderX = EDGE_THRESHOLD - 3;
+        const int minBorderY = minBorderX;
+        const int maxBorderX = e->lw[level] - EDGE_THRESHOLD + 3;
+        const int maxBorderY = e->lh[level] - EDGE_THRESHOLD + 3;
+        const float width = (float)(maxBorderX - minBorderX);
+        const float height = (float)(maxBorderY - minBorderY);
+        const int nCols = (int)(width / W);
+        const int nRows = (int)(height / W);
+        e->ncand[level] = 0;
+        if (nCols > 0 && nRows > 0) {
+            const int wCell = (int)ceilf(width / nCols);
+            const int hCell = (int)ceilf(height / nRows);
+            for (int i = 0; i < nRows; i++) {
+                const float iniY = (float)(minBorderY + i * hCell);
+                float maxY = iniY + hCell + 6;
+                if (iniY >= maxBorderY - 3) continue;
+                if (maxY > maxBorderY) maxY = (float)maxBorderY;
+                for (int j = 0; j < nCols; j++) {
+                    const float iniX = (float)(minBorderX + j * wCell);
+                    float maxX = iniX + wCell + 6;
+                    if (iniX >= maxBorderX - 6) continue;
+                    if (maxX > maxBorderX) maxX = (float)maxBorderX;
+                    const uint8_t* sub = e->level[level] + (size_t)(int)iniY * e->lw[level] + (int)iniX;
+                    int cw = (int)maxX - (int)iniX, ch = (int)maxY - (int)iniY;
+                    int nc = orc_fast9_16(sub, cw, ch, e->lw[level], e->iniTh, 1, cell, 8192);
+                    if (nc == 0) nc = orc_fast9_16(sub, cw, ch, e->lw[level], e->minTh, 1, cell, 8192);
+                    for (int k = 0; k < nc; k++)
+                        cand_push(e, level, (float)(cell[k * 3] + j * wCell), (float)(cell[k * 3 + 1] + i * hCell),
+                                  (float)cell[k * 3 + 2]);
+                }
+            }
+        }
+        int N = e->featuresPerLevel[level];
+        int cap = e->ncand[level] + 8;
+        Cand* kept = (Cand*)malloc(sizeof(Cand) * cap);
+        int nk = 0;
+        if (e->ncand[level] > 0)
+            nk = distribute_octree(e->cand[level], e->ncand[level], minBorderX, maxBorderX, minBorderY, maxBorderY,
+                                   N, kept, cap);
+        const int scaledPatchSize = (int)(PATCH_SIZE * e->scale[level]);
+        e->lkp[level] = (OrcKeyPoint*)malloc(sizeof(OrcKeyPoint) * (nk > 0 ? nk : 1));
+        e->nlkp[level] = nk;
+        for (int i = 0; i < nk; i++) {
+            OrcKeyPoint* kp = &e->lkp[level][i];
+            kp->x = kept[i].x + minBorderX;
+            kp->y = kept[i].y + minBorderY;
+            kp->size = (float)scaledPatchSize;
+            kp->angle = -1;
+            kp->response = kept[i].r;
+            kp->octave = level;
+            kp->class_id = -1;
+        }
+        free(kept);
+    }
+    free(cell);
+    for (int level = 0; level < e->nlevels; ++level)
+        for (int i = 0; i < e->nlkp[level]; i++)
+            e->lkp[level][i].angle = ic_angle(e->level[level], e->lw[level], e->lkp[level][i].x,
+                                              e->lkp[level][i].y, e->umax);
+}
+
+/* ORBextractor::operator(), R/src/ORBextractor.cc:1068-1150 */
+int orc_extract(OrcExtractor* e, const uint8_t* img, int w, int h, int stride, int lap0, int lap1,
+                OrcKeyPoint* kps, uint8_t* desc, int cap, int* n_out)
+{
+    if (n_out) *n_out = 0;
+    if (!img || w <= 0 || h <= 0) return -1;
+    extractor_clear(e);
+    compute_pyramid(e, img, w, h, stride);
+    compute_keypoints_octree(e);
+    int nkeypoints = 0;
+    for (int l = 0; l < e->nlevels; l++) nkeypoints += e->nlkp[l];
+    if (n_out) *n_out = nkeypoints;
+    if (nkeypoints > cap) return -2;
+    int monoIndex = 0, stereoIndex = nkeypoints - 1;
+    uint8_t d[32];
+    for (int level = 0; level < e->nlevels; ++level) {
+        int nl = e->nlkp[level];
+        if (nl == 0) continue;
+        e->blurred[level] = (uint8_t*)malloc((size_t)e->lw[level] * e->lh[level]);
+        orc_gaussian_blur7(e->level[level], e->lw[level], e->lh[level], e->lw[level], e->blurred[level], e->lw[level]);
+        float scale = e->scale[level];
+        for (int i = 0; i < nl; i++) {
+            OrcKeyPoint kp = e->lkp[level][i];
+            orb_descriptor(&kp, e->blurred[level], e->lw[level], d);
+            if (level != 0) { kp.x *= scale; kp.y *= scale; }
+            int slot;
+            if (kp.x >= lap0 && kp.x <= lap1) slot = stereoIndex--;
+            else slot = monoIndex++;
+            kps[slot] = kp;
+            memcpy(desc + (size_t)slot * 32, d, 32);
+        }
+    }
+    return monoIndex;
+}
+
+int orc_level_size(const OrcExtractor* e, int level, int* w, int* h)
+{
+    if (level < 0 || level >= e->nlevels) return -1;
+    *w = e->lw[level]; *h = e->lh[level];
+    return 0;
+}
+const uint8_t* orc_level_image(const OrcExtractor* e, int level) { return e->level[level]; }
+const uint8_t* orc_level_blurred(const OrcExtractor* e, int level) { return e->blurred[level]; }
+int orc_level_candidates(const OrcExtractor* e, int level, const float** xyr)
+{
+    *xyr = (const float*)e->cand[level];
+    return e->ncand[level];
+}
+int orc_level_keypoints(const OrcExtractor* e, int level, const OrcKeyPoint** kps)
+{
+    *kps = e->lkp[level];
+    return e->nlkp[level];
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Matching
+ * ---------------------------------------------------------------------------------------- */
+
+/* ORBmatcher::DescriptorDistance, R/src/ORBmatcher.cc:2358-2374 (SWAR popcount of 8 x 32 bit) */
+int orc_hamming256(const uint8_t* a, const uint8_t* b)
+{
+    int dist = 0;
+    for (int i = 0; i < 8; i++) {
+        uint32_t pa, pb;
+        memcpy(&pa, a + 4 * i, 4); memcpy(&pb, b + 4 * i, 4);
+        uint32_t v = pa ^ pb;
+        v = v - ((v >> 1) & 0x55555555);
+        v = (v & 0x33333333) + ((v >> 2) & 0x33333333);
+        dist += (((v + (v >> 4)) & 0xF0F0F0F) * 0x1010101) >> 24;
+    }
+    return dist;
+}
+
+/* cv::BFMatcher(NORM_HAMMING).knnMatch(q, t, 2) as called at R/src/Frame.cc:1130: top-2 by
+ * (distance, trainIdx) lexicographic. */
+void orc_bf_knn2(const uint8_t* q, int nq, const uint8_t* t, int nt, int32_t* idx, int32_t* dist)
+{
+    for (int i = 0; i < nq; i++) {
+        int b0 = INT_MAX, b1 = INT_MAX, i0 = -1, i1 = -1;
+        for (int j = 0; j < nt; j++) {
+            int d = orc_hamming256(q + (size_t)i * 32, t + (size_t)j * 32);
+            if (d < b0) { b1 = b0; i1 = i0; b0 = d; i0 = j; }
+            else if (d < b1) { b1 = d; i1 = j; }
+        }
+        idx[i * 2] = i0; idx[i * 2 + 1] = i1;
+        dist[i * 2] = i0 >= 0 ? b0 : -1; dist[i * 2 + 1] = i1 >= 0 ? b1 : -1;
+    }
+}
+
+/* Frame::AssignFeaturesToGrid / PosInGrid, R/src/Frame.cc:360-391, 699-709 */
+struct OrcGrid {
+    float minX, minY, maxX, maxY, wInv, hInv;
+    int* start;   /* GRID_COLS*GRID_ROWS+1, cell (ix,iy) -> ix*GRID_ROWS+iy */
+    int* items;
+};
+
+OrcGrid* orc_grid_build(const OrcKeyPoint* kps, int n, float minX, float maxX, float minY, float maxY)
+{
+    OrcGrid* g = (OrcGrid*)calloc(1, sizeof(OrcGrid));
+    g->minX = minX; g->minY = minY; g->maxX = maxX; g->maxY = maxY;
+    g->wInv = (float)GRID_COLS / (maxX - minX);
+    g->hInv = (float)GRID_ROWS / (maxY - minY);
+    const int nc = GRID_COLS * GRID_ROWS;
+    g->start = (int*)calloc(nc + 1, sizeof(int));
+    g->items = (int*)malloc(sizeof(int) * (n > 0 ? n : 1));
+    int* cellOf = (int*)malloc(sizeof(int) * (n > 0 ? n : 1));
+    for (int i = 0; i < n; i++) {
+        int px = (int)roundf((kps[i].x - minX) * g->wInv);
+        int py = (int)roundf((kps[i].y - minY) * g->hInv);
+        if (px < 0 || px >= GRID_COLS || py < 0 || py >= GRID_ROWS) { cellOf[i] = -1; continue; }
+        cellOf[i] = px * GRID_ROWS + py;
+        g->start[cellOf[i] + 1]++;
+    }
+    for (int c = 0; c < nc; c++) g->start[c + 1] += g->start[c];
+    int* fill = (int*)calloc(nc, sizeof(int));
+    for (int i = 0; i < n; i++)
+        if (cellOf[i] >= 0) g->items[g->start[cellOf[i]] + fill[cellOf[i]]++] = i;
+    free(fill); free(cellOf);
+    return g;
+}
+void orc_grid_destroy(OrcGrid* g) { if (g) { free(g->start); free(g->items); free(g); } }
+
+/* Frame::GetFeaturesInArea, R/src/Frame.cc:628-697 */
+int orc_features_in_area(const OrcGrid* g, const OrcKeyPoint* kps, float x, float y, float r,
+                         int minLevel, int maxLevel, int32_t* out, int cap)
+{
+    int n = 0;
+    const float factorX = r, factorY = r;
+    int nMinCellX = (int)floorf((x - g->minX - factorX) * g->wInv); if (nMinCellX < 0) nMinCellX = 0;
+    if (nMinCellX >= GRID_COLS) return 0;
+    int nMaxCellX = (int)ceilf((x - g->minX + factorX) * g->wInv); if (nMaxCellX > GRID_COLS - 1) nMaxCellX = GRID_COLS - 1;
+    if (nMaxCellX < 0) return 0;
+    int nMinCellY = (int)floorf((y - g->minY - factorY) * g->hInv); if (nMinCellY < 0) nMinCellY = 0;
+    if (nMinCellY >= GRID_ROWS) return 0;
+    int nMaxCellY = (int)ceilf((y - g->minY + factorY) * g->hInv); if (nMaxCellY > GRID_ROWS - 1) nMaxCellY = GRID_ROWS - 1;
+    if (nMaxCellY < 0) return 0;
+    const int bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
+    for (int ix = nMinCellX; ix <= nMaxCellX; ix++)
+        for (int iy = nMinCellY; iy <= nMaxCellY; iy++) {
+            int c = ix * GRID_ROWS + iy;
+            for (int j = g->start[c]; j < g->start[c + 1]; j++) {
+                const OrcKeyPoint* kp = &kps[g->items[j]];
+                if (bCheckLevels) {
+                    if (kp->octave < minLevel) continue;
+                    if (maxLevel >= 0 && kp->octave > maxLevel) continue;
+                }
+                const float distx = kp->x - x, disty = kp->y - y;
+                if (fabsf(distx) < factorX && fabsf(disty) < factorY) {
+                    if (n < cap) out[n] = g->items[j];
+                    n++;
+                }
+            }
+        }
+    return n;
+}
+
+/* ORBmatcher::ComputeThreeMaxima, R/src/ORBmatcher.cc:2312-2353 */
+static void three_maxima(const int* sizes, int L, int* ind1, int* ind2, int* ind3)
+{
+    int max1 = 0, max2 = 0, max3 = 0;
+    *ind1 = *ind2 = *ind3 = -1;
+    for (int i = 0; i < L; i++) {
+        const int s = sizes[i];
+        if (s > max1) { max3 = max2; max2 = max1; max1 = s; *ind3 = *ind2; *ind2 = *ind1; *ind1 = i; }
+        else if (s > max2) { max3 = max2; max2 = s; *ind3 = *ind2; *ind2 = i; }
+        else if (s > max3) { max3 = s; *ind3 = i; }
+    }
+    if (max2 < 0.1f * (float)max1) { *ind2 = -1; *ind3 = -1; }
+    else if (max3 < 0.1f * (float)max1) { *ind3 = -1; }
+}
+
+static int rot_bin(float a1, float a2)
+{
+    const float factor = 1.0f / HISTO_LENGTH;
+    float rot = a1 - a2;
+    if (rot < 0.0) rot += 360.0f;
+    int bin = (int)roundf(rot * factor);
+    if (bin == HISTO_LENGTH) bin = 0;
+    return bin;
+}
+
+/* ORBmatcher::SearchForInitialization, R/src/ORBmatcher.cc:702-817 */
+int orc_search_for_initialization(const OrcKeyPoint* k1, const uint8_t* d1, int n1,
+                                  const OrcKeyPoint* k2, const uint8_t* d2, int n2,
+                                  float minX, float maxX, float minY, float maxY,
+                                  float* prev_xy, int32_t* matches12, int window,
+                                  float nnratio, int check_ori)
+{
+    int nmatches = 0;
+    OrcGrid* g = orc_grid_build(k2, n2, minX, maxX, minY, maxY);
+    int* histIdx = (int*)malloc(sizeof(int) * (n1 > 0 ? n1 : 1));   /* bin of each pushed i1, in push order */
+    int* histBin = (int*)malloc(sizeof(int) * (n1 > 0 ? n1 : 1));
+    int nhist = 0;
+    int sizes[HISTO_LENGTH]; memset(sizes, 0, sizeof(sizes));
+    int* matchedDist = (int*)malloc(sizeof(int) * (n2 > 0 ? n2 : 1));
+    int* matches21 = (int*)malloc(sizeof(int) * (n2 > 0 ? n2 : 1));
+    int32_t* cand = (int32_t*)malloc(sizeof(int32_t) * (n2 > 0 ? n2 : 1));
+    for (int i = 0; i < n1; i++) matches12[i] = -1;
+    for (int i = 0; i < n2; i++) { matchedDist[i] = INT_MAX; matches21[i] = -1; }
+    for (int i1 = 0; i1 < n1; i1++) {
+        if (k1[i1].octave > 0) continue;
+        int nc = orc_features_in_area(g, k2, prev_xy[i1 * 2], prev_xy[i1 * 2 + 1], (float)window, 0, 0, cand, n2);
+        if (nc == 0) continue;
+        int bestDist = INT_MAX, bestDist2 = INT_MAX, bestIdx2 = -1;
+        for (int c = 0; c < nc; c++) {
+            int i2 = cand[c];
+            int dist = orc_hamming256(d1 + (size_t)i1 * 32, d2 + (size_t)i2 * 32);
+            if (matchedDist[i2] <= dist) continue;
+            if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestIdx2 = i2; }
+            else if (dist < bestDist2) bestDist2 = dist;
+        }
+        if (bestDist <= TH_LOW) {
+            if (bestDist < (float)bestDist2 * nnratio) {
+                if (matches21[bestIdx2] >= 0) { matches12[matches21[bestIdx2]] = -1; nmatches--; }
+                matches12[i1] = bestIdx2;
+                matches21[bestIdx2] = i1;
+                matchedDist[bestIdx2] = bestDist;
+                nmatches++;
+                if (check_ori) {
+                    int bin = rot_bin(k1[i1].angle, k2[bestIdx2].angle);
+                    histIdx[nhist] = i1; histBin[nhist] = bin; nhist++;
+                    sizes[bin]++;
+                }
+            }
+        }
+    }
+    if (check_ori) {
+        int ind1, ind2, ind3;
+        three_maxima(sizes, HISTO_LENGTH, &ind1, &ind2, &ind3);
+        for (int k = 0; k < nhist; k++) {
+            int b = histBin[k];
+            if (b == ind1 || b == ind2 || b == ind3) continue;
+            int idx1 = histIdx[k];
+            if (matches12[idx1] >= 0) { matches12[idx1] = -1; nmatches--; }
+        }
+    }
+    for (int i1 = 0; i1 < n1; i1++)
+        if (matches12[i1] >= 0) {
+            prev_xy[i1 * 2] = k2[matches12[i1]].x;
+            prev_xy[i1 * 2 + 1] = k2[matches12[i1]].y;
+        }
+    free(histIdx); free(histBin); free(matchedDist); free(matches21); free(cand);
+    orc_grid_destroy(g);
+    return nmatches;
+}
+
+/* SearchByProjection, mono/left-image branches, on flat arrays.
+ * mode 0: R/src/ORBmatcher.cc:1970-2091 + :2163-2185;  mode 1: R/src/ORBmatcher.cc:44-143. */
+int orc_search_by_projection(int mode, const OrcProjQuery* q, const uint8_t* qdesc, int nq,
+                             const OrcKeyPoint* k2, const uint8_t* d2, const float* uright2, int n2,
+                             float minX, float maxX, float minY, float maxY,
+                             int32_t* assigned, float nnratio, int check_ori)
+{
+    int nmatches = 0;
+    OrcGrid* g = orc_grid_build(k2, n2, minX, maxX, minY, maxY);
+    int32_t* cand = (int32_t*)malloc(sizeof(int32_t) * (n2 > 0 ? n2 : 1));
+    int* histIdx = (int*)malloc(sizeof(int) * (nq > 0 ? nq : 1));
+    int* histBin = (int*)malloc(sizeof(int) * (nq > 0 ? nq : 1));
+    int nhist = 0;
+    int sizes[HISTO_LENGTH]; memset(sizes, 0, sizeof(sizes));
+    for (int i = 0; i < nq; i++) {
+        if (!q[i].valid) continue;
+        int nc = orc_features_in_area(g, k2, q[i].u, q[i].v, q[i].r, q[i].minl, q[i].maxl, cand, n2);
+        if (nc == 0) continue;
+        int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+        for (int c = 0; c < nc; c++) {
+            int i2 = cand[c];
+            if (assigned[i2] >= 0) continue;
+            if (uright2 && uright2[i2] > 0) {
+                const float er = fabsf(q[i].ur - uright2[i2]);
+                if (er > q[i].r) continue;
+            }
+            int dist = orc_hamming256(qdesc + (size_t)i * 32, d2 + (size_t)i2 * 32);
+            if (dist < bestDist) {
+                bestDist2 = bestDist; bestDist = dist;
+                bestLevel2 = bestLevel; bestLevel = k2[i2].octave;
+                bestIdx = i2;
+            } else if (mode == 1 && dist < bestDist2) {
+                bestLevel2 = k2[i2].octave; bestDist2 = dist;
+            }
+        }
+        if (bestDist <= TH_HIGH) {
+            if (mode == 1) {
+                if (bestLevel == bestLevel2 && bestDist > nnratio * bestDist2) continue;
+                assigned[bestIdx] = i;
+                nmatches++;
+            } else {
+                assigned[bestIdx] = i;
+                nmatches++;
+                if (check_ori) {
+                    int bin = rot_bin(q[i].angle, k2[bestIdx].angle);
+                    histIdx[nhist] = bestIdx; histBin[nhist] = bin; nhist++;
+                    sizes[bin]++;
+                }
+            }
+        }
+    }
+    if (mode == 0 && check_ori) {
+        int ind1, ind2, ind3;
+        three_maxima(sizes, HISTO_LENGTH, &ind1, &ind2, &ind3);
+        for (int k = 0; k < nhist; k++) {
+            int b = histBin[k];
+            if (b != ind1 && b != ind2 && b != ind3) { assigned[histIdx[k]] = -1; nmatches--; }
+        }
+    }
+    free(cand); free(histIdx); free(histBin);
+    orc_grid_destroy(g);
+    return nmatches;
+}
+
+/* Frame::ComputeStereoMatches, descriptor search, R/src/Frame.cc:785-868 */
+void orc_stereo_band_match(const OrcKeyPoint* kl, const uint8_t* dl, int nl,
+                           const OrcKeyPoint* kr, const uint8_t* dr, int nr,
+                           const float* scale_factors, int nrows, float minD, float maxD,
+                           int32_t* best_idx, int32_t* best_dist)
+{
+    int* cnt = (int*)calloc(nrows + 1, sizeof(int));
+    for (int iR = 0; iR < nr; iR++) {
+        const float kpY = kr[iR].y;
+        const float r = 2.0f * scale_factors[kr[iR].octave];
+        const int maxr = (int)ceilf(kpY + r), minr = (int)floorf(kpY - r);
+        for (int yi = minr; yi <= maxr; yi++) if (yi >= 0 && yi < nrows) cnt[yi + 1]++;
+    }
+    for (int y = 0; y < nrows; y++) cnt[y + 1] += cnt[y];
+    int* items = (int*)malloc(sizeof(int) * (cnt[nrows] > 0 ? cnt[nrows] : 1));
+    int* fill = (int*)calloc(nrows, sizeof(int));
+    for (int iR = 0; iR < nr; iR++) {
+        const float kpY = kr[iR].y;
+        const float r = 2.0f * scale_factors[kr[iR].octave];
+        const int maxr = (int)ceilf(kpY + r), minr = (int)floorf(kpY - r);
+        for (int yi = minr; yi <= maxr; yi++)
+            if (yi >= 0 && yi < nrows) items[cnt[yi] + fill[yi]++] = iR;
+    }
+    for (int iL = 0; iL < nl; iL++) {
+        best_idx[iL] = -1; best_dist[iL] = TH_HIGH;
+        const int levelL = kl[iL].octave;
+        const float vL = kl[iL].y, uL = kl[iL].x;
+        int row = (int)vL;
+        if (row < 0 || row >= nrows) continue;
+        if (cnt[row + 1] == cnt[row]) continue;
+        const float minU = uL - maxD, maxU = uL - minD;
+        if (maxU < 0) continue;
+        int bestDist = TH_HIGH, bestIdxR = -1;
+        for (int c = cnt[row]; c < cnt[row + 1]; c++) {
+            const int iR = items[c];
+            if (kr[iR].octave < levelL - 1 || kr[iR].octave > levelL + 1) continue;
+            const float uR = kr[iR].x;
+            if (uR >= minU && uR <= maxU) {
+                const int dist = orc_hamming256(dl + (size_t)iL * 32, dr + (size_t)iR * 32);
+                if (dist < bestDist) { bestDist = dist; bestIdxR = iR; }
+            }
+        }
+        best_idx[iL] = bestIdxR; best_dist[iL] = bestDist;
+    }
+    free(cnt); free(items); free(fill);
+}

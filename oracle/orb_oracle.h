@@ -1,0 +1,112 @@
+/* orb_oracle.h - CPU oracle (TEST INFRASTRUCTURE, not product code).
+ *
+ * Plain-C restatement of the reference's ORB front-end hot path.  Only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+ * load this library; the product path (multi_orbslam3_b200/) never does.
+ *
+ * R/ = /root/reference/src/orb_slam3_ros/orb_slam3/
+ * Reference logic restated:   R/src/ORBextractor.cc:70-145, 408-878, 1059-1177
+ *                             R/src/ORBmatcher.cc:36-222, 702-817, 1970-2186, 2312-2374
+ *                             R/src/Frame.cc:360-391, 628-709, 785-868, 1127-1137
+ * Third-party arithmetic the reference calls but does not contain (OpenCV, unpinned by
+ * R/../CMakeLists.txt:55-65) is restated from OpenCV 4.x's published algorithms and
+ * PINNED against cv2 4.13.0 by tests/test_oracle_pin_cv2.py and tests/golden/.
+ */
+#ifndef ORB_ORACLE_H
+#define ORB_ORACLE_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* binary-compatible with cv::KeyPoint (28 bytes) */
+typedef struct {
+    float x, y;
+    float size;
+    float angle;
+    float response;
+    int32_t octave;
+    int32_t class_id;
+} OrcKeyPoint;
+
+/* ---- OpenCV primitives (restated) ---- */
+void  orc_resize_linear_u8(const uint8_t* src, int sw, int sh, int sstride,
+                           uint8_t* dst, int dw, int dh, int dstride);
+void  orc_gaussian_blur7(const uint8_t* src, int w, int h, int sstride, uint8_t* dst, int dstride);
+/* cv::FAST(img, t, nonmaxSuppression, TYPE_9_16): writes (x,y,score) int triples, returns count */
+int   orc_fast9_16(const uint8_t* img, int w, int h, int stride, int threshold, int nms,
+                   int32_t* out_xys, int cap);
+float orc_fast_atan2(float y, float x);
+int   orc_cv_round_f(float v);
+
+/* ---- extractor ---- */
+typedef struct OrcExtractor OrcExtractor;
+OrcExtractor* orc_extractor_create(int nfeatures, float scale_factor, int nlevels, int ini_th, int min_th);
+void  orc_extractor_destroy(OrcExtractor* e);
+/* tables: out arrays have nlevels entries */
+void  orc_extractor_tables(const OrcExtractor* e, float* scale, float* inv_scale, float* sigma2,
+                           float* inv_sigma2, int32_t* features_per_level, int32_t* umax16);
+/* ORBextractor::operator(): returns monoIndex, or -1 on empty image; *n_out = #keypoints */
+int   orc_extract(OrcExtractor* e, const uint8_t* img, int w, int h, int stride, int lap0, int lap1,
+                  OrcKeyPoint* kps, uint8_t* desc, int cap, int* n_out);
+/* stage taps (valid until the next orc_extract on this handle) */
+int   orc_level_size(const OrcExtractor* e, int level, int* w, int* h);
+const uint8_t* orc_level_image(const OrcExtractor* e, int level);   /* tight stride = w */
+const uint8_t* orc_level_blurred(const OrcExtractor* e, int level); /* NULL when level had no keypoints */
+/* FAST candidates handed to the octree: float triples (x,y,response), coords relative to (16,16) */
+int   orc_level_candidates(const OrcExtractor* e, int level, const float** xyr);
+/* octree output with border added, octave/size/angle set, BEFORE scaling (list order) */
+int   orc_level_keypoints(const OrcExtractor* e, int level, const OrcKeyPoint** kps);
+
+/* standalone DistributeOctTree (canonical tie rule: equal size -> later-created node first) */
+int   orc_distribute_octree(const float* xyr, int n, int minX, int maxX, int minY, int maxY, int N,
+                            float* out_xyr, int cap);
+
+/* ---- matching ---- */
+int   orc_hamming256(const uint8_t* a, const uint8_t* b);
+/* cv::BFMatcher(NORM_HAMMING).knnMatch(k=2): idx/dist are nq*2; missing -> idx -1 */
+void  orc_bf_knn2(const uint8_t* q, int nq, const uint8_t* t, int nt, int32_t* idx, int32_t* dist);
+
+typedef struct OrcGrid OrcGrid;   /* Frame::mGrid, 64 x 48 */
+OrcGrid* orc_grid_build(const OrcKeyPoint* kps, int n, float minX, float maxX, float minY, float maxY);
+void  orc_grid_destroy(OrcGrid* g);
+int   orc_features_in_area(const OrcGrid* g, const OrcKeyPoint* kps, float x, float y, float r,
+                           int minLevel, int maxLevel, int32_t* out, int cap);
+
+/* ORBmatcher::SearchForInitialization; prev_xy (n1*2) is updated in place; returns nmatches */
+int   orc_search_for_initialization(const OrcKeyPoint* k1, const uint8_t* d1, int n1,
+                                    const OrcKeyPoint* k2, const uint8_t* d2, int n2,
+                                    float minX, float maxX, float minY, float maxY,
+                                    float* prev_xy, int32_t* matches12, int window,
+                                    float nnratio, int check_ori);
+
+/* Projection-guided searches on flat arrays (the drop-in ORBmatcher marshals Frame/MapPoint into these).
+ * query i: window centre (u,v), radius r, level range [minl,maxl], 32-byte descriptor, angle.
+ * frame: keypoints/descriptors/grid bounds, uright[n2] (<=0: mono), assigned[n2] in/out (-1 free,
+ * else the query index that owns the keypoint).
+ * mode 0 = SearchByProjection(Frame&,const Frame&,th,bMono)   (ORBmatcher.cc:1970-2186): best only, <=TH_HIGH
+ * mode 1 = SearchByProjection(Frame&,vector<MapPoint*>&,th..) (ORBmatcher.cc:44-214): best+second, level ratio rule */
+typedef struct {
+    float u, v, r;
+    int32_t minl, maxl;
+    float ur;          /* predicted right coordinate for the stereo gate, used when frame uright>0 */
+    float angle;       /* for the rotation histogram (mode 0) */
+    int32_t valid;     /* 0 = query skipped */
+} OrcProjQuery;
+int   orc_search_by_projection(int mode, const OrcProjQuery* q, const uint8_t* qdesc, int nq,
+                               const OrcKeyPoint* k2, const uint8_t* d2, const float* uright2, int n2,
+                               float minX, float maxX, float minY, float maxY,
+                               int32_t* assigned, float nnratio, int check_ori);
+
+/* Frame::ComputeStereoMatches descriptor part (Frame.cc:785-868): per left keypoint the best right
+ * index and distance (dist starts at TH_HIGH=100; idx -1 if none < 100). nrows = level-0 rows. */
+void  orc_stereo_band_match(const OrcKeyPoint* kl, const uint8_t* dl, int nl,
+                            const OrcKeyPoint* kr, const uint8_t* dr, int nr,
+                            const float* scale_factors, int nrows, float minD, float maxD,
+                            int32_t* best_idx, int32_t* best_dist);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
