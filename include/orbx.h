@@ -1,0 +1,192 @@
+/* orbx.h - C ABI of liborbx_b200.so: the B200-native (sm_100a) ORB front-end hot path.
+ *
+ * Drop-in boundary for multi_orbslam3's ORBextractor / ORBmatcher.  The reference has no FFI or
+ * plugin layer: both are concrete C++ classes.  The replacement keeps the two
+ * class headers unchanged (dropin/ORBextractor.h, dropin/ORBmatcher.h) and routes their bodies to
+ * the entry points below.  Every entry point cites the reference code it replaces;
+ * R/ = src/orb_slam3_ros/orb_slam3/ in the reference tree.
+ *
+ * Conventions: extern "C", plain pointers and sizes, int status return (ORBX_OK == 0), no
+ * exceptions, opaque handles, caller-allocated outputs with a capacity and a count-out.
+ * `stream` arguments are a cudaStream_t passed as void* (NULL = the handle's own stream).
+ * There is no CPU fallback: without a CUDA device every create call fails with ORBX_E_CUDA.
+ */
+#ifndef ORBX_H
+#define ORBX_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORBX_OK            0
+#define ORBX_E_INVALID    -1   /* bad argument */
+#define ORBX_E_EMPTY      -2   /* empty image: ORBextractor::operator() returns -1 (R/src/ORBextractor.cc:1072) */
+#define ORBX_E_CUDA       -3   /* CUDA runtime error; see orbx_last_error() */
+#define ORBX_E_CAPACITY   -4   /* an internal or caller buffer was too small; nothing was truncated silently */
+#define ORBX_E_NOMEM      -5
+
+#define ORBX_MAX_LEVELS   12
+#define ORBX_TH_HIGH      100  /* ORBmatcher::TH_HIGH  (R/src/ORBmatcher.cc:36) */
+#define ORBX_TH_LOW       50   /* ORBmatcher::TH_LOW   (R/src/ORBmatcher.cc:37) */
+#define ORBX_HISTO_LENGTH 30   /* ORBmatcher::HISTO_LENGTH (R/src/ORBmatcher.cc:38) */
+#define ORBX_GRID_COLS    64   /* FRAME_GRID_COLS (R/include/Frame.h:39) */
+#define ORBX_GRID_ROWS    48   /* FRAME_GRID_ROWS (R/include/Frame.h:38) */
+
+/* binary-compatible with cv::KeyPoint (28 bytes): pt.x pt.y size angle response octave class_id */
+typedef struct orbx_keypoint {
+    float x, y, size, angle, response;
+    int32_t octave, class_id;
+} orbx_keypoint;
+
+const char* orbx_last_error(void);          /* thread-local, human readable */
+int  orbx_device_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Extractor: replaces class ORBextractor (R/include/ORBextractor.h:47-113).
+ * One handle per reference ORBextractor instance; like the reference it is not re-entrant, distinct
+ * handles run concurrently (R/src/Frame.cc:92-95 runs left/right extractors on two threads).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct orbx_extractor orbx_extractor;
+
+typedef struct orbx_params {
+    int32_t nfeatures;        /* ORBextractor ctor args, R/src/ORBextractor.cc:408-411 */
+    float   scale_factor;
+    int32_t nlevels;
+    int32_t ini_th_fast;
+    int32_t min_th_fast;
+    int32_t max_width;        /* largest image this handle will see */
+    int32_t max_height;
+    int32_t max_batch;        /* frames per batched call (1 for the class wrapper) */
+    int32_t device;           /* CUDA device ordinal */
+    int32_t max_candidates_per_level; /* 0 = default (32768); FAST corners per level above this -> ORBX_E_CAPACITY */
+} orbx_params;
+
+/* ORBextractor::ORBextractor, R/src/ORBextractor.cc:408-468 */
+int  orbx_extractor_create(const orbx_params* p, orbx_extractor** out);
+void orbx_extractor_destroy(orbx_extractor* h);
+
+/* scale tables / per-level quotas: R/include/ORBextractor.h:64-86 getters, R/src/ORBextractor.cc:413-444.
+ * Each out array has nlevels entries; NULL pointers are skipped. */
+int  orbx_extractor_tables(const orbx_extractor* h, float* scale, float* inv_scale, float* sigma2,
+                           float* inv_sigma2, int32_t* features_per_level);
+/* upper bound on keypoints per frame (nfeatures + 3 per level): size outputs with it */
+int  orbx_extractor_max_keypoints(const orbx_extractor* h);
+
+/* ORBextractor::operator(), R/src/ORBextractor.cc:1068-1150.  Synchronous, one host image.
+ * lap0/lap1 = vLappingArea.  *mono_index receives the return value of operator() (monoIndex).
+ * Returns ORBX_E_EMPTY for an empty image (the class wrapper maps it to -1). */
+int  orbx_extract(orbx_extractor* h, const uint8_t* img, int width, int height, int stride,
+                  int lap0, int lap1, orbx_keypoint* kps, uint8_t* desc, int cap, int* n, int* mono_index);
+
+/* Batched operator() over host frames (the e2e path): `batch` frames of equal geometry at
+ * imgs + i*frame_stride; H2D and D2H copies happen inside.  kps: batch*cap, desc: batch*cap*32. */
+int  orbx_extract_batch(orbx_extractor* h, const uint8_t* imgs, int batch, int width, int height,
+                        int stride, size_t frame_stride, int lap0, int lap1,
+                        orbx_keypoint* kps, uint8_t* desc, int cap, int32_t* n, int32_t* mono_index);
+
+/* Batched operator() over DEVICE-resident frames, asynchronous on `stream`; results stay on the
+ * device in the handle's result slots first_slot .. first_slot+batch-1 (slots 0..max_batch). */
+int  orbx_extract_batch_device(orbx_extractor* h, const uint8_t* d_imgs, int batch, int width, int height,
+                               int stride, size_t frame_stride, int lap0, int lap1, int first_slot, void* stream);
+/* copies result slot `from` onto slot `to` (carry the last frame of a batch over as predecessor) */
+int  orbx_extractor_copy_slot(orbx_extractor* h, int from, int to, void* stream);
+/* device views of the result slots: kps [slots][cap], desc [slots][cap][32], n [slots], mono [slots] */
+int  orbx_extractor_results_device(orbx_extractor* h, orbx_keypoint** d_kps, uint8_t** d_desc,
+                                   int32_t** d_n, int32_t** d_mono, int* cap, int* slots);
+/* D2H of `count` result slots starting at first_slot; synchronises `stream`; reports ORBX_E_CAPACITY
+ * raised by any kernel of the batch. */
+int  orbx_extractor_download(orbx_extractor* h, int first_slot, int count, orbx_keypoint* kps, uint8_t* desc,
+                             int cap, int32_t* n, int32_t* mono_index, void* stream);
+int  orbx_extractor_sync(orbx_extractor* h, void* stream);   /* also returns any deferred device error */
+
+/* mvImagePyramid (R/include/ORBextractor.h:88) stays on the device; this is the explicit download the
+ * stereo SAD refinement (R/src/Frame.cc:882-901) needs.  slot = frame within the last batch. */
+int  orbx_pyramid_level_size(const orbx_extractor* h, int level, int* width, int* height);
+int  orbx_pyramid_to_host(orbx_extractor* h, int slot, int level, uint8_t* dst, int dst_stride);
+/* test taps: blurred level (R/src/ORBextractor.cc:1114-1115) and the FAST candidates handed to
+ * DistributeOctTree (R/src/ORBextractor.cc:845-851) as (x,y,response) float triples */
+int  orbx_blurred_to_host(orbx_extractor* h, int slot, int level, uint8_t* dst, int dst_stride);
+int  orbx_candidates_to_host(orbx_extractor* h, int slot, int level, float* xyr, int cap, int* n);
+int  orbx_level_keypoints_to_host(orbx_extractor* h, int slot, int level, float* xyr, int cap, int* n);
+
+/* ------------------------------------------------------------------------------------------------
+ * Matcher: replaces the Hamming searches of class ORBmatcher (R/include/ORBmatcher.h:35-108).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct orbx_matcher orbx_matcher;
+
+typedef struct orbx_matcher_params {
+    int32_t device;
+    int32_t max_keypoints;     /* per frame */
+    int32_t max_batch;         /* frame pairs per batched call */
+    int32_t max_candidates;    /* CSR pool per pair for windowed searches; 0 = default (131072) */
+} orbx_matcher_params;
+
+int  orbx_matcher_create(const orbx_matcher_params* p, orbx_matcher** out);
+void orbx_matcher_destroy(orbx_matcher* m);
+int  orbx_matcher_sync(orbx_matcher* m, void* stream);
+
+/* ORBmatcher::DescriptorDistance (R/src/ORBmatcher.cc:2358-2374) for n descriptor pairs:
+ * out[i] = hamming(a[i], b[i]); host pointers. */
+int  orbx_hamming_pairs(orbx_matcher* m, const uint8_t* a, const uint8_t* b, int n, int32_t* out);
+
+/* cv::BFMatcher(NORM_HAMMING).knnMatch(q, t, 2) as used at R/src/Frame.cc:1127-1137 and by the server's
+ * cross-agent matching: top-2 by (distance, trainIdx).  idx/dist are nq x 2; missing = -1.  Host pointers. */
+int  orbx_bf_knn2(orbx_matcher* m, const uint8_t* q, int nq, const uint8_t* t, int nt, int32_t* idx, int32_t* dist);
+/* same on device pointers, asynchronous.  idx_base is added to every train index (sharded DBs). */
+int  orbx_bf_knn2_device(orbx_matcher* m, const uint8_t* d_q, int nq, const uint8_t* d_t, long long nt,
+                         int32_t* d_idx, int32_t* d_dist, int idx_base, void* stream);
+/* merges nparts partial top-2 tables ([part][nq][2], e.g. all-gathered from the DB shards of the 8 GPUs)
+ * into the global top-2 by (distance, index); device pointers */
+int  orbx_knn2_merge_device(orbx_matcher* m, const int32_t* d_idx_parts, const int32_t* d_dist_parts, int nparts,
+                            int nq, int32_t* d_idx, int32_t* d_dist, void* stream);
+
+/* ORBmatcher::SearchForInitialization, R/src/ORBmatcher.cc:702-817 (with Frame::AssignFeaturesToGrid /
+ * GetFeaturesInArea, R/src/Frame.cc:360-391, 628-697).  bounds = {mnMinX, mnMaxX, mnMinY, mnMaxY}.
+ * prev_xy (n1 x 2, vbPrevMatched) is updated in place; matches12 has n1 entries.  Host pointers. */
+int  orbx_search_for_initialization(orbx_matcher* m, const orbx_keypoint* k1, const uint8_t* d1, int n1,
+                                    const orbx_keypoint* k2, const uint8_t* d2, int n2, const float bounds[4],
+                                    float* prev_xy, int32_t* matches12, int window, float nnratio, int check_ori,
+                                    int* nmatches);
+/* batched over extractor result slots on the device: pair i matches slot a[i] (F1) against slot b[i] (F2)
+ * with vbPrevMatched = F1's keypoint positions (first call of Tracking.cc:2216-2217).  Also runs
+ * orbx_bf_knn2 for every pair when d_knn_idx != NULL.  Outputs on device: matches12 [npairs][cap],
+ * nmatches [npairs], knn idx/dist [npairs][cap][2]. */
+int  orbx_match_slots_device(orbx_matcher* m, orbx_extractor* ex, const int32_t* a, const int32_t* b, int npairs,
+                             const float bounds[4], int window, float nnratio, int check_ori,
+                             int32_t* d_matches12, int32_t* d_nmatches, int32_t* d_knn_idx, int32_t* d_knn_dist,
+                             void* stream);
+
+/* Projection-guided window searches on flat arrays (the drop-in ORBmatcher marshals Frame/MapPoint into
+ * these).  Query i: window centre (u,v), radius r, octave range [minl,maxl] as GetFeaturesInArea takes them,
+ * predicted right coordinate ur (stereo gate), angle (rotation histogram), valid flag.
+ *   mode 0: SearchByProjection(Frame&, const Frame&, th, bMono)      R/src/ORBmatcher.cc:1970-2186
+ *   mode 1: SearchByProjection(Frame&, vector<MapPoint*>&, th, ...)   R/src/ORBmatcher.cc:44-214
+ * assigned[n2]: in = -1 for free keypoints (anything >= 0 is skipped like an occupied mvpMapPoints slot),
+ * out = index of the query that took the keypoint.  Host pointers. */
+typedef struct orbx_proj_query {
+    float u, v, r;
+    int32_t minl, maxl;
+    float ur;
+    float angle;
+    int32_t valid;
+} orbx_proj_query;
+int  orbx_search_by_projection(orbx_matcher* m, int mode, const orbx_proj_query* q, const uint8_t* qdesc, int nq,
+                               const orbx_keypoint* k2, const uint8_t* d2, const float* uright2, int n2,
+                               const float bounds[4], int32_t* assigned, float nnratio, int check_ori, int* nmatches);
+
+/* Frame::ComputeStereoMatches, descriptor search (R/src/Frame.cc:785-868): per left keypoint the best
+ * right index (-1 if none) and its distance (starts at TH_HIGH).  Host pointers. */
+int  orbx_stereo_band_match(orbx_matcher* m, const orbx_keypoint* kl, const uint8_t* dl, int nl,
+                            const orbx_keypoint* kr, const uint8_t* dr, int nr, const float* scale_factors,
+                            int nlevels, int nrows, float min_d, float max_d, int32_t* best_idx, int32_t* best_dist);
+
+/* register-only popcount micro-benchmark: returns measured 32-bit popc per second on `device` (roofline
+ * denominator for the matching kernels) */
+int  orbx_popc_peak(int device, double* popc_per_s, double* lop3_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,495 @@
+// orbx_api.cu - C ABI of the extractor (include/orbx.h): geometry tables, device buffers, launch order.
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include "orbx_internal.h"
+
+static thread_local std::string g_last_error;
+void orbx_set_error(const char* fmt, const char* a, const char* b2)
+{
+    char buf[512];
+    snprintf(buf, sizeof(buf), fmt, a, b2);
+    g_last_error = buf;
+}
+extern "C" const char* orbx_last_error(void) { return g_last_error.c_str(); }
+
+#define CK(call)                                                                          \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess) {                                                          \
+            orbx_set_error("%s failed: %s", #call, cudaGetErrorString(e_));               \
+            return ORBX_E_CUDA;                                                           \
+        }                                                                                 \
+    } while (0)
+
+extern "C" int orbx_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+static inline int cv_round_f(float v) { return (int)lrintf(v); }
+
+struct orbx_extractor {
+    orbx_params p;
+    double scaleFactor;
+    std::vector<float> scale, invScale, sigma2, invSigma2;
+    std::vector<int> featuresPerLevel;
+    int slots;               // result slots = max_batch + 1
+    OrbxGeom geom;           // geometry of the currently configured image size (width == 0: none)
+    OrbxBuffers buf;
+    cudaStream_t stream;
+    // level-0 staging for host images
+    uint8_t* d_level0; int pitch0; long long stride0;
+    uint8_t* h_stage_in;     // pinned
+    orbx_keypoint* h_kps; uint8_t* h_desc; int* h_n; int* h_mono; unsigned* h_err;   // pinned
+    // what the last batch used as level 0 (for pyramid_to_host)
+    const uint8_t* last_level0; int last_pitch0; long long last_stride0; int last_batch;
+    std::vector<void*> allocs;
+};
+
+static int dev_alloc(orbx_extractor* h, void** p, size_t bytes)
+{
+    if (bytes == 0) bytes = 16;
+    CK(cudaMalloc(p, bytes));
+    h->allocs.push_back(*p);
+    return ORBX_OK;
+}
+
+// cv::resize table for one axis (OpenCV imgproc resize.cpp: fixed-point INTER_LINEAR, coefficient bits = 11)
+static void axis_table(int dn, int sn, bool horizontal, short4* out)
+{
+    const double inv_scale = (double)dn / sn, scale = 1. / inv_scale;
+    for (int d = 0; d < dn; d++) {
+        float fx = (float)((d + 0.5) * scale - 0.5);
+        int s = (int)floorf(fx);
+        fx -= s;
+        int s0, s1;
+        if (horizontal) {
+            if (s < 0) { fx = 0; s = 0; }
+            if (s >= sn - 1) { fx = 0; s = sn - 1; }
+            s0 = s; s1 = s + 1 < sn ? s + 1 : sn - 1;
+        } else {
+            s0 = s < 0 ? 0 : (s > sn - 1 ? sn - 1 : s);
+            s1 = s + 1 < 0 ? 0 : (s + 1 > sn - 1 ? sn - 1 : s + 1);
+        }
+        out[d].x = (short)s0; out[d].y = (short)s1;
+        out[d].z = (short)cv_round_f((1.f - fx) * 2048.f);
+        out[d].w = (short)cv_round_f(fx * 2048.f);
+    }
+}
+
+static int configure_geometry(orbx_extractor* h, int width, int height)
+{
+    OrbxGeom& g = h->geom;
+    if (g.width == width && g.height == height) return ORBX_OK;
+    if (width > h->p.max_width || height > h->p.max_height) {
+        orbx_set_error("%s%s", "image larger than max_width/max_height of the handle", "");
+        return ORBX_E_INVALID;
+    }
+    memset(&g, 0, sizeof(g));
+    g.nlevels = h->p.nlevels; g.width = width; g.height = height;
+    g.ini_th = h->p.ini_th_fast; g.min_th = h->p.min_th_fast;
+    const int B = h->p.max_batch;
+    int rows = 0, kpbase = 0, tab = 0;
+    const int maxcand = h->p.max_candidates_per_level > 0 ? h->p.max_candidates_per_level : 16384;
+    std::vector<int> row_off; std::vector<int> sort_off;
+    long long row_elems = 0, sort_elems = 0;
+    for (int l = 0; l < g.nlevels; l++) {
+        OrbxLevel& L = g.lv[l];
+        const float sc = h->invScale[l];
+        L.w = cv_round_f((float)width * sc); L.h = cv_round_f((float)height * sc);   // R/src/ORBextractor.cc:1157
+        if (L.w < 8 || L.h < 8 || L.w > 4096 + 2 * ORBX_BORDER || L.h > 4096 + 2 * ORBX_BORDER) {
+            orbx_set_error("%s%s", "unsupported level size (need 8..4128 px per side at every level)", "");
+            g.width = 0; return ORBX_E_INVALID;
+        }
+        L.pitch = (L.w + 63) & ~63;
+        L.frame_stride = (long long)L.pitch * L.h;
+        L.maxBX = L.w - ORBX_BORDER; L.maxBY = L.h - ORBX_BORDER;
+        const float fw = (float)(L.maxBX - ORBX_BORDER), fh = (float)(L.maxBY - ORBX_BORDER);
+        L.nCols = fw > 0 ? (int)(fw / (float)ORBX_FAST_W) : 0;
+        L.nRows = fh > 0 ? (int)(fh / (float)ORBX_FAST_W) : 0;
+        if (L.nCols <= 0 || L.nRows <= 0) { L.nCols = L.nRows = 0; L.wCell = L.hCell = 0; }
+        else { L.wCell = (int)ceilf(fw / L.nCols); L.hCell = (int)ceilf(fh / L.nRows); }
+        if (L.nCols > 128 || L.nRows > 127) {
+            orbx_set_error("%s%s", "image too large for the FAST cell tables", ""); g.width = 0; return ORBX_E_INVALID;
+        }
+        L.quota = h->featuresPerLevel[l];
+        L.scale = h->scale[l];
+        L.size = (float)(int)(31 * h->scale[l]);                                    // :862
+        if (L.nRows > 0) {
+            L.nIni = (int)roundf((float)(L.maxBX - ORBX_BORDER) / (L.maxBY - ORBX_BORDER));   // :541
+            if (L.nIni < 1) L.nIni = 1;
+            if (L.nIni > 63) { orbx_set_error("%s%s", "aspect ratio too extreme for the octree key", ""); g.width = 0; return ORBX_E_INVALID; }
+            L.hX = (float)(L.maxBX - ORBX_BORDER) / L.nIni;                         // :543
+        } else { L.nIni = 1; L.hX = 1.f; }
+        L.row_base = rows;
+        // capacity of one cell row: in-cell NMS leaves at most ceil(w/2)*ceil(h/2) corners per cell
+        long long rowcap = 0;
+        for (int j = 0; j < L.nCols; j++) {
+            int c0 = j * L.wCell, c1 = c0 + L.wCell; const int ws = L.maxBX - ORBX_BORDER - 6;
+            if (c1 > ws) c1 = ws;
+            if (c1 > c0) rowcap += (long long)((c1 - c0 + 1) / 2) * ((L.hCell + 1) / 2);
+        }
+        if (rowcap > maxcand) rowcap = maxcand;
+        L.row_cap = (int)rowcap;
+        long long lc = rowcap * L.nRows; if (lc > maxcand) lc = maxcand;
+        L.cand_cap = (int)lc;
+        for (int r = 0; r < L.nRows; r++) { row_off.push_back((int)row_elems); row_elems += L.row_cap; }
+        rows += L.nRows;
+        L.kp_cap = (L.quota > 4 * L.nIni ? L.quota : 4 * L.nIni) + 4;
+        L.kp_base = kpbase; kpbase += L.kp_cap;
+        L.xtab_off = tab; tab += L.w;
+        L.ytab_off = tab; tab += L.h;
+        int npad = 1; while (npad < L.cand_cap) npad <<= 1;
+        sort_off.push_back((int)sort_elems);
+        sort_elems += (npad > 4096) ? (long long)npad + npad / 2 : 0;
+    }
+    g.total_rows = rows;
+    g.kp_total_cap = kpbase;
+    g.out_cap = orbx_extractor_max_keypoints(h);
+
+    // ---- (re)allocate device buffers ----
+    for (void* p : h->allocs) cudaFree(p);
+    h->allocs.clear();
+    OrbxBuffers& b = h->buf;
+    memset(&b, 0, sizeof(b));
+    int rc;
+    for (int l = 0; l < g.nlevels; l++) {
+        if (l > 0 && (rc = dev_alloc(h, (void**)&b.pyr[l], (size_t)g.lv[l].frame_stride * B))) return rc;
+        if ((rc = dev_alloc(h, (void**)&b.blur[l], (size_t)g.lv[l].frame_stride * B))) return rc;
+    }
+    h->pitch0 = g.lv[0].pitch; h->stride0 = g.lv[0].frame_stride;
+    if ((rc = dev_alloc(h, (void**)&h->d_level0, (size_t)h->stride0 * B))) return rc;
+    std::vector<short4> tabs(tab);
+    for (int l = 1; l < g.nlevels; l++) {
+        axis_table(g.lv[l].w, g.lv[l - 1].w, true, tabs.data() + g.lv[l].xtab_off);
+        axis_table(g.lv[l].h, g.lv[l - 1].h, false, tabs.data() + g.lv[l].ytab_off);
+    }
+    if ((rc = dev_alloc(h, (void**)&b.tabs, sizeof(short4) * tab))) return rc;
+    CK(cudaMemcpy(b.tabs, tabs.data(), sizeof(short4) * tab, cudaMemcpyHostToDevice));
+    b.row_cand_stride = row_elems;
+    if ((rc = dev_alloc(h, (void**)&b.row_cand, sizeof(uint32_t) * (size_t)row_elems * B))) return rc;
+    if ((rc = dev_alloc(h, (void**)&b.row_count, sizeof(int) * (size_t)rows * B))) return rc;
+    if ((rc = dev_alloc(h, (void**)&b.row_off, sizeof(int) * (rows + 1)))) return rc;
+    if (rows) CK(cudaMemcpy(b.row_off, row_off.data(), sizeof(int) * rows, cudaMemcpyHostToDevice));
+    if ((rc = dev_alloc(h, (void**)&b.lvl_kp, sizeof(uint32_t) * (size_t)kpbase * B))) return rc;
+    if ((rc = dev_alloc(h, (void**)&b.lvl_n, sizeof(int) * (size_t)g.nlevels * B))) return rc;
+    b.sort_scratch_stride = sort_elems;
+    if ((rc = dev_alloc(h, (void**)&b.sort_scratch, sizeof(unsigned long long) * (size_t)sort_elems * B))) return rc;
+    if ((rc = dev_alloc(h, (void**)&b.sort_off, sizeof(int) * g.nlevels))) return rc;
+    CK(cudaMemcpy(b.sort_off, sort_off.data(), sizeof(int) * g.nlevels, cudaMemcpyHostToDevice));
+    if ((rc = dev_alloc(h, (void**)&b.work, sizeof(uint2) * (size_t)g.out_cap * B))) return rc;
+    if ((rc = dev_alloc(h, (void**)&b.kps, sizeof(orbx_keypoint) * (size_t)g.out_cap * h->slots))) return rc;
+    if ((rc = dev_alloc(h, (void**)&b.desc, (size_t)32 * g.out_cap * h->slots))) return rc;
+    if ((rc = dev_alloc(h, (void**)&b.n, sizeof(int) * h->slots))) return rc;
+    if ((rc = dev_alloc(h, (void**)&b.mono, sizeof(int) * h->slots))) return rc;
+    if ((rc = dev_alloc(h, (void**)&b.err, sizeof(unsigned)))) return rc;
+    CK(cudaMemset(b.n, 0, sizeof(int) * h->slots));
+    CK(cudaMemset(b.mono, 0, sizeof(int) * h->slots));
+    CK(cudaMemset(b.err, 0, sizeof(unsigned)));
+    orbx_octree_configure(g);
+    orbx_fast_configure(g);
+    CK(cudaGetLastError());
+    return ORBX_OK;
+}
+
+extern "C" int orbx_extractor_create(const orbx_params* p, orbx_extractor** out)
+{
+    if (!p || !out || p->nlevels < 1 || p->nlevels > ORBX_MAX_LEVELS || p->nfeatures < 1 || p->max_batch < 1 ||
+        p->scale_factor <= 1.0f || p->max_width < 8 || p->max_height < 8) {
+        orbx_set_error("%s%s", "orbx_extractor_create: invalid parameters", "");
+        return ORBX_E_INVALID;
+    }
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (p->device < 0 || p->device >= ndev) { orbx_set_error("%s%s", "no such CUDA device", ""); return ORBX_E_CUDA; }
+    CK(cudaSetDevice(p->device));
+    orbx_extractor* h = new orbx_extractor();
+    h->p = *p;
+    h->slots = p->max_batch + 1;
+    h->scaleFactor = (double)p->scale_factor;
+    const int nl = p->nlevels;
+    h->scale.resize(nl); h->invScale.resize(nl); h->sigma2.resize(nl); h->invSigma2.resize(nl); h->featuresPerLevel.resize(nl);
+    // R/src/ORBextractor.cc:413-444
+    h->scale[0] = 1.0f; h->sigma2[0] = 1.0f;
+    for (int i = 1; i < nl; i++) {
+        h->scale[i] = (float)(h->scale[i - 1] * h->scaleFactor);
+        h->sigma2[i] = h->scale[i] * h->scale[i];
+    }
+    for (int i = 0; i < nl; i++) { h->invScale[i] = 1.0f / h->scale[i]; h->invSigma2[i] = 1.0f / h->sigma2[i]; }
+    const float factor = (float)(1.0f / h->scaleFactor);
+    float nDesired = p->nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)nl));
+    int sum = 0;
+    for (int l = 0; l < nl - 1; l++) {
+        h->featuresPerLevel[l] = cv_round_f(nDesired);
+        sum += h->featuresPerLevel[l];
+        nDesired *= factor;
+    }
+    h->featuresPerLevel[nl - 1] = p->nfeatures - sum > 0 ? p->nfeatures - sum : 0;
+    memset(&h->geom, 0, sizeof(h->geom));
+    memset(&h->buf, 0, sizeof(h->buf));
+    h->d_level0 = nullptr; h->last_level0 = nullptr; h->last_batch = 0;
+    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    const int cap = orbx_extractor_max_keypoints(h);
+    CK(cudaMallocHost((void**)&h->h_stage_in, (size_t)((p->max_width + 63) & ~63) * p->max_height * p->max_batch));
+    CK(cudaMallocHost((void**)&h->h_kps, sizeof(orbx_keypoint) * (size_t)cap * h->slots));
+    CK(cudaMallocHost((void**)&h->h_desc, (size_t)32 * cap * h->slots));
+    CK(cudaMallocHost((void**)&h->h_n, sizeof(int) * h->slots));
+    CK(cudaMallocHost((void**)&h->h_mono, sizeof(int) * h->slots));
+    CK(cudaMallocHost((void**)&h->h_err, sizeof(unsigned)));
+    orbx_upload_pattern();
+    CK(cudaGetLastError());
+    *out = h;
+    return ORBX_OK;
+}
+
+extern "C" void orbx_extractor_destroy(orbx_extractor* h)
+{
+    if (!h) return;
+    cudaSetDevice(h->p.device);
+    cudaStreamSynchronize(h->stream);
+    for (void* p : h->allocs) cudaFree(p);
+    cudaFreeHost(h->h_stage_in); cudaFreeHost(h->h_kps); cudaFreeHost(h->h_desc);
+    cudaFreeHost(h->h_n); cudaFreeHost(h->h_mono); cudaFreeHost(h->h_err);
+    cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+extern "C" int orbx_extractor_tables(const orbx_extractor* h, float* scale, float* inv_scale, float* sigma2,
+                                     float* inv_sigma2, int32_t* fpl)
+{
+    if (!h) return ORBX_E_INVALID;
+    for (int i = 0; i < h->p.nlevels; i++) {
+        if (scale) scale[i] = h->scale[i];
+        if (inv_scale) inv_scale[i] = h->invScale[i];
+        if (sigma2) sigma2[i] = h->sigma2[i];
+        if (inv_sigma2) inv_sigma2[i] = h->invSigma2[i];
+        if (fpl) fpl[i] = h->featuresPerLevel[i];
+    }
+    return ORBX_OK;
+}
+
+extern "C" int orbx_extractor_max_keypoints(const orbx_extractor* h)
+{
+    // every level can overshoot its quota by up to 3 (a split adds at most 3 nodes), and a level whose
+    // quota is tiny still starts from up to 4 nodes per root
+    int cap = 0;
+    for (int l = 0; l < h->p.nlevels; l++) cap += h->featuresPerLevel[l] + 4;
+    return cap + 64;
+}
+
+static int deferred_error(orbx_extractor* h)
+{
+    const unsigned e = *h->h_err;
+    if (e) {
+        char buf[64]; snprintf(buf, sizeof(buf), "0x%x", e);
+        orbx_set_error("device capacity error flags %s%s", buf, " (raise max_candidates_per_level / capacities)");
+        cudaMemsetAsync(h->buf.err, 0, sizeof(unsigned), h->stream);
+        return ORBX_E_CAPACITY;
+    }
+    return ORBX_OK;
+}
+
+static int run_batch(orbx_extractor* h, const uint8_t* d_level0, int pitch0, long long stride0, int batch,
+                     int lap0, int lap1, int first_slot, cudaStream_t s)
+{
+    const OrbxGeom& g = h->geom;
+    orbx_launch_pyramid(g, h->buf, d_level0, pitch0, stride0, batch, s);
+    orbx_launch_fast(g, h->buf, d_level0, pitch0, stride0, batch, s);
+    orbx_launch_octree(g, h->buf, batch, s);
+    orbx_launch_describe(g, h->buf, d_level0, pitch0, stride0, batch, lap0, lap1, first_slot, s);
+    h->last_level0 = d_level0; h->last_pitch0 = pitch0; h->last_stride0 = stride0; h->last_batch = batch;
+    CK(cudaGetLastError());
+    return ORBX_OK;
+}
+
+extern "C" int orbx_extract_batch_device(orbx_extractor* h, const uint8_t* d_imgs, int batch, int width, int height,
+                                         int stride, size_t frame_stride, int lap0, int lap1, int first_slot, void* stream)
+{
+    if (!h || !d_imgs || batch < 1 || batch > h->p.max_batch || first_slot < 0 || first_slot + batch > h->slots ||
+        stride < width) {
+        orbx_set_error("%s%s", "orbx_extract_batch_device: invalid arguments", "");
+        return ORBX_E_INVALID;
+    }
+    if (width <= 0 || height <= 0) return ORBX_E_EMPTY;
+    CK(cudaSetDevice(h->p.device));
+    int rc = configure_geometry(h, width, height);
+    if (rc) return rc;
+    cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
+    return run_batch(h, d_imgs, stride, (long long)frame_stride, batch, lap0, lap1, first_slot, s);
+}
+
+extern "C" int orbx_extractor_sync(orbx_extractor* h, void* stream)
+{
+    if (!h) return ORBX_E_INVALID;
+    cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
+    if (h->buf.err) CK(cudaMemcpyAsync(h->h_err, h->buf.err, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+    else *h->h_err = 0;
+    CK(cudaStreamSynchronize(s));
+    return deferred_error(h);
+}
+
+extern "C" int orbx_extractor_copy_slot(orbx_extractor* h, int from, int to, void* stream)
+{
+    if (!h || from < 0 || to < 0 || from >= h->slots || to >= h->slots || !h->buf.kps) return ORBX_E_INVALID;
+    cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
+    const size_t cap = h->geom.out_cap;
+    CK(cudaMemcpyAsync(h->buf.kps + to * cap, h->buf.kps + from * cap, sizeof(orbx_keypoint) * cap, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(h->buf.desc + to * cap * 32, h->buf.desc + from * cap * 32, cap * 32, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(h->buf.n + to, h->buf.n + from, sizeof(int), cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(h->buf.mono + to, h->buf.mono + from, sizeof(int), cudaMemcpyDeviceToDevice, s));
+    return ORBX_OK;
+}
+
+extern "C" int orbx_extractor_results_device(orbx_extractor* h, orbx_keypoint** d_kps, uint8_t** d_desc,
+                                             int32_t** d_n, int32_t** d_mono, int* cap, int* slots)
+{
+    if (!h || !h->buf.kps) { orbx_set_error("%s%s", "no batch has been extracted yet", ""); return ORBX_E_INVALID; }
+    if (d_kps) *d_kps = h->buf.kps;
+    if (d_desc) *d_desc = h->buf.desc;
+    if (d_n) *d_n = h->buf.n;
+    if (d_mono) *d_mono = h->buf.mono;
+    if (cap) *cap = h->geom.out_cap;
+    if (slots) *slots = h->slots;
+    return ORBX_OK;
+}
+
+extern "C" int orbx_extractor_download(orbx_extractor* h, int first_slot, int count, orbx_keypoint* kps, uint8_t* desc,
+                                       int cap, int32_t* n, int32_t* mono_index, void* stream)
+{
+    if (!h || !h->buf.kps || first_slot < 0 || count < 1 || first_slot + count > h->slots) return ORBX_E_INVALID;
+    cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
+    const size_t ocap = h->geom.out_cap;
+    CK(cudaMemcpyAsync(h->h_n, h->buf.n + first_slot, sizeof(int) * count, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(h->h_mono, h->buf.mono + first_slot, sizeof(int) * count, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(h->h_err, h->buf.err, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(h->h_kps, h->buf.kps + first_slot * ocap, sizeof(orbx_keypoint) * ocap * count, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(h->h_desc, h->buf.desc + first_slot * ocap * 32, ocap * 32 * count, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    int rc = deferred_error(h);
+    if (rc) return rc;
+    for (int i = 0; i < count; i++) {
+        const int ni = h->h_n[i];
+        if (n) n[i] = ni;
+        if (mono_index) mono_index[i] = h->h_mono[i];
+        if (ni > cap) { orbx_set_error("%s%s", "caller keypoint capacity too small", ""); return ORBX_E_CAPACITY; }
+        if (kps) memcpy(kps + (size_t)i * cap, h->h_kps + (size_t)i * ocap, sizeof(orbx_keypoint) * ni);
+        if (desc) memcpy(desc + (size_t)i * cap * 32, h->h_desc + (size_t)i * ocap * 32, (size_t)32 * ni);
+    }
+    return ORBX_OK;
+}
+
+extern "C" int orbx_extract_batch(orbx_extractor* h, const uint8_t* imgs, int batch, int width, int height,
+                                  int stride, size_t frame_stride, int lap0, int lap1,
+                                  orbx_keypoint* kps, uint8_t* desc, int cap, int32_t* n, int32_t* mono_index)
+{
+    if (!h || batch < 1 || batch > h->p.max_batch) { orbx_set_error("%s%s", "orbx_extract_batch: invalid arguments", ""); return ORBX_E_INVALID; }
+    if (!imgs || width <= 0 || height <= 0) return ORBX_E_EMPTY;
+    if (stride < width) return ORBX_E_INVALID;
+    CK(cudaSetDevice(h->p.device));
+    int rc = configure_geometry(h, width, height);
+    if (rc) return rc;
+    // host frames -> pinned staging (tight pitch0 rows) -> device level 0
+    const int p0 = h->pitch0;
+    for (int f = 0; f < batch; f++)
+        for (int y = 0; y < height; y++)
+            memcpy(h->h_stage_in + (size_t)f * h->stride0 + (size_t)y * p0, imgs + f * frame_stride + (size_t)y * stride, width);
+    CK(cudaMemcpyAsync(h->d_level0, h->h_stage_in, (size_t)h->stride0 * batch, cudaMemcpyHostToDevice, h->stream));
+    rc = run_batch(h, h->d_level0, p0, h->stride0, batch, lap0, lap1, 0, h->stream);
+    if (rc) return rc;
+    return orbx_extractor_download(h, 0, batch, kps, desc, cap, n, mono_index, h->stream);
+}
+
+extern "C" int orbx_extract(orbx_extractor* h, const uint8_t* img, int width, int height, int stride,
+                            int lap0, int lap1, orbx_keypoint* kps, uint8_t* desc, int cap, int* n, int* mono_index)
+{
+    int32_t nn = 0, mm = 0;
+    int rc = orbx_extract_batch(h, img, 1, width, height, stride, (size_t)stride * (height > 0 ? height : 0), lap0, lap1,
+                                kps, desc, cap, &nn, &mm);
+    if (n) *n = nn;
+    if (mono_index) *mono_index = mm;
+    return rc;
+}
+
+extern "C" int orbx_pyramid_level_size(const orbx_extractor* h, int level, int* width, int* height)
+{
+    if (!h || h->geom.width == 0 || level < 0 || level >= h->geom.nlevels) return ORBX_E_INVALID;
+    if (width) *width = h->geom.lv[level].w;
+    if (height) *height = h->geom.lv[level].h;
+    return ORBX_OK;
+}
+
+static int level_to_host(orbx_extractor* h, const uint8_t* base, int pitch, long long fstride, int slot, int level,
+                         uint8_t* dst, int dst_stride)
+{
+    const OrbxLevel& L = h->geom.lv[level];
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy2D(dst, dst_stride, base + (long long)slot * fstride, pitch, L.w, L.h, cudaMemcpyDeviceToHost));
+    return ORBX_OK;
+}
+
+extern "C" int orbx_pyramid_to_host(orbx_extractor* h, int slot, int level, uint8_t* dst, int dst_stride)
+{
+    if (!h || h->geom.width == 0 || level < 0 || level >= h->geom.nlevels || slot < 0 || slot >= h->last_batch || !dst)
+        return ORBX_E_INVALID;
+    CK(cudaSetDevice(h->p.device));
+    if (level == 0) return level_to_host(h, h->last_level0, h->last_pitch0, h->last_stride0, slot, 0, dst, dst_stride);
+    return level_to_host(h, h->buf.pyr[level], h->geom.lv[level].pitch, h->geom.lv[level].frame_stride, slot, level, dst, dst_stride);
+}
+
+extern "C" int orbx_blurred_to_host(orbx_extractor* h, int slot, int level, uint8_t* dst, int dst_stride)
+{
+    if (!h || h->geom.width == 0 || level < 0 || level >= h->geom.nlevels || slot < 0 || slot >= h->last_batch || !dst)
+        return ORBX_E_INVALID;
+    CK(cudaSetDevice(h->p.device));
+    return level_to_host(h, h->buf.blur[level], h->geom.lv[level].pitch, h->geom.lv[level].frame_stride, slot, level, dst, dst_stride);
+}
+
+extern "C" int orbx_candidates_to_host(orbx_extractor* h, int slot, int level, float* xyr, int cap, int* n)
+{
+    if (!h || h->geom.width == 0 || level < 0 || level >= h->geom.nlevels || slot < 0 || slot >= h->last_batch) return ORBX_E_INVALID;
+    CK(cudaSetDevice(h->p.device));
+    CK(cudaStreamSynchronize(h->stream));
+    const OrbxGeom& g = h->geom; const OrbxLevel& L = g.lv[level];
+    std::vector<int> cnt(L.nRows > 0 ? L.nRows : 1), off(L.nRows > 0 ? L.nRows : 1);
+    int total = 0;
+    if (L.nRows > 0) {
+        CK(cudaMemcpy(cnt.data(), h->buf.row_count + (long long)slot * g.total_rows + L.row_base, sizeof(int) * L.nRows, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(off.data(), h->buf.row_off + L.row_base, sizeof(int) * L.nRows, cudaMemcpyDeviceToHost));
+    }
+    std::vector<uint32_t> tmp;
+    for (int r = 0; r < L.nRows; r++) {
+        tmp.resize(cnt[r] > 0 ? cnt[r] : 1);
+        if (cnt[r] > 0)
+            CK(cudaMemcpy(tmp.data(), h->buf.row_cand + (long long)slot * h->buf.row_cand_stride + off[r], sizeof(uint32_t) * cnt[r], cudaMemcpyDeviceToHost));
+        for (int k = 0; k < cnt[r]; k++, total++)
+            if (total < cap) {
+                xyr[total * 3] = (float)(tmp[k] & 0xFFF); xyr[total * 3 + 1] = (float)((tmp[k] >> 12) & 0xFFF);
+                xyr[total * 3 + 2] = (float)(tmp[k] >> 24);
+            }
+    }
+    if (n) *n = total;
+    return total <= cap ? ORBX_OK : ORBX_E_CAPACITY;
+}
+
+extern "C" int orbx_level_keypoints_to_host(orbx_extractor* h, int slot, int level, float* xyr, int cap, int* n)
+{
+    if (!h || h->geom.width == 0 || level < 0 || level >= h->geom.nlevels || slot < 0 || slot >= h->last_batch) return ORBX_E_INVALID;
+    CK(cudaSetDevice(h->p.device));
+    CK(cudaStreamSynchronize(h->stream));
+    const OrbxGeom& g = h->geom; const OrbxLevel& L = g.lv[level];
+    int cnt = 0;
+    CK(cudaMemcpy(&cnt, h->buf.lvl_n + (long long)slot * g.nlevels + level, sizeof(int), cudaMemcpyDeviceToHost));
+    std::vector<uint32_t> tmp(cnt > 0 ? cnt : 1);
+    if (cnt > 0) CK(cudaMemcpy(tmp.data(), h->buf.lvl_kp + (long long)slot * g.kp_total_cap + L.kp_base, sizeof(uint32_t) * cnt, cudaMemcpyDeviceToHost));
+    for (int k = 0; k < cnt && k < cap; k++) {
+        xyr[k * 3] = (float)(tmp[k] & 0xFFF); xyr[k * 3 + 1] = (float)((tmp[k] >> 12) & 0xFFF); xyr[k * 3 + 2] = (float)(tmp[k] >> 24);
+    }
+    if (n) *n = cnt;
+    return cnt <= cap ? ORBX_OK : ORBX_E_CAPACITY;
+}

@@ -1,0 +1,95 @@
+// orbx_internal.h - shared declarations of the sm_100a ORB front-end kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/orbx.h"
+
+#define ORBX_EDGE 19          // EDGE_THRESHOLD, R/src/ORBextractor.cc:72
+#define ORBX_BORDER 16        // minBorderX = EDGE_THRESHOLD-3, R/src/ORBextractor.cc:771
+#define ORBX_HALF_PATCH 15    // HALF_PATCH_SIZE, R/src/ORBextractor.cc:71
+#define ORBX_FAST_W 30        // cell size W, R/src/ORBextractor.cc:767
+
+// device error flag bits (written by kernels, read back at sync/download)
+#define ORBX_DEVERR_CAND_OVERFLOW  1u   // more FAST corners in a cell row / level than the buffers hold
+#define ORBX_DEVERR_OCTREE_DEPTH   2u   // octree node could not be separated within the key depth
+#define ORBX_DEVERR_NODE_OVERFLOW  4u   // octree node table overflow
+#define ORBX_DEVERR_KP_OVERFLOW    8u   // more keypoints than the result capacity
+#define ORBX_DEVERR_POOL_OVERFLOW 16u   // matcher candidate pool overflow
+
+// Geometry of one pyramid level and of its FAST cell grid (R/src/ORBextractor.cc:769-804)
+struct OrbxLevel {
+    int w, h;            // level size
+    int pitch;           // bytes per row
+    long long frame_stride;   // bytes per frame in the batched level buffer
+    int maxBX, maxBY;    // maxBorderX/Y = dim - 16
+    int nCols, nRows;    // cells
+    int wCell, hCell;
+    int quota;           // mnFeaturesPerLevel
+    int nIni;            // octree root count
+    float hX;            // octree root width
+    float scale;         // mvScaleFactor
+    float size;          // keypoint.size = int(31*scale)
+    int row_base;        // index of this level's first cell row in the flattened cell-row list
+    int row_cap;         // candidate capacity of one cell row
+    int cand_cap;        // candidate capacity of the level (octree input)
+    int kp_cap;          // kept-keypoint capacity of the level
+    int kp_base;         // offset of this level in the per-frame kept-keypoint buffer
+    int xtab_off, ytab_off;   // offsets (in short4 units) of the resize tables
+};
+
+struct OrbxGeom {
+    int nlevels;
+    int width, height;
+    int total_rows;      // sum of nRows over levels
+    int kp_total_cap;    // per-frame kept-keypoint buffer length (sum of kp_cap)
+    int out_cap;         // per-frame result capacity
+    int ini_th, min_th;
+    OrbxLevel lv[ORBX_MAX_LEVELS];
+};
+
+// Device buffers of one extractor handle.
+struct OrbxBuffers {
+    uint8_t* pyr[ORBX_MAX_LEVELS];     // level images; pyr[0] may alias the caller's frames
+    uint8_t* blur[ORBX_MAX_LEVELS];    // blurred levels
+    short4* tabs;                      // resize tables: (s0, s1, c0, c1) per dst column / row
+    uint32_t* row_cand;                // [batch][total_rows][row_cap(level)] packed x | y<<12 | score<<24 ... flattened by row offsets
+    int* row_count;                    // [batch][total_rows]
+    long long row_cand_stride;         // elements per frame
+    int* row_off;                      // [total_rows] element offset of each cell row inside a frame
+    uint32_t* lvl_kp;                  // [batch][kp_total_cap] kept keypoints per level, packed
+    int* lvl_n;                        // [batch][nlevels]
+    unsigned long long* sort_scratch;  // global sort scratch for oversized levels [batch][nlevels][...]
+    long long sort_scratch_stride;     // per (frame) elements
+    int* sort_off;                     // [nlevels] offsets into a frame's scratch
+    uint2* work;                       // [batch][out_cap] orientation/descriptor work items
+    orbx_keypoint* kps;                // [slots][out_cap]
+    uint8_t* desc;                     // [slots][out_cap][32]
+    int* n;                            // [slots]
+    int* mono;                         // [slots]
+    unsigned int* err;                 // device error flags
+};
+
+#ifdef __CUDACC__
+__device__ __forceinline__ int orbx_reflect101(int p, int n)
+{
+    // BORDER_REFLECT_101 for |overshoot| < n (n >= 2); n == 1 -> 0
+    if (n == 1) return 0;
+    if (p < 0) p = -p;
+    if (p >= n) p = 2 * (n - 1) - p;
+    return p;
+}
+#endif
+
+// kernel launchers (defined in the .cu files)
+void orbx_launch_pyramid(const OrbxGeom& g, const OrbxBuffers& b, const uint8_t* level0, int pitch0,
+                         long long stride0, int batch, cudaStream_t s);
+void orbx_launch_fast(const OrbxGeom& g, const OrbxBuffers& b, const uint8_t* level0, int pitch0,
+                      long long stride0, int batch, cudaStream_t s);
+void orbx_launch_octree(const OrbxGeom& g, const OrbxBuffers& b, int batch, cudaStream_t s);
+void orbx_launch_describe(const OrbxGeom& g, const OrbxBuffers& b, const uint8_t* level0, int pitch0,
+                          long long stride0, int batch, int lap0, int lap1, int first_slot, cudaStream_t s);
+int  orbx_octree_smem_bytes(const OrbxGeom& g);
+void orbx_octree_configure(const OrbxGeom& g);
+void orbx_fast_configure(const OrbxGeom& g);
+void orbx_upload_pattern();
+void orbx_set_error(const char* fmt, const char* a, const char* b);

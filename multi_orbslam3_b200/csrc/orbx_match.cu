@@ -1,0 +1,922 @@
+// orbx_match.cu - 256-bit Hamming matching: brute-force kNN-2, grid-windowed searches, stereo band search.
+//
+// Replaces (R/ = src/orb_slam3_ros/orb_slam3/):
+//   ORBmatcher::DescriptorDistance                      R/src/ORBmatcher.cc:2358-2374
+//   cv::BFMatcher(NORM_HAMMING).knnMatch(k=2)           R/src/Frame.cc:1127-1137 (+ server cross-agent matching)
+//   Frame::AssignFeaturesToGrid / GetFeaturesInArea     R/src/Frame.cc:360-391, 628-709
+//   ORBmatcher::SearchForInitialization                 R/src/ORBmatcher.cc:702-817
+//   ORBmatcher::SearchByProjection (2 overloads)        R/src/ORBmatcher.cc:44-214, 1970-2186
+//   ORBmatcher::ComputeThreeMaxima                      R/src/ORBmatcher.cc:2312-2353
+//   Frame::ComputeStereoMatches (descriptor search)     R/src/Frame.cc:785-868
+//
+// Structure of the windowed searches: all (query, candidate) distances are order-free and computed in
+// parallel (one warp per query, candidates in the reference's visit order: grid column ix, then row iy,
+// then insertion order) into a CSR pool; the order-dependent bookkeeping of the reference (a keypoint taken
+// by an earlier query is skipped / stolen back) is replayed by one warp per frame pair over that pool.
+#include <stdio.h>
+#include <string.h>
+#include <vector>
+#include "orbx_internal.h"
+
+#define CKM(call)                                                                         \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess) {                                                          \
+            orbx_set_error("%s failed: %s", #call, cudaGetErrorString(e_));               \
+            return ORBX_E_CUDA;                                                           \
+        }                                                                                 \
+    } while (0)
+
+namespace {
+
+constexpr int GC = ORBX_GRID_COLS, GR = ORBX_GRID_ROWS, NCELL = GC * GR;
+
+struct PairDesc {
+    const orbx_keypoint* k1; const uint8_t* d1;       // query frame (SearchForInitialization) or unused
+    const orbx_keypoint* k2; const uint8_t* d2;       // searched frame
+    const float* uright2;                             // may be null
+    const orbx_proj_query* q; const uint8_t* qdesc;   // queries
+    int n1, n2, nq;
+};
+
+__device__ __forceinline__ int hamming256(const uint4& a0, const uint4& a1, const uint4& b0, const uint4& b1)
+{
+    return __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+           __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+}
+
+__global__ void k_hamming_pairs(const uint4* a, const uint4* b, int n, int* out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = hamming256(a[2 * i], a[2 * i + 1], b[2 * i], b[2 * i + 1]);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// brute-force kNN-2.  One thread = one query descriptor held in 8 registers; train descriptors stream
+// through shared memory in tiles and are read by all threads as broadcasts.  Top-2 by (distance, index).
+// ---------------------------------------------------------------------------------------------------
+constexpr int BF_NT = 128;      // queries per CTA
+constexpr int BF_TILE = 256;    // train descriptors per tile (8 KB)
+
+struct BfArgs {
+    // direct mode
+    const uint8_t* q; const uint8_t* t; int nq; long long nt;
+    // slot mode (q == nullptr): descriptors of result slots a[p] / b[p]
+    const uint8_t* desc; const int* n; const int* a; const int* b; int cap;
+    int32_t* idx; int32_t* dist;          // [pair][out_stride][2]
+    int out_stride; int idx_base;
+    long long chunk;                      // train descriptors per split
+    int nsplit;
+    int32_t* part_idx; int32_t* part_dist;   // [pair][split][out_stride][2] when nsplit > 1
+};
+
+__global__ void __launch_bounds__(BF_NT) k_bf_knn2(BfArgs A)
+{
+    __shared__ uint4 tile[BF_TILE * 2];
+    const int p = blockIdx.z, split = blockIdx.y;
+    const uint8_t* q; const uint8_t* t; int nq; long long nt;
+    if (A.q) { q = A.q; t = A.t; nq = A.nq; nt = A.nt; }
+    else {
+        const int sa = A.a[p], sb = A.b[p];
+        q = A.desc + (long long)sa * A.cap * 32; nq = A.n[sa];
+        t = A.desc + (long long)sb * A.cap * 32; nt = A.n[sb];
+    }
+    if ((long long)blockIdx.x * BF_NT >= nq) return;
+    const int qi = blockIdx.x * BF_NT + threadIdx.x;
+    const bool live = qi < nq;
+    uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0;
+    if (live) { q0 = reinterpret_cast<const uint4*>(q)[2 * qi]; q1 = reinterpret_cast<const uint4*>(q)[2 * qi + 1]; }
+    int d0 = 0x7fffffff, d1 = 0x7fffffff, i0 = -1, i1 = -1;
+    const long long t_begin = (long long)split * A.chunk;
+    long long t_end = t_begin + A.chunk; if (t_end > nt) t_end = nt;
+    for (long long base = t_begin; base < t_end; base += BF_TILE) {
+        const int cnt = (int)min((long long)BF_TILE, t_end - base);
+        __syncthreads();
+        for (int k = threadIdx.x; k < cnt * 2; k += BF_NT) tile[k] = __ldg(reinterpret_cast<const uint4*>(t) + base * 2 + k);
+        __syncthreads();
+        if (live) {
+#pragma unroll 4
+            for (int j = 0; j < cnt; j++) {
+                const int d = hamming256(q0, q1, tile[2 * j], tile[2 * j + 1]);
+                if (d < d1) {
+                    const int id = (int)(base + j) + A.idx_base;
+                    if (d < d0) { d1 = d0; i1 = i0; d0 = d; i0 = id; }
+                    else { d1 = d; i1 = id; }
+                }
+            }
+        }
+    }
+    if (!live) return;
+    int32_t* oi; int32_t* od;
+    if (A.nsplit > 1) {
+        const long long o = (((long long)p * A.nsplit + split) * A.out_stride + qi) * 2;
+        oi = A.part_idx + o; od = A.part_dist + o;
+    } else {
+        const long long o = ((long long)p * A.out_stride + qi) * 2;
+        oi = A.idx + o; od = A.dist + o;
+    }
+    oi[0] = i0; oi[1] = i1;
+    od[0] = i0 >= 0 ? d0 : -1; od[1] = i1 >= 0 ? d1 : -1;
+}
+
+// merge partial top-2 tables: parts laid out [pair][part][stride][2]; lexicographic (dist, idx)
+__global__ void k_knn2_merge(const int32_t* pidx, const int32_t* pdist, int nparts, int stride, int nq_fixed,
+                             const int* n, const int* a, int32_t* idx, int32_t* dist)
+{
+    const int p = blockIdx.y;
+    const int nq = n ? n[a[p]] : nq_fixed;
+    const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi >= nq) return;
+    int d0 = 0x7fffffff, d1 = 0x7fffffff, i0 = -1, i1 = -1;
+    for (int s = 0; s < nparts; s++) {
+        const long long o = (((long long)p * nparts + s) * stride + qi) * 2;
+        for (int k = 0; k < 2; k++) {
+            const int id = pidx[o + k], d = pdist[o + k];
+            if (id < 0) continue;
+            if (d < d0 || (d == d0 && id < i0)) { d1 = d0; i1 = i0; d0 = d; i0 = id; }
+            else if (d < d1 || (d == d1 && id < i1)) { d1 = d; i1 = id; }
+        }
+    }
+    const long long o = ((long long)p * stride + qi) * 2;
+    idx[o] = i0; idx[o + 1] = i1;
+    dist[o] = i0 >= 0 ? d0 : -1; dist[o + 1] = i1 >= 0 ? d1 : -1;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// windowed searches
+// ---------------------------------------------------------------------------------------------------
+struct WinBufs {
+    PairDesc* pairs;              // [P]
+    orbx_proj_query* q;           // [P][K]   (queries synthesised for SearchForInitialization)
+    uint16_t* items;              // [P][K]   keypoint indices sorted by (cell, index)
+    int* cell_start;              // [P][NCELL+1]
+    int* q_off; int* q_cnt;       // [P][K]
+    uint32_t* pool; int* pool_used;   // [P][POOL], [P]
+    uint8_t* bin_of;              // [P][K]
+    int K, POOL;
+    float minX, maxX, minY, maxY, wInv, hInv;
+    unsigned* err;
+};
+
+// fills PairDesc for result slots and synthesises the SearchForInitialization queries:
+// level-0 keypoints of F1 search a window around vbPrevMatched = their own position, levels [0,0]
+__global__ void k_setup_slot_pairs(WinBufs W, const orbx_keypoint* kps, const uint8_t* desc, const int* n,
+                                   const int* a, const int* b, int cap, float window)
+{
+    const int p = blockIdx.x;
+    const int sa = a[p], sb = b[p];
+    const orbx_keypoint* k1 = kps + (long long)sa * cap;
+    if (threadIdx.x == 0) {
+        PairDesc d;
+        d.k1 = k1; d.d1 = desc + (long long)sa * cap * 32;
+        d.k2 = kps + (long long)sb * cap; d.d2 = desc + (long long)sb * cap * 32;
+        d.uright2 = nullptr; d.q = W.q + (long long)p * W.K; d.qdesc = d.d1;
+        d.n1 = n[sa]; d.n2 = n[sb]; d.nq = n[sa];
+        W.pairs[p] = d;
+    }
+    const int n1 = n[sa];
+    for (int i = threadIdx.x; i < n1 && i < W.K; i += blockDim.x) {
+        orbx_proj_query q;
+        q.u = k1[i].x; q.v = k1[i].y; q.r = window; q.minl = 0; q.maxl = 0; q.ur = 0.f; q.angle = k1[i].angle;
+        q.valid = k1[i].octave > 0 ? 0 : 1;
+        W.q[(long long)p * W.K + i] = q;
+    }
+}
+
+// host-API variant: queries for SearchForInitialization from explicit prev_xy
+__global__ void k_make_init_queries(orbx_proj_query* q, const orbx_keypoint* k1, const float* prev_xy, int n1, float window)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n1) return;
+    orbx_proj_query o;
+    o.u = prev_xy[2 * i]; o.v = prev_xy[2 * i + 1]; o.r = window; o.minl = 0; o.maxl = 0; o.ur = 0.f;
+    o.angle = k1[i].angle; o.valid = k1[i].octave > 0 ? 0 : 1;
+    q[i] = o;
+}
+
+constexpr int GRID_NT = 512;
+
+// Frame::AssignFeaturesToGrid: keypoints sorted by (cell, index) == per-cell vectors in push_back order.
+// cell = ix*GR + iy so that the cells (ix, iy0..iy1) visited by GetFeaturesInArea are one contiguous range.
+__global__ void __launch_bounds__(GRID_NT) k_grid_build(WinBufs W, int npad_max)
+{
+    extern __shared__ uint32_t keys[];     // [npad]
+    const int p = blockIdx.x;
+    const PairDesc P = W.pairs[p];
+    const int n = min(P.n2, W.K);
+    int npad = 1; while (npad < n) npad <<= 1;
+    if (npad > npad_max) npad = npad_max;
+    for (int i = threadIdx.x; i < npad; i += GRID_NT) {
+        uint32_t key = 0xFFFFFFFFu;
+        if (i < n) {
+            const orbx_keypoint kp = P.k2[i];
+            const int px = (int)roundf(__fmul_rn(__fsub_rn(kp.x, W.minX), W.wInv));      // PosInGrid: round, not floor
+            const int py = (int)roundf(__fmul_rn(__fsub_rn(kp.y, W.minY), W.hInv));
+            if (px >= 0 && px < GC && py >= 0 && py < GR) key = ((uint32_t)(px * GR + py) << 16) | (uint32_t)i;
+        }
+        keys[i] = key;
+    }
+    __syncthreads();
+    for (int k = 2; k <= npad; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < (npad >> 1); t += GRID_NT) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int l = i | j;
+                const bool up = (i & k) == 0;
+                const uint32_t x = keys[i], y = keys[l];
+                if ((x > y) == up) { keys[i] = y; keys[l] = x; }
+            }
+            __syncthreads();
+        }
+    uint16_t* items = W.items + (long long)p * W.K;
+    for (int i = threadIdx.x; i < n; i += GRID_NT) items[i] = (uint16_t)(keys[i] & 0xFFFF);
+    int* cs = W.cell_start + (long long)p * (NCELL + 1);
+    for (int c = threadIdx.x; c <= NCELL; c += GRID_NT) {
+        // first sorted position whose cell >= c (out-of-grid keys sort last)
+        int lo = 0, hi = n;
+        const uint32_t kc = (uint32_t)c << 16;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (keys[mid] < kc) lo = mid + 1; else hi = mid; }
+        cs[c] = lo;
+    }
+}
+
+constexpr int CAND_WARPS = 8;
+
+// Frame::GetFeaturesInArea + descriptor distances, one warp per query.  Pool entry: i2 | dist << 16 | octave << 25
+__global__ void __launch_bounds__(CAND_WARPS * 32) k_window_candidates(WinBufs W)
+{
+    const int lane = threadIdx.x & 31;
+    const int p = blockIdx.y;
+    const PairDesc P = W.pairs[p];
+    const int qi = blockIdx.x * CAND_WARPS + (threadIdx.x >> 5);
+    if (qi >= P.nq || qi >= W.K) return;
+    int* q_off = W.q_off + (long long)p * W.K + qi;
+    int* q_cnt = W.q_cnt + (long long)p * W.K + qi;
+    const orbx_proj_query Q = P.q[qi];
+    bool any = Q.valid != 0;
+    int cx0 = 0, cx1 = -1, cy0 = 0, cy1 = -1;
+    if (any) {
+        // :639-660, all fp32
+        cx0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(Q.u, W.minX), Q.r), W.wInv)));
+        cx1 = min(GC - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(Q.u, W.minX), Q.r), W.wInv)));
+        cy0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(Q.v, W.minY), Q.r), W.hInv)));
+        cy1 = min(GR - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(Q.v, W.minY), Q.r), W.hInv)));
+        if (cx0 >= GC || cx1 < 0 || cy0 >= GR || cy1 < 0) any = false;
+    }
+    if (!any) { if (lane == 0) { *q_off = 0; *q_cnt = 0; } return; }
+    const bool check_levels = (Q.minl > 0) || (Q.maxl >= 0);
+    const int* cs = W.cell_start + (long long)p * (NCELL + 1);
+    const uint16_t* items = W.items + (long long)p * W.K;
+    const uint4 q0 = reinterpret_cast<const uint4*>(P.qdesc)[2 * qi], q1 = reinterpret_cast<const uint4*>(P.qdesc)[2 * qi + 1];
+
+    // pass 0 counts, pass 1 writes (the candidate test is cheap; distances only in pass 1)
+    int base = 0, total = 0;
+    for (int pass = 0; pass < 2; pass++) {
+        int pos = 0;
+        for (int ix = cx0; ix <= cx1; ix++) {
+            const int s = cs[ix * GR + cy0], e = cs[ix * GR + cy1 + 1];
+            for (int k0 = s; k0 < e; k0 += 32) {
+                const int k = k0 + lane;
+                bool ok = false; int i2 = 0; int oct = 0;
+                if (k < e) {
+                    i2 = items[k];
+                    const orbx_keypoint kp = P.k2[i2];
+                    oct = kp.octave;
+                    ok = true;
+                    if (check_levels) {
+                        if (oct < Q.minl) ok = false;
+                        if (Q.maxl >= 0 && oct > Q.maxl) ok = false;
+                    }
+                    const float dx = __fsub_rn(kp.x, Q.u), dy = __fsub_rn(kp.y, Q.v);
+                    if (!(fabsf(dx) < Q.r && fabsf(dy) < Q.r)) ok = false;
+                    // stereo gate (ORBmatcher.cc:93-98 / :2049-2055): not order dependent, applied here
+                    if (ok && P.uright2) {
+                        const float ur2 = P.uright2[i2];
+                        if (ur2 > 0 && fabsf(__fsub_rn(Q.ur, ur2)) > Q.r) ok = false;
+                    }
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, ok);
+                if (pass == 1 && ok) {
+                    const int o = pos + __popc(bal & ((1u << lane) - 1));
+                    const uint4 t0 = reinterpret_cast<const uint4*>(P.d2)[2 * i2], t1 = reinterpret_cast<const uint4*>(P.d2)[2 * i2 + 1];
+                    const int d = hamming256(q0, q1, t0, t1);
+                    if (base + o < W.POOL)
+                        W.pool[(long long)p * W.POOL + base + o] = (uint32_t)i2 | ((uint32_t)d << 16) | ((uint32_t)oct << 25);
+                }
+                pos += __popc(bal);
+            }
+        }
+        if (pass == 0) {
+            total = pos;
+            if (lane == 0) base = total ? atomicAdd(W.pool_used + p, total) : 0;
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base + total > W.POOL) {
+                if (lane == 0) { atomicOr(W.err, ORBX_DEVERR_POOL_OVERFLOW); *q_off = 0; *q_cnt = 0; }
+                return;
+            }
+            if (lane == 0) { *q_off = base; *q_cnt = total; }
+            if (total == 0) return;
+        }
+    }
+}
+
+// warp-wide top-2 merge by (dist, rank): each lane holds (d0, k0, e0) best and (d1, e1) second
+__device__ __forceinline__ void warp_top2(int& d0, int& k0, uint32_t& e0, int& d1, uint32_t& e1, int& k1)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const int od0 = __shfl_xor_sync(0xffffffffu, d0, o), ok0 = __shfl_xor_sync(0xffffffffu, k0, o);
+        const uint32_t oe0 = __shfl_xor_sync(0xffffffffu, e0, o);
+        const int od1 = __shfl_xor_sync(0xffffffffu, d1, o), ok1 = __shfl_xor_sync(0xffffffffu, k1, o);
+        const uint32_t oe1 = __shfl_xor_sync(0xffffffffu, e1, o);
+        // candidates for second place: loser of the firsts, and both seconds
+        int ld, lk; uint32_t le;
+        if (od0 < d0 || (od0 == d0 && ok0 < k0)) { ld = d0; lk = k0; le = e0; d0 = od0; k0 = ok0; e0 = oe0; }
+        else { ld = od0; lk = ok0; le = oe0; }
+        if (od1 < d1 || (od1 == d1 && ok1 < k1)) { d1 = od1; k1 = ok1; e1 = oe1; }
+        if (ld < d1 || (ld == d1 && lk < k1)) { d1 = ld; k1 = lk; e1 = le; }
+    }
+}
+
+__device__ __forceinline__ int rot_bin(float a1, float a2)
+{
+    const float factor = 1.0f / ORBX_HISTO_LENGTH;
+    float rot = __fsub_rn(a1, a2);
+    if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+    int bin = (int)roundf(__fmul_rn(rot, factor));
+    if (bin == ORBX_HISTO_LENGTH) bin = 0;
+    return bin;
+}
+
+// ORBmatcher::ComputeThreeMaxima on bin counts; all lanes compute the same result
+__device__ __forceinline__ void three_maxima(const int* hist, int& ind1, int& ind2, int& ind3)
+{
+    int max1 = 0, max2 = 0, max3 = 0;
+    ind1 = ind2 = ind3 = -1;
+    for (int i = 0; i < ORBX_HISTO_LENGTH; i++) {
+        const int s = hist[i];
+        if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+        else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+        else if (s > max3) { max3 = s; ind3 = i; }
+    }
+    if ((float)max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+    else if ((float)max3 < 0.1f * (float)max1) { ind3 = -1; }
+}
+
+// mode 2 = SearchForInitialization, 0 / 1 = SearchByProjection overloads (see orbx.h)
+// out: mode 2 -> matches12 [P][K] (+ prev_xy update when prev != null); modes 0/1 -> assigned [P][K] (in/out)
+__global__ void __launch_bounds__(32) k_window_resolve(WinBufs W, int mode, float nnratio, int check_ori,
+                                                     int32_t* out, int32_t* nmatches, float* prev_xy)
+{
+    extern __shared__ int s_mem[];
+    const int lane = threadIdx.x;
+    const int p = blockIdx.x;
+    const PairDesc P = W.pairs[p];
+    const int nq = min(P.nq, W.K), n2 = min(P.n2, W.K);
+    int* matchedDist = s_mem;                 // [K] (mode 2)
+    int* matches21 = s_mem + W.K;             // [K] (mode 2)
+    __shared__ int hist[ORBX_HISTO_LENGTH];
+    int32_t* res = out + (long long)p * W.K;
+    uint8_t* bin_of = W.bin_of + (long long)p * W.K;
+    const uint32_t* pool = W.pool + (long long)p * W.POOL;
+    const int* q_off = W.q_off + (long long)p * W.K;
+    const int* q_cnt = W.q_cnt + (long long)p * W.K;
+    if (lane < ORBX_HISTO_LENGTH) hist[lane] = 0;
+    if (mode == 2) {
+        for (int i = lane; i < n2; i += 32) { matchedDist[i] = 0x7fffffff; matches21[i] = -1; }
+        for (int i = lane; i < nq; i += 32) { res[i] = -1; bin_of[i] = 0xFF; }
+    } else {
+        for (int i = lane; i < n2; i += 32) bin_of[i] = 0xFF;
+    }
+    __syncwarp();
+
+    for (int i = 0; i < nq; i++) {
+        const int cnt = q_cnt[i];
+        if (cnt == 0) continue;
+        const int off = q_off[i];
+        int d0 = 0x7fffffff, k0 = 0x7fffffff, d1 = 0x7fffffff, k1 = 0x7fffffff;
+        uint32_t e0 = 0, e1 = 0;
+        for (int k = lane; k < cnt; k += 32) {
+            const uint32_t e = pool[off + k];
+            const int i2 = e & 0xFFFF, d = (e >> 16) & 0x1FF;
+            bool skip;
+            if (mode == 2) skip = matchedDist[i2] <= d;          // ORBmatcher.cc:741
+            else skip = res[i2] >= 0;                            // occupied keypoint, :89-91 / :2045-2047
+            if (skip) continue;
+            if (d < d0) { d1 = d0; k1 = k0; e1 = e0; d0 = d; k0 = k; e0 = e; }
+            else if (d < d1) { d1 = d; k1 = k; e1 = e; }
+        }
+        warp_top2(d0, k0, e0, d1, e1, k1);
+        // every lane now holds the same (best, second); lane 0 applies the sequential rule
+        if (mode == 2) {
+            if (d0 <= ORBX_TH_LOW && (float)d0 < (float)d1 * nnratio) {     // :756-758 (INT_MAX second -> float)
+                const int i2 = e0 & 0xFFFF;
+                if (lane == 0) {
+                    if (matches21[i2] >= 0) res[matches21[i2]] = -1;
+                    res[i] = i2; matches21[i2] = i; matchedDist[i2] = d0;
+                    if (check_ori) {
+                        const int bin = rot_bin(P.q[i].angle, P.k2[i2].angle);
+                        bin_of[i] = (uint8_t)bin; hist[bin]++;
+                    }
+                }
+            }
+        } else if (mode == 0) {
+            // best starts at 256 and must be <= TH_HIGH (:2038, :2068)
+            if (d0 <= ORBX_TH_HIGH) {
+                const int i2 = e0 & 0xFFFF;
+                if (lane == 0) {
+                    res[i2] = i;
+                    if (check_ori) { const int bin = rot_bin(P.q[i].angle, P.k2[i2].angle); bin_of[i2] = (uint8_t)bin; hist[bin]++; }
+                }
+            }
+        } else {
+            // :78-141: best/second start at 256 with level -1
+            const int bd = d0 < 256 ? d0 : 256, bd2 = d1 < 256 ? d1 : 256;
+            const int bl = d0 < 256 ? (int)(e0 >> 25) : -1, bl2 = d1 < 256 ? (int)(e1 >> 25) : -1;
+            if (bd <= ORBX_TH_HIGH && !(bl == bl2 && (float)bd > nnratio * (float)bd2)) {
+                if (lane == 0) res[e0 & 0xFFFF] = i;
+            }
+        }
+        __syncwarp();
+    }
+    __syncwarp();
+    // rotation consistency (:786-809 / :2163-2183)
+    if (check_ori && mode != 1) {
+        int ind1, ind2, ind3;
+        three_maxima(hist, ind1, ind2, ind3);
+        const int lim = mode == 2 ? nq : n2;
+        for (int i = lane; i < lim; i += 32) {
+            const int b = bin_of[i];
+            if (b != 0xFF && b != ind1 && b != ind2 && b != ind3) res[i] = -1;
+        }
+        __syncwarp();
+    }
+    int cntm = 0;
+    const int lim = mode == 2 ? nq : n2;
+    for (int i = lane; i < lim; i += 32) {
+        const int m = res[i];
+        if (mode == 2) {
+            if (m >= 0) { cntm++; if (prev_xy) { prev_xy[((long long)p * W.K + i) * 2] = P.k2[m].x; prev_xy[((long long)p * W.K + i) * 2 + 1] = P.k2[m].y; } }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cntm += __shfl_xor_sync(0xffffffffu, cntm, o);
+    if (lane == 0 && mode == 2) nmatches[p] = cntm;
+}
+
+// modes 0/1 count matches as "queries that own a keypoint they took in this call"
+__global__ void k_count_new_assigned(const int32_t* before, const int32_t* after, int n, int32_t* count)
+{
+    __shared__ int s;
+    if (threadIdx.x == 0) s = 0;
+    __syncthreads();
+    int c = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) c += (after[i] >= 0 && before[i] < 0) ? 1 : 0;
+    atomicAdd(&s, c);
+    __syncthreads();
+    if (threadIdx.x == 0) *count = s;
+}
+
+// Frame::ComputeStereoMatches descriptor search: one warp per left keypoint, right keypoints in index order
+__global__ void __launch_bounds__(256) k_stereo_band(const orbx_keypoint* kl, const uint8_t* dl, int nl,
+                                                   const orbx_keypoint* kr, const uint8_t* dr, int nr,
+                                                   const float* sf, int nrows, float minD, float maxD,
+                                                   int32_t* best_idx, int32_t* best_dist)
+{
+    const int lane = threadIdx.x & 31;
+    const int iL = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (iL >= nl) return;
+    const orbx_keypoint L = kl[iL];
+    const int row = (int)L.y;
+    const float minU = __fsub_rn(L.x, maxD), maxU = __fsub_rn(L.x, minD);
+    int bd = ORBX_TH_HIGH, bi = 0x7fffffff;
+    if (row >= 0 && row < nrows && !(maxU < 0)) {
+        const uint4 q0 = reinterpret_cast<const uint4*>(dl)[2 * iL], q1 = reinterpret_cast<const uint4*>(dl)[2 * iL + 1];
+        for (int iR = lane; iR < nr; iR += 32) {
+            const orbx_keypoint R = kr[iR];
+            const float r = __fmul_rn(2.0f, sf[R.octave]);
+            const int maxr = (int)ceilf(__fadd_rn(R.y, r)), minr = (int)floorf(__fsub_rn(R.y, r));
+            if (row < minr || row > maxr) continue;
+            if (R.octave < L.octave - 1 || R.octave > L.octave + 1) continue;
+            if (!(R.x >= minU && R.x <= maxU)) continue;
+            const uint4 t0 = reinterpret_cast<const uint4*>(dr)[2 * iR], t1 = reinterpret_cast<const uint4*>(dr)[2 * iR + 1];
+            const int d = hamming256(q0, q1, t0, t1);
+            if (d < bd) { bd = d; bi = iR; }     // iR ascending per lane: first wins inside the lane
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const int od = __shfl_xor_sync(0xffffffffu, bd, o), oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+    }
+    if (lane == 0) { best_idx[iL] = bi == 0x7fffffff ? -1 : bi; best_dist[iL] = bd; }
+}
+
+// register-only throughput probes
+__global__ void k_popc_probe(unsigned seed, int iters, unsigned* sink)
+{
+    unsigned a0 = seed + threadIdx.x, a1 = a0 * 3, a2 = a0 * 5, a3 = a0 * 7, a4 = a0 * 11, a5 = a0 * 13, a6 = a0 * 17, a7 = a0 * 19;
+    for (int i = 0; i < iters; i++) {
+        a0 = __popc(a0) + a1; a1 = __popc(a1) + a2; a2 = __popc(a2) + a3; a3 = __popc(a3) + a4;
+        a4 = __popc(a4) + a5; a5 = __popc(a5) + a6; a6 = __popc(a6) + a7; a7 = __popc(a7) + a0;
+    }
+    if ((a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7) == 0x12345678u) *sink = a0;
+}
+__global__ void k_lop3_probe(unsigned seed, int iters, unsigned* sink)
+{
+    unsigned a0 = seed + threadIdx.x, a1 = a0 * 3, a2 = a0 * 5, a3 = a0 * 7, a4 = a0 * 11, a5 = a0 * 13, a6 = a0 * 17, a7 = a0 * 19;
+    for (int i = 0; i < iters; i++) {
+        a0 = (a0 & a1) ^ a2; a1 = (a1 & a2) ^ a3; a2 = (a2 & a3) ^ a4; a3 = (a3 & a4) ^ a5;
+        a4 = (a4 & a5) ^ a6; a5 = (a5 & a6) ^ a7; a6 = (a6 & a7) ^ a0; a7 = (a7 & a0) ^ a1;
+    }
+    if ((a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7) == 0x12345678u) *sink = a0;
+}
+
+}  // namespace
+
+// ===================================================================================================
+struct orbx_matcher {
+    orbx_matcher_params p;
+    int K, P, POOL;
+    cudaStream_t stream;
+    WinBufs W;
+    // device staging for the host-pointer APIs (two frames + queries)
+    orbx_keypoint* d_k1; orbx_keypoint* d_k2; uint8_t* d_d1; uint8_t* d_d2; uint8_t* d_qdesc; float* d_uright;
+    float* d_prev; int32_t* d_out; int32_t* d_out2; int32_t* d_nm; float* d_sf;
+    int32_t* d_knn_idx; int32_t* d_knn_dist;
+    int32_t* d_part_idx; int32_t* d_part_dist; size_t part_elems;
+    uint8_t* d_bfq; uint8_t* d_bft; size_t bfq_bytes, bft_bytes;
+    unsigned* h_err;
+    std::vector<void*> allocs;
+};
+
+static int m_alloc(orbx_matcher* m, void** p, size_t bytes)
+{
+    if (bytes == 0) bytes = 16;
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess) { orbx_set_error("%s: %s", "cudaMalloc", cudaGetErrorString(e)); return ORBX_E_NOMEM; }
+    m->allocs.push_back(*p);
+    return ORBX_OK;
+}
+
+extern "C" int orbx_matcher_create(const orbx_matcher_params* p, orbx_matcher** out)
+{
+    if (!p || !out || p->max_keypoints < 1 || p->max_keypoints > 24000 || p->max_batch < 1) {
+        orbx_set_error("%s%s", "orbx_matcher_create: invalid parameters (max_keypoints must be 1..24000)", "");
+        return ORBX_E_INVALID;
+    }
+    int ndev = 0;
+    CKM(cudaGetDeviceCount(&ndev));
+    if (p->device < 0 || p->device >= ndev) { orbx_set_error("%s%s", "no such CUDA device", ""); return ORBX_E_CUDA; }
+    CKM(cudaSetDevice(p->device));
+    orbx_matcher* m = new orbx_matcher();
+    m->p = *p;
+    m->K = p->max_keypoints; m->P = p->max_batch;
+    m->POOL = p->max_candidates > 0 ? p->max_candidates : 131072;
+    CKM(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+    WinBufs& W = m->W;
+    memset(&W, 0, sizeof(W));
+    W.K = m->K; W.POOL = m->POOL;
+    const size_t K = m->K, P = m->P;
+    int rc;
+#define MA(ptr, bytes) if ((rc = m_alloc(m, (void**)&(ptr), (bytes)))) return rc
+    MA(W.pairs, sizeof(PairDesc) * P);
+    MA(W.q, sizeof(orbx_proj_query) * K * P);
+    MA(W.items, sizeof(uint16_t) * K * P);
+    MA(W.cell_start, sizeof(int) * (NCELL + 1) * P);
+    MA(W.q_off, sizeof(int) * K * P);
+    MA(W.q_cnt, sizeof(int) * K * P);
+    MA(W.pool, sizeof(uint32_t) * (size_t)m->POOL * P);
+    MA(W.pool_used, sizeof(int) * P);
+    MA(W.bin_of, K * P);
+    MA(W.err, sizeof(unsigned));
+    MA(m->d_k1, sizeof(orbx_keypoint) * K); MA(m->d_k2, sizeof(orbx_keypoint) * K);
+    MA(m->d_d1, 32 * K); MA(m->d_d2, 32 * K); MA(m->d_qdesc, 32 * K); MA(m->d_uright, sizeof(float) * K);
+    MA(m->d_prev, sizeof(float) * 2 * K * P); MA(m->d_out, sizeof(int32_t) * K * P); MA(m->d_out2, sizeof(int32_t) * K);
+    MA(m->d_nm, sizeof(int32_t) * P); MA(m->d_sf, sizeof(float) * ORBX_MAX_LEVELS);
+    MA(m->d_knn_idx, sizeof(int32_t) * 2 * K); MA(m->d_knn_dist, sizeof(int32_t) * 2 * K);
+#undef MA
+    m->d_part_idx = m->d_part_dist = nullptr; m->part_elems = 0;
+    m->d_bfq = m->d_bft = nullptr; m->bfq_bytes = m->bft_bytes = 0;
+    CKM(cudaMemset(W.err, 0, sizeof(unsigned)));
+    CKM(cudaMallocHost((void**)&m->h_err, sizeof(unsigned)));
+    if (2 * K * sizeof(int) > 48 * 1024)
+        CKM(cudaFuncSetAttribute(k_window_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * K * sizeof(int))));
+    {
+        size_t npad = 1; while (npad < K) npad <<= 1;
+        if (npad * sizeof(uint32_t) > 48 * 1024)
+            CKM(cudaFuncSetAttribute(k_grid_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(npad * sizeof(uint32_t))));
+    }
+    *out = m;
+    return ORBX_OK;
+}
+
+extern "C" void orbx_matcher_destroy(orbx_matcher* m)
+{
+    if (!m) return;
+    cudaSetDevice(m->p.device);
+    cudaStreamSynchronize(m->stream);
+    for (void* p : m->allocs) cudaFree(p);
+    if (m->d_part_idx) cudaFree(m->d_part_idx);
+    if (m->d_part_dist) cudaFree(m->d_part_dist);
+    if (m->d_bfq) cudaFree(m->d_bfq);
+    if (m->d_bft) cudaFree(m->d_bft);
+    cudaFreeHost(m->h_err);
+    cudaStreamDestroy(m->stream);
+    delete m;
+}
+
+static int m_check_err(orbx_matcher* m, cudaStream_t s)
+{
+    CKM(cudaMemcpyAsync(m->h_err, m->W.err, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+    CKM(cudaStreamSynchronize(s));
+    if (*m->h_err) {
+        char buf[32]; snprintf(buf, sizeof(buf), "0x%x", *m->h_err);
+        orbx_set_error("matcher device capacity error flags %s%s", buf, " (raise max_candidates)");
+        cudaMemsetAsync(m->W.err, 0, sizeof(unsigned), s);
+        return ORBX_E_CAPACITY;
+    }
+    return ORBX_OK;
+}
+
+extern "C" int orbx_matcher_sync(orbx_matcher* m, void* stream)
+{
+    if (!m) return ORBX_E_INVALID;
+    return m_check_err(m, stream ? (cudaStream_t)stream : m->stream);
+}
+
+extern "C" int orbx_hamming_pairs(orbx_matcher* m, const uint8_t* a, const uint8_t* b, int n, int32_t* out)
+{
+    if (!m || n < 0 || (n > 0 && (!a || !b || !out))) return ORBX_E_INVALID;
+    if (n == 0) return ORBX_OK;
+    CKM(cudaSetDevice(m->p.device));
+    for (int done = 0; done < n; done += m->K) {
+        const int c = n - done < m->K ? n - done : m->K;
+        CKM(cudaMemcpyAsync(m->d_d1, a + (size_t)done * 32, (size_t)c * 32, cudaMemcpyHostToDevice, m->stream));
+        CKM(cudaMemcpyAsync(m->d_d2, b + (size_t)done * 32, (size_t)c * 32, cudaMemcpyHostToDevice, m->stream));
+        k_hamming_pairs<<<(c + 255) / 256, 256, 0, m->stream>>>((const uint4*)m->d_d1, (const uint4*)m->d_d2, c, m->d_out);
+        CKM(cudaMemcpyAsync(out + done, m->d_out, sizeof(int32_t) * c, cudaMemcpyDeviceToHost, m->stream));
+        CKM(cudaStreamSynchronize(m->stream));
+    }
+    return ORBX_OK;
+}
+
+static int ensure_parts(orbx_matcher* m, size_t elems)
+{
+    if (elems <= m->part_elems) return ORBX_OK;
+    if (m->d_part_idx) cudaFree(m->d_part_idx);
+    if (m->d_part_dist) cudaFree(m->d_part_dist);
+    CKM(cudaMalloc((void**)&m->d_part_idx, sizeof(int32_t) * elems));
+    CKM(cudaMalloc((void**)&m->d_part_dist, sizeof(int32_t) * elems));
+    m->part_elems = elems;
+    return ORBX_OK;
+}
+
+static int bf_launch(orbx_matcher* m, BfArgs A, int npairs, int nq_max, long long nt_max, cudaStream_t s)
+{
+    // split the train set so that a small query set still fills the 148 SMs
+    const int qblocks = (nq_max + BF_NT - 1) / BF_NT;
+    int nsplit = 1;
+    const long long tiles = (nt_max + BF_TILE - 1) / BF_TILE;
+    if (tiles > 0) {
+        const int want = 148 * 8;
+        while ((long long)qblocks * npairs * nsplit < want && nsplit * 2 <= tiles && nsplit < 1024) nsplit *= 2;
+    }
+    long long chunk = (nt_max + nsplit - 1) / nsplit;
+    chunk = (chunk + BF_TILE - 1) / BF_TILE * BF_TILE;
+    if (chunk < BF_TILE) chunk = BF_TILE;
+    A.chunk = chunk; A.nsplit = nsplit;
+    if (nsplit > 1) {
+        int rc = ensure_parts(m, (size_t)npairs * nsplit * A.out_stride * 2);
+        if (rc) return rc;
+        A.part_idx = m->d_part_idx; A.part_dist = m->d_part_dist;
+    }
+    if (qblocks == 0 || npairs == 0) return ORBX_OK;
+    dim3 grid(qblocks, nsplit, npairs);
+    k_bf_knn2<<<grid, BF_NT, 0, s>>>(A);
+    if (nsplit > 1) {
+        dim3 mg((nq_max + 127) / 128, npairs);
+        k_knn2_merge<<<mg, 128, 0, s>>>(A.part_idx, A.part_dist, nsplit, A.out_stride, A.nq, A.q ? nullptr : A.n, A.a, A.idx, A.dist);
+    }
+    CKM(cudaGetLastError());
+    return ORBX_OK;
+}
+
+extern "C" int orbx_bf_knn2_device(orbx_matcher* m, const uint8_t* d_q, int nq, const uint8_t* d_t, long long nt,
+                                   int32_t* d_idx, int32_t* d_dist, int idx_base, void* stream)
+{
+    if (!m || nq < 0 || nt < 0 || !d_idx || !d_dist) return ORBX_E_INVALID;
+    if (nq == 0) return ORBX_OK;
+    CKM(cudaSetDevice(m->p.device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : m->stream;
+    BfArgs A{};
+    A.q = d_q; A.t = d_t; A.nq = nq; A.nt = nt; A.idx = d_idx; A.dist = d_dist; A.out_stride = nq; A.idx_base = idx_base;
+    return bf_launch(m, A, 1, nq, nt, s);
+}
+
+extern "C" int orbx_bf_knn2(orbx_matcher* m, const uint8_t* q, int nq, const uint8_t* t, int nt, int32_t* idx, int32_t* dist)
+{
+    if (!m || nq < 0 || nt < 0 || (nq > 0 && (!q || !idx || !dist)) || (nt > 0 && !t)) return ORBX_E_INVALID;
+    if (nq == 0) return ORBX_OK;
+    CKM(cudaSetDevice(m->p.device));
+    if ((size_t)nq * 32 > m->bfq_bytes) { if (m->d_bfq) cudaFree(m->d_bfq); m->bfq_bytes = (size_t)nq * 32; CKM(cudaMalloc((void**)&m->d_bfq, m->bfq_bytes + (size_t)nq * 16)); }
+    if ((size_t)nt * 32 > m->bft_bytes) { if (m->d_bft) cudaFree(m->d_bft); m->bft_bytes = (size_t)nt * 32; CKM(cudaMalloc((void**)&m->d_bft, m->bft_bytes + 32)); }
+    // result tables live behind the query copy
+    int32_t* d_idx = reinterpret_cast<int32_t*>(m->d_bfq + (size_t)nq * 32);
+    int32_t* d_dist = d_idx + 2 * nq;
+    CKM(cudaMemcpyAsync(m->d_bfq, q, (size_t)nq * 32, cudaMemcpyHostToDevice, m->stream));
+    if (nt) CKM(cudaMemcpyAsync(m->d_bft, t, (size_t)nt * 32, cudaMemcpyHostToDevice, m->stream));
+    int rc = orbx_bf_knn2_device(m, m->d_bfq, nq, m->d_bft, nt, d_idx, d_dist, 0, m->stream);
+    if (rc) return rc;
+    CKM(cudaMemcpyAsync(idx, d_idx, sizeof(int32_t) * 2 * nq, cudaMemcpyDeviceToHost, m->stream));
+    CKM(cudaMemcpyAsync(dist, d_dist, sizeof(int32_t) * 2 * nq, cudaMemcpyDeviceToHost, m->stream));
+    CKM(cudaStreamSynchronize(m->stream));
+    return ORBX_OK;
+}
+
+extern "C" int orbx_knn2_merge_device(orbx_matcher* m, const int32_t* d_idx_parts, const int32_t* d_dist_parts, int nparts,
+                                      int nq, int32_t* d_idx, int32_t* d_dist, void* stream)
+{
+    if (!m || nparts < 1 || nq < 0) return ORBX_E_INVALID;
+    if (nq == 0) return ORBX_OK;
+    CKM(cudaSetDevice(m->p.device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : m->stream;
+    dim3 mg((nq + 127) / 128, 1);
+    k_knn2_merge<<<mg, 128, 0, s>>>(d_idx_parts, d_dist_parts, nparts, nq, nq, nullptr, nullptr, d_idx, d_dist);
+    CKM(cudaGetLastError());
+    return ORBX_OK;
+}
+
+static void set_bounds(orbx_matcher* m, const float bounds[4])
+{
+    WinBufs& W = m->W;
+    W.minX = bounds[0]; W.maxX = bounds[1]; W.minY = bounds[2]; W.maxY = bounds[3];
+    W.wInv = (float)GC / (W.maxX - W.minX);      // R/src/Frame.cc:318-319
+    W.hInv = (float)GR / (W.maxY - W.minY);
+}
+
+static int run_window(orbx_matcher* m, int npairs, int nq_max, int mode, float nnratio, int check_ori,
+                      int32_t* d_out, int32_t* d_nm, float* d_prev, cudaStream_t s)
+{
+    int npad = 1; while (npad < m->K) npad <<= 1;
+    CKM(cudaMemsetAsync(m->W.pool_used, 0, sizeof(int) * npairs, s));
+    k_grid_build<<<npairs, GRID_NT, sizeof(uint32_t) * npad, s>>>(m->W, npad);
+    dim3 cg((nq_max + CAND_WARPS - 1) / CAND_WARPS, npairs);
+    if (nq_max > 0) k_window_candidates<<<cg, CAND_WARPS * 32, 0, s>>>(m->W);
+    k_window_resolve<<<npairs, 32, 2 * m->K * sizeof(int), s>>>(m->W, mode, nnratio, check_ori, d_out, d_nm, d_prev);
+    CKM(cudaGetLastError());
+    return ORBX_OK;
+}
+
+extern "C" int orbx_search_for_initialization(orbx_matcher* m, const orbx_keypoint* k1, const uint8_t* d1, int n1,
+                                              const orbx_keypoint* k2, const uint8_t* d2, int n2, const float bounds[4],
+                                              float* prev_xy, int32_t* matches12, int window, float nnratio, int check_ori,
+                                              int* nmatches)
+{
+    if (!m || n1 < 0 || n2 < 0 || n1 > m->K || n2 > m->K || !bounds || (n1 > 0 && (!k1 || !d1 || !prev_xy || !matches12)) ||
+        (n2 > 0 && (!k2 || !d2))) {
+        orbx_set_error("%s%s", "orbx_search_for_initialization: invalid arguments / more keypoints than max_keypoints", "");
+        return ORBX_E_INVALID;
+    }
+    if (nmatches) *nmatches = 0;
+    if (n1 == 0) return ORBX_OK;
+    CKM(cudaSetDevice(m->p.device));
+    cudaStream_t s = m->stream;
+    set_bounds(m, bounds);
+    CKM(cudaMemcpyAsync(m->d_k1, k1, sizeof(orbx_keypoint) * n1, cudaMemcpyHostToDevice, s));
+    CKM(cudaMemcpyAsync(m->d_d1, d1, (size_t)32 * n1, cudaMemcpyHostToDevice, s));
+    if (n2) {
+        CKM(cudaMemcpyAsync(m->d_k2, k2, sizeof(orbx_keypoint) * n2, cudaMemcpyHostToDevice, s));
+        CKM(cudaMemcpyAsync(m->d_d2, d2, (size_t)32 * n2, cudaMemcpyHostToDevice, s));
+    }
+    CKM(cudaMemcpyAsync(m->d_prev, prev_xy, sizeof(float) * 2 * n1, cudaMemcpyHostToDevice, s));
+    PairDesc pd{};
+    pd.k1 = m->d_k1; pd.d1 = m->d_d1; pd.k2 = m->d_k2; pd.d2 = m->d_d2; pd.uright2 = nullptr;
+    pd.q = m->W.q; pd.qdesc = m->d_d1; pd.n1 = n1; pd.n2 = n2; pd.nq = n1;
+    CKM(cudaMemcpyAsync(m->W.pairs, &pd, sizeof(pd), cudaMemcpyHostToDevice, s));
+    k_make_init_queries<<<(n1 + 255) / 256, 256, 0, s>>>(m->W.q, m->d_k1, m->d_prev, n1, (float)window);
+    int rc = run_window(m, 1, n1, 2, nnratio, check_ori, m->d_out, m->d_nm, m->d_prev, s);
+    if (rc) return rc;
+    int nm = 0;
+    CKM(cudaMemcpyAsync(matches12, m->d_out, sizeof(int32_t) * n1, cudaMemcpyDeviceToHost, s));
+    CKM(cudaMemcpyAsync(prev_xy, m->d_prev, sizeof(float) * 2 * n1, cudaMemcpyDeviceToHost, s));
+    CKM(cudaMemcpyAsync(&nm, m->d_nm, sizeof(int), cudaMemcpyDeviceToHost, s));
+    rc = m_check_err(m, s);
+    if (rc) return rc;
+    if (nmatches) *nmatches = nm;
+    return ORBX_OK;
+}
+
+extern "C" int orbx_search_by_projection(orbx_matcher* m, int mode, const orbx_proj_query* q, const uint8_t* qdesc, int nq,
+                                         const orbx_keypoint* k2, const uint8_t* d2, const float* uright2, int n2,
+                                         const float bounds[4], int32_t* assigned, float nnratio, int check_ori, int* nmatches)
+{
+    if (!m || (mode != 0 && mode != 1) || nq < 0 || n2 < 0 || nq > m->K || n2 > m->K || !bounds ||
+        (nq > 0 && (!q || !qdesc)) || (n2 > 0 && (!k2 || !d2 || !assigned))) {
+        orbx_set_error("%s%s", "orbx_search_by_projection: invalid arguments / more keypoints than max_keypoints", "");
+        return ORBX_E_INVALID;
+    }
+    if (nmatches) *nmatches = 0;
+    if (nq == 0 || n2 == 0) return ORBX_OK;
+    CKM(cudaSetDevice(m->p.device));
+    cudaStream_t s = m->stream;
+    set_bounds(m, bounds);
+    CKM(cudaMemcpyAsync(m->W.q, q, sizeof(orbx_proj_query) * nq, cudaMemcpyHostToDevice, s));
+    CKM(cudaMemcpyAsync(m->d_qdesc, qdesc, (size_t)32 * nq, cudaMemcpyHostToDevice, s));
+    CKM(cudaMemcpyAsync(m->d_k2, k2, sizeof(orbx_keypoint) * n2, cudaMemcpyHostToDevice, s));
+    CKM(cudaMemcpyAsync(m->d_d2, d2, (size_t)32 * n2, cudaMemcpyHostToDevice, s));
+    if (uright2) CKM(cudaMemcpyAsync(m->d_uright, uright2, sizeof(float) * n2, cudaMemcpyHostToDevice, s));
+    CKM(cudaMemcpyAsync(m->d_out, assigned, sizeof(int32_t) * n2, cudaMemcpyHostToDevice, s));
+    CKM(cudaMemcpyAsync(m->d_out2, assigned, sizeof(int32_t) * n2, cudaMemcpyHostToDevice, s));
+    PairDesc pd{};
+    pd.k1 = nullptr; pd.d1 = nullptr; pd.k2 = m->d_k2; pd.d2 = m->d_d2; pd.uright2 = uright2 ? m->d_uright : nullptr;
+    pd.q = m->W.q; pd.qdesc = m->d_qdesc; pd.n1 = nq; pd.n2 = n2; pd.nq = nq;
+    CKM(cudaMemcpyAsync(m->W.pairs, &pd, sizeof(pd), cudaMemcpyHostToDevice, s));
+    int rc = run_window(m, 1, nq, mode, nnratio, check_ori, m->d_out, m->d_nm, nullptr, s);
+    if (rc) return rc;
+    k_count_new_assigned<<<1, 256, 0, s>>>(m->d_out2, m->d_out, n2, m->d_nm);
+    int nm = 0;
+    CKM(cudaMemcpyAsync(assigned, m->d_out, sizeof(int32_t) * n2, cudaMemcpyDeviceToHost, s));
+    CKM(cudaMemcpyAsync(&nm, m->d_nm, sizeof(int), cudaMemcpyDeviceToHost, s));
+    rc = m_check_err(m, s);
+    if (rc) return rc;
+    if (nmatches) *nmatches = nm;
+    return ORBX_OK;
+}
+
+extern "C" int orbx_match_slots_device(orbx_matcher* m, orbx_extractor* ex, const int32_t* a, const int32_t* b, int npairs,
+                                       const float bounds[4], int window, float nnratio, int check_ori,
+                                       int32_t* d_matches12, int32_t* d_nmatches, int32_t* d_knn_idx, int32_t* d_knn_dist,
+                                       void* stream)
+{
+    if (!m || !ex || !a || !b || npairs < 1 || npairs > m->P || !bounds || !d_matches12 || !d_nmatches) return ORBX_E_INVALID;
+    orbx_keypoint* kps; uint8_t* desc; int32_t* n; int32_t* mono; int cap, slots;
+    int rc = orbx_extractor_results_device(ex, &kps, &desc, &n, &mono, &cap, &slots);
+    if (rc) return rc;
+    if (cap > m->K) { orbx_set_error("%s%s", "matcher max_keypoints smaller than the extractor's result capacity", ""); return ORBX_E_INVALID; }
+    CKM(cudaSetDevice(m->p.device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : m->stream;
+    set_bounds(m, bounds);
+    // NOTE: outputs use row stride K (= matcher max_keypoints)
+    k_setup_slot_pairs<<<npairs, 256, 0, s>>>(m->W, kps, desc, n, a, b, cap, (float)window);
+    rc = run_window(m, npairs, cap, 2, nnratio, check_ori, d_matches12, d_nmatches, nullptr, s);
+    if (rc) return rc;
+    if (d_knn_idx && d_knn_dist) {
+        BfArgs A{};
+        A.q = nullptr; A.desc = desc; A.n = n; A.a = a; A.b = b; A.cap = cap;
+        A.idx = d_knn_idx; A.dist = d_knn_dist; A.out_stride = m->K; A.idx_base = 0;
+        rc = bf_launch(m, A, npairs, cap, cap, s);
+        if (rc) return rc;
+    }
+    return ORBX_OK;
+}
+
+extern "C" int orbx_stereo_band_match(orbx_matcher* m, const orbx_keypoint* kl, const uint8_t* dl, int nl,
+                                      const orbx_keypoint* kr, const uint8_t* dr, int nr, const float* scale_factors,
+                                      int nlevels, int nrows, float min_d, float max_d, int32_t* best_idx, int32_t* best_dist)
+{
+    if (!m || nl < 0 || nr < 0 || nl > m->K || nr > m->K || nlevels < 1 || nlevels > ORBX_MAX_LEVELS || !scale_factors ||
+        (nl > 0 && (!kl || !dl || !best_idx || !best_dist)) || (nr > 0 && (!kr || !dr))) return ORBX_E_INVALID;
+    if (nl == 0) return ORBX_OK;
+    CKM(cudaSetDevice(m->p.device));
+    cudaStream_t s = m->stream;
+    CKM(cudaMemcpyAsync(m->d_k1, kl, sizeof(orbx_keypoint) * nl, cudaMemcpyHostToDevice, s));
+    CKM(cudaMemcpyAsync(m->d_d1, dl, (size_t)32 * nl, cudaMemcpyHostToDevice, s));
+    if (nr) {
+        CKM(cudaMemcpyAsync(m->d_k2, kr, sizeof(orbx_keypoint) * nr, cudaMemcpyHostToDevice, s));
+        CKM(cudaMemcpyAsync(m->d_d2, dr, (size_t)32 * nr, cudaMemcpyHostToDevice, s));
+    }
+    CKM(cudaMemcpyAsync(m->d_sf, scale_factors, sizeof(float) * nlevels, cudaMemcpyHostToDevice, s));
+    k_stereo_band<<<(nl + 7) / 8, 256, 0, s>>>(m->d_k1, m->d_d1, nl, m->d_k2, m->d_d2, nr, m->d_sf, nrows, min_d, max_d,
+                                               m->d_out, m->d_out2);
+    CKM(cudaGetLastError());
+    CKM(cudaMemcpyAsync(best_idx, m->d_out, sizeof(int32_t) * nl, cudaMemcpyDeviceToHost, s));
+    CKM(cudaMemcpyAsync(best_dist, m->d_out2, sizeof(int32_t) * nl, cudaMemcpyDeviceToHost, s));
+    CKM(cudaStreamSynchronize(s));
+    return ORBX_OK;
+}
+
+extern "C" int orbx_popc_peak(int device, double* popc_per_s, double* lop3_per_s)
+{
+    CKM(cudaSetDevice(device));
+    unsigned* sink; CKM(cudaMalloc((void**)&sink, 4));
+    cudaEvent_t e0, e1; CKM(cudaEventCreate(&e0)); CKM(cudaEventCreate(&e1));
+    const int iters = 4096, blocks = 148 * 8, threads = 256;
+    for (int which = 0; which < 2; which++) {
+        float best = 1e30f;
+        for (int rep = 0; rep < 5; rep++) {
+            CKM(cudaEventRecord(e0));
+            if (which == 0) k_popc_probe<<<blocks, threads>>>(rep, iters, sink); else k_lop3_probe<<<blocks, threads>>>(rep, iters, sink);
+            CKM(cudaEventRecord(e1));
+            CKM(cudaEventSynchronize(e1));
+            float ms; CKM(cudaEventElapsedTime(&ms, e0, e1));
+            if (rep > 0 && ms < best) best = ms;
+        }
+        // popc probe: 8 popc per iteration; lop3 probe: 8 LOP3 per iteration (and-xor fuses into one LOP3)
+        const double ops = (double)iters * 8 * blocks * threads;
+        if (which == 0 && popc_per_s) *popc_per_s = ops / (best * 1e-3);
+        if (which == 1 && lop3_per_s) *lop3_per_s = ops / (best * 1e-3);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
+    return ORBX_OK;
+}

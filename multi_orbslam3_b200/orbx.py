@@ -1,0 +1,320 @@
+"""ctypes host layer over liborbx_b200.so (include/orbx.h).
+
+Mirrors the reference's class interface for the hot path so that tests read like calls into the
+reference: ORBextractor(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST) with operator()
+(R/orb_slam3/include/ORBextractor.h:47-113) and ORBmatcher(nnratio, checkOri) with DescriptorDistance,
+SearchForInitialization, SearchByProjection (R/orb_slam3/include/ORBmatcher.h:35-108).
+
+There is no CPU fallback: importing works anywhere (so that the C ABI can be inspected), but creating an
+extractor or matcher without the CUDA library or without a GPU raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liborbx_b200.so")
+
+ORBX_OK, ORBX_E_INVALID, ORBX_E_EMPTY, ORBX_E_CUDA, ORBX_E_CAPACITY, ORBX_E_NOMEM = 0, -1, -2, -3, -4, -5
+TH_HIGH, TH_LOW, HISTO_LENGTH = 100, 50, 30
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
+                     ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])
+PROJQ_DTYPE = np.dtype([("u", "<f4"), ("v", "<f4"), ("r", "<f4"), ("minl", "<i4"), ("maxl", "<i4"),
+                        ("ur", "<f4"), ("angle", "<f4"), ("valid", "<i4")])
+assert KP_DTYPE.itemsize == 28 and PROJQ_DTYPE.itemsize == 32
+
+# every symbol include/orbx.h declares (tests check the library exports all of them)
+EXPORTS = [
+    "orbx_last_error", "orbx_device_count",
+    "orbx_extractor_create", "orbx_extractor_destroy", "orbx_extractor_tables", "orbx_extractor_max_keypoints",
+    "orbx_extract", "orbx_extract_batch", "orbx_extract_batch_device", "orbx_extractor_copy_slot",
+    "orbx_extractor_results_device", "orbx_extractor_download", "orbx_extractor_sync",
+    "orbx_pyramid_level_size", "orbx_pyramid_to_host", "orbx_blurred_to_host", "orbx_candidates_to_host",
+    "orbx_level_keypoints_to_host",
+    "orbx_matcher_create", "orbx_matcher_destroy", "orbx_matcher_sync", "orbx_hamming_pairs",
+    "orbx_bf_knn2", "orbx_bf_knn2_device", "orbx_knn2_merge_device",
+    "orbx_search_for_initialization", "orbx_match_slots_device", "orbx_search_by_projection",
+    "orbx_stereo_band_match", "orbx_popc_peak",
+]
+
+
+class OrbxError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("orbx error %d: %s" % (code, msg))
+        self.code = code
+
+
+class Params(C.Structure):
+    _fields_ = [("nfeatures", C.c_int32), ("scale_factor", C.c_float), ("nlevels", C.c_int32),
+                ("ini_th_fast", C.c_int32), ("min_th_fast", C.c_int32), ("max_width", C.c_int32),
+                ("max_height", C.c_int32), ("max_batch", C.c_int32), ("device", C.c_int32),
+                ("max_candidates_per_level", C.c_int32)]
+
+
+class MatcherParams(C.Structure):
+    _fields_ = [("device", C.c_int32), ("max_keypoints", C.c_int32), ("max_batch", C.c_int32),
+                ("max_candidates", C.c_int32)]
+
+
+_lib = None
+
+
+def lib():
+    """Loads liborbx_b200.so; raises if it has not been built (no fallback path exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise OrbxError(ORBX_E_CUDA, "liborbx_b200.so is missing: run ./build.sh (or __graft_entry__.build())")
+        L = C.CDLL(LIB_PATH)
+        vp, i32, f32, sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+        L.orbx_last_error.restype = C.c_char_p
+        L.orbx_device_count.restype = i32
+        L.orbx_extractor_create.argtypes = [C.POINTER(Params), C.POINTER(vp)]
+        L.orbx_extractor_destroy.argtypes = [vp]
+        L.orbx_extractor_destroy.restype = None
+        L.orbx_extractor_tables.argtypes = [vp] * 6
+        L.orbx_extractor_max_keypoints.argtypes = [vp]
+        L.orbx_extract.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, vp, i32, vp, vp]
+        L.orbx_extract_batch.argtypes = [vp, vp, i32, i32, i32, i32, sz, i32, i32, vp, vp, i32, vp, vp]
+        L.orbx_extract_batch_device.argtypes = [vp, vp, i32, i32, i32, i32, sz, i32, i32, i32, vp]
+        L.orbx_extractor_copy_slot.argtypes = [vp, i32, i32, vp]
+        L.orbx_extractor_results_device.argtypes = [vp] * 7
+        L.orbx_extractor_download.argtypes = [vp, i32, i32, vp, vp, i32, vp, vp, vp]
+        L.orbx_extractor_sync.argtypes = [vp, vp]
+        L.orbx_pyramid_level_size.argtypes = [vp, i32, vp, vp]
+        L.orbx_pyramid_to_host.argtypes = [vp, i32, i32, vp, i32]
+        L.orbx_blurred_to_host.argtypes = [vp, i32, i32, vp, i32]
+        L.orbx_candidates_to_host.argtypes = [vp, i32, i32, vp, i32, vp]
+        L.orbx_level_keypoints_to_host.argtypes = [vp, i32, i32, vp, i32, vp]
+        L.orbx_matcher_create.argtypes = [C.POINTER(MatcherParams), C.POINTER(vp)]
+        L.orbx_matcher_destroy.argtypes = [vp]
+        L.orbx_matcher_destroy.restype = None
+        L.orbx_matcher_sync.argtypes = [vp, vp]
+        L.orbx_hamming_pairs.argtypes = [vp, vp, vp, i32, vp]
+        L.orbx_bf_knn2.argtypes = [vp, vp, i32, vp, i32, vp, vp]
+        L.orbx_bf_knn2_device.argtypes = [vp, vp, i32, vp, C.c_longlong, vp, vp, i32, vp]
+        L.orbx_knn2_merge_device.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp]
+        L.orbx_search_for_initialization.argtypes = [vp, vp, vp, i32, vp, vp, i32, vp, vp, vp, i32, f32, i32, vp]
+        L.orbx_match_slots_device.argtypes = [vp, vp, vp, vp, i32, vp, i32, f32, i32, vp, vp, vp, vp, vp]
+        L.orbx_search_by_projection.argtypes = [vp, i32, vp, vp, i32, vp, vp, vp, i32, vp, vp, f32, i32, vp]
+        L.orbx_stereo_band_match.argtypes = [vp, vp, vp, i32, vp, vp, i32, vp, i32, i32, f32, f32, vp, vp]
+        L.orbx_popc_peak.argtypes = [i32, vp, vp]
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != ORBX_OK:
+        raise OrbxError(rc, lib().orbx_last_error().decode())
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def device_count():
+    return lib().orbx_device_count()
+
+
+class ORBextractor:
+    """Drop-in mirror of ORB_SLAM3::ORBextractor (R/orb_slam3/include/ORBextractor.h:47-113)."""
+
+    def __init__(self, nfeatures=1000, scaleFactor=1.2, nlevels=8, iniThFAST=20, minThFAST=7,
+                 max_width=1280, max_height=1024, max_batch=1, device=0, max_candidates_per_level=0):
+        self._h = C.c_void_p()
+        self.params = Params(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, max_width, max_height,
+                             max_batch, device, max_candidates_per_level)
+        _check(lib().orbx_extractor_create(C.byref(self.params), C.byref(self._h)))
+        self.nfeatures, self.nlevels, self.max_batch = nfeatures, nlevels, max_batch
+        self.cap = lib().orbx_extractor_max_keypoints(self._h)
+        t = [np.empty(nlevels, np.float32) for _ in range(4)] + [np.empty(nlevels, np.int32)]
+        _check(lib().orbx_extractor_tables(self._h, *[_p(x) for x in t]))
+        self.mvScaleFactor, self.mvInvScaleFactor, self.mvLevelSigma2, self.mvInvLevelSigma2, self.mnFeaturesPerLevel = t
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().orbx_extractor_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    # reference getters
+    def GetLevels(self): return self.nlevels
+    def GetScaleFactor(self): return float(self.params.scale_factor)
+    def GetScaleFactors(self): return self.mvScaleFactor
+    def GetInverseScaleFactors(self): return self.mvInvScaleFactor
+    def GetScaleSigmaSquares(self): return self.mvLevelSigma2
+    def GetInverseScaleSigmaSquares(self): return self.mvInvLevelSigma2
+
+    def __call__(self, image, mask=None, vLappingArea=(0, 0)):
+        """operator(): returns (monoIndex, keypoints, descriptors); monoIndex is -1 for an empty image."""
+        img = np.ascontiguousarray(image, np.uint8)
+        if img.size == 0:
+            return -1, np.empty(0, KP_DTYPE), np.empty((0, 32), np.uint8)
+        assert img.ndim == 2, "CV_8UC1 expected (R/src/ORBextractor.cc:1076)"
+        kps = np.zeros(self.cap, KP_DTYPE)
+        desc = np.zeros((self.cap, 32), np.uint8)
+        n, mono = C.c_int(0), C.c_int(0)
+        rc = lib().orbx_extract(self._h, _p(img), img.shape[1], img.shape[0], img.strides[0],
+                                int(vLappingArea[0]), int(vLappingArea[1]), _p(kps), _p(desc), self.cap,
+                                C.byref(n), C.byref(mono))
+        if rc == ORBX_E_EMPTY:
+            return -1, np.empty(0, KP_DTYPE), np.empty((0, 32), np.uint8)
+        _check(rc)
+        return mono.value, kps[:n.value].copy(), desc[:n.value].copy()
+
+    def extract_batch(self, images, vLappingArea=(0, 0)):
+        """Host frames [B,H,W] -> list of (monoIndex, keypoints, descriptors); H2D/D2H inside."""
+        imgs = np.ascontiguousarray(images, np.uint8)
+        B, H, W = imgs.shape
+        kps = np.zeros((B, self.cap), KP_DTYPE)
+        desc = np.zeros((B, self.cap, 32), np.uint8)
+        n = np.zeros(B, np.int32); mono = np.zeros(B, np.int32)
+        _check(lib().orbx_extract_batch(self._h, _p(imgs), B, W, H, imgs.strides[1], imgs.strides[0],
+                                        int(vLappingArea[0]), int(vLappingArea[1]), _p(kps), _p(desc), self.cap,
+                                        _p(n), _p(mono)))
+        return [(int(mono[i]), kps[i, :n[i]].copy(), desc[i, :n[i]].copy()) for i in range(B)]
+
+    def extract_batch_device(self, d_ptr, batch, width, height, stride, frame_stride, vLappingArea=(0, 0),
+                             first_slot=0, stream=None):
+        _check(lib().orbx_extract_batch_device(self._h, C.c_void_p(d_ptr), batch, width, height, stride, frame_stride,
+                                               int(vLappingArea[0]), int(vLappingArea[1]), first_slot,
+                                               C.c_void_p(stream) if stream else None))
+
+    def copy_slot(self, src, dst, stream=None):
+        _check(lib().orbx_extractor_copy_slot(self._h, src, dst, C.c_void_p(stream) if stream else None))
+
+    def sync(self, stream=None):
+        _check(lib().orbx_extractor_sync(self._h, C.c_void_p(stream) if stream else None))
+
+    def download(self, first_slot, count, stream=None):
+        kps = np.zeros((count, self.cap), KP_DTYPE)
+        desc = np.zeros((count, self.cap, 32), np.uint8)
+        n = np.zeros(count, np.int32); mono = np.zeros(count, np.int32)
+        _check(lib().orbx_extractor_download(self._h, first_slot, count, _p(kps), _p(desc), self.cap, _p(n), _p(mono),
+                                             C.c_void_p(stream) if stream else None))
+        return [(int(mono[i]), kps[i, :n[i]].copy(), desc[i, :n[i]].copy()) for i in range(count)]
+
+    def results_device(self):
+        ptrs = [C.c_void_p() for _ in range(4)]
+        cap, slots = C.c_int(), C.c_int()
+        _check(lib().orbx_extractor_results_device(self._h, *[C.byref(p) for p in ptrs], C.byref(cap), C.byref(slots)))
+        return dict(kps=ptrs[0].value, desc=ptrs[1].value, n=ptrs[2].value, mono=ptrs[3].value, cap=cap.value, slots=slots.value)
+
+    # mvImagePyramid and test taps
+    def level_size(self, level):
+        w, h = C.c_int(), C.c_int()
+        _check(lib().orbx_pyramid_level_size(self._h, level, C.byref(w), C.byref(h)))
+        return w.value, h.value
+
+    def _level(self, fn, slot, level):
+        w, h = self.level_size(level)
+        out = np.empty((h, w), np.uint8)
+        _check(fn(self._h, slot, level, _p(out), w))
+        return out
+
+    def pyramid_level(self, level, slot=0):
+        return self._level(lib().orbx_pyramid_to_host, slot, level)
+
+    def blurred_level(self, level, slot=0):
+        return self._level(lib().orbx_blurred_to_host, slot, level)
+
+    def _xyr(self, fn, slot, level, cap):
+        out = np.empty((cap, 3), np.float32)
+        n = C.c_int()
+        _check(fn(self._h, slot, level, _p(out), cap, C.byref(n)))
+        return out[:n.value].copy()
+
+    def level_candidates(self, level, slot=0, cap=1 << 17):
+        return self._xyr(lib().orbx_candidates_to_host, slot, level, cap)
+
+    def level_keypoints(self, level, slot=0):
+        return self._xyr(lib().orbx_level_keypoints_to_host, slot, level, self.cap)
+
+
+class ORBmatcher:
+    """Mirror of ORB_SLAM3::ORBmatcher's Hamming searches on flat arrays (R/orb_slam3/include/ORBmatcher.h:35-108)."""
+    TH_LOW, TH_HIGH, HISTO_LENGTH = TH_LOW, TH_HIGH, HISTO_LENGTH
+
+    def __init__(self, nnratio=0.6, checkOri=True, max_keypoints=8192, max_batch=1, device=0, max_candidates=0):
+        self.mfNNratio, self.mbCheckOrientation = float(nnratio), bool(checkOri)
+        self._h = C.c_void_p()
+        self.params = MatcherParams(device, max_keypoints, max_batch, max_candidates)
+        _check(lib().orbx_matcher_create(C.byref(self.params), C.byref(self._h)))
+        self.K = max_keypoints
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().orbx_matcher_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def sync(self, stream=None):
+        _check(lib().orbx_matcher_sync(self._h, C.c_void_p(stream) if stream else None))
+
+    def DescriptorDistance(self, a, b):
+        """Batched ORBmatcher::DescriptorDistance: a, b are [n,32] (or [32]) uint8."""
+        a = np.ascontiguousarray(a, np.uint8).reshape(-1, 32); b = np.ascontiguousarray(b, np.uint8).reshape(-1, 32)
+        out = np.empty(len(a), np.int32)
+        _check(lib().orbx_hamming_pairs(self._h, _p(a), _p(b), len(a), _p(out)))
+        return out
+
+    def knnMatch2(self, q, t):
+        """cv::BFMatcher(NORM_HAMMING).knnMatch(q, t, k=2) -> (idx[nq,2], dist[nq,2])."""
+        q = np.ascontiguousarray(q, np.uint8).reshape(-1, 32); t = np.ascontiguousarray(t, np.uint8).reshape(-1, 32)
+        idx = np.full((len(q), 2), -1, np.int32); dist = np.full((len(q), 2), -1, np.int32)
+        _check(lib().orbx_bf_knn2(self._h, _p(q), len(q), _p(t), len(t), _p(idx), _p(dist)))
+        return idx, dist
+
+    def SearchForInitialization(self, k1, d1, k2, d2, bounds, vbPrevMatched, windowSize=10):
+        """returns (nmatches, vnMatches12, updated vbPrevMatched); bounds = (mnMinX, mnMaxX, mnMinY, mnMaxY)."""
+        k1 = np.ascontiguousarray(k1, KP_DTYPE); k2 = np.ascontiguousarray(k2, KP_DTYPE)
+        d1 = np.ascontiguousarray(d1, np.uint8); d2 = np.ascontiguousarray(d2, np.uint8)
+        prev = np.ascontiguousarray(vbPrevMatched, np.float32).copy()
+        m12 = np.full(len(k1), -1, np.int32)
+        b = np.array(bounds, np.float32)
+        nm = C.c_int(0)
+        _check(lib().orbx_search_for_initialization(self._h, _p(k1), _p(d1), len(k1), _p(k2), _p(d2), len(k2), _p(b),
+                                                    _p(prev), _p(m12), int(windowSize), self.mfNNratio,
+                                                    int(self.mbCheckOrientation), C.byref(nm)))
+        return nm.value, m12, prev
+
+    def SearchByProjection(self, mode, queries, qdesc, k2, d2, bounds, assigned=None, uright=None):
+        """mode 0: (Frame&, const Frame&, th, bMono); mode 1: (Frame&, vector<MapPoint*>&, th).  Returns (nmatches, assigned)."""
+        q = np.ascontiguousarray(queries, PROJQ_DTYPE); qd = np.ascontiguousarray(qdesc, np.uint8)
+        k2 = np.ascontiguousarray(k2, KP_DTYPE); d2 = np.ascontiguousarray(d2, np.uint8)
+        a = np.full(len(k2), -1, np.int32) if assigned is None else np.ascontiguousarray(assigned, np.int32).copy()
+        ur = None if uright is None else np.ascontiguousarray(uright, np.float32)
+        b = np.array(bounds, np.float32)
+        nm = C.c_int(0)
+        _check(lib().orbx_search_by_projection(self._h, mode, _p(q), _p(qd), len(q), _p(k2), _p(d2), _p(ur), len(k2),
+                                               _p(b), _p(a), self.mfNNratio, int(self.mbCheckOrientation), C.byref(nm)))
+        return nm.value, a
+
+    def StereoBandMatch(self, kl, dl, kr, dr, scale_factors, nrows, minD, maxD):
+        kl = np.ascontiguousarray(kl, KP_DTYPE); kr = np.ascontiguousarray(kr, KP_DTYPE)
+        dl = np.ascontiguousarray(dl, np.uint8); dr = np.ascontiguousarray(dr, np.uint8)
+        sf = np.ascontiguousarray(scale_factors, np.float32)
+        bi = np.full(len(kl), -1, np.int32); bd = np.full(len(kl), TH_HIGH, np.int32)
+        _check(lib().orbx_stereo_band_match(self._h, _p(kl), _p(dl), len(kl), _p(kr), _p(dr), len(kr), _p(sf), len(sf),
+                                            int(nrows), float(minD), float(maxD), _p(bi), _p(bd)))
+        return bi, bd
+
+    def match_slots_device(self, extractor, a, b, bounds, window, d_matches12, d_nmatches, d_knn_idx=None,
+                           d_knn_dist=None, stream=None):
+        """a, b: device pointers to int32 slot indices (npairs each); outputs are device pointers, row stride = max_keypoints."""
+        bb = np.array(bounds, np.float32)
+        _check(lib().orbx_match_slots_device(self._h, extractor._h, C.c_void_p(a[0]), C.c_void_p(b[0]), a[1], _p(bb), int(window),
+                                             self.mfNNratio, int(self.mbCheckOrientation), C.c_void_p(d_matches12),
+                                             C.c_void_p(d_nmatches), C.c_void_p(d_knn_idx) if d_knn_idx else None,
+                                             C.c_void_p(d_knn_dist) if d_knn_dist else None,
+                                             C.c_void_p(stream) if stream else None))
+
+
+def popc_peak(device=0):
+    p, l = C.c_double(), C.c_double()
+    _check(lib().orbx_popc_peak(device, C.byref(p), C.byref(l)))
+    return p.value, l.value

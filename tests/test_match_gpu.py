@@ -1,0 +1,177 @@
+"""GPU parity tests of the matcher kernels (through the C ABI) vs the CPU oracle: bit-exact indices/distances."""
+import os
+
+import numpy as np
+import pytest
+
+from multi_orbslam3_b200 import orbx, synth
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def frames():
+    """Two consecutive frames of a stream, extracted by the oracle (matcher tests do not depend on the GPU extractor)."""
+    st = synth.rects_stream(752, 480, 2, seed=3)
+    e = O.Extractor(1000, 1.2, 8, 20, 7)
+    out = []
+    for f in st:
+        _, k, d = e(f, (0, 0))
+        out.append((k, d))
+    return out
+
+
+def test_descriptor_distance_pairs():
+    m = orbx.ORBmatcher(0.9, True, max_keypoints=4096)
+    a = synth.random_descriptors(5000, 1); b = synth.random_descriptors(5000, 2, 0.3)
+    a[0] = 0; b[0] = 255; b[1] = a[1]
+    got = m.DescriptorDistance(a, b)
+    ref = np.unpackbits(a ^ b, axis=1).sum(1)
+    np.testing.assert_array_equal(got, ref)
+    assert got[0] == 256 and got[1] == 0
+    m.close()
+
+
+@pytest.mark.parametrize("nq,nt", [(1, 1), (1, 2), (5, 3), (100, 257), (1000, 1000), (130, 70000), (3, 0)])
+def test_bf_knn2_parity(nq, nt):
+    m = orbx.ORBmatcher(0.7, True, max_keypoints=2048)
+    q = synth.random_descriptors(nq, 10 + nq, 0.2)
+    t = synth.random_descriptors(max(nt, 1), 20 + nt, 0.5)[:nt]
+    if nt > 300:
+        t[100] = q[0]; t[299] = q[0]; t[nt - 1] = q[0]      # exact ties -> lowest index first
+    idx, dist = m.knnMatch2(q, t)
+    ridx, rdist = O.bf_knn2(q, t)
+    np.testing.assert_array_equal(idx, ridx)
+    np.testing.assert_array_equal(dist, rdist)
+    m.close()
+
+
+def test_search_for_initialization_parity(frames):
+    (k1, d1), (k2, d2) = frames
+    m = orbx.ORBmatcher(0.9, True, max_keypoints=2048)
+    prev = np.stack([k1["x"], k1["y"]], 1)
+    for window, ratio, ori in ((100, 0.9, True), (10, 0.9, True), (100, 0.6, False), (300, 0.99, True)):
+        m.mfNNratio, m.mbCheckOrientation = ratio, ori
+        n, m12, p2 = m.SearchForInitialization(k1, d1, k2, d2, (0, 752, 0, 480), prev, window)
+        rn, rm12, rp2 = O.search_for_initialization(k1, d1, k2, d2, (0, 752, 0, 480), prev, window, ratio, ori)
+        assert n == rn
+        np.testing.assert_array_equal(m12, rm12)
+        np.testing.assert_array_equal(p2, rp2)
+        # second call with the updated vbPrevMatched, as Tracking does on the next frame
+        n2, m12b, _ = m.SearchForInitialization(k1, d1, k2, d2, (0, 752, 0, 480), p2, window)
+        rn2, rm12b, _ = O.search_for_initialization(k1, d1, k2, d2, (0, 752, 0, 480), rp2, window, ratio, ori)
+        assert n2 == rn2
+        np.testing.assert_array_equal(m12b, rm12b)
+    m.close()
+
+
+def test_search_for_initialization_steal_back_and_ties():
+    """Planted duplicates: several F1 keypoints compete for one F2 keypoint (ORBmatcher.cc:741, :760-767)."""
+    rng = np.random.default_rng(4)
+    n = 300
+    k1 = np.zeros(n, O.KP_DTYPE); k2 = np.zeros(n, O.KP_DTYPE)
+    k1["x"] = rng.uniform(20, 620, n).astype(np.float32); k1["y"] = rng.uniform(20, 460, n).astype(np.float32)
+    k2["x"] = k1["x"] + 2; k2["y"] = k1["y"] + 1
+    k1["angle"] = rng.uniform(0, 360, n).astype(np.float32); k2["angle"] = k1["angle"]
+    k1["octave"][::7] = 1
+    d2 = synth.random_descriptors(n, 8)
+    d1 = d2.copy()
+    for i in range(n):                      # a few flipped bits so that distances are small but distinct
+        for b in rng.integers(0, 256, int(rng.integers(0, 12))):
+            d1[i, b >> 3] ^= np.uint8(1 << (b & 7))
+    d1[10] = d1[11] = d1[12] = d2[40]       # three queries want F2 keypoint 40 at distance 0
+    k1["x"][10:13] = k2["x"][40]; k1["y"][10:13] = k2["y"][40]
+    d2[50] = d2[51]; k2["x"][51] = k2["x"][50] + 1; k2["y"][51] = k2["y"][50]   # exact tie between candidates
+    m = orbx.ORBmatcher(0.9, True, max_keypoints=1024)
+    prev = np.stack([k1["x"], k1["y"]], 1)
+    n_, m12, p2 = m.SearchForInitialization(k1, d1, k2, d2, (0, 640, 0, 480), prev, 60)
+    rn, rm12, rp2 = O.search_for_initialization(k1, d1, k2, d2, (0, 640, 0, 480), prev, 60, 0.9, True)
+    assert n_ == rn
+    np.testing.assert_array_equal(m12, rm12)
+    np.testing.assert_array_equal(p2, rp2)
+    m.close()
+
+
+def make_queries(k1, rng, th=15.0, scale=None):
+    q = np.zeros(len(k1), O.PROJQ_DTYPE)
+    q["u"] = k1["x"] + rng.normal(0, 2, len(k1)).astype(np.float32)
+    q["v"] = k1["y"] + rng.normal(0, 2, len(k1)).astype(np.float32)
+    q["r"] = (th * scale[k1["octave"]]).astype(np.float32)
+    q["minl"] = k1["octave"] - 1; q["maxl"] = k1["octave"] + 1
+    q["angle"] = k1["angle"]; q["valid"] = (rng.random(len(k1)) > 0.1).astype(np.int32)
+    q["ur"] = q["u"] - 10
+    return q
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_search_by_projection_parity(frames, mode):
+    (k1, d1), (k2, d2) = frames
+    rng = np.random.default_rng(12)
+    scale = O.Extractor(1000, 1.2, 8, 20, 7).scale
+    q = make_queries(k1, rng, 15.0 if mode == 0 else 4.0 * 3, scale)
+    if mode == 1:
+        q["minl"] = k1["octave"] - 1; q["maxl"] = k1["octave"]
+    pre = np.full(len(k2), -1, np.int32); pre[::9] = 7777       # keypoints that already hold a map point
+    uright = np.where(rng.random(len(k2)) > 0.5, k2["x"] - 10 + rng.normal(0, 8, len(k2)), -1).astype(np.float32)
+    m = orbx.ORBmatcher(0.8, True, max_keypoints=2048)
+    for ur in (None, uright):
+        n, a = m.SearchByProjection(mode, q, d1, k2, d2, (0, 752, 0, 480), pre, ur)
+        rn, ra = O.search_by_projection(mode, q, d1, k2, d2, (0, 752, 0, 480), pre, ur, 0.8, True)
+        assert n == rn
+        np.testing.assert_array_equal(a, ra)
+    m.close()
+
+
+def test_stereo_band_match_parity():
+    L, R = synth.stereo_pair(752, 480, seed=2, disparity=14)
+    e = O.Extractor(1200, 1.2, 8, 20, 7)
+    _, kl, dl = e(L, (0, 0)); _, kr, dr = e(R, (0, 0))
+    m = orbx.ORBmatcher(0.9, True, max_keypoints=2048)
+    bf, b = 47.9, 0.11
+    bi, bd = m.StereoBandMatch(kl, dl, kr, dr, e.scale, 480, 0.0, bf / b * 0.1)
+    ri, rd = O.stereo_band_match(kl, dl, kr, dr, e.scale, 480, 0.0, bf / b * 0.1)
+    np.testing.assert_array_equal(bi, ri)
+    np.testing.assert_array_equal(bd, rd)
+    assert (bi >= 0).sum() > 100
+    m.close()
+
+
+def test_slots_pipeline_matches_oracle():
+    """Device-resident path used by bench.py: extract a batch, match consecutive slots, compare with the oracle."""
+    import torch
+    B = 5
+    frames = synth.rects_stream(640, 480, B, seed=77)
+    ex = orbx.ORBextractor(1000, 1.2, 8, 20, 7, max_width=640, max_height=480, max_batch=B)
+    m = orbx.ORBmatcher(0.9, True, max_keypoints=ex.cap, max_batch=B)
+    d_frames = torch.from_numpy(frames).cuda()
+    stream = torch.cuda.current_stream().cuda_stream
+    ex.extract_batch_device(d_frames.data_ptr(), B, 640, 480, 640, 640 * 480, (0, 0), first_slot=1, stream=stream)
+    ex.copy_slot(B, 0, stream)        # slot 0 = predecessor of the batch's first frame (here: its last frame)
+    a = torch.arange(0, B, dtype=torch.int32, device="cuda"); b = torch.arange(1, B + 1, dtype=torch.int32, device="cuda")
+    K = m.K
+    m12 = torch.full((B, K), -2, dtype=torch.int32, device="cuda"); nm = torch.zeros(B, dtype=torch.int32, device="cuda")
+    kidx = torch.full((B, K, 2), -2, dtype=torch.int32, device="cuda"); kdist = torch.full((B, K, 2), -2, dtype=torch.int32, device="cuda")
+    m.match_slots_device(ex, (a.data_ptr(), B), (b.data_ptr(), B), (0, 640, 0, 480), 100, m12.data_ptr(), nm.data_ptr(),
+                         kidx.data_ptr(), kdist.data_ptr(), stream)
+    ex.sync(stream); m.sync(stream)
+    res = ex.download(0, B + 1, stream)
+    ref = O.Extractor(1000, 1.2, 8, 20, 7)
+    for p in range(B):
+        (_, k1, d1), (_, k2, d2) = res[p], res[p + 1]
+        if p > 0:
+            _, rk, rd = ref(frames[p - 1], (0, 0))
+            assert k1.tobytes()[:0] == b"" and len(k1) == len(rk)
+        prev = np.stack([k1["x"], k1["y"]], 1)
+        rn, rm12, _ = O.search_for_initialization(k1, d1, k2, d2, (0, 640, 0, 480), prev, 100, 0.9, True)
+        assert int(nm[p]) == rn
+        np.testing.assert_array_equal(m12[p, :len(k1)].cpu().numpy(), rm12)
+        ridx, rdist = O.bf_knn2(d1, d2)
+        np.testing.assert_array_equal(kidx[p, :len(k1)].cpu().numpy(), ridx)
+        np.testing.assert_array_equal(kdist[p, :len(k1)].cpu().numpy(), rdist)
+    ex.close(); m.close()
+
+
+def test_popc_probe_runs():
+    p, l = orbx.popc_peak(0)
+    assert p > 1e11 and l > 1e11
