@@ -24,22 +24,24 @@ __device__ __constant__ int8_t c_ring[16][2] = {
     {0, 3}, {1, 3}, {2, 2}, {3, 1}, {3, 0}, {3, -1}, {2, -2}, {1, -3},
     {0, -3}, {-1, -3}, {-2, -2}, {-3, -1}, {-3, 0}, {-3, 1}, {-2, 2}, {-1, 3}};
 
-__device__ __forceinline__ int arc_measure(const int (&d)[16])
+// Arc measure on packed 16-bit lanes.  p[k] holds both polarities of ring pixel k, biased by 256 so that
+// both lanes stay positive: low = v - r_k + 256 (= d_k + 256), high = r_k - v + 256 (= -d_k + 256).
+// One unsigned 16x2 min network (windows of 9 by doubling: 2, 4, 8, +1) then serves "9 darker" and
+// "9 brighter" at once: m = max over arcs of max(min d, min -d).
+// NOTE: the scalar formulation max(min(...), -max(...)) is MIScompiled by ptxas 12.9 / the 580 driver JIT for
+// sm_100 (verified on B200: -Xptxas -O0 and -G give the right answer, -O1..-O3 return max(d)); see DESIGN.md.
+__device__ __forceinline__ int arc_measure(const unsigned (&p)[16])
 {
-    // sliding min / max over windows of 9 (circular) by doubling: 2, 4, 8, then +1
-    int lo2[16], hi2[16], lo4[16], hi4[16];
+    unsigned l2[16], l4[16];
 #pragma unroll
-    for (int k = 0; k < 16; k++) { lo2[k] = min(d[k], d[(k + 1) & 15]); hi2[k] = max(d[k], d[(k + 1) & 15]); }
+    for (int k = 0; k < 16; k++) l2[k] = __vminu2(p[k], p[(k + 1) & 15]);
 #pragma unroll
-    for (int k = 0; k < 16; k++) { lo4[k] = min(lo2[k], lo2[(k + 2) & 15]); hi4[k] = max(hi2[k], hi2[(k + 2) & 15]); }
-    int best = -256;
+    for (int k = 0; k < 16; k++) l4[k] = __vminu2(l2[k], l2[(k + 2) & 15]);
+    unsigned best = 0;
 #pragma unroll
-    for (int k = 0; k < 16; k++) {
-        int mn = min(min(lo4[k], lo4[(k + 4) & 15]), d[(k + 8) & 15]);
-        int mx = max(max(hi4[k], hi4[(k + 4) & 15]), d[(k + 8) & 15]);
-        best = max(best, max(mn, -mx));
-    }
-    return best;
+    for (int k = 0; k < 16; k++) best = __vmaxu2(best, __vminu2(__vminu2(l4[k], l4[(k + 4) & 15]), p[(k + 8) & 15]));
+    const int a = (int)(best & 0xFFFF), b = (int)(best >> 16);
+    return (a > b ? a : b) - 256;
 }
 
 __global__ void __launch_bounds__(NT) k_fast_rows(OrbxGeom g, OrbxBuffers b, const uint8_t* level0, int pitch0,
@@ -112,10 +114,11 @@ __global__ void __launch_bounds__(NT) k_fast_rows(OrbxGeom g, OrbxBuffers b, con
                 if (t) {
                     t &= CLS(1) | CLS(9); t &= CLS(3) | CLS(11); t &= CLS(5) | CLS(13); t &= CLS(7) | CLS(15);
                     if (t) {
-                        int d[16];
+                        unsigned pk[16];
+                        const unsigned cv = (unsigned)(v + 256) | ((unsigned)(256 - v) << 16);
 #pragma unroll
-                        for (int q = 0; q < 16; q++) d[q] = v - p[roff[q]];
-                        m = arc_measure(d);
+                        for (int q = 0; q < 16; q++) pk[q] = cv + (unsigned)p[roff[q]] * 0xFFFFu;   // (v+256-r) | (256-v+r)<<16
+                        m = arc_measure(pk);
                         if (m <= minTh) m = 0;
                     }
                 }
