@@ -42,6 +42,8 @@ typedef struct orbx_keypoint {
 
 const char* orbx_last_error(void);          /* thread-local, human readable */
 int  orbx_device_count(void);
+/* number of CUDA kernels this library has launched since it was loaded (bench.py: gpu_launches) */
+unsigned long long orbx_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------
  * Extractor: replaces class ORBextractor (R/include/ORBextractor.h:47-113).
@@ -60,7 +62,7 @@ typedef struct orbx_params {
     int32_t max_height;
     int32_t max_batch;        /* frames per batched call (1 for the class wrapper) */
     int32_t device;           /* CUDA device ordinal */
-    int32_t max_candidates_per_level; /* 0 = default (32768); FAST corners per level above this -> ORBX_E_CAPACITY */
+    int32_t max_candidates_per_level; /* 0 = default (16384); FAST corners per level above this -> ORBX_E_CAPACITY */
 } orbx_params;
 
 /* ORBextractor::ORBextractor, R/src/ORBextractor.cc:408-468 */
@@ -100,6 +102,10 @@ int  orbx_extractor_results_device(orbx_extractor* h, orbx_keypoint** d_kps, uin
 int  orbx_extractor_download(orbx_extractor* h, int first_slot, int count, orbx_keypoint* kps, uint8_t* desc,
                              int cap, int32_t* n, int32_t* mono_index, void* stream);
 int  orbx_extractor_sync(orbx_extractor* h, void* stream);   /* also returns any deferred device error */
+/* per-stage CUDA-event timing: returns the milliseconds accumulated so far in stage_ms4 = {pyramid+blur, FAST,
+ * octree, finalize+orientation+descriptors} over *batches batches; enable = 1/0 switches it on/off and resets the
+ * sums, -1 only reads. */
+int  orbx_extractor_profile(orbx_extractor* h, int enable, double* stage_ms4, int* batches);
 
 /* mvImagePyramid (R/include/ORBextractor.h:88) stays on the device; this is the explicit download the
  * stereo SAD refinement (R/src/Frame.cc:882-901) needs.  slot = frame within the last batch. */
@@ -151,12 +157,22 @@ int  orbx_search_for_initialization(orbx_matcher* m, const orbx_keypoint* k1, co
                                     int* nmatches);
 /* batched over extractor result slots on the device: pair i matches slot a[i] (F1) against slot b[i] (F2)
  * with vbPrevMatched = F1's keypoint positions (first call of Tracking.cc:2216-2217).  Also runs
- * orbx_bf_knn2 for every pair when d_knn_idx != NULL.  Outputs on device: matches12 [npairs][cap],
- * nmatches [npairs], knn idx/dist [npairs][cap][2]. */
+ * orbx_bf_knn2 for every pair when d_knn_idx != NULL.  a, b are DEVICE pointers.  Outputs on device, rows have
+ * stride K = the matcher's max_keypoints: matches12 [npairs][K], nmatches [npairs], knn idx/dist [npairs][K][2]. */
 int  orbx_match_slots_device(orbx_matcher* m, orbx_extractor* ex, const int32_t* a, const int32_t* b, int npairs,
                              const float bounds[4], int window, float nnratio, int check_ori,
                              int32_t* d_matches12, int32_t* d_nmatches, int32_t* d_knn_idx, int32_t* d_knn_dist,
                              void* stream);
+
+/* One tracking step over a batch of HOST frames (the end-to-end path): H2D, operator() on every frame into result
+ * slots 1..batch, SearchForInitialization of each frame against its predecessor (slot i-1 -> slot i; slot 0 keeps
+ * the last frame of the previous call, as Tracking keeps mLastFrame), D2H of keypoints, descriptors and matches.
+ * Pinned caller buffers are DMA'd directly.  kps: batch*cap, desc: batch*cap*32, matches12: batch*cap. */
+int  orbx_extract_match_batch(orbx_extractor* ex, orbx_matcher* m, const uint8_t* imgs, int batch, int width,
+                              int height, int stride, size_t frame_stride, int lap0, int lap1,
+                              const float bounds[4], int window, float nnratio, int check_ori,
+                              orbx_keypoint* kps, uint8_t* desc, int cap, int32_t* n, int32_t* mono_index,
+                              int32_t* matches12, int32_t* nmatches);
 
 /* Projection-guided window searches on flat arrays (the drop-in ORBmatcher marshals Frame/MapPoint into
  * these).  Query i: window centre (u,v), radius r, octave range [minl,maxl] as GetFeaturesInArea takes them,

@@ -7,6 +7,9 @@
 #include <vector>
 #include "orbx_internal.h"
 
+unsigned long long g_orbx_launches = 0;
+extern "C" unsigned long long orbx_launch_count(void) { return g_orbx_launches; }
+
 static thread_local std::string g_last_error;
 void orbx_set_error(const char* fmt, const char* a, const char* b2)
 {
@@ -50,7 +53,18 @@ struct orbx_extractor {
     // what the last batch used as level 0 (for pyramid_to_host)
     const uint8_t* last_level0; int last_pitch0; long long last_stride0; int last_batch;
     std::vector<void*> allocs;
+    // optional per-stage CUDA-event timing (bench.py): pyramid+blur | FAST | octree | finalize+orient+describe
+    bool profile; cudaEvent_t ev[5]; double stage_ms[4]; int stage_batches; bool ev_pending;
 };
+
+static void harvest_stage_times(orbx_extractor* h)
+{
+    if (!h->profile || !h->ev_pending) return;
+    if (cudaEventSynchronize(h->ev[4]) != cudaSuccess) return;
+    for (int i = 0; i < 4; i++) { float ms = 0; cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]); h->stage_ms[i] += ms; }
+    h->stage_batches++;
+    h->ev_pending = false;
+}
 
 static int dev_alloc(orbx_extractor* h, void** p, size_t bytes)
 {
@@ -234,6 +248,9 @@ extern "C" int orbx_extractor_create(const orbx_params* p, orbx_extractor** out)
     memset(&h->geom, 0, sizeof(h->geom));
     memset(&h->buf, 0, sizeof(h->buf));
     h->d_level0 = nullptr; h->last_level0 = nullptr; h->last_batch = 0;
+    h->profile = false; h->ev_pending = false; h->stage_batches = 0;
+    for (int i = 0; i < 4; i++) h->stage_ms[i] = 0;
+    for (int i = 0; i < 5; i++) CK(cudaEventCreate(&h->ev[i]));
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     const int cap = orbx_extractor_max_keypoints(h);
     CK(cudaMallocHost((void**)&h->h_stage_in, (size_t)((p->max_width + 63) & ~63) * p->max_height * p->max_batch));
@@ -256,6 +273,7 @@ extern "C" void orbx_extractor_destroy(orbx_extractor* h)
     for (void* p : h->allocs) cudaFree(p);
     cudaFreeHost(h->h_stage_in); cudaFreeHost(h->h_kps); cudaFreeHost(h->h_desc);
     cudaFreeHost(h->h_n); cudaFreeHost(h->h_mono); cudaFreeHost(h->h_err);
+    for (int i = 0; i < 5; i++) cudaEventDestroy(h->ev[i]);
     cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -299,10 +317,17 @@ static int run_batch(orbx_extractor* h, const uint8_t* d_level0, int pitch0, lon
                      int lap0, int lap1, int first_slot, cudaStream_t s)
 {
     const OrbxGeom& g = h->geom;
+    harvest_stage_times(h);
+    const bool prof = h->profile;
+    if (prof) cudaEventRecord(h->ev[0], s);
     orbx_launch_pyramid(g, h->buf, d_level0, pitch0, stride0, batch, s);
+    if (prof) cudaEventRecord(h->ev[1], s);
     orbx_launch_fast(g, h->buf, d_level0, pitch0, stride0, batch, s);
+    if (prof) cudaEventRecord(h->ev[2], s);
     orbx_launch_octree(g, h->buf, batch, s);
+    if (prof) cudaEventRecord(h->ev[3], s);
     orbx_launch_describe(g, h->buf, d_level0, pitch0, stride0, batch, lap0, lap1, first_slot, s);
+    if (prof) { cudaEventRecord(h->ev[4], s); h->ev_pending = true; }
     h->last_level0 = d_level0; h->last_pitch0 = pitch0; h->last_stride0 = stride0; h->last_batch = batch;
     CK(cudaGetLastError());
     return ORBX_OK;
@@ -359,20 +384,68 @@ extern "C" int orbx_extractor_results_device(orbx_extractor* h, orbx_keypoint** 
     return ORBX_OK;
 }
 
-extern "C" int orbx_extractor_download(orbx_extractor* h, int first_slot, int count, orbx_keypoint* kps, uint8_t* desc,
-                                       int cap, int32_t* n, int32_t* mono_index, void* stream)
+static bool is_pinned(const void* p)
 {
-    if (!h || !h->buf.kps || first_slot < 0 || count < 1 || first_slot + count > h->slots) return ORBX_E_INVALID;
-    cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
+// ---- host-buffer pipeline pieces (shared with orbx_extract_match_batch in orbx_match.cu) ----
+int orbx_ex_stage_input(orbx_extractor* h, const uint8_t* imgs, int batch, int width, int height, int stride,
+                        size_t frame_stride, cudaStream_t s)
+{
+    CK(cudaSetDevice(h->p.device));
+    int rc = configure_geometry(h, width, height);
+    if (rc) return rc;
+    const int p0 = h->pitch0;
+    if (is_pinned(imgs)) {
+        // pinned caller memory: DMA straight from it
+        if (frame_stride == (size_t)stride * height) {
+            CK(cudaMemcpy2DAsync(h->d_level0, p0, imgs, stride, width, (size_t)height * batch, cudaMemcpyHostToDevice, s));
+        } else {
+            for (int f = 0; f < batch; f++)
+                CK(cudaMemcpy2DAsync(h->d_level0 + (size_t)f * h->stride0, p0, imgs + f * frame_stride, stride, width, height,
+                                     cudaMemcpyHostToDevice, s));
+        }
+    } else {
+        for (int f = 0; f < batch; f++)
+            for (int y = 0; y < height; y++)
+                memcpy(h->h_stage_in + (size_t)f * h->stride0 + (size_t)y * p0, imgs + f * frame_stride + (size_t)y * stride, width);
+        CK(cudaMemcpyAsync(h->d_level0, h->h_stage_in, (size_t)h->stride0 * batch, cudaMemcpyHostToDevice, s));
+    }
+    return ORBX_OK;
+}
+
+int orbx_ex_run_staged(orbx_extractor* h, int batch, int lap0, int lap1, int first_slot, cudaStream_t s)
+{
+    return run_batch(h, h->d_level0, h->pitch0, h->stride0, batch, lap0, lap1, first_slot, s);
+}
+
+cudaStream_t orbx_ex_stream(orbx_extractor* h) { return h->stream; }
+
+// issues the D2H copies of `count` result slots; direct into the caller's buffers when they are pinned and
+// laid out with the handle's own capacity, else into the handle's pinned staging (unpacked by _finish)
+int orbx_ex_fetch_async(orbx_extractor* h, int first_slot, int count, orbx_keypoint* kps, uint8_t* desc, int cap,
+                        int32_t* n, int32_t* mono_index, cudaStream_t s, bool* direct)
+{
     const size_t ocap = h->geom.out_cap;
-    CK(cudaMemcpyAsync(h->h_n, h->buf.n + first_slot, sizeof(int) * count, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(h->h_mono, h->buf.mono + first_slot, sizeof(int) * count, cudaMemcpyDeviceToHost, s));
+    *direct = kps && desc && n && mono_index && cap == (int)ocap && is_pinned(kps) && is_pinned(desc) && is_pinned(n) && is_pinned(mono_index);
     CK(cudaMemcpyAsync(h->h_err, h->buf.err, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(h->h_kps, h->buf.kps + first_slot * ocap, sizeof(orbx_keypoint) * ocap * count, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(h->h_desc, h->buf.desc + first_slot * ocap * 32, ocap * 32 * count, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
+    CK(cudaMemcpyAsync(*direct ? n : h->h_n, h->buf.n + first_slot, sizeof(int) * count, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(*direct ? mono_index : h->h_mono, h->buf.mono + first_slot, sizeof(int) * count, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(*direct ? kps : h->h_kps, h->buf.kps + first_slot * ocap, sizeof(orbx_keypoint) * ocap * count, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(*direct ? desc : h->h_desc, h->buf.desc + first_slot * ocap * 32, ocap * 32 * count, cudaMemcpyDeviceToHost, s));
+    return ORBX_OK;
+}
+
+int orbx_ex_fetch_finish(orbx_extractor* h, int count, orbx_keypoint* kps, uint8_t* desc, int cap,
+                         int32_t* n, int32_t* mono_index, bool direct)
+{
     int rc = deferred_error(h);
     if (rc) return rc;
+    if (direct) return ORBX_OK;
+    const size_t ocap = h->geom.out_cap;
     for (int i = 0; i < count; i++) {
         const int ni = h->h_n[i];
         if (n) n[i] = ni;
@@ -384,6 +457,19 @@ extern "C" int orbx_extractor_download(orbx_extractor* h, int first_slot, int co
     return ORBX_OK;
 }
 
+extern "C" int orbx_extractor_download(orbx_extractor* h, int first_slot, int count, orbx_keypoint* kps, uint8_t* desc,
+                                       int cap, int32_t* n, int32_t* mono_index, void* stream)
+{
+    if (!h || !h->buf.kps || first_slot < 0 || count < 1 || first_slot + count > h->slots) return ORBX_E_INVALID;
+    CK(cudaSetDevice(h->p.device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
+    bool direct;
+    int rc = orbx_ex_fetch_async(h, first_slot, count, kps, desc, cap, n, mono_index, s, &direct);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(s));
+    return orbx_ex_fetch_finish(h, count, kps, desc, cap, n, mono_index, direct);
+}
+
 extern "C" int orbx_extract_batch(orbx_extractor* h, const uint8_t* imgs, int batch, int width, int height,
                                   int stride, size_t frame_stride, int lap0, int lap1,
                                   orbx_keypoint* kps, uint8_t* desc, int cap, int32_t* n, int32_t* mono_index)
@@ -391,16 +477,9 @@ extern "C" int orbx_extract_batch(orbx_extractor* h, const uint8_t* imgs, int ba
     if (!h || batch < 1 || batch > h->p.max_batch) { orbx_set_error("%s%s", "orbx_extract_batch: invalid arguments", ""); return ORBX_E_INVALID; }
     if (!imgs || width <= 0 || height <= 0) return ORBX_E_EMPTY;
     if (stride < width) return ORBX_E_INVALID;
-    CK(cudaSetDevice(h->p.device));
-    int rc = configure_geometry(h, width, height);
+    int rc = orbx_ex_stage_input(h, imgs, batch, width, height, stride, frame_stride, h->stream);
     if (rc) return rc;
-    // host frames -> pinned staging (tight pitch0 rows) -> device level 0
-    const int p0 = h->pitch0;
-    for (int f = 0; f < batch; f++)
-        for (int y = 0; y < height; y++)
-            memcpy(h->h_stage_in + (size_t)f * h->stride0 + (size_t)y * p0, imgs + f * frame_stride + (size_t)y * stride, width);
-    CK(cudaMemcpyAsync(h->d_level0, h->h_stage_in, (size_t)h->stride0 * batch, cudaMemcpyHostToDevice, h->stream));
-    rc = run_batch(h, h->d_level0, p0, h->stride0, batch, lap0, lap1, 0, h->stream);
+    rc = orbx_ex_run_staged(h, batch, lap0, lap1, 0, h->stream);
     if (rc) return rc;
     return orbx_extractor_download(h, 0, batch, kps, desc, cap, n, mono_index, h->stream);
 }
@@ -414,6 +493,20 @@ extern "C" int orbx_extract(orbx_extractor* h, const uint8_t* img, int width, in
     if (n) *n = nn;
     if (mono_index) *mono_index = mm;
     return rc;
+}
+
+extern "C" int orbx_extractor_profile(orbx_extractor* h, int enable, double* stage_ms4, int* batches)
+{
+    if (!h) return ORBX_E_INVALID;
+    harvest_stage_times(h);
+    if (stage_ms4) for (int i = 0; i < 4; i++) stage_ms4[i] = h->stage_ms[i];
+    if (batches) *batches = h->stage_batches;
+    if (enable >= 0) {
+        h->profile = enable != 0;
+        for (int i = 0; i < 4; i++) h->stage_ms[i] = 0;
+        h->stage_batches = 0; h->ev_pending = false;
+    }
+    return ORBX_OK;
 }
 
 extern "C" int orbx_pyramid_level_size(const orbx_extractor* h, int level, int* width, int* height)

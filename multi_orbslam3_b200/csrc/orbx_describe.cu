@@ -195,4 +195,5 @@ void orbx_launch_describe(const OrbxGeom& g, const OrbxBuffers& b, const uint8_t
     k_finalize<<<batch, FIN_NT, 0, s>>>(g, b, lap0, lap1, first_slot);
     dim3 grid((g.out_cap + DESC_WARPS - 1) / DESC_WARPS, batch);
     k_orient_describe<<<grid, DESC_WARPS * 32, 0, s>>>(g, b, level0, pitch0, stride0, first_slot);
+    ORBX_COUNT_LAUNCH(2);
 }

@@ -229,4 +229,5 @@ void orbx_launch_fast(const OrbxGeom& g, const OrbxBuffers& b, const uint8_t* le
     if (g.total_rows == 0) return;
     dim3 grid(g.total_rows, batch);
     k_fast_rows<<<grid, NT, fast_smem_bytes(g), s>>>(g, b, level0, pitch0, stride0);
+    ORBX_COUNT_LAUNCH(1);
 }

@@ -547,6 +547,7 @@ struct orbx_matcher {
     int32_t* d_part_idx; int32_t* d_part_dist; size_t part_elems;
     uint8_t* d_bfq; uint8_t* d_bft; size_t bfq_bytes, bft_bytes;
     unsigned* h_err;
+    int32_t* d_pair_a; int32_t* d_pair_b;
     std::vector<void*> allocs;
 };
 
@@ -598,6 +599,7 @@ extern "C" int orbx_matcher_create(const orbx_matcher_params* p, orbx_matcher** 
 #undef MA
     m->d_part_idx = m->d_part_dist = nullptr; m->part_elems = 0;
     m->d_bfq = m->d_bft = nullptr; m->bfq_bytes = m->bft_bytes = 0;
+    m->d_pair_a = m->d_pair_b = nullptr;
     CKM(cudaMemset(W.err, 0, sizeof(unsigned)));
     CKM(cudaMallocHost((void**)&m->h_err, sizeof(unsigned)));
     if (2 * K * sizeof(int) > 48 * 1024)
@@ -621,6 +623,7 @@ extern "C" void orbx_matcher_destroy(orbx_matcher* m)
     if (m->d_part_dist) cudaFree(m->d_part_dist);
     if (m->d_bfq) cudaFree(m->d_bfq);
     if (m->d_bft) cudaFree(m->d_bft);
+    if (m->d_pair_a) cudaFree(m->d_pair_a);
     cudaFreeHost(m->h_err);
     cudaStreamDestroy(m->stream);
     delete m;
@@ -654,7 +657,7 @@ extern "C" int orbx_hamming_pairs(orbx_matcher* m, const uint8_t* a, const uint8
         const int c = n - done < m->K ? n - done : m->K;
         CKM(cudaMemcpyAsync(m->d_d1, a + (size_t)done * 32, (size_t)c * 32, cudaMemcpyHostToDevice, m->stream));
         CKM(cudaMemcpyAsync(m->d_d2, b + (size_t)done * 32, (size_t)c * 32, cudaMemcpyHostToDevice, m->stream));
-        k_hamming_pairs<<<(c + 255) / 256, 256, 0, m->stream>>>((const uint4*)m->d_d1, (const uint4*)m->d_d2, c, m->d_out);
+        k_hamming_pairs<<<(c + 255) / 256, 256, 0, m->stream>>>((const uint4*)m->d_d1, (const uint4*)m->d_d2, c, m->d_out); ORBX_COUNT_LAUNCH(1);
         CKM(cudaMemcpyAsync(out + done, m->d_out, sizeof(int32_t) * c, cudaMemcpyDeviceToHost, m->stream));
         CKM(cudaStreamSynchronize(m->stream));
     }
@@ -693,10 +696,10 @@ static int bf_launch(orbx_matcher* m, BfArgs A, int npairs, int nq_max, long lon
     }
     if (qblocks == 0 || npairs == 0) return ORBX_OK;
     dim3 grid(qblocks, nsplit, npairs);
-    k_bf_knn2<<<grid, BF_NT, 0, s>>>(A);
+    k_bf_knn2<<<grid, BF_NT, 0, s>>>(A); ORBX_COUNT_LAUNCH(1);
     if (nsplit > 1) {
         dim3 mg((nq_max + 127) / 128, npairs);
-        k_knn2_merge<<<mg, 128, 0, s>>>(A.part_idx, A.part_dist, nsplit, A.out_stride, A.nq, A.q ? nullptr : A.n, A.a, A.idx, A.dist);
+        k_knn2_merge<<<mg, 128, 0, s>>>(A.part_idx, A.part_dist, nsplit, A.out_stride, A.nq, A.q ? nullptr : A.n, A.a, A.idx, A.dist); ORBX_COUNT_LAUNCH(1);
     }
     CKM(cudaGetLastError());
     return ORBX_OK;
@@ -742,7 +745,7 @@ extern "C" int orbx_knn2_merge_device(orbx_matcher* m, const int32_t* d_idx_part
     CKM(cudaSetDevice(m->p.device));
     cudaStream_t s = stream ? (cudaStream_t)stream : m->stream;
     dim3 mg((nq + 127) / 128, 1);
-    k_knn2_merge<<<mg, 128, 0, s>>>(d_idx_parts, d_dist_parts, nparts, nq, nq, nullptr, nullptr, d_idx, d_dist);
+    k_knn2_merge<<<mg, 128, 0, s>>>(d_idx_parts, d_dist_parts, nparts, nq, nq, nullptr, nullptr, d_idx, d_dist); ORBX_COUNT_LAUNCH(1);
     CKM(cudaGetLastError());
     return ORBX_OK;
 }
@@ -760,10 +763,10 @@ static int run_window(orbx_matcher* m, int npairs, int nq_max, int mode, float n
 {
     int npad = 1; while (npad < m->K) npad <<= 1;
     CKM(cudaMemsetAsync(m->W.pool_used, 0, sizeof(int) * npairs, s));
-    k_grid_build<<<npairs, GRID_NT, sizeof(uint32_t) * npad, s>>>(m->W, npad);
+    k_grid_build<<<npairs, GRID_NT, sizeof(uint32_t) * npad, s>>>(m->W, npad); ORBX_COUNT_LAUNCH(1);
     dim3 cg((nq_max + CAND_WARPS - 1) / CAND_WARPS, npairs);
-    if (nq_max > 0) k_window_candidates<<<cg, CAND_WARPS * 32, 0, s>>>(m->W);
-    k_window_resolve<<<npairs, 32, 2 * m->K * sizeof(int), s>>>(m->W, mode, nnratio, check_ori, d_out, d_nm, d_prev);
+    if (nq_max > 0) { k_window_candidates<<<cg, CAND_WARPS * 32, 0, s>>>(m->W); ORBX_COUNT_LAUNCH(1); }
+    k_window_resolve<<<npairs, 32, 2 * m->K * sizeof(int), s>>>(m->W, mode, nnratio, check_ori, d_out, d_nm, d_prev); ORBX_COUNT_LAUNCH(1);
     CKM(cudaGetLastError());
     return ORBX_OK;
 }
@@ -794,7 +797,7 @@ extern "C" int orbx_search_for_initialization(orbx_matcher* m, const orbx_keypoi
     pd.k1 = m->d_k1; pd.d1 = m->d_d1; pd.k2 = m->d_k2; pd.d2 = m->d_d2; pd.uright2 = nullptr;
     pd.q = m->W.q; pd.qdesc = m->d_d1; pd.n1 = n1; pd.n2 = n2; pd.nq = n1;
     CKM(cudaMemcpyAsync(m->W.pairs, &pd, sizeof(pd), cudaMemcpyHostToDevice, s));
-    k_make_init_queries<<<(n1 + 255) / 256, 256, 0, s>>>(m->W.q, m->d_k1, m->d_prev, n1, (float)window);
+    k_make_init_queries<<<(n1 + 255) / 256, 256, 0, s>>>(m->W.q, m->d_k1, m->d_prev, n1, (float)window); ORBX_COUNT_LAUNCH(1);
     int rc = run_window(m, 1, n1, 2, nnratio, check_ori, m->d_out, m->d_nm, m->d_prev, s);
     if (rc) return rc;
     int nm = 0;
@@ -834,7 +837,7 @@ extern "C" int orbx_search_by_projection(orbx_matcher* m, int mode, const orbx_p
     CKM(cudaMemcpyAsync(m->W.pairs, &pd, sizeof(pd), cudaMemcpyHostToDevice, s));
     int rc = run_window(m, 1, nq, mode, nnratio, check_ori, m->d_out, m->d_nm, nullptr, s);
     if (rc) return rc;
-    k_count_new_assigned<<<1, 256, 0, s>>>(m->d_out2, m->d_out, n2, m->d_nm);
+    k_count_new_assigned<<<1, 256, 0, s>>>(m->d_out2, m->d_out, n2, m->d_nm); ORBX_COUNT_LAUNCH(1);
     int nm = 0;
     CKM(cudaMemcpyAsync(assigned, m->d_out, sizeof(int32_t) * n2, cudaMemcpyDeviceToHost, s));
     CKM(cudaMemcpyAsync(&nm, m->d_nm, sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -858,7 +861,7 @@ extern "C" int orbx_match_slots_device(orbx_matcher* m, orbx_extractor* ex, cons
     cudaStream_t s = stream ? (cudaStream_t)stream : m->stream;
     set_bounds(m, bounds);
     // NOTE: outputs use row stride K (= matcher max_keypoints)
-    k_setup_slot_pairs<<<npairs, 256, 0, s>>>(m->W, kps, desc, n, a, b, cap, (float)window);
+    k_setup_slot_pairs<<<npairs, 256, 0, s>>>(m->W, kps, desc, n, a, b, cap, (float)window); ORBX_COUNT_LAUNCH(1);
     rc = run_window(m, npairs, cap, 2, nnratio, check_ori, d_matches12, d_nmatches, nullptr, s);
     if (rc) return rc;
     if (d_knn_idx && d_knn_dist) {
@@ -869,6 +872,56 @@ extern "C" int orbx_match_slots_device(orbx_matcher* m, orbx_extractor* ex, cons
         if (rc) return rc;
     }
     return ORBX_OK;
+}
+
+static bool m_is_pinned(const void* p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
+// One call = one tracking step over a batch of HOST frames: H2D, ORBextractor::operator() on every frame
+// (result slots 1..batch), SearchForInitialization of every frame against its predecessor (slot i-1 -> i; slot 0
+// holds the last frame of the previous call), D2H of keypoints, descriptors and matches.
+extern "C" int orbx_extract_match_batch(orbx_extractor* ex, orbx_matcher* m, const uint8_t* imgs, int batch, int width,
+                                        int height, int stride, size_t frame_stride, int lap0, int lap1,
+                                        const float bounds[4], int window, float nnratio, int check_ori,
+                                        orbx_keypoint* kps, uint8_t* desc, int cap, int32_t* n, int32_t* mono_index,
+                                        int32_t* matches12, int32_t* nmatches)
+{
+    if (!ex || !m || !imgs || batch < 1 || batch > m->P || !bounds) return ORBX_E_INVALID;
+    if (width <= 0 || height <= 0) return ORBX_E_EMPTY;
+    cudaStream_t s = orbx_ex_stream(ex);
+    int rc = orbx_ex_stage_input(ex, imgs, batch, width, height, stride, frame_stride, s);
+    if (rc) return rc;
+    rc = orbx_ex_run_staged(ex, batch, lap0, lap1, 1, s);
+    if (rc) return rc;
+    bool direct = false;
+    rc = orbx_ex_fetch_async(ex, 1, batch, kps, desc, cap, n, mono_index, s, &direct);
+    if (rc) return rc;
+    // slot pairs (i, i+1), i = 0..batch-1
+    if (!m->d_pair_a) {
+        std::vector<int32_t> a(m->P), b(m->P);
+        for (int i = 0; i < m->P; i++) { a[i] = i; b[i] = i + 1; }
+        CKM(cudaMalloc((void**)&m->d_pair_a, sizeof(int32_t) * m->P * 2));
+        m->d_pair_b = m->d_pair_a + m->P;
+        CKM(cudaMemcpy(m->d_pair_a, a.data(), sizeof(int32_t) * m->P, cudaMemcpyHostToDevice));
+        CKM(cudaMemcpy(m->d_pair_b, b.data(), sizeof(int32_t) * m->P, cudaMemcpyHostToDevice));
+    }
+    rc = orbx_match_slots_device(m, ex, m->d_pair_a, m->d_pair_b, batch, bounds, window, nnratio, check_ori,
+                                 m->d_out, m->d_nm, nullptr, nullptr, s);
+    if (rc) return rc;
+    rc = orbx_extractor_copy_slot(ex, batch, 0, s);
+    if (rc) return rc;
+    // matches: device rows have stride K; host rows have stride cap
+    if (matches12) CKM(cudaMemcpy2DAsync(matches12, sizeof(int32_t) * cap, m->d_out, sizeof(int32_t) * m->K,
+                                         sizeof(int32_t) * (cap < m->K ? cap : m->K), batch, cudaMemcpyDeviceToHost, s));
+    if (nmatches) CKM(cudaMemcpyAsync(nmatches, m->d_nm, sizeof(int32_t) * batch, cudaMemcpyDeviceToHost, s));
+    (void)m_is_pinned;
+    rc = m_check_err(m, s);      // synchronises the stream
+    if (rc) return rc;
+    return orbx_ex_fetch_finish(ex, batch, kps, desc, cap, n, mono_index, direct);
 }
 
 extern "C" int orbx_stereo_band_match(orbx_matcher* m, const orbx_keypoint* kl, const uint8_t* dl, int nl,
@@ -906,7 +959,7 @@ extern "C" int orbx_popc_peak(int device, double* popc_per_s, double* lop3_per_s
         float best = 1e30f;
         for (int rep = 0; rep < 5; rep++) {
             CKM(cudaEventRecord(e0));
-            if (which == 0) k_popc_probe<<<blocks, threads>>>(rep, iters, sink); else k_lop3_probe<<<blocks, threads>>>(rep, iters, sink);
+            if (which == 0) k_popc_probe<<<blocks, threads>>>(rep, iters, sink); else k_lop3_probe<<<blocks, threads>>>(rep, iters, sink); ORBX_COUNT_LAUNCH(1);
             CKM(cudaEventRecord(e1));
             CKM(cudaEventSynchronize(e1));
             float ms; CKM(cudaEventElapsedTime(&ms, e0, e1));

@@ -374,8 +374,6 @@ __global__ void __launch_bounds__(NT) k_octree(OrbxGeom g, OrbxBuffers b, int sm
     if (tid == 0) *out_n = nn;
 }
 
-int pow2_at_least(int v) { int p = 1; while (p < v) p <<= 1; return p; }
-
 struct OctCfg { int smem_pts, ncap; size_t smem; };
 
 OctCfg octree_cfg(const OrbxGeom& g)
@@ -401,6 +399,7 @@ void orbx_launch_octree(const OrbxGeom& g, const OrbxBuffers& b, int batch, cuda
     const OctCfg c = octree_cfg(g);
     dim3 grid(g.nlevels, batch);
     k_octree<<<grid, NT, c.smem, s>>>(g, b, c.smem_pts, c.ncap);
+    ORBX_COUNT_LAUNCH(1);
 }
 
 void orbx_octree_configure(const OrbxGeom& g)

@@ -154,6 +154,7 @@ void orbx_launch_pyramid(const OrbxGeom& g, const OrbxBuffers& b, const uint8_t*
         if (l == 0) {
             a.src = level0; a.spitch = pitch0; a.sstride = stride0; a.sw = L.w; a.sh = L.h;
             k_pyr_level<false><<<grid, NT, smem, s>>>(a);
+            ORBX_COUNT_LAUNCH(1);
         } else {
             const OrbxLevel& P = g.lv[l - 1];
             a.src = (l == 1) ? level0 : b.pyr[l - 1];
@@ -168,6 +169,7 @@ void orbx_launch_pyramid(const OrbxGeom& g, const OrbxBuffers& b, const uint8_t*
             a.src_th = (int)(RH * sy) + 4;
             smem += (size_t)a.src_tw * a.src_th;
             k_pyr_level<true><<<grid, NT, smem, s>>>(a);
+            ORBX_COUNT_LAUNCH(1);
         }
     }
 }

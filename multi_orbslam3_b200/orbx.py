@@ -27,15 +27,15 @@ assert KP_DTYPE.itemsize == 28 and PROJQ_DTYPE.itemsize == 32
 
 # every symbol include/orbx.h declares (tests check the library exports all of them)
 EXPORTS = [
-    "orbx_last_error", "orbx_device_count",
+    "orbx_last_error", "orbx_device_count", "orbx_launch_count",
     "orbx_extractor_create", "orbx_extractor_destroy", "orbx_extractor_tables", "orbx_extractor_max_keypoints",
     "orbx_extract", "orbx_extract_batch", "orbx_extract_batch_device", "orbx_extractor_copy_slot",
-    "orbx_extractor_results_device", "orbx_extractor_download", "orbx_extractor_sync",
+    "orbx_extractor_results_device", "orbx_extractor_download", "orbx_extractor_sync", "orbx_extractor_profile",
     "orbx_pyramid_level_size", "orbx_pyramid_to_host", "orbx_blurred_to_host", "orbx_candidates_to_host",
     "orbx_level_keypoints_to_host",
     "orbx_matcher_create", "orbx_matcher_destroy", "orbx_matcher_sync", "orbx_hamming_pairs",
     "orbx_bf_knn2", "orbx_bf_knn2_device", "orbx_knn2_merge_device",
-    "orbx_search_for_initialization", "orbx_match_slots_device", "orbx_search_by_projection",
+    "orbx_search_for_initialization", "orbx_match_slots_device", "orbx_extract_match_batch", "orbx_search_by_projection",
     "orbx_stereo_band_match", "orbx_popc_peak",
 ]
 
@@ -71,6 +71,10 @@ def lib():
         vp, i32, f32, sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
         L.orbx_last_error.restype = C.c_char_p
         L.orbx_device_count.restype = i32
+        L.orbx_launch_count.restype = C.c_ulonglong
+        L.orbx_extractor_profile.argtypes = [vp, i32, vp, vp]
+        L.orbx_extract_match_batch.argtypes = [vp, vp, vp, i32, i32, i32, i32, sz, i32, i32, vp, i32, f32, i32,
+                                               vp, vp, i32, vp, vp, vp, vp]
         L.orbx_extractor_create.argtypes = [C.POINTER(Params), C.POINTER(vp)]
         L.orbx_extractor_destroy.argtypes = [vp]
         L.orbx_extractor_destroy.restype = None
@@ -112,6 +116,14 @@ def _check(rc):
 
 def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _s(stream):
+    """cudaStream_t argument: None -> the handle's own stream (NULL); 0 -> the legacy default stream (torch's
+    default stream has handle 0, which the C ABI spells cudaStreamLegacy = 0x1); anything else verbatim."""
+    if stream is None:
+        return None
+    return C.c_void_p(1 if stream == 0 else stream)
 
 
 def device_count():
@@ -181,21 +193,27 @@ class ORBextractor:
                              first_slot=0, stream=None):
         _check(lib().orbx_extract_batch_device(self._h, C.c_void_p(d_ptr), batch, width, height, stride, frame_stride,
                                                int(vLappingArea[0]), int(vLappingArea[1]), first_slot,
-                                               C.c_void_p(stream) if stream else None))
+                                               _s(stream)))
 
     def copy_slot(self, src, dst, stream=None):
-        _check(lib().orbx_extractor_copy_slot(self._h, src, dst, C.c_void_p(stream) if stream else None))
+        _check(lib().orbx_extractor_copy_slot(self._h, src, dst, _s(stream)))
 
     def sync(self, stream=None):
-        _check(lib().orbx_extractor_sync(self._h, C.c_void_p(stream) if stream else None))
+        _check(lib().orbx_extractor_sync(self._h, _s(stream)))
 
     def download(self, first_slot, count, stream=None):
         kps = np.zeros((count, self.cap), KP_DTYPE)
         desc = np.zeros((count, self.cap, 32), np.uint8)
         n = np.zeros(count, np.int32); mono = np.zeros(count, np.int32)
         _check(lib().orbx_extractor_download(self._h, first_slot, count, _p(kps), _p(desc), self.cap, _p(n), _p(mono),
-                                             C.c_void_p(stream) if stream else None))
+                                             _s(stream)))
         return [(int(mono[i]), kps[i, :n[i]].copy(), desc[i, :n[i]].copy()) for i in range(count)]
+
+    def profile(self, enable=-1):
+        """per-stage CUDA-event milliseconds {pyramid+blur, FAST, octree, describe} summed over `batches` batches"""
+        ms = (C.c_double * 4)(); nb = C.c_int()
+        _check(lib().orbx_extractor_profile(self._h, enable, ms, C.byref(nb)))
+        return list(ms), nb.value
 
     def results_device(self):
         ptrs = [C.c_void_p() for _ in range(4)]
@@ -253,7 +271,7 @@ class ORBmatcher:
     __del__ = close
 
     def sync(self, stream=None):
-        _check(lib().orbx_matcher_sync(self._h, C.c_void_p(stream) if stream else None))
+        _check(lib().orbx_matcher_sync(self._h, _s(stream)))
 
     def DescriptorDistance(self, a, b):
         """Batched ORBmatcher::DescriptorDistance: a, b are [n,32] (or [32]) uint8."""
@@ -311,7 +329,21 @@ class ORBmatcher:
                                              self.mfNNratio, int(self.mbCheckOrientation), C.c_void_p(d_matches12),
                                              C.c_void_p(d_nmatches), C.c_void_p(d_knn_idx) if d_knn_idx else None,
                                              C.c_void_p(d_knn_dist) if d_knn_dist else None,
-                                             C.c_void_p(stream) if stream else None))
+                                             _s(stream)))
+
+
+def launch_count():
+    return int(lib().orbx_launch_count())
+
+
+def extract_match_batch(ex, m, imgs, lap, bounds, window, out):
+    """orbx_extract_match_batch on host arrays; `out` = dict of preallocated (ideally pinned) numpy arrays
+    kps[B,cap] desc[B,cap,32] n[B] mono[B] matches12[B,cap] nmatches[B]; imgs [B,H,W] uint8."""
+    B, H, W = imgs.shape
+    bb = np.array(bounds, np.float32)
+    _check(lib().orbx_extract_match_batch(ex._h, m._h, _p(imgs), B, W, H, imgs.strides[1], imgs.strides[0], int(lap[0]), int(lap[1]),
+                                          _p(bb), int(window), m.mfNNratio, int(m.mbCheckOrientation), _p(out["kps"]), _p(out["desc"]),
+                                          ex.cap, _p(out["n"]), _p(out["mono"]), _p(out["matches12"]), _p(out["nmatches"])))
 
 
 def popc_peak(device=0):

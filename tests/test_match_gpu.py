@@ -145,7 +145,7 @@ def test_slots_pipeline_matches_oracle():
     ex = orbx.ORBextractor(1000, 1.2, 8, 20, 7, max_width=640, max_height=480, max_batch=B)
     m = orbx.ORBmatcher(0.9, True, max_keypoints=ex.cap, max_batch=B)
     d_frames = torch.from_numpy(frames).cuda()
-    stream = torch.cuda.current_stream().cuda_stream
+    stream = torch.cuda.current_stream().cuda_stream   # 0 = legacy default stream; the wrapper maps it to cudaStreamLegacy
     ex.extract_batch_device(d_frames.data_ptr(), B, 640, 480, 640, 640 * 480, (0, 0), first_slot=1, stream=stream)
     ex.copy_slot(B, 0, stream)        # slot 0 = predecessor of the batch's first frame (here: its last frame)
     a = torch.arange(0, B, dtype=torch.int32, device="cuda"); b = torch.arange(1, B + 1, dtype=torch.int32, device="cuda")
