@@ -151,6 +151,7 @@ def main():
     ap.add_argument("--impl", default="orbx", choices=["orbx", "reference"])
     ap.add_argument("--batch", type=int, default=512, help="frames per step per GPU (512 x 361 KB = 185 MB of input > 126 MB L2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "orbx":
         args.warmup = 3
@@ -244,8 +245,8 @@ def main():
         "nmatches": torch.empty(B, dtype=torch.int32).pin_memory().numpy(),
     }
     h_np = h_frames.numpy()
-    e2e_steps = max(3, min(args.steps, 10))
-    for _ in range(2):
+    e2e_steps = 0 if args.no_e2e else max(3, min(args.steps, 10))
+    for _ in range(0 if args.no_e2e else 2):
         orbx.extract_match_batch(ex, m, h_np, (0, 0), bounds, WINDOW, out)
     barrier()
     t0 = time.perf_counter()
@@ -256,7 +257,7 @@ def main():
     t = torch.tensor([dt], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * e2e_steps / float(t.item())
+    e2e_value = world * B * e2e_steps / float(t.item()) if e2e_steps else None
     h2d = B * W * H
     d2h = B * (cap * 28 + cap * 32 + cap * 4 + 4 + 4 + 4)
     clocks = sampler.stop() if rank == 0 else None

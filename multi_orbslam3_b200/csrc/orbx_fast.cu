@@ -3,21 +3,30 @@
 // Replaces the cell loop of ORBextractor::ComputeKeyPointsOctTree (R/src/ORBextractor.cc:787-854) and the
 // cv::FAST(cell, th, nonmax=true) calls inside it (:808, :827).
 //
-// One CTA owns one row of cells of one level of one frame.  It stages rows [iniY, maxY) in shared memory
-// with 16-byte loads, computes the arc measure m (max over the 16 arcs of 9 ring pixels of
-// max(min d, min -d); corner <=> m > t, cv::FAST response = m - 1, independent of t) once per pixel,
-// and derives BOTH thresholds from it: because the reference's non-max suppression compares a corner
-// only with scores inside the same FAST call (= the same cell) and non-corners score 0, a pixel survives
-// at threshold t  <=>  m > t and m is a strict maximum among its in-cell neighbours' m.  Cells with no
-// survivor at iniThFAST fall back to the minThFAST survivors (:825-828).  Survivors are emitted in the
-// reference's order (cell by cell, row-major inside a cell) by warp-ballot compaction.  No score map is
-// ever written to global memory.
+// One CTA owns one row of cells of one level of one frame and never writes a score map to global memory:
+//   1. rows [iniY, maxY) are staged in shared memory with 16-byte loads (x index = absolute column);
+//   2. SWAR screen, 4 pixels per thread-step: |v - ring| per byte (VABSDIFF4.U8) on the 4 compass/diagonal
+//      opposite pairs; a 9-arc contains one pixel of every opposite pair, so a corner at threshold t needs
+//      max(|d_k|, |d_k+8|) > t for every pair.  Survivors (a few % of pixels) go to a shared-memory queue;
+//   3. queue drain, one pixel per thread: signed test on all 8 pairs, then the exact arc measure
+//      m = max over the 16 arcs of 9 of max(min d, min -d) on packed 16x2 lanes (VIMNMX.U16x2).
+//      corner <=> m > t, cv::FAST response = m - 1, independent of t.  m is kept in a shared u8 map;
+//   4. non-max suppression inside the cell: the reference's NMS only sees scores of the same FAST call (= the
+//      same cell) and non-corners score 0, so a pixel survives at threshold t <=> m > t and m is a strict
+//      maximum among its in-cell neighbours' m: ONE suppression pass serves both thresholds.  Survivors are
+//      recorded in two bitmaps (minThFAST / iniThFAST);
+//   5. cells with no iniThFAST survivor fall back to their minThFAST survivors (:825-828); every survivor
+//      computes its own output slot from popcounts (cell by cell, row-major inside a cell = reference order).
 #include "orbx_internal.h"
 
 namespace {
 
 constexpr int NT = 256;
 constexpr int MAX_CELLS = 128;
+constexpr int NW = NT / 32;
+constexpr int QCAP = 2048;           // screen survivors per band (overflow is scored inline, never dropped)
+constexpr int Q2CAP = 1024;          // signed-test survivors per band (same overflow rule)
+constexpr int BAND_ROWS = NW;        // one tile row per warp and band
 
 // ring offsets (dx,dy), OpenCV order
 __device__ __constant__ int8_t c_ring[16][2] = {
@@ -29,7 +38,8 @@ __device__ __constant__ int8_t c_ring[16][2] = {
 // One unsigned 16x2 min network (windows of 9 by doubling: 2, 4, 8, +1) then serves "9 darker" and
 // "9 brighter" at once: m = max over arcs of max(min d, min -d).
 // NOTE: the scalar formulation max(min(...), -max(...)) is MIScompiled by ptxas 12.9 / the 580 driver JIT for
-// sm_100 (verified on B200: -Xptxas -O0 and -G give the right answer, -O1..-O3 return max(d)); see DESIGN.md.
+// sm_100 (verified on B200: -Xptxas -O0 and -G give the right answer, -O1..-O3 return max(d)); see
+// profiles/ptxas_minmax_bug/ and DESIGN.md.
 __device__ __forceinline__ int arc_measure(const unsigned (&p)[16])
 {
     unsigned l2[16], l4[16];
@@ -44,15 +54,67 @@ __device__ __forceinline__ int arc_measure(const unsigned (&p)[16])
     return (a > b ? a : b) - 256;
 }
 
+// packed ring differences of one pixel: pk[q] = (v + 256 - r_q) | (256 - v + r_q) << 16
+__device__ __forceinline__ void load_ring(const uint8_t* p, const int (&roff)[16], unsigned (&pk)[16])
+{
+    const int v = p[0];
+    const unsigned cv = (unsigned)(v + 256) | ((unsigned)(256 - v) << 16);
+#pragma unroll
+    for (int q = 0; q < 16; q++) pk[q] = cv + (unsigned)p[roff[q]] * 0xFFFFu;
+}
+
+// OpenCV's high-speed test on the 8 opposite pairs, both polarities at once and branch-free:
+// "every pair has a member darker than v - t" <=> min_k max(d_k, d_k+8) > t (low lanes); brighter: high lanes.
+__device__ __forceinline__ bool pair_test(const unsigned (&pk)[16], int minTh)
+{
+    unsigned mn = __vmaxu2(pk[0], pk[8]);
+#pragma unroll
+    for (int k = 1; k < 8; k++) mn = __vminu2(mn, __vmaxu2(pk[k], pk[k + 8]));
+    const int lim = 256 + minTh;
+    return (int)(mn & 0xFFFF) > lim || (int)(mn >> 16) > lim;
+}
+
+// exact per-pixel path used when a queue overflows: pair test, then the arc measure
+__device__ __forceinline__ void score_pixel(const uint8_t* T, uint8_t* M, int tp, const int (&roff)[16], int x, int yt, int minTh)
+{
+    unsigned pk[16];
+    load_ring(T + yt * tp + x, roff, pk);
+    if (!pair_test(pk, minTh)) return;
+    const int m = arc_measure(pk);
+    if (m > minTh) M[(yt - 3) * tp + x] = (uint8_t)m;
+}
+
+// per-byte flag (bit 7) of "a > t" for t <= 126: bytes < 128 carry into bit 7 when a + 127 - t >= 128
+__device__ __forceinline__ unsigned gt_flags(unsigned a, unsigned c127mt) { return ((a & 0x7f7f7f7fu) + c127mt) | a; }
+
+// number of set bits in columns [c0, c1) of a bitmap row
+__device__ __forceinline__ int popc_range(const unsigned* row, int c0, int c1)
+{
+    int n = 0;
+    for (int w = c0 >> 5; w <= (c1 - 1) >> 5; w++) {
+        unsigned v = row[w];
+        const int lo = w << 5;
+        if (c0 > lo) v &= 0xFFFFFFFFu << (c0 - lo);
+        if (c1 < lo + 32) v &= 0xFFFFFFFFu >> (lo + 32 - c1);
+        n += __popc(v);
+    }
+    return n;
+}
+
+struct FastSmem {
+    int q_count, q2_count;
+    int cell_off[MAX_CELLS + 1];
+    unsigned char use_ini[MAX_CELLS];
+};
+
 __global__ void __launch_bounds__(NT) k_fast_rows(OrbxGeom g, OrbxBuffers b, const uint8_t* level0, int pitch0,
                                                   long long stride0)
 {
     extern __shared__ __align__(16) uint8_t smem[];
-    __shared__ int s_cnt_ini[MAX_CELLS], s_cnt_min[MAX_CELLS], s_off[MAX_CELLS + 1];
+    __shared__ FastSmem sh;
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
     const int f = blockIdx.y;
-    // locate (level, cell row)
     int l = 0;
     while (l + 1 < g.nlevels && (int)blockIdx.x >= g.lv[l + 1].row_base) l++;
     const OrbxLevel L = g.lv[l];
@@ -63,160 +125,309 @@ __global__ void __launch_bounds__(NT) k_fast_rows(OrbxGeom g, OrbxBuffers b, con
     int maxY = iniY + L.hCell + 6;
     if (iniY >= L.maxBY - 3) { if (tid == 0) *row_count = 0; return; }
     if (maxY > L.maxBY) maxY = L.maxBY;
-    const int nrow = maxY - iniY;                  // staged rows
-    const int ncol = L.maxBX - ORBX_BORDER;        // staged columns (x_rel = abs x - 16)
-    const int tp = (ncol + 15) & ~15;              // smem pitch
-    const int hs = nrow - 6, ws = ncol - 6;        // scored region (rel rows 3.., rel cols 3..)
-    if (hs <= 0 || ws <= 0) { if (tid == 0) *row_count = 0; return; }
-    uint8_t* T = smem;                             // [nrow][tp] pixels, later survivor flags
-    uint8_t* M = smem + (size_t)(L.hCell + 6) * tp;   // [hs][tp] arc measure (0 when <= minTh)
+    const int nrow = maxY - iniY;                      // staged rows
+    const int hs = nrow - 6;                           // scored rows: tile rows 3 .. nrow-4
+    const int xs0 = ORBX_EDGE, xs1 = L.w - ORBX_EDGE;  // scored columns [19, w-19)
+    if (hs <= 0 || xs1 <= xs0) { if (tid == 0) *row_count = 0; return; }
+    const int tp = (L.w + 15) & ~15;                   // smem pitch; x index = absolute column
+    const int bw = (L.w + 31) >> 5;                    // bitmap words per row
+    const int hmax = L.hCell;                          // scored rows of a full cell row of this level
+
+    // ---- smem carve-up (sizes use the level's maxima so that every cell row has the same layout) ----
+    uint8_t* T = smem;                                              // [hmax+6][tp] pixels
+    uint8_t* M = T + (size_t)(hmax + 6) * tp;                       // [hmax][tp]   arc measure (0 = not a corner at minTh)
+    unsigned* Q = reinterpret_cast<unsigned*>(M + (size_t)hmax * tp);   // [QCAP] candidate queue: x | tile row << 16
+    unsigned* Q2 = Q + QCAP;                                        // [Q2CAP] survivors of the signed pair test
+    unsigned* Bmin = Q2 + Q2CAP;                                    // [hmax][bw] survivors at minTh
+    unsigned* Bini = Bmin + hmax * bw;                              // [hmax][bw] survivors at iniTh
+    unsigned short* cnt_min = reinterpret_cast<unsigned short*>(Bini + hmax * bw);   // [nCols][hmax]
+    unsigned short* cnt_ini = cnt_min + L.nCols * hmax;             // [nCols][hmax]; later: exclusive row prefix of the chosen counts
 
     const uint8_t* img; int pitch;
     if (l == 0) { img = level0 + (long long)f * stride0; pitch = pitch0; }
     else { img = b.pyr[l] + (long long)f * L.frame_stride; pitch = L.pitch; }
 
-    // ---- stage rows, 16 bytes per load when the layout allows ----
-    const bool vec = ((pitch & 15) == 0) && ((reinterpret_cast<uintptr_t>(img) & 15) == 0);
+    // ---- 1. stage rows ----
+    const bool vec = ((pitch & 15) == 0) && (pitch >= tp) && ((reinterpret_cast<uintptr_t>(img) & 15) == 0);
+    const int lane = tid & 31, warp = tid >> 5;
     if (vec) {
-        const int nv = tp >> 4;    // may read up to 15 bytes of row padding: pitch is a multiple of 16 >= w
-        for (int k = tid; k < nrow * nv; k += NT) {
-            int r = k / nv, c = k - r * nv;
-            const uint4 v = __ldg(reinterpret_cast<const uint4*>(img + (long long)(iniY + r) * pitch + ORBX_BORDER) + c);
-            *reinterpret_cast<uint4*>(T + r * tp + c * 16) = v;
+        const int nv = tp >> 4;
+        for (int r = warp; r < nrow; r += NW) {
+            const uint4* src = reinterpret_cast<const uint4*>(img + (long long)(iniY + r) * pitch);
+            uint4* dst = reinterpret_cast<uint4*>(T + r * tp);
+            for (int c = lane; c < nv; c += 32) dst[c] = __ldg(src + c);
         }
     } else {
-        for (int k = tid; k < nrow * ncol; k += NT) {
-            int r = k / ncol, c = k - r * ncol;
-            T[r * tp + c] = __ldg(img + (long long)(iniY + r) * pitch + ORBX_BORDER + c);
-        }
+        for (int r = warp; r < nrow; r += NW)
+            for (int c = lane; c < tp; c += 32) T[r * tp + c] = c < L.w ? __ldg(img + (long long)(iniY + r) * pitch + c) : 0;
     }
-    for (int k = tid; k < L.nCols; k += NT) { s_cnt_ini[k] = 0; s_cnt_min[k] = 0; }
+    {
+        uint4* z = reinterpret_cast<uint4*>(M);
+        const int nz = (hs * tp) >> 4;
+        for (int k = tid; k < nz; k += NT) z[k] = make_uint4(0, 0, 0, 0);
+        for (int k = tid; k < 2 * hmax * bw; k += NT) Bmin[k] = 0;
+    }
     __syncthreads();
 
-    // ---- arc measure per scored pixel ----
     const int minTh = g.min_th, iniTh = g.ini_th;
     int roff[16];
 #pragma unroll
     for (int k = 0; k < 16; k++) roff[k] = c_ring[k][1] * tp + c_ring[k][0];
-    for (int k = tid; k < hs * ws; k += NT) {
-        const int r = k / ws, c = k - r * ws;
-        const uint8_t* p = T + (r + 3) * tp + c + 3;
-        const int v = p[0];
-        int m = 0;
-        // high-speed pre-test at minTh on the opposite pairs (k, k+8)
-        const int lo = v - minTh, hi = v + minTh;
-#define CLS(q) ((p[roff[q]] < lo ? 1 : 0) | (p[roff[q]] > hi ? 2 : 0))
-        int t = CLS(0) | CLS(8);
-        if (t) {
-            t &= CLS(4) | CLS(12);
-            if (t) {
-                t &= CLS(2) | CLS(10); t &= CLS(6) | CLS(14);
-                if (t) {
-                    t &= CLS(1) | CLS(9); t &= CLS(3) | CLS(11); t &= CLS(5) | CLS(13); t &= CLS(7) | CLS(15);
-                    if (t) {
-                        unsigned pk[16];
-                        const unsigned cv = (unsigned)(v + 256) | ((unsigned)(256 - v) << 16);
+
+    // ---- 2 + 3. banded screen and drain ----
+    const int gx0 = xs0 >> 2, gx1 = (xs1 - 1) >> 2;    // 4-pixel groups that contain scored columns
+    const unsigned c127 = (unsigned)(127 - (minTh < 126 ? minTh : 126)) * 0x01010101u;
+    const bool screen_ok = minTh <= 126;
+    for (int y0 = 3; y0 < nrow - 3; y0 += BAND_ROWS) {
+        if (tid == 0) { sh.q_count = 0; sh.q2_count = 0; }
+        __syncthreads();
+        // -- screen: one tile row per warp, one 4-pixel group per lane-step --
+        const int yt = y0 + warp;
+        if (yt < nrow - 3) {
+            const unsigned* rc = reinterpret_cast<const unsigned*>(T + yt * tp);
+            const unsigned* rp3 = reinterpret_cast<const unsigned*>(T + (yt + 3) * tp);
+            const unsigned* rm3 = reinterpret_cast<const unsigned*>(T + (yt - 3) * tp);
+            const unsigned* rp2 = reinterpret_cast<const unsigned*>(T + (yt + 2) * tp);
+            const unsigned* rm2 = reinterpret_cast<const unsigned*>(T + (yt - 2) * tp);
+            for (int g0 = gx0; g0 <= gx1; g0 += 32) {      // warp-uniform trip count (ballots below)
+                const int gx = g0 + lane;
+                unsigned cand = 0;
+                if (gx <= gx1) {
+                    cand = 0x80808080u;
+                    if (screen_ok) {
+                        // |d_k| | |d_k+8| >= max(|d_k|, |d_k+8|): one threshold test per pair, still only a necessary
+                        // condition (exact when t = 2^n - 1, e.g. the reference's minThFAST = 7)
+                        const unsigned V = rc[gx];
+                        // pair (0, 8): (0,+3) / (0,-3);  pair (4, 12): (+3,0) / (-3,0)
+                        cand &= gt_flags(__vabsdiffu4(V, rp3[gx]) | __vabsdiffu4(V, rm3[gx]), c127);
+                        cand &= gt_flags(__vabsdiffu4(V, __funnelshift_r(V, rc[gx + 1], 24)) |
+                                         __vabsdiffu4(V, __funnelshift_r(rc[gx - 1], V, 8)), c127);
+                        if (cand) {
+                            // pair (2, 10): (+2,+2) / (-2,-2);  pair (6, 14): (+2,-2) / (-2,+2)
+                            const unsigned p2c = rp2[gx], m2c = rm2[gx];
+                            const unsigned a2 = __funnelshift_r(p2c, rp2[gx + 1], 16), a10 = __funnelshift_r(rm2[gx - 1], m2c, 16);
+                            const unsigned a6 = __funnelshift_r(m2c, rm2[gx + 1], 16), a14 = __funnelshift_r(rp2[gx - 1], p2c, 16);
+                            cand &= gt_flags(__vabsdiffu4(V, a2) | __vabsdiffu4(V, a10), c127);
+                            cand &= gt_flags(__vabsdiffu4(V, a6) | __vabsdiffu4(V, a14), c127);
+                        }
+                    }
+                    // keep scored columns only (only the first and last group straddle the border)
+                    if (gx == gx0 || gx == gx1) {
+                        const int xb = gx << 2;
 #pragma unroll
-                        for (int q = 0; q < 16; q++) pk[q] = cv + (unsigned)p[roff[q]] * 0xFFFFu;   // (v+256-r) | (256-v+r)<<16
-                        m = arc_measure(pk);
-                        if (m <= minTh) m = 0;
+                        for (int q = 0; q < 4; q++)
+                            if (xb + q < xs0 || xb + q >= xs1) cand &= ~(0x80u << (8 * q));
+                    }
+                }
+                // warp-wide ordered compaction: one atomic per warp-step, dense stores
+                const unsigned b0 = __ballot_sync(0xffffffffu, cand & 0x00000080u), b1 = __ballot_sync(0xffffffffu, cand & 0x00008000u);
+                const unsigned b2 = __ballot_sync(0xffffffffu, cand & 0x00800000u), b3 = __ballot_sync(0xffffffffu, cand & 0x80000000u);
+                const int n0 = __popc(b0), n1 = __popc(b1), n2 = __popc(b2), n3 = __popc(b3);
+                const int total = n0 + n1 + n2 + n3;
+                if (total) {
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(&sh.q_count, total);
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    const unsigned lt = (1u << lane) - 1;
+                    const unsigned e = (unsigned)(gx << 2) | ((unsigned)yt << 16);
+                    int o;
+                    if (cand & 0x00000080u) { o = base + __popc(b0 & lt); if (o < QCAP) Q[o] = e; else score_pixel(T, M, tp, roff, e & 0xFFFF, yt, minTh); }
+                    if (cand & 0x00008000u) { o = base + n0 + __popc(b1 & lt); if (o < QCAP) Q[o] = e + 1; else score_pixel(T, M, tp, roff, (e + 1) & 0xFFFF, yt, minTh); }
+                    if (cand & 0x00800000u) { o = base + n0 + n1 + __popc(b2 & lt); if (o < QCAP) Q[o] = e + 2; else score_pixel(T, M, tp, roff, (e + 2) & 0xFFFF, yt, minTh); }
+                    if (cand & 0x80000000u) { o = base + n0 + n1 + n2 + __popc(b3 & lt); if (o < QCAP) Q[o] = e + 3; else score_pixel(T, M, tp, roff, (e + 3) & 0xFFFF, yt, minTh); }
+                }
+            }
+        }
+        __syncthreads();
+        // -- phase A: signed pair test, dense and branch-free; survivors are compacted into Q2 --
+        const int nq = min(sh.q_count, QCAP);
+        for (int e0 = warp * 32; e0 < nq; e0 += NT) {
+            const int e = e0 + lane;
+            bool pass = false; unsigned ent = 0;
+            if (e < nq) {
+                ent = Q[e];
+                unsigned pk[16];
+                load_ring(T + (ent >> 16) * tp + (ent & 0xFFFF), roff, pk);
+                pass = pair_test(pk, minTh);
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, pass);
+            if (bal) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&sh.q2_count, __popc(bal));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (pass) {
+                    const int o = base + __popc(bal & ((1u << lane) - 1));
+                    if (o < Q2CAP) Q2[o] = ent;
+                    else score_pixel(T, M, tp, roff, ent & 0xFFFF, ent >> 16, minTh);
+                }
+            }
+        }
+        __syncthreads();
+        // -- phase B: exact arc measure for the survivors --
+        const int nq2 = min(sh.q2_count, Q2CAP);
+        for (int e = tid; e < nq2; e += NT) {
+            const unsigned ent = Q2[e];
+            const int x = ent & 0xFFFF, yq = ent >> 16;
+            unsigned pk[16];
+            load_ring(T + yq * tp + x, roff, pk);
+            const int m = arc_measure(pk);
+            if (m > minTh) M[(yq - 3) * tp + x] = (uint8_t)m;
+        }
+        __syncthreads();      // every thread has read the band's counters before thread 0 resets them
+    }
+
+    // ---- 4. in-cell non-max suppression ----
+    // The pixel tile is dead now: its memory becomes the list of corners (non-zero entries of M), so that the
+    // suppression itself runs one corner per thread instead of diverging over a sparse map.
+    unsigned* CL = reinterpret_cast<unsigned*>(T);
+    const int clcap = ((hmax + 6) * tp) >> 2;
+    if (tid == 0) sh.q_count = 0;
+    __syncthreads();
+    {
+        const int nw = tp >> 2;
+        for (int r = warp; r < hs; r += NW)
+            for (int w0 = 0; w0 < nw; w0 += 32) {
+                const int wx = w0 + lane;
+                const unsigned word = wx < nw ? reinterpret_cast<const unsigned*>(M + r * tp)[wx] : 0u;
+                const unsigned b0 = __ballot_sync(0xffffffffu, word & 0x000000FFu), b1 = __ballot_sync(0xffffffffu, word & 0x0000FF00u);
+                const unsigned b2 = __ballot_sync(0xffffffffu, word & 0x00FF0000u), b3 = __ballot_sync(0xffffffffu, word & 0xFF000000u);
+                const int n0 = __popc(b0), n1 = __popc(b1), n2 = __popc(b2), n3 = __popc(b3);
+                const int total = n0 + n1 + n2 + n3;
+                if (total) {
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(&sh.q_count, total);
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    const unsigned lt = (1u << lane) - 1;
+                    const unsigned e = (unsigned)(wx << 2) | ((unsigned)r << 16);
+                    int o;
+                    if (word & 0x000000FFu) { o = base + __popc(b0 & lt); if (o < clcap) CL[o] = e; }
+                    if (word & 0x0000FF00u) { o = base + n0 + __popc(b1 & lt); if (o < clcap) CL[o] = e + 1; }
+                    if (word & 0x00FF0000u) { o = base + n0 + n1 + __popc(b2 & lt); if (o < clcap) CL[o] = e + 2; }
+                    if (word & 0xFF000000u) { o = base + n0 + n1 + n2 + __popc(b3 & lt); if (o < clcap) CL[o] = e + 3; }
+                }
+            }
+    }
+    __syncthreads();
+    if (sh.q_count <= clcap) {
+        const int ncl = sh.q_count;
+        for (int e = tid; e < ncl; e += NT) {
+            const unsigned ent = CL[e];
+            const int x = ent & 0xFFFF, r = ent >> 16;
+            const uint8_t* qm = M + r * tp + x;
+            const int sc = qm[0];
+            const int j = (x - xs0) / L.wCell;
+            const int c0 = xs0 + j * L.wCell, c1 = min(c0 + L.wCell, xs1);     // cell interior [c0, c1)
+            const bool hl = x - 1 >= c0, hr = x + 1 < c1, vu = r > 0, vd = r + 1 < hs;
+            // neighbours outside the cell count as 0 (they belong to another FAST call in the reference)
+            const int l0 = hl ? qm[-1] : 0, r0 = hr ? qm[1] : 0;
+            const int u0 = vu ? qm[-tp] : 0, ul = (vu && hl) ? qm[-tp - 1] : 0, ur = (vu && hr) ? qm[-tp + 1] : 0;
+            const int d0 = vd ? qm[tp] : 0, dl = (vd && hl) ? qm[tp - 1] : 0, dr = (vd && hr) ? qm[tp + 1] : 0;
+            const int mx = max(max(max(l0, r0), max(u0, ul)), max(max(ur, d0), max(dl, dr)));
+            if (sc > mx) {
+                atomicOr(&Bmin[r * bw + (x >> 5)], 1u << (x & 31));
+                if (sc > iniTh) atomicOr(&Bini[r * bw + (x >> 5)], 1u << (x & 31));
+            }
+        }
+    } else {
+        // corner-dense tile (more corners than the list holds): suppress in place over the map, still exact
+        const int nw = tp >> 2;
+        for (int r = warp; r < hs; r += NW)
+            for (int wx = lane; wx < nw; wx += 32) {
+                const unsigned word = reinterpret_cast<const unsigned*>(M + r * tp)[wx];
+                if (!word) continue;
+                for (int q = 0; q < 4; q++) {
+                    const int sc = (word >> (8 * q)) & 0xFF;
+                    if (!sc) continue;
+                    const int x = (wx << 2) + q;
+                    const uint8_t* qm = M + r * tp + x;
+                    const int j = (x - xs0) / L.wCell;
+                    const int c0 = xs0 + j * L.wCell, c1 = min(c0 + L.wCell, xs1);
+                    const bool hl = x - 1 >= c0, hr = x + 1 < c1, vu = r > 0, vd = r + 1 < hs;
+                    const int l0 = hl ? qm[-1] : 0, r0 = hr ? qm[1] : 0;
+                    const int u0 = vu ? qm[-tp] : 0, ul = (vu && hl) ? qm[-tp - 1] : 0, ur = (vu && hr) ? qm[-tp + 1] : 0;
+                    const int d0 = vd ? qm[tp] : 0, dl = (vd && hl) ? qm[tp - 1] : 0, dr = (vd && hr) ? qm[tp + 1] : 0;
+                    const int mx = max(max(max(l0, r0), max(u0, ul)), max(max(ur, d0), max(dl, dr)));
+                    if (sc > mx) {
+                        atomicOr(&Bmin[r * bw + (x >> 5)], 1u << (x & 31));
+                        if (sc > iniTh) atomicOr(&Bini[r * bw + (x >> 5)], 1u << (x & 31));
                     }
                 }
             }
-        }
-#undef CLS
-        M[r * tp + c] = (uint8_t)m;
     }
     __syncthreads();
 
-    // ---- in-cell non-max suppression; flags overwrite the pixel tile: bit0 survivor(minTh), bit1 survivor(iniTh) ----
-    for (int k = tid; k < hs * ws; k += NT) {
-        const int r = k / ws, c = k - r * ws;
-        const int s = M[r * tp + c];
-        uint8_t flag = 0;
-        if (s > 0) {
-            const int j = c / L.wCell;
-            const int c0 = j * L.wCell, c1 = min(c0 + L.wCell, ws);   // cell interior [c0, c1)
-            const bool hl = c - 1 >= c0, hr = c + 1 < c1, vu = r > 0, vd = r + 1 < hs;
-            const uint8_t* q = M + r * tp + c;
-            bool keep = true;
-            if (hl) keep &= s > q[-1];
-            if (hr) keep &= s > q[1];
-            if (vu) { keep &= s > q[-tp]; if (hl) keep &= s > q[-tp - 1]; if (hr) keep &= s > q[-tp + 1]; }
-            if (vd) { keep &= s > q[tp]; if (hl) keep &= s > q[tp - 1]; if (hr) keep &= s > q[tp + 1]; }
-            if (keep) {
-                flag = 1;
-                atomicAdd(&s_cnt_min[j], 1);
-                if (s > iniTh) { flag = 3; atomicAdd(&s_cnt_ini[j], 1); }
-            }
-        }
-        T[r * tp + c] = flag;
+    // ---- 5. counts per (cell, row), threshold choice per cell, offsets ----
+    for (int k = tid; k < L.nCols * hs; k += NT) {
+        const int j = k / hs, r = k - j * hs;
+        const int c0 = xs0 + j * L.wCell, c1 = min(c0 + L.wCell, xs1);
+        int a = 0, bq = 0;
+        if (c1 > c0) { a = popc_range(Bmin + r * bw, c0, c1); bq = popc_range(Bini + r * bw, c0, c1); }
+        cnt_min[j * hmax + r] = (unsigned short)a;
+        cnt_ini[j * hmax + r] = (unsigned short)bq;
     }
     __syncthreads();
-
-    // ---- per-cell threshold choice and offsets (cells are skipped like the reference does, :801) ----
-    if (warp == 0) {
+    for (int j = tid; j < L.nCols; j += NT) {
+        int ti = 0;
+        for (int r = 0; r < hs; r++) ti += cnt_ini[j * hmax + r];
+        const bool ui = ti > 0;
         int run = 0;
-        for (int base = 0; base < L.nCols; base += 32) {
-            const int j = base + lane;
-            int cnt = 0;
-            if (j < L.nCols) {
-                const int iniX = ORBX_BORDER + j * L.wCell;
-                if (iniX < L.maxBX - 6) cnt = s_cnt_ini[j] > 0 ? s_cnt_ini[j] : s_cnt_min[j];
-            }
-            int inc = cnt;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-            if (j < L.nCols) s_off[j] = run + inc - cnt;
-            run += __shfl_sync(0xffffffffu, inc, 31);
+        for (int r = 0; r < hs; r++) {
+            const int c = ui ? cnt_ini[j * hmax + r] : cnt_min[j * hmax + r];
+            cnt_ini[j * hmax + r] = (unsigned short)run;        // exclusive prefix inside the cell
+            run += c;
         }
-        if (lane == 0) {
-            s_off[L.nCols] = run;
-            *row_count = min(run, L.row_cap);
-            if (run > L.row_cap) atomicOr(b.err, ORBX_DEVERR_CAND_OVERFLOW);
-        }
+        sh.use_ini[j] = ui;
+        sh.cell_off[j + 1] = run;                               // cell totals, scanned below
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int run = 0;
+        sh.cell_off[0] = 0;
+        for (int j = 0; j < L.nCols; j++) { run += sh.cell_off[j + 1]; sh.cell_off[j + 1] = run; }   // cell_off[j] = first slot of cell j
+        *row_count = min(run, L.row_cap);
+        if (run > L.row_cap) atomicOr(b.err, ORBX_DEVERR_CAND_OVERFLOW);
     }
     __syncthreads();
 
-    // ---- ordered emission: one warp per cell, row-major inside the cell ----
+    // ---- ordered emission: every survivor computes its own slot ----
     uint32_t* out = b.row_cand + (long long)f * b.row_cand_stride + b.row_off[blockIdx.x];
     const int yrel0 = iniY - ORBX_BORDER + 3;
-    for (int j = warp; j < L.nCols; j += NT / 32) {
-        const int total = s_off[j + 1] - s_off[j];
-        if (total == 0) continue;
-        const uint8_t need = s_cnt_ini[j] > 0 ? 2 : 1;
-        const int c0 = j * L.wCell, c1 = min(c0 + L.wCell, ws);
-        int pos = s_off[j];
-        for (int r = 0; r < hs; r++) {
-            for (int cb = c0; cb < c1; cb += 32) {
-                const int c = cb + lane;
-                const bool on = c < c1 && (T[r * tp + c] & need);
-                const unsigned bal = __ballot_sync(0xffffffffu, on);
-                if (on) {
-                    const int o = pos + __popc(bal & ((1u << lane) - 1));
-                    if (o < L.row_cap)
-                        out[o] = (uint32_t)(c + 3) | ((uint32_t)(yrel0 + r) << 12) | ((uint32_t)(M[r * tp + c] - 1) << 24);
-                }
-                pos += __popc(bal);
-            }
+    for (int k = tid; k < hs * bw; k += NT) {
+        const int r = k / bw, wi = k - r * bw;
+        unsigned bits = Bmin[r * bw + wi];
+        const unsigned ibits = Bini[r * bw + wi];
+        while (bits) {
+            const int bpos = __ffs(bits) - 1;
+            bits &= bits - 1;
+            const int x = (wi << 5) + bpos;
+            const int j = (x - xs0) / L.wCell;
+            const bool ui = sh.use_ini[j];
+            if (ui && !((ibits >> bpos) & 1u)) continue;
+            const int c0 = xs0 + j * L.wCell;
+            const int rank = x > c0 ? popc_range((ui ? Bini : Bmin) + r * bw, c0, x) : 0;
+            const int o = sh.cell_off[j] + cnt_ini[j * hmax + r] + rank;
+            if (o < L.row_cap)
+                out[o] = (uint32_t)(x - ORBX_BORDER) | ((uint32_t)(yrel0 + r) << 12) | ((uint32_t)(M[r * tp + x] - 1) << 24);
         }
     }
 }
 
-}  // namespace
-
-static size_t fast_smem_bytes(const OrbxGeom& g)
+size_t fast_smem_bytes(const OrbxGeom& g)
 {
     size_t smem = 0;
     for (int l = 0; l < g.nlevels; l++) {
         const OrbxLevel& L = g.lv[l];
         if (L.nCols <= 0 || L.nRows <= 0) continue;
-        const size_t tp = ((L.maxBX - ORBX_BORDER) + 15) & ~15;
-        const size_t need = (size_t)(L.hCell + 6) * tp + (size_t)L.hCell * tp;
+        const size_t tp = (L.w + 15) & ~15;
+        const size_t bw = (L.w + 31) >> 5;
+        const size_t need = (size_t)(L.hCell + 6) * tp + (size_t)L.hCell * tp + (QCAP + Q2CAP) * 4 + 2 * L.hCell * bw * 4 +
+                            2 * (size_t)L.nCols * L.hCell * 2 + 16;
         if (need > smem) smem = need;
     }
     return smem;
 }
+
+}  // namespace
 
 void orbx_fast_configure(const OrbxGeom& g)
 {
