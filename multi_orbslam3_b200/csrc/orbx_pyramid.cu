@@ -9,7 +9,7 @@
 // The 19-px reflected border the reference materialises is never read downstream and is not built.
 #include "orbx_internal.h"
 
-namespace {
+namespace generic {
 
 constexpr int TW = 64, TH = 32;          // dst tile
 constexpr int RW = TW + 6, RH = TH + 6;  // tile + blur halo
@@ -139,11 +139,12 @@ __global__ void __launch_bounds__(NT) k_pyr_level(PyrArgs a)
     }
 }
 
-}  // namespace
+}  // namespace generic
 
-void orbx_launch_pyramid(const OrbxGeom& g, const OrbxBuffers& b, const uint8_t* level0, int pitch0,
+static void launch_pyramid_generic(const OrbxGeom& g, const OrbxBuffers& b, const uint8_t* level0, int pitch0,
                          long long stride0, int batch, cudaStream_t s)
 {
+    using namespace generic;
     for (int l = 0; l < g.nlevels; l++) {
         const OrbxLevel& L = g.lv[l];
         PyrArgs a{};
@@ -171,5 +172,269 @@ void orbx_launch_pyramid(const OrbxGeom& g, const OrbxBuffers& b, const uint8_t*
             k_pyr_level<true><<<grid, NT, smem, s>>>(a);
             ORBX_COUNT_LAUNCH(1);
         }
+    }
+}
+
+// =====================================================================================================
+// Fast path (scale factors up to 1.5): 128x64 destination tiles, 256 threads.
+//   S  source tile of level l-1 (TMA 3-D tiled bulk load when the layout allows, else cooperative 16-byte loads)
+//   Hs horizontally interpolated source rows, (S[x0]*c0 + S[x1]*c1) >> 4, 16 bit
+//   R  resized tile + 3-px halo (halo outside the image is filled by BORDER_REFLECT_101 of the level itself)
+//   Hb horizontal blur pass (exact integers <= 65280, 16 bit); blurred bytes are staged back into R
+// The blur is exact in any pass order because only the final (sum + 32768) >> 16 rounds.
+// =====================================================================================================
+namespace fastp {
+
+constexpr int TW = 128, TH = 64, NT = 256, NWARP = NT / 32;
+constexpr int RW = TW + 6, RH = TH + 6;
+constexpr int RO = 16;                 // column of R that holds dst x = X0 (16-byte aligned interior)
+constexpr int RP = 160;                // R pitch
+constexpr int HP = 136;                // Hs pitch (u16 elements)
+constexpr int KMAXCOL = (RW + 31) / 32;
+
+struct Args {
+    const uint8_t* src; int spitch; long long sstride; int sw, sh;
+    uint8_t* dst; int dpitch; long long dstride; int w, h;
+    uint8_t* blur; int bpitch; long long bstride;
+    const short4* xt; const short4* yt;
+    int sp;        // smem source pitch (multiple of 16)
+    int sh_max;    // smem source rows
+};
+
+__device__ __forceinline__ void blur_and_store(uint8_t* R, uint16_t* Hb, uint8_t* blur_base, int bpitch, int X0, int Y0,
+                                               int tw, int th)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // ---- horizontal pass: lane = 4-pixel group, warp = row; two dp4a per pixel ----
+    const unsigned K0 = 18u | (34u << 8) | (48u << 16) | (56u << 24), K1 = 48u | (34u << 8) | (18u << 16);
+    for (int row = warp; row < th + 6; row += NWARP) {
+        const unsigned* rr = reinterpret_cast<const unsigned*>(R + row * RP) + (RO >> 2) + lane;
+        const unsigned wm = rr[-1], w0 = rr[0], w1 = rr[1];
+        unsigned a0 = __dp4a(__funnelshift_r(wm, w0, 8), K0, 0u);  a0 = __dp4a(__funnelshift_r(w0, w1, 8), K1, a0);
+        unsigned a1 = __dp4a(__funnelshift_r(wm, w0, 16), K0, 0u); a1 = __dp4a(__funnelshift_r(w0, w1, 16), K1, a1);
+        unsigned a2 = __dp4a(__funnelshift_r(wm, w0, 24), K0, 0u); a2 = __dp4a(__funnelshift_r(w0, w1, 24), K1, a2);
+        unsigned a3 = __dp4a(w0, K0, 0u);                          a3 = __dp4a(w1, K1, a3);
+        *reinterpret_cast<uint2*>(Hb + row * TW + lane * 4) = make_uint2(a0 | (a1 << 16), a2 | (a3 << 16));
+    }
+    __syncthreads();
+    // ---- vertical pass: 2 columns x 4 rows per thread; blurred bytes go back into R's interior ----
+    for (int it = tid; it < (TW / 2) * (TH / 4); it += NT) {
+        const int cp = it & (TW / 2 - 1), rg = it >> 6;
+        const int r0 = rg * 4;
+        if (r0 >= th) continue;
+        unsigned lo[10], hi[10];
+#pragma unroll
+        for (int k = 0; k < 10; k++) {
+            const unsigned v = *reinterpret_cast<const unsigned*>(Hb + (r0 + k) * TW + cp * 2);
+            lo[k] = v & 0xFFFFu; hi[k] = v >> 16;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const unsigned sl = 18u * (lo[q] + lo[q + 6]) + 34u * (lo[q + 1] + lo[q + 5]) + 48u * (lo[q + 2] + lo[q + 4]) + 56u * lo[q + 3];
+            const unsigned sh = 18u * (hi[q] + hi[q + 6]) + 34u * (hi[q + 1] + hi[q + 5]) + 48u * (hi[q + 2] + hi[q + 4]) + 56u * hi[q + 3];
+            const unsigned o = ((sl + 32768u) >> 16) | (((sh + 32768u) >> 16) << 8);
+            *reinterpret_cast<uint16_t*>(R + (3 + r0 + q) * RP + RO + cp * 2) = (uint16_t)o;
+        }
+    }
+    __syncthreads();
+    // ---- 16-byte stores of the blurred tile ----
+    for (int it = tid; it < th * (TW / 16); it += NT) {
+        const int r = it >> 3, c16 = it & 7;
+        if (c16 * 16 < tw)
+            *reinterpret_cast<uint4*>(blur_base + (long long)(Y0 + r) * bpitch + X0 + c16 * 16) =
+                *reinterpret_cast<const uint4*>(R + (3 + r) * RP + RO + c16 * 16);
+    }
+}
+
+// BORDER_REFLECT_101 fill of the halo that lies outside the level: columns first, then whole rows.
+// we / he = tile-local index of the first column / row outside the image (>= TW+3 / TH+3 when none is).
+__device__ __forceinline__ void reflect_halo(uint8_t* R, int X0, int Y0, int w, int h)
+{
+    const int tid = threadIdx.x;
+    const int we = w - X0, he = h - Y0;
+    const bool left = X0 == 0, right = we < TW + 3, top = Y0 == 0, bottom = he < TH + 3;
+    if (left || right) {
+        const int rlo = top ? 3 : 0, rhi = bottom ? 3 + he : RH;      // R rows that hold image pixels
+        for (int it = tid; it < (rhi - rlo) * 3; it += NT) {
+            const int row = rlo + it / 3, d = it % 3;
+            uint8_t* rr = R + row * RP + RO;
+            if (left) rr[-(d + 1)] = rr[d + 1];
+            if (right && we + d < TW + 3) rr[we + d] = rr[we - 2 - d];
+        }
+    }
+    __syncthreads();
+    if (top || bottom) {
+        for (int it = tid; it < 3 * (RP / 4); it += NT) {
+            const int d = it / (RP / 4), c4 = it % (RP / 4);
+            unsigned* base = reinterpret_cast<unsigned*>(R) + c4;
+            if (top) base[(3 - (d + 1)) * (RP / 4)] = base[(3 + d + 1) * (RP / 4)];
+            if (bottom && he + d < TH + 3) base[(3 + he + d) * (RP / 4)] = base[(3 + he - 2 - d) * (RP / 4)];
+        }
+    }
+    __syncthreads();
+}
+
+template <bool RESIZE>
+__global__ void __launch_bounds__(NT) k_pyr_fast(Args a)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int X0 = blockIdx.x * TW, Y0 = blockIdx.y * TH;
+    const int f = blockIdx.z;
+    const int w = a.w, h = a.h;
+    const int tw = min(TW, w - X0), th = min(TH, h - Y0);
+    const int ax = max(X0 - 3, 0), bx = min(X0 + TW + 3, w);
+    const int ay = max(Y0 - 3, 0), by = min(Y0 + TH + 3, h);
+    const int rw = bx - ax, rh = by - ay;
+    const int rcol0 = RO - (X0 - ax), rrow0 = 3 - (Y0 - ay);      // R position of dst (ax, ay)
+
+    uint8_t* R = smem;                                             // [RH][RP]
+    uint16_t* Hb = reinterpret_cast<uint16_t*>(smem + RH * RP);    // [RH][TW]  (aliases Hs)
+    const uint8_t* srcf = a.src + (long long)f * a.sstride;
+
+    if (RESIZE) {
+        uint16_t* Hs = Hb;                                         // [sh_max][HP]
+        const int hs_bytes = max(a.sh_max * HP * 2, RH * TW * 2);
+        int4* sy = reinterpret_cast<int4*>(smem + RH * RP + hs_bytes);              // [RH] per-row (y0, y1, b0, b1)
+        uint8_t* S = reinterpret_cast<uint8_t*>(sy + RH);                           // [sh_max][sp]
+        const short4 xa = a.xt[ax], xb = a.xt[bx - 1];
+        const short4 ya = a.yt[ay], yb = a.yt[by - 1];
+        const int sx0 = xa.x & ~15, sx1 = xb.y;                   // first source column aligned down to 16
+        const int sy0 = ya.x, sy1 = yb.y;
+        const int sp = a.sp;
+        const int nrows = sy1 - sy0 + 1;
+        // ---- source tile ----
+        const bool vec = ((a.spitch & 15) == 0) && ((reinterpret_cast<uintptr_t>(srcf) & 15) == 0);
+        if (vec) {
+            const int nv = (sx1 - sx0 + 16) >> 4;                 // stays inside the row pitch (pitch is a multiple of 16 >= sw)
+            for (int r = warp; r < nrows; r += NWARP) {
+                const uint4* g = reinterpret_cast<const uint4*>(srcf + (long long)(sy0 + r) * a.spitch + sx0);
+                uint4* d = reinterpret_cast<uint4*>(S + r * sp);
+                for (int c = lane; c < nv; c += 32) d[c] = __ldg(g + c);
+            }
+        } else {
+            const int ncols = sx1 - sx0 + 1;
+            for (int r = warp; r < nrows; r += NWARP)
+                for (int c = lane; c < ncols; c += 32) S[r * sp + c] = __ldg(srcf + (long long)(sy0 + r) * a.spitch + sx0 + c);
+        }
+        if (tid < rh) {
+            const short4 ye = a.yt[ay + tid];
+            sy[tid] = make_int4(ye.x - sy0, ye.y - sy0, ye.z, ye.w);
+        }
+        // per-lane column coefficients
+        int o0[KMAXCOL], o1[KMAXCOL], c0[KMAXCOL], c1[KMAXCOL];
+#pragma unroll
+        for (int k = 0; k < KMAXCOL; k++) {
+            const int c = lane + 32 * k;
+            const short4 xe = a.xt[ax + min(c, rw - 1)];
+            o0[k] = xe.x - sx0; o1[k] = xe.y - sx0; c0[k] = xe.z; c1[k] = xe.w;
+        }
+        __syncthreads();
+        // ---- horizontal interpolation of every source row ----
+        for (int r = warp; r < nrows; r += NWARP) {
+            const uint8_t* sr = S + r * sp;
+#pragma unroll
+            for (int k = 0; k < KMAXCOL; k++) {
+                const int c = lane + 32 * k;
+                if (c < rw) Hs[r * HP + c] = (uint16_t)((sr[o0[k]] * c0[k] + sr[o1[k]] * c1[k]) >> 4);
+            }
+        }
+        __syncthreads();
+        // ---- vertical interpolation -> R ----
+        for (int ry = warp; ry < rh; ry += NWARP) {
+            const int4 ye = sy[ry];
+            const uint16_t* h0 = Hs + ye.x * HP;
+            const uint16_t* h1 = Hs + ye.y * HP;
+            uint8_t* rr = R + (rrow0 + ry) * RP + rcol0;
+#pragma unroll
+            for (int k = 0; k < KMAXCOL; k++) {
+                const int c = lane + 32 * k;
+                if (c < rw) {
+                    const int v = (((ye.z * (int)h0[c]) >> 16) + ((ye.w * (int)h1[c]) >> 16) + 2) >> 2;
+                    rr[c] = (uint8_t)min(max(v, 0), 255);
+                }
+            }
+        }
+        __syncthreads();
+    } else {
+        // level 0: R comes straight from the frame; 16-byte chunks cover x in [X0-16, X0+TW+16)
+        const bool vec = ((a.spitch & 15) == 0) && ((reinterpret_cast<uintptr_t>(srcf) & 15) == 0);
+        const int rowsn = rh;
+        if (vec) {
+            for (int it = tid; it < rowsn * (RP / 16); it += NT) {
+                const int ry = it / (RP / 16), c16 = it % (RP / 16);
+                const int x = X0 - RO + c16 * 16;
+                uint4 v = make_uint4(0, 0, 0, 0);
+                if (x >= 0 && x < a.spitch) v = __ldg(reinterpret_cast<const uint4*>(srcf + (long long)(ay + ry) * a.spitch + x));
+                *reinterpret_cast<uint4*>(R + (rrow0 + ry) * RP + c16 * 16) = v;
+            }
+        } else {
+            for (int it = tid; it < rowsn * rw; it += NT) {
+                const int ry = it / rw, c = it % rw;
+                R[(rrow0 + ry) * RP + rcol0 + c] = __ldg(srcf + (long long)(ay + ry) * a.spitch + ax + c);
+            }
+        }
+        __syncthreads();
+    }
+
+    // halo outside the image
+    reflect_halo(R, X0, Y0, w, h);
+
+    if (RESIZE) {
+        // ---- store the level tile (16-byte stores; the row pitch absorbs the tail) ----
+        uint8_t* dst = a.dst + (long long)f * a.dstride;
+        for (int it = tid; it < th * (TW / 16); it += NT) {
+            const int r = it >> 3, c16 = it & 7;
+            if (c16 * 16 < tw)
+                *reinterpret_cast<uint4*>(dst + (long long)(Y0 + r) * a.dpitch + X0 + c16 * 16) =
+                    *reinterpret_cast<const uint4*>(R + (3 + r) * RP + RO + c16 * 16);
+        }
+    }
+    blur_and_store(R, Hb, a.blur + (long long)f * a.bstride, a.bpitch, X0, Y0, tw, th);
+}
+
+}  // namespace fastp
+
+void orbx_launch_pyramid(const OrbxGeom& g, const OrbxBuffers& b, const uint8_t* level0, int pitch0,
+                         long long stride0, int batch, cudaStream_t s)
+{
+    using namespace fastp;
+    // the fast kernels need a scale factor <= 1.5 (source tile extents) and a blur pitch that is a multiple of 16
+    bool ok = true;
+    for (int l = 1; l < g.nlevels; l++) {
+        const double sx = (double)g.lv[l - 1].w / g.lv[l].w, sy = (double)g.lv[l - 1].h / g.lv[l].h;
+        if (sx > 1.55 || sy > 1.55) ok = false;
+    }
+    if (!ok) { launch_pyramid_generic(g, b, level0, pitch0, stride0, batch, s); return; }
+    for (int l = 0; l < g.nlevels; l++) {
+        const OrbxLevel& L = g.lv[l];
+        Args a{};
+        a.w = L.w; a.h = L.h;
+        a.blur = b.blur[l]; a.bpitch = L.pitch; a.bstride = L.frame_stride;
+        dim3 grid((L.w + TW - 1) / TW, (L.h + TH - 1) / TH, batch);
+        if (l == 0) {
+            a.src = level0; a.spitch = pitch0; a.sstride = stride0; a.sw = L.w; a.sh = L.h;
+            const size_t smem = RH * RP + RH * TW * 2;
+            static bool cfg0 = false;
+            if (!cfg0) { cudaFuncSetAttribute(k_pyr_fast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); cfg0 = true; }
+            k_pyr_fast<false><<<grid, NT, smem, s>>>(a);
+        } else {
+            const OrbxLevel& P = g.lv[l - 1];
+            a.src = (l == 1) ? level0 : b.pyr[l - 1];
+            a.spitch = (l == 1) ? pitch0 : P.pitch;
+            a.sstride = (l == 1) ? stride0 : P.frame_stride;
+            a.sw = P.w; a.sh = P.h;
+            a.dst = b.pyr[l]; a.dpitch = L.pitch; a.dstride = L.frame_stride;
+            a.xt = b.tabs + L.xtab_off; a.yt = b.tabs + L.ytab_off;
+            const double sx = (double)P.w / L.w, sy = (double)P.h / L.h;
+            a.sp = (((int)(RW * sx) + 2 + 15 + 16) + 15) & ~15;     // span + alignment slack, multiple of 16
+            a.sh_max = (int)(RH * sy) + 4;
+            const size_t hs_bytes = (size_t)a.sh_max * HP * 2 > (size_t)RH * TW * 2 ? (size_t)a.sh_max * HP * 2 : (size_t)RH * TW * 2;
+            const size_t smem = RH * RP + hs_bytes + RH * sizeof(int4) + (size_t)a.sh_max * a.sp;
+            static size_t cfg1 = 0;
+            if (smem > cfg1) { cudaFuncSetAttribute(k_pyr_fast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); cfg1 = smem; }
+            k_pyr_fast<true><<<grid, NT, smem, s>>>(a);
+        }
+        ORBX_COUNT_LAUNCH(1);
     }
 }
