@@ -80,7 +80,7 @@ def reference_arm(args):
     O.build()
     cores = os.cpu_count() or 1
     frames = synth.rects_stream(W, H, 16, seed=0)
-    per_thread = 4
+    per_thread = 16
     for _ in range(args.warmup):
         cpu_run(frames, cores, 1)
     tot_frames, tot_time = 0, 0.0
@@ -303,7 +303,8 @@ def main():
         from oracle import oracle as O
         O.build()
         cores = os.cpu_count() or 1
-        per_thread = 6
+        _, dcal, ncal = cpu_run(base[:16], cores, 2)                 # calibration: 2 frames per thread
+        per_thread = int(min(2000, max(6, 15.0 / max(dcal / 2.0, 1e-3))))   # ~15 s of wall time on all cores
         fps, dtc, nf = cpu_run(base[:16], cores, per_thread)
         cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
                "sample": "%d frames (%d threads x %d frames of the same S-rects stream), %.1f s wall" % (nf, cores, per_thread, dtc)}

@@ -177,7 +177,8 @@ static int configure_geometry(orbx_extractor* h, int width, int height)
         if (l > 0 && (rc = dev_alloc(h, (void**)&b.pyr[l], (size_t)g.lv[l].frame_stride * B))) return rc;
         if ((rc = dev_alloc(h, (void**)&b.blur[l], (size_t)g.lv[l].frame_stride * B))) return rc;
     }
-    h->pitch0 = g.lv[0].pitch; h->stride0 = g.lv[0].frame_stride;
+    // staged level 0: tight 16-byte-multiple pitch so that a pinned frame batch with the same stride is ONE contiguous DMA
+    h->pitch0 = (g.lv[0].w + 15) & ~15; h->stride0 = (long long)h->pitch0 * g.lv[0].h;
     if ((rc = dev_alloc(h, (void**)&h->d_level0, (size_t)h->stride0 * B))) return rc;
     std::vector<short4> tabs(tab);
     for (int l = 1; l < g.nlevels; l++) {
@@ -401,7 +402,9 @@ int orbx_ex_stage_input(orbx_extractor* h, const uint8_t* imgs, int batch, int w
     const int p0 = h->pitch0;
     if (is_pinned(imgs)) {
         // pinned caller memory: DMA straight from it
-        if (frame_stride == (size_t)stride * height) {
+        if (frame_stride == (size_t)stride * height && stride == p0) {
+            CK(cudaMemcpyAsync(h->d_level0, imgs, (size_t)h->stride0 * batch, cudaMemcpyHostToDevice, s));
+        } else if (frame_stride == (size_t)stride * height) {
             CK(cudaMemcpy2DAsync(h->d_level0, p0, imgs, stride, width, (size_t)height * batch, cudaMemcpyHostToDevice, s));
         } else {
             for (int f = 0; f < batch; f++)

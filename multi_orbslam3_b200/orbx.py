@@ -146,8 +146,8 @@ class ORBextractor:
         self.mvScaleFactor, self.mvInvScaleFactor, self.mvLevelSigma2, self.mvInvLevelSigma2, self.mnFeaturesPerLevel = t
 
     def close(self):
-        if getattr(self, "_h", None) and self._h.value:
-            lib().orbx_extractor_destroy(self._h)
+        if getattr(self, "_h", None) and self._h.value and _lib is not None:
+            _lib.orbx_extractor_destroy(self._h)
             self._h = C.c_void_p()
 
     __del__ = close
@@ -264,8 +264,8 @@ class ORBmatcher:
         self.K = max_keypoints
 
     def close(self):
-        if getattr(self, "_h", None) and self._h.value:
-            lib().orbx_matcher_destroy(self._h)
+        if getattr(self, "_h", None) and self._h.value and _lib is not None:
+            _lib.orbx_matcher_destroy(self._h)
             self._h = C.c_void_p()
 
     __del__ = close
