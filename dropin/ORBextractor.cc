@@ -1,0 +1,93 @@
+// Drop-in body of ORB_SLAM3::ORBextractor over the B200 C ABI.  Replaces R/orb_slam3/src/ORBextractor.cc.
+#include "ORBextractor.h"
+#include <stdexcept>
+#include <string>
+#include "../include/orbx.h"
+
+namespace ORB_SLAM3
+{
+
+static int g_orbx_device = 0;
+void ORBextractor::SetDevice(int device) { g_orbx_device = device; }
+
+static void create_handle(orbx_extractor** out, int nfeatures, float scaleFactor, int nlevels, int ini, int min, int w, int h)
+{
+    orbx_params p;
+    p.nfeatures = nfeatures; p.scale_factor = scaleFactor; p.nlevels = nlevels; p.ini_th_fast = ini; p.min_th_fast = min;
+    p.max_width = w; p.max_height = h; p.max_batch = 1; p.device = g_orbx_device; p.max_candidates_per_level = 0;
+    if (orbx_extractor_create(&p, out) != ORBX_OK)
+        throw std::runtime_error(std::string("ORBextractor (B200): ") + orbx_last_error());   // no CPU fallback exists
+}
+
+// R/src/ORBextractor.cc:408-468: the tables come from the library so that both sides agree bit for bit
+ORBextractor::ORBextractor(int _nfeatures, float _scaleFactor, int _nlevels, int _iniThFAST, int _minThFAST):
+    nfeatures(_nfeatures), scaleFactor(_scaleFactor), nlevels(_nlevels),
+    iniThFAST(_iniThFAST), minThFAST(_minThFAST), mpHandle(nullptr), mnHandleW(0), mnHandleH(0)
+{
+    // a small probe handle gives the tables without knowing the camera resolution yet
+    orbx_extractor* probe = nullptr;
+    create_handle(&probe, nfeatures, (float)scaleFactor, nlevels, iniThFAST, minThFAST, 64, 64);
+    mvScaleFactor.resize(nlevels); mvInvScaleFactor.resize(nlevels);
+    mvLevelSigma2.resize(nlevels); mvInvLevelSigma2.resize(nlevels); mnFeaturesPerLevel.resize(nlevels);
+    orbx_extractor_tables(probe, mvScaleFactor.data(), mvInvScaleFactor.data(), mvLevelSigma2.data(),
+                          mvInvLevelSigma2.data(), mnFeaturesPerLevel.data());
+    orbx_extractor_destroy(probe);
+    mvImagePyramid.resize(nlevels);
+}
+
+ORBextractor::~ORBextractor()
+{
+    if (mpHandle) orbx_extractor_destroy(mpHandle);
+}
+
+// R/src/ORBextractor.cc:1068-1150
+int ORBextractor::operator()( cv::InputArray _image, cv::InputArray _mask, std::vector<cv::KeyPoint>& _keypoints,
+                              cv::OutputArray _descriptors, std::vector<int> &vLappingArea)
+{
+    (void)_mask;                                       // ignored by the reference too (ORBextractor.h:60)
+    if(_image.empty())
+        return -1;
+
+    cv::Mat image = _image.getMat();
+    // assert(image.type() == CV_8UC1) in the reference (:1076)
+
+    if (!mpHandle || image.cols > mnHandleW || image.rows > mnHandleH) {
+        if (mpHandle) orbx_extractor_destroy(mpHandle);
+        mpHandle = nullptr;
+        mnHandleW = image.cols; mnHandleH = image.rows;
+        create_handle(&mpHandle, nfeatures, (float)scaleFactor, nlevels, iniThFAST, minThFAST, mnHandleW, mnHandleH);
+    }
+    const int cap = orbx_extractor_max_keypoints(mpHandle);
+    _keypoints.resize(cap);                            // cv::KeyPoint is layout-compatible with orbx_keypoint
+    std::vector<unsigned char> desc((size_t)cap * 32);
+    int n = 0, mono = 0;
+    const int rc = orbx_extract(mpHandle, image.ptr(0), image.cols, image.rows, (int)image.step,
+                                vLappingArea[0], vLappingArea[1],
+                                reinterpret_cast<orbx_keypoint*>(_keypoints.data()), desc.data(), cap, &n, &mono);
+    if (rc == ORBX_E_EMPTY) return -1;
+    if (rc != ORBX_OK) throw std::runtime_error(std::string("ORBextractor (B200): ") + orbx_last_error());
+    _keypoints.resize(n);
+    if (n == 0) _descriptors.release();
+    else {
+        _descriptors.create(n, 32, CV_8U);
+        cv::Mat d = _descriptors.getMat();
+        for (int i = 0; i < n; i++) std::memcpy(d.ptr(i), desc.data() + (size_t)i * 32, 32);
+    }
+    for (auto& m : mvImagePyramid) m.release();        // stale until SyncPyramidToHost()
+    return mono;
+}
+
+// explicit download of mvImagePyramid (R/include/ORBextractor.h:88); only the stereo SAD refinement reads it
+void ORBextractor::SyncPyramidToHost()
+{
+    if (!mpHandle) return;
+    for (int l = 0; l < nlevels; l++) {
+        int w = 0, h = 0;
+        if (orbx_pyramid_level_size(mpHandle, l, &w, &h) != ORBX_OK) return;
+        mvImagePyramid[l].create(h, w, CV_8UC1);
+        if (orbx_pyramid_to_host(mpHandle, 0, l, mvImagePyramid[l].ptr(0), (int)mvImagePyramid[l].step) != ORBX_OK)
+            throw std::runtime_error(std::string("ORBextractor (B200): ") + orbx_last_error());
+    }
+}
+
+} //namespace ORB_SLAM

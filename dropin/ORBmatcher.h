@@ -1,0 +1,53 @@
+// Drop-in replacement of R/orb_slam3/include/ORBmatcher.h:35-108 (class ORB_SLAM3::ORBmatcher) for the methods on
+// the B200 hot path.  Public signatures are the reference's.  Methods not listed here (SearchByBoW, the Sim3 /
+// KeyFrame SearchByProjection overloads, SearchForTriangulation, SearchBySim3, Fuse) keep the reference's own
+// bodies from ORBmatcher.cc: they are host-side candidate gathering around DescriptorDistance and are marked
+// "glue" in SURVEY.md section 8a; see INTEGRATION.md for how both translation units live side by side.
+#ifndef ORBMATCHER_H
+#define ORBMATCHER_H
+
+#include <vector>
+#include "frame_shim.h"
+
+struct orbx_matcher;   // include/orbx.h
+
+namespace ORB_SLAM3
+{
+
+class ORBmatcher
+{
+public:
+
+    ORBmatcher(float nnratio=0.6, bool checkOri=true);
+
+    // Computes the Hamming distance between two ORB descriptors
+    static int DescriptorDistance(const cv::Mat &a, const cv::Mat &b);
+
+    // Search matches between Frame keypoints and projected MapPoints. Returns number of matches
+    // Used to track the local map (Tracking)
+    int SearchByProjection(Frame &F, const std::vector<MapPoint*> &vpMapPoints, const float th=3, const bool bFarPoints = false, const float thFarPoints = 50.0f);
+
+    // Project MapPoints tracked in last frame into the current frame and search matches.
+    // Used to track from previous frame (Tracking)
+    int SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, const float th, const bool bMono);
+
+    // Matching for the Map Initialization (only used in the monocular case)
+    int SearchForInitialization(Frame &F1, Frame &F2, std::vector<cv::Point2f> &vbPrevMatched, std::vector<int> &vnMatches12, int windowSize=10);
+
+public:
+
+    static const int TH_LOW;
+    static const int TH_HIGH;
+    static const int HISTO_LENGTH;
+
+protected:
+
+    float RadiusByViewingCos(const float &viewCos);
+
+    float mfNNratio;
+    bool mbCheckOrientation;
+};
+
+}// namespace ORB_SLAM
+
+#endif // ORBMATCHER_H

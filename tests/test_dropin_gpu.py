@@ -1,0 +1,55 @@
+"""The drop-in C++ classes (dropin/ORBextractor, dropin/ORBmatcher: the reference's public signatures over the C ABI)
+driven the way Frame/Tracking drive them, compared with the oracle."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+from multi_orbslam3_b200 import synth
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_dropin_classes_match_oracle(tmp_path):
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "dropin")])
+    W, H = 752, 480
+    st = synth.rects_stream(W, H, 2, seed=5)
+    for k in range(2):
+        st[k].tofile(tmp_path / ("f%d.raw" % k))
+    out = tmp_path / "out.bin"
+    subprocess.check_call([os.path.join(ROOT, "dropin", "_build", "test_dropin"), str(W), str(H),
+                           str(tmp_path / "f0.raw"), str(tmp_path / "f1.raw"), str(out)])
+    buf = out.read_bytes()
+    off = 0
+    ref = O.Extractor(1000, 1.2, 8, 20, 7)
+    frames = []
+    for k in range(2):
+        n, mono = struct.unpack_from("<ii", buf, off); off += 8
+        kps = np.frombuffer(buf, O.KP_DTYPE, n, off); off += 28 * n
+        desc = np.frombuffer(buf, np.uint8, 32 * n, off).reshape(n, 32); off += 32 * n
+        rmono, rk, rd = ref(st[k], (0, 0))
+        assert (mono, n) == (rmono, len(rk))
+        for name in ("x", "y", "size", "response", "octave", "class_id"):
+            np.testing.assert_array_equal(kps[name], rk[name])
+        assert np.abs(kps["angle"] - rk["angle"]).max() <= 1e-3
+        same = kps["angle"] == rk["angle"]
+        np.testing.assert_array_equal(desc[same], rd[same])
+        frames.append((kps, desc))
+        if k == 1:
+            lvl3 = ref.level_image(3)
+    nm, = struct.unpack_from("<i", buf, off); off += 4
+    n0 = len(frames[0][0])
+    m12 = np.frombuffer(buf, np.int32, n0, off); off += 4 * n0
+    (k1, d1), (k2, d2) = frames
+    rn, rm12, _ = O.search_for_initialization(k1, d1, k2, d2, (0, W, 0, H), np.stack([k1["x"], k1["y"]], 1), 100, 0.9, True)
+    assert nm == rn
+    np.testing.assert_array_equal(m12, rm12)
+    lw, lh = struct.unpack_from("<ii", buf, off); off += 8
+    pyr3 = np.frombuffer(buf, np.uint8, lw * lh, off).reshape(lh, lw); off += lw * lh
+    np.testing.assert_array_equal(pyr3, lvl3)           # mvImagePyramid after SyncPyramidToHost()
+    d, = struct.unpack_from("<i", buf, off)
+    assert d == O.hamming256(d1[0], d2[0])
