@@ -102,6 +102,54 @@ def reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------------------
+def server_bench(args, world, rank, local):
+    """BASELINE config C5: one query keyframe (1000 descriptors) per step against a 65 536-keyframe DB sharded by
+    agent/GPU; NCCL all-gathers either the partial top-2 tables (default) or the descriptor shards."""
+    import torch
+    import torch.distributed as dist
+    from multi_orbslam3_b200 import orbx
+    from multi_orbslam3_b200.server import ShardedDescriptorDB, gpu_fns
+    n_local = args.db_keyframes // world * 1000
+    g = torch.Generator(device="cuda"); g.manual_seed(1234 + rank)
+    shard = torch.randint(0, 256, (n_local, 32), dtype=torch.uint8, device="cuda", generator=g)
+    q = torch.randint(0, 256, (1000, 32), dtype=torch.uint8, device="cuda", generator=g)
+    m = orbx.ORBmatcher(0.7, True, max_keypoints=2048, device=local)
+    match_fn, merge_fn = gpu_fns(m)
+    db = ShardedDescriptorDB(shard, match_fn, merge_fn)
+    fn = db.knn2_allgather_top2 if args.exchange == "top2" else db.knn2_allgather_db
+    db.broadcast_queries(q, 0)
+    for _ in range(args.warmup):
+        fn(q)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    l0 = orbx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        idx, d = fn(q)
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / args.steps
+    pairs = 1000.0 * n_local * world
+    if rank == 0:
+        popc, _ = orbx.popc_peak(local)
+        line = {"metric": "server BF kNN-2 query keyframes/sec vs %d-keyframe DB" % args.db_keyframes, "value": 1e3 / ms,
+                "unit": "query keyframes/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "config": {"workload": "C5: 1000-descriptor query keyframe vs %d x 1000 descriptors sharded over %d GPU(s), exchange=%s" % (args.db_keyframes, world, args.exchange)},
+                "gpu_launches": int(orbx.launch_count() - l0),
+                "roofline": {"bound": "popc", "achieved": pairs * 8 / (ms * 1e-3) / world, "peak": popc, "unit": "popc32/s per GPU",
+                             "frac": pairs * 8 / (ms * 1e-3) / world / popc, "traffic": None}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -152,6 +200,10 @@ def main():
     ap.add_argument("--batch", type=int, default=512, help="frames per step per GPU (512 x 361 KB = 185 MB of input > 126 MB L2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
+    ap.add_argument("--workload", default="c1", choices=["c1", "c5"],
+                    help="c1 (default, the BASELINE metric): extract+match streams; c5: server cross-agent BF matching over a sharded DB")
+    ap.add_argument("--db-keyframes", type=int, default=65536, help="c5: keyframes in the whole DB (x1000 descriptors)")
+    ap.add_argument("--exchange", default="top2", choices=["top2", "db"], help="c5: all-gather partial top-2 tables or the DB shards")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "orbx":
         args.warmup = 3
@@ -173,6 +225,9 @@ def main():
     if world > 1:
         dist.barrier()
     from multi_orbslam3_b200 import orbx, synth
+
+    if args.workload == "c5":
+        return server_bench(args, world, rank, local)
 
     B = args.batch
     ex = orbx.ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, max_width=W, max_height=H, max_batch=B, device=local)

@@ -1,0 +1,87 @@
+"""Server-side cross-agent descriptor matching over a keyframe-descriptor DB sharded across the GPUs of one box
+(BASELINE config C5).
+
+The reference's server matches keyframes of different agents through BoW buckets (LoopClosing.cc:605-657); the
+north star asks for brute-force Hamming kNN-2 against the whole DB with cv::BFMatcher semantics (Frame.cc:1127-1137:
+top-2 by (distance, trainIdx)).  The DB is sharded by owning agent = GPU (rank r holds global rows
+[r*shard, (r+1)*shard)).  Two exchange strategies, identical results:
+
+  * allgather_db  (the north star's wording): all-gather the descriptor shards over NVLink (32 B per descriptor), then
+    every rank matches its own queries against the full DB.
+  * allgather_top2 (less traffic): every rank matches ALL queries against its local shard, then all-gathers only the
+    per-query partial top-2 tables (16 B per query and rank) and merges them by (distance, global index).
+
+The device work (orbx_bf_knn2_device / orbx_knn2_merge_device) is injected as `match_fn` / `merge_fn` so that the
+collective and index logic can be exercised on CPU with gloo (tests/test_server_dist.py injects the oracle).
+"""
+import torch
+import torch.distributed as dist
+
+
+def _world(group):
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(group), dist.get_rank(group)
+    return 1, 0
+
+
+def _all_gather(t, group):
+    w, _ = _world(group)
+    if w == 1:
+        return t.unsqueeze(0).clone()
+    out = torch.empty((w * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)   # concatenated along dim 0
+    dist.all_gather_into_tensor(out, t.contiguous(), group=group)
+    return out.view((w,) + tuple(t.shape))
+
+
+class ShardedDescriptorDB:
+    """shard: uint8 tensor [n_local, 32] (every rank holds the same n_local; pad with a copy of row 0 if needed)."""
+
+    def __init__(self, shard, match_fn, merge_fn, group=None):
+        assert shard.dtype == torch.uint8 and shard.dim() == 2 and shard.shape[1] == 32
+        self.shard, self.match_fn, self.merge_fn, self.group = shard.contiguous(), match_fn, merge_fn, group
+        self.world, self.rank = _world(group)
+        self.n_local = shard.shape[0]
+
+    def knn2_allgather_top2(self, queries):
+        """queries: the same uint8 [nq, 32] tensor on every rank (the query keyframe is broadcast by its owner).
+        Returns (idx [nq,2] global row indices, dist [nq,2])."""
+        idx, d = self.match_fn(queries, self.shard, self.rank * self.n_local)      # partial top-2 on the local shard
+        parts_i = _all_gather(idx, self.group)                                      # [world, nq, 2]
+        parts_d = _all_gather(d, self.group)
+        return self.merge_fn(parts_i, parts_d)
+
+    def knn2_allgather_db(self, queries):
+        """all-gather the shards (world * n_local * 32 bytes per rank), then match against the full DB."""
+        full = _all_gather(self.shard, self.group).reshape(-1, 32)
+        return self.match_fn(queries, full, 0)
+
+    def broadcast_queries(self, queries, src):
+        if self.world > 1:
+            dist.broadcast(queries, src=src, group=self.group)
+        return queries
+
+
+def gpu_fns(matcher):
+    """match_fn / merge_fn backed by the CUDA kernels of an orbx.ORBmatcher (tensors on its device)."""
+    import ctypes as C
+    from . import orbx
+
+    def match_fn(q, t, idx_base):
+        nq = q.shape[0]
+        idx = torch.empty((nq, 2), dtype=torch.int32, device=q.device)
+        d = torch.empty((nq, 2), dtype=torch.int32, device=q.device)
+        s = torch.cuda.current_stream(q.device).cuda_stream
+        orbx._check(orbx.lib().orbx_bf_knn2_device(matcher._h, C.c_void_p(q.data_ptr()), nq, C.c_void_p(t.data_ptr()), t.shape[0],
+                                                   C.c_void_p(idx.data_ptr()), C.c_void_p(d.data_ptr()), int(idx_base), orbx._s(s)))
+        return idx, d
+
+    def merge_fn(parts_i, parts_d):
+        nparts, nq = parts_i.shape[0], parts_i.shape[1]
+        idx = torch.empty((nq, 2), dtype=torch.int32, device=parts_i.device)
+        d = torch.empty((nq, 2), dtype=torch.int32, device=parts_i.device)
+        s = torch.cuda.current_stream(parts_i.device).cuda_stream
+        orbx._check(orbx.lib().orbx_knn2_merge_device(matcher._h, C.c_void_p(parts_i.data_ptr()), C.c_void_p(parts_d.data_ptr()), nparts, nq,
+                                                      C.c_void_p(idx.data_ptr()), C.c_void_p(d.data_ptr()), orbx._s(s)))
+        return idx, d
+
+    return match_fn, merge_fn
