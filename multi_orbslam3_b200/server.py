@@ -51,9 +51,19 @@ class ShardedDescriptorDB:
         return self.merge_fn(parts_i, parts_d)
 
     def knn2_allgather_db(self, queries):
-        """all-gather the shards (world * n_local * 32 bytes per rank), then match against the full DB."""
+        """all-gather the shards (world * n_local * 32 bytes into every rank), then every rank matches ITS slice of the
+        queries against the full DB and the per-slice results are all-gathered (nq is padded to a multiple of world)."""
         full = _all_gather(self.shard, self.group).reshape(-1, 32)
-        return self.match_fn(queries, full, 0)
+        nq = queries.shape[0]
+        per = (nq + self.world - 1) // self.world
+        lo = min(self.rank * per, nq); hi = min(lo + per, nq)
+        mine = queries[lo:hi]
+        if hi - lo < per:                                            # pad the last slice with copies of query 0
+            mine = torch.cat([mine, queries[:1].expand(per - (hi - lo), 32)], 0)
+        idx, d = self.match_fn(mine.contiguous(), full, 0)
+        idx = _all_gather(idx, self.group).reshape(-1, 2)[:nq]
+        d = _all_gather(d, self.group).reshape(-1, 2)[:nq]
+        return idx.contiguous(), d.contiguous()
 
     def broadcast_queries(self, queries, src):
         if self.world > 1:
