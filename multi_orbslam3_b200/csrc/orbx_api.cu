@@ -314,22 +314,44 @@ static int deferred_error(orbx_extractor* h)
     return ORBX_OK;
 }
 
+// OrbxBuffers view whose per-frame arrays start at frame `off` (chunked pipelines reuse the same kernels)
+static OrbxBuffers shifted(const orbx_extractor* h, int off)
+{
+    OrbxBuffers b = h->buf;
+    if (off == 0) return b;
+    const OrbxGeom& g = h->geom;
+    for (int l = 0; l < g.nlevels; l++) {
+        if (b.pyr[l]) b.pyr[l] += (long long)off * g.lv[l].frame_stride;
+        b.blur[l] += (long long)off * g.lv[l].frame_stride;
+    }
+    b.row_cand += (long long)off * b.row_cand_stride;
+    b.row_count += (long long)off * g.total_rows;
+    b.lvl_kp += (long long)off * g.kp_total_cap;
+    b.lvl_n += (long long)off * g.nlevels;
+    b.sort_scratch += (long long)off * b.sort_scratch_stride;
+    b.work += (long long)off * g.out_cap;
+    return b;
+}
+
 static int run_batch(orbx_extractor* h, const uint8_t* d_level0, int pitch0, long long stride0, int batch,
-                     int lap0, int lap1, int first_slot, cudaStream_t s)
+                     int lap0, int lap1, int first_slot, cudaStream_t s, int frame_off = 0)
 {
     const OrbxGeom& g = h->geom;
+    const OrbxBuffers buf = shifted(h, frame_off);
+    const uint8_t* l0 = d_level0 + (long long)frame_off * stride0;
     harvest_stage_times(h);
     const bool prof = h->profile;
     if (prof) cudaEventRecord(h->ev[0], s);
-    orbx_launch_pyramid(g, h->buf, d_level0, pitch0, stride0, batch, s);
+    orbx_launch_pyramid(g, buf, l0, pitch0, stride0, batch, s);
     if (prof) cudaEventRecord(h->ev[1], s);
-    orbx_launch_fast(g, h->buf, d_level0, pitch0, stride0, batch, s);
+    orbx_launch_fast(g, buf, l0, pitch0, stride0, batch, s);
     if (prof) cudaEventRecord(h->ev[2], s);
-    orbx_launch_octree(g, h->buf, batch, s);
+    orbx_launch_octree(g, buf, batch, s);
     if (prof) cudaEventRecord(h->ev[3], s);
-    orbx_launch_describe(g, h->buf, d_level0, pitch0, stride0, batch, lap0, lap1, first_slot, s);
+    orbx_launch_describe(g, buf, l0, pitch0, stride0, batch, lap0, lap1, first_slot, s);
     if (prof) { cudaEventRecord(h->ev[4], s); h->ev_pending = true; }
-    h->last_level0 = d_level0; h->last_pitch0 = pitch0; h->last_stride0 = stride0; h->last_batch = batch;
+    h->last_level0 = d_level0; h->last_pitch0 = pitch0; h->last_stride0 = stride0;
+    if (frame_off + batch > h->last_batch || frame_off == 0) h->last_batch = frame_off + batch;
     CK(cudaGetLastError());
     return ORBX_OK;
 }
@@ -393,58 +415,73 @@ static bool is_pinned(const void* p)
 }
 
 // ---- host-buffer pipeline pieces (shared with orbx_extract_match_batch in orbx_match.cu) ----
-int orbx_ex_stage_input(orbx_extractor* h, const uint8_t* imgs, int batch, int width, int height, int stride,
-                        size_t frame_stride, cudaStream_t s)
+int orbx_ex_configure(orbx_extractor* h, int width, int height)
 {
     CK(cudaSetDevice(h->p.device));
-    int rc = configure_geometry(h, width, height);
-    if (rc) return rc;
+    return configure_geometry(h, width, height);
+}
+
+// H2D of frames [f0, f0+count) of a host batch into the staged level 0 (geometry already configured)
+int orbx_ex_stage_input(orbx_extractor* h, const uint8_t* imgs, int f0, int count, int width, int height, int stride,
+                        size_t frame_stride, cudaStream_t s)
+{
     const int p0 = h->pitch0;
+    uint8_t* dst = h->d_level0 + (size_t)f0 * h->stride0;
+    const uint8_t* src = imgs + (size_t)f0 * frame_stride;
     if (is_pinned(imgs)) {
         // pinned caller memory: DMA straight from it
         if (frame_stride == (size_t)stride * height && stride == p0) {
-            CK(cudaMemcpyAsync(h->d_level0, imgs, (size_t)h->stride0 * batch, cudaMemcpyHostToDevice, s));
+            CK(cudaMemcpyAsync(dst, src, (size_t)h->stride0 * count, cudaMemcpyHostToDevice, s));
         } else if (frame_stride == (size_t)stride * height) {
-            CK(cudaMemcpy2DAsync(h->d_level0, p0, imgs, stride, width, (size_t)height * batch, cudaMemcpyHostToDevice, s));
+            CK(cudaMemcpy2DAsync(dst, p0, src, stride, width, (size_t)height * count, cudaMemcpyHostToDevice, s));
         } else {
-            for (int f = 0; f < batch; f++)
-                CK(cudaMemcpy2DAsync(h->d_level0 + (size_t)f * h->stride0, p0, imgs + f * frame_stride, stride, width, height,
+            for (int f = 0; f < count; f++)
+                CK(cudaMemcpy2DAsync(dst + (size_t)f * h->stride0, p0, src + f * frame_stride, stride, width, height,
                                      cudaMemcpyHostToDevice, s));
         }
     } else {
-        for (int f = 0; f < batch; f++)
+        uint8_t* stage = h->h_stage_in + (size_t)f0 * h->stride0;
+        for (int f = 0; f < count; f++)
             for (int y = 0; y < height; y++)
-                memcpy(h->h_stage_in + (size_t)f * h->stride0 + (size_t)y * p0, imgs + f * frame_stride + (size_t)y * stride, width);
-        CK(cudaMemcpyAsync(h->d_level0, h->h_stage_in, (size_t)h->stride0 * batch, cudaMemcpyHostToDevice, s));
+                memcpy(stage + (size_t)f * h->stride0 + (size_t)y * p0, src + f * frame_stride + (size_t)y * stride, width);
+        CK(cudaMemcpyAsync(dst, stage, (size_t)h->stride0 * count, cudaMemcpyHostToDevice, s));
     }
     return ORBX_OK;
 }
 
-int orbx_ex_run_staged(orbx_extractor* h, int batch, int lap0, int lap1, int first_slot, cudaStream_t s)
+int orbx_ex_run_staged(orbx_extractor* h, int f0, int count, int lap0, int lap1, int first_slot, cudaStream_t s)
 {
-    return run_batch(h, h->d_level0, h->pitch0, h->stride0, batch, lap0, lap1, first_slot, s);
+    return run_batch(h, h->d_level0, h->pitch0, h->stride0, count, lap0, lap1, first_slot, s, f0);
 }
 
 cudaStream_t orbx_ex_stream(orbx_extractor* h) { return h->stream; }
+int orbx_ex_out_cap(orbx_extractor* h) { return h->geom.out_cap; }
 
-// issues the D2H copies of `count` result slots; direct into the caller's buffers when they are pinned and
-// laid out with the handle's own capacity, else into the handle's pinned staging (unpacked by _finish)
-int orbx_ex_fetch_async(orbx_extractor* h, int first_slot, int count, orbx_keypoint* kps, uint8_t* desc, int cap,
-                        int32_t* n, int32_t* mono_index, cudaStream_t s, bool* direct)
+// issues the D2H copies of `count` result slots starting at first_slot into host frame positions host_off..;
+// direct into the caller's buffers when they are pinned and laid out with the handle's own capacity, else into the
+// handle's pinned staging (unpacked by _finish)
+int orbx_ex_fetch_async(orbx_extractor* h, int first_slot, int count, int host_off, orbx_keypoint* kps, uint8_t* desc, int cap,
+                        int32_t* n, int32_t* mono_index, cudaStream_t s, bool direct)
 {
     const size_t ocap = h->geom.out_cap;
-    *direct = kps && desc && n && mono_index && cap == (int)ocap && is_pinned(kps) && is_pinned(desc) && is_pinned(n) && is_pinned(mono_index);
-    CK(cudaMemcpyAsync(h->h_err, h->buf.err, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(*direct ? n : h->h_n, h->buf.n + first_slot, sizeof(int) * count, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(*direct ? mono_index : h->h_mono, h->buf.mono + first_slot, sizeof(int) * count, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(*direct ? kps : h->h_kps, h->buf.kps + first_slot * ocap, sizeof(orbx_keypoint) * ocap * count, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(*direct ? desc : h->h_desc, h->buf.desc + first_slot * ocap * 32, ocap * 32 * count, cudaMemcpyDeviceToHost, s));
+    const size_t ho = (size_t)host_off;
+    CK(cudaMemcpyAsync(direct ? n + ho : h->h_n + ho, h->buf.n + first_slot, sizeof(int) * count, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(direct ? mono_index + ho : h->h_mono + ho, h->buf.mono + first_slot, sizeof(int) * count, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(direct ? kps + ho * ocap : h->h_kps + ho * ocap, h->buf.kps + first_slot * ocap, sizeof(orbx_keypoint) * ocap * count, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(direct ? desc + ho * ocap * 32 : h->h_desc + ho * ocap * 32, h->buf.desc + first_slot * ocap * 32, ocap * 32 * count, cudaMemcpyDeviceToHost, s));
     return ORBX_OK;
 }
 
+bool orbx_ex_can_fetch_direct(orbx_extractor* h, orbx_keypoint* kps, uint8_t* desc, int cap, int32_t* n, int32_t* mono_index)
+{
+    return kps && desc && n && mono_index && cap == h->geom.out_cap && is_pinned(kps) && is_pinned(desc) && is_pinned(n) && is_pinned(mono_index);
+}
+
+// after the stream(s) were synchronised: device error flags, then unpack the staging if the fetch was not direct
 int orbx_ex_fetch_finish(orbx_extractor* h, int count, orbx_keypoint* kps, uint8_t* desc, int cap,
                          int32_t* n, int32_t* mono_index, bool direct)
 {
+    CK(cudaMemcpy(h->h_err, h->buf.err, sizeof(unsigned), cudaMemcpyDeviceToHost));
     int rc = deferred_error(h);
     if (rc) return rc;
     if (direct) return ORBX_OK;
@@ -466,8 +503,8 @@ extern "C" int orbx_extractor_download(orbx_extractor* h, int first_slot, int co
     if (!h || !h->buf.kps || first_slot < 0 || count < 1 || first_slot + count > h->slots) return ORBX_E_INVALID;
     CK(cudaSetDevice(h->p.device));
     cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
-    bool direct;
-    int rc = orbx_ex_fetch_async(h, first_slot, count, kps, desc, cap, n, mono_index, s, &direct);
+    const bool direct = orbx_ex_can_fetch_direct(h, kps, desc, cap, n, mono_index);
+    int rc = orbx_ex_fetch_async(h, first_slot, count, 0, kps, desc, cap, n, mono_index, s, direct);
     if (rc) return rc;
     CK(cudaStreamSynchronize(s));
     return orbx_ex_fetch_finish(h, count, kps, desc, cap, n, mono_index, direct);
@@ -480,9 +517,11 @@ extern "C" int orbx_extract_batch(orbx_extractor* h, const uint8_t* imgs, int ba
     if (!h || batch < 1 || batch > h->p.max_batch) { orbx_set_error("%s%s", "orbx_extract_batch: invalid arguments", ""); return ORBX_E_INVALID; }
     if (!imgs || width <= 0 || height <= 0) return ORBX_E_EMPTY;
     if (stride < width) return ORBX_E_INVALID;
-    int rc = orbx_ex_stage_input(h, imgs, batch, width, height, stride, frame_stride, h->stream);
+    int rc = orbx_ex_configure(h, width, height);
     if (rc) return rc;
-    rc = orbx_ex_run_staged(h, batch, lap0, lap1, 0, h->stream);
+    rc = orbx_ex_stage_input(h, imgs, 0, batch, width, height, stride, frame_stride, h->stream);
+    if (rc) return rc;
+    rc = orbx_ex_run_staged(h, 0, batch, lap0, lap1, 0, h->stream);
     if (rc) return rc;
     return orbx_extractor_download(h, 0, batch, kps, desc, cap, n, mono_index, h->stream);
 }

@@ -99,11 +99,14 @@ extern unsigned long long g_orbx_launches;
 
 // host-buffer pipeline pieces of the extractor (orbx_api.cu), used by orbx_extract_match_batch
 struct orbx_extractor;
-int orbx_ex_stage_input(orbx_extractor* h, const uint8_t* imgs, int batch, int width, int height, int stride,
+int orbx_ex_configure(orbx_extractor* h, int width, int height);
+int orbx_ex_stage_input(orbx_extractor* h, const uint8_t* imgs, int f0, int count, int width, int height, int stride,
                         size_t frame_stride, cudaStream_t s);
-int orbx_ex_run_staged(orbx_extractor* h, int batch, int lap0, int lap1, int first_slot, cudaStream_t s);
+int orbx_ex_run_staged(orbx_extractor* h, int f0, int count, int lap0, int lap1, int first_slot, cudaStream_t s);
 cudaStream_t orbx_ex_stream(orbx_extractor* h);
-int orbx_ex_fetch_async(orbx_extractor* h, int first_slot, int count, orbx_keypoint* kps, uint8_t* desc, int cap,
-                        int32_t* n, int32_t* mono_index, cudaStream_t s, bool* direct);
+int orbx_ex_out_cap(orbx_extractor* h);
+bool orbx_ex_can_fetch_direct(orbx_extractor* h, orbx_keypoint* kps, uint8_t* desc, int cap, int32_t* n, int32_t* mono_index);
+int orbx_ex_fetch_async(orbx_extractor* h, int first_slot, int count, int host_off, orbx_keypoint* kps, uint8_t* desc, int cap,
+                        int32_t* n, int32_t* mono_index, cudaStream_t s, bool direct);
 int orbx_ex_fetch_finish(orbx_extractor* h, int count, orbx_keypoint* kps, uint8_t* desc, int cap,
                          int32_t* n, int32_t* mono_index, bool direct);

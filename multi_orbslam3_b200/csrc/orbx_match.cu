@@ -27,6 +27,8 @@
         }                                                                                 \
     } while (0)
 
+#define ORBX_MAX_CHUNKS 4
+
 namespace {
 
 constexpr int GC = ORBX_GRID_COLS, GR = ORBX_GRID_ROWS, NCELL = GC * GR;
@@ -548,6 +550,7 @@ struct orbx_matcher {
     uint8_t* d_bfq; uint8_t* d_bft; size_t bfq_bytes, bft_bytes;
     unsigned* h_err;
     int32_t* d_pair_a; int32_t* d_pair_b;
+    cudaStream_t s_h2d, s_d2h; cudaEvent_t ev[2 * ORBX_MAX_CHUNKS]; cudaEvent_t ev_start;
     std::vector<void*> allocs;
 };
 
@@ -600,6 +603,7 @@ extern "C" int orbx_matcher_create(const orbx_matcher_params* p, orbx_matcher** 
     m->d_part_idx = m->d_part_dist = nullptr; m->part_elems = 0;
     m->d_bfq = m->d_bft = nullptr; m->bfq_bytes = m->bft_bytes = 0;
     m->d_pair_a = m->d_pair_b = nullptr;
+    m->s_h2d = m->s_d2h = nullptr;
     CKM(cudaMemset(W.err, 0, sizeof(unsigned)));
     CKM(cudaMallocHost((void**)&m->h_err, sizeof(unsigned)));
     if (2 * K * sizeof(int) > 48 * 1024)
@@ -624,6 +628,11 @@ extern "C" void orbx_matcher_destroy(orbx_matcher* m)
     if (m->d_bfq) cudaFree(m->d_bfq);
     if (m->d_bft) cudaFree(m->d_bft);
     if (m->d_pair_a) cudaFree(m->d_pair_a);
+    if (m->s_h2d) {
+        cudaStreamDestroy(m->s_h2d); cudaStreamDestroy(m->s_d2h);
+        for (int i = 0; i < 2 * ORBX_MAX_CHUNKS; i++) cudaEventDestroy(m->ev[i]);
+        cudaEventDestroy(m->ev_start);
+    }
     cudaFreeHost(m->h_err);
     cudaStreamDestroy(m->stream);
     delete m;
@@ -874,16 +883,11 @@ extern "C" int orbx_match_slots_device(orbx_matcher* m, orbx_extractor* ex, cons
     return ORBX_OK;
 }
 
-static bool m_is_pinned(const void* p)
-{
-    cudaPointerAttributes at;
-    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
-    return at.type == cudaMemoryTypeHost;
-}
-
 // One call = one tracking step over a batch of HOST frames: H2D, ORBextractor::operator() on every frame
 // (result slots 1..batch), SearchForInitialization of every frame against its predecessor (slot i-1 -> i; slot 0
 // holds the last frame of the previous call), D2H of keypoints, descriptors and matches.
+// The batch is cut into chunks that flow through three streams (H2D | kernels | D2H) so that the PCIe copies of
+// chunk c+1 / c-1 overlap the kernels of chunk c.
 extern "C" int orbx_extract_match_batch(orbx_extractor* ex, orbx_matcher* m, const uint8_t* imgs, int batch, int width,
                                         int height, int stride, size_t frame_stride, int lap0, int lap1,
                                         const float bounds[4], int window, float nnratio, int check_ori,
@@ -892,15 +896,16 @@ extern "C" int orbx_extract_match_batch(orbx_extractor* ex, orbx_matcher* m, con
 {
     if (!ex || !m || !imgs || batch < 1 || batch > m->P || !bounds) return ORBX_E_INVALID;
     if (width <= 0 || height <= 0) return ORBX_E_EMPTY;
+    int rc = orbx_ex_configure(ex, width, height);
+    if (rc) return rc;
+    CKM(cudaSetDevice(m->p.device));
     cudaStream_t s = orbx_ex_stream(ex);
-    int rc = orbx_ex_stage_input(ex, imgs, batch, width, height, stride, frame_stride, s);
-    if (rc) return rc;
-    rc = orbx_ex_run_staged(ex, batch, lap0, lap1, 1, s);
-    if (rc) return rc;
-    bool direct = false;
-    rc = orbx_ex_fetch_async(ex, 1, batch, kps, desc, cap, n, mono_index, s, &direct);
-    if (rc) return rc;
-    // slot pairs (i, i+1), i = 0..batch-1
+    if (!m->s_h2d) {
+        CKM(cudaStreamCreateWithFlags(&m->s_h2d, cudaStreamNonBlocking));
+        CKM(cudaStreamCreateWithFlags(&m->s_d2h, cudaStreamNonBlocking));
+        for (int i = 0; i < 2 * ORBX_MAX_CHUNKS; i++) CKM(cudaEventCreateWithFlags(&m->ev[i], cudaEventDisableTiming));
+        CKM(cudaEventCreateWithFlags(&m->ev_start, cudaEventDisableTiming));
+    }
     if (!m->d_pair_a) {
         std::vector<int32_t> a(m->P), b(m->P);
         for (int i = 0; i < m->P; i++) { a[i] = i; b[i] = i + 1; }
@@ -909,17 +914,44 @@ extern "C" int orbx_extract_match_batch(orbx_extractor* ex, orbx_matcher* m, con
         CKM(cudaMemcpy(m->d_pair_a, a.data(), sizeof(int32_t) * m->P, cudaMemcpyHostToDevice));
         CKM(cudaMemcpy(m->d_pair_b, b.data(), sizeof(int32_t) * m->P, cudaMemcpyHostToDevice));
     }
-    rc = orbx_match_slots_device(m, ex, m->d_pair_a, m->d_pair_b, batch, bounds, window, nnratio, check_ori,
-                                 m->d_out, m->d_nm, nullptr, nullptr, s);
-    if (rc) return rc;
+    const bool direct = orbx_ex_can_fetch_direct(ex, kps, desc, cap, n, mono_index);
+    const int ocap = orbx_ex_out_cap(ex);
+    int nchunks = batch >= 64 ? ORBX_MAX_CHUNKS : 1;
+    const int per = (batch + nchunks - 1) / nchunks;
+    nchunks = (batch + per - 1) / per;
+    // the copy streams must not run ahead of work already queued on the kernel stream (previous call's carry)
+    CKM(cudaEventRecord(m->ev_start, s));
+    CKM(cudaStreamWaitEvent(m->s_h2d, m->ev_start, 0));
+    CKM(cudaStreamWaitEvent(m->s_d2h, m->ev_start, 0));
+    for (int c = 0; c < nchunks; c++) {
+        const int f0 = c * per, cnt = (f0 + per <= batch) ? per : batch - f0;
+        rc = orbx_ex_stage_input(ex, imgs, f0, cnt, width, height, stride, frame_stride, m->s_h2d);
+        if (rc) return rc;
+        CKM(cudaEventRecord(m->ev[c], m->s_h2d));
+    }
+    for (int c = 0; c < nchunks; c++) {
+        const int f0 = c * per, cnt = (f0 + per <= batch) ? per : batch - f0;
+        CKM(cudaStreamWaitEvent(s, m->ev[c], 0));
+        rc = orbx_ex_run_staged(ex, f0, cnt, lap0, lap1, 1 + f0, s);
+        if (rc) return rc;
+        // pairs (slot f0+i, slot f0+i+1); the matcher's per-pair scratch is reused chunk after chunk (stream order)
+        rc = orbx_match_slots_device(m, ex, m->d_pair_a + f0, m->d_pair_b + f0, cnt, bounds, window, nnratio, check_ori,
+                                     m->d_out + (size_t)f0 * m->K, m->d_nm + f0, nullptr, nullptr, s);
+        if (rc) return rc;
+        CKM(cudaEventRecord(m->ev[ORBX_MAX_CHUNKS + c], s));
+        CKM(cudaStreamWaitEvent(m->s_d2h, m->ev[ORBX_MAX_CHUNKS + c], 0));
+        rc = orbx_ex_fetch_async(ex, 1 + f0, cnt, f0, kps, desc, cap, n, mono_index, m->s_d2h, direct);
+        if (rc) return rc;
+        // matches: device rows have stride K; host rows have stride cap
+        if (matches12) CKM(cudaMemcpy2DAsync(matches12 + (size_t)f0 * cap, sizeof(int32_t) * cap, m->d_out + (size_t)f0 * m->K, sizeof(int32_t) * m->K,
+                                             sizeof(int32_t) * (cap < m->K ? cap : m->K), cnt, cudaMemcpyDeviceToHost, m->s_d2h));
+        if (nmatches) CKM(cudaMemcpyAsync(nmatches + f0, m->d_nm + f0, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, m->s_d2h));
+    }
     rc = orbx_extractor_copy_slot(ex, batch, 0, s);
     if (rc) return rc;
-    // matches: device rows have stride K; host rows have stride cap
-    if (matches12) CKM(cudaMemcpy2DAsync(matches12, sizeof(int32_t) * cap, m->d_out, sizeof(int32_t) * m->K,
-                                         sizeof(int32_t) * (cap < m->K ? cap : m->K), batch, cudaMemcpyDeviceToHost, s));
-    if (nmatches) CKM(cudaMemcpyAsync(nmatches, m->d_nm, sizeof(int32_t) * batch, cudaMemcpyDeviceToHost, s));
-    (void)m_is_pinned;
-    rc = m_check_err(m, s);      // synchronises the stream
+    (void)ocap;
+    CKM(cudaStreamSynchronize(m->s_d2h));
+    rc = m_check_err(m, s);      // synchronises the kernel stream
     if (rc) return rc;
     return orbx_ex_fetch_finish(ex, batch, kps, desc, cap, n, mono_index, direct);
 }

@@ -175,3 +175,49 @@ def test_slots_pipeline_matches_oracle():
 def test_popc_probe_runs():
     p, l = orbx.popc_peak(0)
     assert p > 1e11 and l > 1e11
+
+
+def test_extract_match_batch_host_pipeline():
+    """orbx_extract_match_batch (the e2e call): chunked H2D | kernels | D2H pipeline, predecessor carried across calls."""
+    import torch
+    B, W, H = 70, 640, 480
+    frames = synth.rects_stream(W, H, 2 * B, seed=91)
+    ex = orbx.ORBextractor(1000, 1.2, 8, 20, 7, max_width=W, max_height=H, max_batch=B)
+    m = orbx.ORBmatcher(0.9, True, max_keypoints=ex.cap, max_batch=B)
+    cap = ex.cap
+    ref = O.Extractor(1000, 1.2, 8, 20, 7)
+    prev = None
+    for call, pinned in ((0, True), (1, False)):
+        chunk = np.ascontiguousarray(frames[call * B:(call + 1) * B])
+        if pinned:
+            hold = torch.from_numpy(chunk).pin_memory(); chunk = hold.numpy()
+            mk = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory().numpy()
+            out = {"kps": mk((B, cap, 7), torch.float32).view(np.uint8).reshape(B, cap, 28).view(orbx.KP_DTYPE).reshape(B, cap),
+                   "desc": mk((B, cap, 32), torch.uint8), "n": mk((B,), torch.int32), "mono": mk((B,), torch.int32),
+                   "matches12": mk((B, cap), torch.int32), "nmatches": mk((B,), torch.int32)}
+        else:
+            out = {"kps": np.zeros((B, cap), orbx.KP_DTYPE), "desc": np.zeros((B, cap, 32), np.uint8), "n": np.zeros(B, np.int32),
+                   "mono": np.zeros(B, np.int32), "matches12": np.zeros((B, cap), np.int32), "nmatches": np.zeros(B, np.int32)}
+        orbx.extract_match_batch(ex, m, chunk, (0, 0), (0, W, 0, H), 100, out)
+        for f in (0, 1, 17, 18, 35, 36, B - 1):
+            n = int(out["n"][f])
+            rmono, rk, rd = ref(chunk[f], (0, 0))
+            assert n == len(rk) and int(out["mono"][f]) == rmono
+            k = out["kps"][f, :n]; d = out["desc"][f, :n]
+            for name in ("x", "y", "size", "response", "octave"):
+                np.testing.assert_array_equal(k[name], rk[name])
+            same = k["angle"] == rk["angle"]
+            np.testing.assert_array_equal(d[same], rd[same])
+            # predecessor: previous frame of the stream (previous call's last frame for f == 0)
+            if f > 0:
+                _, pk, pd = ref(chunk[f - 1], (0, 0))
+            elif prev is not None:
+                pk, pd = prev
+            else:
+                continue
+            rn, rm12, _ = O.search_for_initialization(pk, pd, rk, rd, (0, W, 0, H), np.stack([pk["x"], pk["y"]], 1), 100, 0.9, True)
+            assert int(out["nmatches"][f]) == rn
+            np.testing.assert_array_equal(out["matches12"][f, :len(pk)], rm12)
+        _, lk, ld = ref(chunk[B - 1], (0, 0))
+        prev = (lk, ld)
+    ex.close(); m.close()
