@@ -21,12 +21,21 @@
 
 namespace {
 
-constexpr int NT = 256;
+constexpr int NT = 512;
 constexpr int MAX_CELLS = 128;
 constexpr int NW = NT / 32;
-constexpr int QCAP = 2048;           // screen survivors per band (overflow is scored inline, never dropped)
-constexpr int Q2CAP = 1024;          // signed-test survivors per band (same overflow rule)
+constexpr int QCAP = 4096;           // screen survivors per band (overflow is scored inline, never dropped)
+constexpr int Q2CAP = 2048;          // signed-test survivors per band (same overflow rule)
+constexpr int CLCAP = 2048;          // corners (m > minTh) of the whole cell row; overflow -> map scan (still exact)
 constexpr int BAND_ROWS = NW;        // one tile row per warp and band
+
+// shared-memory atomic add as ONE instruction (the CUDA intrinsic expands to a warp-aggregation sequence)
+__device__ __forceinline__ int atoms_add(int* p, int v)
+{
+    int old;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+    return old;
+}
 
 // ring offsets (dx,dy), OpenCV order
 __device__ __constant__ int8_t c_ring[16][2] = {
@@ -75,13 +84,14 @@ __device__ __forceinline__ bool pair_test(const unsigned (&pk)[16], int minTh)
 }
 
 // exact per-pixel path used when a queue overflows: pair test, then the arc measure
-__device__ __forceinline__ void score_pixel(const uint8_t* T, uint8_t* M, int tp, const int (&roff)[16], int x, int yt, int minTh)
+__device__ __forceinline__ void score_pixel(const uint8_t* T, uint8_t* M, int tp, const int (&roff)[16], int x, int yt, int minTh,
+                                            int* cl_count)
 {
     unsigned pk[16];
     load_ring(T + yt * tp + x, roff, pk);
     if (!pair_test(pk, minTh)) return;
     const int m = arc_measure(pk);
-    if (m > minTh) M[(yt - 3) * tp + x] = (uint8_t)m;
+    if (m > minTh) { M[(yt - 3) * tp + x] = (uint8_t)m; atoms_add(cl_count, CLCAP + 1); }   // forces the exact map-scan NMS path
 }
 
 // per-byte flag (bit 7) of "a > t" for t <= 126: bytes < 128 carry into bit 7 when a + 127 - t >= 128
@@ -102,7 +112,7 @@ __device__ __forceinline__ int popc_range(const unsigned* row, int c0, int c1)
 }
 
 struct FastSmem {
-    int q_count, q2_count;
+    int q_count, q2_count, cl_count;
     int cell_off[MAX_CELLS + 1];
     unsigned char use_ini[MAX_CELLS];
 };
@@ -138,7 +148,8 @@ __global__ void __launch_bounds__(NT) k_fast_rows(OrbxGeom g, OrbxBuffers b, con
     uint8_t* M = T + (size_t)(hmax + 6) * tp;                       // [hmax][tp]   arc measure (0 = not a corner at minTh)
     unsigned* Q = reinterpret_cast<unsigned*>(M + (size_t)hmax * tp);   // [QCAP] candidate queue: x | tile row << 16
     unsigned* Q2 = Q + QCAP;                                        // [Q2CAP] survivors of the signed pair test
-    unsigned* Bmin = Q2 + Q2CAP;                                    // [hmax][bw] survivors at minTh
+    unsigned* CL = Q2 + Q2CAP;                                      // [CLCAP] corners: x | scored row << 16
+    unsigned* Bmin = CL + CLCAP;                                    // [hmax][bw] survivors at minTh
     unsigned* Bini = Bmin + hmax * bw;                              // [hmax][bw] survivors at iniTh
     unsigned short* cnt_min = reinterpret_cast<unsigned short*>(Bini + hmax * bw);   // [nCols][hmax]
     unsigned short* cnt_ini = cnt_min + L.nCols * hmax;             // [nCols][hmax]; later: exclusive row prefix of the chosen counts
@@ -166,6 +177,7 @@ __global__ void __launch_bounds__(NT) k_fast_rows(OrbxGeom g, OrbxBuffers b, con
         const int nz = (hs * tp) >> 4;
         for (int k = tid; k < nz; k += NT) z[k] = make_uint4(0, 0, 0, 0);
         for (int k = tid; k < 2 * hmax * bw; k += NT) Bmin[k] = 0;
+        if (tid == 0) sh.cl_count = 0;
     }
     __syncthreads();
 
@@ -226,15 +238,15 @@ __global__ void __launch_bounds__(NT) k_fast_rows(OrbxGeom g, OrbxBuffers b, con
                 const int total = n0 + n1 + n2 + n3;
                 if (total) {
                     int base = 0;
-                    if (lane == 0) base = atomicAdd(&sh.q_count, total);
+                    if (lane == 0) base = atoms_add(&sh.q_count, total);
                     base = __shfl_sync(0xffffffffu, base, 0);
                     const unsigned lt = (1u << lane) - 1;
                     const unsigned e = (unsigned)(gx << 2) | ((unsigned)yt << 16);
                     int o;
-                    if (cand & 0x00000080u) { o = base + __popc(b0 & lt); if (o < QCAP) Q[o] = e; else score_pixel(T, M, tp, roff, e & 0xFFFF, yt, minTh); }
-                    if (cand & 0x00008000u) { o = base + n0 + __popc(b1 & lt); if (o < QCAP) Q[o] = e + 1; else score_pixel(T, M, tp, roff, (e + 1) & 0xFFFF, yt, minTh); }
-                    if (cand & 0x00800000u) { o = base + n0 + n1 + __popc(b2 & lt); if (o < QCAP) Q[o] = e + 2; else score_pixel(T, M, tp, roff, (e + 2) & 0xFFFF, yt, minTh); }
-                    if (cand & 0x80000000u) { o = base + n0 + n1 + n2 + __popc(b3 & lt); if (o < QCAP) Q[o] = e + 3; else score_pixel(T, M, tp, roff, (e + 3) & 0xFFFF, yt, minTh); }
+                    if (cand & 0x00000080u) { o = base + __popc(b0 & lt); if (o < QCAP) Q[o] = e; else score_pixel(T, M, tp, roff, e & 0xFFFF, yt, minTh, &sh.cl_count); }
+                    if (cand & 0x00008000u) { o = base + n0 + __popc(b1 & lt); if (o < QCAP) Q[o] = e + 1; else score_pixel(T, M, tp, roff, (e + 1) & 0xFFFF, yt, minTh, &sh.cl_count); }
+                    if (cand & 0x00800000u) { o = base + n0 + n1 + __popc(b2 & lt); if (o < QCAP) Q[o] = e + 2; else score_pixel(T, M, tp, roff, (e + 2) & 0xFFFF, yt, minTh, &sh.cl_count); }
+                    if (cand & 0x80000000u) { o = base + n0 + n1 + n2 + __popc(b3 & lt); if (o < QCAP) Q[o] = e + 3; else score_pixel(T, M, tp, roff, (e + 3) & 0xFFFF, yt, minTh, &sh.cl_count); }
                 }
             }
         }
@@ -253,12 +265,12 @@ __global__ void __launch_bounds__(NT) k_fast_rows(OrbxGeom g, OrbxBuffers b, con
             const unsigned bal = __ballot_sync(0xffffffffu, pass);
             if (bal) {
                 int base = 0;
-                if (lane == 0) base = atomicAdd(&sh.q2_count, __popc(bal));
+                if (lane == 0) base = atoms_add(&sh.q2_count, __popc(bal));
                 base = __shfl_sync(0xffffffffu, base, 0);
                 if (pass) {
                     const int o = base + __popc(bal & ((1u << lane) - 1));
                     if (o < Q2CAP) Q2[o] = ent;
-                    else score_pixel(T, M, tp, roff, ent & 0xFFFF, ent >> 16, minTh);
+                    else score_pixel(T, M, tp, roff, ent & 0xFFFF, ent >> 16, minTh, &sh.cl_count);
                 }
             }
         }
@@ -271,45 +283,21 @@ __global__ void __launch_bounds__(NT) k_fast_rows(OrbxGeom g, OrbxBuffers b, con
             unsigned pk[16];
             load_ring(T + yq * tp + x, roff, pk);
             const int m = arc_measure(pk);
-            if (m > minTh) M[(yq - 3) * tp + x] = (uint8_t)m;
+            if (m > minTh) {
+                M[(yq - 3) * tp + x] = (uint8_t)m;
+                const int o = atoms_add(&sh.cl_count, 1);
+                if (o < CLCAP) CL[o] = (unsigned)x | ((unsigned)(yq - 3) << 16);
+            }
         }
         __syncthreads();      // every thread has read the band's counters before thread 0 resets them
     }
 
     // ---- 4. in-cell non-max suppression ----
-    // The pixel tile is dead now: its memory becomes the list of corners (non-zero entries of M), so that the
-    // suppression itself runs one corner per thread instead of diverging over a sparse map.
-    unsigned* CL = reinterpret_cast<unsigned*>(T);
-    const int clcap = ((hmax + 6) * tp) >> 2;
-    if (tid == 0) sh.q_count = 0;
-    __syncthreads();
-    {
-        const int nw = tp >> 2;
-        for (int r = warp; r < hs; r += NW)
-            for (int w0 = 0; w0 < nw; w0 += 32) {
-                const int wx = w0 + lane;
-                const unsigned word = wx < nw ? reinterpret_cast<const unsigned*>(M + r * tp)[wx] : 0u;
-                const unsigned b0 = __ballot_sync(0xffffffffu, word & 0x000000FFu), b1 = __ballot_sync(0xffffffffu, word & 0x0000FF00u);
-                const unsigned b2 = __ballot_sync(0xffffffffu, word & 0x00FF0000u), b3 = __ballot_sync(0xffffffffu, word & 0xFF000000u);
-                const int n0 = __popc(b0), n1 = __popc(b1), n2 = __popc(b2), n3 = __popc(b3);
-                const int total = n0 + n1 + n2 + n3;
-                if (total) {
-                    int base = 0;
-                    if (lane == 0) base = atomicAdd(&sh.q_count, total);
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    const unsigned lt = (1u << lane) - 1;
-                    const unsigned e = (unsigned)(wx << 2) | ((unsigned)r << 16);
-                    int o;
-                    if (word & 0x000000FFu) { o = base + __popc(b0 & lt); if (o < clcap) CL[o] = e; }
-                    if (word & 0x0000FF00u) { o = base + n0 + __popc(b1 & lt); if (o < clcap) CL[o] = e + 1; }
-                    if (word & 0x00FF0000u) { o = base + n0 + n1 + __popc(b2 & lt); if (o < clcap) CL[o] = e + 2; }
-                    if (word & 0xFF000000u) { o = base + n0 + n1 + n2 + __popc(b3 & lt); if (o < clcap) CL[o] = e + 3; }
-                }
-            }
-    }
-    __syncthreads();
-    if (sh.q_count <= clcap) {
-        const int ncl = sh.q_count;
+    // Corners were listed by phase B, so the suppression runs one corner per thread instead of diverging over a
+    // sparse map; a corner-dense tile (list overflow) falls back to scanning the map, still exact.
+    const int clcap = CLCAP;
+    if (sh.cl_count <= clcap) {
+        const int ncl = sh.cl_count;
         for (int e = tid; e < ncl; e += NT) {
             const unsigned ent = CL[e];
             const int x = ent & 0xFFFF, r = ent >> 16;
@@ -420,7 +408,7 @@ size_t fast_smem_bytes(const OrbxGeom& g)
         if (L.nCols <= 0 || L.nRows <= 0) continue;
         const size_t tp = (L.w + 15) & ~15;
         const size_t bw = (L.w + 31) >> 5;
-        const size_t need = (size_t)(L.hCell + 6) * tp + (size_t)L.hCell * tp + (QCAP + Q2CAP) * 4 + 2 * L.hCell * bw * 4 +
+        const size_t need = (size_t)(L.hCell + 6) * tp + (size_t)L.hCell * tp + (QCAP + Q2CAP + CLCAP) * 4 + 2 * L.hCell * bw * 4 +
                             2 * (size_t)L.nCols * L.hCell * 2 + 16;
         if (need > smem) smem = need;
     }

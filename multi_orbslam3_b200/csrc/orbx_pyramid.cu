@@ -7,6 +7,8 @@
 // stores the tile, then runs the separable integer blur [18,34,48,56,48,34,18]/256 out of shared
 // memory and stores the blurred tile.  Level l-1 is read once, level l and blur(l) are written once.
 // The 19-px reflected border the reference materialises is never read downstream and is not built.
+#include <cuda.h>
+#include <string.h>
 #include "orbx_internal.h"
 
 namespace generic {
@@ -197,9 +199,37 @@ struct Args {
     uint8_t* dst; int dpitch; long long dstride; int w, h;
     uint8_t* blur; int bpitch; long long bstride;
     const short4* xt; const short4* yt;
-    int sp;        // smem source pitch (multiple of 16)
-    int sh_max;    // smem source rows
+    int sp;        // smem source pitch (multiple of 16) = TMA box width
+    int sh_max;    // smem source rows = TMA box height
+    int use_tma;   // source tile arrives by cp.async.bulk.tensor (3-D tiled map: x, y, frame)
 };
+
+// ---- TMA / mbarrier primitives (sm_90+ PTX; SASS: UTMALDG, SYNCS) ----
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, int x, int y, int z, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(map), "r"(x), "r"(y), "r"(z),
+                   "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
 
 __device__ __forceinline__ void blur_and_store(uint8_t* R, uint16_t* Hb, uint8_t* blur_base, int bpitch, int X0, int Y0,
                                                int tw, int th)
@@ -275,9 +305,10 @@ __device__ __forceinline__ void reflect_halo(uint8_t* R, int X0, int Y0, int w, 
 }
 
 template <bool RESIZE>
-__global__ void __launch_bounds__(NT) k_pyr_fast(Args a)
+__global__ void __launch_bounds__(NT) k_pyr_fast(Args a, const __grid_constant__ CUtensorMap tmap)
 {
     extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) unsigned long long s_bar;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int X0 = blockIdx.x * TW, Y0 = blockIdx.y * TH;
     const int f = blockIdx.z;
@@ -288,24 +319,35 @@ __global__ void __launch_bounds__(NT) k_pyr_fast(Args a)
     const int rw = bx - ax, rh = by - ay;
     const int rcol0 = RO - (X0 - ax), rrow0 = 3 - (Y0 - ay);      // R position of dst (ax, ay)
 
-    uint8_t* R = smem;                                             // [RH][RP]
-    uint16_t* Hb = reinterpret_cast<uint16_t*>(smem + RH * RP);    // [RH][TW]  (aliases Hs)
+    // smem: S (source tile, first: TMA wants a 128-byte aligned destination) | R | Hb/Hs | sy
+    const int s_bytes = RESIZE ? ((a.sh_max * a.sp + 127) & ~127) : 0;
+    uint8_t* R = smem + s_bytes;                                   // [RH][RP]
+    uint16_t* Hb = reinterpret_cast<uint16_t*>(R + RH * RP);       // [RH][TW]  (aliases Hs)
     const uint8_t* srcf = a.src + (long long)f * a.sstride;
 
     if (RESIZE) {
         uint16_t* Hs = Hb;                                         // [sh_max][HP]
         const int hs_bytes = max(a.sh_max * HP * 2, RH * TW * 2);
-        int4* sy = reinterpret_cast<int4*>(smem + RH * RP + hs_bytes);              // [RH] per-row (y0, y1, b0, b1)
-        uint8_t* S = reinterpret_cast<uint8_t*>(sy + RH);                           // [sh_max][sp]
+        int4* sy = reinterpret_cast<int4*>(reinterpret_cast<uint8_t*>(Hb) + hs_bytes);   // [RH] per-row (y0, y1, b0, b1)
+        uint8_t* S = smem;                                                               // [sh_max][sp]
         const short4 xa = a.xt[ax], xb = a.xt[bx - 1];
         const short4 ya = a.yt[ay], yb = a.yt[by - 1];
-        const int sx0 = xa.x & ~15, sx1 = xb.y;                   // first source column aligned down to 16
+        const int sx0 = xa.x & ~15, sx1 = xb.y;   // first source column aligned down to 16 bytes (TMA moves 16-byte granules)
         const int sy0 = ya.x, sy1 = yb.y;
         const int sp = a.sp;
         const int nrows = sy1 - sy0 + 1;
         // ---- source tile ----
         const bool vec = ((a.spitch & 15) == 0) && ((reinterpret_cast<uintptr_t>(srcf) & 15) == 0);
-        if (vec) {
+        if (a.use_tma) {
+            // one elected thread arms the mbarrier with the box size and issues the 3-D tiled bulk load;
+            // out-of-image parts of the box are zero-filled by the TMA unit and never indexed (tables clamp)
+            if (tid == 0) mbar_init(&s_bar, 1);
+            __syncthreads();
+            if (tid == 0) {
+                mbar_expect_tx(&s_bar, (unsigned)(a.sp * a.sh_max));
+                tma_load_3d(S, &tmap, sx0, sy0, f, &s_bar);
+            }
+        } else if (vec) {
             const int nv = (sx1 - sx0 + 16) >> 4;                 // stays inside the row pitch (pitch is a multiple of 16 >= sw)
             for (int r = warp; r < nrows; r += NWARP) {
                 const uint4* g = reinterpret_cast<const uint4*>(srcf + (long long)(sy0 + r) * a.spitch + sx0);
@@ -329,6 +371,7 @@ __global__ void __launch_bounds__(NT) k_pyr_fast(Args a)
             const short4 xe = a.xt[ax + min(c, rw - 1)];
             o0[k] = xe.x - sx0; o1[k] = xe.y - sx0; c0[k] = xe.z; c1[k] = xe.w;
         }
+        if (a.use_tma) mbar_wait(&s_bar, 0);       // table loads above overlap the bulk copy
         __syncthreads();
         // ---- horizontal interpolation of every source row ----
         for (int r = warp; r < nrows; r += NWARP) {
@@ -395,6 +438,38 @@ __global__ void __launch_bounds__(NT) k_pyr_fast(Args a)
 
 }  // namespace fastp
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode()
+{
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+        else cudaGetLastError();
+    }
+    return fn;
+}
+
+// 3-D u8 tensor (x, y, frame) over a batch of pitched images; box = (bw, bh, 1).  Returns false when the layout
+// is not TMA-legal (base 16-byte aligned, strides multiples of 16) so that the caller uses the plain-load path.
+static bool make_map(CUtensorMap* m, const uint8_t* base, int w, int h, int pitch, long long fstride, int frames, int bw, int bh)
+{
+    EncodeTiledFn enc = get_encode();
+    if (!enc || (reinterpret_cast<uintptr_t>(base) & 15) || (pitch & 15) || (fstride & 15) || bw > 256 || bh > 256) return false;
+    cuuint64_t dims[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)frames};
+    cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)fstride};
+    cuuint32_t box[3] = {(cuuint32_t)bw, (cuuint32_t)bh, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 void orbx_launch_pyramid(const OrbxGeom& g, const OrbxBuffers& b, const uint8_t* level0, int pitch0,
                          long long stride0, int batch, cudaStream_t s)
 {
@@ -417,7 +492,8 @@ void orbx_launch_pyramid(const OrbxGeom& g, const OrbxBuffers& b, const uint8_t*
             const size_t smem = RH * RP + RH * TW * 2;
             static bool cfg0 = false;
             if (!cfg0) { cudaFuncSetAttribute(k_pyr_fast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); cfg0 = true; }
-            k_pyr_fast<false><<<grid, NT, smem, s>>>(a);
+            CUtensorMap none; memset(&none, 0, sizeof(none));
+            k_pyr_fast<false><<<grid, NT, smem, s>>>(a, none);
         } else {
             const OrbxLevel& P = g.lv[l - 1];
             a.src = (l == 1) ? level0 : b.pyr[l - 1];
@@ -430,10 +506,12 @@ void orbx_launch_pyramid(const OrbxGeom& g, const OrbxBuffers& b, const uint8_t*
             a.sp = (((int)(RW * sx) + 2 + 15 + 16) + 15) & ~15;     // span + alignment slack, multiple of 16
             a.sh_max = (int)(RH * sy) + 4;
             const size_t hs_bytes = (size_t)a.sh_max * HP * 2 > (size_t)RH * TW * 2 ? (size_t)a.sh_max * HP * 2 : (size_t)RH * TW * 2;
-            const size_t smem = RH * RP + hs_bytes + RH * sizeof(int4) + (size_t)a.sh_max * a.sp;
+            const size_t smem = (((size_t)a.sh_max * a.sp + 127) & ~(size_t)127) + RH * RP + hs_bytes + RH * sizeof(int4);
             static size_t cfg1 = 0;
             if (smem > cfg1) { cudaFuncSetAttribute(k_pyr_fast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); cfg1 = smem; }
-            k_pyr_fast<true><<<grid, NT, smem, s>>>(a);
+            CUtensorMap map; memset(&map, 0, sizeof(map));
+            a.use_tma = make_map(&map, a.src, a.sw, a.sh, a.spitch, a.sstride, batch, a.sp, a.sh_max) ? 1 : 0;
+            k_pyr_fast<true><<<grid, NT, smem, s>>>(a, map);
         }
         ORBX_COUNT_LAUNCH(1);
     }
