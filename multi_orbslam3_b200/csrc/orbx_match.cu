@@ -322,22 +322,21 @@ __global__ void __launch_bounds__(CAND_WARPS * 32) k_window_candidates(WinBufs W
     }
 }
 
-// warp-wide top-2 merge by (dist, rank): each lane holds (d0, k0, e0) best and (d1, e1) second
+// warp-wide top-2 by (dist, rank): each lane holds its local best (d0, k0, e0) and second (d1, k1, e1); ranks are unique,
+// so (dist << 16 | rank) keys are unique and two REDUX.MIN + two ballots replace a 5-round shuffle tree.
 __device__ __forceinline__ void warp_top2(int& d0, int& k0, uint32_t& e0, int& d1, uint32_t& e1, int& k1)
 {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const int od0 = __shfl_xor_sync(0xffffffffu, d0, o), ok0 = __shfl_xor_sync(0xffffffffu, k0, o);
-        const uint32_t oe0 = __shfl_xor_sync(0xffffffffu, e0, o);
-        const int od1 = __shfl_xor_sync(0xffffffffu, d1, o), ok1 = __shfl_xor_sync(0xffffffffu, k1, o);
-        const uint32_t oe1 = __shfl_xor_sync(0xffffffffu, e1, o);
-        // candidates for second place: loser of the firsts, and both seconds
-        int ld, lk; uint32_t le;
-        if (od0 < d0 || (od0 == d0 && ok0 < k0)) { ld = d0; lk = k0; le = e0; d0 = od0; k0 = ok0; e0 = oe0; }
-        else { ld = od0; lk = ok0; le = oe0; }
-        if (od1 < d1 || (od1 == d1 && ok1 < k1)) { d1 = od1; k1 = ok1; e1 = oe1; }
-        if (ld < d1 || (ld == d1 && lk < k1)) { d1 = ld; k1 = lk; e1 = le; }
-    }
+    const unsigned key0 = d0 == 0x7fffffff ? 0xFFFFFFFFu : (((unsigned)d0 << 16) | (unsigned)k0);
+    const unsigned key1 = d1 == 0x7fffffff ? 0xFFFFFFFFu : (((unsigned)d1 << 16) | (unsigned)k1);
+    const unsigned B = __reduce_min_sync(0xffffffffu, key0);
+    const unsigned c2 = key0 == B ? key1 : key0;
+    const unsigned S = __reduce_min_sync(0xffffffffu, c2);
+    const uint32_t sel = (key0 == S) ? e0 : e1;
+    const unsigned wb = __ballot_sync(0xffffffffu, key0 == B), ws = __ballot_sync(0xffffffffu, c2 == S);
+    const uint32_t be = __shfl_sync(0xffffffffu, e0, __ffs(wb) - 1);
+    const uint32_t se = __shfl_sync(0xffffffffu, sel, __ffs(ws) - 1);
+    if (B == 0xFFFFFFFFu) { d0 = 0x7fffffff; k0 = 0x7fffffff; e0 = 0; } else { d0 = (int)(B >> 16); k0 = (int)(B & 0xFFFF); e0 = be; }
+    if (S == 0xFFFFFFFFu) { d1 = 0x7fffffff; k1 = 0x7fffffff; e1 = 0; } else { d1 = (int)(S >> 16); k1 = (int)(S & 0xFFFF); e1 = se; }
 }
 
 __device__ __forceinline__ int rot_bin(float a1, float a2)
@@ -392,22 +391,46 @@ __global__ void __launch_bounds__(32) k_window_resolve(WinBufs W, int mode, floa
     }
     __syncwarp();
 
-    for (int i = 0; i < nq; i++) {
-        const int cnt = q_cnt[i];
-        if (cnt == 0) continue;
-        const int off = q_off[i];
+    // Queries are visited in order, but their CSR headers are fetched 32 at a time and empty queries are skipped by
+    // ballot; the candidates of the NEXT live query are prefetched while the current one is resolved, so the
+    // sequential loop pays one L2 latency per live query instead of several per query.
+    for (int qb = 0; qb < nq; qb += 32) {
+      const int my_q = qb + lane;
+      const int my_cnt = my_q < nq ? q_cnt[my_q] : 0;
+      const int my_off = my_q < nq ? q_off[my_q] : 0;
+      unsigned live = __ballot_sync(0xffffffffu, my_cnt > 0);
+      uint32_t pre[4] = {0, 0, 0, 0};
+      if (live) {
+          const int src = __ffs(live) - 1;
+          const int c = __shfl_sync(0xffffffffu, my_cnt, src), o = __shfl_sync(0xffffffffu, my_off, src);
+#pragma unroll
+          for (int j = 0; j < 4; j++) if (lane + 32 * j < c) pre[j] = pool[o + lane + 32 * j];
+      }
+      while (live) {
+        const int src = __ffs(live) - 1;
+        live &= live - 1;
+        const int i = qb + src;
+        const int cnt = __shfl_sync(0xffffffffu, my_cnt, src), off = __shfl_sync(0xffffffffu, my_off, src);
+        uint32_t cur[4] = {pre[0], pre[1], pre[2], pre[3]};
+        if (live) {                                  // prefetch the next live query of this group of 32
+            const int ns = __ffs(live) - 1;
+            const int c = __shfl_sync(0xffffffffu, my_cnt, ns), o = __shfl_sync(0xffffffffu, my_off, ns);
+#pragma unroll
+            for (int j = 0; j < 4; j++) if (lane + 32 * j < c) pre[j] = pool[o + lane + 32 * j];
+        }
         int d0 = 0x7fffffff, k0 = 0x7fffffff, d1 = 0x7fffffff, k1 = 0x7fffffff;
         uint32_t e0 = 0, e1 = 0;
-        for (int k = lane; k < cnt; k += 32) {
-            const uint32_t e = pool[off + k];
+        auto consume = [&](uint32_t e, int k) {
             const int i2 = e & 0xFFFF, d = (e >> 16) & 0x1FF;
-            bool skip;
-            if (mode == 2) skip = matchedDist[i2] <= d;          // ORBmatcher.cc:741
-            else skip = res[i2] >= 0;                            // occupied keypoint, :89-91 / :2045-2047
-            if (skip) continue;
+            const bool skip = (mode == 2) ? (matchedDist[i2] <= d)      // ORBmatcher.cc:741
+                                          : (res[i2] >= 0);             // occupied keypoint, :89-91 / :2045-2047
+            if (skip) return;
             if (d < d0) { d1 = d0; k1 = k0; e1 = e0; d0 = d; k0 = k; e0 = e; }
             else if (d < d1) { d1 = d; k1 = k; e1 = e; }
-        }
+        };
+#pragma unroll
+        for (int j = 0; j < 4; j++) if (lane + 32 * j < cnt) consume(cur[j], lane + 32 * j);
+        for (int k = lane + 128; k < cnt; k += 32) consume(pool[off + k], k);
         warp_top2(d0, k0, e0, d1, e1, k1);
         // every lane now holds the same (best, second); lane 0 applies the sequential rule
         if (mode == 2) {
@@ -440,6 +463,7 @@ __global__ void __launch_bounds__(32) k_window_resolve(WinBufs W, int mode, floa
             }
         }
         __syncwarp();
+      }
     }
     __syncwarp();
     // rotation consistency (:786-809 / :2163-2183)
