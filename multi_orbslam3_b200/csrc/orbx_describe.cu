@@ -129,15 +129,46 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_orient_describe(OrbxGeom g,
     if (lvl == 0) { img = level0 + (long long)f * stride0; pitch = pitch0; }
     else { img = b.pyr[lvl] + (long long)f * L.frame_stride; pitch = L.pitch; }
 
-    // ---- orientation ----
+    // ---- orientation: integer moments over the 749-pixel circular patch (rows v = -15..15, |u| <= umax[|v|]) ----
+    // The patch is read as aligned 32-bit words, 9 per row; the 31 x 9 words are dealt to the lanes in row-major
+    // order (neighbouring lanes read neighbouring words), masked to the row's extent and reduced with dp4a:
+    // m10 += sum(u * I) uses signed byte weights u, m01 += v * sum(I).
     int m10 = 0, m01 = 0;
-    if (lane < 31) {
-        const int v = lane - ORBX_HALF_PATCH;
-        const int d = c_umax[v < 0 ? -v : v];
-        const uint8_t* row = img + (long long)(cy + v) * pitch + cx;
-        int rs = 0;
-        for (int u = -d; u <= d; ++u) { const int val = __ldg(row + u); m10 += u * val; rs += val; }
-        m01 = v * rs;
+    {
+        const uint8_t* p0 = img + (long long)(cy - ORBX_HALF_PATCH) * pitch + (cx - ORBX_HALF_PATCH);
+        const int sh = (int)(reinterpret_cast<uintptr_t>(p0) & 3);        // same for every row when pitch % 4 == 0
+        if ((pitch & 3) == 0) {
+            const uint32_t* w0 = reinterpret_cast<const uint32_t*>(p0 - sh);
+            const int pw = pitch >> 2;
+#pragma unroll
+            for (int it = 0; it < 9; it++) {
+                const int t = lane + 32 * it;                              // item = (row, word)
+                if (t < 31 * 9) {
+                    const int row = t / 9, w = t - row * 9;
+                    const int v = row - ORBX_HALF_PATCH;
+                    const int d = c_umax[v < 0 ? -v : v];
+                    const uint32_t word = __ldg(w0 + row * pw + w);
+                    // byte j of word w sits at u = 4w + j - sh - 15
+                    const int u0 = 4 * w - sh - ORBX_HALF_PATCH;
+                    uint32_t mask = 0, wu = 0;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const int u = u0 + j;
+                        if (u >= -d && u <= d) { mask |= 0xFFu << (8 * j); wu |= (uint32_t)(uint8_t)(int8_t)u << (8 * j); }
+                    }
+                    const uint32_t mw = word & mask;
+                    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(m10) : "r"(mw), "r"(wu), "r"(m10));   // unsigned pixels x signed weights
+                    m01 += v * (int)__dp4a(mw, 0x01010101u, 0u);
+                }
+            }
+        } else if (lane < 31) {
+            const int v = lane - ORBX_HALF_PATCH;
+            const int d = c_umax[v < 0 ? -v : v];
+            const uint8_t* row = img + (long long)(cy + v) * pitch + cx;
+            int rs = 0;
+            for (int u = -d; u <= d; ++u) { const int val = __ldg(row + u); m10 += u * val; rs += val; }
+            m01 = v * rs;
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {

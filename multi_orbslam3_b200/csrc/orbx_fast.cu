@@ -24,7 +24,8 @@ namespace {
 constexpr int NT = 512;
 constexpr int MAX_CELLS = 128;
 constexpr int NW = NT / 32;
-constexpr int QCAP = 4096;           // screen survivors per band (overflow is scored inline, never dropped)
+constexpr int QGCAP = 4096;          // 4-pixel groups with a screen survivor per band: 16 rows x <= 256 groups, cannot overflow
+constexpr int QCAP = 4096;           // screen survivors (pixels) per band (overflow is scored inline, never dropped)
 constexpr int Q2CAP = 2048;          // signed-test survivors per band (same overflow rule)
 constexpr int CLCAP = 2048;          // corners (m > minTh) of the whole cell row; overflow -> map scan (still exact)
 constexpr int BAND_ROWS = NW;        // one tile row per warp and band
@@ -112,7 +113,7 @@ __device__ __forceinline__ int popc_range(const unsigned* row, int c0, int c1)
 }
 
 struct FastSmem {
-    int q_count, q2_count, cl_count;
+    int qg_count, q_count, q2_count, cl_count;
     int cell_off[MAX_CELLS + 1];
     unsigned char use_ini[MAX_CELLS];
 };
@@ -147,7 +148,8 @@ __global__ void __launch_bounds__(NT) k_fast_rows(OrbxGeom g, OrbxBuffers b, con
     uint8_t* T = smem;                                              // [hmax+6][tp] pixels
     uint8_t* M = T + (size_t)(hmax + 6) * tp;                       // [hmax][tp]   arc measure (0 = not a corner at minTh)
     unsigned* Q = reinterpret_cast<unsigned*>(M + (size_t)hmax * tp);   // [QCAP] candidate queue: x | tile row << 16
-    unsigned* Q2 = Q + QCAP;                                        // [Q2CAP] survivors of the signed pair test
+    unsigned* QG = Q + QCAP;                                        // [QGCAP] groups with survivors: gx | tile row << 12 | mask << 20
+    unsigned* Q2 = QG + QGCAP;                                      // [Q2CAP] survivors of the signed pair test
     unsigned* CL = Q2 + Q2CAP;                                      // [CLCAP] corners: x | scored row << 16
     unsigned* Bmin = CL + CLCAP;                                    // [hmax][bw] survivors at minTh
     unsigned* Bini = Bmin + hmax * bw;                              // [hmax][bw] survivors at iniTh
@@ -191,7 +193,7 @@ __global__ void __launch_bounds__(NT) k_fast_rows(OrbxGeom g, OrbxBuffers b, con
     const unsigned c127 = (unsigned)(127 - (minTh < 126 ? minTh : 126)) * 0x01010101u;
     const bool screen_ok = minTh <= 126;
     for (int y0 = 3; y0 < nrow - 3; y0 += BAND_ROWS) {
-        if (tid == 0) { sh.q_count = 0; sh.q2_count = 0; }
+        if (tid == 0) { sh.qg_count = 0; sh.q_count = 0; sh.q2_count = 0; }
         __syncthreads();
         // -- screen: one tile row per warp, one 4-pixel group per lane-step --
         const int yt = y0 + warp;
@@ -231,23 +233,46 @@ __global__ void __launch_bounds__(NT) k_fast_rows(OrbxGeom g, OrbxBuffers b, con
                             if (xb + q < xs0 || xb + q >= xs1) cand &= ~(0x80u << (8 * q));
                     }
                 }
-                // warp-wide ordered compaction: one atomic per warp-step, dense stores
-                const unsigned b0 = __ballot_sync(0xffffffffu, cand & 0x00000080u), b1 = __ballot_sync(0xffffffffu, cand & 0x00008000u);
-                const unsigned b2 = __ballot_sync(0xffffffffu, cand & 0x00800000u), b3 = __ballot_sync(0xffffffffu, cand & 0x80000000u);
-                const int n0 = __popc(b0), n1 = __popc(b1), n2 = __popc(b2), n3 = __popc(b3);
-                const int total = n0 + n1 + n2 + n3;
-                if (total) {
+                // one queue entry per 4-pixel group that still has a candidate: one ballot, one atomic per warp-step
+                const unsigned bal = __ballot_sync(0xffffffffu, cand != 0);
+                if (bal) {
                     int base = 0;
-                    if (lane == 0) base = atoms_add(&sh.q_count, total);
+                    if (lane == 0) base = atoms_add(&sh.qg_count, __popc(bal));
                     base = __shfl_sync(0xffffffffu, base, 0);
-                    const unsigned lt = (1u << lane) - 1;
-                    const unsigned e = (unsigned)(gx << 2) | ((unsigned)yt << 16);
-                    int o;
-                    if (cand & 0x00000080u) { o = base + __popc(b0 & lt); if (o < QCAP) Q[o] = e; else score_pixel(T, M, tp, roff, e & 0xFFFF, yt, minTh, &sh.cl_count); }
-                    if (cand & 0x00008000u) { o = base + n0 + __popc(b1 & lt); if (o < QCAP) Q[o] = e + 1; else score_pixel(T, M, tp, roff, (e + 1) & 0xFFFF, yt, minTh, &sh.cl_count); }
-                    if (cand & 0x00800000u) { o = base + n0 + n1 + __popc(b2 & lt); if (o < QCAP) Q[o] = e + 2; else score_pixel(T, M, tp, roff, (e + 2) & 0xFFFF, yt, minTh, &sh.cl_count); }
-                    if (cand & 0x80000000u) { o = base + n0 + n1 + n2 + __popc(b3 & lt); if (o < QCAP) Q[o] = e + 3; else score_pixel(T, M, tp, roff, (e + 3) & 0xFFFF, yt, minTh, &sh.cl_count); }
+                    if (cand) {
+                        const unsigned m4 = ((cand >> 7) & 1u) | ((cand >> 14) & 2u) | ((cand >> 21) & 4u) | ((cand >> 28) & 8u);
+                        const int o = base + __popc(bal & ((1u << lane) - 1));
+                        if (o < QGCAP) QG[o] = (unsigned)gx | ((unsigned)yt << 12) | (m4 << 20);
+                        else atomicOr(b.err, ORBX_DEVERR_CAND_OVERFLOW);      // unreachable for widths <= 4128
+                    }
                 }
+            }
+        }
+        __syncthreads();
+        // -- expand the group entries into pixel entries (dense queue for phase A) --
+        {
+            const int ng = min(sh.qg_count, QGCAP);
+            for (int g0 = warp * 32; g0 < ng; g0 += NT) {
+                const int gi = g0 + lane;
+                const unsigned ge = gi < ng ? QG[gi] : 0u;
+                const unsigned m4 = ge >> 20;
+                const int n = __popc(m4);
+                int inc = n;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+                const int total = __shfl_sync(0xffffffffu, inc, 31);
+                int base = 0;
+                if (lane == 0 && total) base = atoms_add(&sh.q_count, total);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                int o = base + inc - n;
+                const unsigned e = ((ge & 0xFFFu) << 2) | (((ge >> 12) & 0xFFu) << 16);
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    if (m4 & (1u << q)) {
+                        if (o < QCAP) Q[o] = e + q;
+                        else score_pixel(T, M, tp, roff, (e + q) & 0xFFFF, (int)((ge >> 12) & 0xFFu), minTh, &sh.cl_count);   // queue full: score inline
+                        o++;
+                    }
             }
         }
         __syncthreads();
@@ -408,7 +433,7 @@ size_t fast_smem_bytes(const OrbxGeom& g)
         if (L.nCols <= 0 || L.nRows <= 0) continue;
         const size_t tp = (L.w + 15) & ~15;
         const size_t bw = (L.w + 31) >> 5;
-        const size_t need = (size_t)(L.hCell + 6) * tp + (size_t)L.hCell * tp + (QCAP + Q2CAP + CLCAP) * 4 + 2 * L.hCell * bw * 4 +
+        const size_t need = (size_t)(L.hCell + 6) * tp + (size_t)L.hCell * tp + (QCAP + QGCAP + Q2CAP + CLCAP) * 4 + 2 * L.hCell * bw * 4 +
                             2 * (size_t)L.nCols * L.hCell * 2 + 16;
         if (need > smem) smem = need;
     }
