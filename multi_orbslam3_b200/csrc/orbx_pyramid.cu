@@ -191,8 +191,7 @@ constexpr int TW = 128, TH = 64, NT = 256, NWARP = NT / 32;
 constexpr int RW = TW + 6, RH = TH + 6;
 constexpr int RO = 16;                 // column of R that holds dst x = X0 (16-byte aligned interior)
 constexpr int RP = 160;                // R pitch
-constexpr int HP = 136;                // Hs pitch (u16 elements)
-constexpr int KMAXCOL = (RW + 31) / 32;
+constexpr int HP = 144;                // Hs pitch (u16 elements): 36 groups of 4 columns
 
 struct Args {
     const uint8_t* src; int spitch; long long sstride; int sw, sh;
@@ -363,39 +362,63 @@ __global__ void __launch_bounds__(NT) k_pyr_fast(Args a, const __grid_constant__
             const short4 ye = a.yt[ay + tid];
             sy[tid] = make_int4(ye.x - sy0, ye.y - sy0, ye.z, ye.w);
         }
-        // per-lane column coefficients
-        int o0[KMAXCOL], o1[KMAXCOL], c0[KMAXCOL], c1[KMAXCOL];
+        // ---- per-thread constants: one thread owns 4 consecutive R columns (one aligned word of R) ----
+        // R column rho <-> dst x = ax + (rho - rcol0), clamped to the tile's valid range (clamped duplicates land in
+        // cells that are either unused or rewritten by reflect_halo).
+        constexpr int NG = 36, RL = 7;                 // groups per row, row lanes: 252 of the 256 threads work
+        const int g0 = rcol0 >> 2;
+        const int ng = ((rcol0 + rw - 1) >> 2) - g0 + 1;
+        const int gq = tid % NG, rl = tid / NG;
+        const bool worker = rl < RL && gq < ng;
+        unsigned coef[4], sel = 0, wb = 0;
+        if (worker) {
+            int o0[4], o1[4];
 #pragma unroll
-        for (int k = 0; k < KMAXCOL; k++) {
-            const int c = lane + 32 * k;
-            const short4 xe = a.xt[ax + min(c, rw - 1)];
-            o0[k] = xe.x - sx0; o1[k] = xe.y - sx0; c0[k] = xe.z; c1[k] = xe.w;
+            for (int i = 0; i < 4; i++) {
+                const int c = min(max(4 * (g0 + gq) + i - rcol0, 0), rw - 1);
+                const short4 xe = a.xt[ax + c];
+                o0[i] = xe.x - sx0; o1[i] = xe.y - sx0;
+                coef[i] = (unsigned)xe.z | ((unsigned)xe.w << 16);
+            }
+            wb = (unsigned)(o0[0] >> 2);                // the 4 columns read bytes [4wb, 4wb+12): words A, B, C
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int p0 = o0[i] - 4 * (int)wb, p1 = o1[i] - 4 * (int)wb;      // 0..11
+                const int hi = p0 >= 4 ? 1 : 0;          // take the pair (B,C) instead of (A,B)
+                sel |= (unsigned)((p0 - 4 * hi) | ((p1 - 4 * hi) << 3) | (hi << 6)) << (8 * i);       // 7 bits per column
+            }
         }
         if (a.use_tma) mbar_wait(&s_bar, 0);       // table loads above overlap the bulk copy
         __syncthreads();
-        // ---- horizontal interpolation of every source row ----
-        for (int r = warp; r < nrows; r += NWARP) {
-            const uint8_t* sr = S + r * sp;
+        // ---- horizontal interpolation of every source row: 3 word loads, 4 x (PRMT + DP2A) per 4 columns ----
+        if (worker) {
+            for (int r = rl; r < nrows; r += RL) {
+                const unsigned* sr = reinterpret_cast<const unsigned*>(S + r * sp) + wb;
+                const unsigned A = sr[0], B = sr[1], C = sr[2];
+                unsigned hv[4];
 #pragma unroll
-            for (int k = 0; k < KMAXCOL; k++) {
-                const int c = lane + 32 * k;
-                if (c < rw) Hs[r * HP + c] = (uint16_t)((sr[o0[k]] * c0[k] + sr[o1[k]] * c1[k]) >> 4);
+                for (int i = 0; i < 4; i++) {
+                    const unsigned sl = sel >> (8 * i);
+                    const unsigned ps = (sl & 7u) | ((sl & 0x38u) << 1);                                            // PRMT nibbles
+                    const unsigned pair = (sl & 0x40u) ? __byte_perm(B, C, ps) : __byte_perm(A, B, ps);              // bytes (S0, S1)
+                    hv[i] = __dp2a_lo(coef[i], pair, 0u) >> 4;                                                      // (S0*c0 + S1*c1) >> 4
+                }
+                *reinterpret_cast<uint2*>(Hs + r * HP + 4 * gq) = make_uint2(hv[0] | (hv[1] << 16), hv[2] | (hv[3] << 16));
             }
         }
         __syncthreads();
-        // ---- vertical interpolation -> R ----
-        for (int ry = warp; ry < rh; ry += NWARP) {
-            const int4 ye = sy[ry];
-            const uint16_t* h0 = Hs + ye.x * HP;
-            const uint16_t* h1 = Hs + ye.y * HP;
-            uint8_t* rr = R + (rrow0 + ry) * RP + rcol0;
-#pragma unroll
-            for (int k = 0; k < KMAXCOL; k++) {
-                const int c = lane + 32 * k;
-                if (c < rw) {
-                    const int v = (((ye.z * (int)h0[c]) >> 16) + ((ye.w * (int)h1[c]) >> 16) + 2) >> 2;
-                    rr[c] = (uint8_t)min(max(v, 0), 255);
-                }
+        // ---- vertical interpolation -> R: ((b0*h0)>>16 + (b1*h1)>>16 + 2) >> 2, one aligned word of R per step ----
+        if (worker) {
+            for (int ry = rl; ry < rh; ry += RL) {
+                const int4 ye = sy[ry];
+                const uint2 h0 = *reinterpret_cast<const uint2*>(Hs + ye.x * HP + 4 * gq);
+                const uint2 h1 = *reinterpret_cast<const uint2*>(Hs + ye.y * HP + 4 * gq);
+                const unsigned b0 = (unsigned)ye.z << 16, b1 = (unsigned)ye.w << 16;
+                const unsigned v0 = (__umulhi(b0, h0.x & 0xFFFFu) + __umulhi(b1, h1.x & 0xFFFFu) + 2u) >> 2;
+                const unsigned v1 = (__umulhi(b0, h0.x >> 16) + __umulhi(b1, h1.x >> 16) + 2u) >> 2;
+                const unsigned v2 = (__umulhi(b0, h0.y & 0xFFFFu) + __umulhi(b1, h1.y & 0xFFFFu) + 2u) >> 2;
+                const unsigned v3 = (__umulhi(b0, h0.y >> 16) + __umulhi(b1, h1.y >> 16) + 2u) >> 2;
+                *reinterpret_cast<unsigned*>(R + (rrow0 + ry) * RP + 4 * (g0 + gq)) = v0 | (v1 << 8) | (v2 << 16) | (v3 << 24);   // <= 255 by construction
             }
         }
         __syncthreads();
