@@ -151,6 +151,7 @@ struct WinBufs {
     PairDesc* pairs;              // [P]
     orbx_proj_query* q;           // [P][K]   (queries synthesised for SearchForInitialization)
     uint16_t* items;              // [P][K]   keypoint indices sorted by (cell, index)
+    float4* skp;                  // [P][K]   the same order as records (x, y, octave, index): one load per candidate
     int* cell_start;              // [P][NCELL+1]
     int* q_off; int* q_cnt;       // [P][K]
     uint32_t* pool; int* pool_used;   // [P][POOL], [P]
@@ -231,7 +232,16 @@ __global__ void __launch_bounds__(GRID_NT) k_grid_build(WinBufs W, int npad_max)
             __syncthreads();
         }
     uint16_t* items = W.items + (long long)p * W.K;
-    for (int i = threadIdx.x; i < n; i += GRID_NT) items[i] = (uint16_t)(keys[i] & 0xFFFF);
+    float4* skp = W.skp + (long long)p * W.K;
+    for (int i = threadIdx.x; i < n; i += GRID_NT) {
+        const uint32_t key = keys[i];
+        const int idx = (int)(key & 0xFFFF);
+        items[i] = (uint16_t)idx;
+        if (key != 0xFFFFFFFFu) {
+            const orbx_keypoint kp = P.k2[idx];
+            skp[i] = make_float4(kp.x, kp.y, __int_as_float(kp.octave), __int_as_float(idx));
+        }
+    }
     int* cs = W.cell_start + (long long)p * (NCELL + 1);
     for (int c = threadIdx.x; c <= NCELL; c += GRID_NT) {
         // first sorted position whose cell >= c (out-of-grid keys sort last)
@@ -268,45 +278,63 @@ __global__ void __launch_bounds__(CAND_WARPS * 32) k_window_candidates(WinBufs W
     if (!any) { if (lane == 0) { *q_off = 0; *q_cnt = 0; } return; }
     const bool check_levels = (Q.minl > 0) || (Q.maxl >= 0);
     const int* cs = W.cell_start + (long long)p * (NCELL + 1);
-    const uint16_t* items = W.items + (long long)p * W.K;
+    const float4* skp = W.skp + (long long)p * W.K;
     const uint4 q0 = reinterpret_cast<const uint4*>(P.qdesc)[2 * qi], q1 = reinterpret_cast<const uint4*>(P.qdesc)[2 * qi + 1];
 
-    // pass 0 counts, pass 1 writes (the candidate test is cheap; distances only in pass 1)
+    // The cells (ix, cy0..cy1) of one grid column are one contiguous range of the sorted records, so the window is
+    // nr <= 64 ranges.  Their bounds are fetched by the lanes in parallel, prefix-summed, and the concatenation of
+    // the ranges (= the reference's visit order) is walked 32 records per step: pass 0 counts the records that pass
+    // the octave / window / stereo tests, pass 1 computes their distances into the reserved CSR segment.
+    __shared__ int s_rs[CAND_WARPS][GC], s_rp[CAND_WARPS][GC + 1];
+    int* rs = s_rs[threadIdx.x >> 5]; int* rp = s_rp[threadIdx.x >> 5];
+    const int nr = cx1 - cx0 + 1;
+    int T = 0;
+    for (int r0 = 0; r0 < nr; r0 += 32) {
+        const int r = r0 + lane;
+        int st = 0, len = 0;
+        if (r < nr) { st = cs[(cx0 + r) * GR + cy0]; len = cs[(cx0 + r) * GR + cy1 + 1] - st; }
+        int inc = len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        if (r < nr) { rs[r] = st; rp[r] = T + inc - len; }
+        T += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) rp[nr] = T;
+    __syncwarp();
+
     int base = 0, total = 0;
     for (int pass = 0; pass < 2; pass++) {
         int pos = 0;
-        for (int ix = cx0; ix <= cx1; ix++) {
-            const int s = cs[ix * GR + cy0], e = cs[ix * GR + cy1 + 1];
-            for (int k0 = s; k0 < e; k0 += 32) {
-                const int k = k0 + lane;
-                bool ok = false; int i2 = 0; int oct = 0;
-                if (k < e) {
-                    i2 = items[k];
-                    const orbx_keypoint kp = P.k2[i2];
-                    oct = kp.octave;
-                    ok = true;
-                    if (check_levels) {
-                        if (oct < Q.minl) ok = false;
-                        if (Q.maxl >= 0 && oct > Q.maxl) ok = false;
-                    }
-                    const float dx = __fsub_rn(kp.x, Q.u), dy = __fsub_rn(kp.y, Q.v);
-                    if (!(fabsf(dx) < Q.r && fabsf(dy) < Q.r)) ok = false;
-                    // stereo gate (ORBmatcher.cc:93-98 / :2049-2055): not order dependent, applied here
-                    if (ok && P.uright2) {
-                        const float ur2 = P.uright2[i2];
-                        if (ur2 > 0 && fabsf(__fsub_rn(Q.ur, ur2)) > Q.r) ok = false;
-                    }
+        for (int j0 = 0; j0 < T; j0 += 32) {
+            const int j = j0 + lane;
+            bool ok = false; int i2 = 0, oct = 0;
+            if (j < T) {
+                int lo = 0, hi = nr - 1;                      // last range whose prefix <= j
+                while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (rp[mid] <= j) lo = mid; else hi = mid - 1; }
+                const float4 rec = __ldg(skp + rs[lo] + (j - rp[lo]));
+                oct = __float_as_int(rec.z); i2 = __float_as_int(rec.w);
+                ok = true;
+                if (check_levels) {
+                    if (oct < Q.minl) ok = false;
+                    if (Q.maxl >= 0 && oct > Q.maxl) ok = false;
                 }
-                const unsigned bal = __ballot_sync(0xffffffffu, ok);
-                if (pass == 1 && ok) {
-                    const int o = pos + __popc(bal & ((1u << lane) - 1));
-                    const uint4 t0 = reinterpret_cast<const uint4*>(P.d2)[2 * i2], t1 = reinterpret_cast<const uint4*>(P.d2)[2 * i2 + 1];
-                    const int d = hamming256(q0, q1, t0, t1);
-                    if (base + o < W.POOL)
-                        W.pool[(long long)p * W.POOL + base + o] = (uint32_t)i2 | ((uint32_t)d << 16) | ((uint32_t)oct << 25);
+                const float dx = __fsub_rn(rec.x, Q.u), dy = __fsub_rn(rec.y, Q.v);
+                if (!(fabsf(dx) < Q.r && fabsf(dy) < Q.r)) ok = false;
+                // stereo gate (ORBmatcher.cc:93-98 / :2049-2055): not order dependent, applied here
+                if (ok && P.uright2) {
+                    const float ur2 = P.uright2[i2];
+                    if (ur2 > 0 && fabsf(__fsub_rn(Q.ur, ur2)) > Q.r) ok = false;
                 }
-                pos += __popc(bal);
             }
+            const unsigned bal = __ballot_sync(0xffffffffu, ok);
+            if (pass == 1 && ok) {
+                const int o = pos + __popc(bal & ((1u << lane) - 1));
+                const uint4 t0 = reinterpret_cast<const uint4*>(P.d2)[2 * i2], t1 = reinterpret_cast<const uint4*>(P.d2)[2 * i2 + 1];
+                const int d = hamming256(q0, q1, t0, t1);
+                if (base + o < W.POOL)
+                    W.pool[(long long)p * W.POOL + base + o] = (uint32_t)i2 | ((uint32_t)d << 16) | ((uint32_t)oct << 25);
+            }
+            pos += __popc(bal);
         }
         if (pass == 0) {
             total = pos;
@@ -611,6 +639,7 @@ extern "C" int orbx_matcher_create(const orbx_matcher_params* p, orbx_matcher** 
     MA(W.pairs, sizeof(PairDesc) * P);
     MA(W.q, sizeof(orbx_proj_query) * K * P);
     MA(W.items, sizeof(uint16_t) * K * P);
+    MA(W.skp, sizeof(float4) * K * P);
     MA(W.cell_start, sizeof(int) * (NCELL + 1) * P);
     MA(W.q_off, sizeof(int) * K * P);
     MA(W.q_cnt, sizeof(int) * K * P);
