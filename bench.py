@@ -161,7 +161,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -194,7 +194,7 @@ class ClockSampler:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="orbx", choices=["orbx", "reference"])
     ap.add_argument("--batch", type=int, default=512, help="frames per step per GPU (512 x 361 KB = 185 MB of input > 126 MB L2)")
@@ -317,6 +317,24 @@ def main():
     d2h = B * (cap * 28 + cap * 32 + cap * 4 + 4 + 4 + 4)
     clocks = sampler.stop() if rank == 0 else None
 
+    # ---------------- p50 per-frame latency: batch = 1, synchronous class-API calls with host buffers ----------------
+    latency = None
+    if rank == 0 and not args.no_e2e:
+        ex1 = orbx.ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, max_width=W, max_height=H, max_batch=1, device=local)
+        m1 = orbx.ORBmatcher(NNRATIO, True, max_keypoints=ex1.cap, max_batch=1, device=local)
+        out1 = {k: v[:1] for k, v in out.items()}
+        nlat = 300
+        ts = []
+        for i in range(nlat + 20):
+            f1 = h_np[i % B:i % B + 1]
+            t1 = time.perf_counter()
+            orbx.extract_match_batch(ex1, m1, f1, (0, 0), bounds, WINDOW, out1)     # operator() + SearchForInitialization, H2D/D2H inside
+            ts.append(time.perf_counter() - t1)
+        ts = np.array(ts[20:]) * 1e3
+        latency = {"p50_ms": float(np.percentile(ts, 50)), "p95_ms": float(np.percentile(ts, 95)), "frames": nlat,
+                   "what": "one frame per call: orbx_extract_match_batch(batch=1) = H2D + extract + SearchForInitialization vs previous frame + D2H"}
+        ex1.close(); m1.close()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -342,9 +360,21 @@ def main():
     if dom is None:
         dom = 1   # roofline is reported for the HBM-bound stage the north star names (FAST); shares are in `stages`
     achieved = stage_bytes[dom] / (per_batch[dom] * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_fast_rows" if dom == 1 else "k_pyr_level x8", "achieved": achieved, "peak": hbm_peak,
-                "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": stage_bytes[dom], "stages": stages}
+    # DRAM traffic per launch from the committed `ncu --set full` capture of the same command (profiles/r1_ncu_summary.json,
+    # taken at 512 frames per launch; scaled to this run's batch)
+    traffic, limiter = None, None
+    try:
+        ncu = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_summary.json")))
+        rec = ncu["k_fast_rows"][0] if dom == 1 else None
+        if rec:
+            traffic = rec["dram_traffic_bytes"] * B / 512.0
+            limiter = ("instruction issue, not HBM: ncu issue-active %.0f%%, DRAM %.1f%% of peak, %.2f warp-instructions per pixel"
+                       % (rec["issue_active_pct"], rec["dram_pct_of_peak"], rec["warp_instructions"] / (512.0 * P)))
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": "k_fast_rows" if dom == 1 else "k_pyr_fast x8", "achieved": achieved, "peak": hbm_peak,
+                "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": stage_bytes[dom], "limiter": limiter, "stages": stages}
     try:
         popc, lop3 = orbx.popc_peak(local)
         pairs = B * nkp_mean * nkp_mean
@@ -361,8 +391,21 @@ def main():
         _, dcal, ncal = cpu_run(base[:16], cores, 2)                 # calibration: 2 frames per thread
         per_thread = int(min(2000, max(6, 15.0 / max(dcal / 2.0, 1e-3))))   # ~15 s of wall time on all cores
         fps, dtc, nf = cpu_run(base[:16], cores, per_thread)
+        # reference-faithful latency: one thread per image (mono), extract + SearchForInitialization + BF kNN-2
+        lat = []
+        exo = O.Extractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH)
+        prevf = None
+        for i in range(24):
+            t1 = time.perf_counter()
+            _, k, d = exo(base[i % 16], (0, 0))
+            if prevf is not None:
+                O.search_for_initialization(prevf[0], prevf[1], k, d, (0, W, 0, H), np.stack([prevf[0]["x"], prevf[0]["y"]], 1), WINDOW, NNRATIO, True)
+                O.bf_knn2(prevf[1], d)
+            prevf = (k, d)
+            lat.append(time.perf_counter() - t1)
         cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-               "sample": "%d frames (%d threads x %d frames of the same S-rects stream), %.1f s wall" % (nf, cores, per_thread, dtc)}
+               "sample": "%d frames (%d threads x %d frames of the same S-rects stream), %.1f s wall" % (nf, cores, per_thread, dtc),
+               "p50_ms_per_frame_1_thread": float(np.percentile(np.array(lat[4:]) * 1e3, 50))}
 
     line = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -376,6 +419,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                 "api": "orbx_extract_match_batch (pinned host frames -> keypoints, descriptors, matches on host)"},
         "gpu_launches": int(launches),
+        "latency": latency,
         "roofline": roofline,
         "cpu_baseline": cpu,
     }
