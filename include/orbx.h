@@ -198,6 +198,15 @@ int  orbx_stereo_band_match(orbx_matcher* m, const orbx_keypoint* kl, const uint
                             const orbx_keypoint* kr, const uint8_t* dr, int nr, const float* scale_factors,
                             int nlevels, int nrows, float min_d, float max_d, int32_t* best_idx, int32_t* best_dist);
 
+/* Frame::ComputeStereoMatches in full (R/src/Frame.cc:785-962) on the device-resident results and pyramids of the left
+ * and right extractor (R/src/Frame.cc:92-95 runs one ORBextractor per camera): descriptor search, 11x11 SAD refinement
+ * over +-5 px on the pyramid level of the left keypoint, parabola sub-pixel fit, median-based outlier cut.
+ * slot_* = result slot, frame_* = frame index inside each extractor's last batch (0 for orbx_extract).
+ * uright/depth receive mvuRight/mvDepth (-1 = no match), sad_dist (optional) the SAD distance or -1. */
+int  orbx_stereo_matches(orbx_matcher* m, orbx_extractor* left, orbx_extractor* right, int slot_l, int slot_r,
+                         int frame_l, int frame_r, float mb, float mbf, float* uright, float* depth,
+                         int32_t* sad_dist, int cap, int* n_left);
+
 /* register-only popcount micro-benchmark: returns measured 32-bit popc per second on `device` (roofline
  * denominator for the matching kernels) */
 int  orbx_popc_peak(int device, double* popc_per_s, double* lop3_per_s);

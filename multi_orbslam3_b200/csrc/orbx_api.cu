@@ -455,6 +455,21 @@ int orbx_ex_run_staged(orbx_extractor* h, int f0, int count, int lap0, int lap1,
 }
 
 cudaStream_t orbx_ex_stream(orbx_extractor* h) { return h->stream; }
+int orbx_ex_device(orbx_extractor* h) { return h->p.device; }
+
+int orbx_ex_pyramid_view(orbx_extractor* h, int frame, OrbxPyrView* out)
+{
+    if (!h || h->geom.width == 0 || frame < 0 || frame >= h->last_batch || !h->last_level0) return ORBX_E_INVALID;
+    const OrbxGeom& g = h->geom;
+    out->nlevels = g.nlevels;
+    for (int l = 0; l < g.nlevels; l++) {
+        if (l == 0) { out->lv[0] = h->last_level0 + (long long)frame * h->last_stride0; out->pitch[0] = h->last_pitch0; }
+        else { out->lv[l] = h->buf.pyr[l] + (long long)frame * g.lv[l].frame_stride; out->pitch[l] = g.lv[l].pitch; }
+        out->w[l] = g.lv[l].w; out->h[l] = g.lv[l].h;
+        out->scale[l] = h->scale[l]; out->inv_scale[l] = h->invScale[l];
+    }
+    return ORBX_OK;
+}
 int orbx_ex_out_cap(orbx_extractor* h) { return h->geom.out_cap; }
 
 // issues the D2H copies of `count` result slots starting at first_slot into host frame positions host_off..;

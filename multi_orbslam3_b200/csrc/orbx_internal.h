@@ -110,3 +110,13 @@ int orbx_ex_fetch_async(orbx_extractor* h, int first_slot, int count, int host_o
                         int32_t* n, int32_t* mono_index, cudaStream_t s, bool direct);
 int orbx_ex_fetch_finish(orbx_extractor* h, int count, orbx_keypoint* kps, uint8_t* desc, int cap,
                          int32_t* n, int32_t* mono_index, bool direct);
+
+// device view of one frame's pyramid of an extractor handle (stereo refinement reads both cameras' pyramids)
+struct OrbxPyrView {
+    const uint8_t* lv[ORBX_MAX_LEVELS];
+    int pitch[ORBX_MAX_LEVELS], w[ORBX_MAX_LEVELS], h[ORBX_MAX_LEVELS];
+    float scale[ORBX_MAX_LEVELS], inv_scale[ORBX_MAX_LEVELS];
+    int nlevels;
+};
+int orbx_ex_pyramid_view(orbx_extractor* h, int frame, OrbxPyrView* out);
+int orbx_ex_device(orbx_extractor* h);

@@ -566,6 +566,99 @@ __global__ void __launch_bounds__(256) k_stereo_band(const orbx_keypoint* kl, co
     if (lane == 0) { best_idx[iL] = bi == 0x7fffffff ? -1 : bi; best_dist[iL] = bd; }
 }
 
+// Frame::ComputeStereoMatches, sub-pixel refinement (R/src/Frame.cc:871-946): one warp per left keypoint.
+// 11x11 patches around the keypoint (left) and around the matched right keypoint shifted by incR = -5..5, both centred on
+// their own middle pixel, L1 distance per shift, parabola through the best shift and its neighbours.
+__global__ void __launch_bounds__(256) k_stereo_refine(const orbx_keypoint* kl, int nl, const orbx_keypoint* kr,
+                                                     const int32_t* best_idx, const int32_t* best_dist,
+                                                     OrbxPyrView L, OrbxPyrView R, float mbf, float minD, float maxD,
+                                                     float* uright, float* depth, int32_t* sad)
+{
+    __shared__ int s_d[8][12];
+    const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
+    const int iL = blockIdx.x * 8 + wq;
+    if (iL >= nl) return;
+    float out_u = -1.0f, out_z = -1.0f; int out_s = -1;
+    const int bi = best_idx[iL];
+    const int thOrbDist = (ORBX_TH_HIGH + ORBX_TH_LOW) / 2;
+    if (bi >= 0 && best_dist[iL] < thOrbDist) {
+        const orbx_keypoint kp = kl[iL];
+        const int oct = kp.octave;
+        const float uL = kp.x;
+        const float uR0 = kr[bi].x;
+        const float sf = L.inv_scale[oct];
+        const float scaleduL = roundf(__fmul_rn(kp.x, sf)), scaledvL = roundf(__fmul_rn(kp.y, sf)), scaleduR0 = roundf(__fmul_rn(uR0, sf));
+        const int w = 5, Lr = 5;
+        const float iniu = scaleduR0 + Lr - w, endu = scaleduR0 + Lr + w + 1;
+        if (!(iniu < 0 || endu >= (float)R.w[oct])) {
+            const int r0 = (int)(scaledvL - w), c0 = (int)(scaleduL - w), cr0 = (int)(scaleduR0 - w);
+            const uint8_t* imL = L.lv[oct]; const int pL = L.pitch[oct];
+            const uint8_t* imR = R.lv[oct]; const int pR = R.pitch[oct];
+            if (lane < 11) s_d[wq][lane] = 0;
+            __syncwarp();
+            const int ctrL = imL[(long long)(r0 + w) * pL + c0 + w];
+            // 121 (shift, row) tasks of 11 pixels each
+            for (int t = lane; t < 121; t += 32) {
+                const int inc = t / 11 - Lr, r = t - (t / 11) * 11;
+                const int cr = cr0 + inc;
+                const int ctrR = imR[(long long)(r0 + w) * pR + cr + w];
+                const uint8_t* a = imL + (long long)(r0 + r) * pL + c0;
+                const uint8_t* b = imR + (long long)(r0 + r) * pR + cr;
+                int acc = 0;
+#pragma unroll
+                for (int c = 0; c < 11; c++) acc += abs(((int)a[c] - ctrL) - ((int)b[c] - ctrR));
+                atomicAdd(&s_d[wq][inc + Lr], acc);
+            }
+            __syncwarp();
+            int bestDist = 0x7fffffff, bestinc = 0;
+            for (int k = 0; k < 11; k++) { const int d = s_d[wq][k]; if (d < bestDist) { bestDist = d; bestinc = k - Lr; } }   // first minimum wins (:905-909)
+            if (bestinc != -Lr && bestinc != Lr) {
+                const float d1 = (float)s_d[wq][Lr + bestinc - 1], d2 = (float)s_d[wq][Lr + bestinc], d3 = (float)s_d[wq][Lr + bestinc + 1];
+                const float deltaR = __fdiv_rn(__fsub_rn(d1, d3), __fmul_rn(2.0f, __fsub_rn(__fadd_rn(d1, d3), __fmul_rn(2.0f, d2))));
+                if (!(deltaR < -1 || deltaR > 1)) {
+                    float bestuR = __fmul_rn(L.scale[oct], __fadd_rn(__fadd_rn(scaleduR0, (float)bestinc), deltaR));
+                    float disparity = __fsub_rn(uL, bestuR);
+                    if (disparity >= minD && disparity < maxD) {
+                        if (disparity <= 0) { disparity = 0.01f; bestuR = (float)((double)uL - 0.01); }
+                        out_z = __fdiv_rn(mbf, disparity); out_u = bestuR; out_s = bestDist;
+                    }
+                }
+            }
+        }
+    }
+    if (lane == 0) { uright[iL] = out_u; depth[iL] = out_z; sad[iL] = out_s; }
+}
+
+// median-based outlier cut (R/src/Frame.cc:949-962): one CTA; bitonic sort of the SAD distances of the matched keypoints
+__global__ void __launch_bounds__(1024) k_stereo_outliers(int nl, float* uright, float* depth, const int32_t* sad, int npad)
+{
+    extern __shared__ int s_v[];
+    __shared__ int s_n;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    int local = 0;
+    for (int i = threadIdx.x; i < nl; i += 1024) local += sad[i] >= 0;
+    atomicAdd(&s_n, local);
+    for (int i = threadIdx.x; i < npad; i += 1024) s_v[i] = (i < nl && sad[i] >= 0) ? sad[i] : 0x7fffffff;
+    __syncthreads();
+    const int n = s_n;
+    if (n == 0) return;
+    for (int k = 2; k <= npad; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < (npad >> 1); t += 1024) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), l = i | j;
+                const bool up = (i & k) == 0;
+                const int x = s_v[i], y = s_v[l];
+                if ((x > y) == up) { s_v[i] = y; s_v[l] = x; }
+            }
+            __syncthreads();
+        }
+    const float median = (float)s_v[n / 2];
+    const float thDist = __fmul_rn(1.5f * 1.4f, median);
+    for (int i = threadIdx.x; i < nl; i += 1024)
+        if (sad[i] >= 0 && !((float)sad[i] < thDist)) { uright[i] = -1.0f; depth[i] = -1.0f; }
+}
+
 // register-only throughput probes
 __global__ void k_popc_probe(unsigned seed, int iters, unsigned* sink)
 {
@@ -1030,6 +1123,49 @@ extern "C" int orbx_stereo_band_match(orbx_matcher* m, const orbx_keypoint* kl, 
     CKM(cudaGetLastError());
     CKM(cudaMemcpyAsync(best_idx, m->d_out, sizeof(int32_t) * nl, cudaMemcpyDeviceToHost, s));
     CKM(cudaMemcpyAsync(best_dist, m->d_out2, sizeof(int32_t) * nl, cudaMemcpyDeviceToHost, s));
+    CKM(cudaStreamSynchronize(s));
+    return ORBX_OK;
+}
+
+// Frame::ComputeStereoMatches (R/src/Frame.cc:785-962) on two extractors' device-resident results and pyramids
+extern "C" int orbx_stereo_matches(orbx_matcher* m, orbx_extractor* left, orbx_extractor* right, int slot_l, int slot_r,
+                                   int frame_l, int frame_r, float mb, float mbf, float* uright, float* depth,
+                                   int32_t* sad_dist, int cap, int* n_left)
+{
+    if (!m || !left || !right || !uright || !depth) return ORBX_E_INVALID;
+    orbx_keypoint *kL, *kR; uint8_t *dL, *dR; int32_t *nL, *nR; int capL, capR, slotsL, slotsR;
+    int rc = orbx_extractor_results_device(left, &kL, &dL, &nL, nullptr, &capL, &slotsL);
+    if (rc) return rc;
+    rc = orbx_extractor_results_device(right, &kR, &dR, &nR, nullptr, &capR, &slotsR);
+    if (rc) return rc;
+    if (slot_l < 0 || slot_l >= slotsL || slot_r < 0 || slot_r >= slotsR || capL > m->K || capR > m->K) return ORBX_E_INVALID;
+    OrbxPyrView vL, vR;
+    if ((rc = orbx_ex_pyramid_view(left, frame_l, &vL)) || (rc = orbx_ex_pyramid_view(right, frame_r, &vR))) return rc;
+    CKM(cudaSetDevice(m->p.device));
+    // the extractors run on their own streams: wait for both, then work on the matcher's stream
+    CKM(cudaStreamSynchronize(orbx_ex_stream(left)));
+    CKM(cudaStreamSynchronize(orbx_ex_stream(right)));
+    cudaStream_t s = m->stream;
+    int nl = 0, nr = 0;
+    CKM(cudaMemcpyAsync(&nl, nL + slot_l, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CKM(cudaMemcpyAsync(&nr, nR + slot_r, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CKM(cudaStreamSynchronize(s));
+    if (n_left) *n_left = nl;
+    if (nl > cap) { orbx_set_error("%s%s", "orbx_stereo_matches: output capacity too small", ""); return ORBX_E_CAPACITY; }
+    if (nl == 0) return ORBX_OK;
+    const orbx_keypoint* dkl = kL + (size_t)slot_l * capL; const uint8_t* ddl = dL + (size_t)slot_l * capL * 32;
+    const orbx_keypoint* dkr = kR + (size_t)slot_r * capR; const uint8_t* ddr = dR + (size_t)slot_r * capR * 32;
+    CKM(cudaMemcpyAsync(m->d_sf, vL.scale, sizeof(float) * vL.nlevels, cudaMemcpyHostToDevice, s));
+    const float minD = 0.0f, maxD = mbf / mb;          // minZ = mb (:815-818)
+    float* d_u = m->d_prev; float* d_z = m->d_prev + m->K;
+    k_stereo_band<<<(nl + 7) / 8, 256, 0, s>>>(dkl, ddl, nl, dkr, ddr, nr, m->d_sf, vL.h[0], minD, maxD, m->d_out, m->d_out2); ORBX_COUNT_LAUNCH(1);
+    k_stereo_refine<<<(nl + 7) / 8, 256, 0, s>>>(dkl, nl, dkr, m->d_out, m->d_out2, vL, vR, mbf, minD, maxD, d_u, d_z, m->d_knn_idx); ORBX_COUNT_LAUNCH(1);
+    int npad = 1; while (npad < nl) npad <<= 1;
+    k_stereo_outliers<<<1, 1024, sizeof(int) * npad, s>>>(nl, d_u, d_z, m->d_knn_idx, npad); ORBX_COUNT_LAUNCH(1);
+    CKM(cudaGetLastError());
+    CKM(cudaMemcpyAsync(uright, d_u, sizeof(float) * nl, cudaMemcpyDeviceToHost, s));
+    CKM(cudaMemcpyAsync(depth, d_z, sizeof(float) * nl, cudaMemcpyDeviceToHost, s));
+    if (sad_dist) CKM(cudaMemcpyAsync(sad_dist, m->d_knn_idx, sizeof(int32_t) * nl, cudaMemcpyDeviceToHost, s));
     CKM(cudaStreamSynchronize(s));
     return ORBX_OK;
 }

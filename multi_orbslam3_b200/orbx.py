@@ -36,7 +36,7 @@ EXPORTS = [
     "orbx_matcher_create", "orbx_matcher_destroy", "orbx_matcher_sync", "orbx_hamming_pairs",
     "orbx_bf_knn2", "orbx_bf_knn2_device", "orbx_knn2_merge_device",
     "orbx_search_for_initialization", "orbx_match_slots_device", "orbx_extract_match_batch", "orbx_search_by_projection",
-    "orbx_stereo_band_match", "orbx_popc_peak",
+    "orbx_stereo_band_match", "orbx_stereo_matches", "orbx_popc_peak",
 ]
 
 
@@ -105,6 +105,7 @@ def lib():
         L.orbx_search_by_projection.argtypes = [vp, i32, vp, vp, i32, vp, vp, vp, i32, vp, vp, f32, i32, vp]
         L.orbx_stereo_band_match.argtypes = [vp, vp, vp, i32, vp, vp, i32, vp, i32, i32, f32, f32, vp, vp]
         L.orbx_popc_peak.argtypes = [i32, vp, vp]
+        L.orbx_stereo_matches.argtypes = [vp, vp, vp, i32, i32, i32, i32, f32, f32, vp, vp, vp, i32, vp]
         _lib = L
     return _lib
 
@@ -320,6 +321,15 @@ class ORBmatcher:
         _check(lib().orbx_stereo_band_match(self._h, _p(kl), _p(dl), len(kl), _p(kr), _p(dr), len(kr), _p(sf), len(sf),
                                             int(nrows), float(minD), float(maxD), _p(bi), _p(bd)))
         return bi, bd
+
+    def ComputeStereoMatches(self, ex_left, ex_right, mb, mbf, slot_l=0, slot_r=0, frame_l=0, frame_r=0):
+        """Frame::ComputeStereoMatches on the two extractors' last results -> (mvuRight, mvDepth, SAD distance)."""
+        cap = max(ex_left.cap, ex_right.cap)
+        ur = np.empty(cap, np.float32); dp = np.empty(cap, np.float32); sd = np.empty(cap, np.int32)
+        n = C.c_int(0)
+        _check(lib().orbx_stereo_matches(self._h, ex_left._h, ex_right._h, slot_l, slot_r, frame_l, frame_r, float(mb), float(mbf),
+                                         _p(ur), _p(dp), _p(sd), cap, C.byref(n)))
+        return ur[:n.value].copy(), dp[:n.value].copy(), sd[:n.value].copy()
 
     def match_slots_device(self, extractor, a, b, bounds, window, d_matches12, d_nmatches, d_knn_idx=None,
                            d_knn_dist=None, stream=None):

@@ -84,6 +84,7 @@ def lib():
                                                vp, f32, i32]
         L.orc_search_by_projection.restype = i32
         L.orc_stereo_band_match.argtypes = [vp, vp, i32, vp, vp, i32, vp, i32, f32, f32, vp, vp]
+        L.orc_compute_stereo_matches.argtypes = [vp, vp, vp, vp, i32, vp, vp, i32, f32, f32, vp, vp, vp]
         _lib = L
     return _lib
 
@@ -252,3 +253,13 @@ def stereo_band_match(kl, dl, kr, dr, scale_factors, nrows, min_d, max_d):
     lib().orc_stereo_band_match(_p(kl), _p(dl), len(kl), _p(kr), _p(dr), len(kr), _p(sf), int(nrows),
                                 float(min_d), float(max_d), _p(bi), _p(bd))
     return bi, bd
+
+
+def compute_stereo_matches(ex_left, ex_right, kl, dl, kr, dr, mb, mbf):
+    """Frame::ComputeStereoMatches on the two oracle extractors' last pyramids -> (mvuRight, mvDepth, sad best distance)."""
+    kl = np.ascontiguousarray(kl, KP_DTYPE); kr = np.ascontiguousarray(kr, KP_DTYPE)
+    dl = _u8(dl); dr = _u8(dr)
+    ur = np.empty(len(kl), np.float32); dp = np.empty(len(kl), np.float32); sd = np.empty(len(kl), np.int32)
+    lib().orc_compute_stereo_matches(ex_left._h, ex_right._h, _p(kl), _p(dl), len(kl), _p(kr), _p(dr), len(kr),
+                                     float(mb), float(mbf), _p(ur), _p(dp), _p(sd))
+    return ur, dp, sd

@@ -997,3 +997,86 @@ void orc_stereo_band_match(const OrcKeyPoint* kl, const uint8_t* dl, int nl,
     }
     free(cnt); free(items); free(fill);
 }
+
+/* Frame::ComputeStereoMatches, R/src/Frame.cc:785-962 (descriptor search :785-868 as above, then the SAD refinement) */
+typedef struct { int dist; int idx; } DistIdx;
+static int cmp_distidx(const void* a, const void* b)
+{
+    const DistIdx* A = (const DistIdx*)a; const DistIdx* B = (const DistIdx*)b;
+    if (A->dist != B->dist) return A->dist < B->dist ? -1 : 1;
+    return A->idx < B->idx ? -1 : (A->idx > B->idx ? 1 : 0);
+}
+
+void orc_compute_stereo_matches(const OrcExtractor* left, const OrcExtractor* right,
+                                const OrcKeyPoint* kl, const uint8_t* dl, int nl,
+                                const OrcKeyPoint* kr, const uint8_t* dr, int nr,
+                                float mb, float mbf, float* uright, float* depth, int32_t* sad_dist)
+{
+    const int thOrbDist = (TH_HIGH + TH_LOW) / 2;
+    const int nRows = left->lh[0];
+    const float minZ = mb, minD = 0, maxD = mbf / minZ;
+    int32_t* bi = (int32_t*)malloc(sizeof(int32_t) * (nl > 0 ? nl : 1));
+    int32_t* bd = (int32_t*)malloc(sizeof(int32_t) * (nl > 0 ? nl : 1));
+    orc_stereo_band_match(kl, dl, nl, kr, dr, nr, left->scale, nRows, minD, maxD, bi, bd);
+    DistIdx* vDistIdx = (DistIdx*)malloc(sizeof(DistIdx) * (nl > 0 ? nl : 1));
+    int nvd = 0;
+    for (int iL = 0; iL < nl; iL++) {
+        uright[iL] = -1.0f; depth[iL] = -1.0f;
+        if (sad_dist) sad_dist[iL] = -1;
+        if (bi[iL] < 0 || !(bd[iL] < thOrbDist)) continue;
+        const OrcKeyPoint* kpL = &kl[iL];
+        const float uL = kpL->x;
+        const int oct = kpL->octave;
+        const float uR0 = kr[bi[iL]].x;
+        const float scaleFactor = left->invScale[oct];
+        const float scaleduL = roundf(kpL->x * scaleFactor);
+        const float scaledvL = roundf(kpL->y * scaleFactor);
+        const float scaleduR0 = roundf(uR0 * scaleFactor);
+        const int w = 5, L = 5;
+        const uint8_t* imL = left->level[oct]; const int wL = left->lw[oct];
+        const uint8_t* imR = right->level[oct]; const int wR = right->lw[oct];
+        const int r0 = (int)(scaledvL - w), c0 = (int)(scaleduL - w);
+        short IL[11][11];
+        {
+            const int ctr = imL[(size_t)(r0 + w) * wL + c0 + w];
+            for (int r = 0; r < 11; r++) for (int c = 0; c < 11; c++) IL[r][c] = (short)(imL[(size_t)(r0 + r) * wL + c0 + c] - ctr);
+        }
+        int bestDist = INT_MAX, bestincR = 0;
+        float vDists[11];
+        const float iniu = scaleduR0 + L - w, endu = scaleduR0 + L + w + 1;
+        if (iniu < 0 || endu >= right->lw[oct]) continue;
+        for (int incR = -L; incR <= +L; incR++) {
+            const int cr = (int)(scaleduR0 + incR - w);
+            const int ctr = imR[(size_t)(r0 + w) * wR + cr + w];
+            double acc = 0;
+            for (int r = 0; r < 11; r++)
+                for (int c = 0; c < 11; c++) acc += abs((int)IL[r][c] - ((int)imR[(size_t)(r0 + r) * wR + cr + c] - ctr));
+            const float dist = (float)acc;                       /* cv::norm(IL, IR, NORM_L1) */
+            if (dist < bestDist) { bestDist = (int)dist; bestincR = incR; }
+            vDists[L + incR] = dist;
+        }
+        if (bestincR == -L || bestincR == L) continue;
+        const float dist1 = vDists[L + bestincR - 1], dist2 = vDists[L + bestincR], dist3 = vDists[L + bestincR + 1];
+        const float deltaR = (dist1 - dist3) / (2.0f * (dist1 + dist3 - 2.0f * dist2));
+        if (deltaR < -1 || deltaR > 1) continue;
+        float bestuR = left->scale[oct] * ((float)scaleduR0 + (float)bestincR + deltaR);
+        float disparity = (uL - bestuR);
+        if (disparity >= minD && disparity < maxD) {
+            if (disparity <= 0) { disparity = 0.01; bestuR = uL - 0.01; }
+            depth[iL] = mbf / disparity;
+            uright[iL] = bestuR;
+            if (sad_dist) sad_dist[iL] = bestDist;
+            vDistIdx[nvd].dist = bestDist; vDistIdx[nvd].idx = iL; nvd++;
+        }
+    }
+    if (nvd > 0) {     /* the reference indexes an empty vector here when nothing matched (:950) */
+        qsort(vDistIdx, nvd, sizeof(DistIdx), cmp_distidx);
+        const float median = (float)vDistIdx[nvd / 2].dist;
+        const float thDist = 1.5f * 1.4f * median;
+        for (int i = nvd - 1; i >= 0; i--) {
+            if (vDistIdx[i].dist < thDist) break;
+            uright[vDistIdx[i].idx] = -1; depth[vDistIdx[i].idx] = -1;
+        }
+    }
+    free(bi); free(bd); free(vDistIdx);
+}

@@ -106,6 +106,14 @@ void  orc_stereo_band_match(const OrcKeyPoint* kl, const uint8_t* dl, int nl,
                             const float* scale_factors, int nrows, float minD, float maxD,
                             int32_t* best_idx, int32_t* best_dist);
 
+/* Frame::ComputeStereoMatches in full (Frame.cc:785-962): descriptor search, 11x11 SAD sliding-window refinement on
+ * the two extractors' pyramids (their last orc_extract), parabola sub-pixel fit, median-based outlier cut.
+ * uright/depth have nl entries (-1 = no match); sad_dist (optional) receives the SAD best distance or -1. */
+void  orc_compute_stereo_matches(const OrcExtractor* left, const OrcExtractor* right,
+                                 const OrcKeyPoint* kl, const uint8_t* dl, int nl,
+                                 const OrcKeyPoint* kr, const uint8_t* dr, int nr,
+                                 float mb, float mbf, float* uright, float* depth, int32_t* sad_dist);
+
 #ifdef __cplusplus
 }
 #endif

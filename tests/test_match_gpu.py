@@ -221,3 +221,28 @@ def test_extract_match_batch_host_pipeline():
         _, lk, ld = ref(chunk[B - 1], (0, 0))
         prev = (lk, ld)
     ex.close(); m.close()
+
+
+@pytest.mark.parametrize("shape,nf,disp", [((752, 480), 1200, 14), ((1241, 376), 2000, 23)], ids=["C2_euroc", "C3_kitti"])
+def test_compute_stereo_matches_full(shape, nf, disp):
+    """BASELINE configs C2 / C3: stereo pair, extraction on both cameras + Frame::ComputeStereoMatches (SAD refinement,
+    sub-pixel fit, outlier cut) entirely on the device, against the oracle: mvuRight / mvDepth bit-exact."""
+    W, H = shape
+    L, R = synth.stereo_pair(W, H, seed=8, disparity=disp)
+    exl = orbx.ORBextractor(nf, 1.2, 8, 20, 7, max_width=W, max_height=H)
+    exr = orbx.ORBextractor(nf, 1.2, 8, 20, 7, max_width=W, max_height=H)
+    gl = exl(L, None, (0, 0)); gr = exr(R, None, (0, 0))
+    m = orbx.ORBmatcher(0.9, True, max_keypoints=max(exl.cap, exr.cap))
+    mb, mbf = 0.11, 47.9
+    ur, dp, sd = m.ComputeStereoMatches(exl, exr, mb, mbf)
+    ol, orr = O.Extractor(nf, 1.2, 8, 20, 7), O.Extractor(nf, 1.2, 8, 20, 7)
+    _, kl, dl = ol(L, (0, 0)); _, kr, dr = orr(R, (0, 0))
+    rur, rdp, rsd = O.compute_stereo_matches(ol, orr, kl, dl, kr, dr, mb, mbf)
+    assert len(ur) == len(rur)
+    np.testing.assert_array_equal(sd, rsd)
+    np.testing.assert_array_equal(ur, rur)          # bit-exact fp32
+    np.testing.assert_array_equal(dp, rdp)
+    ok = rur >= 0
+    assert ok.sum() > 0.4 * len(rur)
+    assert abs(np.median(kl["x"][ok] - rur[ok]) - disp) < 0.5
+    exl.close(); exr.close(); m.close()
