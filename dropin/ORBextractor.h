@@ -62,6 +62,8 @@ public:
 
     // device selection for multi-agent boxes: one agent (= one ORBextractor pair) per GPU
     static void SetDevice(int device);
+    // C-ABI handle of this extractor (for orbx_stereo_matches, which replaces Frame::ComputeStereoMatches)
+    orbx_extractor* handle() { return mpHandle; }
 
 protected:
 

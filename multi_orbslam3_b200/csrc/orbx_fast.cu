@@ -30,6 +30,32 @@ constexpr int Q2CAP = 2048;          // signed-test survivors per band (same ove
 constexpr int CLCAP = 2048;          // corners (m > minTh) of the whole cell row; overflow -> map scan (still exact)
 constexpr int BAND_ROWS = NW;        // one tile row per warp and band
 
+// ---- bulk asynchronous copy (TMA engine, 1-D form: SASS UBLKCP) + mbarrier ----
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+
 // shared-memory atomic add as ONE instruction (the CUDA intrinsic expands to a warp-aggregation sequence)
 __device__ __forceinline__ int atoms_add(int* p, int v)
 {
@@ -163,12 +189,16 @@ __global__ void __launch_bounds__(NT) k_fast_rows(OrbxGeom g, OrbxBuffers b, con
     // ---- 1. stage rows ----
     const bool vec = ((pitch & 15) == 0) && (pitch >= tp) && ((reinterpret_cast<uintptr_t>(img) & 15) == 0);
     const int lane = tid & 31, warp = tid >> 5;
+    __shared__ __align__(8) unsigned long long s_bar;
     if (vec) {
-        const int nv = tp >> 4;
-        for (int r = warp; r < nrow; r += NW) {
-            const uint4* src = reinterpret_cast<const uint4*>(img + (long long)(iniY + r) * pitch);
-            uint4* dst = reinterpret_cast<uint4*>(T + r * tp);
-            for (int c = lane; c < nv; c += 32) dst[c] = __ldg(src + c);
+        // one bulk copy per row, issued by the lanes of warp 0; completion is counted in bytes on an mbarrier, and the
+        // zero-fill of the score map / bitmaps below overlaps the copies
+        if (tid == 0) mbar_init(&s_bar, 1);
+        __syncthreads();
+        if (warp == 0) {
+            if (lane == 0) mbar_expect_tx(&s_bar, (unsigned)(nrow * tp));
+            __syncwarp();
+            for (int r = lane; r < nrow; r += 32) bulk_g2s(T + r * tp, img + (long long)(iniY + r) * pitch, (unsigned)tp, &s_bar);
         }
     } else {
         for (int r = warp; r < nrow; r += NW)
@@ -181,12 +211,12 @@ __global__ void __launch_bounds__(NT) k_fast_rows(OrbxGeom g, OrbxBuffers b, con
         for (int k = tid; k < 2 * hmax * bw; k += NT) Bmin[k] = 0;
         if (tid == 0) sh.cl_count = 0;
     }
-    __syncthreads();
-
     const int minTh = g.min_th, iniTh = g.ini_th;
     int roff[16];
 #pragma unroll
     for (int k = 0; k < 16; k++) roff[k] = c_ring[k][1] * tp + c_ring[k][0];
+    if (vec) mbar_wait(&s_bar, 0);
+    __syncthreads();
 
     // ---- 2 + 3. banded screen and drain ----
     const int gx0 = xs0 >> 2, gx1 = (xs1 - 1) >> 2;    // 4-pixel groups that contain scored columns
