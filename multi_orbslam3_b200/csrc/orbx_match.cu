@@ -695,7 +695,7 @@ struct orbx_matcher {
     uint8_t* d_bfq; uint8_t* d_bft; size_t bfq_bytes, bft_bytes;
     unsigned* h_err;
     int32_t* d_pair_a; int32_t* d_pair_b;
-    cudaStream_t s_h2d, s_d2h; cudaEvent_t ev[2 * ORBX_MAX_CHUNKS]; cudaEvent_t ev_start;
+    cudaStream_t s_h2d, s_d2h, s_match; cudaEvent_t ev[2 * ORBX_MAX_CHUNKS]; cudaEvent_t ev_ext[ORBX_MAX_CHUNKS]; cudaEvent_t ev_start;
     std::vector<void*> allocs;
 };
 
@@ -775,7 +775,8 @@ extern "C" void orbx_matcher_destroy(orbx_matcher* m)
     if (m->d_bft) cudaFree(m->d_bft);
     if (m->d_pair_a) cudaFree(m->d_pair_a);
     if (m->s_h2d) {
-        cudaStreamDestroy(m->s_h2d); cudaStreamDestroy(m->s_d2h);
+        cudaStreamDestroy(m->s_h2d); cudaStreamDestroy(m->s_d2h); cudaStreamDestroy(m->s_match);
+        for (int i = 0; i < ORBX_MAX_CHUNKS; i++) cudaEventDestroy(m->ev_ext[i]);
         for (int i = 0; i < 2 * ORBX_MAX_CHUNKS; i++) cudaEventDestroy(m->ev[i]);
         cudaEventDestroy(m->ev_start);
     }
@@ -913,15 +914,25 @@ static void set_bounds(orbx_matcher* m, const float bounds[4])
     W.hInv = (float)GR / (W.maxY - W.minY);
 }
 
-static int run_window(orbx_matcher* m, int npairs, int nq_max, int mode, float nnratio, int check_ori,
+// the matcher's per-pair scratch starting at pair `pb` (chunks of one batch may be matched concurrently)
+static WinBufs shifted_pairs(const orbx_matcher* m, int pb)
+{
+    WinBufs W = m->W;
+    const long long K = m->K;
+    W.pairs += pb; W.q += pb * K; W.items += pb * K; W.skp += pb * K; W.cell_start += (long long)pb * (NCELL + 1);
+    W.q_off += pb * K; W.q_cnt += pb * K; W.pool += (long long)pb * m->POOL; W.pool_used += pb; W.bin_of += pb * K;
+    return W;
+}
+
+static int run_window(orbx_matcher* m, const WinBufs& W, int npairs, int nq_max, int mode, float nnratio, int check_ori,
                       int32_t* d_out, int32_t* d_nm, float* d_prev, cudaStream_t s)
 {
     int npad = 1; while (npad < m->K) npad <<= 1;
-    CKM(cudaMemsetAsync(m->W.pool_used, 0, sizeof(int) * npairs, s));
-    k_grid_build<<<npairs, GRID_NT, sizeof(uint32_t) * npad, s>>>(m->W, npad); ORBX_COUNT_LAUNCH(1);
+    CKM(cudaMemsetAsync(W.pool_used, 0, sizeof(int) * npairs, s));
+    k_grid_build<<<npairs, GRID_NT, sizeof(uint32_t) * npad, s>>>(W, npad); ORBX_COUNT_LAUNCH(1);
     dim3 cg((nq_max + CAND_WARPS - 1) / CAND_WARPS, npairs);
-    if (nq_max > 0) { k_window_candidates<<<cg, CAND_WARPS * 32, 0, s>>>(m->W); ORBX_COUNT_LAUNCH(1); }
-    k_window_resolve<<<npairs, 32, 2 * m->K * sizeof(int), s>>>(m->W, mode, nnratio, check_ori, d_out, d_nm, d_prev); ORBX_COUNT_LAUNCH(1);
+    if (nq_max > 0) { k_window_candidates<<<cg, CAND_WARPS * 32, 0, s>>>(W); ORBX_COUNT_LAUNCH(1); }
+    k_window_resolve<<<npairs, 32, 2 * m->K * sizeof(int), s>>>(W, mode, nnratio, check_ori, d_out, d_nm, d_prev); ORBX_COUNT_LAUNCH(1);
     CKM(cudaGetLastError());
     return ORBX_OK;
 }
@@ -953,7 +964,7 @@ extern "C" int orbx_search_for_initialization(orbx_matcher* m, const orbx_keypoi
     pd.q = m->W.q; pd.qdesc = m->d_d1; pd.n1 = n1; pd.n2 = n2; pd.nq = n1;
     CKM(cudaMemcpyAsync(m->W.pairs, &pd, sizeof(pd), cudaMemcpyHostToDevice, s));
     k_make_init_queries<<<(n1 + 255) / 256, 256, 0, s>>>(m->W.q, m->d_k1, m->d_prev, n1, (float)window); ORBX_COUNT_LAUNCH(1);
-    int rc = run_window(m, 1, n1, 2, nnratio, check_ori, m->d_out, m->d_nm, m->d_prev, s);
+    int rc = run_window(m, m->W, 1, n1, 2, nnratio, check_ori, m->d_out, m->d_nm, m->d_prev, s);
     if (rc) return rc;
     int nm = 0;
     CKM(cudaMemcpyAsync(matches12, m->d_out, sizeof(int32_t) * n1, cudaMemcpyDeviceToHost, s));
@@ -990,7 +1001,7 @@ extern "C" int orbx_search_by_projection(orbx_matcher* m, int mode, const orbx_p
     pd.k1 = nullptr; pd.d1 = nullptr; pd.k2 = m->d_k2; pd.d2 = m->d_d2; pd.uright2 = uright2 ? m->d_uright : nullptr;
     pd.q = m->W.q; pd.qdesc = m->d_qdesc; pd.n1 = nq; pd.n2 = n2; pd.nq = nq;
     CKM(cudaMemcpyAsync(m->W.pairs, &pd, sizeof(pd), cudaMemcpyHostToDevice, s));
-    int rc = run_window(m, 1, nq, mode, nnratio, check_ori, m->d_out, m->d_nm, nullptr, s);
+    int rc = run_window(m, m->W, 1, nq, mode, nnratio, check_ori, m->d_out, m->d_nm, nullptr, s);
     if (rc) return rc;
     k_count_new_assigned<<<1, 256, 0, s>>>(m->d_out2, m->d_out, n2, m->d_nm); ORBX_COUNT_LAUNCH(1);
     int nm = 0;
@@ -1002,22 +1013,20 @@ extern "C" int orbx_search_by_projection(orbx_matcher* m, int mode, const orbx_p
     return ORBX_OK;
 }
 
-extern "C" int orbx_match_slots_device(orbx_matcher* m, orbx_extractor* ex, const int32_t* a, const int32_t* b, int npairs,
-                                       const float bounds[4], int window, float nnratio, int check_ori,
-                                       int32_t* d_matches12, int32_t* d_nmatches, int32_t* d_knn_idx, int32_t* d_knn_dist,
-                                       void* stream)
+static int match_slots_impl(orbx_matcher* m, orbx_extractor* ex, const int32_t* a, const int32_t* b, int npairs, int pair_base,
+                            const float bounds[4], int window, float nnratio, int check_ori,
+                            int32_t* d_matches12, int32_t* d_nmatches, int32_t* d_knn_idx, int32_t* d_knn_dist, cudaStream_t s)
 {
-    if (!m || !ex || !a || !b || npairs < 1 || npairs > m->P || !bounds || !d_matches12 || !d_nmatches) return ORBX_E_INVALID;
     orbx_keypoint* kps; uint8_t* desc; int32_t* n; int32_t* mono; int cap, slots;
     int rc = orbx_extractor_results_device(ex, &kps, &desc, &n, &mono, &cap, &slots);
     if (rc) return rc;
     if (cap > m->K) { orbx_set_error("%s%s", "matcher max_keypoints smaller than the extractor's result capacity", ""); return ORBX_E_INVALID; }
     CKM(cudaSetDevice(m->p.device));
-    cudaStream_t s = stream ? (cudaStream_t)stream : m->stream;
     set_bounds(m, bounds);
+    const WinBufs W = shifted_pairs(m, pair_base);
     // NOTE: outputs use row stride K (= matcher max_keypoints)
-    k_setup_slot_pairs<<<npairs, 256, 0, s>>>(m->W, kps, desc, n, a, b, cap, (float)window); ORBX_COUNT_LAUNCH(1);
-    rc = run_window(m, npairs, cap, 2, nnratio, check_ori, d_matches12, d_nmatches, nullptr, s);
+    k_setup_slot_pairs<<<npairs, 256, 0, s>>>(W, kps, desc, n, a, b, cap, (float)window); ORBX_COUNT_LAUNCH(1);
+    rc = run_window(m, W, npairs, cap, 2, nnratio, check_ori, d_matches12, d_nmatches, nullptr, s);
     if (rc) return rc;
     if (d_knn_idx && d_knn_dist) {
         BfArgs A{};
@@ -1027,6 +1036,16 @@ extern "C" int orbx_match_slots_device(orbx_matcher* m, orbx_extractor* ex, cons
         if (rc) return rc;
     }
     return ORBX_OK;
+}
+
+extern "C" int orbx_match_slots_device(orbx_matcher* m, orbx_extractor* ex, const int32_t* a, const int32_t* b, int npairs,
+                                       const float bounds[4], int window, float nnratio, int check_ori,
+                                       int32_t* d_matches12, int32_t* d_nmatches, int32_t* d_knn_idx, int32_t* d_knn_dist,
+                                       void* stream)
+{
+    if (!m || !ex || !a || !b || npairs < 1 || npairs > m->P || !bounds || !d_matches12 || !d_nmatches) return ORBX_E_INVALID;
+    return match_slots_impl(m, ex, a, b, npairs, 0, bounds, window, nnratio, check_ori, d_matches12, d_nmatches, d_knn_idx, d_knn_dist,
+                            stream ? (cudaStream_t)stream : m->stream);
 }
 
 // One call = one tracking step over a batch of HOST frames: H2D, ORBextractor::operator() on every frame
@@ -1049,6 +1068,8 @@ extern "C" int orbx_extract_match_batch(orbx_extractor* ex, orbx_matcher* m, con
     if (!m->s_h2d) {
         CKM(cudaStreamCreateWithFlags(&m->s_h2d, cudaStreamNonBlocking));
         CKM(cudaStreamCreateWithFlags(&m->s_d2h, cudaStreamNonBlocking));
+        CKM(cudaStreamCreateWithFlags(&m->s_match, cudaStreamNonBlocking));
+        for (int i = 0; i < ORBX_MAX_CHUNKS; i++) CKM(cudaEventCreateWithFlags(&m->ev_ext[i], cudaEventDisableTiming));
         for (int i = 0; i < 2 * ORBX_MAX_CHUNKS; i++) CKM(cudaEventCreateWithFlags(&m->ev[i], cudaEventDisableTiming));
         CKM(cudaEventCreateWithFlags(&m->ev_start, cudaEventDisableTiming));
     }
@@ -1069,6 +1090,7 @@ extern "C" int orbx_extract_match_batch(orbx_extractor* ex, orbx_matcher* m, con
     CKM(cudaEventRecord(m->ev_start, s));
     CKM(cudaStreamWaitEvent(m->s_h2d, m->ev_start, 0));
     CKM(cudaStreamWaitEvent(m->s_d2h, m->ev_start, 0));
+    CKM(cudaStreamWaitEvent(m->s_match, m->ev_start, 0));
     for (int c = 0; c < nchunks; c++) {
         const int f0 = c * per, cnt = (f0 + per <= batch) ? per : batch - f0;
         rc = orbx_ex_stage_input(ex, imgs, f0, cnt, width, height, stride, frame_stride, m->s_h2d);
@@ -1080,11 +1102,14 @@ extern "C" int orbx_extract_match_batch(orbx_extractor* ex, orbx_matcher* m, con
         CKM(cudaStreamWaitEvent(s, m->ev[c], 0));
         rc = orbx_ex_run_staged(ex, f0, cnt, lap0, lap1, 1 + f0, s);
         if (rc) return rc;
-        // pairs (slot f0+i, slot f0+i+1); the matcher's per-pair scratch is reused chunk after chunk (stream order)
-        rc = orbx_match_slots_device(m, ex, m->d_pair_a + f0, m->d_pair_b + f0, cnt, bounds, window, nnratio, check_ori,
-                                     m->d_out + (size_t)f0 * m->K, m->d_nm + f0, nullptr, nullptr, s);
+        CKM(cudaEventRecord(m->ev_ext[c], s));
+        // pairs (slot f0+i, slot f0+i+1) are matched on a second kernel stream, concurrently with the extraction of the
+        // next chunk (the latency-bound matcher kernels hide under it); each chunk owns its slice of the pair scratch
+        CKM(cudaStreamWaitEvent(m->s_match, m->ev_ext[c], 0));
+        rc = match_slots_impl(m, ex, m->d_pair_a + f0, m->d_pair_b + f0, cnt, f0, bounds, window, nnratio, check_ori,
+                              m->d_out + (size_t)f0 * m->K, m->d_nm + f0, nullptr, nullptr, m->s_match);
         if (rc) return rc;
-        CKM(cudaEventRecord(m->ev[ORBX_MAX_CHUNKS + c], s));
+        CKM(cudaEventRecord(m->ev[ORBX_MAX_CHUNKS + c], m->s_match));
         CKM(cudaStreamWaitEvent(m->s_d2h, m->ev[ORBX_MAX_CHUNKS + c], 0));
         rc = orbx_ex_fetch_async(ex, 1 + f0, cnt, f0, kps, desc, cap, n, mono_index, m->s_d2h, direct);
         if (rc) return rc;
@@ -1093,10 +1118,13 @@ extern "C" int orbx_extract_match_batch(orbx_extractor* ex, orbx_matcher* m, con
                                              sizeof(int32_t) * (cap < m->K ? cap : m->K), cnt, cudaMemcpyDeviceToHost, m->s_d2h));
         if (nmatches) CKM(cudaMemcpyAsync(nmatches + f0, m->d_nm + f0, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, m->s_d2h));
     }
+    // slot 0 is read by the first chunk's matcher: carry the last frame over only after every matcher finished
+    CKM(cudaStreamWaitEvent(s, m->ev[ORBX_MAX_CHUNKS + nchunks - 1], 0));
     rc = orbx_extractor_copy_slot(ex, batch, 0, s);
     if (rc) return rc;
     (void)ocap;
     CKM(cudaStreamSynchronize(m->s_d2h));
+    CKM(cudaStreamSynchronize(m->s_match));
     rc = m_check_err(m, s);      // synchronises the kernel stream
     if (rc) return rc;
     return orbx_ex_fetch_finish(ex, batch, kps, desc, cap, n, mono_index, direct);
