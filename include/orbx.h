@@ -174,6 +174,16 @@ int  orbx_extract_match_batch(orbx_extractor* ex, orbx_matcher* m, const uint8_t
                               orbx_keypoint* kps, uint8_t* desc, int cap, int32_t* n, int32_t* mono_index,
                               int32_t* matches12, int32_t* nmatches);
 
+/* The same step on DEVICE-resident frames, asynchronous on `stream` (results stay in the slots; matches12 [batch][K],
+ * nmatches [batch] and the optional BF kNN-2 tables [batch][K][2] are device arrays, K = the matcher's max_keypoints).
+ * Internally the batch is cut into chunks whose matcher kernels run on a second stream under the next chunk's
+ * extraction; `stream` waits for all of it before the slot carry, so synchronising `stream` completes the step. */
+int  orbx_extract_match_batch_device(orbx_extractor* ex, orbx_matcher* m, const uint8_t* d_imgs, int batch, int width,
+                                     int height, int stride, size_t frame_stride, int lap0, int lap1,
+                                     const float bounds[4], int window, float nnratio, int check_ori,
+                                     int32_t* d_matches12, int32_t* d_nmatches, int32_t* d_knn_idx, int32_t* d_knn_dist,
+                                     void* stream);
+
 /* Projection-guided window searches on flat arrays (the drop-in ORBmatcher marshals Frame/MapPoint into
  * these).  Query i: window centre (u,v), radius r, octave range [minl,maxl] as GetFeaturesInArea takes them,
  * predicted right coordinate ur (stereo gate), angle (rotation histogram), valid flag.

@@ -54,16 +54,23 @@ struct orbx_extractor {
     const uint8_t* last_level0; int last_pitch0; long long last_stride0; int last_batch;
     std::vector<void*> allocs;
     // optional per-stage CUDA-event timing (bench.py): pyramid+blur | FAST | octree | finalize+orient+describe
-    bool profile; cudaEvent_t ev[5]; double stage_ms[4]; int stage_batches; bool ev_pending;
+    // a ring of event sets so that recording never makes the host wait inside a timed region; harvested on query
+    bool profile; std::vector<cudaEvent_t> ev; int ev_head, ev_count; double stage_ms[4]; int stage_batches;
 };
+#define ORBX_EV_SETS 512
 
-static void harvest_stage_times(orbx_extractor* h)
+static void harvest_stage_times(orbx_extractor* h, bool all)
 {
-    if (!h->profile || !h->ev_pending) return;
-    if (cudaEventSynchronize(h->ev[4]) != cudaSuccess) return;
-    for (int i = 0; i < 4; i++) { float ms = 0; cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]); h->stage_ms[i] += ms; }
-    h->stage_batches++;
-    h->ev_pending = false;
+    // oldest first; `all` == false only frees one set when the ring is full
+    while (h->ev_count > 0) {
+        const int set = (h->ev_head - h->ev_count + ORBX_EV_SETS) % ORBX_EV_SETS;
+        cudaEvent_t* e = h->ev.data() + set * 5;
+        if (cudaEventSynchronize(e[4]) != cudaSuccess) { cudaGetLastError(); break; }
+        for (int i = 0; i < 4; i++) { float ms = 0; cudaEventElapsedTime(&ms, e[i], e[i + 1]); h->stage_ms[i] += ms; }
+        h->stage_batches++;
+        h->ev_count--;
+        if (!all) break;
+    }
 }
 
 static int dev_alloc(orbx_extractor* h, void** p, size_t bytes)
@@ -249,9 +256,8 @@ extern "C" int orbx_extractor_create(const orbx_params* p, orbx_extractor** out)
     memset(&h->geom, 0, sizeof(h->geom));
     memset(&h->buf, 0, sizeof(h->buf));
     h->d_level0 = nullptr; h->last_level0 = nullptr; h->last_batch = 0;
-    h->profile = false; h->ev_pending = false; h->stage_batches = 0;
+    h->profile = false; h->ev_head = 0; h->ev_count = 0; h->stage_batches = 0;
     for (int i = 0; i < 4; i++) h->stage_ms[i] = 0;
-    for (int i = 0; i < 5; i++) CK(cudaEventCreate(&h->ev[i]));
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     const int cap = orbx_extractor_max_keypoints(h);
     CK(cudaMallocHost((void**)&h->h_stage_in, (size_t)((p->max_width + 63) & ~63) * p->max_height * p->max_batch));
@@ -274,7 +280,7 @@ extern "C" void orbx_extractor_destroy(orbx_extractor* h)
     for (void* p : h->allocs) cudaFree(p);
     cudaFreeHost(h->h_stage_in); cudaFreeHost(h->h_kps); cudaFreeHost(h->h_desc);
     cudaFreeHost(h->h_n); cudaFreeHost(h->h_mono); cudaFreeHost(h->h_err);
-    for (int i = 0; i < 5; i++) cudaEventDestroy(h->ev[i]);
+    for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
     cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -339,17 +345,22 @@ static int run_batch(orbx_extractor* h, const uint8_t* d_level0, int pitch0, lon
     const OrbxGeom& g = h->geom;
     const OrbxBuffers buf = shifted(h, frame_off);
     const uint8_t* l0 = d_level0 + (long long)frame_off * stride0;
-    harvest_stage_times(h);
     const bool prof = h->profile;
-    if (prof) cudaEventRecord(h->ev[0], s);
+    cudaEvent_t* e = nullptr;
+    if (prof) {
+        if (h->ev_count == ORBX_EV_SETS) harvest_stage_times(h, false);
+        e = h->ev.data() + h->ev_head * 5;
+        h->ev_head = (h->ev_head + 1) % ORBX_EV_SETS; h->ev_count++;
+        cudaEventRecord(e[0], s);
+    }
     orbx_launch_pyramid(g, buf, l0, pitch0, stride0, batch, s);
-    if (prof) cudaEventRecord(h->ev[1], s);
+    if (prof) cudaEventRecord(e[1], s);
     orbx_launch_fast(g, buf, l0, pitch0, stride0, batch, s);
-    if (prof) cudaEventRecord(h->ev[2], s);
+    if (prof) cudaEventRecord(e[2], s);
     orbx_launch_octree(g, buf, batch, s);
-    if (prof) cudaEventRecord(h->ev[3], s);
+    if (prof) cudaEventRecord(e[3], s);
     orbx_launch_describe(g, buf, l0, pitch0, stride0, batch, lap0, lap1, first_slot, s);
-    if (prof) { cudaEventRecord(h->ev[4], s); h->ev_pending = true; }
+    if (prof) cudaEventRecord(e[4], s);
     h->last_level0 = d_level0; h->last_pitch0 = pitch0; h->last_stride0 = stride0;
     if (frame_off + batch > h->last_batch || frame_off == 0) h->last_batch = frame_off + batch;
     CK(cudaGetLastError());
@@ -454,6 +465,13 @@ int orbx_ex_run_staged(orbx_extractor* h, int f0, int count, int lap0, int lap1,
     return run_batch(h, h->d_level0, h->pitch0, h->stride0, count, lap0, lap1, first_slot, s, f0);
 }
 
+// frames [f0, f0+count) of a DEVICE batch (geometry already configured); per-frame scratch slice f0..
+int orbx_ex_run_device(orbx_extractor* h, const uint8_t* d_imgs, int pitch, long long fstride, int f0, int count,
+                       int lap0, int lap1, int first_slot, cudaStream_t s)
+{
+    return run_batch(h, d_imgs, pitch, fstride, count, lap0, lap1, first_slot, s, f0);
+}
+
 cudaStream_t orbx_ex_stream(orbx_extractor* h) { return h->stream; }
 int orbx_ex_device(orbx_extractor* h) { return h->p.device; }
 
@@ -555,13 +573,17 @@ extern "C" int orbx_extract(orbx_extractor* h, const uint8_t* img, int width, in
 extern "C" int orbx_extractor_profile(orbx_extractor* h, int enable, double* stage_ms4, int* batches)
 {
     if (!h) return ORBX_E_INVALID;
-    harvest_stage_times(h);
+    harvest_stage_times(h, true);
     if (stage_ms4) for (int i = 0; i < 4; i++) stage_ms4[i] = h->stage_ms[i];
     if (batches) *batches = h->stage_batches;
     if (enable >= 0) {
         h->profile = enable != 0;
+        if (h->profile && h->ev.empty()) {
+            h->ev.resize(ORBX_EV_SETS * 5);
+            for (cudaEvent_t& e : h->ev) CK(cudaEventCreate(&e));
+        }
         for (int i = 0; i < 4; i++) h->stage_ms[i] = 0;
-        h->stage_batches = 0; h->ev_pending = false;
+        h->stage_batches = 0; h->ev_head = 0; h->ev_count = 0;
     }
     return ORBX_OK;
 }

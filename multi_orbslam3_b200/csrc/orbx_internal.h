@@ -103,6 +103,8 @@ int orbx_ex_configure(orbx_extractor* h, int width, int height);
 int orbx_ex_stage_input(orbx_extractor* h, const uint8_t* imgs, int f0, int count, int width, int height, int stride,
                         size_t frame_stride, cudaStream_t s);
 int orbx_ex_run_staged(orbx_extractor* h, int f0, int count, int lap0, int lap1, int first_slot, cudaStream_t s);
+int orbx_ex_run_device(orbx_extractor* h, const uint8_t* d_imgs, int pitch, long long fstride, int f0, int count,
+                       int lap0, int lap1, int first_slot, cudaStream_t s);
 cudaStream_t orbx_ex_stream(orbx_extractor* h);
 int orbx_ex_out_cap(orbx_extractor* h);
 bool orbx_ex_can_fetch_direct(orbx_extractor* h, orbx_keypoint* kps, uint8_t* desc, int cap, int32_t* n, int32_t* mono_index);

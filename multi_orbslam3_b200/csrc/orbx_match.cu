@@ -14,6 +14,7 @@
 // then insertion order) into a CSR pool; the order-dependent bookkeeping of the reference (a keypoint taken
 // by an earlier query is skipped / stolen back) is replayed by one warp per frame pair over that pool.
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 #include "orbx_internal.h"
@@ -27,7 +28,7 @@
         }                                                                                 \
     } while (0)
 
-#define ORBX_MAX_CHUNKS 4
+#define ORBX_MAX_CHUNKS 8
 
 namespace {
 
@@ -1048,29 +1049,14 @@ extern "C" int orbx_match_slots_device(orbx_matcher* m, orbx_extractor* ex, cons
                             stream ? (cudaStream_t)stream : m->stream);
 }
 
-// One call = one tracking step over a batch of HOST frames: H2D, ORBextractor::operator() on every frame
-// (result slots 1..batch), SearchForInitialization of every frame against its predecessor (slot i-1 -> i; slot 0
-// holds the last frame of the previous call), D2H of keypoints, descriptors and matches.
-// The batch is cut into chunks that flow through three streams (H2D | kernels | D2H) so that the PCIe copies of
-// chunk c+1 / c-1 overlap the kernels of chunk c.
-extern "C" int orbx_extract_match_batch(orbx_extractor* ex, orbx_matcher* m, const uint8_t* imgs, int batch, int width,
-                                        int height, int stride, size_t frame_stride, int lap0, int lap1,
-                                        const float bounds[4], int window, float nnratio, int check_ori,
-                                        orbx_keypoint* kps, uint8_t* desc, int cap, int32_t* n, int32_t* mono_index,
-                                        int32_t* matches12, int32_t* nmatches)
+static int ensure_pipeline(orbx_matcher* m)
 {
-    if (!ex || !m || !imgs || batch < 1 || batch > m->P || !bounds) return ORBX_E_INVALID;
-    if (width <= 0 || height <= 0) return ORBX_E_EMPTY;
-    int rc = orbx_ex_configure(ex, width, height);
-    if (rc) return rc;
-    CKM(cudaSetDevice(m->p.device));
-    cudaStream_t s = orbx_ex_stream(ex);
     if (!m->s_h2d) {
         CKM(cudaStreamCreateWithFlags(&m->s_h2d, cudaStreamNonBlocking));
         CKM(cudaStreamCreateWithFlags(&m->s_d2h, cudaStreamNonBlocking));
         CKM(cudaStreamCreateWithFlags(&m->s_match, cudaStreamNonBlocking));
-        for (int i = 0; i < ORBX_MAX_CHUNKS; i++) CKM(cudaEventCreateWithFlags(&m->ev_ext[i], cudaEventDisableTiming));
         for (int i = 0; i < 2 * ORBX_MAX_CHUNKS; i++) CKM(cudaEventCreateWithFlags(&m->ev[i], cudaEventDisableTiming));
+        for (int i = 0; i < ORBX_MAX_CHUNKS; i++) CKM(cudaEventCreateWithFlags(&m->ev_ext[i], cudaEventDisableTiming));
         CKM(cudaEventCreateWithFlags(&m->ev_start, cudaEventDisableTiming));
     }
     if (!m->d_pair_a) {
@@ -1081,53 +1067,116 @@ extern "C" int orbx_extract_match_batch(orbx_extractor* ex, orbx_matcher* m, con
         CKM(cudaMemcpy(m->d_pair_a, a.data(), sizeof(int32_t) * m->P, cudaMemcpyHostToDevice));
         CKM(cudaMemcpy(m->d_pair_b, b.data(), sizeof(int32_t) * m->P, cudaMemcpyHostToDevice));
     }
-    const bool direct = orbx_ex_can_fetch_direct(ex, kps, desc, cap, n, mono_index);
-    const int ocap = orbx_ex_out_cap(ex);
-    int nchunks = batch >= 64 ? ORBX_MAX_CHUNKS : 1;
+    return ORBX_OK;
+}
+
+// One call = one tracking step over a batch of frames: ORBextractor::operator() on every frame (result slots
+// 1..batch), SearchForInitialization (+ optional BF kNN-2) of every frame against its predecessor (slot i-1 -> i; slot 0
+// holds the last frame of the previous call).  The batch is cut into chunks that flow through up to four streams
+// (H2D | extraction kernels | matcher kernels | D2H): copies of chunk c+1 / c-1 and the latency-bound matcher kernels of
+// chunk c-1 overlap the extraction of chunk c.  host == true: imgs/outputs are host buffers; else imgs is a device pointer
+// and nothing is copied back (results stay in the slots / the caller's device arrays).
+static int extract_match_pipeline(orbx_extractor* ex, orbx_matcher* m, bool host, const uint8_t* imgs, int batch, int width,
+                                  int height, int stride, size_t frame_stride, int lap0, int lap1,
+                                  const float bounds[4], int window, float nnratio, int check_ori,
+                                  orbx_keypoint* kps, uint8_t* desc, int cap, int32_t* n, int32_t* mono_index,
+                                  int32_t* matches12, int32_t* nmatches,
+                                  int32_t* d_matches12, int32_t* d_nmatches, int32_t* d_knn_idx, int32_t* d_knn_dist,
+                                  cudaStream_t s)
+{
+    int rc = orbx_ex_configure(ex, width, height);
+    if (rc) return rc;
+    CKM(cudaSetDevice(m->p.device));
+    if ((rc = ensure_pipeline(m))) return rc;
+    const bool direct = host && orbx_ex_can_fetch_direct(ex, kps, desc, cap, n, mono_index);
+    // host path: 4 chunks hide the PCIe copies; device path: chunking only shrinks the kernels and makes the two kernel
+    // streams fight for the SMs (measured: 1 chunk 5.7 ms, 4 chunks 6.2 ms per 512 frames), so one chunk unless overridden
+    int nchunks = host ? (batch >= 64 ? 4 : 1) : 1;
+    if (const char* e = getenv(host ? "ORBX_HOST_CHUNKS" : "ORBX_DEVICE_CHUNKS")) { const int v = atoi(e); if (v >= 1 && v <= ORBX_MAX_CHUNKS) nchunks = v; }
+    if (nchunks > batch) nchunks = batch;
     const int per = (batch + nchunks - 1) / nchunks;
     nchunks = (batch + per - 1) / per;
-    // the copy streams must not run ahead of work already queued on the kernel stream (previous call's carry)
+    int32_t* dm12 = host ? m->d_out : d_matches12;
+    int32_t* dnm = host ? m->d_nm : d_nmatches;
+    // the side streams must not run ahead of work already queued on the kernel stream (previous call's carry)
     CKM(cudaEventRecord(m->ev_start, s));
-    CKM(cudaStreamWaitEvent(m->s_h2d, m->ev_start, 0));
-    CKM(cudaStreamWaitEvent(m->s_d2h, m->ev_start, 0));
     CKM(cudaStreamWaitEvent(m->s_match, m->ev_start, 0));
-    for (int c = 0; c < nchunks; c++) {
-        const int f0 = c * per, cnt = (f0 + per <= batch) ? per : batch - f0;
-        rc = orbx_ex_stage_input(ex, imgs, f0, cnt, width, height, stride, frame_stride, m->s_h2d);
-        if (rc) return rc;
-        CKM(cudaEventRecord(m->ev[c], m->s_h2d));
+    if (host) {
+        CKM(cudaStreamWaitEvent(m->s_h2d, m->ev_start, 0));
+        CKM(cudaStreamWaitEvent(m->s_d2h, m->ev_start, 0));
+        for (int c = 0; c < nchunks; c++) {
+            const int f0 = c * per, cnt = (f0 + per <= batch) ? per : batch - f0;
+            rc = orbx_ex_stage_input(ex, imgs, f0, cnt, width, height, stride, frame_stride, m->s_h2d);
+            if (rc) return rc;
+            CKM(cudaEventRecord(m->ev[c], m->s_h2d));
+        }
     }
     for (int c = 0; c < nchunks; c++) {
         const int f0 = c * per, cnt = (f0 + per <= batch) ? per : batch - f0;
-        CKM(cudaStreamWaitEvent(s, m->ev[c], 0));
-        rc = orbx_ex_run_staged(ex, f0, cnt, lap0, lap1, 1 + f0, s);
+        if (host) {
+            CKM(cudaStreamWaitEvent(s, m->ev[c], 0));
+            rc = orbx_ex_run_staged(ex, f0, cnt, lap0, lap1, 1 + f0, s);
+        } else {
+            rc = orbx_ex_run_device(ex, imgs, stride, (long long)frame_stride, f0, cnt, lap0, lap1, 1 + f0, s);
+        }
         if (rc) return rc;
         CKM(cudaEventRecord(m->ev_ext[c], s));
         // pairs (slot f0+i, slot f0+i+1) are matched on a second kernel stream, concurrently with the extraction of the
-        // next chunk (the latency-bound matcher kernels hide under it); each chunk owns its slice of the pair scratch
+        // next chunk; each chunk owns its slice of the pair scratch
         CKM(cudaStreamWaitEvent(m->s_match, m->ev_ext[c], 0));
         rc = match_slots_impl(m, ex, m->d_pair_a + f0, m->d_pair_b + f0, cnt, f0, bounds, window, nnratio, check_ori,
-                              m->d_out + (size_t)f0 * m->K, m->d_nm + f0, nullptr, nullptr, m->s_match);
+                              dm12 + (size_t)f0 * m->K, dnm + f0,
+                              d_knn_idx ? d_knn_idx + (size_t)f0 * m->K * 2 : nullptr, d_knn_dist ? d_knn_dist + (size_t)f0 * m->K * 2 : nullptr,
+                              m->s_match);
         if (rc) return rc;
         CKM(cudaEventRecord(m->ev[ORBX_MAX_CHUNKS + c], m->s_match));
-        CKM(cudaStreamWaitEvent(m->s_d2h, m->ev[ORBX_MAX_CHUNKS + c], 0));
-        rc = orbx_ex_fetch_async(ex, 1 + f0, cnt, f0, kps, desc, cap, n, mono_index, m->s_d2h, direct);
-        if (rc) return rc;
-        // matches: device rows have stride K; host rows have stride cap
-        if (matches12) CKM(cudaMemcpy2DAsync(matches12 + (size_t)f0 * cap, sizeof(int32_t) * cap, m->d_out + (size_t)f0 * m->K, sizeof(int32_t) * m->K,
-                                             sizeof(int32_t) * (cap < m->K ? cap : m->K), cnt, cudaMemcpyDeviceToHost, m->s_d2h));
-        if (nmatches) CKM(cudaMemcpyAsync(nmatches + f0, m->d_nm + f0, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, m->s_d2h));
+        if (host) {
+            CKM(cudaStreamWaitEvent(m->s_d2h, m->ev[ORBX_MAX_CHUNKS + c], 0));
+            rc = orbx_ex_fetch_async(ex, 1 + f0, cnt, f0, kps, desc, cap, n, mono_index, m->s_d2h, direct);
+            if (rc) return rc;
+            // matches: device rows have stride K; host rows have stride cap
+            if (matches12) CKM(cudaMemcpy2DAsync(matches12 + (size_t)f0 * cap, sizeof(int32_t) * cap, dm12 + (size_t)f0 * m->K, sizeof(int32_t) * m->K,
+                                                 sizeof(int32_t) * (cap < m->K ? cap : m->K), cnt, cudaMemcpyDeviceToHost, m->s_d2h));
+            if (nmatches) CKM(cudaMemcpyAsync(nmatches + f0, dnm + f0, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, m->s_d2h));
+        }
     }
-    // slot 0 is read by the first chunk's matcher: carry the last frame over only after every matcher finished
+    // slot 0 is read by the first chunk's matcher: carry the last frame over only after every matcher finished; the
+    // caller's stream `s` thereby also waits for the matcher stream
     CKM(cudaStreamWaitEvent(s, m->ev[ORBX_MAX_CHUNKS + nchunks - 1], 0));
     rc = orbx_extractor_copy_slot(ex, batch, 0, s);
     if (rc) return rc;
-    (void)ocap;
+    if (!host) return ORBX_OK;                       // asynchronous: the caller synchronises `s`
     CKM(cudaStreamSynchronize(m->s_d2h));
     CKM(cudaStreamSynchronize(m->s_match));
     rc = m_check_err(m, s);      // synchronises the kernel stream
     if (rc) return rc;
     return orbx_ex_fetch_finish(ex, batch, kps, desc, cap, n, mono_index, direct);
+}
+
+extern "C" int orbx_extract_match_batch(orbx_extractor* ex, orbx_matcher* m, const uint8_t* imgs, int batch, int width,
+                                        int height, int stride, size_t frame_stride, int lap0, int lap1,
+                                        const float bounds[4], int window, float nnratio, int check_ori,
+                                        orbx_keypoint* kps, uint8_t* desc, int cap, int32_t* n, int32_t* mono_index,
+                                        int32_t* matches12, int32_t* nmatches)
+{
+    if (!ex || !m || !imgs || batch < 1 || batch > m->P || !bounds) return ORBX_E_INVALID;
+    if (width <= 0 || height <= 0) return ORBX_E_EMPTY;
+    return extract_match_pipeline(ex, m, true, imgs, batch, width, height, stride, frame_stride, lap0, lap1, bounds, window, nnratio,
+                                  check_ori, kps, desc, cap, n, mono_index, matches12, nmatches, nullptr, nullptr, nullptr, nullptr,
+                                  orbx_ex_stream(ex));
+}
+
+extern "C" int orbx_extract_match_batch_device(orbx_extractor* ex, orbx_matcher* m, const uint8_t* d_imgs, int batch, int width,
+                                               int height, int stride, size_t frame_stride, int lap0, int lap1,
+                                               const float bounds[4], int window, float nnratio, int check_ori,
+                                               int32_t* d_matches12, int32_t* d_nmatches, int32_t* d_knn_idx, int32_t* d_knn_dist,
+                                               void* stream)
+{
+    if (!ex || !m || !d_imgs || batch < 1 || batch > m->P || !bounds || !d_matches12 || !d_nmatches || stride < width) return ORBX_E_INVALID;
+    if (width <= 0 || height <= 0) return ORBX_E_EMPTY;
+    return extract_match_pipeline(ex, m, false, d_imgs, batch, width, height, stride, frame_stride, lap0, lap1, bounds, window, nnratio,
+                                  check_ori, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr, d_matches12, d_nmatches, d_knn_idx,
+                                  d_knn_dist, stream ? (cudaStream_t)stream : orbx_ex_stream(ex));
 }
 
 extern "C" int orbx_stereo_band_match(orbx_matcher* m, const orbx_keypoint* kl, const uint8_t* dl, int nl,

@@ -35,7 +35,8 @@ EXPORTS = [
     "orbx_level_keypoints_to_host",
     "orbx_matcher_create", "orbx_matcher_destroy", "orbx_matcher_sync", "orbx_hamming_pairs",
     "orbx_bf_knn2", "orbx_bf_knn2_device", "orbx_knn2_merge_device",
-    "orbx_search_for_initialization", "orbx_match_slots_device", "orbx_extract_match_batch", "orbx_search_by_projection",
+    "orbx_search_for_initialization", "orbx_match_slots_device", "orbx_extract_match_batch", "orbx_extract_match_batch_device",
+    "orbx_search_by_projection",
     "orbx_stereo_band_match", "orbx_stereo_matches", "orbx_popc_peak",
 ]
 
@@ -75,6 +76,8 @@ def lib():
         L.orbx_extractor_profile.argtypes = [vp, i32, vp, vp]
         L.orbx_extract_match_batch.argtypes = [vp, vp, vp, i32, i32, i32, i32, sz, i32, i32, vp, i32, f32, i32,
                                                vp, vp, i32, vp, vp, vp, vp]
+        L.orbx_extract_match_batch_device.argtypes = [vp, vp, vp, i32, i32, i32, i32, sz, i32, i32, vp, i32, f32, i32,
+                                                      vp, vp, vp, vp, vp]
         L.orbx_extractor_create.argtypes = [C.POINTER(Params), C.POINTER(vp)]
         L.orbx_extractor_destroy.argtypes = [vp]
         L.orbx_extractor_destroy.restype = None
@@ -354,6 +357,17 @@ def extract_match_batch(ex, m, imgs, lap, bounds, window, out):
     _check(lib().orbx_extract_match_batch(ex._h, m._h, _p(imgs), B, W, H, imgs.strides[1], imgs.strides[0], int(lap[0]), int(lap[1]),
                                           _p(bb), int(window), m.mfNNratio, int(m.mbCheckOrientation), _p(out["kps"]), _p(out["desc"]),
                                           ex.cap, _p(out["n"]), _p(out["mono"]), _p(out["matches12"]), _p(out["nmatches"])))
+
+
+def extract_match_batch_device(ex, m, d_ptr, batch, width, height, stride, frame_stride, lap, bounds, window,
+                               d_matches12, d_nmatches, d_knn_idx=None, d_knn_dist=None, stream=None):
+    """orbx_extract_match_batch_device: one asynchronous extract + match step on device-resident frames."""
+    bb = np.array(bounds, np.float32)
+    _check(lib().orbx_extract_match_batch_device(ex._h, m._h, C.c_void_p(d_ptr), batch, width, height, stride, frame_stride,
+                                                 int(lap[0]), int(lap[1]), _p(bb), int(window), m.mfNNratio, int(m.mbCheckOrientation),
+                                                 C.c_void_p(d_matches12), C.c_void_p(d_nmatches),
+                                                 C.c_void_p(d_knn_idx) if d_knn_idx else None,
+                                                 C.c_void_p(d_knn_dist) if d_knn_dist else None, _s(stream)))
 
 
 def popc_peak(device=0):
