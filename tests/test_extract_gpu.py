@@ -134,3 +134,23 @@ def test_capacity_error_is_loud():
         ex(img)
     assert ei.value.code == orbx.ORBX_E_CAPACITY
     ex.close()
+
+
+def test_kitti_batched_stream_c3():
+    """BASELINE C3: KITTI-shape 1241x376, 2000 kp, batched frame stream on one GPU (device-resident frames)."""
+    import torch
+    B, W, H = 6, 1241, 376
+    frames = synth.rects_stream(W, H, B, seed=13)
+    ex = orbx.ORBextractor(2000, 1.2, 8, 20, 7, max_width=W, max_height=H, max_batch=B)
+    # a pitched device batch (stride 1248) exercises the TMA path with stride != width
+    d = torch.zeros((B, H, 1248), dtype=torch.uint8, device="cuda")
+    d[:, :, :W] = torch.from_numpy(frames).cuda()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        ex.extract_batch_device(d.data_ptr(), B, W, H, 1248, 1248 * H, (0, 0), first_slot=1, stream=s.cuda_stream)
+    ex.sync(s.cuda_stream)
+    res = ex.download(1, B, s.cuda_stream)
+    ref = O.Extractor(2000, 1.2, 8, 20, 7)
+    for f in range(B):
+        check_frame(res[f], ref(frames[f], (0, 0)))
+    ex.close()

@@ -31,3 +31,36 @@ def test_partial_top2_merge_equals_full_search():
         np.testing.assert_array_equal(i2.cpu().numpy(), want_i)
         np.testing.assert_array_equal(d2.cpu().numpy(), want_d)
     m.close()
+
+
+def test_full_size_shard_properties():
+    """BASELINE C5 scale on one GPU shard (8 192 keyframes x 1000 descriptors = 8.2 M x 32 B): too big for the CPU oracle,
+    so check size-independent properties: planted copies are found at distance 0 with the LOWEST index first, results do not
+    depend on how the DB is cut into shards, and the distances of the reported neighbours are their true Hamming distances."""
+    m = orbx.ORBmatcher(0.7, True, max_keypoints=2048)
+    match_fn, merge_fn = gpu_fns(m)
+    n = 8192 * 1000
+    g = torch.Generator(device="cuda"); g.manual_seed(7)
+    db = torch.randint(0, 256, (n, 32), dtype=torch.uint8, device="cuda", generator=g)
+    q = torch.randint(0, 256, (1000, 32), dtype=torch.uint8, device="cuda", generator=g)
+    plant = torch.tensor([5, 4_000_000, n - 1], device="cuda")
+    db[plant] = q[0]                                    # three exact copies of query 0
+    db[123_456] = q[1]; db[123_456, 0] ^= 1             # a 1-bit neighbour of query 1
+    i_full, d_full = match_fn(q, db, 0)
+    torch.cuda.synchronize()
+    assert i_full[0].tolist() == [5, 4_000_000] and d_full[0].tolist() == [0, 0]
+    assert int(i_full[1, 0]) == 123_456 and int(d_full[1, 0]) == 1
+    # shard invariance: 8 shards + merge == one pass
+    parts = [match_fn(q, db[r * (n // 8):(r + 1) * (n // 8)], r * (n // 8)) for r in range(8)]
+    i_m, d_m = merge_fn(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]))
+    torch.cuda.synchronize()
+    assert torch.equal(i_m, i_full) and torch.equal(d_m, d_full)
+    # reported distances are the true distances of the reported rows (checked with torch on the gathered rows)
+    rows = db[i_full.long().reshape(-1)].reshape(1000, 2, 32)
+    x = (rows ^ q[:, None, :]).to(torch.int32)
+    pop = torch.zeros_like(x)
+    for b in range(8):
+        pop += (x >> b) & 1
+    assert torch.equal(pop.sum(-1).to(torch.int32), d_full)
+    assert bool((d_full[:, 0] <= d_full[:, 1]).all())
+    m.close()
