@@ -4,12 +4,16 @@
 //           computeOrientation / IC_Angle (:75-102, :470-477),
 //           computeOrbDescriptor / computeDescriptors (:105-145, :1059-1066),
 //           the scale + two-ended mono/stereo placement of operator() (:1102-1149).
+#include <string.h>
 #include "orbx_internal.h"
 
 namespace {
 
 // 256 test pairs, (x0,y0,x1,y1) as int8 packed into one 32-bit word per pair
 __device__ uint32_t d_pattern[256];
+// IC_Angle item table: for each byte alignment sh (0..3) of the patch's first column and each of the 31 x 9 aligned
+// words of the patch: {byte mask of the pixels inside the circular patch, signed byte weights u, row, word}.
+__device__ uint4 d_ic_table[4 * 288];
 // IC_Angle patch half-widths per |v| (umax, R/src/ORBextractor.cc:452-467)
 __device__ __constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
 
@@ -140,25 +144,15 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_orient_describe(OrbxGeom g,
         if ((pitch & 3) == 0) {
             const uint32_t* w0 = reinterpret_cast<const uint32_t*>(p0 - sh);
             const int pw = pitch >> 2;
+            const uint4* tab = d_ic_table + sh * 288;
 #pragma unroll
             for (int it = 0; it < 9; it++) {
-                const int t = lane + 32 * it;                              // item = (row, word)
+                const int t = lane + 32 * it;                              // item = (row, word), 279 items
                 if (t < 31 * 9) {
-                    const int row = t / 9, w = t - row * 9;
-                    const int v = row - ORBX_HALF_PATCH;
-                    const int d = c_umax[v < 0 ? -v : v];
-                    const uint32_t word = __ldg(w0 + row * pw + w);
-                    // byte j of word w sits at u = 4w + j - sh - 15
-                    const int u0 = 4 * w - sh - ORBX_HALF_PATCH;
-                    uint32_t mask = 0, wu = 0;
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        const int u = u0 + j;
-                        if (u >= -d && u <= d) { mask |= 0xFFu << (8 * j); wu |= (uint32_t)(uint8_t)(int8_t)u << (8 * j); }
-                    }
-                    const uint32_t mw = word & mask;
-                    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(m10) : "r"(mw), "r"(wu), "r"(m10));   // unsigned pixels x signed weights
-                    m01 += v * (int)__dp4a(mw, 0x01010101u, 0u);
+                    const uint4 e = __ldg(tab + t);                        // mask, weights, row, word
+                    const uint32_t mw = __ldg(w0 + (int)e.z * pw + (int)e.w) & e.x;
+                    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(m10) : "r"(mw), "r"(e.y), "r"(m10));   // unsigned pixels x signed weights u
+                    m01 += ((int)e.z - ORBX_HALF_PATCH) * (int)__dp4a(mw, 0x01010101u, 0u);
                 }
             }
         } else if (lane < 31) {
@@ -209,8 +203,27 @@ static const int32_t h_pattern[1024] = {
 #include "orb_pattern.inc"
 };
 
+static void upload_ic_table()
+{
+    static const int umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+    static uint4 tab[4 * 288];
+    memset(tab, 0, sizeof(tab));
+    for (int sh = 0; sh < 4; sh++)
+        for (int t = 0; t < 31 * 9; t++) {
+            const int row = t / 9, w = t % 9, v = row - ORBX_HALF_PATCH, d = umax[v < 0 ? -v : v];
+            uint32_t mask = 0, wu = 0;
+            for (int j = 0; j < 4; j++) {
+                const int u = 4 * w + j - sh - ORBX_HALF_PATCH;          // byte j of word w sits at u
+                if (u >= -d && u <= d) { mask |= 0xFFu << (8 * j); wu |= (uint32_t)(uint8_t)(int8_t)u << (8 * j); }
+            }
+            tab[sh * 288 + t] = make_uint4(mask, wu, (uint32_t)row, (uint32_t)w);
+        }
+    cudaMemcpyToSymbol(d_ic_table, tab, sizeof(tab));
+}
+
 void orbx_upload_pattern()
 {
+    upload_ic_table();
     uint32_t packed[256];
     for (int i = 0; i < 256; i++) {
         const int32_t* p = h_pattern + 4 * i;

@@ -34,10 +34,12 @@ __device__ __forceinline__ u64 block_scan_excl(u64 v, u64* total, u64* s_warp)
     __syncthreads();                      // protect s_warp reuse
     if (lane == 31) s_warp[warp] = inc;
     __syncthreads();
-    u64 base = 0, tot = 0;
+    // every warp scans the NT/32 warp totals with shuffles (lane = warp index)
+    u64 ws = lane < NT / 32 ? s_warp[lane] : 0ull, wi = ws;
 #pragma unroll
-    for (int wi = 0; wi < NT / 32; wi++) { u64 t = s_warp[wi]; if (wi < warp) base += t; tot += t; }
-    *total = tot;
+    for (int o = 1; o < NT / 32; o <<= 1) { u64 t = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += t; }
+    *total = __shfl_sync(0xffffffffu, wi, NT / 32 - 1);
+    const u64 base = __shfl_sync(0xffffffffu, wi - ws, warp);
     return base + inc - v;
 }
 
