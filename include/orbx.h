@@ -202,6 +202,13 @@ int  orbx_search_by_projection(orbx_matcher* m, int mode, const orbx_proj_query*
                                const orbx_keypoint* k2, const uint8_t* d2, const float* uright2, int n2,
                                const float bounds[4], int32_t* assigned, float nnratio, int check_ori, int* nmatches);
 
+/* Generic candidate matching for the searches whose candidate gathering stays on the host: SearchByBoW
+ * (R/src/ORBmatcher.cc:269-471, 819-959), SearchForTriangulation (:961-1394), Fuse (:1395-1742), SearchBySim3 (:1744-1968).
+ * Query i is compared with train rows indices[offsets[i] .. offsets[i+1]) in list order; idx/dist (nq x 2) receive the
+ * best and second best by (distance, list position), -1 when missing.  Host pointers. */
+int  orbx_match_candidates(orbx_matcher* m, const uint8_t* q, int nq, const uint8_t* t, int nt, const int32_t* offsets,
+                           const int32_t* indices, int32_t* idx, int32_t* dist);
+
 /* Frame::ComputeStereoMatches, descriptor search (R/src/Frame.cc:785-868): per left keypoint the best
  * right index (-1 if none) and its distance (starts at TH_HIGH).  Host pointers. */
 int  orbx_stereo_band_match(orbx_matcher* m, const orbx_keypoint* kl, const uint8_t* dl, int nl,

@@ -660,6 +660,46 @@ __global__ void __launch_bounds__(1024) k_stereo_outliers(int nl, float* uright,
         if (sad[i] >= 0 && !((float)sad[i] < thDist)) { uright[i] = -1.0f; depth[i] = -1.0f; }
 }
 
+// generic CSR candidate matching: one warp per query, candidates in list order, top-2 by (distance, list position)
+__global__ void __launch_bounds__(256) k_match_candidates(const uint8_t* q, int nq, const uint8_t* t, const int32_t* offsets,
+                                                        const int32_t* indices, int32_t* out_idx, int32_t* out_dist)
+{
+    const int lane = threadIdx.x & 31;
+    const int qi = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (qi >= nq) return;
+    const int o0 = offsets[qi], o1 = offsets[qi + 1];
+    const uint4 a0 = reinterpret_cast<const uint4*>(q)[2 * qi], a1 = reinterpret_cast<const uint4*>(q)[2 * qi + 1];
+    int d0 = 0x7fffffff, k0 = 0x7fffffff, d1 = 0x7fffffff, k1 = 0x7fffffff;
+    uint32_t e0 = 0, e1 = 0;
+    for (int k = o0 + lane; k < o1; k += 32) {
+        const int j = indices[k];
+        const int d = hamming256(a0, a1, reinterpret_cast<const uint4*>(t)[2 * j], reinterpret_cast<const uint4*>(t)[2 * j + 1]);
+        const int r = k - o0;
+        if (d < d0) { d1 = d0; k1 = k0; e1 = e0; d0 = d; k0 = r; e0 = (uint32_t)j; }
+        else if (d < d1) { d1 = d; k1 = r; e1 = (uint32_t)j; }
+    }
+    if (o1 - o0 > 65535) {     // ranks beyond 16 bits: fall back to the shuffle tree on (dist, rank) pairs
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const int od0 = __shfl_xor_sync(0xffffffffu, d0, o), ok0 = __shfl_xor_sync(0xffffffffu, k0, o);
+            const uint32_t oe0 = __shfl_xor_sync(0xffffffffu, e0, o);
+            const int od1 = __shfl_xor_sync(0xffffffffu, d1, o), ok1 = __shfl_xor_sync(0xffffffffu, k1, o);
+            const uint32_t oe1 = __shfl_xor_sync(0xffffffffu, e1, o);
+            int ld, lk; uint32_t le;
+            if (od0 < d0 || (od0 == d0 && ok0 < k0)) { ld = d0; lk = k0; le = e0; d0 = od0; k0 = ok0; e0 = oe0; }
+            else { ld = od0; lk = ok0; le = oe0; }
+            if (od1 < d1 || (od1 == d1 && ok1 < k1)) { d1 = od1; k1 = ok1; e1 = oe1; }
+            if (ld < d1 || (ld == d1 && lk < k1)) { d1 = ld; k1 = lk; e1 = le; }
+        }
+    } else {
+        warp_top2(d0, k0, e0, d1, e1, k1);
+    }
+    if (lane == 0) {
+        out_idx[2 * qi] = d0 == 0x7fffffff ? -1 : (int)e0; out_dist[2 * qi] = d0 == 0x7fffffff ? -1 : d0;
+        out_idx[2 * qi + 1] = d1 == 0x7fffffff ? -1 : (int)e1; out_dist[2 * qi + 1] = d1 == 0x7fffffff ? -1 : d1;
+    }
+}
+
 // register-only throughput probes
 __global__ void k_popc_probe(unsigned seed, int iters, unsigned* sink)
 {
@@ -696,6 +736,7 @@ struct orbx_matcher {
     uint8_t* d_bfq; uint8_t* d_bft; size_t bfq_bytes, bft_bytes;
     unsigned* h_err;
     int32_t* d_pair_a; int32_t* d_pair_b;
+    uint8_t* d_gen; size_t gen_bytes;
     cudaStream_t s_h2d, s_d2h, s_match; cudaEvent_t ev[2 * ORBX_MAX_CHUNKS]; cudaEvent_t ev_ext[ORBX_MAX_CHUNKS]; cudaEvent_t ev_start;
     std::vector<void*> allocs;
 };
@@ -750,6 +791,7 @@ extern "C" int orbx_matcher_create(const orbx_matcher_params* p, orbx_matcher** 
     m->d_part_idx = m->d_part_dist = nullptr; m->part_elems = 0;
     m->d_bfq = m->d_bft = nullptr; m->bfq_bytes = m->bft_bytes = 0;
     m->d_pair_a = m->d_pair_b = nullptr;
+    m->d_gen = nullptr; m->gen_bytes = 0;
     m->s_h2d = m->s_d2h = nullptr;
     CKM(cudaMemset(W.err, 0, sizeof(unsigned)));
     CKM(cudaMallocHost((void**)&m->h_err, sizeof(unsigned)));
@@ -775,6 +817,7 @@ extern "C" void orbx_matcher_destroy(orbx_matcher* m)
     if (m->d_bfq) cudaFree(m->d_bfq);
     if (m->d_bft) cudaFree(m->d_bft);
     if (m->d_pair_a) cudaFree(m->d_pair_a);
+    if (m->d_gen) cudaFree(m->d_gen);
     if (m->s_h2d) {
         cudaStreamDestroy(m->s_h2d); cudaStreamDestroy(m->s_d2h); cudaStreamDestroy(m->s_match);
         for (int i = 0; i < ORBX_MAX_CHUNKS; i++) cudaEventDestroy(m->ev_ext[i]);
@@ -1243,6 +1286,37 @@ extern "C" int orbx_stereo_matches(orbx_matcher* m, orbx_extractor* left, orbx_e
     CKM(cudaMemcpyAsync(uright, d_u, sizeof(float) * nl, cudaMemcpyDeviceToHost, s));
     CKM(cudaMemcpyAsync(depth, d_z, sizeof(float) * nl, cudaMemcpyDeviceToHost, s));
     if (sad_dist) CKM(cudaMemcpyAsync(sad_dist, m->d_knn_idx, sizeof(int32_t) * nl, cudaMemcpyDeviceToHost, s));
+    CKM(cudaStreamSynchronize(s));
+    return ORBX_OK;
+}
+
+// generic candidate matching for the host-side searches (SearchByBoW, SearchForTriangulation, Fuse, SearchBySim3)
+extern "C" int orbx_match_candidates(orbx_matcher* m, const uint8_t* q, int nq, const uint8_t* t, int nt, const int32_t* offsets,
+                                     const int32_t* indices, int32_t* idx, int32_t* dist)
+{
+    if (!m || nq < 0 || nt < 0 || (nq > 0 && (!q || !offsets || !idx || !dist))) return ORBX_E_INVALID;
+    if (nq == 0) return ORBX_OK;
+    const int ncand = offsets[nq];
+    if (ncand < 0 || (ncand > 0 && (!indices || !t))) return ORBX_E_INVALID;
+    CKM(cudaSetDevice(m->p.device));
+    cudaStream_t s = m->stream;
+    uint8_t *dq, *dt; int32_t *doff, *dind, *dres;
+    const size_t bytes = (size_t)nq * 32 + (size_t)(nt > 0 ? nt : 1) * 32 + sizeof(int32_t) * ((size_t)nq + 1 + (ncand > 0 ? ncand : 1) + 4 * (size_t)nq) + 256;
+    if (bytes > m->gen_bytes) {
+        if (m->d_gen) cudaFree(m->d_gen);
+        CKM(cudaMalloc((void**)&m->d_gen, bytes)); m->gen_bytes = bytes;
+    }
+    dq = m->d_gen; dt = dq + (((size_t)nq * 32 + 63) & ~(size_t)63);
+    doff = reinterpret_cast<int32_t*>(dt + (((size_t)(nt > 0 ? nt : 1) * 32 + 63) & ~(size_t)63));
+    dind = doff + nq + 1; dres = dind + (ncand > 0 ? ncand : 1);
+    CKM(cudaMemcpyAsync(dq, q, (size_t)nq * 32, cudaMemcpyHostToDevice, s));
+    if (nt) CKM(cudaMemcpyAsync(dt, t, (size_t)nt * 32, cudaMemcpyHostToDevice, s));
+    CKM(cudaMemcpyAsync(doff, offsets, sizeof(int32_t) * (nq + 1), cudaMemcpyHostToDevice, s));
+    if (ncand) CKM(cudaMemcpyAsync(dind, indices, sizeof(int32_t) * ncand, cudaMemcpyHostToDevice, s));
+    k_match_candidates<<<(nq + 7) / 8, 256, 0, s>>>(dq, nq, dt, doff, dind, dres, dres + 2 * nq); ORBX_COUNT_LAUNCH(1);
+    CKM(cudaGetLastError());
+    CKM(cudaMemcpyAsync(idx, dres, sizeof(int32_t) * 2 * nq, cudaMemcpyDeviceToHost, s));
+    CKM(cudaMemcpyAsync(dist, dres + 2 * nq, sizeof(int32_t) * 2 * nq, cudaMemcpyDeviceToHost, s));
     CKM(cudaStreamSynchronize(s));
     return ORBX_OK;
 }

@@ -37,7 +37,7 @@ EXPORTS = [
     "orbx_bf_knn2", "orbx_bf_knn2_device", "orbx_knn2_merge_device",
     "orbx_search_for_initialization", "orbx_match_slots_device", "orbx_extract_match_batch", "orbx_extract_match_batch_device",
     "orbx_search_by_projection",
-    "orbx_stereo_band_match", "orbx_stereo_matches", "orbx_popc_peak",
+    "orbx_stereo_band_match", "orbx_stereo_matches", "orbx_match_candidates", "orbx_popc_peak",
 ]
 
 
@@ -108,6 +108,7 @@ def lib():
         L.orbx_search_by_projection.argtypes = [vp, i32, vp, vp, i32, vp, vp, vp, i32, vp, vp, f32, i32, vp]
         L.orbx_stereo_band_match.argtypes = [vp, vp, vp, i32, vp, vp, i32, vp, i32, i32, f32, f32, vp, vp]
         L.orbx_popc_peak.argtypes = [i32, vp, vp]
+        L.orbx_match_candidates.argtypes = [vp, vp, i32, vp, i32, vp, vp, vp, vp]
         L.orbx_stereo_matches.argtypes = [vp, vp, vp, i32, i32, i32, i32, f32, f32, vp, vp, vp, i32, vp]
         _lib = L
     return _lib
@@ -324,6 +325,14 @@ class ORBmatcher:
         _check(lib().orbx_stereo_band_match(self._h, _p(kl), _p(dl), len(kl), _p(kr), _p(dr), len(kr), _p(sf), len(sf),
                                             int(nrows), float(minD), float(maxD), _p(bi), _p(bd)))
         return bi, bd
+
+    def MatchCandidates(self, q, t, offsets, indices):
+        """best / second best of every query over its explicit candidate list (SearchByBoW-style inner loop)."""
+        q = np.ascontiguousarray(q, np.uint8).reshape(-1, 32); t = np.ascontiguousarray(t, np.uint8).reshape(-1, 32)
+        off = np.ascontiguousarray(offsets, np.int32); ind = np.ascontiguousarray(indices, np.int32)
+        idx = np.full((len(q), 2), -1, np.int32); dist = np.full((len(q), 2), -1, np.int32)
+        _check(lib().orbx_match_candidates(self._h, _p(q), len(q), _p(t), len(t), _p(off), _p(ind), _p(idx), _p(dist)))
+        return idx, dist
 
     def ComputeStereoMatches(self, ex_left, ex_right, mb, mbf, slot_l=0, slot_r=0, frame_l=0, frame_r=0):
         """Frame::ComputeStereoMatches on the two extractors' last results -> (mvuRight, mvDepth, SAD distance)."""

@@ -84,6 +84,7 @@ def lib():
                                                vp, f32, i32]
         L.orc_search_by_projection.restype = i32
         L.orc_stereo_band_match.argtypes = [vp, vp, i32, vp, vp, i32, vp, i32, f32, f32, vp, vp]
+        L.orc_match_candidates.argtypes = [vp, i32, vp, vp, vp, vp, vp]
         L.orc_compute_stereo_matches.argtypes = [vp, vp, vp, vp, i32, vp, vp, i32, f32, f32, vp, vp, vp]
         _lib = L
     return _lib
@@ -263,3 +264,11 @@ def compute_stereo_matches(ex_left, ex_right, kl, dl, kr, dr, mb, mbf):
     lib().orc_compute_stereo_matches(ex_left._h, ex_right._h, _p(kl), _p(dl), len(kl), _p(kr), _p(dr), len(kr),
                                      float(mb), float(mbf), _p(ur), _p(dp), _p(sd))
     return ur, dp, sd
+
+
+def match_candidates(q, t, offsets, indices):
+    q = _u8(q); t = _u8(t)
+    off = np.ascontiguousarray(offsets, np.int32); ind = np.ascontiguousarray(indices, np.int32)
+    idx = np.empty((len(q), 2), np.int32); dist = np.empty((len(q), 2), np.int32)
+    lib().orc_match_candidates(_p(q), len(q), _p(t), _p(off), _p(ind), _p(idx), _p(dist))
+    return idx, dist

@@ -1080,3 +1080,20 @@ void orc_compute_stereo_matches(const OrcExtractor* left, const OrcExtractor* ri
     }
     free(bi); free(bd); free(vDistIdx);
 }
+
+/* best / second-best over an explicit candidate list, e.g. ORBmatcher.cc:320-340 (SearchByBoW inner loop) */
+void orc_match_candidates(const uint8_t* q, int nq, const uint8_t* t, const int32_t* offsets, const int32_t* indices,
+                          int32_t* out_idx, int32_t* out_dist)
+{
+    for (int i = 0; i < nq; i++) {
+        int b0 = INT_MAX, b1 = INT_MAX, i0 = -1, i1 = -1;
+        for (int k = offsets[i]; k < offsets[i + 1]; k++) {
+            const int j = indices[k];
+            const int d = orc_hamming256(q + (size_t)i * 32, t + (size_t)j * 32);
+            if (d < b0) { b1 = b0; i1 = i0; b0 = d; i0 = j; }
+            else if (d < b1) { b1 = d; i1 = j; }
+        }
+        out_idx[i * 2] = i0; out_idx[i * 2 + 1] = i1;
+        out_dist[i * 2] = i0 >= 0 ? b0 : -1; out_dist[i * 2 + 1] = i1 >= 0 ? b1 : -1;
+    }
+}

@@ -106,6 +106,13 @@ void  orc_stereo_band_match(const OrcKeyPoint* kl, const uint8_t* dl, int nl,
                             const float* scale_factors, int nrows, float minD, float maxD,
                             int32_t* best_idx, int32_t* best_dist);
 
+/* Generic candidate matching used by the host-side searches (SearchByBoW ORBmatcher.cc:269-471/819-959,
+ * SearchForTriangulation :961-1394, Fuse :1395-1742, SearchBySim3 :1744-1968): for query i the candidates are
+ * indices[offsets[i] .. offsets[i+1]) into the train descriptors, visited in list order; strict '<' updates give the
+ * top-2 by (distance, list position).  out_idx/out_dist are nq x 2 (train index / distance, -1 when missing). */
+void  orc_match_candidates(const uint8_t* q, int nq, const uint8_t* t, const int32_t* offsets, const int32_t* indices,
+                           int32_t* out_idx, int32_t* out_dist);
+
 /* Frame::ComputeStereoMatches in full (Frame.cc:785-962): descriptor search, 11x11 SAD sliding-window refinement on
  * the two extractors' pyramids (their last orc_extract), parabola sub-pixel fit, median-based outlier cut.
  * uright/depth have nl entries (-1 = no match); sad_dist (optional) receives the SAD best distance or -1. */

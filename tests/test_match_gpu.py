@@ -246,3 +246,20 @@ def test_compute_stereo_matches_full(shape, nf, disp):
     assert ok.sum() > 0.4 * len(rur)
     assert abs(np.median(kl["x"][ok] - rur[ok]) - disp) < 0.5
     exl.close(); exr.close(); m.close()
+
+
+def test_match_candidates_generic():
+    """orbx_match_candidates: the primitive behind SearchByBoW / SearchForTriangulation / Fuse (explicit candidate lists)."""
+    rng = np.random.default_rng(3)
+    q = synth.random_descriptors(700, 31, 0.2); t = synth.random_descriptors(3000, 32, 0.4)
+    counts = rng.integers(0, 90, 700); counts[5] = 0; counts[6] = 1; counts[7] = 2500
+    off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    ind = rng.integers(0, 3000, off[-1]).astype(np.int32)
+    t[ind[off[10]]] = q[10]; t[ind[off[10] + 3]] = q[10]          # exact ties: first in list order wins
+    m = orbx.ORBmatcher(0.9, True, max_keypoints=1024)
+    gi, gd = m.MatchCandidates(q, t, off, ind)
+    ri, rd = O.match_candidates(q, t, off, ind)
+    np.testing.assert_array_equal(gi, ri)
+    np.testing.assert_array_equal(gd, rd)
+    assert list(gi[5]) == [-1, -1] and gi[6, 1] == -1
+    m.close()
