@@ -368,14 +368,14 @@ def main():
     traffic, limiter = None, None
     try:
         ncu = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_summary.json")))
-        rec = ncu["k_fast_rows"][0] if dom == 1 else None
+        rec = ncu["k_fast_seg"][0] if dom == 1 else None
         if rec:
             traffic = rec["dram_traffic_bytes"] * B / 512.0
             limiter = ("instruction issue, not HBM: ncu issue-active %.0f%%, DRAM %.1f%% of peak, %.2f warp-instructions per pixel"
                        % (rec["issue_active_pct"], rec["dram_pct_of_peak"], rec["warp_instructions"] / (512.0 * P)))
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "k_fast_rows" if dom == 1 else "k_pyr_fast x8", "achieved": achieved, "peak": hbm_peak,
+    roofline = {"bound": "hbm", "kernel": "k_fast_seg" if dom == 1 else "k_pyr_fast x8", "achieved": achieved, "peak": hbm_peak,
                 "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": stage_bytes[dom] / chunks, "launches_per_step": chunks,
                 "limiter": limiter, "stages": stages}

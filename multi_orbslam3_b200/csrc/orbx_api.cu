@@ -149,19 +149,29 @@ static int configure_geometry(orbx_extractor* h, int width, int height)
             L.hX = (float)(L.maxBX - ORBX_BORDER) / L.nIni;                         // :543
         } else { L.nIni = 1; L.hX = 1.f; }
         L.row_base = rows;
-        // capacity of one cell row: in-cell NMS leaves at most ceil(w/2)*ceil(h/2) corners per cell
-        long long rowcap = 0;
-        for (int j = 0; j < L.nCols; j++) {
-            int c0 = j * L.wCell, c1 = c0 + L.wCell; const int ws = L.maxBX - ORBX_BORDER - 6;
-            if (c1 > ws) c1 = ws;
-            if (c1 > c0) rowcap += (long long)((c1 - c0 + 1) / 2) * ((L.hCell + 1) / 2);
+        L.segCells = orbx_fast_plan(L.w, L.nCols, L.wCell);
+        L.nSeg = L.nCols > 0 ? (L.nCols + L.segCells - 1) / L.segCells : 0;
+        if (L.nRows * L.nSeg > ORBX_MAX_UNITS) {
+            orbx_set_error("%s%s", "image too large for the FAST segment tables", ""); g.width = 0; return ORBX_E_INVALID;
+        }
+        // capacity of one segment: in-cell NMS leaves at most ceil(w/2)*ceil(h/2) corners per cell
+        long long rowcap = 0, rowsum = 0;
+        for (int sg = 0; sg < L.nSeg; sg++) {
+            long long segcap = 0;
+            for (int j = sg * L.segCells; j < L.nCols && j < (sg + 1) * L.segCells; j++) {
+                int c0 = j * L.wCell, c1 = c0 + L.wCell; const int ws = L.maxBX - ORBX_BORDER - 6;
+                if (c1 > ws) c1 = ws;
+                if (c1 > c0) segcap += (long long)((c1 - c0 + 1) / 2) * ((L.hCell + 1) / 2);
+            }
+            rowsum += segcap;
+            if (segcap > rowcap) rowcap = segcap;
         }
         if (rowcap > maxcand) rowcap = maxcand;
         L.row_cap = (int)rowcap;
-        long long lc = rowcap * L.nRows; if (lc > maxcand) lc = maxcand;
+        long long lc = rowsum * L.nRows; if (lc > maxcand) lc = maxcand;
         L.cand_cap = (int)lc;
-        for (int r = 0; r < L.nRows; r++) { row_off.push_back((int)row_elems); row_elems += L.row_cap; }
-        rows += L.nRows;
+        for (int r = 0; r < L.nRows * L.nSeg; r++) { row_off.push_back((int)row_elems); row_elems += L.row_cap; }
+        rows += L.nRows * L.nSeg;
         L.kp_cap = (L.quota > 4 * L.nIni ? L.quota : 4 * L.nIni) + 4;
         L.kp_base = kpbase; kpbase += L.kp_cap;
         L.xtab_off = tab; tab += L.w;
@@ -628,14 +638,15 @@ extern "C" int orbx_candidates_to_host(orbx_extractor* h, int slot, int level, f
     CK(cudaSetDevice(h->p.device));
     CK(cudaStreamSynchronize(h->stream));
     const OrbxGeom& g = h->geom; const OrbxLevel& L = g.lv[level];
-    std::vector<int> cnt(L.nRows > 0 ? L.nRows : 1), off(L.nRows > 0 ? L.nRows : 1);
+    const int nUnits = L.nRows * L.nSeg;
+    std::vector<int> cnt(nUnits > 0 ? nUnits : 1), off(nUnits > 0 ? nUnits : 1);
     int total = 0;
-    if (L.nRows > 0) {
-        CK(cudaMemcpy(cnt.data(), h->buf.row_count + (long long)slot * g.total_rows + L.row_base, sizeof(int) * L.nRows, cudaMemcpyDeviceToHost));
-        CK(cudaMemcpy(off.data(), h->buf.row_off + L.row_base, sizeof(int) * L.nRows, cudaMemcpyDeviceToHost));
+    if (nUnits > 0) {
+        CK(cudaMemcpy(cnt.data(), h->buf.row_count + (long long)slot * g.total_rows + L.row_base, sizeof(int) * nUnits, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(off.data(), h->buf.row_off + L.row_base, sizeof(int) * nUnits, cudaMemcpyDeviceToHost));
     }
     std::vector<uint32_t> tmp;
-    for (int r = 0; r < L.nRows; r++) {
+    for (int r = 0; r < nUnits; r++) {
         tmp.resize(cnt[r] > 0 ? cnt[r] : 1);
         if (cnt[r] > 0)
             CK(cudaMemcpy(tmp.data(), h->buf.row_cand + (long long)slot * h->buf.row_cand_stride + off[r], sizeof(uint32_t) * cnt[r], cudaMemcpyDeviceToHost));

@@ -3,8 +3,10 @@
 // Replaces the cell loop of ORBextractor::ComputeKeyPointsOctTree (R/src/ORBextractor.cc:787-854) and the
 // cv::FAST(cell, th, nonmax=true) calls inside it (:808, :827).
 //
-// One CTA owns one row of cells of one level of one frame and never writes a score map to global memory:
-//   1. rows [iniY, maxY) are staged in shared memory with 16-byte loads (x index = absolute column);
+// One CTA owns one SEGMENT (a run of whole cells, at most ORBX_FAST_TP staged columns) of one row of cells of one
+// level of one frame and never writes a score map to global memory.  Segments bound the shared-memory footprint
+// independently of the image width (4 CTAs per SM) and every phase runs once over the whole tile:
+//   1. rows [iniY, maxY) x columns [xa0, xa1) are staged in shared memory by bulk copies (x index = column - xa0);
 //   2. SWAR screen, 4 pixels per thread-step: |v - ring| per byte (VABSDIFF4.U8) on the 4 compass/diagonal
 //      opposite pairs; a 9-arc contains one pixel of every opposite pair, so a corner at threshold t needs
 //      max(|d_k|, |d_k+8|) > t for every pair.  Survivors (a few % of pixels) go to a shared-memory queue;
@@ -21,14 +23,13 @@
 
 namespace {
 
-constexpr int NT = 512;
-constexpr int MAX_CELLS = 128;
+constexpr int NT = 256;
 constexpr int NW = NT / 32;
-constexpr int QGCAP = 4096;          // 4-pixel groups with a screen survivor per band: 16 rows x <= 256 groups, cannot overflow
-constexpr int QCAP = 4096;           // screen survivors (pixels) per band (overflow is scored inline, never dropped)
-constexpr int Q2CAP = 2048;          // signed-test survivors per band (same overflow rule)
-constexpr int CLCAP = 2048;          // corners (m > minTh) of the whole cell row; overflow -> map scan (still exact)
-constexpr int BAND_ROWS = NW;        // one tile row per warp and band
+constexpr int TP = ORBX_FAST_TP;     // shared-memory pitch of a segment tile (compile time: ring offsets become immediates)
+constexpr int MAX_SEG_CELLS = 16;    // cells per segment (TP / 35 rounded up)
+constexpr int CLCAP = 1024;          // corners (m > minTh) of the whole tile; overflow -> map scan (still exact)
+constexpr int QMIN = 1024;           // smallest pixel queue the launch is sized for (overflow is scored inline, never dropped)
+constexpr int SMEM_TARGET = 54 * 1024;   // 4 CTAs per SM
 
 // ---- bulk asynchronous copy (TMA engine, 1-D form: SASS UBLKCP) + mbarrier ----
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count)
@@ -111,14 +112,35 @@ __device__ __forceinline__ bool pair_test(const unsigned (&pk)[16], int minTh)
 }
 
 // exact per-pixel path used when a queue overflows: pair test, then the arc measure
-__device__ __forceinline__ void score_pixel(const uint8_t* T, uint8_t* M, int tp, const int (&roff)[16], int x, int yt, int minTh,
+__device__ __forceinline__ void score_pixel(const uint8_t* T, uint8_t* M, const int (&roff)[16], int x, int yt, int minTh,
                                             int* cl_count)
 {
     unsigned pk[16];
-    load_ring(T + yt * tp + x, roff, pk);
+    load_ring(T + yt * TP + x, roff, pk);
     if (!pair_test(pk, minTh)) return;
     const int m = arc_measure(pk);
-    if (m > minTh) { M[(yt - 3) * tp + x] = (uint8_t)m; atoms_add(cl_count, CLCAP + 1); }   // forces the exact map-scan NMS path
+    if (m > minTh) { M[(yt - 3) * TP + x] = (uint8_t)m; atoms_add(cl_count, CLCAP + 1); }   // forces the exact map-scan NMS path
+}
+
+// in-cell non-max suppression of one corner (tile column x, scored row r): neighbours outside the cell count as 0
+// (they belong to another FAST call in the reference)
+__device__ __forceinline__ void nms_pixel(const uint8_t* M, unsigned* Bmin, unsigned* Bini, int x, int r, int X0, int X1, int hs,
+                                          int wCell, unsigned wrcp, int iniTh)
+{
+    const uint8_t* qm = M + r * TP + x;
+    const int sc = qm[0];
+    const int j = (int)(((unsigned)(x - X0) * wrcp) >> 16);
+    const int c0 = X0 + j * wCell, c1 = min(c0 + wCell, X1);     // cell interior [c0, c1)
+    const bool hl = x - 1 >= c0, hr = x + 1 < c1, vu = r > 0, vd = r + 1 < hs;
+    const int l0 = hl ? qm[-1] : 0, r0 = hr ? qm[1] : 0;
+    const int u0 = vu ? qm[-TP] : 0, ul = (vu && hl) ? qm[-TP - 1] : 0, ur = (vu && hr) ? qm[-TP + 1] : 0;
+    const int d0 = vd ? qm[TP] : 0, dl = (vd && hl) ? qm[TP - 1] : 0, dr = (vd && hr) ? qm[TP + 1] : 0;
+    const int mx = max(max(max(l0, r0), max(u0, ul)), max(max(ur, d0), max(dl, dr)));
+    if (sc > mx) {
+        constexpr int bw = TP / 32;
+        atomicOr(&Bmin[r * bw + (x >> 5)], 1u << (x & 31));
+        if (sc > iniTh) atomicOr(&Bini[r * bw + (x >> 5)], 1u << (x & 31));
+    }
 }
 
 // per-byte flag (bit 7) of "a > t" for t <= 126: bytes < 128 carry into bit 7 when a + 127 - t >= 128
@@ -140,181 +162,182 @@ __device__ __forceinline__ int popc_range(const unsigned* row, int c0, int c1)
 
 struct FastSmem {
     int qg_count, q_count, q2_count, cl_count;
-    int cell_off[MAX_CELLS + 1];
-    unsigned char use_ini[MAX_CELLS];
+    int cell_off[MAX_SEG_CELLS + 1];
+    unsigned char use_ini[MAX_SEG_CELLS];
 };
 
-__global__ void __launch_bounds__(NT) k_fast_rows(OrbxGeom g, OrbxBuffers b, const uint8_t* level0, int pitch0,
-                                                  long long stride0)
+// shared-memory bytes of one segment tile, without the pixel queue
+__host__ __device__ inline int tile_bytes(int nrow, int hs, int ng, int ncell)
+{
+    return nrow * TP + hs * TP + hs * ng * 4 + CLCAP * 4 + 2 * hs * (TP / 32) * 4 + ((2 * ncell * hs * 2 + 15) & ~15);
+}
+
+__global__ void __launch_bounds__(NT, 4) k_fast_seg(OrbxGeom g, OrbxBuffers b, const uint8_t* level0, int pitch0,
+                                                    long long stride0, int smem_total)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ FastSmem sh;
+    __shared__ __align__(8) unsigned long long s_bar;
 
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int f = blockIdx.y;
     int l = 0;
     while (l + 1 < g.nlevels && (int)blockIdx.x >= g.lv[l + 1].row_base) l++;
     const OrbxLevel L = g.lv[l];
-    const int i = blockIdx.x - L.row_base;
+    const int u = blockIdx.x - L.row_base;
     int* row_count = b.row_count + (long long)f * g.total_rows + blockIdx.x;
-    if (i >= L.nRows) return;
+    if (u >= L.nRows * L.nSeg) return;
+    const int i = u / L.nSeg, sgm = u - i * L.nSeg;
     const int iniY = ORBX_BORDER + i * L.hCell;
     int maxY = iniY + L.hCell + 6;
-    if (iniY >= L.maxBY - 3) { if (tid == 0) *row_count = 0; return; }
     if (maxY > L.maxBY) maxY = L.maxBY;
     const int nrow = maxY - iniY;                      // staged rows
     const int hs = nrow - 6;                           // scored rows: tile rows 3 .. nrow-4
-    const int xs0 = ORBX_EDGE, xs1 = L.w - ORBX_EDGE;  // scored columns [19, w-19)
-    if (hs <= 0 || xs1 <= xs0) { if (tid == 0) *row_count = 0; return; }
-    const int tp = (L.w + 15) & ~15;                   // smem pitch; x index = absolute column
-    const int bw = (L.w + 31) >> 5;                    // bitmap words per row
-    const int hmax = L.hCell;                          // scored rows of a full cell row of this level
+    const int j0 = sgm * L.segCells, ncell = min(L.segCells, L.nCols - j0);
+    const int xs1 = L.w - ORBX_EDGE;
+    const int cs0 = ORBX_EDGE + j0 * L.wCell, cs1 = min(cs0 + ncell * L.wCell, xs1);   // scored columns of the segment
+    if (iniY >= L.maxBY - 3 || hs <= 0 || cs1 <= cs0) { if (tid == 0) *row_count = 0; return; }
+    const int xa0 = (cs0 - 3) & ~15, xa1 = (cs1 + 3 + 15) & ~15;      // staged columns [xa0, xa1), xa1 <= w
+    const int sw = xa1 - xa0;                                          // <= TP (orbx_fast_plan)
+    const int X0 = cs0 - xa0, X1 = cs1 - xa0;                          // scored columns in tile coordinates
+    const int g0 = X0 >> 2, g1 = (X1 - 1) >> 2, ng = g1 - g0 + 1;      // 4-pixel groups holding scored columns
+    constexpr int bw = TP / 32;                                        // bitmap words per row
+    const unsigned wrcp = (65536u + L.wCell - 1) / L.wCell;            // (n * wrcp) >> 16 == n / wCell for n < TP
 
-    // ---- smem carve-up (sizes use the level's maxima so that every cell row has the same layout) ----
-    uint8_t* T = smem;                                              // [hmax+6][tp] pixels
-    uint8_t* M = T + (size_t)(hmax + 6) * tp;                       // [hmax][tp]   arc measure (0 = not a corner at minTh)
-    unsigned* Q = reinterpret_cast<unsigned*>(M + (size_t)hmax * tp);   // [QCAP] candidate queue: x | tile row << 16
-    unsigned* QG = Q + QCAP;                                        // [QGCAP] groups with survivors: gx | tile row << 12 | mask << 20
-    unsigned* Q2 = QG + QGCAP;                                      // [Q2CAP] survivors of the signed pair test
-    unsigned* CL = Q2 + Q2CAP;                                      // [CLCAP] corners: x | scored row << 16
-    unsigned* Bmin = CL + CLCAP;                                    // [hmax][bw] survivors at minTh
-    unsigned* Bini = Bmin + hmax * bw;                              // [hmax][bw] survivors at iniTh
-    unsigned short* cnt_min = reinterpret_cast<unsigned short*>(Bini + hmax * bw);   // [nCols][hmax]
-    unsigned short* cnt_ini = cnt_min + L.nCols * hmax;             // [nCols][hmax]; later: exclusive row prefix of the chosen counts
+    // ---- smem carve-up (per CTA: tiles of different levels have different shapes) ----
+    uint8_t* T = smem;                                              // [nrow][TP] pixels
+    uint8_t* M = T + nrow * TP;                                     // [hs][TP]   arc measure (0 = not a corner at minTh)
+    unsigned* QG = reinterpret_cast<unsigned*>(M + hs * TP);        // [hs*ng] groups with survivors: gx | tile row << 12 | mask << 20
+    unsigned* Q2 = QG;                                              // survivors of the signed pair test (QG is dead by then)
+    const int q2cap = hs * ng;
+    unsigned* CL = QG + hs * ng;                                    // [CLCAP] corners: x | scored row << 16
+    unsigned* Bmin = CL + CLCAP;                                    // [hs][bw] survivors at minTh
+    unsigned* Bini = Bmin + hs * bw;                                // [hs][bw] survivors at iniTh
+    unsigned short* cnt_min = reinterpret_cast<unsigned short*>(Bini + hs * bw);   // [ncell][hs]
+    unsigned short* cnt_ini = cnt_min + ncell * hs;                 // [ncell][hs]; later: exclusive row prefix of the chosen counts
+    unsigned* Q = reinterpret_cast<unsigned*>(smem + tile_bytes(nrow, hs, ng, ncell));   // [qcap] candidate queue: x | tile row << 16
+    const int qcap = (smem_total - tile_bytes(nrow, hs, ng, ncell)) >> 2;
 
     const uint8_t* img; int pitch;
     if (l == 0) { img = level0 + (long long)f * stride0; pitch = pitch0; }
     else { img = b.pyr[l] + (long long)f * L.frame_stride; pitch = L.pitch; }
 
     // ---- 1. stage rows ----
-    const bool vec = ((pitch & 15) == 0) && (pitch >= tp) && ((reinterpret_cast<uintptr_t>(img) & 15) == 0);
-    const int lane = tid & 31, warp = tid >> 5;
-    __shared__ __align__(8) unsigned long long s_bar;
+    const bool vec = ((pitch & 15) == 0) && (pitch >= xa1) && ((reinterpret_cast<uintptr_t>(img) & 15) == 0);
     if (vec) {
         // one bulk copy per row, issued by the lanes of warp 0; completion is counted in bytes on an mbarrier, and the
         // zero-fill of the score map / bitmaps below overlaps the copies
         if (tid == 0) mbar_init(&s_bar, 1);
         __syncthreads();
         if (warp == 0) {
-            if (lane == 0) mbar_expect_tx(&s_bar, (unsigned)(nrow * tp));
+            if (lane == 0) mbar_expect_tx(&s_bar, (unsigned)(nrow * sw));
             __syncwarp();
-            for (int r = lane; r < nrow; r += 32) bulk_g2s(T + r * tp, img + (long long)(iniY + r) * pitch, (unsigned)tp, &s_bar);
+            for (int r = lane; r < nrow; r += 32) bulk_g2s(T + r * TP, img + (long long)(iniY + r) * pitch + xa0, (unsigned)sw, &s_bar);
         }
     } else {
         for (int r = warp; r < nrow; r += NW)
-            for (int c = lane; c < tp; c += 32) T[r * tp + c] = c < L.w ? __ldg(img + (long long)(iniY + r) * pitch + c) : 0;
+            for (int c = lane; c < sw; c += 32) T[r * TP + c] = xa0 + c < L.w ? __ldg(img + (long long)(iniY + r) * pitch + xa0 + c) : 0;
     }
     {
         uint4* z = reinterpret_cast<uint4*>(M);
-        const int nz = (hs * tp) >> 4;
+        const int nz = (hs * TP) >> 4;
         for (int k = tid; k < nz; k += NT) z[k] = make_uint4(0, 0, 0, 0);
-        for (int k = tid; k < 2 * hmax * bw; k += NT) Bmin[k] = 0;
-        if (tid == 0) sh.cl_count = 0;
+        for (int k = tid; k < 2 * hs * bw; k += NT) Bmin[k] = 0;
+        if (tid == 0) { sh.cl_count = 0; sh.qg_count = 0; sh.q_count = 0; sh.q2_count = 0; }
     }
     const int minTh = g.min_th, iniTh = g.ini_th;
     int roff[16];
 #pragma unroll
-    for (int k = 0; k < 16; k++) roff[k] = c_ring[k][1] * tp + c_ring[k][0];
+    for (int k = 0; k < 16; k++) roff[k] = c_ring[k][1] * TP + c_ring[k][0];
     if (vec) mbar_wait(&s_bar, 0);
     __syncthreads();
 
-    // ---- 2 + 3. banded screen and drain ----
-    const int gx0 = xs0 >> 2, gx1 = (xs1 - 1) >> 2;    // 4-pixel groups that contain scored columns
+    // ---- 2. screen: one (tile row, 32-group step) item per warp ----
     const unsigned c127 = (unsigned)(127 - (minTh < 126 ? minTh : 126)) * 0x01010101u;
     const bool screen_ok = minTh <= 126;
-    for (int y0 = 3; y0 < nrow - 3; y0 += BAND_ROWS) {
-        if (tid == 0) { sh.qg_count = 0; sh.q_count = 0; sh.q2_count = 0; }
-        __syncthreads();
-        // -- screen: one tile row per warp, one 4-pixel group per lane-step --
-        const int yt = y0 + warp;
-        if (yt < nrow - 3) {
-            const unsigned* rc = reinterpret_cast<const unsigned*>(T + yt * tp);
-            const unsigned* rp3 = reinterpret_cast<const unsigned*>(T + (yt + 3) * tp);
-            const unsigned* rm3 = reinterpret_cast<const unsigned*>(T + (yt - 3) * tp);
-            const unsigned* rp2 = reinterpret_cast<const unsigned*>(T + (yt + 2) * tp);
-            const unsigned* rm2 = reinterpret_cast<const unsigned*>(T + (yt - 2) * tp);
-            for (int g0 = gx0; g0 <= gx1; g0 += 32) {      // warp-uniform trip count (ballots below)
-                const int gx = g0 + lane;
-                unsigned cand = 0;
-                if (gx <= gx1) {
-                    cand = 0x80808080u;
-                    if (screen_ok) {
-                        // |d_k| | |d_k+8| >= max(|d_k|, |d_k+8|): one threshold test per pair, still only a necessary
-                        // condition (exact when t = 2^n - 1, e.g. the reference's minThFAST = 7)
-                        const unsigned V = rc[gx];
-                        // pair (0, 8): (0,+3) / (0,-3);  pair (4, 12): (+3,0) / (-3,0)
-                        cand &= gt_flags(__vabsdiffu4(V, rp3[gx]) | __vabsdiffu4(V, rm3[gx]), c127);
-                        cand &= gt_flags(__vabsdiffu4(V, __funnelshift_r(V, rc[gx + 1], 24)) |
-                                         __vabsdiffu4(V, __funnelshift_r(rc[gx - 1], V, 8)), c127);
-                        if (cand) {
-                            // pair (2, 10): (+2,+2) / (-2,-2);  pair (6, 14): (+2,-2) / (-2,+2)
-                            const unsigned p2c = rp2[gx], m2c = rm2[gx];
-                            const unsigned a2 = __funnelshift_r(p2c, rp2[gx + 1], 16), a10 = __funnelshift_r(rm2[gx - 1], m2c, 16);
-                            const unsigned a6 = __funnelshift_r(m2c, rm2[gx + 1], 16), a14 = __funnelshift_r(rp2[gx - 1], p2c, 16);
-                            cand &= gt_flags(__vabsdiffu4(V, a2) | __vabsdiffu4(V, a10), c127);
-                            cand &= gt_flags(__vabsdiffu4(V, a6) | __vabsdiffu4(V, a14), c127);
-                        }
-                    }
-                    // keep scored columns only (only the first and last group straddle the border)
-                    if (gx == gx0 || gx == gx1) {
-                        const int xb = gx << 2;
-#pragma unroll
-                        for (int q = 0; q < 4; q++)
-                            if (xb + q < xs0 || xb + q >= xs1) cand &= ~(0x80u << (8 * q));
-                    }
-                }
-                // one queue entry per 4-pixel group that still has a candidate: one ballot, one atomic per warp-step
-                const unsigned bal = __ballot_sync(0xffffffffu, cand != 0);
-                if (bal) {
-                    int base = 0;
-                    if (lane == 0) base = atoms_add(&sh.qg_count, __popc(bal));
-                    base = __shfl_sync(0xffffffffu, base, 0);
+    {
+        const int nsteps = (ng + 31) >> 5;
+        const int items = hs * nsteps;
+        for (int it = warp; it < items; it += NW) {            // warp-uniform trip count (ballots below)
+            const int ry = it / nsteps, yt = 3 + ry;
+            const int gx = g0 + ((it - ry * nsteps) << 5) + lane;
+            const unsigned* rc = reinterpret_cast<const unsigned*>(T + yt * TP) + gx;
+            constexpr int W = TP / 4;
+            unsigned cand = 0;
+            if (gx <= g1) {
+                cand = 0x80808080u;
+                if (screen_ok) {
+                    // |d_k| | |d_k+8| >= max(|d_k|, |d_k+8|): one threshold test per pair, still only a necessary
+                    // condition (exact when t = 2^n - 1, e.g. the reference's minThFAST = 7)
+                    const unsigned V = rc[0];
+                    // pair (0, 8): (0,+3) / (0,-3);  pair (4, 12): (+3,0) / (-3,0)
+                    cand &= gt_flags(__vabsdiffu4(V, rc[3 * W]) | __vabsdiffu4(V, rc[-3 * W]), c127);
+                    cand &= gt_flags(__vabsdiffu4(V, __funnelshift_r(V, rc[1], 24)) |
+                                     __vabsdiffu4(V, __funnelshift_r(rc[-1], V, 8)), c127);
                     if (cand) {
-                        const unsigned m4 = ((cand >> 7) & 1u) | ((cand >> 14) & 2u) | ((cand >> 21) & 4u) | ((cand >> 28) & 8u);
-                        const int o = base + __popc(bal & ((1u << lane) - 1));
-                        if (o < QGCAP) QG[o] = (unsigned)gx | ((unsigned)yt << 12) | (m4 << 20);
-                        else atomicOr(b.err, ORBX_DEVERR_CAND_OVERFLOW);      // unreachable for widths <= 4128
+                        // pair (2, 10): (+2,+2) / (-2,-2);  pair (6, 14): (+2,-2) / (-2,+2)
+                        const unsigned p2c = rc[2 * W], m2c = rc[-2 * W];
+                        const unsigned a2 = __funnelshift_r(p2c, rc[2 * W + 1], 16), a10 = __funnelshift_r(rc[-2 * W - 1], m2c, 16);
+                        const unsigned a6 = __funnelshift_r(m2c, rc[-2 * W + 1], 16), a14 = __funnelshift_r(rc[2 * W - 1], p2c, 16);
+                        cand &= gt_flags(__vabsdiffu4(V, a2) | __vabsdiffu4(V, a10), c127);
+                        cand &= gt_flags(__vabsdiffu4(V, a6) | __vabsdiffu4(V, a14), c127);
                     }
+                }
+                // keep scored columns only (only the first and last group straddle the segment's edges)
+                if (gx == g0) cand &= 0x80808080u << (8 * (X0 & 3));
+                if (gx == g1) cand &= 0x80808080u >> (8 * (3 - ((X1 - 1) & 3)));
+            }
+            // one queue entry per 4-pixel group that still has a candidate: one ballot, one atomic per warp-step
+            const unsigned bal = __ballot_sync(0xffffffffu, cand != 0);
+            if (bal) {
+                int base = 0;
+                if (lane == 0) base = atoms_add(&sh.qg_count, __popc(bal));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (cand) {
+                    const unsigned m4 = ((cand >> 7) & 1u) | ((cand >> 14) & 2u) | ((cand >> 21) & 4u) | ((cand >> 28) & 8u);
+                    QG[base + __popc(bal & ((1u << lane) - 1))] = (unsigned)gx | ((unsigned)yt << 12) | (m4 << 20);   // <= hs*ng entries by construction
                 }
             }
         }
-        __syncthreads();
-        // -- expand the group entries into pixel entries (dense queue for phase A) --
-        {
-            const int ng = min(sh.qg_count, QGCAP);
-            for (int g0 = warp * 32; g0 < ng; g0 += NT) {
-                const int gi = g0 + lane;
-                const unsigned ge = gi < ng ? QG[gi] : 0u;
-                const unsigned m4 = ge >> 20;
-                const int n = __popc(m4);
-                int inc = n;
+    }
+    __syncthreads();
+    // ---- expand the group entries into pixel entries (dense queue for phase A) ----
+    {
+        const int ngq = sh.qg_count;
+        for (int gb = warp * 32; gb < ngq; gb += NT) {
+            const int gi = gb + lane;
+            const unsigned ge = gi < ngq ? QG[gi] : 0u;
+            const unsigned m4 = ge >> 20;
+            const int n = __popc(m4);
+            int inc = n;
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-                const int total = __shfl_sync(0xffffffffu, inc, 31);
-                int base = 0;
-                if (lane == 0 && total) base = atoms_add(&sh.q_count, total);
-                base = __shfl_sync(0xffffffffu, base, 0);
-                int o = base + inc - n;
-                const unsigned e = ((ge & 0xFFFu) << 2) | (((ge >> 12) & 0xFFu) << 16);
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+            const int total = __shfl_sync(0xffffffffu, inc, 31);
+            int base = 0;
+            if (lane == 0 && total) base = atoms_add(&sh.q_count, total);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            int o = base + inc - n;
+            const unsigned e = ((ge & 0xFFFu) << 2) | (((ge >> 12) & 0xFFu) << 16);
 #pragma unroll
-                for (int q = 0; q < 4; q++)
-                    if (m4 & (1u << q)) {
-                        if (o < QCAP) Q[o] = e + q;
-                        else score_pixel(T, M, tp, roff, (e + q) & 0xFFFF, (int)((ge >> 12) & 0xFFu), minTh, &sh.cl_count);   // queue full: score inline
-                        o++;
-                    }
-            }
+            for (int q = 0; q < 4; q++)
+                if (m4 & (1u << q)) {
+                    if (o < qcap) Q[o] = e + q;
+                    else score_pixel(T, M, roff, (e + q) & 0xFFFF, (int)((ge >> 12) & 0xFFu), minTh, &sh.cl_count);   // queue full: score inline
+                    o++;
+                }
         }
-        __syncthreads();
-        // -- phase A: signed pair test, dense and branch-free; survivors are compacted into Q2 --
-        const int nq = min(sh.q_count, QCAP);
+    }
+    __syncthreads();
+    // ---- 3a. signed pair test, dense and branch-free; survivors are compacted into Q2 ----
+    {
+        const int nq = min(sh.q_count, qcap);
         for (int e0 = warp * 32; e0 < nq; e0 += NT) {
             const int e = e0 + lane;
             bool pass = false; unsigned ent = 0;
             if (e < nq) {
                 ent = Q[e];
                 unsigned pk[16];
-                load_ring(T + (ent >> 16) * tp + (ent & 0xFFFF), roff, pk);
+                load_ring(T + (ent >> 16) * TP + (ent & 0xFFFF), roff, pk);
                 pass = pair_test(pk, minTh);
             }
             const unsigned bal = __ballot_sync(0xffffffffu, pass);
@@ -324,99 +347,71 @@ __global__ void __launch_bounds__(NT) k_fast_rows(OrbxGeom g, OrbxBuffers b, con
                 base = __shfl_sync(0xffffffffu, base, 0);
                 if (pass) {
                     const int o = base + __popc(bal & ((1u << lane) - 1));
-                    if (o < Q2CAP) Q2[o] = ent;
-                    else score_pixel(T, M, tp, roff, ent & 0xFFFF, ent >> 16, minTh, &sh.cl_count);
+                    if (o < q2cap) Q2[o] = ent;
+                    else score_pixel(T, M, roff, ent & 0xFFFF, ent >> 16, minTh, &sh.cl_count);
                 }
             }
         }
-        __syncthreads();
-        // -- phase B: exact arc measure for the survivors --
-        const int nq2 = min(sh.q2_count, Q2CAP);
+    }
+    __syncthreads();
+    // ---- 3b. exact arc measure for the survivors ----
+    {
+        const int nq2 = min(sh.q2_count, q2cap);
         for (int e = tid; e < nq2; e += NT) {
             const unsigned ent = Q2[e];
             const int x = ent & 0xFFFF, yq = ent >> 16;
             unsigned pk[16];
-            load_ring(T + yq * tp + x, roff, pk);
+            load_ring(T + yq * TP + x, roff, pk);
             const int m = arc_measure(pk);
             if (m > minTh) {
-                M[(yq - 3) * tp + x] = (uint8_t)m;
+                M[(yq - 3) * TP + x] = (uint8_t)m;
                 const int o = atoms_add(&sh.cl_count, 1);
                 if (o < CLCAP) CL[o] = (unsigned)x | ((unsigned)(yq - 3) << 16);
             }
         }
-        __syncthreads();      // every thread has read the band's counters before thread 0 resets them
     }
+    __syncthreads();
 
     // ---- 4. in-cell non-max suppression ----
-    // Corners were listed by phase B, so the suppression runs one corner per thread instead of diverging over a
+    // Corners were listed by phase 3b, so the suppression runs one corner per thread instead of diverging over a
     // sparse map; a corner-dense tile (list overflow) falls back to scanning the map, still exact.
-    const int clcap = CLCAP;
-    if (sh.cl_count <= clcap) {
+    if (sh.cl_count <= CLCAP) {
         const int ncl = sh.cl_count;
         for (int e = tid; e < ncl; e += NT) {
             const unsigned ent = CL[e];
             const int x = ent & 0xFFFF, r = ent >> 16;
-            const uint8_t* qm = M + r * tp + x;
-            const int sc = qm[0];
-            const int j = (x - xs0) / L.wCell;
-            const int c0 = xs0 + j * L.wCell, c1 = min(c0 + L.wCell, xs1);     // cell interior [c0, c1)
-            const bool hl = x - 1 >= c0, hr = x + 1 < c1, vu = r > 0, vd = r + 1 < hs;
-            // neighbours outside the cell count as 0 (they belong to another FAST call in the reference)
-            const int l0 = hl ? qm[-1] : 0, r0 = hr ? qm[1] : 0;
-            const int u0 = vu ? qm[-tp] : 0, ul = (vu && hl) ? qm[-tp - 1] : 0, ur = (vu && hr) ? qm[-tp + 1] : 0;
-            const int d0 = vd ? qm[tp] : 0, dl = (vd && hl) ? qm[tp - 1] : 0, dr = (vd && hr) ? qm[tp + 1] : 0;
-            const int mx = max(max(max(l0, r0), max(u0, ul)), max(max(ur, d0), max(dl, dr)));
-            if (sc > mx) {
-                atomicOr(&Bmin[r * bw + (x >> 5)], 1u << (x & 31));
-                if (sc > iniTh) atomicOr(&Bini[r * bw + (x >> 5)], 1u << (x & 31));
-            }
+            nms_pixel(M, Bmin, Bini, x, r, X0, X1, hs, L.wCell, wrcp, iniTh);
         }
     } else {
-        // corner-dense tile (more corners than the list holds): suppress in place over the map, still exact
-        const int nw = tp >> 2;
         for (int r = warp; r < hs; r += NW)
-            for (int wx = lane; wx < nw; wx += 32) {
-                const unsigned word = reinterpret_cast<const unsigned*>(M + r * tp)[wx];
+            for (int wx = lane; wx < TP / 4; wx += 32) {
+                const unsigned word = reinterpret_cast<const unsigned*>(M + r * TP)[wx];
                 if (!word) continue;
-                for (int q = 0; q < 4; q++) {
-                    const int sc = (word >> (8 * q)) & 0xFF;
-                    if (!sc) continue;
-                    const int x = (wx << 2) + q;
-                    const uint8_t* qm = M + r * tp + x;
-                    const int j = (x - xs0) / L.wCell;
-                    const int c0 = xs0 + j * L.wCell, c1 = min(c0 + L.wCell, xs1);
-                    const bool hl = x - 1 >= c0, hr = x + 1 < c1, vu = r > 0, vd = r + 1 < hs;
-                    const int l0 = hl ? qm[-1] : 0, r0 = hr ? qm[1] : 0;
-                    const int u0 = vu ? qm[-tp] : 0, ul = (vu && hl) ? qm[-tp - 1] : 0, ur = (vu && hr) ? qm[-tp + 1] : 0;
-                    const int d0 = vd ? qm[tp] : 0, dl = (vd && hl) ? qm[tp - 1] : 0, dr = (vd && hr) ? qm[tp + 1] : 0;
-                    const int mx = max(max(max(l0, r0), max(u0, ul)), max(max(ur, d0), max(dl, dr)));
-                    if (sc > mx) {
-                        atomicOr(&Bmin[r * bw + (x >> 5)], 1u << (x & 31));
-                        if (sc > iniTh) atomicOr(&Bini[r * bw + (x >> 5)], 1u << (x & 31));
-                    }
-                }
+                for (int q = 0; q < 4; q++)
+                    if ((word >> (8 * q)) & 0xFF) nms_pixel(M, Bmin, Bini, (wx << 2) + q, r, X0, X1, hs, L.wCell, wrcp, iniTh);
             }
     }
     __syncthreads();
 
     // ---- 5. counts per (cell, row), threshold choice per cell, offsets ----
-    for (int k = tid; k < L.nCols * hs; k += NT) {
+    for (int k = tid; k < ncell * hs; k += NT) {
         const int j = k / hs, r = k - j * hs;
-        const int c0 = xs0 + j * L.wCell, c1 = min(c0 + L.wCell, xs1);
+        const int c0 = X0 + j * L.wCell, c1 = min(c0 + L.wCell, X1);
         int a = 0, bq = 0;
         if (c1 > c0) { a = popc_range(Bmin + r * bw, c0, c1); bq = popc_range(Bini + r * bw, c0, c1); }
-        cnt_min[j * hmax + r] = (unsigned short)a;
-        cnt_ini[j * hmax + r] = (unsigned short)bq;
+        cnt_min[j * hs + r] = (unsigned short)a;
+        cnt_ini[j * hs + r] = (unsigned short)bq;
     }
     __syncthreads();
-    for (int j = tid; j < L.nCols; j += NT) {
+    if (tid < ncell) {
+        const int j = tid;
         int ti = 0;
-        for (int r = 0; r < hs; r++) ti += cnt_ini[j * hmax + r];
+        for (int r = 0; r < hs; r++) ti += cnt_ini[j * hs + r];
         const bool ui = ti > 0;
         int run = 0;
         for (int r = 0; r < hs; r++) {
-            const int c = ui ? cnt_ini[j * hmax + r] : cnt_min[j * hmax + r];
-            cnt_ini[j * hmax + r] = (unsigned short)run;        // exclusive prefix inside the cell
+            const int c = ui ? cnt_ini[j * hs + r] : cnt_min[j * hs + r];
+            cnt_ini[j * hs + r] = (unsigned short)run;          // exclusive prefix inside the cell
             run += c;
         }
         sh.use_ini[j] = ui;
@@ -426,7 +421,7 @@ __global__ void __launch_bounds__(NT) k_fast_rows(OrbxGeom g, OrbxBuffers b, con
     if (tid == 0) {
         int run = 0;
         sh.cell_off[0] = 0;
-        for (int j = 0; j < L.nCols; j++) { run += sh.cell_off[j + 1]; sh.cell_off[j + 1] = run; }   // cell_off[j] = first slot of cell j
+        for (int j = 0; j < ncell; j++) { run += sh.cell_off[j + 1]; sh.cell_off[j + 1] = run; }   // cell_off[j] = first slot of cell j
         *row_count = min(run, L.row_cap);
         if (run > L.row_cap) atomicOr(b.err, ORBX_DEVERR_CAND_OVERFLOW);
     }
@@ -437,44 +432,64 @@ __global__ void __launch_bounds__(NT) k_fast_rows(OrbxGeom g, OrbxBuffers b, con
     const int yrel0 = iniY - ORBX_BORDER + 3;
     for (int k = tid; k < hs * bw; k += NT) {
         const int r = k / bw, wi = k - r * bw;
-        unsigned bits = Bmin[r * bw + wi];
-        const unsigned ibits = Bini[r * bw + wi];
+        unsigned bits = Bmin[k];
+        const unsigned ibits = Bini[k];
         while (bits) {
             const int bpos = __ffs(bits) - 1;
             bits &= bits - 1;
             const int x = (wi << 5) + bpos;
-            const int j = (x - xs0) / L.wCell;
+            const int j = (int)(((unsigned)(x - X0) * wrcp) >> 16);
             const bool ui = sh.use_ini[j];
             if (ui && !((ibits >> bpos) & 1u)) continue;
-            const int c0 = xs0 + j * L.wCell;
+            const int c0 = X0 + j * L.wCell;
             const int rank = x > c0 ? popc_range((ui ? Bini : Bmin) + r * bw, c0, x) : 0;
-            const int o = sh.cell_off[j] + cnt_ini[j * hmax + r] + rank;
+            const int o = sh.cell_off[j] + cnt_ini[j * hs + r] + rank;
             if (o < L.row_cap)
-                out[o] = (uint32_t)(x - ORBX_BORDER) | ((uint32_t)(yrel0 + r) << 12) | ((uint32_t)(M[r * tp + x] - 1) << 24);
+                out[o] = (uint32_t)(x + xa0 - ORBX_BORDER) | ((uint32_t)(yrel0 + r) << 12) | ((uint32_t)(M[r * TP + x] - 1) << 24);
         }
     }
 }
 
+// shared memory of the launch: the largest tile of any level plus a pixel queue, rounded up to the 4-CTA target
 size_t fast_smem_bytes(const OrbxGeom& g)
 {
-    size_t smem = 0;
+    size_t need = 0;
     for (int l = 0; l < g.nlevels; l++) {
         const OrbxLevel& L = g.lv[l];
         if (L.nCols <= 0 || L.nRows <= 0) continue;
-        const size_t tp = (L.w + 15) & ~15;
-        const size_t bw = (L.w + 31) >> 5;
-        const size_t need = (size_t)(L.hCell + 6) * tp + (size_t)L.hCell * tp + (QCAP + QGCAP + Q2CAP + CLCAP) * 4 + 2 * L.hCell * bw * 4 +
-                            2 * (size_t)L.nCols * L.hCell * 2 + 16;
-        if (need > smem) smem = need;
+        const int hs = L.hCell, ng = TP / 4;
+        const size_t n = (size_t)tile_bytes(hs + 6, hs, ng, L.segCells) + QMIN * 4;
+        if (n > need) need = n;
     }
-    return smem;
+    return need > (size_t)SMEM_TARGET ? need : (size_t)SMEM_TARGET;
 }
 
 }  // namespace
 
+// Segments of a cell row: the fewest equal runs of whole cells whose staged width (3-pixel halo, 16-byte aligned on
+// both sides) fits the tile pitch.  Returns cells per segment.
+int orbx_fast_plan(int w, int nCols, int wCell)
+{
+    if (nCols <= 0) return 0;
+    for (int ns = 1; ns <= nCols; ns++) {
+        const int sc = (nCols + ns - 1) / ns;
+        bool ok = true;
+        for (int j0 = 0; j0 < nCols && ok; j0 += sc) {
+            const int j1 = j0 + sc < nCols ? j0 + sc : nCols;
+            const int cs0 = ORBX_EDGE + j0 * wCell;
+            int cs1 = ORBX_EDGE + j1 * wCell; if (cs1 > w - ORBX_EDGE) cs1 = w - ORBX_EDGE;
+            if (cs1 <= cs0) continue;
+            const int xa0 = (cs0 - 3) & ~15, xa1 = (cs1 + 3 + 15) & ~15;
+            if (xa1 - xa0 > TP || sc > MAX_SEG_CELLS) ok = false;
+        }
+        if (ok) return sc;
+    }
+    return 1;
+}
+
 void orbx_fast_configure(const OrbxGeom& g)
 {
-    cudaFuncSetAttribute(k_fast_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem_bytes(g));
+    cudaFuncSetAttribute(k_fast_seg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem_bytes(g));
 }
 
 void orbx_launch_fast(const OrbxGeom& g, const OrbxBuffers& b, const uint8_t* level0, int pitch0,
@@ -482,6 +497,7 @@ void orbx_launch_fast(const OrbxGeom& g, const OrbxBuffers& b, const uint8_t* le
 {
     if (g.total_rows == 0) return;
     dim3 grid(g.total_rows, batch);
-    k_fast_rows<<<grid, NT, fast_smem_bytes(g), s>>>(g, b, level0, pitch0, stride0);
+    const size_t smem = fast_smem_bytes(g);
+    k_fast_seg<<<grid, NT, smem, s>>>(g, b, level0, pitch0, stride0, (int)smem);
     ORBX_COUNT_LAUNCH(1);
 }

@@ -7,6 +7,8 @@
 #define ORBX_EDGE 19          // EDGE_THRESHOLD, R/src/ORBextractor.cc:72
 #define ORBX_BORDER 16        // minBorderX = EDGE_THRESHOLD-3, R/src/ORBextractor.cc:771
 #define ORBX_HALF_PATCH 15    // HALF_PATCH_SIZE, R/src/ORBextractor.cc:71
+#define ORBX_FAST_TP 288      // staged width limit (bytes) of one FAST segment tile
+#define ORBX_MAX_UNITS 2048   // FAST segments (cell row x segment) per level
 #define ORBX_FAST_W 30        // cell size W, R/src/ORBextractor.cc:767
 
 // device error flag bits (written by kernels, read back at sync/download)
@@ -24,13 +26,14 @@ struct OrbxLevel {
     int maxBX, maxBY;    // maxBorderX/Y = dim - 16
     int nCols, nRows;    // cells
     int wCell, hCell;
+    int nSeg, segCells;  // FAST segments per cell row, cells per segment
     int quota;           // mnFeaturesPerLevel
     int nIni;            // octree root count
     float hX;            // octree root width
     float scale;         // mvScaleFactor
     float size;          // keypoint.size = int(31*scale)
-    int row_base;        // index of this level's first cell row in the flattened cell-row list
-    int row_cap;         // candidate capacity of one cell row
+    int row_base;        // index of this level's first segment (cell row x segment, row-major) in the flattened list
+    int row_cap;         // candidate capacity of one segment
     int cand_cap;        // candidate capacity of the level (octree input)
     int kp_cap;          // kept-keypoint capacity of the level
     int kp_base;         // offset of this level in the per-frame kept-keypoint buffer
@@ -40,7 +43,7 @@ struct OrbxLevel {
 struct OrbxGeom {
     int nlevels;
     int width, height;
-    int total_rows;      // sum of nRows over levels
+    int total_rows;      // sum of nRows * nSeg over levels
     int kp_total_cap;    // per-frame kept-keypoint buffer length (sum of kp_cap)
     int out_cap;         // per-frame result capacity
     int ini_th, min_th;
@@ -91,6 +94,7 @@ void orbx_launch_describe(const OrbxGeom& g, const OrbxBuffers& b, const uint8_t
 int  orbx_octree_smem_bytes(const OrbxGeom& g);
 void orbx_octree_configure(const OrbxGeom& g);
 void orbx_fast_configure(const OrbxGeom& g);
+int orbx_fast_plan(int w, int nCols, int wCell);
 void orbx_upload_pattern();
 void orbx_set_error(const char* fmt, const char* a, const char* b);
 // number of kernels this library launched since load (bench.py reports the delta as gpu_launches)

@@ -93,7 +93,7 @@ struct OctShared {
     u64 warp_sums[NT / 32];
     int n_pts, n_nodes, n_vec, jstar, flag_overflow;
     int tot_c, tot_e;
-    int row_prefix[128];
+    int row_prefix[ORBX_MAX_UNITS + 1];
 };
 
 __global__ void __launch_bounds__(NT) k_octree(OrbxGeom g, OrbxBuffers b, int smem_pts, int ncap)
@@ -119,12 +119,24 @@ __global__ void __launch_bounds__(NT) k_octree(OrbxGeom g, OrbxBuffers b, int sm
     // ---- gather the level's candidates in reference order (cell rows top to bottom) ----
     if (L.nRows <= 0 || L.nCols <= 0) { if (tid == 0) *out_n = 0; return; }
     const int* rc = b.row_count + (long long)f * g.total_rows + L.row_base;
-    if (tid == 0) {
+    const int nUnits = L.nRows * L.nSeg;               // FAST segments of the level, reference order
+    if (tid < 32) {
+        // exclusive prefix of the segment counts, 32 segments per step
         int run = 0;
-        for (int r = 0; r < L.nRows; r++) { sh.row_prefix[r] = run; run += rc[r]; }
-        sh.row_prefix[L.nRows] = run;
-        if (run > L.cand_cap) { atomicOr(b.err, ORBX_DEVERR_CAND_OVERFLOW); run = L.cand_cap; }
-        sh.n_pts = run;
+        for (int r0 = 0; r0 < nUnits; r0 += 32) {
+            const int r = r0 + tid;
+            const int c = r < nUnits ? rc[r] : 0;
+            int inc = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (tid >= o) inc += t; }
+            if (r < nUnits) sh.row_prefix[r] = run + inc - c;
+            run += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (tid == 0) {
+            sh.row_prefix[nUnits] = run;
+            if (run > L.cand_cap) { atomicOr(b.err, ORBX_DEVERR_CAND_OVERFLOW); run = L.cand_cap; }
+            sh.n_pts = run;
+        }
     }
     __syncthreads();
     const int n = sh.n_pts;
@@ -137,10 +149,10 @@ __global__ void __launch_bounds__(NT) k_octree(OrbxGeom g, OrbxBuffers b, int sm
         buf = scratch; pts = reinterpret_cast<uint32_t*>(scratch + npad);
     }
     const uint32_t* cand = b.row_cand + (long long)f * b.row_cand_stride;
-    for (int r = 0; r < L.nRows; r++) {
+    for (int r = tid >> 5; r < nUnits; r += NT / 32) {
         const int base = sh.row_prefix[r], cnt = min(sh.row_prefix[r + 1], n) - base;
         const uint32_t* src = cand + b.row_off[L.row_base + r];
-        for (int k = tid; k < cnt; k += NT) pts[base + k] = src[k];
+        for (int k = tid & 31; k < cnt; k += 32) pts[base + k] = src[k];
     }
     __syncthreads();
 
