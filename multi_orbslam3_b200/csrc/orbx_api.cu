@@ -209,6 +209,12 @@ static int configure_geometry(orbx_extractor* h, int width, int height)
     if ((rc = dev_alloc(h, (void**)&b.row_count, sizeof(int) * (size_t)rows * B))) return rc;
     if ((rc = dev_alloc(h, (void**)&b.row_off, sizeof(int) * (rows + 1)))) return rc;
     if (rows) CK(cudaMemcpy(b.row_off, row_off.data(), sizeof(int) * rows, cudaMemcpyHostToDevice));
+    {
+        std::vector<int4> units;
+        orbx_fast_units(g, units);
+        if ((rc = dev_alloc(h, (void**)&b.unit_tab, sizeof(int4) * (units.size() + 1)))) return rc;
+        if (!units.empty()) CK(cudaMemcpy(b.unit_tab, units.data(), sizeof(int4) * units.size(), cudaMemcpyHostToDevice));
+    }
     if ((rc = dev_alloc(h, (void**)&b.lvl_kp, sizeof(uint32_t) * (size_t)kpbase * B))) return rc;
     if ((rc = dev_alloc(h, (void**)&b.lvl_n, sizeof(int) * (size_t)g.nlevels * B))) return rc;
     b.sort_scratch_stride = sort_elems;

@@ -66,9 +66,12 @@ __device__ __forceinline__ int atoms_add(int* p, int v)
 }
 
 // ring offsets (dx,dy), OpenCV order
-__device__ __constant__ int8_t c_ring[16][2] = {
-    {0, 3}, {1, 3}, {2, 2}, {3, 1}, {3, 0}, {3, -1}, {2, -2}, {1, -3},
-    {0, -3}, {-1, -3}, {-2, -2}, {-3, -1}, {-3, 0}, {-3, 1}, {-2, 2}, {-1, 3}};
+__host__ __device__ constexpr int ring_off(int k)
+{
+    constexpr int dx[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
+    constexpr int dy[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
+    return dy[k] * TP + dx[k];
+}
 
 // Arc measure on packed 16-bit lanes.  p[k] holds both polarities of ring pixel k, biased by 256 so that
 // both lanes stay positive: low = v - r_k + 256 (= d_k + 256), high = r_k - v + 256 (= -d_k + 256).
@@ -92,12 +95,12 @@ __device__ __forceinline__ int arc_measure(const unsigned (&p)[16])
 }
 
 // packed ring differences of one pixel: pk[q] = (v + 256 - r_q) | (256 - v + r_q) << 16
-__device__ __forceinline__ void load_ring(const uint8_t* p, const int (&roff)[16], unsigned (&pk)[16])
+__device__ __forceinline__ void load_ring(const uint8_t* p, unsigned (&pk)[16])
 {
     const int v = p[0];
     const unsigned cv = (unsigned)(v + 256) | ((unsigned)(256 - v) << 16);
 #pragma unroll
-    for (int q = 0; q < 16; q++) pk[q] = cv + (unsigned)p[roff[q]] * 0xFFFFu;
+    for (int q = 0; q < 16; q++) pk[q] = cv + (unsigned)p[ring_off(q)] * 0xFFFFu;   // immediate offsets
 }
 
 // OpenCV's high-speed test on the 8 opposite pairs, both polarities at once and branch-free:
@@ -112,11 +115,11 @@ __device__ __forceinline__ bool pair_test(const unsigned (&pk)[16], int minTh)
 }
 
 // exact per-pixel path used when a queue overflows: pair test, then the arc measure
-__device__ __forceinline__ void score_pixel(const uint8_t* T, uint8_t* M, const int (&roff)[16], int x, int yt, int minTh,
+__device__ __forceinline__ void score_pixel(const uint8_t* T, uint8_t* M, int x, int yt, int minTh,
                                             int* cl_count)
 {
     unsigned pk[16];
-    load_ring(T + yt * TP + x, roff, pk);
+    load_ring(T + yt * TP + x, pk);
     if (!pair_test(pk, minTh)) return;
     const int m = arc_measure(pk);
     if (m > minTh) { M[(yt - 3) * TP + x] = (uint8_t)m; atoms_add(cl_count, CLCAP + 1); }   // forces the exact map-scan NMS path
@@ -146,18 +149,13 @@ __device__ __forceinline__ void nms_pixel(const uint8_t* M, unsigned* Bmin, unsi
 // per-byte flag (bit 7) of "a > t" for t <= 126: bytes < 128 carry into bit 7 when a + 127 - t >= 128
 __device__ __forceinline__ unsigned gt_flags(unsigned a, unsigned c127mt) { return ((a & 0x7f7f7f7fu) + c127mt) | a; }
 
-// number of set bits in columns [c0, c1) of a bitmap row
+// number of set bits in columns [c0, c1) of a bitmap row, 0 <= c1 - c0 < 64 (a cell is narrower than 60 columns);
+// the word after the range's first word is read unconditionally: the bitmaps are padded by one word
 __device__ __forceinline__ int popc_range(const unsigned* row, int c0, int c1)
 {
-    int n = 0;
-    for (int w = c0 >> 5; w <= (c1 - 1) >> 5; w++) {
-        unsigned v = row[w];
-        const int lo = w << 5;
-        if (c0 > lo) v &= 0xFFFFFFFFu << (c0 - lo);
-        if (c1 < lo + 32) v &= 0xFFFFFFFFu >> (lo + 32 - c1);
-        n += __popc(v);
-    }
-    return n;
+    const int w = c0 >> 5;
+    const unsigned long long v = ((unsigned long long)row[w + 1] << 32 | row[w]) >> (c0 & 31);
+    return __popcll(v & ((1ull << (c1 - c0)) - 1ull));
 }
 
 struct FastSmem {
@@ -169,7 +167,7 @@ struct FastSmem {
 // shared-memory bytes of one segment tile, without the pixel queue
 __host__ __device__ inline int tile_bytes(int nrow, int hs, int ng, int ncell)
 {
-    return nrow * TP + hs * TP + hs * ng * 4 + CLCAP * 4 + 2 * hs * (TP / 32) * 4 + ((2 * ncell * hs * 2 + 15) & ~15);
+    return nrow * TP + hs * TP + hs * ng * 4 + CLCAP * 4 + (2 * hs * (TP / 32) + 4) * 4 + ((2 * ncell * hs * 2 + 15) & ~15);
 }
 
 __global__ void __launch_bounds__(NT, 4) k_fast_seg(OrbxGeom g, OrbxBuffers b, const uint8_t* level0, int pitch0,
@@ -181,28 +179,18 @@ __global__ void __launch_bounds__(NT, 4) k_fast_seg(OrbxGeom g, OrbxBuffers b, c
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int f = blockIdx.y;
-    int l = 0;
-    while (l + 1 < g.nlevels && (int)blockIdx.x >= g.lv[l + 1].row_base) l++;
-    const OrbxLevel L = g.lv[l];
-    const int u = blockIdx.x - L.row_base;
+    // per-segment record precomputed by the host (orbx_fast_units)
+    const int4 u0 = __ldg(b.unit_tab + 4 * blockIdx.x), u1 = __ldg(b.unit_tab + 4 * blockIdx.x + 1), u2 = __ldg(b.unit_tab + 4 * blockIdx.x + 2);
+    const int l = u0.x, iniY = u0.y, nrow = u0.z, hs = u0.w;          // level, first staged row, staged rows, scored rows (tile rows 3 .. nrow-4)
+    const int xa0 = u1.x, sw = u1.y, X0 = u1.z, X1 = u1.w;            // staged columns [xa0, xa0+sw), scored tile columns [X0, X1)
+    const int ncell = u2.x, tbytes = u2.y;
+    const unsigned hrcp = (unsigned)__ldg(&b.unit_tab[4 * blockIdx.x + 3].x);     // (n * hrcp) >> 16 == n / hs
+    const unsigned wrcp = (unsigned)u2.z, srcp = (unsigned)u2.w;      // (n * wrcp) >> 16 == n / wCell; (n * srcp) >> 16 == n / nsteps
     int* row_count = b.row_count + (long long)f * g.total_rows + blockIdx.x;
-    if (u >= L.nRows * L.nSeg) return;
-    const int i = u / L.nSeg, sgm = u - i * L.nSeg;
-    const int iniY = ORBX_BORDER + i * L.hCell;
-    int maxY = iniY + L.hCell + 6;
-    if (maxY > L.maxBY) maxY = L.maxBY;
-    const int nrow = maxY - iniY;                      // staged rows
-    const int hs = nrow - 6;                           // scored rows: tile rows 3 .. nrow-4
-    const int j0 = sgm * L.segCells, ncell = min(L.segCells, L.nCols - j0);
-    const int xs1 = L.w - ORBX_EDGE;
-    const int cs0 = ORBX_EDGE + j0 * L.wCell, cs1 = min(cs0 + ncell * L.wCell, xs1);   // scored columns of the segment
-    if (iniY >= L.maxBY - 3 || hs <= 0 || cs1 <= cs0) { if (tid == 0) *row_count = 0; return; }
-    const int xa0 = (cs0 - 3) & ~15, xa1 = (cs1 + 3 + 15) & ~15;      // staged columns [xa0, xa1), xa1 <= w
-    const int sw = xa1 - xa0;                                          // <= TP (orbx_fast_plan)
-    const int X0 = cs0 - xa0, X1 = cs1 - xa0;                          // scored columns in tile coordinates
+    if (hs <= 0) { if (tid == 0) *row_count = 0; return; }
+    const int wCell = g.lv[l].wCell, row_cap = g.lv[l].row_cap;
     const int g0 = X0 >> 2, g1 = (X1 - 1) >> 2, ng = g1 - g0 + 1;      // 4-pixel groups holding scored columns
     constexpr int bw = TP / 32;                                        // bitmap words per row
-    const unsigned wrcp = (65536u + L.wCell - 1) / L.wCell;            // (n * wrcp) >> 16 == n / wCell for n < TP
 
     // ---- smem carve-up (per CTA: tiles of different levels have different shapes) ----
     uint8_t* T = smem;                                              // [nrow][TP] pixels
@@ -212,18 +200,18 @@ __global__ void __launch_bounds__(NT, 4) k_fast_seg(OrbxGeom g, OrbxBuffers b, c
     const int q2cap = hs * ng;
     unsigned* CL = QG + hs * ng;                                    // [CLCAP] corners: x | scored row << 16
     unsigned* Bmin = CL + CLCAP;                                    // [hs][bw] survivors at minTh
-    unsigned* Bini = Bmin + hs * bw;                                // [hs][bw] survivors at iniTh
-    unsigned short* cnt_min = reinterpret_cast<unsigned short*>(Bini + hs * bw);   // [ncell][hs]
+    unsigned* Bini = Bmin + hs * bw;                                // [hs][bw] (+4 words of padding) survivors at iniTh
+    unsigned short* cnt_min = reinterpret_cast<unsigned short*>(Bini + hs * bw + 4);   // [ncell][hs]
     unsigned short* cnt_ini = cnt_min + ncell * hs;                 // [ncell][hs]; later: exclusive row prefix of the chosen counts
-    unsigned* Q = reinterpret_cast<unsigned*>(smem + tile_bytes(nrow, hs, ng, ncell));   // [qcap] candidate queue: x | tile row << 16
-    const int qcap = (smem_total - tile_bytes(nrow, hs, ng, ncell)) >> 2;
+    unsigned* Q = reinterpret_cast<unsigned*>(smem + tbytes);       // [qcap] candidate queue: x | tile row << 16
+    const int qcap = (smem_total - tbytes) >> 2;
 
     const uint8_t* img; int pitch;
     if (l == 0) { img = level0 + (long long)f * stride0; pitch = pitch0; }
-    else { img = b.pyr[l] + (long long)f * L.frame_stride; pitch = L.pitch; }
+    else { img = b.pyr[l] + (long long)f * g.lv[l].frame_stride; pitch = g.lv[l].pitch; }
 
     // ---- 1. stage rows ----
-    const bool vec = ((pitch & 15) == 0) && (pitch >= xa1) && ((reinterpret_cast<uintptr_t>(img) & 15) == 0);
+    const bool vec = ((pitch & 15) == 0) && (pitch >= xa0 + sw) && ((reinterpret_cast<uintptr_t>(img) & 15) == 0);
     if (vec) {
         // one bulk copy per row, issued by the lanes of warp 0; completion is counted in bytes on an mbarrier, and the
         // zero-fill of the score map / bitmaps below overlaps the copies
@@ -236,19 +224,16 @@ __global__ void __launch_bounds__(NT, 4) k_fast_seg(OrbxGeom g, OrbxBuffers b, c
         }
     } else {
         for (int r = warp; r < nrow; r += NW)
-            for (int c = lane; c < sw; c += 32) T[r * TP + c] = xa0 + c < L.w ? __ldg(img + (long long)(iniY + r) * pitch + xa0 + c) : 0;
+            for (int c = lane; c < sw; c += 32) T[r * TP + c] = xa0 + c < g.lv[l].w ? __ldg(img + (long long)(iniY + r) * pitch + xa0 + c) : 0;
     }
     {
         uint4* z = reinterpret_cast<uint4*>(M);
         const int nz = (hs * TP) >> 4;
         for (int k = tid; k < nz; k += NT) z[k] = make_uint4(0, 0, 0, 0);
-        for (int k = tid; k < 2 * hs * bw; k += NT) Bmin[k] = 0;
+        for (int k = tid; k < 2 * hs * bw + 4; k += NT) Bmin[k] = 0;
         if (tid == 0) { sh.cl_count = 0; sh.qg_count = 0; sh.q_count = 0; sh.q2_count = 0; }
     }
     const int minTh = g.min_th, iniTh = g.ini_th;
-    int roff[16];
-#pragma unroll
-    for (int k = 0; k < 16; k++) roff[k] = c_ring[k][1] * TP + c_ring[k][0];
     if (vec) mbar_wait(&s_bar, 0);
     __syncthreads();
 
@@ -259,7 +244,7 @@ __global__ void __launch_bounds__(NT, 4) k_fast_seg(OrbxGeom g, OrbxBuffers b, c
         const int nsteps = (ng + 31) >> 5;
         const int items = hs * nsteps;
         for (int it = warp; it < items; it += NW) {            // warp-uniform trip count (ballots below)
-            const int ry = it / nsteps, yt = 3 + ry;
+            const int ry = (int)(((unsigned)it * srcp) >> 16), yt = 3 + ry;
             const int gx = g0 + ((it - ry * nsteps) << 5) + lane;
             const unsigned* rc = reinterpret_cast<const unsigned*>(T + yt * TP) + gx;
             constexpr int W = TP / 4;
@@ -322,7 +307,7 @@ __global__ void __launch_bounds__(NT, 4) k_fast_seg(OrbxGeom g, OrbxBuffers b, c
             for (int q = 0; q < 4; q++)
                 if (m4 & (1u << q)) {
                     if (o < qcap) Q[o] = e + q;
-                    else score_pixel(T, M, roff, (e + q) & 0xFFFF, (int)((ge >> 12) & 0xFFu), minTh, &sh.cl_count);   // queue full: score inline
+                    else score_pixel(T, M, (e + q) & 0xFFFF, (int)((ge >> 12) & 0xFFu), minTh, &sh.cl_count);   // queue full: score inline
                     o++;
                 }
         }
@@ -337,7 +322,7 @@ __global__ void __launch_bounds__(NT, 4) k_fast_seg(OrbxGeom g, OrbxBuffers b, c
             if (e < nq) {
                 ent = Q[e];
                 unsigned pk[16];
-                load_ring(T + (ent >> 16) * TP + (ent & 0xFFFF), roff, pk);
+                load_ring(T + (ent >> 16) * TP + (ent & 0xFFFF), pk);
                 pass = pair_test(pk, minTh);
             }
             const unsigned bal = __ballot_sync(0xffffffffu, pass);
@@ -348,7 +333,7 @@ __global__ void __launch_bounds__(NT, 4) k_fast_seg(OrbxGeom g, OrbxBuffers b, c
                 if (pass) {
                     const int o = base + __popc(bal & ((1u << lane) - 1));
                     if (o < q2cap) Q2[o] = ent;
-                    else score_pixel(T, M, roff, ent & 0xFFFF, ent >> 16, minTh, &sh.cl_count);
+                    else score_pixel(T, M, ent & 0xFFFF, ent >> 16, minTh, &sh.cl_count);
                 }
             }
         }
@@ -361,7 +346,7 @@ __global__ void __launch_bounds__(NT, 4) k_fast_seg(OrbxGeom g, OrbxBuffers b, c
             const unsigned ent = Q2[e];
             const int x = ent & 0xFFFF, yq = ent >> 16;
             unsigned pk[16];
-            load_ring(T + yq * TP + x, roff, pk);
+            load_ring(T + yq * TP + x, pk);
             const int m = arc_measure(pk);
             if (m > minTh) {
                 M[(yq - 3) * TP + x] = (uint8_t)m;
@@ -380,7 +365,7 @@ __global__ void __launch_bounds__(NT, 4) k_fast_seg(OrbxGeom g, OrbxBuffers b, c
         for (int e = tid; e < ncl; e += NT) {
             const unsigned ent = CL[e];
             const int x = ent & 0xFFFF, r = ent >> 16;
-            nms_pixel(M, Bmin, Bini, x, r, X0, X1, hs, L.wCell, wrcp, iniTh);
+            nms_pixel(M, Bmin, Bini, x, r, X0, X1, hs, wCell, wrcp, iniTh);
         }
     } else {
         for (int r = warp; r < hs; r += NW)
@@ -388,15 +373,15 @@ __global__ void __launch_bounds__(NT, 4) k_fast_seg(OrbxGeom g, OrbxBuffers b, c
                 const unsigned word = reinterpret_cast<const unsigned*>(M + r * TP)[wx];
                 if (!word) continue;
                 for (int q = 0; q < 4; q++)
-                    if ((word >> (8 * q)) & 0xFF) nms_pixel(M, Bmin, Bini, (wx << 2) + q, r, X0, X1, hs, L.wCell, wrcp, iniTh);
+                    if ((word >> (8 * q)) & 0xFF) nms_pixel(M, Bmin, Bini, (wx << 2) + q, r, X0, X1, hs, wCell, wrcp, iniTh);
             }
     }
     __syncthreads();
 
     // ---- 5. counts per (cell, row), threshold choice per cell, offsets ----
     for (int k = tid; k < ncell * hs; k += NT) {
-        const int j = k / hs, r = k - j * hs;
-        const int c0 = X0 + j * L.wCell, c1 = min(c0 + L.wCell, X1);
+        const int j = (int)(((unsigned)k * hrcp) >> 16), r = k - j * hs;
+        const int c0 = X0 + j * wCell, c1 = min(c0 + wCell, X1);
         int a = 0, bq = 0;
         if (c1 > c0) { a = popc_range(Bmin + r * bw, c0, c1); bq = popc_range(Bini + r * bw, c0, c1); }
         cnt_min[j * hs + r] = (unsigned short)a;
@@ -422,8 +407,8 @@ __global__ void __launch_bounds__(NT, 4) k_fast_seg(OrbxGeom g, OrbxBuffers b, c
         int run = 0;
         sh.cell_off[0] = 0;
         for (int j = 0; j < ncell; j++) { run += sh.cell_off[j + 1]; sh.cell_off[j + 1] = run; }   // cell_off[j] = first slot of cell j
-        *row_count = min(run, L.row_cap);
-        if (run > L.row_cap) atomicOr(b.err, ORBX_DEVERR_CAND_OVERFLOW);
+        *row_count = min(run, row_cap);
+        if (run > row_cap) atomicOr(b.err, ORBX_DEVERR_CAND_OVERFLOW);
     }
     __syncthreads();
 
@@ -431,7 +416,7 @@ __global__ void __launch_bounds__(NT, 4) k_fast_seg(OrbxGeom g, OrbxBuffers b, c
     uint32_t* out = b.row_cand + (long long)f * b.row_cand_stride + b.row_off[blockIdx.x];
     const int yrel0 = iniY - ORBX_BORDER + 3;
     for (int k = tid; k < hs * bw; k += NT) {
-        const int r = k / bw, wi = k - r * bw;
+        const int r = k / bw, wi = k - r * bw;                 // bw is a compile-time constant
         unsigned bits = Bmin[k];
         const unsigned ibits = Bini[k];
         while (bits) {
@@ -441,10 +426,10 @@ __global__ void __launch_bounds__(NT, 4) k_fast_seg(OrbxGeom g, OrbxBuffers b, c
             const int j = (int)(((unsigned)(x - X0) * wrcp) >> 16);
             const bool ui = sh.use_ini[j];
             if (ui && !((ibits >> bpos) & 1u)) continue;
-            const int c0 = X0 + j * L.wCell;
+            const int c0 = X0 + j * wCell;
             const int rank = x > c0 ? popc_range((ui ? Bini : Bmin) + r * bw, c0, x) : 0;
             const int o = sh.cell_off[j] + cnt_ini[j * hs + r] + rank;
-            if (o < L.row_cap)
+            if (o < row_cap)
                 out[o] = (uint32_t)(x + xa0 - ORBX_BORDER) | ((uint32_t)(yrel0 + r) << 12) | ((uint32_t)(M[r * TP + x] - 1) << 24);
         }
     }
@@ -485,6 +470,38 @@ int orbx_fast_plan(int w, int nCols, int wCell)
         if (ok) return sc;
     }
     return 1;
+}
+
+// Per-segment records read by k_fast_seg, 4 x int4 per segment in launch order (level, cell row, segment):
+//   {level, first staged row, staged rows, scored rows (<= 0: empty segment)}
+//   {xa0, staged width, X0, X1}     {cells, tile bytes, 2^16 / wCell, 2^16 / screen steps per row}   {2^16 / scored rows, -, -, -}
+void orbx_fast_units(const OrbxGeom& g, std::vector<int4>& tab)
+{
+    tab.clear();
+    for (int l = 0; l < g.nlevels; l++) {
+        const OrbxLevel& L = g.lv[l];
+        for (int i = 0; i < L.nRows; i++)
+            for (int sg = 0; sg < L.nSeg; sg++) {
+                int4 a = make_int4(l, 0, 0, 0), bq = make_int4(0, 0, 0, 0), c = make_int4(0, 0, 0, 0);
+                const int iniY = ORBX_BORDER + i * L.hCell;
+                int maxY = iniY + L.hCell + 6; if (maxY > L.maxBY) maxY = L.maxBY;
+                const int nrow = maxY - iniY, hs = nrow - 6;
+                const int j0 = sg * L.segCells, ncell = L.segCells < L.nCols - j0 ? L.segCells : L.nCols - j0;
+                const int xs1 = L.w - ORBX_EDGE;
+                const int cs0 = ORBX_EDGE + j0 * L.wCell;
+                int cs1 = cs0 + ncell * L.wCell; if (cs1 > xs1) cs1 = xs1;
+                if (iniY < L.maxBY - 3 && hs > 0 && cs1 > cs0) {
+                    const int xa0 = (cs0 - 3) & ~15, xa1 = (cs1 + 3 + 15) & ~15;
+                    const int X0 = cs0 - xa0, X1 = cs1 - xa0;
+                    const int ng = ((X1 - 1) >> 2) - (X0 >> 2) + 1, nsteps = (ng + 31) >> 5;
+                    a = make_int4(l, iniY, nrow, hs);
+                    bq = make_int4(xa0, xa1 - xa0, X0, X1);
+                    c = make_int4(ncell, tile_bytes(nrow, hs, ng, ncell), (65536 + L.wCell - 1) / L.wCell, (65536 + nsteps - 1) / nsteps);
+                }
+                tab.push_back(a); tab.push_back(bq); tab.push_back(c);
+                tab.push_back(make_int4(hs > 0 ? (65536 + hs - 1) / hs : 0, 0, 0, 0));
+            }
+    }
 }
 
 void orbx_fast_configure(const OrbxGeom& g)

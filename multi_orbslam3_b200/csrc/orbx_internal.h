@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <vector>
 #include "../../include/orbx.h"
 
 #define ORBX_EDGE 19          // EDGE_THRESHOLD, R/src/ORBextractor.cc:72
@@ -58,6 +59,7 @@ struct OrbxBuffers {
     uint32_t* row_cand;                // [batch][total_rows][row_cap(level)] packed x | y<<12 | score<<24 ... flattened by row offsets
     int* row_count;                    // [batch][total_rows]
     long long row_cand_stride;         // elements per frame
+    int4* unit_tab;                    // [total_rows][4] FAST segment records (orbx_fast_units)
     int* row_off;                      // [total_rows] element offset of each cell row inside a frame
     uint32_t* lvl_kp;                  // [batch][kp_total_cap] kept keypoints per level, packed
     int* lvl_n;                        // [batch][nlevels]
@@ -95,6 +97,7 @@ int  orbx_octree_smem_bytes(const OrbxGeom& g);
 void orbx_octree_configure(const OrbxGeom& g);
 void orbx_fast_configure(const OrbxGeom& g);
 int orbx_fast_plan(int w, int nCols, int wCell);
+void orbx_fast_units(const OrbxGeom& g, std::vector<int4>& tab);
 void orbx_upload_pattern();
 void orbx_set_error(const char* fmt, const char* a, const char* b);
 // number of kernels this library launched since load (bench.py reports the delta as gpu_launches)
