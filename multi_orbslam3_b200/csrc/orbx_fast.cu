@@ -19,6 +19,7 @@
 //      recorded in two bitmaps (minThFAST / iniThFAST);
 //   5. cells with no iniThFAST survivor fall back to their minThFAST survivors (:825-828); every survivor
 //      computes its own output slot from popcounts (cell by cell, row-major inside a cell = reference order).
+#include <cstdlib>
 #include "orbx_internal.h"
 
 namespace {
@@ -29,7 +30,7 @@ constexpr int TP = ORBX_FAST_TP;     // shared-memory pitch of a segment tile (c
 constexpr int MAX_SEG_CELLS = 16;    // cells per segment (TP / 35 rounded up)
 constexpr int CLCAP = 1024;          // corners (m > minTh) of the whole tile; overflow -> map scan (still exact)
 constexpr int QMIN = 1024;           // smallest pixel queue the launch is sized for (overflow is scored inline, never dropped)
-constexpr int SMEM_TARGET = 54 * 1024;   // 4 CTAs per SM
+constexpr int SMEM_TARGET = 44 * 1024;   // 5 CTAs per SM
 
 // ---- bulk asynchronous copy (TMA engine, 1-D form: SASS UBLKCP) + mbarrier ----
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count)
@@ -164,13 +165,16 @@ struct FastSmem {
     unsigned char use_ini[MAX_SEG_CELLS];
 };
 
+// group-queue capacity: every group of the tile (cannot overflow)
+__host__ __device__ inline int qg_cap(int hs, int ng) { return hs * ng; }
+
 // shared-memory bytes of one segment tile, without the pixel queue
 __host__ __device__ inline int tile_bytes(int nrow, int hs, int ng, int ncell)
 {
-    return nrow * TP + hs * TP + hs * ng * 4 + CLCAP * 4 + (2 * hs * (TP / 32) + 4) * 4 + ((2 * ncell * hs * 2 + 15) & ~15);
+    return nrow * TP + hs * TP + qg_cap(hs, ng) * 4 + CLCAP * 4 + (2 * hs * (TP / 32) + 4) * 4 + ((2 * ncell * hs * 2 + 15) & ~15);
 }
 
-__global__ void __launch_bounds__(NT, 4) k_fast_seg(OrbxGeom g, OrbxBuffers b, const uint8_t* level0, int pitch0,
+__global__ void __launch_bounds__(NT, 5) k_fast_seg(OrbxGeom g, OrbxBuffers b, const uint8_t* level0, int pitch0,
                                                     long long stride0, int smem_total)
 {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -195,10 +199,10 @@ __global__ void __launch_bounds__(NT, 4) k_fast_seg(OrbxGeom g, OrbxBuffers b, c
     // ---- smem carve-up (per CTA: tiles of different levels have different shapes) ----
     uint8_t* T = smem;                                              // [nrow][TP] pixels
     uint8_t* M = T + nrow * TP;                                     // [hs][TP]   arc measure (0 = not a corner at minTh)
-    unsigned* QG = reinterpret_cast<unsigned*>(M + hs * TP);        // [hs*ng] groups with survivors: gx | tile row << 12 | mask << 20
+    unsigned* QG = reinterpret_cast<unsigned*>(M + hs * TP);        // [qgcap] 4-pixel groups with screen survivors
     unsigned* Q2 = QG;                                              // survivors of the signed pair test (QG is dead by then)
-    const int q2cap = hs * ng;
-    unsigned* CL = QG + hs * ng;                                    // [CLCAP] corners: x | scored row << 16
+    const int qgcap = qg_cap(hs, ng), q2cap = qgcap;
+    unsigned* CL = QG + qgcap;                                    // [CLCAP] corners: x | scored row << 16
     unsigned* Bmin = CL + CLCAP;                                    // [hs][bw] survivors at minTh
     unsigned* Bini = Bmin + hs * bw;                                // [hs][bw] (+4 words of padding) survivors at iniTh
     unsigned short* cnt_min = reinterpret_cast<unsigned short*>(Bini + hs * bw + 4);   // [ncell][hs]
@@ -241,13 +245,18 @@ __global__ void __launch_bounds__(NT, 4) k_fast_seg(OrbxGeom g, OrbxBuffers b, c
     const unsigned c127 = (unsigned)(127 - (minTh < 126 ? minTh : 126)) * 0x01010101u;
     const bool screen_ok = minTh <= 126;
     {
+        constexpr int W = TP / 4;
         const int nsteps = (ng + 31) >> 5;
-        const int items = hs * nsteps;
-        for (int it = warp; it < items; it += NW) {            // warp-uniform trip count (ballots below)
-            const int ry = (int)(((unsigned)it * srcp) >> 16), yt = 3 + ry;
-            const int gx = g0 + ((it - ry * nsteps) << 5) + lane;
-            const unsigned* rc = reinterpret_cast<const unsigned*>(T + yt * TP) + gx;
-            constexpr int W = TP / 4;
+        // items (row, step) are dealt round-robin to the warps; the pair advances by NW items per iteration
+        int ry = (int)(((unsigned)warp * srcp) >> 16), st = warp - ry * nsteps;
+        const int dq = (int)(((unsigned)NW * srcp) >> 16), dr = NW - dq * nsteps;
+        // scored columns only: the first and last group straddle the segment's edges
+        const unsigned mask0 = 0x80808080u << (8 * (X0 & 3)), mask1 = 0x80808080u >> (8 * (3 - ((X1 - 1) & 3)));
+        const unsigned lt = (1u << lane) - 1;
+        const unsigned* Tw = reinterpret_cast<const unsigned*>(T + 3 * TP) + g0 + lane;
+        while (ry < hs) {                                       // warp-uniform (ballots below)
+            const int gx = g0 + (st << 5) + lane;
+            const unsigned* rc = Tw + ry * W + (st << 5);
             unsigned cand = 0;
             if (gx <= g1) {
                 cand = 0x80808080u;
@@ -268,32 +277,31 @@ __global__ void __launch_bounds__(NT, 4) k_fast_seg(OrbxGeom g, OrbxBuffers b, c
                         cand &= gt_flags(__vabsdiffu4(V, a6) | __vabsdiffu4(V, a14), c127);
                     }
                 }
-                // keep scored columns only (only the first and last group straddle the segment's edges)
-                if (gx == g0) cand &= 0x80808080u << (8 * (X0 & 3));
-                if (gx == g1) cand &= 0x80808080u >> (8 * (3 - ((X1 - 1) & 3)));
+                if (gx == g0) cand &= mask0;
+                if (gx == g1) cand &= mask1;
             }
-            // one queue entry per 4-pixel group that still has a candidate: one ballot, one atomic per warp-step
+            // one queue entry per 4-pixel group that still has a candidate: one ballot, one atomic per warp-step.
+            // entry = flags (bits 7, 15, 23, 31) | gx (bits 0-6) | tile row (bits 8-14)
             const unsigned bal = __ballot_sync(0xffffffffu, cand != 0);
             if (bal) {
                 int base = 0;
                 if (lane == 0) base = atoms_add(&sh.qg_count, __popc(bal));
                 base = __shfl_sync(0xffffffffu, base, 0);
-                if (cand) {
-                    const unsigned m4 = ((cand >> 7) & 1u) | ((cand >> 14) & 2u) | ((cand >> 21) & 4u) | ((cand >> 28) & 8u);
-                    QG[base + __popc(bal & ((1u << lane) - 1))] = (unsigned)gx | ((unsigned)yt << 12) | (m4 << 20);   // <= hs*ng entries by construction
-                }
+                if (cand) QG[base + __popc(bal & lt)] = cand | (unsigned)gx | ((unsigned)(ry + 3) << 8);   // <= hs*ng entries by construction
             }
+            st += dr; ry += dq;
+            if (st >= nsteps) { st -= nsteps; ry++; }
         }
     }
     __syncthreads();
-    // ---- expand the group entries into pixel entries (dense queue for phase A) ----
+    // ---- expand the group entries into pixel entries (dense queue for phase 3a) ----
     {
-        const int ngq = sh.qg_count;
+        const int ngq = min(sh.qg_count, qgcap);
         for (int gb = warp * 32; gb < ngq; gb += NT) {
             const int gi = gb + lane;
             const unsigned ge = gi < ngq ? QG[gi] : 0u;
-            const unsigned m4 = ge >> 20;
-            const int n = __popc(m4);
+            const unsigned fl = ge & 0x80808080u;
+            const int n = __popc(fl);
             int inc = n;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
@@ -302,12 +310,12 @@ __global__ void __launch_bounds__(NT, 4) k_fast_seg(OrbxGeom g, OrbxBuffers b, c
             if (lane == 0 && total) base = atoms_add(&sh.q_count, total);
             base = __shfl_sync(0xffffffffu, base, 0);
             int o = base + inc - n;
-            const unsigned e = ((ge & 0xFFFu) << 2) | (((ge >> 12) & 0xFFu) << 16);
+            const unsigned e = ((ge & 0x7Fu) << 2) | ((ge & 0x7F00u) << 8);
 #pragma unroll
             for (int q = 0; q < 4; q++)
-                if (m4 & (1u << q)) {
+                if (fl & (0x80u << (8 * q))) {
                     if (o < qcap) Q[o] = e + q;
-                    else score_pixel(T, M, (e + q) & 0xFFFF, (int)((ge >> 12) & 0xFFu), minTh, &sh.cl_count);   // queue full: score inline
+                    else score_pixel(T, M, (e + q) & 0xFFFF, (int)(e >> 16), minTh, &sh.cl_count);   // queue full: score inline
                     o++;
                 }
         }
@@ -446,7 +454,8 @@ size_t fast_smem_bytes(const OrbxGeom& g)
         const size_t n = (size_t)tile_bytes(hs + 6, hs, ng, L.segCells) + QMIN * 4;
         if (n > need) need = n;
     }
-    return need > (size_t)SMEM_TARGET ? need : (size_t)SMEM_TARGET;
+    static const int target = getenv("ORBX_FAST_SMEM_KB") ? atoi(getenv("ORBX_FAST_SMEM_KB")) * 1024 : SMEM_TARGET;
+    return need > (size_t)target ? need : (size_t)target;
 }
 
 }  // namespace

@@ -58,6 +58,10 @@ CASES = [
     ("odd_size", lambda: synth.rects_frame(333, 259, 7), (700, 1.2, 6, 20, 7), (0, 0)),
     ("scale15", lambda: synth.rects_frame(480, 360, 8), (600, 1.5, 4, 15, 5), (0, 0)),
     ("flat", lambda: np.full((240, 320), 77, np.uint8), (500, 1.2, 6, 20, 7), (0, 0)),
+    ("fullhd1920", lambda: synth.rects_frame(1920, 1080, 10), (3000, 1.2, 8, 20, 7), (0, 0)),
+    ("noise_wide", lambda: synth.noise_frame(1241, 150, 11), (2000, 1.2, 8, 20, 7), (0, 0)),
+    ("one_level", lambda: synth.rects_frame(600, 400, 12), (800, 1.2, 1, 20, 7), (0, 0)),
+    ("narrow_strip", lambda: synth.rects_frame(900, 96, 13), (300, 1.2, 4, 20, 7), (0, 0)),
     ("few_corners", lambda: synth.rects_frame(400, 300, 9, n_rect=3, noise_sigma=0.0), (1000, 1.2, 8, 20, 7), (0, 0)),
 ]
 
