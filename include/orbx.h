@@ -223,6 +223,15 @@ int  orbx_stereo_band_match(orbx_matcher* m, const orbx_keypoint* kl, const uint
 int  orbx_stereo_matches(orbx_matcher* m, orbx_extractor* left, orbx_extractor* right, int slot_l, int slot_r,
                          int frame_l, int frame_r, float mb, float mbf, float* uright, float* depth,
                          int32_t* sad_dist, int cap, int* n_left);
+/* The same for a batch of stereo pairs (a KITTI / EuRoC stereo stream): pair p uses result slot and frame (first + p) of
+ * both extractors' last batch.  _device: outputs are DEVICE arrays [count][orbx_extractor_max_keypoints(left)], d_sad may
+ * be NULL, all work is enqueued on `stream` (the stream of the two orbx_extract_batch_device calls) and nothing is
+ * synchronised.  Host form: uright/depth are host arrays [count][cap]; synchronises. */
+int  orbx_stereo_matches_batch_device(orbx_matcher* m, orbx_extractor* left, orbx_extractor* right, int first, int count,
+                                      float mb, float mbf, float* d_uright, float* d_depth, int32_t* d_sad, void* stream);
+int  orbx_stereo_matches_batch(orbx_matcher* m, orbx_extractor* left, orbx_extractor* right, int first, int count,
+                               float mb, float mbf, float* uright, float* depth, int cap);
+
 
 /* register-only popcount micro-benchmark: returns measured 32-bit popc per second on `device` (roofline
  * denominator for the matching kernels) */

@@ -497,8 +497,8 @@ int orbx_ex_pyramid_view(orbx_extractor* h, int frame, OrbxPyrView* out)
     const OrbxGeom& g = h->geom;
     out->nlevels = g.nlevels;
     for (int l = 0; l < g.nlevels; l++) {
-        if (l == 0) { out->lv[0] = h->last_level0 + (long long)frame * h->last_stride0; out->pitch[0] = h->last_pitch0; }
-        else { out->lv[l] = h->buf.pyr[l] + (long long)frame * g.lv[l].frame_stride; out->pitch[l] = g.lv[l].pitch; }
+        if (l == 0) { out->lv[0] = h->last_level0 + (long long)frame * h->last_stride0; out->pitch[0] = h->last_pitch0; out->fstride[0] = h->last_stride0; }
+        else { out->lv[l] = h->buf.pyr[l] + (long long)frame * g.lv[l].frame_stride; out->pitch[l] = g.lv[l].pitch; out->fstride[l] = g.lv[l].frame_stride; }
         out->w[l] = g.lv[l].w; out->h[l] = g.lv[l].h;
         out->scale[l] = h->scale[l]; out->inv_scale[l] = h->invScale[l];
     }

@@ -124,6 +124,7 @@ int orbx_ex_fetch_finish(orbx_extractor* h, int count, orbx_keypoint* kps, uint8
 struct OrbxPyrView {
     const uint8_t* lv[ORBX_MAX_LEVELS];
     int pitch[ORBX_MAX_LEVELS], w[ORBX_MAX_LEVELS], h[ORBX_MAX_LEVELS];
+    long long fstride[ORBX_MAX_LEVELS];     // bytes between consecutive frames of the batch
     float scale[ORBX_MAX_LEVELS], inv_scale[ORBX_MAX_LEVELS];
     int nlevels;
 };

@@ -532,24 +532,38 @@ __global__ void k_count_new_assigned(const int32_t* before, const int32_t* after
     if (threadIdx.x == 0) *count = s;
 }
 
-// Frame::ComputeStereoMatches descriptor search: one warp per left keypoint, right keypoints in index order
-__global__ void __launch_bounds__(256) k_stereo_band(const orbx_keypoint* kl, const uint8_t* dl, int nl,
-                                                   const orbx_keypoint* kr, const uint8_t* dr, int nr,
-                                                   const float* sf, int nrows, float minD, float maxD,
-                                                   int32_t* best_idx, int32_t* best_dist)
+// ---- Frame::ComputeStereoMatches, batched: blockIdx.y = stereo pair of the batch ----
+struct StereoArgs {
+    const orbx_keypoint* kL; const uint8_t* dL; const int32_t* nL; int capL;     // left results: [slot][capL]
+    const orbx_keypoint* kR; const uint8_t* dR; const int32_t* nR; int capR;     // right results
+    int slotL0, slotR0;                 // result slot of pair 0 (pair p uses slot*0 + p); nL/nR == nullptr: counts in nl1/nr1
+    int nl1, nr1;
+    int nrows;                          // level-0 rows
+    float minD, maxD, mbf;
+    float sf[ORBX_MAX_LEVELS];          // mvScaleFactors
+    int32_t* best_idx; int32_t* best_dist;      // [pair][capL]
+    float* uright; float* depth; int32_t* sad;  // [pair][ostride]
+    int ostride;
+};
+
+// descriptor search (R/src/Frame.cc:785-868): one warp per left keypoint, right keypoints in index order
+__global__ void __launch_bounds__(256) k_stereo_band(StereoArgs A)
 {
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, p = blockIdx.y;
     const int iL = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int nl = A.nL ? A.nL[A.slotL0 + p] : A.nl1, nr = A.nR ? A.nR[A.slotR0 + p] : A.nr1;
     if (iL >= nl) return;
+    const orbx_keypoint* kl = A.kL + (size_t)(A.slotL0 + p) * A.capL; const uint8_t* dl = A.dL + (size_t)(A.slotL0 + p) * A.capL * 32;
+    const orbx_keypoint* kr = A.kR + (size_t)(A.slotR0 + p) * A.capR; const uint8_t* dr = A.dR + (size_t)(A.slotR0 + p) * A.capR * 32;
     const orbx_keypoint L = kl[iL];
     const int row = (int)L.y;
-    const float minU = __fsub_rn(L.x, maxD), maxU = __fsub_rn(L.x, minD);
+    const float minU = __fsub_rn(L.x, A.maxD), maxU = __fsub_rn(L.x, A.minD);
     int bd = ORBX_TH_HIGH, bi = 0x7fffffff;
-    if (row >= 0 && row < nrows && !(maxU < 0)) {
+    if (row >= 0 && row < A.nrows && !(maxU < 0)) {
         const uint4 q0 = reinterpret_cast<const uint4*>(dl)[2 * iL], q1 = reinterpret_cast<const uint4*>(dl)[2 * iL + 1];
         for (int iR = lane; iR < nr; iR += 32) {
             const orbx_keypoint R = kr[iR];
-            const float r = __fmul_rn(2.0f, sf[R.octave]);
+            const float r = __fmul_rn(2.0f, A.sf[R.octave]);
             const int maxr = (int)ceilf(__fadd_rn(R.y, r)), minr = (int)floorf(__fsub_rn(R.y, r));
             if (row < minr || row > maxr) continue;
             if (R.octave < L.octave - 1 || R.octave > L.octave + 1) continue;
@@ -564,25 +578,25 @@ __global__ void __launch_bounds__(256) k_stereo_band(const orbx_keypoint* kl, co
         const int od = __shfl_xor_sync(0xffffffffu, bd, o), oi = __shfl_xor_sync(0xffffffffu, bi, o);
         if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
     }
-    if (lane == 0) { best_idx[iL] = bi == 0x7fffffff ? -1 : bi; best_dist[iL] = bd; }
+    if (lane == 0) { A.best_idx[(size_t)p * A.capL + iL] = bi == 0x7fffffff ? -1 : bi; A.best_dist[(size_t)p * A.capL + iL] = bd; }
 }
 
-// Frame::ComputeStereoMatches, sub-pixel refinement (R/src/Frame.cc:871-946): one warp per left keypoint.
+// sub-pixel refinement (R/src/Frame.cc:871-946): one warp per left keypoint.
 // 11x11 patches around the keypoint (left) and around the matched right keypoint shifted by incR = -5..5, both centred on
 // their own middle pixel, L1 distance per shift, parabola through the best shift and its neighbours.
-__global__ void __launch_bounds__(256) k_stereo_refine(const orbx_keypoint* kl, int nl, const orbx_keypoint* kr,
-                                                     const int32_t* best_idx, const int32_t* best_dist,
-                                                     OrbxPyrView L, OrbxPyrView R, float mbf, float minD, float maxD,
-                                                     float* uright, float* depth, int32_t* sad)
+__global__ void __launch_bounds__(256) k_stereo_refine(StereoArgs A, OrbxPyrView L, OrbxPyrView R)
 {
     __shared__ int s_d[8][12];
-    const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5, p = blockIdx.y;
     const int iL = blockIdx.x * 8 + wq;
+    const int nl = A.nL ? A.nL[A.slotL0 + p] : A.nl1;
     if (iL >= nl) return;
+    const orbx_keypoint* kl = A.kL + (size_t)(A.slotL0 + p) * A.capL;
+    const orbx_keypoint* kr = A.kR + (size_t)(A.slotR0 + p) * A.capR;
     float out_u = -1.0f, out_z = -1.0f; int out_s = -1;
-    const int bi = best_idx[iL];
+    const int bi = A.best_idx[(size_t)p * A.capL + iL];
     const int thOrbDist = (ORBX_TH_HIGH + ORBX_TH_LOW) / 2;
-    if (bi >= 0 && best_dist[iL] < thOrbDist) {
+    if (bi >= 0 && A.best_dist[(size_t)p * A.capL + iL] < thOrbDist) {
         const orbx_keypoint kp = kl[iL];
         const int oct = kp.octave;
         const float uL = kp.x;
@@ -593,8 +607,8 @@ __global__ void __launch_bounds__(256) k_stereo_refine(const orbx_keypoint* kl, 
         const float iniu = scaleduR0 + Lr - w, endu = scaleduR0 + Lr + w + 1;
         if (!(iniu < 0 || endu >= (float)R.w[oct])) {
             const int r0 = (int)(scaledvL - w), c0 = (int)(scaleduL - w), cr0 = (int)(scaleduR0 - w);
-            const uint8_t* imL = L.lv[oct]; const int pL = L.pitch[oct];
-            const uint8_t* imR = R.lv[oct]; const int pR = R.pitch[oct];
+            const uint8_t* imL = L.lv[oct] + (long long)p * L.fstride[oct]; const int pL = L.pitch[oct];
+            const uint8_t* imR = R.lv[oct] + (long long)p * R.fstride[oct]; const int pR = R.pitch[oct];
             if (lane < 11) s_d[wq][lane] = 0;
             __syncwarp();
             const int ctrL = imL[(long long)(r0 + w) * pL + c0 + w];
@@ -619,27 +633,34 @@ __global__ void __launch_bounds__(256) k_stereo_refine(const orbx_keypoint* kl, 
                 if (!(deltaR < -1 || deltaR > 1)) {
                     float bestuR = __fmul_rn(L.scale[oct], __fadd_rn(__fadd_rn(scaleduR0, (float)bestinc), deltaR));
                     float disparity = __fsub_rn(uL, bestuR);
-                    if (disparity >= minD && disparity < maxD) {
+                    if (disparity >= A.minD && disparity < A.maxD) {
                         if (disparity <= 0) { disparity = 0.01f; bestuR = (float)((double)uL - 0.01); }
-                        out_z = __fdiv_rn(mbf, disparity); out_u = bestuR; out_s = bestDist;
+                        out_z = __fdiv_rn(A.mbf, disparity); out_u = bestuR; out_s = bestDist;
                     }
                 }
             }
         }
     }
-    if (lane == 0) { uright[iL] = out_u; depth[iL] = out_z; sad[iL] = out_s; }
+    if (lane == 0) {
+        const size_t o = (size_t)p * A.ostride + iL;
+        A.uright[o] = out_u; A.depth[o] = out_z; A.sad[o] = out_s;
+    }
 }
 
-// median-based outlier cut (R/src/Frame.cc:949-962): one CTA; bitonic sort of the SAD distances of the matched keypoints
-__global__ void __launch_bounds__(1024) k_stereo_outliers(int nl, float* uright, float* depth, const int32_t* sad, int npad)
+// median-based outlier cut (R/src/Frame.cc:949-962): one CTA per pair; bitonic sort of the SAD distances of the matched keypoints
+__global__ void __launch_bounds__(1024) k_stereo_outliers(StereoArgs A, int npad)
 {
     extern __shared__ int s_v[];
     __shared__ int s_n;
+    const int p = blockIdx.x;
+    const int nl = A.nL ? A.nL[A.slotL0 + p] : A.nl1;
+    float* uright = A.uright + (size_t)p * A.ostride; float* depth = A.depth + (size_t)p * A.ostride;
+    const int32_t* sad = A.sad + (size_t)p * A.ostride;
     if (threadIdx.x == 0) s_n = 0;
     __syncthreads();
     int local = 0;
     for (int i = threadIdx.x; i < nl; i += 1024) local += sad[i] >= 0;
-    atomicAdd(&s_n, local);
+    if (local) atomicAdd(&s_n, local);
     for (int i = threadIdx.x; i < npad; i += 1024) s_v[i] = (i < nl && sad[i] >= 0) ? sad[i] : 0x7fffffff;
     __syncthreads();
     const int n = s_n;
@@ -737,6 +758,7 @@ struct orbx_matcher {
     unsigned* h_err;
     int32_t* d_pair_a; int32_t* d_pair_b;
     uint8_t* d_gen; size_t gen_bytes;
+    uint8_t* d_st; size_t st_bytes;          // stereo scratch
     cudaStream_t s_h2d, s_d2h, s_match; cudaEvent_t ev[2 * ORBX_MAX_CHUNKS]; cudaEvent_t ev_ext[ORBX_MAX_CHUNKS]; cudaEvent_t ev_start;
     std::vector<void*> allocs;
 };
@@ -792,6 +814,7 @@ extern "C" int orbx_matcher_create(const orbx_matcher_params* p, orbx_matcher** 
     m->d_bfq = m->d_bft = nullptr; m->bfq_bytes = m->bft_bytes = 0;
     m->d_pair_a = m->d_pair_b = nullptr;
     m->d_gen = nullptr; m->gen_bytes = 0;
+    m->d_st = nullptr; m->st_bytes = 0;
     m->s_h2d = m->s_d2h = nullptr;
     CKM(cudaMemset(W.err, 0, sizeof(unsigned)));
     CKM(cudaMallocHost((void**)&m->h_err, sizeof(unsigned)));
@@ -818,6 +841,7 @@ extern "C" void orbx_matcher_destroy(orbx_matcher* m)
     if (m->d_bft) cudaFree(m->d_bft);
     if (m->d_pair_a) cudaFree(m->d_pair_a);
     if (m->d_gen) cudaFree(m->d_gen);
+    if (m->d_st) cudaFree(m->d_st);
     if (m->s_h2d) {
         cudaStreamDestroy(m->s_h2d); cudaStreamDestroy(m->s_d2h); cudaStreamDestroy(m->s_match);
         for (int i = 0; i < ORBX_MAX_CHUNKS; i++) cudaEventDestroy(m->ev_ext[i]);
@@ -1237,9 +1261,14 @@ extern "C" int orbx_stereo_band_match(orbx_matcher* m, const orbx_keypoint* kl, 
         CKM(cudaMemcpyAsync(m->d_k2, kr, sizeof(orbx_keypoint) * nr, cudaMemcpyHostToDevice, s));
         CKM(cudaMemcpyAsync(m->d_d2, dr, (size_t)32 * nr, cudaMemcpyHostToDevice, s));
     }
-    CKM(cudaMemcpyAsync(m->d_sf, scale_factors, sizeof(float) * nlevels, cudaMemcpyHostToDevice, s));
-    k_stereo_band<<<(nl + 7) / 8, 256, 0, s>>>(m->d_k1, m->d_d1, nl, m->d_k2, m->d_d2, nr, m->d_sf, nrows, min_d, max_d,
-                                               m->d_out, m->d_out2);
+    {
+        StereoArgs A{};
+        A.kL = m->d_k1; A.dL = m->d_d1; A.capL = nl; A.kR = m->d_k2; A.dR = m->d_d2; A.capR = nr; A.nl1 = nl; A.nr1 = nr;
+        A.nrows = nrows; A.minD = min_d; A.maxD = max_d;
+        for (int l = 0; l < nlevels && l < ORBX_MAX_LEVELS; l++) A.sf[l] = scale_factors[l];
+        A.best_idx = m->d_out; A.best_dist = m->d_out2;
+        k_stereo_band<<<dim3((nl + 7) / 8, 1), 256, 0, s>>>(A); ORBX_COUNT_LAUNCH(1);
+    }
     CKM(cudaGetLastError());
     CKM(cudaMemcpyAsync(best_idx, m->d_out, sizeof(int32_t) * nl, cudaMemcpyDeviceToHost, s));
     CKM(cudaMemcpyAsync(best_dist, m->d_out2, sizeof(int32_t) * nl, cudaMemcpyDeviceToHost, s));
@@ -1248,44 +1277,113 @@ extern "C" int orbx_stereo_band_match(orbx_matcher* m, const orbx_keypoint* kl, 
 }
 
 // Frame::ComputeStereoMatches (R/src/Frame.cc:785-962) on two extractors' device-resident results and pyramids
+// Launches the three stereo kernels for `count` pairs: pair p = (left slot slot_l + p, frame frame_l + p) x (right ...).
+// d_best: 2 x count x capL ints of scratch; outputs have row stride `ostride`.
+static int stereo_launch(orbx_matcher* m, orbx_extractor* left, orbx_extractor* right, int slot_l, int slot_r, int frame_l, int frame_r,
+                         int count, float mb, float mbf, int32_t* d_best, float* d_u, float* d_z, int32_t* d_sad, int ostride, cudaStream_t s)
+{
+    orbx_keypoint *kL, *kR; uint8_t *dL, *dR; int32_t *nL, *nR; int capL, capR, slotsL, slotsR;
+    int rc = orbx_extractor_results_device(left, &kL, &dL, &nL, nullptr, &capL, &slotsL);
+    if (rc) return rc;
+    if ((rc = orbx_extractor_results_device(right, &kR, &dR, &nR, nullptr, &capR, &slotsR))) return rc;
+    if (count <= 0 || slot_l < 0 || slot_l + count > slotsL || slot_r < 0 || slot_r + count > slotsR || ostride < capL) return ORBX_E_INVALID;
+    OrbxPyrView vL, vR, tmp;
+    if ((rc = orbx_ex_pyramid_view(left, frame_l, &vL)) || (rc = orbx_ex_pyramid_view(right, frame_r, &vR))) return rc;
+    if ((rc = orbx_ex_pyramid_view(left, frame_l + count - 1, &tmp)) || (rc = orbx_ex_pyramid_view(right, frame_r + count - 1, &tmp))) return rc;
+    StereoArgs A{};
+    A.kL = kL; A.dL = dL; A.nL = nL; A.capL = capL; A.kR = kR; A.dR = dR; A.nR = nR; A.capR = capR;
+    A.slotL0 = slot_l; A.slotR0 = slot_r;
+    A.nrows = vL.h[0]; A.minD = 0.0f; A.maxD = mbf / mb; A.mbf = mbf;      // minZ = mb (R/src/Frame.cc:815-818)
+    for (int l = 0; l < vL.nlevels; l++) A.sf[l] = vL.scale[l];
+    A.best_idx = d_best; A.best_dist = d_best + (size_t)count * capL;
+    A.uright = d_u; A.depth = d_z; A.sad = d_sad; A.ostride = ostride;
+    const dim3 grid((capL + 7) / 8, count);
+    k_stereo_band<<<grid, 256, 0, s>>>(A); ORBX_COUNT_LAUNCH(1);
+    k_stereo_refine<<<grid, 256, 0, s>>>(A, vL, vR); ORBX_COUNT_LAUNCH(1);
+    int npad = 1; while (npad < capL) npad <<= 1;
+    if (sizeof(int) * npad > 48 * 1024) CKM(cudaFuncSetAttribute(k_stereo_outliers, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(int) * npad)));
+    k_stereo_outliers<<<count, 1024, sizeof(int) * npad, s>>>(A, npad); ORBX_COUNT_LAUNCH(1);
+    CKM(cudaGetLastError());
+    return ORBX_OK;
+}
+
+static int stereo_scratch(orbx_matcher* m, size_t bytes)
+{
+    if (bytes <= m->st_bytes) return ORBX_OK;
+    if (m->d_st) cudaFree(m->d_st);
+    m->d_st = nullptr; m->st_bytes = 0;
+    CKM(cudaMalloc((void**)&m->d_st, bytes));
+    m->st_bytes = bytes;
+    return ORBX_OK;
+}
+
 extern "C" int orbx_stereo_matches(orbx_matcher* m, orbx_extractor* left, orbx_extractor* right, int slot_l, int slot_r,
                                    int frame_l, int frame_r, float mb, float mbf, float* uright, float* depth,
                                    int32_t* sad_dist, int cap, int* n_left)
 {
     if (!m || !left || !right || !uright || !depth) return ORBX_E_INVALID;
-    orbx_keypoint *kL, *kR; uint8_t *dL, *dR; int32_t *nL, *nR; int capL, capR, slotsL, slotsR;
+    orbx_keypoint* kL; uint8_t* dL; int32_t* nL; int capL, slotsL;
     int rc = orbx_extractor_results_device(left, &kL, &dL, &nL, nullptr, &capL, &slotsL);
     if (rc) return rc;
-    rc = orbx_extractor_results_device(right, &kR, &dR, &nR, nullptr, &capR, &slotsR);
-    if (rc) return rc;
-    if (slot_l < 0 || slot_l >= slotsL || slot_r < 0 || slot_r >= slotsR || capL > m->K || capR > m->K) return ORBX_E_INVALID;
-    OrbxPyrView vL, vR;
-    if ((rc = orbx_ex_pyramid_view(left, frame_l, &vL)) || (rc = orbx_ex_pyramid_view(right, frame_r, &vR))) return rc;
+    if (slot_l < 0 || slot_l >= slotsL) return ORBX_E_INVALID;
     CKM(cudaSetDevice(m->p.device));
     // the extractors run on their own streams: wait for both, then work on the matcher's stream
     CKM(cudaStreamSynchronize(orbx_ex_stream(left)));
     CKM(cudaStreamSynchronize(orbx_ex_stream(right)));
     cudaStream_t s = m->stream;
-    int nl = 0, nr = 0;
+    int nl = 0;
     CKM(cudaMemcpyAsync(&nl, nL + slot_l, sizeof(int), cudaMemcpyDeviceToHost, s));
-    CKM(cudaMemcpyAsync(&nr, nR + slot_r, sizeof(int), cudaMemcpyDeviceToHost, s));
     CKM(cudaStreamSynchronize(s));
     if (n_left) *n_left = nl;
     if (nl > cap) { orbx_set_error("%s%s", "orbx_stereo_matches: output capacity too small", ""); return ORBX_E_CAPACITY; }
     if (nl == 0) return ORBX_OK;
-    const orbx_keypoint* dkl = kL + (size_t)slot_l * capL; const uint8_t* ddl = dL + (size_t)slot_l * capL * 32;
-    const orbx_keypoint* dkr = kR + (size_t)slot_r * capR; const uint8_t* ddr = dR + (size_t)slot_r * capR * 32;
-    CKM(cudaMemcpyAsync(m->d_sf, vL.scale, sizeof(float) * vL.nlevels, cudaMemcpyHostToDevice, s));
-    const float minD = 0.0f, maxD = mbf / mb;          // minZ = mb (:815-818)
-    float* d_u = m->d_prev; float* d_z = m->d_prev + m->K;
-    k_stereo_band<<<(nl + 7) / 8, 256, 0, s>>>(dkl, ddl, nl, dkr, ddr, nr, m->d_sf, vL.h[0], minD, maxD, m->d_out, m->d_out2); ORBX_COUNT_LAUNCH(1);
-    k_stereo_refine<<<(nl + 7) / 8, 256, 0, s>>>(dkl, nl, dkr, m->d_out, m->d_out2, vL, vR, mbf, minD, maxD, d_u, d_z, m->d_knn_idx); ORBX_COUNT_LAUNCH(1);
-    int npad = 1; while (npad < nl) npad <<= 1;
-    k_stereo_outliers<<<1, 1024, sizeof(int) * npad, s>>>(nl, d_u, d_z, m->d_knn_idx, npad); ORBX_COUNT_LAUNCH(1);
-    CKM(cudaGetLastError());
+    if ((rc = stereo_scratch(m, (size_t)capL * 5 * sizeof(int32_t)))) return rc;
+    int32_t* d_best = reinterpret_cast<int32_t*>(m->d_st);
+    float* d_u = reinterpret_cast<float*>(d_best + 2 * (size_t)capL); float* d_z = d_u + capL;
+    int32_t* d_sad = reinterpret_cast<int32_t*>(d_z + capL);
+    if ((rc = stereo_launch(m, left, right, slot_l, slot_r, frame_l, frame_r, 1, mb, mbf, d_best, d_u, d_z, d_sad, capL, s))) return rc;
     CKM(cudaMemcpyAsync(uright, d_u, sizeof(float) * nl, cudaMemcpyDeviceToHost, s));
     CKM(cudaMemcpyAsync(depth, d_z, sizeof(float) * nl, cudaMemcpyDeviceToHost, s));
-    if (sad_dist) CKM(cudaMemcpyAsync(sad_dist, m->d_knn_idx, sizeof(int32_t) * nl, cudaMemcpyDeviceToHost, s));
+    if (sad_dist) CKM(cudaMemcpyAsync(sad_dist, d_sad, sizeof(int32_t) * nl, cudaMemcpyDeviceToHost, s));
+    CKM(cudaStreamSynchronize(s));
+    return ORBX_OK;
+}
+
+// batched form on device buffers: pair p = slot / frame (first + p) of both extractors; everything is enqueued on `stream`
+// (the stream the two orbx_extract_batch_device calls used); outputs are [count][capacity of the left extractor]
+extern "C" int orbx_stereo_matches_batch_device(orbx_matcher* m, orbx_extractor* left, orbx_extractor* right, int first, int count,
+                                                float mb, float mbf, float* d_uright, float* d_depth, int32_t* d_sad, void* stream)
+{
+    if (!m || !left || !right || !d_uright || !d_depth || count <= 0) return ORBX_E_INVALID;
+    CKM(cudaSetDevice(m->p.device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : m->stream;
+    const int capL = orbx_ex_out_cap(left);
+    int rc = stereo_scratch(m, (size_t)count * capL * 3 * sizeof(int32_t));
+    if (rc) return rc;
+    int32_t* d_best = reinterpret_cast<int32_t*>(m->d_st);
+    int32_t* sad = d_sad ? d_sad : d_best + 2 * (size_t)count * capL;
+    return stereo_launch(m, left, right, first, first, first, first, count, mb, mbf, d_best, d_uright, d_depth, sad, capL, s);
+}
+
+// batched form with host outputs: uright/depth are [count][cap] (rows beyond a frame's keypoint count are unspecified)
+extern "C" int orbx_stereo_matches_batch(orbx_matcher* m, orbx_extractor* left, orbx_extractor* right, int first, int count,
+                                         float mb, float mbf, float* uright, float* depth, int cap)
+{
+    if (!m || !left || !right || !uright || !depth || count <= 0 || cap <= 0) return ORBX_E_INVALID;
+    CKM(cudaSetDevice(m->p.device));
+    CKM(cudaStreamSynchronize(orbx_ex_stream(left)));
+    CKM(cudaStreamSynchronize(orbx_ex_stream(right)));
+    cudaStream_t s = m->stream;
+    const int capL = orbx_ex_out_cap(left);
+    int rc = stereo_scratch(m, (size_t)count * capL * 5 * sizeof(int32_t));
+    if (rc) return rc;
+    int32_t* d_best = reinterpret_cast<int32_t*>(m->d_st);
+    float* d_u = reinterpret_cast<float*>(d_best + 2 * (size_t)count * capL); float* d_z = d_u + (size_t)count * capL;
+    int32_t* d_sad = reinterpret_cast<int32_t*>(d_z + (size_t)count * capL);
+    if ((rc = stereo_launch(m, left, right, first, first, first, first, count, mb, mbf, d_best, d_u, d_z, d_sad, capL, s))) return rc;
+    const int wcopy = cap < capL ? cap : capL;
+    CKM(cudaMemcpy2DAsync(uright, sizeof(float) * cap, d_u, sizeof(float) * capL, sizeof(float) * wcopy, count, cudaMemcpyDeviceToHost, s));
+    CKM(cudaMemcpy2DAsync(depth, sizeof(float) * cap, d_z, sizeof(float) * capL, sizeof(float) * wcopy, count, cudaMemcpyDeviceToHost, s));
     CKM(cudaStreamSynchronize(s));
     return ORBX_OK;
 }
@@ -1304,6 +1402,7 @@ extern "C" int orbx_match_candidates(orbx_matcher* m, const uint8_t* q, int nq, 
     const size_t bytes = (size_t)nq * 32 + (size_t)(nt > 0 ? nt : 1) * 32 + sizeof(int32_t) * ((size_t)nq + 1 + (ncand > 0 ? ncand : 1) + 4 * (size_t)nq) + 256;
     if (bytes > m->gen_bytes) {
         if (m->d_gen) cudaFree(m->d_gen);
+    if (m->d_st) cudaFree(m->d_st);
         CKM(cudaMalloc((void**)&m->d_gen, bytes)); m->gen_bytes = bytes;
     }
     dq = m->d_gen; dt = dq + (((size_t)nq * 32 + 63) & ~(size_t)63);

@@ -37,7 +37,8 @@ EXPORTS = [
     "orbx_bf_knn2", "orbx_bf_knn2_device", "orbx_knn2_merge_device",
     "orbx_search_for_initialization", "orbx_match_slots_device", "orbx_extract_match_batch", "orbx_extract_match_batch_device",
     "orbx_search_by_projection",
-    "orbx_stereo_band_match", "orbx_stereo_matches", "orbx_match_candidates", "orbx_popc_peak",
+    "orbx_stereo_band_match", "orbx_stereo_matches", "orbx_stereo_matches_batch", "orbx_stereo_matches_batch_device",
+    "orbx_match_candidates", "orbx_popc_peak",
 ]
 
 
@@ -110,6 +111,8 @@ def lib():
         L.orbx_popc_peak.argtypes = [i32, vp, vp]
         L.orbx_match_candidates.argtypes = [vp, vp, i32, vp, i32, vp, vp, vp, vp]
         L.orbx_stereo_matches.argtypes = [vp, vp, vp, i32, i32, i32, i32, f32, f32, vp, vp, vp, i32, vp]
+        L.orbx_stereo_matches_batch.argtypes = [vp, vp, vp, i32, i32, f32, f32, vp, vp, i32]
+        L.orbx_stereo_matches_batch_device.argtypes = [vp, vp, vp, i32, i32, f32, f32, vp, vp, vp, vp]
         _lib = L
     return _lib
 
@@ -342,6 +345,19 @@ class ORBmatcher:
         _check(lib().orbx_stereo_matches(self._h, ex_left._h, ex_right._h, slot_l, slot_r, frame_l, frame_r, float(mb), float(mbf),
                                          _p(ur), _p(dp), _p(sd), cap, C.byref(n)))
         return ur[:n.value].copy(), dp[:n.value].copy(), sd[:n.value].copy()
+
+    def ComputeStereoMatchesBatch(self, ex_left, ex_right, mb, mbf, first=0, count=1):
+        """Frame::ComputeStereoMatches for `count` stereo pairs of the two extractors' last batch -> (mvuRight, mvDepth) [count, cap]."""
+        cap = ex_left.cap
+        ur = np.empty((count, cap), np.float32); dp = np.empty((count, cap), np.float32)
+        _check(lib().orbx_stereo_matches_batch(self._h, ex_left._h, ex_right._h, first, count, float(mb), float(mbf), _p(ur), _p(dp), cap))
+        return ur, dp
+
+    def stereo_matches_batch_device(self, ex_left, ex_right, mb, mbf, first, count, d_uright, d_depth, d_sad=None, stream=None):
+        """device form: d_* are device pointers to [count][ex_left.cap] arrays; enqueued on `stream`, not synchronised."""
+        _check(lib().orbx_stereo_matches_batch_device(self._h, ex_left._h, ex_right._h, first, count, float(mb), float(mbf),
+                                                      C.c_void_p(d_uright), C.c_void_p(d_depth),
+                                                      C.c_void_p(d_sad) if d_sad else None, _s(stream)))
 
     def match_slots_device(self, extractor, a, b, bounds, window, d_matches12, d_nmatches, d_knn_idx=None,
                            d_knn_dist=None, stream=None):

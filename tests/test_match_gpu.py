@@ -248,6 +248,33 @@ def test_compute_stereo_matches_full(shape, nf, disp):
     exl.close(); exr.close(); m.close()
 
 
+def test_stereo_matches_batched_stream():
+    """C3 as a stream: a batch of KITTI-shape stereo pairs, both cameras extracted in batch, ComputeStereoMatches for all
+    pairs in three launches; every pair equals the oracle's per-pair result."""
+    W, H, nf, B = 1241, 376, 2000, 4
+    pairs = [synth.stereo_pair(W, H, seed=20 + i, disparity=15 + 3 * i) for i in range(B)]
+    Ls = np.stack([p[0] for p in pairs]); Rs = np.stack([p[1] for p in pairs])
+    exl = orbx.ORBextractor(nf, 1.2, 8, 20, 7, max_width=W, max_height=H, max_batch=B)
+    exr = orbx.ORBextractor(nf, 1.2, 8, 20, 7, max_width=W, max_height=H, max_batch=B)
+    gl = exl.extract_batch(Ls); gr = exr.extract_batch(Rs)
+    m = orbx.ORBmatcher(0.9, True, max_keypoints=exl.cap)
+    mb, mbf = 0.54, 386.1
+    ur, dp = m.ComputeStereoMatchesBatch(exl, exr, mb, mbf, 0, B)
+    for i in range(B):
+        ol, orr = O.Extractor(nf, 1.2, 8, 20, 7), O.Extractor(nf, 1.2, 8, 20, 7)
+        _, kl, dl = ol(Ls[i], (0, 0)); _, kr, dr = orr(Rs[i], (0, 0))
+        rur, rdp, _ = O.compute_stereo_matches(ol, orr, kl, dl, kr, dr, mb, mbf)
+        n = len(rur)
+        assert n == len(gl[i][1])
+        np.testing.assert_array_equal(ur[i, :n], rur)
+        np.testing.assert_array_equal(dp[i, :n], rdp)
+        assert (rur >= 0).sum() > 0.3 * n
+    # single-pair entry point on a slot of the batch agrees with the batched one
+    u1, d1, _ = m.ComputeStereoMatches(exl, exr, mb, mbf, slot_l=2, slot_r=2, frame_l=2, frame_r=2)
+    np.testing.assert_array_equal(u1, ur[2, :len(u1)])
+    exl.close(); exr.close(); m.close()
+
+
 def test_match_candidates_generic():
     """orbx_match_candidates: the primitive behind SearchByBoW / SearchForTriangulation / Fuse (explicit candidate lists)."""
     rng = np.random.default_rng(3)
