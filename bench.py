@@ -28,12 +28,13 @@ WINDOW, NNRATIO = 100, 0.9
 METRIC = "ORB frames/sec (extract+match) at 752x480, 1000 kp"
 
 
-def level_pixels():
+def level_pixels(w=None, h=None):
+    w = W if w is None else w; h = H if h is None else h
     s, out = 1.0, []
     sc = np.float32(1.0)
     for l in range(NLEVELS):
         inv = np.float32(1.0) / sc
-        out.append(int(np.rint(np.float32(W) * inv)) * int(np.rint(np.float32(H) * inv)))
+        out.append(int(np.rint(np.float32(w) * inv)) * int(np.rint(np.float32(h) * inv)))
         sc = np.float32(float(sc) * float(np.float32(SCALE)))
     return out
 
@@ -92,7 +93,7 @@ def reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_time / max(args.steps, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "C1: 752x480 mono, 1000 kp, 8 levels, scale 1.2, FAST 20/7; extract + SearchForInitialization(window 100) + BF kNN-2 vs previous frame"},
+        "config": {"workload": ("C4: 640x480 TUM-shape" if args.workload == "c4" else "C1: 752x480") + " mono, 1000 kp, 8 levels, scale 1.2, FAST 20/7; extract + SearchForInitialization(window 100) + BF kNN-2 vs previous frame"},
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port",
                          "sample": "%d frames per step (%d threads x %d frames of a 16-frame S-rects stream), %d steps" % (cores * per_thread, cores, per_thread, args.steps)},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -149,6 +150,154 @@ def server_bench(args, world, rank, local):
         dist.destroy_process_group()
 
 
+def stereo_bench(args, world, rank, local):
+    """BASELINE configs C2 (EuRoC 752x480, 1200 kp) and C3 (KITTI 1241x376, 2000 kp): a stream of stereo pairs per GPU.
+    Step = ORBextractor::operator() on every left and right frame + Frame::ComputeStereoMatches for every pair."""
+    import torch
+    import torch.distributed as dist
+    from multi_orbslam3_b200 import orbx, synth
+    if args.workload == "c2":
+        w, h, nf, mb, mbf, name = 752, 480, 1200, 0.11, 47.9, "C2: EuRoC-shape 752x480 stereo, 1200 kp per image"
+    else:
+        w, h, nf, mb, mbf, name = 1241, 376, 2000, 0.54, 386.1, "C3: KITTI-shape 1241x376 stereo, 2000 kp per image"
+    P = args.batch // 2 if args.batch != 512 else (256 if args.workload == "c2" else 192)     # pairs per step per GPU
+    exl = orbx.ORBextractor(nf, SCALE, NLEVELS, INI_TH, MIN_TH, max_width=w, max_height=h, max_batch=P, device=local)
+    exr = orbx.ORBextractor(nf, SCALE, NLEVELS, INI_TH, MIN_TH, max_width=w, max_height=h, max_batch=P, device=local)
+    m = orbx.ORBmatcher(NNRATIO, True, max_keypoints=exl.cap, device=local)
+    cap = exl.cap
+    uniq = min(P, 16)
+    pairs = [synth.stereo_pair(w, h, seed=1000 * rank + i, disparity=10 + (i % 8) * 3) for i in range(uniq)]
+    reps = (P + uniq - 1) // uniq
+    hl = torch.from_numpy(np.ascontiguousarray(np.concatenate([np.stack([p[0] for p in pairs])] * reps)[:P])).pin_memory()
+    hr = torch.from_numpy(np.ascontiguousarray(np.concatenate([np.stack([p[1] for p in pairs])] * reps)[:P])).pin_memory()
+    dl, dr = hl.cuda(), hr.cuda()
+    tstream = torch.cuda.Stream(); torch.cuda.set_stream(tstream); stream = tstream.cuda_stream
+    d_u = torch.empty((P, cap), dtype=torch.float32, device="cuda"); d_z = torch.empty((P, cap), dtype=torch.float32, device="cuda")
+
+    def step_device():
+        exl.extract_batch_device(dl.data_ptr(), P, w, h, w, w * h, (0, 0), 0, stream)
+        exr.extract_batch_device(dr.data_ptr(), P, w, h, w, w * h, (0, 0), 0, stream)
+        m.stereo_matches_batch_device(exl, exr, mb, mbf, 0, P, d_u.data_ptr(), d_z.data_ptr(), None, stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_device()
+    exl.sync(stream); exr.sync(stream)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = orbx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_device()
+    e1.record()
+    barrier()
+    launches = orbx.launch_count() - l0
+    exl.sync(stream); exr.sync(stream)
+    # stereo share of the step: the three stereo launches alone
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for _ in range(args.steps):
+        m.stereo_matches_batch_device(exl, exr, mb, mbf, 0, P, d_u.data_ptr(), d_z.data_ptr(), None, stream)
+    s1.record()
+    torch.cuda.synchronize()
+    stereo_ms = s0.elapsed_time(s1) / args.steps
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    value = world * 2 * P / (ms_step * 1e-3)
+    matched = float((d_u >= 0).float().sum(1).mean().item())
+
+    # end to end: pinned host frames of both cameras in; keypoints, descriptors, mvuRight, mvDepth on the host
+    e2e = None
+    if not args.no_e2e:
+        L = orbx.lib()
+        def pin(shape, dt):
+            return torch.empty(shape, dtype=dt).pin_memory().numpy()
+        ok = [pin((P, cap, 7), torch.float32) for _ in range(2)]; od = [pin((P, cap, 32), torch.uint8) for _ in range(2)]
+        on = [pin((P,), torch.int32) for _ in range(4)]
+        hu, hz = pin((P, cap), torch.float32), pin((P, cap), torch.float32)
+        hln, hrn = hl.numpy(), hr.numpy()
+
+        def step_host():
+            for ex, img, k, d, n, mo in ((exl, hln, ok[0], od[0], on[0], on[1]), (exr, hrn, ok[1], od[1], on[2], on[3])):
+                orbx._check(L.orbx_extract_batch(ex._h, orbx._p(img), P, w, h, w, w * h, 0, 0, orbx._p(k), orbx._p(d), cap, orbx._p(n), orbx._p(mo)))
+            orbx._check(L.orbx_stereo_matches_batch(m._h, exl._h, exr._h, 0, P, mb, mbf, orbx._p(hu), orbx._p(hz), cap))
+        for _ in range(2):
+            step_host()
+        barrier()
+        ns = max(3, min(args.steps, 8))
+        t0 = time.perf_counter()
+        for _ in range(ns):
+            step_host()
+        torch.cuda.synchronize()
+        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * 2 * P * ns / float(t.item()), "unit": "frames/s", "h2d_bytes_per_step": 2 * P * w * h,
+               "d2h_bytes_per_step": 2 * P * (cap * 60 + 8) + 2 * P * cap * 4, "steps": ns,
+               "api": "orbx_extract_batch x2 + orbx_stereo_matches_batch (pinned host frames -> keypoints, descriptors, mvuRight, mvDepth on host)"}
+    clocks = sampler.stop() if rank == 0 else None
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle as O
+        O.build()
+        cores = os.cpu_count() or 1
+        res = [0] * cores
+
+        def work(i, npairs):
+            ol, orr = O.Extractor(nf, SCALE, NLEVELS, INI_TH, MIN_TH), O.Extractor(nf, SCALE, NLEVELS, INI_TH, MIN_TH)
+            for j in range(npairs):
+                a, b = pairs[(i + j) % uniq]
+                _, kl, dsl = ol(a, (0, 0)); _, kr, dsr = orr(b, (0, 0))
+                O.compute_stereo_matches(ol, orr, kl, dsl, kr, dsr, mb, mbf)
+                res[i] += 2
+
+        def run(npairs):
+            for i in range(cores):
+                res[i] = 0
+            th = [threading.Thread(target=work, args=(i, npairs)) for i in range(cores)]
+            t0 = time.perf_counter()
+            [x.start() for x in th]; [x.join() for x in th]
+            return time.perf_counter() - t0
+        dcal = run(1)
+        per = int(min(500, max(2, 12.0 / max(dcal, 1e-3))))
+        dtc = run(per)
+        cpu = {"value": sum(res) / dtc, "unit": "frames/s", "cores": cores, "kind": "port",
+               "sample": "%d stereo pairs (%d threads x %d pairs), %.1f s wall" % (sum(res) // 2, cores, per, dtc)}
+
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    hbm_peak = float(json.load(open(peaks_path))["hbm_gbs"]) if os.path.exists(peaks_path) else 6650.0
+    px = level_pixels(w, h); Ppx = sum(px)
+    bytes_step = 2 * P * ((Ppx - px[-1]) + (Ppx - px[0]) + 2 * Ppx + Ppx)         # pyramid + blur + FAST, both cameras
+    line = {"metric": "ORB frames/sec (extract both cameras + ComputeStereoMatches) at %dx%d, %d kp" % (w, h, nf), "value": value,
+            "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": name + "; 8 levels, scale 1.2, FAST 20/7; extract L + R, stereo descriptor search + SAD refinement + outlier cut",
+                       "pairs_per_step_per_gpu": P, "l2": "inputs larger than L2 (%d MB of frames per step)" % (2 * P * w * h // 2 ** 20),
+                       "mean_stereo_matches": matched},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "image kernels (pyramid+blur+FAST) of both cameras", "achieved": bytes_step / ((ms_step - stereo_ms) * 1e-3) / 1e9,
+                         "peak": hbm_peak, "unit": "GB/s", "frac": bytes_step / ((ms_step - stereo_ms) * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+                         "stages": {"extract L+R": {"ms_per_step": ms_step - stereo_ms}, "stereo band + refine + outliers (3 launches)": {"ms_per_step": stereo_ms}}},
+            "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+    exl.close(); exr.close(); m.close()
+
+
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
@@ -200,8 +349,10 @@ def main():
     ap.add_argument("--batch", type=int, default=512, help="frames per step per GPU (512 x 361 KB = 185 MB of input > 126 MB L2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
-    ap.add_argument("--workload", default="c1", choices=["c1", "c5"],
-                    help="c1 (default, the BASELINE metric): extract+match streams; c5: server cross-agent BF matching over a sharded DB")
+    ap.add_argument("--workload", default="c1", choices=["c1", "c2", "c3", "c4", "c5"],
+                    help="c1 (default, the BASELINE metric): extract+match streams; c2 / c3: EuRoC / KITTI stereo streams "
+                         "(extract both cameras + ComputeStereoMatches); c4: c1 at TUM shape 640x480; "
+                         "c5: server cross-agent BF matching over a sharded DB")
     ap.add_argument("--db-keyframes", type=int, default=65536, help="c5: keyframes in the whole DB (x1000 descriptors)")
     ap.add_argument("--exchange", default="top2", choices=["top2", "db"], help="c5: all-gather partial top-2 tables or the DB shards")
     args = ap.parse_args()
@@ -228,6 +379,12 @@ def main():
 
     if args.workload == "c5":
         return server_bench(args, world, rank, local)
+    if args.workload in ("c2", "c3"):
+        return stereo_bench(args, world, rank, local)
+    global W, H, METRIC
+    if args.workload == "c4":
+        W, H = 640, 480
+        METRIC = "ORB frames/sec (extract+match) at 640x480, 1000 kp"
 
     B = args.batch
     ex = orbx.ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, max_width=W, max_height=H, max_batch=B, device=local)
@@ -415,7 +572,7 @@ def main():
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
         "data": "synthetic",
-        "config": {"workload": "C1: 752x480 mono, 1000 kp, 8 levels, scale 1.2, FAST 20/7; extract + SearchForInitialization(window 100) + BF kNN-2 vs previous frame",
+        "config": {"workload": ("C4: 640x480 TUM-shape" if args.workload == "c4" else "C1: 752x480") + " mono, 1000 kp, 8 levels, scale 1.2, FAST 20/7; extract + SearchForInitialization(window 100) + BF kNN-2 vs previous frame",
                    "frames_per_step_per_gpu": B, "streams": "one S-rects camera stream per GPU, no collective",
                    "l2": "inputs larger than L2 (%d MB of frames per step, >1 GB touched)" % (B * W * H // 2 ** 20),
                    "mean_keypoints": nkp_mean, "mean_init_matches": nmatch_mean},

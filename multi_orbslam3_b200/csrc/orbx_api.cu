@@ -49,6 +49,7 @@ struct orbx_extractor {
     // level-0 staging for host images
     uint8_t* d_level0; int pitch0; long long stride0;
     uint8_t* h_stage_in;     // pinned
+    uint8_t* d_raw; size_t raw_bytes;   // device landing zone for host rows whose stride is not the staging pitch
     orbx_keypoint* h_kps; uint8_t* h_desc; int* h_n; int* h_mono; unsigned* h_err;   // pinned
     // what the last batch used as level 0 (for pyramid_to_host)
     const uint8_t* last_level0; int last_pitch0; long long last_stride0; int last_batch;
@@ -272,6 +273,7 @@ extern "C" int orbx_extractor_create(const orbx_params* p, orbx_extractor** out)
     memset(&h->geom, 0, sizeof(h->geom));
     memset(&h->buf, 0, sizeof(h->buf));
     h->d_level0 = nullptr; h->last_level0 = nullptr; h->last_batch = 0;
+    h->d_raw = nullptr; h->raw_bytes = 0;
     h->profile = false; h->ev_head = 0; h->ev_count = 0; h->stage_batches = 0;
     for (int i = 0; i < 4; i++) h->stage_ms[i] = 0;
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
@@ -294,6 +296,7 @@ extern "C" void orbx_extractor_destroy(orbx_extractor* h)
     cudaSetDevice(h->p.device);
     cudaStreamSynchronize(h->stream);
     for (void* p : h->allocs) cudaFree(p);
+    if (h->d_raw) cudaFree(h->d_raw);
     cudaFreeHost(h->h_stage_in); cudaFreeHost(h->h_kps); cudaFreeHost(h->h_desc);
     cudaFreeHost(h->h_n); cudaFreeHost(h->h_mono); cudaFreeHost(h->h_err);
     for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
@@ -460,7 +463,16 @@ int orbx_ex_stage_input(orbx_extractor* h, const uint8_t* imgs, int f0, int coun
         if (frame_stride == (size_t)stride * height && stride == p0) {
             CK(cudaMemcpyAsync(dst, src, (size_t)h->stride0 * count, cudaMemcpyHostToDevice, s));
         } else if (frame_stride == (size_t)stride * height) {
-            CK(cudaMemcpy2DAsync(dst, p0, src, stride, width, (size_t)height * count, cudaMemcpyHostToDevice, s));
+            // rows at another pitch (e.g. a 1241-px-wide KITTI frame): one contiguous DMA into a device landing zone, then
+            // a device-side 2-D copy to the staging pitch (a strided host->device DMA runs at a fraction of the link rate)
+            const size_t need = frame_stride * (size_t)h->p.max_batch;
+            if (need > h->raw_bytes) {
+                if (h->d_raw) { CK(cudaStreamSynchronize(s)); cudaFree(h->d_raw); h->d_raw = nullptr; h->raw_bytes = 0; }
+                CK(cudaMalloc((void**)&h->d_raw, need)); h->raw_bytes = need;
+            }
+            uint8_t* raw = h->d_raw + (size_t)f0 * frame_stride;
+            CK(cudaMemcpyAsync(raw, src, frame_stride * count, cudaMemcpyHostToDevice, s));
+            CK(cudaMemcpy2DAsync(dst, p0, raw, stride, width, (size_t)height * count, cudaMemcpyDeviceToDevice, s));
         } else {
             for (int f = 0; f < count; f++)
                 CK(cudaMemcpy2DAsync(dst + (size_t)f * h->stride0, p0, src + f * frame_stride, stride, width, height,

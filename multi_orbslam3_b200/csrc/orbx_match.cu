@@ -546,39 +546,99 @@ struct StereoArgs {
     int ostride;
 };
 
-// descriptor search (R/src/Frame.cc:785-868): one warp per left keypoint, right keypoints in index order
-__global__ void __launch_bounds__(256) k_stereo_band(StereoArgs A)
+// descriptor search (R/src/Frame.cc:785-868), one CTA per stereo pair:
+//   1. vRowIndices (:798-812): every right keypoint is listed under the level-0 rows [floor(y - r), ceil(y + r)],
+//      r = 2 * scale(octave), as a CSR table (row histogram in shared memory, block scan, fill into `lists`);
+//   2. one warp per left keypoint walks the list of its own row (:826-865): octave gate, disparity gate, Hamming distance;
+//      best = smallest distance, ties -> smallest right index (the reference visits a row's list in index order).
+constexpr int STEREO_NT = 1024;
+__device__ __forceinline__ void stereo_row_range(const orbx_keypoint& R, const float* sf, int nrows, int& minr, int& maxr)
 {
-    const int lane = threadIdx.x & 31, p = blockIdx.y;
-    const int iL = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const float r = __fmul_rn(2.0f, sf[R.octave]);
+    maxr = (int)ceilf(__fadd_rn(R.y, r)); minr = (int)floorf(__fsub_rn(R.y, r));
+    if (minr < 0) minr = 0;
+    if (maxr > nrows - 1) maxr = nrows - 1;
+}
+
+__global__ void __launch_bounds__(STEREO_NT) k_stereo_band(StereoArgs A, int32_t* lists, int list_cap)
+{
+    extern __shared__ int s_rows[];                 // [nrows + 1] starts, [nrows + 1] fill cursors
+    __shared__ int s_warp[STEREO_NT / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, p = blockIdx.x;
     const int nl = A.nL ? A.nL[A.slotL0 + p] : A.nl1, nr = A.nR ? A.nR[A.slotR0 + p] : A.nr1;
-    if (iL >= nl) return;
+    const int nrows = A.nrows;
+    int* start = s_rows; int* cur = s_rows + nrows + 1;
     const orbx_keypoint* kl = A.kL + (size_t)(A.slotL0 + p) * A.capL; const uint8_t* dl = A.dL + (size_t)(A.slotL0 + p) * A.capL * 32;
     const orbx_keypoint* kr = A.kR + (size_t)(A.slotR0 + p) * A.capR; const uint8_t* dr = A.dR + (size_t)(A.slotR0 + p) * A.capR * 32;
-    const orbx_keypoint L = kl[iL];
-    const int row = (int)L.y;
-    const float minU = __fsub_rn(L.x, A.maxD), maxU = __fsub_rn(L.x, A.minD);
-    int bd = ORBX_TH_HIGH, bi = 0x7fffffff;
-    if (row >= 0 && row < A.nrows && !(maxU < 0)) {
-        const uint4 q0 = reinterpret_cast<const uint4*>(dl)[2 * iL], q1 = reinterpret_cast<const uint4*>(dl)[2 * iL + 1];
-        for (int iR = lane; iR < nr; iR += 32) {
-            const orbx_keypoint R = kr[iR];
-            const float r = __fmul_rn(2.0f, A.sf[R.octave]);
-            const int maxr = (int)ceilf(__fadd_rn(R.y, r)), minr = (int)floorf(__fsub_rn(R.y, r));
-            if (row < minr || row > maxr) continue;
-            if (R.octave < L.octave - 1 || R.octave > L.octave + 1) continue;
-            if (!(R.x >= minU && R.x <= maxU)) continue;
-            const uint4 t0 = reinterpret_cast<const uint4*>(dr)[2 * iR], t1 = reinterpret_cast<const uint4*>(dr)[2 * iR + 1];
-            const int d = hamming256(q0, q1, t0, t1);
-            if (d < bd) { bd = d; bi = iR; }     // iR ascending per lane: first wins inside the lane
-        }
+    int32_t* list = lists + (size_t)p * list_cap;
+    for (int i = tid; i <= nrows; i += STEREO_NT) start[i] = 0;
+    __syncthreads();
+    for (int iR = tid; iR < nr; iR += STEREO_NT) {
+        int minr, maxr;
+        stereo_row_range(kr[iR], A.sf, nrows, minr, maxr);
+        for (int y = minr; y <= maxr; y++) atomicAdd(&start[y], 1);
     }
+    __syncthreads();
+    {   // exclusive scan of the row histogram: each thread owns a run of consecutive rows
+        const int per = (nrows + STEREO_NT) / STEREO_NT;
+        const int r0 = tid * per, r1 = min(r0 + per, nrows + 1);
+        int sum = 0;
+        for (int r = r0; r < r1; r++) sum += start[r];
+        int inc = sum;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const int od = __shfl_xor_sync(0xffffffffu, bd, o), oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            int w = s_warp[lane], wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += t; }
+            s_warp[lane] = wi - w;
+        }
+        __syncthreads();
+        int run = s_warp[warp] + inc - sum;
+        for (int r = r0; r < r1; r++) { const int c = start[r]; start[r] = run; cur[r] = run; run += c; }
     }
-    if (lane == 0) { A.best_idx[(size_t)p * A.capL + iL] = bi == 0x7fffffff ? -1 : bi; A.best_dist[(size_t)p * A.capL + iL] = bd; }
+    __syncthreads();
+    for (int iR = tid; iR < nr; iR += STEREO_NT) {
+        int minr, maxr;
+        stereo_row_range(kr[iR], A.sf, nrows, minr, maxr);
+        for (int y = minr; y <= maxr; y++) { const int o = atomicAdd(&cur[y], 1); if (o < list_cap) list[o] = iR; }
+    }
+    __syncthreads();
+    for (int iL = warp; iL < nl; iL += STEREO_NT / 32) {
+        const orbx_keypoint L = kl[iL];
+        const int row = (int)L.y;
+        const float minU = __fsub_rn(L.x, A.maxD), maxU = __fsub_rn(L.x, A.minD);
+        int bd = ORBX_TH_HIGH, bi = 0x7fffffff;
+        if (row >= 0 && row < nrows && !(maxU < 0)) {
+            const uint4 q0 = reinterpret_cast<const uint4*>(dl)[2 * iL], q1 = reinterpret_cast<const uint4*>(dl)[2 * iL + 1];
+            const int k1 = min(start[row + 1], list_cap);
+            for (int k = start[row] + lane; k < k1; k += 32) {
+                const int iR = list[k];
+                const int oct = kr[iR].octave; const float xr = kr[iR].x;
+                if (oct < L.octave - 1 || oct > L.octave + 1) continue;
+                if (!(xr >= minU && xr <= maxU)) continue;
+                const uint4 t0 = reinterpret_cast<const uint4*>(dr)[2 * iR], t1 = reinterpret_cast<const uint4*>(dr)[2 * iR + 1];
+                const int d = hamming256(q0, q1, t0, t1);
+                if (d < bd || (d == bd && iR < bi && d < ORBX_TH_HIGH)) { bd = d; bi = iR; }    // strict '<' from TH_HIGH (:829)
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const int od = __shfl_xor_sync(0xffffffffu, bd, o), oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+        }
+        if (lane == 0) { A.best_idx[(size_t)p * A.capL + iL] = bi == 0x7fffffff ? -1 : bi; A.best_dist[(size_t)p * A.capL + iL] = bd; }
+    }
+}
+
+// rows a right keypoint can be listed under: 2 * ceil(2 * largest scale factor) + 3
+static int stereo_rows_per_kp(const float* sf, int nlevels)
+{
+    float mx = 1.0f;
+    for (int l = 0; l < nlevels; l++) if (sf[l] > mx) mx = sf[l];
+    return 2 * (int)ceilf(2.0f * mx) + 3;
 }
 
 // sub-pixel refinement (R/src/Frame.cc:871-946): one warp per left keypoint.
@@ -1246,6 +1306,8 @@ extern "C" int orbx_extract_match_batch_device(orbx_extractor* ex, orbx_matcher*
                                   d_knn_dist, stream ? (cudaStream_t)stream : orbx_ex_stream(ex));
 }
 
+static int stereo_scratch(orbx_matcher* m, size_t bytes);
+
 extern "C" int orbx_stereo_band_match(orbx_matcher* m, const orbx_keypoint* kl, const uint8_t* dl, int nl,
                                       const orbx_keypoint* kr, const uint8_t* dr, int nr, const float* scale_factors,
                                       int nlevels, int nrows, float min_d, float max_d, int32_t* best_idx, int32_t* best_dist)
@@ -1267,7 +1329,13 @@ extern "C" int orbx_stereo_band_match(orbx_matcher* m, const orbx_keypoint* kl, 
         A.nrows = nrows; A.minD = min_d; A.maxD = max_d;
         for (int l = 0; l < nlevels && l < ORBX_MAX_LEVELS; l++) A.sf[l] = scale_factors[l];
         A.best_idx = m->d_out; A.best_dist = m->d_out2;
-        k_stereo_band<<<dim3((nl + 7) / 8, 1), 256, 0, s>>>(A); ORBX_COUNT_LAUNCH(1);
+        const int list_cap = (nr > 0 ? nr : 1) * stereo_rows_per_kp(A.sf, nlevels < ORBX_MAX_LEVELS ? nlevels : ORBX_MAX_LEVELS);
+        int rc = stereo_scratch(m, sizeof(int32_t) * (size_t)list_cap);
+        if (rc) return rc;
+        const size_t smem = sizeof(int) * 2 * ((size_t)nrows + 1);
+        if (smem > 200 * 1024) return ORBX_E_INVALID;
+        if (smem > 48 * 1024) CKM(cudaFuncSetAttribute(k_stereo_band, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_stereo_band<<<1, STEREO_NT, smem, s>>>(A, reinterpret_cast<int32_t*>(m->d_st), list_cap); ORBX_COUNT_LAUNCH(1);
     }
     CKM(cudaGetLastError());
     CKM(cudaMemcpyAsync(best_idx, m->d_out, sizeof(int32_t) * nl, cudaMemcpyDeviceToHost, s));
@@ -1277,10 +1345,30 @@ extern "C" int orbx_stereo_band_match(orbx_matcher* m, const orbx_keypoint* kl, 
 }
 
 // Frame::ComputeStereoMatches (R/src/Frame.cc:785-962) on two extractors' device-resident results and pyramids
+// Device scratch of one stereo call: row lists, best index / distance, and (when the caller's outputs live on the host)
+// mvuRight / mvDepth / SAD rows.
+struct StereoScratch { int32_t* lists; int list_cap; int32_t* best; float* u; float* z; int32_t* sad; };
+static int stereo_prepare(orbx_matcher* m, orbx_extractor* left, orbx_extractor* right, int count, StereoScratch* S)
+{
+    const int capL = orbx_ex_out_cap(left), capR = orbx_ex_out_cap(right);
+    OrbxPyrView v;
+    int rc = orbx_ex_pyramid_view(left, 0, &v);
+    if (rc) return rc;
+    S->list_cap = capR * stereo_rows_per_kp(v.scale, v.nlevels);
+    const size_t n_lists = (size_t)count * S->list_cap, n_row = (size_t)count * capL;
+    if ((rc = stereo_scratch(m, sizeof(int32_t) * (n_lists + 5 * n_row)))) return rc;
+    S->lists = reinterpret_cast<int32_t*>(m->d_st);
+    S->best = S->lists + n_lists;
+    S->u = reinterpret_cast<float*>(S->best + 2 * n_row); S->z = S->u + n_row;
+    S->sad = reinterpret_cast<int32_t*>(S->z + n_row);
+    return ORBX_OK;
+}
+
 // Launches the three stereo kernels for `count` pairs: pair p = (left slot slot_l + p, frame frame_l + p) x (right ...).
-// d_best: 2 x count x capL ints of scratch; outputs have row stride `ostride`.
+// Outputs have row stride `ostride`.
 static int stereo_launch(orbx_matcher* m, orbx_extractor* left, orbx_extractor* right, int slot_l, int slot_r, int frame_l, int frame_r,
-                         int count, float mb, float mbf, int32_t* d_best, float* d_u, float* d_z, int32_t* d_sad, int ostride, cudaStream_t s)
+                         int count, float mb, float mbf, const StereoScratch& S, float* d_u, float* d_z, int32_t* d_sad, int ostride,
+                         cudaStream_t s)
 {
     orbx_keypoint *kL, *kR; uint8_t *dL, *dR; int32_t *nL, *nR; int capL, capR, slotsL, slotsR;
     int rc = orbx_extractor_results_device(left, &kL, &dL, &nL, nullptr, &capL, &slotsL);
@@ -1295,11 +1383,15 @@ static int stereo_launch(orbx_matcher* m, orbx_extractor* left, orbx_extractor* 
     A.slotL0 = slot_l; A.slotR0 = slot_r;
     A.nrows = vL.h[0]; A.minD = 0.0f; A.maxD = mbf / mb; A.mbf = mbf;      // minZ = mb (R/src/Frame.cc:815-818)
     for (int l = 0; l < vL.nlevels; l++) A.sf[l] = vL.scale[l];
-    A.best_idx = d_best; A.best_dist = d_best + (size_t)count * capL;
+    A.best_idx = S.best; A.best_dist = S.best + (size_t)count * capL;
     A.uright = d_u; A.depth = d_z; A.sad = d_sad; A.ostride = ostride;
-    const dim3 grid((capL + 7) / 8, count);
-    k_stereo_band<<<grid, 256, 0, s>>>(A); ORBX_COUNT_LAUNCH(1);
-    k_stereo_refine<<<grid, 256, 0, s>>>(A, vL, vR); ORBX_COUNT_LAUNCH(1);
+    {
+        const size_t smem = sizeof(int) * 2 * ((size_t)A.nrows + 1);
+        if (smem > 200 * 1024) return ORBX_E_INVALID;
+        if (smem > 48 * 1024) CKM(cudaFuncSetAttribute(k_stereo_band, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_stereo_band<<<count, STEREO_NT, smem, s>>>(A, S.lists, S.list_cap); ORBX_COUNT_LAUNCH(1);
+    }
+    k_stereo_refine<<<dim3((capL + 7) / 8, count), 256, 0, s>>>(A, vL, vR); ORBX_COUNT_LAUNCH(1);
     int npad = 1; while (npad < capL) npad <<= 1;
     if (sizeof(int) * npad > 48 * 1024) CKM(cudaFuncSetAttribute(k_stereo_outliers, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(int) * npad)));
     k_stereo_outliers<<<count, 1024, sizeof(int) * npad, s>>>(A, npad); ORBX_COUNT_LAUNCH(1);
@@ -1310,7 +1402,7 @@ static int stereo_launch(orbx_matcher* m, orbx_extractor* left, orbx_extractor* 
 static int stereo_scratch(orbx_matcher* m, size_t bytes)
 {
     if (bytes <= m->st_bytes) return ORBX_OK;
-    if (m->d_st) cudaFree(m->d_st);
+    if (m->d_st) { cudaDeviceSynchronize(); cudaFree(m->d_st); }
     m->d_st = nullptr; m->st_bytes = 0;
     CKM(cudaMalloc((void**)&m->d_st, bytes));
     m->st_bytes = bytes;
@@ -1337,14 +1429,12 @@ extern "C" int orbx_stereo_matches(orbx_matcher* m, orbx_extractor* left, orbx_e
     if (n_left) *n_left = nl;
     if (nl > cap) { orbx_set_error("%s%s", "orbx_stereo_matches: output capacity too small", ""); return ORBX_E_CAPACITY; }
     if (nl == 0) return ORBX_OK;
-    if ((rc = stereo_scratch(m, (size_t)capL * 5 * sizeof(int32_t)))) return rc;
-    int32_t* d_best = reinterpret_cast<int32_t*>(m->d_st);
-    float* d_u = reinterpret_cast<float*>(d_best + 2 * (size_t)capL); float* d_z = d_u + capL;
-    int32_t* d_sad = reinterpret_cast<int32_t*>(d_z + capL);
-    if ((rc = stereo_launch(m, left, right, slot_l, slot_r, frame_l, frame_r, 1, mb, mbf, d_best, d_u, d_z, d_sad, capL, s))) return rc;
-    CKM(cudaMemcpyAsync(uright, d_u, sizeof(float) * nl, cudaMemcpyDeviceToHost, s));
-    CKM(cudaMemcpyAsync(depth, d_z, sizeof(float) * nl, cudaMemcpyDeviceToHost, s));
-    if (sad_dist) CKM(cudaMemcpyAsync(sad_dist, d_sad, sizeof(int32_t) * nl, cudaMemcpyDeviceToHost, s));
+    StereoScratch S;
+    if ((rc = stereo_prepare(m, left, right, 1, &S))) return rc;
+    if ((rc = stereo_launch(m, left, right, slot_l, slot_r, frame_l, frame_r, 1, mb, mbf, S, S.u, S.z, S.sad, capL, s))) return rc;
+    CKM(cudaMemcpyAsync(uright, S.u, sizeof(float) * nl, cudaMemcpyDeviceToHost, s));
+    CKM(cudaMemcpyAsync(depth, S.z, sizeof(float) * nl, cudaMemcpyDeviceToHost, s));
+    if (sad_dist) CKM(cudaMemcpyAsync(sad_dist, S.sad, sizeof(int32_t) * nl, cudaMemcpyDeviceToHost, s));
     CKM(cudaStreamSynchronize(s));
     return ORBX_OK;
 }
@@ -1357,12 +1447,11 @@ extern "C" int orbx_stereo_matches_batch_device(orbx_matcher* m, orbx_extractor*
     if (!m || !left || !right || !d_uright || !d_depth || count <= 0) return ORBX_E_INVALID;
     CKM(cudaSetDevice(m->p.device));
     cudaStream_t s = stream ? (cudaStream_t)stream : m->stream;
-    const int capL = orbx_ex_out_cap(left);
-    int rc = stereo_scratch(m, (size_t)count * capL * 3 * sizeof(int32_t));
+    StereoScratch S;
+    int rc = stereo_prepare(m, left, right, count, &S);
     if (rc) return rc;
-    int32_t* d_best = reinterpret_cast<int32_t*>(m->d_st);
-    int32_t* sad = d_sad ? d_sad : d_best + 2 * (size_t)count * capL;
-    return stereo_launch(m, left, right, first, first, first, first, count, mb, mbf, d_best, d_uright, d_depth, sad, capL, s);
+    return stereo_launch(m, left, right, first, first, first, first, count, mb, mbf, S, d_uright, d_depth, d_sad ? d_sad : S.sad,
+                         orbx_ex_out_cap(left), s);
 }
 
 // batched form with host outputs: uright/depth are [count][cap] (rows beyond a frame's keypoint count are unspecified)
@@ -1375,15 +1464,13 @@ extern "C" int orbx_stereo_matches_batch(orbx_matcher* m, orbx_extractor* left, 
     CKM(cudaStreamSynchronize(orbx_ex_stream(right)));
     cudaStream_t s = m->stream;
     const int capL = orbx_ex_out_cap(left);
-    int rc = stereo_scratch(m, (size_t)count * capL * 5 * sizeof(int32_t));
+    StereoScratch S;
+    int rc = stereo_prepare(m, left, right, count, &S);
     if (rc) return rc;
-    int32_t* d_best = reinterpret_cast<int32_t*>(m->d_st);
-    float* d_u = reinterpret_cast<float*>(d_best + 2 * (size_t)count * capL); float* d_z = d_u + (size_t)count * capL;
-    int32_t* d_sad = reinterpret_cast<int32_t*>(d_z + (size_t)count * capL);
-    if ((rc = stereo_launch(m, left, right, first, first, first, first, count, mb, mbf, d_best, d_u, d_z, d_sad, capL, s))) return rc;
+    if ((rc = stereo_launch(m, left, right, first, first, first, first, count, mb, mbf, S, S.u, S.z, S.sad, capL, s))) return rc;
     const int wcopy = cap < capL ? cap : capL;
-    CKM(cudaMemcpy2DAsync(uright, sizeof(float) * cap, d_u, sizeof(float) * capL, sizeof(float) * wcopy, count, cudaMemcpyDeviceToHost, s));
-    CKM(cudaMemcpy2DAsync(depth, sizeof(float) * cap, d_z, sizeof(float) * capL, sizeof(float) * wcopy, count, cudaMemcpyDeviceToHost, s));
+    CKM(cudaMemcpy2DAsync(uright, sizeof(float) * cap, S.u, sizeof(float) * capL, sizeof(float) * wcopy, count, cudaMemcpyDeviceToHost, s));
+    CKM(cudaMemcpy2DAsync(depth, sizeof(float) * cap, S.z, sizeof(float) * capL, sizeof(float) * wcopy, count, cudaMemcpyDeviceToHost, s));
     CKM(cudaStreamSynchronize(s));
     return ORBX_OK;
 }
