@@ -7,8 +7,8 @@
 #include <vector>
 #include "orbx_internal.h"
 
-unsigned long long g_orbx_launches = 0;
-extern "C" unsigned long long orbx_launch_count(void) { return g_orbx_launches; }
+std::atomic<unsigned long long> g_orbx_launches{0};
+extern "C" unsigned long long orbx_launch_count(void) { return g_orbx_launches.load(std::memory_order_relaxed); }
 
 static thread_local std::string g_last_error;
 void orbx_set_error(const char* fmt, const char* a, const char* b2)

@@ -101,8 +101,9 @@ void orbx_fast_units(const OrbxGeom& g, std::vector<int4>& tab);
 void orbx_upload_pattern();
 void orbx_set_error(const char* fmt, const char* a, const char* b);
 // number of kernels this library launched since load (bench.py reports the delta as gpu_launches)
-extern unsigned long long g_orbx_launches;
-#define ORBX_COUNT_LAUNCH(n) (g_orbx_launches += (n))
+#include <atomic>
+extern std::atomic<unsigned long long> g_orbx_launches;     // extractor instances may run on different host threads
+#define ORBX_COUNT_LAUNCH(n) (g_orbx_launches.fetch_add((n), std::memory_order_relaxed))
 
 // host-buffer pipeline pieces of the extractor (orbx_api.cu), used by orbx_extract_match_batch
 struct orbx_extractor;

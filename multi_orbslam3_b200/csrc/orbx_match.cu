@@ -647,6 +647,7 @@ static int stereo_rows_per_kp(const float* sf, int nlevels)
 __global__ void __launch_bounds__(256) k_stereo_refine(StereoArgs A, OrbxPyrView L, OrbxPyrView R)
 {
     __shared__ int s_d[8][12];
+    __shared__ uint8_t s_patch[8][11 * 32];
     const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5, p = blockIdx.y;
     const int iL = blockIdx.x * 8 + wq;
     const int nl = A.nL ? A.nL[A.slotL0 + p] : A.nl1;
@@ -670,19 +671,24 @@ __global__ void __launch_bounds__(256) k_stereo_refine(StereoArgs A, OrbxPyrView
             const uint8_t* imL = L.lv[oct] + (long long)p * L.fstride[oct]; const int pL = L.pitch[oct];
             const uint8_t* imR = R.lv[oct] + (long long)p * R.fstride[oct]; const int pR = R.pitch[oct];
             if (lane < 11) s_d[wq][lane] = 0;
-            __syncwarp();
-            const int ctrL = imL[(long long)(r0 + w) * pL + c0 + w];
-            // 121 (shift, row) tasks of 11 pixels each
-            for (int t = lane; t < 121; t += 32) {
-                const int inc = t / 11 - Lr, r = t - (t / 11) * 11;
-                const int cr = cr0 + inc;
-                const int ctrR = imR[(long long)(r0 + w) * pR + cr + w];
-                const uint8_t* a = imL + (long long)(r0 + r) * pL + c0;
-                const uint8_t* b = imR + (long long)(r0 + r) * pR + cr;
-                int acc = 0;
+            // stage the 11x11 left patch and the 11x21 right strip (all 11 shifts) in shared memory: 32 bytes per row
+            uint8_t* sp = s_patch[wq];
 #pragma unroll
-                for (int c = 0; c < 11; c++) acc += abs(((int)a[c] - ctrL) - ((int)b[c] - ctrR));
-                atomicAdd(&s_d[wq][inc + Lr], acc);
+            for (int r = 0; r < 11; r++)
+                sp[r * 32 + lane] = lane < 11 ? imL[(long long)(r0 + r) * pL + c0 + lane]
+                                              : imR[(long long)(r0 + r) * pR + cr0 - Lr + (lane - 11)];
+            __syncwarp();
+            const int ctrL = sp[w * 32 + w];
+            // 121 (shift, row) tasks of 11 pixels each: |(a - ctrL) - (b - ctrR)| = |(a + ctrR - ctrL) - b|
+            for (int t = lane; t < 121; t += 32) {
+                const int inc = t / 11, r = t - inc * 11;
+                const int kd = (int)sp[w * 32 + 11 + inc + w] - ctrL;
+                const uint8_t* a = sp + r * 32;
+                const uint8_t* b = sp + r * 32 + 11 + inc;
+                unsigned acc = 0;
+#pragma unroll
+                for (int c = 0; c < 11; c++) acc = __sad((int)a[c] + kd, (int)b[c], acc);
+                atomicAdd(&s_d[wq][inc], (int)acc);
             }
             __syncwarp();
             int bestDist = 0x7fffffff, bestinc = 0;
