@@ -174,7 +174,9 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_orient_describe(OrbxGeom g,
     // ---- descriptor on the blurred level ----
     const float factorPI = (float)(3.1415926535897932384626433832795 / 180.f);
     const float ang = __fmul_rn(angle, factorPI);
-    const float ca = (float)cos((double)ang), sa = (float)sin((double)ang);
+    double sd, cd;
+    sincos((double)ang, &sd, &cd);                  // same kernels as cos() / sin(), one range reduction
+    const float ca = (float)cd, sa = (float)sd;
     const uint8_t* bl = b.blur[lvl] + (long long)f * L.frame_stride;
     const uint8_t* center = bl + (long long)cy * L.pitch + cx;
     const uint4 w0 = reinterpret_cast<const uint4*>(d_pattern)[lane * 2];
