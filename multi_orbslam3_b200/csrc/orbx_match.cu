@@ -48,6 +48,27 @@ __device__ __forceinline__ int hamming256(const uint4& a0, const uint4& a1, cons
            __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
 }
 
+// The same distance with carry-save compression for the popc-bound brute-force kernel: three full adders (2 LOP3 each)
+// fold 7 of the 8 difference words into 2 "ones" and 3 "twos" words, so a pair costs 5 POPC (the 16-lane XU pipe) instead
+// of 8, at the price of 6 LOP3 on the 64-lane ALU pipe: d = popc(s3) + popc(x7) + 2 * (popc(c1) + popc(c2) + popc(c3)).
+__device__ __forceinline__ unsigned xor3(unsigned a, unsigned b, unsigned c)
+{
+    unsigned r; asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r;
+}
+__device__ __forceinline__ unsigned maj3(unsigned a, unsigned b, unsigned c)
+{
+    unsigned r; asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r;
+}
+__device__ __forceinline__ int hamming256_csa(const uint4& a0, const uint4& a1, const uint4& b0, const uint4& b1)
+{
+    const unsigned x0 = a0.x ^ b0.x, x1 = a0.y ^ b0.y, x2 = a0.z ^ b0.z, x3 = a0.w ^ b0.w;
+    const unsigned x4 = a1.x ^ b1.x, x5 = a1.y ^ b1.y, x6 = a1.z ^ b1.z, x7 = a1.w ^ b1.w;
+    const unsigned s1 = xor3(x0, x1, x2), c1 = maj3(x0, x1, x2);
+    const unsigned s2 = xor3(x3, x4, x5), c2 = maj3(x3, x4, x5);
+    const unsigned s3 = xor3(s1, s2, x6), c3 = maj3(s1, s2, x6);
+    return __popc(s3) + __popc(x7) + 2 * (__popc(c1) + __popc(c2) + __popc(c3));
+}
+
 __global__ void k_hamming_pairs(const uint4* a, const uint4* b, int n, int* out)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -100,7 +121,7 @@ __global__ void __launch_bounds__(BF_NT) k_bf_knn2(BfArgs A)
         if (live) {
 #pragma unroll 4
             for (int j = 0; j < cnt; j++) {
-                const int d = hamming256(q0, q1, tile[2 * j], tile[2 * j + 1]);
+                const int d = hamming256_csa(q0, q1, tile[2 * j], tile[2 * j + 1]);
                 if (d < d1) {
                     const int id = (int)(base + j) + A.idx_base;
                     if (d < d0) { d1 = d0; i1 = i0; d0 = d; i0 = id; }
