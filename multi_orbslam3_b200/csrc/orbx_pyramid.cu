@@ -234,35 +234,47 @@ __device__ __forceinline__ void blur_and_store(uint8_t* R, uint16_t* Hb, uint8_t
                                                int tw, int th)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // ---- horizontal pass: lane = 4-pixel group, warp = row; two dp4a per pixel ----
+    // ---- horizontal pass: lane = 4-pixel group, warp = PAIR of rows; two dp4a per pixel.  The 16-bit results of rows
+    //      (2k, 2k+1) are stored interleaved, one 32-bit word per column, so that the vertical pass can feed them to dp2a ----
     const unsigned K0 = 18u | (34u << 8) | (48u << 16) | (56u << 24), K1 = 48u | (34u << 8) | (18u << 16);
-    for (int row = warp; row < th + 6; row += NWARP) {
-        const unsigned* rr = reinterpret_cast<const unsigned*>(R + row * RP) + (RO >> 2) + lane;
-        const unsigned wm = rr[-1], w0 = rr[0], w1 = rr[1];
-        unsigned a0 = __dp4a(__funnelshift_r(wm, w0, 8), K0, 0u);  a0 = __dp4a(__funnelshift_r(w0, w1, 8), K1, a0);
-        unsigned a1 = __dp4a(__funnelshift_r(wm, w0, 16), K0, 0u); a1 = __dp4a(__funnelshift_r(w0, w1, 16), K1, a1);
-        unsigned a2 = __dp4a(__funnelshift_r(wm, w0, 24), K0, 0u); a2 = __dp4a(__funnelshift_r(w0, w1, 24), K1, a2);
-        unsigned a3 = __dp4a(w0, K0, 0u);                          a3 = __dp4a(w1, K1, a3);
-        *reinterpret_cast<uint2*>(Hb + row * TW + lane * 4) = make_uint2(a0 | (a1 << 16), a2 | (a3 << 16));
+    unsigned* Hp = reinterpret_cast<unsigned*>(Hb);               // [(TH+6)/2][TW] words: H(2k, x) | H(2k+1, x) << 16
+    for (int pr = warp; pr < (th + 7) / 2; pr += NWARP) {
+        unsigned v[2][4];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const unsigned* rr = reinterpret_cast<const unsigned*>(R + (2 * pr + h) * RP) + (RO >> 2) + lane;
+            const unsigned wm = rr[-1], w0 = rr[0], w1 = rr[1];
+            v[h][0] = __dp4a(__funnelshift_r(w0, w1, 8), K1, __dp4a(__funnelshift_r(wm, w0, 8), K0, 0u));
+            v[h][1] = __dp4a(__funnelshift_r(w0, w1, 16), K1, __dp4a(__funnelshift_r(wm, w0, 16), K0, 0u));
+            v[h][2] = __dp4a(__funnelshift_r(w0, w1, 24), K1, __dp4a(__funnelshift_r(wm, w0, 24), K0, 0u));
+            v[h][3] = __dp4a(w1, K1, __dp4a(w0, K0, 0u));
+        }
+        *reinterpret_cast<uint4*>(Hp + pr * TW + lane * 4) =
+            make_uint4(v[0][0] | (v[1][0] << 16), v[0][1] | (v[1][1] << 16), v[0][2] | (v[1][2] << 16), v[0][3] | (v[1][3] << 16));
     }
     __syncthreads();
-    // ---- vertical pass: 2 columns x 4 rows per thread; blurred bytes go back into R's interior ----
-    for (int it = tid; it < (TW / 2) * (TH / 4); it += NT) {
-        const int cp = it & (TW / 2 - 1), rg = it >> 6;
-        const int r0 = rg * 4;
-        if (r0 >= th) continue;
-        unsigned lo[10], hi[10];
+    // ---- vertical pass: 4 columns x 8 rows per thread, 4 dp2a per pixel (two taps each); blurred bytes go back into R ----
+    {
+        const int cg = tid & 31, r0 = (tid >> 5) * 8;             // NT == 32 * TH / 8
+        if (r0 < th) {
+            uint4 P[7];
 #pragma unroll
-        for (int k = 0; k < 10; k++) {
-            const unsigned v = *reinterpret_cast<const unsigned*>(Hb + (r0 + k) * TW + cp * 2);
-            lo[k] = v & 0xFFFFu; hi[k] = v >> 16;
-        }
+            for (int k = 0; k < 7; k++) P[k] = *reinterpret_cast<const uint4*>(Hp + (r0 / 2 + k) * TW + cg * 4);
+            // taps (18,34,48,56,48,34,18) over rows q..q+6: even q starts on a pair, odd q on the high half of one
+            const unsigned WE0 = 18u | (34u << 8), WE1 = 48u | (56u << 8), WE2 = 48u | (34u << 8), WE3 = 18u;
+            const unsigned WO0 = 18u << 8, WO1 = 34u | (48u << 8), WO2 = 56u | (48u << 8), WO3 = 34u | (18u << 8);
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const unsigned sl = 18u * (lo[q] + lo[q + 6]) + 34u * (lo[q + 1] + lo[q + 5]) + 48u * (lo[q + 2] + lo[q + 4]) + 56u * lo[q + 3];
-            const unsigned sh = 18u * (hi[q] + hi[q + 6]) + 34u * (hi[q + 1] + hi[q + 5]) + 48u * (hi[q + 2] + hi[q + 4]) + 56u * hi[q + 3];
-            const unsigned o = ((sl + 32768u) >> 16) | (((sh + 32768u) >> 16) << 8);
-            *reinterpret_cast<uint16_t*>(R + (3 + r0 + q) * RP + RO + cp * 2) = (uint16_t)o;
+            for (int q = 0; q < 8; q++) {
+                const int m = q >> 1;
+                const unsigned w0 = (q & 1) ? WO0 : WE0, w1 = (q & 1) ? WO1 : WE1, w2 = (q & 1) ? WO2 : WE2, w3 = (q & 1) ? WO3 : WE3;
+                const unsigned ax = __dp2a_lo(P[m + 3].x, w3, __dp2a_lo(P[m + 2].x, w2, __dp2a_lo(P[m + 1].x, w1, __dp2a_lo(P[m].x, w0, 32768u))));
+                const unsigned ay = __dp2a_lo(P[m + 3].y, w3, __dp2a_lo(P[m + 2].y, w2, __dp2a_lo(P[m + 1].y, w1, __dp2a_lo(P[m].y, w0, 32768u))));
+                const unsigned az = __dp2a_lo(P[m + 3].z, w3, __dp2a_lo(P[m + 2].z, w2, __dp2a_lo(P[m + 1].z, w1, __dp2a_lo(P[m].z, w0, 32768u))));
+                const unsigned aw = __dp2a_lo(P[m + 3].w, w3, __dp2a_lo(P[m + 2].w, w2, __dp2a_lo(P[m + 1].w, w1, __dp2a_lo(P[m].w, w0, 32768u))));
+                // byte 2 of each accumulator = (sum + 2^15) >> 16
+                const unsigned o = __byte_perm(__byte_perm(ax, ay, 0x0062), __byte_perm(az, aw, 0x0062), 0x5410);
+                *reinterpret_cast<unsigned*>(R + (3 + r0 + q) * RP + RO + cg * 4) = o;
+            }
         }
     }
     __syncthreads();
