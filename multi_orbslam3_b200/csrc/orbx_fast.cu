@@ -241,53 +241,65 @@ __global__ void __launch_bounds__(NT, 5) k_fast_seg(OrbxGeom g, OrbxBuffers b, c
     if (vec) mbar_wait(&s_bar, 0);
     __syncthreads();
 
-    // ---- 2. screen: one (tile row, 32-group step) item per warp ----
+    // ---- 2. screen: one (tile row, 32 x 8-pixel step) item per warp; a lane screens two adjacent 4-pixel groups ----
     const unsigned c127 = (unsigned)(127 - (minTh < 126 ? minTh : 126)) * 0x01010101u;
     const bool screen_ok = minTh <= 126;
     {
         constexpr int W = TP / 4;
-        const int nsteps = (ng + 31) >> 5;
+        const int k0 = g0 >> 1, k1 = g1 >> 1;                   // pairs of groups (8-byte aligned)
+        const int nsteps = (k1 - k0 + 32) >> 5;
         // items (row, step) are dealt round-robin to the warps; the pair advances by NW items per iteration
         int ry = (int)(((unsigned)warp * srcp) >> 16), st = warp - ry * nsteps;
         const int dq = (int)(((unsigned)NW * srcp) >> 16), dr = NW - dq * nsteps;
         // scored columns only: the first and last group straddle the segment's edges
         const unsigned mask0 = 0x80808080u << (8 * (X0 & 3)), mask1 = 0x80808080u >> (8 * (3 - ((X1 - 1) & 3)));
         const unsigned lt = (1u << lane) - 1;
-        const unsigned* Tw = reinterpret_cast<const unsigned*>(T + 3 * TP) + g0 + lane;
+        const unsigned* Tw = reinterpret_cast<const unsigned*>(T + 3 * TP) + 2 * (k0 + lane);
         while (ry < hs) {                                       // warp-uniform (ballots below)
-            const int gx = g0 + (st << 5) + lane;
-            const unsigned* rc = Tw + ry * W + (st << 5);
-            unsigned cand = 0;
-            if (gx <= g1) {
-                cand = 0x80808080u;
+            const int ga = 2 * (k0 + (st << 5) + lane);         // groups ga, ga + 1
+            const unsigned* rc = Tw + ry * W + (st << 6);
+            unsigned ca = 0, cb = 0;
+            if (ga <= g1) {
+                ca = cb = 0x80808080u;
                 if (screen_ok) {
                     // |d_k| | |d_k+8| >= max(|d_k|, |d_k+8|): one threshold test per pair, still only a necessary
                     // condition (exact when t = 2^n - 1, e.g. the reference's minThFAST = 7)
-                    const unsigned V = rc[0];
+                    const uint2 V = *reinterpret_cast<const uint2*>(rc);
+                    const uint2 P3 = *reinterpret_cast<const uint2*>(rc + 3 * W), M3 = *reinterpret_cast<const uint2*>(rc - 3 * W);
+                    const unsigned Lw = rc[-1], Rw = rc[2];
                     // pair (0, 8): (0,+3) / (0,-3);  pair (4, 12): (+3,0) / (-3,0)
-                    cand &= gt_flags(__vabsdiffu4(V, rc[3 * W]) | __vabsdiffu4(V, rc[-3 * W]), c127);
-                    cand &= gt_flags(__vabsdiffu4(V, __funnelshift_r(V, rc[1], 24)) |
-                                     __vabsdiffu4(V, __funnelshift_r(rc[-1], V, 8)), c127);
-                    if (cand) {
+                    ca &= gt_flags(__vabsdiffu4(V.x, P3.x) | __vabsdiffu4(V.x, M3.x), c127);
+                    cb &= gt_flags(__vabsdiffu4(V.y, P3.y) | __vabsdiffu4(V.y, M3.y), c127);
+                    ca &= gt_flags(__vabsdiffu4(V.x, __funnelshift_r(V.x, V.y, 24)) | __vabsdiffu4(V.x, __funnelshift_r(Lw, V.x, 8)), c127);
+                    cb &= gt_flags(__vabsdiffu4(V.y, __funnelshift_r(V.y, Rw, 24)) | __vabsdiffu4(V.y, __funnelshift_r(V.x, V.y, 8)), c127);
+                    if (ca | cb) {
                         // pair (2, 10): (+2,+2) / (-2,-2);  pair (6, 14): (+2,-2) / (-2,+2)
-                        const unsigned p2c = rc[2 * W], m2c = rc[-2 * W];
-                        const unsigned a2 = __funnelshift_r(p2c, rc[2 * W + 1], 16), a10 = __funnelshift_r(rc[-2 * W - 1], m2c, 16);
-                        const unsigned a6 = __funnelshift_r(m2c, rc[-2 * W + 1], 16), a14 = __funnelshift_r(rc[2 * W - 1], p2c, 16);
-                        cand &= gt_flags(__vabsdiffu4(V, a2) | __vabsdiffu4(V, a10), c127);
-                        cand &= gt_flags(__vabsdiffu4(V, a6) | __vabsdiffu4(V, a14), c127);
+                        const uint2 P2 = *reinterpret_cast<const uint2*>(rc + 2 * W), M2 = *reinterpret_cast<const uint2*>(rc - 2 * W);
+                        const unsigned P2l = rc[2 * W - 1], P2r = rc[2 * W + 2], M2l = rc[-2 * W - 1], M2r = rc[-2 * W + 2];
+                        ca &= gt_flags(__vabsdiffu4(V.x, __funnelshift_r(P2.x, P2.y, 16)) | __vabsdiffu4(V.x, __funnelshift_r(M2l, M2.x, 16)), c127);
+                        ca &= gt_flags(__vabsdiffu4(V.x, __funnelshift_r(M2.x, M2.y, 16)) | __vabsdiffu4(V.x, __funnelshift_r(P2l, P2.x, 16)), c127);
+                        cb &= gt_flags(__vabsdiffu4(V.y, __funnelshift_r(P2.y, P2r, 16)) | __vabsdiffu4(V.y, __funnelshift_r(M2.x, M2.y, 16)), c127);
+                        cb &= gt_flags(__vabsdiffu4(V.y, __funnelshift_r(M2.y, M2r, 16)) | __vabsdiffu4(V.y, __funnelshift_r(P2.x, P2.y, 16)), c127);
                     }
                 }
-                if (gx == g0) cand &= mask0;
-                if (gx == g1) cand &= mask1;
+                if (ga < g0) ca = 0;
+                if (ga == g0) ca &= mask0;
+                if (ga == g1) ca &= mask1;
+                if (ga + 1 > g1) cb = 0;
+                if (ga + 1 == g0) cb &= mask0;
+                if (ga + 1 == g1) cb &= mask1;
             }
-            // one queue entry per 4-pixel group that still has a candidate: one ballot, one atomic per warp-step.
+            // one queue entry per 4-pixel group that still has a candidate: two ballots, one atomic per warp-step.
             // entry = flags (bits 7, 15, 23, 31) | gx (bits 0-6) | tile row (bits 8-14)
-            const unsigned bal = __ballot_sync(0xffffffffu, cand != 0);
-            if (bal) {
+            const unsigned ba = __ballot_sync(0xffffffffu, ca != 0), bb = __ballot_sync(0xffffffffu, cb != 0);
+            if (ba | bb) {
                 int base = 0;
-                if (lane == 0) base = atoms_add(&sh.qg_count, __popc(bal));
+                const int na = __popc(ba);
+                if (lane == 0) base = atoms_add(&sh.qg_count, na + __popc(bb));
                 base = __shfl_sync(0xffffffffu, base, 0);
-                if (cand) QG[base + __popc(bal & lt)] = cand | (unsigned)gx | ((unsigned)(ry + 3) << 8);   // <= hs*ng entries by construction
+                const unsigned tag = (unsigned)ga | ((unsigned)(ry + 3) << 8);
+                if (ca) QG[base + __popc(ba & lt)] = ca | tag;                      // <= hs*ng entries by construction
+                if (cb) QG[base + na + __popc(bb & lt)] = cb | (tag + 1u);
             }
             st += dr; ry += dq;
             if (st >= nsteps) { st -= nsteps; ry++; }
@@ -502,7 +514,8 @@ void orbx_fast_units(const OrbxGeom& g, std::vector<int4>& tab)
                 if (iniY < L.maxBY - 3 && hs > 0 && cs1 > cs0) {
                     const int xa0 = (cs0 - 3) & ~15, xa1 = (cs1 + 3 + 15) & ~15;
                     const int X0 = cs0 - xa0, X1 = cs1 - xa0;
-                    const int ng = ((X1 - 1) >> 2) - (X0 >> 2) + 1, nsteps = (ng + 31) >> 5;
+                    const int ng = ((X1 - 1) >> 2) - (X0 >> 2) + 1;
+                    const int nsteps = ((((X1 - 1) >> 2) >> 1) - ((X0 >> 2) >> 1) + 32) >> 5;      // 32 lanes x 2 groups per screen step
                     a = make_int4(l, iniY, nrow, hs);
                     bq = make_int4(xa0, xa1 - xa0, X0, X1);
                     c = make_int4(ncell, tile_bytes(nrow, hs, ng, ncell), (65536 + L.wCell - 1) / L.wCell, (65536 + nsteps - 1) / nsteps);

@@ -1510,6 +1510,10 @@ extern "C" int orbx_match_candidates(orbx_matcher* m, const uint8_t* q, int nq, 
     if (nq == 0) return ORBX_OK;
     const int ncand = offsets[nq];
     if (ncand < 0 || (ncand > 0 && (!indices || !t))) return ORBX_E_INVALID;
+    for (int i = 0; i < nq; i++)
+        if (offsets[i] < 0 || offsets[i] > offsets[i + 1]) { orbx_set_error("%s%s", "orbx_match_candidates: offsets must be non-decreasing", ""); return ORBX_E_INVALID; }
+    for (int k = 0; k < ncand; k++)
+        if ((unsigned)indices[k] >= (unsigned)nt) { orbx_set_error("%s%s", "orbx_match_candidates: candidate index out of range", ""); return ORBX_E_INVALID; }
     CKM(cudaSetDevice(m->p.device));
     cudaStream_t s = m->stream;
     uint8_t *dq, *dt; int32_t *doff, *dind, *dres;

@@ -289,4 +289,7 @@ def test_match_candidates_generic():
     np.testing.assert_array_equal(gi, ri)
     np.testing.assert_array_equal(gd, rd)
     assert list(gi[5]) == [-1, -1] and gi[6, 1] == -1
+    bad = ind.copy(); bad[3] = 3000
+    with pytest.raises(orbx.OrbxError):
+        m.MatchCandidates(q, t, off, bad)              # out-of-range candidate index is refused, not read
     m.close()
