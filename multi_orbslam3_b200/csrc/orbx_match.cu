@@ -1243,13 +1243,27 @@ static int extract_match_pipeline(orbx_extractor* ex, orbx_matcher* m, bool host
     CKM(cudaSetDevice(m->p.device));
     if ((rc = ensure_pipeline(m))) return rc;
     const bool direct = host && orbx_ex_can_fetch_direct(ex, kps, desc, cap, n, mono_index);
-    // host path: 4 chunks hide the PCIe copies; device path: chunking only shrinks the kernels and makes the two kernel
-    // streams fight for the SMs (measured: 1 chunk 5.7 ms, 4 chunks 6.2 ms per 512 frames), so one chunk unless overridden
-    int nchunks = host ? (batch >= 64 ? 4 : 1) : 1;
+    // host path: chunks hide the PCIe copies under the kernels.  The call is H2D-bound in the middle, so what is left is
+    // the fill (first chunk's copy) and the drain (last chunk's kernels + D2H): the first and last chunk are small
+    // (1/16 of the batch each), the rest is split evenly.  Device path: chunking only shrinks the kernels and makes the
+    // two kernel streams fight for the SMs (measured: 1 chunk 5.7 ms, 4 chunks 6.2 ms per 512 frames): one chunk.
+    int nchunks = host ? (batch >= 64 ? 6 : 1) : 1;
     if (const char* e = getenv(host ? "ORBX_HOST_CHUNKS" : "ORBX_DEVICE_CHUNKS")) { const int v = atoi(e); if (v >= 1 && v <= ORBX_MAX_CHUNKS) nchunks = v; }
     if (nchunks > batch) nchunks = batch;
-    const int per = (batch + nchunks - 1) / nchunks;
-    nchunks = (batch + per - 1) / per;
+    int c_f0[ORBX_MAX_CHUNKS], c_cnt[ORBX_MAX_CHUNKS];
+    {
+        const bool taper = host && nchunks >= 4 && batch >= 16 * nchunks && !getenv("ORBX_UNIFORM_CHUNKS");
+        const int edge = taper ? batch / 16 : 0;
+        const int mid = taper ? nchunks - 2 : nchunks, rest = batch - 2 * edge;
+        int f = 0, k = 0;
+        if (taper) { c_f0[k] = 0; c_cnt[k++] = edge; f = edge; }
+        for (int i = 0; i < mid; i++) {
+            const int cnt = rest / mid + (i < rest % mid ? 1 : 0);
+            c_f0[k] = f; c_cnt[k++] = cnt; f += cnt;
+        }
+        if (taper) { c_f0[k] = f; c_cnt[k++] = edge; }
+        nchunks = k;
+    }
     int32_t* dm12 = host ? m->d_out : d_matches12;
     int32_t* dnm = host ? m->d_nm : d_nmatches;
     // the side streams must not run ahead of work already queued on the kernel stream (previous call's carry)
@@ -1259,14 +1273,14 @@ static int extract_match_pipeline(orbx_extractor* ex, orbx_matcher* m, bool host
         CKM(cudaStreamWaitEvent(m->s_h2d, m->ev_start, 0));
         CKM(cudaStreamWaitEvent(m->s_d2h, m->ev_start, 0));
         for (int c = 0; c < nchunks; c++) {
-            const int f0 = c * per, cnt = (f0 + per <= batch) ? per : batch - f0;
+            const int f0 = c_f0[c], cnt = c_cnt[c];
             rc = orbx_ex_stage_input(ex, imgs, f0, cnt, width, height, stride, frame_stride, m->s_h2d);
             if (rc) return rc;
             CKM(cudaEventRecord(m->ev[c], m->s_h2d));
         }
     }
     for (int c = 0; c < nchunks; c++) {
-        const int f0 = c * per, cnt = (f0 + per <= batch) ? per : batch - f0;
+        const int f0 = c_f0[c], cnt = c_cnt[c];
         if (host) {
             CKM(cudaStreamWaitEvent(s, m->ev[c], 0));
             rc = orbx_ex_run_staged(ex, f0, cnt, lap0, lap1, 1 + f0, s);
