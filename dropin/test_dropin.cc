@@ -1,6 +1,7 @@
 // Exercises the drop-in classes the way Frame / Tracking do (Frame.cc:393-400, Tracking.cc:2216-2217):
 //   test_dropin <w> <h> <frame0.raw> <frame1.raw> <out.bin>
-// writes: n0, mono0, keypoints0, descriptors0, n1, keypoints1, descriptors1, nmatches, vnMatches12
+// writes: n0, mono0, keypoints0, descriptors0, n1, keypoints1, descriptors1, nmatches, vnMatches12, pyramid level 3,
+//         one descriptor distance, then the two SearchByProjection results (count + per-keypoint map-point index)
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -52,7 +53,42 @@ int main(int argc, char** argv)
     for (int y = 0; y < lh; y++) fwrite(ext->mvImagePyramid[3].ptr(y), 1, lw, o);
     const int d = ORBmatcher::DescriptorDistance(F[0].mDescriptors.row(0), F[1].mDescriptors.row(0));
     fwrite(&d, 4, 1, o);
+
+    // ---- SearchByProjection(Frame&, vector<MapPoint*>&, th): local-map tracking (Tracking::SearchLocalPoints) ----
+    // one map point per keypoint of frame 0, predicted in frame 1 at its own position + the stream's (3, 2) motion
+    const int n0 = F[0].N;
+    std::vector<MapPoint> mps(n0);
+    std::vector<MapPoint*> vmp(n0);
+    for (int i = 0; i < n0; i++) {
+        MapPoint& mp = mps[i];
+        mp.mTrackProjX = F[0].mvKeysUn[i].pt.x + 3.f; mp.mTrackProjY = F[0].mvKeysUn[i].pt.y + 2.f; mp.mTrackProjXR = 0.f;
+        mp.mnTrackScaleLevel = F[0].mvKeysUn[i].octave; mp.mTrackViewCos = (i % 3) ? 0.9995f : 0.9f;
+        mp.mbTrackInView = (i % 7) != 0; mp.mDescriptor = F[0].mDescriptors.row(i);
+        mp.mWorldPos[0] = mp.mTrackProjX; mp.mWorldPos[1] = mp.mTrackProjY; mp.mWorldPos[2] = 1.f;
+        vmp[i] = &mp;
+    }
+    Frame A = F[1];
+    A.mvScaleFactors = ext->GetScaleFactors();
+    A.mvpMapPoints.assign(A.N, nullptr); A.mvbOutlier.assign(A.N, false);
+    ORBmatcher mA(0.8f, true);
+    const int nA = mA.SearchByProjection(A, vmp, 3.f);
+    fwrite(&nA, 4, 1, o);
+    for (int i = 0; i < A.N; i++) { int v = A.mvpMapPoints[i] ? (int)(A.mvpMapPoints[i] - mps.data()) : -1; fwrite(&v, 4, 1, o); }
+
+    // ---- SearchByProjection(Frame& Current, const Frame& Last, th, bMono): TrackWithMotionModel ----
+    GeometricCamera cam;                                            // identity pose and intrinsics: project(X) = (X, Y) / Z
+    Frame Last = F[0];
+    Last.mvScaleFactors = ext->GetScaleFactors();
+    Last.mvpMapPoints = vmp; Last.mvbOutlier.assign(n0, false);
+    for (int i = 0; i < n0; i += 11) Last.mvbOutlier[i] = true;
+    Frame Cur = F[1];
+    Cur.mvScaleFactors = ext->GetScaleFactors(); Cur.mpCamera = &cam;
+    Cur.mvpMapPoints.assign(Cur.N, nullptr); Cur.mvbOutlier.assign(Cur.N, false);
+    ORBmatcher mB(0.9f, true);
+    const int nB = mB.SearchByProjection(Cur, Last, 7.f, true);
+    fwrite(&nB, 4, 1, o);
+    for (int i = 0; i < Cur.N; i++) { int v = Cur.mvpMapPoints[i] ? (int)(Cur.mvpMapPoints[i] - mps.data()) : -1; fwrite(&v, 4, 1, o); }
     fclose(o);
-    printf("dropin ok: %d / %d keypoints, %d matches\n", F[0].N, F[1].N, nm);
+    printf("dropin ok: %d / %d keypoints, %d init matches, %d / %d projection matches\n", F[0].N, F[1].N, nm, nA, nB);
     return 0;
 }

@@ -51,5 +51,35 @@ def test_dropin_classes_match_oracle(tmp_path):
     lw, lh = struct.unpack_from("<ii", buf, off); off += 8
     pyr3 = np.frombuffer(buf, np.uint8, lw * lh, off).reshape(lh, lw); off += lw * lh
     np.testing.assert_array_equal(pyr3, lvl3)           # mvImagePyramid after SyncPyramidToHost()
-    d, = struct.unpack_from("<i", buf, off)
+    d, = struct.unpack_from("<i", buf, off); off += 4
     assert d == O.hamming256(d1[0], d2[0])
+
+    # SearchByProjection(Frame&, vector<MapPoint*>&, th = 3): the drop-in marshals MapPoints into flat queries
+    scale = np.asarray(ref.scale, np.float32)
+    n1 = len(k1); n2 = len(k2)
+    q = np.zeros(n1, O.PROJQ_DTYPE)
+    idx = np.arange(n1)
+    view = np.where(idx % 3 != 0, np.float32(0.9995), np.float32(0.9))
+    r = np.where(view > 0.998, np.float32(2.5), np.float32(4.0)).astype(np.float32) * np.float32(3.0)
+    q["u"] = k1["x"] + np.float32(3); q["v"] = k1["y"] + np.float32(2)
+    q["r"] = r * scale[k1["octave"]]
+    q["minl"] = k1["octave"] - 1; q["maxl"] = k1["octave"]
+    q["valid"] = (idx % 7 != 0).astype(np.int32)
+    nA, = struct.unpack_from("<i", buf, off); off += 4
+    gotA = np.frombuffer(buf, np.int32, n2, off); off += 4 * n2
+    rnA, rA = O.search_by_projection(1, q, d1, k2, d2, (0, W, 0, H), nnratio=0.8, check_ori=True)
+    assert nA == rnA and nA > 100
+    np.testing.assert_array_equal(gotA, rA)
+
+    # SearchByProjection(Frame& Current, const Frame& Last, th = 7, bMono): projection of the last frame's map points
+    q = np.zeros(n1, O.PROJQ_DTYPE)
+    q["u"] = k1["x"] + np.float32(3); q["v"] = k1["y"] + np.float32(2)
+    q["r"] = np.float32(7.0) * scale[k1["octave"]]
+    q["minl"] = k1["octave"] - 1; q["maxl"] = k1["octave"] + 1
+    q["ur"] = q["u"]; q["angle"] = k1["angle"]
+    q["valid"] = (idx % 11 != 0).astype(np.int32)
+    nB, = struct.unpack_from("<i", buf, off); off += 4
+    gotB = np.frombuffer(buf, np.int32, n2, off); off += 4 * n2
+    rnB, rB = O.search_by_projection(0, q, d1, k2, d2, (0, W, 0, H), nnratio=0.9, check_ori=True)
+    assert nB == rnB and nB > 100
+    np.testing.assert_array_equal(gotB, rB)
