@@ -8,6 +8,7 @@
 #include <stdexcept>
 #include <string>
 #include "../include/orbx.h"
+#include "ORBextractor.h"
 
 namespace ORB_SLAM3
 {
@@ -161,6 +162,18 @@ int ORBmatcher::SearchByProjection(Frame &F, const std::vector<MapPoint*> &vpMap
     for (int i = 0; i < n2; i++)
         if (assigned[i] >= 0 && assigned[i] < nq) F.mvpMapPoints[i] = vpMapPoints[assigned[i]];
     return nmatches;
+}
+
+// R/src/Frame.cc:785-962 (see ORBmatcher.h)
+void ORBmatcher::ComputeStereoMatches(ORBextractor* pLeft, ORBextractor* pRight, float mb, float mbf,
+                                      std::vector<float> &mvuRight, std::vector<float> &mvDepth)
+{
+    const int cap = orbx_extractor_max_keypoints(pLeft->handle());
+    mvuRight.assign(cap, -1.0f); mvDepth.assign(cap, -1.0f);
+    int n = 0;
+    check(orbx_stereo_matches(context(), pLeft->handle(), pRight->handle(), 0, 0, 0, 0, mb, mbf, mvuRight.data(), mvDepth.data(),
+                              nullptr, cap, &n));
+    mvuRight.resize(n); mvDepth.resize(n);
 }
 
 } //namespace ORB_SLAM

@@ -14,6 +14,8 @@ struct orbx_matcher;   // include/orbx.h
 namespace ORB_SLAM3
 {
 
+class ORBextractor;
+
 class ORBmatcher
 {
 public:
@@ -33,6 +35,13 @@ public:
 
     // Matching for the Map Initialization (only used in the monocular case)
     int SearchForInitialization(Frame &F1, Frame &F2, std::vector<cv::Point2f> &vbPrevMatched, std::vector<int> &vnMatches12, int windowSize=10);
+
+    // Addition (not in the reference class): the body of Frame::ComputeStereoMatches (R/src/Frame.cc:785-962) on the
+    // device-resident results and pyramids of the frame's two extractors, so that mvImagePyramid never leaves the GPU.
+    // Frame::ComputeStereoMatches() becomes: ORBmatcher::ComputeStereoMatches(mpORBextractorLeft, mpORBextractorRight,
+    // mb, mbf, mvuRight, mvDepth);  (N = mvKeys.size() entries each, -1 where there is no match)
+    static void ComputeStereoMatches(ORBextractor* pLeft, ORBextractor* pRight, float mb, float mbf,
+                                     std::vector<float> &mvuRight, std::vector<float> &mvDepth);
 
 public:
 

@@ -88,7 +88,23 @@ int main(int argc, char** argv)
     const int nB = mB.SearchByProjection(Cur, Last, 7.f, true);
     fwrite(&nB, 4, 1, o);
     for (int i = 0; i < Cur.N; i++) { int v = Cur.mvpMapPoints[i] ? (int)(Cur.mvpMapPoints[i] - mps.data()) : -1; fwrite(&v, 4, 1, o); }
+
+    // ---- Frame::ComputeStereoMatches: one extractor per camera (Frame.cc:92-95); frame 1 is the left view, frame 0 the
+    //      right view (the stream moves by +3 px in x: disparity 3, 2 px of vertical offset inside the row band) ----
+    ORBextractor* extR = new ORBextractor(1000, 1.2f, 8, 20, 7);
+    Frame SL, SR;
+    {
+        cv::Mat iml(h, w, CV_8UC1, i1.data()), imr(h, w, CV_8UC1, i0.data());
+        (*ext)(iml, cv::Mat(), SL.mvKeys, SL.mDescriptors, lap);
+        (*extR)(imr, cv::Mat(), SR.mvKeys, SR.mDescriptors, lap);
+    }
+    std::vector<float> uR, depth;
+    ORBmatcher::ComputeStereoMatches(ext, extR, 0.11f, 47.9f, uR, depth);
+    int ns = (int)uR.size();
+    fwrite(&ns, 4, 1, o);
+    fwrite(uR.data(), 4, ns, o); fwrite(depth.data(), 4, ns, o);
     fclose(o);
+    delete extR;
     printf("dropin ok: %d / %d keypoints, %d init matches, %d / %d projection matches\n", F[0].N, F[1].N, nm, nA, nB);
     return 0;
 }

@@ -83,3 +83,15 @@ def test_dropin_classes_match_oracle(tmp_path):
     rnB, rB = O.search_by_projection(0, q, d1, k2, d2, (0, W, 0, H), nnratio=0.9, check_ori=True)
     assert nB == rnB and nB > 100
     np.testing.assert_array_equal(gotB, rB)
+
+    # ORBmatcher::ComputeStereoMatches(left extractor, right extractor, ...): frame 1 as the left view, frame 0 as the right
+    ns, = struct.unpack_from("<i", buf, off); off += 4
+    uR = np.frombuffer(buf, np.float32, ns, off); off += 4 * ns
+    dep = np.frombuffer(buf, np.float32, ns, off); off += 4 * ns
+    ol, orr = O.Extractor(1000, 1.2, 8, 20, 7), O.Extractor(1000, 1.2, 8, 20, 7)
+    _, skl, sdl = ol(st[1], (0, 0)); _, skr, sdr = orr(st[0], (0, 0))
+    rur, rdp, _ = O.compute_stereo_matches(ol, orr, skl, sdl, skr, sdr, 0.11, 47.9)
+    assert ns == len(rur)
+    np.testing.assert_array_equal(uR, rur)
+    np.testing.assert_array_equal(dep, rdp)
+    assert (rur >= 0).sum() > 10
