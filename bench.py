@@ -305,6 +305,8 @@ def stereo_bench(args, world, rank, local):
             "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
     exl.close(); exr.close(); m.close()
+    if world > 1:
+        dist.destroy_process_group()
 
 
 # ------------------------------------------------------------------------------------------------
