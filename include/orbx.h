@@ -237,6 +237,31 @@ int  orbx_stereo_matches_batch(orbx_matcher* m, orbx_extractor* left, orbx_extra
  * denominator for the matching kernels) */
 int  orbx_popc_peak(int device, double* popc_per_s, double* lop3_per_s);
 
+/* ---- bag of words: DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB> as Frame::ComputeBoW
+ * (R/src/Frame.cc:712-719) and KeyFrame::ComputeBoW (R/src/KeyFrame.cc:168-176) use it ---- */
+typedef struct orbx_vocab orbx_vocab;
+/* Vocabulary from its node table = the rows of ORBvoc.txt after the header, in file order
+ * (R/Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h, loadFromTextFile): node 0 is the root, parent[i] < i, children keep
+ * their order of appearance, is_leaf marks exactly the childless nodes = the words, numbered in node order; desc is
+ * [n_nodes][32], weight [n_nodes] (idf of the words); L = depth (6 for ORBvoc). */
+int  orbx_vocab_create(int device, int n_nodes, const int32_t* parent, const uint8_t* is_leaf, const uint8_t* desc,
+                       const double* weight, int L, orbx_vocab** out);
+void orbx_vocab_destroy(orbx_vocab* v);
+int  orbx_vocab_words(const orbx_vocab* v);
+int  orbx_vocab_word_weights(const orbx_vocab* v, double* w, int cap);
+/* Per-feature part of transform(features, BowVector&, FeatureVector&, levelsup) (TemplatedVocabulary.h:1127-1200,
+ * :1218-1259; distance FORB.cpp:81-101): word id, word weight (may be NULL) and the node at level L - levelsup of every
+ * descriptor (0 = root when that level is <= 0; the last node reached when a leaf lies above it, where the reference
+ * leaves the value uninitialised).  The first child with the smallest distance wins, as the reference's strict '<'.
+ * Host pointers, synchronous.  The BowVector / FeatureVector maps are assembled from these arrays by the caller
+ * (dropin/ORBVocabulary, multi_orbslam3_b200/orbx.py): sums of equal weights and an L1 norm over ~1000 words. */
+int  orbx_bow_transform(orbx_vocab* v, const uint8_t* desc, int n, int levelsup, int32_t* word_id, double* weight,
+                        int32_t* node_id);
+/* The same on the descriptors of an extractor's result slots (never leaving the GPU): d_word / d_node are DEVICE arrays
+ * [count][orbx_extractor_max_keypoints(ex)]; asynchronous on `stream`. */
+int  orbx_bow_transform_slots_device(orbx_vocab* v, orbx_extractor* ex, int first_slot, int count, int levelsup,
+                                     int32_t* d_word, int32_t* d_node, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -38,7 +38,8 @@ EXPORTS = [
     "orbx_search_for_initialization", "orbx_match_slots_device", "orbx_extract_match_batch", "orbx_extract_match_batch_device",
     "orbx_search_by_projection",
     "orbx_stereo_band_match", "orbx_stereo_matches", "orbx_stereo_matches_batch", "orbx_stereo_matches_batch_device",
-    "orbx_match_candidates", "orbx_popc_peak",
+    "orbx_match_candidates", "orbx_vocab_create", "orbx_vocab_destroy", "orbx_vocab_words", "orbx_vocab_word_weights",
+    "orbx_bow_transform", "orbx_bow_transform_slots_device", "orbx_popc_peak",
 ]
 
 
@@ -110,6 +111,12 @@ def lib():
         L.orbx_stereo_band_match.argtypes = [vp, vp, vp, i32, vp, vp, i32, vp, i32, i32, f32, f32, vp, vp]
         L.orbx_popc_peak.argtypes = [i32, vp, vp]
         L.orbx_match_candidates.argtypes = [vp, vp, i32, vp, i32, vp, vp, vp, vp]
+        L.orbx_vocab_create.argtypes = [i32, i32, vp, vp, vp, vp, i32, vp]
+        L.orbx_vocab_destroy.argtypes = [vp]; L.orbx_vocab_destroy.restype = None
+        L.orbx_vocab_words.argtypes = [vp]
+        L.orbx_vocab_word_weights.argtypes = [vp, vp, i32]
+        L.orbx_bow_transform.argtypes = [vp, vp, i32, i32, vp, vp, vp]
+        L.orbx_bow_transform_slots_device.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp]
         L.orbx_stereo_matches.argtypes = [vp, vp, vp, i32, i32, i32, i32, f32, f32, vp, vp, vp, i32, vp]
         L.orbx_stereo_matches_batch.argtypes = [vp, vp, vp, i32, i32, f32, f32, vp, vp, i32]
         L.orbx_stereo_matches_batch_device.argtypes = [vp, vp, vp, i32, i32, f32, f32, vp, vp, vp, vp]
@@ -368,6 +375,68 @@ class ORBmatcher:
                                              C.c_void_p(d_nmatches), C.c_void_p(d_knn_idx) if d_knn_idx else None,
                                              C.c_void_p(d_knn_dist) if d_knn_dist else None,
                                              _s(stream)))
+
+
+class ORBVocabulary:
+    """Mirror of ORB_SLAM3::ORBVocabulary = DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB> (R/include/ORBVocabulary.h)
+    for the path Frame::ComputeBoW uses: transform(features, BowVector, FeatureVector, levelsup)."""
+
+    def __init__(self, parent, is_leaf, desc, weight, L, device=0):
+        parent = np.ascontiguousarray(parent, np.int32); is_leaf = np.ascontiguousarray(is_leaf, np.uint8)
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32); weight = np.ascontiguousarray(weight, np.float64)
+        h = C.c_void_p()
+        _check(lib().orbx_vocab_create(device, len(parent), _p(parent), _p(is_leaf), _p(desc), _p(weight), int(L), C.byref(h)))
+        self._h = h
+        self.n_words = int(lib().orbx_vocab_words(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            lib().orbx_vocab_destroy(self._h)
+        self._h = None
+
+    __del__ = close
+
+    def transform_features(self, desc, levelsup=4):
+        """per-descriptor (word id, word weight, node id at level L - levelsup)"""
+        d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32); n = len(d)
+        w = np.empty(n, np.int32); wt = np.empty(n, np.float64); nd = np.empty(n, np.int32)
+        _check(lib().orbx_bow_transform(self._h, _p(d), n, int(levelsup), _p(w), _p(wt), _p(nd)))
+        return w, wt, nd
+
+    def transform(self, desc, levelsup=4):
+        """transform(features, BowVector&, FeatureVector&, levelsup): ((word ids, L1-normalised values), (node ids, feature lists)),
+        both sorted by key like the std::map the reference fills (TF_IDF weighting, L1 scoring as in ORBvoc.txt)."""
+        w, wt, nd = self.transform_features(desc, levelsup)
+        return assemble_bow(w, wt, nd)
+
+    def transform_slots_device(self, extractor, first_slot, count, d_word, d_node, levelsup=4, stream=None):
+        _check(lib().orbx_bow_transform_slots_device(self._h, extractor._h, first_slot, count, int(levelsup), C.c_void_p(d_word),
+                                                     C.c_void_p(d_node), _s(stream)))
+
+
+def assemble_bow(word, weight, node):
+    """BowVector::addWeight / normalize(L1) and FeatureVector::addFeature over per-feature (word, weight, node) arrays
+    (R/Thirdparty/DBoW2/DBoW2/BowVector.cpp, FeatureVector.cpp): stopped words (weight 0) are skipped; a word's value is its
+    weight added once per feature, in feature order; the L1 norm is summed in word order."""
+    keep = np.nonzero(weight > 0)[0]
+    order = keep[np.argsort(word[keep], kind="stable")]
+    words, first, counts = np.unique(word[order], return_index=True, return_counts=True)
+    vals = np.empty(len(words), np.float64)
+    for i, (f0, c) in enumerate(zip(first, counts)):
+        wv = weight[order[f0]]
+        acc = wv
+        for _ in range(c - 1):
+            acc += wv
+        vals[i] = acc
+    norm = 0.0
+    for v in vals:
+        norm += abs(v)
+    if norm > 0.0:
+        vals = vals / norm
+    order = keep[np.argsort(node[keep], kind="stable")]
+    nodes, first, counts = np.unique(node[order], return_index=True, return_counts=True)
+    feats = [order[f0:f0 + c].astype(np.int32) for f0, c in zip(first, counts)]
+    return (words.astype(np.int32), vals), (nodes.astype(np.int32), feats)
 
 
 def launch_count():

@@ -71,3 +71,64 @@ def random_descriptors(n, seed=0, dup_frac=0.0):
                 row[b >> 3] ^= np.uint8(1 << (b & 7))
             d[j] = row
     return d
+
+
+def random_vocabulary(k=10, L=3, seed=0, irregular=False, shuffle=False, stop_frac=0.02):
+    """Synthetic DBoW2 ORB vocabulary as a node table in text-file order (ORBvoc.txt itself is not redistributable here):
+    returns (parent int32[n], is_leaf uint8[n], desc uint8[n,32], weight float64[n]); node 0 is the root, parent[i] < i.
+    A child's descriptor is its parent's with ~24 random bits flipped; leaf weights look like idf values, a few are 0
+    (stopped words).  irregular: early leaves and nodes with fewer than k children; shuffle: siblings not contiguous."""
+    rng = np.random.default_rng(seed)
+    parent = [np.array([-1], np.int32)]; desc = [rng.integers(0, 256, (1, 32), dtype=np.uint8)]
+    leaf = [np.array([0], np.uint8)]
+    prev_ids = np.array([0], np.int64); prev_desc = desc[0]; n = 1
+    for level in range(1, L + 1):
+        cnt = np.full(len(prev_ids), k, np.int64)
+        if irregular and level > 1:
+            cnt = rng.integers(2, k + 1, len(prev_ids))
+            cnt[rng.random(len(prev_ids)) < 0.1] = 0                      # early leaf
+        par = np.repeat(prev_ids, cnt)
+        m = len(par)
+        if m == 0:
+            break
+        flips = np.zeros((m, 256), np.uint8)
+        cols = rng.integers(0, 256, (m, 24))
+        np.put_along_axis(flips, cols, 1, axis=1)
+        d = np.repeat(prev_desc, cnt, axis=0) ^ np.packbits(flips, axis=1, bitorder="little")
+        ids = n + np.arange(m)
+        parent.append(par.astype(np.int32)); desc.append(d); leaf.append(np.zeros(m, np.uint8))
+        if irregular and level > 1:
+            early = prev_ids[cnt == 0]
+            flat = np.concatenate(leaf); flat[early] = 1
+            leaf = [flat]
+        prev_ids, prev_desc, n = ids, d, n + m
+    parent = np.concatenate(parent); desc = np.concatenate(desc); leaf = np.concatenate(leaf)
+    has_child = np.zeros(n, bool); has_child[parent[1:]] = True
+    leaf = (~has_child).astype(np.uint8); leaf[0] = 0
+    weight = np.where(leaf == 1, rng.uniform(0.5, 9.0, n), 0.0)
+    stopped = (leaf == 1) & (rng.random(n) < stop_frac)
+    weight[stopped] = 0.0
+    if shuffle:
+        # random order that keeps every parent before its children
+        pri = np.zeros(n); step = rng.uniform(0.01, 1.0, n)
+        for i in range(1, n):
+            pri[i] = pri[parent[i]] + step[i]
+        order = np.argsort(pri, kind="stable")
+        new_id = np.empty(n, np.int64); new_id[order] = np.arange(n)
+        parent = np.where(parent[order] >= 0, new_id[np.maximum(parent[order], 0)], -1).astype(np.int32)
+        desc, leaf, weight = desc[order], leaf[order], weight[order]
+    return parent, leaf, np.ascontiguousarray(desc), weight.astype(np.float64)
+
+
+def vocabulary_queries(vocab, n, seed=0):
+    """n descriptors: noisy copies of random leaf descriptors (most) and uniformly random ones (some)."""
+    parent, leaf, desc, _ = vocab
+    rng = np.random.default_rng(seed)
+    leaves = np.nonzero(leaf)[0]
+    q = desc[rng.choice(leaves, n)].copy()
+    flips = np.zeros((n, 256), np.uint8)
+    np.put_along_axis(flips, rng.integers(0, 256, (n, 12)), 1, axis=1)
+    q ^= np.packbits(flips, axis=1, bitorder="little")
+    rnd = rng.random(n) < 0.1
+    q[rnd] = rng.integers(0, 256, (int(rnd.sum()), 32), dtype=np.uint8)
+    return np.ascontiguousarray(q)

@@ -297,10 +297,98 @@ def golden_primitives(outdir):
     print("primitives ok")
 
 
+class PyVocabulary:
+    """Second, independent restatement of DBoW2's vocabulary for the golden vectors: a literal node list with Python
+    children lists, std::map semantics via dicts kept in key order (TemplatedVocabulary.h loadFromTextFile, transform
+    :1127-1200 / :1218-1259, BowVector.cpp addWeight / normalize, FeatureVector.cpp addFeature)."""
+
+    def __init__(self, parent, is_leaf, desc, weight, L):
+        n = len(parent)
+        self.children = [[] for _ in range(n)]
+        for i in range(1, n):
+            self.children[int(parent[i])].append(i)
+        self.bits = np.unpackbits(np.asarray(desc, np.uint8), axis=1)
+        self.weight = [float(w) for w in weight]
+        self.word = [-1] * n
+        words = 0
+        for i in range(1, n):
+            if is_leaf[i]:
+                self.word[i] = words; words += 1
+        self.L = L
+
+    def descend(self, d, levelsup):
+        bits = np.unpackbits(np.asarray(d, np.uint8))
+        nid_level = self.L - levelsup
+        nid = 0 if nid_level <= 0 else None
+        final, level = 0, 0
+        while True:
+            level += 1
+            nodes = self.children[final]
+            final = nodes[0]
+            best = int((bits != self.bits[final]).sum())
+            for c in nodes[1:]:
+                dd = int((bits != self.bits[c]).sum())
+                if dd < best:
+                    best, final = dd, c
+            if level == nid_level:
+                nid = final
+            if not self.children[final]:
+                break
+        if nid is None:
+            nid = final            # the reference leaves *nid uninitialised here; canonical choice: the leaf
+        return self.word[final], self.weight[final], nid
+
+    def transform(self, descs, levelsup):
+        bow, fv = {}, {}
+        for i, d in enumerate(descs):
+            w, wt, nid = self.descend(d, levelsup)
+            if wt > 0:
+                if w in bow:
+                    bow[w] += wt
+                else:
+                    bow[w] = wt
+                fv.setdefault(nid, []).append(i)
+        norm = 0.0
+        for k in sorted(bow):
+            norm += abs(bow[k])
+        if norm > 0.0:
+            for k in bow:
+                bow[k] /= norm
+        return bow, fv
+
+
+def golden_bow(outdir):
+    cases = {"k10_L3": dict(k=10, L=3), "irregular_k6_L4": dict(k=6, L=4, irregular=True, shuffle=True), "wide_k20_L2": dict(k=20, L=2)}
+    out = {}
+    for name, kw in cases.items():
+        vocab = synth.random_vocabulary(seed=7, **kw)
+        q = synth.vocabulary_queries(vocab, 300, seed=8)
+        L = kw["L"]
+        py = PyVocabulary(*vocab, L=L)
+        oc = O.Vocabulary(*vocab, L=L)
+        for levelsup in (1, L - 1, L + 2):
+            bow, fv = py.transform(q, levelsup)
+            (bw, bv), (fn, ff) = oc.transform(q, levelsup)
+            assert list(bw) == sorted(bow) and [bow[k] for k in sorted(bow)] == list(bv), name
+            assert list(fn) == sorted(fv) and all(list(a) == fv[k] for a, k in zip(ff, sorted(fv))), name
+            w, wt, nd = oc.transform_features(q, levelsup)
+            ref = [py.descend(d, levelsup) for d in q]
+            assert [r[0] for r in ref] == list(w) and [r[1] for r in ref] == list(wt) and [r[2] for r in ref] == list(nd), name
+            out["%s_ls%d_word" % (name, levelsup)] = w; out["%s_ls%d_node" % (name, levelsup)] = nd
+            out["%s_ls%d_bow_words" % (name, levelsup)] = bw; out["%s_ls%d_bow_values" % (name, levelsup)] = bv
+        for key, arr in zip(("parent", "leaf", "desc", "weight"), vocab):
+            out["%s_%s" % (name, key)] = arr
+        out["%s_queries" % name] = q
+        out["%s_L" % name] = np.int32(L)
+    np.savez_compressed(os.path.join(outdir, "bow.npz"), **out)
+    print("bow ok")
+
+
 def main():
     outdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
     os.makedirs(outdir, exist_ok=True)
     golden_primitives(outdir)
+    golden_bow(outdir)
     st = synth.rects_stream(320, 240, 2, seed=11)
     k0, d0 = golden_extract("extract_320x240_nf300_f0", st[0], (300, 1.2, 8, 20, 7), (0, 0), outdir)
     k1, d1 = golden_extract("extract_320x240_nf300_f1", st[1], (300, 1.2, 8, 20, 7), (0, 0), outdir)

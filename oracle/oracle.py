@@ -85,6 +85,12 @@ def lib():
         L.orc_search_by_projection.restype = i32
         L.orc_stereo_band_match.argtypes = [vp, vp, i32, vp, vp, i32, vp, i32, f32, f32, vp, vp]
         L.orc_match_candidates.argtypes = [vp, i32, vp, vp, vp, vp, vp]
+        L.orc_vocab_create.restype = vp
+        L.orc_vocab_create.argtypes = [i32, vp, vp, vp, vp, i32]
+        L.orc_vocab_destroy.argtypes = [vp]
+        L.orc_bow_transform_features.argtypes = [vp, vp, i32, i32, vp, vp, vp]
+        L.orc_bow_transform.restype = i32
+        L.orc_bow_transform.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, vp, vp]
         L.orc_compute_stereo_matches.argtypes = [vp, vp, vp, vp, i32, vp, vp, i32, f32, f32, vp, vp, vp]
         _lib = L
     return _lib
@@ -272,3 +278,34 @@ def match_candidates(q, t, offsets, indices):
     idx = np.empty((len(q), 2), np.int32); dist = np.empty((len(q), 2), np.int32)
     lib().orc_match_candidates(_p(q), len(q), _p(t), _p(off), _p(ind), _p(idx), _p(dist))
     return idx, dist
+
+
+class Vocabulary:
+    """DBoW2 ORB vocabulary (node table in file order, see orb_oracle.h)."""
+
+    def __init__(self, parent, is_leaf, desc, weight, L):
+        self.parent = np.ascontiguousarray(parent, np.int32); self.is_leaf = np.ascontiguousarray(is_leaf, np.uint8)
+        self.desc = _u8(desc); self.weight = np.ascontiguousarray(weight, np.float64); self.L = int(L)
+        self._h = lib().orc_vocab_create(len(self.parent), _p(self.parent), _p(self.is_leaf), _p(self.desc), _p(self.weight), self.L)
+        if not self._h:
+            raise ValueError("invalid vocabulary")
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_vocab_destroy(self._h); self._h = None
+
+    def transform_features(self, desc, levelsup=4):
+        d = _u8(desc); n = len(d)
+        w = np.empty(n, np.int32); wt = np.empty(n, np.float64); nd = np.empty(n, np.int32)
+        lib().orc_bow_transform_features(self._h, _p(d), n, levelsup, _p(w), _p(wt), _p(nd))
+        return w, wt, nd
+
+    def transform(self, desc, levelsup=4):
+        """-> (bow word ids, bow values), (fv node ids, list of feature-index arrays)"""
+        d = _u8(desc); n = len(d)
+        bw = np.empty(n + 1, np.int32); bv = np.empty(n + 1, np.float64)
+        fn = np.empty(n + 1, np.int32); fs = np.empty(n + 2, np.int32); ff = np.empty(n + 1, np.int32)
+        nfv = C.c_int(0)
+        nb = lib().orc_bow_transform(self._h, _p(d), n, levelsup, _p(bw), _p(bv), _p(fn), _p(fs), _p(ff), C.byref(nfv))
+        k = nfv.value
+        return (bw[:nb].copy(), bv[:nb].copy()), (fn[:k].copy(), [ff[fs[i]:fs[i + 1]].copy() for i in range(k)])

@@ -1097,3 +1097,115 @@ void orc_match_candidates(const uint8_t* q, int nq, const uint8_t* t, const int3
         out_dist[i * 2] = i0 >= 0 ? b0 : -1; out_dist[i * 2 + 1] = i1 >= 0 ? b1 : -1;
     }
 }
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Bag of words (DBoW2 as vendored by the reference, R/Thirdparty/DBoW2/DBoW2)
+ * ------------------------------------------------------------------------------------------------------------------ */
+struct OrcVocab {
+    int n_nodes, L;
+    int32_t* child_start;   /* CSR over children, order of appearance (loadFromTextFile: m_nodes[pid].children.push_back) */
+    int32_t* child;
+    uint8_t* desc;
+    double* weight;
+    int32_t* word_id;       /* -1 for inner nodes */
+};
+
+OrcVocab* orc_vocab_create(int n_nodes, const int32_t* parent, const uint8_t* is_leaf, const uint8_t* desc,
+                           const double* weight, int L)
+{
+    if (n_nodes < 1) return NULL;
+    for (int i = 1; i < n_nodes; i++) if (parent[i] < 0 || parent[i] >= i) return NULL;
+    OrcVocab* v = (OrcVocab*)calloc(1, sizeof(OrcVocab));
+    v->n_nodes = n_nodes; v->L = L;
+    v->child_start = (int32_t*)calloc((size_t)n_nodes + 1, sizeof(int32_t));
+    v->child = (int32_t*)calloc((size_t)n_nodes, sizeof(int32_t));
+    v->desc = (uint8_t*)malloc((size_t)n_nodes * 32); memcpy(v->desc, desc, (size_t)n_nodes * 32);
+    v->weight = (double*)malloc(sizeof(double) * n_nodes); memcpy(v->weight, weight, sizeof(double) * n_nodes);
+    v->word_id = (int32_t*)malloc(sizeof(int32_t) * n_nodes);
+    for (int i = 1; i < n_nodes; i++) v->child_start[parent[i] + 1]++;
+    for (int i = 0; i < n_nodes; i++) v->child_start[i + 1] += v->child_start[i];
+    int32_t* cur = (int32_t*)malloc(sizeof(int32_t) * n_nodes);
+    memcpy(cur, v->child_start, sizeof(int32_t) * n_nodes);
+    for (int i = 1; i < n_nodes; i++) v->child[cur[parent[i]]++] = i;
+    free(cur);
+    int words = 0;
+    for (int i = 0; i < n_nodes; i++) v->word_id[i] = (i > 0 && is_leaf[i]) ? words++ : -1;   /* :TemplatedVocabulary.h loadFromTextFile */
+    return v;
+}
+
+void orc_vocab_destroy(OrcVocab* v)
+{
+    if (!v) return;
+    free(v->child_start); free(v->child); free(v->desc); free(v->weight); free(v->word_id); free(v);
+}
+
+void orc_bow_transform_features(const OrcVocab* v, const uint8_t* desc, int n, int levelsup,
+                                int32_t* word_id, double* weight, int32_t* node_id)
+{
+    const int nid_level = v->L - levelsup;
+    for (int f = 0; f < n; f++) {
+        const uint8_t* d = desc + (size_t)f * 32;
+        int final_id = 0, level = 0, nid = 0, have_nid = nid_level <= 0;
+        if (v->child_start[1] == v->child_start[0]) { word_id[f] = -1; weight[f] = 0.0; node_id[f] = 0; continue; }   /* empty vocabulary */
+        do {                                                         /* TemplatedVocabulary.h:1234-1254 */
+            ++level;
+            const int c0 = v->child_start[final_id], c1 = v->child_start[final_id + 1];
+            int best = v->child[c0];
+            int best_d = orc_hamming256(d, v->desc + (size_t)best * 32);
+            for (int c = c0 + 1; c < c1; c++) {
+                const int id = v->child[c];
+                const int dd = orc_hamming256(d, v->desc + (size_t)id * 32);
+                if (dd < best_d) { best_d = dd; best = id; }
+            }
+            final_id = best;
+            if (level == nid_level) { nid = final_id; have_nid = 1; }
+        } while (v->child_start[final_id + 1] > v->child_start[final_id]);
+        if (!have_nid) nid = final_id;
+        word_id[f] = v->word_id[final_id]; weight[f] = v->weight[final_id]; node_id[f] = nid;
+    }
+}
+
+typedef struct { int32_t key; int32_t idx; } OrcKI;
+static int orc_ki_cmp(const void* a, const void* b)
+{
+    const OrcKI* x = (const OrcKI*)a; const OrcKI* y = (const OrcKI*)b;
+    if (x->key != y->key) return x->key < y->key ? -1 : 1;
+    return x->idx < y->idx ? -1 : (x->idx > y->idx);
+}
+
+int orc_bow_transform(const OrcVocab* v, const uint8_t* desc, int n, int levelsup,
+                      int32_t* bow_words, double* bow_values,
+                      int32_t* fv_nodes, int32_t* fv_start, int32_t* fv_features, int* n_fv)
+{
+    int32_t* w = (int32_t*)malloc(sizeof(int32_t) * (n + 1)); double* wt = (double*)malloc(sizeof(double) * (n + 1));
+    int32_t* nd = (int32_t*)malloc(sizeof(int32_t) * (n + 1));
+    orc_bow_transform_features(v, desc, n, levelsup, w, wt, nd);
+    OrcKI* kw = (OrcKI*)malloc(sizeof(OrcKI) * (n + 1)); OrcKI* kn = (OrcKI*)malloc(sizeof(OrcKI) * (n + 1));
+    int m = 0;
+    for (int i = 0; i < n; i++)
+        if (wt[i] > 0) { kw[m].key = w[i]; kw[m].idx = i; kn[m].key = nd[i]; kn[m].idx = i; m++; }      /* "not stopped" :1157 */
+    qsort(kw, m, sizeof(OrcKI), orc_ki_cmp); qsort(kn, m, sizeof(OrcKI), orc_ki_cmp);
+    /* BowVector::addWeight in feature order: the value of a word is w added once per feature that hit it */
+    int nb = 0;
+    for (int i = 0; i < m; ) {
+        int j = i; double acc = 0.0;
+        while (j < m && kw[j].key == kw[i].key) { if (j == i) acc = wt[kw[j].idx]; else acc += wt[kw[j].idx]; j++; }
+        bow_words[nb] = kw[i].key; bow_values[nb] = acc; nb++;
+        i = j;
+    }
+    /* BowVector::normalize(L1): norm summed in map (word id) order */
+    double norm = 0.0;
+    for (int i = 0; i < nb; i++) norm += fabs(bow_values[i]);
+    if (norm > 0.0) for (int i = 0; i < nb; i++) bow_values[i] /= norm;
+    int nf = 0;
+    for (int i = 0; i < m; ) {
+        int j = i;
+        fv_nodes[nf] = kn[i].key; fv_start[nf] = i;
+        while (j < m && kn[j].key == kn[i].key) { fv_features[j] = kn[j].idx; j++; }
+        nf++; i = j;
+    }
+    fv_start[nf] = m;
+    *n_fv = nf;
+    free(w); free(wt); free(nd); free(kw); free(kn);
+    return nb;
+}

@@ -121,6 +121,26 @@ void  orc_compute_stereo_matches(const OrcExtractor* left, const OrcExtractor* r
                                  const OrcKeyPoint* kr, const uint8_t* dr, int nr,
                                  float mb, float mbf, float* uright, float* depth, int32_t* sad_dist);
 
+/* ---- bag of words: DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB> as ORB-SLAM3 uses it ----
+ * Restated from R/Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h (loadFromTextFile, transform :1127-1200, :1218-1259),
+ * BowVector.cpp (addWeight, normalize), FeatureVector.cpp (addFeature), FORB.cpp:81-101 (distance).
+ * Vocabulary = node table in file order: node 0 is the root; node i > 0 has parent[i] < i; children keep their order of
+ * appearance; nodes flagged is_leaf are the words, numbered in node order.  TF_IDF weighting, L1 scoring (ORBvoc.txt). */
+typedef struct OrcVocab OrcVocab;
+OrcVocab* orc_vocab_create(int n_nodes, const int32_t* parent, const uint8_t* is_leaf, const uint8_t* desc,
+                           const double* weight, int L);
+void  orc_vocab_destroy(OrcVocab* v);
+/* per-feature descent (:1218-1259): word id, word weight and the node at level L - levelsup (0 = root when that level
+ * is <= 0; the last node reached when the leaf lies above that level, where the reference leaves it uninitialised) */
+void  orc_bow_transform_features(const OrcVocab* v, const uint8_t* desc, int n, int levelsup,
+                                 int32_t* word_id, double* weight, int32_t* node_id);
+/* transform(features, BowVector&, FeatureVector&, levelsup) (:1127-1200): bow_words/bow_values sorted by word id and L1
+ * normalised (capacity n), fv_nodes sorted node ids with fv_start[i] .. fv_start[i+1] into fv_features (feature indices
+ * in insertion order).  Returns the BowVector size; *n_fv = FeatureVector size. */
+int   orc_bow_transform(const OrcVocab* v, const uint8_t* desc, int n, int levelsup,
+                        int32_t* bow_words, double* bow_values,
+                        int32_t* fv_nodes, int32_t* fv_start, int32_t* fv_features, int* n_fv);
+
 #ifdef __cplusplus
 }
 #endif
