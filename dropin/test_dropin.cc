@@ -7,6 +7,7 @@
 #include <vector>
 #include "ORBextractor.h"
 #include "ORBmatcher.h"
+#include "ORBVocabulary.h"
 using namespace ORB_SLAM3;
 
 static std::vector<unsigned char> slurp(const char* p, size_t n)
@@ -103,6 +104,27 @@ int main(int argc, char** argv)
     int ns = (int)uR.size();
     fwrite(&ns, 4, 1, o);
     fwrite(uR.data(), 4, ns, o); fwrite(depth.data(), 4, ns, o);
+
+    // ---- Frame::ComputeBoW: ORBVocabulary::loadFromTextFile + transform(features, BowVector, FeatureVector, 4) ----
+    int nbow = -1;
+    if (argc > 6) {
+        ORBVocabulary voc;
+        if (!voc.loadFromTextFile(argv[6])) { fprintf(stderr, "cannot load vocabulary %s\n", argv[6]); return 3; }
+        std::vector<cv::Mat> vDesc;                                   // Converter::toDescriptorVector
+        for (int i = 0; i < F[0].N; i++) vDesc.push_back(F[0].mDescriptors.row(i));
+        DBoW2::BowVector bow; DBoW2::FeatureVector fv;
+        voc.transform(vDesc, bow, fv, 4);
+        nbow = (int)bow.size();
+        fwrite(&nbow, 4, 1, o);
+        for (DBoW2::BowVector::const_iterator it = bow.begin(); it != bow.end(); ++it) { unsigned w = it->first; double x = it->second; fwrite(&w, 4, 1, o); fwrite(&x, 8, 1, o); }
+        int nfv = (int)fv.size();
+        fwrite(&nfv, 4, 1, o);
+        for (DBoW2::FeatureVector::const_iterator it = fv.begin(); it != fv.end(); ++it) {
+            unsigned nid = it->first; int c = (int)it->second.size();
+            fwrite(&nid, 4, 1, o); fwrite(&c, 4, 1, o); fwrite(it->second.data(), 4, c, o);
+        }
+        unsigned nw = voc.size(); fwrite(&nw, 4, 1, o);
+    }
     fclose(o);
     delete extR;
     printf("dropin ok: %d / %d keypoints, %d init matches, %d / %d projection matches\n", F[0].N, F[1].N, nm, nA, nB);

@@ -21,8 +21,14 @@ def test_dropin_classes_match_oracle(tmp_path):
     for k in range(2):
         st[k].tofile(tmp_path / ("f%d.raw" % k))
     out = tmp_path / "out.bin"
+    # a synthetic vocabulary in the text format of ORBvoc.txt ("k L scoring weighting", then parent isLeaf 32 bytes weight)
+    vocab = synth.random_vocabulary(k=10, L=5, seed=21)
+    with open(tmp_path / "voc.txt", "w") as fh:
+        fh.write("10 5 0 0\n")
+        for i in range(1, len(vocab[0])):
+            fh.write("%d %d %s %r\n" % (vocab[0][i], vocab[1][i], " ".join(str(int(b)) for b in vocab[2][i]), float(vocab[3][i])))
     subprocess.check_call([os.path.join(ROOT, "dropin", "_build", "test_dropin"), str(W), str(H),
-                           str(tmp_path / "f0.raw"), str(tmp_path / "f1.raw"), str(out)])
+                           str(tmp_path / "f0.raw"), str(tmp_path / "f1.raw"), str(out), str(tmp_path / "voc.txt")])
     buf = out.read_bytes()
     off = 0
     ref = O.Extractor(1000, 1.2, 8, 20, 7)
@@ -95,3 +101,21 @@ def test_dropin_classes_match_oracle(tmp_path):
     np.testing.assert_array_equal(uR, rur)
     np.testing.assert_array_equal(dep, rdp)
     assert (rur >= 0).sum() > 10
+
+    # ORBVocabulary::loadFromTextFile + transform(features, BowVector, FeatureVector, 4) on frame 0's descriptors
+    RV = O.Vocabulary(*vocab, L=5)
+    (rbw, rbv), (rfn, rff) = RV.transform(d1, 4)
+    nbow, = struct.unpack_from("<i", buf, off); off += 4
+    assert nbow == len(rbw)
+    rec = np.frombuffer(buf, np.dtype([("w", "<u4"), ("v", "<f8")]), nbow, off); off += 12 * nbow
+    np.testing.assert_array_equal(rec["w"], rbw)
+    np.testing.assert_array_equal(rec["v"], rbv)                  # doubles, bit for bit (values survive the text round trip via repr)
+    nfv, = struct.unpack_from("<i", buf, off); off += 4
+    assert nfv == len(rfn)
+    for k in range(nfv):
+        nid, c = struct.unpack_from("<Ii", buf, off); off += 8
+        feats = np.frombuffer(buf, np.uint32, c, off); off += 4 * c
+        assert nid == rfn[k]
+        np.testing.assert_array_equal(feats, rff[k])
+    nw, = struct.unpack_from("<I", buf, off)
+    assert nw == int(vocab[1].sum())
