@@ -154,6 +154,113 @@ def server_bench(args, world, rank, local):
         dist.destroy_process_group()
 
 
+def bow_bench(args, world, rank, local):
+    """SURVEY 8f row 2: Frame::ComputeBoW = DBoW2 transform(features, BowVector, FeatureVector, 4) with an ORBvoc-shaped
+    vocabulary (k = 10, L = 6: 1 111 111 nodes, 10^6 words; synthetic, ORBvoc.txt is not in the image).  Step = the tree
+    descent of every descriptor of a batch of extracted frames (descriptors resident in the extractor's result slots)."""
+    import torch
+    import torch.distributed as dist
+    from multi_orbslam3_b200 import orbx, synth
+    B = args.batch
+    ex = orbx.ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, max_width=W, max_height=H, max_batch=B, device=local)
+    uniq = min(B, 64)
+    base = synth.rects_stream(W, H, uniq, seed=1000 * rank)
+    frames = np.ascontiguousarray(np.concatenate([base] * ((B + uniq - 1) // uniq))[:B])
+    d_frames = torch.from_numpy(frames).cuda()
+    tstream = torch.cuda.Stream(); torch.cuda.set_stream(tstream); stream = tstream.cuda_stream
+    ex.extract_batch_device(d_frames.data_ptr(), B, W, H, W, W * H, (0, 0), 0, stream)
+    ex.sync(stream)
+    res = ex.download(0, B)
+    ndesc = int(sum(len(r[1]) for r in res))
+    vocab = synth.random_vocabulary(k=10, L=6, seed=77)
+    V = orbx.ORBVocabulary(*vocab, L=6, device=local)
+    dw = torch.empty((B, ex.cap), dtype=torch.int32, device="cuda"); dn = torch.empty((B, ex.cap), dtype=torch.int32, device="cuda")
+
+    def step():
+        V.transform_slots_device(ex, 0, B, dw.data_ptr(), dn.data_ptr(), 4, stream)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = orbx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches = orbx.launch_count() - l0
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / args.steps
+    # end to end: host descriptors of the whole batch in, word / node ids and weights out (one C-ABI call)
+    hd = torch.from_numpy(np.concatenate([r[2] for r in res])).pin_memory().numpy()
+    e2e = None
+    if not args.no_e2e:
+        V.transform_features(hd, 4)
+        ns = max(3, min(args.steps, 10))
+        t0 = time.perf_counter()
+        for _ in range(ns):
+            V.transform_features(hd, 4)
+        dt = (time.perf_counter() - t0) / ns
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * B / float(t.item()), "unit": "frames/s", "h2d_bytes_per_step": ndesc * 32, "d2h_bytes_per_step": ndesc * 8,
+               "steps": ns, "api": "orbx_bow_transform (host descriptors -> word ids, weights, node ids on host)"}
+    clocks = sampler.stop() if rank == 0 else None
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle as O
+        O.build()
+        cores = os.cpu_count() or 1
+        RV = [O.Vocabulary(*vocab, L=6) for _ in range(1)][0]
+        per = [r[2] for r in res[:uniq]]
+        done = [0] * cores
+
+        def work(i, reps):
+            for j in range(reps):
+                RV.transform(per[(i + j) % len(per)], 4)
+                done[i] += 1
+        t0 = time.perf_counter(); work(0, 4); dcal = (time.perf_counter() - t0) / 4
+        reps = int(min(5000, max(8, 10.0 / max(dcal, 1e-4))))
+        for i in range(cores):
+            done[i] = 0
+        th = [threading.Thread(target=work, args=(i, reps)) for i in range(cores)]
+        t0 = time.perf_counter(); [x.start() for x in th]; [x.join() for x in th]
+        dtc = time.perf_counter() - t0
+        cpu = {"value": sum(done) / dtc, "unit": "frames/s", "cores": cores, "kind": "port",
+               "sample": "%d frames (%d threads x %d transforms of ~%d descriptors), %.1f s wall" % (sum(done), cores, reps, ndesc // B, dtc)}
+    popc, _ = orbx.popc_peak(local)
+    dist_per_desc = 60.0                      # 10 children x 6 levels
+    line = {"metric": "BoW transform frames/sec (DBoW2 k=10 L=6, ~1000 descriptors per frame)", "value": world * B / (ms * 1e-3), "unit": "frames/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "BoW: Frame::ComputeBoW tree descent on the descriptors of %d extracted 752x480 frames per step; synthetic ORBvoc-shaped vocabulary (1 111 111 nodes, 35 MB, L2-resident)" % B,
+                       "descriptors_per_step_per_gpu": ndesc},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": {"bound": "popc", "kernel": "k_bow_transform", "achieved": ndesc * dist_per_desc * 8 / (ms * 1e-3), "peak": popc,
+                         "unit": "popc32/s", "frac": ndesc * dist_per_desc * 8 / (ms * 1e-3) / popc, "traffic": None,
+                         "note": "6 dependent levels of 10 distances each: latency- and L2-bound (1.9 KB of child descriptors per descriptor), far below the popc pipe"},
+            "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+    V.close(); ex.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def stereo_bench(args, world, rank, local):
     """BASELINE configs C2 (EuRoC 752x480, 1200 kp) and C3 (KITTI 1241x376, 2000 kp): a stream of stereo pairs per GPU.
     Step = ORBextractor::operator() on every left and right frame + Frame::ComputeStereoMatches for every pair."""
@@ -360,10 +467,10 @@ def main():
     ap.add_argument("--batch", type=int, default=512, help="frames per step per GPU (512 x 361 KB = 185 MB of input > 126 MB L2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
-    ap.add_argument("--workload", default="c1", choices=["c1", "c2", "c3", "c4", "c5"],
+    ap.add_argument("--workload", default="c1", choices=["c1", "c2", "c3", "c4", "c5", "bow"],
                     help="c1 (default, the BASELINE metric): extract+match streams; c2 / c3: EuRoC / KITTI stereo streams "
                          "(extract both cameras + ComputeStereoMatches); c4: c1 at TUM shape 640x480; "
-                         "c5: server cross-agent BF matching over a sharded DB")
+                         "c5: server cross-agent BF matching over a sharded DB; bow: Frame::ComputeBoW (DBoW2 transform, k=10 L=6) on extracted frames")
     ap.add_argument("--db-keyframes", type=int, default=65536, help="c5: keyframes in the whole DB (x1000 descriptors)")
     ap.add_argument("--exchange", default="top2", choices=["top2", "db"], help="c5: all-gather partial top-2 tables or the DB shards")
     args = ap.parse_args()
@@ -392,6 +499,8 @@ def main():
         return server_bench(args, world, rank, local)
     if args.workload in ("c2", "c3"):
         return stereo_bench(args, world, rank, local)
+    if args.workload == "bow":
+        return bow_bench(args, world, rank, local)
     global W, H, METRIC
     if args.workload == "c4":
         W, H = 640, 480

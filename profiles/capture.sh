@@ -6,6 +6,7 @@ python bench.py > $O/r1_bench_1gpu.json 2> $O/r1_bench_1gpu.err
 python bench.py --impl reference --steps 3 --warmup 1 > $O/r1_bench_reference.json 2>> $O/r1_bench_1gpu.err
 for w in c2 c3 c4; do python bench.py --workload $w --steps 20 > $O/r1_bench_${w}_1gpu.json 2>> $O/r1_bench_1gpu.err; done
 python bench.py --workload c5 --steps 5 > $O/r1_bench_c5_1gpu.json 2>> $O/r1_bench_1gpu.err
+python bench.py --workload bow --steps 20 > $O/r1_bench_bow_1gpu.json 2>> $O/r1_bench_1gpu.err
 python profiles/h2d_probe.py > $O/r1_h2d_probe.txt 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/r1_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/bench_under_ncu.log 2>&1
