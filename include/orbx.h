@@ -237,6 +237,22 @@ int  orbx_stereo_matches_batch(orbx_matcher* m, orbx_extractor* left, orbx_extra
  * denominator for the matching kernels) */
 int  orbx_popc_peak(int device, double* popc_per_s, double* lop3_per_s);
 
+/* ORBmatcher::SearchByBoW on flat arrays.  The two FeatureVectors are CSR tables sorted by node id (the order of the
+ * std::map the reference iterates): fv_nodes[nfv], fv_start[nfv + 1], fv_feat[fv_start[nfv]].  valid = "the feature has a
+ * MapPoint that is not bad".  matches12[i1] receives the matched index in set 2, or -1; *nmatches the return value.
+ * mode 0 = SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&) (R/src/ORBmatcher.cc:269-471, Nleft == -1 branch): set 1 =
+ *          keyframe, set 2 = frame, valid2 ignored, accept bestDist1 <= TH_LOW; the caller stores
+ *          vpMapPointMatches[matches12[i1]] = MapPoint of i1;
+ * mode 1 = SearchByBoW(KeyFrame*, KeyFrame*, vector<MapPoint*>&) (R/src/ORBmatcher.cc:819-959): candidates need valid2,
+ *          accept bestDist1 < TH_LOW; vpMatches12[i1] = MapPoint of matches12[i1].
+ * Host pointers, synchronous. */
+int  orbx_search_by_bow(orbx_matcher* m, int mode,
+                        const orbx_keypoint* k1, const uint8_t* d1, const uint8_t* valid1, int n1,
+                        const int32_t* fv1_nodes, const int32_t* fv1_start, const int32_t* fv1_feat, int nfv1,
+                        const orbx_keypoint* k2, const uint8_t* d2, const uint8_t* valid2, int n2,
+                        const int32_t* fv2_nodes, const int32_t* fv2_start, const int32_t* fv2_feat, int nfv2,
+                        float nnratio, int check_ori, int32_t* matches12, int* nmatches);
+
 /* ---- bag of words: DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB> as Frame::ComputeBoW
  * (R/src/Frame.cc:712-719) and KeyFrame::ComputeBoW (R/src/KeyFrame.cc:168-176) use it ---- */
 typedef struct orbx_vocab orbx_vocab;

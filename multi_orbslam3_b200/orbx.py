@@ -38,7 +38,7 @@ EXPORTS = [
     "orbx_search_for_initialization", "orbx_match_slots_device", "orbx_extract_match_batch", "orbx_extract_match_batch_device",
     "orbx_search_by_projection",
     "orbx_stereo_band_match", "orbx_stereo_matches", "orbx_stereo_matches_batch", "orbx_stereo_matches_batch_device",
-    "orbx_match_candidates", "orbx_vocab_create", "orbx_vocab_destroy", "orbx_vocab_words", "orbx_vocab_word_weights",
+    "orbx_match_candidates", "orbx_search_by_bow", "orbx_vocab_create", "orbx_vocab_destroy", "orbx_vocab_words", "orbx_vocab_word_weights",
     "orbx_bow_transform", "orbx_bow_transform_slots_device", "orbx_popc_peak",
 ]
 
@@ -111,6 +111,7 @@ def lib():
         L.orbx_stereo_band_match.argtypes = [vp, vp, vp, i32, vp, vp, i32, vp, i32, i32, f32, f32, vp, vp]
         L.orbx_popc_peak.argtypes = [i32, vp, vp]
         L.orbx_match_candidates.argtypes = [vp, vp, i32, vp, i32, vp, vp, vp, vp]
+        L.orbx_search_by_bow.argtypes = [vp, i32, vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, vp, i32, f32, i32, vp, vp]
         L.orbx_vocab_create.argtypes = [i32, i32, vp, vp, vp, vp, i32, vp]
         L.orbx_vocab_destroy.argtypes = [vp]; L.orbx_vocab_destroy.restype = None
         L.orbx_vocab_words.argtypes = [vp]
@@ -352,6 +353,27 @@ class ORBmatcher:
         _check(lib().orbx_stereo_matches(self._h, ex_left._h, ex_right._h, slot_l, slot_r, frame_l, frame_r, float(mb), float(mbf),
                                          _p(ur), _p(dp), _p(sd), cap, C.byref(n)))
         return ur[:n.value].copy(), dp[:n.value].copy(), sd[:n.value].copy()
+
+    def SearchByBoW(self, mode, k1, d1, valid1, fv1, k2, d2, valid2, fv2):
+        """ORBmatcher::SearchByBoW: mode 0 = (KeyFrame, Frame), mode 1 = (KeyFrame, KeyFrame); fv = (node ids, feature lists)
+        as ORBVocabulary.transform returns them.  -> (nmatches, matches12)"""
+        k1 = np.ascontiguousarray(k1, KP_DTYPE); k2 = np.ascontiguousarray(k2, KP_DTYPE)
+        d1 = np.ascontiguousarray(d1, np.uint8).reshape(-1, 32); d2 = np.ascontiguousarray(d2, np.uint8).reshape(-1, 32)
+        v1 = np.ascontiguousarray(valid1, np.uint8); v2 = None if valid2 is None else np.ascontiguousarray(valid2, np.uint8)
+
+        def csr(fv):
+            nodes, feats = fv
+            start = np.zeros(len(nodes) + 1, np.int32)
+            if len(nodes):
+                start[1:] = np.cumsum([len(f) for f in feats])
+            flat = np.concatenate(feats).astype(np.int32) if len(nodes) else np.zeros(0, np.int32)
+            return np.ascontiguousarray(nodes, np.int32), start, np.ascontiguousarray(flat)
+        n1, s1, f1 = csr(fv1); n2, s2, f2 = csr(fv2)
+        m12 = np.empty(len(k1), np.int32); nm = C.c_int(0)
+        _check(lib().orbx_search_by_bow(self._h, int(mode), _p(k1), _p(d1), _p(v1), len(k1), _p(n1), _p(s1), _p(f1), len(n1),
+                                        _p(k2), _p(d2), _p(v2) if v2 is not None else None, len(k2), _p(n2), _p(s2), _p(f2), len(n2),
+                                        self.mfNNratio, int(self.mbCheckOrientation), _p(m12), C.byref(nm)))
+        return nm.value, m12
 
     def ComputeStereoMatchesBatch(self, ex_left, ex_right, mb, mbf, first=0, count=1):
         """Frame::ComputeStereoMatches for `count` stereo pairs of the two extractors' last batch -> (mvuRight, mvDepth) [count, cap]."""

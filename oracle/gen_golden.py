@@ -357,6 +357,100 @@ class PyVocabulary:
         return bow, fv
 
 
+def py_search_by_bow(mode, k1, d1, valid1, fv1, k2, d2, valid2, fv2, nnratio, check_ori):
+    """Literal restatement of ORBmatcher::SearchByBoW (ORBmatcher.cc:269-471 mono branch / :819-959) on dict FeatureVectors."""
+    TH_LOW, HL = 50, 30
+    bits1 = np.unpackbits(d1, axis=1); bits2 = np.unpackbits(d2, axis=1)
+    m12 = [-1] * len(k1); matched2 = [False] * len(k2)
+    rot = [[] for _ in range(HL)]
+    n = 0
+    keys1, keys2 = sorted(fv1), sorted(fv2)
+    a = b = 0
+    while a < len(keys1) and b < len(keys2):
+        if keys1[a] == keys2[b]:
+            for i1 in fv1[keys1[a]]:
+                if not valid1[i1]:
+                    continue
+                b1, bi, b2 = 256, -1, 256
+                for i2 in fv2[keys2[b]]:
+                    if matched2[i2]:
+                        continue
+                    if mode == 1 and not valid2[i2]:
+                        continue
+                    dist = int((bits1[i1] != bits2[i2]).sum())
+                    if dist < b1:
+                        b2, b1, bi = b1, dist, i2
+                    elif dist < b2:
+                        b2 = dist
+                ok = b1 <= TH_LOW if mode == 0 else b1 < TH_LOW
+                if ok and np.float32(b1) < np.float32(nnratio) * np.float32(b2):
+                    m12[i1] = bi; matched2[bi] = True
+                    if check_ori:
+                        r = np.float32(k1["angle"][i1]) - np.float32(k2["angle"][bi])
+                        if r < 0:
+                            r = np.float32(r + np.float32(360.0))
+                        x = np.float32(r * np.float32(np.float32(1.0) / np.float32(HL)))
+                        bn = int(np.floor(x + np.float32(0.5))) if x >= 0 else int(np.ceil(x - np.float32(0.5)))     # C round()
+                        if bn == HL:
+                            bn = 0
+                        rot[bn].append(i1)
+                    n += 1
+            a += 1; b += 1
+        elif keys1[a] < keys2[b]:
+            while a < len(keys1) and keys1[a] < keys2[b]:
+                a += 1
+        else:
+            while b < len(keys2) and keys2[b] < keys1[a]:
+                b += 1
+    if check_ori:
+        sizes = [len(r) for r in rot]
+        mx = [0, 0, 0]; ind = [-1, -1, -1]
+        for i, s_ in enumerate(sizes):                  # ComputeThreeMaxima, ORBmatcher.cc:2312-2353
+            if s_ > mx[0]:
+                mx = [s_, mx[0], mx[1]]; ind = [i, ind[0], ind[1]]
+            elif s_ > mx[1]:
+                mx = [mx[0], s_, mx[1]]; ind = [ind[0], i, ind[1]]
+            elif s_ > mx[2]:
+                mx[2] = s_; ind[2] = i
+        if mx[1] < np.float32(0.1) * np.float32(mx[0]):
+            ind[1] = ind[2] = -1
+        elif mx[2] < np.float32(0.1) * np.float32(mx[0]):
+            ind[2] = -1
+        for i in range(HL):
+            if i in ind:
+                continue
+            for i1 in rot[i]:
+                m12[i1] = -1; n -= 1
+    return n, np.array(m12, np.int32)
+
+
+def golden_search_by_bow(outdir):
+    st = synth.rects_stream(480, 360, 2, seed=31)
+    e = O.Extractor(600, 1.2, 8, 20, 7)
+    _, k1, d1 = e(st[0], (0, 0)); _, k2, d2 = e(st[1], (0, 0))
+    vocab = synth.random_vocabulary(k=10, L=4, seed=9)
+    V = O.Vocabulary(*vocab, L=4); P = PyVocabulary(*vocab, L=4)
+    out = dict(k1=k1, d1=d1, k2=k2, d2=d2)
+    for key, arr in zip(("parent", "leaf", "desc", "weight"), vocab):
+        out["voc_" + key] = arr
+    v1 = (np.arange(len(k1)) % 6 != 0).astype(np.uint8); v2 = (np.arange(len(k2)) % 5 != 0).astype(np.uint8)
+    out["valid1"] = v1; out["valid2"] = v2
+    for levelsup in (3, 2):
+        fv1 = P.transform(d1, levelsup)[1]; fv2 = P.transform(d2, levelsup)[1]
+        ofv1 = V.transform(d1, levelsup)[1]; ofv2 = V.transform(d2, levelsup)[1]
+        for mode, ratio in ((0, 0.7), (1, 0.8), (0, 0.95)):
+            n, m12 = py_search_by_bow(mode, k1, d1, v1, fv1, k2, d2, v2, fv2, ratio, True)
+            on, om12 = O.search_by_bow(mode, k1, d1, v1, ofv1, k2, d2, v2 if mode == 1 else None, ofv2, ratio, True)
+            assert n == on and np.array_equal(m12, om12), (levelsup, mode)
+            n2_, m2 = py_search_by_bow(mode, k1, d1, v1, fv1, k2, d2, v2, fv2, ratio, False)
+            on2, om2 = O.search_by_bow(mode, k1, d1, v1, ofv1, k2, d2, v2 if mode == 1 else None, ofv2, ratio, False)
+            assert n2_ == on2 and np.array_equal(m2, om2)
+            tag = "ls%d_m%d_r%d" % (levelsup, mode, int(ratio * 100))
+            out[tag + "_n"] = np.int32(n); out[tag + "_m12"] = m12; out[tag + "_noori_n"] = np.int32(n2_); out[tag + "_noori_m12"] = m2
+            print("search_by_bow", tag, n, n2_)
+    np.savez_compressed(os.path.join(outdir, "search_by_bow.npz"), **out)
+
+
 def golden_bow(outdir):
     cases = {"k10_L3": dict(k=10, L=3), "irregular_k6_L4": dict(k=6, L=4, irregular=True, shuffle=True), "wide_k20_L2": dict(k=20, L=2)}
     out = {}
@@ -389,6 +483,7 @@ def main():
     os.makedirs(outdir, exist_ok=True)
     golden_primitives(outdir)
     golden_bow(outdir)
+    golden_search_by_bow(outdir)
     st = synth.rects_stream(320, 240, 2, seed=11)
     k0, d0 = golden_extract("extract_320x240_nf300_f0", st[0], (300, 1.2, 8, 20, 7), (0, 0), outdir)
     k1, d1 = golden_extract("extract_320x240_nf300_f1", st[1], (300, 1.2, 8, 20, 7), (0, 0), outdir)

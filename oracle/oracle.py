@@ -85,6 +85,8 @@ def lib():
         L.orc_search_by_projection.restype = i32
         L.orc_stereo_band_match.argtypes = [vp, vp, i32, vp, vp, i32, vp, i32, f32, f32, vp, vp]
         L.orc_match_candidates.argtypes = [vp, i32, vp, vp, vp, vp, vp]
+        L.orc_search_by_bow.restype = i32
+        L.orc_search_by_bow.argtypes = [i32, vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, vp, i32, f32, i32, vp]
         L.orc_vocab_create.restype = vp
         L.orc_vocab_create.argtypes = [i32, vp, vp, vp, vp, i32]
         L.orc_vocab_destroy.argtypes = [vp]
@@ -309,3 +311,24 @@ class Vocabulary:
         nb = lib().orc_bow_transform(self._h, _p(d), n, levelsup, _p(bw), _p(bv), _p(fn), _p(fs), _p(ff), C.byref(nfv))
         k = nfv.value
         return (bw[:nb].copy(), bv[:nb].copy()), (fn[:k].copy(), [ff[fs[i]:fs[i + 1]].copy() for i in range(k)])
+
+
+def fv_to_csr(fv):
+    """(node ids, list of feature arrays) -> (nodes int32, start int32[n+1], features int32)"""
+    nodes, feats = fv
+    start = np.zeros(len(nodes) + 1, np.int32)
+    if len(nodes):
+        start[1:] = np.cumsum([len(f) for f in feats])
+    flat = np.concatenate(feats).astype(np.int32) if len(nodes) else np.zeros(0, np.int32)
+    return np.ascontiguousarray(nodes, np.int32), start, np.ascontiguousarray(flat)
+
+
+def search_by_bow(mode, k1, d1, valid1, fv1, k2, d2, valid2, fv2, nnratio=0.7, check_ori=True):
+    k1 = np.ascontiguousarray(k1, KP_DTYPE); k2 = np.ascontiguousarray(k2, KP_DTYPE); d1 = _u8(d1); d2 = _u8(d2)
+    v1 = np.ascontiguousarray(valid1, np.uint8); v2 = None if valid2 is None else np.ascontiguousarray(valid2, np.uint8)
+    n1, s1, f1 = fv_to_csr(fv1); n2, s2, f2 = fv_to_csr(fv2)
+    m12 = np.empty(len(k1), np.int32)
+    n = lib().orc_search_by_bow(mode, _p(k1), _p(d1), _p(v1), len(k1), _p(n1), _p(s1), _p(f1), len(n1),
+                                _p(k2), _p(d2), _p(v2) if v2 is not None else None, len(k2), _p(n2), _p(s2), _p(f2), len(n2),
+                                float(nnratio), int(check_ori), _p(m12))
+    return n, m12

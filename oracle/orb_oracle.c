@@ -1209,3 +1209,57 @@ int orc_bow_transform(const OrcVocab* v, const uint8_t* desc, int n, int levelsu
     free(w); free(wt); free(nd); free(kw); free(kn);
     return nb;
 }
+
+/* ORBmatcher::SearchByBoW, R/src/ORBmatcher.cc:269-471 (mode 0) and :819-959 (mode 1) */
+int orc_search_by_bow(int mode, const OrcKeyPoint* k1, const uint8_t* d1, const uint8_t* valid1, int n1,
+                      const int32_t* fv1_nodes, const int32_t* fv1_start, const int32_t* fv1_feat, int nfv1,
+                      const OrcKeyPoint* k2, const uint8_t* d2, const uint8_t* valid2, int n2,
+                      const int32_t* fv2_nodes, const int32_t* fv2_start, const int32_t* fv2_feat, int nfv2,
+                      float nnratio, int check_ori, int32_t* matches12)
+{
+    int nmatches = 0;
+    uint8_t* matched2 = (uint8_t*)calloc(n2 > 0 ? n2 : 1, 1);
+    int* histIdx = (int*)malloc(sizeof(int) * (n1 > 0 ? n1 : 1));
+    int* histBin = (int*)malloc(sizeof(int) * (n1 > 0 ? n1 : 1));
+    int hist[HISTO_LENGTH]; int nh = 0;
+    for (int i = 0; i < HISTO_LENGTH; i++) hist[i] = 0;
+    for (int i = 0; i < n1; i++) matches12[i] = -1;
+    int a = 0, b = 0;
+    while (a < nfv1 && b < nfv2) {
+        if (fv1_nodes[a] == fv2_nodes[b]) {
+            for (int ia = fv1_start[a]; ia < fv1_start[a + 1]; ia++) {
+                const int i1 = fv1_feat[ia];
+                if (!valid1[i1]) continue;
+                int bestDist1 = 256, bestIdx2 = -1, bestDist2 = 256;
+                for (int ib = fv2_start[b]; ib < fv2_start[b + 1]; ib++) {
+                    const int i2 = fv2_feat[ib];
+                    if (matched2[i2]) continue;
+                    if (mode == 1 && valid2 && !valid2[i2]) continue;
+                    const int dist = orc_hamming256(d1 + (size_t)i1 * 32, d2 + (size_t)i2 * 32);
+                    if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdx2 = i2; }
+                    else if (dist < bestDist2) bestDist2 = dist;
+                }
+                const int pass = mode == 0 ? bestDist1 <= TH_LOW : bestDist1 < TH_LOW;
+                if (pass && (float)bestDist1 < nnratio * (float)bestDist2) {
+                    matches12[i1] = bestIdx2; matched2[bestIdx2] = 1;
+                    if (check_ori) { const int bin = rot_bin(k1[i1].angle, k2[bestIdx2].angle); histIdx[nh] = i1; histBin[nh] = bin; nh++; hist[bin]++; }
+                    nmatches++;
+                }
+            }
+            a++; b++;
+        } else if (fv1_nodes[a] < fv2_nodes[b]) {
+            while (a < nfv1 && fv1_nodes[a] < fv2_nodes[b]) a++;          /* lower_bound */
+        } else {
+            while (b < nfv2 && fv2_nodes[b] < fv1_nodes[a]) b++;
+        }
+    }
+    if (check_ori) {
+        int ind1, ind2, ind3;
+        three_maxima(hist, HISTO_LENGTH, &ind1, &ind2, &ind3);
+        for (int j = 0; j < nh; j++)
+            if (histBin[j] != ind1 && histBin[j] != ind2 && histBin[j] != ind3) { matches12[histIdx[j]] = -1; nmatches--; }
+    }
+    free(matched2); free(histIdx); free(histBin);
+    (void)n2;
+    return nmatches;
+}

@@ -141,6 +141,18 @@ int   orc_bow_transform(const OrcVocab* v, const uint8_t* desc, int n, int level
                         int32_t* bow_words, double* bow_values,
                         int32_t* fv_nodes, int32_t* fv_start, int32_t* fv_features, int* n_fv);
 
+/* ORBmatcher::SearchByBoW on flat arrays.  FeatureVectors are CSR tables sorted by node id (std::map order):
+ * fv_nodes[nfv], fv_start[nfv+1], fv_feat[].  valid1 / valid2 = "has a MapPoint that is not bad" (valid2 NULL = every
+ * feature is a candidate).  matches12[i1] = matched index in set 2 or -1; returns nmatches.
+ * mode 0 = SearchByBoW(KeyFrame*, Frame&, ...)  (ORBmatcher.cc:269-471, Nleft == -1 branch): accept bestDist1 <= TH_LOW;
+ *          set 1 = keyframe, set 2 = frame (the reference stores the result per frame feature: vpMapPointMatches[i2]);
+ * mode 1 = SearchByBoW(KeyFrame*, KeyFrame*, ...) (ORBmatcher.cc:819-959): candidates need valid2, accept bestDist1 < TH_LOW. */
+int   orc_search_by_bow(int mode, const OrcKeyPoint* k1, const uint8_t* d1, const uint8_t* valid1, int n1,
+                        const int32_t* fv1_nodes, const int32_t* fv1_start, const int32_t* fv1_feat, int nfv1,
+                        const OrcKeyPoint* k2, const uint8_t* d2, const uint8_t* valid2, int n2,
+                        const int32_t* fv2_nodes, const int32_t* fv2_start, const int32_t* fv2_feat, int nfv2,
+                        float nnratio, int check_ori, int32_t* matches12);
+
 #ifdef __cplusplus
 }
 #endif

@@ -73,3 +73,28 @@ def test_first_child_wins_ties_and_invalid_tables():
     assert (w[0], wt[0], nd[0]) == (1, 2.0, 2)
     with pytest.raises(ValueError):
         O.Vocabulary(np.array([-1, 2, 0], np.int32), np.array([0, 1, 0], np.uint8), np.zeros((3, 32), np.uint8), np.zeros(3), L=2)
+
+
+def _sbb_fixture():
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "search_by_bow.npz"))
+    vocab = tuple(g["voc_" + k] for k in ("parent", "leaf", "desc", "weight"))
+    return g, O.Vocabulary(*vocab, L=4), vocab
+
+
+@pytest.mark.parametrize("levelsup", [3, 2])
+@pytest.mark.parametrize("mode,ratio", [(0, 0.7), (1, 0.8), (0, 0.95)])
+def test_search_by_bow_oracle_matches_golden(levelsup, mode, ratio):
+    """ORBmatcher::SearchByBoW (KeyFrame-Frame and KeyFrame-KeyFrame): the C oracle against the vectors written by the
+    literal Python restatement in oracle/gen_golden.py (both with and without the rotation-consistency filter)."""
+    g, V, _ = _sbb_fixture()
+    k1, d1, k2, d2, v1, v2 = g["k1"], g["d1"], g["k2"], g["d2"], g["valid1"], g["valid2"]
+    fv1 = V.transform(d1, levelsup)[1]; fv2 = V.transform(d2, levelsup)[1]
+    tag = "ls%d_m%d_r%d" % (levelsup, mode, int(ratio * 100))
+    for ori, suffix in ((True, ""), (False, "_noori")):
+        n, m12 = O.search_by_bow(mode, k1, d1, v1, fv1, k2, d2, v2 if mode == 1 else None, fv2, ratio, ori)
+        assert n == int(g[tag + suffix + "_n"])
+        np.testing.assert_array_equal(m12, g[tag + suffix + "_m12"])
+        assert n == (m12 >= 0).sum()
+        got = m12[m12 >= 0]
+        assert len(np.unique(got)) == len(got)                     # a set-2 feature is claimed at most once
+        assert v1[m12 >= 0].all() and (mode == 0 or v2[got].all())

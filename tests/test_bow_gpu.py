@@ -81,3 +81,54 @@ def test_bow_rejects_bad_tables():
     w0, _, n0 = V.transform_features(np.zeros((0, 32), np.uint8), 0)
     assert len(w0) == 0 and len(n0) == 0
     V.close()
+
+
+@pytest.mark.parametrize("levelsup", [3, 2])
+@pytest.mark.parametrize("mode,ratio", [(0, 0.7), (1, 0.8), (0, 0.95)])
+def test_search_by_bow_golden(levelsup, mode, ratio):
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "search_by_bow.npz"))
+    vocab = tuple(g["voc_" + k] for k in ("parent", "leaf", "desc", "weight"))
+    V = orbx.ORBVocabulary(*vocab, L=4)
+    k1, d1, k2, d2, v1, v2 = g["k1"], g["d1"], g["k2"], g["d2"], g["valid1"], g["valid2"]
+    fv1 = V.transform(d1, levelsup)[1]; fv2 = V.transform(d2, levelsup)[1]
+    tag = "ls%d_m%d_r%d" % (levelsup, mode, int(ratio * 100))
+    for ori, suffix in ((True, ""), (False, "_noori")):
+        m = orbx.ORBmatcher(ratio, ori, max_keypoints=2048)
+        n, m12 = m.SearchByBoW(mode, k1, d1, v1, fv1, k2, d2, v2 if mode == 1 else None, fv2)
+        assert n == int(g[tag + suffix + "_n"])
+        np.testing.assert_array_equal(m12, g[tag + suffix + "_m12"])
+        m.close()
+    V.close()
+
+
+def test_search_by_bow_matches_oracle_c1_and_duplicates():
+    """C1-size frames with planted duplicate descriptors (ties inside a node: first in list order wins, a claimed feature
+    is skipped by later keyframe features), BoW on the GPU for both sides."""
+    W, H = 752, 480
+    st = synth.rects_stream(W, H, 2, seed=41)
+    ex = orbx.ORBextractor(1000, 1.2, 8, 20, 7, max_width=W, max_height=H)
+    (_, k1, d1), (_, k2, d2) = ex(st[0], None, (0, 0)), ex(st[1], None, (0, 0))
+    d2 = d2.copy(); d1 = d1.copy()
+    d2[10:40] = d1[10:40]; d2[40:70] = d1[10:40]              # exact copies, twice: best == second -> ratio test fails
+    d1[100:130] = d1[130:160]                                  # two keyframe features compete for the same frame feature
+    d2[100:130] = d1[100:130]
+    vocab = synth.random_vocabulary(k=10, L=5, seed=13)
+    V = orbx.ORBVocabulary(*vocab, L=5); R = O.Vocabulary(*vocab, L=5)
+    fv1 = V.transform(d1, 4)[1]; fv2 = V.transform(d2, 4)[1]
+    rf1 = R.transform(d1, 4)[1]; rf2 = R.transform(d2, 4)[1]
+    assert all(np.array_equal(a, b) for a, b in zip(fv1[1], rf1[1]))
+    v1 = np.ones(len(k1), np.uint8); v1[::9] = 0
+    v2 = np.ones(len(k2), np.uint8); v2[::7] = 0
+    for mode, ratio in ((0, 0.7), (1, 0.9)):
+        m = orbx.ORBmatcher(ratio, True, max_keypoints=2048)
+        n, m12 = m.SearchByBoW(mode, k1, d1, v1, fv1, k2, d2, v2 if mode == 1 else None, fv2)
+        rn, rm12 = O.search_by_bow(mode, k1, d1, v1, rf1, k2, d2, v2 if mode == 1 else None, rf2, ratio, True)
+        assert n == rn and n > 20
+        np.testing.assert_array_equal(m12, rm12)
+        m.close()
+    # malformed tables are refused
+    m = orbx.ORBmatcher(0.7, True, max_keypoints=2048)
+    bad = (fv2[0][::-1].copy(), fv2[1][::-1])
+    with pytest.raises(orbx.OrbxError):
+        m.SearchByBoW(0, k1, d1, v1, fv1, k2, d2, None, bad)
+    m.close(); V.close(); ex.close()
