@@ -17,13 +17,7 @@
 #include "Thirdparty/DBoW2/DBoW2/BowVector.h"
 #include "Thirdparty/DBoW2/DBoW2/FeatureVector.h"
 #else
-namespace DBoW2 {      // same value types as R/Thirdparty/DBoW2/DBoW2/BowVector.h:23-29, FeatureVector.h
-typedef unsigned int WordId;
-typedef double WordValue;
-typedef unsigned int NodeId;
-class BowVector : public std::map<WordId, WordValue> {};
-class FeatureVector : public std::map<NodeId, std::vector<unsigned int> > {};
-}  // namespace DBoW2
+#include "frame_shim.h"   // DBoW2::BowVector / FeatureVector value types
 #endif
 
 struct orbx_vocab;   // include/orbx.h

@@ -164,6 +164,64 @@ int ORBmatcher::SearchByProjection(Frame &F, const std::vector<MapPoint*> &vpMap
     return nmatches;
 }
 
+// FeatureVector (std::map<NodeId, vector<unsigned>>) -> CSR sorted by node id
+static void fv_csr(const DBoW2::FeatureVector& fv, std::vector<int32_t>& nodes, std::vector<int32_t>& start, std::vector<int32_t>& feat)
+{
+    nodes.clear(); start.assign(1, 0); feat.clear();
+    for (DBoW2::FeatureVector::const_iterator it = fv.begin(); it != fv.end(); ++it) {
+        nodes.push_back((int32_t)it->first);
+        for (size_t j = 0; j < it->second.size(); j++) feat.push_back((int32_t)it->second[j]);
+        start.push_back((int32_t)feat.size());
+    }
+}
+static void valid_flags(const std::vector<MapPoint*>& mps, int n, std::vector<uint8_t>& valid)
+{
+    valid.assign(n, 0);
+    for (int i = 0; i < n && i < (int)mps.size(); i++) valid[i] = (mps[i] && !mps[i]->isBad()) ? 1 : 0;
+}
+
+// R/src/ORBmatcher.cc:269-471, monocular branch (F.Nleft == -1)
+int ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame &F, std::vector<MapPoint*> &vpMapPointMatches)
+{
+    const std::vector<MapPoint*> vpMapPointsKF = pKF->GetMapPointMatches();
+    vpMapPointMatches = std::vector<MapPoint*>(F.N, static_cast<MapPoint*>(NULL));
+    const int n1 = pKF->mDescriptors.rows, n2 = F.N;
+    if (n1 == 0 || n2 == 0) return 0;
+    std::vector<int32_t> nd1, st1, ft1, nd2, st2, ft2, m12(n1, -1);
+    fv_csr(pKF->mFeatVec, nd1, st1, ft1); fv_csr(F.mFeatVec, nd2, st2, ft2);
+    std::vector<uint8_t> v1, t1, t2;
+    valid_flags(vpMapPointsKF, n1, v1);
+    int nmatches = 0;
+    check(orbx_search_by_bow(context(), 0, reinterpret_cast<const orbx_keypoint*>(pKF->mvKeysUn.data()), rows32(pKF->mDescriptors, t1), v1.data(), n1,
+                             nd1.data(), st1.data(), ft1.data(), (int)nd1.size(),
+                             reinterpret_cast<const orbx_keypoint*>(F.mvKeys.data()), rows32(F.mDescriptors, t2), nullptr, n2,
+                             nd2.data(), st2.data(), ft2.data(), (int)nd2.size(), mfNNratio, mbCheckOrientation ? 1 : 0, m12.data(), &nmatches));
+    for (int i1 = 0; i1 < n1; i1++)
+        if (m12[i1] >= 0) vpMapPointMatches[m12[i1]] = vpMapPointsKF[i1];
+    return nmatches;
+}
+
+// R/src/ORBmatcher.cc:819-959
+int ORBmatcher::SearchByBoW(KeyFrame *pKF1, KeyFrame *pKF2, std::vector<MapPoint *> &vpMatches12)
+{
+    const std::vector<MapPoint*> vpMapPoints1 = pKF1->GetMapPointMatches(), vpMapPoints2 = pKF2->GetMapPointMatches();
+    vpMatches12 = std::vector<MapPoint*>(vpMapPoints1.size(), static_cast<MapPoint*>(NULL));
+    const int n1 = pKF1->mDescriptors.rows, n2 = pKF2->mDescriptors.rows;
+    if (n1 == 0 || n2 == 0) return 0;
+    std::vector<int32_t> nd1, st1, ft1, nd2, st2, ft2, m12(n1, -1);
+    fv_csr(pKF1->mFeatVec, nd1, st1, ft1); fv_csr(pKF2->mFeatVec, nd2, st2, ft2);
+    std::vector<uint8_t> v1, v2, t1, t2;
+    valid_flags(vpMapPoints1, n1, v1); valid_flags(vpMapPoints2, n2, v2);
+    int nmatches = 0;
+    check(orbx_search_by_bow(context(), 1, reinterpret_cast<const orbx_keypoint*>(pKF1->mvKeysUn.data()), rows32(pKF1->mDescriptors, t1), v1.data(), n1,
+                             nd1.data(), st1.data(), ft1.data(), (int)nd1.size(),
+                             reinterpret_cast<const orbx_keypoint*>(pKF2->mvKeysUn.data()), rows32(pKF2->mDescriptors, t2), v2.data(), n2,
+                             nd2.data(), st2.data(), ft2.data(), (int)nd2.size(), mfNNratio, mbCheckOrientation ? 1 : 0, m12.data(), &nmatches));
+    for (int i1 = 0; i1 < n1 && i1 < (int)vpMatches12.size(); i1++)
+        if (m12[i1] >= 0) vpMatches12[i1] = vpMapPoints2[m12[i1]];
+    return nmatches;
+}
+
 // R/src/Frame.cc:785-962 (see ORBmatcher.h)
 void ORBmatcher::ComputeStereoMatches(ORBextractor* pLeft, ORBextractor* pRight, float mb, float mbf,
                                       std::vector<float> &mvuRight, std::vector<float> &mvDepth)

@@ -7,11 +7,21 @@
 #include "KeyFrame.h"
 #include "Frame.h"
 #else
+#include <map>
 #include <set>
 #include <vector>
 #include "cv_shim.h"
+#ifndef ORBX_DBOW2_SHIM
+#define ORBX_DBOW2_SHIM
+namespace DBoW2 {      // same value types as R/Thirdparty/DBoW2/DBoW2/BowVector.h:23-29, FeatureVector.h
+typedef unsigned int WordId;
+typedef double WordValue;
+typedef unsigned int NodeId;
+class BowVector : public std::map<WordId, WordValue> {};
+class FeatureVector : public std::map<NodeId, std::vector<unsigned int> > {};
+}  // namespace DBoW2
+#endif
 namespace ORB_SLAM3 {
-class KeyFrame;
 class MapPoint {
 public:
     // tracking state written by Frame::isInFrustum (MapPoint.h)
@@ -28,9 +38,22 @@ public:
 };
 struct GeometricCamera { float fx = 1, fy = 1, cx = 0, cy = 0;
     cv::Point2f project(const float p[3]) const { return cv::Point2f(fx * p[0] / p[2] + cx, fy * p[1] / p[2] + cy); } };
+class KeyFrame {          // the members SearchByBoW reads (R/include/KeyFrame.h)
+public:
+    int N = 0, NLeft = -1;
+    std::vector<cv::KeyPoint> mvKeys, mvKeysUn, mvKeysRight;
+    cv::Mat mDescriptors;
+    DBoW2::BowVector mBowVec;
+    DBoW2::FeatureVector mFeatVec;
+    std::vector<MapPoint*> mvpMapPoints;
+    GeometricCamera* mpCamera = nullptr; GeometricCamera* mpCamera2 = nullptr;
+    std::vector<MapPoint*> GetMapPointMatches() const { return mvpMapPoints; }
+};
 class Frame {
 public:
     int N = 0, Nleft = -1;
+    DBoW2::BowVector mBowVec;
+    DBoW2::FeatureVector mFeatVec;
     std::vector<cv::KeyPoint> mvKeys, mvKeysUn, mvKeysRight;
     cv::Mat mDescriptors;
     std::vector<MapPoint*> mvpMapPoints;

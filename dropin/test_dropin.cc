@@ -124,6 +124,29 @@ int main(int argc, char** argv)
             fwrite(&nid, 4, 1, o); fwrite(&c, 4, 1, o); fwrite(it->second.data(), 4, c, o);
         }
         unsigned nw = voc.size(); fwrite(&nw, 4, 1, o);
+
+        // ---- ORBmatcher::SearchByBoW(KeyFrame*, Frame&) (relocalisation) and (KeyFrame*, KeyFrame*) (loop detection) ----
+        KeyFrame KF1, KF2;
+        KF1.N = F[0].N; KF1.mvKeys = F[0].mvKeys; KF1.mvKeysUn = F[0].mvKeysUn; KF1.mDescriptors = F[0].mDescriptors;
+        KF2.N = F[1].N; KF2.mvKeys = F[1].mvKeys; KF2.mvKeysUn = F[1].mvKeysUn; KF2.mDescriptors = F[1].mDescriptors;
+        voc.transform(KF1.mDescriptors, KF1.mBowVec, KF1.mFeatVec, 4);
+        voc.transform(KF2.mDescriptors, KF2.mBowVec, KF2.mFeatVec, 4);
+        std::vector<MapPoint> mps2(F[1].N);
+        KF1.mvpMapPoints.assign(KF1.N, nullptr); KF2.mvpMapPoints.assign(KF2.N, nullptr);
+        for (int i = 0; i < KF1.N; i++) { if (i % 6) KF1.mvpMapPoints[i] = &mps[i]; mps[i].bad = (i % 10) == 3; }
+        for (int i = 0; i < KF2.N; i++) { if (i % 5) KF2.mvpMapPoints[i] = &mps2[i]; mps2[i].bad = (i % 13) == 4; }
+        Frame FB = F[1];
+        FB.mFeatVec = KF2.mFeatVec;
+        ORBmatcher mbow(0.7f, true);
+        std::vector<MapPoint*> vpm;
+        const int nR = mbow.SearchByBoW(&KF1, FB, vpm);
+        fwrite(&nR, 4, 1, o);
+        for (int i = 0; i < FB.N; i++) { int v = vpm[i] ? (int)(vpm[i] - mps.data()) : -1; fwrite(&v, 4, 1, o); }
+        ORBmatcher mloop(0.8f, true);
+        std::vector<MapPoint*> vpm12;
+        const int nL = mloop.SearchByBoW(&KF1, &KF2, vpm12);
+        fwrite(&nL, 4, 1, o);
+        for (int i = 0; i < KF1.N; i++) { int v = vpm12[i] ? (int)(vpm12[i] - mps2.data()) : -1; fwrite(&v, 4, 1, o); }
     }
     fclose(o);
     delete extR;

@@ -117,5 +117,23 @@ def test_dropin_classes_match_oracle(tmp_path):
         feats = np.frombuffer(buf, np.uint32, c, off); off += 4 * c
         assert nid == rfn[k]
         np.testing.assert_array_equal(feats, rff[k])
-    nw, = struct.unpack_from("<I", buf, off)
+    nw, = struct.unpack_from("<I", buf, off); off += 4
     assert nw == int(vocab[1].sum())
+
+    # ORBmatcher::SearchByBoW(KeyFrame*, Frame&): result per frame feature = index of the keyframe's map point
+    fv1 = RV.transform(d1, 4)[1]; fv2 = RV.transform(d2, 4)[1]
+    i1 = np.arange(n1); i2 = np.arange(n2)
+    v1 = ((i1 % 6 != 0) & (i1 % 10 != 3)).astype(np.uint8)
+    v2 = ((i2 % 5 != 0) & (i2 % 13 != 4)).astype(np.uint8)
+    nR, = struct.unpack_from("<i", buf, off); off += 4
+    got = np.frombuffer(buf, np.int32, n2, off); off += 4 * n2
+    rn, rm12 = O.search_by_bow(0, k1, d1, v1, fv1, k2, d2, None, fv2, 0.7, True)
+    want = np.full(n2, -1, np.int32); want[rm12[rm12 >= 0]] = np.nonzero(rm12 >= 0)[0]
+    assert nR == rn and nR > 5
+    np.testing.assert_array_equal(got, want)
+    # ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*): result per feature of keyframe 1 = index of keyframe 2's map point
+    nL, = struct.unpack_from("<i", buf, off); off += 4
+    got = np.frombuffer(buf, np.int32, n1, off); off += 4 * n1
+    rn, rm12 = O.search_by_bow(1, k1, d1, v1, fv1, k2, d2, v2, fv2, 0.8, True)
+    assert nL == rn and nL > 5
+    np.testing.assert_array_equal(got, rm12)
