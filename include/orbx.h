@@ -237,6 +237,14 @@ int  orbx_stereo_matches_batch(orbx_matcher* m, orbx_extractor* left, orbx_extra
  * denominator for the matching kernels) */
 int  orbx_popc_peak(int device, double* popc_per_s, double* lop3_per_s);
 
+/* MapPoint::ComputeDistinctiveDescriptors (R/src/MapPoint.cc:448-524) for a batch of map points, as
+ * LocalMapping runs it for every point a new keyframe observes: the observed descriptors of point p are rows
+ * offsets[p] .. offsets[p+1] of desc ([total][32], gathered by the caller from the observing keyframes); best[p] receives
+ * the index inside that run of the descriptor with the least median Hamming distance to the others (median = sorted row
+ * [(int)(0.5 * (N - 1))] with the 0 of the diagonal included; first minimum wins), -1 for a point without observations.
+ * Host pointers, synchronous. */
+int  orbx_distinctive_descriptors(orbx_matcher* m, const uint8_t* desc, const int32_t* offsets, int npoints, int32_t* best);
+
 /* ORBmatcher::SearchByBoW on flat arrays.  The two FeatureVectors are CSR tables sorted by node id (the order of the
  * std::map the reference iterates): fv_nodes[nfv], fv_start[nfv + 1], fv_feat[fv_start[nfv]].  valid = "the feature has a
  * MapPoint that is not bad".  matches12[i1] receives the matched index in set 2, or -1; *nmatches the return value.

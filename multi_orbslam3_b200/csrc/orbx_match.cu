@@ -887,6 +887,48 @@ __global__ void __launch_bounds__(256) k_bow_finish(BowArgs A, int32_t* nmatches
     if (threadIdx.x == 0) *nmatches = A.hist[ORBX_HISTO_LENGTH] - removed;
 }
 
+// ---- MapPoint::ComputeDistinctiveDescriptors (R/src/MapPoint.cc:448-524), batched over map points ----
+// One warp per map point.  For observation i the lanes compute its distances to all observations (kept in registers for
+// up to 256 of them, recomputed beyond), and the median of the row (its (N-1)/2-th smallest value, the 0 of the diagonal
+// included) is found by bisection on the value range [0, 256] with ballot counts instead of a sort.
+constexpr int DD_R = 8;
+__global__ void __launch_bounds__(256) k_distinctive(const uint8_t* desc, const int32_t* offsets, int npoints, int32_t* best)
+{
+    const int lane = threadIdx.x & 31;
+    const int p = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (p >= npoints) return;
+    const int o = offsets[p], N = offsets[p + 1] - o;
+    if (N <= 0) { if (lane == 0) best[p] = -1; return; }
+    const uint4* D = reinterpret_cast<const uint4*>(desc) + 2 * (size_t)o;
+    const int k = (N - 1) >> 1;                       // (int)(0.5 * (N - 1))
+    const int steps = (N + 31) >> 5;
+    int bestMedian = 0x7fffffff, bestIdx = 0;
+    for (int i = 0; i < N; i++) {
+        const uint4 q0 = D[2 * i], q1 = D[2 * i + 1];
+        int cache[DD_R];
+#pragma unroll
+        for (int s = 0; s < DD_R; s++) {
+            const int j = s * 32 + lane;
+            cache[s] = (s < steps && j < N) ? hamming256(q0, q1, D[2 * j], D[2 * j + 1]) : 0x7fff;
+        }
+        int lo = 0, hi = 256;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            int cnt = 0;
+#pragma unroll
+            for (int s = 0; s < DD_R; s++) cnt += __popc(__ballot_sync(0xffffffffu, cache[s] <= mid));
+            for (int s = DD_R; s < steps; s++) {
+                const int j = s * 32 + lane;
+                const bool le = j < N && hamming256(q0, q1, D[2 * j], D[2 * j + 1]) <= mid;
+                cnt += __popc(__ballot_sync(0xffffffffu, le));
+            }
+            if (cnt >= k + 1) hi = mid; else lo = mid + 1;
+        }
+        if (lo < bestMedian) { bestMedian = lo; bestIdx = i; }
+    }
+    if (lane == 0) best[p] = bestIdx;
+}
+
 // register-only throughput probes
 __global__ void k_popc_probe(unsigned seed, int iters, unsigned* sink)
 {
@@ -1699,6 +1741,36 @@ extern "C" int orbx_search_by_bow(orbx_matcher* m, int mode,
     CKM(cudaMemcpyAsync(&nm, A.hist + ORBX_HISTO_LENGTH + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     CKM(cudaStreamSynchronize(s));
     if (nmatches) *nmatches = nm;
+    return ORBX_OK;
+}
+
+// MapPoint::ComputeDistinctiveDescriptors for a batch of map points (see include/orbx.h).  Host pointers, synchronous.
+extern "C" int orbx_distinctive_descriptors(orbx_matcher* m, const uint8_t* desc, const int32_t* offsets, int npoints, int32_t* best)
+{
+    if (!m || npoints < 0 || (npoints > 0 && (!offsets || !best))) return ORBX_E_INVALID;
+    if (npoints == 0) return ORBX_OK;
+    if (offsets[0] != 0) return ORBX_E_INVALID;
+    for (int p = 0; p < npoints; p++) if (offsets[p] > offsets[p + 1]) { orbx_set_error("%s%s", "orbx_distinctive_descriptors: offsets must be non-decreasing", ""); return ORBX_E_INVALID; }
+    const int total = offsets[npoints];
+    if (total > 0 && !desc) return ORBX_E_INVALID;
+    CKM(cudaSetDevice(m->p.device));
+    cudaStream_t s = m->stream;
+    const size_t o_d = 0, o_o = ((size_t)(total > 0 ? total : 1) * 32 + 255) & ~(size_t)255;
+    const size_t o_b = o_o + ((sizeof(int32_t) * ((size_t)npoints + 1) + 255) & ~(size_t)255);
+    const size_t bytes = o_b + sizeof(int32_t) * (size_t)npoints;
+    if (bytes > m->gen_bytes) {
+        if (m->d_gen) cudaFree(m->d_gen);
+        m->d_gen = nullptr; m->gen_bytes = 0;
+        CKM(cudaMalloc((void**)&m->d_gen, bytes)); m->gen_bytes = bytes;
+    }
+    uint8_t* B = m->d_gen;
+    if (total) CKM(cudaMemcpyAsync(B + o_d, desc, (size_t)total * 32, cudaMemcpyHostToDevice, s));
+    CKM(cudaMemcpyAsync(B + o_o, offsets, sizeof(int32_t) * ((size_t)npoints + 1), cudaMemcpyHostToDevice, s));
+    k_distinctive<<<(npoints + 7) / 8, 256, 0, s>>>(B + o_d, reinterpret_cast<const int32_t*>(B + o_o), npoints, reinterpret_cast<int32_t*>(B + o_b));
+    ORBX_COUNT_LAUNCH(1);
+    CKM(cudaGetLastError());
+    CKM(cudaMemcpyAsync(best, B + o_b, sizeof(int32_t) * (size_t)npoints, cudaMemcpyDeviceToHost, s));
+    CKM(cudaStreamSynchronize(s));
     return ORBX_OK;
 }
 

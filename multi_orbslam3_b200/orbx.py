@@ -38,7 +38,7 @@ EXPORTS = [
     "orbx_search_for_initialization", "orbx_match_slots_device", "orbx_extract_match_batch", "orbx_extract_match_batch_device",
     "orbx_search_by_projection",
     "orbx_stereo_band_match", "orbx_stereo_matches", "orbx_stereo_matches_batch", "orbx_stereo_matches_batch_device",
-    "orbx_match_candidates", "orbx_search_by_bow", "orbx_vocab_create", "orbx_vocab_destroy", "orbx_vocab_words", "orbx_vocab_word_weights",
+    "orbx_match_candidates", "orbx_search_by_bow", "orbx_distinctive_descriptors", "orbx_vocab_create", "orbx_vocab_destroy", "orbx_vocab_words", "orbx_vocab_word_weights",
     "orbx_bow_transform", "orbx_bow_transform_slots_device", "orbx_popc_peak",
 ]
 
@@ -112,6 +112,7 @@ def lib():
         L.orbx_popc_peak.argtypes = [i32, vp, vp]
         L.orbx_match_candidates.argtypes = [vp, vp, i32, vp, i32, vp, vp, vp, vp]
         L.orbx_search_by_bow.argtypes = [vp, i32, vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, vp, i32, f32, i32, vp, vp]
+        L.orbx_distinctive_descriptors.argtypes = [vp, vp, vp, i32, vp]
         L.orbx_vocab_create.argtypes = [i32, i32, vp, vp, vp, vp, i32, vp]
         L.orbx_vocab_destroy.argtypes = [vp]; L.orbx_vocab_destroy.restype = None
         L.orbx_vocab_words.argtypes = [vp]
@@ -374,6 +375,13 @@ class ORBmatcher:
                                         _p(k2), _p(d2), _p(v2) if v2 is not None else None, len(k2), _p(n2), _p(s2), _p(f2), len(n2),
                                         self.mfNNratio, int(self.mbCheckOrientation), _p(m12), C.byref(nm)))
         return nm.value, m12
+
+    def DistinctiveDescriptors(self, desc, offsets):
+        """MapPoint::ComputeDistinctiveDescriptors for a batch of map points (CSR runs of observed descriptors) -> best index per point"""
+        d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32); off = np.ascontiguousarray(offsets, np.int32)
+        best = np.empty(len(off) - 1, np.int32)
+        _check(lib().orbx_distinctive_descriptors(self._h, _p(d), _p(off), len(off) - 1, _p(best)))
+        return best
 
     def ComputeStereoMatchesBatch(self, ex_left, ex_right, mb, mbf, first=0, count=1):
         """Frame::ComputeStereoMatches for `count` stereo pairs of the two extractors' last batch -> (mvuRight, mvDepth) [count, cap]."""

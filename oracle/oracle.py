@@ -85,6 +85,7 @@ def lib():
         L.orc_search_by_projection.restype = i32
         L.orc_stereo_band_match.argtypes = [vp, vp, i32, vp, vp, i32, vp, i32, f32, f32, vp, vp]
         L.orc_match_candidates.argtypes = [vp, i32, vp, vp, vp, vp, vp]
+        L.orc_distinctive_descriptors.argtypes = [vp, vp, i32, vp]
         L.orc_search_by_bow.restype = i32
         L.orc_search_by_bow.argtypes = [i32, vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, vp, i32, f32, i32, vp]
         L.orc_vocab_create.restype = vp
@@ -332,3 +333,10 @@ def search_by_bow(mode, k1, d1, valid1, fv1, k2, d2, valid2, fv2, nnratio=0.7, c
                                 _p(k2), _p(d2), _p(v2) if v2 is not None else None, len(k2), _p(n2), _p(s2), _p(f2), len(n2),
                                 float(nnratio), int(check_ori), _p(m12))
     return n, m12
+
+
+def distinctive_descriptors(desc, offsets):
+    d = _u8(desc); off = np.ascontiguousarray(offsets, np.int32)
+    best = np.empty(len(off) - 1, np.int32)
+    lib().orc_distinctive_descriptors(_p(d), _p(off), len(off) - 1, _p(best))
+    return best

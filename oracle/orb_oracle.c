@@ -1263,3 +1263,24 @@ int orc_search_by_bow(int mode, const OrcKeyPoint* k1, const uint8_t* d1, const 
     (void)n2;
     return nmatches;
 }
+
+/* MapPoint::ComputeDistinctiveDescriptors, R/src/MapPoint.cc:487-518 */
+static int orc_int_cmp(const void* a, const void* b) { const int x = *(const int*)a, y = *(const int*)b; return x < y ? -1 : (x > y); }
+void orc_distinctive_descriptors(const uint8_t* desc, const int32_t* offsets, int npoints, int32_t* best)
+{
+    for (int p = 0; p < npoints; p++) {
+        const int N = offsets[p + 1] - offsets[p];
+        if (N <= 0) { best[p] = -1; continue; }
+        const uint8_t* d = desc + (size_t)offsets[p] * 32;
+        int* row = (int*)malloc(sizeof(int) * N);
+        int BestMedian = INT_MAX, BestIdx = 0;
+        for (int i = 0; i < N; i++) {
+            for (int j = 0; j < N; j++) row[j] = i == j ? 0 : orc_hamming256(d + (size_t)i * 32, d + (size_t)j * 32);
+            qsort(row, N, sizeof(int), orc_int_cmp);
+            const int median = row[(int)(0.5 * (N - 1))];
+            if (median < BestMedian) { BestMedian = median; BestIdx = i; }
+        }
+        best[p] = BestIdx;
+        free(row);
+    }
+}

@@ -141,6 +141,12 @@ int   orc_bow_transform(const OrcVocab* v, const uint8_t* desc, int n, int level
                         int32_t* bow_words, double* bow_values,
                         int32_t* fv_nodes, int32_t* fv_start, int32_t* fv_features, int* n_fv);
 
+/* MapPoint::ComputeDistinctiveDescriptors (R/src/MapPoint.cc:448-524) for a batch of map points: the observed
+ * descriptors of point p are rows offsets[p] .. offsets[p+1] of desc; best[p] = index inside that run of the descriptor
+ * with the least median distance to the others (median = sorted row [(int)(0.5 * (N - 1))], the row includes the 0 on
+ * the diagonal; first minimum wins); -1 for a point without observations. */
+void  orc_distinctive_descriptors(const uint8_t* desc, const int32_t* offsets, int npoints, int32_t* best);
+
 /* ORBmatcher::SearchByBoW on flat arrays.  FeatureVectors are CSR tables sorted by node id (std::map order):
  * fv_nodes[nfv], fv_start[nfv+1], fv_feat[].  valid1 / valid2 = "has a MapPoint that is not bad" (valid2 NULL = every
  * feature is a candidate).  matches12[i1] = matched index in set 2 or -1; returns nmatches.
