@@ -5,11 +5,12 @@
 //
 // One CTA owns one SEGMENT (a run of whole cells, at most ORBX_FAST_TP staged columns) of one row of cells of one
 // level of one frame and never writes a score map to global memory.  Segments bound the shared-memory footprint
-// independently of the image width (4 CTAs per SM) and every phase runs once over the whole tile:
+// independently of the image width (44 KB: 5 CTAs per SM) and every phase runs once over the whole tile:
 //   1. rows [iniY, maxY) x columns [xa0, xa1) are staged in shared memory by bulk copies (x index = column - xa0);
-//   2. SWAR screen, 4 pixels per thread-step: |v - ring| per byte (VABSDIFF4.U8) on the 4 compass/diagonal
+//   2. SWAR screen, two 4-pixel groups per lane-step: |v - ring| per byte (VABSDIFF4.U8) on the 4 compass/diagonal
 //      opposite pairs; a 9-arc contains one pixel of every opposite pair, so a corner at threshold t needs
-//      max(|d_k|, |d_k+8|) > t for every pair.  Survivors (a few % of pixels) go to a shared-memory queue;
+//      max(|d_k|, |d_k+8|) > t for every pair.  Groups with a survivor go to a group queue and are expanded into a
+//      dense pixel queue (~13 % of the pixels of the bench frames);
 //   3. queue drain, one pixel per thread: signed test on all 8 pairs, then the exact arc measure
 //      m = max over the 16 arcs of 9 of max(min d, min -d) on packed 16x2 lanes (VIMNMX.U16x2).
 //      corner <=> m > t, cv::FAST response = m - 1, independent of t.  m is kept in a shared u8 map;
@@ -27,7 +28,7 @@ namespace {
 constexpr int NT = 256;
 constexpr int NW = NT / 32;
 constexpr int TP = ORBX_FAST_TP;     // shared-memory pitch of a segment tile (compile time: ring offsets become immediates)
-constexpr int MAX_SEG_CELLS = 16;    // cells per segment (TP / 35 rounded up)
+constexpr int MAX_SEG_CELLS = 16;    // cells per segment (a cell is at least 30 columns wide: TP / 30 rounded up)
 constexpr int CLCAP = 1024;          // corners (m > minTh) of the whole tile; overflow -> map scan (still exact)
 constexpr int QMIN = 1024;           // smallest pixel queue the launch is sized for (overflow is scored inline, never dropped)
 constexpr int SMEM_TARGET = 44 * 1024;   // 5 CTAs per SM
