@@ -107,6 +107,11 @@ int  orbx_extractor_sync(orbx_extractor* h, void* stream);   /* also returns any
  * sums, -1 only reads. */
 int  orbx_extractor_profile(orbx_extractor* h, int enable, double* stage_ms4, int* batches);
 
+/* Host-only introspection (no device needed): the FAST cell grid of a pyramid level of width level_width
+ * (R/src/ORBextractor.cc:779-785: nCols = width/30, wCell = ceil(width/nCols) over the 16-px-bordered area) and how the
+ * kernel cuts a cell row into segments of whole cells (cells per segment, segments per row, widest staged tile). */
+int  orbx_fast_segment_plan(int level_width, int* n_cols, int* w_cell, int* seg_cells, int* n_seg, int* max_staged_width);
+
 /* mvImagePyramid (R/include/ORBextractor.h:88) stays on the device; this is the explicit download the
  * stereo SAD refinement (R/src/Frame.cc:882-901) needs.  slot = frame within the last batch. */
 int  orbx_pyramid_level_size(const orbx_extractor* h, int level, int* width, int* height);

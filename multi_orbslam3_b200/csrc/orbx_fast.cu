@@ -20,6 +20,7 @@
 //      recorded in two bitmaps (minThFAST / iniThFAST);
 //   5. cells with no iniThFAST survivor fall back to their minThFAST survivors (:825-828); every survivor
 //      computes its own output slot from popcounts (cell by cell, row-major inside a cell = reference order).
+#include <cmath>
 #include <cstdlib>
 #include "orbx_internal.h"
 
@@ -525,6 +526,28 @@ void orbx_fast_units(const OrbxGeom& g, std::vector<int4>& tab)
                 tab.push_back(make_int4(hs > 0 ? (65536 + hs - 1) / hs : 0, 0, 0, 0));
             }
     }
+}
+
+// host-only introspection of the segment plan of one pyramid level (no device needed; used by the CPU test-suite)
+extern "C" int orbx_fast_segment_plan(int level_width, int* n_cols, int* w_cell, int* seg_cells, int* n_seg, int* max_staged_width)
+{
+    if (level_width < 8 || !n_cols || !w_cell || !seg_cells || !n_seg || !max_staged_width) return ORBX_E_INVALID;
+    const float fw = (float)(level_width - 2 * ORBX_BORDER);
+    const int nc = fw > 0 ? (int)(fw / (float)ORBX_FAST_W) : 0;                       // R/src/ORBextractor.cc:779-785
+    *n_cols = nc; *w_cell = 0; *seg_cells = 0; *n_seg = 0; *max_staged_width = 0;
+    if (nc <= 0) return ORBX_OK;
+    const int wc = (int)ceilf(fw / nc);
+    const int sc = orbx_fast_plan(level_width, nc, wc);
+    *w_cell = wc; *seg_cells = sc; *n_seg = (nc + sc - 1) / sc;
+    for (int j0 = 0; j0 < nc; j0 += sc) {
+        const int j1 = j0 + sc < nc ? j0 + sc : nc;
+        const int cs0 = ORBX_EDGE + j0 * wc;
+        int cs1 = ORBX_EDGE + j1 * wc; if (cs1 > level_width - ORBX_EDGE) cs1 = level_width - ORBX_EDGE;
+        if (cs1 <= cs0) continue;
+        const int wst = ((cs1 + 3 + 15) & ~15) - ((cs0 - 3) & ~15);
+        if (wst > *max_staged_width) *max_staged_width = wst;
+    }
+    return ORBX_OK;
 }
 
 void orbx_fast_configure(const OrbxGeom& g)

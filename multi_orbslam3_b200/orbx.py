@@ -38,7 +38,7 @@ EXPORTS = [
     "orbx_search_for_initialization", "orbx_match_slots_device", "orbx_extract_match_batch", "orbx_extract_match_batch_device",
     "orbx_search_by_projection",
     "orbx_stereo_band_match", "orbx_stereo_matches", "orbx_stereo_matches_batch", "orbx_stereo_matches_batch_device",
-    "orbx_match_candidates", "orbx_search_by_bow", "orbx_distinctive_descriptors", "orbx_vocab_create", "orbx_vocab_destroy", "orbx_vocab_words", "orbx_vocab_word_weights",
+    "orbx_fast_segment_plan", "orbx_match_candidates", "orbx_search_by_bow", "orbx_distinctive_descriptors", "orbx_vocab_create", "orbx_vocab_destroy", "orbx_vocab_words", "orbx_vocab_word_weights",
     "orbx_bow_transform", "orbx_bow_transform_slots_device", "orbx_popc_peak",
 ]
 
@@ -112,6 +112,7 @@ def lib():
         L.orbx_popc_peak.argtypes = [i32, vp, vp]
         L.orbx_match_candidates.argtypes = [vp, vp, i32, vp, i32, vp, vp, vp, vp]
         L.orbx_search_by_bow.argtypes = [vp, i32, vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, vp, i32, f32, i32, vp, vp]
+        L.orbx_fast_segment_plan.argtypes = [i32, vp, vp, vp, vp, vp]
         L.orbx_distinctive_descriptors.argtypes = [vp, vp, vp, i32, vp]
         L.orbx_vocab_create.argtypes = [i32, i32, vp, vp, vp, vp, i32, vp]
         L.orbx_vocab_destroy.argtypes = [vp]; L.orbx_vocab_destroy.restype = None

@@ -3,6 +3,7 @@ import ctypes
 import os
 import re
 
+import numpy as np
 import pytest
 
 import __graft_entry__ as ge
@@ -60,3 +61,22 @@ def test_product_never_imports_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 for pat in (r"^\s*(from|import)\s+oracle", r"#\s*include.*oracle", r"liborb_oracle", r"orb_oracle", r"\borc_[a-z]"):
                     assert not re.search(pat, src, flags=re.M), (os.path.join(dirpath, f), pat)
+
+
+def test_fast_segment_plan_host_logic():
+    """Host-side geometry of the FAST kernel (no device needed): for every level width the cell grid follows the
+    reference's formulas and the segments are whole cells, cover every cell and fit the 288-byte tile."""
+    import ctypes as C
+    L = orbx.lib()
+    for w in list(range(40, 700)) + [752, 1241, 1920, 2048, 3840, 4128]:
+        v = [C.c_int() for _ in range(5)]
+        assert L.orbx_fast_segment_plan(w, *[C.byref(x) for x in v]) == 0
+        ncols, wcell, segcells, nseg, wmax = [x.value for x in v]
+        fw = w - 32
+        assert ncols == max(int(np.float32(fw) / np.float32(30)), 0) if fw > 0 else ncols == 0
+        if ncols == 0:
+            continue
+        assert wcell == int(np.ceil(np.float32(fw) / np.float32(ncols)))
+        assert 1 <= segcells <= 16 and nseg == -(-ncols // segcells) and nseg * segcells >= ncols
+        assert 0 < wmax <= 288 and wmax % 16 == 0
+    assert L.orbx_fast_segment_plan(4, *[C.byref(C.c_int()) for _ in range(5)]) != 0
