@@ -178,6 +178,7 @@ struct WinBufs {
     int* q_off; int* q_cnt;       // [P][K]
     uint32_t* pool; int* pool_used;   // [P][POOL], [P]
     uint8_t* bin_of;              // [P][K]
+    uint2* top2;                  // [P][K]   best / second pool entry of every query by (distance, list rank), 0xFFFFFFFF = none
     int K, POOL;
     float minX, maxX, minY, maxY, wInv, hInv;
     unsigned* err;
@@ -276,6 +277,23 @@ __global__ void __launch_bounds__(GRID_NT) k_grid_build(WinBufs W, int npad_max)
 
 constexpr int CAND_WARPS = 8;
 
+// warp-wide top-2 by (dist, rank): each lane holds its local best (d0, k0, e0) and second (d1, k1, e1); ranks are unique,
+// so (dist << 16 | rank) keys are unique and two REDUX.MIN + two ballots replace a 5-round shuffle tree.
+__device__ __forceinline__ void warp_top2(int& d0, int& k0, uint32_t& e0, int& d1, uint32_t& e1, int& k1)
+{
+    const unsigned key0 = d0 == 0x7fffffff ? 0xFFFFFFFFu : (((unsigned)d0 << 16) | (unsigned)k0);
+    const unsigned key1 = d1 == 0x7fffffff ? 0xFFFFFFFFu : (((unsigned)d1 << 16) | (unsigned)k1);
+    const unsigned B = __reduce_min_sync(0xffffffffu, key0);
+    const unsigned c2 = key0 == B ? key1 : key0;
+    const unsigned S = __reduce_min_sync(0xffffffffu, c2);
+    const uint32_t sel = (key0 == S) ? e0 : e1;
+    const unsigned wb = __ballot_sync(0xffffffffu, key0 == B), ws = __ballot_sync(0xffffffffu, c2 == S);
+    const uint32_t be = __shfl_sync(0xffffffffu, e0, __ffs(wb) - 1);
+    const uint32_t se = __shfl_sync(0xffffffffu, sel, __ffs(ws) - 1);
+    if (B == 0xFFFFFFFFu) { d0 = 0x7fffffff; k0 = 0x7fffffff; e0 = 0; } else { d0 = (int)(B >> 16); k0 = (int)(B & 0xFFFF); e0 = be; }
+    if (S == 0xFFFFFFFFu) { d1 = 0x7fffffff; k1 = 0x7fffffff; e1 = 0; } else { d1 = (int)(S >> 16); k1 = (int)(S & 0xFFFF); e1 = se; }
+}
+
 // Frame::GetFeaturesInArea + descriptor distances, one warp per query.  Pool entry: i2 | dist << 16 | octave << 25
 __global__ void __launch_bounds__(CAND_WARPS * 32) k_window_candidates(WinBufs W)
 {
@@ -325,6 +343,8 @@ __global__ void __launch_bounds__(CAND_WARPS * 32) k_window_candidates(WinBufs W
     __syncwarp();
 
     int base = 0, total = 0;
+    int td0 = 0x7fffffff, tk0 = 0x7fffffff, td1 = 0x7fffffff, tk1 = 0x7fffffff;      // unfiltered top-2 by (distance, rank)
+    uint32_t te0 = 0, te1 = 0;
     for (int pass = 0; pass < 2; pass++) {
         int pos = 0;
         for (int j0 = 0; j0 < T; j0 += 32) {
@@ -353,8 +373,10 @@ __global__ void __launch_bounds__(CAND_WARPS * 32) k_window_candidates(WinBufs W
                 const int o = pos + __popc(bal & ((1u << lane) - 1));
                 const uint4 t0 = reinterpret_cast<const uint4*>(P.d2)[2 * i2], t1 = reinterpret_cast<const uint4*>(P.d2)[2 * i2 + 1];
                 const int d = hamming256(q0, q1, t0, t1);
-                if (base + o < W.POOL)
-                    W.pool[(long long)p * W.POOL + base + o] = (uint32_t)i2 | ((uint32_t)d << 16) | ((uint32_t)oct << 25);
+                const uint32_t e = (uint32_t)i2 | ((uint32_t)d << 16) | ((uint32_t)oct << 25);
+                if (base + o < W.POOL) W.pool[(long long)p * W.POOL + base + o] = e;
+                if (d < td0) { td1 = td0; tk1 = tk0; te1 = te0; td0 = d; tk0 = o; te0 = e; }      // ranks grow per lane: first minimum kept
+                else if (d < td1) { td1 = d; tk1 = o; te1 = e; }
             }
             pos += __popc(bal);
         }
@@ -370,24 +392,12 @@ __global__ void __launch_bounds__(CAND_WARPS * 32) k_window_candidates(WinBufs W
             if (total == 0) return;
         }
     }
+    // the resolve kernel starts from these two and rescans the list only when one of them has been taken meanwhile
+    warp_top2(td0, tk0, te0, td1, te1, tk1);
+    if (lane == 0)
+        W.top2[(long long)p * W.K + qi] = make_uint2(td0 == 0x7fffffff ? 0xFFFFFFFFu : te0, td1 == 0x7fffffff ? 0xFFFFFFFFu : te1);
 }
 
-// warp-wide top-2 by (dist, rank): each lane holds its local best (d0, k0, e0) and second (d1, k1, e1); ranks are unique,
-// so (dist << 16 | rank) keys are unique and two REDUX.MIN + two ballots replace a 5-round shuffle tree.
-__device__ __forceinline__ void warp_top2(int& d0, int& k0, uint32_t& e0, int& d1, uint32_t& e1, int& k1)
-{
-    const unsigned key0 = d0 == 0x7fffffff ? 0xFFFFFFFFu : (((unsigned)d0 << 16) | (unsigned)k0);
-    const unsigned key1 = d1 == 0x7fffffff ? 0xFFFFFFFFu : (((unsigned)d1 << 16) | (unsigned)k1);
-    const unsigned B = __reduce_min_sync(0xffffffffu, key0);
-    const unsigned c2 = key0 == B ? key1 : key0;
-    const unsigned S = __reduce_min_sync(0xffffffffu, c2);
-    const uint32_t sel = (key0 == S) ? e0 : e1;
-    const unsigned wb = __ballot_sync(0xffffffffu, key0 == B), ws = __ballot_sync(0xffffffffu, c2 == S);
-    const uint32_t be = __shfl_sync(0xffffffffu, e0, __ffs(wb) - 1);
-    const uint32_t se = __shfl_sync(0xffffffffu, sel, __ffs(ws) - 1);
-    if (B == 0xFFFFFFFFu) { d0 = 0x7fffffff; k0 = 0x7fffffff; e0 = 0; } else { d0 = (int)(B >> 16); k0 = (int)(B & 0xFFFF); e0 = be; }
-    if (S == 0xFFFFFFFFu) { d1 = 0x7fffffff; k1 = 0x7fffffff; e1 = 0; } else { d1 = (int)(S >> 16); k1 = (int)(S & 0xFFFF); e1 = se; }
-}
 
 __device__ __forceinline__ int rot_bin(float a1, float a2)
 {
@@ -441,47 +451,51 @@ __global__ void __launch_bounds__(32) k_window_resolve(WinBufs W, int mode, floa
     }
     __syncwarp();
 
-    // Queries are visited in order, but their CSR headers are fetched 32 at a time and empty queries are skipped by
-    // ballot; the candidates of the NEXT live query are prefetched while the current one is resolved, so the
-    // sequential loop pays one L2 latency per live query instead of several per query.
+    // Queries are visited in order; their CSR headers and their unfiltered (best, second) entries from k_window_candidates
+    // are fetched 32 at a time and empty queries are skipped by ballot.  The order-dependent rule only REMOVES candidates
+    // (:741 / :89-91), so when neither of the two entries has been taken meanwhile they are still the best and the second
+    // of the filtered list and the query costs two shared-memory lookups; otherwise its list is rescanned.
+    const uint2* top2 = W.top2 + (long long)p * W.K;
     for (int qb = 0; qb < nq; qb += 32) {
       const int my_q = qb + lane;
       const int my_cnt = my_q < nq ? q_cnt[my_q] : 0;
       const int my_off = my_q < nq ? q_off[my_q] : 0;
+      const uint2 my_t2 = (my_q < nq && my_cnt > 0) ? top2[my_q] : make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
+      // the two angles of the rotation histogram, fetched with the headers instead of inside the sequential rule
+      float my_a1 = 0.f, my_a2 = 0.f;
+      if (check_ori && mode != 1 && my_t2.x != 0xFFFFFFFFu) { my_a1 = P.q[my_q].angle; my_a2 = P.k2[my_t2.x & 0xFFFF].angle; }
       unsigned live = __ballot_sync(0xffffffffu, my_cnt > 0);
-      uint32_t pre[4] = {0, 0, 0, 0};
-      if (live) {
-          const int src = __ffs(live) - 1;
-          const int c = __shfl_sync(0xffffffffu, my_cnt, src), o = __shfl_sync(0xffffffffu, my_off, src);
-#pragma unroll
-          for (int j = 0; j < 4; j++) if (lane + 32 * j < c) pre[j] = pool[o + lane + 32 * j];
-      }
       while (live) {
         const int src = __ffs(live) - 1;
         live &= live - 1;
         const int i = qb + src;
-        const int cnt = __shfl_sync(0xffffffffu, my_cnt, src), off = __shfl_sync(0xffffffffu, my_off, src);
-        uint32_t cur[4] = {pre[0], pre[1], pre[2], pre[3]};
-        if (live) {                                  // prefetch the next live query of this group of 32
-            const int ns = __ffs(live) - 1;
-            const int c = __shfl_sync(0xffffffffu, my_cnt, ns), o = __shfl_sync(0xffffffffu, my_off, ns);
-#pragma unroll
-            for (int j = 0; j < 4; j++) if (lane + 32 * j < c) pre[j] = pool[o + lane + 32 * j];
+        uint32_t e0 = __shfl_sync(0xffffffffu, my_t2.x, src), e1 = __shfl_sync(0xffffffffu, my_t2.y, src);
+        int d0 = e0 == 0xFFFFFFFFu ? 0x7fffffff : (int)((e0 >> 16) & 0x1FF);
+        int d1 = e1 == 0xFFFFFFFFu ? 0x7fffffff : (int)((e1 >> 16) & 0x1FF);
+        const float a1 = __shfl_sync(0xffffffffu, my_a1, src);
+        float a2 = __shfl_sync(0xffffffffu, my_a2, src);
+        bool taken = false;
+        if (mode == 2) {
+            taken = (d0 != 0x7fffffff && matchedDist[e0 & 0xFFFF] <= d0) || (d1 != 0x7fffffff && matchedDist[e1 & 0xFFFF] <= d1);
+        } else {
+            taken = (d0 != 0x7fffffff && res[e0 & 0xFFFF] >= 0) || (mode == 1 && d1 != 0x7fffffff && res[e1 & 0xFFFF] >= 0);
         }
-        int d0 = 0x7fffffff, k0 = 0x7fffffff, d1 = 0x7fffffff, k1 = 0x7fffffff;
-        uint32_t e0 = 0, e1 = 0;
-        auto consume = [&](uint32_t e, int k) {
-            const int i2 = e & 0xFFFF, d = (e >> 16) & 0x1FF;
-            const bool skip = (mode == 2) ? (matchedDist[i2] <= d)      // ORBmatcher.cc:741
-                                          : (res[i2] >= 0);             // occupied keypoint, :89-91 / :2045-2047
-            if (skip) return;
-            if (d < d0) { d1 = d0; k1 = k0; e1 = e0; d0 = d; k0 = k; e0 = e; }
-            else if (d < d1) { d1 = d; k1 = k; e1 = e; }
-        };
-#pragma unroll
-        for (int j = 0; j < 4; j++) if (lane + 32 * j < cnt) consume(cur[j], lane + 32 * j);
-        for (int k = lane + 128; k < cnt; k += 32) consume(pool[off + k], k);
-        warp_top2(d0, k0, e0, d1, e1, k1);
+        if (taken) {                                     // warp-uniform: rescan the query's list with the skip rule
+            const int cnt = __shfl_sync(0xffffffffu, my_cnt, src), off = __shfl_sync(0xffffffffu, my_off, src);
+            int k0 = 0x7fffffff, k1 = 0x7fffffff;
+            d0 = 0x7fffffff; d1 = 0x7fffffff; e0 = 0; e1 = 0;
+            for (int k = lane; k < cnt; k += 32) {
+                const uint32_t e = pool[off + k];
+                const int i2 = e & 0xFFFF, d = (e >> 16) & 0x1FF;
+                const bool skip = (mode == 2) ? (matchedDist[i2] <= d)      // ORBmatcher.cc:741
+                                              : (res[i2] >= 0);             // occupied keypoint, :89-91 / :2045-2047
+                if (skip) continue;
+                if (d < d0) { d1 = d0; k1 = k0; e1 = e0; d0 = d; k0 = k; e0 = e; }
+                else if (d < d1) { d1 = d; k1 = k; e1 = e; }
+            }
+            warp_top2(d0, k0, e0, d1, e1, k1);
+            if (check_ori && mode != 1 && d0 != 0x7fffffff) a2 = P.k2[e0 & 0xFFFF].angle;
+        }
         // every lane now holds the same (best, second); lane 0 applies the sequential rule
         if (mode == 2) {
             if (d0 <= ORBX_TH_LOW && (float)d0 < (float)d1 * nnratio) {     // :756-758 (INT_MAX second -> float)
@@ -490,7 +504,7 @@ __global__ void __launch_bounds__(32) k_window_resolve(WinBufs W, int mode, floa
                     if (matches21[i2] >= 0) res[matches21[i2]] = -1;
                     res[i] = i2; matches21[i2] = i; matchedDist[i2] = d0;
                     if (check_ori) {
-                        const int bin = rot_bin(P.q[i].angle, P.k2[i2].angle);
+                        const int bin = rot_bin(a1, a2);
                         bin_of[i] = (uint8_t)bin; hist[bin]++;
                     }
                 }
@@ -501,7 +515,7 @@ __global__ void __launch_bounds__(32) k_window_resolve(WinBufs W, int mode, floa
                 const int i2 = e0 & 0xFFFF;
                 if (lane == 0) {
                     res[i2] = i;
-                    if (check_ori) { const int bin = rot_bin(P.q[i].angle, P.k2[i2].angle); bin_of[i2] = (uint8_t)bin; hist[bin]++; }
+                    if (check_ori) { const int bin = rot_bin(a1, a2); bin_of[i2] = (uint8_t)bin; hist[bin]++; }
                 }
             }
         } else {
@@ -521,6 +535,7 @@ __global__ void __launch_bounds__(32) k_window_resolve(WinBufs W, int mode, floa
         int ind1, ind2, ind3;
         three_maxima(hist, ind1, ind2, ind3);
         const int lim = mode == 2 ? nq : n2;
+#pragma unroll 4
         for (int i = lane; i < lim; i += 32) {
             const int b = bin_of[i];
             if (b != 0xFF && b != ind1 && b != ind2 && b != ind3) res[i] = -1;
@@ -529,6 +544,7 @@ __global__ void __launch_bounds__(32) k_window_resolve(WinBufs W, int mode, floa
     }
     int cntm = 0;
     const int lim = mode == 2 ? nq : n2;
+#pragma unroll 4
     for (int i = lane; i < lim; i += 32) {
         const int m = res[i];
         if (mode == 2) {
@@ -1011,6 +1027,7 @@ extern "C" int orbx_matcher_create(const orbx_matcher_params* p, orbx_matcher** 
     MA(W.pool, sizeof(uint32_t) * (size_t)m->POOL * P);
     MA(W.pool_used, sizeof(int) * P);
     MA(W.bin_of, K * P);
+    MA(W.top2, sizeof(uint2) * K * P);
     MA(W.err, sizeof(unsigned));
     MA(m->d_k1, sizeof(orbx_keypoint) * K); MA(m->d_k2, sizeof(orbx_keypoint) * K);
     MA(m->d_d1, 32 * K); MA(m->d_d2, 32 * K); MA(m->d_qdesc, 32 * K); MA(m->d_uright, sizeof(float) * K);
@@ -1196,7 +1213,7 @@ static WinBufs shifted_pairs(const orbx_matcher* m, int pb)
     WinBufs W = m->W;
     const long long K = m->K;
     W.pairs += pb; W.q += pb * K; W.items += pb * K; W.skp += pb * K; W.cell_start += (long long)pb * (NCELL + 1);
-    W.q_off += pb * K; W.q_cnt += pb * K; W.pool += (long long)pb * m->POOL; W.pool_used += pb; W.bin_of += pb * K;
+    W.q_off += pb * K; W.q_cnt += pb * K; W.pool += (long long)pb * m->POOL; W.pool_used += pb; W.bin_of += pb * K; W.top2 += pb * K;
     return W;
 }
 
