@@ -78,7 +78,8 @@ int  orbx_extractor_max_keypoints(const orbx_extractor* h);
 
 /* ORBextractor::operator(), R/src/ORBextractor.cc:1068-1150.  Synchronous, one host image.
  * lap0/lap1 = vLappingArea.  *mono_index receives the return value of operator() (monoIndex).
- * Returns ORBX_E_EMPTY for an empty image (the class wrapper maps it to -1). */
+ * Returns ORBX_E_EMPTY for an empty image (the class wrapper maps it to -1).  kps and / or desc may be NULL when only
+ * the count is wanted. */
 int  orbx_extract(orbx_extractor* h, const uint8_t* img, int width, int height, int stride,
                   int lap0, int lap1, orbx_keypoint* kps, uint8_t* desc, int cap, int* n, int* mono_index);
 

@@ -158,3 +158,49 @@ def test_kitti_batched_stream_c3():
     for f in range(B):
         check_frame(res[f], ref(frames[f], (0, 0)))
     ex.close()
+
+
+def test_c_abi_rejects_bad_arguments():
+    """Every misuse returns an ORBX_E_* code with a message (never a crash, never a silent truncation)."""
+    import ctypes as C
+    L = orbx.lib()
+    W, H = 320, 240
+    img = synth.rects_frame(W, H, 3)
+    ex = orbx.ORBextractor(300, 1.2, 8, 20, 7, max_width=W, max_height=H, max_batch=2)
+    cap = ex.cap
+    kps = np.zeros(cap, orbx.KP_DTYPE); desc = np.zeros((cap, 32), np.uint8); n = C.c_int(); mono = C.c_int()
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    INVALID, EMPTY = -1, -2
+    # null handle / null image / null outputs
+    assert L.orbx_extract(None, p(img), W, H, W, 0, 0, p(kps), p(desc), cap, C.byref(n), C.byref(mono)) == INVALID
+    assert L.orbx_extract(ex._h, None, W, H, W, 0, 0, p(kps), p(desc), cap, C.byref(n), C.byref(mono)) in (INVALID, EMPTY)
+    # keypoint / descriptor outputs are optional (a caller may only want the count)
+    assert L.orbx_extract(ex._h, p(img), W, H, W, 0, 0, None, None, cap, C.byref(n), C.byref(mono)) == 0 and n.value > 100
+    # empty image -> ORBX_E_EMPTY (operator() returns -1), stride smaller than the width, image larger than the handle
+    assert L.orbx_extract(ex._h, p(img), 0, 0, 0, 0, 0, p(kps), p(desc), cap, C.byref(n), C.byref(mono)) == EMPTY
+    assert L.orbx_extract(ex._h, p(img), W, H, W - 1, 0, 0, p(kps), p(desc), cap, C.byref(n), C.byref(mono)) == INVALID
+    big = synth.rects_frame(W + 16, H, 3)
+    assert L.orbx_extract(ex._h, p(big), W + 16, H, W + 16, 0, 0, p(kps), p(desc), cap, C.byref(n), C.byref(mono)) == INVALID
+    assert len(L.orbx_last_error()) > 0
+    # more frames than max_batch
+    batch = np.stack([img] * 3)
+    kb = np.zeros((3, cap), orbx.KP_DTYPE); db = np.zeros((3, cap, 32), np.uint8); nb = np.zeros(3, np.int32); mb = np.zeros(3, np.int32)
+    assert L.orbx_extract_batch(ex._h, p(batch), 3, W, H, W, C.c_size_t(W * H), 0, 0, p(kb), p(db), cap, p(nb), p(mb)) == INVALID
+    # slot / level queries out of range
+    ex(img, None, (0, 0))
+    w_, h_ = C.c_int(), C.c_int()
+    assert L.orbx_pyramid_level_size(ex._h, 8, C.byref(w_), C.byref(h_)) == INVALID
+    lvl = np.zeros((H, W), np.uint8)
+    assert L.orbx_pyramid_to_host(ex._h, 5, 0, p(lvl), W) == INVALID             # slot 5 of a batch of 1
+    # the handle still works after all of that
+    mono_ok, k_ok, d_ok = ex(img, None, (0, 0))
+    ref = O.Extractor(300, 1.2, 8, 20, 7)(img, (0, 0))
+    check_frame((mono_ok, k_ok, d_ok), ref)
+    # matcher: bad sizes
+    m = orbx.ORBmatcher(0.9, True, max_keypoints=256)
+    out = np.zeros(10, np.int32)
+    assert L.orbx_hamming_pairs(None, p(d_ok), p(d_ok), 10, p(out)) == INVALID
+    assert L.orbx_hamming_pairs(m._h, p(d_ok), p(d_ok), -1, p(out)) == INVALID
+    idx = np.zeros((300, 2), np.int32); dist = np.zeros((300, 2), np.int32)
+    assert L.orbx_bf_knn2(m._h, None, 10, p(d_ok), 10, p(idx), p(dist)) == INVALID
+    m.close(); ex.close()
