@@ -338,15 +338,11 @@ def stereo_bench(args, world, rank, local):
         hu, hz = pin((P, cap), torch.float32), pin((P, cap), torch.float32)
         hln, hrn = hl.numpy(), hr.numpy()
 
-        def one(ex, img, k, d, n, mo):
-            orbx._check(L.orbx_extract_batch(ex._h, orbx._p(img), P, w, h, w, w * h, 0, 0, orbx._p(k), orbx._p(d), cap, orbx._p(n), orbx._p(mo)))
-
         def step_host():
-            # one host thread per camera, as the reference does (Frame.cc:92-95): the two extractor instances overlap
-            # each other's copies and kernels on their own streams
-            th = [threading.Thread(target=one, args=a) for a in ((exl, hln, ok[0], od[0], on[0], on[1]), (exr, hrn, ok[1], od[1], on[2], on[3]))]
-            [x.start() for x in th]; [x.join() for x in th]
-            orbx._check(L.orbx_stereo_matches_batch(m._h, exl._h, exr._h, 0, P, mb, mbf, orbx._p(hu), orbx._p(hz), cap))
+            # one C-ABI call: both cameras' frames from pinned host memory -> keypoints, descriptors, mvuRight, mvDepth
+            orbx._check(L.orbx_extract_stereo_batch(m._h, exl._h, exr._h, orbx._p(hln), orbx._p(hrn), P, w, h, w, w * h, mb, mbf,
+                                                    orbx._p(ok[0]), orbx._p(od[0]), orbx._p(on[0]), orbx._p(ok[1]), orbx._p(od[1]), orbx._p(on[2]),
+                                                    cap, orbx._p(hu), orbx._p(hz)))
         for _ in range(2):
             step_host()
         barrier()
@@ -360,7 +356,7 @@ def stereo_bench(args, world, rank, local):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e = {"value": world * 2 * P * ns / float(t.item()), "unit": "frames/s", "h2d_bytes_per_step": 2 * P * w * h,
                "d2h_bytes_per_step": 2 * P * (cap * 60 + 8) + 2 * P * cap * 4, "steps": ns,
-               "api": "orbx_extract_batch on two host threads (left / right camera) + orbx_stereo_matches_batch (pinned host frames -> keypoints, descriptors, mvuRight, mvDepth on host)"}
+               "api": "orbx_extract_stereo_batch (pinned host frames of both cameras -> keypoints, descriptors, mvuRight, mvDepth on host)"}
     clocks = sampler.stop() if rank == 0 else None
     if rank != 0:
         if world > 1:

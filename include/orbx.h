@@ -237,6 +237,17 @@ int  orbx_stereo_matches_batch_device(orbx_matcher* m, orbx_extractor* left, orb
                                       float mb, float mbf, float* d_uright, float* d_depth, int32_t* d_sad, void* stream);
 int  orbx_stereo_matches_batch(orbx_matcher* m, orbx_extractor* left, orbx_extractor* right, int first, int count,
                                float mb, float mbf, float* uright, float* depth, int cap);
+/* A batch of stereo frames from HOST memory to HOST results in one call: ORBextractor::operator() on every left and right
+ * frame (two extractor instances, as R/src/Frame.cc:92-95) and Frame::ComputeStereoMatches for every pair; chunks of the
+ * batch flow through separate copy / kernel streams.  kps_* [batch][cap], desc_* [batch][cap][32], n_* [batch],
+ * uright / depth [batch][cap]; any of kps_*, desc_* may be NULL.  batch <= max_batch of both extractors. */
+int  orbx_extract_stereo_batch(orbx_matcher* m, orbx_extractor* left, orbx_extractor* right,
+                               const uint8_t* imgs_left, const uint8_t* imgs_right, int batch, int width, int height,
+                               int stride, size_t frame_stride, float mb, float mbf,
+                               orbx_keypoint* kps_l, uint8_t* desc_l, int32_t* n_l,
+                               orbx_keypoint* kps_r, uint8_t* desc_r, int32_t* n_r, int cap,
+                               float* uright, float* depth);
+
 
 
 /* register-only popcount micro-benchmark: returns measured 32-bit popc per second on `device` (roofline

@@ -983,7 +983,9 @@ struct orbx_matcher {
     int32_t* d_pair_a; int32_t* d_pair_b;
     uint8_t* d_gen; size_t gen_bytes;
     uint8_t* d_st; size_t st_bytes;          // stereo scratch
+    int32_t* h_mono2; int mono2_cap;         // pinned monoIndex landing zone of the stereo pipeline (2 x batch)
     cudaStream_t s_h2d, s_d2h, s_match; cudaEvent_t ev[2 * ORBX_MAX_CHUNKS]; cudaEvent_t ev_ext[ORBX_MAX_CHUNKS]; cudaEvent_t ev_start;
+    cudaEvent_t ev_r[2 * ORBX_MAX_CHUNKS];      // right camera of the stereo pipeline: [c] copy done, [MAX + c] extraction done
     std::vector<void*> allocs;
 };
 
@@ -1040,6 +1042,7 @@ extern "C" int orbx_matcher_create(const orbx_matcher_params* p, orbx_matcher** 
     m->d_pair_a = m->d_pair_b = nullptr;
     m->d_gen = nullptr; m->gen_bytes = 0;
     m->d_st = nullptr; m->st_bytes = 0;
+    m->h_mono2 = nullptr; m->mono2_cap = 0;
     m->s_h2d = m->s_d2h = nullptr;
     CKM(cudaMemset(W.err, 0, sizeof(unsigned)));
     CKM(cudaMallocHost((void**)&m->h_err, sizeof(unsigned)));
@@ -1067,10 +1070,11 @@ extern "C" void orbx_matcher_destroy(orbx_matcher* m)
     if (m->d_pair_a) cudaFree(m->d_pair_a);
     if (m->d_gen) cudaFree(m->d_gen);
     if (m->d_st) cudaFree(m->d_st);
+    if (m->h_mono2) cudaFreeHost(m->h_mono2);
     if (m->s_h2d) {
         cudaStreamDestroy(m->s_h2d); cudaStreamDestroy(m->s_d2h); cudaStreamDestroy(m->s_match);
         for (int i = 0; i < ORBX_MAX_CHUNKS; i++) cudaEventDestroy(m->ev_ext[i]);
-        for (int i = 0; i < 2 * ORBX_MAX_CHUNKS; i++) cudaEventDestroy(m->ev[i]);
+        for (int i = 0; i < 2 * ORBX_MAX_CHUNKS; i++) { cudaEventDestroy(m->ev[i]); cudaEventDestroy(m->ev_r[i]); }
         cudaEventDestroy(m->ev_start);
     }
     cudaFreeHost(m->h_err);
@@ -1349,6 +1353,7 @@ static int ensure_pipeline(orbx_matcher* m)
         CKM(cudaStreamCreateWithFlags(&m->s_match, cudaStreamNonBlocking));
         for (int i = 0; i < 2 * ORBX_MAX_CHUNKS; i++) CKM(cudaEventCreateWithFlags(&m->ev[i], cudaEventDisableTiming));
         for (int i = 0; i < ORBX_MAX_CHUNKS; i++) CKM(cudaEventCreateWithFlags(&m->ev_ext[i], cudaEventDisableTiming));
+        for (int i = 0; i < 2 * ORBX_MAX_CHUNKS; i++) CKM(cudaEventCreateWithFlags(&m->ev_r[i], cudaEventDisableTiming));
         CKM(cudaEventCreateWithFlags(&m->ev_start, cudaEventDisableTiming));
     }
     if (!m->d_pair_a) {
@@ -1654,6 +1659,85 @@ extern "C" int orbx_stereo_matches_batch(orbx_matcher* m, orbx_extractor* left, 
     return ORBX_OK;
 }
 
+// One call = a batch of stereo frames from host memory to host results: both cameras extracted (Frame.cc:92-95 runs the
+// two extractors side by side) and Frame::ComputeStereoMatches for every pair.  The batch is cut into chunks that flow
+// through five streams (H2D | left extractor | right extractor | stereo kernels | D2H), so the copies and the stereo
+// kernels of one chunk hide under the extraction of its neighbours.
+extern "C" int orbx_extract_stereo_batch(orbx_matcher* m, orbx_extractor* left, orbx_extractor* right,
+                                         const uint8_t* imgs_left, const uint8_t* imgs_right, int batch, int width, int height,
+                                         int stride, size_t frame_stride, float mb, float mbf,
+                                         orbx_keypoint* kps_l, uint8_t* desc_l, int32_t* n_l,
+                                         orbx_keypoint* kps_r, uint8_t* desc_r, int32_t* n_r, int cap,
+                                         float* uright, float* depth)
+{
+    if (!m || !left || !right || left == right || !imgs_left || !imgs_right || batch < 1 || !uright || !depth || cap <= 0) return ORBX_E_INVALID;
+    if (width <= 0 || height <= 0) return ORBX_E_EMPTY;
+    int rc;
+    if ((rc = orbx_ex_configure(left, width, height)) || (rc = orbx_ex_configure(right, width, height))) return rc;
+    if (orbx_ex_device(left) != m->p.device || orbx_ex_device(right) != m->p.device) return ORBX_E_INVALID;
+    int slotsL = 0, slotsR = 0, capL = 0, capR = 0;
+    { orbx_keypoint* k; uint8_t* d; int32_t* n;
+      if ((rc = orbx_extractor_results_device(left, &k, &d, &n, nullptr, &capL, &slotsL)) || (rc = orbx_extractor_results_device(right, &k, &d, &n, nullptr, &capR, &slotsR))) return rc; }
+    if (batch > slotsL - 1 || batch > slotsR - 1) { orbx_set_error("%s%s", "orbx_extract_stereo_batch: batch larger than max_batch of an extractor", ""); return ORBX_E_INVALID; }
+    CKM(cudaSetDevice(m->p.device));
+    if ((rc = ensure_pipeline(m))) return rc;
+    cudaStream_t sL = orbx_ex_stream(left), sR = orbx_ex_stream(right);
+    if (m->mono2_cap < batch) {
+        if (m->h_mono2) cudaFreeHost(m->h_mono2);
+        m->h_mono2 = nullptr; m->mono2_cap = 0;
+        CKM(cudaMallocHost((void**)&m->h_mono2, sizeof(int32_t) * 2 * (size_t)batch));
+        m->mono2_cap = batch;
+    }
+    int32_t* mono_l = m->h_mono2; int32_t* mono_r = m->h_mono2 + batch;      // monoIndex is not part of this call's results
+    const bool directL = orbx_ex_can_fetch_direct(left, kps_l, desc_l, cap, n_l, mono_l), directR = orbx_ex_can_fetch_direct(right, kps_r, desc_r, cap, n_r, mono_r);
+    int nchunks = batch >= 48 ? 6 : (batch >= 16 ? 4 : 1);      // measured on C2 / C3: 6 chunks 88.9 k / 62.0 k frames/s, 4: 87.6 / 61.2, 8: 86.6 / 59.1
+    if (const char* e = getenv("ORBX_HOST_CHUNKS")) { const int v = atoi(e); if (v >= 1 && v <= ORBX_MAX_CHUNKS) nchunks = v; }
+    if (nchunks > batch) nchunks = batch;
+    const int per = (batch + nchunks - 1) / nchunks;
+    nchunks = (batch + per - 1) / per;
+    StereoScratch S{};
+    // the side streams start after whatever the caller queued on the extractors' streams
+    CKM(cudaEventRecord(m->ev_start, sL));
+    CKM(cudaStreamWaitEvent(m->s_h2d, m->ev_start, 0));
+    CKM(cudaStreamWaitEvent(m->s_match, m->ev_start, 0));
+    CKM(cudaStreamWaitEvent(m->s_d2h, m->ev_start, 0));
+    for (int c = 0; c < nchunks; c++) {
+        const int f0 = c * per, cnt = f0 + per <= batch ? per : batch - f0;
+        if ((rc = orbx_ex_stage_input(left, imgs_left, f0, cnt, width, height, stride, frame_stride, m->s_h2d))) return rc;
+        CKM(cudaEventRecord(m->ev[c], m->s_h2d));
+        if ((rc = orbx_ex_stage_input(right, imgs_right, f0, cnt, width, height, stride, frame_stride, m->s_h2d))) return rc;
+        CKM(cudaEventRecord(m->ev_r[c], m->s_h2d));
+    }
+    for (int c = 0; c < nchunks; c++) {
+        const int f0 = c * per, cnt = f0 + per <= batch ? per : batch - f0;
+        CKM(cudaStreamWaitEvent(sL, m->ev[c], 0));
+        if ((rc = orbx_ex_run_staged(left, f0, cnt, 0, 0, f0, sL))) return rc;
+        CKM(cudaEventRecord(m->ev_ext[c], sL));
+        CKM(cudaStreamWaitEvent(sR, m->ev_r[c], 0));
+        if ((rc = orbx_ex_run_staged(right, f0, cnt, 0, 0, f0, sR))) return rc;
+        CKM(cudaEventRecord(m->ev_r[ORBX_MAX_CHUNKS + c], sR));
+        if (c == 0 && (rc = stereo_prepare(m, left, right, batch, &S))) return rc;      // needs the geometry of a queued batch
+        CKM(cudaStreamWaitEvent(m->s_match, m->ev_ext[c], 0));
+        CKM(cudaStreamWaitEvent(m->s_match, m->ev_r[ORBX_MAX_CHUNKS + c], 0));
+        StereoScratch C = S;                                   // this chunk's slice of the scratch
+        C.lists = S.lists + (size_t)f0 * S.list_cap; C.best = S.best + 2 * (size_t)f0 * capL;
+        float* du = S.u + (size_t)f0 * capL; float* dz = S.z + (size_t)f0 * capL; int32_t* ds = S.sad + (size_t)f0 * capL;
+        if ((rc = stereo_launch(m, left, right, f0, f0, f0, f0, cnt, mb, mbf, C, du, dz, ds, capL, m->s_match))) return rc;
+        CKM(cudaEventRecord(m->ev[ORBX_MAX_CHUNKS + c], m->s_match));
+        CKM(cudaStreamWaitEvent(m->s_d2h, m->ev[ORBX_MAX_CHUNKS + c], 0));
+        if ((rc = orbx_ex_fetch_async(left, f0, cnt, f0, kps_l, desc_l, cap, n_l, mono_l, m->s_d2h, directL))) return rc;
+        if ((rc = orbx_ex_fetch_async(right, f0, cnt, f0, kps_r, desc_r, cap, n_r, mono_r, m->s_d2h, directR))) return rc;
+        const int wcopy = cap < capL ? cap : capL;
+        CKM(cudaMemcpy2DAsync(uright + (size_t)f0 * cap, sizeof(float) * cap, du, sizeof(float) * capL, sizeof(float) * wcopy, cnt, cudaMemcpyDeviceToHost, m->s_d2h));
+        CKM(cudaMemcpy2DAsync(depth + (size_t)f0 * cap, sizeof(float) * cap, dz, sizeof(float) * capL, sizeof(float) * wcopy, cnt, cudaMemcpyDeviceToHost, m->s_d2h));
+    }
+    CKM(cudaStreamSynchronize(m->s_d2h));
+    CKM(cudaStreamSynchronize(sL));
+    CKM(cudaStreamSynchronize(sR));
+    if ((rc = orbx_ex_fetch_finish(left, batch, kps_l, desc_l, cap, n_l, nullptr, directL))) return rc;
+    return orbx_ex_fetch_finish(right, batch, kps_r, desc_r, cap, n_r, nullptr, directR);
+}
+
 // generic candidate matching for the host-side searches (SearchByBoW, SearchForTriangulation, Fuse, SearchBySim3)
 extern "C" int orbx_match_candidates(orbx_matcher* m, const uint8_t* q, int nq, const uint8_t* t, int nt, const int32_t* offsets,
                                      const int32_t* indices, int32_t* idx, int32_t* dist)
@@ -1673,6 +1757,7 @@ extern "C" int orbx_match_candidates(orbx_matcher* m, const uint8_t* q, int nq, 
     if (bytes > m->gen_bytes) {
         if (m->d_gen) cudaFree(m->d_gen);
     if (m->d_st) cudaFree(m->d_st);
+    if (m->h_mono2) cudaFreeHost(m->h_mono2);
         CKM(cudaMalloc((void**)&m->d_gen, bytes)); m->gen_bytes = bytes;
     }
     dq = m->d_gen; dt = dq + (((size_t)nq * 32 + 63) & ~(size_t)63);

@@ -38,6 +38,7 @@ EXPORTS = [
     "orbx_search_for_initialization", "orbx_match_slots_device", "orbx_extract_match_batch", "orbx_extract_match_batch_device",
     "orbx_search_by_projection",
     "orbx_stereo_band_match", "orbx_stereo_matches", "orbx_stereo_matches_batch", "orbx_stereo_matches_batch_device",
+    "orbx_extract_stereo_batch",
     "orbx_fast_segment_plan", "orbx_match_candidates", "orbx_search_by_bow", "orbx_distinctive_descriptors", "orbx_vocab_create", "orbx_vocab_destroy", "orbx_vocab_words", "orbx_vocab_word_weights",
     "orbx_bow_transform", "orbx_bow_transform_slots_device", "orbx_popc_peak",
 ]
@@ -123,6 +124,7 @@ def lib():
         L.orbx_stereo_matches.argtypes = [vp, vp, vp, i32, i32, i32, i32, f32, f32, vp, vp, vp, i32, vp]
         L.orbx_stereo_matches_batch.argtypes = [vp, vp, vp, i32, i32, f32, f32, vp, vp, i32]
         L.orbx_stereo_matches_batch_device.argtypes = [vp, vp, vp, i32, i32, f32, f32, vp, vp, vp, vp]
+        L.orbx_extract_stereo_batch.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, sz, f32, f32, vp, vp, vp, vp, vp, vp, i32, vp, vp]
         _lib = L
     return _lib
 
@@ -390,6 +392,20 @@ class ORBmatcher:
         ur = np.empty((count, cap), np.float32); dp = np.empty((count, cap), np.float32)
         _check(lib().orbx_stereo_matches_batch(self._h, ex_left._h, ex_right._h, first, count, float(mb), float(mbf), _p(ur), _p(dp), cap))
         return ur, dp
+
+    def ExtractStereoBatch(self, ex_left, ex_right, imgs_left, imgs_right, mb, mbf, out=None):
+        """host frames [B,H,W] x 2 -> dict(kps_l, desc_l, n_l, kps_r, desc_r, n_r, uright, depth), one C-ABI call"""
+        il = np.ascontiguousarray(imgs_left, np.uint8); ir = np.ascontiguousarray(imgs_right, np.uint8)
+        B, H, W = il.shape
+        cap = ex_left.cap
+        if out is None:
+            out = {"kps_l": np.zeros((B, cap), KP_DTYPE), "desc_l": np.zeros((B, cap, 32), np.uint8), "n_l": np.zeros(B, np.int32),
+                   "kps_r": np.zeros((B, cap), KP_DTYPE), "desc_r": np.zeros((B, cap, 32), np.uint8), "n_r": np.zeros(B, np.int32),
+                   "uright": np.empty((B, cap), np.float32), "depth": np.empty((B, cap), np.float32)}
+        _check(lib().orbx_extract_stereo_batch(self._h, ex_left._h, ex_right._h, _p(il), _p(ir), B, W, H, W, W * H, float(mb), float(mbf),
+                                               _p(out["kps_l"]), _p(out["desc_l"]), _p(out["n_l"]), _p(out["kps_r"]), _p(out["desc_r"]),
+                                               _p(out["n_r"]), cap, _p(out["uright"]), _p(out["depth"])))
+        return out
 
     def stereo_matches_batch_device(self, ex_left, ex_right, mb, mbf, first, count, d_uright, d_depth, d_sad=None, stream=None):
         """device form: d_* are device pointers to [count][ex_left.cap] arrays; enqueued on `stream`, not synchronised."""

@@ -293,3 +293,38 @@ def test_match_candidates_generic():
     with pytest.raises(orbx.OrbxError):
         m.MatchCandidates(q, t, off, bad)              # out-of-range candidate index is refused, not read
     m.close()
+
+
+def test_extract_stereo_batch_host_pipeline():
+    """orbx_extract_stereo_batch (host frames of both cameras in, keypoints + mvuRight + mvDepth out, chunked over five
+    streams) equals the step-by-step path and the oracle, with pageable and with pinned caller buffers."""
+    import torch
+    W, H, nf, B = 752, 480, 1200, 40                       # 40 pairs -> 4 chunks of 10
+    pairs = [synth.stereo_pair(W, H, seed=60 + i, disparity=12 + (i % 5) * 4) for i in range(6)]
+    Ls = np.stack([pairs[i % 6][0] for i in range(B)]); Rs = np.stack([pairs[i % 6][1] for i in range(B)])
+    exl = orbx.ORBextractor(nf, 1.2, 8, 20, 7, max_width=W, max_height=H, max_batch=B)
+    exr = orbx.ORBextractor(nf, 1.2, 8, 20, 7, max_width=W, max_height=H, max_batch=B)
+    m = orbx.ORBmatcher(0.9, True, max_keypoints=exl.cap)
+    mb, mbf = 0.11, 47.9
+    out = m.ExtractStereoBatch(exl, exr, Ls, Rs, mb, mbf)
+    cap = exl.cap
+    pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory().numpy()
+    pout = {"kps_l": pin((B, cap, 7), torch.float32).view(np.uint8).reshape(B, cap, 28).view(orbx.KP_DTYPE).reshape(B, cap),
+            "desc_l": pin((B, cap, 32), torch.uint8), "n_l": pin((B,), torch.int32),
+            "kps_r": pin((B, cap, 7), torch.float32).view(np.uint8).reshape(B, cap, 28).view(orbx.KP_DTYPE).reshape(B, cap),
+            "desc_r": pin((B, cap, 32), torch.uint8), "n_r": pin((B,), torch.int32),
+            "uright": pin((B, cap), torch.float32), "depth": pin((B, cap), torch.float32)}
+    m.ExtractStereoBatch(exl, exr, torch.from_numpy(Ls).pin_memory().numpy(), torch.from_numpy(Rs).pin_memory().numpy(), mb, mbf, pout)
+    for i in range(6):
+        ol, orr = O.Extractor(nf, 1.2, 8, 20, 7), O.Extractor(nf, 1.2, 8, 20, 7)
+        _, kl, dl = ol(pairs[i][0], (0, 0)); _, kr, dr = orr(pairs[i][1], (0, 0))
+        rur, rdp, _ = O.compute_stereo_matches(ol, orr, kl, dl, kr, dr, mb, mbf)
+        for j in (i, i + 6 * ((B - 1 - i) // 6)):           # the first and the last copy of this pair in the batch (different chunks)
+            for o in (out, pout):
+                n = int(o["n_l"][j])
+                assert n == len(kl) and int(o["n_r"][j]) == len(kr)
+                assert o["kps_l"][j, :n].tobytes() == kl.tobytes() and o["kps_r"][j, :len(kr)].tobytes() == kr.tobytes()
+                np.testing.assert_array_equal(o["desc_l"][j, :n], dl)
+                np.testing.assert_array_equal(o["uright"][j, :n], rur)
+                np.testing.assert_array_equal(o["depth"][j, :n], rdp)
+    exl.close(); exr.close(); m.close()
