@@ -1,0 +1,295 @@
+// orbx_search.cu - searches over explicit candidate sets: the generic CSR candidate matcher (inner loops of
+// SearchForTriangulation / Fuse / SearchBySim3), ORBmatcher::SearchByBoW (R/src/ORBmatcher.cc:269-471, :819-959) and
+// MapPoint::ComputeDistinctiveDescriptors (R/src/MapPoint.cc:448-524).
+#include "orbx_match_internal.h"
+
+namespace {
+
+// generic CSR candidate matching: one warp per query, candidates in list order, top-2 by (distance, list position)
+__global__ void __launch_bounds__(256) k_match_candidates(const uint8_t* q, int nq, const uint8_t* t, const int32_t* offsets,
+                                                        const int32_t* indices, int32_t* out_idx, int32_t* out_dist)
+{
+    const int lane = threadIdx.x & 31;
+    const int qi = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (qi >= nq) return;
+    const int o0 = offsets[qi], o1 = offsets[qi + 1];
+    const uint4 a0 = reinterpret_cast<const uint4*>(q)[2 * qi], a1 = reinterpret_cast<const uint4*>(q)[2 * qi + 1];
+    int d0 = 0x7fffffff, k0 = 0x7fffffff, d1 = 0x7fffffff, k1 = 0x7fffffff;
+    uint32_t e0 = 0, e1 = 0;
+    for (int k = o0 + lane; k < o1; k += 32) {
+        const int j = indices[k];
+        const int d = hamming256(a0, a1, reinterpret_cast<const uint4*>(t)[2 * j], reinterpret_cast<const uint4*>(t)[2 * j + 1]);
+        const int r = k - o0;
+        if (d < d0) { d1 = d0; k1 = k0; e1 = e0; d0 = d; k0 = r; e0 = (uint32_t)j; }
+        else if (d < d1) { d1 = d; k1 = r; e1 = (uint32_t)j; }
+    }
+    if (o1 - o0 > 65535) {     // ranks beyond 16 bits: fall back to the shuffle tree on (dist, rank) pairs
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const int od0 = __shfl_xor_sync(0xffffffffu, d0, o), ok0 = __shfl_xor_sync(0xffffffffu, k0, o);
+            const uint32_t oe0 = __shfl_xor_sync(0xffffffffu, e0, o);
+            const int od1 = __shfl_xor_sync(0xffffffffu, d1, o), ok1 = __shfl_xor_sync(0xffffffffu, k1, o);
+            const uint32_t oe1 = __shfl_xor_sync(0xffffffffu, e1, o);
+            int ld, lk; uint32_t le;
+            if (od0 < d0 || (od0 == d0 && ok0 < k0)) { ld = d0; lk = k0; le = e0; d0 = od0; k0 = ok0; e0 = oe0; }
+            else { ld = od0; lk = ok0; le = oe0; }
+            if (od1 < d1 || (od1 == d1 && ok1 < k1)) { d1 = od1; k1 = ok1; e1 = oe1; }
+            if (ld < d1 || (ld == d1 && lk < k1)) { d1 = ld; k1 = lk; e1 = le; }
+        }
+    } else {
+        warp_top2(d0, k0, e0, d1, e1, k1);
+    }
+    if (lane == 0) {
+        out_idx[2 * qi] = d0 == 0x7fffffff ? -1 : (int)e0; out_dist[2 * qi] = d0 == 0x7fffffff ? -1 : d0;
+        out_idx[2 * qi + 1] = d1 == 0x7fffffff ? -1 : (int)e1; out_dist[2 * qi + 1] = d1 == 0x7fffffff ? -1 : d1;
+    }
+}
+
+// ---- ORBmatcher::SearchByBoW (R/src/ORBmatcher.cc:269-471, :819-959) ----
+// The FeatureVectors of both sides are CSR tables sorted by node id.  Features of different nodes never interact (a
+// feature belongs to one node), so one warp owns one common node and walks its set-1 features in list order exactly as
+// the reference does: lanes score the node's set-2 features that are still free, warp top-2 by (distance, list rank),
+// threshold + ratio test, claim.  The rotation histogram is global: bins are counted with atomics and applied by
+// k_bow_finish.
+struct BowArgs {
+    int mode;
+    const orbx_keypoint* k1; const uint8_t* d1; const uint8_t* valid1; int n1;
+    const int32_t* fv1_nodes; const int32_t* fv1_start; const int32_t* fv1_feat; int nfv1;
+    const orbx_keypoint* k2; const uint8_t* d2; const uint8_t* valid2; int n2;
+    const int32_t* fv2_nodes; const int32_t* fv2_start; const int32_t* fv2_feat; int nfv2;
+    float nnratio; int check_ori;
+    int32_t* matches12;      // [n1], preset to -1
+    uint8_t* claimed2;       // [n2], preset to 0
+    uint8_t* bin_of;         // [n1]
+    int32_t* hist;           // [HISTO_LENGTH + 1]: bins, then the match count; preset to 0
+};
+
+__global__ void __launch_bounds__(256) k_bow_match(BowArgs A)
+{
+    const int lane = threadIdx.x & 31;
+    const int w = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (w >= A.nfv1) return;
+    const int node = A.fv1_nodes[w];
+    int lo = 0, hi = A.nfv2;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (A.fv2_nodes[mid] < node) lo = mid + 1; else hi = mid; }
+    if (lo >= A.nfv2 || A.fv2_nodes[lo] != node) return;
+    const int a0 = A.fv1_start[w], a1 = A.fv1_start[w + 1], b0 = A.fv2_start[lo], b1 = A.fv2_start[lo + 1];
+    for (int ia = a0; ia < a1; ia++) {
+        const int i1 = A.fv1_feat[ia];
+        if (!A.valid1[i1]) continue;
+        const uint4 q0 = reinterpret_cast<const uint4*>(A.d1)[2 * i1], q1 = reinterpret_cast<const uint4*>(A.d1)[2 * i1 + 1];
+        int d0 = 0x7fffffff, r0 = 0x7fffffff, d1 = 0x7fffffff, r1 = 0x7fffffff;
+        uint32_t e0 = 0, e1 = 0;
+        for (int ib = b0 + lane; ib < b1; ib += 32) {
+            const int i2 = A.fv2_feat[ib];
+            if (A.claimed2[i2]) continue;
+            if (A.mode == 1 && A.valid2 && !A.valid2[i2]) continue;
+            const int d = hamming256(q0, q1, reinterpret_cast<const uint4*>(A.d2)[2 * i2], reinterpret_cast<const uint4*>(A.d2)[2 * i2 + 1]);
+            const int r = ib - b0;
+            if (d < d0) { d1 = d0; r1 = r0; e1 = e0; d0 = d; r0 = r; e0 = (uint32_t)i2; }
+            else if (d < d1) { d1 = d; r1 = r; e1 = (uint32_t)i2; }
+        }
+        warp_top2(d0, r0, e0, d1, e1, r1);
+        const int best1 = d0 == 0x7fffffff ? 256 : d0, best2 = d1 == 0x7fffffff ? 256 : d1;
+        const bool pass = A.mode == 0 ? best1 <= ORBX_TH_LOW : best1 < ORBX_TH_LOW;
+        if (pass && (float)best1 < __fmul_rn(A.nnratio, (float)best2)) {
+            if (lane == 0) {
+                A.matches12[i1] = (int32_t)e0; A.claimed2[e0] = 1;
+                if (A.check_ori) { const int bin = rot_bin(A.k1[i1].angle, A.k2[e0].angle); A.bin_of[i1] = (uint8_t)bin; atomicAdd(&A.hist[bin], 1); }
+                atomicAdd(&A.hist[ORBX_HISTO_LENGTH], 1);
+            }
+        }
+        __syncwarp();          // the claim is visible to every lane before the next set-1 feature is scored
+    }
+}
+
+// rotation consistency (:437-460): keep the three dominant bins
+__global__ void __launch_bounds__(256) k_bow_finish(BowArgs A, int32_t* nmatches)
+{
+    __shared__ int removed;
+    if (threadIdx.x == 0) removed = 0;
+    __syncthreads();
+    if (A.check_ori) {
+        int ind1, ind2, ind3;
+        three_maxima(A.hist, ind1, ind2, ind3);
+        int local = 0;
+        for (int i = threadIdx.x; i < A.n1; i += blockDim.x)
+            if (A.matches12[i] >= 0) {
+                const int bin = A.bin_of[i];
+                if (bin != ind1 && bin != ind2 && bin != ind3) { A.matches12[i] = -1; local++; }
+            }
+        if (local) atomicAdd(&removed, local);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *nmatches = A.hist[ORBX_HISTO_LENGTH] - removed;
+}
+
+// ---- MapPoint::ComputeDistinctiveDescriptors (R/src/MapPoint.cc:448-524), batched over map points ----
+// One warp per map point.  For observation i the lanes compute its distances to all observations (kept in registers for
+// up to 256 of them, recomputed beyond), and the median of the row (its (N-1)/2-th smallest value, the 0 of the diagonal
+// included) is found by bisection on the value range [0, 256] with ballot counts instead of a sort.
+constexpr int DD_R = 8;
+__global__ void __launch_bounds__(256) k_distinctive(const uint8_t* desc, const int32_t* offsets, int npoints, int32_t* best)
+{
+    const int lane = threadIdx.x & 31;
+    const int p = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (p >= npoints) return;
+    const int o = offsets[p], N = offsets[p + 1] - o;
+    if (N <= 0) { if (lane == 0) best[p] = -1; return; }
+    const uint4* D = reinterpret_cast<const uint4*>(desc) + 2 * (size_t)o;
+    const int k = (N - 1) >> 1;                       // (int)(0.5 * (N - 1))
+    const int steps = (N + 31) >> 5;
+    int bestMedian = 0x7fffffff, bestIdx = 0;
+    for (int i = 0; i < N; i++) {
+        const uint4 q0 = D[2 * i], q1 = D[2 * i + 1];
+        int cache[DD_R];
+#pragma unroll
+        for (int s = 0; s < DD_R; s++) {
+            const int j = s * 32 + lane;
+            cache[s] = (s < steps && j < N) ? hamming256(q0, q1, D[2 * j], D[2 * j + 1]) : 0x7fff;
+        }
+        int lo = 0, hi = 256;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            int cnt = 0;
+#pragma unroll
+            for (int s = 0; s < DD_R; s++) cnt += __popc(__ballot_sync(0xffffffffu, cache[s] <= mid));
+            for (int s = DD_R; s < steps; s++) {
+                const int j = s * 32 + lane;
+                const bool le = j < N && hamming256(q0, q1, D[2 * j], D[2 * j + 1]) <= mid;
+                cnt += __popc(__ballot_sync(0xffffffffu, le));
+            }
+            if (cnt >= k + 1) hi = mid; else lo = mid + 1;
+        }
+        if (lo < bestMedian) { bestMedian = lo; bestIdx = i; }
+    }
+    if (lane == 0) best[p] = bestIdx;
+}
+
+}  // namespace
+
+// generic candidate matching for the host-side searches (SearchByBoW, SearchForTriangulation, Fuse, SearchBySim3)
+extern "C" int orbx_match_candidates(orbx_matcher* m, const uint8_t* q, int nq, const uint8_t* t, int nt, const int32_t* offsets,
+                                     const int32_t* indices, int32_t* idx, int32_t* dist)
+{
+    if (!m || nq < 0 || nt < 0 || (nq > 0 && (!q || !offsets || !idx || !dist))) return ORBX_E_INVALID;
+    if (nq == 0) return ORBX_OK;
+    const int ncand = offsets[nq];
+    if (ncand < 0 || (ncand > 0 && (!indices || !t))) return ORBX_E_INVALID;
+    for (int i = 0; i < nq; i++)
+        if (offsets[i] < 0 || offsets[i] > offsets[i + 1]) { orbx_set_error("%s%s", "orbx_match_candidates: offsets must be non-decreasing", ""); return ORBX_E_INVALID; }
+    for (int k = 0; k < ncand; k++)
+        if ((unsigned)indices[k] >= (unsigned)nt) { orbx_set_error("%s%s", "orbx_match_candidates: candidate index out of range", ""); return ORBX_E_INVALID; }
+    CKM(cudaSetDevice(m->p.device));
+    cudaStream_t s = m->stream;
+    uint8_t *dq, *dt; int32_t *doff, *dind, *dres;
+    const size_t bytes = (size_t)nq * 32 + (size_t)(nt > 0 ? nt : 1) * 32 + sizeof(int32_t) * ((size_t)nq + 1 + (ncand > 0 ? ncand : 1) + 4 * (size_t)nq) + 256;
+    { const int rcs = orbx_m_gen_scratch(m, bytes); if (rcs) return rcs; }
+    dq = m->d_gen; dt = dq + (((size_t)nq * 32 + 63) & ~(size_t)63);
+    doff = reinterpret_cast<int32_t*>(dt + (((size_t)(nt > 0 ? nt : 1) * 32 + 63) & ~(size_t)63));
+    dind = doff + nq + 1; dres = dind + (ncand > 0 ? ncand : 1);
+    CKM(cudaMemcpyAsync(dq, q, (size_t)nq * 32, cudaMemcpyHostToDevice, s));
+    if (nt) CKM(cudaMemcpyAsync(dt, t, (size_t)nt * 32, cudaMemcpyHostToDevice, s));
+    CKM(cudaMemcpyAsync(doff, offsets, sizeof(int32_t) * (nq + 1), cudaMemcpyHostToDevice, s));
+    if (ncand) CKM(cudaMemcpyAsync(dind, indices, sizeof(int32_t) * ncand, cudaMemcpyHostToDevice, s));
+    k_match_candidates<<<(nq + 7) / 8, 256, 0, s>>>(dq, nq, dt, doff, dind, dres, dres + 2 * nq); ORBX_COUNT_LAUNCH(1);
+    CKM(cudaGetLastError());
+    CKM(cudaMemcpyAsync(idx, dres, sizeof(int32_t) * 2 * nq, cudaMemcpyDeviceToHost, s));
+    CKM(cudaMemcpyAsync(dist, dres + 2 * nq, sizeof(int32_t) * 2 * nq, cudaMemcpyDeviceToHost, s));
+    CKM(cudaStreamSynchronize(s));
+    return ORBX_OK;
+}
+
+// ORBmatcher::SearchByBoW on flat arrays (see include/orbx.h).  Host pointers, synchronous.
+extern "C" int orbx_search_by_bow(orbx_matcher* m, int mode,
+                                  const orbx_keypoint* k1, const uint8_t* d1, const uint8_t* valid1, int n1,
+                                  const int32_t* fv1_nodes, const int32_t* fv1_start, const int32_t* fv1_feat, int nfv1,
+                                  const orbx_keypoint* k2, const uint8_t* d2, const uint8_t* valid2, int n2,
+                                  const int32_t* fv2_nodes, const int32_t* fv2_start, const int32_t* fv2_feat, int nfv2,
+                                  float nnratio, int check_ori, int32_t* matches12, int* nmatches)
+{
+    if (!m || (mode != 0 && mode != 1) || n1 < 0 || n2 < 0 || n2 > 65535 || nfv1 < 0 || nfv2 < 0 || !matches12) return ORBX_E_INVALID;
+    if (nmatches) *nmatches = 0;
+    for (int i = 0; i < n1; i++) matches12[i] = -1;
+    if (n1 == 0 || n2 == 0 || nfv1 == 0 || nfv2 == 0) return ORBX_OK;
+    if (!k1 || !d1 || !valid1 || !k2 || !d2 || !fv1_nodes || !fv1_start || !fv1_feat || !fv2_nodes || !fv2_start || !fv2_feat) return ORBX_E_INVALID;
+    const int nf1 = fv1_start[nfv1], nf2 = fv2_start[nfv2];
+    if (nf1 < 0 || nf2 < 0 || fv1_start[0] != 0 || fv2_start[0] != 0) return ORBX_E_INVALID;
+    for (int i = 0; i < nfv1; i++) if (fv1_start[i] > fv1_start[i + 1] || (i && fv1_nodes[i - 1] >= fv1_nodes[i])) { orbx_set_error("%s%s", "orbx_search_by_bow: FeatureVector 1 must be sorted by node id", ""); return ORBX_E_INVALID; }
+    for (int i = 0; i < nfv2; i++) if (fv2_start[i] > fv2_start[i + 1] || (i && fv2_nodes[i - 1] >= fv2_nodes[i])) { orbx_set_error("%s%s", "orbx_search_by_bow: FeatureVector 2 must be sorted by node id", ""); return ORBX_E_INVALID; }
+    for (int i = 0; i < nf1; i++) if ((unsigned)fv1_feat[i] >= (unsigned)n1) { orbx_set_error("%s%s", "orbx_search_by_bow: feature index out of range", ""); return ORBX_E_INVALID; }
+    for (int i = 0; i < nf2; i++) if ((unsigned)fv2_feat[i] >= (unsigned)n2) { orbx_set_error("%s%s", "orbx_search_by_bow: feature index out of range", ""); return ORBX_E_INVALID; }
+    CKM(cudaSetDevice(m->p.device));
+    cudaStream_t s = m->stream;
+    // one scratch block: [k1][d1][valid1][k2][d2][valid2][fv tables][outputs]
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_k1 = take(sizeof(orbx_keypoint) * n1), o_d1 = take((size_t)32 * n1), o_v1 = take(n1);
+    const size_t o_k2 = take(sizeof(orbx_keypoint) * n2), o_d2 = take((size_t)32 * n2), o_v2 = take(n2);
+    const size_t o_n1 = take(sizeof(int32_t) * nfv1), o_s1 = take(sizeof(int32_t) * (nfv1 + 1)), o_f1 = take(sizeof(int32_t) * (nf1 + 1));
+    const size_t o_n2 = take(sizeof(int32_t) * nfv2), o_s2 = take(sizeof(int32_t) * (nfv2 + 1)), o_f2 = take(sizeof(int32_t) * (nf2 + 1));
+    const size_t o_m = take(sizeof(int32_t) * n1), o_c = take(n2), o_b = take(n1), o_h = take(sizeof(int32_t) * (ORBX_HISTO_LENGTH + 2));
+    { const int rcs = orbx_m_gen_scratch(m, off); if (rcs) return rcs; }
+    uint8_t* B = m->d_gen;
+    CKM(cudaMemcpyAsync(B + o_k1, k1, sizeof(orbx_keypoint) * n1, cudaMemcpyHostToDevice, s));
+    CKM(cudaMemcpyAsync(B + o_d1, d1, (size_t)32 * n1, cudaMemcpyHostToDevice, s));
+    CKM(cudaMemcpyAsync(B + o_v1, valid1, n1, cudaMemcpyHostToDevice, s));
+    CKM(cudaMemcpyAsync(B + o_k2, k2, sizeof(orbx_keypoint) * n2, cudaMemcpyHostToDevice, s));
+    CKM(cudaMemcpyAsync(B + o_d2, d2, (size_t)32 * n2, cudaMemcpyHostToDevice, s));
+    if (valid2) CKM(cudaMemcpyAsync(B + o_v2, valid2, n2, cudaMemcpyHostToDevice, s));
+    CKM(cudaMemcpyAsync(B + o_n1, fv1_nodes, sizeof(int32_t) * nfv1, cudaMemcpyHostToDevice, s));
+    CKM(cudaMemcpyAsync(B + o_s1, fv1_start, sizeof(int32_t) * (nfv1 + 1), cudaMemcpyHostToDevice, s));
+    if (nf1) CKM(cudaMemcpyAsync(B + o_f1, fv1_feat, sizeof(int32_t) * nf1, cudaMemcpyHostToDevice, s));
+    CKM(cudaMemcpyAsync(B + o_n2, fv2_nodes, sizeof(int32_t) * nfv2, cudaMemcpyHostToDevice, s));
+    CKM(cudaMemcpyAsync(B + o_s2, fv2_start, sizeof(int32_t) * (nfv2 + 1), cudaMemcpyHostToDevice, s));
+    if (nf2) CKM(cudaMemcpyAsync(B + o_f2, fv2_feat, sizeof(int32_t) * nf2, cudaMemcpyHostToDevice, s));
+    CKM(cudaMemsetAsync(B + o_m, 0xFF, sizeof(int32_t) * n1, s));
+    CKM(cudaMemsetAsync(B + o_c, 0, n2, s));
+    CKM(cudaMemsetAsync(B + o_h, 0, sizeof(int32_t) * (ORBX_HISTO_LENGTH + 2), s));
+    BowArgs A;
+    A.mode = mode;
+    A.k1 = reinterpret_cast<const orbx_keypoint*>(B + o_k1); A.d1 = B + o_d1; A.valid1 = B + o_v1; A.n1 = n1;
+    A.fv1_nodes = reinterpret_cast<const int32_t*>(B + o_n1); A.fv1_start = reinterpret_cast<const int32_t*>(B + o_s1);
+    A.fv1_feat = reinterpret_cast<const int32_t*>(B + o_f1); A.nfv1 = nfv1;
+    A.k2 = reinterpret_cast<const orbx_keypoint*>(B + o_k2); A.d2 = B + o_d2; A.valid2 = valid2 ? B + o_v2 : nullptr; A.n2 = n2;
+    A.fv2_nodes = reinterpret_cast<const int32_t*>(B + o_n2); A.fv2_start = reinterpret_cast<const int32_t*>(B + o_s2);
+    A.fv2_feat = reinterpret_cast<const int32_t*>(B + o_f2); A.nfv2 = nfv2;
+    A.nnratio = nnratio; A.check_ori = check_ori;
+    A.matches12 = reinterpret_cast<int32_t*>(B + o_m); A.claimed2 = B + o_c; A.bin_of = B + o_b; A.hist = reinterpret_cast<int32_t*>(B + o_h);
+    k_bow_match<<<(nfv1 + 7) / 8, 256, 0, s>>>(A); ORBX_COUNT_LAUNCH(1);
+    k_bow_finish<<<1, 256, 0, s>>>(A, A.hist + ORBX_HISTO_LENGTH + 1); ORBX_COUNT_LAUNCH(1);
+    CKM(cudaGetLastError());
+    int nm = 0;
+    CKM(cudaMemcpyAsync(matches12, A.matches12, sizeof(int32_t) * n1, cudaMemcpyDeviceToHost, s));
+    CKM(cudaMemcpyAsync(&nm, A.hist + ORBX_HISTO_LENGTH + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    CKM(cudaStreamSynchronize(s));
+    if (nmatches) *nmatches = nm;
+    return ORBX_OK;
+}
+
+// MapPoint::ComputeDistinctiveDescriptors for a batch of map points (see include/orbx.h).  Host pointers, synchronous.
+extern "C" int orbx_distinctive_descriptors(orbx_matcher* m, const uint8_t* desc, const int32_t* offsets, int npoints, int32_t* best)
+{
+    if (!m || npoints < 0 || (npoints > 0 && (!offsets || !best))) return ORBX_E_INVALID;
+    if (npoints == 0) return ORBX_OK;
+    if (offsets[0] != 0) return ORBX_E_INVALID;
+    for (int p = 0; p < npoints; p++) if (offsets[p] > offsets[p + 1]) { orbx_set_error("%s%s", "orbx_distinctive_descriptors: offsets must be non-decreasing", ""); return ORBX_E_INVALID; }
+    const int total = offsets[npoints];
+    if (total > 0 && !desc) return ORBX_E_INVALID;
+    CKM(cudaSetDevice(m->p.device));
+    cudaStream_t s = m->stream;
+    const size_t o_d = 0, o_o = ((size_t)(total > 0 ? total : 1) * 32 + 255) & ~(size_t)255;
+    const size_t o_b = o_o + ((sizeof(int32_t) * ((size_t)npoints + 1) + 255) & ~(size_t)255);
+    const size_t bytes = o_b + sizeof(int32_t) * (size_t)npoints;
+    { const int rcs = orbx_m_gen_scratch(m, bytes); if (rcs) return rcs; }
+    uint8_t* B = m->d_gen;
+    if (total) CKM(cudaMemcpyAsync(B + o_d, desc, (size_t)total * 32, cudaMemcpyHostToDevice, s));
+    CKM(cudaMemcpyAsync(B + o_o, offsets, sizeof(int32_t) * ((size_t)npoints + 1), cudaMemcpyHostToDevice, s));
+    k_distinctive<<<(npoints + 7) / 8, 256, 0, s>>>(B + o_d, reinterpret_cast<const int32_t*>(B + o_o), npoints, reinterpret_cast<int32_t*>(B + o_b));
+    ORBX_COUNT_LAUNCH(1);
+    CKM(cudaGetLastError());
+    CKM(cudaMemcpyAsync(best, B + o_b, sizeof(int32_t) * (size_t)npoints, cudaMemcpyDeviceToHost, s));
+    CKM(cudaStreamSynchronize(s));
+    return ORBX_OK;
+}
+
