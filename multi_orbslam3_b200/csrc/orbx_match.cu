@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(GRID_NT) k_grid_build(WinBufs W, int npad_max)
 constexpr int CAND_WARPS = 8;
 
 // Frame::GetFeaturesInArea + descriptor distances, one warp per query.  Pool entry: i2 | dist << 16 | octave << 25
-__global__ void __launch_bounds__(CAND_WARPS * 32) k_window_candidates(WinBufs W)
+__global__ void __launch_bounds__(CAND_WARPS * 32, 6) k_window_candidates(WinBufs W)
 {
     const int lane = threadIdx.x & 31;
     const int p = blockIdx.y;
