@@ -160,6 +160,23 @@ def test_kitti_batched_stream_c3():
     ex.close()
 
 
+def test_uhd_4k_frame():
+    """3840x2160: 63 k FAST candidates at level 0 (octree sort in global scratch), 16 FAST segments per cell row."""
+    W, H = 3840, 2160
+    img = synth.rects_frame(W, H, 14, n_rect=1600)
+    params = (5000, 1.2, 8, 20, 7)
+    ex = orbx.ORBextractor(*params, max_width=W, max_height=H, max_batch=1, max_candidates_per_level=80000)
+    ref = O.Extractor(*params)
+    got = ex(img, None, (0, 0)); want = ref(img, (0, 0))
+    stage_parity(ex, ref)
+    check_frame(got, want)
+    # the default candidate capacity is too small for this frame: loud error, nothing truncated
+    small = orbx.ORBextractor(*params, max_width=W, max_height=H, max_batch=1)
+    with pytest.raises(orbx.OrbxError):
+        small(img, None, (0, 0))
+    small.close(); ex.close()
+
+
 def test_c_abi_rejects_bad_arguments():
     """Every misuse returns an ORBX_E_* code with a message (never a crash, never a silent truncation)."""
     import ctypes as C
