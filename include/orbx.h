@@ -254,6 +254,16 @@ int  orbx_extract_stereo_batch(orbx_matcher* m, orbx_extractor* left, orbx_extra
  * denominator for the matching kernels) */
 int  orbx_popc_peak(int device, double* popc_per_s, double* lop3_per_s);
 
+/* Frame::UndistortKeyPoints (R/src/Frame.cc:721-754): mvKeysUn = cv::undistortPoints(mvKeys, K, mDistCoef,
+ * R = I, P = mK) exactly as OpenCV 4.x computes it (double arithmetic, five fixed-point iterations, float result); K and P
+ * are 3x3 row-major float, dist has ndist = 4..12 coefficients (k1, k2, p1, p2[, k3 ...]); dist[0] == 0 copies the
+ * keypoints (:723-727).  Host form: synchronous.  _slots_device: on the result slots of an extractor, d_kps_un is a
+ * DEVICE array [count][orbx_extractor_max_keypoints(ex)], asynchronous on `stream`. */
+int  orbx_undistort_keypoints(orbx_matcher* m, const orbx_keypoint* kps, int n, const float* K, const float* dist, int ndist,
+                              const float* P, orbx_keypoint* kps_un);
+int  orbx_undistort_slots_device(orbx_extractor* ex, int first_slot, int count, const float* K, const float* dist, int ndist,
+                                 const float* P, orbx_keypoint* d_kps_un, void* stream);
+
 /* MapPoint::ComputeDistinctiveDescriptors (R/src/MapPoint.cc:448-524) for a batch of map points, as
  * LocalMapping runs it for every point a new keyframe observes: the observed descriptors of point p are rows
  * offsets[p] .. offsets[p+1] of desc ([total][32], gathered by the caller from the observing keyframes); best[p] receives

@@ -166,7 +166,104 @@ __global__ void __launch_bounds__(256) k_distinctive(const uint8_t* desc, const 
     if (lane == 0) best[p] = bestIdx;
 }
 
+// ---- Frame::UndistortKeyPoints (R/src/Frame.cc:721-754) = cv::undistortPoints(pts, K, distCoef, I, K_new) ----
+// Double arithmetic in OpenCV's operation order with explicitly rounded operations (no FMA contraction), exactly five
+// iterations of the radial-tangential fixed point, result rounded to float: bit-identical to the CPU.
+struct UndistortArgs { double k[12]; double fx, fy, cx, cy, ifx, ify; double RR[9]; };
+
+__global__ void __launch_bounds__(256) k_undistort(const orbx_keypoint* in, const int32_t* n_slot, int n_fixed, int cap, UndistortArgs A,
+                                                   orbx_keypoint* out)
+{
+    const int slot = blockIdx.y;
+    const int n = n_slot ? n_slot[slot] : n_fixed;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    orbx_keypoint kp = in[(size_t)slot * cap + i];
+    const double u = kp.x, v = kp.y;
+    double x = __dmul_rn(__dsub_rn(u, A.cx), A.ifx), y = __dmul_rn(__dsub_rn(v, A.cy), A.ify);
+    const double x0 = x, y0 = y;
+    const double* k = A.k;
+#pragma unroll 1
+    for (int j = 0; j < 5; j++) {
+        const double r2 = __dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y));
+        const double num = __dadd_rn(1.0, __dmul_rn(__dadd_rn(__dmul_rn(__dadd_rn(__dmul_rn(k[7], r2), k[6]), r2), k[5]), r2));
+        const double den = __dadd_rn(1.0, __dmul_rn(__dadd_rn(__dmul_rn(__dadd_rn(__dmul_rn(k[4], r2), k[1]), r2), k[0]), r2));
+        const double icdist = __ddiv_rn(num, den);
+        if (icdist < 0) { x = __dmul_rn(__dsub_rn(u, A.cx), A.ifx); y = __dmul_rn(__dsub_rn(v, A.cy), A.ify); break; }
+        // deltaX = 2*k2*x*y + k3*(r2 + 2*x*x) + k8*r2 + k9*r2*r2, left to right
+        const double dX = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(__dmul_rn(__dmul_rn(2.0, k[2]), x), y),
+                                                        __dmul_rn(k[3], __dadd_rn(r2, __dmul_rn(__dmul_rn(2.0, x), x)))),
+                                              __dmul_rn(k[8], r2)), __dmul_rn(__dmul_rn(k[9], r2), r2));
+        const double dY = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(k[2], __dadd_rn(r2, __dmul_rn(__dmul_rn(2.0, y), y))),
+                                                        __dmul_rn(__dmul_rn(__dmul_rn(2.0, k[3]), x), y)),
+                                              __dmul_rn(k[10], r2)), __dmul_rn(__dmul_rn(k[11], r2), r2));
+        x = __dmul_rn(__dsub_rn(x0, dX), icdist);
+        y = __dmul_rn(__dsub_rn(y0, dY), icdist);
+    }
+    const double xx = __dadd_rn(__dadd_rn(__dmul_rn(A.RR[0], x), __dmul_rn(A.RR[1], y)), A.RR[2]);
+    const double yy = __dadd_rn(__dadd_rn(__dmul_rn(A.RR[3], x), __dmul_rn(A.RR[4], y)), A.RR[5]);
+    const double ww = __ddiv_rn(1.0, __dadd_rn(__dadd_rn(__dmul_rn(A.RR[6], x), __dmul_rn(A.RR[7], y)), A.RR[8]));
+    kp.x = (float)__dmul_rn(xx, ww); kp.y = (float)__dmul_rn(yy, ww);
+    out[(size_t)slot * cap + i] = kp;
+}
+
 }  // namespace
+
+static int undistort_args(const float* K, const float* dist, int ndist, const float* P, UndistortArgs* A)
+{
+    if (!K || !P || !dist || ndist < 4 || ndist > 12) return ORBX_E_INVALID;
+    for (int i = 0; i < 12; i++) A->k[i] = i < ndist ? (double)dist[i] : 0.0;
+    A->fx = K[0]; A->fy = K[4]; A->cx = K[2]; A->cy = K[5];
+    A->ifx = 1. / A->fx; A->ify = 1. / A->fy;
+    for (int i = 0; i < 9; i++) A->RR[i] = (double)P[i];
+    return ORBX_OK;
+}
+
+// Frame::UndistortKeyPoints on host arrays (see include/orbx.h).  Synchronous.
+extern "C" int orbx_undistort_keypoints(orbx_matcher* m, const orbx_keypoint* kps, int n, const float* K, const float* dist, int ndist,
+                                        const float* P, orbx_keypoint* kps_un)
+{
+    if (!m || n < 0 || (n > 0 && (!kps || !kps_un))) return ORBX_E_INVALID;
+    if (n == 0) return ORBX_OK;
+    UndistortArgs A;
+    int rc = undistort_args(K, dist, ndist, P, &A);
+    if (rc) return rc;
+    if (dist[0] == 0.0f) { memcpy(kps_un, kps, sizeof(orbx_keypoint) * n); return ORBX_OK; }       // R/src/Frame.cc:723-727
+    CKM(cudaSetDevice(m->p.device));
+    if ((rc = orbx_m_gen_scratch(m, 2 * sizeof(orbx_keypoint) * (size_t)n))) return rc;
+    cudaStream_t s = m->stream;
+    orbx_keypoint* din = reinterpret_cast<orbx_keypoint*>(m->d_gen); orbx_keypoint* dout = din + n;
+    CKM(cudaMemcpyAsync(din, kps, sizeof(orbx_keypoint) * n, cudaMemcpyHostToDevice, s));
+    k_undistort<<<dim3((n + 255) / 256, 1), 256, 0, s>>>(din, nullptr, n, n, A, dout); ORBX_COUNT_LAUNCH(1);
+    CKM(cudaGetLastError());
+    CKM(cudaMemcpyAsync(kps_un, dout, sizeof(orbx_keypoint) * n, cudaMemcpyDeviceToHost, s));
+    CKM(cudaStreamSynchronize(s));
+    return ORBX_OK;
+}
+
+// The same on the keypoints an extractor holds in its result slots: d_kps_un is a DEVICE array
+// [count][orbx_extractor_max_keypoints(ex)] (mvKeysUn of every frame of the batch); asynchronous on `stream`.
+extern "C" int orbx_undistort_slots_device(orbx_extractor* ex, int first_slot, int count, const float* K, const float* dist, int ndist,
+                                           const float* P, orbx_keypoint* d_kps_un, void* stream)
+{
+    if (!ex || !d_kps_un || count <= 0) return ORBX_E_INVALID;
+    orbx_keypoint* dk; uint8_t* dd; int32_t* dn; int cap, slots;
+    int rc = orbx_extractor_results_device(ex, &dk, &dd, &dn, nullptr, &cap, &slots);
+    if (rc) return rc;
+    if (first_slot < 0 || first_slot + count > slots) return ORBX_E_INVALID;
+    UndistortArgs A;
+    if ((rc = undistort_args(K, dist, ndist, P, &A))) return rc;
+    CKM(cudaSetDevice(orbx_ex_device(ex)));
+    cudaStream_t s = stream ? (cudaStream_t)stream : orbx_ex_stream(ex);
+    if (dist[0] == 0.0f) {
+        CKM(cudaMemcpyAsync(d_kps_un, dk + (size_t)first_slot * cap, sizeof(orbx_keypoint) * (size_t)cap * count, cudaMemcpyDeviceToDevice, s));
+        return ORBX_OK;
+    }
+    k_undistort<<<dim3((cap + 255) / 256, count), 256, 0, s>>>(dk + (size_t)first_slot * cap, dn + first_slot, 0, cap, A, d_kps_un);
+    ORBX_COUNT_LAUNCH(1);
+    CKM(cudaGetLastError());
+    return ORBX_OK;
+}
 
 // generic candidate matching for the host-side searches (SearchByBoW, SearchForTriangulation, Fuse, SearchBySim3)
 extern "C" int orbx_match_candidates(orbx_matcher* m, const uint8_t* q, int nq, const uint8_t* t, int nt, const int32_t* offsets,

@@ -39,7 +39,7 @@ EXPORTS = [
     "orbx_search_by_projection",
     "orbx_stereo_band_match", "orbx_stereo_matches", "orbx_stereo_matches_batch", "orbx_stereo_matches_batch_device",
     "orbx_extract_stereo_batch",
-    "orbx_fast_segment_plan", "orbx_match_candidates", "orbx_search_by_bow", "orbx_distinctive_descriptors", "orbx_vocab_create", "orbx_vocab_destroy", "orbx_vocab_words", "orbx_vocab_word_weights",
+    "orbx_fast_segment_plan", "orbx_match_candidates", "orbx_search_by_bow", "orbx_distinctive_descriptors", "orbx_undistort_keypoints", "orbx_undistort_slots_device", "orbx_vocab_create", "orbx_vocab_destroy", "orbx_vocab_words", "orbx_vocab_word_weights",
     "orbx_bow_transform", "orbx_bow_transform_slots_device", "orbx_popc_peak",
 ]
 
@@ -115,6 +115,8 @@ def lib():
         L.orbx_search_by_bow.argtypes = [vp, i32, vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, vp, i32, f32, i32, vp, vp]
         L.orbx_fast_segment_plan.argtypes = [i32, vp, vp, vp, vp, vp]
         L.orbx_distinctive_descriptors.argtypes = [vp, vp, vp, i32, vp]
+        L.orbx_undistort_keypoints.argtypes = [vp, vp, i32, vp, vp, i32, vp, vp]
+        L.orbx_undistort_slots_device.argtypes = [vp, i32, i32, vp, vp, i32, vp, vp, vp]
         L.orbx_vocab_create.argtypes = [i32, i32, vp, vp, vp, vp, i32, vp]
         L.orbx_vocab_destroy.argtypes = [vp]; L.orbx_vocab_destroy.restype = None
         L.orbx_vocab_words.argtypes = [vp]
@@ -378,6 +380,14 @@ class ORBmatcher:
                                         _p(k2), _p(d2), _p(v2) if v2 is not None else None, len(k2), _p(n2), _p(s2), _p(f2), len(n2),
                                         self.mfNNratio, int(self.mbCheckOrientation), _p(m12), C.byref(nm)))
         return nm.value, m12
+
+    def UndistortKeyPoints(self, kps, K, dist, P):
+        """Frame::UndistortKeyPoints: cv::undistortPoints(mvKeys, K, distCoef, I, P) -> mvKeysUn"""
+        k = np.ascontiguousarray(kps, KP_DTYPE); out = np.empty_like(k)
+        Kf = np.ascontiguousarray(K, np.float32).reshape(9); Pf = np.ascontiguousarray(P, np.float32).reshape(9)
+        d = np.ascontiguousarray(dist, np.float32)
+        _check(lib().orbx_undistort_keypoints(self._h, _p(k), len(k), _p(Kf), _p(d), len(d), _p(Pf), _p(out)))
+        return out
 
     def DistinctiveDescriptors(self, desc, offsets):
         """MapPoint::ComputeDistinctiveDescriptors for a batch of map points (CSR runs of observed descriptors) -> best index per point"""

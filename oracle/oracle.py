@@ -85,6 +85,7 @@ def lib():
         L.orc_search_by_projection.restype = i32
         L.orc_stereo_band_match.argtypes = [vp, vp, i32, vp, vp, i32, vp, i32, f32, f32, vp, vp]
         L.orc_match_candidates.argtypes = [vp, i32, vp, vp, vp, vp, vp]
+        L.orc_undistort_keypoints.argtypes = [vp, i32, vp, vp, i32, vp, vp]
         L.orc_distinctive_descriptors.argtypes = [vp, vp, i32, vp]
         L.orc_search_by_bow.restype = i32
         L.orc_search_by_bow.argtypes = [i32, vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, vp, i32, f32, i32, vp]
@@ -340,3 +341,11 @@ def distinctive_descriptors(desc, offsets):
     best = np.empty(len(off) - 1, np.int32)
     lib().orc_distinctive_descriptors(_p(d), _p(off), len(off) - 1, _p(best))
     return best
+
+
+def undistort_keypoints(kps, K, dist, P):
+    k = np.ascontiguousarray(kps, KP_DTYPE); out = np.empty_like(k)
+    Kf = np.ascontiguousarray(K, np.float32).reshape(9); Pf = np.ascontiguousarray(P, np.float32).reshape(9)
+    d = np.ascontiguousarray(dist, np.float32)
+    lib().orc_undistort_keypoints(_p(k), len(k), _p(Kf), _p(d), len(d), _p(Pf), _p(out))
+    return out

@@ -1284,3 +1284,35 @@ void orc_distinctive_descriptors(const uint8_t* desc, const int32_t* offsets, in
         free(row);
     }
 }
+
+/* Frame::UndistortKeyPoints, R/src/Frame.cc:721-754; the arithmetic is cv::undistortPoints of OpenCV 4.x
+ * (modules/calib3d/src/undistort.dispatch.cpp, cvUndistortPointsInternal) with the default TermCriteria(MAX_ITER, 5, 0.01) */
+void orc_undistort_keypoints(const OrcKeyPoint* kps, int n, const float* K, const float* dist, int ndist, const float* P,
+                             OrcKeyPoint* out)
+{
+    if (ndist < 1 || dist[0] == 0.0f) { for (int i = 0; i < n; i++) out[i] = kps[i]; return; }
+    double k[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < ndist && i < 12; i++) k[i] = (double)dist[i];
+    const double fx = K[0], fy = K[4], cx = K[2], cy = K[5];
+    const double ifx = 1. / fx, ify = 1. / fy;
+    double RR[9];
+    for (int i = 0; i < 9; i++) RR[i] = (double)P[i];
+    for (int i = 0; i < n; i++) {
+        const double u = kps[i].x, v = kps[i].y;
+        double x = (u - cx) * ifx, y = (v - cy) * ify;
+        const double x0 = x, y0 = y;
+        for (int j = 0; j < 5; j++) {
+            const double r2 = x * x + y * y;
+            const double icdist = (1 + ((k[7] * r2 + k[6]) * r2 + k[5]) * r2) / (1 + ((k[4] * r2 + k[1]) * r2 + k[0]) * r2);
+            if (icdist < 0) { x = (u - cx) * ifx; y = (v - cy) * ify; break; }
+            const double deltaX = 2 * k[2] * x * y + k[3] * (r2 + 2 * x * x) + k[8] * r2 + k[9] * r2 * r2;
+            const double deltaY = k[2] * (r2 + 2 * y * y) + 2 * k[3] * x * y + k[10] * r2 + k[11] * r2 * r2;
+            x = (x0 - deltaX) * icdist;
+            y = (y0 - deltaY) * icdist;
+        }
+        const double xx = RR[0] * x + RR[1] * y + RR[2], yy = RR[3] * x + RR[4] * y + RR[5];
+        const double ww = 1. / (RR[6] * x + RR[7] * y + RR[8]);
+        out[i] = kps[i];
+        out[i].x = (float)(xx * ww); out[i].y = (float)(yy * ww);
+    }
+}

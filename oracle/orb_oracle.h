@@ -141,6 +141,13 @@ int   orc_bow_transform(const OrcVocab* v, const uint8_t* desc, int n, int level
                         int32_t* bow_words, double* bow_values,
                         int32_t* fv_nodes, int32_t* fv_start, int32_t* fv_features, int* n_fv);
 
+/* Frame::UndistortKeyPoints (R/src/Frame.cc:721-754): cv::undistortPoints(pts, K, distCoef, R = I, P = K_new) as OpenCV 4.x
+ * computes it (double arithmetic, exactly 5 fixed-point iterations of the radial-tangential model, result rounded to
+ * float).  K and P are 3x3 row-major float; dist holds ndist = 4 or 5 coefficients (k1, k2, p1, p2[, k3]).  The x / y
+ * of every keypoint is replaced, the other fields are copied.  dist[0] == 0 copies the keypoints unchanged (:723-727). */
+void  orc_undistort_keypoints(const OrcKeyPoint* kps, int n, const float* K, const float* dist, int ndist, const float* P,
+                              OrcKeyPoint* out);
+
 /* MapPoint::ComputeDistinctiveDescriptors (R/src/MapPoint.cc:448-524) for a batch of map points: the observed
  * descriptors of point p are rows offsets[p] .. offsets[p+1] of desc; best[p] = index inside that run of the descriptor
  * with the least median distance to the others (median = sorted row [(int)(0.5 * (N - 1))], the row includes the 0 on

@@ -1,0 +1,60 @@
+"""Frame::UndistortKeyPoints (R/src/Frame.cc:721-754): the oracle is pinned against cv2.undistortPoints (OpenCV 4.13) on the
+CPU; the CUDA path is compared with the oracle on the GPU (both bit for bit)."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+EUROC_K = np.array([[458.654, 0, 367.215], [0, 457.296, 248.375], [0, 0, 1]], np.float32)
+EUROC_D = np.array([-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05], np.float32)
+TUM_K = np.array([[517.306408, 0, 318.643040], [0, 516.469215, 255.313989], [0, 0, 1]], np.float32)
+TUM_D = np.array([0.262383, -0.953104, -0.005358, 0.002628, 1.163314], np.float32)
+
+
+def keypoints(n, w, h, seed):
+    rng = np.random.default_rng(seed)
+    k = np.zeros(n, O.KP_DTYPE)
+    k["x"] = rng.uniform(-20, w + 20, n).astype(np.float32); k["y"] = rng.uniform(-20, h + 20, n).astype(np.float32)
+    k["size"] = 31; k["angle"] = rng.uniform(0, 360, n).astype(np.float32); k["response"] = rng.integers(7, 200, n)
+    k["octave"] = rng.integers(0, 8, n); k["class_id"] = -1
+    return k
+
+
+@pytest.mark.parametrize("K,D,w,h", [(EUROC_K, EUROC_D, 752, 480), (TUM_K, TUM_D, 640, 480)], ids=["euroc_4coef", "tum_5coef"])
+def test_oracle_pinned_to_cv2(K, D, w, h):
+    cv2 = pytest.importorskip("cv2")
+    kps = keypoints(20000, w, h, 1)
+    P = K.copy(); P[0, 0] *= np.float32(0.9); P[0, 2] += np.float32(3.5)          # a new camera matrix different from K
+    for Pm in (K, P):
+        ref = cv2.undistortPoints(np.stack([kps["x"], kps["y"]], 1).reshape(-1, 1, 2), K, D, None, Pm).reshape(-1, 2)
+        got = O.undistort_keypoints(kps, K, D, Pm)
+        np.testing.assert_array_equal(got["x"], ref[:, 0]); np.testing.assert_array_equal(got["y"], ref[:, 1])
+        for f in ("size", "angle", "response", "octave", "class_id"):
+            np.testing.assert_array_equal(got[f], kps[f])
+    same = O.undistort_keypoints(kps, K, np.zeros(4, np.float32), K)              # mDistCoef[0] == 0: mvKeysUn = mvKeys
+    assert same.tobytes() == kps.tobytes()
+
+
+@pytest.mark.gpu
+def test_gpu_matches_oracle_host_and_slots():
+    import torch
+    from multi_orbslam3_b200 import orbx, synth
+    m = orbx.ORBmatcher(0.9, True, max_keypoints=1024)
+    for K, D, w, h in ((EUROC_K, EUROC_D, 752, 480), (TUM_K, TUM_D, 640, 480)):
+        kps = keypoints(50000, w, h, 2)
+        got = m.UndistortKeyPoints(kps, K, D, K)
+        assert got.tobytes() == O.undistort_keypoints(kps, K, D, K).tobytes()
+    assert m.UndistortKeyPoints(kps, K, np.zeros(5, np.float32), K).tobytes() == kps.tobytes()
+    # on the result slots of an extractor (mvKeysUn of a batch stays on the device)
+    W, H, B = 752, 480, 3
+    ex = orbx.ORBextractor(1000, 1.2, 8, 20, 7, max_width=W, max_height=H, max_batch=B)
+    res = ex.extract_batch(synth.rects_stream(W, H, B, seed=4))
+    d_un = torch.zeros((B, ex.cap, 7), dtype=torch.float32, device="cuda")
+    Kf = np.ascontiguousarray(EUROC_K.reshape(9)); Df = np.ascontiguousarray(EUROC_D)
+    orbx._check(orbx.lib().orbx_undistort_slots_device(ex._h, 0, B, orbx._p(Kf), orbx._p(Df), 4, orbx._p(Kf), d_un.data_ptr(), None))
+    ex.sync()
+    torch.cuda.synchronize()
+    h_un = d_un.cpu().numpy().view(np.uint8).reshape(B, ex.cap, 28).view(orbx.KP_DTYPE).reshape(B, ex.cap)
+    for i, (_, k, _) in enumerate(res):
+        assert h_un[i, :len(k)].tobytes() == O.undistort_keypoints(k, EUROC_K, EUROC_D, EUROC_K).tobytes()
+    ex.close(); m.close()
