@@ -264,6 +264,16 @@ int  orbx_undistort_keypoints(orbx_matcher* m, const orbx_keypoint* kps, int n, 
 int  orbx_undistort_slots_device(orbx_extractor* ex, int first_slot, int count, const float* K, const float* dist, int ndist,
                                  const float* P, orbx_keypoint* d_kps_un, void* stream);
 
+/* KF.msg wire format of the keypoints: msg/CvKeyPoint.msg as ROS1 serialises it, 15 packed bytes per
+ * keypoint (float32 x, float32 y, uint8 size, float32 angle, uint8 response, int8 octave); Converter::toCvKeyPointMsg /
+ * fromCvKeyPointMsg (R/src/Converter.cc:218-244) called from KeyFrame.cc:1430 and :1929.  size / response are truncated
+ * to 8 bits, class_id is not transmitted (-1 after unpacking).  Descriptor.msg is the 32-byte descriptor row itself.
+ * Host forms: synchronous.  _slot_..._device: one result slot of an extractor into a DEVICE buffer of
+ * orbx_extractor_max_keypoints(ex) * 15 bytes, asynchronous on `stream`. */
+int  orbx_keypoints_to_msg(orbx_matcher* m, const orbx_keypoint* kps, int n, uint8_t* msg15);
+int  orbx_keypoints_from_msg(orbx_matcher* m, const uint8_t* msg15, int n, orbx_keypoint* kps);
+int  orbx_slot_keypoints_to_msg_device(orbx_extractor* ex, int slot, uint8_t* d_msg15, void* stream);
+
 /* MapPoint::ComputeDistinctiveDescriptors (R/src/MapPoint.cc:448-524) for a batch of map points, as
  * LocalMapping runs it for every point a new keyframe observes: the observed descriptors of point p are rows
  * offsets[p] .. offsets[p+1] of desc ([total][32], gathered by the caller from the observing keyframes); best[p] receives

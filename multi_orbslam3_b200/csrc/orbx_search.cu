@@ -207,7 +207,90 @@ __global__ void __launch_bounds__(256) k_undistort(const orbx_keypoint* in, cons
     out[(size_t)slot * cap + i] = kp;
 }
 
+// ---- KF.msg wire format of the keypoints (msg/CvKeyPoint.msg, R/src/Converter.cc:218-244): 15 packed bytes ----
+__global__ void k_kp_to_msg(const orbx_keypoint* kps, const int32_t* n_dev, int n_fixed, uint8_t* msg)
+{
+    const int n = n_dev ? *n_dev : n_fixed;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const orbx_keypoint k = kps[i];
+    uint8_t* o = msg + (size_t)i * 15;
+    const unsigned x = __float_as_uint(k.x), y = __float_as_uint(k.y), a = __float_as_uint(k.angle);
+    o[0] = x; o[1] = x >> 8; o[2] = x >> 16; o[3] = x >> 24;
+    o[4] = y; o[5] = y >> 8; o[6] = y >> 16; o[7] = y >> 24;
+    o[8] = (uint8_t)(int)k.size;                          // (u_int8_t)kp.size, :228
+    o[9] = a; o[10] = a >> 8; o[11] = a >> 16; o[12] = a >> 24;
+    o[13] = (uint8_t)(int)k.response;                     // (u_int8_t)kp.response, :227
+    o[14] = (uint8_t)(int8_t)k.octave;
+}
+
+__global__ void k_kp_from_msg(const uint8_t* msg, int n, orbx_keypoint* kps)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint8_t* o = msg + (size_t)i * 15;
+    orbx_keypoint k;
+    k.x = __uint_as_float((unsigned)o[0] | ((unsigned)o[1] << 8) | ((unsigned)o[2] << 16) | ((unsigned)o[3] << 24));
+    k.y = __uint_as_float((unsigned)o[4] | ((unsigned)o[5] << 8) | ((unsigned)o[6] << 16) | ((unsigned)o[7] << 24));
+    k.size = (float)o[8];
+    k.angle = __uint_as_float((unsigned)o[9] | ((unsigned)o[10] << 8) | ((unsigned)o[11] << 16) | ((unsigned)o[12] << 24));
+    k.response = (float)o[13]; k.octave = (int)(int8_t)o[14]; k.class_id = -1;
+    kps[i] = k;
+}
+
 }  // namespace
+
+// Keypoints -> KF.msg records (15 bytes each) and back; host pointers, synchronous.
+extern "C" int orbx_keypoints_to_msg(orbx_matcher* m, const orbx_keypoint* kps, int n, uint8_t* msg15)
+{
+    if (!m || n < 0 || (n > 0 && (!kps || !msg15))) return ORBX_E_INVALID;
+    if (n == 0) return ORBX_OK;
+    CKM(cudaSetDevice(m->p.device));
+    int rc = orbx_m_gen_scratch(m, (sizeof(orbx_keypoint) + 16) * (size_t)n);
+    if (rc) return rc;
+    cudaStream_t s = m->stream;
+    orbx_keypoint* dk = reinterpret_cast<orbx_keypoint*>(m->d_gen); uint8_t* dm = reinterpret_cast<uint8_t*>(dk + n);
+    CKM(cudaMemcpyAsync(dk, kps, sizeof(orbx_keypoint) * n, cudaMemcpyHostToDevice, s));
+    k_kp_to_msg<<<(n + 255) / 256, 256, 0, s>>>(dk, nullptr, n, dm); ORBX_COUNT_LAUNCH(1);
+    CKM(cudaGetLastError());
+    CKM(cudaMemcpyAsync(msg15, dm, (size_t)15 * n, cudaMemcpyDeviceToHost, s));
+    CKM(cudaStreamSynchronize(s));
+    return ORBX_OK;
+}
+
+extern "C" int orbx_keypoints_from_msg(orbx_matcher* m, const uint8_t* msg15, int n, orbx_keypoint* kps)
+{
+    if (!m || n < 0 || (n > 0 && (!kps || !msg15))) return ORBX_E_INVALID;
+    if (n == 0) return ORBX_OK;
+    CKM(cudaSetDevice(m->p.device));
+    int rc = orbx_m_gen_scratch(m, (sizeof(orbx_keypoint) + 16) * (size_t)n);
+    if (rc) return rc;
+    cudaStream_t s = m->stream;
+    orbx_keypoint* dk = reinterpret_cast<orbx_keypoint*>(m->d_gen); uint8_t* dm = reinterpret_cast<uint8_t*>(dk + n);
+    CKM(cudaMemcpyAsync(dm, msg15, (size_t)15 * n, cudaMemcpyHostToDevice, s));
+    k_kp_from_msg<<<(n + 255) / 256, 256, 0, s>>>(dm, n, dk); ORBX_COUNT_LAUNCH(1);
+    CKM(cudaGetLastError());
+    CKM(cudaMemcpyAsync(kps, dk, sizeof(orbx_keypoint) * n, cudaMemcpyDeviceToHost, s));
+    CKM(cudaStreamSynchronize(s));
+    return ORBX_OK;
+}
+
+// The keypoints of one result slot of an extractor as KF.msg records, written to a DEVICE buffer of
+// orbx_extractor_max_keypoints(ex) * 15 bytes (the descriptors of the slot are already the 32-byte rows of Descriptor.msg);
+// asynchronous on `stream`.
+extern "C" int orbx_slot_keypoints_to_msg_device(orbx_extractor* ex, int slot, uint8_t* d_msg15, void* stream)
+{
+    if (!ex || !d_msg15) return ORBX_E_INVALID;
+    orbx_keypoint* dk; uint8_t* dd; int32_t* dn; int cap, slots;
+    int rc = orbx_extractor_results_device(ex, &dk, &dd, &dn, nullptr, &cap, &slots);
+    if (rc) return rc;
+    if (slot < 0 || slot >= slots) return ORBX_E_INVALID;
+    CKM(cudaSetDevice(orbx_ex_device(ex)));
+    cudaStream_t s = stream ? (cudaStream_t)stream : orbx_ex_stream(ex);
+    k_kp_to_msg<<<(cap + 255) / 256, 256, 0, s>>>(dk + (size_t)slot * cap, dn + slot, 0, d_msg15); ORBX_COUNT_LAUNCH(1);
+    CKM(cudaGetLastError());
+    return ORBX_OK;
+}
 
 static int undistort_args(const float* K, const float* dist, int ndist, const float* P, UndistortArgs* A)
 {

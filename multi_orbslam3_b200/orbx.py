@@ -39,7 +39,8 @@ EXPORTS = [
     "orbx_search_by_projection",
     "orbx_stereo_band_match", "orbx_stereo_matches", "orbx_stereo_matches_batch", "orbx_stereo_matches_batch_device",
     "orbx_extract_stereo_batch",
-    "orbx_fast_segment_plan", "orbx_match_candidates", "orbx_search_by_bow", "orbx_distinctive_descriptors", "orbx_undistort_keypoints", "orbx_undistort_slots_device", "orbx_vocab_create", "orbx_vocab_destroy", "orbx_vocab_words", "orbx_vocab_word_weights",
+    "orbx_fast_segment_plan", "orbx_match_candidates", "orbx_search_by_bow", "orbx_distinctive_descriptors", "orbx_undistort_keypoints", "orbx_undistort_slots_device",
+    "orbx_keypoints_to_msg", "orbx_keypoints_from_msg", "orbx_slot_keypoints_to_msg_device", "orbx_vocab_create", "orbx_vocab_destroy", "orbx_vocab_words", "orbx_vocab_word_weights",
     "orbx_bow_transform", "orbx_bow_transform_slots_device", "orbx_popc_peak",
 ]
 
@@ -116,6 +117,9 @@ def lib():
         L.orbx_fast_segment_plan.argtypes = [i32, vp, vp, vp, vp, vp]
         L.orbx_distinctive_descriptors.argtypes = [vp, vp, vp, i32, vp]
         L.orbx_undistort_keypoints.argtypes = [vp, vp, i32, vp, vp, i32, vp, vp]
+        L.orbx_keypoints_to_msg.argtypes = [vp, vp, i32, vp]
+        L.orbx_keypoints_from_msg.argtypes = [vp, vp, i32, vp]
+        L.orbx_slot_keypoints_to_msg_device.argtypes = [vp, i32, vp, vp]
         L.orbx_undistort_slots_device.argtypes = [vp, i32, i32, vp, vp, i32, vp, vp, vp]
         L.orbx_vocab_create.argtypes = [i32, i32, vp, vp, vp, vp, i32, vp]
         L.orbx_vocab_destroy.argtypes = [vp]; L.orbx_vocab_destroy.restype = None
@@ -380,6 +384,17 @@ class ORBmatcher:
                                         _p(k2), _p(d2), _p(v2) if v2 is not None else None, len(k2), _p(n2), _p(s2), _p(f2), len(n2),
                                         self.mfNNratio, int(self.mbCheckOrientation), _p(m12), C.byref(nm)))
         return nm.value, m12
+
+    def KeyPointsToMsg(self, kps):
+        """Converter::toCvKeyPointMsg for an array of keypoints -> [n, 15] bytes (ROS1 layout of CvKeyPoint.msg)"""
+        k = np.ascontiguousarray(kps, KP_DTYPE); out = np.empty((len(k), 15), np.uint8)
+        _check(lib().orbx_keypoints_to_msg(self._h, _p(k), len(k), _p(out)))
+        return out
+
+    def KeyPointsFromMsg(self, msg):
+        mm = np.ascontiguousarray(msg, np.uint8).reshape(-1, 15); out = np.empty(len(mm), KP_DTYPE)
+        _check(lib().orbx_keypoints_from_msg(self._h, _p(mm), len(mm), _p(out)))
+        return out
 
     def UndistortKeyPoints(self, kps, K, dist, P):
         """Frame::UndistortKeyPoints: cv::undistortPoints(mvKeys, K, distCoef, I, P) -> mvKeysUn"""

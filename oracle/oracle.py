@@ -86,6 +86,8 @@ def lib():
         L.orc_stereo_band_match.argtypes = [vp, vp, i32, vp, vp, i32, vp, i32, f32, f32, vp, vp]
         L.orc_match_candidates.argtypes = [vp, i32, vp, vp, vp, vp, vp]
         L.orc_undistort_keypoints.argtypes = [vp, i32, vp, vp, i32, vp, vp]
+        L.orc_keypoints_to_msg.argtypes = [vp, i32, vp]
+        L.orc_keypoints_from_msg.argtypes = [vp, i32, vp]
         L.orc_distinctive_descriptors.argtypes = [vp, vp, i32, vp]
         L.orc_search_by_bow.restype = i32
         L.orc_search_by_bow.argtypes = [i32, vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, vp, i32, f32, i32, vp]
@@ -348,4 +350,16 @@ def undistort_keypoints(kps, K, dist, P):
     Kf = np.ascontiguousarray(K, np.float32).reshape(9); Pf = np.ascontiguousarray(P, np.float32).reshape(9)
     d = np.ascontiguousarray(dist, np.float32)
     lib().orc_undistort_keypoints(_p(k), len(k), _p(Kf), _p(d), len(d), _p(Pf), _p(out))
+    return out
+
+
+def keypoints_to_msg(kps):
+    k = np.ascontiguousarray(kps, KP_DTYPE); out = np.empty((len(k), 15), np.uint8)
+    lib().orc_keypoints_to_msg(_p(k), len(k), _p(out))
+    return out
+
+
+def keypoints_from_msg(msg):
+    m = np.ascontiguousarray(msg, np.uint8).reshape(-1, 15); out = np.empty(len(m), KP_DTYPE)
+    lib().orc_keypoints_from_msg(_p(m), len(m), _p(out))
     return out

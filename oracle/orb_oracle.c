@@ -1316,3 +1316,24 @@ void orc_undistort_keypoints(const OrcKeyPoint* kps, int n, const float* K, cons
         out[i].x = (float)(xx * ww); out[i].y = (float)(yy * ww);
     }
 }
+
+/* Converter::toCvKeyPointMsg / fromCvKeyPointMsg, R/src/Converter.cc:218-244, in ROS1 wire layout (15 bytes per keypoint) */
+void orc_keypoints_to_msg(const OrcKeyPoint* kps, int n, uint8_t* msg)
+{
+    for (int i = 0; i < n; i++) {
+        uint8_t* o = msg + (size_t)i * 15;
+        const uint8_t size = (uint8_t)(int32_t)kps[i].size, response = (uint8_t)(int32_t)kps[i].response;
+        const int8_t octave = (int8_t)kps[i].octave;
+        memcpy(o, &kps[i].x, 4); memcpy(o + 4, &kps[i].y, 4); o[8] = size; memcpy(o + 9, &kps[i].angle, 4);
+        o[13] = response; o[14] = (uint8_t)octave;
+    }
+}
+
+void orc_keypoints_from_msg(const uint8_t* msg, int n, OrcKeyPoint* kps)
+{
+    for (int i = 0; i < n; i++) {
+        const uint8_t* o = msg + (size_t)i * 15;
+        memcpy(&kps[i].x, o, 4); memcpy(&kps[i].y, o + 4, 4); memcpy(&kps[i].angle, o + 9, 4);
+        kps[i].size = (float)o[8]; kps[i].response = (float)o[13]; kps[i].octave = (int8_t)o[14]; kps[i].class_id = -1;
+    }
+}

@@ -148,6 +148,13 @@ int   orc_bow_transform(const OrcVocab* v, const uint8_t* desc, int n, int level
 void  orc_undistort_keypoints(const OrcKeyPoint* kps, int n, const float* K, const float* dist, int ndist, const float* P,
                               OrcKeyPoint* out);
 
+/* KF.msg wire format of the keypoints (R/../msg/CvKeyPoint.msg; Converter::toCvKeyPointMsg / fromCvKeyPointMsg,
+ * R/src/Converter.cc:218-244; used by KeyFrame.cc:1430 and :1929): ROS1 serialises the record without padding as
+ * float32 x, float32 y, uint8 size, float32 angle, uint8 response, int8 octave = 15 bytes; size and response are
+ * truncated to 8 bits on the way out, class_id is not transmitted (-1 after unpacking). */
+void  orc_keypoints_to_msg(const OrcKeyPoint* kps, int n, uint8_t* msg15);
+void  orc_keypoints_from_msg(const uint8_t* msg15, int n, OrcKeyPoint* kps);
+
 /* MapPoint::ComputeDistinctiveDescriptors (R/src/MapPoint.cc:448-524) for a batch of map points: the observed
  * descriptors of point p are rows offsets[p] .. offsets[p+1] of desc; best[p] = index inside that run of the descriptor
  * with the least median distance to the others (median = sorted row [(int)(0.5 * (N - 1))], the row includes the 0 on

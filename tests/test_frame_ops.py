@@ -1,4 +1,4 @@
-"""Frame::UndistortKeyPoints (R/src/Frame.cc:721-754): the oracle is pinned against cv2.undistortPoints (OpenCV 4.13) on the
+"""Frame-level helpers.  Frame::UndistortKeyPoints (R/src/Frame.cc:721-754): the oracle is pinned against cv2.undistortPoints (OpenCV 4.13) on the
 CPU; the CUDA path is compared with the oracle on the GPU (both bit for bit)."""
 import numpy as np
 import pytest
@@ -57,4 +57,44 @@ def test_gpu_matches_oracle_host_and_slots():
     h_un = d_un.cpu().numpy().view(np.uint8).reshape(B, ex.cap, 28).view(orbx.KP_DTYPE).reshape(B, ex.cap)
     for i, (_, k, _) in enumerate(res):
         assert h_un[i, :len(k)].tobytes() == O.undistort_keypoints(k, EUROC_K, EUROC_D, EUROC_K).tobytes()
+    ex.close(); m.close()
+
+
+MSG_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "u1"), ("angle", "<f4"), ("response", "u1"), ("octave", "i1")])   # packed: 15 bytes
+
+
+def test_kf_msg_keypoint_records_oracle():
+    """KF.msg keypoint records (msg/CvKeyPoint.msg in ROS1 wire layout): the oracle against a packed numpy dtype."""
+    assert MSG_DTYPE.itemsize == 15
+    kps = keypoints(3000, 752, 480, 5)
+    kps["size"] = np.float32(31) * np.float32(1.2) ** kps["octave"]
+    msg = O.keypoints_to_msg(kps)
+    rec = msg.reshape(-1).view(MSG_DTYPE)
+    np.testing.assert_array_equal(rec["x"], kps["x"]); np.testing.assert_array_equal(rec["angle"], kps["angle"])
+    np.testing.assert_array_equal(rec["size"], kps["size"].astype(np.int32).astype(np.uint8))
+    np.testing.assert_array_equal(rec["response"], kps["response"].astype(np.int32).astype(np.uint8))
+    np.testing.assert_array_equal(rec["octave"], kps["octave"].astype(np.int8))
+    back = O.keypoints_from_msg(msg)
+    np.testing.assert_array_equal(back["x"], kps["x"]); np.testing.assert_array_equal(back["y"], kps["y"])
+    np.testing.assert_array_equal(back["size"], np.floor(kps["size"])); np.testing.assert_array_equal(back["response"], kps["response"])
+    assert (back["class_id"] == -1).all() and (back["octave"] == kps["octave"]).all()
+
+
+@pytest.mark.gpu
+def test_kf_msg_keypoint_records_gpu():
+    import torch
+    from multi_orbslam3_b200 import orbx, synth
+    m = orbx.ORBmatcher(0.9, True, max_keypoints=1024)
+    kps = keypoints(5000, 752, 480, 6)
+    kps["size"] = np.float32(31) * np.float32(1.2) ** kps["octave"]
+    msg = m.KeyPointsToMsg(kps)
+    np.testing.assert_array_equal(msg, O.keypoints_to_msg(kps))
+    assert m.KeyPointsFromMsg(msg).tobytes() == O.keypoints_from_msg(msg).tobytes()
+    W, H = 640, 480
+    ex = orbx.ORBextractor(1000, 1.2, 8, 20, 7, max_width=W, max_height=H)
+    _, k, _ = ex(synth.rects_frame(W, H, 3), None, (0, 0))
+    d = torch.zeros(ex.cap * 15, dtype=torch.uint8, device="cuda")
+    orbx._check(orbx.lib().orbx_slot_keypoints_to_msg_device(ex._h, 0, d.data_ptr(), None))
+    ex.sync(); torch.cuda.synchronize()
+    np.testing.assert_array_equal(d.cpu().numpy()[:len(k) * 15].reshape(-1, 15), O.keypoints_to_msg(k))
     ex.close(); m.close()
