@@ -472,6 +472,10 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "orbx":
         args.warmup = 3
+    global W, H, METRIC
+    if args.workload == "c4":
+        W, H = 640, 480
+        METRIC = "ORB frames/sec (extract+match) at 640x480, 1000 kp"
     if args.impl == "reference":
         return reference_arm(args)
 
@@ -497,11 +501,6 @@ def main():
         return stereo_bench(args, world, rank, local)
     if args.workload == "bow":
         return bow_bench(args, world, rank, local)
-    global W, H, METRIC
-    if args.workload == "c4":
-        W, H = 640, 480
-        METRIC = "ORB frames/sec (extract+match) at 640x480, 1000 kp"
-
     B = args.batch
     ex = orbx.ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, max_width=W, max_height=H, max_batch=B, device=local)
     m = orbx.ORBmatcher(NNRATIO, True, max_keypoints=ex.cap, max_batch=B, device=local)
