@@ -207,6 +207,22 @@ typedef struct orbx_proj_query {
 int  orbx_search_by_projection(orbx_matcher* m, int mode, const orbx_proj_query* q, const uint8_t* qdesc, int nq,
                                const orbx_keypoint* k2, const uint8_t* d2, const float* uright2, int n2,
                                const float bounds[4], int32_t* assigned, float nnratio, int check_ori, int* nmatches);
+/* The same machinery with the knobs of the reference's other projection searches:
+ *   mode 0 + max_dist: acceptance bound of the best distance: ORBX_TH_HIGH for :1970-2186; floor(TH_LOW * ratioHamming) for
+ *       the Sim3 overloads SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th, ratioHamming) (:473-586, :588-700), where
+ *       assigned[] is preset from vpMatched and check_ori = 0; ORBdist for the relocalisation overload
+ *       SearchByProjection(Frame&, KeyFrame*, sAlreadyFound, th, ORBdist) (:2188-2310);
+ *   inv_level_sigma2[nlevels] + chi2: per-candidate gate of Fuse (:1497-1505), a candidate is skipped when
+ *       |q - kp|^2 * invSigma2[octave] (float) > chi2 (5.99 mono, 7.8 stereo); chi2 = 0 disables it;
+ *   mode 3: the best candidate of every query on its own, no bookkeeping between queries (Fuse :1395-1742, where the map
+ *       update that follows stays on the host): best_idx / best_dist [nq] (-1 / 256 without a candidate), assigned unused;
+ *       *nmatches = queries with a candidate. */
+int  orbx_search_by_projection_ex(orbx_matcher* m, int mode, const orbx_proj_query* q, const uint8_t* qdesc, int nq,
+                                  const orbx_keypoint* k2, const uint8_t* d2, const float* uright2, int n2,
+                                  const float bounds[4], int32_t* assigned, float nnratio, int check_ori, int max_dist,
+                                  const float* inv_level_sigma2, int nlevels, double chi2,
+                                  int32_t* best_idx, int32_t* best_dist, int* nmatches);
+
 
 /* Generic candidate matching for the searches whose candidate gathering stays on the host: SearchByBoW
  * (R/src/ORBmatcher.cc:269-471, 819-959), SearchForTriangulation (:961-1394), Fuse (:1395-1742), SearchBySim3 (:1744-1968).

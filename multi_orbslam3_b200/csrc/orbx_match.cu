@@ -278,6 +278,9 @@ __global__ void __launch_bounds__(CAND_WARPS * 32, 6) k_window_candidates(WinBuf
                 }
                 const float dx = __fsub_rn(rec.x, Q.u), dy = __fsub_rn(rec.y, Q.v);
                 if (!(fabsf(dx) < Q.r && fabsf(dy) < Q.r)) ok = false;
+                // Fuse (ORBmatcher.cc:1497-1505): e2 * invSigma2 (float) against the double chi-square bound
+                if (ok && W.gate_chi2 > 0.0 &&
+                    (double)__fmul_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), W.inv_sigma2[min(oct, ORBX_MAX_LEVELS - 1)]) > W.gate_chi2) ok = false;
                 // stereo gate (ORBmatcher.cc:93-98 / :2049-2055): not order dependent, applied here
                 if (ok && P.uright2) {
                     const float ur2 = P.uright2[i2];
@@ -317,7 +320,7 @@ __global__ void __launch_bounds__(CAND_WARPS * 32, 6) k_window_candidates(WinBuf
 
 // mode 2 = SearchForInitialization, 0 / 1 = SearchByProjection overloads (see orbx.h)
 // out: mode 2 -> matches12 [P][K] (+ prev_xy update when prev != null); modes 0/1 -> assigned [P][K] (in/out)
-__global__ void __launch_bounds__(32) k_window_resolve(WinBufs W, int mode, float nnratio, int check_ori,
+__global__ void __launch_bounds__(32) k_window_resolve(WinBufs W, int mode, float nnratio, int check_ori, int max_dist,
                                                      int32_t* out, int32_t* nmatches, float* prev_xy)
 {
     extern __shared__ int s_mem[];
@@ -401,8 +404,8 @@ __global__ void __launch_bounds__(32) k_window_resolve(WinBufs W, int mode, floa
                 }
             }
         } else if (mode == 0) {
-            // best starts at 256 and must be <= TH_HIGH (:2038, :2068)
-            if (d0 <= ORBX_TH_HIGH) {
+            // best starts at 256 and must be <= TH_HIGH (:2038, :2068), or the caller's bound for the other overloads
+            if (d0 <= max_dist) {
                 const int i2 = e0 & 0xFFFF;
                 if (lane == 0) {
                     res[i2] = i;
@@ -715,15 +718,26 @@ static WinBufs shifted_pairs(const orbx_matcher* m, int pb)
     return W;
 }
 
+// mode 3: the independent best of every query is the first entry of its top-2 record
+__global__ void k_best_from_top2(WinBufs W, int nq, int32_t* best_idx, int32_t* best_dist)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    const unsigned e = W.q_cnt[i] > 0 ? W.top2[i].x : 0xFFFFFFFFu;
+    best_idx[i] = e == 0xFFFFFFFFu ? -1 : (int)(e & 0xFFFF);
+    best_dist[i] = e == 0xFFFFFFFFu ? 256 : (int)((e >> 16) & 0x1FF);
+}
+
 static int run_window(orbx_matcher* m, const WinBufs& W, int npairs, int nq_max, int mode, float nnratio, int check_ori,
-                      int32_t* d_out, int32_t* d_nm, float* d_prev, cudaStream_t s)
+                      int32_t* d_out, int32_t* d_nm, float* d_prev, cudaStream_t s, int max_dist = ORBX_TH_HIGH)
 {
     int npad = 1; while (npad < m->K) npad <<= 1;
     CKM(cudaMemsetAsync(W.pool_used, 0, sizeof(int) * npairs, s));
     k_grid_build<<<npairs, GRID_NT, sizeof(uint32_t) * npad, s>>>(W, npad); ORBX_COUNT_LAUNCH(1);
     dim3 cg((nq_max + CAND_WARPS - 1) / CAND_WARPS, npairs);
     if (nq_max > 0) { k_window_candidates<<<cg, CAND_WARPS * 32, 0, s>>>(W); ORBX_COUNT_LAUNCH(1); }
-    k_window_resolve<<<npairs, 32, 2 * m->K * sizeof(int), s>>>(W, mode, nnratio, check_ori, d_out, d_nm, d_prev); ORBX_COUNT_LAUNCH(1);
+    if (mode == 3) { CKM(cudaGetLastError()); return ORBX_OK; }
+    k_window_resolve<<<npairs, 32, 2 * m->K * sizeof(int), s>>>(W, mode, nnratio, check_ori, max_dist, d_out, d_nm, d_prev); ORBX_COUNT_LAUNCH(1);
     CKM(cudaGetLastError());
     return ORBX_OK;
 }
@@ -767,41 +781,69 @@ extern "C" int orbx_search_for_initialization(orbx_matcher* m, const orbx_keypoi
     return ORBX_OK;
 }
 
-extern "C" int orbx_search_by_projection(orbx_matcher* m, int mode, const orbx_proj_query* q, const uint8_t* qdesc, int nq,
-                                         const orbx_keypoint* k2, const uint8_t* d2, const float* uright2, int n2,
-                                         const float bounds[4], int32_t* assigned, float nnratio, int check_ori, int* nmatches)
+extern "C" int orbx_search_by_projection_ex(orbx_matcher* m, int mode, const orbx_proj_query* q, const uint8_t* qdesc, int nq,
+                                            const orbx_keypoint* k2, const uint8_t* d2, const float* uright2, int n2,
+                                            const float bounds[4], int32_t* assigned, float nnratio, int check_ori, int max_dist,
+                                            const float* inv_level_sigma2, int nlevels, double chi2,
+                                            int32_t* best_idx, int32_t* best_dist, int* nmatches)
 {
-    if (!m || (mode != 0 && mode != 1) || nq < 0 || n2 < 0 || nq > m->K || n2 > m->K || !bounds ||
-        (nq > 0 && (!q || !qdesc)) || (n2 > 0 && (!k2 || !d2 || !assigned))) {
+    const bool indep = mode == 3;
+    if (!m || (mode != 0 && mode != 1 && mode != 3) || nq < 0 || n2 < 0 || nq > m->K || n2 > m->K || !bounds ||
+        (nq > 0 && (!q || !qdesc)) || (n2 > 0 && (!k2 || !d2)) || (!indep && n2 > 0 && !assigned) || (indep && nq > 0 && (!best_idx || !best_dist)) ||
+        (chi2 > 0 && (!inv_level_sigma2 || nlevels < 1 || nlevels > ORBX_MAX_LEVELS))) {
         orbx_set_error("%s%s", "orbx_search_by_projection: invalid arguments / more keypoints than max_keypoints", "");
         return ORBX_E_INVALID;
     }
     if (nmatches) *nmatches = 0;
+    if (indep) for (int i = 0; i < nq; i++) { best_idx[i] = -1; best_dist[i] = 256; }
     if (nq == 0 || n2 == 0) return ORBX_OK;
     CKM(cudaSetDevice(m->p.device));
     cudaStream_t s = m->stream;
     set_bounds(m, bounds);
+    m->W.gate_chi2 = chi2 > 0 ? chi2 : 0.0;
+    for (int l = 0; l < ORBX_MAX_LEVELS; l++) m->W.inv_sigma2[l] = (chi2 > 0 && l < nlevels) ? inv_level_sigma2[l] : 0.f;
     CKM(cudaMemcpyAsync(m->W.q, q, sizeof(orbx_proj_query) * nq, cudaMemcpyHostToDevice, s));
     CKM(cudaMemcpyAsync(m->d_qdesc, qdesc, (size_t)32 * nq, cudaMemcpyHostToDevice, s));
     CKM(cudaMemcpyAsync(m->d_k2, k2, sizeof(orbx_keypoint) * n2, cudaMemcpyHostToDevice, s));
     CKM(cudaMemcpyAsync(m->d_d2, d2, (size_t)32 * n2, cudaMemcpyHostToDevice, s));
     if (uright2) CKM(cudaMemcpyAsync(m->d_uright, uright2, sizeof(float) * n2, cudaMemcpyHostToDevice, s));
-    CKM(cudaMemcpyAsync(m->d_out, assigned, sizeof(int32_t) * n2, cudaMemcpyHostToDevice, s));
-    CKM(cudaMemcpyAsync(m->d_out2, assigned, sizeof(int32_t) * n2, cudaMemcpyHostToDevice, s));
+    if (!indep) {
+        CKM(cudaMemcpyAsync(m->d_out, assigned, sizeof(int32_t) * n2, cudaMemcpyHostToDevice, s));
+        CKM(cudaMemcpyAsync(m->d_out2, assigned, sizeof(int32_t) * n2, cudaMemcpyHostToDevice, s));
+    }
     PairDesc pd{};
     pd.k1 = nullptr; pd.d1 = nullptr; pd.k2 = m->d_k2; pd.d2 = m->d_d2; pd.uright2 = uright2 ? m->d_uright : nullptr;
     pd.q = m->W.q; pd.qdesc = m->d_qdesc; pd.n1 = nq; pd.n2 = n2; pd.nq = nq;
     CKM(cudaMemcpyAsync(m->W.pairs, &pd, sizeof(pd), cudaMemcpyHostToDevice, s));
-    int rc = run_window(m, m->W, 1, nq, mode, nnratio, check_ori, m->d_out, m->d_nm, nullptr, s);
+    int rc = run_window(m, m->W, 1, nq, mode, nnratio, check_ori, m->d_out, m->d_nm, nullptr, s, max_dist);
+    m->W.gate_chi2 = 0.0;
     if (rc) return rc;
-    k_count_new_assigned<<<1, 256, 0, s>>>(m->d_out2, m->d_out, n2, m->d_nm); ORBX_COUNT_LAUNCH(1);
     int nm = 0;
-    CKM(cudaMemcpyAsync(assigned, m->d_out, sizeof(int32_t) * n2, cudaMemcpyDeviceToHost, s));
-    CKM(cudaMemcpyAsync(&nm, m->d_nm, sizeof(int), cudaMemcpyDeviceToHost, s));
-    rc = m_check_err(m, s);
-    if (rc) return rc;
+    if (indep) {
+        k_best_from_top2<<<(nq + 255) / 256, 256, 0, s>>>(m->W, nq, m->d_knn_idx, m->d_knn_dist); ORBX_COUNT_LAUNCH(1);
+        CKM(cudaMemcpyAsync(best_idx, m->d_knn_idx, sizeof(int32_t) * nq, cudaMemcpyDeviceToHost, s));
+        CKM(cudaMemcpyAsync(best_dist, m->d_knn_dist, sizeof(int32_t) * nq, cudaMemcpyDeviceToHost, s));
+        rc = m_check_err(m, s);
+        if (rc) return rc;
+        for (int i = 0; i < nq; i++) nm += best_idx[i] >= 0;
+    } else {
+        k_count_new_assigned<<<1, 256, 0, s>>>(m->d_out2, m->d_out, n2, m->d_nm); ORBX_COUNT_LAUNCH(1);
+        CKM(cudaMemcpyAsync(assigned, m->d_out, sizeof(int32_t) * n2, cudaMemcpyDeviceToHost, s));
+        CKM(cudaMemcpyAsync(&nm, m->d_nm, sizeof(int), cudaMemcpyDeviceToHost, s));
+        rc = m_check_err(m, s);
+        if (rc) return rc;
+    }
     if (nmatches) *nmatches = nm;
     return ORBX_OK;
+}
+
+extern "C" int orbx_search_by_projection(orbx_matcher* m, int mode, const orbx_proj_query* q, const uint8_t* qdesc, int nq,
+                                         const orbx_keypoint* k2, const uint8_t* d2, const float* uright2, int n2,
+                                         const float bounds[4], int32_t* assigned, float nnratio, int check_ori, int* nmatches)
+{
+    if (mode != 0 && mode != 1) return ORBX_E_INVALID;
+    return orbx_search_by_projection_ex(m, mode, q, qdesc, nq, k2, d2, uright2, n2, bounds, assigned, nnratio, check_ori, ORBX_TH_HIGH,
+                                        nullptr, 0, 0.0, nullptr, nullptr, nmatches);
 }
 
 static int match_slots_impl(orbx_matcher* m, orbx_extractor* ex, const int32_t* a, const int32_t* b, int npairs, int pair_base,

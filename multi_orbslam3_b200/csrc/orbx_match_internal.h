@@ -111,6 +111,8 @@ struct WinBufs {
     uint2* top2;                  // [P][K]   best / second pool entry of every query by (distance, list rank), 0xFFFFFFFF = none
     int K, POOL;
     float minX, maxX, minY, maxY, wInv, hInv;
+    double gate_chi2;             // > 0: per-candidate reprojection gate (Fuse), with the per-level 1 / sigma^2 below
+    float inv_sigma2[ORBX_MAX_LEVELS];
     unsigned* err;
 };
 

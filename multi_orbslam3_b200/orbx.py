@@ -39,7 +39,7 @@ EXPORTS = [
     "orbx_search_by_projection",
     "orbx_stereo_band_match", "orbx_stereo_matches", "orbx_stereo_matches_batch", "orbx_stereo_matches_batch_device",
     "orbx_extract_stereo_batch",
-    "orbx_fast_segment_plan", "orbx_match_candidates", "orbx_search_by_bow", "orbx_distinctive_descriptors", "orbx_undistort_keypoints", "orbx_undistort_slots_device",
+    "orbx_fast_segment_plan", "orbx_search_by_projection_ex", "orbx_match_candidates", "orbx_search_by_bow", "orbx_distinctive_descriptors", "orbx_undistort_keypoints", "orbx_undistort_slots_device",
     "orbx_keypoints_to_msg", "orbx_keypoints_from_msg", "orbx_slot_keypoints_to_msg_device", "orbx_vocab_create", "orbx_vocab_destroy", "orbx_vocab_words", "orbx_vocab_word_weights",
     "orbx_bow_transform", "orbx_bow_transform_slots_device", "orbx_popc_peak",
 ]
@@ -115,6 +115,7 @@ def lib():
         L.orbx_match_candidates.argtypes = [vp, vp, i32, vp, i32, vp, vp, vp, vp]
         L.orbx_search_by_bow.argtypes = [vp, i32, vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, vp, i32, f32, i32, vp, vp]
         L.orbx_fast_segment_plan.argtypes = [i32, vp, vp, vp, vp, vp]
+        L.orbx_search_by_projection_ex.argtypes = [vp, i32, vp, vp, i32, vp, vp, vp, i32, vp, vp, f32, i32, i32, vp, i32, C.c_double, vp, vp, vp]
         L.orbx_distinctive_descriptors.argtypes = [vp, vp, vp, i32, vp]
         L.orbx_undistort_keypoints.argtypes = [vp, vp, i32, vp, vp, i32, vp, vp]
         L.orbx_keypoints_to_msg.argtypes = [vp, vp, i32, vp]
@@ -363,6 +364,22 @@ class ORBmatcher:
         _check(lib().orbx_stereo_matches(self._h, ex_left._h, ex_right._h, slot_l, slot_r, frame_l, frame_r, float(mb), float(mbf),
                                          _p(ur), _p(dp), _p(sd), cap, C.byref(n)))
         return ur[:n.value].copy(), dp[:n.value].copy(), sd[:n.value].copy()
+
+    def SearchByProjectionEx(self, mode, queries, qdesc, k2, d2, bounds, assigned=None, uright=None, max_dist=100, inv_sigma2=None, chi2=0.0):
+        """mode 0 / 1 with an acceptance bound, or mode 3 = independent best per query (Fuse); see include/orbx.h.
+        -> (count, assigned) for modes 0 / 1, (count, best_idx, best_dist) for mode 3"""
+        q = np.ascontiguousarray(queries, PROJQ_DTYPE); qd = np.ascontiguousarray(qdesc, np.uint8).reshape(-1, 32)
+        k2 = np.ascontiguousarray(k2, KP_DTYPE); d2 = np.ascontiguousarray(d2, np.uint8).reshape(-1, 32)
+        a = np.full(len(k2), -1, np.int32) if assigned is None else np.ascontiguousarray(assigned, np.int32).copy()
+        ur = None if uright is None else np.ascontiguousarray(uright, np.float32)
+        sg = None if inv_sigma2 is None else np.ascontiguousarray(inv_sigma2, np.float32)
+        bb = np.array(bounds, np.float32); nm = C.c_int(0)
+        bi = np.empty(len(q), np.int32); bd = np.empty(len(q), np.int32)
+        _check(lib().orbx_search_by_projection_ex(self._h, int(mode), _p(q), _p(qd), len(q), _p(k2), _p(d2), _p(ur) if ur is not None else None,
+                                                  len(k2), _p(bb), _p(a), self.mfNNratio, int(self.mbCheckOrientation), int(max_dist),
+                                                  _p(sg) if sg is not None else None, 0 if sg is None else len(sg), float(chi2),
+                                                  _p(bi), _p(bd), C.byref(nm)))
+        return (nm.value, bi, bd) if mode == 3 else (nm.value, a)
 
     def SearchByBoW(self, mode, k1, d1, valid1, fv1, k2, d2, valid2, fv2):
         """ORBmatcher::SearchByBoW: mode 0 = (KeyFrame, Frame), mode 1 = (KeyFrame, KeyFrame); fv = (node ids, feature lists)

@@ -889,12 +889,14 @@ int orc_search_for_initialization(const OrcKeyPoint* k1, const uint8_t* d1, int 
 
 /* SearchByProjection, mono/left-image branches, on flat arrays.
  * mode 0: R/src/ORBmatcher.cc:1970-2091 + :2163-2185;  mode 1: R/src/ORBmatcher.cc:44-143. */
-int orc_search_by_projection(int mode, const OrcProjQuery* q, const uint8_t* qdesc, int nq,
-                             const OrcKeyPoint* k2, const uint8_t* d2, const float* uright2, int n2,
-                             float minX, float maxX, float minY, float maxY,
-                             int32_t* assigned, float nnratio, int check_ori)
+int orc_search_by_projection_ex(int mode, const OrcProjQuery* q, const uint8_t* qdesc, int nq,
+                                const OrcKeyPoint* k2, const uint8_t* d2, const float* uright2, int n2,
+                                float minX, float maxX, float minY, float maxY,
+                                int32_t* assigned, float nnratio, int check_ori, int max_dist,
+                                const float* inv_sigma2, double chi2, int32_t* best_idx, int32_t* best_dist)
 {
     int nmatches = 0;
+    if (mode == 3) for (int i = 0; i < nq; i++) { best_idx[i] = -1; best_dist[i] = 256; }
     OrcGrid* g = orc_grid_build(k2, n2, minX, maxX, minY, maxY);
     int32_t* cand = (int32_t*)malloc(sizeof(int32_t) * (n2 > 0 ? n2 : 1));
     int* histIdx = (int*)malloc(sizeof(int) * (nq > 0 ? nq : 1));
@@ -908,7 +910,12 @@ int orc_search_by_projection(int mode, const OrcProjQuery* q, const uint8_t* qde
         int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
         for (int c = 0; c < nc; c++) {
             int i2 = cand[c];
-            if (assigned[i2] >= 0) continue;
+            if (mode != 3 && assigned[i2] >= 0) continue;
+            if (inv_sigma2 && chi2 > 0) {                  /* Fuse: reprojection error gate, ORBmatcher.cc:1497-1505 */
+                const float ex = q[i].u - k2[i2].x, ey = q[i].v - k2[i2].y;
+                const float e2 = ex * ex + ey * ey;
+                if ((double)(e2 * inv_sigma2[k2[i2].octave]) > chi2) continue;       /* float product against the double literal 5.99 */
+            }
             if (uright2 && uright2[i2] > 0) {
                 const float er = fabsf(q[i].ur - uright2[i2]);
                 if (er > q[i].r) continue;
@@ -922,7 +929,8 @@ int orc_search_by_projection(int mode, const OrcProjQuery* q, const uint8_t* qde
                 bestLevel2 = k2[i2].octave; bestDist2 = dist;
             }
         }
-        if (bestDist <= TH_HIGH) {
+        if (mode == 3) { best_idx[i] = bestIdx; best_dist[i] = bestDist; if (bestIdx >= 0) nmatches++; continue; }
+        if (bestDist <= max_dist) {
             if (mode == 1) {
                 if (bestLevel == bestLevel2 && bestDist > nnratio * bestDist2) continue;
                 assigned[bestIdx] = i;
@@ -949,6 +957,15 @@ int orc_search_by_projection(int mode, const OrcProjQuery* q, const uint8_t* qde
     free(cand); free(histIdx); free(histBin);
     orc_grid_destroy(g);
     return nmatches;
+}
+
+int orc_search_by_projection(int mode, const OrcProjQuery* q, const uint8_t* qdesc, int nq,
+                             const OrcKeyPoint* k2, const uint8_t* d2, const float* uright2, int n2,
+                             float minX, float maxX, float minY, float maxY,
+                             int32_t* assigned, float nnratio, int check_ori)
+{
+    return orc_search_by_projection_ex(mode, q, qdesc, nq, k2, d2, uright2, n2, minX, maxX, minY, maxY, assigned, nnratio, check_ori,
+                                       TH_HIGH, NULL, 0.0, NULL, NULL);
 }
 
 /* Frame::ComputeStereoMatches, descriptor search, R/src/Frame.cc:785-868 */

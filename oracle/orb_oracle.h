@@ -99,6 +99,19 @@ int   orc_search_by_projection(int mode, const OrcProjQuery* q, const uint8_t* q
                                float minX, float maxX, float minY, float maxY,
                                int32_t* assigned, float nnratio, int check_ori);
 
+/* The same with the knobs the other projection searches of the reference use:
+ *   max_dist  acceptance threshold of mode 0 (TH_HIGH for :1970-2186; TH_LOW * ratioHamming for the Sim3 overloads :473-700,
+ *             ORBdist for the relocalisation overload :2188-2310);
+ *   inv_sigma2 / chi2  per-candidate reprojection gate of Fuse (:1497-1505): skip when |q - kp|^2 * inv_sigma2[octave] > chi2
+ *             (the product in float, the comparison against the double literal 5.99); NULL / 0 = no gate;
+ *   mode 3    independent best per query, no bookkeeping (Fuse :1395-1742): best_idx / best_dist [nq] (-1 / 256 if none);
+ *             returns the number of queries with a candidate. */
+int   orc_search_by_projection_ex(int mode, const OrcProjQuery* q, const uint8_t* qdesc, int nq,
+                                  const OrcKeyPoint* k2, const uint8_t* d2, const float* uright2, int n2,
+                                  float minX, float maxX, float minY, float maxY,
+                                  int32_t* assigned, float nnratio, int check_ori, int max_dist,
+                                  const float* inv_sigma2, double chi2, int32_t* best_idx, int32_t* best_dist);
+
 /* Frame::ComputeStereoMatches descriptor part (Frame.cc:785-868): per left keypoint the best right
  * index and distance (dist starts at TH_HIGH=100; idx -1 if none < 100). nrows = level-0 rows. */
 void  orc_stereo_band_match(const OrcKeyPoint* kl, const uint8_t* dl, int nl,

@@ -328,3 +328,49 @@ def test_extract_stereo_batch_host_pipeline():
                 np.testing.assert_array_equal(o["uright"][j, :n], rur)
                 np.testing.assert_array_equal(o["depth"][j, :n], rdp)
     exl.close(); exr.close(); m.close()
+
+
+def _proj_setup(seed=71):
+    W, H = 752, 480
+    st = synth.rects_stream(W, H, 2, seed=seed)
+    e = O.Extractor(1000, 1.2, 8, 20, 7)
+    _, k1, d1 = e(st[0], (0, 0)); _, k2, d2 = e(st[1], (0, 0))
+    q = np.zeros(len(k1), O.PROJQ_DTYPE)
+    q["u"] = k1["x"] + np.float32(3); q["v"] = k1["y"] + np.float32(2)
+    q["r"] = np.float32(4.0) * np.asarray(e.scale, np.float32)[k1["octave"]]
+    q["minl"] = k1["octave"] - 1; q["maxl"] = k1["octave"]
+    q["ur"] = q["u"]; q["angle"] = k1["angle"]; q["valid"] = (np.arange(len(k1)) % 9 != 0).astype(np.int32)
+    return W, H, e, k1, d1, k2, d2, q
+
+
+def test_projection_search_with_distance_bound():
+    """The Sim3 / relocalisation SearchByProjection overloads = mode 0 with their own acceptance bound and a preset
+    'already matched' table (ORBmatcher.cc:473-700, :2188-2310)."""
+    W, H, e, k1, d1, k2, d2, q = _proj_setup()
+    pre = np.full(len(k2), -1, np.int32); pre[::17] = len(k1)                 # keypoints that already have a map point
+    for max_dist, ori in ((50, False), (25, False), (100, True), (64, True)):
+        m = orbx.ORBmatcher(0.9, ori, max_keypoints=2048)
+        n, a = m.SearchByProjectionEx(0, q, d1, k2, d2, (0, W, 0, H), assigned=pre, max_dist=max_dist)
+        rn, ra = O.search_by_projection_ex(0, q, d1, k2, d2, (0, W, 0, H), assigned=pre, nnratio=0.9, check_ori=ori, max_dist=max_dist)
+        assert n == rn and n > 50
+        np.testing.assert_array_equal(a, ra)
+        m.close()
+    # independent check of the rule with the grid query of the oracle: nothing above the bound is accepted
+    n25, a25 = O.search_by_projection_ex(0, q, d1, k2, d2, (0, W, 0, H), assigned=pre, check_ori=False, max_dist=25)
+    for i2 in np.nonzero((a25 >= 0) & (a25 < len(k1)))[0]:
+        assert O.hamming256(d1[a25[i2]], d2[i2]) <= 25
+
+
+def test_fuse_style_independent_best_with_chi2_gate():
+    """Fuse (ORBmatcher.cc:1395-1742): best candidate of every projected map point on its own, candidates gated by the
+    reprojection error e2 * invSigma2[level] > 5.99; compared with the oracle and with a brute-force numpy restatement
+    built on the oracle's GetFeaturesInArea."""
+    W, H, e, k1, d1, k2, d2, q = _proj_setup(seed=72)
+    inv_sigma2 = np.asarray(e.inv_sigma2, np.float32)
+    m = orbx.ORBmatcher(0.9, True, max_keypoints=2048)
+    for chi2, sg in ((5.99, inv_sigma2), (0.0, None)):
+        n, bi, bd = m.SearchByProjectionEx(3, q, d1, k2, d2, (0, W, 0, H), inv_sigma2=sg, chi2=chi2)
+        rn, rbi, rbd = O.search_by_projection_ex(3, q, d1, k2, d2, (0, W, 0, H), inv_sigma2=sg, chi2=chi2)
+        assert n == rn and n > 100
+        np.testing.assert_array_equal(bi, rbi); np.testing.assert_array_equal(bd, rbd)
+    m.close()

@@ -197,3 +197,53 @@ class TestPinAgainstCv2:
         idx, dist = O.bf_knn2(q, t)
         np.testing.assert_array_equal(idx, np.array([[m.trainIdx for m in r] for r in knn]))
         np.testing.assert_array_equal(dist, np.array([[int(m.distance) for m in r] for r in knn]))
+
+
+def test_projection_search_ex_against_python_rules():
+    """orc_search_by_projection_ex: mode 3 (Fuse-style independent best with the chi-square gate) and the mode 0 distance
+    bound, re-derived in Python from the oracle's own GetFeaturesInArea lists."""
+    from multi_orbslam3_b200 import synth
+    W, H = 480, 360
+    st = synth.rects_stream(W, H, 2, seed=81)
+    e = O.Extractor(500, 1.2, 8, 20, 7)
+    _, k1, d1 = e(st[0], (0, 0)); _, k2, d2 = e(st[1], (0, 0))
+    scale = np.asarray(e.scale, np.float32); inv_sigma2 = np.asarray(e.inv_sigma2, np.float32)
+    q = np.zeros(len(k1), O.PROJQ_DTYPE)
+    q["u"] = k1["x"] + np.float32(3); q["v"] = k1["y"] + np.float32(2)
+    q["r"] = np.float32(4.0) * scale[k1["octave"]]
+    q["minl"] = k1["octave"] - 1; q["maxl"] = k1["octave"]
+    q["valid"] = (np.arange(len(k1)) % 7 != 0).astype(np.int32)
+    n, bi, bd = O.search_by_projection_ex(3, q, d1, k2, d2, (0, W, 0, H), inv_sigma2=inv_sigma2, chi2=5.99)
+    cnt = 0
+    for i in range(len(q)):
+        best, bidx = 256, -1
+        if q["valid"][i]:
+            for i2 in O.features_in_area(k2, (0, W, 0, H), q["u"][i], q["v"][i], q["r"][i], int(q["minl"][i]), int(q["maxl"][i])):
+                ex = np.float32(q["u"][i] - k2["x"][i2]); ey = np.float32(q["v"][i] - k2["y"][i2])
+                e2 = np.float32(np.float32(ex * ex) + np.float32(ey * ey))
+                if float(np.float32(e2 * inv_sigma2[k2["octave"][i2]])) > 5.99:
+                    continue
+                d = O.hamming256(d1[i], d2[i2])
+                if d < best:
+                    best, bidx = d, int(i2)
+        assert (bi[i], bd[i]) == (bidx, best), i
+        cnt += bidx >= 0
+    assert n == cnt and cnt > 20
+    # mode 0 with a bound: sequential 'taken' rule, best only
+    pre = np.full(len(k2), -1, np.int32)
+    n0, a0 = O.search_by_projection_ex(0, q, d1, k2, d2, (0, W, 0, H), assigned=pre, check_ori=False, max_dist=30)
+    taken = np.full(len(k2), -1, np.int32)
+    for i in range(len(q)):
+        if not q["valid"][i]:
+            continue
+        best, bidx = 256, -1
+        for i2 in O.features_in_area(k2, (0, W, 0, H), q["u"][i], q["v"][i], q["r"][i], int(q["minl"][i]), int(q["maxl"][i])):
+            if taken[i2] >= 0:
+                continue
+            d = O.hamming256(d1[i], d2[i2])
+            if d < best:
+                best, bidx = d, int(i2)
+        if best <= 30:
+            taken[bidx] = i
+    np.testing.assert_array_equal(a0, taken)
+    assert n0 == (taken >= 0).sum()
