@@ -314,6 +314,23 @@ int  orbx_search_by_bow(orbx_matcher* m, int mode,
                         const int32_t* fv2_nodes, const int32_t* fv2_start, const int32_t* fv2_feat, int nfv2,
                         float nnratio, int check_ori, int32_t* matches12, int* nmatches);
 
+/* ORBmatcher::SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, bOnlyStereo, bCoarse) (R/src/ORBmatcher.cc:961-1202) for
+ * pinhole cameras without a second camera, as LocalMapping::CreateNewMapPoints calls it for every neighbour keyframe.
+ * free* = the feature has no MapPoint; stereo* (may be NULL) = mvuRight >= 0; FeatureVectors as CSR tables sorted by node id.
+ * A candidate needs distance <= TH_LOW, (mono-mono) at least 100 * scale_factors2[octave2] squared pixels from the epipole
+ * (ep_x, ep_y) and, unless coarse, to lie within 3.84 * level_sigma2_2[octave2] of the epipolar line of F12 (3x3 row
+ * major, Pinhole::epipolarConstrain, CameraModels/Pinhole.cpp:121-143); smallest distance wins, among equals the last in
+ * list order.  The reference never marks keyframe-2 features as taken in this function, so queries do not interact.
+ * matches12[i1] = index in keyframe 2 or -1.  Host pointers, synchronous. */
+int  orbx_search_for_triangulation(orbx_matcher* m,
+                                   const orbx_keypoint* k1, const uint8_t* d1, const uint8_t* free1, const uint8_t* stereo1, int n1,
+                                   const int32_t* fv1_nodes, const int32_t* fv1_start, const int32_t* fv1_feat, int nfv1,
+                                   const orbx_keypoint* k2, const uint8_t* d2, const uint8_t* free2, const uint8_t* stereo2, int n2,
+                                   const int32_t* fv2_nodes, const int32_t* fv2_start, const int32_t* fv2_feat, int nfv2,
+                                   const float* F12, float ep_x, float ep_y, const float* scale_factors2,
+                                   const float* level_sigma2_2, int nlevels, int only_stereo, int coarse, int check_ori,
+                                   int32_t* matches12, int* nmatches);
+
 /* ---- bag of words: DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB> as Frame::ComputeBoW
  * (R/src/Frame.cc:712-719) and KeyFrame::ComputeBoW (R/src/KeyFrame.cc:168-176) use it ---- */
 typedef struct orbx_vocab orbx_vocab;

@@ -124,6 +124,75 @@ __global__ void __launch_bounds__(256) k_bow_finish(BowArgs A, int32_t* nmatches
     if (threadIdx.x == 0) *nmatches = A.hist[ORBX_HISTO_LENGTH] - removed;
 }
 
+// ---- ORBmatcher::SearchForTriangulation (R/src/ORBmatcher.cc:961-1202), pinhole, no second camera ----
+// Same node-by-node structure as SearchByBoW, but the queries of this fork do not interact (vbMatched2 is never set), so a
+// warp handles one (node, keyframe-1 feature) at a time without claims: lanes score the node's free keyframe-2 features
+// (distance <= TH_LOW, epipole distance, epipolar line), the best is the smallest distance and among equals the LAST in
+// list order (the reference's `dist > bestDist` test lets a later equal candidate replace an earlier one).
+struct TriArgs {
+    BowArgs B;                         // feature sets, FeatureVectors, outputs (valid1 / valid2 = "has no MapPoint")
+    const uint8_t* stereo1; const uint8_t* stereo2;
+    float F[9]; float ep_x, ep_y;
+    float scale2[ORBX_MAX_LEVELS], sigma2_2[ORBX_MAX_LEVELS];
+    int only_stereo, coarse;
+};
+
+__global__ void __launch_bounds__(256) k_triangulation_match(TriArgs T)
+{
+    const BowArgs& A = T.B;
+    const int lane = threadIdx.x & 31;
+    const int w = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (w >= A.nfv1) return;
+    const int node = A.fv1_nodes[w];
+    int lo = 0, hi = A.nfv2;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (A.fv2_nodes[mid] < node) lo = mid + 1; else hi = mid; }
+    if (lo >= A.nfv2 || A.fv2_nodes[lo] != node) return;
+    const int a0 = A.fv1_start[w], a1 = A.fv1_start[w + 1], b0 = A.fv2_start[lo], b1 = A.fv2_start[lo + 1];
+    for (int ia = a0; ia < a1; ia++) {
+        const int i1 = A.fv1_feat[ia];
+        if (!A.valid1[i1]) continue;
+        const bool st1 = T.stereo1 ? T.stereo1[i1] != 0 : false;
+        if (T.only_stereo && !st1) continue;
+        const orbx_keypoint kp1 = A.k1[i1];
+        // epipolar line of kp1 in image 2: l = x1' F12 (Pinhole.cpp:129-131), float operations in the reference's order
+        const float la = __fadd_rn(__fadd_rn(__fmul_rn(kp1.x, T.F[0]), __fmul_rn(kp1.y, T.F[3])), T.F[6]);
+        const float lb = __fadd_rn(__fadd_rn(__fmul_rn(kp1.x, T.F[1]), __fmul_rn(kp1.y, T.F[4])), T.F[7]);
+        const float lc = __fadd_rn(__fadd_rn(__fmul_rn(kp1.x, T.F[2]), __fmul_rn(kp1.y, T.F[5])), T.F[8]);
+        const float den = __fadd_rn(__fmul_rn(la, la), __fmul_rn(lb, lb));
+        const uint4 q0 = reinterpret_cast<const uint4*>(A.d1)[2 * i1], q1 = reinterpret_cast<const uint4*>(A.d1)[2 * i1 + 1];
+        unsigned best = 0xFFFFFFFFu;                   // dist << 16 | (0xFFFF - rank): smallest distance, then the latest candidate
+        for (int ib = b0 + lane; ib < b1; ib += 32) {
+            const int i2 = A.fv2_feat[ib];
+            if (!A.valid2[i2]) continue;
+            const bool st2 = T.stereo2 ? T.stereo2[i2] != 0 : false;
+            if (T.only_stereo && !st2) continue;
+            const int d = hamming256(q0, q1, reinterpret_cast<const uint4*>(A.d2)[2 * i2], reinterpret_cast<const uint4*>(A.d2)[2 * i2 + 1]);
+            if (d > ORBX_TH_LOW) continue;
+            const orbx_keypoint kp2 = A.k2[i2];
+            const int oct = min(max(kp2.octave, 0), ORBX_MAX_LEVELS - 1);
+            if (!st1 && !st2) {
+                const float ex = __fsub_rn(T.ep_x, kp2.x), ey = __fsub_rn(T.ep_y, kp2.y);
+                if (__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)) < __fmul_rn(100.0f, T.scale2[oct])) continue;
+            }
+            if (!T.coarse) {
+                if (den == 0.0f) continue;
+                const float num = __fadd_rn(__fadd_rn(__fmul_rn(la, kp2.x), __fmul_rn(lb, kp2.y)), lc);
+                const float dsqr = __fdiv_rn(__fmul_rn(num, num), den);
+                if (!((double)dsqr < __dmul_rn(3.84, (double)T.sigma2_2[oct]))) continue;
+            }
+            const unsigned key = ((unsigned)d << 16) | (unsigned)(0xFFFF - (ib - b0));
+            best = min(best, key);
+        }
+        best = __reduce_min_sync(0xffffffffu, best);
+        if (best != 0xFFFFFFFFu && lane == 0) {
+            const int i2 = A.fv2_feat[b0 + (0xFFFF - (int)(best & 0xFFFF))];
+            A.matches12[i1] = i2;
+            if (A.check_ori) { const int bin = rot_bin(kp1.angle, A.k2[i2].angle); A.bin_of[i1] = (uint8_t)bin; atomicAdd(&A.hist[bin], 1); }
+            atomicAdd(&A.hist[ORBX_HISTO_LENGTH], 1);
+        }
+    }
+}
+
 // ---- MapPoint::ComputeDistinctiveDescriptors (R/src/MapPoint.cc:448-524), batched over map points ----
 // One warp per map point.  For observation i the lanes compute its distances to all observations (kept in registers for
 // up to 256 of them, recomputed beyond), and the median of the row (its (N-1)/2-th smallest value, the 0 of the diagonal
@@ -381,27 +450,25 @@ extern "C" int orbx_match_candidates(orbx_matcher* m, const uint8_t* q, int nq, 
 }
 
 // ORBmatcher::SearchByBoW on flat arrays (see include/orbx.h).  Host pointers, synchronous.
-extern "C" int orbx_search_by_bow(orbx_matcher* m, int mode,
-                                  const orbx_keypoint* k1, const uint8_t* d1, const uint8_t* valid1, int n1,
-                                  const int32_t* fv1_nodes, const int32_t* fv1_start, const int32_t* fv1_feat, int nfv1,
-                                  const orbx_keypoint* k2, const uint8_t* d2, const uint8_t* valid2, int n2,
-                                  const int32_t* fv2_nodes, const int32_t* fv2_start, const int32_t* fv2_feat, int nfv2,
-                                  float nnratio, int check_ori, int32_t* matches12, int* nmatches)
+// validates the two feature sets + FeatureVectors, uploads them and fills BowArgs; `extra` more bytes are reserved behind
+// the block (returned in *d_extra).  who = name for the error messages.
+static int bow_stage(orbx_matcher* m, const char* who,
+                     const orbx_keypoint* k1, const uint8_t* d1, const uint8_t* valid1, int n1,
+                     const int32_t* fv1_nodes, const int32_t* fv1_start, const int32_t* fv1_feat, int nfv1,
+                     const orbx_keypoint* k2, const uint8_t* d2, const uint8_t* valid2, int n2,
+                     const int32_t* fv2_nodes, const int32_t* fv2_start, const int32_t* fv2_feat, int nfv2,
+                     size_t extra, BowArgs* out, uint8_t** d_extra)
 {
-    if (!m || (mode != 0 && mode != 1) || n1 < 0 || n2 < 0 || n2 > 65535 || nfv1 < 0 || nfv2 < 0 || !matches12) return ORBX_E_INVALID;
-    if (nmatches) *nmatches = 0;
-    for (int i = 0; i < n1; i++) matches12[i] = -1;
-    if (n1 == 0 || n2 == 0 || nfv1 == 0 || nfv2 == 0) return ORBX_OK;
     if (!k1 || !d1 || !valid1 || !k2 || !d2 || !fv1_nodes || !fv1_start || !fv1_feat || !fv2_nodes || !fv2_start || !fv2_feat) return ORBX_E_INVALID;
     const int nf1 = fv1_start[nfv1], nf2 = fv2_start[nfv2];
     if (nf1 < 0 || nf2 < 0 || fv1_start[0] != 0 || fv2_start[0] != 0) return ORBX_E_INVALID;
-    for (int i = 0; i < nfv1; i++) if (fv1_start[i] > fv1_start[i + 1] || (i && fv1_nodes[i - 1] >= fv1_nodes[i])) { orbx_set_error("%s%s", "orbx_search_by_bow: FeatureVector 1 must be sorted by node id", ""); return ORBX_E_INVALID; }
-    for (int i = 0; i < nfv2; i++) if (fv2_start[i] > fv2_start[i + 1] || (i && fv2_nodes[i - 1] >= fv2_nodes[i])) { orbx_set_error("%s%s", "orbx_search_by_bow: FeatureVector 2 must be sorted by node id", ""); return ORBX_E_INVALID; }
-    for (int i = 0; i < nf1; i++) if ((unsigned)fv1_feat[i] >= (unsigned)n1) { orbx_set_error("%s%s", "orbx_search_by_bow: feature index out of range", ""); return ORBX_E_INVALID; }
-    for (int i = 0; i < nf2; i++) if ((unsigned)fv2_feat[i] >= (unsigned)n2) { orbx_set_error("%s%s", "orbx_search_by_bow: feature index out of range", ""); return ORBX_E_INVALID; }
+    for (int i = 0; i < nfv1; i++) if (fv1_start[i] > fv1_start[i + 1] || (i && fv1_nodes[i - 1] >= fv1_nodes[i])) { orbx_set_error("%s%s", who, ": FeatureVector 1 must be sorted by node id"); return ORBX_E_INVALID; }
+    for (int i = 0; i < nfv2; i++) if (fv2_start[i] > fv2_start[i + 1] || (i && fv2_nodes[i - 1] >= fv2_nodes[i])) { orbx_set_error("%s%s", who, ": FeatureVector 2 must be sorted by node id"); return ORBX_E_INVALID; }
+    for (int i = 0; i < nf1; i++) if ((unsigned)fv1_feat[i] >= (unsigned)n1) { orbx_set_error("%s%s", who, ": feature index out of range"); return ORBX_E_INVALID; }
+    for (int i = 0; i < nf2; i++) if ((unsigned)fv2_feat[i] >= (unsigned)n2) { orbx_set_error("%s%s", who, ": feature index out of range"); return ORBX_E_INVALID; }
     CKM(cudaSetDevice(m->p.device));
     cudaStream_t s = m->stream;
-    // one scratch block: [k1][d1][valid1][k2][d2][valid2][fv tables][outputs]
+    // one scratch block: [k1][d1][valid1][k2][d2][valid2][fv tables][outputs][extra]
     size_t off = 0;
     auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
     const size_t o_k1 = take(sizeof(orbx_keypoint) * n1), o_d1 = take((size_t)32 * n1), o_v1 = take(n1);
@@ -409,6 +476,7 @@ extern "C" int orbx_search_by_bow(orbx_matcher* m, int mode,
     const size_t o_n1 = take(sizeof(int32_t) * nfv1), o_s1 = take(sizeof(int32_t) * (nfv1 + 1)), o_f1 = take(sizeof(int32_t) * (nf1 + 1));
     const size_t o_n2 = take(sizeof(int32_t) * nfv2), o_s2 = take(sizeof(int32_t) * (nfv2 + 1)), o_f2 = take(sizeof(int32_t) * (nf2 + 1));
     const size_t o_m = take(sizeof(int32_t) * n1), o_c = take(n2), o_b = take(n1), o_h = take(sizeof(int32_t) * (ORBX_HISTO_LENGTH + 2));
+    const size_t o_x = take(extra);
     { const int rcs = orbx_m_gen_scratch(m, off); if (rcs) return rcs; }
     uint8_t* B = m->d_gen;
     CKM(cudaMemcpyAsync(B + o_k1, k1, sizeof(orbx_keypoint) * n1, cudaMemcpyHostToDevice, s));
@@ -426,25 +494,87 @@ extern "C" int orbx_search_by_bow(orbx_matcher* m, int mode,
     CKM(cudaMemsetAsync(B + o_m, 0xFF, sizeof(int32_t) * n1, s));
     CKM(cudaMemsetAsync(B + o_c, 0, n2, s));
     CKM(cudaMemsetAsync(B + o_h, 0, sizeof(int32_t) * (ORBX_HISTO_LENGTH + 2), s));
-    BowArgs A;
-    A.mode = mode;
+    BowArgs& A = *out;
+    A.mode = 0;
     A.k1 = reinterpret_cast<const orbx_keypoint*>(B + o_k1); A.d1 = B + o_d1; A.valid1 = B + o_v1; A.n1 = n1;
     A.fv1_nodes = reinterpret_cast<const int32_t*>(B + o_n1); A.fv1_start = reinterpret_cast<const int32_t*>(B + o_s1);
     A.fv1_feat = reinterpret_cast<const int32_t*>(B + o_f1); A.nfv1 = nfv1;
     A.k2 = reinterpret_cast<const orbx_keypoint*>(B + o_k2); A.d2 = B + o_d2; A.valid2 = valid2 ? B + o_v2 : nullptr; A.n2 = n2;
     A.fv2_nodes = reinterpret_cast<const int32_t*>(B + o_n2); A.fv2_start = reinterpret_cast<const int32_t*>(B + o_s2);
     A.fv2_feat = reinterpret_cast<const int32_t*>(B + o_f2); A.nfv2 = nfv2;
-    A.nnratio = nnratio; A.check_ori = check_ori;
+    A.nnratio = 0.f; A.check_ori = 0;
     A.matches12 = reinterpret_cast<int32_t*>(B + o_m); A.claimed2 = B + o_c; A.bin_of = B + o_b; A.hist = reinterpret_cast<int32_t*>(B + o_h);
-    k_bow_match<<<(nfv1 + 7) / 8, 256, 0, s>>>(A); ORBX_COUNT_LAUNCH(1);
+    if (d_extra) *d_extra = B + o_x;
+    return ORBX_OK;
+}
+
+// rotation filter + result download shared by the node-based searches
+static int bow_finish(orbx_matcher* m, const BowArgs& A, int32_t* matches12, int* nmatches)
+{
+    cudaStream_t s = m->stream;
     k_bow_finish<<<1, 256, 0, s>>>(A, A.hist + ORBX_HISTO_LENGTH + 1); ORBX_COUNT_LAUNCH(1);
     CKM(cudaGetLastError());
     int nm = 0;
-    CKM(cudaMemcpyAsync(matches12, A.matches12, sizeof(int32_t) * n1, cudaMemcpyDeviceToHost, s));
+    CKM(cudaMemcpyAsync(matches12, A.matches12, sizeof(int32_t) * A.n1, cudaMemcpyDeviceToHost, s));
     CKM(cudaMemcpyAsync(&nm, A.hist + ORBX_HISTO_LENGTH + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     CKM(cudaStreamSynchronize(s));
     if (nmatches) *nmatches = nm;
     return ORBX_OK;
+}
+
+extern "C" int orbx_search_by_bow(orbx_matcher* m, int mode,
+                                  const orbx_keypoint* k1, const uint8_t* d1, const uint8_t* valid1, int n1,
+                                  const int32_t* fv1_nodes, const int32_t* fv1_start, const int32_t* fv1_feat, int nfv1,
+                                  const orbx_keypoint* k2, const uint8_t* d2, const uint8_t* valid2, int n2,
+                                  const int32_t* fv2_nodes, const int32_t* fv2_start, const int32_t* fv2_feat, int nfv2,
+                                  float nnratio, int check_ori, int32_t* matches12, int* nmatches)
+{
+    if (!m || (mode != 0 && mode != 1) || n1 < 0 || n2 < 0 || n2 > 65535 || nfv1 < 0 || nfv2 < 0 || !matches12) return ORBX_E_INVALID;
+    if (nmatches) *nmatches = 0;
+    for (int i = 0; i < n1; i++) matches12[i] = -1;
+    if (n1 == 0 || n2 == 0 || nfv1 == 0 || nfv2 == 0) return ORBX_OK;
+    BowArgs A;
+    int rc = bow_stage(m, "orbx_search_by_bow", k1, d1, valid1, n1, fv1_nodes, fv1_start, fv1_feat, nfv1,
+                       k2, d2, valid2, n2, fv2_nodes, fv2_start, fv2_feat, nfv2, 0, &A, nullptr);
+    if (rc) return rc;
+    A.mode = mode; A.nnratio = nnratio; A.check_ori = check_ori;
+    k_bow_match<<<(nfv1 + 7) / 8, 256, 0, m->stream>>>(A); ORBX_COUNT_LAUNCH(1);
+    return bow_finish(m, A, matches12, nmatches);
+}
+
+// ORBmatcher::SearchForTriangulation on flat arrays (see include/orbx.h).  Host pointers, synchronous.
+extern "C" int orbx_search_for_triangulation(orbx_matcher* m,
+                                             const orbx_keypoint* k1, const uint8_t* d1, const uint8_t* free1, const uint8_t* stereo1, int n1,
+                                             const int32_t* fv1_nodes, const int32_t* fv1_start, const int32_t* fv1_feat, int nfv1,
+                                             const orbx_keypoint* k2, const uint8_t* d2, const uint8_t* free2, const uint8_t* stereo2, int n2,
+                                             const int32_t* fv2_nodes, const int32_t* fv2_start, const int32_t* fv2_feat, int nfv2,
+                                             const float* F12, float ep_x, float ep_y, const float* scale_factors2,
+                                             const float* level_sigma2_2, int nlevels, int only_stereo, int coarse, int check_ori,
+                                             int32_t* matches12, int* nmatches)
+{
+    if (!m || n1 < 0 || n2 < 0 || n2 > 65535 || nfv1 < 0 || nfv2 < 0 || !matches12 || !F12 || !scale_factors2 || !level_sigma2_2 ||
+        nlevels < 1 || nlevels > ORBX_MAX_LEVELS) return ORBX_E_INVALID;
+    if (nmatches) *nmatches = 0;
+    for (int i = 0; i < n1; i++) matches12[i] = -1;
+    if (n1 == 0 || n2 == 0 || nfv1 == 0 || nfv2 == 0) return ORBX_OK;
+    if (!free2) return ORBX_E_INVALID;
+    TriArgs T;
+    uint8_t* dx = nullptr;
+    int rc = bow_stage(m, "orbx_search_for_triangulation", k1, d1, free1, n1, fv1_nodes, fv1_start, fv1_feat, nfv1,
+                       k2, d2, free2, n2, fv2_nodes, fv2_start, fv2_feat, nfv2, (size_t)n1 + n2 + 512, &T.B, &dx);
+    if (rc) return rc;
+    cudaStream_t s = m->stream;
+    T.stereo1 = nullptr; T.stereo2 = nullptr;
+    if (stereo1) { CKM(cudaMemcpyAsync(dx, stereo1, n1, cudaMemcpyHostToDevice, s)); T.stereo1 = dx; }
+    uint8_t* dx2 = dx + (((size_t)n1 + 255) & ~(size_t)255);
+    if (stereo2) { CKM(cudaMemcpyAsync(dx2, stereo2, n2, cudaMemcpyHostToDevice, s)); T.stereo2 = dx2; }
+    for (int i = 0; i < 9; i++) T.F[i] = F12[i];
+    T.ep_x = ep_x; T.ep_y = ep_y;
+    for (int l = 0; l < ORBX_MAX_LEVELS; l++) { T.scale2[l] = l < nlevels ? scale_factors2[l] : 0.f; T.sigma2_2[l] = l < nlevels ? level_sigma2_2[l] : 0.f; }
+    T.only_stereo = only_stereo; T.coarse = coarse;
+    T.B.check_ori = check_ori;
+    k_triangulation_match<<<(nfv1 + 7) / 8, 256, 0, s>>>(T); ORBX_COUNT_LAUNCH(1);
+    return bow_finish(m, T.B, matches12, nmatches);
 }
 
 // MapPoint::ComputeDistinctiveDescriptors for a batch of map points (see include/orbx.h).  Host pointers, synchronous.

@@ -39,7 +39,7 @@ EXPORTS = [
     "orbx_search_by_projection",
     "orbx_stereo_band_match", "orbx_stereo_matches", "orbx_stereo_matches_batch", "orbx_stereo_matches_batch_device",
     "orbx_extract_stereo_batch",
-    "orbx_fast_segment_plan", "orbx_search_by_projection_ex", "orbx_match_candidates", "orbx_search_by_bow", "orbx_distinctive_descriptors", "orbx_undistort_keypoints", "orbx_undistort_slots_device",
+    "orbx_fast_segment_plan", "orbx_search_by_projection_ex", "orbx_match_candidates", "orbx_search_by_bow", "orbx_search_for_triangulation", "orbx_distinctive_descriptors", "orbx_undistort_keypoints", "orbx_undistort_slots_device",
     "orbx_keypoints_to_msg", "orbx_keypoints_from_msg", "orbx_slot_keypoints_to_msg_device", "orbx_vocab_create", "orbx_vocab_destroy", "orbx_vocab_words", "orbx_vocab_word_weights",
     "orbx_bow_transform", "orbx_bow_transform_slots_device", "orbx_popc_peak",
 ]
@@ -122,6 +122,8 @@ def lib():
         L.orbx_keypoints_from_msg.argtypes = [vp, vp, i32, vp]
         L.orbx_slot_keypoints_to_msg_device.argtypes = [vp, i32, vp, vp]
         L.orbx_undistort_slots_device.argtypes = [vp, i32, i32, vp, vp, i32, vp, vp, vp]
+        L.orbx_search_for_triangulation.argtypes = [vp, vp, vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, vp, vp, i32, vp, vp, vp, i32,
+                                                    vp, f32, f32, vp, vp, i32, i32, i32, i32, vp, vp]
         L.orbx_vocab_create.argtypes = [i32, i32, vp, vp, vp, vp, i32, vp]
         L.orbx_vocab_destroy.argtypes = [vp]; L.orbx_vocab_destroy.restype = None
         L.orbx_vocab_words.argtypes = [vp]
@@ -380,6 +382,32 @@ class ORBmatcher:
                                                   _p(sg) if sg is not None else None, 0 if sg is None else len(sg), float(chi2),
                                                   _p(bi), _p(bd), C.byref(nm)))
         return (nm.value, bi, bd) if mode == 3 else (nm.value, a)
+
+    def SearchForTriangulation(self, k1, d1, free1, stereo1, fv1, k2, d2, free2, stereo2, fv2, F12, ep, scale2, sigma2_2,
+                               only_stereo=False, coarse=False):
+        """ORBmatcher::SearchForTriangulation (pinhole, one camera per keyframe) -> (nmatches, matches12)"""
+        k1 = np.ascontiguousarray(k1, KP_DTYPE); k2 = np.ascontiguousarray(k2, KP_DTYPE)
+        d1 = np.ascontiguousarray(d1, np.uint8).reshape(-1, 32); d2 = np.ascontiguousarray(d2, np.uint8).reshape(-1, 32)
+        f1 = np.ascontiguousarray(free1, np.uint8); f2 = np.ascontiguousarray(free2, np.uint8)
+        s1 = None if stereo1 is None else np.ascontiguousarray(stereo1, np.uint8)
+        s2 = None if stereo2 is None else np.ascontiguousarray(stereo2, np.uint8)
+
+        def csr(fv):
+            nodes, feats = fv
+            start = np.zeros(len(nodes) + 1, np.int32)
+            if len(nodes):
+                start[1:] = np.cumsum([len(f) for f in feats])
+            flat = np.concatenate(feats).astype(np.int32) if len(nodes) else np.zeros(0, np.int32)
+            return np.ascontiguousarray(nodes, np.int32), start, np.ascontiguousarray(flat)
+        n1, st1, ft1 = csr(fv1); n2, st2, ft2 = csr(fv2)
+        F = np.ascontiguousarray(F12, np.float32).reshape(9)
+        sc = np.ascontiguousarray(scale2, np.float32); sg = np.ascontiguousarray(sigma2_2, np.float32)
+        m12 = np.empty(len(k1), np.int32); nm = C.c_int(0)
+        _check(lib().orbx_search_for_triangulation(self._h, _p(k1), _p(d1), _p(f1), _p(s1) if s1 is not None else None, len(k1),
+                                                   _p(n1), _p(st1), _p(ft1), len(n1), _p(k2), _p(d2), _p(f2), _p(s2) if s2 is not None else None,
+                                                   len(k2), _p(n2), _p(st2), _p(ft2), len(n2), _p(F), float(ep[0]), float(ep[1]), _p(sc), _p(sg),
+                                                   len(sc), int(only_stereo), int(coarse), int(self.mbCheckOrientation), _p(m12), C.byref(nm)))
+        return nm.value, m12
 
     def SearchByBoW(self, mode, k1, d1, valid1, fv1, k2, d2, valid2, fv2):
         """ORBmatcher::SearchByBoW: mode 0 = (KeyFrame, Frame), mode 1 = (KeyFrame, KeyFrame); fv = (node ids, feature lists)

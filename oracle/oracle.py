@@ -91,6 +91,9 @@ def lib():
         L.orc_keypoints_to_msg.argtypes = [vp, i32, vp]
         L.orc_keypoints_from_msg.argtypes = [vp, i32, vp]
         L.orc_distinctive_descriptors.argtypes = [vp, vp, i32, vp]
+        L.orc_search_for_triangulation.restype = i32
+        L.orc_search_for_triangulation.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, vp, vp, i32, vp, vp, vp, i32,
+                                                   vp, f32, f32, vp, vp, i32, i32, i32, vp]
         L.orc_search_by_bow.restype = i32
         L.orc_search_by_bow.argtypes = [i32, vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, vp, i32, f32, i32, vp]
         L.orc_vocab_create.restype = vp
@@ -380,3 +383,18 @@ def search_by_projection_ex(mode, queries, qdesc, k2, d2, bounds, assigned=None,
                                           *[float(b) for b in bounds], _p(a), float(nnratio), int(check_ori), int(max_dist),
                                           _p(sg) if sg is not None else None, float(chi2), _p(bi), _p(bd))
     return (n, bi, bd) if mode == 3 else (n, a)
+
+
+def search_for_triangulation(k1, d1, free1, stereo1, fv1, k2, d2, free2, stereo2, fv2, F12, ep, scale2, sigma2_2,
+                             only_stereo=False, coarse=False, check_ori=True):
+    k1 = np.ascontiguousarray(k1, KP_DTYPE); k2 = np.ascontiguousarray(k2, KP_DTYPE); d1 = _u8(d1); d2 = _u8(d2)
+    f1 = np.ascontiguousarray(free1, np.uint8); f2 = np.ascontiguousarray(free2, np.uint8)
+    s1 = None if stereo1 is None else np.ascontiguousarray(stereo1, np.uint8)
+    s2 = None if stereo2 is None else np.ascontiguousarray(stereo2, np.uint8)
+    n1, st1, ft1 = fv_to_csr(fv1); n2, st2, ft2 = fv_to_csr(fv2)
+    F = np.ascontiguousarray(F12, np.float32).reshape(9); sc = np.ascontiguousarray(scale2, np.float32); sg = np.ascontiguousarray(sigma2_2, np.float32)
+    m12 = np.empty(len(k1), np.int32)
+    n = lib().orc_search_for_triangulation(_p(k1), _p(d1), _p(f1), _p(s1) if s1 is not None else None, len(k1), _p(n1), _p(st1), _p(ft1), len(n1),
+                                           _p(k2), _p(d2), _p(f2), _p(s2) if s2 is not None else None, len(k2), _p(n2), _p(st2), _p(ft2), len(n2),
+                                           _p(F), float(ep[0]), float(ep[1]), _p(sc), _p(sg), int(only_stereo), int(coarse), int(check_ori), _p(m12))
+    return n, m12

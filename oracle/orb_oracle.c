@@ -1354,3 +1354,75 @@ void orc_keypoints_from_msg(const uint8_t* msg, int n, OrcKeyPoint* kps)
         kps[i].size = (float)o[8]; kps[i].response = (float)o[13]; kps[i].octave = (int8_t)o[14]; kps[i].class_id = -1;
     }
 }
+
+/* Pinhole::epipolarConstrain with F12 given, R/src/CameraModels/Pinhole.cpp:128-142 */
+static int epipolar_ok(const OrcKeyPoint* kp1, const OrcKeyPoint* kp2, const float* F, float unc)
+{
+    const float a = kp1->x * F[0] + kp1->y * F[3] + F[6];
+    const float b = kp1->x * F[1] + kp1->y * F[4] + F[7];
+    const float c = kp1->x * F[2] + kp1->y * F[5] + F[8];
+    const float num = a * kp2->x + b * kp2->y + c;
+    const float den = a * a + b * b;
+    if (den == 0) return 0;
+    const float dsqr = num * num / den;
+    return dsqr < 3.84 * unc;
+}
+
+/* ORBmatcher::SearchForTriangulation, R/src/ORBmatcher.cc:961-1202 (mpCamera2 == NULL) */
+int orc_search_for_triangulation(const OrcKeyPoint* k1, const uint8_t* d1, const uint8_t* free1, const uint8_t* stereo1, int n1,
+                                 const int32_t* fv1_nodes, const int32_t* fv1_start, const int32_t* fv1_feat, int nfv1,
+                                 const OrcKeyPoint* k2, const uint8_t* d2, const uint8_t* free2, const uint8_t* stereo2, int n2,
+                                 const int32_t* fv2_nodes, const int32_t* fv2_start, const int32_t* fv2_feat, int nfv2,
+                                 const float* F12, float ep_x, float ep_y, const float* scale_factors2, const float* level_sigma2_2,
+                                 int only_stereo, int coarse, int check_ori, int32_t* matches12)
+{
+    int nmatches = 0;
+    int* histIdx = (int*)malloc(sizeof(int) * (n1 > 0 ? n1 : 1));
+    int* histBin = (int*)malloc(sizeof(int) * (n1 > 0 ? n1 : 1));
+    int hist[HISTO_LENGTH]; int nh = 0;
+    for (int i = 0; i < HISTO_LENGTH; i++) hist[i] = 0;
+    for (int i = 0; i < n1; i++) matches12[i] = -1;
+    int a = 0, b = 0;
+    while (a < nfv1 && b < nfv2) {
+        if (fv1_nodes[a] == fv2_nodes[b]) {
+            for (int ia = fv1_start[a]; ia < fv1_start[a + 1]; ia++) {
+                const int idx1 = fv1_feat[ia];
+                if (!free1[idx1]) continue;
+                const int bStereo1 = stereo1 ? stereo1[idx1] : 0;
+                if (only_stereo && !bStereo1) continue;
+                int bestDist = TH_LOW, bestIdx2 = -1;
+                for (int ib = fv2_start[b]; ib < fv2_start[b + 1]; ib++) {
+                    const int idx2 = fv2_feat[ib];
+                    if (!free2[idx2]) continue;
+                    const int bStereo2 = stereo2 ? stereo2[idx2] : 0;
+                    if (only_stereo && !bStereo2) continue;
+                    const int dist = orc_hamming256(d1 + (size_t)idx1 * 32, d2 + (size_t)idx2 * 32);
+                    if (dist > TH_LOW || dist > bestDist) continue;
+                    if (!bStereo1 && !bStereo2) {
+                        const float distex = ep_x - k2[idx2].x, distey = ep_y - k2[idx2].y;
+                        if (distex * distex + distey * distey < 100 * scale_factors2[k2[idx2].octave]) continue;
+                    }
+                    if (epipolar_ok(&k1[idx1], &k2[idx2], F12, level_sigma2_2[k2[idx2].octave]) || coarse) { bestIdx2 = idx2; bestDist = dist; }
+                }
+                if (bestIdx2 >= 0) {
+                    matches12[idx1] = bestIdx2; nmatches++;
+                    if (check_ori) { const int bin = rot_bin(k1[idx1].angle, k2[bestIdx2].angle); histIdx[nh] = idx1; histBin[nh] = bin; nh++; hist[bin]++; }
+                }
+            }
+            a++; b++;
+        } else if (fv1_nodes[a] < fv2_nodes[b]) {
+            while (a < nfv1 && fv1_nodes[a] < fv2_nodes[b]) a++;
+        } else {
+            while (b < nfv2 && fv2_nodes[b] < fv1_nodes[a]) b++;
+        }
+    }
+    if (check_ori) {
+        int ind1, ind2, ind3;
+        three_maxima(hist, HISTO_LENGTH, &ind1, &ind2, &ind3);
+        for (int j = 0; j < nh; j++)
+            if (histBin[j] != ind1 && histBin[j] != ind2 && histBin[j] != ind3) { matches12[histIdx[j]] = -1; nmatches--; }
+    }
+    free(histIdx); free(histBin);
+    (void)n2;
+    return nmatches;
+}

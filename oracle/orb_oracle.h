@@ -168,6 +168,22 @@ void  orc_undistort_keypoints(const OrcKeyPoint* kps, int n, const float* K, con
 void  orc_keypoints_to_msg(const OrcKeyPoint* kps, int n, uint8_t* msg15);
 void  orc_keypoints_from_msg(const uint8_t* msg15, int n, OrcKeyPoint* kps);
 
+/* ORBmatcher::SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, bOnlyStereo, bCoarse) (R/src/ORBmatcher.cc:961-1202),
+ * pinhole cameras without a second camera (mpCamera2 == NULL): for every feature of keyframe 1 without a MapPoint, the
+ * features of keyframe 2 in the same vocabulary node that have no MapPoint either; Hamming distance <= TH_LOW and <= the
+ * best so far (a later candidate with the same distance replaces an earlier one); monocular-monocular candidates closer
+ * to the epipole than 100 * scaleFactor[octave2] (squared pixels) are skipped; the candidate must lie within
+ * 3.84 * levelSigma2[octave2] of the epipolar line of F12 (Pinhole::epipolarConstrain, CameraModels/Pinhole.cpp:121-143)
+ * unless coarse; rotation consistency as everywhere.  This fork never sets vbMatched2, so queries do not interact.
+ * free1 / free2: 1 = the feature has no MapPoint; stereo1 / stereo2 (may be NULL): mvuRight >= 0.
+ * matches12[i1] = index in keyframe 2 or -1; returns nmatches. */
+int   orc_search_for_triangulation(const OrcKeyPoint* k1, const uint8_t* d1, const uint8_t* free1, const uint8_t* stereo1, int n1,
+                                   const int32_t* fv1_nodes, const int32_t* fv1_start, const int32_t* fv1_feat, int nfv1,
+                                   const OrcKeyPoint* k2, const uint8_t* d2, const uint8_t* free2, const uint8_t* stereo2, int n2,
+                                   const int32_t* fv2_nodes, const int32_t* fv2_start, const int32_t* fv2_feat, int nfv2,
+                                   const float* F12, float ep_x, float ep_y, const float* scale_factors2, const float* level_sigma2_2,
+                                   int only_stereo, int coarse, int check_ori, int32_t* matches12);
+
 /* MapPoint::ComputeDistinctiveDescriptors (R/src/MapPoint.cc:448-524) for a batch of map points: the observed
  * descriptors of point p are rows offsets[p] .. offsets[p+1] of desc; best[p] = index inside that run of the descriptor
  * with the least median distance to the others (median = sorted row [(int)(0.5 * (N - 1))], the row includes the 0 on

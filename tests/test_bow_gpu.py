@@ -132,3 +132,20 @@ def test_search_by_bow_matches_oracle_c1_and_duplicates():
     with pytest.raises(orbx.OrbxError):
         m.SearchByBoW(0, k1, d1, v1, fv1, k2, d2, None, bad)
     m.close(); V.close(); ex.close()
+
+
+@pytest.mark.parametrize("only_stereo,coarse,ep,use_stereo", [(False, False, (1e6, 1e6), False), (False, False, (240.0, 180.0), True),
+                                                             (True, False, (1e6, 1e6), True), (False, True, (100.0, 100.0), False)])
+def test_search_for_triangulation_matches_oracle(only_stereo, coarse, ep, use_stereo):
+    """ORBmatcher::SearchForTriangulation: epipole gate, epipolar-line gate, last-of-equals rule, rotation filter."""
+    from test_bow import triangulation_case
+    e, k1, d1, k2, d2, fv1, fv2, F12, free1, free2, st1, st2, _ = triangulation_case()
+    d2 = d2.copy(); d2[40:60] = d1[40:60]                      # exact duplicates: equal distances inside a node
+    s1, s2 = (st1, st2) if use_stereo else (None, None)
+    for ori in (True, False):
+        m = orbx.ORBmatcher(0.6, ori, max_keypoints=2048)
+        n, m12 = m.SearchForTriangulation(k1, d1, free1, s1, fv1, k2, d2, free2, s2, fv2, F12, ep, e.scale, e.sigma2, only_stereo, coarse)
+        rn, rm12 = O.search_for_triangulation(k1, d1, free1, s1, fv1, k2, d2, free2, s2, fv2, F12, ep, e.scale, e.sigma2, only_stereo, coarse, ori)
+        assert n == rn
+        np.testing.assert_array_equal(m12, rm12)
+        m.close()
