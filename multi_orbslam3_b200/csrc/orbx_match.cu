@@ -209,6 +209,7 @@ __global__ void __launch_bounds__(GRID_NT) k_grid_build(WinBufs W, int npad_max)
 }
 
 constexpr int CAND_WARPS = 8;
+constexpr int CAND_CACHE = 4;           // warp-steps (x 32 records) of a window whose test outcome is kept in registers between the two passes
 
 // Frame::GetFeaturesInArea + descriptor distances, one warp per query.  Pool entry: i2 | dist << 16 | octave << 25
 __global__ void __launch_bounds__(CAND_WARPS * 32, 6) k_window_candidates(WinBufs W)
@@ -261,34 +262,66 @@ __global__ void __launch_bounds__(CAND_WARPS * 32, 6) k_window_candidates(WinBuf
     int base = 0, total = 0;
     int td0 = 0x7fffffff, tk0 = 0x7fffffff, td1 = 0x7fffffff, tk1 = 0x7fffffff;      // unfiltered top-2 by (distance, rank)
     uint32_t te0 = 0, te1 = 0;
-    for (int pass = 0; pass < 2; pass++) {
+    // pass 0 counts the records that pass the tests and keeps the outcome of the first CAND_CACHE warp-steps in registers
+    // (index | octave << 16, or ~0), so that pass 1 does not search, load and test those records a second time
+    uint32_t cache[CAND_CACHE];
+#pragma unroll
+    for (int c = 0; c < CAND_CACHE; c++) cache[c] = 0xFFFFFFFFu;
+    auto test_record = [&](int j, int& i2, int& oct) -> bool {
+        int lo = 0, hi = nr - 1;                          // last range whose prefix <= j
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (rp[mid] <= j) lo = mid; else hi = mid - 1; }
+        const float4 rec = __ldg(skp + rs[lo] + (j - rp[lo]));
+        oct = __float_as_int(rec.z); i2 = __float_as_int(rec.w);
+        bool ok = true;
+        if (check_levels) {
+            if (oct < Q.minl) ok = false;
+            if (Q.maxl >= 0 && oct > Q.maxl) ok = false;
+        }
+        const float dx = __fsub_rn(rec.x, Q.u), dy = __fsub_rn(rec.y, Q.v);
+        if (!(fabsf(dx) < Q.r && fabsf(dy) < Q.r)) ok = false;
+        // Fuse (ORBmatcher.cc:1497-1505): e2 * invSigma2 (float) against the double chi-square bound
+        if (ok && W.gate_chi2 > 0.0 &&
+            (double)__fmul_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), W.inv_sigma2[min(oct, ORBX_MAX_LEVELS - 1)]) > W.gate_chi2) ok = false;
+        // stereo gate (ORBmatcher.cc:93-98 / :2049-2055): not order dependent, applied here
+        if (ok && P.uright2) {
+            const float ur2 = P.uright2[i2];
+            if (ur2 > 0 && fabsf(__fsub_rn(Q.ur, ur2)) > Q.r) ok = false;
+        }
+        return ok;
+    };
+    {
         int pos = 0;
-        for (int j0 = 0; j0 < T; j0 += 32) {
-            const int j = j0 + lane;
-            bool ok = false; int i2 = 0, oct = 0;
-            if (j < T) {
-                int lo = 0, hi = nr - 1;                      // last range whose prefix <= j
-                while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (rp[mid] <= j) lo = mid; else hi = mid - 1; }
-                const float4 rec = __ldg(skp + rs[lo] + (j - rp[lo]));
-                oct = __float_as_int(rec.z); i2 = __float_as_int(rec.w);
-                ok = true;
-                if (check_levels) {
-                    if (oct < Q.minl) ok = false;
-                    if (Q.maxl >= 0 && oct > Q.maxl) ok = false;
-                }
-                const float dx = __fsub_rn(rec.x, Q.u), dy = __fsub_rn(rec.y, Q.v);
-                if (!(fabsf(dx) < Q.r && fabsf(dy) < Q.r)) ok = false;
-                // Fuse (ORBmatcher.cc:1497-1505): e2 * invSigma2 (float) against the double chi-square bound
-                if (ok && W.gate_chi2 > 0.0 &&
-                    (double)__fmul_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), W.inv_sigma2[min(oct, ORBX_MAX_LEVELS - 1)]) > W.gate_chi2) ok = false;
-                // stereo gate (ORBmatcher.cc:93-98 / :2049-2055): not order dependent, applied here
-                if (ok && P.uright2) {
-                    const float ur2 = P.uright2[i2];
-                    if (ur2 > 0 && fabsf(__fsub_rn(Q.ur, ur2)) > Q.r) ok = false;
-                }
+#pragma unroll
+        for (int c = 0; c < CAND_CACHE; c++) {
+            const int j = c * 32 + lane;
+            if (c * 32 < T) {                               // warp-uniform
+                int i2 = 0, oct = 0;
+                const bool ok = j < T && test_record(j, i2, oct);
+                if (ok) cache[c] = (uint32_t)i2 | ((uint32_t)oct << 16);
+                pos += __popc(__ballot_sync(0xffffffffu, ok));
             }
+        }
+        for (int j0 = CAND_CACHE * 32; j0 < T; j0 += 32) {
+            const int j = j0 + lane;
+            int i2 = 0, oct = 0;
+            const bool ok = j < T && test_record(j, i2, oct);
+            pos += __popc(__ballot_sync(0xffffffffu, ok));
+        }
+        total = pos;
+        if (lane == 0) base = total ? atomicAdd(W.pool_used + p, total) : 0;
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base + total > W.POOL) {
+            if (lane == 0) { atomicOr(W.err, ORBX_DEVERR_POOL_OVERFLOW); *q_off = 0; *q_cnt = 0; }
+            return;
+        }
+        if (lane == 0) { *q_off = base; *q_cnt = total; }
+        if (total == 0) return;
+    }
+    {
+        int pos = 0;
+        auto emit = [&](bool ok, int i2, int oct) {
             const unsigned bal = __ballot_sync(0xffffffffu, ok);
-            if (pass == 1 && ok) {
+            if (ok) {
                 const int o = pos + __popc(bal & ((1u << lane) - 1));
                 const uint4 t0 = reinterpret_cast<const uint4*>(P.d2)[2 * i2], t1 = reinterpret_cast<const uint4*>(P.d2)[2 * i2 + 1];
                 const int d = hamming256(q0, q1, t0, t1);
@@ -298,17 +331,15 @@ __global__ void __launch_bounds__(CAND_WARPS * 32, 6) k_window_candidates(WinBuf
                 else if (d < td1) { td1 = d; tk1 = o; te1 = e; }
             }
             pos += __popc(bal);
-        }
-        if (pass == 0) {
-            total = pos;
-            if (lane == 0) base = total ? atomicAdd(W.pool_used + p, total) : 0;
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (base + total > W.POOL) {
-                if (lane == 0) { atomicOr(W.err, ORBX_DEVERR_POOL_OVERFLOW); *q_off = 0; *q_cnt = 0; }
-                return;
-            }
-            if (lane == 0) { *q_off = base; *q_cnt = total; }
-            if (total == 0) return;
+        };
+#pragma unroll
+        for (int c = 0; c < CAND_CACHE; c++)
+            if (c * 32 < T) emit(cache[c] != 0xFFFFFFFFu, (int)(cache[c] & 0xFFFF), (int)((cache[c] >> 16) & 0xFF));
+        for (int j0 = CAND_CACHE * 32; j0 < T; j0 += 32) {
+            const int j = j0 + lane;
+            int i2 = 0, oct = 0;
+            const bool ok = j < T && test_record(j, i2, oct);
+            emit(ok, i2, oct);
         }
     }
     // the resolve kernel starts from these two and rescans the list only when one of them has been taken meanwhile
