@@ -400,29 +400,28 @@ __global__ void __launch_bounds__(NT, 5) k_fast_seg(OrbxGeom g, OrbxBuffers b, c
     }
     __syncthreads();
 
-    // ---- 5. counts per (cell, row), threshold choice per cell, offsets ----
-    for (int k = tid; k < ncell * hs; k += NT) {
-        const int j = (int)(((unsigned)k * hrcp) >> 16), r = k - j * hs;
+    // ---- 5. counts per (cell, row), threshold choice per cell, offsets: one warp per cell, one lane per scored row ----
+    for (int j = warp; j < ncell; j += NW) {
         const int c0 = X0 + j * wCell, c1 = min(c0 + wCell, X1);
-        int a = 0, bq = 0;
-        if (c1 > c0) { a = popc_range(Bmin + r * bw, c0, c1); bq = popc_range(Bini + r * bw, c0, c1); }
-        cnt_min[j * hs + r] = (unsigned short)a;
-        cnt_ini[j * hs + r] = (unsigned short)bq;
-    }
-    __syncthreads();
-    if (tid < ncell) {
-        const int j = tid;
-        int ti = 0;
-        for (int r = 0; r < hs; r++) ti += cnt_ini[j * hs + r];
-        const bool ui = ti > 0;
-        int run = 0;
-        for (int r = 0; r < hs; r++) {
-            const int c = ui ? cnt_ini[j * hs + r] : cnt_min[j * hs + r];
-            cnt_ini[j * hs + r] = (unsigned short)run;          // exclusive prefix inside the cell
-            run += c;
+        int run = 0, ti = 0;
+        // first sweep: does the cell have an iniThFAST survivor at all?
+        for (int r0 = 0; r0 < hs; r0 += 32) {
+            const int r = r0 + lane;
+            const int bq = (r < hs && c1 > c0) ? popc_range(Bini + r * bw, c0, c1) : 0;
+            ti += __popc(__ballot_sync(0xffffffffu, bq > 0));
         }
-        sh.use_ini[j] = ui;
-        sh.cell_off[j + 1] = run;                               // cell totals, scanned below
+        const bool ui = ti > 0;
+        const unsigned* Bsel = ui ? Bini : Bmin;
+        for (int r0 = 0; r0 < hs; r0 += 32) {
+            const int r = r0 + lane;
+            const int c = (r < hs && c1 > c0) ? popc_range(Bsel + r * bw, c0, c1) : 0;
+            int inc = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+            if (r < hs) cnt_ini[j * hs + r] = (unsigned short)(run + inc - c);      // exclusive prefix inside the cell
+            run += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (lane == 0) { sh.use_ini[j] = ui; sh.cell_off[j + 1] = run; }            // cell totals, scanned below
     }
     __syncthreads();
     if (tid == 0) {
