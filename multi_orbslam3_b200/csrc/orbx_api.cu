@@ -79,6 +79,7 @@ static int dev_alloc(orbx_extractor* h, void** p, size_t bytes)
     if (bytes == 0) bytes = 16;
     CK(cudaMalloc(p, bytes));
     h->allocs.push_back(*p);
+    CK(cudaMemset(*p, 0, bytes));        // capacity tails that travel to the host with the results are zeros, not stale memory
     return ORBX_OK;
 }
 

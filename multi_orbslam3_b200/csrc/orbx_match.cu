@@ -523,6 +523,7 @@ static int m_alloc(orbx_matcher* m, void** p, size_t bytes)
     cudaError_t e = cudaMalloc(p, bytes);
     if (e != cudaSuccess) { orbx_set_error("%s: %s", "cudaMalloc", cudaGetErrorString(e)); return ORBX_E_NOMEM; }
     m->allocs.push_back(*p);
+    if (cudaMemset(*p, 0, bytes) != cudaSuccess) { orbx_set_error("%s%s", "cudaMemset failed", ""); return ORBX_E_CUDA; }
     return ORBX_OK;
 }
 
