@@ -6,6 +6,11 @@
  * the entry points below.  Every entry point cites the reference code it replaces;
  * R/ = src/orb_slam3_ros/orb_slam3/ in the reference tree.
  *
+ * Groups: extractor (orbx_extractor_*, orbx_extract*), pyramid access and test taps, matcher (Hamming pairs, brute-force
+ * kNN-2, SearchForInitialization, SearchByProjection family, SearchByBoW, SearchForTriangulation, candidate lists),
+ * stereo (orbx_stereo_*, orbx_extract_stereo_batch), stream pipelines (orbx_extract_match_batch*), bag of words
+ * (orbx_vocab_*, orbx_bow_transform*), frame / map-point helpers (undistortion, distinctive descriptors, KF.msg records).
+ *
  * Conventions: extern "C", plain pointers and sizes, int status return (ORBX_OK == 0), no
  * exceptions, opaque handles, caller-allocated outputs with a capacity and a count-out.
  * `stream` arguments are a cudaStream_t passed as void* (NULL = the handle's own stream).
