@@ -174,6 +174,12 @@ int  orbx_match_slots_device(orbx_matcher* m, orbx_extractor* ex, const int32_t*
                              const float bounds[4], int window, float nnratio, int check_ori,
                              int32_t* d_matches12, int32_t* d_nmatches, int32_t* d_knn_idx, int32_t* d_knn_dist,
                              void* stream);
+/* The reference matches on mvKeysUn (R/src/Frame.cc:721-754 feeds R/src/ORBmatcher.cc:702-817).  For a distorted camera
+ * give the slot-based searches (orbx_match_slots_device, orbx_extract_match_batch*) the undistorted keypoints: a DEVICE
+ * array laid out like the extractor's results, [slots][orbx_extractor_max_keypoints(ex)], typically written by
+ * orbx_undistort_slots_device.  NULL (default) = the extractor's own keypoints (mvKeysUn == mvKeys when mDistCoef[0] == 0). */
+int  orbx_matcher_set_slot_keypoints(orbx_matcher* m, const orbx_keypoint* d_kps_un);
+
 
 /* One tracking step over a batch of HOST frames (the end-to-end path): H2D, operator() on every frame into result
  * slots 1..batch, SearchForInitialization of each frame against its predecessor (slot i-1 -> slot i; slot 0 keeps

@@ -570,6 +570,7 @@ extern "C" int orbx_matcher_create(const orbx_matcher_params* p, orbx_matcher** 
     m->d_bfq = m->d_bft = nullptr; m->bfq_bytes = m->bft_bytes = 0;
     m->d_pair_a = m->d_pair_b = nullptr;
     m->d_gen = nullptr; m->gen_bytes = 0;
+    m->d_kps_src = nullptr;
     m->d_st = nullptr; m->st_bytes = 0;
     m->h_mono2 = nullptr; m->mono2_cap = 0;
     m->s_h2d = m->s_d2h = nullptr;
@@ -890,7 +891,8 @@ static int match_slots_impl(orbx_matcher* m, orbx_extractor* ex, const int32_t* 
     set_bounds(m, bounds);
     const WinBufs W = shifted_pairs(m, pair_base);
     // NOTE: outputs use row stride K (= matcher max_keypoints)
-    k_setup_slot_pairs<<<npairs, 256, 0, s>>>(W, kps, desc, n, a, b, cap, (float)window); ORBX_COUNT_LAUNCH(1);
+    // mvKeysUn when the caller supplied undistorted keypoints (same [slot][cap] layout), mvKeys otherwise
+    k_setup_slot_pairs<<<npairs, 256, 0, s>>>(W, m->d_kps_src ? m->d_kps_src : kps, desc, n, a, b, cap, (float)window); ORBX_COUNT_LAUNCH(1);
     rc = run_window(m, W, npairs, cap, 2, nnratio, check_ori, d_matches12, d_nmatches, nullptr, s);
     if (rc) return rc;
     if (d_knn_idx && d_knn_dist) {
@@ -900,6 +902,15 @@ static int match_slots_impl(orbx_matcher* m, orbx_extractor* ex, const int32_t* 
         rc = bf_launch(m, A, npairs, cap, cap, s);
         if (rc) return rc;
     }
+    return ORBX_OK;
+}
+
+// Undistorted keypoints for the slot-based searches: a DEVICE array laid out like the extractor's results
+// ([slots][orbx_extractor_max_keypoints]), e.g. the output of orbx_undistort_slots_device; NULL = use the extractor's own.
+extern "C" int orbx_matcher_set_slot_keypoints(orbx_matcher* m, const orbx_keypoint* d_kps_un)
+{
+    if (!m) return ORBX_E_INVALID;
+    m->d_kps_src = d_kps_un;
     return ORBX_OK;
 }
 

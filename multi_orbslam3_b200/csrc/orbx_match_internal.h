@@ -131,6 +131,7 @@ struct orbx_matcher {
     uint8_t* d_bfq; uint8_t* d_bft; size_t bfq_bytes, bft_bytes;
     unsigned* h_err;
     int32_t* d_pair_a; int32_t* d_pair_b;
+    const orbx_keypoint* d_kps_src;          // optional replacement of the extractor's keypoints in the slot-based searches (mvKeysUn)
     uint8_t* d_gen; size_t gen_bytes;
     uint8_t* d_st; size_t st_bytes;          // stereo scratch
     int32_t* h_mono2; int mono2_cap;         // pinned monoIndex landing zone of the stereo pipeline (2 x batch)

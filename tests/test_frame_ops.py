@@ -98,3 +98,35 @@ def test_kf_msg_keypoint_records_gpu():
     ex.sync(); torch.cuda.synchronize()
     np.testing.assert_array_equal(d.cpu().numpy()[:len(k) * 15].reshape(-1, 15), O.keypoints_to_msg(k))
     ex.close(); m.close()
+
+
+@pytest.mark.gpu
+def test_device_pipeline_with_undistorted_keypoints():
+    """Distorted camera, everything device-resident: extract a batch -> undistort the result slots -> SearchForInitialization
+    between consecutive frames on mvKeysUn (as Tracking does) == oracle on undistorted keypoints."""
+    import torch
+    from multi_orbslam3_b200 import orbx, synth
+    W, H, B = 752, 480, 3
+    frames = synth.rects_stream(W, H, B, seed=12)
+    ex = orbx.ORBextractor(1000, 1.2, 8, 20, 7, max_width=W, max_height=H, max_batch=B)
+    m = orbx.ORBmatcher(0.9, True, max_keypoints=ex.cap, max_batch=B)
+    d_frames = torch.from_numpy(frames).cuda()
+    ex.extract_batch_device(d_frames.data_ptr(), B, W, H, W, W * H, (0, 0), 0, None)
+    d_un = torch.zeros((B + 1, ex.cap, 7), dtype=torch.float32, device="cuda")
+    Kf = np.ascontiguousarray(EUROC_K.reshape(9)); Df = np.ascontiguousarray(EUROC_D)
+    orbx._check(orbx.lib().orbx_undistort_slots_device(ex._h, 0, B, orbx._p(Kf), orbx._p(Df), 4, orbx._p(Kf), d_un.data_ptr(), None))
+    orbx._check(orbx.lib().orbx_matcher_set_slot_keypoints(m._h, d_un.data_ptr()))
+    a = torch.arange(0, B - 1, dtype=torch.int32, device="cuda"); b = torch.arange(1, B, dtype=torch.int32, device="cuda")
+    m12 = torch.empty((B - 1, m.K), dtype=torch.int32, device="cuda"); nm = torch.empty(B - 1, dtype=torch.int32, device="cuda")
+    bounds = (-30.0, W + 30.0, -30.0, H + 30.0)                # ComputeImageBounds of the undistorted corners (host side)
+    m.match_slots_device(ex, (a.data_ptr(), B - 1), (b.data_ptr(), B - 1), bounds, 100, m12.data_ptr(), nm.data_ptr())
+    ex.sync(); m.sync(); torch.cuda.synchronize()
+    res = ex.download(0, B)
+    hm12, hnm = m12.cpu().numpy(), nm.cpu().numpy()
+    for i in range(B - 1):
+        k1 = O.undistort_keypoints(res[i][1], EUROC_K, EUROC_D, EUROC_K); k2 = O.undistort_keypoints(res[i + 1][1], EUROC_K, EUROC_D, EUROC_K)
+        rn, rm12, _ = O.search_for_initialization(k1, res[i][2], k2, res[i + 1][2], bounds, np.stack([k1["x"], k1["y"]], 1), 100, 0.9, True)
+        assert hnm[i] == rn and rn > 20
+        np.testing.assert_array_equal(hm12[i, :len(k1)], rm12)
+    orbx._check(orbx.lib().orbx_matcher_set_slot_keypoints(m._h, None))
+    ex.close(); m.close()
