@@ -179,6 +179,12 @@ int  orbx_match_slots_device(orbx_matcher* m, orbx_extractor* ex, const int32_t*
  * array laid out like the extractor's results, [slots][orbx_extractor_max_keypoints(ex)], typically written by
  * orbx_undistort_slots_device.  NULL (default) = the extractor's own keypoints (mvKeysUn == mvKeys when mDistCoef[0] == 0). */
 int  orbx_matcher_set_slot_keypoints(orbx_matcher* m, const orbx_keypoint* d_kps_un);
+/* The stream pipelines do that by themselves once the camera is known: K, P 3x3 row-major, dist = ndist (4..12) distortion
+ * coefficients as in Frame::UndistortKeyPoints (R/src/Frame.cc:721-754); every chunk is undistorted right after extraction
+ * and matched on mvKeysUn.  K = NULL clears the camera.  orbx_matcher_undistorted_device returns the device view of
+ * mvKeysUn of the last pipeline call ([slots][orbx_extractor_max_keypoints], slot i + 1 = frame i; NULL without camera). */
+int  orbx_matcher_set_camera(orbx_matcher* m, const float* K, const float* dist, int ndist, const float* P);
+int  orbx_matcher_undistorted_device(orbx_matcher* m, orbx_keypoint** d_kps_un);
 
 
 /* One tracking step over a batch of HOST frames (the end-to-end path): H2D, operator() on every frame into result

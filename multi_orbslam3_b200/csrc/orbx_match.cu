@@ -571,6 +571,7 @@ extern "C" int orbx_matcher_create(const orbx_matcher_params* p, orbx_matcher** 
     m->d_pair_a = m->d_pair_b = nullptr;
     m->d_gen = nullptr; m->gen_bytes = 0;
     m->d_kps_src = nullptr;
+    m->cam_set = false; m->cam_ndist = 0; m->d_kps_un = nullptr; m->kps_un_elems = 0;
     m->d_st = nullptr; m->st_bytes = 0;
     m->h_mono2 = nullptr; m->mono2_cap = 0;
     m->s_h2d = m->s_d2h = nullptr;
@@ -599,6 +600,7 @@ extern "C" void orbx_matcher_destroy(orbx_matcher* m)
     if (m->d_bft) cudaFree(m->d_bft);
     if (m->d_pair_a) cudaFree(m->d_pair_a);
     if (m->d_gen) cudaFree(m->d_gen);
+    if (m->d_kps_un) cudaFree(m->d_kps_un);
     if (m->d_st) cudaFree(m->d_st);
     if (m->h_mono2) cudaFreeHost(m->h_mono2);
     if (m->s_h2d) {
@@ -905,6 +907,30 @@ static int match_slots_impl(orbx_matcher* m, orbx_extractor* ex, const int32_t* 
     return ORBX_OK;
 }
 
+// Camera of the stream pipelines (orbx_extract_match_batch*): with distortion coefficients set, every chunk's keypoints
+// are undistorted on the device (Frame::UndistortKeyPoints) right after extraction and the matching runs on mvKeysUn, as
+// the reference does.  K = NULL clears it.
+extern "C" int orbx_matcher_set_camera(orbx_matcher* m, const float* K, const float* dist, int ndist, const float* P)
+{
+    if (!m) return ORBX_E_INVALID;
+    if (!K) { m->cam_set = false; return ORBX_OK; }
+    if (!dist || !P || ndist < 4 || ndist > 12) return ORBX_E_INVALID;
+    for (int i = 0; i < 9; i++) { m->cam_K[i] = K[i]; m->cam_P[i] = P[i]; }
+    for (int i = 0; i < 12; i++) m->cam_dist[i] = i < ndist ? dist[i] : 0.f;
+    m->cam_ndist = ndist;
+    m->cam_set = dist[0] != 0.0f;                       // R/src/Frame.cc:723-727: mvKeysUn = mvKeys without distortion
+    return ORBX_OK;
+}
+
+// device view of mvKeysUn of the last pipeline call ([slots][orbx_extractor_max_keypoints], slot i + 1 = frame i); NULL when
+// no camera is set
+extern "C" int orbx_matcher_undistorted_device(orbx_matcher* m, orbx_keypoint** d_kps_un)
+{
+    if (!m || !d_kps_un) return ORBX_E_INVALID;
+    *d_kps_un = m->cam_set ? m->d_kps_un : nullptr;
+    return ORBX_OK;
+}
+
 // Undistorted keypoints for the slot-based searches: a DEVICE array laid out like the extractor's results
 // ([slots][orbx_extractor_max_keypoints]), e.g. the output of orbx_undistort_slots_device; NULL = use the extractor's own.
 extern "C" int orbx_matcher_set_slot_keypoints(orbx_matcher* m, const orbx_keypoint* d_kps_un)
@@ -975,6 +1001,21 @@ static int extract_match_pipeline(orbx_extractor* ex, orbx_matcher* m, bool host
     if (rc) return rc;
     CKM(cudaSetDevice(m->p.device));
     if ((rc = orbx_m_ensure_pipeline(m))) return rc;
+    struct SrcGuard {                                  // the pipeline's own mvKeysUn is the source only for the duration of the call
+        orbx_matcher* m; const orbx_keypoint* saved;
+        ~SrcGuard() { m->d_kps_src = saved; }
+    } guard{m, m->d_kps_src};
+    if (m->cam_set) {
+        const size_t need = (size_t)(m->P + 1) * orbx_ex_out_cap(ex);
+        if (need > m->kps_un_elems) {
+            // a fresh buffer has no predecessor in slot 0: the first frame of the first call matches against an empty slot anyway
+            if (m->d_kps_un) { CKM(cudaDeviceSynchronize()); cudaFree(m->d_kps_un); m->d_kps_un = nullptr; m->kps_un_elems = 0; }
+            CKM(cudaMalloc((void**)&m->d_kps_un, sizeof(orbx_keypoint) * need));
+            CKM(cudaMemset(m->d_kps_un, 0, sizeof(orbx_keypoint) * need));
+            m->kps_un_elems = need;
+        }
+        m->d_kps_src = m->d_kps_un;
+    }
     const bool direct = host && orbx_ex_can_fetch_direct(ex, kps, desc, cap, n, mono_index);
     // host path: chunks hide the PCIe copies under the kernels.  The call is H2D-bound in the middle, so what is left is
     // the fill (first chunk's copy) and the drain (last chunk's kernels + D2H): the first and last chunk are small
@@ -1021,6 +1062,11 @@ static int extract_match_pipeline(orbx_extractor* ex, orbx_matcher* m, bool host
             rc = orbx_ex_run_device(ex, imgs, stride, (long long)frame_stride, f0, cnt, lap0, lap1, 1 + f0, s);
         }
         if (rc) return rc;
+        if (m->cam_set) {                                // mvKeysUn of this chunk (result slots 1 + f0 ..)
+            rc = orbx_undistort_slots_device(ex, 1 + f0, cnt, m->cam_K, m->cam_dist, m->cam_ndist, m->cam_P,
+                                             m->d_kps_un + (size_t)(1 + f0) * orbx_ex_out_cap(ex), s);
+            if (rc) return rc;
+        }
         CKM(cudaEventRecord(m->ev_ext[c], s));
         // pairs (slot f0+i, slot f0+i+1) are matched on a second kernel stream, concurrently with the extraction of the
         // next chunk; each chunk owns its slice of the pair scratch
@@ -1046,6 +1092,10 @@ static int extract_match_pipeline(orbx_extractor* ex, orbx_matcher* m, bool host
     CKM(cudaStreamWaitEvent(s, m->ev[ORBX_MAX_CHUNKS + nchunks - 1], 0));
     rc = orbx_extractor_copy_slot(ex, batch, 0, s);
     if (rc) return rc;
+    if (m->cam_set) {
+        const size_t capx = orbx_ex_out_cap(ex);
+        CKM(cudaMemcpyAsync(m->d_kps_un, m->d_kps_un + (size_t)batch * capx, sizeof(orbx_keypoint) * capx, cudaMemcpyDeviceToDevice, s));
+    }
     if (!host) return ORBX_OK;                       // asynchronous: the caller synchronises `s`
     CKM(cudaStreamSynchronize(m->s_d2h));
     CKM(cudaStreamSynchronize(m->s_match));

@@ -132,6 +132,9 @@ struct orbx_matcher {
     unsigned* h_err;
     int32_t* d_pair_a; int32_t* d_pair_b;
     const orbx_keypoint* d_kps_src;          // optional replacement of the extractor's keypoints in the slot-based searches (mvKeysUn)
+    // camera of the stream pipelines (orbx_matcher_set_camera): when set, every chunk is undistorted into d_kps_un
+    bool cam_set; float cam_K[9], cam_P[9], cam_dist[12]; int cam_ndist;
+    orbx_keypoint* d_kps_un; size_t kps_un_elems;
     uint8_t* d_gen; size_t gen_bytes;
     uint8_t* d_st; size_t st_bytes;          // stereo scratch
     int32_t* h_mono2; int mono2_cap;         // pinned monoIndex landing zone of the stereo pipeline (2 x batch)

@@ -39,7 +39,7 @@ EXPORTS = [
     "orbx_search_by_projection",
     "orbx_stereo_band_match", "orbx_stereo_matches", "orbx_stereo_matches_batch", "orbx_stereo_matches_batch_device",
     "orbx_extract_stereo_batch",
-    "orbx_fast_segment_plan", "orbx_matcher_set_slot_keypoints", "orbx_search_by_projection_ex", "orbx_match_candidates", "orbx_search_by_bow", "orbx_search_for_triangulation", "orbx_distinctive_descriptors", "orbx_undistort_keypoints", "orbx_undistort_slots_device",
+    "orbx_fast_segment_plan", "orbx_matcher_set_slot_keypoints", "orbx_matcher_set_camera", "orbx_matcher_undistorted_device", "orbx_search_by_projection_ex", "orbx_match_candidates", "orbx_search_by_bow", "orbx_search_for_triangulation", "orbx_distinctive_descriptors", "orbx_undistort_keypoints", "orbx_undistort_slots_device",
     "orbx_keypoints_to_msg", "orbx_keypoints_from_msg", "orbx_slot_keypoints_to_msg_device", "orbx_vocab_create", "orbx_vocab_destroy", "orbx_vocab_words", "orbx_vocab_word_weights",
     "orbx_bow_transform", "orbx_bow_transform_slots_device", "orbx_popc_peak",
 ]
@@ -116,6 +116,8 @@ def lib():
         L.orbx_search_by_bow.argtypes = [vp, i32, vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, vp, i32, f32, i32, vp, vp]
         L.orbx_fast_segment_plan.argtypes = [i32, vp, vp, vp, vp, vp]
         L.orbx_matcher_set_slot_keypoints.argtypes = [vp, vp]
+        L.orbx_matcher_set_camera.argtypes = [vp, vp, vp, i32, vp]
+        L.orbx_matcher_undistorted_device.argtypes = [vp, vp]
         L.orbx_search_by_projection_ex.argtypes = [vp, i32, vp, vp, i32, vp, vp, vp, i32, vp, vp, f32, i32, i32, vp, i32, C.c_double, vp, vp, vp]
         L.orbx_distinctive_descriptors.argtypes = [vp, vp, vp, i32, vp]
         L.orbx_undistort_keypoints.argtypes = [vp, vp, i32, vp, vp, i32, vp, vp]

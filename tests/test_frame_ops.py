@@ -130,3 +130,38 @@ def test_device_pipeline_with_undistorted_keypoints():
         np.testing.assert_array_equal(hm12[i, :len(k1)], rm12)
     orbx._check(orbx.lib().orbx_matcher_set_slot_keypoints(m._h, None))
     ex.close(); m.close()
+
+
+@pytest.mark.gpu
+def test_stream_pipeline_with_camera():
+    """orbx_extract_match_batch with a distorted camera set on the matcher: every frame is matched against its predecessor on
+    mvKeysUn (predecessor carried across calls), equal to the oracle on undistorted keypoints."""
+    from multi_orbslam3_b200 import orbx, synth
+    W, H = 752, 480
+    frames = synth.rects_stream(W, H, 5, seed=14)
+    ex = orbx.ORBextractor(1000, 1.2, 8, 20, 7, max_width=W, max_height=H, max_batch=3)
+    m = orbx.ORBmatcher(0.9, True, max_keypoints=ex.cap, max_batch=3)
+    Kf = np.ascontiguousarray(EUROC_K.reshape(9)); Df = np.ascontiguousarray(EUROC_D)
+    orbx._check(orbx.lib().orbx_matcher_set_camera(m._h, orbx._p(Kf), orbx._p(Df), 4, orbx._p(Kf)))
+    bounds = (-30.0, W + 30.0, -30.0, H + 30.0)
+    got = []
+    for lo, hi in ((0, 3), (3, 5)):                      # two calls: the second one starts from the carried predecessor
+        nb, cap = hi - lo, ex.cap
+        out = {"kps": np.zeros((nb, cap), orbx.KP_DTYPE), "desc": np.zeros((nb, cap, 32), np.uint8), "n": np.zeros(nb, np.int32),
+               "mono": np.zeros(nb, np.int32), "matches12": np.zeros((nb, cap), np.int32), "nmatches": np.zeros(nb, np.int32)}
+        orbx.extract_match_batch(ex, m, np.ascontiguousarray(frames[lo:hi]), (0, 0), bounds, 100, out)
+        for i in range(hi - lo):
+            n = int(out["n"][i])
+            got.append((out["kps"][i, :n].copy(), out["desc"][i, :n].copy(), out["matches12"][i].copy(), int(out["nmatches"][i])))
+    ref = O.Extractor(1000, 1.2, 8, 20, 7)
+    prev = None
+    for i in range(5):
+        _, k, d = ref(frames[i], (0, 0))
+        assert got[i][0].tobytes() == k.tobytes()                              # the returned keypoints are mvKeys (distorted)
+        ku = O.undistort_keypoints(k, EUROC_K, EUROC_D, EUROC_K)
+        if prev is not None:
+            rn, rm12, _ = O.search_for_initialization(prev[0], prev[1], ku, d, bounds, np.stack([prev[0]["x"], prev[0]["y"]], 1), 100, 0.9, True)
+            assert got[i][3] == rn and rn > 20
+            np.testing.assert_array_equal(got[i][2][:len(prev[0])], rm12)
+        prev = (ku, d)
+    ex.close(); m.close()
