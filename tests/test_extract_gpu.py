@@ -221,3 +221,27 @@ def test_c_abi_rejects_bad_arguments():
     idx = np.zeros((300, 2), np.int32); dist = np.zeros((300, 2), np.int32)
     assert L.orbx_bf_knn2(m._h, None, 10, p(d_ok), 10, p(idx), p(dist)) == INVALID
     m.close(); ex.close()
+
+
+def test_full_c1_batch_properties():
+    """BASELINE config C1 at the bench size (512 frames of 752x480 per call, device-resident): size-independent properties.
+    Frames repeat with period 32, so every repetition must give byte-identical keypoints and descriptors wherever it sits
+    in the batch; one period is compared with the oracle; counts stay within the reference's quota bounds."""
+    import torch
+    W, H, B, PER = 752, 480, 512, 32
+    base = synth.rects_stream(W, H, PER, seed=123)
+    frames = np.ascontiguousarray(np.concatenate([base] * (B // PER)))
+    ex = orbx.ORBextractor(1000, 1.2, 8, 20, 7, max_width=W, max_height=H, max_batch=B)
+    d = torch.from_numpy(frames).cuda()
+    ex.extract_batch_device(d.data_ptr(), B, W, H, W, W * H, (0, 0), 0, None)
+    ex.sync()
+    res = ex.download(0, B)
+    for i in range(PER, B):
+        a, b_ = res[i], res[i - PER]
+        assert a[0] == b_[0] and a[1].tobytes() == b_[1].tobytes() and a[2].tobytes() == b_[2].tobytes(), i
+    ref = O.Extractor(1000, 1.2, 8, 20, 7)
+    for i in (0, 7, 31):
+        check_frame(res[i], ref(base[i], (0, 0)))
+    n = np.array([len(r[1]) for r in res])
+    assert n.min() >= 900 and n.max() <= 1000 + 8 * 4          # quota + at most a few extra nodes per level (:736)
+    ex.close()
