@@ -173,7 +173,7 @@ __host__ __device__ inline int qg_cap(int hs, int ng) { return hs * ng; }
 // shared-memory bytes of one segment tile, without the pixel queue
 __host__ __device__ inline int tile_bytes(int nrow, int hs, int ng, int ncell)
 {
-    return nrow * TP + hs * TP + qg_cap(hs, ng) * 4 + CLCAP * 4 + (2 * hs * (TP / 32) + 4) * 4 + ((2 * ncell * hs * 2 + 15) & ~15);
+    return nrow * TP + hs * TP + qg_cap(hs, ng) * 4 + CLCAP * 4 + (2 * hs * (TP / 32) + 4) * 4 + ((ncell * hs * 2 + 15) & ~15);
 }
 
 __global__ void __launch_bounds__(NT, 5) k_fast_seg(OrbxGeom g, OrbxBuffers b, const uint8_t* level0, int pitch0,
@@ -207,8 +207,7 @@ __global__ void __launch_bounds__(NT, 5) k_fast_seg(OrbxGeom g, OrbxBuffers b, c
     unsigned* CL = QG + qgcap;                                    // [CLCAP] corners: x | scored row << 16
     unsigned* Bmin = CL + CLCAP;                                    // [hs][bw] survivors at minTh
     unsigned* Bini = Bmin + hs * bw;                                // [hs][bw] (+4 words of padding) survivors at iniTh
-    unsigned short* cnt_min = reinterpret_cast<unsigned short*>(Bini + hs * bw + 4);   // [ncell][hs]
-    unsigned short* cnt_ini = cnt_min + ncell * hs;                 // [ncell][hs]; later: exclusive row prefix of the chosen counts
+    unsigned short* cnt_ini = reinterpret_cast<unsigned short*>(Bini + hs * bw + 4);   // [ncell][hs] exclusive row prefix of the chosen counts inside a cell
     unsigned* Q = reinterpret_cast<unsigned*>(smem + tbytes);       // [qcap] candidate queue: x | tile row << 16
     const int qcap = (smem_total - tbytes) >> 2;
 
