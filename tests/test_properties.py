@@ -9,7 +9,7 @@ from oracle import oracle as O
 desc_rows = lambda lo, hi: hnp.arrays(np.uint8, st.tuples(st.integers(lo, hi), st.just(32)))
 
 
-@settings(max_examples=40, deadline=None)
+@settings(max_examples=40, deadline=None, derandomize=True)
 @given(desc_rows(1, 40), desc_rows(1, 40))
 def test_hamming_and_knn2(q, t):
     D = (np.unpackbits(q, axis=1)[:, None, :] != np.unpackbits(t, axis=1)[None, :, :]).sum(2)
@@ -24,7 +24,7 @@ def test_hamming_and_knn2(q, t):
             assert idx[i, 1] == -1
 
 
-@settings(max_examples=30, deadline=None)
+@settings(max_examples=30, deadline=None, derandomize=True)
 @given(st.integers(0, 2 ** 31 - 1), st.integers(1, 600), st.integers(1, 120))
 def test_octree_selection_invariants(seed, n, N):
     rng = np.random.default_rng(seed)
@@ -40,11 +40,11 @@ def test_octree_selection_invariants(seed, n, N):
     assert len({(r[0], r[1]) for r in out.tolist()}) == len(out)                   # at most one keypoint per node
     assert len(out) <= max(N, 2) + 3 * 2 + 2                                       # N plus the last expansion's surplus (:736)
     assert len(out) >= min(len(cand), 1)
-    if len(cand) <= N // 4:
-        assert len(out) == len(cand)                                               # far below the quota every candidate survives
+    # NB: even far below the quota a candidate can be dropped: the reference stops as soon as a sweep does not increase the
+    # node count (ORBextractor.cc:667), e.g. when two points share the only non-empty child of every multi-point node
 
 
-@settings(max_examples=25, deadline=None)
+@settings(max_examples=25, deadline=None, derandomize=True)
 @given(st.integers(0, 255), st.integers(8, 70), st.integers(8, 70), st.integers(8, 60), st.integers(8, 60))
 def test_constant_images_stay_constant(v, sw, sh, dw, dh):
     img = np.full((sh, sw), v, np.uint8)
@@ -52,7 +52,7 @@ def test_constant_images_stay_constant(v, sw, sh, dw, dh):
     assert (O.gaussian_blur7(img) == v).all()                                      # kernel sums to 256
 
 
-@settings(max_examples=30, deadline=None)
+@settings(max_examples=30, deadline=None, derandomize=True)
 @given(desc_rows(1, 24))
 def test_distinctive_descriptor_is_a_median_minimiser(d):
     off = np.array([0, len(d)], np.int32)
