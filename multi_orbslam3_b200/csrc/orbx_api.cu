@@ -277,16 +277,27 @@ extern "C" int orbx_extractor_create(const orbx_params* p, orbx_extractor** out)
     h->d_raw = nullptr; h->raw_bytes = 0;
     h->profile = false; h->ev_head = 0; h->ev_count = 0; h->stage_batches = 0;
     for (int i = 0; i < 4; i++) h->stage_ms[i] = 0;
-    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    // value-initialised above: every pointer the destructor frees is null until it is allocated
+#define CKH(call)                                                                         \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess) {                                                          \
+            orbx_set_error("%s failed: %s", #call, cudaGetErrorString(e_));               \
+            orbx_extractor_destroy(h);                                                    \
+            return ORBX_E_CUDA;                                                           \
+        }                                                                                 \
+    } while (0)
+    CKH(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     const int cap = orbx_extractor_max_keypoints(h);
-    CK(cudaMallocHost((void**)&h->h_stage_in, (size_t)((p->max_width + 63) & ~63) * p->max_height * p->max_batch));
-    CK(cudaMallocHost((void**)&h->h_kps, sizeof(orbx_keypoint) * (size_t)cap * h->slots));
-    CK(cudaMallocHost((void**)&h->h_desc, (size_t)32 * cap * h->slots));
-    CK(cudaMallocHost((void**)&h->h_n, sizeof(int) * h->slots));
-    CK(cudaMallocHost((void**)&h->h_mono, sizeof(int) * h->slots));
-    CK(cudaMallocHost((void**)&h->h_err, sizeof(unsigned)));
+    CKH(cudaMallocHost((void**)&h->h_stage_in, (size_t)((p->max_width + 63) & ~63) * p->max_height * p->max_batch));
+    CKH(cudaMallocHost((void**)&h->h_kps, sizeof(orbx_keypoint) * (size_t)cap * h->slots));
+    CKH(cudaMallocHost((void**)&h->h_desc, (size_t)32 * cap * h->slots));
+    CKH(cudaMallocHost((void**)&h->h_n, sizeof(int) * h->slots));
+    CKH(cudaMallocHost((void**)&h->h_mono, sizeof(int) * h->slots));
+    CKH(cudaMallocHost((void**)&h->h_err, sizeof(unsigned)));
     orbx_upload_pattern();
-    CK(cudaGetLastError());
+    CKH(cudaGetLastError());
+#undef CKH
     *out = h;
     return ORBX_OK;
 }

@@ -541,13 +541,15 @@ extern "C" int orbx_matcher_create(const orbx_matcher_params* p, orbx_matcher** 
     m->p = *p;
     m->K = p->max_keypoints; m->P = p->max_batch;
     m->POOL = p->max_candidates > 0 ? p->max_candidates : 131072;
-    CKM(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+    if (cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        orbx_set_error("%s%s", "cudaStreamCreate failed", ""); delete m; return ORBX_E_CUDA;
+    }
     WinBufs& W = m->W;
     memset(&W, 0, sizeof(W));
     W.K = m->K; W.POOL = m->POOL;
     const size_t K = m->K, P = m->P;
     int rc;
-#define MA(ptr, bytes) if ((rc = m_alloc(m, (void**)&(ptr), (bytes)))) return rc
+#define MA(ptr, bytes) if ((rc = m_alloc(m, (void**)&(ptr), (bytes)))) { orbx_matcher_destroy(m); return rc; }
     MA(W.pairs, sizeof(PairDesc) * P);
     MA(W.q, sizeof(orbx_proj_query) * K * P);
     MA(W.items, sizeof(uint16_t) * K * P);

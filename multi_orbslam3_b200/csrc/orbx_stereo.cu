@@ -228,7 +228,7 @@ extern "C" int orbx_stereo_band_match(orbx_matcher* m, const orbx_keypoint* kl, 
                                       const orbx_keypoint* kr, const uint8_t* dr, int nr, const float* scale_factors,
                                       int nlevels, int nrows, float min_d, float max_d, int32_t* best_idx, int32_t* best_dist)
 {
-    if (!m || nl < 0 || nr < 0 || nl > m->K || nr > m->K || nlevels < 1 || nlevels > ORBX_MAX_LEVELS || !scale_factors ||
+    if (!m || nl < 0 || nr < 0 || nl > m->K || nr > m->K || nrows < 1 || nlevels < 1 || nlevels > ORBX_MAX_LEVELS || !scale_factors ||
         (nl > 0 && (!kl || !dl || !best_idx || !best_dist)) || (nr > 0 && (!kr || !dr))) return ORBX_E_INVALID;
     if (nl == 0) return ORBX_OK;
     CKM(cudaSetDevice(m->p.device));
