@@ -39,6 +39,13 @@ def level_pixels(w=None, h=None):
     return out
 
 
+def workload_config(args):
+    """`config` of the JSON line: the same dict in both arms (the driver compares them)."""
+    return {"workload": ("C4: 640x480 TUM-shape" if args.workload == "c4" else "C1: 752x480") +
+            " mono, 1000 kp, 8 levels, scale 1.2, FAST 20/7; extract + SearchForInitialization(window 100) + BF kNN-2 vs previous frame",
+            "l2": "inputs larger than L2 (frames per step exceed the 126 MB L2)"}
+
+
 # ------------------------------------------------------------------------------------------------
 # CPU oracle legs (cpu_baseline and --impl reference)
 # ------------------------------------------------------------------------------------------------
@@ -93,7 +100,7 @@ def reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_time / max(args.steps, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": ("C4: 640x480 TUM-shape" if args.workload == "c4" else "C1: 752x480") + " mono, 1000 kp, 8 levels, scale 1.2, FAST 20/7; extract + SearchForInitialization(window 100) + BF kNN-2 vs previous frame"},
+        "config": workload_config(args),
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port",
                          "sample": "%d frames per step (%d threads x %d frames of a 16-frame S-rects stream), %d steps" % (cores * per_thread, cores, per_thread, args.steps)},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -457,7 +464,7 @@ class ClockSampler:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=250, help="timed steps (default: > 1 s of device time, so that the clock record has real samples)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="orbx", choices=["orbx", "reference"])
     ap.add_argument("--batch", type=int, default=512, help="frames per step per GPU (512 x 361 KB = 185 MB of input > 126 MB L2)")
@@ -571,9 +578,12 @@ def main():
         "mono": torch.empty(B, dtype=torch.int32).pin_memory().numpy(),
         "matches12": torch.empty((B, cap), dtype=torch.int32).pin_memory().numpy(),
         "nmatches": torch.empty(B, dtype=torch.int32).pin_memory().numpy(),
+        # BF kNN-2 tables of every (previous frame, frame) pair: part of the C1 workload, so part of the e2e / latency legs
+        "knn_idx": torch.empty((B, cap, 2), dtype=torch.int32).pin_memory().numpy(),
+        "knn_dist": torch.empty((B, cap, 2), dtype=torch.int32).pin_memory().numpy(),
     }
     h_np = h_frames.numpy()
-    e2e_steps = 0 if args.no_e2e else max(3, min(args.steps, 10))
+    e2e_steps = 0 if args.no_e2e else max(3, min(args.steps, 60))
     for _ in range(0 if args.no_e2e else 2):
         orbx.extract_match_batch(ex, m, h_np, (0, 0), bounds, WINDOW, out)
     barrier()
@@ -587,7 +597,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * B * e2e_steps / float(t.item()) if e2e_steps else None
     h2d = B * W * H
-    d2h = B * (cap * 28 + cap * 32 + cap * 4 + 4 + 4 + 4)
+    d2h = B * (cap * 28 + cap * 32 + cap * 4 + 2 * cap * 8 + 4 + 4 + 4)
     clocks = sampler.stop() if rank == 0 else None
 
     # ---------------- p50 per-frame latency: batch = 1, synchronous class-API calls with host buffers ----------------
@@ -605,7 +615,7 @@ def main():
             ts.append(time.perf_counter() - t1)
         ts = np.array(ts[20:]) * 1e3
         latency = {"p50_ms": float(np.percentile(ts, 50)), "p95_ms": float(np.percentile(ts, 95)), "frames": nlat,
-                   "what": "one frame per call: orbx_extract_match_batch(batch=1) = H2D + extract + SearchForInitialization vs previous frame + D2H"}
+                   "what": "one frame per call: orbx_extract_match_batch(batch=1) = H2D + extract + SearchForInitialization + BF kNN-2 vs previous frame + D2H"}
         ex1.close(); m1.close()
 
     if rank != 0:
@@ -688,13 +698,13 @@ def main():
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
         "data": "synthetic",
-        "config": {"workload": ("C4: 640x480 TUM-shape" if args.workload == "c4" else "C1: 752x480") + " mono, 1000 kp, 8 levels, scale 1.2, FAST 20/7; extract + SearchForInitialization(window 100) + BF kNN-2 vs previous frame",
-                   "frames_per_step_per_gpu": B, "streams": "one S-rects camera stream per GPU, no collective",
-                   "l2": "inputs larger than L2 (%d MB of frames per step, >1 GB touched)" % (B * W * H // 2 ** 20),
-                   "mean_keypoints": nkp_mean, "mean_init_matches": nmatch_mean},
+        "config": workload_config(args),
+        "run": {"frames_per_step_per_gpu": B, "streams": "one S-rects camera stream per GPU, no collective",
+                "l2": "inputs larger than L2 (%d MB of frames per step, >1 GB touched)" % (B * W * H // 2 ** 20),
+                "mean_keypoints": nkp_mean, "mean_init_matches": nmatch_mean},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                "api": "orbx_extract_match_batch (pinned host frames -> keypoints, descriptors, matches on host)"},
+                "api": "orbx_extract_match_batch (pinned host frames -> keypoints, descriptors, SearchForInitialization matches and BF kNN-2 tables on host)"},
         "gpu_launches": int(launches),
         "latency": latency,
         "roofline": roofline,

@@ -190,12 +190,15 @@ int  orbx_matcher_undistorted_device(orbx_matcher* m, orbx_keypoint** d_kps_un);
 /* One tracking step over a batch of HOST frames (the end-to-end path): H2D, operator() on every frame into result
  * slots 1..batch, SearchForInitialization of each frame against its predecessor (slot i-1 -> slot i; slot 0 keeps
  * the last frame of the previous call, as Tracking keeps mLastFrame), D2H of keypoints, descriptors and matches.
- * Pinned caller buffers are DMA'd directly.  kps: batch*cap, desc: batch*cap*32, matches12: batch*cap. */
+ * Pinned caller buffers are DMA'd directly.  kps: batch*cap, desc: batch*cap*32, matches12: batch*cap.
+ * knn_idx / knn_dist (both or neither; batch*cap*2 each): when given, the brute-force kNN-2 of every frame's predecessor
+ * against the frame (cv::BFMatcher::knnMatch(k = 2), R/src/Frame.cc:1127-1137; rows = the predecessor's keypoints) is run
+ * and copied back as well.  batch must fit both handles (matcher max_batch, extractor max_batch); both handles on one device. */
 int  orbx_extract_match_batch(orbx_extractor* ex, orbx_matcher* m, const uint8_t* imgs, int batch, int width,
                               int height, int stride, size_t frame_stride, int lap0, int lap1,
                               const float bounds[4], int window, float nnratio, int check_ori,
                               orbx_keypoint* kps, uint8_t* desc, int cap, int32_t* n, int32_t* mono_index,
-                              int32_t* matches12, int32_t* nmatches);
+                              int32_t* matches12, int32_t* nmatches, int32_t* knn_idx, int32_t* knn_dist);
 
 /* The same step on DEVICE-resident frames, asynchronous on `stream` (results stay in the slots; matches12 [batch][K],
  * nmatches [batch] and the optional BF kNN-2 tables [batch][K][2] are device arrays, K = the matcher's max_keypoints).

@@ -3,7 +3,10 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <mutex>
+#include <set>
 #include <string>
+#include <utility>
 #include <vector>
 #include "orbx_internal.h"
 
@@ -27,6 +30,24 @@ extern "C" const char* orbx_last_error(void) { return g_last_error.c_str(); }
             return ORBX_E_CUDA;                                                           \
         }                                                                                 \
     } while (0)
+
+cudaError_t orbx_optin_smem(const void* kernel)
+{
+    static std::mutex mu;
+    static std::set<std::pair<const void*, int>> done;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lock(mu);
+    if (done.count(std::make_pair(kernel, dev))) return cudaSuccess;
+    int optin = 0;
+    if ((e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess) return e;
+    cudaFuncAttributes fa;
+    if ((e = cudaFuncGetAttributes(&fa, kernel)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes)) != cudaSuccess) return e;
+    done.insert(std::make_pair(kernel, dev));
+    return cudaSuccess;
+}
 
 extern "C" int orbx_device_count(void)
 {
@@ -106,10 +127,20 @@ static void axis_table(int dn, int sn, bool horizontal, short4* out)
     }
 }
 
+static int configure_geometry_impl(orbx_extractor* h, int width, int height);
+// The geometry is committed only when every table and buffer of it exists: a failure half way (out of memory, a bad size)
+// leaves the handle unconfigured (width == 0) so that the next call starts over instead of launching on partial buffers.
 static int configure_geometry(orbx_extractor* h, int width, int height)
 {
+    if (h->geom.width == width && h->geom.height == height) return ORBX_OK;
+    const int rc = configure_geometry_impl(h, width, height);
+    if (rc != ORBX_OK) { h->geom.width = 0; h->geom.height = 0; }
+    return rc;
+}
+
+static int configure_geometry_impl(orbx_extractor* h, int width, int height)
+{
     OrbxGeom& g = h->geom;
-    if (g.width == width && g.height == height) return ORBX_OK;
     if (width > h->p.max_width || height > h->p.max_height) {
         orbx_set_error("%s%s", "image larger than max_width/max_height of the handle", "");
         return ORBX_E_INVALID;
@@ -271,6 +302,13 @@ extern "C" int orbx_extractor_create(const orbx_params* p, orbx_extractor** out)
         nDesired *= factor;
     }
     h->featuresPerLevel[nl - 1] = p->nfeatures - sum > 0 ? p->nfeatures - sum : 0;
+    // k_octree keeps a level's node table on chip: quota + 8 nodes must fit its ORBX_OCTREE_MAX_NODES entries
+    for (int l = 0; l < nl; l++)
+        if (h->featuresPerLevel[l] + 8 > ORBX_OCTREE_MAX_NODES) {
+            orbx_set_error("%s%s", "orbx_extractor_create: nfeatures too large (a level quota exceeds the octree node table, 4088)", "");
+            delete h;
+            return ORBX_E_INVALID;
+        }
     memset(&h->geom, 0, sizeof(h->geom));
     memset(&h->buf, 0, sizeof(h->buf));
     h->d_level0 = nullptr; h->last_level0 = nullptr; h->last_batch = 0;
@@ -514,6 +552,7 @@ int orbx_ex_run_device(orbx_extractor* h, const uint8_t* d_imgs, int pitch, long
 
 cudaStream_t orbx_ex_stream(orbx_extractor* h) { return h->stream; }
 int orbx_ex_device(orbx_extractor* h) { return h->p.device; }
+int orbx_ex_max_batch(orbx_extractor* h) { return h->p.max_batch; }
 
 int orbx_ex_pyramid_view(orbx_extractor* h, int frame, OrbxPyrView* out)
 {

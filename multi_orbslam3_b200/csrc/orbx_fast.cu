@@ -550,7 +550,8 @@ extern "C" int orbx_fast_segment_plan(int level_width, int* n_cols, int* w_cell,
 
 void orbx_fast_configure(const OrbxGeom& g)
 {
-    cudaFuncSetAttribute(k_fast_seg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem_bytes(g));
+    (void)g;
+    ORBX_OPTIN_SMEM(k_fast_seg);
 }
 
 void orbx_launch_fast(const OrbxGeom& g, const OrbxBuffers& b, const uint8_t* level0, int pitch0,
@@ -559,6 +560,7 @@ void orbx_launch_fast(const OrbxGeom& g, const OrbxBuffers& b, const uint8_t* le
     if (g.total_rows == 0) return;
     dim3 grid(g.total_rows, batch);
     const size_t smem = fast_smem_bytes(g);
+    ORBX_OPTIN_SMEM(k_fast_seg);
     k_fast_seg<<<grid, NT, smem, s>>>(g, b, level0, pitch0, stride0, (int)smem);
     ORBX_COUNT_LAUNCH(1);
 }

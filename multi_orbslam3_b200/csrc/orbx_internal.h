@@ -10,6 +10,7 @@
 #define ORBX_HALF_PATCH 15    // HALF_PATCH_SIZE, R/src/ORBextractor.cc:71
 #define ORBX_FAST_TP 288      // staged width limit (bytes) of one FAST segment tile
 #define ORBX_MAX_UNITS 2048   // FAST segments (cell row x segment) per level
+#define ORBX_OCTREE_MAX_NODES 4096   // k_octree: MAX_IPT (8) node items per thread x 512 threads; creation index packed in 12 bits
 #define ORBX_FAST_W 30        // cell size W, R/src/ORBextractor.cc:767
 
 // device error flag bits (written by kernels, read back at sync/download)
@@ -100,6 +101,11 @@ int orbx_fast_plan(int w, int nCols, int wCell);
 void orbx_fast_units(const OrbxGeom& g, std::vector<int4>& tab);
 void orbx_upload_pattern();
 void orbx_set_error(const char* fmt, const char* a, const char* b);
+// Raises a kernel's dynamic shared-memory limit to the opt-in maximum of the CURRENT device, once per (kernel, device).
+// The attribute is per function and per device, shared by every handle of the process: it is never tied to one handle's
+// configuration and never lowered, so handles with different sizes and handles on different devices cannot interfere.
+cudaError_t orbx_optin_smem(const void* kernel);
+#define ORBX_OPTIN_SMEM(k) orbx_optin_smem(reinterpret_cast<const void*>(k))
 // number of kernels this library launched since load (bench.py reports the delta as gpu_launches)
 #include <atomic>
 extern std::atomic<unsigned long long> g_orbx_launches;     // extractor instances may run on different host threads
@@ -131,3 +137,4 @@ struct OrbxPyrView {
 };
 int orbx_ex_pyramid_view(orbx_extractor* h, int frame, OrbxPyrView* out);
 int orbx_ex_device(orbx_extractor* h);
+int orbx_ex_max_batch(orbx_extractor* h);

@@ -571,21 +571,28 @@ extern "C" int orbx_matcher_create(const orbx_matcher_params* p, orbx_matcher** 
     m->d_part_idx = m->d_part_dist = nullptr; m->part_elems = 0;
     m->d_bfq = m->d_bft = nullptr; m->bfq_bytes = m->bft_bytes = 0;
     m->d_pair_a = m->d_pair_b = nullptr;
+    m->d_pipe_knn = nullptr; m->pipe_knn_elems = 0;
     m->d_gen = nullptr; m->gen_bytes = 0;
     m->d_kps_src = nullptr;
     m->cam_set = false; m->cam_ndist = 0; m->d_kps_un = nullptr; m->kps_un_elems = 0;
     m->d_st = nullptr; m->st_bytes = 0;
     m->h_mono2 = nullptr; m->mono2_cap = 0;
     m->s_h2d = m->s_d2h = nullptr;
-    CKM(cudaMemset(W.err, 0, sizeof(unsigned)));
-    CKM(cudaMallocHost((void**)&m->h_err, sizeof(unsigned)));
-    if (2 * K * sizeof(int) > 48 * 1024)
-        CKM(cudaFuncSetAttribute(k_window_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * K * sizeof(int))));
-    {
-        size_t npad = 1; while (npad < K) npad <<= 1;
-        if (npad * sizeof(uint32_t) > 48 * 1024)
-            CKM(cudaFuncSetAttribute(k_grid_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(npad * sizeof(uint32_t))));
-    }
+    m->h_err = nullptr;
+#define CKD(call)                                                                         \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess) {                                                          \
+            orbx_set_error("%s failed: %s", #call, cudaGetErrorString(e_));               \
+            orbx_matcher_destroy(m);                                                      \
+            return ORBX_E_CUDA;                                                           \
+        }                                                                                 \
+    } while (0)
+    CKD(cudaMemset(W.err, 0, sizeof(unsigned)));
+    CKD(cudaMallocHost((void**)&m->h_err, sizeof(unsigned)));
+    CKD(ORBX_OPTIN_SMEM(k_window_resolve));
+    CKD(ORBX_OPTIN_SMEM(k_grid_build));
+#undef CKD
     *out = m;
     return ORBX_OK;
 }
@@ -601,6 +608,7 @@ extern "C" void orbx_matcher_destroy(orbx_matcher* m)
     if (m->d_bfq) cudaFree(m->d_bfq);
     if (m->d_bft) cudaFree(m->d_bft);
     if (m->d_pair_a) cudaFree(m->d_pair_a);
+    if (m->d_pipe_knn) cudaFree(m->d_pipe_knn);
     if (m->d_gen) cudaFree(m->d_gen);
     if (m->d_kps_un) cudaFree(m->d_kps_un);
     if (m->d_st) cudaFree(m->d_st);
@@ -611,7 +619,7 @@ extern "C" void orbx_matcher_destroy(orbx_matcher* m)
         for (int i = 0; i < 2 * ORBX_MAX_CHUNKS; i++) { cudaEventDestroy(m->ev[i]); cudaEventDestroy(m->ev_r[i]); }
         cudaEventDestroy(m->ev_start);
     }
-    cudaFreeHost(m->h_err);
+    if (m->h_err) cudaFreeHost(m->h_err);
     cudaStreamDestroy(m->stream);
     delete m;
 }
@@ -770,10 +778,12 @@ static int run_window(orbx_matcher* m, const WinBufs& W, int npairs, int nq_max,
 {
     int npad = 1; while (npad < m->K) npad <<= 1;
     CKM(cudaMemsetAsync(W.pool_used, 0, sizeof(int) * npairs, s));
+    CKM(ORBX_OPTIN_SMEM(k_grid_build));
     k_grid_build<<<npairs, GRID_NT, sizeof(uint32_t) * npad, s>>>(W, npad); ORBX_COUNT_LAUNCH(1);
     dim3 cg((nq_max + CAND_WARPS - 1) / CAND_WARPS, npairs);
     if (nq_max > 0) { k_window_candidates<<<cg, CAND_WARPS * 32, 0, s>>>(W); ORBX_COUNT_LAUNCH(1); }
     if (mode == 3) { CKM(cudaGetLastError()); return ORBX_OK; }
+    CKM(ORBX_OPTIN_SMEM(k_window_resolve));
     k_window_resolve<<<npairs, 32, 2 * m->K * sizeof(int), s>>>(W, mode, nnratio, check_ori, max_dist, d_out, d_nm, d_prev); ORBX_COUNT_LAUNCH(1);
     CKM(cudaGetLastError());
     return ORBX_OK;
@@ -991,11 +1001,11 @@ int orbx_m_ensure_pipeline(orbx_matcher* m)
 // (H2D | extraction kernels | matcher kernels | D2H): copies of chunk c+1 / c-1 and the latency-bound matcher kernels of
 // chunk c-1 overlap the extraction of chunk c.  host == true: imgs/outputs are host buffers; else imgs is a device pointer
 // and nothing is copied back (results stay in the slots / the caller's device arrays).
-static int extract_match_pipeline(orbx_extractor* ex, orbx_matcher* m, bool host, const uint8_t* imgs, int batch, int width,
+static int extract_match_pipeline_impl(orbx_extractor* ex, orbx_matcher* m, bool host, const uint8_t* imgs, int batch, int width,
                                   int height, int stride, size_t frame_stride, int lap0, int lap1,
                                   const float bounds[4], int window, float nnratio, int check_ori,
                                   orbx_keypoint* kps, uint8_t* desc, int cap, int32_t* n, int32_t* mono_index,
-                                  int32_t* matches12, int32_t* nmatches,
+                                  int32_t* matches12, int32_t* nmatches, int32_t* knn_idx, int32_t* knn_dist,
                                   int32_t* d_matches12, int32_t* d_nmatches, int32_t* d_knn_idx, int32_t* d_knn_dist,
                                   cudaStream_t s)
 {
@@ -1003,6 +1013,16 @@ static int extract_match_pipeline(orbx_extractor* ex, orbx_matcher* m, bool host
     if (rc) return rc;
     CKM(cudaSetDevice(m->p.device));
     if ((rc = orbx_m_ensure_pipeline(m))) return rc;
+    if (host && knn_idx && knn_dist) {
+        // device landing zone of the BF kNN-2 tables (rows of stride K like every matcher output)
+        const size_t need = (size_t)m->P * m->K * 2;
+        if (need > m->pipe_knn_elems) {
+            if (m->d_pipe_knn) { CKM(cudaDeviceSynchronize()); cudaFree(m->d_pipe_knn); m->d_pipe_knn = nullptr; m->pipe_knn_elems = 0; }
+            CKM(cudaMalloc((void**)&m->d_pipe_knn, sizeof(int32_t) * need * 2));
+            m->pipe_knn_elems = need;
+        }
+        d_knn_idx = m->d_pipe_knn; d_knn_dist = m->d_pipe_knn + need;
+    }
     struct SrcGuard {                                  // the pipeline's own mvKeysUn is the source only for the duration of the call
         orbx_matcher* m; const orbx_keypoint* saved;
         ~SrcGuard() { m->d_kps_src = saved; }
@@ -1087,6 +1107,13 @@ static int extract_match_pipeline(orbx_extractor* ex, orbx_matcher* m, bool host
             if (matches12) CKM(cudaMemcpy2DAsync(matches12 + (size_t)f0 * cap, sizeof(int32_t) * cap, dm12 + (size_t)f0 * m->K, sizeof(int32_t) * m->K,
                                                  sizeof(int32_t) * (cap < m->K ? cap : m->K), cnt, cudaMemcpyDeviceToHost, m->s_d2h));
             if (nmatches) CKM(cudaMemcpyAsync(nmatches + f0, dnm + f0, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, m->s_d2h));
+            if (knn_idx && knn_dist) {
+                const size_t wbytes = sizeof(int32_t) * 2 * (cap < m->K ? cap : m->K);
+                CKM(cudaMemcpy2DAsync(knn_idx + (size_t)f0 * cap * 2, sizeof(int32_t) * 2 * cap, d_knn_idx + (size_t)f0 * m->K * 2,
+                                      sizeof(int32_t) * 2 * m->K, wbytes, cnt, cudaMemcpyDeviceToHost, m->s_d2h));
+                CKM(cudaMemcpy2DAsync(knn_dist + (size_t)f0 * cap * 2, sizeof(int32_t) * 2 * cap, d_knn_dist + (size_t)f0 * m->K * 2,
+                                      sizeof(int32_t) * 2 * m->K, wbytes, cnt, cudaMemcpyDeviceToHost, m->s_d2h));
+            }
         }
     }
     // slot 0 is read by the first chunk's matcher: carry the last frame over only after every matcher finished; the
@@ -1106,17 +1133,51 @@ static int extract_match_pipeline(orbx_extractor* ex, orbx_matcher* m, bool host
     return orbx_ex_fetch_finish(ex, batch, kps, desc, cap, n, mono_index, direct);
 }
 
+// A failure in the middle of the pipeline leaves copies / kernels queued on the side streams that read the caller's buffers:
+// drain them before the error is returned.
+static int extract_match_pipeline(orbx_extractor* ex, orbx_matcher* m, bool host, const uint8_t* imgs, int batch, int width,
+                                  int height, int stride, size_t frame_stride, int lap0, int lap1,
+                                  const float bounds[4], int window, float nnratio, int check_ori,
+                                  orbx_keypoint* kps, uint8_t* desc, int cap, int32_t* n, int32_t* mono_index,
+                                  int32_t* matches12, int32_t* nmatches, int32_t* knn_idx, int32_t* knn_dist,
+                                  int32_t* d_matches12, int32_t* d_nmatches, int32_t* d_knn_idx, int32_t* d_knn_dist,
+                                  cudaStream_t s)
+{
+    const int rc = extract_match_pipeline_impl(ex, m, host, imgs, batch, width, height, stride, frame_stride, lap0, lap1, bounds, window,
+                                               nnratio, check_ori, kps, desc, cap, n, mono_index, matches12, nmatches, knn_idx, knn_dist,
+                                               d_matches12, d_nmatches, d_knn_idx, d_knn_dist, s);
+    if (rc != ORBX_OK && m->s_h2d) {
+        cudaStreamSynchronize(m->s_h2d); cudaStreamSynchronize(m->s_match); cudaStreamSynchronize(m->s_d2h); cudaStreamSynchronize(s);
+        cudaGetLastError();
+    }
+    return rc;
+}
+
+// argument checks shared by the two entry points: the batch must fit the matcher's pair scratch AND the extractor's result slots
+// 1..batch / per-frame scratch, both handles must live on the same device
+static int pipeline_args_ok(orbx_extractor* ex, orbx_matcher* m, const void* imgs, int batch, int width, int stride, const float* bounds)
+{
+    if (!ex || !m || !imgs || !bounds || batch < 1) { orbx_set_error("%s%s", "orbx_extract_match_batch: null argument or batch < 1", ""); return ORBX_E_INVALID; }
+    if (batch > m->P) { orbx_set_error("%s%s", "orbx_extract_match_batch: batch larger than the matcher's max_batch", ""); return ORBX_E_INVALID; }
+    if (batch > orbx_ex_max_batch(ex)) { orbx_set_error("%s%s", "orbx_extract_match_batch: batch larger than the extractor's max_batch", ""); return ORBX_E_INVALID; }
+    if (orbx_ex_device(ex) != m->p.device) { orbx_set_error("%s%s", "orbx_extract_match_batch: extractor and matcher are on different devices", ""); return ORBX_E_INVALID; }
+    if (width > 0 && stride < width) { orbx_set_error("%s%s", "orbx_extract_match_batch: stride smaller than width", ""); return ORBX_E_INVALID; }
+    return ORBX_OK;
+}
+
 extern "C" int orbx_extract_match_batch(orbx_extractor* ex, orbx_matcher* m, const uint8_t* imgs, int batch, int width,
                                         int height, int stride, size_t frame_stride, int lap0, int lap1,
                                         const float bounds[4], int window, float nnratio, int check_ori,
                                         orbx_keypoint* kps, uint8_t* desc, int cap, int32_t* n, int32_t* mono_index,
-                                        int32_t* matches12, int32_t* nmatches)
+                                        int32_t* matches12, int32_t* nmatches, int32_t* knn_idx, int32_t* knn_dist)
 {
-    if (!ex || !m || !imgs || batch < 1 || batch > m->P || !bounds) return ORBX_E_INVALID;
+    int rc = pipeline_args_ok(ex, m, imgs, batch, width, stride, bounds);
+    if (rc) return rc;
+    if ((knn_idx == nullptr) != (knn_dist == nullptr)) return ORBX_E_INVALID;
     if (width <= 0 || height <= 0) return ORBX_E_EMPTY;
     return extract_match_pipeline(ex, m, true, imgs, batch, width, height, stride, frame_stride, lap0, lap1, bounds, window, nnratio,
-                                  check_ori, kps, desc, cap, n, mono_index, matches12, nmatches, nullptr, nullptr, nullptr, nullptr,
-                                  orbx_ex_stream(ex));
+                                  check_ori, kps, desc, cap, n, mono_index, matches12, nmatches, knn_idx, knn_dist,
+                                  nullptr, nullptr, nullptr, nullptr, orbx_ex_stream(ex));
 }
 
 extern "C" int orbx_extract_match_batch_device(orbx_extractor* ex, orbx_matcher* m, const uint8_t* d_imgs, int batch, int width,
@@ -1125,10 +1186,12 @@ extern "C" int orbx_extract_match_batch_device(orbx_extractor* ex, orbx_matcher*
                                                int32_t* d_matches12, int32_t* d_nmatches, int32_t* d_knn_idx, int32_t* d_knn_dist,
                                                void* stream)
 {
-    if (!ex || !m || !d_imgs || batch < 1 || batch > m->P || !bounds || !d_matches12 || !d_nmatches || stride < width) return ORBX_E_INVALID;
+    int rc = pipeline_args_ok(ex, m, d_imgs, batch, width, stride, bounds);
+    if (rc) return rc;
+    if (!d_matches12 || !d_nmatches) return ORBX_E_INVALID;
     if (width <= 0 || height <= 0) return ORBX_E_EMPTY;
     return extract_match_pipeline(ex, m, false, d_imgs, batch, width, height, stride, frame_stride, lap0, lap1, bounds, window, nnratio,
-                                  check_ori, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr, d_matches12, d_nmatches, d_knn_idx,
+                                  check_ori, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, d_matches12, d_nmatches, d_knn_idx,
                                   d_knn_dist, stream ? (cudaStream_t)stream : orbx_ex_stream(ex));
 }
 

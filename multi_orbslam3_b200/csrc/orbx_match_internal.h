@@ -127,6 +127,7 @@ struct orbx_matcher {
     orbx_keypoint* d_k1; orbx_keypoint* d_k2; uint8_t* d_d1; uint8_t* d_d2; uint8_t* d_qdesc; float* d_uright;
     float* d_prev; int32_t* d_out; int32_t* d_out2; int32_t* d_nm; float* d_sf;
     int32_t* d_knn_idx; int32_t* d_knn_dist;
+    int32_t* d_pipe_knn; size_t pipe_knn_elems;   // BF kNN-2 tables of the host pipeline: idx [P][K][2] then dist [P][K][2]
     int32_t* d_part_idx; int32_t* d_part_dist; size_t part_elems;
     uint8_t* d_bfq; uint8_t* d_bft; size_t bfq_bytes, bft_bytes;
     unsigned* h_err;

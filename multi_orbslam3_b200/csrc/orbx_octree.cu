@@ -23,6 +23,7 @@ namespace {
 constexpr int NT = 512;
 constexpr int DMAX = 13;                 // path depth: 26 bits; root index: 6 bits
 constexpr int MAX_IPT = 8;               // node items per thread -> up to 4096 nodes
+static_assert(MAX_IPT * NT == ORBX_OCTREE_MAX_NODES, "orbx_extractor_create validates level quotas against this bound");
 typedef unsigned long long u64;
 
 __device__ __forceinline__ u64 block_scan_excl(u64 v, u64* total, u64* s_warp)
@@ -412,12 +413,13 @@ void orbx_launch_octree(const OrbxGeom& g, const OrbxBuffers& b, int batch, cuda
 {
     const OctCfg c = octree_cfg(g);
     dim3 grid(g.nlevels, batch);
+    ORBX_OPTIN_SMEM(k_octree);
     k_octree<<<grid, NT, c.smem, s>>>(g, b, c.smem_pts, c.ncap);
     ORBX_COUNT_LAUNCH(1);
 }
 
 void orbx_octree_configure(const OrbxGeom& g)
 {
-    const OctCfg c = octree_cfg(g);
-    cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
+    (void)g;
+    ORBX_OPTIN_SMEM(k_octree);
 }

@@ -156,6 +156,7 @@ static void launch_pyramid_generic(const OrbxGeom& g, const OrbxBuffers& b, cons
         size_t smem = RH * RP + RH * TW * 2;
         if (l == 0) {
             a.src = level0; a.spitch = pitch0; a.sstride = stride0; a.sw = L.w; a.sh = L.h;
+            ORBX_OPTIN_SMEM(k_pyr_level<false>);
             k_pyr_level<false><<<grid, NT, smem, s>>>(a);
             ORBX_COUNT_LAUNCH(1);
         } else {
@@ -171,6 +172,7 @@ static void launch_pyramid_generic(const OrbxGeom& g, const OrbxBuffers& b, cons
             a.src_tw = (((int)(RW * sx) + 12) + 3) & ~3;
             a.src_th = (int)(RH * sy) + 4;
             smem += (size_t)a.src_tw * a.src_th;
+            ORBX_OPTIN_SMEM(k_pyr_level<true>);
             k_pyr_level<true><<<grid, NT, smem, s>>>(a);
             ORBX_COUNT_LAUNCH(1);
         }
@@ -525,8 +527,7 @@ void orbx_launch_pyramid(const OrbxGeom& g, const OrbxBuffers& b, const uint8_t*
         if (l == 0) {
             a.src = level0; a.spitch = pitch0; a.sstride = stride0; a.sw = L.w; a.sh = L.h;
             const size_t smem = RH * RP + RH * TW * 2;
-            static bool cfg0 = false;
-            if (!cfg0) { cudaFuncSetAttribute(k_pyr_fast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); cfg0 = true; }
+            ORBX_OPTIN_SMEM(k_pyr_fast<false>);
             CUtensorMap none; memset(&none, 0, sizeof(none));
             k_pyr_fast<false><<<grid, NT, smem, s>>>(a, none);
         } else {
@@ -542,8 +543,7 @@ void orbx_launch_pyramid(const OrbxGeom& g, const OrbxBuffers& b, const uint8_t*
             a.sh_max = (int)(RH * sy) + 4;
             const size_t hs_bytes = (size_t)a.sh_max * HP * 2 > (size_t)RH * TW * 2 ? (size_t)a.sh_max * HP * 2 : (size_t)RH * TW * 2;
             const size_t smem = (((size_t)a.sh_max * a.sp + 127) & ~(size_t)127) + RH * RP + hs_bytes + RH * sizeof(int4);
-            static size_t cfg1 = 0;
-            if (smem > cfg1) { cudaFuncSetAttribute(k_pyr_fast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); cfg1 = smem; }
+            ORBX_OPTIN_SMEM(k_pyr_fast<true>);
             CUtensorMap map; memset(&map, 0, sizeof(map));
             a.use_tma = make_map(&map, a.src, a.sw, a.sh, a.spitch, a.sstride, batch, a.sp, a.sh_max) ? 1 : 0;
             k_pyr_fast<true><<<grid, NT, smem, s>>>(a, map);

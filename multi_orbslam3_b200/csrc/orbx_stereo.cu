@@ -250,7 +250,7 @@ extern "C" int orbx_stereo_band_match(orbx_matcher* m, const orbx_keypoint* kl, 
         if (rc) return rc;
         const size_t smem = sizeof(int) * 2 * ((size_t)nrows + 1);
         if (smem > 200 * 1024) return ORBX_E_INVALID;
-        if (smem > 48 * 1024) CKM(cudaFuncSetAttribute(k_stereo_band, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (smem > 48 * 1024) CKM(ORBX_OPTIN_SMEM(k_stereo_band));
         k_stereo_band<<<1, STEREO_NT, smem, s>>>(A, reinterpret_cast<int32_t*>(m->d_st), list_cap); ORBX_COUNT_LAUNCH(1);
     }
     CKM(cudaGetLastError());
@@ -304,12 +304,12 @@ static int stereo_launch(orbx_matcher* m, orbx_extractor* left, orbx_extractor* 
     {
         const size_t smem = sizeof(int) * 2 * ((size_t)A.nrows + 1);
         if (smem > 200 * 1024) return ORBX_E_INVALID;
-        if (smem > 48 * 1024) CKM(cudaFuncSetAttribute(k_stereo_band, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (smem > 48 * 1024) CKM(ORBX_OPTIN_SMEM(k_stereo_band));
         k_stereo_band<<<count, STEREO_NT, smem, s>>>(A, S.lists, S.list_cap); ORBX_COUNT_LAUNCH(1);
     }
     k_stereo_refine<<<dim3((capL + 7) / 8, count), 256, 0, s>>>(A, vL, vR); ORBX_COUNT_LAUNCH(1);
     int npad = 1; while (npad < capL) npad <<= 1;
-    if (sizeof(int) * npad > 48 * 1024) CKM(cudaFuncSetAttribute(k_stereo_outliers, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(int) * npad)));
+    if (sizeof(int) * npad > 48 * 1024) CKM(ORBX_OPTIN_SMEM(k_stereo_outliers));
     k_stereo_outliers<<<count, 1024, sizeof(int) * npad, s>>>(A, npad); ORBX_COUNT_LAUNCH(1);
     CKM(cudaGetLastError());
     return ORBX_OK;

@@ -79,7 +79,7 @@ def lib():
         L.orbx_launch_count.restype = C.c_ulonglong
         L.orbx_extractor_profile.argtypes = [vp, i32, vp, vp]
         L.orbx_extract_match_batch.argtypes = [vp, vp, vp, i32, i32, i32, i32, sz, i32, i32, vp, i32, f32, i32,
-                                               vp, vp, i32, vp, vp, vp, vp]
+                                               vp, vp, i32, vp, vp, vp, vp, vp, vp]
         L.orbx_extract_match_batch_device.argtypes = [vp, vp, vp, i32, i32, i32, i32, sz, i32, i32, vp, i32, f32, i32,
                                                       vp, vp, vp, vp, vp]
         L.orbx_extractor_create.argtypes = [C.POINTER(Params), C.POINTER(vp)]
@@ -565,12 +565,15 @@ def launch_count():
 
 def extract_match_batch(ex, m, imgs, lap, bounds, window, out):
     """orbx_extract_match_batch on host arrays; `out` = dict of preallocated (ideally pinned) numpy arrays
-    kps[B,cap] desc[B,cap,32] n[B] mono[B] matches12[B,cap] nmatches[B]; imgs [B,H,W] uint8."""
+    kps[B,cap] desc[B,cap,32] n[B] mono[B] matches12[B,cap] nmatches[B] and, optionally, the BF kNN-2 tables
+    knn_idx[B,cap,2] knn_dist[B,cap,2] (predecessor x frame); imgs [B,H,W] uint8."""
     B, H, W = imgs.shape
     bb = np.array(bounds, np.float32)
     _check(lib().orbx_extract_match_batch(ex._h, m._h, _p(imgs), B, W, H, imgs.strides[1], imgs.strides[0], int(lap[0]), int(lap[1]),
                                           _p(bb), int(window), m.mfNNratio, int(m.mbCheckOrientation), _p(out["kps"]), _p(out["desc"]),
-                                          ex.cap, _p(out["n"]), _p(out["mono"]), _p(out["matches12"]), _p(out["nmatches"])))
+                                          ex.cap, _p(out["n"]), _p(out["mono"]), _p(out["matches12"]), _p(out["nmatches"]),
+                                          _p(out["knn_idx"]) if "knn_idx" in out else None,
+                                          _p(out["knn_dist"]) if "knn_dist" in out else None))
 
 
 def extract_match_batch_device(ex, m, d_ptr, batch, width, height, stride, frame_stride, lap, bounds, window,

@@ -245,3 +245,64 @@ def test_full_c1_batch_properties():
     n = np.array([len(r[1]) for r in res])
     assert n.min() >= 900 and n.max() <= 1000 + 8 * 4          # quota + at most a few extra nodes per level (:736)
     ex.close()
+
+
+def test_interleaved_handles_keep_their_shared_memory_limits():
+    """the dynamic shared-memory opt-in is per kernel and per device, shared by all handles.  The init
+    extractor (5 x nFeatures: the octree needs ~85 KB) must keep working after a smaller extractor was configured, and two
+    matchers with different max_keypoints must not lower each other's limits."""
+    W, H = 752, 480
+    img = synth.rects_stream(W, H, 1, seed=12)[0]
+    big = orbx.ORBextractor(5000, 1.2, 8, 20, 7, max_width=W, max_height=H)
+    rb = O.Extractor(5000, 1.2, 8, 20, 7)
+    small = orbx.ORBextractor(1000, 1.2, 8, 20, 7, max_width=W, max_height=H)
+    rs = O.Extractor(1000, 1.2, 8, 20, 7)
+    for _ in range(2):                       # big -> small -> big again (the geometry of `big` is cached the second time)
+        for ex, ref in ((big, rb), (small, rs)):
+            mono, k, d = ex(img, None, (0, 0))
+            rmono, rk, rd = ref(img, (0, 0))
+            assert mono == rmono and len(k) == len(rk)
+            for name in ("x", "y", "response", "octave"):
+                np.testing.assert_array_equal(k[name], rk[name])
+    m_big = orbx.ORBmatcher(0.9, True, max_keypoints=16000)
+    m_small = orbx.ORBmatcher(0.9, True, max_keypoints=1200)
+    _, k1, d1 = big(img, None, (0, 0))
+    prev = np.stack([k1["x"], k1["y"]], 1)
+    for m in (m_big, m_small, m_big):
+        kk, dd = (k1, d1) if m is m_big else (k1[:1100], d1[:1100])
+        n, m12, _ = m.SearchForInitialization(kk, dd, kk, dd, (0, W, 0, H), prev[:len(kk)].copy(), 100)
+        rn, rm12, _ = O.search_for_initialization(kk, dd, kk, dd, (0, W, 0, H), prev[:len(kk)].copy(), 100, 0.9, True)
+        assert n == rn
+        np.testing.assert_array_equal(m12, rm12)
+    for h in (big, small, m_big, m_small):
+        h.close()
+
+
+def test_nfeatures_beyond_octree_capacity_is_rejected():
+    """A level quota above the on-chip node table of k_octree (4088) must fail loudly at creation, not overrun it."""
+    with pytest.raises(orbx.OrbxError) as e:
+        orbx.ORBextractor(20000, 1.2, 8, 20, 7, max_width=752, max_height=480)
+    assert e.value.code == orbx.ORBX_E_INVALID
+    ex = orbx.ORBextractor(18000, 1.2, 8, 20, 7, max_width=752, max_height=480)      # level-0 quota 3909: accepted
+    ex.close()
+
+
+def test_second_device_in_one_process():
+    """extraction + stereo matching on device 1 after device 0 in ONE process (per-device kernel attributes,
+    matcher context on the extractor's device)."""
+    if orbx.lib().orbx_device_count() < 2:
+        pytest.skip("needs two GPUs in one process")
+    W, H = 752, 480
+    L, R = synth.stereo_pair(W, H, seed=8, disparity=14)
+    ref_l, ref_r = O.Extractor(1200, 1.2, 8, 20, 7), O.Extractor(1200, 1.2, 8, 20, 7)
+    _, rkl, rdl = ref_l(L, (0, 0)); _, rkr, rdr = ref_r(R, (0, 0))
+    ru, rz, _ = O.compute_stereo_matches(ref_l, ref_r, rkl, rdl, rkr, rdr, 0.11, 47.9)
+    for dev in (0, 1, 0):
+        exl = orbx.ORBextractor(1200, 1.2, 8, 20, 7, max_width=W, max_height=H, device=dev)
+        exr = orbx.ORBextractor(1200, 1.2, 8, 20, 7, max_width=W, max_height=H, device=dev)
+        m = orbx.ORBmatcher(0.9, True, max_keypoints=max(exl.cap, exr.cap), device=dev)
+        gl = exl(L, None, (0, 0)); gr = exr(R, None, (0, 0))
+        np.testing.assert_array_equal(gl[1]["x"], rkl["x"]); np.testing.assert_array_equal(gr[1]["x"], rkr["x"])
+        u, z = m.ComputeStereoMatches(exl, exr, 0.11, 47.9)[:2]
+        np.testing.assert_array_equal(u, ru); np.testing.assert_array_equal(z, rz)
+        exl.close(); exr.close(); m.close()

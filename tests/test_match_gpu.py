@@ -194,10 +194,12 @@ def test_extract_match_batch_host_pipeline():
             mk = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory().numpy()
             out = {"kps": mk((B, cap, 7), torch.float32).view(np.uint8).reshape(B, cap, 28).view(orbx.KP_DTYPE).reshape(B, cap),
                    "desc": mk((B, cap, 32), torch.uint8), "n": mk((B,), torch.int32), "mono": mk((B,), torch.int32),
-                   "matches12": mk((B, cap), torch.int32), "nmatches": mk((B,), torch.int32)}
+                   "matches12": mk((B, cap), torch.int32), "nmatches": mk((B,), torch.int32),
+                   "knn_idx": mk((B, cap, 2), torch.int32), "knn_dist": mk((B, cap, 2), torch.int32)}
         else:
             out = {"kps": np.zeros((B, cap), orbx.KP_DTYPE), "desc": np.zeros((B, cap, 32), np.uint8), "n": np.zeros(B, np.int32),
-                   "mono": np.zeros(B, np.int32), "matches12": np.zeros((B, cap), np.int32), "nmatches": np.zeros(B, np.int32)}
+                   "mono": np.zeros(B, np.int32), "matches12": np.zeros((B, cap), np.int32), "nmatches": np.zeros(B, np.int32),
+                   "knn_idx": np.zeros((B, cap, 2), np.int32), "knn_dist": np.zeros((B, cap, 2), np.int32)}
         orbx.extract_match_batch(ex, m, chunk, (0, 0), (0, W, 0, H), 100, out)
         for f in (0, 1, 17, 18, 35, 36, B - 1):
             n = int(out["n"][f])
@@ -218,6 +220,10 @@ def test_extract_match_batch_host_pipeline():
             rn, rm12, _ = O.search_for_initialization(pk, pd, rk, rd, (0, W, 0, H), np.stack([pk["x"], pk["y"]], 1), 100, 0.9, True)
             assert int(out["nmatches"][f]) == rn
             np.testing.assert_array_equal(out["matches12"][f, :len(pk)], rm12)
+            # BF kNN-2 of the pair (the other half of the C1 "match"): rows = the predecessor's keypoints
+            ridx, rdist = O.bf_knn2(pd, rd)
+            np.testing.assert_array_equal(out["knn_idx"][f, :len(pk)], ridx)
+            np.testing.assert_array_equal(out["knn_dist"][f, :len(pk)], rdist)
         _, lk, ld = ref(chunk[B - 1], (0, 0))
         prev = (lk, ld)
     ex.close(); m.close()
@@ -374,3 +380,22 @@ def test_fuse_style_independent_best_with_chi2_gate():
         assert n == rn and n > 100
         np.testing.assert_array_equal(bi, rbi); np.testing.assert_array_equal(bd, rbd)
     m.close()
+
+
+def test_pipeline_rejects_batch_beyond_extractor():
+    """the pipeline must validate the batch against BOTH handles (the extractor's result slots / scratch are sized
+    by its own max_batch), reject a stride below the width and handles on different devices; nothing is launched."""
+    W, H = 320, 240
+    ex = orbx.ORBextractor(300, 1.2, 8, 20, 7, max_width=W, max_height=H, max_batch=2)
+    m = orbx.ORBmatcher(0.9, True, max_keypoints=ex.cap, max_batch=8)
+    cap = ex.cap
+    frames = synth.rects_stream(W, H, 4, seed=3)
+    out = {"kps": np.zeros((4, cap), orbx.KP_DTYPE), "desc": np.zeros((4, cap, 32), np.uint8), "n": np.zeros(4, np.int32),
+           "mono": np.zeros(4, np.int32), "matches12": np.zeros((4, cap), np.int32), "nmatches": np.zeros(4, np.int32)}
+    with pytest.raises(orbx.OrbxError) as e:
+        orbx.extract_match_batch(ex, m, frames, (0, 0), (0, W, 0, H), 100, out)
+    assert e.value.code == orbx.ORBX_E_INVALID and "extractor" in str(e.value)
+    # a legal batch on the same handles still works afterwards
+    orbx.extract_match_batch(ex, m, np.ascontiguousarray(frames[:2]), (0, 0), (0, W, 0, H), 100, {k: v[:2] for k, v in out.items()})
+    assert out["n"][0] > 0
+    ex.close(); m.close()
