@@ -19,8 +19,16 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <cfloat>
+#include <climits>
+#include <fstream>
 #include <iostream>
+#include <limits>
+#include <map>
 #include <memory>
+#include <numeric>
+#include <set>
+#include <sstream>
 #include <string>
 #include <vector>
 
@@ -246,6 +254,9 @@ public:
     Mat rowRange(const Range& r) const { return rowRange(r.start, r.end); }
     Mat colRange(const Range& r) const { return colRange(r.start, r.end); }
 
+    // channels do not exist here: an N x 2 CV_32F matrix stands for both its 1- and its 2-channel view (Frame::UndistortKeyPoints
+    // reshapes between them around cv::undistortPoints, which takes the N x 2 layout directly in this stand-in)
+    Mat reshape(int /*cn*/, int /*rows*/ = 0) const { return *this; }
     Mat clone() const { Mat m; copyTo(m); return m; }
     void copyTo(Mat& dst) const
     {
@@ -274,6 +285,9 @@ public:
     {
         switch (flags) {
         case CV_8U: return at<uchar>(r, c);
+        case CV_8S: return at<signed char>(r, c);
+        case CV_16U: return at<unsigned short>(r, c);
+        case CV_16S: return at<short>(r, c);
         case CV_32S: return at<int>(r, c);
         case CV_32F: return at<float>(r, c);
         case CV_64F: return at<double>(r, c);
@@ -284,6 +298,9 @@ public:
     {
         switch (flags) {
         case CV_8U: at<uchar>(r, c) = saturate_cast<uchar>(v); break;
+        case CV_8S: { const int i = cvRound(v); at<signed char>(r, c) = (signed char)(i < -128 ? -128 : i > 127 ? 127 : i); break; }
+        case CV_16U: { const int i = cvRound(v); at<unsigned short>(r, c) = (unsigned short)(i < 0 ? 0 : i > 65535 ? 65535 : i); break; }
+        case CV_16S: { const int i = cvRound(v); at<short>(r, c) = (short)(i < -32768 ? -32768 : i > 32767 ? 32767 : i); break; }
         case CV_32S: at<int>(r, c) = cvRound(v); break;
         case CV_32F: at<float>(r, c) = (float)v; break;
         case CV_64F: at<double>(r, c) = v; break;
@@ -398,6 +415,19 @@ static inline Mat operator*(const Mat& a, const Mat& b)
             m.setd(i, j, s);
         }
     return m;
+}
+static inline Mat operator+(const Mat& a, double s) { Mat m(a.rows, a.cols, a.flags); for (int r = 0; r < a.rows; r++) for (int c = 0; c < a.cols; c++) m.setd(r, c, a.getd(r, c) + s); return m; }
+static inline Mat operator-(const Mat& a, double s) { return a + (-s); }
+static inline void hconcat(const Mat& a, const Mat& b, Mat& dst)
+{
+    if (a.rows != b.rows || a.flags != b.flags) cvmin_fail("hconcat operands");
+    Mat m(a.rows, a.cols + b.cols, a.flags);
+    const size_t e = Mat::esz(a.flags);
+    for (int r = 0; r < a.rows; r++) {
+        memcpy(m.ptr(r), a.ptr(r), (size_t)a.cols * e);
+        memcpy(m.ptr(r) + (size_t)a.cols * e, b.ptr(r), (size_t)b.cols * e);
+    }
+    dst = m;
 }
 static inline Mat& operator+=(Mat& a, const Mat& b) { a = a + b; return a; }
 static inline Mat& operator-=(Mat& a, const Mat& b) { a = a - b; return a; }

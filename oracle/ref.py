@@ -67,7 +67,23 @@ def lib(variant="arena"):
 
 
 def _bind_matcher(L):
-    pass
+    vp, i32, f32 = C.c_void_p, C.c_int, C.c_float
+    L.ref_hamming256.argtypes = [vp, vp]
+    L.ref_hamming256.restype = i32
+    L.ref_features_in_area.argtypes = [vp, i32, f32, f32, f32, f32, f32, f32, f32, i32, i32, vp, i32]
+    L.ref_features_in_area.restype = i32
+    L.ref_search_for_initialization.argtypes = [vp, vp, i32, vp, vp, i32, f32, f32, f32, f32, vp, vp, i32, f32, i32]
+    L.ref_search_for_initialization.restype = i32
+    L.ref_compute_stereo_matches.argtypes = [vp, vp, vp, vp, i32, vp, vp, i32, vp, i32, f32, f32, vp, vp]
+    L.ref_vocab_create.argtypes = [i32, vp, vp, vp, vp, i32, i32]
+    L.ref_vocab_create.restype = vp
+    L.ref_vocab_destroy.argtypes = [vp]
+    L.ref_bow_transform.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, vp, vp]
+    L.ref_bow_transform.restype = i32
+    L.ref_bow_transform_features.argtypes = [vp, vp, i32, i32, vp, vp, vp]
+    L.ref_search_by_bow.argtypes = [i32, vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, vp, i32, f32, i32, vp]
+    L.ref_search_by_bow.restype = i32
+    L.ref_distinctive_descriptors.argtypes = [vp, vp, i32, vp]
 
 
 class Extractor:
@@ -130,3 +146,87 @@ class Extractor:
         out = np.empty((len(xyr) + 8, 3), np.float32)
         n = self._L.ref_distribute_octree(self._h, _p(xyr), len(xyr), min_x, max_x, min_y, max_y, n_features, level, _p(out), len(out))
         return out[:n].copy()
+
+
+# ---- matcher side: same call shapes as oracle.oracle ----
+def hamming256(a, b):
+    a = _u8(a); b = _u8(b)
+    return lib().ref_hamming256(_p(a), _p(b))
+
+
+def features_in_area(kps, bounds, x, y, r, min_level=-1, max_level=-1):
+    kps = np.ascontiguousarray(kps, KP_DTYPE)
+    out = np.empty(len(kps) + 1, np.int32)
+    n = lib().ref_features_in_area(_p(kps), len(kps), *[float(b) for b in bounds], float(x), float(y), float(r), min_level, max_level,
+                                   _p(out), len(out))
+    return out[:n].copy()
+
+
+def search_for_initialization(k1, d1, k2, d2, bounds, prev_xy, window=100, nnratio=0.9, check_ori=True):
+    k1 = np.ascontiguousarray(k1, KP_DTYPE); k2 = np.ascontiguousarray(k2, KP_DTYPE)
+    d1 = _u8(d1); d2 = _u8(d2)
+    prev = np.ascontiguousarray(prev_xy, np.float32).copy()
+    m12 = np.empty(len(k1), np.int32)
+    n = lib().ref_search_for_initialization(_p(k1), _p(d1), len(k1), _p(k2), _p(d2), len(k2), *[float(b) for b in bounds], _p(prev), _p(m12),
+                                            int(window), float(nnratio), int(check_ori))
+    return n, m12, prev
+
+
+def compute_stereo_matches(ex_left, ex_right, kl, dl, kr, dr, mb, mbf):
+    """Frame::ComputeStereoMatches on two reference extractors' last pyramids -> (mvuRight, mvDepth)"""
+    kl = np.ascontiguousarray(kl, KP_DTYPE); kr = np.ascontiguousarray(kr, KP_DTYPE)
+    dl = _u8(dl); dr = _u8(dr)
+    ur = np.empty(len(kl), np.float32); dp = np.empty(len(kl), np.float32)
+    sc = np.ascontiguousarray(ex_left.scale, np.float32)
+    lib().ref_compute_stereo_matches(ex_left._h, ex_right._h, _p(kl), _p(dl), len(kl), _p(kr), _p(dr), len(kr), _p(sc), len(sc),
+                                     float(mb), float(mbf), _p(ur), _p(dp))
+    return ur, dp
+
+
+class Vocabulary:
+    """DBoW2::TemplatedVocabulary<FORB> of the reference, loaded from a node table through its own text loader."""
+
+    def __init__(self, parent, is_leaf, desc, weight, L, k=10):
+        parent = np.ascontiguousarray(parent, np.int32); is_leaf = np.ascontiguousarray(is_leaf, np.uint8)
+        desc = _u8(desc); weight = np.ascontiguousarray(weight, np.float64)
+        self._h = lib().ref_vocab_create(len(parent), _p(parent), _p(is_leaf), _p(desc), _p(weight), int(k), int(L))
+        if not self._h:
+            raise ValueError("the reference's loader rejected the vocabulary")
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().ref_vocab_destroy(self._h); self._h = None
+
+    def transform_features(self, desc, levelsup=4):
+        d = _u8(desc); n = len(d)
+        w = np.empty(n, np.int32); wt = np.empty(n, np.float64); nd = np.empty(n, np.int32)
+        lib().ref_bow_transform_features(self._h, _p(d), n, levelsup, _p(w), _p(wt), _p(nd))
+        return w, wt, nd
+
+    def transform(self, desc, levelsup=4):
+        d = _u8(desc); n = len(d)
+        bw = np.empty(n + 1, np.int32); bv = np.empty(n + 1, np.float64)
+        fn = np.empty(n + 1, np.int32); fs = np.empty(n + 2, np.int32); ff = np.empty(n + 1, np.int32)
+        nfv = C.c_int(0)
+        nb = lib().ref_bow_transform(self._h, _p(d), n, levelsup, _p(bw), _p(bv), _p(fn), _p(fs), _p(ff), C.byref(nfv))
+        k = nfv.value
+        return (bw[:nb].copy(), bv[:nb].copy()), (fn[:k].copy(), [ff[fs[i]:fs[i + 1]].copy() for i in range(k)])
+
+
+def search_by_bow(mode, k1, d1, valid1, fv1, k2, d2, valid2, fv2, nnratio=0.7, check_ori=True):
+    from .oracle import fv_to_csr
+    k1 = np.ascontiguousarray(k1, KP_DTYPE); k2 = np.ascontiguousarray(k2, KP_DTYPE); d1 = _u8(d1); d2 = _u8(d2)
+    v1 = np.ascontiguousarray(valid1, np.uint8); v2 = None if valid2 is None else np.ascontiguousarray(valid2, np.uint8)
+    n1, s1, f1 = fv_to_csr(fv1); n2, s2, f2 = fv_to_csr(fv2)
+    m12 = np.empty(len(k1), np.int32)
+    n = lib().ref_search_by_bow(mode, _p(k1), _p(d1), _p(v1), len(k1), _p(n1), _p(s1), _p(f1), len(n1),
+                                _p(k2), _p(d2), _p(v2) if v2 is not None else None, len(k2), _p(n2), _p(s2), _p(f2), len(n2),
+                                float(nnratio), int(check_ori), _p(m12))
+    return n, m12
+
+
+def distinctive_descriptors(desc, offsets):
+    d = _u8(desc); off = np.ascontiguousarray(offsets, np.int32)
+    best = np.empty(len(off) - 1, np.int32)
+    lib().ref_distinctive_descriptors(_p(d), _p(off), len(off) - 1, _p(best))
+    return best

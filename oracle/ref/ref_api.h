@@ -31,6 +31,36 @@ int   ref_octree_keypoints(RefExtractor* e, const uint8_t* img, int w, int h, in
 int   ref_distribute_octree(RefExtractor* e, const float* xyr, int n, int minX, int maxX, int minY, int maxY, int N, int level,
                             float* out_xyr, int cap);
 
+
+/* ---- ORB_SLAM3::ORBmatcher (R/src/ORBmatcher.cc, whole file) over the reference's own Frame / KeyFrame / MapPoint bodies ---- */
+int   ref_hamming256(const uint8_t* a, const uint8_t* b);                                   /* ORBmatcher::DescriptorDistance */
+/* Frame::AssignFeaturesToGrid + GetFeaturesInArea (R/src/Frame.cc:360-391, 628-709) */
+int   ref_features_in_area(const OrcKeyPoint* kps, int n, float minX, float maxX, float minY, float maxY,
+                           float x, float y, float r, int minLevel, int maxLevel, int32_t* out, int cap);
+/* same contract as orc_search_for_initialization */
+int   ref_search_for_initialization(const OrcKeyPoint* k1, const uint8_t* d1, int n1, const OrcKeyPoint* k2, const uint8_t* d2, int n2,
+                                    float minX, float maxX, float minY, float maxY, float* prev_xy, int32_t* matches12, int window,
+                                    float nnratio, int check_ori);
+/* Frame::ComputeStereoMatches (R/src/Frame.cc:785-962) on the pyramids of the two extractors' last ref_extract calls */
+void  ref_compute_stereo_matches(RefExtractor* left, RefExtractor* right, const OrcKeyPoint* kl, const uint8_t* dl, int nl,
+                                 const OrcKeyPoint* kr, const uint8_t* dr, int nr, const float* scale, int nlevels,
+                                 float mb, float mbf, float* uright, float* depth);
+/* DBoW2 vocabulary from a node table (through TemplatedVocabulary::loadFromTextFile); transform as orc_bow_transform[_features] */
+typedef struct RefVocab RefVocab;
+RefVocab* ref_vocab_create(int n_nodes, const int32_t* parent, const uint8_t* is_leaf, const uint8_t* desc, const double* weight, int k, int L);
+void  ref_vocab_destroy(RefVocab* v);
+int   ref_bow_transform(RefVocab* v, const uint8_t* desc, int n, int levelsup, int32_t* bow_words, double* bow_values,
+                        int32_t* fv_nodes, int32_t* fv_start, int32_t* fv_features, int* n_fv);
+void  ref_bow_transform_features(RefVocab* v, const uint8_t* desc, int n, int levelsup, int32_t* word_id, double* weight, int32_t* node_id);
+/* same contract as orc_search_by_bow */
+int   ref_search_by_bow(int mode, const OrcKeyPoint* k1, const uint8_t* d1, const uint8_t* valid1, int n1,
+                        const int32_t* fv1_nodes, const int32_t* fv1_start, const int32_t* fv1_feat, int nfv1,
+                        const OrcKeyPoint* k2, const uint8_t* d2, const uint8_t* valid2, int n2,
+                        const int32_t* fv2_nodes, const int32_t* fv2_start, const int32_t* fv2_feat, int nfv2,
+                        float nnratio, int check_ori, int32_t* matches12);
+/* same contract as orc_distinctive_descriptors (MapPoint::ComputeDistinctiveDescriptors, R/src/MapPoint.cc:448-524) */
+void  ref_distinctive_descriptors(const uint8_t* desc, const int32_t* offsets, int npoints, int32_t* best);
+
 #ifdef __cplusplus
 }
 #endif

@@ -115,3 +115,6 @@ extern "C" int ref_distribute_octree(RefExtractor* e, const float* xyr, int n, i
     for (int i = 0; i < (int)out.size() && i < cap; i++) { out_xyr[3 * i] = out[i].pt.x; out_xyr[3 * i + 1] = out[i].pt.y; out_xyr[3 * i + 2] = out[i].response; }
     return (int)out.size();
 }
+
+// for ref_matcher_api.cc (Frame::ComputeStereoMatches reads mpORBextractorLeft/Right->mvImagePyramid)
+ORB_SLAM3::ORBextractor* ref_extractor_object(RefExtractor* e) { return &e->ex; }
