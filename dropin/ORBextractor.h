@@ -1,14 +1,27 @@
-// Drop-in replacement of R/orb_slam3/include/ORBextractor.h:47-113 (class ORB_SLAM3::ORBextractor).
-// The PUBLIC interface is the reference's, member for member: constructor, operator(), the six getters and the
-// public mvImagePyramid.  The private part is a handle of the B200 C ABI (include/orbx.h) instead of the
-// reference's tables; every caller in the reference (Frame.cc:80-86, :397-399, :792-901; Tracking.cc:145-151)
-// is compiled from source in the same package, so the changed private layout is safe.
+/**
+* Drop-in replacement of ORB-SLAM3's include/ORBextractor.h (class ORB_SLAM3::ORBextractor) for the B200 front-end.
+*
+* The PUBLIC interface reproduces the reference's member for member (R/orb_slam3/include/ORBextractor.h:47-113: constructor,
+* operator(), the six getters, the public mvImagePyramid); that declaration is part of ORB-SLAM3:
+*   Copyright (C) 2017-2020 Carlos Campos, Richard Elvira, Juan J. Gómez Rodríguez, José M.M. Montiel and Juan D. Tardós, University of Zaragoza.
+*   Copyright (C) 2014-2016 Raúl Mur-Artal, José M.M. Montiel and Juan D. Tardós, University of Zaragoza.
+* ORB-SLAM3 is free software under the GNU General Public License v3 (or later); this interface declaration is used under
+* the same license.  tests/test_dropin_signatures.py checks that every public signature here equals the reference's.
+*
+* The private part is a handle of the B200 C ABI (include/orbx.h) instead of the reference's tables; every caller in the
+* reference (Frame.cc:80-86, :397-399, :792-901; Tracking.cc:145-151) is compiled from source in the same package, so the
+* changed private layout is safe.
+*/
 #ifndef ORBEXTRACTOR_H
 #define ORBEXTRACTOR_H
 
-#include <list>
 #include <vector>
-#include "cv_shim.h"
+#include <list>
+#if (CV_MAJOR_VERSION > 3)
+#include <opencv2/opencv.hpp>
+#else
+#include <opencv/cv.h>
+#endif
 
 struct orbx_extractor;   // include/orbx.h
 
@@ -55,14 +68,19 @@ public:
         return mvInvLevelSigma2;
     }
 
-    // The pyramid of the last frame.  It lives on the GPU; the host copies are refreshed lazily by
-    // SyncPyramidToHost(), which the stereo SAD refinement (Frame.cc:871-946) must call before it reads them.
     std::vector<cv::Mat> mvImagePyramid;
-    void SyncPyramidToHost();
 
-    // device selection for multi-agent boxes: one agent (= one ORBextractor pair) per GPU
+    // ---- additions of the B200 drop-in (not in the reference class) ----
+    // The pyramid lives on the GPU.  By default operator() also downloads it into mvImagePyramid, exactly as the reference leaves
+    // it (Frame::ComputeStereoMatches reads it, R/src/Frame.cc:792, :882-901).  A stereo integration that calls
+    // ORBmatcher::ComputeStereoMatches (device-side) turns the download off and saves 1.1 MB of D2H per 752x480 frame;
+    // SyncPyramidToHost() then fetches the levels of the last frame on demand.
+    static void SetPyramidSync(bool on);
+    void SyncPyramidToHost();
+    // The GPU that extractors constructed from now on live on (multi-agent boxes: one agent per GPU); default 0
     static void SetDevice(int device);
-    // C-ABI handle of this extractor (for orbx_stereo_matches, which replaces Frame::ComputeStereoMatches)
+    int device() const { return mnDevice; }
+    // C-ABI handle of this extractor (NULL before the first frame)
     orbx_extractor* handle() { return mpHandle; }
 
 protected:
@@ -82,7 +100,7 @@ protected:
 
     orbx_extractor* mpHandle;      // created lazily at the first frame (the image size is not a ctor argument)
     int mnHandleW, mnHandleH;
-    std::vector<unsigned char> mvTightImage;
+    int mnDevice;
 };
 
 } //namespace ORB_SLAM

@@ -1,23 +1,35 @@
-// Drop-in replacement of R/orb_slam3/include/ORBmatcher.h:35-108 (class ORB_SLAM3::ORBmatcher) for the methods on
-// the B200 hot path.  Public signatures are the reference's.  Methods not listed here (SearchByBoW, the Sim3 /
-// KeyFrame SearchByProjection overloads, SearchForTriangulation, SearchBySim3, Fuse) keep the reference's own
-// bodies from ORBmatcher.cc: they are host-side candidate gathering around DescriptorDistance and are marked
-// "glue" in SURVEY.md section 8a; see INTEGRATION.md for how both translation units live side by side.
+/**
+* Drop-in replacement of ORB-SLAM3's include/ORBmatcher.h (class ORB_SLAM3::ORBmatcher) for the B200 front-end.
+*
+* The class declaration below reproduces, member for member, the public and protected interface of the reference
+* (R/orb_slam3/include/ORBmatcher.h:35-108), which is part of ORB-SLAM3:
+*   Copyright (C) 2017-2020 Carlos Campos, Richard Elvira, Juan J. Gómez Rodríguez, José M.M. Montiel and Juan D. Tardós, University of Zaragoza.
+*   Copyright (C) 2014-2016 Raúl Mur-Artal, José M.M. Montiel and Juan D. Tardós, University of Zaragoza.
+* ORB-SLAM3 is free software under the GNU General Public License v3 (or later); this interface declaration is used under
+* the same license.  tests/test_dropin_signatures.py checks that every signature here equals the reference's.
+*
+* The bodies (dropin/ORBmatcher.cc) are new: the geometry of every search (projection, frustum / depth / viewing-angle tests)
+* stays on the host with the reference's arithmetic, the 256-bit Hamming searches run on the GPU through the C ABI
+* (include/orbx.h).  Everything the reference's callers use is here, so ORBmatcher.cc of the reference is simply replaced.
+*/
+
 #ifndef ORBMATCHER_H
 #define ORBMATCHER_H
 
-#include <vector>
-#include "frame_shim.h"
+#include<vector>
+#include<opencv2/core/core.hpp>
+#include<opencv2/features2d/features2d.hpp>
 
-struct orbx_matcher;   // include/orbx.h
+#include"MapPoint.h"
+#include"KeyFrame.h"
+#include"Frame.h"
+
 
 namespace ORB_SLAM3
 {
 
-class ORBextractor;
-
 class ORBmatcher
-{
+{    
 public:
 
     ORBmatcher(float nnratio=0.6, bool checkOri=true);
@@ -33,6 +45,18 @@ public:
     // Used to track from previous frame (Tracking)
     int SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, const float th, const bool bMono);
 
+    // Project MapPoints seen in KeyFrame into the Frame and search matches.
+    // Used in relocalisation (Tracking)
+    int SearchByProjection(Frame &CurrentFrame, KeyFrame* pKF, const std::set<MapPoint*> &sAlreadyFound, const float th, const int ORBdist);
+
+    // Project MapPoints using a Similarity Transformation and search matches.
+    // Used in loop detection (Loop Closing)
+    int SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const std::vector<MapPoint*> &vpPoints, std::vector<MapPoint*> &vpMatched, int th, float ratioHamming=1.0);
+
+    // Project MapPoints using a Similarity Transformation and search matches.
+    // Used in Place Recognition (Loop Closing and Merging)
+    int SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const std::vector<MapPoint*> &vpPoints, const std::vector<KeyFrame*> &vpPointsKFs, std::vector<MapPoint*> &vpMatched, std::vector<KeyFrame*> &vpMatchedKF, int th, float ratioHamming=1.0);
+
     // Search matches between MapPoints in a KeyFrame and ORB in a Frame.
     // Brute force constrained to ORB that belong to the same vocabulary node (at a certain level)
     // Used in Relocalisation and Loop Detection
@@ -42,12 +66,22 @@ public:
     // Matching for the Map Initialization (only used in the monocular case)
     int SearchForInitialization(Frame &F1, Frame &F2, std::vector<cv::Point2f> &vbPrevMatched, std::vector<int> &vnMatches12, int windowSize=10);
 
-    // Addition (not in the reference class): the body of Frame::ComputeStereoMatches (R/src/Frame.cc:785-962) on the
-    // device-resident results and pyramids of the frame's two extractors, so that mvImagePyramid never leaves the GPU.
-    // Frame::ComputeStereoMatches() becomes: ORBmatcher::ComputeStereoMatches(mpORBextractorLeft, mpORBextractorRight,
-    // mb, mbf, mvuRight, mvDepth);  (N = mvKeys.size() entries each, -1 where there is no match)
-    static void ComputeStereoMatches(ORBextractor* pLeft, ORBextractor* pRight, float mb, float mbf,
-                                     std::vector<float> &mvuRight, std::vector<float> &mvDepth);
+    // Matching to triangulate new MapPoints. Check Epipolar Constraint.
+    int SearchForTriangulation(KeyFrame *pKF1, KeyFrame* pKF2, cv::Mat F12,
+                               std::vector<pair<size_t, size_t> > &vMatchedPairs, const bool bOnlyStereo, const bool bCoarse = false);
+
+    int SearchForTriangulation(KeyFrame *pKF1, KeyFrame *pKF2, cv::Mat F12,
+                                           vector<pair<size_t, size_t> > &vMatchedPairs, const bool bOnlyStereo, vector<cv::Mat> &vMatchedPoints);
+
+    // Search matches between MapPoints seen in KF1 and KF2 transforming by a Sim3 [s12*R12|t12]
+    // In the stereo and RGB-D case, s12=1
+    int SearchBySim3(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoint *> &vpMatches12, const float &s12, const cv::Mat &R12, const cv::Mat &t12, const float th);
+
+    // Project MapPoints into KeyFrame and search for duplicated MapPoints.
+    int Fuse(KeyFrame* pKF, const vector<MapPoint *> &vpMapPoints, const float th=3.0, const bool bRight = false);
+
+    // Project MapPoints into KeyFrame using a given Sim3 and search for duplicated MapPoints.
+    int Fuse(KeyFrame* pKF, cv::Mat Scw, const std::vector<MapPoint*> &vpPoints, float th, vector<MapPoint *> &vpReplacePoint);
 
 public:
 
@@ -55,9 +89,24 @@ public:
     static const int TH_HIGH;
     static const int HISTO_LENGTH;
 
+    // ---- additions of the B200 drop-in (not in the reference class) ----
+    // Frame::ComputeStereoMatches (R/src/Frame.cc:785-962) on the device-resident results and pyramids of the frame's two
+    // extractors, so that mvImagePyramid never has to leave the GPU (see ORBextractor::SetPyramidSync).  Optional: without it
+    // the reference's Frame::ComputeStereoMatches keeps working unchanged on the host copies of the pyramids.
+    static void ComputeStereoMatches(ORBextractor* pLeft, ORBextractor* pRight, float mb, float mbf,
+                                     std::vector<float> &mvuRight, std::vector<float> &mvDepth);
+    // The GPU every ORBmatcher call of the CALLING THREAD runs on (default: the device of the last ORBextractor this thread
+    // called, else ORBextractor's default device).
+    static void SetDevice(int device);
+
 protected:
 
+    bool CheckDistEpipolarLine(const cv::KeyPoint &kp1, const cv::KeyPoint &kp2, const cv::Mat &F12, const KeyFrame *pKF, const bool b1=false);
+    bool CheckDistEpipolarLine2(const cv::KeyPoint &kp1, const cv::KeyPoint &kp2, const cv::Mat &F12, const KeyFrame *pKF, const float unc);
+
     float RadiusByViewingCos(const float &viewCos);
+
+    void ComputeThreeMaxima(std::vector<int>* histo, const int L, int &ind1, int &ind2, int &ind3);
 
     float mfNNratio;
     bool mbCheckOrientation;

@@ -212,7 +212,10 @@ int  orbx_extract_match_batch_device(orbx_extractor* ex, orbx_matcher* m, const 
 
 /* Projection-guided window searches on flat arrays (the drop-in ORBmatcher marshals Frame/MapPoint into
  * these).  Query i: window centre (u,v), radius r, octave range [minl,maxl] as GetFeaturesInArea takes them,
- * predicted right coordinate ur (stereo gate), angle (rotation histogram), valid flag.
+ * predicted right coordinate ur (stereo gate), angle (rotation histogram), valid flags: bit 0 = the query takes part; bit 1
+ * (value 2) = the query's MapPoint has Observations() == 0, so a keypoint it claims stays free for later queries (the
+ * reference only skips keypoints whose MapPoint has observations, R/src/ORBmatcher.cc:89-91, :2045-2047; the temporal points
+ * of Tracking::UpdateLastFrame have none), every accepting query counts as a match.
  *   mode 0: SearchByProjection(Frame&, const Frame&, th, bMono)      R/src/ORBmatcher.cc:1970-2186
  *   mode 1: SearchByProjection(Frame&, vector<MapPoint*>&, th, ...)   R/src/ORBmatcher.cc:44-214
  * assigned[n2]: in = -1 for free keypoints (anything >= 0 is skipped like an occupied mvpMapPoints slot),
@@ -242,6 +245,30 @@ int  orbx_search_by_projection_ex(orbx_matcher* m, int mode, const orbx_proj_que
                                   const float bounds[4], int32_t* assigned, float nnratio, int check_ori, int max_dist,
                                   const float* inv_level_sigma2, int nlevels, double chi2,
                                   int32_t* best_idx, int32_t* best_dist, int* nmatches);
+/* The full set of knobs in one record (the entry the drop-in ORBmatcher calls):
+ *   bounds        the grid of the searched frame: Frame::mnMinX, mnMaxX, mnMinY, mnMaxY (R/src/Frame.cc:314-327);
+ *   query_origin  origin of the query cell range.  Frame::GetFeaturesInArea (R/src/Frame.cc:639-657) uses the same float
+ *                 mnMinX / mnMinY; KeyFrame::GetFeaturesInArea (R/src/KeyFrame.cc:897-911) uses KeyFrame::mnMinX / mnMinY, which
+ *                 are `const int` copies (R/include/KeyFrame.h:501-504): pass (float)(int)mnMinX for a keyframe whose grid
+ *                 was built on a distorted camera's fractional bounds;
+ *   chi2_mono / chi2_stereo / inv_level_sigma2[nlevels]  the reprojection gates of Fuse (R/src/ORBmatcher.cc:1525-1552): a
+ *                 candidate with mvuRight >= 0 is skipped when (ex^2 + ey^2 + er^2) * invSigma2[octave] > chi2_stereo (7.8, er
+ *                 from the query's `ur`), any other candidate when (ex^2 + ey^2) * invSigma2[octave] > chi2_mono (5.99);
+ *                 chi2_mono = 0 disables both, chi2_stereo = 0 applies the mono form to every candidate. */
+typedef struct orbx_proj_options {
+    float bounds[4];
+    float query_origin[2];
+    float nnratio;
+    int32_t check_ori;
+    int32_t max_dist;
+    int32_t nlevels;
+    float inv_level_sigma2[ORBX_MAX_LEVELS];
+    double chi2_mono, chi2_stereo;
+} orbx_proj_options;
+int  orbx_search_by_projection_opts(orbx_matcher* m, int mode, const orbx_proj_query* q, const uint8_t* qdesc, int nq,
+                                    const orbx_keypoint* k2, const uint8_t* d2, const float* uright2, int n2,
+                                    const orbx_proj_options* opt, int32_t* assigned,
+                                    int32_t* best_idx, int32_t* best_dist, int* nmatches);
 
 
 /* Generic candidate matching for the searches whose candidate gathering stays on the host: SearchByBoW

@@ -222,14 +222,14 @@ __global__ void __launch_bounds__(CAND_WARPS * 32, 6) k_window_candidates(WinBuf
     int* q_off = W.q_off + (long long)p * W.K + qi;
     int* q_cnt = W.q_cnt + (long long)p * W.K + qi;
     const orbx_proj_query Q = P.q[qi];
-    bool any = Q.valid != 0;
+    bool any = (Q.valid & 1) != 0;
     int cx0 = 0, cx1 = -1, cy0 = 0, cy1 = -1;
     if (any) {
         // :639-660, all fp32
-        cx0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(Q.u, W.minX), Q.r), W.wInv)));
-        cx1 = min(GC - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(Q.u, W.minX), Q.r), W.wInv)));
-        cy0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(Q.v, W.minY), Q.r), W.hInv)));
-        cy1 = min(GR - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(Q.v, W.minY), Q.r), W.hInv)));
+        cx0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(Q.u, W.qminX), Q.r), W.wInv)));
+        cx1 = min(GC - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(Q.u, W.qminX), Q.r), W.wInv)));
+        cy0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(Q.v, W.qminY), Q.r), W.hInv)));
+        cy1 = min(GR - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(Q.v, W.qminY), Q.r), W.hInv)));
         if (cx0 >= GC || cx1 < 0 || cy0 >= GR || cy1 < 0) any = false;
     }
     if (!any) { if (lane == 0) { *q_off = 0; *q_cnt = 0; } return; }
@@ -279,11 +279,19 @@ __global__ void __launch_bounds__(CAND_WARPS * 32, 6) k_window_candidates(WinBuf
         }
         const float dx = __fsub_rn(rec.x, Q.u), dy = __fsub_rn(rec.y, Q.v);
         if (!(fabsf(dx) < Q.r && fabsf(dy) < Q.r)) ok = false;
-        // Fuse (ORBmatcher.cc:1497-1505): e2 * invSigma2 (float) against the double chi-square bound
-        if (ok && W.gate_chi2 > 0.0 &&
-            (double)__fmul_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), W.inv_sigma2[min(oct, ORBX_MAX_LEVELS - 1)]) > W.gate_chi2) ok = false;
+        // Fuse (ORBmatcher.cc:1525-1552): e2 * invSigma2 (float) against the double chi-square bound; a keypoint with a right
+        // coordinate (mvuRight >= 0) adds the squared right-image error and uses the 3-dof bound
+        if (ok && W.gate_chi2 > 0.0) {
+            float e2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+            double bound = W.gate_chi2;
+            if (W.gate_chi2_stereo > 0.0 && P.uright2) {
+                const float ur2 = P.uright2[i2];
+                if (ur2 >= 0) { const float er = __fsub_rn(Q.ur, ur2); e2 = __fadd_rn(e2, __fmul_rn(er, er)); bound = W.gate_chi2_stereo; }
+            }
+            if ((double)__fmul_rn(e2, W.inv_sigma2[min(oct, ORBX_MAX_LEVELS - 1)]) > bound) ok = false;
+        }
         // stereo gate (ORBmatcher.cc:93-98 / :2049-2055): not order dependent, applied here
-        if (ok && P.uright2) {
+        if (ok && P.uright2 && !(W.gate_chi2 > 0.0)) {
             const float ur2 = P.uright2[i2];
             if (ur2 > 0 && fabsf(__fsub_rn(Q.ur, ur2)) > Q.r) ok = false;
         }
@@ -361,6 +369,12 @@ __global__ void __launch_bounds__(32) k_window_resolve(WinBufs W, int mode, floa
     const int nq = min(P.nq, W.K), n2 = min(P.n2, W.K);
     int* matchedDist = s_mem;                 // [K] (mode 2)
     int* matches21 = s_mem + W.K;             // [K] (mode 2)
+    // modes 0 / 1: "occupied" (= holds a MapPoint with Observations() > 0, :89-91 / :2045-2047) is kept apart from the owner in
+    // res[]: a claim by a 0-observation MapPoint (query valid bit 1) leaves the keypoint free for later queries, which may take
+    // it over; every accepting query counts as a match and enters the rotation histogram on its own (:2068-2090)
+    int* occ = s_mem;                         // [K] by keypoint
+    int* claim_of = s_mem + W.K;              // [K] by query: the keypoint the query claimed, or -1
+    int accepted = 0;
     __shared__ int hist[ORBX_HISTO_LENGTH];
     int32_t* res = out + (long long)p * W.K;
     uint8_t* bin_of = W.bin_of + (long long)p * W.K;
@@ -372,7 +386,8 @@ __global__ void __launch_bounds__(32) k_window_resolve(WinBufs W, int mode, floa
         for (int i = lane; i < n2; i += 32) { matchedDist[i] = 0x7fffffff; matches21[i] = -1; }
         for (int i = lane; i < nq; i += 32) { res[i] = -1; bin_of[i] = 0xFF; }
     } else {
-        for (int i = lane; i < n2; i += 32) bin_of[i] = 0xFF;
+        for (int i = lane; i < n2; i += 32) occ[i] = res[i] >= 0;
+        for (int i = lane; i < nq; i += 32) { claim_of[i] = -1; bin_of[i] = 0xFF; }
     }
     __syncwarp();
 
@@ -403,7 +418,7 @@ __global__ void __launch_bounds__(32) k_window_resolve(WinBufs W, int mode, floa
         if (mode == 2) {
             taken = (d0 != 0x7fffffff && matchedDist[e0 & 0xFFFF] <= d0) || (d1 != 0x7fffffff && matchedDist[e1 & 0xFFFF] <= d1);
         } else {
-            taken = (d0 != 0x7fffffff && res[e0 & 0xFFFF] >= 0) || (mode == 1 && d1 != 0x7fffffff && res[e1 & 0xFFFF] >= 0);
+            taken = (d0 != 0x7fffffff && occ[e0 & 0xFFFF]) || (mode == 1 && d1 != 0x7fffffff && occ[e1 & 0xFFFF]);
         }
         if (taken) {                                     // warp-uniform: rescan the query's list with the skip rule
             const int cnt = __shfl_sync(0xffffffffu, my_cnt, src), off = __shfl_sync(0xffffffffu, my_off, src);
@@ -413,7 +428,7 @@ __global__ void __launch_bounds__(32) k_window_resolve(WinBufs W, int mode, floa
                 const uint32_t e = pool[off + k];
                 const int i2 = e & 0xFFFF, d = (e >> 16) & 0x1FF;
                 const bool skip = (mode == 2) ? (matchedDist[i2] <= d)      // ORBmatcher.cc:741
-                                              : (res[i2] >= 0);             // occupied keypoint, :89-91 / :2045-2047
+                                              : (occ[i2] != 0);             // occupied keypoint, :89-91 / :2045-2047
                 if (skip) continue;
                 if (d < d0) { d1 = d0; k1 = k0; e1 = e0; d0 = d; k0 = k; e0 = e; }
                 else if (d < d1) { d1 = d; k1 = k; e1 = e; }
@@ -439,8 +454,9 @@ __global__ void __launch_bounds__(32) k_window_resolve(WinBufs W, int mode, floa
             if (d0 <= max_dist) {
                 const int i2 = e0 & 0xFFFF;
                 if (lane == 0) {
-                    res[i2] = i;
-                    if (check_ori) { const int bin = rot_bin(a1, a2); bin_of[i2] = (uint8_t)bin; hist[bin]++; }
+                    res[i2] = i; claim_of[i] = i2; accepted++;
+                    if (!(P.q[i].valid & 2)) occ[i2] = 1;
+                    if (check_ori) { const int bin = rot_bin(a1, a2); bin_of[i] = (uint8_t)bin; hist[bin]++; }
                 }
             }
         } else {
@@ -448,7 +464,7 @@ __global__ void __launch_bounds__(32) k_window_resolve(WinBufs W, int mode, floa
             const int bd = d0 < 256 ? d0 : 256, bd2 = d1 < 256 ? d1 : 256;
             const int bl = d0 < 256 ? (int)(e0 >> 25) : -1, bl2 = d1 < 256 ? (int)(e1 >> 25) : -1;
             if (bd <= ORBX_TH_HIGH && !(bl == bl2 && (float)bd > nnratio * (float)bd2)) {
-                if (lane == 0) res[e0 & 0xFFFF] = i;
+                if (lane == 0) { res[e0 & 0xFFFF] = i; accepted++; if (!(P.q[i].valid & 2)) occ[e0 & 0xFFFF] = 1; }
             }
         }
         __syncwarp();
@@ -459,12 +475,19 @@ __global__ void __launch_bounds__(32) k_window_resolve(WinBufs W, int mode, floa
     if (check_ori && mode != 1) {
         int ind1, ind2, ind3;
         three_maxima(hist, ind1, ind2, ind3);
-        const int lim = mode == 2 ? nq : n2;
+        // both tables are indexed by query; mode 0 clears the CLAIMED keypoint (a keypoint claimed twice is cleared when either claim
+        // falls into a rejected bin, exactly as the reference's rotHist lists do)
+        int culled = 0;
 #pragma unroll 4
-        for (int i = lane; i < lim; i += 32) {
+        for (int i = lane; i < nq; i += 32) {
             const int b = bin_of[i];
-            if (b != 0xFF && b != ind1 && b != ind2 && b != ind3) res[i] = -1;
+            if (b != 0xFF && b != ind1 && b != ind2 && b != ind3) {
+                if (mode == 2) res[i] = -1; else { res[claim_of[i]] = -1; culled++; }
+            }
         }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) culled += __shfl_xor_sync(0xffffffffu, culled, o);
+        accepted -= culled;                               // only lane 0's value is used
         __syncwarp();
     }
     int cntm = 0;
@@ -478,20 +501,7 @@ __global__ void __launch_bounds__(32) k_window_resolve(WinBufs W, int mode, floa
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) cntm += __shfl_xor_sync(0xffffffffu, cntm, o);
-    if (lane == 0 && mode == 2) nmatches[p] = cntm;
-}
-
-// modes 0/1 count matches as "queries that own a keypoint they took in this call"
-__global__ void k_count_new_assigned(const int32_t* before, const int32_t* after, int n, int32_t* count)
-{
-    __shared__ int s;
-    if (threadIdx.x == 0) s = 0;
-    __syncthreads();
-    int c = 0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) c += (after[i] >= 0 && before[i] < 0) ? 1 : 0;
-    atomicAdd(&s, c);
-    __syncthreads();
-    if (threadIdx.x == 0) *count = s;
+    if (lane == 0) nmatches[p] = mode == 2 ? cntm : accepted;
 }
 
 // register-only throughput probes
@@ -751,6 +761,7 @@ static void set_bounds(orbx_matcher* m, const float bounds[4])
     W.minX = bounds[0]; W.maxX = bounds[1]; W.minY = bounds[2]; W.maxY = bounds[3];
     W.wInv = (float)GC / (W.maxX - W.minX);      // R/src/Frame.cc:318-319
     W.hInv = (float)GR / (W.maxY - W.minY);
+    W.qminX = W.minX; W.qminY = W.minY;
 }
 
 // the matcher's per-pair scratch starting at pair `pb` (chunks of one batch may be matched concurrently)
@@ -834,20 +845,45 @@ extern "C" int orbx_search_by_projection_ex(orbx_matcher* m, int mode, const orb
                                             const float* inv_level_sigma2, int nlevels, double chi2,
                                             int32_t* best_idx, int32_t* best_dist, int* nmatches)
 {
+    if (!bounds || (chi2 > 0 && (!inv_level_sigma2 || nlevels < 1 || nlevels > ORBX_MAX_LEVELS))) {
+        orbx_set_error("%s%s", "orbx_search_by_projection: invalid arguments", "");
+        return ORBX_E_INVALID;
+    }
+    orbx_proj_options o;
+    memset(&o, 0, sizeof(o));
+    for (int i = 0; i < 4; i++) o.bounds[i] = bounds[i];
+    o.query_origin[0] = bounds[0]; o.query_origin[1] = bounds[2];
+    o.nnratio = nnratio; o.check_ori = check_ori; o.max_dist = max_dist;
+    o.nlevels = chi2 > 0 ? nlevels : 0;
+    for (int l = 0; l < o.nlevels; l++) o.inv_level_sigma2[l] = inv_level_sigma2[l];
+    o.chi2_mono = chi2; o.chi2_stereo = 0.0;
+    return orbx_search_by_projection_opts(m, mode, q, qdesc, nq, k2, d2, uright2, n2, &o, assigned, best_idx, best_dist, nmatches);
+}
+
+extern "C" int orbx_search_by_projection_opts(orbx_matcher* m, int mode, const orbx_proj_query* q, const uint8_t* qdesc, int nq,
+                                              const orbx_keypoint* k2, const uint8_t* d2, const float* uright2, int n2,
+                                              const orbx_proj_options* opt, int32_t* assigned,
+                                              int32_t* best_idx, int32_t* best_dist, int* nmatches)
+{
     const bool indep = mode == 3;
-    if (!m || (mode != 0 && mode != 1 && mode != 3) || nq < 0 || n2 < 0 || nq > m->K || n2 > m->K || !bounds ||
+    if (!m || !opt || (mode != 0 && mode != 1 && mode != 3) || nq < 0 || n2 < 0 || nq > m->K || n2 > m->K ||
         (nq > 0 && (!q || !qdesc)) || (n2 > 0 && (!k2 || !d2)) || (!indep && n2 > 0 && !assigned) || (indep && nq > 0 && (!best_idx || !best_dist)) ||
-        (chi2 > 0 && (!inv_level_sigma2 || nlevels < 1 || nlevels > ORBX_MAX_LEVELS))) {
+        (opt->chi2_mono > 0 && (opt->nlevels < 1 || opt->nlevels > ORBX_MAX_LEVELS)) || (opt->chi2_stereo > 0 && !(opt->chi2_mono > 0))) {
         orbx_set_error("%s%s", "orbx_search_by_projection: invalid arguments / more keypoints than max_keypoints", "");
         return ORBX_E_INVALID;
     }
+    const float* bounds = opt->bounds;
+    const float nnratio = opt->nnratio; const int check_ori = opt->check_ori, max_dist = opt->max_dist;
+    const double chi2 = opt->chi2_mono; const int nlevels = opt->nlevels; const float* inv_level_sigma2 = opt->inv_level_sigma2;
     if (nmatches) *nmatches = 0;
     if (indep) for (int i = 0; i < nq; i++) { best_idx[i] = -1; best_dist[i] = 256; }
     if (nq == 0 || n2 == 0) return ORBX_OK;
     CKM(cudaSetDevice(m->p.device));
     cudaStream_t s = m->stream;
     set_bounds(m, bounds);
+    m->W.qminX = opt->query_origin[0]; m->W.qminY = opt->query_origin[1];
     m->W.gate_chi2 = chi2 > 0 ? chi2 : 0.0;
+    m->W.gate_chi2_stereo = opt->chi2_stereo > 0 ? opt->chi2_stereo : 0.0;
     for (int l = 0; l < ORBX_MAX_LEVELS; l++) m->W.inv_sigma2[l] = (chi2 > 0 && l < nlevels) ? inv_level_sigma2[l] : 0.f;
     CKM(cudaMemcpyAsync(m->W.q, q, sizeof(orbx_proj_query) * nq, cudaMemcpyHostToDevice, s));
     CKM(cudaMemcpyAsync(m->d_qdesc, qdesc, (size_t)32 * nq, cudaMemcpyHostToDevice, s));
@@ -856,14 +892,14 @@ extern "C" int orbx_search_by_projection_ex(orbx_matcher* m, int mode, const orb
     if (uright2) CKM(cudaMemcpyAsync(m->d_uright, uright2, sizeof(float) * n2, cudaMemcpyHostToDevice, s));
     if (!indep) {
         CKM(cudaMemcpyAsync(m->d_out, assigned, sizeof(int32_t) * n2, cudaMemcpyHostToDevice, s));
-        CKM(cudaMemcpyAsync(m->d_out2, assigned, sizeof(int32_t) * n2, cudaMemcpyHostToDevice, s));
     }
     PairDesc pd{};
     pd.k1 = nullptr; pd.d1 = nullptr; pd.k2 = m->d_k2; pd.d2 = m->d_d2; pd.uright2 = uright2 ? m->d_uright : nullptr;
     pd.q = m->W.q; pd.qdesc = m->d_qdesc; pd.n1 = nq; pd.n2 = n2; pd.nq = nq;
     CKM(cudaMemcpyAsync(m->W.pairs, &pd, sizeof(pd), cudaMemcpyHostToDevice, s));
     int rc = run_window(m, m->W, 1, nq, mode, nnratio, check_ori, m->d_out, m->d_nm, nullptr, s, max_dist);
-    m->W.gate_chi2 = 0.0;
+    m->W.gate_chi2 = 0.0; m->W.gate_chi2_stereo = 0.0;
+    m->W.qminX = m->W.minX; m->W.qminY = m->W.minY;
     if (rc) return rc;
     int nm = 0;
     if (indep) {
@@ -874,7 +910,6 @@ extern "C" int orbx_search_by_projection_ex(orbx_matcher* m, int mode, const orb
         if (rc) return rc;
         for (int i = 0; i < nq; i++) nm += best_idx[i] >= 0;
     } else {
-        k_count_new_assigned<<<1, 256, 0, s>>>(m->d_out2, m->d_out, n2, m->d_nm); ORBX_COUNT_LAUNCH(1);
         CKM(cudaMemcpyAsync(assigned, m->d_out, sizeof(int32_t) * n2, cudaMemcpyDeviceToHost, s));
         CKM(cudaMemcpyAsync(&nm, m->d_nm, sizeof(int), cudaMemcpyDeviceToHost, s));
         rc = m_check_err(m, s);

@@ -111,7 +111,9 @@ struct WinBufs {
     uint2* top2;                  // [P][K]   best / second pool entry of every query by (distance, list rank), 0xFFFFFFFF = none
     int K, POOL;
     float minX, maxX, minY, maxY, wInv, hInv;
+    float qminX, qminY;           // origin of the query cell range (= minX, minY for a Frame; the int-truncated KeyFrame::mnMinX/Y for a KeyFrame)
     double gate_chi2;             // > 0: per-candidate reprojection gate (Fuse), with the per-level 1 / sigma^2 below
+    double gate_chi2_stereo;      // > 0: keypoints with a right coordinate use (ex^2 + ey^2 + er^2) against this bound instead
     float inv_sigma2[ORBX_MAX_LEVELS];
     unsigned* err;
 };

@@ -39,7 +39,7 @@ EXPORTS = [
     "orbx_search_by_projection",
     "orbx_stereo_band_match", "orbx_stereo_matches", "orbx_stereo_matches_batch", "orbx_stereo_matches_batch_device",
     "orbx_extract_stereo_batch",
-    "orbx_fast_segment_plan", "orbx_matcher_set_slot_keypoints", "orbx_matcher_set_camera", "orbx_matcher_undistorted_device", "orbx_search_by_projection_ex", "orbx_match_candidates", "orbx_search_by_bow", "orbx_search_for_triangulation", "orbx_distinctive_descriptors", "orbx_undistort_keypoints", "orbx_undistort_slots_device",
+    "orbx_fast_segment_plan", "orbx_matcher_set_slot_keypoints", "orbx_matcher_set_camera", "orbx_matcher_undistorted_device", "orbx_search_by_projection_ex", "orbx_search_by_projection_opts", "orbx_match_candidates", "orbx_search_by_bow", "orbx_search_for_triangulation", "orbx_distinctive_descriptors", "orbx_undistort_keypoints", "orbx_undistort_slots_device",
     "orbx_keypoints_to_msg", "orbx_keypoints_from_msg", "orbx_slot_keypoints_to_msg_device", "orbx_vocab_create", "orbx_vocab_destroy", "orbx_vocab_words", "orbx_vocab_word_weights",
     "orbx_bow_transform", "orbx_bow_transform_slots_device", "orbx_popc_peak",
 ]
@@ -61,6 +61,13 @@ class Params(C.Structure):
 class MatcherParams(C.Structure):
     _fields_ = [("device", C.c_int32), ("max_keypoints", C.c_int32), ("max_batch", C.c_int32),
                 ("max_candidates", C.c_int32)]
+
+
+class ProjOptions(C.Structure):
+    """orbx_proj_options (include/orbx.h)"""
+    _fields_ = [("bounds", C.c_float * 4), ("query_origin", C.c_float * 2), ("nnratio", C.c_float), ("check_ori", C.c_int32),
+                ("max_dist", C.c_int32), ("nlevels", C.c_int32), ("inv_level_sigma2", C.c_float * 12),
+                ("chi2_mono", C.c_double), ("chi2_stereo", C.c_double)]
 
 
 _lib = None
@@ -119,6 +126,7 @@ def lib():
         L.orbx_matcher_set_camera.argtypes = [vp, vp, vp, i32, vp]
         L.orbx_matcher_undistorted_device.argtypes = [vp, vp]
         L.orbx_search_by_projection_ex.argtypes = [vp, i32, vp, vp, i32, vp, vp, vp, i32, vp, vp, f32, i32, i32, vp, i32, C.c_double, vp, vp, vp]
+        L.orbx_search_by_projection_opts.argtypes = [vp, i32, vp, vp, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp]
         L.orbx_distinctive_descriptors.argtypes = [vp, vp, vp, i32, vp]
         L.orbx_undistort_keypoints.argtypes = [vp, vp, i32, vp, vp, i32, vp, vp]
         L.orbx_keypoints_to_msg.argtypes = [vp, vp, i32, vp]
@@ -369,6 +377,29 @@ class ORBmatcher:
         _check(lib().orbx_stereo_matches(self._h, ex_left._h, ex_right._h, slot_l, slot_r, frame_l, frame_r, float(mb), float(mbf),
                                          _p(ur), _p(dp), _p(sd), cap, C.byref(n)))
         return ur[:n.value].copy(), dp[:n.value].copy(), sd[:n.value].copy()
+
+    def SearchByProjectionOpts(self, mode, queries, qdesc, k2, d2, bounds, assigned=None, uright=None, max_dist=100, inv_sigma2=None,
+                               chi2=0.0, chi2_stereo=0.0, query_origin=None):
+        """orbx_search_by_projection_opts: every knob (query origin of a KeyFrame grid, both Fuse gates); same returns as below"""
+        q = np.ascontiguousarray(queries, PROJQ_DTYPE); qd = np.ascontiguousarray(qdesc, np.uint8).reshape(-1, 32)
+        k2 = np.ascontiguousarray(k2, KP_DTYPE); d2 = np.ascontiguousarray(d2, np.uint8).reshape(-1, 32)
+        a = np.full(len(k2), -1, np.int32) if assigned is None else np.ascontiguousarray(assigned, np.int32).copy()
+        ur = None if uright is None else np.ascontiguousarray(uright, np.float32)
+        o = ProjOptions()
+        for i in range(4):
+            o.bounds[i] = float(bounds[i])
+        qo = (bounds[0], bounds[2]) if query_origin is None else query_origin
+        o.query_origin[0], o.query_origin[1] = float(qo[0]), float(qo[1])
+        o.nnratio = self.mfNNratio; o.check_ori = int(self.mbCheckOrientation); o.max_dist = int(max_dist)
+        o.nlevels = 0 if inv_sigma2 is None else len(inv_sigma2)
+        for i in range(o.nlevels):
+            o.inv_level_sigma2[i] = float(inv_sigma2[i])
+        o.chi2_mono = float(chi2); o.chi2_stereo = float(chi2_stereo)
+        nm = C.c_int(0)
+        bi = np.empty(len(q), np.int32); bd = np.empty(len(q), np.int32)
+        _check(lib().orbx_search_by_projection_opts(self._h, int(mode), _p(q), _p(qd), len(q), _p(k2), _p(d2), _p(ur) if ur is not None else None,
+                                                    len(k2), C.byref(o), _p(a), _p(bi), _p(bd), C.byref(nm)))
+        return (nm.value, bi, bd) if mode == 3 else (nm.value, a)
 
     def SearchByProjectionEx(self, mode, queries, qdesc, k2, d2, bounds, assigned=None, uright=None, max_dist=100, inv_sigma2=None, chi2=0.0):
         """mode 0 / 1 with an acceptance bound, or mode 3 = independent best per query (Fuse); see include/orbx.h.

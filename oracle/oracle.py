@@ -87,6 +87,9 @@ def lib():
         L.orc_match_candidates.argtypes = [vp, i32, vp, vp, vp, vp, vp]
         L.orc_search_by_projection_ex.restype = i32
         L.orc_search_by_projection_ex.argtypes = [i32, vp, vp, i32, vp, vp, vp, i32, f32, f32, f32, f32, vp, f32, i32, i32, vp, C.c_double, vp, vp]
+        L.orc_search_by_projection_full.restype = i32
+        L.orc_search_by_projection_full.argtypes = [i32, vp, vp, i32, vp, vp, vp, i32, f32, f32, f32, f32, f32, f32, vp, f32, i32, i32, vp,
+                                                    C.c_double, C.c_double, vp, vp]
         L.orc_undistort_keypoints.argtypes = [vp, i32, vp, vp, i32, vp, vp]
         L.orc_keypoints_to_msg.argtypes = [vp, i32, vp]
         L.orc_keypoints_from_msg.argtypes = [vp, i32, vp]
@@ -368,6 +371,22 @@ def keypoints_from_msg(msg):
     m = np.ascontiguousarray(msg, np.uint8).reshape(-1, 15); out = np.empty(len(m), KP_DTYPE)
     lib().orc_keypoints_from_msg(_p(m), len(m), _p(out))
     return out
+
+
+def search_by_projection_full(mode, queries, qdesc, k2, d2, bounds, assigned=None, uright=None, nnratio=0.8, check_ori=True,
+                              max_dist=100, inv_sigma2=None, chi2=0.0, chi2_stereo=0.0, query_origin=None):
+    """orc_search_by_projection_full -> (count, assigned) for modes 0 / 1, (count, best_idx, best_dist) for mode 3"""
+    q = np.ascontiguousarray(queries, PROJQ_DTYPE)
+    qdesc = _u8(qdesc); k2 = np.ascontiguousarray(k2, KP_DTYPE); d2 = _u8(d2)
+    a = np.full(len(k2), -1, np.int32) if assigned is None else np.ascontiguousarray(assigned, np.int32).copy()
+    ur = None if uright is None else np.ascontiguousarray(uright, np.float32)
+    sg = None if inv_sigma2 is None else np.ascontiguousarray(inv_sigma2, np.float32)
+    bi = np.empty(len(q), np.int32); bd = np.empty(len(q), np.int32)
+    qo = (bounds[0], bounds[2]) if query_origin is None else query_origin
+    n = lib().orc_search_by_projection_full(mode, _p(q), _p(qdesc), len(q), _p(k2), _p(d2), _p(ur) if ur is not None else None, len(k2),
+                                            *[float(b) for b in bounds], float(qo[0]), float(qo[1]), _p(a), float(nnratio), int(check_ori),
+                                            int(max_dist), _p(sg) if sg is not None else None, float(chi2), float(chi2_stereo), _p(bi), _p(bd))
+    return (n, bi, bd) if mode == 3 else (n, a)
 
 
 def search_by_projection_ex(mode, queries, qdesc, k2, d2, bounds, assigned=None, uright=None, nnratio=0.8, check_ori=True,

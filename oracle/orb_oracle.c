@@ -733,6 +733,8 @@ void orc_bf_knn2(const uint8_t* q, int nq, const uint8_t* t, int nt, int32_t* id
 /* Frame::AssignFeaturesToGrid / PosInGrid, R/src/Frame.cc:360-391, 699-709 */
 struct OrcGrid {
     float minX, minY, maxX, maxY, wInv, hInv;
+    float qminX, qminY;   /* origin of the query cell range: = minX, minY for Frame::GetFeaturesInArea (Frame.cc:639-657); the int-truncated
+                           * KeyFrame::mnMinX / mnMinY for KeyFrame::GetFeaturesInArea (KeyFrame.cc:897-911, KeyFrame.h:501-504) */
     int* start;   /* GRID_COLS*GRID_ROWS+1, cell (ix,iy) -> ix*GRID_ROWS+iy */
     int* items;
 };
@@ -741,6 +743,7 @@ OrcGrid* orc_grid_build(const OrcKeyPoint* kps, int n, float minX, float maxX, f
 {
     OrcGrid* g = (OrcGrid*)calloc(1, sizeof(OrcGrid));
     g->minX = minX; g->minY = minY; g->maxX = maxX; g->maxY = maxY;
+    g->qminX = minX; g->qminY = minY;
     g->wInv = (float)GRID_COLS / (maxX - minX);
     g->hInv = (float)GRID_ROWS / (maxY - minY);
     const int nc = GRID_COLS * GRID_ROWS;
@@ -761,6 +764,7 @@ OrcGrid* orc_grid_build(const OrcKeyPoint* kps, int n, float minX, float maxX, f
     free(fill); free(cellOf);
     return g;
 }
+void orc_grid_set_query_origin(OrcGrid* g, float qminX, float qminY) { g->qminX = qminX; g->qminY = qminY; }
 void orc_grid_destroy(OrcGrid* g) { if (g) { free(g->start); free(g->items); free(g); } }
 
 /* Frame::GetFeaturesInArea, R/src/Frame.cc:628-697 */
@@ -769,13 +773,13 @@ int orc_features_in_area(const OrcGrid* g, const OrcKeyPoint* kps, float x, floa
 {
     int n = 0;
     const float factorX = r, factorY = r;
-    int nMinCellX = (int)floorf((x - g->minX - factorX) * g->wInv); if (nMinCellX < 0) nMinCellX = 0;
+    int nMinCellX = (int)floorf((x - g->qminX - factorX) * g->wInv); if (nMinCellX < 0) nMinCellX = 0;
     if (nMinCellX >= GRID_COLS) return 0;
-    int nMaxCellX = (int)ceilf((x - g->minX + factorX) * g->wInv); if (nMaxCellX > GRID_COLS - 1) nMaxCellX = GRID_COLS - 1;
+    int nMaxCellX = (int)ceilf((x - g->qminX + factorX) * g->wInv); if (nMaxCellX > GRID_COLS - 1) nMaxCellX = GRID_COLS - 1;
     if (nMaxCellX < 0) return 0;
-    int nMinCellY = (int)floorf((y - g->minY - factorY) * g->hInv); if (nMinCellY < 0) nMinCellY = 0;
+    int nMinCellY = (int)floorf((y - g->qminY - factorY) * g->hInv); if (nMinCellY < 0) nMinCellY = 0;
     if (nMinCellY >= GRID_ROWS) return 0;
-    int nMaxCellY = (int)ceilf((y - g->minY + factorY) * g->hInv); if (nMaxCellY > GRID_ROWS - 1) nMaxCellY = GRID_ROWS - 1;
+    int nMaxCellY = (int)ceilf((y - g->qminY + factorY) * g->hInv); if (nMaxCellY > GRID_ROWS - 1) nMaxCellY = GRID_ROWS - 1;
     if (nMaxCellY < 0) return 0;
     const int bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
     for (int ix = nMinCellX; ix <= nMaxCellX; ix++)
@@ -895,28 +899,50 @@ int orc_search_by_projection_ex(int mode, const OrcProjQuery* q, const uint8_t* 
                                 int32_t* assigned, float nnratio, int check_ori, int max_dist,
                                 const float* inv_sigma2, double chi2, int32_t* best_idx, int32_t* best_dist)
 {
+    return orc_search_by_projection_full(mode, q, qdesc, nq, k2, d2, uright2, n2, minX, maxX, minY, maxY, minX, minY, assigned, nnratio,
+                                         check_ori, max_dist, inv_sigma2, chi2, 0.0, best_idx, best_dist);
+}
+
+int orc_search_by_projection_full(int mode, const OrcProjQuery* q, const uint8_t* qdesc, int nq,
+                                  const OrcKeyPoint* k2, const uint8_t* d2, const float* uright2, int n2,
+                                  float minX, float maxX, float minY, float maxY, float qminX, float qminY,
+                                  int32_t* assigned, float nnratio, int check_ori, int max_dist,
+                                  const float* inv_sigma2, double chi2, double chi2_stereo, int32_t* best_idx, int32_t* best_dist)
+{
     int nmatches = 0;
     if (mode == 3) for (int i = 0; i < nq; i++) { best_idx[i] = -1; best_dist[i] = 256; }
     OrcGrid* g = orc_grid_build(k2, n2, minX, maxX, minY, maxY);
+    orc_grid_set_query_origin(g, qminX, qminY);
     int32_t* cand = (int32_t*)malloc(sizeof(int32_t) * (n2 > 0 ? n2 : 1));
     int* histIdx = (int*)malloc(sizeof(int) * (nq > 0 ? nq : 1));
     int* histBin = (int*)malloc(sizeof(int) * (nq > 0 ? nq : 1));
     int nhist = 0;
     int sizes[HISTO_LENGTH]; memset(sizes, 0, sizeof(sizes));
+    /* "occupied" = the keypoint holds a MapPoint with Observations() > 0 (ORBmatcher.cc:89-91, :2045-2047).  The caller encodes the
+     * state before the call in assigned[] (>= 0 = occupied); a claim made during the call occupies the keypoint only when the
+     * claiming MapPoint has observations (valid bit 1 clear): a 0-observation owner (the temporal points Tracking::UpdateLastFrame
+     * creates for stereo / RGB-D) leaves it free, so a later query may take it over and both count as matches. */
+    uint8_t* occ = (uint8_t*)calloc(n2 > 0 ? n2 : 1, 1);
+    if (mode != 3) for (int i = 0; i < n2; i++) occ[i] = assigned[i] >= 0;
     for (int i = 0; i < nq; i++) {
-        if (!q[i].valid) continue;
+        if (!(q[i].valid & 1)) continue;
         int nc = orc_features_in_area(g, k2, q[i].u, q[i].v, q[i].r, q[i].minl, q[i].maxl, cand, n2);
         if (nc == 0) continue;
         int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
         for (int c = 0; c < nc; c++) {
             int i2 = cand[c];
-            if (mode != 3 && assigned[i2] >= 0) continue;
-            if (inv_sigma2 && chi2 > 0) {                  /* Fuse: reprojection error gate, ORBmatcher.cc:1497-1505 */
+            if (mode != 3 && occ[i2]) continue;
+            if (inv_sigma2 && chi2 > 0) {                  /* Fuse: reprojection error gates, ORBmatcher.cc:1525-1552 */
                 const float ex = q[i].u - k2[i2].x, ey = q[i].v - k2[i2].y;
-                const float e2 = ex * ex + ey * ey;
-                if ((double)(e2 * inv_sigma2[k2[i2].octave]) > chi2) continue;       /* float product against the double literal 5.99 */
-            }
-            if (uright2 && uright2[i2] > 0) {
+                if (chi2_stereo > 0 && uright2 && uright2[i2] >= 0) {
+                    const float er = q[i].ur - uright2[i2];
+                    const float e2 = ex * ex + ey * ey + er * er;
+                    if ((double)(e2 * inv_sigma2[k2[i2].octave]) > chi2_stereo) continue;   /* 7.8 */
+                } else {
+                    const float e2 = ex * ex + ey * ey;
+                    if ((double)(e2 * inv_sigma2[k2[i2].octave]) > chi2) continue;       /* float product against the double literal 5.99 */
+                }
+            } else if (uright2 && uright2[i2] > 0) {
                 const float er = fabsf(q[i].ur - uright2[i2]);
                 if (er > q[i].r) continue;
             }
@@ -934,9 +960,11 @@ int orc_search_by_projection_ex(int mode, const OrcProjQuery* q, const uint8_t* 
             if (mode == 1) {
                 if (bestLevel == bestLevel2 && bestDist > nnratio * bestDist2) continue;
                 assigned[bestIdx] = i;
+                if (!(q[i].valid & 2)) occ[bestIdx] = 1;
                 nmatches++;
             } else {
                 assigned[bestIdx] = i;
+                if (!(q[i].valid & 2)) occ[bestIdx] = 1;
                 nmatches++;
                 if (check_ori) {
                     int bin = rot_bin(q[i].angle, k2[bestIdx].angle);
@@ -954,7 +982,7 @@ int orc_search_by_projection_ex(int mode, const OrcProjQuery* q, const uint8_t* 
             if (b != ind1 && b != ind2 && b != ind3) { assigned[histIdx[k]] = -1; nmatches--; }
         }
     }
-    free(cand); free(histIdx); free(histBin);
+    free(cand); free(histIdx); free(histBin); free(occ);
     orc_grid_destroy(g);
     return nmatches;
 }

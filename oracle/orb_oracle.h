@@ -92,7 +92,8 @@ typedef struct {
     int32_t minl, maxl;
     float ur;          /* predicted right coordinate for the stereo gate, used when frame uright>0 */
     float angle;       /* for the rotation histogram (mode 0) */
-    int32_t valid;     /* 0 = query skipped */
+    int32_t valid;     /* bit 0: the query takes part; bit 1 (value 2): its MapPoint has Observations() == 0, so a keypoint it
+                        * claims stays free for later queries (ORBmatcher.cc:89-91, :2045-2047) */
 } OrcProjQuery;
 int   orc_search_by_projection(int mode, const OrcProjQuery* q, const uint8_t* qdesc, int nq,
                                const OrcKeyPoint* k2, const uint8_t* d2, const float* uright2, int n2,
@@ -111,6 +112,16 @@ int   orc_search_by_projection_ex(int mode, const OrcProjQuery* q, const uint8_t
                                   float minX, float maxX, float minY, float maxY,
                                   int32_t* assigned, float nnratio, int check_ori, int max_dist,
                                   const float* inv_sigma2, double chi2, int32_t* best_idx, int32_t* best_dist);
+
+/* The same with the two remaining knobs: (qminX, qminY) = origin of the query cell range (KeyFrame::GetFeaturesInArea uses the
+ * int-truncated KeyFrame::mnMinX / mnMinY, R/src/KeyFrame.cc:897-911), and chi2_stereo = Fuse's 3-dof gate for keypoints with
+ * mvuRight >= 0 (R/src/ORBmatcher.cc:1525-1540; 0 = mono form for every candidate). */
+int   orc_search_by_projection_full(int mode, const OrcProjQuery* q, const uint8_t* qdesc, int nq,
+                                    const OrcKeyPoint* k2, const uint8_t* d2, const float* uright2, int n2,
+                                    float minX, float maxX, float minY, float maxY, float qminX, float qminY,
+                                    int32_t* assigned, float nnratio, int check_ori, int max_dist,
+                                    const float* inv_sigma2, double chi2, double chi2_stereo, int32_t* best_idx, int32_t* best_dist);
+void  orc_grid_set_query_origin(OrcGrid* g, float qminX, float qminY);
 
 /* Frame::ComputeStereoMatches descriptor part (Frame.cc:785-868): per left keypoint the best right
  * index and distance (dist starts at TH_HIGH=100; idx -1 if none < 100). nrows = level-0 rows. */
