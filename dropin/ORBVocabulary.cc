@@ -6,7 +6,7 @@
 #include <fstream>
 #include <sstream>
 #include <stdexcept>
-#include "../include/orbx.h"
+#include "orbx.h"
 
 namespace ORB_SLAM3
 {

@@ -11,14 +11,10 @@
 #include <map>
 #include <string>
 #include <vector>
-#include "cv_shim.h"
+#include <opencv2/core/core.hpp>
 
-#ifdef ORBX_USE_REAL_OPENCV
 #include "Thirdparty/DBoW2/DBoW2/BowVector.h"
 #include "Thirdparty/DBoW2/DBoW2/FeatureVector.h"
-#else
-#include "frame_shim.h"   // DBoW2::BowVector / FeatureVector value types
-#endif
 
 struct orbx_vocab;   // include/orbx.h
 

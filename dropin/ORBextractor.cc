@@ -1,20 +1,27 @@
 // Drop-in body of ORB_SLAM3::ORBextractor over the B200 C ABI.  Replaces R/orb_slam3/src/ORBextractor.cc.
 #include "ORBextractor.h"
+#include <atomic>
+#include <cstring>
 #include <stdexcept>
 #include <string>
-#include "../include/orbx.h"
+#include "orbx.h"
 
 namespace ORB_SLAM3
 {
 
-static int g_orbx_device = 0;
+static std::atomic<int> g_orbx_device(0);
+static std::atomic<bool> g_pyramid_sync(true);
+static thread_local int tl_last_device = -1;
 void ORBextractor::SetDevice(int device) { g_orbx_device = device; }
+int ORBextractor::DefaultDevice() { return g_orbx_device; }
+int ORBextractor::ThreadDevice() { return tl_last_device >= 0 ? tl_last_device : (int)g_orbx_device; }
+void ORBextractor::SetPyramidSync(bool on) { g_pyramid_sync = on; }
 
-static void create_handle(orbx_extractor** out, int nfeatures, float scaleFactor, int nlevels, int ini, int min, int w, int h)
+static void create_handle(orbx_extractor** out, int device, int nfeatures, float scaleFactor, int nlevels, int ini, int min, int w, int h)
 {
     orbx_params p;
     p.nfeatures = nfeatures; p.scale_factor = scaleFactor; p.nlevels = nlevels; p.ini_th_fast = ini; p.min_th_fast = min;
-    p.max_width = w; p.max_height = h; p.max_batch = 1; p.device = g_orbx_device; p.max_candidates_per_level = 0;
+    p.max_width = w; p.max_height = h; p.max_batch = 1; p.device = device; p.max_candidates_per_level = 0;
     if (orbx_extractor_create(&p, out) != ORBX_OK)
         throw std::runtime_error(std::string("ORBextractor (B200): ") + orbx_last_error());   // no CPU fallback exists
 }
@@ -22,11 +29,11 @@ static void create_handle(orbx_extractor** out, int nfeatures, float scaleFactor
 // R/src/ORBextractor.cc:408-468: the tables come from the library so that both sides agree bit for bit
 ORBextractor::ORBextractor(int _nfeatures, float _scaleFactor, int _nlevels, int _iniThFAST, int _minThFAST):
     nfeatures(_nfeatures), scaleFactor(_scaleFactor), nlevels(_nlevels),
-    iniThFAST(_iniThFAST), minThFAST(_minThFAST), mpHandle(nullptr), mnHandleW(0), mnHandleH(0)
+    iniThFAST(_iniThFAST), minThFAST(_minThFAST), mpHandle(nullptr), mnHandleW(0), mnHandleH(0), mnDevice(g_orbx_device)
 {
     // a small probe handle gives the tables without knowing the camera resolution yet
     orbx_extractor* probe = nullptr;
-    create_handle(&probe, nfeatures, (float)scaleFactor, nlevels, iniThFAST, minThFAST, 64, 64);
+    create_handle(&probe, mnDevice, nfeatures, (float)scaleFactor, nlevels, iniThFAST, minThFAST, 64, 64);
     mvScaleFactor.resize(nlevels); mvInvScaleFactor.resize(nlevels);
     mvLevelSigma2.resize(nlevels); mvInvLevelSigma2.resize(nlevels); mnFeaturesPerLevel.resize(nlevels);
     orbx_extractor_tables(probe, mvScaleFactor.data(), mvInvScaleFactor.data(), mvLevelSigma2.data(),
@@ -55,8 +62,9 @@ int ORBextractor::operator()( cv::InputArray _image, cv::InputArray _mask, std::
         if (mpHandle) orbx_extractor_destroy(mpHandle);
         mpHandle = nullptr;
         mnHandleW = image.cols; mnHandleH = image.rows;
-        create_handle(&mpHandle, nfeatures, (float)scaleFactor, nlevels, iniThFAST, minThFAST, mnHandleW, mnHandleH);
+        create_handle(&mpHandle, mnDevice, nfeatures, (float)scaleFactor, nlevels, iniThFAST, minThFAST, mnHandleW, mnHandleH);
     }
+    tl_last_device = mnDevice;                         // ORBmatcher calls of this thread follow the extractor's device
     const int cap = orbx_extractor_max_keypoints(mpHandle);
     _keypoints.resize(cap);                            // cv::KeyPoint is layout-compatible with orbx_keypoint
     std::vector<unsigned char> desc((size_t)cap * 32);
@@ -73,7 +81,9 @@ int ORBextractor::operator()( cv::InputArray _image, cv::InputArray _mask, std::
         cv::Mat d = _descriptors.getMat();
         for (int i = 0; i < n; i++) std::memcpy(d.ptr(i), desc.data() + (size_t)i * 32, 32);
     }
-    for (auto& m : mvImagePyramid) m.release();        // stale until SyncPyramidToHost()
+    // mvImagePyramid as the reference leaves it (Frame::ComputeStereoMatches reads it), unless the integration keeps it on the GPU
+    if (g_pyramid_sync) SyncPyramidToHost();
+    else for (auto& m : mvImagePyramid) m.release();   // stale until SyncPyramidToHost()
     return mono;
 }
 

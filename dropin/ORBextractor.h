@@ -79,6 +79,9 @@ public:
     void SyncPyramidToHost();
     // The GPU that extractors constructed from now on live on (multi-agent boxes: one agent per GPU); default 0
     static void SetDevice(int device);
+    static int DefaultDevice();
+    // the device of the extractor the calling thread used last (what ORBmatcher calls of that thread follow), else the default
+    static int ThreadDevice();
     int device() const { return mnDevice; }
     // C-ABI handle of this extractor (NULL before the first frame)
     orbx_extractor* handle() { return mpHandle; }

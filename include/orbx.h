@@ -219,7 +219,9 @@ int  orbx_extract_match_batch_device(orbx_extractor* ex, orbx_matcher* m, const 
  *   mode 0: SearchByProjection(Frame&, const Frame&, th, bMono)      R/src/ORBmatcher.cc:1970-2186
  *   mode 1: SearchByProjection(Frame&, vector<MapPoint*>&, th, ...)   R/src/ORBmatcher.cc:44-214
  * assigned[n2]: in = -1 for free keypoints (anything >= 0 is skipped like an occupied mvpMapPoints slot),
- * out = index of the query that took the keypoint.  Host pointers. */
+ * out = index of the query that took the keypoint; -2 = a keypoint that was claimed during the call and then cleared by the
+ * rotation check (the reference sets such a slot to NULL even when it held a 0-observation MapPoint before, :2176-2180).
+ * Host pointers. */
 typedef struct orbx_proj_query {
     float u, v, r;
     int32_t minl, maxl;

@@ -482,7 +482,7 @@ __global__ void __launch_bounds__(32) k_window_resolve(WinBufs W, int mode, floa
         for (int i = lane; i < nq; i += 32) {
             const int b = bin_of[i];
             if (b != 0xFF && b != ind1 && b != ind2 && b != ind3) {
-                if (mode == 2) res[i] = -1; else { res[claim_of[i]] = -1; culled++; }
+                if (mode == 2) res[i] = -1; else { res[claim_of[i]] = -2; culled++; }      // -2: claimed, then cleared (the caller NULLs the slot)
             }
         }
 #pragma unroll

@@ -979,7 +979,7 @@ int orc_search_by_projection_full(int mode, const OrcProjQuery* q, const uint8_t
         three_maxima(sizes, HISTO_LENGTH, &ind1, &ind2, &ind3);
         for (int k = 0; k < nhist; k++) {
             int b = histBin[k];
-            if (b != ind1 && b != ind2 && b != ind3) { assigned[histIdx[k]] = -1; nmatches--; }
+            if (b != ind1 && b != ind2 && b != ind3) { assigned[histIdx[k]] = -2; nmatches--; }   /* -2: claimed, then cleared (:2176-2180) */
         }
     }
     free(cand); free(histIdx); free(histBin); free(occ);
