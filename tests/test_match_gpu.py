@@ -399,3 +399,45 @@ def test_pipeline_rejects_batch_beyond_extractor():
     orbx.extract_match_batch(ex, m, np.ascontiguousarray(frames[:2]), (0, 0), (0, W, 0, H), 100, {k: v[:2] for k, v in out.items()})
     assert out["n"][0] > 0
     ex.close(); m.close()
+
+
+def test_projection_options_occupancy_origin_and_stereo_gate():
+    """orbx_search_by_projection_opts: (1) claims by 0-observation MapPoints (valid bit 1) leave the keypoint free, later queries
+    take it over and both count (R/src/ORBmatcher.cc:89-91, :2045-2047), claims cleared by the rotation check come back as -2;
+    (2) the query origin of a KeyFrame grid (int-truncated mnMinX / mnMinY, R/src/KeyFrame.cc:897-911); (3) Fuse's 3-dof gate for
+    keypoints with a right coordinate (:1525-1540).  Against the C oracle (whose class-level behaviour tests/test_dropin_scenario.py
+    pins to the reference's ORBmatcher.cc)."""
+    W, H, e, k1, d1, k2, d2, q = _proj_setup(seed=73)
+    rng = np.random.default_rng(5)
+    # (1) duplicate every query so that two queries compete for the same keypoint; a third of them do not occupy
+    q2 = np.concatenate([q, q]); dd = np.concatenate([d1, d1])
+    q2["valid"] = np.where(q2["valid"] > 0, np.where(rng.random(len(q2)) < 0.35, 3, 1), 0).astype(np.int32)
+    pre = np.full(len(k2), -1, np.int32); pre[::23] = len(q2)
+    for mode, ori in ((0, True), (0, False), (1, False)):
+        m = orbx.ORBmatcher(0.9, ori, max_keypoints=4096)
+        n, a = m.SearchByProjectionOpts(mode, q2, dd, k2, d2, (0, W, 0, H), assigned=pre)
+        rn, ra = O.search_by_projection_full(mode, q2, dd, k2, d2, (0, W, 0, H), assigned=pre, nnratio=0.9, check_ori=ori)
+        assert n == rn and n > 100
+        np.testing.assert_array_equal(a, ra)
+        owners = a[(a >= 0) & (a < len(q2))]
+        assert n > len(owners) or mode == 0 and ori            # takeovers: more accepting queries than owned keypoints
+        if mode == 0 and ori:
+            assert (a == -2).any()                              # something was claimed and then cleared by the rotation check
+        m.close()
+    # (2) fractional grid bounds (a distorted camera) with the truncated query origin
+    bounds = (-3.7, W + 2.4, -2.6, H + 1.9)
+    m = orbx.ORBmatcher(0.9, False, max_keypoints=4096)
+    n, a = m.SearchByProjectionOpts(0, q, d1, k2, d2, bounds, query_origin=(-3.0, -2.0), max_dist=60)
+    rn, ra = O.search_by_projection_full(0, q, d1, k2, d2, bounds, query_origin=(-3.0, -2.0), nnratio=0.9, check_ori=False, max_dist=60)
+    assert n == rn and n > 100
+    np.testing.assert_array_equal(a, ra)
+    # (3) both chi-square gates: two thirds of the keypoints have a right coordinate
+    ur = np.where(np.arange(len(k2)) % 3 != 0, k2["x"] - np.float32(9.0), np.float32(-1)).astype(np.float32)
+    q["ur"] = q["u"] - np.float32(9.0) + rng.normal(0, 0.7, len(q)).astype(np.float32)
+    sg = np.asarray(e.inv_sigma2, np.float32)
+    n, bi, bd = m.SearchByProjectionOpts(3, q, d1, k2, d2, (0, W, 0, H), uright=ur, inv_sigma2=sg, chi2=5.99, chi2_stereo=7.8)
+    rn, rbi, rbd = O.search_by_projection_full(3, q, d1, k2, d2, (0, W, 0, H), uright=ur, inv_sigma2=sg, chi2=5.99, chi2_stereo=7.8)
+    n1, bi1, _ = O.search_by_projection_full(3, q, d1, k2, d2, (0, W, 0, H), uright=ur, inv_sigma2=sg, chi2=5.99, chi2_stereo=0.0)
+    assert n == rn and n > 40 and not np.array_equal(rbi, bi1)       # the stereo form changes the outcome on this input
+    np.testing.assert_array_equal(bi, rbi); np.testing.assert_array_equal(bd, rbd)
+    m.close()
