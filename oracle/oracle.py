@@ -6,6 +6,7 @@ import this module.  The product package (multi_orbslam3_b200) never does.
 import ctypes as C
 import os
 import subprocess
+import sys
 
 import numpy as np
 
@@ -31,7 +32,7 @@ assert PROJQ_DTYPE.itemsize == 32
 def build(force=False):
     src = os.path.join(_HERE, "orb_oracle.c")
     if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
-        subprocess.check_call(["make", "-s", "-C", _HERE])
+        subprocess.check_call(["make", "-s", "-C", _HERE], stdout=sys.stderr)
     return _LIB_PATH
 
 

@@ -9,6 +9,7 @@ libraries that travelled with the snapshot are used as they are.
 import ctypes as C
 import os
 import subprocess
+import sys
 
 import numpy as np
 
@@ -34,7 +35,7 @@ def _path(variant):
 def build():
     """make -C oracle/ref when the reference sources are here; otherwise the prebuilt oracle/_ref is used."""
     if reference_present():
-        subprocess.check_call(["make", "-s", "-C", os.path.join(_HERE, "ref")])
+        subprocess.check_call(["make", "-s", "-C", os.path.join(_HERE, "ref")], stdout=sys.stderr)
     return os.path.exists(_path("arena"))
 
 
