@@ -7,8 +7,8 @@ A step = one pass of the hot path over one batch of synthetic frames of ONE came
   nnratio 0.9, checkOri) + brute-force kNN-2 of the two descriptor sets.
 Prints ONE JSON line (rank 0).  `value` = frames/s with the frames resident in HBM; `e2e` = the same metric
 through the host-buffer C-ABI call orbx_extract_match_batch (pinned host frames in, keypoints + descriptors +
-matches out, copies inside the timed region).  --impl reference times the CPU oracle (the reference's own
-sources cannot be built here) on all host cores.
+matches out, copies inside the timed region).  --impl reference times the reference's own CPU code (oracle/_ref:
+ORBextractor.cc + ORBmatcher.cc compiled unmodified) on all host cores.
 """
 import argparse
 import json
@@ -46,21 +46,41 @@ def workload_config(args):
             "l2": "inputs larger than L2 (frames per step exceed the 126 MB L2)"}
 
 
+CPU_WHAT = {
+    "reference": "oracle/_ref: the reference's own ORBextractor.cc and ORBmatcher.cc compiled unmodified (-O3, no -march=native as its "
+                 "CMakeLists), one extractor per thread; OpenCV primitives (resize, blur, FAST, BFMatcher) = scalar C restatements "
+                 "pinned to cv2 4.13, not OpenCV's SIMD builds",
+    "port": "oracle/orb_oracle.c: C restatement of the reference path (oracle/_ref was not prebuilt)",
+}
+
 # ------------------------------------------------------------------------------------------------
 # CPU oracle legs (cpu_baseline and --impl reference)
 # ------------------------------------------------------------------------------------------------
+def cpu_impl():
+    """(module with Extractor / search_for_initialization, kind): the reference's OWN code when oracle/_ref is there (compiled
+    unmodified from /root/reference, prebuilt for the GPU box), else the C restatement."""
+    from oracle import ref as R
+    if R.available():
+        R.lib()
+        return R, "reference"
+    from oracle import oracle as O
+    return O, "port"
+
+
 def cpu_worker(frames, nframes, out, idx):
     from oracle import oracle as O
-    ex = O.Extractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH)
+    impl, _ = cpu_impl()
+    ex = impl.Extractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH)
     prev = None
     done = 0
     for i in range(nframes):
         f = frames[i % len(frames)]
-        _, k, d = ex(f, (0, 0))
+        _, k, d = ex(f, (0, 0))                 # ORBextractor::operator() (R/src/ORBextractor.cc)
         if prev is not None:
             pk, pd = prev
-            O.search_for_initialization(pk, pd, k, d, (0, W, 0, H), np.stack([pk["x"], pk["y"]], 1), WINDOW, NNRATIO, True)
-            O.bf_knn2(pd, d)
+            # ORBmatcher::SearchForInitialization (R/src/ORBmatcher.cc:702-817)
+            impl.search_for_initialization(pk, pd, k, d, (0, W, 0, H), np.stack([pk["x"], pk["y"]], 1), WINDOW, NNRATIO, True)
+            O.bf_knn2(pd, d)                    # cv::BFMatcher::knnMatch(k = 2) is OpenCV, not reference code: the pinned restatement
         prev = (k, d)
         done += 1
     out[idx] = done
@@ -86,6 +106,7 @@ def reference_arm(args):
     from multi_orbslam3_b200 import synth
     from oracle import oracle as O
     O.build()
+    _, kind = cpu_impl()
     cores = os.cpu_count() or 1
     frames = synth.rects_stream(W, H, 16, seed=0)
     per_thread = 16
@@ -101,8 +122,9 @@ def reference_arm(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_time / max(args.steps, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": workload_config(args),
-        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port",
-                         "sample": "%d frames per step (%d threads x %d frames of a 16-frame S-rects stream), %d steps" % (cores * per_thread, cores, per_thread, args.steps)},
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": kind,
+                         "sample": "%d frames per step (%d threads x %d frames of a 16-frame S-rects stream), %d steps" % (cores * per_thread, cores, per_thread, args.steps),
+                         "what": CPU_WHAT[kind]},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -121,6 +143,19 @@ def server_bench(args, world, rank, local):
     g = torch.Generator(device="cuda"); g.manual_seed(1234 + rank)
     shard = torch.randint(0, 256, (n_local, 32), dtype=torch.uint8, device="cuda", generator=g)
     q = torch.randint(0, 256, (1000, 32), dtype=torch.uint8, device="cuda", generator=g)
+    # planted answers (the result of the timed steps is verified against them below): query j < 8 has an exact copy on rank
+    # j % world at local row 1000 + j and, for j < 4, a second copy on the LAST rank at local row 17 + j (a tie across shards:
+    # the lower global index must come first); query 8 has a 1-bit neighbour on rank 0
+    if world > 1:
+        dist.broadcast(q, src=0)
+    for j in range(8):
+        if rank == j % world:
+            shard[1000 + j] = q[j]
+    if rank == world - 1:
+        for j in range(4):
+            shard[17 + j] = q[j]
+    if rank == 0:
+        shard[555] = q[8]; shard[555, 3] ^= 16
     m = orbx.ORBmatcher(0.7, True, max_keypoints=2048, device=local)
     match_fn, merge_fn = gpu_fns(m)
     db = ShardedDescriptorDB(shard, match_fn, merge_fn)
@@ -143,6 +178,21 @@ def server_bench(args, world, rank, local):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item()) / args.steps
     pairs = 1000.0 * n_local * world
+    # the last step's answer against what was planted
+    idx_h, d_h = idx.cpu().numpy(), d.cpu().numpy()
+    want = []
+    for j in range(8):
+        first = (j % world) * n_local + 1000 + j
+        rows = sorted([first] + ([(world - 1) * n_local + 17 + j] if j < 4 else []))
+        want.append(rows)
+    for j, rows in enumerate(want):
+        assert idx_h[j, 0] == rows[0] and d_h[j, 0] == 0, ("planted copy of query %d not found first" % j, idx_h[j], d_h[j], rows)
+        if len(rows) > 1:
+            assert idx_h[j, 1] == rows[1] and d_h[j, 1] == 0, ("second planted copy of query %d (other shard)" % j, idx_h[j], d_h[j], rows)
+        else:
+            assert d_h[j, 1] > 0
+    assert idx_h[8, 0] == 555 and d_h[8, 0] == 1, (idx_h[8], d_h[8])
+    assert (d_h[:, 0] <= d_h[:, 1]).all() and (d_h[9:, 0] > 40).all()       # random 256-bit rows: nearest neighbours far away
     if rank == 0:
         popc, _ = orbx.popc_peak(local)
         line = {"metric": "server BF kNN-2 query keyframes/sec vs %d-keyframe DB" % args.db_keyframes, "value": 1e3 / ms,
@@ -150,6 +200,7 @@ def server_bench(args, world, rank, local):
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
                 "config": {"workload": "C5: 1000-descriptor query keyframe vs %d x 1000 descriptors sharded over %d GPU(s), exchange=%s" % (args.db_keyframes, world, args.exchange)},
                 "gpu_launches": int(orbx.launch_count() - l0),
+                "result_check": "planted exact copies (8 queries, 4 of them tied across two shards: lower global index first) and a 1-bit neighbour found on every rank",
                 # the kernel executes 5 POPC per 256-bit pair (carry-save compression of the 8 difference words) on the
                 # 16-lane XU pipe and 6 extra LOP3 on the ALU pipe; both pipes are near balance at that point
                 "roofline": {"bound": "popc", "achieved": pairs * 5 / (ms * 1e-3) / world, "peak": popc, "unit": "executed popc32/s per GPU",
@@ -674,23 +725,24 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         from oracle import oracle as O
         O.build()
+        impl, kind = cpu_impl()
         cores = os.cpu_count() or 1
         _, dcal, ncal = cpu_run(base[:16], cores, 2)                 # calibration: 2 frames per thread
         per_thread = int(min(2000, max(6, 15.0 / max(dcal / 2.0, 1e-3))))   # ~15 s of wall time on all cores
         fps, dtc, nf = cpu_run(base[:16], cores, per_thread)
         # reference-faithful latency: one thread per image (mono), extract + SearchForInitialization + BF kNN-2
         lat = []
-        exo = O.Extractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH)
+        exo = impl.Extractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH)
         prevf = None
         for i in range(24):
             t1 = time.perf_counter()
             _, k, d = exo(base[i % 16], (0, 0))
             if prevf is not None:
-                O.search_for_initialization(prevf[0], prevf[1], k, d, (0, W, 0, H), np.stack([prevf[0]["x"], prevf[0]["y"]], 1), WINDOW, NNRATIO, True)
+                impl.search_for_initialization(prevf[0], prevf[1], k, d, (0, W, 0, H), np.stack([prevf[0]["x"], prevf[0]["y"]], 1), WINDOW, NNRATIO, True)
                 O.bf_knn2(prevf[1], d)
             prevf = (k, d)
             lat.append(time.perf_counter() - t1)
-        cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+        cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind, "what": CPU_WHAT[kind],
                "sample": "%d frames (%d threads x %d frames of the same S-rects stream), %.1f s wall" % (nf, cores, per_thread, dtc),
                "p50_ms_per_frame_1_thread": float(np.percentile(np.array(lat[4:]) * 1e3, 50))}
 

@@ -34,18 +34,25 @@ def _all_gather(t, group):
 
 
 class ShardedDescriptorDB:
-    """shard: uint8 tensor [n_local, 32] (every rank holds the same n_local; pad with a copy of row 0 if needed)."""
+    """shard: uint8 tensor [n_local, 32]; every rank allocates the same n_local rows (the all-gather needs equal shapes) and says
+    how many of them are real with n_valid (default: all).  Rows beyond n_valid are never matched: padding with copies of a real
+    row would plant duplicates that become the second-best match and defeat the ratio test.  Global row index = rank * n_local +
+    local row."""
 
-    def __init__(self, shard, match_fn, merge_fn, group=None):
+    def __init__(self, shard, match_fn, merge_fn, group=None, n_valid=None):
         assert shard.dtype == torch.uint8 and shard.dim() == 2 and shard.shape[1] == 32
         self.shard, self.match_fn, self.merge_fn, self.group = shard.contiguous(), match_fn, merge_fn, group
         self.world, self.rank = _world(group)
         self.n_local = shard.shape[0]
+        self.n_valid = self.n_local if n_valid is None else int(n_valid)
+        assert 0 <= self.n_valid <= self.n_local
+        counts = torch.tensor([self.n_valid], dtype=torch.int64, device=shard.device)
+        self.valid_counts = [int(v) for v in _all_gather(counts, group).reshape(-1).tolist()]     # every rank's n_valid
 
     def knn2_allgather_top2(self, queries):
         """queries: the same uint8 [nq, 32] tensor on every rank (the query keyframe is broadcast by its owner).
         Returns (idx [nq,2] global row indices, dist [nq,2])."""
-        idx, d = self.match_fn(queries, self.shard, self.rank * self.n_local)      # partial top-2 on the local shard
+        idx, d = self.match_fn(queries, self.shard[:self.n_valid], self.rank * self.n_local)      # partial top-2 on the local shard
         parts_i = _all_gather(idx, self.group)                                      # [world, nq, 2]
         parts_d = _all_gather(d, self.group)
         return self.merge_fn(parts_i, parts_d)
@@ -53,14 +60,19 @@ class ShardedDescriptorDB:
     def knn2_allgather_db(self, queries):
         """all-gather the shards (world * n_local * 32 bytes into every rank), then every rank matches ITS slice of the
         queries against the full DB and the per-slice results are all-gathered (nq is padded to a multiple of world)."""
-        full = _all_gather(self.shard, self.group).reshape(-1, 32)
+        full = _all_gather(self.shard, self.group)                   # [world, n_local, 32]
         nq = queries.shape[0]
         per = (nq + self.world - 1) // self.world
         lo = min(self.rank * per, nq); hi = min(lo + per, nq)
         mine = queries[lo:hi]
-        if hi - lo < per:                                            # pad the last slice with copies of query 0
+        if hi - lo < per:                                            # pad the last slice with copies of query 0 (QUERIES: harmless, cut off below)
             mine = torch.cat([mine, queries[:1].expand(per - (hi - lo), 32)], 0)
-        idx, d = self.match_fn(mine.contiguous(), full, 0)
+        mine = mine.contiguous()
+        if all(v == self.n_local for v in self.valid_counts):
+            idx, d = self.match_fn(mine, full.reshape(-1, 32), 0)
+        else:                                                        # ragged shards: one pass per owner over its real rows, then the merge
+            parts = [self.match_fn(mine, full[r, :self.valid_counts[r]], r * self.n_local) for r in range(self.world)]
+            idx, d = self.merge_fn(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]))
         idx = _all_gather(idx, self.group).reshape(-1, 2)[:nq]
         d = _all_gather(d, self.group).reshape(-1, 2)[:nq]
         return idx.contiguous(), d.contiguous()
