@@ -21,7 +21,7 @@ def test_reference_arm_json_line():
         d = json.loads(lines[0])
         assert d["impl"] == "reference" and d["unit"] == "frames/s" and d["higher_is_better"] is True and d["value"] > 0
         assert shape in d["metric"] and shape in d["config"]["workload"]
-        assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+        assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
         assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
         assert d["gpu_launches"] == 0 and d["vs_baseline"] is None and d["dtype"] == "u8"
 
