@@ -21,7 +21,8 @@ static void create_handle(orbx_extractor** out, int device, int nfeatures, float
 {
     orbx_params p;
     p.nfeatures = nfeatures; p.scale_factor = scaleFactor; p.nlevels = nlevels; p.ini_th_fast = ini; p.min_th_fast = min;
-    p.max_width = w; p.max_height = h; p.max_batch = 1; p.device = device; p.max_candidates_per_level = 0;
+    p.max_width = w; p.max_height = h; p.max_batch = 1; p.device = device;
+    p.max_candidates_per_level = 1 << 30;      // clamped to the geometric NMS bound of every level: a corner-dense frame can never overflow
     if (orbx_extractor_create(&p, out) != ORBX_OK)
         throw std::runtime_error(std::string("ORBextractor (B200): ") + orbx_last_error());   // no CPU fallback exists
 }

@@ -254,7 +254,7 @@ static int configure_geometry_impl(orbx_extractor* h, int width, int height)
     if ((rc = dev_alloc(h, (void**)&b.sort_scratch, sizeof(unsigned long long) * (size_t)sort_elems * B))) return rc;
     if ((rc = dev_alloc(h, (void**)&b.sort_off, sizeof(int) * g.nlevels))) return rc;
     CK(cudaMemcpy(b.sort_off, sort_off.data(), sizeof(int) * g.nlevels, cudaMemcpyHostToDevice));
-    if ((rc = dev_alloc(h, (void**)&b.work, sizeof(uint2) * (size_t)g.out_cap * B))) return rc;
+    if ((rc = dev_alloc(h, (void**)&b.work, sizeof(uint4) * (size_t)g.out_cap * B))) return rc;
     if ((rc = dev_alloc(h, (void**)&b.kps, sizeof(orbx_keypoint) * (size_t)g.out_cap * h->slots))) return rc;
     if ((rc = dev_alloc(h, (void**)&b.desc, (size_t)32 * g.out_cap * h->slots))) return rc;
     if ((rc = dev_alloc(h, (void**)&b.n, sizeof(int) * h->slots))) return rc;

@@ -4,6 +4,8 @@
 //           computeOrientation / IC_Angle (:75-102, :470-477),
 //           computeOrbDescriptor / computeDescriptors (:105-145, :1059-1066),
 //           the scale + two-ended mono/stereo placement of operator() (:1102-1149).
+#include <cuda.h>
+#include <stdlib.h>
 #include <string.h>
 #include "orbx_internal.h"
 
@@ -42,7 +44,7 @@ __global__ void __launch_bounds__(FIN_NT) k_finalize(OrbxGeom g, OrbxBuffers b, 
     if (total > g.out_cap) { if (tid == 0) atomicOr(b.err, ORBX_DEVERR_KP_OVERFLOW); total = g.out_cap; }
     const uint32_t* lk = b.lvl_kp + (long long)f * g.kp_total_cap;
     orbx_keypoint* okp = b.kps + (long long)slot_f * g.out_cap;
-    uint2* work = b.work + (long long)f * g.out_cap;
+    uint4* work = b.work + (long long)f * g.out_cap;
 
     // total number of keypoints in the lapping area is needed up front? No: stereo slots count down from
     // total-1, mono slots count up from 0; both only need the running counts.
@@ -74,8 +76,8 @@ __global__ void __launch_bounds__(FIN_NT) k_finalize(OrbxGeom g, OrbxBuffers b, 
             kp.response = (float)(p >> 24); kp.octave = lvl; kp.class_id = -1;
             okp[slot] = kp;
             // work item: level coords (with border), level, output slot
-            work[i] = make_uint2(((p & 0xFFF) + ORBX_BORDER) | ((((p >> 12) & 0xFFF) + ORBX_BORDER) << 12) | ((uint32_t)lvl << 24),
-                                 (uint32_t)slot);
+            work[i] = make_uint4(((p & 0xFFF) + ORBX_BORDER) | ((((p >> 12) & 0xFFF) + ORBX_BORDER) << 12) | ((uint32_t)lvl << 24),
+                                 (uint32_t)slot, 0u, 0u);
         }
         __syncthreads();
         if (tid == 0) s_run += tot;
@@ -110,93 +112,221 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x)
     return a;
 }
 
+constexpr int ORI_WARPS = 8;
+constexpr int ORI_GROUP = 4;          // keypoints per warp in k_orient, processed interleaved (independent load chains)
 constexpr int DESC_WARPS = 8;
+constexpr int DESC_GROUP = 8;         // keypoints per warp in k_describe, one after the other through two staged boxes
+constexpr int PATCH_R = 18;           // |rotated pattern offset| <= round(18.385) = 18
+constexpr int PATCH_W = 64;           // box width in bytes.  The box must START on a 16-byte boundary of the image row (an unaligned
+                                      // inner coordinate faults with "illegal instruction": profiles/probes/tma_box_probe_b200.txt),
+                                      // so it begins at (cx - 18) & ~15 and needs 15 + 37 <= 64 columns
+constexpr int PATCH_H = 2 * PATCH_R + 1;
+constexpr int PATCH_BYTES = PATCH_W * PATCH_H;               // 2368
+constexpr int PATCH_SLOT = (PATCH_BYTES + 127) & ~127;       // 2432: every buffer starts 128-byte aligned
+constexpr int DESC_SMEM = DESC_WARPS * 2 * PATCH_SLOT;
 
-// ---- k_orient_describe: one warp per keypoint -------------------------------------------------
-// IC_Angle: lane v' = lane-15 owns patch row v = lane-15 (31 rows), integer moments, shuffle reduce.
-// Descriptor: lane j produces byte j = tests 8j..8j+7; the rotated sample offsets use separately
-// rounded fp32 products (no FMA) and round-half-even, cos/sin in fp64 rounded to fp32.
-__global__ void __launch_bounds__(DESC_WARPS * 32) k_orient_describe(OrbxGeom g, OrbxBuffers b, const uint8_t* level0,
-                                                                   int pitch0, long long stride0, int first_slot)
+// the 256 test pairs as floats, laid out for conflict-free 16-byte shared-memory reads: entry [k][lane] = (x0, y0, x1, y1) of
+// pair 8 * lane + k (lane j produces descriptor byte j = tests 8j .. 8j+7)
+__device__ float4 d_pattern_f[8 * 32];
+
+struct DescMaps { CUtensorMap blur[ORBX_MAX_LEVELS]; };
+
+// ---- TMA / mbarrier primitives (SASS: UTMALDG, SYNCS) ----
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count)
 {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, int x, int y, int z, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(map), "r"(x), "r"(y), "r"(z),
+                   "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+
+// ---- k_orient: IC_Angle + the rotation of every keypoint ------------------------------------------
+// One warp per group of ORI_GROUP keypoints.  The phase is bound by the latency of the patch loads (every 31 x 31 patch is fresh
+// from L2 / HBM), so the kernel keeps no large shared-memory state and runs at full occupancy, and a warp keeps the loads of its
+// four keypoints in flight together.
+//   moments: integer m10, m01 over the 749-pixel circular patch of the un-blurred level, read as aligned words dealt row-major to
+//     the lanes (coalesced: ~6 sectors per load) and reduced with dp4a; the item table (byte mask, byte weights, row, word per
+//     alignment) lives in shared memory;
+//   angle: lane j = keypoint j: cv::fastAtan2 and ONE fp64 sincos per keypoint (the one-warp-per-keypoint kernel of round 1
+//     executed both on all 32 lanes: 15 % of its instructions); angle -> the keypoint record, (cos, sin) -> the work item.
+__global__ void __launch_bounds__(ORI_WARPS * 32, 5) k_orient(OrbxGeom g, OrbxBuffers b, const uint8_t* level0, int pitch0, long long stride0,
+                                                          int first_slot)
+{
+    constexpr int G = ORI_GROUP;
+    __shared__ uint4 s_ic[4 * 288];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int f = blockIdx.y;
     const int slot_f = first_slot + f;
     const int total = b.n[slot_f];
-    const int i = blockIdx.x * DESC_WARPS + warp;
-    if (i >= total) return;
-    const uint2 wk = b.work[(long long)f * g.out_cap + i];
-    const int cx = wk.x & 0xFFF, cy = (wk.x >> 12) & 0xFFF, lvl = wk.x >> 24;
-    const int slot = (int)wk.y;
-    const OrbxLevel& L = g.lv[lvl];
-    const uint8_t* img; int pitch;
-    if (lvl == 0) { img = level0 + (long long)f * stride0; pitch = pitch0; }
-    else { img = b.pyr[lvl] + (long long)f * L.frame_stride; pitch = L.pitch; }
-
-    // ---- orientation: integer moments over the 749-pixel circular patch (rows v = -15..15, |u| <= umax[|v|]) ----
-    // The patch is read as aligned 32-bit words, 9 per row; the 31 x 9 words are dealt to the lanes in row-major
-    // order (neighbouring lanes read neighbouring words), masked to the row's extent and reduced with dp4a:
-    // m10 += sum(u * I) uses signed byte weights u, m01 += v * sum(I).
-    int m10 = 0, m01 = 0;
-    {
-        const uint8_t* p0 = img + (long long)(cy - ORBX_HALF_PATCH) * pitch + (cx - ORBX_HALF_PATCH);
-        const int sh = (int)(reinterpret_cast<uintptr_t>(p0) & 3);        // same for every row when pitch % 4 == 0
-        if ((pitch & 3) == 0) {
-            const uint32_t* w0 = reinterpret_cast<const uint32_t*>(p0 - sh);
-            const int pw = pitch >> 2;
-            const uint4* tab = d_ic_table + sh * 288;
+    // a CTA walks groups blockIdx.x, blockIdx.x + gridDim.x, ...: the table copy is paid once per CTA, not once per 32 keypoints
+    if (blockIdx.x * ORI_WARPS * G >= total) return;
+    for (int k = threadIdx.x; k < 4 * 288; k += ORI_WARPS * 32) s_ic[k] = d_ic_table[k];
+    __syncthreads();
+    uint4* work = b.work + (long long)f * g.out_cap;
+    for (int i0 = (blockIdx.x * ORI_WARPS + warp) * G; i0 < total; i0 += gridDim.x * ORI_WARPS * G) {
+        const int cnt = min(G, total - i0);
+        // lane j < cnt holds the work item of keypoint i0 + j; the lanes of missing keypoints repeat keypoint i0 so that every
+        // address below stays valid (their results are dropped)
+        const uint4 wk = work[i0 + (lane < cnt ? lane : 0)];
+        int m10[G], m01[G];
+        const uint32_t* w0[G]; int pw[G]; const uint4* tab[G];
+        bool aligned = true;
+#pragma unroll
+        for (int j = 0; j < G; j++) {
+            const uint32_t w = __shfl_sync(0xffffffffu, wk.x, j);
+            const int cx = w & 0xFFF, cy = (w >> 12) & 0xFFF, lvl = w >> 24;
+            const uint8_t* img; int pitch;
+            if (lvl == 0) { img = level0 + (long long)f * stride0; pitch = pitch0; }
+            else { img = b.pyr[lvl] + (long long)f * g.lv[lvl].frame_stride; pitch = g.lv[lvl].pitch; }
+            const uint8_t* p0 = img + (long long)(cy - ORBX_HALF_PATCH) * pitch + (cx - ORBX_HALF_PATCH);
+            const int sh = (int)(reinterpret_cast<uintptr_t>(p0) & 3);    // same for every row when pitch % 4 == 0
+            w0[j] = reinterpret_cast<const uint32_t*>(p0 - sh); pw[j] = pitch >> 2; tab[j] = s_ic + sh * 288;
+            aligned = aligned && (pitch & 3) == 0;
+            m10[j] = 0; m01[j] = 0;
+        }
+        if (aligned) {
 #pragma unroll
             for (int it = 0; it < 9; it++) {
                 const int t = lane + 32 * it;                              // item = (row, word), 279 items
                 if (t < 31 * 9) {
-                    const uint4 e = __ldg(tab + t);                        // mask, weights, row, word
-                    const uint32_t mw = __ldg(w0 + (int)e.z * pw + (int)e.w) & e.x;
-                    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(m10) : "r"(mw), "r"(e.y), "r"(m10));   // unsigned pixels x signed weights u
-                    m01 += ((int)e.z - ORBX_HALF_PATCH) * (int)__dp4a(mw, 0x01010101u, 0u);
+#pragma unroll
+                    for (int j = 0; j < G; j++) {
+                        const uint4 e = tab[j][t];                         // mask, weights, row, word
+                        const uint32_t mw = __ldg(w0[j] + (int)e.z * pw[j] + (int)e.w) & e.x;
+                        asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(m10[j]) : "r"(mw), "r"(e.y), "r"(m10[j]));   // unsigned pixels x signed weights u
+                        m01[j] += ((int)e.z - ORBX_HALF_PATCH) * (int)__dp4a(mw, 0x01010101u, 0u);
+                    }
                 }
             }
-        } else if (lane < 31) {
-            const int v = lane - ORBX_HALF_PATCH;
-            const int d = c_umax[v < 0 ? -v : v];
-            const uint8_t* row = img + (long long)(cy + v) * pitch + cx;
-            int rs = 0;
-            for (int u = -d; u <= d; ++u) { const int val = __ldg(row + u); m10 += u * val; rs += val; }
-            m01 = v * rs;
+        } else {
+            // a caller's level-0 pitch that is not a multiple of 4: plain byte loads, lane = patch row
+#pragma unroll
+            for (int j = 0; j < G; j++) {
+                const uint32_t w = __shfl_sync(0xffffffffu, wk.x, j);
+                const int cx = w & 0xFFF, cy = (w >> 12) & 0xFFF, lvl = w >> 24;
+                const uint8_t* img; int pitch;
+                if (lvl == 0) { img = level0 + (long long)f * stride0; pitch = pitch0; }
+                else { img = b.pyr[lvl] + (long long)f * g.lv[lvl].frame_stride; pitch = g.lv[lvl].pitch; }
+                if (lane < 31) {
+                    const int v = lane - ORBX_HALF_PATCH;
+                    const int d = c_umax[v < 0 ? -v : v];
+                    const uint8_t* row = img + (long long)(cy + v) * pitch + cx;
+                    int rs = 0;
+                    for (int u = -d; u <= d; ++u) { const int val = __ldg(row + u); m10[j] += u * val; rs += val; }
+                    m01[j] = v * rs;
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < G; j++) { m10[j] = __reduce_add_sync(0xffffffffu, m10[j]); m01[j] = __reduce_add_sync(0xffffffffu, m01[j]); }
+        int mm10 = m10[0], mm01 = m01[0];
+#pragma unroll
+        for (int j = 1; j < G; j++) if (lane == j) { mm10 = m10[j]; mm01 = m01[j]; }
+        if (lane < cnt) {
+            const float angle = fast_atan2_deg((float)mm01, (float)mm10);
+            const float factorPI = (float)(3.1415926535897932384626433832795 / 180.f);
+            const float ang = __fmul_rn(angle, factorPI);
+            double sd, cd;
+            sincos((double)ang, &sd, &cd);          // same kernels as cos() / sin(), one range reduction
+            b.kps[(long long)slot_f * g.out_cap + (int)wk.y].angle = angle;
+            work[i0 + lane] = make_uint4(wk.x, wk.y, __float_as_uint((float)cd), __float_as_uint((float)sd));
         }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        m10 += __shfl_xor_sync(0xffffffffu, m10, o);
-        m01 += __shfl_xor_sync(0xffffffffu, m01, o);
-    }
-    const float angle = fast_atan2_deg((float)m01, (float)m10);
+}
 
-    // ---- descriptor on the blurred level ----
-    const float factorPI = (float)(3.1415926535897932384626433832795 / 180.f);
-    const float ang = __fmul_rn(angle, factorPI);
-    double sd, cd;
-    sincos((double)ang, &sd, &cd);                  // same kernels as cos() / sin(), one range reduction
-    const float ca = (float)cd, sa = (float)sd;
-    const uint8_t* bl = b.blur[lvl] + (long long)f * L.frame_stride;
-    const uint8_t* center = bl + (long long)cy * L.pitch + cx;
-    const uint4 w0 = reinterpret_cast<const uint4*>(d_pattern)[lane * 2];
-    const uint4 w1 = reinterpret_cast<const uint4*>(d_pattern)[lane * 2 + 1];
-    const uint32_t pw[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-    uint32_t val = 0;
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-        const float x0 = (float)(int8_t)(pw[k] & 0xFF), y0 = (float)(int8_t)((pw[k] >> 8) & 0xFF);
-        const float x1 = (float)(int8_t)((pw[k] >> 16) & 0xFF), y1 = (float)(int8_t)(pw[k] >> 24);
-        const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, sa), __fmul_rn(y0, ca)));
-        const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, ca), __fmul_rn(y0, sa)));
-        const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, sa), __fmul_rn(y1, ca)));
-        const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, ca), __fmul_rn(y1, sa)));
-        const int t0 = __ldg(center + r0 * L.pitch + c0);
-        const int t1 = __ldg(center + r1 * L.pitch + c1);
-        val |= (uint32_t)(t0 < t1) << k;
+// ---- k_describe: steered BRIEF from TMA-staged patches --------------------------------------------
+// One warp per group of DESC_GROUP keypoints.  The 37 x 37 window of the BLURRED level that the rotated pattern can reach is
+// staged in shared memory, one TMA box (64 x 37 bytes, cp.async.bulk.tensor on a per-level 3-D map) per keypoint, issued by one
+// lane, double-buffered per warp and completed on an mbarrier: the 512 scattered byte reads of a descriptor hit shared memory
+// instead of ~17 different L1 sectors per load instruction (with __ldg the kernel sat at 86 % of the L1TEX pipe, ncu r2_desc_v3).
+// Lane j produces descriptor byte j; the rotated sample offsets use separately rounded fp32 products (no FMA) and round-half-even,
+// exactly the reference's arithmetic.  TMA == false: the same with plain loads (driver without cuTensorMapEncodeTiled).
+template <bool TMA>
+__global__ void __launch_bounds__(DESC_WARPS * 32, 4) k_describe(OrbxGeom g, OrbxBuffers b, int first_slot, const __grid_constant__ DescMaps maps)
+{
+    constexpr int G = DESC_GROUP;
+    extern __shared__ __align__(128) uint8_t s_patch[];                   // [warp][2][PATCH_SLOT] (TMA only)
+    __shared__ float4 s_pat[8 * 32];
+    __shared__ __align__(8) unsigned long long s_bar[DESC_WARPS][2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int f = blockIdx.y;
+    const int slot_f = first_slot + f;
+    const int total = b.n[slot_f];
+    if (blockIdx.x * DESC_WARPS * G >= total) return;                     // whole CTA past the frame's keypoints
+    for (int k = threadIdx.x; k < 8 * 32; k += DESC_WARPS * 32) s_pat[k] = d_pattern_f[k];
+    if (TMA && threadIdx.x < DESC_WARPS * 2) mbar_init(&s_bar[threadIdx.x >> 1][threadIdx.x & 1], 1);
+    if (TMA) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    const int i0 = (blockIdx.x * DESC_WARPS + warp) * G;
+    if (i0 >= total) return;
+    const int cnt = min(G, total - i0);
+    const uint4 wk = b.work[(long long)f * g.out_cap + i0 + (lane < cnt ? lane : 0)];
+    uint8_t* mybuf = s_patch + warp * 2 * PATCH_SLOT;
+    // (a bulk tensor copy is issued by ONE lane: the instruction takes warp-uniform operands)
+    auto issue = [&](int j) {
+        const uint32_t w = __shfl_sync(0xffffffffu, wk.x, j);
+        if (lane == 0) {
+            const int cx = w & 0xFFF, cy = (w >> 12) & 0xFFF, lvl = w >> 24;
+            mbar_expect_tx(&s_bar[warp][j & 1], PATCH_BYTES);
+            tma_load_3d(mybuf + (j & 1) * PATCH_SLOT, &maps.blur[lvl], (cx - PATCH_R) & ~15, cy - PATCH_R, f, &s_bar[warp][j & 1]);
+        }
+    };
+    if (TMA) {
+        issue(0);
+        if (cnt > 1) issue(1);
     }
-    b.desc[((long long)slot_f * g.out_cap + slot) * 32 + lane] = (uint8_t)val;
-    if (lane == 0) b.kps[(long long)slot_f * g.out_cap + slot].angle = angle;
+    float4 pt[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) pt[k] = s_pat[k * 32 + lane];
+#pragma unroll 2
+    for (int j = 0; j < cnt; j++) {
+        const uint32_t w = __shfl_sync(0xffffffffu, wk.x, j);
+        const int slot = (int)__shfl_sync(0xffffffffu, wk.y, j);
+        const float c = __uint_as_float(__shfl_sync(0xffffffffu, wk.z, j)), s_ = __uint_as_float(__shfl_sync(0xffffffffu, wk.w, j));
+        const int cx = w & 0xFFF, cy = (w >> 12) & 0xFFF, lvl = w >> 24;
+        const uint8_t* center; int bp;
+        if (TMA) {
+            center = mybuf + (j & 1) * PATCH_SLOT + PATCH_R * PATCH_W + PATCH_R + ((cx - PATCH_R) & 15);
+            bp = PATCH_W;
+            mbar_wait(&s_bar[warp][j & 1], (j >> 1) & 1);
+        } else {
+            bp = g.lv[lvl].pitch;
+            center = b.blur[lvl] + (long long)f * g.lv[lvl].frame_stride + (long long)cy * bp + cx;
+        }
+        uint32_t val = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(pt[k].x, s_), __fmul_rn(pt[k].y, c)));
+            const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(pt[k].x, c), __fmul_rn(pt[k].y, s_)));
+            const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(pt[k].z, s_), __fmul_rn(pt[k].w, c)));
+            const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(pt[k].z, c), __fmul_rn(pt[k].w, s_)));
+            const int t0 = TMA ? (int)center[r0 * PATCH_W + c0] : (int)__ldg(center + r0 * bp + c0);
+            const int t1 = TMA ? (int)center[r1 * PATCH_W + c1] : (int)__ldg(center + r1 * bp + c1);
+            val |= (uint32_t)(t0 < t1) << k;
+        }
+        b.desc[((long long)slot_f * g.out_cap + slot) * 32 + lane] = (uint8_t)val;
+        if (TMA && j + 2 < cnt) {
+            __syncwarp();                                                 // every lane has read its samples: the buffer is free again
+            issue(j + 2);
+        }
+    }
 }
 
 }  // namespace
@@ -233,13 +363,39 @@ void orbx_upload_pattern()
                     ((uint32_t)(uint8_t)(int8_t)p[2] << 16) | ((uint32_t)(uint8_t)(int8_t)p[3] << 24);
     }
     cudaMemcpyToSymbol(d_pattern, packed, sizeof(packed));
+    static float4 pf[8 * 32];
+    for (int lane = 0; lane < 32; lane++)
+        for (int k = 0; k < 8; k++) {
+            const int32_t* p = h_pattern + 4 * (8 * lane + k);
+            pf[k * 32 + lane] = make_float4((float)p[0], (float)p[1], (float)p[2], (float)p[3]);
+        }
+    cudaMemcpyToSymbol(d_pattern_f, pf, sizeof(pf));
 }
 
 void orbx_launch_describe(const OrbxGeom& g, const OrbxBuffers& b, const uint8_t* level0, int pitch0,
                           long long stride0, int batch, int lap0, int lap1, int first_slot, cudaStream_t s)
 {
     k_finalize<<<batch, FIN_NT, 0, s>>>(g, b, lap0, lap1, first_slot);
-    dim3 grid((g.out_cap + DESC_WARPS - 1) / DESC_WARPS, batch);
-    k_orient_describe<<<grid, DESC_WARPS * 32, 0, s>>>(g, b, level0, pitch0, stride0, first_slot);
-    ORBX_COUNT_LAUNCH(2);
+    // orientation: CTAs walk the keypoint groups of a frame in strides (the item table is copied once per CTA)
+    {
+        const int groups = (g.out_cap + ORI_WARPS * ORI_GROUP - 1) / (ORI_WARPS * ORI_GROUP);
+        // big batches: 8 CTAs per frame amortise the table copy; a single frame spreads over the whole GPU instead
+        dim3 grid(batch >= 32 && groups > 8 ? 8 : groups, batch);
+        k_orient<<<grid, ORI_WARPS * 32, 0, s>>>(g, b, level0, pitch0, stride0, first_slot);
+    }
+    dim3 grid((g.out_cap + DESC_WARPS * DESC_GROUP - 1) / (DESC_WARPS * DESC_GROUP), batch);
+    // one 3-D tensor map (x, y, frame) per blurred level with a 64 x 37 box; the blurred levels are this library's own buffers
+    // (64-byte pitches), so the layout is always TMA-legal; if the driver entry point is missing the plain-load kernel runs
+    alignas(64) DescMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    bool tma = getenv("ORBX_DESC_NO_TMA") == nullptr;
+    for (int l = 0; l < g.nlevels && tma; l++)
+        tma = orbx_make_tensor_map_3d(&maps.blur[l], b.blur[l], g.lv[l].w, g.lv[l].h, g.lv[l].pitch, g.lv[l].frame_stride, batch, PATCH_W, PATCH_H);
+    if (tma) {
+        ORBX_OPTIN_SMEM(k_describe<true>);
+        k_describe<true><<<grid, DESC_WARPS * 32, DESC_SMEM, s>>>(g, b, first_slot, maps);
+    } else {
+        k_describe<false><<<grid, DESC_WARPS * 32, 0, s>>>(g, b, first_slot, maps);
+    }
+    ORBX_COUNT_LAUNCH(3);
 }

@@ -67,7 +67,7 @@ struct OrbxBuffers {
     unsigned long long* sort_scratch;  // global sort scratch for oversized levels [batch][nlevels][...]
     long long sort_scratch_stride;     // per (frame) elements
     int* sort_off;                     // [nlevels] offsets into a frame's scratch
-    uint2* work;                       // [batch][out_cap] orientation/descriptor work items
+    uint4* work;                       // [batch][out_cap] work items: level coords | level, output slot, cos, sin (k_orient fills the last two)
     orbx_keypoint* kps;                // [slots][out_cap]
     uint8_t* desc;                     // [slots][out_cap][32]
     int* n;                            // [slots]
@@ -100,6 +100,9 @@ void orbx_fast_configure(const OrbxGeom& g);
 int orbx_fast_plan(int w, int nCols, int wCell);
 void orbx_fast_units(const OrbxGeom& g, std::vector<int4>& tab);
 void orbx_upload_pattern();
+// 3-D u8 tensor map (x, y, frame) over a batch of pitched images, box = (bw, bh, 1); map128 points at a CUtensorMap (128 bytes,
+// 64-byte aligned).  false when the layout is not TMA-legal (base / strides not multiples of 16) or the driver entry is missing.
+bool orbx_make_tensor_map_3d(void* map128, const uint8_t* base, int w, int h, int pitch, long long fstride, int frames, int bw, int bh);
 void orbx_set_error(const char* fmt, const char* a, const char* b);
 // Raises a kernel's dynamic shared-memory limit to the opt-in maximum of the CURRENT device, once per (kernel, device).
 // The attribute is per function and per device, shared by every handle of the process: it is never tied to one handle's

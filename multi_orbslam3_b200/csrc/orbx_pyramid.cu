@@ -495,8 +495,14 @@ static EncodeTiledFn get_encode()
 
 // 3-D u8 tensor (x, y, frame) over a batch of pitched images; box = (bw, bh, 1).  Returns false when the layout
 // is not TMA-legal (base 16-byte aligned, strides multiples of 16) so that the caller uses the plain-load path.
+bool orbx_make_tensor_map_3d(void* map128, const uint8_t* base, int w, int h, int pitch, long long fstride, int frames, int bw, int bh);
 static bool make_map(CUtensorMap* m, const uint8_t* base, int w, int h, int pitch, long long fstride, int frames, int bw, int bh)
 {
+    return orbx_make_tensor_map_3d(m, base, w, h, pitch, fstride, frames, bw, bh);
+}
+bool orbx_make_tensor_map_3d(void* map128, const uint8_t* base, int w, int h, int pitch, long long fstride, int frames, int bw, int bh)
+{
+    CUtensorMap* m = reinterpret_cast<CUtensorMap*>(map128);
     EncodeTiledFn enc = get_encode();
     if (!enc || (reinterpret_cast<uintptr_t>(base) & 15) || (pitch & 15) || (fstride & 15) || bw > 256 || bh > 256) return false;
     cuuint64_t dims[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)frames};

@@ -27,7 +27,8 @@ def assert_bit_exact(got, ref):
                          ids=["C1_mono", "C1_init5000", "C2_stereo", "C3_kitti", "C4_tum"])
 def test_extraction_equals_reference(w, h, nf, lap, B):
     frames = np.ascontiguousarray(np.concatenate([synth.rects_stream(w, h, B - 1, seed=40), synth.noise_frame(w, h, seed=4)[None]]))
-    ex = orbx.ORBextractor(nf, 1.2, 8, 20, 7, max_width=w, max_height=h, max_batch=B)
+    # the noise frame has ~30 k FAST corners: candidate capacity = the geometric bound instead of the streaming default of 16384
+    ex = orbx.ORBextractor(nf, 1.2, 8, 20, 7, max_width=w, max_height=h, max_batch=B, max_candidates_per_level=1 << 30)
     ref = R.Extractor(nf, 1.2, 8, 20, 7)
     got = ex.extract_batch(frames, lap)
     for f in range(B):
