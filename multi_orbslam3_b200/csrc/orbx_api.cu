@@ -590,10 +590,17 @@ bool orbx_ex_can_fetch_direct(orbx_extractor* h, orbx_keypoint* kps, uint8_t* de
 }
 
 // after the stream(s) were synchronised: device error flags, then unpack the staging if the fetch was not direct
-int orbx_ex_fetch_finish(orbx_extractor* h, int count, orbx_keypoint* kps, uint8_t* desc, int cap,
-                         int32_t* n, int32_t* mono_index, bool direct)
+// queues the D2H copy of the device error flags on `s` (the caller synchronises s, then calls orbx_ex_fetch_finish with err_fetched)
+int orbx_ex_fetch_err_async(orbx_extractor* h, cudaStream_t s)
 {
-    CK(cudaMemcpy(h->h_err, h->buf.err, sizeof(unsigned), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpyAsync(h->h_err, h->buf.err, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+    return ORBX_OK;
+}
+
+int orbx_ex_fetch_finish(orbx_extractor* h, int count, orbx_keypoint* kps, uint8_t* desc, int cap,
+                         int32_t* n, int32_t* mono_index, bool direct, bool err_fetched)
+{
+    if (!err_fetched) CK(cudaMemcpy(h->h_err, h->buf.err, sizeof(unsigned), cudaMemcpyDeviceToHost));
     int rc = deferred_error(h);
     if (rc) return rc;
     if (direct) return ORBX_OK;
@@ -619,7 +626,7 @@ extern "C" int orbx_extractor_download(orbx_extractor* h, int first_slot, int co
     int rc = orbx_ex_fetch_async(h, first_slot, count, 0, kps, desc, cap, n, mono_index, s, direct);
     if (rc) return rc;
     CK(cudaStreamSynchronize(s));
-    return orbx_ex_fetch_finish(h, count, kps, desc, cap, n, mono_index, direct);
+    return orbx_ex_fetch_finish(h, count, kps, desc, cap, n, mono_index, direct, false);
 }
 
 extern "C" int orbx_extract_batch(orbx_extractor* h, const uint8_t* imgs, int batch, int width, int height,

@@ -128,7 +128,8 @@ bool orbx_ex_can_fetch_direct(orbx_extractor* h, orbx_keypoint* kps, uint8_t* de
 int orbx_ex_fetch_async(orbx_extractor* h, int first_slot, int count, int host_off, orbx_keypoint* kps, uint8_t* desc, int cap,
                         int32_t* n, int32_t* mono_index, cudaStream_t s, bool direct);
 int orbx_ex_fetch_finish(orbx_extractor* h, int count, orbx_keypoint* kps, uint8_t* desc, int cap,
-                         int32_t* n, int32_t* mono_index, bool direct);
+                         int32_t* n, int32_t* mono_index, bool direct, bool err_fetched = false);
+int orbx_ex_fetch_err_async(orbx_extractor* h, cudaStream_t s);
 
 // device view of one frame's pyramid of an extractor handle (stereo refinement reads both cameras' pyramids)
 struct OrbxPyrView {
