@@ -167,8 +167,8 @@ struct FastSmem {
     unsigned char use_ini[MAX_SEG_CELLS];
 };
 
-// group-queue capacity: every group of the tile (cannot overflow)
-__host__ __device__ inline int qg_cap(int hs, int ng) { return hs * ng; }
+// group-queue capacity: every pair of groups of the tile (cannot overflow)
+__host__ __device__ inline int qg_cap(int hs, int ng) { return hs * (ng + 2); }      // words: one 64-bit entry per pair of groups
 
 // shared-memory bytes of one segment tile, without the pixel queue
 __host__ __device__ inline int tile_bytes(int nrow, int hs, int ng, int ncell)
@@ -190,8 +190,7 @@ __global__ void __launch_bounds__(NT, 5) k_fast_seg(OrbxGeom g, OrbxBuffers b, c
     const int l = u0.x, iniY = u0.y, nrow = u0.z, hs = u0.w;          // level, first staged row, staged rows, scored rows (tile rows 3 .. nrow-4)
     const int xa0 = u1.x, sw = u1.y, X0 = u1.z, X1 = u1.w;            // staged columns [xa0, xa0+sw), scored tile columns [X0, X1)
     const int ncell = u2.x, tbytes = u2.y;
-    const unsigned hrcp = (unsigned)__ldg(&b.unit_tab[4 * blockIdx.x + 3].x);     // (n * hrcp) >> 16 == n / hs
-    const unsigned wrcp = (unsigned)u2.z, srcp = (unsigned)u2.w;      // (n * wrcp) >> 16 == n / wCell; (n * srcp) >> 16 == n / nsteps
+    const unsigned wrcp = (unsigned)u2.z, prcp = (unsigned)u2.w;      // (n * wrcp) >> 16 == n / wCell; (n * prcp) >> 20 == n / (pairs of groups per row)
     int* row_count = b.row_count + (long long)f * g.total_rows + blockIdx.x;
     if (hs <= 0) { if (tid == 0) *row_count = 0; return; }
     const int wCell = g.lv[l].wCell, row_cap = g.lv[l].row_cap;
@@ -242,91 +241,89 @@ __global__ void __launch_bounds__(NT, 5) k_fast_seg(OrbxGeom g, OrbxBuffers b, c
     if (vec) mbar_wait(&s_bar, 0);
     __syncthreads();
 
-    // ---- 2. screen: one (tile row, 32 x 8-pixel step) item per warp; a lane screens two adjacent 4-pixel groups ----
+    // ---- 2. screen: items = (scored row, pair of adjacent 4-pixel groups), dealt linearly to the threads (no idle lanes at
+    //      narrow levels).  Stage 1 (compass pairs) runs here on every item; an item with a survivor is queued as one 64-bit
+    //      entry by a per-lane shared-memory atomic (the order of the queue is irrelevant: the output order comes from the
+    //      bitmaps).  Stage 2 (diagonal pairs) and the segment-edge masks run in the expansion below, where every lane holds
+    //      a queued item: dense lanes instead of the 12-of-32 of a branch inside this loop. ----
     const unsigned c127 = (unsigned)(127 - (minTh < 126 ? minTh : 126)) * 0x01010101u;
     const bool screen_ok = minTh <= 126;
+    constexpr int W = TP / 4;
+    const int k0 = g0 >> 1, npairs = (g1 >> 1) - k0 + 1;          // pairs of groups (8-byte aligned)
+    uint2* QG2 = reinterpret_cast<uint2*>(QG);
     {
-        constexpr int W = TP / 4;
-        const int k0 = g0 >> 1, k1 = g1 >> 1;                   // pairs of groups (8-byte aligned)
-        const int nsteps = (k1 - k0 + 32) >> 5;
-        // items (row, step) are dealt round-robin to the warps; the pair advances by NW items per iteration
-        int ry = (int)(((unsigned)warp * srcp) >> 16), st = warp - ry * nsteps;
-        const int dq = (int)(((unsigned)NW * srcp) >> 16), dr = NW - dq * nsteps;
+        const int nitems = hs * npairs;
+        const unsigned* Tw = reinterpret_cast<const unsigned*>(T + 3 * TP);
+        for (int i = tid; i < nitems; i += NT) {
+            const int ry = (int)(((unsigned)i * prcp) >> 20), kp = k0 + i - ry * npairs;
+            const unsigned* rc = Tw + ry * W + 2 * kp;
+            unsigned ca = 0x80808080u, cb = 0x80808080u;
+            if (screen_ok) {
+                // |d_k| | |d_k+8| >= max(|d_k|, |d_k+8|): one threshold test per pair, still only a necessary
+                // condition (exact when t = 2^n - 1, e.g. the reference's minThFAST = 7)
+                const uint2 V = *reinterpret_cast<const uint2*>(rc);
+                const uint2 P3 = *reinterpret_cast<const uint2*>(rc + 3 * W), M3 = *reinterpret_cast<const uint2*>(rc - 3 * W);
+                const unsigned Lw = rc[-1], Rw = rc[2];
+                // pair (0, 8): (0,+3) / (0,-3);  pair (4, 12): (+3,0) / (-3,0)
+                ca = gt_flags(__vabsdiffu4(V.x, P3.x) | __vabsdiffu4(V.x, M3.x), c127);
+                cb = gt_flags(__vabsdiffu4(V.y, P3.y) | __vabsdiffu4(V.y, M3.y), c127);
+                ca &= gt_flags(__vabsdiffu4(V.x, __funnelshift_r(V.x, V.y, 24)) | __vabsdiffu4(V.x, __funnelshift_r(Lw, V.x, 8)), c127);
+                cb &= gt_flags(__vabsdiffu4(V.y, __funnelshift_r(V.y, Rw, 24)) | __vabsdiffu4(V.y, __funnelshift_r(V.x, V.y, 8)), c127);
+                ca &= 0x80808080u; cb &= 0x80808080u;
+            }
+            if (ca | cb) {
+                // entry.x = flags of the first group (bits 7, 15, 23, 31) | pair index (bits 0-6) | tile row (bits 8-14); entry.y = flags of the second
+                const int o = atoms_add(&sh.qg_count, 1);                 // <= hs * npairs entries by construction
+                QG2[o] = make_uint2(ca | (unsigned)kp | ((unsigned)(ry + 3) << 8), cb);
+            }
+        }
+    }
+    __syncthreads();
+    // ---- stage 2 of the screen on the queued items, then expansion into pixel entries (dense queue for phase 3a) ----
+    {
+        const int ngq = sh.qg_count;
         // scored columns only: the first and last group straddle the segment's edges
         const unsigned mask0 = 0x80808080u << (8 * (X0 & 3)), mask1 = 0x80808080u >> (8 * (3 - ((X1 - 1) & 3)));
-        const unsigned lt = (1u << lane) - 1;
-        const unsigned* Tw = reinterpret_cast<const unsigned*>(T + 3 * TP) + 2 * (k0 + lane);
-        while (ry < hs) {                                       // warp-uniform (ballots below)
-            const int ga = 2 * (k0 + (st << 5) + lane);         // groups ga, ga + 1
-            const unsigned* rc = Tw + ry * W + (st << 6);
-            unsigned ca = 0, cb = 0;
-            if (ga <= g1) {
-                ca = cb = 0x80808080u;
+        for (int gb = warp * 32; gb < ngq; gb += NT) {
+            const int gi = gb + lane;
+            unsigned ca = 0, cb = 0, e = 0;
+            if (gi < ngq) {
+                const uint2 ge = QG2[gi];
+                const int kp = ge.x & 0x7F, yt = (ge.x >> 8) & 0x7F;
+                ca = ge.x & 0x80808080u; cb = ge.y;
                 if (screen_ok) {
-                    // |d_k| | |d_k+8| >= max(|d_k|, |d_k+8|): one threshold test per pair, still only a necessary
-                    // condition (exact when t = 2^n - 1, e.g. the reference's minThFAST = 7)
+                    const unsigned* rc = reinterpret_cast<const unsigned*>(T + yt * TP) + 2 * kp;
                     const uint2 V = *reinterpret_cast<const uint2*>(rc);
-                    const uint2 P3 = *reinterpret_cast<const uint2*>(rc + 3 * W), M3 = *reinterpret_cast<const uint2*>(rc - 3 * W);
-                    const unsigned Lw = rc[-1], Rw = rc[2];
-                    // pair (0, 8): (0,+3) / (0,-3);  pair (4, 12): (+3,0) / (-3,0)
-                    ca &= gt_flags(__vabsdiffu4(V.x, P3.x) | __vabsdiffu4(V.x, M3.x), c127);
-                    cb &= gt_flags(__vabsdiffu4(V.y, P3.y) | __vabsdiffu4(V.y, M3.y), c127);
-                    ca &= gt_flags(__vabsdiffu4(V.x, __funnelshift_r(V.x, V.y, 24)) | __vabsdiffu4(V.x, __funnelshift_r(Lw, V.x, 8)), c127);
-                    cb &= gt_flags(__vabsdiffu4(V.y, __funnelshift_r(V.y, Rw, 24)) | __vabsdiffu4(V.y, __funnelshift_r(V.x, V.y, 8)), c127);
-                    if (ca | cb) {
-                        // pair (2, 10): (+2,+2) / (-2,-2);  pair (6, 14): (+2,-2) / (-2,+2)
-                        const uint2 P2 = *reinterpret_cast<const uint2*>(rc + 2 * W), M2 = *reinterpret_cast<const uint2*>(rc - 2 * W);
-                        const unsigned P2l = rc[2 * W - 1], P2r = rc[2 * W + 2], M2l = rc[-2 * W - 1], M2r = rc[-2 * W + 2];
-                        ca &= gt_flags(__vabsdiffu4(V.x, __funnelshift_r(P2.x, P2.y, 16)) | __vabsdiffu4(V.x, __funnelshift_r(M2l, M2.x, 16)), c127);
-                        ca &= gt_flags(__vabsdiffu4(V.x, __funnelshift_r(M2.x, M2.y, 16)) | __vabsdiffu4(V.x, __funnelshift_r(P2l, P2.x, 16)), c127);
-                        cb &= gt_flags(__vabsdiffu4(V.y, __funnelshift_r(P2.y, P2r, 16)) | __vabsdiffu4(V.y, __funnelshift_r(M2.x, M2.y, 16)), c127);
-                        cb &= gt_flags(__vabsdiffu4(V.y, __funnelshift_r(M2.y, M2r, 16)) | __vabsdiffu4(V.y, __funnelshift_r(P2.x, P2.y, 16)), c127);
-                    }
+                    // pair (2, 10): (+2,+2) / (-2,-2);  pair (6, 14): (+2,-2) / (-2,+2)
+                    const uint2 P2 = *reinterpret_cast<const uint2*>(rc + 2 * W), M2 = *reinterpret_cast<const uint2*>(rc - 2 * W);
+                    const unsigned P2l = rc[2 * W - 1], P2r = rc[2 * W + 2], M2l = rc[-2 * W - 1], M2r = rc[-2 * W + 2];
+                    ca &= gt_flags(__vabsdiffu4(V.x, __funnelshift_r(P2.x, P2.y, 16)) | __vabsdiffu4(V.x, __funnelshift_r(M2l, M2.x, 16)), c127);
+                    ca &= gt_flags(__vabsdiffu4(V.x, __funnelshift_r(M2.x, M2.y, 16)) | __vabsdiffu4(V.x, __funnelshift_r(P2l, P2.x, 16)), c127);
+                    cb &= gt_flags(__vabsdiffu4(V.y, __funnelshift_r(P2.y, P2r, 16)) | __vabsdiffu4(V.y, __funnelshift_r(M2.x, M2.y, 16)), c127);
+                    cb &= gt_flags(__vabsdiffu4(V.y, __funnelshift_r(M2.y, M2r, 16)) | __vabsdiffu4(V.y, __funnelshift_r(P2.x, P2.y, 16)), c127);
                 }
+                const int ga = 2 * kp;
                 if (ga < g0) ca = 0;
                 if (ga == g0) ca &= mask0;
                 if (ga == g1) ca &= mask1;
                 if (ga + 1 > g1) cb = 0;
                 if (ga + 1 == g0) cb &= mask0;
                 if (ga + 1 == g1) cb &= mask1;
+                e = ((unsigned)ga << 2) | ((unsigned)yt << 16);
             }
-            // one queue entry per 4-pixel group that still has a candidate: two ballots, one atomic per warp-step.
-            // entry = flags (bits 7, 15, 23, 31) | gx (bits 0-6) | tile row (bits 8-14)
-            const unsigned ba = __ballot_sync(0xffffffffu, ca != 0), bb = __ballot_sync(0xffffffffu, cb != 0);
-            if (ba | bb) {
-                int base = 0;
-                const int na = __popc(ba);
-                if (lane == 0) base = atoms_add(&sh.qg_count, na + __popc(bb));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                const unsigned tag = (unsigned)ga | ((unsigned)(ry + 3) << 8);
-                if (ca) QG[base + __popc(ba & lt)] = ca | tag;                      // <= hs*ng entries by construction
-                if (cb) QG[base + na + __popc(bb & lt)] = cb | (tag + 1u);
-            }
-            st += dr; ry += dq;
-            if (st >= nsteps) { st -= nsteps; ry++; }
-        }
-    }
-    __syncthreads();
-    // ---- expand the group entries into pixel entries (dense queue for phase 3a) ----
-    {
-        const int ngq = min(sh.qg_count, qgcap);
-        for (int gb = warp * 32; gb < ngq; gb += NT) {
-            const int gi = gb + lane;
-            const unsigned ge = gi < ngq ? QG[gi] : 0u;
-            const unsigned fl = ge & 0x80808080u;
-            const int n = __popc(fl);
+            const int n = __popc(ca) + __popc(cb);
             int inc = n;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
             const int total = __shfl_sync(0xffffffffu, inc, 31);
+            if (!total) continue;                                       // warp-uniform
             int base = 0;
-            if (lane == 0 && total) base = atoms_add(&sh.q_count, total);
+            if (lane == 0) base = atoms_add(&sh.q_count, total);
             base = __shfl_sync(0xffffffffu, base, 0);
             int o = base + inc - n;
-            const unsigned e = ((ge & 0x7Fu) << 2) | ((ge & 0x7F00u) << 8);
 #pragma unroll
-            for (int q = 0; q < 4; q++)
-                if (fl & (0x80u << (8 * q))) {
+            for (int q = 0; q < 8; q++)
+                if ((q < 4 ? ca : cb) & (0x80u << (8 * (q & 3)))) {
                     if (o < qcap) Q[o] = e + q;
                     else score_pixel(T, M, (e + q) & 0xFFFF, (int)(e >> 16), minTh, &sh.cl_count);   // queue full: score inline
                     o++;
@@ -435,6 +432,23 @@ __global__ void __launch_bounds__(NT, 5) k_fast_seg(OrbxGeom g, OrbxBuffers b, c
     // ---- ordered emission: every survivor computes its own slot ----
     uint32_t* out = b.row_cand + (long long)f * b.row_cand_stride + b.row_off[blockIdx.x];
     const int yrel0 = iniY - ORBX_BORDER + 3;
+    if (sh.cl_count <= CLCAP) {
+        // one listed corner per thread: survivors of the NMS look up their own slot (dense lanes; the bitmap walk below
+        // runs at ~5 threads per instruction)
+        const int ncl = sh.cl_count;
+        for (int e = tid; e < ncl; e += NT) {
+            const unsigned ent = CL[e];
+            const int x = ent & 0xFFFF, r = ent >> 16;
+            const int j = (int)(((unsigned)(x - X0) * wrcp) >> 16);
+            const unsigned* Bsel = (sh.use_ini[j] ? Bini : Bmin) + r * bw;
+            if (!((Bsel[x >> 5] >> (x & 31)) & 1u)) continue;
+            const int c0 = X0 + j * wCell;
+            const int o = sh.cell_off[j] + cnt_ini[j * hs + r] + (x > c0 ? popc_range(Bsel, c0, x) : 0);
+            if (o < row_cap)
+                out[o] = (uint32_t)(x + xa0 - ORBX_BORDER) | ((uint32_t)(yrel0 + r) << 12) | ((uint32_t)(M[r * TP + x] - 1) << 24);
+        }
+        return;
+    }
     for (int k = tid; k < hs * bw; k += NT) {
         const int r = k / bw, wi = k - r * bw;                 // bw is a compile-time constant
         unsigned bits = Bmin[k];
@@ -495,7 +509,7 @@ int orbx_fast_plan(int w, int nCols, int wCell)
 
 // Per-segment records read by k_fast_seg, 4 x int4 per segment in launch order (level, cell row, segment):
 //   {level, first staged row, staged rows, scored rows (<= 0: empty segment)}
-//   {xa0, staged width, X0, X1}     {cells, tile bytes, 2^16 / wCell, 2^16 / screen steps per row}   {2^16 / scored rows, -, -, -}
+//   {xa0, staged width, X0, X1}     {cells, tile bytes, 2^16 / wCell, 2^20 / screen items per row}   {2^16 / scored rows, -, -, -}
 void orbx_fast_units(const OrbxGeom& g, std::vector<int4>& tab)
 {
     tab.clear();
@@ -515,10 +529,10 @@ void orbx_fast_units(const OrbxGeom& g, std::vector<int4>& tab)
                     const int xa0 = (cs0 - 3) & ~15, xa1 = (cs1 + 3 + 15) & ~15;
                     const int X0 = cs0 - xa0, X1 = cs1 - xa0;
                     const int ng = ((X1 - 1) >> 2) - (X0 >> 2) + 1;
-                    const int nsteps = ((((X1 - 1) >> 2) >> 1) - ((X0 >> 2) >> 1) + 32) >> 5;      // 32 lanes x 2 groups per screen step
+                    const int npairs = (((X1 - 1) >> 2) >> 1) - ((X0 >> 2) >> 1) + 1;              // screen items per row: 2 groups each
                     a = make_int4(l, iniY, nrow, hs);
                     bq = make_int4(xa0, xa1 - xa0, X0, X1);
-                    c = make_int4(ncell, tile_bytes(nrow, hs, ng, ncell), (65536 + L.wCell - 1) / L.wCell, (65536 + nsteps - 1) / nsteps);
+                    c = make_int4(ncell, tile_bytes(nrow, hs, ng, ncell), (65536 + L.wCell - 1) / L.wCell, ((1 << 20) + npairs - 1) / npairs);
                 }
                 tab.push_back(a); tab.push_back(bq); tab.push_back(c);
                 tab.push_back(make_int4(hs > 0 ? (65536 + hs - 1) / hs : 0, 0, 0, 0));
