@@ -168,12 +168,15 @@ struct FastSmem {
 };
 
 // group-queue capacity: every pair of groups of the tile (cannot overflow)
-__host__ __device__ inline int qg_cap(int hs, int ng) { return hs * (ng + 2); }      // words: one 64-bit entry per pair of groups
+__host__ __device__ inline int qg_cap(int hs, int ng) { return (hs * (ng + 2) + 3) & ~3; }      // words: one 64-bit entry per pair of groups
+
+// words of the two survivor bitmaps [hs][TP/32] + one padding word for popc_range, rounded to 16 bytes (zeroed together with M)
+__host__ __device__ inline int bitmap_words(int hs) { return (2 * hs * (TP / 32) + 1 + 3) & ~3; }
 
 // shared-memory bytes of one segment tile, without the pixel queue
 __host__ __device__ inline int tile_bytes(int nrow, int hs, int ng, int ncell)
 {
-    return nrow * TP + hs * TP + qg_cap(hs, ng) * 4 + CLCAP * 4 + (2 * hs * (TP / 32) + 4) * 4 + ((ncell * hs * 2 + 15) & ~15);
+    return nrow * TP + hs * TP + bitmap_words(hs) * 4 + qg_cap(hs, ng) * 4 + CLCAP * 4 + ((ncell * hs * 2 + 15) & ~15);
 }
 
 __global__ void __launch_bounds__(NT, 5) k_fast_seg(OrbxGeom g, OrbxBuffers b, const uint8_t* level0, int pitch0,
@@ -200,13 +203,13 @@ __global__ void __launch_bounds__(NT, 5) k_fast_seg(OrbxGeom g, OrbxBuffers b, c
     // ---- smem carve-up (per CTA: tiles of different levels have different shapes) ----
     uint8_t* T = smem;                                              // [nrow][TP] pixels
     uint8_t* M = T + nrow * TP;                                     // [hs][TP]   arc measure (0 = not a corner at minTh)
-    unsigned* QG = reinterpret_cast<unsigned*>(M + hs * TP);        // [qgcap] 4-pixel groups with screen survivors
+    unsigned* Bmin = reinterpret_cast<unsigned*>(M + hs * TP);      // [hs][bw] survivors at minTh
+    unsigned* Bini = Bmin + hs * bw;                                // [hs][bw] (+ padding) survivors at iniTh
+    unsigned* QG = Bmin + bitmap_words(hs);                         // [qgcap] pairs of 4-pixel groups with screen survivors (64-bit entries)
     unsigned* Q2 = QG;                                              // survivors of the signed pair test (QG is dead by then)
     const int qgcap = qg_cap(hs, ng), q2cap = qgcap;
-    unsigned* CL = QG + qgcap;                                    // [CLCAP] corners: x | scored row << 16
-    unsigned* Bmin = CL + CLCAP;                                    // [hs][bw] survivors at minTh
-    unsigned* Bini = Bmin + hs * bw;                                // [hs][bw] (+4 words of padding) survivors at iniTh
-    unsigned short* cnt_ini = reinterpret_cast<unsigned short*>(Bini + hs * bw + 4);   // [ncell][hs] exclusive row prefix of the chosen counts inside a cell
+    unsigned* CL = QG + qgcap;                                      // [CLCAP] corners: x | scored row << 16
+    unsigned short* cnt_ini = reinterpret_cast<unsigned short*>(CL + CLCAP);   // [ncell][hs] exclusive row prefix of the chosen counts inside a cell
     unsigned* Q = reinterpret_cast<unsigned*>(smem + tbytes);       // [qcap] candidate queue: x | tile row << 16
     const int qcap = (smem_total - tbytes) >> 2;
 
@@ -231,10 +234,9 @@ __global__ void __launch_bounds__(NT, 5) k_fast_seg(OrbxGeom g, OrbxBuffers b, c
             for (int c = lane; c < sw; c += 32) T[r * TP + c] = xa0 + c < g.lv[l].w ? __ldg(img + (long long)(iniY + r) * pitch + xa0 + c) : 0;
     }
     {
-        uint4* z = reinterpret_cast<uint4*>(M);
-        const int nz = (hs * TP) >> 4;
+        uint4* z = reinterpret_cast<uint4*>(M);                         // score map and both bitmaps are contiguous
+        const int nz = (hs * TP + bitmap_words(hs) * 4) >> 4;
         for (int k = tid; k < nz; k += NT) z[k] = make_uint4(0, 0, 0, 0);
-        for (int k = tid; k < 2 * hs * bw + 4; k += NT) Bmin[k] = 0;
         if (tid == 0) { sh.cl_count = 0; sh.qg_count = 0; sh.q_count = 0; sh.q2_count = 0; }
     }
     const int minTh = g.min_th, iniTh = g.ini_th;
@@ -284,10 +286,9 @@ __global__ void __launch_bounds__(NT, 5) k_fast_seg(OrbxGeom g, OrbxBuffers b, c
         const int ngq = sh.qg_count;
         // scored columns only: the first and last group straddle the segment's edges
         const unsigned mask0 = 0x80808080u << (8 * (X0 & 3)), mask1 = 0x80808080u >> (8 * (3 - ((X1 - 1) & 3)));
-        for (int gb = warp * 32; gb < ngq; gb += NT) {
-            const int gi = gb + lane;
-            unsigned ca = 0, cb = 0, e = 0;
-            if (gi < ngq) {
+        for (int gi = tid; gi < ngq; gi += NT) {
+            unsigned ca, cb, e;
+            {
                 const uint2 ge = QG2[gi];
                 const int kp = ge.x & 0x7F, yt = (ge.x >> 8) & 0x7F;
                 ca = ge.x & 0x80808080u; cb = ge.y;
@@ -312,47 +313,35 @@ __global__ void __launch_bounds__(NT, 5) k_fast_seg(OrbxGeom g, OrbxBuffers b, c
                 e = ((unsigned)ga << 2) | ((unsigned)yt << 16);
             }
             const int n = __popc(ca) + __popc(cb);
-            int inc = n;
+            if (!n) continue;
+            int o = atoms_add(&sh.q_count, n);                          // per-lane: the queue order is irrelevant
+            if (o + n <= qcap) {
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-            const int total = __shfl_sync(0xffffffffu, inc, 31);
-            if (!total) continue;                                       // warp-uniform
-            int base = 0;
-            if (lane == 0) base = atoms_add(&sh.q_count, total);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            int o = base + inc - n;
-#pragma unroll
-            for (int q = 0; q < 8; q++)
-                if ((q < 4 ? ca : cb) & (0x80u << (8 * (q & 3)))) {
-                    if (o < qcap) Q[o] = e + q;
-                    else score_pixel(T, M, (e + q) & 0xFFFF, (int)(e >> 16), minTh, &sh.cl_count);   // queue full: score inline
-                    o++;
-                }
+                for (int q = 0; q < 8; q++)
+                    if ((q < 4 ? ca : cb) & (0x80u << (8 * (q & 3)))) Q[o++] = e + q;
+            } else {
+#pragma unroll 1
+                for (int q = 0; q < 8; q++)
+                    if ((q < 4 ? ca : cb) & (0x80u << (8 * (q & 3)))) {
+                        if (o < qcap) Q[o] = e + q;
+                        else score_pixel(T, M, (e + q) & 0xFFFF, (int)(e >> 16), minTh, &sh.cl_count);   // queue full: score inline
+                        o++;
+                    }
+            }
         }
     }
     __syncthreads();
     // ---- 3a. signed pair test, dense and branch-free; survivors are compacted into Q2 ----
     {
         const int nq = min(sh.q_count, qcap);
-        for (int e0 = warp * 32; e0 < nq; e0 += NT) {
-            const int e = e0 + lane;
-            bool pass = false; unsigned ent = 0;
-            if (e < nq) {
-                ent = Q[e];
-                unsigned pk[16];
-                load_ring(T + (ent >> 16) * TP + (ent & 0xFFFF), pk);
-                pass = pair_test(pk, minTh);
-            }
-            const unsigned bal = __ballot_sync(0xffffffffu, pass);
-            if (bal) {
-                int base = 0;
-                if (lane == 0) base = atoms_add(&sh.q2_count, __popc(bal));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (pass) {
-                    const int o = base + __popc(bal & ((1u << lane) - 1));
-                    if (o < q2cap) Q2[o] = ent;
-                    else score_pixel(T, M, ent & 0xFFFF, ent >> 16, minTh, &sh.cl_count);
-                }
+        for (int e = tid; e < nq; e += NT) {
+            const unsigned ent = Q[e];
+            unsigned pk[16];
+            load_ring(T + (ent >> 16) * TP + (ent & 0xFFFF), pk);
+            if (pair_test(pk, minTh)) {
+                const int o = atoms_add(&sh.q2_count, 1);
+                if (o < q2cap) Q2[o] = ent;
+                else score_pixel(T, M, ent & 0xFFFF, ent >> 16, minTh, &sh.cl_count);
             }
         }
     }
