@@ -379,12 +379,14 @@ __global__ void __launch_bounds__(NT) k_pyr_fast(Args a, const __grid_constant__
         // ---- per-thread constants: one thread owns 4 consecutive R columns (one aligned word of R) ----
         // R column rho <-> dst x = ax + (rho - rcol0), clamped to the tile's valid range (clamped duplicates land in
         // cells that are either unused or rewritten by reflect_halo).
-        constexpr int NG = 36, RL = 7;                 // groups per row, row lanes: 252 of the 256 threads work
+        // The ng (<= 36) column groups of THIS tile times RL = NT / ng row lanes: a narrow tile at the right image edge keeps
+        // (almost) every thread busy instead of idling the lanes of its missing columns.
         const int g0 = rcol0 >> 2;
         const int ng = ((rcol0 + rw - 1) >> 2) - g0 + 1;
-        const int gq = tid % NG, rl = tid / NG;
-        const bool worker = rl < RL && gq < ng;
-        unsigned coef[4], sel = 0, wb = 0;
+        const int RL = NT / ng;
+        const int rl = tid / ng, gq = tid - rl * ng;
+        const bool worker = rl < RL;
+        unsigned coef[4], psel[4], wb = 0, wsh = 0;
         if (worker) {
             int o0[4], o1[4];
 #pragma unroll
@@ -394,29 +396,23 @@ __global__ void __launch_bounds__(NT) k_pyr_fast(Args a, const __grid_constant__
                 o0[i] = xe.x - sx0; o1[i] = xe.y - sx0;
                 coef[i] = (unsigned)xe.z | ((unsigned)xe.w << 16);
             }
-            wb = (unsigned)(o0[0] >> 2);                // the 4 columns read bytes [4wb, 4wb+12): words A, B, C
+            // the 4 columns read source bytes [o0[0], o0[0] + 8) (scale <= 1.55: o1[3] - o0[0] <= 6): two funnel shifts bring that
+            // window into a register pair, and one loop-invariant PRMT selector per column picks its (S0, S1)
+            wb = (unsigned)(o0[0] >> 2); wsh = 8u * (unsigned)(o0[0] & 3);
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const int p0 = o0[i] - 4 * (int)wb, p1 = o1[i] - 4 * (int)wb;      // 0..11
-                const int hi = p0 >= 4 ? 1 : 0;          // take the pair (B,C) instead of (A,B)
-                sel |= (unsigned)((p0 - 4 * hi) | ((p1 - 4 * hi) << 3) | (hi << 6)) << (8 * i);       // 7 bits per column
-            }
+            for (int i = 0; i < 4; i++) psel[i] = (unsigned)(o0[i] - o0[0]) | ((unsigned)(o1[i] - o0[0]) << 4);
         }
         if (a.use_tma) mbar_wait(&s_bar, 0);       // table loads above overlap the bulk copy
         __syncthreads();
-        // ---- horizontal interpolation of every source row: 3 word loads, 4 x (PRMT + DP2A) per 4 columns ----
+        // ---- horizontal interpolation of every source row: 3 word loads, 2 funnel shifts, 4 x (PRMT + DP2A) per 4 columns ----
         if (worker) {
             for (int r = rl; r < nrows; r += RL) {
                 const unsigned* sr = reinterpret_cast<const unsigned*>(S + r * sp) + wb;
                 const unsigned A = sr[0], B = sr[1], C = sr[2];
+                const unsigned W0 = __funnelshift_r(A, B, wsh), W1 = __funnelshift_r(B, C, wsh);
                 unsigned hv[4];
 #pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const unsigned sl = sel >> (8 * i);
-                    const unsigned ps = (sl & 7u) | ((sl & 0x38u) << 1);                                            // PRMT nibbles
-                    const unsigned pair = (sl & 0x40u) ? __byte_perm(B, C, ps) : __byte_perm(A, B, ps);              // bytes (S0, S1)
-                    hv[i] = __dp2a_lo(coef[i], pair, 0u) >> 4;                                                      // (S0*c0 + S1*c1) >> 4
-                }
+                for (int i = 0; i < 4; i++) hv[i] = __dp2a_lo(coef[i], __byte_perm(W0, W1, psel[i]), 0u) >> 4;      // (S0*c0 + S1*c1) >> 4
                 *reinterpret_cast<uint2*>(Hs + r * HP + 4 * gq) = make_uint2(hv[0] | (hv[1] << 16), hv[2] | (hv[3] << 16));
             }
         }
