@@ -405,6 +405,34 @@ int  orbx_bow_transform(orbx_vocab* v, const uint8_t* desc, int n, int levelsup,
 int  orbx_bow_transform_slots_device(orbx_vocab* v, orbx_extractor* ex, int first_slot, int count, int levelsup,
                                      int32_t* d_word, int32_t* d_node, void* stream);
 
+/* ---- server keyframe database on one GPU (SURVEY 8f row 3 -> 8e) ----
+ * A keyframe reaches the server as a KF.msg (R/msg/KF.msg:24-29): `CvKeyPoint[] mvKeysUn` = N records of 15 packed bytes
+ * (R/msg/CvKeyPoint.msg; Converter::toCvKeyPointMsg, R/src/Converter.cc:218-230) and `Descriptor[] mDescriptors` = N x
+ * uint8[32] (R/msg/Descriptor.msg:1: fixed-size arrays carry no length prefix, the N descriptors are 32 N contiguous bytes
+ * of the serialised message).  Replaces the element-by-element rebuild of KeyFrame.cc:1929-1944 / Converter.cc:232-244:
+ * both byte runs go to the device as they are, the descriptors straight into this GPU's shard of the descriptor DB, the
+ * keypoint records through the device unpack kernel.  The shard is searched by orbx_kfdb_knn2 / orbx_bf_knn2_device
+ * (multi_orbslam3_b200.server.ShardedDescriptorDB for the multi-GPU exchange).  Ingestion is asynchronous on the DB's own
+ * stream and thread-safe (one communication thread per client in the reference, Communicator.cc:110-148). */
+typedef struct orbx_kfdb orbx_kfdb;
+int  orbx_kfdb_create(int device, long long capacity_rows, int max_keyframes, orbx_kfdb** out);
+void orbx_kfdb_destroy(orbx_kfdb* db);
+/* appends one keyframe (host pointers into the received message; msg_keys15 may be NULL = descriptors only).
+ * *first_row = DB row of its first descriptor.  ORBX_E_CAPACITY when rows or keyframes are exhausted: nothing is appended. */
+int  orbx_kfdb_ingest_msg(orbx_kfdb* db, int64_t kf_id, const uint8_t* msg_keys15, const uint8_t* msg_desc32, int n,
+                          long long* first_row);
+/* the same from a result slot of an extractor on the same device (an agent whose frames are extracted on this GPU: no host hop) */
+int  orbx_kfdb_ingest_slot_device(orbx_kfdb* db, int64_t kf_id, orbx_extractor* ex, int slot, long long* first_row);
+int  orbx_kfdb_size(orbx_kfdb* db, long long* rows, int* keyframes, long long* capacity_rows);
+/* device views [capacity_rows][32] / [capacity_rows]; rows ingested before the last orbx_kfdb_sync are complete */
+int  orbx_kfdb_device(orbx_kfdb* db, const uint8_t** d_desc, const orbx_keypoint** d_kps);
+int  orbx_kfdb_sync(orbx_kfdb* db);
+/* DB row -> (keyframe id, feature index inside that keyframe); -1 / -1 for rows outside the DB.  Host arrays. */
+int  orbx_kfdb_locate(orbx_kfdb* db, const long long* rows, int n, int64_t* kf_id, int32_t* feature);
+/* cv::BFMatcher kNN-2 (Frame.cc:1127-1137 semantics) of host queries against everything ingested so far;
+ * idx = idx_base + DB row (idx_base = first global row of this GPU's shard). */
+int  orbx_kfdb_knn2(orbx_kfdb* db, orbx_matcher* m, const uint8_t* q, int nq, long long idx_base, int32_t* idx, int32_t* dist);
+
 #ifdef __cplusplus
 }
 #endif

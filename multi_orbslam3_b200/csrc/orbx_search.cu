@@ -309,6 +309,13 @@ __global__ void k_kp_from_msg(const uint8_t* msg, int n, orbx_keypoint* kps)
 
 }  // namespace
 
+// device-to-device unpack of n wire records (used by the keyframe DB, orbx_kfdb.cu)
+void orbx_launch_kp_from_msg(const uint8_t* d_msg15, int n, orbx_keypoint* d_kps, cudaStream_t s)
+{
+    if (n <= 0) return;
+    k_kp_from_msg<<<(n + 255) / 256, 256, 0, s>>>(d_msg15, n, d_kps); ORBX_COUNT_LAUNCH(1);
+}
+
 // Keypoints -> KF.msg records (15 bytes each) and back; host pointers, synchronous.
 extern "C" int orbx_keypoints_to_msg(orbx_matcher* m, const orbx_keypoint* kps, int n, uint8_t* msg15)
 {

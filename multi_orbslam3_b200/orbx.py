@@ -42,6 +42,8 @@ EXPORTS = [
     "orbx_fast_segment_plan", "orbx_matcher_set_slot_keypoints", "orbx_matcher_set_camera", "orbx_matcher_undistorted_device", "orbx_search_by_projection_ex", "orbx_search_by_projection_opts", "orbx_match_candidates", "orbx_search_by_bow", "orbx_search_for_triangulation", "orbx_distinctive_descriptors", "orbx_undistort_keypoints", "orbx_undistort_slots_device",
     "orbx_keypoints_to_msg", "orbx_keypoints_from_msg", "orbx_slot_keypoints_to_msg_device", "orbx_vocab_create", "orbx_vocab_destroy", "orbx_vocab_words", "orbx_vocab_word_weights",
     "orbx_bow_transform", "orbx_bow_transform_slots_device", "orbx_popc_peak",
+    "orbx_kfdb_create", "orbx_kfdb_destroy", "orbx_kfdb_ingest_msg", "orbx_kfdb_ingest_slot_device", "orbx_kfdb_size", "orbx_kfdb_device",
+    "orbx_kfdb_sync", "orbx_kfdb_locate", "orbx_kfdb_knn2",
 ]
 
 
@@ -135,6 +137,15 @@ def lib():
         L.orbx_undistort_slots_device.argtypes = [vp, i32, i32, vp, vp, i32, vp, vp, vp]
         L.orbx_search_for_triangulation.argtypes = [vp, vp, vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, vp, vp, i32, vp, vp, vp, i32,
                                                     vp, f32, f32, vp, vp, i32, i32, i32, i32, vp, vp]
+        L.orbx_kfdb_create.argtypes = [i32, C.c_longlong, i32, C.POINTER(vp)]
+        L.orbx_kfdb_destroy.argtypes = [vp]; L.orbx_kfdb_destroy.restype = None
+        L.orbx_kfdb_ingest_msg.argtypes = [vp, C.c_int64, vp, vp, i32, vp]
+        L.orbx_kfdb_ingest_slot_device.argtypes = [vp, C.c_int64, vp, i32, vp]
+        L.orbx_kfdb_size.argtypes = [vp, vp, vp, vp]
+        L.orbx_kfdb_device.argtypes = [vp, vp, vp]
+        L.orbx_kfdb_sync.argtypes = [vp]
+        L.orbx_kfdb_locate.argtypes = [vp, vp, i32, vp, vp]
+        L.orbx_kfdb_knn2.argtypes = [vp, vp, vp, i32, C.c_longlong, vp, vp]
         L.orbx_vocab_create.argtypes = [i32, i32, vp, vp, vp, vp, i32, vp]
         L.orbx_vocab_destroy.argtypes = [vp]; L.orbx_vocab_destroy.restype = None
         L.orbx_vocab_words.argtypes = [vp]
@@ -565,6 +576,70 @@ class ORBVocabulary:
                                                      C.c_void_p(d_node), _s(stream)))
 
 
+class _DeviceView:
+    """__cuda_array_interface__ over a raw device pointer (torch.as_tensor(view, device=...) wraps it without a copy)."""
+
+    def __init__(self, ptr, shape, typestr, owner):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+        self._owner = owner            # keeps the handle alive as long as the view
+
+
+class KeyframeDB:
+    """The server's keyframe-descriptor database on one GPU (include/orbx.h, orbx_kfdb_*): KF.msg byte runs
+    (R/msg/KF.msg:24-29) land in the device shard that the brute-force search and server.ShardedDescriptorDB read."""
+
+    def __init__(self, capacity_rows, max_keyframes=65536, device=0):
+        self._h = C.c_void_p()
+        self.device, self.capacity = device, int(capacity_rows)
+        _check(lib().orbx_kfdb_create(device, self.capacity, max_keyframes, C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().orbx_kfdb_destroy(self._h); self._h = C.c_void_p()
+
+    __del__ = close
+
+    def ingest_msg(self, kf_id, msg_keys15, msg_desc32):
+        """msg_keys15: uint8 [n, 15] (or None), msg_desc32: uint8 [n, 32], exactly the bytes of the received message."""
+        d = np.ascontiguousarray(msg_desc32, np.uint8).reshape(-1, 32)
+        k = None if msg_keys15 is None else np.ascontiguousarray(msg_keys15, np.uint8).reshape(-1, 15)
+        assert k is None or len(k) == len(d)
+        first = C.c_longlong(-1)
+        _check(lib().orbx_kfdb_ingest_msg(self._h, int(kf_id), None if k is None else _p(k), _p(d), len(d), C.byref(first)))
+        return first.value
+
+    def ingest_slot(self, kf_id, extractor, slot):
+        first = C.c_longlong(-1)
+        _check(lib().orbx_kfdb_ingest_slot_device(self._h, int(kf_id), extractor._h, slot, C.byref(first)))
+        return first.value
+
+    def size(self):
+        rows, cap, kfs = C.c_longlong(), C.c_longlong(), C.c_int()
+        _check(lib().orbx_kfdb_size(self._h, C.byref(rows), C.byref(kfs), C.byref(cap)))
+        return rows.value, kfs.value, cap.value
+
+    def sync(self):
+        _check(lib().orbx_kfdb_sync(self._h))
+
+    def device_views(self):
+        """(descriptors [capacity, 32] u8, keypoints [capacity, 7] f32-sized words) as __cuda_array_interface__ objects."""
+        dd, dk = C.c_void_p(), C.c_void_p()
+        _check(lib().orbx_kfdb_device(self._h, C.byref(dd), C.byref(dk)))
+        return _DeviceView(dd.value, (self.capacity, 32), "|u1", self), _DeviceView(dk.value, (self.capacity, 7), "<i4", self)
+
+    def locate(self, rows):
+        r = np.ascontiguousarray(rows, np.int64).reshape(-1)
+        kf = np.empty(len(r), np.int64); ft = np.empty(len(r), np.int32)
+        _check(lib().orbx_kfdb_locate(self._h, _p(r), len(r), _p(kf), _p(ft)))
+        return kf, ft
+
+    def knn2(self, matcher, queries, idx_base=0):
+        q = np.ascontiguousarray(queries, np.uint8).reshape(-1, 32)
+        idx = np.empty((len(q), 2), np.int32); dist = np.empty((len(q), 2), np.int32)
+        _check(lib().orbx_kfdb_knn2(self._h, matcher._h, _p(q), len(q), int(idx_base), _p(idx), _p(dist)))
+        return idx, dist
+
+
 def assemble_bow(word, weight, node):
     """BowVector::addWeight / normalize(L1) and FeatureVector::addFeature over per-feature (word, weight, node) arrays
     (R/Thirdparty/DBoW2/DBoW2/BowVector.cpp, FeatureVector.cpp): stopped words (weight 0) are skipped; a word's value is its
@@ -622,3 +697,36 @@ def popc_peak(device=0):
     p, l = C.c_double(), C.c_double()
     _check(lib().orbx_popc_peak(device, C.byref(p), C.byref(l)))
     return p.value, l.value
+
+
+def bind_to_gpu_numa(device=0):
+    """Pins the calling process to the CPUs of the NUMA node GPU `device` hangs off, so that pinned host buffers allocated
+    afterwards (first touch) and the threads that feed them are local to that GPU's PCIe root.  With one process per GPU this keeps
+    eight concurrent host<->device streams off the inter-socket link.  Returns {"pci", "node", "cpus"}; a box without NUMA
+    information (one node, sysfs absent) is left untouched."""
+    info = {"pci": None, "node": None, "cpus": None}
+    try:
+        rt = C.CDLL("libcudart.so.12")
+        buf = C.create_string_buffer(32)
+        if rt.cudaDeviceGetPCIBusId(buf, C.c_int(32), C.c_int(device)) != 0:
+            return info
+        pci = buf.value.decode().lower()
+        info["pci"] = pci
+        with open("/sys/bus/pci/devices/%s/numa_node" % pci) as f:
+            node = int(f.read().strip())
+        info["node"] = node
+        if node < 0:
+            return info
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            cpulist = f.read().strip()
+        cpus = set()
+        for part in cpulist.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info["cpus"] = "%d cpus of node %d" % (len(allowed), node)
+    except (OSError, ValueError, AttributeError):
+        pass
+    return info

@@ -49,6 +49,18 @@ class ShardedDescriptorDB:
         counts = torch.tensor([self.n_valid], dtype=torch.int64, device=shard.device)
         self.valid_counts = [int(v) for v in _all_gather(counts, group).reshape(-1).tolist()]     # every rank's n_valid
 
+    @classmethod
+    def from_kfdb(cls, kfdb, match_fn, merge_fn, group=None):
+        """The shard IS the device storage of an orbx.KeyframeDB (keyframes ingested from KF.msg byte runs):
+        no copy, n_valid = the rows ingested so far (every rank allocates the same capacity).  Call again after further ingests."""
+        kfdb.sync()
+        rows, _, _ = kfdb.size()
+        dd, _ = kfdb.device_views()
+        shard = torch.as_tensor(dd, device=torch.device("cuda", kfdb.device))
+        db = cls(shard, match_fn, merge_fn, group=group, n_valid=rows)
+        db.kfdb = kfdb
+        return db
+
     def knn2_allgather_top2(self, queries):
         """queries: the same uint8 [nq, 32] tensor on every rank (the query keyframe is broadcast by its owner).
         Returns (idx [nq,2] global row indices, dist [nq,2])."""
