@@ -14,6 +14,7 @@
 // then insertion order) into a CSR pool; the order-dependent bookkeeping of the reference (a keypoint taken
 // by an earlier query is skipped / stolen back) is replayed by one warp per frame pair over that pool.
 #include "orbx_match_internal.h"
+#include "orbx_bfknn_tc.cuh"
 
 namespace {
 
@@ -89,6 +90,32 @@ __global__ void __launch_bounds__(BF_NT) k_bf_knn2(BfArgs A)
     }
     oi[0] = i0; oi[1] = i1;
     od[0] = i0 >= 0 ? d0 : -1; od[1] = i1 >= 0 ? d1 : -1;
+}
+
+// The same search on the tensor cores (orbx_bfknn_tc.cuh): grid (query tiles of 128, train splits, pairs), one CTA per SM.
+__global__ void __launch_bounds__(bftc::NT, 1) k_bf_knn2_tc(BfArgs A)
+{
+    extern __shared__ __align__(128) uint8_t bf_smem[];
+    const int p = blockIdx.z, split = blockIdx.y;
+    const uint8_t* q; const uint8_t* t; int nq; long long nt;
+    if (A.q) { q = A.q; t = A.t; nq = A.nq; nt = A.nt; }
+    else {
+        const int sa = A.a[p], sb = A.b[p];
+        q = A.desc + (long long)sa * A.cap * 32; nq = A.n[sa];
+        t = A.desc + (long long)sb * A.cap * 32; nt = A.n[sb];
+    }
+    if ((long long)blockIdx.x * bftc::M >= nq) return;
+    const long long t_begin = (long long)split * A.chunk;
+    long long t_end = t_begin + A.chunk; if (t_end > nt) t_end = nt;
+    int32_t* oi; int32_t* od;
+    if (A.nsplit > 1) {
+        const long long o = (((long long)p * A.nsplit + split) * A.out_stride) * 2;
+        oi = A.part_idx + o; od = A.part_dist + o;
+    } else {
+        const long long o = ((long long)p * A.out_stride) * 2;
+        oi = A.idx + o; od = A.dist + o;
+    }
+    bftc::bf_tile_body(q, nq, blockIdx.x * bftc::M, t, t_begin, t_end, A.idx_base, oi, od, bf_smem);
 }
 
 // merge partial top-2 tables: parts laid out [pair][part][stride][2]; lexicographic (dist, idx)
@@ -803,26 +830,48 @@ static int ensure_parts(orbx_matcher* m, size_t elems)
 
 static int bf_launch(orbx_matcher* m, BfArgs A, int npairs, int nq_max, long long nt_max, cudaStream_t s)
 {
-    // split the train set so that a small query set still fills the 148 SMs
-    const int qblocks = (nq_max + BF_NT - 1) / BF_NT;
-    int nsplit = 1;
-    const long long tiles = (nt_max + BF_TILE - 1) / BF_TILE;
-    if (tiles > 0) {
-        const int want = 148 * 8;
-        while ((long long)qblocks * npairs * nsplit < want && nsplit * 2 <= tiles && nsplit < 1024) nsplit *= 2;
+    static const bool use_popc = getenv("ORBX_BF_POPC") != nullptr;      // the popc-pipe kernel of round 1 (kept for comparison runs)
+    if (npairs == 0 || nq_max <= 0) return ORBX_OK;
+    const int want = 148 * 8;
+    int qblocks, nsplit = 1; long long chunk;
+    if (!use_popc) {
+        // tensor-core kernel: 128 queries x 256 train rows per tile, one CTA per SM; split the train set so that about 8 CTAs per
+        // SM exist, but keep at least 4 tiles per CTA (the query tile and the TMEM allocation are per CTA)
+        qblocks = (nq_max + bftc::M - 1) / bftc::M;
+        const long long tiles = (nt_max + bftc::N - 1) / bftc::N;
+        const long long per = (long long)qblocks * npairs;
+        if (per < want && tiles > 4) {
+            long long ns = (want + per - 1) / per;
+            if (ns > tiles / 4) ns = tiles / 4;
+            if (ns > 4096) ns = 4096;
+            nsplit = (int)(ns < 1 ? 1 : ns);
+        }
+        const long long tpc = (tiles + nsplit - 1) / nsplit;              // tiles per CTA
+        chunk = (tpc < 1 ? 1 : tpc) * bftc::N;
+        nsplit = (int)((nt_max + chunk - 1) / chunk); if (nsplit < 1) nsplit = 1;
+    } else {
+        // split the train set so that a small query set still fills the 148 SMs
+        qblocks = (nq_max + BF_NT - 1) / BF_NT;
+        const long long tiles = (nt_max + BF_TILE - 1) / BF_TILE;
+        if (tiles > 0)
+            while ((long long)qblocks * npairs * nsplit < want && nsplit * 2 <= tiles && nsplit < 1024) nsplit *= 2;
+        chunk = (nt_max + nsplit - 1) / nsplit;
+        chunk = (chunk + BF_TILE - 1) / BF_TILE * BF_TILE;
+        if (chunk < BF_TILE) chunk = BF_TILE;
     }
-    long long chunk = (nt_max + nsplit - 1) / nsplit;
-    chunk = (chunk + BF_TILE - 1) / BF_TILE * BF_TILE;
-    if (chunk < BF_TILE) chunk = BF_TILE;
     A.chunk = chunk; A.nsplit = nsplit;
     if (nsplit > 1) {
         int rc = ensure_parts(m, (size_t)npairs * nsplit * A.out_stride * 2);
         if (rc) return rc;
         A.part_idx = m->d_part_idx; A.part_dist = m->d_part_dist;
     }
-    if (qblocks == 0 || npairs == 0) return ORBX_OK;
     dim3 grid(qblocks, nsplit, npairs);
-    k_bf_knn2<<<grid, BF_NT, 0, s>>>(A); ORBX_COUNT_LAUNCH(1);
+    if (!use_popc) {
+        CKM(ORBX_OPTIN_SMEM(k_bf_knn2_tc));
+        k_bf_knn2_tc<<<grid, bftc::NT, bftc::SMEM_BYTES, s>>>(A); ORBX_COUNT_LAUNCH(1);
+    } else {
+        k_bf_knn2<<<grid, BF_NT, 0, s>>>(A); ORBX_COUNT_LAUNCH(1);
+    }
     if (nsplit > 1) {
         dim3 mg((nq_max + 127) / 128, npairs);
         k_knn2_merge<<<mg, 128, 0, s>>>(A.part_idx, A.part_dist, nsplit, A.out_stride, A.nq, A.q ? nullptr : A.n, A.a, A.idx, A.dist); ORBX_COUNT_LAUNCH(1);
