@@ -3,10 +3,11 @@
 // cv::BFMatcher(NORM_HAMMING).knnMatch(q, t, 2) (R/src/Frame.cc:1127-1137 and the server's cross-agent matching) is a
 // distance MATRIX between two sets of 256-bit vectors: hamming(a, b) = |a| + |b| - 2 <a, b> with <a, b> the dot product of the bit
 // vectors.  That contraction is the one GEMM-shaped piece of the hot path, so it runs as an integer GEMM:
-//   * the descriptor bits are expanded to u8 {0, 1} in shared memory in the canonical K-major no-swizzle core-matrix layout
-//     (8 rows x 16 bytes per core matrix; row-group stride 2048 B, K stride 128 B), 3 ALU instructions per 4 bits;
-//   * one elected thread issues tcgen05.mma.kind::i8 (M = 128 queries, N = 256 train descriptors, K = 32 per instruction, 8 per
-//     tile) with the s32 accumulators in TMEM: two accumulator stages of 256 columns, so the tensor core works on tile t+1
+//   * the descriptor bits are expanded to signed bytes in shared memory in the canonical K-major no-swizzle core-matrix layout
+//     (8 rows x 16 bytes per core matrix; row-group stride 2048 B, K stride 128 B) by shifts + sign-replicating PRMT, 2.9
+//     instructions per 4 bits (expand_word); a CTA holds 256 queries, so every expanded train tile serves two MMA row tiles;
+//   * one elected thread issues tcgen05.mma.kind::i8 (M = 128 queries, N = 128 train descriptors, K = 32 per instruction, 2 x 8
+//     per train tile) with the s32 accumulators in TMEM: two stages of 2 x 128 columns, so the tensor core works on tile t+1
 //     while all warps run the epilogue of tile t;
 //   * epilogue: tcgen05.ld (32 lanes x 32 columns per warp and load), one IMAD per column builds sortable 16-bit keys
 //     (distance << 7 | column), two columns per register, and packed 16x2 min / max keep the two smallest keys of the row
@@ -19,16 +20,19 @@
 
 namespace bftc {
 
-constexpr int M = 128;              // queries per CTA = TMEM lanes
-constexpr int N = 256;              // train descriptors per tile = TMEM columns of one accumulator stage
+constexpr int M = 128;              // rows of one MMA = TMEM lanes
+constexpr int MT = 2;               // query tiles per CTA: every expanded train tile is used by 256 queries
+constexpr int MQ = M * MT;          // queries per CTA
+constexpr int N = 128;              // train descriptors per tile = TMEM columns of one accumulator
 constexpr int NT = 512;             // threads: 16 warps; warp w reads TMEM lanes 32 (w % 4) .., columns QW (w / 4) ..
 constexpr int NQ = NT / 128;        // column quarters
-constexpr int QW = N / NQ;          // columns per thread and tile
+constexpr int QW = N / NQ;          // columns per thread, tile and query tile (32: one tcgen05.ld)
 constexpr int ROWB = 256;           // expanded bytes per descriptor (one 8-bit element per bit)
-constexpr int A_BYTES = M * ROWB;   // 32 KB
-constexpr int B_BYTES = N * ROWB;   // 64 KB per stage
+constexpr int A_BYTES = M * ROWB;   // 32 KB per query tile
+constexpr int B_BYTES = N * ROWB;   // 32 KB per stage
 constexpr int SUB = 65536;          // train rows per key space (16-bit local index)
-constexpr size_t SMEM_BYTES = A_BYTES + 2 * B_BYTES + 2 * N * 2 + NQ * M * 2 * 4 + 64;
+constexpr size_t SMEM_BYTES = MT * A_BYTES + 2 * B_BYTES + 2 * N * 2 + NQ * MQ * 2 * 4 + 64;
+static_assert(QW == 32 && MT * N * 2 == 512, "TMEM: 2 stages x MT accumulators of N columns = all 512 columns");
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
@@ -88,28 +92,27 @@ __device__ __forceinline__ void tmem_ld32(unsigned taddr, int (&r)[32])
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// 16 descriptor bits -> 16 signed bytes.  nibble * (1 + 2^7 + 2^14 + 2^21) puts bit i of the nibble at bit 8 i (the four partial
-// products do not overlap: no carries), the mask drops the rest: bytes {0, 1}.  Queries keep that (mul = 1, add = 0); train rows
-// become 1 - 2 b = {+1, -1} (mul = 0xFE, add = 0x01010101: 0x01 * 0xFE stays inside its byte), so that the accumulator is
-// sum a (1 - 2 b) = |a| - 2 <a, b> and only |b| is left for the epilogue; rows past the end are all-zero bytes (mul = add = 0).
-__device__ __forceinline__ uint4 expand16(unsigned h, unsigned mul, unsigned add)
+// One 32-bit word of a descriptor -> 32 signed bytes = two 16-byte K chunks of its row, 2.9 instructions per output word:
+// w << (7 - i) brings bits i, 8 + i, 16 + i, 24 + i to the sign positions of the four bytes, and PRMT in sign-replicate mode
+// (selector nibbles 8 | k) turns them into 0x00 / 0xFF; (x | orv) & andv then gives {0, 1} for a query row (orv = 0, andv =
+// 0x01010101) and {+1, -1} for a train row (orv = 0x01010101, andv = ~0): the accumulator becomes sum a (1 - 2 b) = |a| - 2 <a, b>
+// and only |b| is left for the epilogue.  A row past the end is all-zero bytes (orv = 0, w = 0).  Output word i holds bits
+// i + 8 k: a permutation of the K axis, the same for both operands, which a dot product does not see.
+// The row lives at (r >> 3) * 2048 + (r & 7) * 16 of its tile (core matrices of 8 rows x 16 bytes), its 16 K chunks 128 bytes apart.
+__device__ __forceinline__ unsigned sign_bytes(unsigned x)       // byte k = 0xFF if bit 7 of byte k of x is set, else 0x00
 {
-    uint4 o;
-    o.x = (((h & 0xFu) * 0x00204081u) & 0x01010101u) * mul + add;
-    o.y = ((((h >> 4) & 0xFu) * 0x00204081u) & 0x01010101u) * mul + add;
-    o.z = ((((h >> 8) & 0xFu) * 0x00204081u) & 0x01010101u) * mul + add;
-    o.w = ((((h >> 12) & 0xFu) * 0x00204081u) & 0x01010101u) * mul + add;
-    return o;
+    unsigned r;                                                  // (the __byte_perm intrinsic masks the selector to 3 bits per nibble)
+    asm("prmt.b32 %0, %1, %1, 0xBA98;" : "=r"(r) : "r"(x));
+    return r;
 }
-
-// NC consecutive chunks (16 bits each, NC / 2 words `w`) starting at chunk c0 of one descriptor row -> the core-matrix layout:
-// row r lives at (r >> 3) * 2048 + (r & 7) * 16, its 16 K chunks 128 bytes apart
-template <int NC>
-__device__ __forceinline__ void expand_chunks(uint8_t* tile, int r, int c0, const unsigned (&w)[NC / 2], unsigned mul, unsigned add)
+__device__ __forceinline__ void expand_word(uint8_t* row_base, int word, unsigned w, unsigned orv, unsigned andv)
 {
-    uint8_t* dst = tile + (r >> 3) * 2048 + (r & 7) * 16 + c0 * 128;
+    unsigned o[8];
 #pragma unroll
-    for (int i = 0; i < NC; i++) *reinterpret_cast<uint4*>(dst + i * 128) = expand16((w[i >> 1] >> ((i & 1) * 16)) & 0xFFFFu, mul, add);
+    for (int i = 0; i < 8; i++) o[i] = (sign_bytes(w << (7 - i)) | orv) & andv;
+    uint8_t* dst = row_base + word * 256;
+    *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<uint4*>(dst + 128) = make_uint4(o[4], o[5], o[6], o[7]);
 }
 
 __device__ __forceinline__ int popc256(const uint4& lo, const uint4& hi)
@@ -125,41 +128,41 @@ __device__ __forceinline__ void top2_insert(int d, int i, int& d0, int& i0, int&
     else if (i1 < 0 || d < d1 || (d == d1 && i < i1)) { d1 = d; i1 = i; }
 }
 
-// One CTA: queries [q_first, q_first + 128) of `q` (nq rows) against train rows [t_begin, t_end) of `t`.
+// One CTA: queries [q_first, q_first + 256) of `q` (nq rows) against train rows [t_begin, t_end) of `t`.
 // Writes (idx, dist) x 2 per live query to oi / od (row stride 2 ints, indexed by the query's row in the whole set).
 //
-// Keys.  Inside a tile a thread owns QW (<= 128) columns of its query row, so (distance << 7 | column) fits 16 bits (distance <=
-// 256) and TWO columns share a register: one IMAD per column adds (|a| - 2 <a, b>) << 7 to the packed bases (|b| << 7 | column) of
-// an even / odd column pair, three VIMNMX.U16x2 keep the two smallest keys of both lanes, and two independent accumulators halve
-// the dependency chain.  After the tile the (at most) two survivors become 32-bit keys (distance << 16 | local train index),
-// skipped outright when the tile's best distance cannot enter the row's top-2.
+// Keys.  Inside a tile a thread owns 32 columns of its query row, so (distance << 7 | column) fits 16 bits (distance <= 256) and
+// TWO columns share a register: one IMAD per column adds (|a| - 2 <a, b>) << 7 to the packed bases (|b| << 7 | column) of an even /
+// odd column pair, three VIMNMX.U16x2 keep the two smallest keys of both lanes, and two independent accumulators halve the
+// dependency chain.  After the tile the (at most) two survivors become 32-bit keys (distance << 16 | local train index), skipped
+// outright when the tile's best distance cannot enter the row's top-2.
 __device__ __forceinline__ void bf_tile_body(const uint8_t* __restrict__ q, int nq, int q_first, const uint8_t* __restrict__ t,
                                              long long t_begin, long long t_end, int idx_base, int32_t* oi, int32_t* od, uint8_t* smem)
 {
-    uint8_t* As = smem;
-    uint8_t* Bs = smem + A_BYTES;                                                          // 2 stages
-    unsigned short* base_s = reinterpret_cast<unsigned short*>(smem + A_BYTES + 2 * B_BYTES);   // [2][N] 16-bit key bases of the stage's columns
-    unsigned* keys_s = reinterpret_cast<unsigned*>(base_s + 2 * N);                        // [NQ][M][2] best keys of the column quarters
-    unsigned long long* bar = reinterpret_cast<unsigned long long*>(keys_s + NQ * M * 2);  // [2] MMA-complete barriers of the accumulator stages
+    uint8_t* As = smem;                                                                    // MT query tiles
+    uint8_t* Bs = smem + MT * A_BYTES;                                                     // 2 stages
+    unsigned short* base_s = reinterpret_cast<unsigned short*>(Bs + 2 * B_BYTES);          // [2][N] 16-bit key bases of the stage's columns
+    unsigned* keys_s = reinterpret_cast<unsigned*>(base_s + 2 * N);                        // [NQ][MQ][2] best keys of the column quarters
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(keys_s + NQ * MQ * 2); // [2] MMA-complete barriers of the two stages
     unsigned* tmem_slot = reinterpret_cast<unsigned*>(bar + 2);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int row = (warp & 3) * 32 + lane, quarter = warp >> 2;              // this thread's TMEM lane (query row) and column range
+    const int row = (warp & 3) * 32 + lane, quarter = warp >> 2;              // this thread's TMEM lane (query row of both tiles) and column range
 
-    // ---- prologue: TMEM (all 512 columns: 2 accumulator stages), barriers, the query tile ----
+    // ---- prologue: TMEM (all 512 columns: 2 stages x MT accumulators), barriers, the query tiles ----
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 32) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     {
-        const int r = tid & (M - 1), qi = q_first + r;
-        uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
-        if (qi < nq) { lo = __ldg(reinterpret_cast<const uint4*>(q) + 2 * (long long)qi); hi = __ldg(reinterpret_cast<const uint4*>(q) + 2 * (long long)qi + 1); }
-        static_assert(NQ == 4, "the query tile is expanded 4 chunks (2 words) per thread");
-        const int part = tid >> 7;                                             // chunks 4 part .. 4 part + 3 = words 2 part, 2 part + 1
-        const uint4 src = (part & 2) ? hi : lo;
-        const unsigned w2[2] = {(part & 1) ? src.z : src.x, (part & 1) ? src.w : src.y};
-        expand_chunks<4>(As, r, part * 4, w2, 1u, 0u);
+        // 256 query rows x 8 words over 512 threads: thread -> row tid & 255, words 4 (tid >> 8) .. + 3
+        const int r = tid & (MQ - 1), qi = q_first + r;
+        uint4 src = make_uint4(0, 0, 0, 0);
+        if (qi < nq) src = __ldg(reinterpret_cast<const uint4*>(q) + 2 * (long long)qi + (tid >> 8));
+        uint8_t* rb = As + (r >> 7) * A_BYTES + ((r & 127) >> 3) * 2048 + (r & 7) * 16;
+        const int w0 = (tid >> 8) * 4;
+        expand_word(rb, w0, src.x, 0u, 0x01010101u); expand_word(rb, w0 + 1, src.y, 0u, 0x01010101u);
+        expand_word(rb, w0 + 2, src.z, 0u, 0x01010101u); expand_word(rb, w0 + 3, src.w, 0u, 0x01010101u);
     }
     tc_fence_before();
     __syncthreads();
@@ -167,30 +170,40 @@ __device__ __forceinline__ void bf_tile_body(const uint8_t* __restrict__ q, int 
     const unsigned tmem = *tmem_slot;
 
     auto expand_b = [&](long long tile_first, int stage) {
-        const int r = tid & (N - 1);
-        const long long g = tile_first + r;                                    // train row; NT / N threads share it
-        uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
+        // 128 train rows x 8 words over 512 threads: thread -> row tid & 127, words 2 (tid >> 7), + 1
+        const int r = tid & (N - 1), part = tid >> 7;
+        const long long g = tile_first + r;
         const bool valid = g < t_end;
-        if (valid) { lo = __ldg(reinterpret_cast<const uint4*>(t) + 2 * g); hi = __ldg(reinterpret_cast<const uint4*>(t) + 2 * g + 1); }
-        static_assert(NT == 2 * N, "a train row is expanded by two threads, 8 chunks (4 words) each");
-        const uint4 src = (tid >= N) ? hi : lo;
-        const unsigned w4[4] = {src.x, src.y, src.z, src.w};
-        expand_chunks<8>(Bs + stage * B_BYTES, r, (tid / N) * 8, w4, valid ? 0xFEu : 0u, valid ? 0x01010101u : 0u);
-        if (tid < N) base_s[stage * N + r] = valid ? (unsigned short)((popc256(lo, hi) << 7) | (r & (QW - 1))) : (unsigned short)0xFFFFu;
+        uint2 src = make_uint2(0, 0);
+        if (valid) src = __ldg(reinterpret_cast<const uint2*>(t) + 4 * g + part);
+        uint8_t* rb = Bs + stage * B_BYTES + (r >> 3) * 2048 + (r & 7) * 16;
+        const unsigned orv = valid ? 0x01010101u : 0u;
+        expand_word(rb, 2 * part, src.x, orv, 0xFFFFFFFFu); expand_word(rb, 2 * part + 1, src.y, orv, 0xFFFFFFFFu);
+        if (part == 0) {                                                       // key base of the column: |b| << 7 | column inside the quarter
+            unsigned short kb = 0xFFFFu;
+            if (valid) kb = (unsigned short)((popc256(__ldg(reinterpret_cast<const uint4*>(t) + 2 * g), __ldg(reinterpret_cast<const uint4*>(t) + 2 * g + 1)) << 7) | (r & (QW - 1)));
+            base_s[stage * N + r] = kb;
+        }
     };
-    auto issue = [&](int stage) {                                              // one thread: 8 x (128 x 256 x 32) into accumulator `stage`
+    auto issue = [&](int stage) {                                              // one thread: MT x 8 x (128 x 128 x 32) into the accumulators of `stage`
         const unsigned a0 = smem_u32(As), b0 = smem_u32(Bs + stage * B_BYTES);
 #pragma unroll
-        for (int k = 0; k < 8; k++) mma_i8(tmem + stage * N, smem_desc(a0 + k * 256), smem_desc(b0 + k * 256), k > 0);
+        for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+                mma_i8(tmem + (stage * MT + mt) * N, smem_desc(a0 + mt * A_BYTES + k * 256), smem_desc(b0 + k * 256), k > 0);
         mma_commit(&bar[stage]);
     };
-
-    int D0 = 0, I0 = -1, D1 = 0, I1 = -1;                                      // running top-2 over the sub-ranges (decoded)
+    int D0[MT], I0[MT], D1[MT], I1[MT];                                        // running top-2 over the sub-ranges (decoded)
+#pragma unroll
+    for (int mt = 0; mt < MT; mt++) { D0[mt] = 0; I0[mt] = -1; D1[mt] = 0; I1[mt] = -1; }
     unsigned uses = 0;                                                         // tiles issued so far (stage = uses & 1, parity = (uses >> 1) & 1)
     for (long long sub = t_begin; sub < t_end; sub += SUB) {
         const long long sub_end = sub + SUB < t_end ? sub + SUB : t_end;
         const int ntiles = (int)((sub_end - sub + N - 1) / N);
-        unsigned G1 = 0xFFFFFFFFu, G2 = 0xFFFFFFFFu;                           // two smallest (distance << 16 | local index) of this sub-range
+        unsigned G1[MT], G2[MT];                                               // two smallest (distance << 16 | local index) of this sub-range
+#pragma unroll
+        for (int mt = 0; mt < MT; mt++) { G1[mt] = 0xFFFFFFFFu; G2[mt] = 0xFFFFFFFFu; }
         expand_b(sub, uses & 1);
         proxy_fence(); tc_fence_before();
         __syncthreads();
@@ -199,22 +212,23 @@ __device__ __forceinline__ void bf_tile_body(const uint8_t* __restrict__ q, int 
             const unsigned cur = uses + tl;
             if (tl + 1 < ntiles) expand_b(sub + (long long)(tl + 1) * N, (cur + 1) & 1);
             proxy_fence(); tc_fence_before();
-            __syncthreads();                       // stage (cur+1)&1: its smem is written, its accumulator was drained by the epilogue of tile cur-1
+            __syncthreads();                       // stage (cur+1)&1: its smem is written, its accumulators were drained by the epilogue of tile cur-1
             if (tid == 0 && tl + 1 < ntiles) { tc_fence_after(); issue((cur + 1) & 1); }
             mbar_wait(&bar[cur & 1], (cur >> 1) & 1);
             tc_fence_after();
-            // ---- epilogue of tile cur: QW columns of this thread's row ----
-            const unsigned taddr = tmem + ((unsigned)((warp & 3) * 32) << 16) + (cur & 1) * N + quarter * QW;
+            // ---- epilogue of tile cur: 32 columns of this thread's row in each query tile ----
             const uint4* kb4 = reinterpret_cast<const uint4*>(base_s + (cur & 1) * N + quarter * QW);
-            unsigned m1a = 0xFFFFFFFFu, m2a = 0xFFFFFFFFu, m1b = 0xFFFFFFFFu, m2b = 0xFFFFFFFFu;
+            const unsigned colbase = (unsigned)(tl * N + quarter * QW);
 #pragma unroll
-            for (int c = 0; c < QW / 32; c++) {
+            for (int mt = 0; mt < MT; mt++) {
+                const unsigned taddr = tmem + ((unsigned)((warp & 3) * 32) << 16) + ((cur & 1) * MT + mt) * N + quarter * QW;
+                unsigned m1a = 0xFFFFFFFFu, m2a = 0xFFFFFFFFu, m1b = 0xFFFFFFFFu, m2b = 0xFFFFFFFFu;
                 int acc[32];
-                tmem_ld32(taddr + c * 32, acc);
+                tmem_ld32(taddr, acc);
                 tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 32; j += 8) {
-                    const uint4 kb = kb4[c * 4 + (j >> 3)];                    // packed bases of 8 columns
+                    const uint4 kb = kb4[j >> 3];                              // packed bases of 8 columns
                     // (|a| - 2 <a, b>) << 7 onto both 16-bit lanes; mod 2^32 arithmetic, every lane ends in [0, 2^16)
                     const unsigned p0 = (unsigned)acc[j] * 128u + (unsigned)acc[j + 1] * (1u << 23) + kb.x;
                     const unsigned p1 = (unsigned)acc[j + 2] * 128u + (unsigned)acc[j + 3] * (1u << 23) + kb.y;
@@ -225,42 +239,52 @@ __device__ __forceinline__ void bf_tile_body(const uint8_t* __restrict__ q, int 
                     m2a = __vminu2(m2a, __vmaxu2(m1a, p2)); m1a = __vminu2(m1a, p2);
                     m2b = __vminu2(m2b, __vmaxu2(m1b, p3)); m1b = __vminu2(m1b, p3);
                 }
-            }
-            // ---- the tile's survivors -> 32-bit keys of the sub-range ----
-            const unsigned n1 = __vminu2(m1a, m1b);
-            const unsigned t1 = min(n1 & 0xFFFFu, n1 >> 16);
-            if ((t1 >> 7) <= (G2 >> 16)) {                                     // otherwise nothing of this tile can enter the top-2
-                const unsigned n2 = __vminu2(__vmaxu2(m1a, m1b), __vminu2(m2a, m2b));
-                const unsigned a1 = n1 & 0xFFFFu, b1 = n1 >> 16, a2 = n2 & 0xFFFFu, b2 = n2 >> 16;
-                const unsigned t2 = min(max(a1, b1), min(a2, b2));
-                const unsigned colbase = (unsigned)(tl * N + quarter * QW);
-                const unsigned g1 = ((t1 >> 7) << 16) | (colbase + (t1 & 127u)), g2 = ((t2 >> 7) << 16) | (colbase + (t2 & 127u));
-                G2 = min(G2, max(G1, g1)); G1 = min(G1, g1);
-                G2 = min(G2, max(G1, g2)); G1 = min(G1, g2);
+                // ---- the tile's survivors -> 32-bit keys of the sub-range ----
+                const unsigned n1 = __vminu2(m1a, m1b);
+                const unsigned t1 = min(n1 & 0xFFFFu, n1 >> 16);
+                if ((t1 >> 7) <= (G2[mt] >> 16)) {                             // otherwise nothing of this tile can enter the top-2
+                    const unsigned n2 = __vminu2(__vmaxu2(m1a, m1b), __vminu2(m2a, m2b));
+                    const unsigned a1 = n1 & 0xFFFFu, b1 = n1 >> 16, a2 = n2 & 0xFFFFu, b2 = n2 >> 16;
+                    const unsigned t2 = min(max(a1, b1), min(a2, b2));
+                    const unsigned g1 = ((t1 >> 7) << 16) | (colbase + (t1 & 127u)), g2 = ((t2 >> 7) << 16) | (colbase + (t2 & 127u));
+                    G2[mt] = min(G2[mt], max(G1[mt], g1)); G1[mt] = min(G1[mt], g1);
+                    G2[mt] = min(G2[mt], max(G1[mt], g2)); G1[mt] = min(G1[mt], g2);
+                }
             }
         }
         uses += ntiles;
         // ---- the column quarters of a row meet in shared memory; quarter 0's thread decodes and merges ----
         tc_fence_before();
         __syncthreads();
-        keys_s[(quarter * M + row) * 2] = G1; keys_s[(quarter * M + row) * 2 + 1] = G2;
+#pragma unroll
+        for (int mt = 0; mt < MT; mt++) {
+            keys_s[(quarter * MQ + mt * M + row) * 2] = G1[mt]; keys_s[(quarter * MQ + mt * M + row) * 2 + 1] = G2[mt];
+        }
         __syncthreads();
         if (quarter == 0) {
-            unsigned b1 = 0xFFFFFFFFu, b2 = 0xFFFFFFFFu;
 #pragma unroll
-            for (int k = 0; k < NQ; k++) {
-                const unsigned o1 = keys_s[(k * M + row) * 2], o2 = keys_s[(k * M + row) * 2 + 1];
-                b2 = min(b2, max(b1, o1)); b1 = min(b1, o1);
-                b2 = min(b2, max(b1, o2)); b1 = min(b1, o2);
+            for (int mt = 0; mt < MT; mt++) {
+                unsigned b1 = 0xFFFFFFFFu, b2 = 0xFFFFFFFFu;
+#pragma unroll
+                for (int k = 0; k < NQ; k++) {
+                    const unsigned o1 = keys_s[(k * MQ + mt * M + row) * 2], o2 = keys_s[(k * MQ + mt * M + row) * 2 + 1];
+                    b2 = min(b2, max(b1, o1)); b1 = min(b1, o1);
+                    b2 = min(b2, max(b1, o2)); b1 = min(b1, o2);
+                }
+                if ((b1 >> 16) <= 256u) top2_insert((int)(b1 >> 16), (int)(sub + (b1 & 0xFFFFu)) + idx_base, D0[mt], I0[mt], D1[mt], I1[mt]);
+                if ((b2 >> 16) <= 256u) top2_insert((int)(b2 >> 16), (int)(sub + (b2 & 0xFFFFu)) + idx_base, D0[mt], I0[mt], D1[mt], I1[mt]);
             }
-            if ((b1 >> 16) <= 256u) top2_insert((int)(b1 >> 16), (int)(sub + (b1 & 0xFFFFu)) + idx_base, D0, I0, D1, I1);
-            if ((b2 >> 16) <= 256u) top2_insert((int)(b2 >> 16), (int)(sub + (b2 & 0xFFFFu)) + idx_base, D0, I0, D1, I1);
         }
     }
-    if (quarter == 0 && q_first + row < nq) {
-        const long long o = 2ll * (q_first + row);
-        oi[o] = I0; oi[o + 1] = I1;
-        od[o] = I0 >= 0 ? D0 : -1; od[o + 1] = I1 >= 0 ? D1 : -1;
+    if (quarter == 0) {
+#pragma unroll
+        for (int mt = 0; mt < MT; mt++) {
+            const int qi = q_first + mt * M + row;
+            if (qi < nq) {
+                oi[2ll * qi] = I0[mt]; oi[2ll * qi + 1] = I1[mt];
+                od[2ll * qi] = I0[mt] >= 0 ? D0[mt] : -1; od[2ll * qi + 1] = I1[mt] >= 0 ? D1[mt] : -1;
+            }
+        }
     }
     tc_fence_before();
     __syncthreads();

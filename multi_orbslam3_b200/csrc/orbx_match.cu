@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(bftc::NT, 1) k_bf_knn2_tc(BfArgs A)
         q = A.desc + (long long)sa * A.cap * 32; nq = A.n[sa];
         t = A.desc + (long long)sb * A.cap * 32; nt = A.n[sb];
     }
-    if ((long long)blockIdx.x * bftc::M >= nq) return;
+    if ((long long)blockIdx.x * bftc::MQ >= nq) return;
     const long long t_begin = (long long)split * A.chunk;
     long long t_end = t_begin + A.chunk; if (t_end > nt) t_end = nt;
     int32_t* oi; int32_t* od;
@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(bftc::NT, 1) k_bf_knn2_tc(BfArgs A)
         const long long o = ((long long)p * A.out_stride) * 2;
         oi = A.idx + o; od = A.dist + o;
     }
-    bftc::bf_tile_body(q, nq, blockIdx.x * bftc::M, t, t_begin, t_end, A.idx_base, oi, od, bf_smem);
+    bftc::bf_tile_body(q, nq, blockIdx.x * bftc::MQ, t, t_begin, t_end, A.idx_base, oi, od, bf_smem);
 }
 
 // merge partial top-2 tables: parts laid out [pair][part][stride][2]; lexicographic (dist, idx)
@@ -835,9 +835,9 @@ static int bf_launch(orbx_matcher* m, BfArgs A, int npairs, int nq_max, long lon
     const int want = 148 * 8;
     int qblocks, nsplit = 1; long long chunk;
     if (!use_popc) {
-        // tensor-core kernel: 128 queries x 256 train rows per tile, one CTA per SM; split the train set so that about 8 CTAs per
+        // tensor-core kernel: 256 queries x 128 train rows per tile, one CTA per SM; split the train set so that about 8 CTAs per
         // SM exist, but keep at least 4 tiles per CTA (the query tile and the TMEM allocation are per CTA)
-        qblocks = (nq_max + bftc::M - 1) / bftc::M;
+        qblocks = (nq_max + bftc::MQ - 1) / bftc::MQ;
         const long long tiles = (nt_max + bftc::N - 1) / bftc::N;
         const long long per = (long long)qblocks * npairs;
         if (per < want && tiles > 4) {
