@@ -169,21 +169,27 @@ __device__ __forceinline__ void bf_tile_body(const uint8_t* __restrict__ q, int 
     tc_fence_after();
     const unsigned tmem = *tmem_slot;
 
-    auto expand_b = [&](long long tile_first, int stage) {
-        // 128 train rows x 8 words over 512 threads: thread -> row tid & 127, words 2 (tid >> 7), + 1
-        const int r = tid & (N - 1), part = tid >> 7;
-        const long long g = tile_first + r;
-        const bool valid = g < t_end;
-        uint2 src = make_uint2(0, 0);
-        if (valid) src = __ldg(reinterpret_cast<const uint2*>(t) + 4 * g + part);
-        uint8_t* rb = Bs + stage * B_BYTES + (r >> 3) * 2048 + (r & 7) * 16;
-        const unsigned orv = valid ? 0x01010101u : 0u;
-        expand_word(rb, 2 * part, src.x, orv, 0xFFFFFFFFu); expand_word(rb, 2 * part + 1, src.y, orv, 0xFFFFFFFFu);
-        if (part == 0) {                                                       // key base of the column: |b| << 7 | column inside the quarter
-            unsigned short kb = 0xFFFFu;
-            if (valid) kb = (unsigned short)((popc256(__ldg(reinterpret_cast<const uint4*>(t) + 2 * g), __ldg(reinterpret_cast<const uint4*>(t) + 2 * g + 1)) << 7) | (r & (QW - 1)));
-            base_s[stage * N + r] = kb;
+    // A train tile goes through registers: its words are requested one iteration ahead (fetch_b), so that the global-memory
+    // latency hides under the epilogue of the tile before, and are expanded when their stage is free (expand_b).
+    // 128 train rows x 8 words over 512 threads: thread -> row tid & 127, words 2 (tid >> 7), + 1; the first thread of a row
+    // also reads the whole row for |b|.
+    const int br = tid & (N - 1), bpart = tid >> 7;
+    uint2 nsrc = make_uint2(0, 0); uint4 nlo = make_uint4(0, 0, 0, 0), nhi = nlo; bool nvalid = false;
+    auto fetch_b = [&](long long tile_first) {
+        const long long g = tile_first + br;
+        nvalid = g < t_end;
+        nsrc = make_uint2(0, 0);
+        if (nvalid) {
+            nsrc = __ldg(reinterpret_cast<const uint2*>(t) + 4 * g + bpart);
+            if (bpart == 0) { nlo = __ldg(reinterpret_cast<const uint4*>(t) + 2 * g); nhi = __ldg(reinterpret_cast<const uint4*>(t) + 2 * g + 1); }
         }
+    };
+    auto expand_b = [&](int stage) {
+        uint8_t* rb = Bs + stage * B_BYTES + (br >> 3) * 2048 + (br & 7) * 16;
+        const unsigned orv = nvalid ? 0x01010101u : 0u;
+        expand_word(rb, 2 * bpart, nsrc.x, orv, 0xFFFFFFFFu); expand_word(rb, 2 * bpart + 1, nsrc.y, orv, 0xFFFFFFFFu);
+        if (bpart == 0)                                                        // key base of the column: |b| << 7 | column inside the quarter
+            base_s[stage * N + br] = nvalid ? (unsigned short)((popc256(nlo, nhi) << 7) | (br & (QW - 1))) : (unsigned short)0xFFFFu;
     };
     auto issue = [&](int stage) {                                              // one thread: MT x 8 x (128 x 128 x 32) into the accumulators of `stage`
         const unsigned a0 = smem_u32(As), b0 = smem_u32(Bs + stage * B_BYTES);
@@ -204,16 +210,19 @@ __device__ __forceinline__ void bf_tile_body(const uint8_t* __restrict__ q, int 
         unsigned G1[MT], G2[MT];                                               // two smallest (distance << 16 | local index) of this sub-range
 #pragma unroll
         for (int mt = 0; mt < MT; mt++) { G1[mt] = 0xFFFFFFFFu; G2[mt] = 0xFFFFFFFFu; }
-        expand_b(sub, uses & 1);
+        fetch_b(sub);
+        expand_b(uses & 1);
+        if (ntiles > 1) fetch_b(sub + N);
         proxy_fence(); tc_fence_before();
         __syncthreads();
         if (tid == 0) { tc_fence_after(); issue(uses & 1); }
         for (int tl = 0; tl < ntiles; tl++) {
             const unsigned cur = uses + tl;
-            if (tl + 1 < ntiles) expand_b(sub + (long long)(tl + 1) * N, (cur + 1) & 1);
+            if (tl + 1 < ntiles) expand_b((cur + 1) & 1);
             proxy_fence(); tc_fence_before();
             __syncthreads();                       // stage (cur+1)&1: its smem is written, its accumulators were drained by the epilogue of tile cur-1
             if (tid == 0 && tl + 1 < ntiles) { tc_fence_after(); issue((cur + 1) & 1); }
+            if (tl + 2 < ntiles) fetch_b(sub + (long long)(tl + 2) * N);       // in flight during the epilogue below
             mbar_wait(&bar[cur & 1], (cur >> 1) & 1);
             tc_fence_after();
             // ---- epilogue of tile cur: 32 columns of this thread's row in each query tile ----
