@@ -75,7 +75,7 @@ Context& context(int need, int min_pool = 0)
     if (!c.m || K != c.K || pool != c.pool) {
         if (c.m) orbx_matcher_destroy(c.m);
         c.m = NULL;
-        orbx_matcher_params p; p.device = dev; p.max_keypoints = K; p.max_batch = 1; p.max_candidates = pool;
+        orbx_matcher_params p; p.device = dev; p.max_keypoints = K; p.max_batch = 2; p.max_candidates = pool;      // two pairs: the halves of a two-camera frame
         if (orbx_matcher_create(&p, &c.m) != ORBX_OK) fail("orbx_matcher_create");
         c.K = K; c.pool = pool;
     }
@@ -206,6 +206,65 @@ int run_search(const SearchSpec& spec, const Queries& Q, const Target& T, std::v
     return total;
 }
 
+// ---- two-camera frames (KannalaBrandt8 rig, Frame::Nleft != -1) ----
+// The frame's keypoints are mvKeys (left, [0, Nleft)) followed by mvKeysRight ([Nleft, N)); descriptor rows follow the same order
+// (Frame.cc:1079-1082).  Every map point has a left and a right query; the device call interleaves them over one occupancy table
+// as the reference's loop does (orbx_search_by_projection_rig).
+struct RigQueries {
+    std::vector<orbx_proj_query> ql, qr;
+    std::vector<uint8_t> desc;
+    std::vector<int> tag;
+    int add(const cv::Mat& d, bool occupies, int t)
+    {
+        orbx_proj_query e; std::memset(&e, 0, sizeof(e));
+        e.valid = occupies ? 0 : 2;                               // bit 0 is set by left() / right()
+        ql.push_back(e); qr.push_back(e);
+        const size_t o = desc.size();
+        desc.resize(o + 32);
+        std::memcpy(desc.data() + o, d.ptr(0), 32);
+        tag.push_back(t);
+        return (int)ql.size() - 1;
+    }
+    static void fill(orbx_proj_query& e, float u, float v, float r, int minl, int maxl, float angle)
+    {
+        e.u = u; e.v = v; e.r = r; e.minl = minl; e.maxl = maxl; e.ur = 0.f; e.angle = angle; e.valid |= 1;
+    }
+    void left(int i, float u, float v, float r, int minl, int maxl, float angle) { fill(ql[i], u, v, r, minl, maxl, angle); }
+    void right(int i, float u, float v, float r, int minl, int maxl, float angle) { fill(qr[i], u, v, r, minl, maxl, angle); }
+    int size() const { return (int)ql.size(); }
+};
+
+int run_rig_search(int mode, float nnratio, bool check_ori, int max_dist, const RigQueries& Q, const Frame& F, bool partners,
+                   std::vector<int32_t>& assigned)
+{
+    const int nq = Q.size(), n2 = F.N;
+    if (nq == 0 || n2 == 0) return 0;
+    if (n2 > 24000 || nq > 24000) fail("more than 24000 keypoints / map points in a two-camera search");
+    std::vector<cv::KeyPoint> keys(F.mvKeys.begin(), F.mvKeys.begin() + F.Nleft);
+    keys.insert(keys.end(), F.mvKeysRight.begin(), F.mvKeysRight.begin() + F.Nright);
+    std::vector<uint8_t> tmp;
+    const uint8_t* d2 = rows32(F.mDescriptors, tmp);
+    orbx_proj_options o;
+    std::memset(&o, 0, sizeof(o));
+    o.bounds[0] = Frame::mnMinX; o.bounds[1] = Frame::mnMaxX; o.bounds[2] = Frame::mnMinY; o.bounds[3] = Frame::mnMaxY;
+    o.query_origin[0] = Frame::mnMinX; o.query_origin[1] = Frame::mnMinY;
+    o.nnratio = nnratio; o.check_ori = check_ori ? 1 : 0; o.max_dist = max_dist;
+    std::vector<int32_t> l2r, r2l;
+    if (partners) { l2r.assign(F.mvLeftToRightMatch.begin(), F.mvLeftToRightMatch.end()); r2l.assign(F.mvRightToLeftMatch.begin(), F.mvRightToLeftMatch.end()); }
+    int min_pool = 0, nm = 0;
+    for (int attempt = 0;; attempt++) {
+        Context& c = context(nq > n2 ? nq : n2, min_pool);
+        std::vector<int32_t> a = assigned;
+        const int rc = orbx_search_by_projection_rig(c.m, mode, Q.ql.data(), Q.qr.data(), Q.desc.data(), nq, kp_ptr(keys), d2, F.Nleft, F.Nright,
+                                                     partners ? l2r.data() : NULL, partners ? r2l.data() : NULL, &o, a.data(), &nm);
+        if (rc == ORBX_E_CAPACITY && attempt < 6) { min_pool = c.pool * 4; continue; }
+        if (rc != ORBX_OK) fail("orbx_search_by_projection_rig");
+        assigned.swap(a);
+        break;
+    }
+    return nm;
+}
+
 // pose split of a similarity transformation as the Sim3 overloads do it (R/src/ORBmatcher.cc:484-488, :598-602, :1616-1620)
 struct Sim3Pose {
     cv::Mat Rcw, tcw, Ow;
@@ -315,8 +374,41 @@ void ORBmatcher::ComputeThreeMaxima(vector<int>* histo, const int L, int &ind1, 
 // R/src/ORBmatcher.cc:44-214  Tracking::SearchLocalPoints: local-map points (already tested by Frame::isInFrustum) against F
 int ORBmatcher::SearchByProjection(Frame &F, const vector<MapPoint*> &vpMapPoints, const float th, const bool bFarPoints, const float thFarPoints)
 {
-    if (F.Nleft != -1) unsupported("SearchByProjection(Frame&, vector<MapPoint*>&) on a two-camera frame");
     const bool bFactor = th!=1.0;
+    if (F.Nleft != -1) {
+        // :144-212: every point searches the left image (mbTrackInView) and then the right one (mbTrackInViewR); a match also takes
+        // the keypoint's stereo partner (mvLeftToRightMatch / mvRightToLeftMatch)
+        RigQueries Q;
+        for (size_t iMP = 0; iMP < vpMapPoints.size(); iMP++) {
+            MapPoint* pMP = vpMapPoints[iMP];
+            if (!pMP->mbTrackInView && !pMP->mbTrackInViewR) continue;
+            if (bFarPoints && pMP->mTrackDepth>thFarPoints) continue;
+            if (pMP->isBad()) continue;
+            const int qi = Q.add(pMP->GetDescriptor(), pMP->Observations()>0, (int)iMP);
+            if (pMP->mbTrackInView) {
+                const int &nPredictedLevel = pMP->mnTrackScaleLevel;
+                float r = RadiusByViewingCos(pMP->mTrackViewCos);
+                if(bFactor)
+                    r*=th;
+                Q.left(qi, pMP->mTrackProjX, pMP->mTrackProjY, r*F.mvScaleFactors[nPredictedLevel], nPredictedLevel-1, nPredictedLevel, 0.f);
+            }
+            if (pMP->mbTrackInViewR) {
+                const int &nPredictedLevel = pMP->mnTrackScaleLevelR;
+                if (nPredictedLevel != -1) {
+                    float r = RadiusByViewingCos(pMP->mTrackViewCosR);                 // no th factor on this side (:148)
+                    Q.right(qi, pMP->mTrackProjXR, pMP->mTrackProjYR, r*F.mvScaleFactors[nPredictedLevel], nPredictedLevel-1, nPredictedLevel, 0.f);
+                }
+            }
+        }
+        std::vector<int32_t> assigned(F.N, -1);
+        const int occupied = Q.size();
+        for (int i = 0; i < F.N; i++)
+            if (F.mvpMapPoints[i] && F.mvpMapPoints[i]->Observations()>0) assigned[i] = occupied;
+        const int nmatches = run_rig_search(1, mfNNratio, false, TH_HIGH, Q, F, true, assigned);
+        for (int i = 0; i < F.N; i++)
+            if (assigned[i] >= 0 && assigned[i] < occupied) F.mvpMapPoints[i] = vpMapPoints[Q.tag[assigned[i]]];
+        return nmatches;
+    }
     Queries Q;
     for (size_t iMP = 0; iMP < vpMapPoints.size(); iMP++) {
         MapPoint* pMP = vpMapPoints[iMP];
@@ -357,7 +449,7 @@ static void write_claims(std::vector<MapPoint*>& slots, const std::vector<int32_
 // R/src/ORBmatcher.cc:1970-2186  Tracking::TrackWithMotionModel: the last frame's points projected with the predicted pose
 int ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, const float th, const bool bMono)
 {
-    if (CurrentFrame.Nleft != -1 || LastFrame.Nleft != -1) unsupported("SearchByProjection(Frame&, const Frame&) on a two-camera frame");
+    if (CurrentFrame.Nleft == -1 && LastFrame.Nleft != -1) unsupported("SearchByProjection(Frame&, const Frame&) from a two-camera frame into a one-camera frame");
     const cv::Mat Rcw = CurrentFrame.mTcw.rowRange(0,3).colRange(0,3);
     const cv::Mat tcw = CurrentFrame.mTcw.rowRange(0,3).col(3);
     const cv::Mat twc = -Rcw.t()*tcw;
@@ -368,6 +460,46 @@ int ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, 
     const bool bForward = tlc.at<float>(2)>CurrentFrame.mb && !bMono;
     const bool bBackward = -tlc.at<float>(2)>CurrentFrame.mb && !bMono;
 
+    if (CurrentFrame.Nleft != -1) {
+        // :2093-2160: after the left image, the point is projected into the right camera (mTrl) and the best free keypoint of
+        // mvKeysRight within the same radius / octave range takes it; both claims enter the one rotation histogram
+        RigQueries Q;
+        for (int i = 0; i < LastFrame.N; i++) {
+            MapPoint* pMP = LastFrame.mvpMapPoints[i];
+            if (!pMP || LastFrame.mvbOutlier[i]) continue;
+            cv::Mat x3Dw = pMP->GetWorldPos();
+            cv::Mat x3Dc = Rcw*x3Dw+tcw;
+            const float invzc = 1.0/x3Dc.at<float>(2);
+            if(invzc<0)
+                continue;
+            cv::Point2f uv = CurrentFrame.mpCamera->project(x3Dc);
+            if(uv.x<CurrentFrame.mnMinX || uv.x>CurrentFrame.mnMaxX)
+                continue;
+            if(uv.y<CurrentFrame.mnMinY || uv.y>CurrentFrame.mnMaxY)
+                continue;
+            const cv::KeyPoint& kpLF = (LastFrame.Nleft == -1) ? LastFrame.mvKeysUn[i]
+                                                                : (i < LastFrame.Nleft) ? LastFrame.mvKeys[i] : LastFrame.mvKeysRight[i - LastFrame.Nleft];
+            const int nLastOctave = (LastFrame.Nleft == -1 || i < LastFrame.Nleft) ? LastFrame.mvKeys[i].octave
+                                                                                   : LastFrame.mvKeysRight[i - LastFrame.Nleft].octave;
+            const float radius = th*CurrentFrame.mvScaleFactors[nLastOctave];
+            int minl, maxl;
+            if (bForward) { minl = nLastOctave; maxl = -1; }
+            else if (bBackward) { minl = 0; maxl = nLastOctave; }
+            else { minl = nLastOctave-1; maxl = nLastOctave+1; }
+            const int qi = Q.add(pMP->GetDescriptor(), pMP->Observations()>0, i);
+            Q.left(qi, uv.x, uv.y, radius, minl, maxl, kpLF.angle);
+            cv::Mat x3Dr = CurrentFrame.mTrl.colRange(0,3).rowRange(0,3) * x3Dc + CurrentFrame.mTrl.col(3);
+            cv::Point2f uvr = CurrentFrame.mpCamera->project(x3Dr);
+            Q.right(qi, uvr.x, uvr.y, radius, minl, maxl, kpLF.angle);
+        }
+        std::vector<int32_t> assigned(CurrentFrame.N, -1);
+        const int occupied = Q.size();
+        for (int i = 0; i < CurrentFrame.N; i++)
+            if (CurrentFrame.mvpMapPoints[i] && CurrentFrame.mvpMapPoints[i]->Observations()>0) assigned[i] = occupied;
+        const int nmatches = run_rig_search(0, mfNNratio, mbCheckOrientation, TH_HIGH, Q, CurrentFrame, false, assigned);
+        write_claims(CurrentFrame.mvpMapPoints, assigned, occupied, [&](int q) { return LastFrame.mvpMapPoints[Q.tag[q]]; });
+        return nmatches;
+    }
     Queries Q;
     for (int i = 0; i < LastFrame.N; i++) {
         MapPoint* pMP = LastFrame.mvpMapPoints[i];

@@ -405,6 +405,26 @@ int  orbx_bow_transform(orbx_vocab* v, const uint8_t* desc, int n, int levelsup,
 int  orbx_bow_transform_slots_device(orbx_vocab* v, orbx_extractor* ex, int first_slot, int count, int levelsup,
                                      int32_t* d_word, int32_t* d_node, void* stream);
 
+/* Modes 0 and 1 on a two-camera frame (KannalaBrandt8 rig, Frame::Nleft != -1; R/src/ORBmatcher.cc:144-213, :2093-2160).
+ * k2 / d2 hold the left camera's keypoints (indices [0, n_left): Frame::mvKeys) followed by the right camera's ([n_left, n_left +
+ * n_right): Frame::mvKeysRight, descriptor rows Nleft ..), each half with its own grid (mGrid / mGridRight, R/src/Frame.cc:360-391,
+ * GetFeaturesInArea(..., bRight) :628-697) over the same bounds.  Map point i has a left query ql[i] and a right query qr[i] (valid
+ * bit 0 = that search takes part, bit 1 = the point has no observations) and one descriptor qdesc[i]; the reference interleaves
+ * them - left of point i, right of point i, left of point i+1, ... - over ONE occupancy table, and so does this call:
+ *   mode 1  SearchByProjection(Frame&, vector<MapPoint*>&): best / second with the level rule on both sides; an accepted left match
+ *           also takes the keypoint's stereo partner l2r[i2] (Frame::mvLeftToRightMatch, -1 = none) and counts twice, likewise r2l
+ *           (mvRightToLeftMatch) for a right match; a left search rejected by the ratio test leaves the point (the `continue` of
+ *           :116-117 skips its right search);
+ *   mode 0  SearchByProjection(Frame&, const Frame&, th, bMono): left as in the one-camera form without the stereo gate, right: the
+ *           best candidate alone, accepted when <= opt->max_dist; both feed the one rotation histogram; a left search that takes
+ *           part but finds no keypoint in its window leaves the point (the `continue` of :2033-2034 skips its right search).
+ * assigned[n_left + n_right] in / out as for orbx_search_by_projection (-2 = cleared by the rotation check).  Needs a matcher with
+ * max_batch >= 2 and n_left + n_right <= max_keypoints.  Host pointers. */
+int  orbx_search_by_projection_rig(orbx_matcher* m, int mode, const orbx_proj_query* ql, const orbx_proj_query* qr,
+                                   const uint8_t* qdesc, int nq, const orbx_keypoint* k2, const uint8_t* d2, int n_left, int n_right,
+                                   const int32_t* l2r, const int32_t* r2l, const orbx_proj_options* opt, int32_t* assigned,
+                                   int* nmatches);
+
 /* ---- server keyframe database on one GPU (SURVEY 8f row 3 -> 8e) ----
  * A keyframe reaches the server as a KF.msg (R/msg/KF.msg:24-29): `CvKeyPoint[] mvKeysUn` = N records of 15 packed bytes
  * (R/msg/CvKeyPoint.msg; Converter::toCvKeyPointMsg, R/src/Converter.cc:218-230) and `Descriptor[] mDescriptors` = N x

@@ -954,6 +954,94 @@ __global__ void k_best_from_top2(WinBufs W, int nq, int32_t* best_idx, int32_t* 
     best_dist[i] = e == 0xFFFFFFFFu ? 256 : (int)((e >> 16) & 0x1FF);
 }
 
+// ---- k_rig_resolve: modes 0 / 1 on a two-camera frame (Frame::Nleft != -1; R/src/ORBmatcher.cc:144-213, :2093-2160) ----
+// Pair 0 = the left camera's keypoints [0, nL), pair 1 = the right camera's [nL, nL + nR), each with its own grid and candidate
+// pool; map point i has a left query (pair 0, query i) and a right query (pair 1, query i).  The reference walks the points in
+// order - left of i, right of i, left of i+1, ... - over ONE occupancy table, so one warp does the same: 32 lanes scan a
+// query's candidate list, lane 0 applies the rule.  res / occ are indexed by the combined keypoint index.
+__global__ void __launch_bounds__(32) k_rig_resolve(WinBufs W, int mode, float nnratio, int check_ori, int max_dist, int nL, int nR, int nq,
+                                                   const int32_t* l2r, const int32_t* r2l, int32_t* res, int32_t* nmatches)
+{
+    extern __shared__ int s_mem[];
+    const int lane = threadIdx.x;
+    int* occ = s_mem;                          // [nL + nR] by combined keypoint
+    int* claim_of = occ + nL + nR;             // [2][nq] by (side, query): the combined keypoint the query claimed, or -1
+    uint8_t* bin_of = reinterpret_cast<uint8_t*>(claim_of + 2 * nq);   // [2][nq]
+    __shared__ int hist[ORBX_HISTO_LENGTH];
+    if (lane < ORBX_HISTO_LENGTH) hist[lane] = 0;
+    for (int i = lane; i < nL + nR; i += 32) occ[i] = res[i] >= 0;
+    for (int i = lane; i < 2 * nq; i += 32) { claim_of[i] = -1; bin_of[i] = 0xFF; }
+    __syncwarp();
+    int accepted = 0;
+    for (int i = 0; i < nq; i++) {
+        bool skip_right = false;
+        for (int side = 0; side < 2; side++) {
+            if (side == 1 && skip_right) break;
+            const PairDesc P = W.pairs[side];
+            const int cnt = W.q_cnt[(long long)side * W.K + i];
+            if (cnt <= 0) {
+                // mode 0: a left search that takes part but finds its window empty leaves the point (`continue` of :2033-2034)
+                if (mode == 0 && side == 0 && (P.q[i].valid & 1)) skip_right = true;
+                continue;
+            }
+            const int off = W.q_off[(long long)side * W.K + i];
+            const uint32_t* pool = W.pool + (long long)side * W.POOL;
+            const int kbase = side ? nL : 0;
+            int d0 = 0x7fffffff, d1 = 0x7fffffff, k0 = 0x7fffffff, k1 = 0x7fffffff;
+            uint32_t e0 = 0, e1 = 0;
+            for (int k = lane; k < cnt; k += 32) {
+                const uint32_t e = pool[off + k];
+                const int i2 = e & 0xFFFF, d = (e >> 16) & 0x1FF;
+                if (occ[kbase + i2]) continue;                                 // :89-91 / :159-161 / :2045-2047 / :2117-2119
+                if (d < d0) { d1 = d0; k1 = k0; e1 = e0; d0 = d; k0 = k; e0 = e; }
+                else if (d < d1) { d1 = d; k1 = k; e1 = e; }
+            }
+            warp_top2(d0, k0, e0, d1, e1, k1);
+            const int obs = !(P.q[i].valid & 2);                              // the claiming MapPoint has observations: it occupies what it takes
+            if (mode == 1) {
+                const int bd = d0 < 256 ? d0 : 256, bd2 = d1 < 256 ? d1 : 256;
+                const int bl = d0 < 256 ? (int)(e0 >> 25) : -1, bl2 = d1 < 256 ? (int)(e1 >> 25) : -1;
+                if (bd <= ORBX_TH_HIGH) {
+                    if (bl == bl2 && (float)bd > nnratio * (float)bd2) { if (side == 0) skip_right = true; continue; }   // `continue` of :116-117 leaves the point
+                    const int i2 = e0 & 0xFFFF;
+                    if (lane == 0) {
+                        const int32_t* partner = side ? r2l : l2r;
+                        const int pi = partner ? partner[i2] : -1;
+                        if (pi >= 0) { const int pk = side ? pi : nL + pi; res[pk] = i; occ[pk] = obs; accepted++; }      // :123-127 / :191-195
+                        res[kbase + i2] = i; occ[kbase + i2] = obs; accepted++;
+                    }
+                }
+            } else {
+                // left: :2038-2090 (best <= TH_HIGH or the caller's bound); right: :2106-2155 (the best alone)
+                if (d0 <= max_dist) {
+                    const int i2 = e0 & 0xFFFF;
+                    if (lane == 0) {
+                        res[kbase + i2] = i; claim_of[side * nq + i] = kbase + i2; accepted++;
+                        if (obs) occ[kbase + i2] = 1;
+                        if (check_ori) { const int bin = rot_bin(P.q[i].angle, P.k2[i2].angle); bin_of[side * nq + i] = (uint8_t)bin; hist[bin]++; }
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        __syncwarp();
+    }
+    __syncwarp();
+    if (check_ori && mode == 0) {                                             // :2163-2183
+        int ind1, ind2, ind3;
+        three_maxima(hist, ind1, ind2, ind3);
+        int culled = 0;
+        for (int i = lane; i < 2 * nq; i += 32) {
+            const int b = bin_of[i];
+            if (b != 0xFF && b != ind1 && b != ind2 && b != ind3) { res[claim_of[i]] = -2; culled++; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) culled += __shfl_xor_sync(0xffffffffu, culled, o);
+        accepted -= culled;
+    }
+    if (lane == 0) *nmatches = accepted;
+}
+
 static int run_window(orbx_matcher* m, const WinBufs& W, int npairs, int nq_max, int mode, float nnratio, int check_ori,
                       int32_t* d_out, int32_t* d_nm, float* d_prev, cudaStream_t s, int max_dist = ORBX_TH_HIGH)
 {
@@ -1092,6 +1180,61 @@ extern "C" int orbx_search_by_projection_opts(orbx_matcher* m, int mode, const o
         rc = m_check_err(m, s);
         if (rc) return rc;
     }
+    if (nmatches) *nmatches = nm;
+    return ORBX_OK;
+}
+
+extern "C" int orbx_search_by_projection_rig(orbx_matcher* m, int mode, const orbx_proj_query* ql, const orbx_proj_query* qr,
+                                             const uint8_t* qdesc, int nq, const orbx_keypoint* k2, const uint8_t* d2, int n_left, int n_right,
+                                             const int32_t* l2r, const int32_t* r2l, const orbx_proj_options* opt, int32_t* assigned,
+                                             int* nmatches)
+{
+    const int n2 = n_left + n_right;
+    if (!m || !opt || (mode != 0 && mode != 1) || nq < 0 || n_left < 0 || n_right < 0 || nq > m->K || n2 > m->K || m->P < 2 ||
+        (nq > 0 && (!ql || !qr || !qdesc)) || (n2 > 0 && (!k2 || !d2 || !assigned)) || (size_t)(n2 + 3 * nq) * sizeof(int) > 200 * 1024) {
+        orbx_set_error("%s%s", "orbx_search_by_projection_rig: invalid arguments (needs max_batch >= 2, n_left + n_right <= max_keypoints)", "");
+        return ORBX_E_INVALID;
+    }
+    if (nmatches) *nmatches = 0;
+    if (nq == 0 || n2 == 0) return ORBX_OK;
+    CKM(cudaSetDevice(m->p.device));
+    cudaStream_t s = m->stream;
+    set_bounds(m, opt->bounds);
+    m->W.qminX = opt->query_origin[0]; m->W.qminY = opt->query_origin[1];
+    // combined keypoints / descriptors in the single-frame staging; pair 0 reads the left half, pair 1 the right half
+    CKM(cudaMemcpyAsync(m->W.q, ql, sizeof(orbx_proj_query) * nq, cudaMemcpyHostToDevice, s));
+    CKM(cudaMemcpyAsync(m->W.q + m->K, qr, sizeof(orbx_proj_query) * nq, cudaMemcpyHostToDevice, s));
+    CKM(cudaMemcpyAsync(m->d_qdesc, qdesc, (size_t)32 * nq, cudaMemcpyHostToDevice, s));
+    CKM(cudaMemcpyAsync(m->d_k2, k2, sizeof(orbx_keypoint) * n2, cudaMemcpyHostToDevice, s));
+    CKM(cudaMemcpyAsync(m->d_d2, d2, (size_t)32 * n2, cudaMemcpyHostToDevice, s));
+    CKM(cudaMemcpyAsync(m->d_out, assigned, sizeof(int32_t) * n2, cudaMemcpyHostToDevice, s));
+    int32_t* d_partner = nullptr;
+    if (l2r || r2l) {
+        int rc = orbx_m_gen_scratch(m, sizeof(int32_t) * (size_t)(n2 > 0 ? n2 : 1));
+        if (rc) return rc;
+        d_partner = reinterpret_cast<int32_t*>(m->d_gen);
+        if (l2r && n_left) CKM(cudaMemcpyAsync(d_partner, l2r, sizeof(int32_t) * n_left, cudaMemcpyHostToDevice, s));
+        if (r2l && n_right) CKM(cudaMemcpyAsync(d_partner + n_left, r2l, sizeof(int32_t) * n_right, cudaMemcpyHostToDevice, s));
+    }
+    PairDesc pd[2] = {};
+    for (int side = 0; side < 2; side++) {
+        pd[side].k2 = m->d_k2 + (side ? n_left : 0); pd[side].d2 = m->d_d2 + (size_t)(side ? n_left : 0) * 32; pd[side].uright2 = nullptr;
+        pd[side].q = m->W.q + (size_t)side * m->K; pd[side].qdesc = m->d_qdesc; pd[side].n1 = nq; pd[side].n2 = side ? n_right : n_left; pd[side].nq = nq;
+    }
+    CKM(cudaMemcpyAsync(m->W.pairs, pd, sizeof(pd), cudaMemcpyHostToDevice, s));
+    int rc = run_window(m, m->W, 2, nq, 3, opt->nnratio, opt->check_ori, nullptr, nullptr, nullptr, s);      // grids + candidate pools of both halves
+    m->W.qminX = m->W.minX; m->W.qminY = m->W.minY;
+    if (rc) return rc;
+    CKM(ORBX_OPTIN_SMEM(k_rig_resolve));
+    const size_t smem = (size_t)(n2 + 2 * nq) * sizeof(int) + 2 * (size_t)nq;
+    k_rig_resolve<<<1, 32, smem, s>>>(m->W, mode, opt->nnratio, opt->check_ori, opt->max_dist > 0 ? opt->max_dist : ORBX_TH_HIGH, n_left, n_right, nq,
+                                      l2r ? d_partner : nullptr, r2l ? d_partner + n_left : nullptr, m->d_out, m->d_nm); ORBX_COUNT_LAUNCH(1);
+    CKM(cudaGetLastError());
+    int nm = 0;
+    CKM(cudaMemcpyAsync(assigned, m->d_out, sizeof(int32_t) * n2, cudaMemcpyDeviceToHost, s));
+    CKM(cudaMemcpyAsync(&nm, m->d_nm, sizeof(int), cudaMemcpyDeviceToHost, s));
+    rc = m_check_err(m, s);
+    if (rc) return rc;
     if (nmatches) *nmatches = nm;
     return ORBX_OK;
 }

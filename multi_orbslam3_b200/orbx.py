@@ -42,6 +42,7 @@ EXPORTS = [
     "orbx_fast_segment_plan", "orbx_matcher_set_slot_keypoints", "orbx_matcher_set_camera", "orbx_matcher_undistorted_device", "orbx_search_by_projection_ex", "orbx_search_by_projection_opts", "orbx_match_candidates", "orbx_search_by_bow", "orbx_search_for_triangulation", "orbx_distinctive_descriptors", "orbx_undistort_keypoints", "orbx_undistort_slots_device",
     "orbx_keypoints_to_msg", "orbx_keypoints_from_msg", "orbx_slot_keypoints_to_msg_device", "orbx_vocab_create", "orbx_vocab_destroy", "orbx_vocab_words", "orbx_vocab_word_weights",
     "orbx_bow_transform", "orbx_bow_transform_slots_device", "orbx_popc_peak",
+    "orbx_search_by_projection_rig",
     "orbx_kfdb_create", "orbx_kfdb_destroy", "orbx_kfdb_ingest_msg", "orbx_kfdb_ingest_slot_device", "orbx_kfdb_size", "orbx_kfdb_device",
     "orbx_kfdb_sync", "orbx_kfdb_locate", "orbx_kfdb_knn2",
 ]
@@ -137,6 +138,7 @@ def lib():
         L.orbx_undistort_slots_device.argtypes = [vp, i32, i32, vp, vp, i32, vp, vp, vp]
         L.orbx_search_for_triangulation.argtypes = [vp, vp, vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, vp, vp, i32, vp, vp, vp, i32,
                                                     vp, f32, f32, vp, vp, i32, i32, i32, i32, vp, vp]
+        L.orbx_search_by_projection_rig.argtypes = [vp, i32, vp, vp, vp, i32, vp, vp, i32, i32, vp, vp, vp, vp, vp]
         L.orbx_kfdb_create.argtypes = [i32, C.c_longlong, i32, C.POINTER(vp)]
         L.orbx_kfdb_destroy.argtypes = [vp]; L.orbx_kfdb_destroy.restype = None
         L.orbx_kfdb_ingest_msg.argtypes = [vp, C.c_int64, vp, vp, i32, vp]
@@ -427,6 +429,21 @@ class ORBmatcher:
                                                   _p(sg) if sg is not None else None, 0 if sg is None else len(sg), float(chi2),
                                                   _p(bi), _p(bd), C.byref(nm)))
         return (nm.value, bi, bd) if mode == 3 else (nm.value, a)
+
+    def SearchByProjectionRig(self, mode, ql, qr, qdesc, k2, d2, n_left, bounds, assigned=None, l2r=None, r2l=None, max_dist=100):
+        """modes 0 / 1 on a two-camera frame (orbx_search_by_projection_rig): k2 / d2 = left keypoints then right keypoints"""
+        ql = np.ascontiguousarray(ql, PROJQ_DTYPE); qr = np.ascontiguousarray(qr, PROJQ_DTYPE)
+        qdesc = np.ascontiguousarray(qdesc, np.uint8); k2 = np.ascontiguousarray(k2, KP_DTYPE); d2 = np.ascontiguousarray(d2, np.uint8)
+        a = np.full(len(k2), -1, np.int32) if assigned is None else np.ascontiguousarray(assigned, np.int32).copy()
+        pl = None if l2r is None else np.ascontiguousarray(l2r, np.int32); pr = None if r2l is None else np.ascontiguousarray(r2l, np.int32)
+        o = ProjOptions()
+        for i in range(4): o.bounds[i] = float(bounds[i])
+        o.query_origin[0] = float(bounds[0]); o.query_origin[1] = float(bounds[2])
+        o.nnratio = self.mfNNratio; o.check_ori = int(self.mbCheckOrientation); o.max_dist = int(max_dist)
+        nm = C.c_int(0)
+        _check(lib().orbx_search_by_projection_rig(self._h, mode, _p(ql), _p(qr), _p(qdesc), len(ql), _p(k2), _p(d2), int(n_left), len(k2) - int(n_left),
+                                                   None if pl is None else _p(pl), None if pr is None else _p(pr), C.byref(o), _p(a), C.byref(nm)))
+        return nm.value, a
 
     def SearchForTriangulation(self, k1, d1, free1, stereo1, fv1, k2, d2, free2, stereo2, fv2, F12, ep, scale2, sigma2_2,
                                only_stereo=False, coarse=False):

@@ -390,6 +390,22 @@ def search_by_projection_full(mode, queries, qdesc, k2, d2, bounds, assigned=Non
     return (n, bi, bd) if mode == 3 else (n, a)
 
 
+def search_by_projection_rig(mode, ql, qr, qdesc, k2, d2, n_left, bounds, assigned=None, l2r=None, r2l=None, nnratio=0.8, check_ori=True,
+                             max_dist=100):
+    """orc_search_by_projection_rig (two-camera frame: k2 = left keypoints then right keypoints) -> (count, assigned)"""
+    ql = np.ascontiguousarray(ql, PROJQ_DTYPE); qr = np.ascontiguousarray(qr, PROJQ_DTYPE)
+    qdesc = _u8(qdesc); k2 = np.ascontiguousarray(k2, KP_DTYPE); d2 = _u8(d2)
+    a = np.full(len(k2), -1, np.int32) if assigned is None else np.ascontiguousarray(assigned, np.int32).copy()
+    pl = None if l2r is None else np.ascontiguousarray(l2r, np.int32); pr = None if r2l is None else np.ascontiguousarray(r2l, np.int32)
+    L = lib()
+    L.orc_search_by_projection_rig.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                               C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_float, C.c_int, C.c_int]
+    n = L.orc_search_by_projection_rig(mode, _p(ql), _p(qr), _p(qdesc), len(ql), _p(k2), _p(d2), int(n_left), len(k2) - int(n_left),
+                                       _p(pl) if pl is not None else None, _p(pr) if pr is not None else None,
+                                       *[float(b) for b in bounds], _p(a), float(nnratio), int(check_ori), int(max_dist))
+    return n, a
+
+
 def search_by_projection_ex(mode, queries, qdesc, k2, d2, bounds, assigned=None, uright=None, nnratio=0.8, check_ori=True,
                             max_dist=100, inv_sigma2=None, chi2=0.0):
     """-> (count, assigned) for modes 0 / 1, (count, best_idx, best_dist) for mode 3"""

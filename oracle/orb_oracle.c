@@ -987,6 +987,92 @@ int orc_search_by_projection_full(int mode, const OrcProjQuery* q, const uint8_t
     return nmatches;
 }
 
+/* Modes 0 / 1 on a two-camera frame (Frame::Nleft != -1), R/src/ORBmatcher.cc:44-214 (mode 1) and :1970-2186 (mode 0), restated on
+ * flat arrays: keypoints [0, nL) = mvKeys with grid mGrid, [nL, nL + nR) = mvKeysRight with grid mGridRight (Frame.cc:360-391), the
+ * point loop visits the left query of point i, then its right query; one occupancy table over the combined indices. */
+int orc_search_by_projection_rig(int mode, const OrcProjQuery* ql, const OrcProjQuery* qr, const uint8_t* qdesc, int nq,
+                                 const OrcKeyPoint* k2, const uint8_t* d2, int nL, int nR, const int32_t* l2r, const int32_t* r2l,
+                                 float minX, float maxX, float minY, float maxY, int32_t* assigned, float nnratio, int check_ori, int max_dist)
+{
+    int nmatches = 0;
+    const int n2 = nL + nR;
+    OrcGrid* gl = orc_grid_build(k2, nL, minX, maxX, minY, maxY);
+    OrcGrid* gr = orc_grid_build(k2 + nL, nR, minX, maxX, minY, maxY);
+    int32_t* cand = (int32_t*)malloc(sizeof(int32_t) * (n2 > 0 ? n2 : 1));
+    int* histIdx = (int*)malloc(sizeof(int) * (nq > 0 ? 2 * nq : 1));
+    int* histBin = (int*)malloc(sizeof(int) * (nq > 0 ? 2 * nq : 1));
+    int nhist = 0;
+    int sizes[HISTO_LENGTH]; memset(sizes, 0, sizeof(sizes));
+    uint8_t* occ = (uint8_t*)calloc(n2 > 0 ? n2 : 1, 1);
+    for (int i = 0; i < n2; i++) occ[i] = assigned[i] >= 0;
+    for (int i = 0; i < nq; i++) {
+        const int obs = !(ql[i].valid & 2);
+        /* ---- left camera ---- */
+        if (ql[i].valid & 1) {
+            int nc = orc_features_in_area(gl, k2, ql[i].u, ql[i].v, ql[i].r, ql[i].minl, ql[i].maxl, cand, nL);
+            if (nc == 0 && mode == 0) continue;                   /* :2033-2034: an empty left window leaves the point (mode 1 wraps it in an if, :75) */
+            if (nc > 0) {
+                int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+                for (int c = 0; c < nc; c++) {
+                    int i2 = cand[c];
+                    if (occ[i2]) continue;
+                    int dist = orc_hamming256(qdesc + (size_t)i * 32, d2 + (size_t)i2 * 32);
+                    if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestLevel = k2[i2].octave; bestIdx = i2; }
+                    else if (mode == 1 && dist < bestDist2) { bestLevel2 = k2[i2].octave; bestDist2 = dist; }
+                }
+                if (mode == 1) {
+                    if (bestDist <= TH_HIGH) {
+                        if (bestLevel == bestLevel2 && bestDist > nnratio * bestDist2) continue;      /* :116-117: leaves the point, right search included */
+                        assigned[bestIdx] = i; occ[bestIdx] = (uint8_t)obs;
+                        if (l2r && l2r[bestIdx] != -1) { assigned[nL + l2r[bestIdx]] = i; occ[nL + l2r[bestIdx]] = (uint8_t)obs; nmatches++; }   /* :123-127 */
+                        nmatches++;
+                    }
+                } else if (bestDist <= max_dist) {
+                    assigned[bestIdx] = i; if (obs) occ[bestIdx] = 1;
+                    nmatches++;
+                    if (check_ori) { int bin = rot_bin(ql[i].angle, k2[bestIdx].angle); histIdx[nhist] = bestIdx; histBin[nhist] = bin; nhist++; sizes[bin]++; }
+                }
+            }
+        }
+        /* ---- right camera (:144-212 / :2093-2160) ---- */
+        if (qr[i].valid & 1) {
+            int nc = orc_features_in_area(gr, k2 + nL, qr[i].u, qr[i].v, qr[i].r, qr[i].minl, qr[i].maxl, cand, nR);
+            if (nc == 0) continue;
+            int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+            for (int c = 0; c < nc; c++) {
+                int i2 = cand[c];
+                if (occ[nL + i2]) continue;
+                int dist = orc_hamming256(qdesc + (size_t)i * 32, d2 + (size_t)(nL + i2) * 32);
+                if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestLevel = k2[nL + i2].octave; bestIdx = i2; }
+                else if (mode == 1 && dist < bestDist2) { bestLevel2 = k2[nL + i2].octave; bestDist2 = dist; }
+            }
+            if (mode == 1) {
+                if (bestDist <= TH_HIGH) {
+                    if (bestLevel == bestLevel2 && bestDist > nnratio * bestDist2) continue;
+                    if (r2l && r2l[bestIdx] != -1) { assigned[r2l[bestIdx]] = i; occ[r2l[bestIdx]] = (uint8_t)obs; nmatches++; }   /* :191-195 */
+                    assigned[nL + bestIdx] = i; occ[nL + bestIdx] = (uint8_t)obs;
+                    nmatches++;
+                }
+            } else if (bestDist <= max_dist) {
+                assigned[nL + bestIdx] = i; if (obs) occ[nL + bestIdx] = 1;
+                nmatches++;
+                if (check_ori) { int bin = rot_bin(qr[i].angle, k2[nL + bestIdx].angle); histIdx[nhist] = nL + bestIdx; histBin[nhist] = bin; nhist++; sizes[bin]++; }
+            }
+        }
+    }
+    if (mode == 0 && check_ori) {
+        int ind1, ind2, ind3;
+        three_maxima(sizes, HISTO_LENGTH, &ind1, &ind2, &ind3);
+        for (int k = 0; k < nhist; k++) {
+            int b = histBin[k];
+            if (b != ind1 && b != ind2 && b != ind3) { assigned[histIdx[k]] = -2; nmatches--; }
+        }
+    }
+    free(cand); free(histIdx); free(histBin); free(occ);
+    orc_grid_destroy(gl); orc_grid_destroy(gr);
+    return nmatches;
+}
+
 int orc_search_by_projection(int mode, const OrcProjQuery* q, const uint8_t* qdesc, int nq,
                              const OrcKeyPoint* k2, const uint8_t* d2, const float* uright2, int n2,
                              float minX, float maxX, float minY, float maxY,

@@ -122,6 +122,10 @@ int   orc_search_by_projection_full(int mode, const OrcProjQuery* q, const uint8
                                     int32_t* assigned, float nnratio, int check_ori, int max_dist,
                                     const float* inv_sigma2, double chi2, double chi2_stereo, int32_t* best_idx, int32_t* best_dist);
 void  orc_grid_set_query_origin(OrcGrid* g, float qminX, float qminY);
+/* modes 0 / 1 on a two-camera frame (Frame::Nleft != -1; R/src/ORBmatcher.cc:144-213, :2093-2160): see orb_oracle.c */
+int   orc_search_by_projection_rig(int mode, const OrcProjQuery* ql, const OrcProjQuery* qr, const uint8_t* qdesc, int nq,
+                                   const OrcKeyPoint* k2, const uint8_t* d2, int nL, int nR, const int32_t* l2r, const int32_t* r2l,
+                                   float minX, float maxX, float minY, float maxY, int32_t* assigned, float nnratio, int check_ori, int max_dist);
 
 /* Frame::ComputeStereoMatches descriptor part (Frame.cc:785-868): per left keypoint the best right
  * index and distance (dist starts at TH_HIGH=100; idx -1 if none < 100). nrows = level-0 rows. */

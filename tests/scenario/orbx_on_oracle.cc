@@ -106,6 +106,18 @@ extern "C" int orbx_search_by_projection_opts(orbx_matcher* m, int mode, const o
     return ORBX_OK;
 }
 
+extern "C" int orbx_search_by_projection_rig(orbx_matcher* m, int mode, const orbx_proj_query* ql, const orbx_proj_query* qr, const uint8_t* qdesc, int nq,
+                                             const orbx_keypoint* k2, const uint8_t* d2, int n_left, int n_right, const int32_t* l2r, const int32_t* r2l,
+                                             const orbx_proj_options* o, int32_t* assigned, int* nmatches)
+{
+    if (nq > m->p.max_keypoints || n_left + n_right > m->p.max_keypoints) { g_err = "more keypoints than max_keypoints"; return ORBX_E_INVALID; }
+    const int nm = orc_search_by_projection_rig(mode, reinterpret_cast<const OrcProjQuery*>(ql), reinterpret_cast<const OrcProjQuery*>(qr), qdesc, nq,
+                                                reinterpret_cast<const OrcKeyPoint*>(k2), d2, n_left, n_right, l2r, r2l, o->bounds[0], o->bounds[1],
+                                                o->bounds[2], o->bounds[3], assigned, o->nnratio, o->check_ori, o->max_dist);
+    if (nmatches) *nmatches = nm;
+    return ORBX_OK;
+}
+
 extern "C" int orbx_search_by_bow(orbx_matcher*, int mode, const orbx_keypoint* k1, const uint8_t* d1, const uint8_t* valid1, int n1,
                                   const int32_t* fv1_nodes, const int32_t* fv1_start, const int32_t* fv1_feat, int nfv1,
                                   const orbx_keypoint* k2, const uint8_t* d2, const uint8_t* valid2, int n2,

@@ -129,6 +129,62 @@ MapPoint* point_from_feature(World& w, Frame& F, KeyFrame* pKF, int idx, float z
     return p;
 }
 
+// A two-camera frame as the rig constructor leaves it (R/src/Frame.cc:1040-1095), minus IMU and ComputeStereoFishEyeMatches
+// (KannalaBrandt8 triangulation): left and right extraction, the stacked descriptor matrix, both grids, the rig calibration;
+// the stereo partner tables hold mutual nearest descriptors (any consistent pairing serves the matcher).
+Frame* make_rig_frame(World& w, const uint8_t* imgL, const uint8_t* imgR, ORBextractor* exL, ORBextractor* exR, const cv::Mat& Tlr)
+{
+    Frame* F = new Frame();
+    F->mpORBextractorLeft = exL; F->mpORBextractorRight = exR;
+    cv::Mat imL(w.H, w.W, CV_8UC1, (void*)imgL, (size_t)w.W), imR(w.H, w.W, CV_8UC1, (void*)imgR, (size_t)w.W);
+    scenario_before_extract();
+    F->ExtractORB(0, imL, 0, 0);
+    scenario_before_extract();
+    F->ExtractORB(1, imR, 0, 0);
+    scenario_after_extract();
+    F->Nleft = F->mvKeys.size(); F->Nright = F->mvKeysRight.size(); F->N = F->Nleft + F->Nright;
+    F->mnScaleLevels = exL->GetLevels();
+    F->mfScaleFactor = exL->GetScaleFactor();
+    F->mfLogScaleFactor = log(F->mfScaleFactor);
+    F->mvScaleFactors = exL->GetScaleFactors();
+    F->mvInvScaleFactors = exL->GetInverseScaleFactors();
+    F->mvLevelSigma2 = exL->GetScaleSigmaSquares();
+    F->mvInvLevelSigma2 = exL->GetInverseScaleSigmaSquares();
+    F->mK = w.K.clone(); F->mDistCoef = w.dist.clone();
+    F->mbf = w.bf; F->mb = w.bf / w.fx; F->mThDepth = 35.f * F->mb;
+    F->mpCamera = w.camera; F->mpCamera2 = w.camera;
+    F->mTlr = Tlr.clone();
+    F->mRlr = F->mTlr.rowRange(0, 3).colRange(0, 3);
+    F->mtlr = F->mTlr.col(3);
+    cv::Mat Rrl = F->mTlr.rowRange(0, 3).colRange(0, 3).t();
+    cv::Mat trl = Rrl * (-1 * F->mTlr.col(3));
+    cv::hconcat(Rrl, trl, F->mTrl);
+    // stereo partners: mutual nearest neighbours under 40 bits
+    F->mvLeftToRightMatch.assign(F->Nleft, -1); F->mvRightToLeftMatch.assign(F->Nright, -1);
+    vector<int> bestR(F->Nleft, -1), bestL(F->Nright, -1), distL(F->Nright, 256);
+    for (int i = 0; i < F->Nleft; i++) {
+        int bd = 256;
+        for (int j = 0; j < F->Nright; j++) {
+            const int d = ORBmatcher::DescriptorDistance(F->mDescriptors.row(i), F->mDescriptorsRight.row(j));
+            if (d < bd) { bd = d; bestR[i] = j; }
+            if (d < distL[j]) { distL[j] = d; bestL[j] = i; }
+        }
+        if (bd >= 40) bestR[i] = -1;
+    }
+    for (int i = 0; i < F->Nleft; i++)
+        if (bestR[i] >= 0 && bestL[bestR[i]] == i) { F->mvLeftToRightMatch[i] = bestR[i]; F->mvRightToLeftMatch[bestR[i]] = i; }
+    // all descriptors in one matrix (cv::vconcat, :1081)
+    cv::Mat all(F->N, 32, CV_8UC1);
+    for (int i = 0; i < F->Nleft; i++) memcpy(all.ptr(i), F->mDescriptors.ptr(i), 32);
+    for (int i = 0; i < F->Nright; i++) memcpy(all.ptr(F->Nleft + i), F->mDescriptorsRight.ptr(i), 32);
+    F->mDescriptors = all;
+    F->mvpMapPoints.assign(F->N, static_cast<MapPoint*>(NULL));
+    F->mvbOutlier.assign(F->N, false);
+    F->AssignFeaturesToGrid();
+    F->UndistortKeyPoints();
+    return F;
+}
+
 void hash_extraction(const char* name, const Frame& F)
 {
     unsigned long long h = 1469598103934665603ull;
@@ -385,6 +441,53 @@ int main(int argc, char** argv)
                 fprintf(stderr, "device ComputeStereoMatches unavailable: %s\n", e.what());
             }
 #endif
+        }
+
+        // ---- two-camera frames (Frame::Nleft != -1): the rig branches of the two tracking searches (R/src/ORBmatcher.cc:144-213,
+        //      :2093-2160).  Left camera = stream frame t, right camera = stream frame t+1 (the scene shifted by (3, 2) px), so the
+        //      rig calibration is the pose step between two stream frames. ----
+        {
+            cv::Mat Tlr = cv::Mat::eye(3, 4, CV_32F);
+            Tlr.at<float>(0, 3) = -(3.0f * z0 / w.fx + 0.004f); Tlr.at<float>(1, 3) = -(2.0f * z0 / w.fy); Tlr.at<float>(2, 3) = -0.03f;
+            std::unique_ptr<Frame> LastRig(make_rig_frame(w, raw.data(), raw.data() + fsz, &ex, &exRight, Tlr));
+            std::unique_ptr<Frame> CurRig(make_rig_frame(w, raw.data() + fsz * 2, raw.data() + fsz * 3, &ex, &exRight, Tlr));
+            LastRig->SetPose(F[0]->mTcw); CurRig->SetPose(F[2]->mTcw);
+            fprintf(g_out, "rig frames: last %d + %d, current %d + %d, partners %zu\n", LastRig->Nleft, LastRig->Nright, CurRig->Nleft, CurRig->Nright,
+                    (size_t)std::count_if(CurRig->mvLeftToRightMatch.begin(), CurRig->mvLeftToRightMatch.end(), [](int v) { return v >= 0; }));
+            // the last rig frame sees the points of frame 0 with its left camera and those of frame 1 with its right camera
+            // (same images and extractor parameters: the keypoints coincide index by index)
+            if (LastRig->Nleft == F[0]->N && LastRig->Nright == F[1]->N) {
+                for (int i = 0; i < F[0]->N; i++) LastRig->mvpMapPoints[i] = pts0[i];
+                for (int i = 0; i < F[1]->N; i++) LastRig->mvpMapPoints[LastRig->Nleft + i] = pts1[i];
+                for (int i = 0; i < LastRig->N; i += 17) LastRig->mvbOutlier[i] = true;
+            }
+            for (int variant = 0; variant < 3; variant++) {
+                CurRig->mvpMapPoints.assign(CurRig->N, static_cast<MapPoint*>(NULL));
+                if (variant == 2)
+                    for (int i = 0; i < CurRig->N; i += 9) CurRig->mvpMapPoints[i] = pts0[(i * 3) % F[0]->N];
+                ORBmatcher matcher(0.9, variant != 1);
+                const Frame& Last = variant == 1 ? *F[0] : *LastRig;          // a one-camera last frame is legal too (:2018-2019)
+                const int n = matcher.SearchByProjection(*CurRig, Last, variant == 1 ? 7.f : 15.f, variant == 1);
+                fprintf(g_out, "SearchByProjection(CurRig,Last)[%d] n=%d\n", variant, n);
+                dump_points("  mvpMapPoints", CurRig->mvpMapPoints);
+            }
+            {
+                CurRig->mvpMapPoints.assign(CurRig->N, static_cast<MapPoint*>(NULL));
+                for (int i = 0; i < CurRig->N; i += 11) CurRig->mvpMapPoints[i] = pts1[(i / 11 * 4) % F[1]->N];
+                vector<MapPoint*> local;
+                for (size_t i = 0; i < pts0.size(); i++) if (pts0[i]) local.push_back(pts0[i]);
+                for (size_t i = 0; i < pts1.size(); i++) if (pts1[i]) local.push_back(pts1[i]);
+                int nl = 0, nr = 0;
+                for (size_t i = 0; i < local.size(); i++) { CurRig->isInFrustum(local[i], 0.5); nl += local[i]->mbTrackInView; nr += local[i]->mbTrackInViewR; }
+                for (int th = 1; th <= 5; th += 2) {
+                    vector<MapPoint*> keep = CurRig->mvpMapPoints;
+                    ORBmatcher matcher(0.8, true);
+                    const int n = matcher.SearchByProjection(*CurRig, local, (float)th, th == 5, 4.1f);
+                    fprintf(g_out, "SearchByProjection(Rig,MapPoints) th=%d visible=%d/%d n=%d\n", th, nl, nr, n);
+                    dump_points("  mvpMapPoints", CurRig->mvpMapPoints);
+                    CurRig->mvpMapPoints = keep;
+                }
+            }
         }
 
         // ---- DescriptorDistance ----

@@ -123,6 +123,48 @@ def test_search_by_projection_parity(frames, mode):
     m.close()
 
 
+@pytest.mark.parametrize("mode", [0, 1])
+def test_search_by_projection_two_camera_parity(mode):
+    """Two-camera frame (Frame::Nleft != -1; R/src/ORBmatcher.cc:144-213, :2093-2160): left + right halves with their own grids, the
+    queries of a point interleaved over one occupancy table, stereo partners (mode 1), 0-observation owners, one rotation histogram
+    (mode 0).  Oracle: orc_search_by_projection_rig, a literal restatement of the reference's loops."""
+    rng = np.random.default_rng(31 + mode)
+    e = O.Extractor(800, 1.2, 8, 20, 7)
+    L, R = synth.stereo_pair(752, 480, seed=5, disparity=9)
+    _, kl, dl = e(L, (0, 0)); _, kr, dr = e(R, (0, 0))
+    nL, nR = len(kl), len(kr)
+    k2 = np.concatenate([kl, kr]); d2 = np.concatenate([dl, dr])
+    # map points = the left keypoints of a slightly shifted view; descriptors a few bits away
+    nq = nL
+    qd = dl.copy()
+    for i in range(nq):
+        for b in rng.integers(0, 256, int(rng.integers(0, 20))):
+            qd[i, b >> 3] ^= np.uint8(1 << (b & 7))
+    ql = make_queries(kl, rng, 15.0 if mode == 0 else 12.0, e.scale)
+    qr = make_queries(kl, rng, 15.0 if mode == 0 else 12.0, e.scale)
+    qr["u"] -= 9                                               # the right camera sees the point 9 px to the left
+    if mode == 1:
+        for q in (ql, qr):
+            q["minl"] = kl["octave"] - 1; q["maxl"] = kl["octave"]
+    noobs = rng.random(nq) < 0.3                               # temporal points without observations: they do not occupy what they take
+    ql["valid"] |= np.where(noobs, 2, 0).astype(np.int32); qr["valid"] |= np.where(noobs, 2, 0).astype(np.int32)
+    # stereo partners from a brute-force match of the two halves (as Frame::ComputeStereoFishEyeMatches fills them)
+    bi, bd = O.bf_knn2(dl, dr)
+    l2r = np.where(bd[:, 0] < 40, bi[:, 0], -1).astype(np.int32)
+    r2l = np.full(nR, -1, np.int32)
+    for i in np.nonzero(l2r >= 0)[0]:
+        r2l[l2r[i]] = i
+    pre = np.full(nL + nR, -1, np.int32); pre[::11] = 4242
+    m = orbx.ORBmatcher(0.8, True, max_keypoints=4096, max_batch=2)
+    for partners in ((l2r, r2l), (None, None)):
+        n, a = m.SearchByProjectionRig(mode, ql, qr, qd, k2, d2, nL, (0, 752, 0, 480), pre, partners[0], partners[1], 100)
+        rn, ra = O.search_by_projection_rig(mode, ql, qr, qd, k2, d2, nL, (0, 752, 0, 480), pre, partners[0], partners[1], 0.8, True, 100)
+        assert n == rn and n > 200
+        np.testing.assert_array_equal(a, ra)
+        assert (a[nL:] >= 0).sum() > 50 and (a[:nL] >= 0).sum() > 50      # both cameras took part
+    m.close()
+
+
 def test_stereo_band_match_parity():
     L, R = synth.stereo_pair(752, 480, seed=2, disparity=14)
     e = O.Extractor(1200, 1.2, 8, 20, 7)
