@@ -115,6 +115,7 @@ struct Queries {
 struct Target {                                    // the searched frame / keyframe
     const std::vector<cv::KeyPoint>* keys;
     const cv::Mat* desc;
+    int row0 = 0;                                  // first descriptor row of `keys` (NLeft for the right camera of a two-camera keyframe)
     const float* uright;                           // may be NULL
     float bounds[4];
     float qorigin[2];
@@ -160,7 +161,7 @@ int run_search(const SearchSpec& spec, const Queries& Q, const Target& T, std::v
     if (nq == 0 || n2 == 0) return 0;
     if (n2 > 24000) fail("more than 24000 keypoints in one frame");
     std::vector<uint8_t> tmp;
-    const uint8_t* d2 = rows32(*T.desc, tmp);
+    const uint8_t* d2 = rows32(*T.desc, tmp) + (size_t)T.row0 * 32;
     orbx_proj_options o;
     std::memset(&o, 0, sizeof(o));
     for (int i = 0; i < 4; i++) o.bounds[i] = T.bounds[i];
@@ -983,12 +984,20 @@ int ORBmatcher::SearchForTriangulation(KeyFrame *pKF1, KeyFrame *pKF2, cv::Mat F
 // returns all of them; the map update that follows is sequential and stays here, re-checking what earlier fusions changed.
 int ORBmatcher::Fuse(KeyFrame *pKF, const vector<MapPoint *> &vpMapPoints, const float th, const bool bRight)
 {
-    if (bRight || pKF->NLeft != -1) unsupported("Fuse on a two-camera keyframe");
-    cv::Mat Rcw = pKF->GetRotation();
-    cv::Mat tcw = pKF->GetTranslation();
-    cv::Mat Ow = pKF->GetCameraCenter();
-    GeometricCamera* pCamera = pKF->mpCamera;
+    // :1400-1413: the right camera of a two-camera keyframe has its own pose, model, keypoints (mvKeysRight) and grid (mGridRight)
+    cv::Mat Rcw = bRight ? pKF->GetRightRotation() : pKF->GetRotation();
+    cv::Mat tcw = bRight ? pKF->GetRightTranslation() : pKF->GetTranslation();
+    cv::Mat Ow = bRight ? pKF->GetRightCameraCenter() : pKF->GetCameraCenter();
+    GeometricCamera* pCamera = bRight ? pKF->mpCamera2 : pKF->mpCamera;
     const float &bf = pKF->mbf;
+    Target target = target_of(pKF, true);
+    int first = 0;                                                  // keyframe index of the searched camera's first keypoint (:1555)
+    if (pKF->NLeft != -1) {
+        // :1520-1522; mvuRight of a two-camera frame is all -1 (Frame.cc:1123): every candidate takes the 2-dof gate
+        target.keys = bRight ? &pKF->mvKeysRight : &pKF->mvKeys;
+        target.uright = NULL;
+        if (bRight) { target.row0 = pKF->NLeft; first = pKF->NLeft; }
+    } else if (bRight) unsupported("Fuse(bRight) on a one-camera keyframe");
 
     Queries Q;
     const int nMPs = vpMapPoints.size();
@@ -1019,13 +1028,14 @@ int ORBmatcher::Fuse(KeyFrame *pKF, const vector<MapPoint *> &vpMapPoints, const
     SearchSpec spec(3, mfNNratio, false, 256);
     spec.inv_sigma2 = &pKF->mvInvLevelSigma2; spec.chi2_mono = 5.99; spec.chi2_stereo = 7.8;
     std::vector<int32_t> none, bestIdx, bestDist;
-    run_search(spec, Q, target_of(pKF, true), none, &bestIdx, &bestDist);
+    run_search(spec, Q, target, none, &bestIdx, &bestDist);
 
     int nFused=0;
     for (int q = 0; q < Q.size(); q++) {
         MapPoint* pMP = vpMapPoints[Q.tag[q]];
         if (pMP->isBad() || pMP->IsInKeyFrame(pKF)) continue;          // an earlier fusion of this call may have changed either
         if (bestIdx[q] < 0 || bestDist[q] > TH_LOW) continue;
+        bestIdx[q] += first;
         MapPoint* pMPinKF = pKF->GetMapPoint(bestIdx[q]);
         if (pMPinKF) {
             if (!pMPinKF->isBad()) {

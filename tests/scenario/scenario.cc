@@ -178,6 +178,7 @@ Frame* make_rig_frame(World& w, const uint8_t* imgL, const uint8_t* imgR, ORBext
     for (int i = 0; i < F->Nleft; i++) memcpy(all.ptr(i), F->mDescriptors.ptr(i), 32);
     for (int i = 0; i < F->Nright; i++) memcpy(all.ptr(F->Nleft + i), F->mDescriptorsRight.ptr(i), 32);
     F->mDescriptors = all;
+    F->mvuRight.assign(F->Nleft, -1.f); F->mvDepth.assign(F->Nleft, -1.f);      // ComputeStereoFishEyeMatches, :1123-1124
     F->mvpMapPoints.assign(F->N, static_cast<MapPoint*>(NULL));
     F->mvbOutlier.assign(F->N, false);
     F->AssignFeaturesToGrid();
@@ -487,6 +488,33 @@ int main(int argc, char** argv)
                     dump_points("  mvpMapPoints", CurRig->mvpMapPoints);
                     CurRig->mvpMapPoints = keep;
                 }
+            }
+
+            // ---- Fuse on a two-camera keyframe, left camera then right camera (LocalMapping::SearchInNeighbors, :1395-1560) ----
+            {
+                // (the reference reads mvuRight[idx] with the RIGHT camera's index although the vector has Nleft entries, :1527: the
+                // keyframe used here has Nright <= Nleft, so that the read stays inside the vector)
+                const bool last_ok = LastRig->Nright <= LastRig->Nleft, cur_ok = CurRig->Nright <= CurRig->Nleft;
+                Frame& Rig = (last_ok || !cur_ok) ? *LastRig : *CurRig;
+                Rig.SetPose(&Rig == LastRig.get() ? F[0]->mTcw : F[2]->mTcw);
+                Rig.mvpMapPoints.assign(Rig.N, static_cast<MapPoint*>(NULL));
+                for (int i = 0; i < Rig.N; i += 7) Rig.mvpMapPoints[i] = pts1[(i / 7 * 4) % F[1]->N];
+                KeyFrame KFR(Rig);
+                vector<MapPoint*> all0, all1;
+                for (size_t i = 0; i < pts0.size(); i++) all0.push_back(pts0[i]);
+                for (size_t i = 0; i < pts1.size(); i++) all1.push_back(pts1[i]);
+                ORBmatcher matcher(0.8, true);
+                int n = matcher.Fuse(&KFR, all0, 3.f, false);
+                fprintf(g_out, "Fuse(RigKF,left) n=%d\n", n);
+                dump_points("  KFR points", KFR.GetMapPointMatches());
+                if (last_ok || cur_ok) {
+                    n = matcher.Fuse(&KFR, all1, 3.f, true);
+                    fprintf(g_out, "Fuse(RigKF,right) n=%d\n", n);
+                    dump_points("  KFR points", KFR.GetMapPointMatches());
+                }
+                vector<int> bad, obs;
+                for (size_t i = 0; i < w.points.size(); i++) { bad.push_back(w.points[i]->isBad() ? 1 : 0); obs.push_back(w.points[i]->Observations()); }
+                dump_ints("  bad", bad); dump_ints("  observations", obs);
             }
         }
 
