@@ -689,11 +689,38 @@ int ORBmatcher::SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const std::vector
 // R/src/ORBmatcher.cc:269-471  relocalisation / loop detection: keyframe MapPoints against the features of a frame, node by node
 int ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame &F, vector<MapPoint*> &vpMapPointMatches)
 {
-    if (F.Nleft != -1 || pKF->NLeft != -1) unsupported("SearchByBoW on a two-camera frame");
     const vector<MapPoint*> vpMapPointsKF = pKF->GetMapPointMatches();
     vpMapPointMatches = vector<MapPoint*>(F.N,static_cast<MapPoint*>(NULL));
     const int n1 = pKF->N, n2 = F.N;
     if (n1 == 0 || n2 == 0) return 0;
+    if (F.Nleft != -1) {
+        // :344-431: a best / second pair per camera of the frame; the keyframe's keypoint is taken from the camera it belongs to
+        // (:379-382), the frame's from mvKeys / mvKeysRight (:386-389, :416-419)
+        if (pKF->NLeft == -1 && pKF->mpCamera2) unsupported("SearchByBoW: a one-camera keyframe with a second camera model");
+        std::vector<cv::KeyPoint> k1v(n1), k2v(F.mvKeys.begin(), F.mvKeys.begin() + F.Nleft);
+        for (int i = 0; i < n1; i++)
+            k1v[i] = (!pKF->mpCamera2) ? pKF->mvKeysUn[i] : (i >= pKF->NLeft) ? pKF->mvKeysRight[i - pKF->NLeft] : pKF->mvKeys[i];
+        k2v.insert(k2v.end(), F.mvKeysRight.begin(), F.mvKeysRight.begin() + F.Nright);
+        std::vector<uint8_t> valid1(n1, 0);
+        for (int i = 0; i < n1 && i < (int)vpMapPointsKF.size(); i++)
+            valid1[i] = (vpMapPointsKF[i] && !vpMapPointsKF[i]->isBad()) ? 1 : 0;
+        std::vector<int32_t> n1v, s1v, f1v, n2v, s2v, f2v, ml(n1, -1), mr(n1, -1);
+        feature_vector_csr(pKF->mFeatVec, n1v, s1v, f1v);
+        feature_vector_csr(F.mFeatVec, n2v, s2v, f2v);
+        std::vector<uint8_t> t1, t2;
+        int nmatches = 0;
+        Context& c = context(n1 > n2 ? n1 : n2);
+        if (orbx_search_by_bow_rig(c.m, kp_ptr(k1v), rows32(pKF->mDescriptors, t1), valid1.data(), n1, n1v.data(), s1v.data(), f1v.data(),
+                                   (int)n1v.size(), kp_ptr(k2v), rows32(F.mDescriptors, t2), n2, F.Nleft, n2v.data(), s2v.data(), f2v.data(),
+                                   (int)n2v.size(), mfNNratio, mbCheckOrientation ? 1 : 0, ml.data(), mr.data(), &nmatches) != ORBX_OK)
+            fail("orbx_search_by_bow_rig");
+        for (int i1 = 0; i1 < n1; i1++) {
+            if (ml[i1] >= 0) vpMapPointMatches[ml[i1]] = vpMapPointsKF[i1];
+            if (mr[i1] >= 0) vpMapPointMatches[mr[i1]] = vpMapPointsKF[i1];
+        }
+        return nmatches;
+    }
+    if (pKF->NLeft != -1) unsupported("SearchByBoW(KeyFrame*, Frame&) from a two-camera keyframe into a one-camera frame");
     std::vector<uint8_t> valid1(n1, 0);
     for (int i = 0; i < n1 && i < (int)vpMapPointsKF.size(); i++)
         valid1[i] = (vpMapPointsKF[i] && !vpMapPointsKF[i]->isBad()) ? 1 : 0;          // :301-307

@@ -425,6 +425,18 @@ int  orbx_search_by_projection_rig(orbx_matcher* m, int mode, const orbx_proj_qu
                                    const int32_t* l2r, const int32_t* r2l, const orbx_proj_options* opt, int32_t* assigned,
                                    int* nmatches);
 
+/* SearchByBoW(KeyFrame*, Frame&) when the frame has two cameras (Frame::Nleft != -1; R/src/ORBmatcher.cc:344-431): features
+ * [0, n2_left) of set 2 are the left camera's (Frame::mvKeys), the rest the right camera's (mvKeysRight).  Per keyframe feature the
+ * reference keeps a best / second pair per camera: the left match needs best <= TH_LOW and the ratio test; the right match needs
+ * bestLeft <= TH_LOW (it sits inside that branch) and bestRight <= TH_LOW (its ratio test is disabled by `|| true`, :402).  Both
+ * claim their feature and share the rotation histogram.  matches12_left / matches12_right [n1]; *nmatches counts both. */
+int  orbx_search_by_bow_rig(orbx_matcher* m,
+                            const orbx_keypoint* k1, const uint8_t* d1, const uint8_t* valid1, int n1,
+                            const int32_t* fv1_nodes, const int32_t* fv1_start, const int32_t* fv1_feat, int nfv1,
+                            const orbx_keypoint* k2, const uint8_t* d2, int n2, int n2_left,
+                            const int32_t* fv2_nodes, const int32_t* fv2_start, const int32_t* fv2_feat, int nfv2,
+                            float nnratio, int check_ori, int32_t* matches12_left, int32_t* matches12_right, int* nmatches);
+
 /* ---- server keyframe database on one GPU (SURVEY 8f row 3 -> 8e) ----
  * A keyframe reaches the server as a KF.msg (R/msg/KF.msg:24-29): `CvKeyPoint[] mvKeysUn` = N records of 15 packed bytes
  * (R/msg/CvKeyPoint.msg; Converter::toCvKeyPointMsg, R/src/Converter.cc:218-230) and `Descriptor[] mDescriptors` = N x

@@ -124,6 +124,79 @@ __global__ void __launch_bounds__(256) k_bow_finish(BowArgs A, int32_t* nmatches
     if (threadIdx.x == 0) *nmatches = A.hist[ORBX_HISTO_LENGTH] - removed;
 }
 
+// ---- SearchByBoW(KeyFrame*, Frame&) on a two-camera frame (Frame::Nleft != -1, R/src/ORBmatcher.cc:344-431) ----
+// The frame's features [0, n2_left) are the left camera's, the rest the right camera's.  Per keyframe feature the reference keeps a
+// (best, second) pair for each camera; the left match needs best <= TH_LOW and the ratio test, the right match needs
+// bestLeft <= TH_LOW (it sits inside that branch) and bestRight <= TH_LOW (its ratio test is disabled by `|| true`, :402).
+// Both claim their feature and enter the one rotation histogram.
+__global__ void __launch_bounds__(256) k_bow_match_rig(BowArgs A, int n2_left, int32_t* matches12r, uint8_t* bin_of_r)
+{
+    const int lane = threadIdx.x & 31;
+    const int w = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (w >= A.nfv1) return;
+    const int node = A.fv1_nodes[w];
+    int lo = 0, hi = A.nfv2;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (A.fv2_nodes[mid] < node) lo = mid + 1; else hi = mid; }
+    if (lo >= A.nfv2 || A.fv2_nodes[lo] != node) return;
+    const int a0 = A.fv1_start[w], a1 = A.fv1_start[w + 1], b0 = A.fv2_start[lo], b1 = A.fv2_start[lo + 1];
+    for (int ia = a0; ia < a1; ia++) {
+        const int i1 = A.fv1_feat[ia];
+        if (!A.valid1[i1]) continue;
+        const uint4 q0 = reinterpret_cast<const uint4*>(A.d1)[2 * i1], q1 = reinterpret_cast<const uint4*>(A.d1)[2 * i1 + 1];
+        int d0 = 0x7fffffff, r0 = 0x7fffffff, d1 = 0x7fffffff, r1 = 0x7fffffff;          // left camera
+        int f0 = 0x7fffffff, s0 = 0x7fffffff, f1 = 0x7fffffff, s1 = 0x7fffffff;          // right camera
+        uint32_t e0 = 0, e1 = 0, g0 = 0, g1 = 0;
+        for (int ib = b0 + lane; ib < b1; ib += 32) {
+            const int i2 = A.fv2_feat[ib];
+            if (A.claimed2[i2]) continue;
+            const int d = hamming256(q0, q1, reinterpret_cast<const uint4*>(A.d2)[2 * i2], reinterpret_cast<const uint4*>(A.d2)[2 * i2 + 1]);
+            const int r = ib - b0;
+            if (i2 < n2_left) {
+                if (d < d0) { d1 = d0; r1 = r0; e1 = e0; d0 = d; r0 = r; e0 = (uint32_t)i2; }
+                else if (d < d1) { d1 = d; r1 = r; e1 = (uint32_t)i2; }
+            } else {
+                if (d < f0) { f1 = f0; s1 = s0; g1 = g0; f0 = d; s0 = r; g0 = (uint32_t)i2; }
+                else if (d < f1) { f1 = d; s1 = r; g1 = (uint32_t)i2; }
+            }
+        }
+        warp_top2(d0, r0, e0, d1, e1, r1);
+        warp_top2(f0, s0, g0, f1, g1, s1);
+        const int best1 = d0 == 0x7fffffff ? 256 : d0, best2 = d1 == 0x7fffffff ? 256 : d1, best1R = f0 == 0x7fffffff ? 256 : f0;
+        if (best1 <= ORBX_TH_LOW && lane == 0) {
+            if ((float)best1 < __fmul_rn(A.nnratio, (float)best2)) {
+                A.matches12[i1] = (int32_t)e0; A.claimed2[e0] = 1;
+                if (A.check_ori) { const int bin = rot_bin(A.k1[i1].angle, A.k2[e0].angle); A.bin_of[i1] = (uint8_t)bin; atomicAdd(&A.hist[bin], 1); }
+                atomicAdd(&A.hist[ORBX_HISTO_LENGTH], 1);
+            }
+            if (best1R <= ORBX_TH_LOW) {
+                matches12r[i1] = (int32_t)g0; A.claimed2[g0] = 1;
+                if (A.check_ori) { const int bin = rot_bin(A.k1[i1].angle, A.k2[g0].angle); bin_of_r[i1] = (uint8_t)bin; atomicAdd(&A.hist[bin], 1); }
+                atomicAdd(&A.hist[ORBX_HISTO_LENGTH], 1);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(256) k_bow_finish_rig(BowArgs A, int32_t* matches12r, const uint8_t* bin_of_r, int32_t* nmatches)
+{
+    __shared__ int removed;
+    if (threadIdx.x == 0) removed = 0;
+    __syncthreads();
+    if (A.check_ori) {
+        int ind1, ind2, ind3;
+        three_maxima(A.hist, ind1, ind2, ind3);
+        int local = 0;
+        for (int i = threadIdx.x; i < A.n1; i += blockDim.x) {
+            if (A.matches12[i] >= 0) { const int bin = A.bin_of[i]; if (bin != ind1 && bin != ind2 && bin != ind3) { A.matches12[i] = -1; local++; } }
+            if (matches12r[i] >= 0) { const int bin = bin_of_r[i]; if (bin != ind1 && bin != ind2 && bin != ind3) { matches12r[i] = -1; local++; } }
+        }
+        if (local) atomicAdd(&removed, local);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *nmatches = A.hist[ORBX_HISTO_LENGTH] - removed;
+}
+
 // ---- ORBmatcher::SearchForTriangulation (R/src/ORBmatcher.cc:961-1202), pinhole, no second camera ----
 // Same node-by-node structure as SearchByBoW, but the queries of this fork do not interact (vbMatched2 is never set), so a
 // warp handles one (node, keyframe-1 feature) at a time without claims: lanes score the node's free keyframe-2 features
@@ -547,6 +620,40 @@ extern "C" int orbx_search_by_bow(orbx_matcher* m, int mode,
     A.mode = mode; A.nnratio = nnratio; A.check_ori = check_ori;
     k_bow_match<<<(nfv1 + 7) / 8, 256, 0, m->stream>>>(A); ORBX_COUNT_LAUNCH(1);
     return bow_finish(m, A, matches12, nmatches);
+}
+
+// SearchByBoW(KeyFrame*, Frame&) on a two-camera frame (see include/orbx.h).  Host pointers, synchronous.
+extern "C" int orbx_search_by_bow_rig(orbx_matcher* m,
+                                      const orbx_keypoint* k1, const uint8_t* d1, const uint8_t* valid1, int n1,
+                                      const int32_t* fv1_nodes, const int32_t* fv1_start, const int32_t* fv1_feat, int nfv1,
+                                      const orbx_keypoint* k2, const uint8_t* d2, int n2, int n2_left,
+                                      const int32_t* fv2_nodes, const int32_t* fv2_start, const int32_t* fv2_feat, int nfv2,
+                                      float nnratio, int check_ori, int32_t* matches12_left, int32_t* matches12_right, int* nmatches)
+{
+    if (!m || n1 < 0 || n2 < 0 || n2 > 65535 || n2_left < 0 || n2_left > n2 || nfv1 < 0 || nfv2 < 0 || !matches12_left || !matches12_right) return ORBX_E_INVALID;
+    if (nmatches) *nmatches = 0;
+    for (int i = 0; i < n1; i++) { matches12_left[i] = -1; matches12_right[i] = -1; }
+    if (n1 == 0 || n2 == 0 || nfv1 == 0 || nfv2 == 0) return ORBX_OK;
+    BowArgs A;
+    uint8_t* dx = nullptr;
+    const size_t mbytes = (sizeof(int32_t) * (size_t)n1 + 255) & ~(size_t)255;
+    int rc = bow_stage(m, "orbx_search_by_bow_rig", k1, d1, valid1, n1, fv1_nodes, fv1_start, fv1_feat, nfv1,
+                       k2, d2, nullptr, n2, fv2_nodes, fv2_start, fv2_feat, nfv2, mbytes + n1, &A, &dx);
+    if (rc) return rc;
+    cudaStream_t s = m->stream;
+    int32_t* d_m12r = reinterpret_cast<int32_t*>(dx); uint8_t* d_binr = dx + mbytes;
+    CKM(cudaMemsetAsync(d_m12r, 0xFF, sizeof(int32_t) * n1, s));
+    A.mode = 0; A.nnratio = nnratio; A.check_ori = check_ori;
+    k_bow_match_rig<<<(nfv1 + 7) / 8, 256, 0, s>>>(A, n2_left, d_m12r, d_binr); ORBX_COUNT_LAUNCH(1);
+    k_bow_finish_rig<<<1, 256, 0, s>>>(A, d_m12r, d_binr, A.hist + ORBX_HISTO_LENGTH + 1); ORBX_COUNT_LAUNCH(1);
+    CKM(cudaGetLastError());
+    int nm = 0;
+    CKM(cudaMemcpyAsync(matches12_left, A.matches12, sizeof(int32_t) * n1, cudaMemcpyDeviceToHost, s));
+    CKM(cudaMemcpyAsync(matches12_right, d_m12r, sizeof(int32_t) * n1, cudaMemcpyDeviceToHost, s));
+    CKM(cudaMemcpyAsync(&nm, A.hist + ORBX_HISTO_LENGTH + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    CKM(cudaStreamSynchronize(s));
+    if (nmatches) *nmatches = nm;
+    return ORBX_OK;
 }
 
 // ORBmatcher::SearchForTriangulation on flat arrays (see include/orbx.h).  Host pointers, synchronous.

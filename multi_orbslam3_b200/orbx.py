@@ -42,7 +42,7 @@ EXPORTS = [
     "orbx_fast_segment_plan", "orbx_matcher_set_slot_keypoints", "orbx_matcher_set_camera", "orbx_matcher_undistorted_device", "orbx_search_by_projection_ex", "orbx_search_by_projection_opts", "orbx_match_candidates", "orbx_search_by_bow", "orbx_search_for_triangulation", "orbx_distinctive_descriptors", "orbx_undistort_keypoints", "orbx_undistort_slots_device",
     "orbx_keypoints_to_msg", "orbx_keypoints_from_msg", "orbx_slot_keypoints_to_msg_device", "orbx_vocab_create", "orbx_vocab_destroy", "orbx_vocab_words", "orbx_vocab_word_weights",
     "orbx_bow_transform", "orbx_bow_transform_slots_device", "orbx_popc_peak",
-    "orbx_search_by_projection_rig",
+    "orbx_search_by_projection_rig", "orbx_search_by_bow_rig",
     "orbx_kfdb_create", "orbx_kfdb_destroy", "orbx_kfdb_ingest_msg", "orbx_kfdb_ingest_slot_device", "orbx_kfdb_size", "orbx_kfdb_device",
     "orbx_kfdb_sync", "orbx_kfdb_locate", "orbx_kfdb_knn2",
 ]
@@ -139,6 +139,7 @@ def lib():
         L.orbx_search_for_triangulation.argtypes = [vp, vp, vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, vp, vp, i32, vp, vp, vp, i32,
                                                     vp, f32, f32, vp, vp, i32, i32, i32, i32, vp, vp]
         L.orbx_search_by_projection_rig.argtypes = [vp, i32, vp, vp, vp, i32, vp, vp, i32, i32, vp, vp, vp, vp, vp]
+        L.orbx_search_by_bow_rig.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, i32, i32, vp, vp, vp, i32, f32, i32, vp, vp, vp]
         L.orbx_kfdb_create.argtypes = [i32, C.c_longlong, i32, C.POINTER(vp)]
         L.orbx_kfdb_destroy.argtypes = [vp]; L.orbx_kfdb_destroy.restype = None
         L.orbx_kfdb_ingest_msg.argtypes = [vp, C.c_int64, vp, vp, i32, vp]

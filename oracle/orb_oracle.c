@@ -1395,6 +1395,71 @@ int orc_search_by_bow(int mode, const OrcKeyPoint* k1, const uint8_t* d1, const 
     return nmatches;
 }
 
+/* SearchByBoW(KeyFrame*, Frame&) on a two-camera frame (Frame::Nleft != -1), R/src/ORBmatcher.cc:344-431 restated: features
+ * [0, n2_left) of the frame are the left camera's.  matches12l / matches12r [n1]: the left / right feature taken by KF feature i1. */
+int orc_search_by_bow_rig(const OrcKeyPoint* k1, const uint8_t* d1, const uint8_t* valid1, int n1,
+                          const int32_t* fv1_nodes, const int32_t* fv1_start, const int32_t* fv1_feat, int nfv1,
+                          const OrcKeyPoint* k2, const uint8_t* d2, int n2, int n2_left,
+                          const int32_t* fv2_nodes, const int32_t* fv2_start, const int32_t* fv2_feat, int nfv2,
+                          float nnratio, int check_ori, int32_t* matches12l, int32_t* matches12r)
+{
+    int nmatches = 0;
+    uint8_t* matched2 = (uint8_t*)calloc(n2 > 0 ? n2 : 1, 1);
+    int* histIdx = (int*)malloc(sizeof(int) * (n1 > 0 ? 2 * n1 : 1));     /* i1, or n1 + i1 for the right match */
+    int* histBin = (int*)malloc(sizeof(int) * (n1 > 0 ? 2 * n1 : 1));
+    int hist[HISTO_LENGTH]; int nh = 0;
+    for (int i = 0; i < HISTO_LENGTH; i++) hist[i] = 0;
+    for (int i = 0; i < n1; i++) { matches12l[i] = -1; matches12r[i] = -1; }
+    int a = 0, b = 0;
+    while (a < nfv1 && b < nfv2) {
+        if (fv1_nodes[a] == fv2_nodes[b]) {
+            for (int ia = fv1_start[a]; ia < fv1_start[a + 1]; ia++) {
+                const int i1 = fv1_feat[ia];
+                if (!valid1[i1]) continue;
+                int bestDist1 = 256, bestIdxF = -1, bestDist2 = 256, bestDist1R = 256, bestIdxFR = -1, bestDist2R = 256;
+                for (int ib = fv2_start[b]; ib < fv2_start[b + 1]; ib++) {
+                    const int i2 = fv2_feat[ib];
+                    if (matched2[i2]) continue;
+                    const int dist = orc_hamming256(d1 + (size_t)i1 * 32, d2 + (size_t)i2 * 32);
+                    if (i2 < n2_left && dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdxF = i2; }
+                    else if (i2 < n2_left && dist < bestDist2) bestDist2 = dist;
+                    if (i2 >= n2_left && dist < bestDist1R) { bestDist2R = bestDist1R; bestDist1R = dist; bestIdxFR = i2; }
+                    else if (i2 >= n2_left && dist < bestDist2R) bestDist2R = dist;
+                }
+                if (bestDist1 <= TH_LOW) {
+                    if ((float)bestDist1 < nnratio * (float)bestDist2) {
+                        matches12l[i1] = bestIdxF; matched2[bestIdxF] = 1;
+                        if (check_ori) { const int bin = rot_bin(k1[i1].angle, k2[bestIdxF].angle); histIdx[nh] = i1; histBin[nh] = bin; nh++; hist[bin]++; }
+                        nmatches++;
+                    }
+                    if (bestDist1R <= TH_LOW) {                                  /* `|| true`: no ratio test on this side (:402) */
+                        matches12r[i1] = bestIdxFR; matched2[bestIdxFR] = 1;
+                        if (check_ori) { const int bin = rot_bin(k1[i1].angle, k2[bestIdxFR].angle); histIdx[nh] = n1 + i1; histBin[nh] = bin; nh++; hist[bin]++; }
+                        nmatches++;
+                    }
+                }
+                (void)bestDist2R;
+            }
+            a++; b++;
+        } else if (fv1_nodes[a] < fv2_nodes[b]) {
+            while (a < nfv1 && fv1_nodes[a] < fv2_nodes[b]) a++;
+        } else {
+            while (b < nfv2 && fv2_nodes[b] < fv1_nodes[a]) b++;
+        }
+    }
+    if (check_ori) {
+        int ind1, ind2, ind3;
+        three_maxima(hist, HISTO_LENGTH, &ind1, &ind2, &ind3);
+        for (int j = 0; j < nh; j++)
+            if (histBin[j] != ind1 && histBin[j] != ind2 && histBin[j] != ind3) {
+                if (histIdx[j] < n1) matches12l[histIdx[j]] = -1; else matches12r[histIdx[j] - n1] = -1;
+                nmatches--;
+            }
+    }
+    free(matched2); free(histIdx); free(histBin);
+    return nmatches;
+}
+
 /* MapPoint::ComputeDistinctiveDescriptors, R/src/MapPoint.cc:487-518 */
 static int orc_int_cmp(const void* a, const void* b) { const int x = *(const int*)a, y = *(const int*)b; return x < y ? -1 : (x > y); }
 void orc_distinctive_descriptors(const uint8_t* desc, const int32_t* offsets, int npoints, int32_t* best)

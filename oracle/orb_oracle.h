@@ -199,6 +199,12 @@ int   orc_search_for_triangulation(const OrcKeyPoint* k1, const uint8_t* d1, con
                                    const float* F12, float ep_x, float ep_y, const float* scale_factors2, const float* level_sigma2_2,
                                    int only_stereo, int coarse, int check_ori, int32_t* matches12);
 
+/* SearchByBoW(KeyFrame*, Frame&) on a two-camera frame (R/src/ORBmatcher.cc:344-431): see orb_oracle.c */
+int   orc_search_by_bow_rig(const OrcKeyPoint* k1, const uint8_t* d1, const uint8_t* valid1, int n1,
+                            const int32_t* fv1_nodes, const int32_t* fv1_start, const int32_t* fv1_feat, int nfv1,
+                            const OrcKeyPoint* k2, const uint8_t* d2, int n2, int n2_left,
+                            const int32_t* fv2_nodes, const int32_t* fv2_start, const int32_t* fv2_feat, int nfv2,
+                            float nnratio, int check_ori, int32_t* matches12l, int32_t* matches12r);
 /* MapPoint::ComputeDistinctiveDescriptors (R/src/MapPoint.cc:448-524) for a batch of map points: the observed
  * descriptors of point p are rows offsets[p] .. offsets[p+1] of desc; best[p] = index inside that run of the descriptor
  * with the least median distance to the others (median = sorted row [(int)(0.5 * (N - 1))], the row includes the 0 on

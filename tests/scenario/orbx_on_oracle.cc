@@ -131,6 +131,19 @@ extern "C" int orbx_search_by_bow(orbx_matcher*, int mode, const orbx_keypoint* 
     return ORBX_OK;
 }
 
+extern "C" int orbx_search_by_bow_rig(orbx_matcher*, const orbx_keypoint* k1, const uint8_t* d1, const uint8_t* valid1, int n1,
+                                      const int32_t* fv1_nodes, const int32_t* fv1_start, const int32_t* fv1_feat, int nfv1,
+                                      const orbx_keypoint* k2, const uint8_t* d2, int n2, int n2_left,
+                                      const int32_t* fv2_nodes, const int32_t* fv2_start, const int32_t* fv2_feat, int nfv2,
+                                      float nnratio, int check_ori, int32_t* ml, int32_t* mr, int* nmatches)
+{
+    const int nm = orc_search_by_bow_rig(reinterpret_cast<const OrcKeyPoint*>(k1), d1, valid1, n1, fv1_nodes, fv1_start, fv1_feat, nfv1,
+                                         reinterpret_cast<const OrcKeyPoint*>(k2), d2, n2, n2_left, fv2_nodes, fv2_start, fv2_feat, nfv2,
+                                         nnratio, check_ori, ml, mr);
+    if (nmatches) *nmatches = nm;
+    return ORBX_OK;
+}
+
 extern "C" int orbx_stereo_matches(orbx_matcher*, orbx_extractor* left, orbx_extractor* right, int, int, int, int, float mb, float mbf,
                                    float* uright, float* depth, int32_t* sad_dist, int cap, int* n_left)
 {

@@ -490,6 +490,22 @@ int main(int argc, char** argv)
                 }
             }
 
+            // ---- SearchByBoW(KeyFrame*, Frame&) into a two-camera frame, from a one-camera and from a two-camera keyframe (:344-431) ----
+            {
+                CurRig->mpORBvocabulary = &w.voc; LastRig->mpORBvocabulary = &w.voc;
+                CurRig->ComputeBoW(); LastRig->ComputeBoW();
+                ORBmatcher matcher(0.75, true);
+                vector<MapPoint*> vp;
+                int n = matcher.SearchByBoW(&KF0, *CurRig, vp);
+                fprintf(g_out, "SearchByBoW(KF,Rig) n=%d\n", n);
+                dump_points("  matches", vp);
+                KeyFrame KFL(*LastRig);
+                ORBmatcher matcher2(0.9, false);
+                n = matcher2.SearchByBoW(&KFL, *CurRig, vp);
+                fprintf(g_out, "SearchByBoW(RigKF,Rig) n=%d\n", n);
+                dump_points("  matches", vp);
+            }
+
             // ---- Fuse on a two-camera keyframe, left camera then right camera (LocalMapping::SearchInNeighbors, :1395-1560) ----
             {
                 // (the reference reads mvuRight[idx] with the RIGHT camera's index although the vector has Nleft entries, :1527: the

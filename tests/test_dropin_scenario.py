@@ -64,7 +64,8 @@ EXPECT_NONZERO = ("SearchForInitialization n=", "SearchByProjection(Cur,Last)[0]
                   "SearchByBoW(KF,F) n=", "SearchByBoW(KF,KF) n=", "SearchByProjection(Sim3) n=", "SearchByProjection(Sim3,KFs) n=",
                   "SearchForTriangulation[0] n=", "SearchForTriangulation[2] n=", "SearchBySim3 n=", "Fuse(Sim3) n=", "Fuse n=",
                   "SearchByProjection(CurRig,Last)[0] n=", "SearchByProjection(CurRig,Last)[1] n=", "SearchByProjection(CurRig,Last)[2] n=",
-                  "SearchByProjection(Rig,MapPoints) th=1", "SearchByProjection(Rig,MapPoints) th=3", "Fuse(RigKF,left) n=")
+                  "SearchByProjection(Rig,MapPoints) th=1", "SearchByProjection(Rig,MapPoints) th=3", "Fuse(RigKF,left) n=",
+                  "SearchByBoW(KF,Rig) n=", "SearchByBoW(RigKF,Rig) n=")
 
 
 def check_coverage(lines):
