@@ -12,9 +12,13 @@
 // one source builds against the real headers in the reference tree and against the stand-ins of dropin/shim here.
 // There is no CPU fallback: a failing device call throws std::runtime_error.
 //
-// Not implemented: the two-camera (KannalaBrandt8 rig, Frame::Nleft != -1) branches of SearchByProjection / SearchByBoW, which
-// interleave left and right occupancy (R/src/ORBmatcher.cc:144-213, 2093-2160); such frames throw.  SearchForTriangulation and
-// Fuse handle both cameras (their candidate geometry goes through the camera's virtual interface).
+// Two-camera frames (KannalaBrandt8 rig, Frame::Nleft != -1): SearchByProjection(Frame&, vector<MapPoint*>&), SearchByProjection(
+// Frame&, const Frame&), SearchByBoW(KeyFrame*, Frame&), Fuse(..., bRight) and both SearchForTriangulation overloads follow the
+// reference's left / right branches (orbx_search_by_projection_rig, orbx_search_by_bow_rig; R/src/ORBmatcher.cc:144-213, :344-431,
+// :1395-1560, :2093-2160); SearchByBoW(KeyFrame*, KeyFrame*) skips the right camera's features as the reference does (:854-876).
+// The relocalisation overload SearchByProjection(Frame&, KeyFrame*, ...) has no two-camera branch in the reference either (it
+// indexes mvKeysUn with right-camera indices there); it throws for such frames, as do mixed one- / two-camera argument pairs the
+// reference does not produce.
 #include "ORBmatcher.h"
 
 #include <limits.h>
@@ -292,12 +296,15 @@ inline int rotation_bin(float a1, float a2)
     return bin;
 }
 
-void feature_vector_csr(const DBoW2::FeatureVector& fv, std::vector<int32_t>& nodes, std::vector<int32_t>& start, std::vector<int32_t>& feat)
+// limit >= 0: features with an index >= limit are left out (the right camera's features of a two-camera keyframe, which
+// SearchByBoW(KeyFrame*, KeyFrame*) skips, R/src/ORBmatcher.cc:854-856, :874-876)
+void feature_vector_csr(const DBoW2::FeatureVector& fv, std::vector<int32_t>& nodes, std::vector<int32_t>& start, std::vector<int32_t>& feat, int limit = -1)
 {
     nodes.clear(); start.assign(1, 0); feat.clear();
     for (DBoW2::FeatureVector::const_iterator it = fv.begin(); it != fv.end(); ++it) {
         nodes.push_back((int32_t)it->first);
-        for (size_t j = 0; j < it->second.size(); j++) feat.push_back((int32_t)it->second[j]);
+        for (size_t j = 0; j < it->second.size(); j++)
+            if (limit < 0 || (int)it->second[j] < limit) feat.push_back((int32_t)it->second[j]);
         start.push_back((int32_t)feat.size());
     }
 }
@@ -751,8 +758,8 @@ int ORBmatcher::SearchByBoW(KeyFrame *pKF1, KeyFrame *pKF2, vector<MapPoint *> &
     for (int i = 0; i < n1 && i < (int)vpMapPoints1.size(); i++) valid1[i] = (vpMapPoints1[i] && !vpMapPoints1[i]->isBad()) ? 1 : 0;
     for (int i = 0; i < n2 && i < (int)vpMapPoints2.size(); i++) valid2[i] = (vpMapPoints2[i] && !vpMapPoints2[i]->isBad()) ? 1 : 0;
     std::vector<int32_t> n1v, s1v, f1v, n2v, s2v, f2v, m12(n1, -1);
-    feature_vector_csr(pKF1->mFeatVec, n1v, s1v, f1v);
-    feature_vector_csr(pKF2->mFeatVec, n2v, s2v, f2v);
+    feature_vector_csr(pKF1->mFeatVec, n1v, s1v, f1v, pKF1->NLeft != -1 ? n1 : -1);
+    feature_vector_csr(pKF2->mFeatVec, n2v, s2v, f2v, pKF2->NLeft != -1 ? n2 : -1);
     std::vector<uint8_t> t1, t2;
     int nmatches = 0;
     Context& c = context(n1 > n2 ? n1 : n2);
