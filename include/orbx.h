@@ -200,6 +200,14 @@ int  orbx_extract_match_batch(orbx_extractor* ex, orbx_matcher* m, const uint8_t
                               orbx_keypoint* kps, uint8_t* desc, int cap, int32_t* n, int32_t* mono_index,
                               int32_t* matches12, int32_t* nmatches, int32_t* knn_idx, int32_t* knn_dist);
 
+/* Input prefetch for a stream of host batches: starts the host-to-device copy of the frames of the NEXT orbx_extract_match_batch
+ * call and returns at once, so that the PCIe transfer of batch k+1 runs under the kernels of batch k.  The frames must be pinned
+ * and packed at the staging pitch (stride = width rounded up to 16, frame_stride = stride * height) and must stay unchanged until
+ * the orbx_extract_match_batch call with the same (imgs, batch, width, height) consumes them; at most two batches can wait.  A
+ * call with other arguments drops what waits and copies its own input as usual.  Results are those of the plain call. */
+int  orbx_extract_match_batch_prefetch(orbx_extractor* ex, orbx_matcher* m, const uint8_t* imgs, int batch, int width,
+                                       int height, int stride, size_t frame_stride);
+
 /* The same step on DEVICE-resident frames, asynchronous on `stream` (results stay in the slots; matches12 [batch][K],
  * nmatches [batch] and the optional BF kNN-2 tables [batch][K][2] are device arrays, K = the matcher's max_keypoints).
  * Internally the batch is cut into chunks whose matcher kernels run on a second stream under the next chunk's

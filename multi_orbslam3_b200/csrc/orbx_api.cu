@@ -71,6 +71,9 @@ struct orbx_extractor {
     uint8_t* d_level0; int pitch0; long long stride0;
     uint8_t* h_stage_in;     // pinned
     uint8_t* d_raw; size_t raw_bytes;   // device landing zone for host rows whose stride is not the staging pitch
+    // input prefetch (orbx_extract_match_batch_prefetch): two extra staging buffers; entries are consumed first in, first out
+    struct Prefetch { const uint8_t* src; int batch, width, height; uint8_t* buf; cudaEvent_t ev; };
+    uint8_t* pf_buf[2]; size_t pf_bytes; cudaEvent_t pf_ev[2]; Prefetch pf[2]; int pf_count, pf_next;
     orbx_keypoint* h_kps; uint8_t* h_desc; int* h_n; int* h_mono; unsigned* h_err;   // pinned
     // what the last batch used as level 0 (for pyramid_to_host)
     const uint8_t* last_level0; int last_pitch0; long long last_stride0; int last_batch;
@@ -312,6 +315,7 @@ extern "C" int orbx_extractor_create(const orbx_params* p, orbx_extractor** out)
     memset(&h->geom, 0, sizeof(h->geom));
     memset(&h->buf, 0, sizeof(h->buf));
     h->d_level0 = nullptr; h->last_level0 = nullptr; h->last_batch = 0;
+    h->pf_buf[0] = h->pf_buf[1] = nullptr; h->pf_bytes = 0; h->pf_ev[0] = h->pf_ev[1] = nullptr; h->pf_count = 0; h->pf_next = 0;
     h->d_raw = nullptr; h->raw_bytes = 0;
     h->profile = false; h->ev_head = 0; h->ev_count = 0; h->stage_batches = 0;
     for (int i = 0; i < 4; i++) h->stage_ms[i] = 0;
@@ -347,6 +351,7 @@ extern "C" void orbx_extractor_destroy(orbx_extractor* h)
     cudaStreamSynchronize(h->stream);
     for (void* p : h->allocs) cudaFree(p);
     if (h->d_raw) cudaFree(h->d_raw);
+    for (int i = 0; i < 2; i++) { if (h->pf_buf[i]) cudaFree(h->pf_buf[i]); if (h->pf_ev[i]) cudaEventDestroy(h->pf_ev[i]); }
     cudaFreeHost(h->h_stage_in); cudaFreeHost(h->h_kps); cudaFreeHost(h->h_desc);
     cudaFreeHost(h->h_n); cudaFreeHost(h->h_mono); cudaFreeHost(h->h_err);
     for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
@@ -537,6 +542,50 @@ int orbx_ex_stage_input(orbx_extractor* h, const uint8_t* imgs, int f0, int coun
     }
     return ORBX_OK;
 }
+
+// ---- input prefetch: the frames of the NEXT host-buffer call travel to the device while the current call computes ----
+// copies `batch` pinned, tightly packed frames into one of two extra staging buffers on stream `s_copy`
+int orbx_ex_prefetch(orbx_extractor* h, const uint8_t* imgs, int batch, int width, int height, int stride, size_t frame_stride, cudaStream_t s_copy)
+{
+    int rc = orbx_ex_configure(h, width, height);
+    if (rc) return rc;
+    if (batch < 1 || batch > h->p.max_batch || !is_pinned(imgs) || frame_stride != (size_t)stride * height || stride != h->pitch0) {
+        orbx_set_error("%s%s", "orbx_extract_match_batch_prefetch: needs pinned frames packed at the staging pitch (width rounded up to 16)", "");
+        return ORBX_E_INVALID;
+    }
+    if (h->pf_count == 2) { orbx_set_error("%s%s", "orbx_extract_match_batch_prefetch: two batches are already waiting", ""); return ORBX_E_CAPACITY; }
+    const size_t need = (size_t)h->stride0 * h->p.max_batch;
+    if (need > h->pf_bytes) {
+        if (h->pf_count) { orbx_set_error("%s%s", "orbx_extract_match_batch_prefetch: image size changed with a batch waiting", ""); return ORBX_E_INVALID; }
+        for (int i = 0; i < 2; i++) { if (h->pf_buf[i]) { CK(cudaDeviceSynchronize()); cudaFree(h->pf_buf[i]); h->pf_buf[i] = nullptr; } }
+        for (int i = 0; i < 2; i++) { CK(cudaMalloc((void**)&h->pf_buf[i], need)); if (!h->pf_ev[i]) CK(cudaEventCreateWithFlags(&h->pf_ev[i], cudaEventDisableTiming)); }
+        h->pf_bytes = need;
+    }
+    const int slot = h->pf_next; h->pf_next ^= 1;
+    orbx_extractor::Prefetch& e = h->pf[h->pf_count++];
+    e.src = imgs; e.batch = batch; e.width = width; e.height = height; e.buf = h->pf_buf[slot]; e.ev = h->pf_ev[slot];
+    CK(cudaMemcpyAsync(e.buf, imgs, (size_t)h->stride0 * batch, cudaMemcpyHostToDevice, s_copy));
+    CK(cudaEventRecord(e.ev, s_copy));
+    return ORBX_OK;
+}
+
+// the oldest waiting batch if it is exactly this call's input (then *d_frames / *ready describe it and it is consumed);
+// any other waiting batch is stale (the caller changed its mind): dropped after its copy finished
+bool orbx_ex_take_prefetched(orbx_extractor* h, const uint8_t* imgs, int batch, int width, int height, const uint8_t** d_frames, cudaEvent_t* ready)
+{
+    if (h->pf_count == 0) return false;
+    const orbx_extractor::Prefetch e = h->pf[0];
+    if (e.src == imgs && e.batch == batch && e.width == width && e.height == height) {
+        h->pf[0] = h->pf[1]; h->pf_count--;
+        *d_frames = e.buf; *ready = e.ev;
+        return true;
+    }
+    for (int i = 0; i < h->pf_count; i++) cudaEventSynchronize(h->pf[i].ev);
+    h->pf_count = 0;
+    return false;
+}
+int orbx_ex_pitch0(orbx_extractor* h) { return h->pitch0; }
+long long orbx_ex_stride0(orbx_extractor* h) { return h->stride0; }
 
 int orbx_ex_run_staged(orbx_extractor* h, int f0, int count, int lap0, int lap1, int first_slot, cudaStream_t s)
 {

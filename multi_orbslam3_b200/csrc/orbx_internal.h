@@ -130,6 +130,11 @@ int orbx_ex_fetch_async(orbx_extractor* h, int first_slot, int count, int host_o
 int orbx_ex_fetch_finish(orbx_extractor* h, int count, orbx_keypoint* kps, uint8_t* desc, int cap,
                          int32_t* n, int32_t* mono_index, bool direct, bool err_fetched = false);
 int orbx_ex_fetch_err_async(orbx_extractor* h, cudaStream_t s);
+// input prefetch of the host pipeline (orbx_extract_match_batch_prefetch)
+int orbx_ex_prefetch(orbx_extractor* h, const uint8_t* imgs, int batch, int width, int height, int stride, size_t frame_stride, cudaStream_t s_copy);
+bool orbx_ex_take_prefetched(orbx_extractor* h, const uint8_t* imgs, int batch, int width, int height, const uint8_t** d_frames, cudaEvent_t* ready);
+int orbx_ex_pitch0(orbx_extractor* h);
+long long orbx_ex_stride0(orbx_extractor* h);
 
 // device view of one frame's pyramid of an extractor handle (stereo refinement reads both cameras' pyramids)
 struct OrbxPyrView {

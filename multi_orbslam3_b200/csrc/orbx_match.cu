@@ -1398,12 +1398,16 @@ static int extract_match_pipeline_impl(orbx_extractor* ex, orbx_matcher* m, bool
     // the fill (first chunk's copy) and the drain (last chunk's kernels + D2H): the first and last chunk are small
     // (1/16 of the batch each), the rest is split evenly.  Device path: chunking only shrinks the kernels and makes the
     // two kernel streams fight for the SMs (measured: 1 chunk 5.7 ms, 4 chunks 6.2 ms per 512 frames): one chunk.
-    int nchunks = host ? (batch >= 64 ? 6 : 1) : 1;
-    if (const char* e = getenv(host ? "ORBX_HOST_CHUNKS" : "ORBX_DEVICE_CHUNKS")) { const int v = atoi(e); if (v >= 1 && v <= ORBX_MAX_CHUNKS) nchunks = v; }
+    // a batch whose frames were prefetched (orbx_extract_match_batch_prefetch) is already on the device: its chunks only overlap the
+    // result copies with the kernels
+    const uint8_t* d_pref = nullptr; cudaEvent_t pref_ready = nullptr;
+    const bool prefetched = host && orbx_ex_take_prefetched(ex, imgs, batch, width, height, &d_pref, &pref_ready);
+    int nchunks = host ? (batch >= 64 ? (prefetched ? 3 : 6) : 1) : 1;
+    if (const char* e = getenv(host ? (prefetched ? "ORBX_PREFETCH_CHUNKS" : "ORBX_HOST_CHUNKS") : "ORBX_DEVICE_CHUNKS")) { const int v = atoi(e); if (v >= 1 && v <= ORBX_MAX_CHUNKS) nchunks = v; }
     if (nchunks > batch) nchunks = batch;
     int c_f0[ORBX_MAX_CHUNKS], c_cnt[ORBX_MAX_CHUNKS];
     {
-        const bool taper = host && nchunks >= 4 && batch >= 16 * nchunks && !getenv("ORBX_UNIFORM_CHUNKS");
+        const bool taper = host && !prefetched && nchunks >= 4 && batch >= 16 * nchunks && !getenv("ORBX_UNIFORM_CHUNKS");
         const int edge = taper ? batch / 16 : 0;
         const int mid = taper ? nchunks - 2 : nchunks, rest = batch - 2 * edge;
         int f = 0, k = 0;
@@ -1417,7 +1421,7 @@ static int extract_match_pipeline_impl(orbx_extractor* ex, orbx_matcher* m, bool
     }
     int32_t* dm12 = host ? m->d_out : d_matches12;
     int32_t* dnm = host ? m->d_nm : d_nmatches;
-    if (host && nchunks == 1) {
+    if (host && nchunks == 1 && !prefetched) {
         // One chunk (small batches, the single-frame latency path): everything in order on ONE stream, no cross-stream events, and
         // one synchronisation at the end that also brings back both handles' error flags.
         rc = orbx_ex_stage_input(ex, imgs, 0, batch, width, height, stride, frame_stride, s);
@@ -1455,9 +1459,10 @@ static int extract_match_pipeline_impl(orbx_extractor* ex, orbx_matcher* m, bool
     CKM(cudaEventRecord(m->ev_start, s));
     CKM(cudaStreamWaitEvent(m->s_match, m->ev_start, 0));
     if (host) {
-        CKM(cudaStreamWaitEvent(m->s_h2d, m->ev_start, 0));
+        if (!prefetched) CKM(cudaStreamWaitEvent(m->s_h2d, m->ev_start, 0));      // (the copy stream may already carry the NEXT batch's prefetch)
         CKM(cudaStreamWaitEvent(m->s_d2h, m->ev_start, 0));
-        for (int c = 0; c < nchunks; c++) {
+        if (prefetched) CKM(cudaStreamWaitEvent(s, pref_ready, 0));
+        for (int c = 0; c < nchunks && !prefetched; c++) {
             const int f0 = c_f0[c], cnt = c_cnt[c];
             rc = orbx_ex_stage_input(ex, imgs, f0, cnt, width, height, stride, frame_stride, m->s_h2d);
             if (rc) return rc;
@@ -1466,7 +1471,9 @@ static int extract_match_pipeline_impl(orbx_extractor* ex, orbx_matcher* m, bool
     }
     for (int c = 0; c < nchunks; c++) {
         const int f0 = c_f0[c], cnt = c_cnt[c];
-        if (host) {
+        if (prefetched) {
+            rc = orbx_ex_run_device(ex, d_pref, orbx_ex_pitch0(ex), orbx_ex_stride0(ex), f0, cnt, lap0, lap1, 1 + f0, s);
+        } else if (host) {
             CKM(cudaStreamWaitEvent(s, m->ev[c], 0));
             rc = orbx_ex_run_staged(ex, f0, cnt, lap0, lap1, 1 + f0, s);
         } else {
@@ -1552,6 +1559,18 @@ static int pipeline_args_ok(orbx_extractor* ex, orbx_matcher* m, const void* img
     if (orbx_ex_device(ex) != m->p.device) { orbx_set_error("%s%s", "orbx_extract_match_batch: extractor and matcher are on different devices", ""); return ORBX_E_INVALID; }
     if (width > 0 && stride < width) { orbx_set_error("%s%s", "orbx_extract_match_batch: stride smaller than width", ""); return ORBX_E_INVALID; }
     return ORBX_OK;
+}
+
+// Starts the host-to-device copy of the frames of the NEXT orbx_extract_match_batch call (same arguments) and returns at once.
+extern "C" int orbx_extract_match_batch_prefetch(orbx_extractor* ex, orbx_matcher* m, const uint8_t* imgs, int batch, int width,
+                                                 int height, int stride, size_t frame_stride)
+{
+    if (!ex || !m || !imgs || batch < 1 || width <= 0 || height <= 0 || stride < width) return ORBX_E_INVALID;
+    if (orbx_ex_device(ex) != m->p.device) { orbx_set_error("%s%s", "orbx_extract_match_batch_prefetch: extractor and matcher live on different devices", ""); return ORBX_E_INVALID; }
+    CKM(cudaSetDevice(m->p.device));
+    int rc = orbx_m_ensure_pipeline(m);
+    if (rc) return rc;
+    return orbx_ex_prefetch(ex, imgs, batch, width, height, stride, frame_stride, m->s_h2d);
 }
 
 extern "C" int orbx_extract_match_batch(orbx_extractor* ex, orbx_matcher* m, const uint8_t* imgs, int batch, int width,

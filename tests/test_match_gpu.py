@@ -271,6 +271,51 @@ def test_extract_match_batch_host_pipeline():
     ex.close(); m.close()
 
 
+def test_extract_match_batch_prefetch_equals_plain_call():
+    """orbx_extract_match_batch_prefetch: the input of the next call travels on its own stream into a second staging buffer; the
+    results (and the predecessor carried from call to call) must be those of the plain calls, whatever is prefetched when."""
+    import torch
+    B, W, H = 64, 640, 480
+    frames = synth.rects_stream(W, H, 3 * B, seed=92)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    batches = [pin(frames[i * B:(i + 1) * B]) for i in range(3)]
+
+    def run(prefetch):
+        ex = orbx.ORBextractor(800, 1.2, 8, 20, 7, max_width=W, max_height=H, max_batch=B)
+        m = orbx.ORBmatcher(0.9, True, max_keypoints=ex.cap, max_batch=B)
+        cap = ex.cap
+        outs = []
+        if prefetch:
+            orbx.extract_match_batch_prefetch(ex, m, batches[0])
+        for i, b in enumerate(batches):
+            if prefetch and i + 1 < len(batches):
+                orbx.extract_match_batch_prefetch(ex, m, batches[i + 1])          # two batches wait at this moment
+            out = {"kps": np.zeros((B, cap), orbx.KP_DTYPE), "desc": np.zeros((B, cap, 32), np.uint8), "n": np.zeros(B, np.int32),
+                   "mono": np.zeros(B, np.int32), "matches12": np.zeros((B, cap), np.int32), "nmatches": np.zeros(B, np.int32),
+                   "knn_idx": np.zeros((B, cap, 2), np.int32), "knn_dist": np.zeros((B, cap, 2), np.int32)}
+            orbx.extract_match_batch(ex, m, b, (0, 0), (0, W, 0, H), 100, out)
+            outs.append(out)
+        if prefetch:                                   # a stale prefetch is dropped by a call with another buffer
+            orbx.extract_match_batch_prefetch(ex, m, batches[0])
+            out = {k: np.zeros_like(v) for k, v in outs[0].items()}
+            orbx.extract_match_batch(ex, m, batches[1], (0, 0), (0, W, 0, H), 100, out)
+            outs.append(out)
+            with pytest.raises(orbx.OrbxError):        # pageable frames cannot be prefetched
+                orbx.extract_match_batch_prefetch(ex, m, np.array(batches[0]))
+        ex.close(); m.close()
+        return outs
+
+    plain, pre = run(False), run(True)
+    for a, b in zip(plain, pre[:3]):
+        for k in a:
+            np.testing.assert_array_equal(a[k], b[k], err_msg=k)
+    # the fourth call of the prefetch run = batch 1 after batch 2: only its own frames matter for extraction
+    np.testing.assert_array_equal(pre[3]["n"], plain[1]["n"]); np.testing.assert_array_equal(pre[3]["desc"], plain[1]["desc"])
+    for f in range(1, B):                               # rows are defined for the predecessor's keypoints
+        npk = int(plain[1]["n"][f - 1])
+        np.testing.assert_array_equal(pre[3]["matches12"][f, :npk], plain[1]["matches12"][f, :npk])
+
+
 @pytest.mark.parametrize("shape,nf,disp", [((752, 480), 1200, 14), ((1241, 376), 2000, 23)], ids=["C2_euroc", "C3_kitti"])
 def test_compute_stereo_matches_full(shape, nf, disp):
     """BASELINE configs C2 / C3: stereo pair, extraction on both cameras + Frame::ComputeStereoMatches (SAD refinement,
