@@ -1408,15 +1408,27 @@ static int extract_match_pipeline_impl(orbx_extractor* ex, orbx_matcher* m, bool
     int c_f0[ORBX_MAX_CHUNKS], c_cnt[ORBX_MAX_CHUNKS];
     {
         const bool taper = host && !prefetched && nchunks >= 4 && batch >= 16 * nchunks && !getenv("ORBX_UNIFORM_CHUNKS");
+        int f = 0, k = 0;
+        if (prefetched && nchunks >= 3 && batch >= 64 && !getenv("ORBX_UNIFORM_CHUNKS")) {
+            // input already resident: only the result copies are left to hide, so the chunks shrink towards the end (the drain is
+            // the last chunk's kernels + copies): 1/2, 1/4, ..., the last two share the rest
+            int left = batch;
+            for (int i = 0; i < nchunks; i++) {
+                int cnt = (i + 1 < nchunks) ? left / 2 : left;
+                if (cnt < 1) cnt = left;
+                c_f0[k] = f; c_cnt[k++] = cnt; f += cnt; left -= cnt;
+                if (left == 0) break;
+            }
+        } else {
         const int edge = taper ? batch / 16 : 0;
         const int mid = taper ? nchunks - 2 : nchunks, rest = batch - 2 * edge;
-        int f = 0, k = 0;
         if (taper) { c_f0[k] = 0; c_cnt[k++] = edge; f = edge; }
         for (int i = 0; i < mid; i++) {
             const int cnt = rest / mid + (i < rest % mid ? 1 : 0);
             c_f0[k] = f; c_cnt[k++] = cnt; f += cnt;
         }
         if (taper) { c_f0[k] = f; c_cnt[k++] = edge; }
+        }
         nchunks = k;
     }
     int32_t* dm12 = host ? m->d_out : d_matches12;
