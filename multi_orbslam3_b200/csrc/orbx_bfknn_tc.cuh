@@ -31,7 +31,7 @@ constexpr int ROWB = 256;           // expanded bytes per descriptor (one 8-bit 
 constexpr int A_BYTES = M * ROWB;   // 32 KB per query tile
 constexpr int B_BYTES = N * ROWB;   // 32 KB per stage
 constexpr int SUB = 65536;          // train rows per key space (16-bit local index)
-constexpr size_t SMEM_BYTES = MT * A_BYTES + 2 * B_BYTES + 2 * N * 2 + NQ * MQ * 2 * 4 + 64;
+constexpr size_t SMEM_BYTES = MT * A_BYTES + 2 * B_BYTES + 3 * N * 2 + NQ * MQ * 2 * 4 + 64;
 static_assert(QW == 32 && MT * N * 2 == 512, "TMEM: 2 stages x MT accumulators of N columns = all 512 columns");
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -141,8 +141,10 @@ __device__ __forceinline__ void bf_tile_body(const uint8_t* __restrict__ q, int 
 {
     uint8_t* As = smem;                                                                    // MT query tiles
     uint8_t* Bs = smem + MT * A_BYTES;                                                     // 2 stages
-    unsigned short* base_s = reinterpret_cast<unsigned short*>(Bs + 2 * B_BYTES);          // [2][N] 16-bit key bases of the stage's columns
-    unsigned* keys_s = reinterpret_cast<unsigned*>(base_s + 2 * N);                        // [NQ][MQ][2] best keys of the column quarters
+    // [3][N] 16-bit key bases of a tile's columns.  THREE slots (tile % 3): the bases of tile t+2 are written while slower warps
+    // may still read those of tile t in its epilogue (no barrier separates an epilogue from the next expansion)
+    unsigned short* base_s = reinterpret_cast<unsigned short*>(Bs + 2 * B_BYTES);
+    unsigned* keys_s = reinterpret_cast<unsigned*>(base_s + 3 * N);                        // [NQ][MQ][2] best keys of the column quarters
     unsigned long long* bar = reinterpret_cast<unsigned long long*>(keys_s + NQ * MQ * 2); // [2] MMA-complete barriers of the two stages
     unsigned* tmem_slot = reinterpret_cast<unsigned*>(bar + 2);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -184,12 +186,12 @@ __device__ __forceinline__ void bf_tile_body(const uint8_t* __restrict__ q, int 
             if (bpart == 0) { nlo = __ldg(reinterpret_cast<const uint4*>(t) + 2 * g); nhi = __ldg(reinterpret_cast<const uint4*>(t) + 2 * g + 1); }
         }
     };
-    auto expand_b = [&](int stage) {
+    auto expand_b = [&](int stage, unsigned tile) {
         uint8_t* rb = Bs + stage * B_BYTES + (br >> 3) * 2048 + (br & 7) * 16;
         const unsigned orv = nvalid ? 0x01010101u : 0u;
         expand_word(rb, 2 * bpart, nsrc.x, orv, 0xFFFFFFFFu); expand_word(rb, 2 * bpart + 1, nsrc.y, orv, 0xFFFFFFFFu);
         if (bpart == 0)                                                        // key base of the column: |b| << 7 | column inside the quarter
-            base_s[stage * N + br] = nvalid ? (unsigned short)((popc256(nlo, nhi) << 7) | (br & (QW - 1))) : (unsigned short)0xFFFFu;
+            base_s[(tile % 3u) * N + br] = nvalid ? (unsigned short)((popc256(nlo, nhi) << 7) | (br & (QW - 1))) : (unsigned short)0xFFFFu;
     };
     auto issue = [&](int stage) {                                              // one thread: MT x 8 x (128 x 128 x 32) into the accumulators of `stage`
         const unsigned a0 = smem_u32(As), b0 = smem_u32(Bs + stage * B_BYTES);
@@ -211,14 +213,14 @@ __device__ __forceinline__ void bf_tile_body(const uint8_t* __restrict__ q, int 
 #pragma unroll
         for (int mt = 0; mt < MT; mt++) { G1[mt] = 0xFFFFFFFFu; G2[mt] = 0xFFFFFFFFu; }
         fetch_b(sub);
-        expand_b(uses & 1);
+        expand_b(uses & 1, uses);
         if (ntiles > 1) fetch_b(sub + N);
         proxy_fence(); tc_fence_before();
         __syncthreads();
         if (tid == 0) { tc_fence_after(); issue(uses & 1); }
         for (int tl = 0; tl < ntiles; tl++) {
             const unsigned cur = uses + tl;
-            if (tl + 1 < ntiles) expand_b((cur + 1) & 1);
+            if (tl + 1 < ntiles) expand_b((cur + 1) & 1, cur + 1);
             proxy_fence(); tc_fence_before();
             __syncthreads();                       // stage (cur+1)&1: its smem is written, its accumulators were drained by the epilogue of tile cur-1
             if (tid == 0 && tl + 1 < ntiles) { tc_fence_after(); issue((cur + 1) & 1); }
@@ -226,7 +228,7 @@ __device__ __forceinline__ void bf_tile_body(const uint8_t* __restrict__ q, int 
             mbar_wait(&bar[cur & 1], (cur >> 1) & 1);
             tc_fence_after();
             // ---- epilogue of tile cur: 32 columns of this thread's row in each query tile ----
-            const uint4* kb4 = reinterpret_cast<const uint4*>(base_s + (cur & 1) * N + quarter * QW);
+            const uint4* kb4 = reinterpret_cast<const uint4*>(base_s + (cur % 3u) * N + quarter * QW);
             const unsigned colbase = (unsigned)(tl * N + quarter * QW);
 #pragma unroll
             for (int mt = 0; mt < MT; mt++) {

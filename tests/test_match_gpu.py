@@ -306,9 +306,18 @@ def test_extract_match_batch_prefetch_equals_plain_call():
         return outs
 
     plain, pre = run(False), run(True)
-    for a, b in zip(plain, pre[:3]):
-        for k in a:
+    for ci, (a, b) in enumerate(zip(plain, pre[:3])):
+        for k in ("n", "mono", "nmatches"):
             np.testing.assert_array_equal(a[k], b[k], err_msg=k)
+        for f in range(B):                              # rows are defined up to the frame's / its predecessor's keypoint count
+            n = int(a["n"][f])
+            assert a["kps"][f, :n].tobytes() == b["kps"][f, :n].tobytes()
+            np.testing.assert_array_equal(a["desc"][f, :n], b["desc"][f, :n])
+            if f == 0 and ci == 0:
+                continue                                # the very first frame has no predecessor
+            npk = int(a["n"][f - 1]) if f else int(plain[ci - 1]["n"][B - 1])
+            for k in ("matches12", "knn_idx", "knn_dist"):
+                np.testing.assert_array_equal(a[k][f, :npk], b[k][f, :npk], err_msg="%s call %d frame %d" % (k, ci, f))
     # the fourth call of the prefetch run = batch 1 after batch 2: only its own frames matter for extraction
     np.testing.assert_array_equal(pre[3]["n"], plain[1]["n"]); np.testing.assert_array_equal(pre[3]["desc"], plain[1]["desc"])
     for f in range(1, B):                               # rows are defined for the predecessor's keypoints
