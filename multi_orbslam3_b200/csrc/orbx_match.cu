@@ -997,6 +997,7 @@ __global__ void __launch_bounds__(32) k_rig_resolve(WinBufs W, int mode, float n
                 else if (d < d1) { d1 = d; k1 = k; e1 = e; }
             }
             warp_top2(d0, k0, e0, d1, e1, k1);
+            __syncwarp();                                                      // every lane's reads of occ[] precede lane 0's writes below
             const int obs = !(P.q[i].valid & 2);                              // the claiming MapPoint has observations: it occupies what it takes
             if (mode == 1) {
                 const int bd = d0 < 256 ? d0 : 256, bd2 = d1 < 256 ? d1 : 256;
