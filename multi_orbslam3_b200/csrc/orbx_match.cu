@@ -1484,13 +1484,17 @@ static int extract_match_pipeline_impl(orbx_extractor* ex, orbx_matcher* m, bool
     }
     for (int c = 0; c < nchunks; c++) {
         const int f0 = c_f0[c], cnt = c_cnt[c];
+        // experiment (ORBX_DEVICE_STREAMS=2): the chunks of a device-resident batch alternate between two extraction streams
+        static const bool two_streams = getenv("ORBX_DEVICE_STREAMS") && atoi(getenv("ORBX_DEVICE_STREAMS")) == 2;
+        cudaStream_t sc = (!host && two_streams && (c & 1)) ? m->s_h2d : s;
+        if (sc != s && c == 1) CKM(cudaStreamWaitEvent(sc, m->ev_start, 0));
         if (prefetched) {
             rc = orbx_ex_run_device(ex, d_pref, orbx_ex_pitch0(ex), orbx_ex_stride0(ex), f0, cnt, lap0, lap1, 1 + f0, s);
         } else if (host) {
             CKM(cudaStreamWaitEvent(s, m->ev[c], 0));
             rc = orbx_ex_run_staged(ex, f0, cnt, lap0, lap1, 1 + f0, s);
         } else {
-            rc = orbx_ex_run_device(ex, imgs, stride, (long long)frame_stride, f0, cnt, lap0, lap1, 1 + f0, s);
+            rc = orbx_ex_run_device(ex, imgs, stride, (long long)frame_stride, f0, cnt, lap0, lap1, 1 + f0, sc);
         }
         if (rc) return rc;
         if (m->cam_set) {                                // mvKeysUn of this chunk (result slots 1 + f0 ..)
@@ -1498,10 +1502,11 @@ static int extract_match_pipeline_impl(orbx_extractor* ex, orbx_matcher* m, bool
                                              m->d_kps_un + (size_t)(1 + f0) * orbx_ex_out_cap(ex), s);
             if (rc) return rc;
         }
-        CKM(cudaEventRecord(m->ev_ext[c], s));
+        CKM(cudaEventRecord(m->ev_ext[c], sc));
         // pairs (slot f0+i, slot f0+i+1) are matched on a second kernel stream, concurrently with the extraction of the
         // next chunk; each chunk owns its slice of the pair scratch
         CKM(cudaStreamWaitEvent(m->s_match, m->ev_ext[c], 0));
+        if (sc != s || (two_streams && !host && c > 0)) CKM(cudaStreamWaitEvent(m->s_match, m->ev_ext[c - 1], 0));   // the pair's other slot
         rc = match_slots_impl(m, ex, m->d_pair_a + f0, m->d_pair_b + f0, cnt, f0, bounds, window, nnratio, check_ori,
                               dm12 + (size_t)f0 * m->K, dnm + f0,
                               d_knn_idx ? d_knn_idx + (size_t)f0 * m->K * 2 : nullptr, d_knn_dist ? d_knn_dist + (size_t)f0 * m->K * 2 : nullptr,
