@@ -302,4 +302,197 @@ __device__ __forceinline__ void bf_tile_body(const uint8_t* __restrict__ q, int 
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
 }
 
+// ---- warp-specialised form of the same search: no block-wide barrier inside the tile loop --------------------------------
+//   warps 0-3   producers: expand the next train tile (one row per thread) into a shared-memory stage, write its key bases
+//   warps 4-11  consumers: epilogue of an accumulator stage (warp w: TMEM lanes 32 (w % 4) .., columns 64 ((w - 4) / 4) ..)
+//   warp 12     one elected thread waits for a full stage and a drained accumulator, issues the 2 x 8 MMAs, commits twice
+// Four mbarrier families hand the stages around: b_full (128 producer arrivals), b_empty (tcgen05.commit: the MMAs that read the
+// stage completed), acc_full (tcgen05.commit), acc_empty (256 consumer arrivals after their tcgen05.ld completed).  A thread of
+// the epilogue owns 64 columns of its row in both query tiles: 128 pairs per tile and thread, which halves the per-tile overhead
+// of the lock-step kernel above, and the expansion of tile t+1/t+2 overlaps the epilogue of tile t instead of preceding it.
+namespace ws {
+constexpr int NT = 13 * 32;
+constexpr int NPROD = 128, NCONS = 256;
+constexpr int HW = N / 2;                                // columns per consumer thread, tile and query tile
+constexpr int BASE_SLOTS = 4;                            // key bases of tile t are read until the epilogue of t ends: tile t+4 is the first
+                                                         // whose expansion provably starts after that (its stage waits MMA(t+2), which waited acc_empty(t))
+constexpr size_t SMEM_BYTES = MT * A_BYTES + 2 * B_BYTES + BASE_SLOTS * N * 2 + 2 * MQ * 2 * 4 + 8 * 8 + 16;
+
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void cons_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }    // the 256 consumer threads only
+
+__device__ __forceinline__ void bf_tile_body(const uint8_t* __restrict__ q, int nq, int q_first, const uint8_t* __restrict__ t,
+                                             long long t_begin, long long t_end, int idx_base, int32_t* oi, int32_t* od, uint8_t* smem)
+{
+    uint8_t* As = smem;
+    uint8_t* Bs = smem + MT * A_BYTES;
+    unsigned short* base_s = reinterpret_cast<unsigned short*>(Bs + 2 * B_BYTES);          // [BASE_SLOTS][N]
+    unsigned* keys_s = reinterpret_cast<unsigned*>(base_s + BASE_SLOTS * N);               // [MQ][2] best keys of the upper column half
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(keys_s + MQ * 2 * 2);
+    unsigned long long *b_full = bars, *b_empty = bars + 2, *acc_full = bars + 4, *acc_empty = bars + 6;
+    unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 8);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (warp == 12) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        for (int i = 0; i < 2; i++) { mbar_init(&b_full[i], NPROD); mbar_init(&b_empty[i], 1); mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], NCONS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // the query tiles: 256 rows x 8 words, every thread helps
+    for (int task = tid; task < MQ * 8; task += NT) {
+        const int r = task >> 3, word = task & 7, qi = q_first + r;
+        const unsigned w = qi < nq ? __ldg(reinterpret_cast<const unsigned*>(q) + 8 * (long long)qi + word) : 0u;
+        expand_word(As + (r >> 7) * A_BYTES + ((r & 127) >> 3) * 2048 + (r & 7) * 16, word, w, 0u, 0x01010101u);
+    }
+    proxy_fence();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const unsigned tmem = *tmem_slot;
+    const long long ntiles_total = (t_end - t_begin + N - 1) / N;          // sub-ranges are multiples of N rows: tiles never straddle them
+
+    if (warp < 4) {
+        // ================= producers =================
+        const int r = tid;                                                 // row of the tile
+        uint4 lo = make_uint4(0, 0, 0, 0), hi = lo; bool valid = false;
+        auto fetch = [&](long long tile) {
+            const long long g = t_begin + tile * N + r;
+            valid = tile < ntiles_total && g < t_end;
+            lo = make_uint4(0, 0, 0, 0); hi = lo;
+            if (valid) { lo = __ldg(reinterpret_cast<const uint4*>(t) + 2 * g); hi = __ldg(reinterpret_cast<const uint4*>(t) + 2 * g + 1); }
+        };
+        fetch(0);
+        for (long long tile = 0; tile < ntiles_total; tile++) {
+            const int s = (int)(tile & 1);
+            const uint4 clo = lo, chi = hi; const bool cvalid = valid;
+            fetch(tile + 1);                                               // in flight while this tile is expanded
+            mbar_wait(&b_empty[s], (unsigned)(((tile >> 1) & 1) ^ 1));     // the MMAs that read this stage two tiles ago completed
+            uint8_t* rb = Bs + s * B_BYTES + (r >> 3) * 2048 + (r & 7) * 16;
+            const unsigned orv = cvalid ? 0x01010101u : 0u;
+            expand_word(rb, 0, clo.x, orv, 0xFFFFFFFFu); expand_word(rb, 1, clo.y, orv, 0xFFFFFFFFu);
+            expand_word(rb, 2, clo.z, orv, 0xFFFFFFFFu); expand_word(rb, 3, clo.w, orv, 0xFFFFFFFFu);
+            expand_word(rb, 4, chi.x, orv, 0xFFFFFFFFu); expand_word(rb, 5, chi.y, orv, 0xFFFFFFFFu);
+            expand_word(rb, 6, chi.z, orv, 0xFFFFFFFFu); expand_word(rb, 7, chi.w, orv, 0xFFFFFFFFu);
+            base_s[(int)(tile % BASE_SLOTS) * N + r] = cvalid ? (unsigned short)((popc256(clo, chi) << 7) | (r & (HW - 1))) : (unsigned short)0xFFFFu;
+            proxy_fence();                                                 // generic-proxy writes -> visible to the tensor core's async proxy
+            mbar_arrive(&b_full[s]);
+        }
+    } else if (warp == 12) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            const unsigned a0 = smem_u32(As);
+            for (long long tile = 0; tile < ntiles_total; tile++) {
+                const int s = (int)(tile & 1);
+                const unsigned ph = (unsigned)((tile >> 1) & 1);
+                mbar_wait(&acc_empty[s], ph ^ 1);                          // the epilogue drained this accumulator stage
+                mbar_wait(&b_full[s], ph);                                 // the stage is expanded (and its base row written)
+                tc_fence_after();
+                const unsigned b0 = smem_u32(Bs + s * B_BYTES);
+#pragma unroll
+                for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+                    for (int k = 0; k < 8; k++)
+                        mma_i8(tmem + (s * MT + mt) * N, smem_desc(a0 + mt * A_BYTES + k * 256), smem_desc(b0 + k * 256), k > 0);
+                mma_commit(&b_empty[s]);
+                mma_commit(&acc_full[s]);
+            }
+        }
+    } else {
+        // ================= consumers =================
+        const int ew = warp - 4, row = (warp & 3) * 32 + lane, half = ew >> 2;
+        int D0[MT], I0[MT], D1[MT], I1[MT];
+#pragma unroll
+        for (int mt = 0; mt < MT; mt++) { D0[mt] = 0; I0[mt] = -1; D1[mt] = 0; I1[mt] = -1; }
+        long long tile = 0;
+        for (long long sub = t_begin; sub < t_end; sub += SUB) {
+            const long long sub_end = sub + SUB < t_end ? sub + SUB : t_end;
+            const int ntiles = (int)((sub_end - sub + N - 1) / N);
+            unsigned G1[MT], G2[MT];
+#pragma unroll
+            for (int mt = 0; mt < MT; mt++) { G1[mt] = 0xFFFFFFFFu; G2[mt] = 0xFFFFFFFFu; }
+            for (int tl = 0; tl < ntiles; tl++, tile++) {
+                const int s = (int)(tile & 1);
+                mbar_wait(&acc_full[s], (unsigned)((tile >> 1) & 1));
+                tc_fence_after();
+                const uint4* kb4 = reinterpret_cast<const uint4*>(base_s + (int)(tile % BASE_SLOTS) * N + half * HW);
+                const unsigned colbase = (unsigned)(tl * N + half * HW);
+#pragma unroll
+                for (int mt = 0; mt < MT; mt++) {
+                    const unsigned taddr = tmem + ((unsigned)((warp & 3) * 32) << 16) + (s * MT + mt) * N + half * HW;
+                    unsigned m1a = 0xFFFFFFFFu, m2a = 0xFFFFFFFFu, m1b = 0xFFFFFFFFu, m2b = 0xFFFFFFFFu;
+#pragma unroll
+                    for (int c = 0; c < HW / 32; c++) {
+                        int acc[32];
+                        tmem_ld32(taddr + c * 32, acc);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            const uint4 kb = kb4[c * 4 + (j >> 3)];
+                            const unsigned p0 = (unsigned)acc[j] * 128u + (unsigned)acc[j + 1] * (1u << 23) + kb.x;
+                            const unsigned p1 = (unsigned)acc[j + 2] * 128u + (unsigned)acc[j + 3] * (1u << 23) + kb.y;
+                            const unsigned p2 = (unsigned)acc[j + 4] * 128u + (unsigned)acc[j + 5] * (1u << 23) + kb.z;
+                            const unsigned p3 = (unsigned)acc[j + 6] * 128u + (unsigned)acc[j + 7] * (1u << 23) + kb.w;
+                            m2a = __vminu2(m2a, __vmaxu2(m1a, p0)); m1a = __vminu2(m1a, p0);
+                            m2b = __vminu2(m2b, __vmaxu2(m1b, p1)); m1b = __vminu2(m1b, p1);
+                            m2a = __vminu2(m2a, __vmaxu2(m1a, p2)); m1a = __vminu2(m1a, p2);
+                            m2b = __vminu2(m2b, __vmaxu2(m1b, p3)); m1b = __vminu2(m1b, p3);
+                        }
+                    }
+                    const unsigned n1 = __vminu2(m1a, m1b);
+                    const unsigned t1 = min(n1 & 0xFFFFu, n1 >> 16);
+                    if ((t1 >> 7) <= (G2[mt] >> 16)) {
+                        const unsigned n2 = __vminu2(__vmaxu2(m1a, m1b), __vminu2(m2a, m2b));
+                        const unsigned a1 = n1 & 0xFFFFu, b1 = n1 >> 16, a2 = n2 & 0xFFFFu, b2 = n2 >> 16;
+                        const unsigned t2 = min(max(a1, b1), min(a2, b2));
+                        const unsigned g1 = ((t1 >> 7) << 16) | (colbase + (t1 & 127u)), g2 = ((t2 >> 7) << 16) | (colbase + (t2 & 127u));
+                        G2[mt] = min(G2[mt], max(G1[mt], g1)); G1[mt] = min(G1[mt], g1);
+                        G2[mt] = min(G2[mt], max(G1[mt], g2)); G1[mt] = min(G1[mt], g2);
+                    }
+                }
+                // accumulators read, key bases of the tile no longer needed: the stage goes back to the MMA issuer
+                tc_fence_before();
+                mbar_arrive(&acc_empty[s]);
+            }
+            // the two column halves of a row meet in shared memory (consumer-only barrier); the lower half decodes and merges
+            cons_barrier();
+            if (half == 1) {
+#pragma unroll
+                for (int mt = 0; mt < MT; mt++) { keys_s[(mt * M + row) * 2] = G1[mt]; keys_s[(mt * M + row) * 2 + 1] = G2[mt]; }
+            }
+            cons_barrier();
+            if (half == 0) {
+#pragma unroll
+                for (int mt = 0; mt < MT; mt++) {
+                    const unsigned o1 = keys_s[(mt * M + row) * 2], o2 = keys_s[(mt * M + row) * 2 + 1];
+                    unsigned b1 = G1[mt], b2 = G2[mt];
+                    b2 = min(b2, max(b1, o1)); b1 = min(b1, o1);
+                    b2 = min(b2, max(b1, o2)); b1 = min(b1, o2);
+                    if ((b1 >> 16) <= 256u) top2_insert((int)(b1 >> 16), (int)(sub + (b1 & 0xFFFFu)) + idx_base, D0[mt], I0[mt], D1[mt], I1[mt]);
+                    if ((b2 >> 16) <= 256u) top2_insert((int)(b2 >> 16), (int)(sub + (b2 & 0xFFFFu)) + idx_base, D0[mt], I0[mt], D1[mt], I1[mt]);
+                }
+            }
+        }
+        if (half == 0) {
+#pragma unroll
+            for (int mt = 0; mt < MT; mt++) {
+                const int qi = q_first + mt * M + row;
+                if (qi < nq) {
+                    oi[2ll * qi] = I0[mt]; oi[2ll * qi + 1] = I1[mt];
+                    od[2ll * qi] = I0[mt] >= 0 ? D0[mt] : -1; od[2ll * qi + 1] = I1[mt] >= 0 ? D1[mt] : -1;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 12) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+}
+}  // namespace ws
+
 }  // namespace bftc

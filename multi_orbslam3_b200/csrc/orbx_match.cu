@@ -118,6 +118,32 @@ __global__ void __launch_bounds__(bftc::NT, 1) k_bf_knn2_tc(BfArgs A)
     bftc::bf_tile_body(q, nq, blockIdx.x * bftc::MQ, t, t_begin, t_end, A.idx_base, oi, od, bf_smem);
 }
 
+// The warp-specialised form (producers / MMA issuer / consumers, no block-wide barrier per tile): the default.
+__global__ void __launch_bounds__(bftc::ws::NT, 1) k_bf_knn2_tcws(BfArgs A)
+{
+    extern __shared__ __align__(128) uint8_t bf_smem[];
+    const int p = blockIdx.z, split = blockIdx.y;
+    const uint8_t* q; const uint8_t* t; int nq; long long nt;
+    if (A.q) { q = A.q; t = A.t; nq = A.nq; nt = A.nt; }
+    else {
+        const int sa = A.a[p], sb = A.b[p];
+        q = A.desc + (long long)sa * A.cap * 32; nq = A.n[sa];
+        t = A.desc + (long long)sb * A.cap * 32; nt = A.n[sb];
+    }
+    if ((long long)blockIdx.x * bftc::MQ >= nq) return;
+    const long long t_begin = (long long)split * A.chunk;
+    long long t_end = t_begin + A.chunk; if (t_end > nt) t_end = nt;
+    int32_t* oi; int32_t* od;
+    if (A.nsplit > 1) {
+        const long long o = (((long long)p * A.nsplit + split) * A.out_stride) * 2;
+        oi = A.part_idx + o; od = A.part_dist + o;
+    } else {
+        const long long o = ((long long)p * A.out_stride) * 2;
+        oi = A.idx + o; od = A.dist + o;
+    }
+    bftc::ws::bf_tile_body(q, nq, blockIdx.x * bftc::MQ, t, t_begin, t_end, A.idx_base, oi, od, bf_smem);
+}
+
 // merge partial top-2 tables: parts laid out [pair][part][stride][2]; lexicographic (dist, idx)
 __global__ void k_knn2_merge(const int32_t* pidx, const int32_t* pdist, int nparts, int stride, int nq_fixed,
                              const int* n, const int* a, int32_t* idx, int32_t* dist)
@@ -866,7 +892,11 @@ static int bf_launch(orbx_matcher* m, BfArgs A, int npairs, int nq_max, long lon
         A.part_idx = m->d_part_idx; A.part_dist = m->d_part_dist;
     }
     dim3 grid(qblocks, nsplit, npairs);
-    if (!use_popc) {
+    static const bool lockstep = getenv("ORBX_BF_LOCKSTEP") != nullptr;   // the first tensor-core kernel (all warps do everything), for comparison
+    if (!use_popc && !lockstep) {
+        CKM(ORBX_OPTIN_SMEM(k_bf_knn2_tcws));
+        k_bf_knn2_tcws<<<grid, bftc::ws::NT, bftc::ws::SMEM_BYTES, s>>>(A); ORBX_COUNT_LAUNCH(1);
+    } else if (!use_popc) {
         CKM(ORBX_OPTIN_SMEM(k_bf_knn2_tc));
         k_bf_knn2_tc<<<grid, bftc::NT, bftc::SMEM_BYTES, s>>>(A); ORBX_COUNT_LAUNCH(1);
     } else {
