@@ -640,20 +640,23 @@ def main():
     }
     h_np = h_frames.numpy()
     e2e_steps = 0 if args.no_e2e else max(3, min(args.steps, 150))
-    # A camera stream: while step k computes, the frames of step k+1 are already on their way (orbx_extract_match_batch_prefetch:
-    # a second staging buffer, the copy on its own stream).  Every step still moves its own h2d bytes from pinned host memory and
-    # its results back to the host inside the timed region; the copy of step k+1's input overlaps step k's kernels.
-    for _ in range(0 if args.no_e2e else 2):
-        orbx.extract_match_batch(ex, m, h_np, (0, 0), bounds, WINDOW, out)
+    # A camera stream through the streaming form of the call: orbx_stream_submit(k + 1); orbx_stream_wait(k).  Every step moves its
+    # own h2d bytes from pinned host memory and its results (d2h bytes) back into pinned host buffers inside the timed region; with
+    # two batches in flight the input copy of step k+1, the kernels of step k and the result copy of step k-1 run at the same time.
+    out_b = {k: torch.empty_like(torch.from_numpy(v.view(np.uint8) if v.dtype.fields else v)).pin_memory().numpy().view(v.dtype).reshape(v.shape) for k, v in out.items()}
+    outs2 = [out, out_b]
+    for _ in range(0 if args.no_e2e else 3):           # untimed warm-up through the same calls (staging buffers are allocated on first use)
+        orbx.stream_wait(ex, m, orbx.stream_submit(ex, m, h_np, (0, 0), bounds, WINDOW, out))
     barrier()
     t0 = time.perf_counter()
-    if e2e_steps:
-        orbx.extract_match_batch_prefetch(ex, m, h_np)
     seg_marks = [t0]                                   # the host link is shared with the box's other tenants: thirds of the run are reported too
+    tickets = []
+    if e2e_steps:
+        tickets.append(orbx.stream_submit(ex, m, h_np, (0, 0), bounds, WINDOW, outs2[0]))
     for i in range(e2e_steps):
         if i + 1 < e2e_steps:
-            orbx.extract_match_batch_prefetch(ex, m, h_np)
-        orbx.extract_match_batch(ex, m, h_np, (0, 0), bounds, WINDOW, out)
+            tickets.append(orbx.stream_submit(ex, m, h_np, (0, 0), bounds, WINDOW, outs2[(i + 1) & 1]))
+        orbx.stream_wait(ex, m, tickets[i])             # the results of step i are in outs2[i & 1]
         if e2e_steps >= 30 and (i + 1) % (e2e_steps // 3) == 0 and len(seg_marks) < 4:
             seg_marks.append(time.perf_counter())
     torch.cuda.synchronize()
@@ -770,7 +773,7 @@ def main():
                 "mean_keypoints": nkp_mean, "mean_init_matches": nmatch_mean},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps, "rank0_frames_per_s_by_third": e2e_segments,
-                "api": "orbx_extract_match_batch_prefetch(next batch) + orbx_extract_match_batch (pinned host frames -> keypoints, descriptors, SearchForInitialization matches and BF kNN-2 tables on host); one input copy and one result copy per step, the input copy of step k+1 under the kernels of step k"},
+                "api": "orbx_stream_submit(step k+1) + orbx_stream_wait(step k): pinned host frames -> keypoints, descriptors, SearchForInitialization matches and BF kNN-2 tables in pinned host buffers; one input copy and one result copy per step, two steps in flight (input copy of k+1 | kernels of k | result copy of k-1)"},
         "gpu_launches": int(launches),
         "latency": latency,
         "roofline": roofline,

@@ -208,6 +208,21 @@ int  orbx_extract_match_batch(orbx_extractor* ex, orbx_matcher* m, const uint8_t
 int  orbx_extract_match_batch_prefetch(orbx_extractor* ex, orbx_matcher* m, const uint8_t* imgs, int batch, int width,
                                        int height, int stride, size_t frame_stride);
 
+/* Streaming form of orbx_extract_match_batch for a camera stream: submit queues one batch (input copy on the copy stream, the
+ * kernels of the step, result copy on the D2H stream) and returns at once with a ticket; wait blocks until THAT batch's results
+ * are in the buffers given at submit (and reports its device error flags).  Two batches may be in flight: with
+ *     submit(k + 1); wait(k);
+ * the input copy of batch k+1, the kernels of batch k and the result copy of batch k-1 ... run at the same time, and every frame
+ * still finds its predecessor (batches are processed in submission order on one kernel stream).  The frames must be pinned and
+ * packed at the staging pitch (as for the prefetch call), the result buffers pinned with cap = orbx_extractor_max_keypoints(ex)
+ * and distinct for the two batches in flight; all must stay untouched until the wait returns.  Results are those of the plain
+ * call.  ORBX_E_CAPACITY from submit: two batches are already in flight. */
+int  orbx_stream_submit(orbx_extractor* ex, orbx_matcher* m, const uint8_t* imgs, int batch, int width, int height, int stride,
+                        size_t frame_stride, int lap0, int lap1, const float bounds[4], int window, float nnratio, int check_ori,
+                        orbx_keypoint* kps, uint8_t* desc, int cap, int32_t* n, int32_t* mono_index,
+                        int32_t* matches12, int32_t* nmatches, int32_t* knn_idx, int32_t* knn_dist, long long* ticket);
+int  orbx_stream_wait(orbx_extractor* ex, orbx_matcher* m, long long ticket);
+
 /* The same step on DEVICE-resident frames, asynchronous on `stream` (results stay in the slots; matches12 [batch][K],
  * nmatches [batch] and the optional BF kNN-2 tables [batch][K][2] are device arrays, K = the matcher's max_keypoints).
  * Internally the batch is cut into chunks whose matcher kernels run on a second stream under the next chunk's

@@ -585,6 +585,8 @@ bool orbx_ex_take_prefetched(orbx_extractor* h, const uint8_t* imgs, int batch, 
     return false;
 }
 int orbx_ex_pitch0(orbx_extractor* h) { return h->pitch0; }
+unsigned* orbx_ex_err_device(orbx_extractor* h) { return h->buf.err; }
+bool orbx_host_pinned(const void* p) { return is_pinned(p); }
 long long orbx_ex_stride0(orbx_extractor* h) { return h->stride0; }
 
 int orbx_ex_run_staged(orbx_extractor* h, int f0, int count, int lap0, int lap1, int first_slot, cudaStream_t s)

@@ -799,6 +799,7 @@ extern "C" void orbx_matcher_destroy(orbx_matcher* m)
     if (m->h_mono2) cudaFreeHost(m->h_mono2);
     if (m->s_h2d) {
         cudaStreamDestroy(m->s_h2d); cudaStreamDestroy(m->s_d2h); cudaStreamDestroy(m->s_match);
+        if (m->st_init) for (int i = 0; i < 2; i++) { cudaEventDestroy(m->st[i].ev_kernels); cudaEventDestroy(m->st[i].ev_host); cudaFreeHost(m->st[i].h_err); }
         for (int i = 0; i < ORBX_MAX_CHUNKS; i++) cudaEventDestroy(m->ev_ext[i]);
         for (int i = 0; i < 2 * ORBX_MAX_CHUNKS; i++) { cudaEventDestroy(m->ev[i]); cudaEventDestroy(m->ev_r[i]); }
         cudaEventDestroy(m->ev_start);
@@ -1606,6 +1607,133 @@ static int pipeline_args_ok(orbx_extractor* ex, orbx_matcher* m, const void* img
     if (batch > orbx_ex_max_batch(ex)) { orbx_set_error("%s%s", "orbx_extract_match_batch: batch larger than the extractor's max_batch", ""); return ORBX_E_INVALID; }
     if (orbx_ex_device(ex) != m->p.device) { orbx_set_error("%s%s", "orbx_extract_match_batch: extractor and matcher are on different devices", ""); return ORBX_E_INVALID; }
     if (width > 0 && stride < width) { orbx_set_error("%s%s", "orbx_extract_match_batch: stride smaller than width", ""); return ORBX_E_INVALID; }
+    return ORBX_OK;
+}
+
+// ---- streaming form: submit queues one batch and returns at once, wait blocks until that batch's results are on the host ----
+// Per batch: the input copy (the prefetch path: own stream, one of two staging buffers), the kernels of the device-resident step
+// (one chunk), a device-to-device copy of the results into one of two staging sets (~45 MB, microseconds), and the result copy to
+// the caller's pinned buffers on the D2H stream.  With two batches in flight the three run at the same time for batches k+1, k
+// and k-1.
+static int stream_init(orbx_matcher* m, orbx_extractor* ex)
+{
+    const int cap = orbx_ex_out_cap(ex);
+    if (m->st_init && m->st_cap == cap) return ORBX_OK;
+    if (m->st_init) { orbx_set_error("%s%s", "orbx_stream_submit: the extractor's result capacity changed", ""); return ORBX_E_INVALID; }
+    const size_t rows = (size_t)m->P;
+    for (int i = 0; i < 2; i++) {
+        orbx_matcher::StreamSet& S = m->st[i];
+        CKM(cudaMalloc((void**)&S.kps, sizeof(orbx_keypoint) * rows * cap)); m->allocs.push_back(S.kps);
+        CKM(cudaMalloc((void**)&S.desc, (size_t)32 * rows * cap)); m->allocs.push_back(S.desc);
+        CKM(cudaMalloc((void**)&S.n, sizeof(int32_t) * rows * 3)); m->allocs.push_back(S.n);
+        S.mono = S.n + rows; S.nm = S.mono + rows;
+        CKM(cudaMalloc((void**)&S.m12, sizeof(int32_t) * rows * m->K * 5)); m->allocs.push_back(S.m12);
+        S.knn_idx = S.m12 + rows * m->K; S.knn_dist = S.knn_idx + rows * m->K * 2;
+        CKM(cudaEventCreateWithFlags(&S.ev_kernels, cudaEventDisableTiming));
+        CKM(cudaEventCreateWithFlags(&S.ev_host, cudaEventDisableTiming));
+        CKM(cudaMallocHost((void**)&S.h_err, 2 * sizeof(unsigned)));
+        S.busy = false; S.batch = 0;
+    }
+    m->st_rows = rows; m->st_cap = cap; m->st_ticket = 0; m->st_init = true;
+    return ORBX_OK;
+}
+
+extern "C" int orbx_stream_submit(orbx_extractor* ex, orbx_matcher* m, const uint8_t* imgs, int batch, int width, int height, int stride,
+                                  size_t frame_stride, int lap0, int lap1, const float bounds[4], int window, float nnratio, int check_ori,
+                                  orbx_keypoint* kps, uint8_t* desc, int cap, int32_t* n, int32_t* mono_index,
+                                  int32_t* matches12, int32_t* nmatches, int32_t* knn_idx, int32_t* knn_dist, long long* ticket)
+{
+    int rc = pipeline_args_ok(ex, m, imgs, batch, width, stride, bounds);
+    if (rc) return rc;
+    if (!ticket || !kps || !desc || !n || !mono_index || !matches12 || !nmatches || (knn_idx == nullptr) != (knn_dist == nullptr)) return ORBX_E_INVALID;
+    if (width <= 0 || height <= 0) return ORBX_E_EMPTY;
+    CKM(cudaSetDevice(m->p.device));
+    if ((rc = orbx_ex_configure(ex, width, height))) return rc;
+    if ((rc = orbx_m_ensure_pipeline(m))) return rc;
+    if ((rc = stream_init(m, ex))) return rc;
+    if (cap != orbx_ex_out_cap(ex) || !orbx_host_pinned(kps) || !orbx_host_pinned(desc) || !orbx_host_pinned(n) || !orbx_host_pinned(mono_index) ||
+        !orbx_host_pinned(matches12) || !orbx_host_pinned(nmatches) || (knn_idx && (!orbx_host_pinned(knn_idx) || !orbx_host_pinned(knn_dist)))) {
+        orbx_set_error("%s%s", "orbx_stream_submit: result buffers must be pinned host memory with cap = orbx_extractor_max_keypoints", "");
+        return ORBX_E_INVALID;
+    }
+    orbx_matcher::StreamSet& S = m->st[m->st_ticket & 1];
+    if (S.busy) { orbx_set_error("%s%s", "orbx_stream_submit: two batches are in flight, wait for the older one first", ""); return ORBX_E_CAPACITY; }
+    cudaStream_t s = orbx_ex_stream(ex);
+    // input: already prefetched, or copied now on the copy stream (after the kernels that last read that staging buffer)
+    const uint8_t* d_in = nullptr; cudaEvent_t ready = nullptr;
+    if (!orbx_ex_take_prefetched(ex, imgs, batch, width, height, &d_in, &ready)) {
+        rc = orbx_ex_prefetch(ex, imgs, batch, width, height, stride, frame_stride, m->s_h2d);
+        if (rc) return rc;
+        if (!orbx_ex_take_prefetched(ex, imgs, batch, width, height, &d_in, &ready)) return ORBX_E_INVALID;
+    }
+    CKM(cudaStreamWaitEvent(s, ready, 0));
+    // kernels: the device-resident step (one chunk; matcher kernels on the second stream, joined into s at the end)
+    if (knn_idx) {
+        const size_t need = (size_t)m->P * m->K * 2;
+        if (need > m->pipe_knn_elems) {
+            if (m->d_pipe_knn) { CKM(cudaDeviceSynchronize()); cudaFree(m->d_pipe_knn); m->d_pipe_knn = nullptr; m->pipe_knn_elems = 0; }
+            CKM(cudaMalloc((void**)&m->d_pipe_knn, sizeof(int32_t) * need * 2));
+            m->pipe_knn_elems = need;
+        }
+    }
+    int32_t* d_ki = knn_idx ? m->d_pipe_knn : nullptr; int32_t* d_kd = knn_idx ? m->d_pipe_knn + (size_t)m->P * m->K * 2 : nullptr;
+    rc = extract_match_pipeline(ex, m, false, d_in, batch, width, height, orbx_ex_pitch0(ex), (size_t)orbx_ex_stride0(ex), lap0, lap1, bounds, window,
+                                nnratio, check_ori, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                m->d_out, m->d_nm, d_ki, d_kd, s);
+    if (rc) return rc;
+    // results -> staging set (device to device, on the kernel stream), flags included
+    orbx_keypoint* dk; uint8_t* dd; int32_t* dn; int32_t* dmono; int ocap, slots;
+    if ((rc = orbx_extractor_results_device(ex, &dk, &dd, &dn, &dmono, &ocap, &slots))) return rc;
+    const size_t B = (size_t)batch;
+    CKM(cudaMemcpyAsync(S.kps, dk + (size_t)ocap, sizeof(orbx_keypoint) * ocap * B, cudaMemcpyDeviceToDevice, s));          // slots 1 .. batch
+    CKM(cudaMemcpyAsync(S.desc, dd + (size_t)ocap * 32, (size_t)32 * ocap * B, cudaMemcpyDeviceToDevice, s));
+    CKM(cudaMemcpyAsync(S.n, dn + 1, sizeof(int32_t) * B, cudaMemcpyDeviceToDevice, s));
+    CKM(cudaMemcpyAsync(S.mono, dmono + 1, sizeof(int32_t) * B, cudaMemcpyDeviceToDevice, s));
+    CKM(cudaMemcpyAsync(S.nm, m->d_nm, sizeof(int32_t) * B, cudaMemcpyDeviceToDevice, s));
+    CKM(cudaMemcpyAsync(S.m12, m->d_out, sizeof(int32_t) * B * m->K, cudaMemcpyDeviceToDevice, s));
+    if (knn_idx) {
+        CKM(cudaMemcpyAsync(S.knn_idx, d_ki, sizeof(int32_t) * B * m->K * 2, cudaMemcpyDeviceToDevice, s));
+        CKM(cudaMemcpyAsync(S.knn_dist, d_kd, sizeof(int32_t) * B * m->K * 2, cudaMemcpyDeviceToDevice, s));
+    }
+    CKM(cudaEventRecord(S.ev_kernels, s));
+    // results -> the caller's pinned buffers on the D2H stream; device rows have stride K, host rows stride cap
+    cudaStream_t sd = m->s_d2h;
+    CKM(cudaStreamWaitEvent(sd, S.ev_kernels, 0));
+    CKM(cudaMemcpyAsync(S.h_err, orbx_ex_err_device(ex), sizeof(unsigned), cudaMemcpyDeviceToHost, sd));
+    CKM(cudaMemcpyAsync(S.h_err + 1, m->W.err, sizeof(unsigned), cudaMemcpyDeviceToHost, sd));
+    CKM(cudaMemcpyAsync(n, S.n, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, sd));
+    CKM(cudaMemcpyAsync(mono_index, S.mono, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, sd));
+    CKM(cudaMemcpyAsync(nmatches, S.nm, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, sd));
+    CKM(cudaMemcpyAsync(kps, S.kps, sizeof(orbx_keypoint) * ocap * B, cudaMemcpyDeviceToHost, sd));
+    CKM(cudaMemcpyAsync(desc, S.desc, (size_t)32 * ocap * B, cudaMemcpyDeviceToHost, sd));
+    const size_t wcols = (size_t)(cap < m->K ? cap : m->K);
+    CKM(cudaMemcpy2DAsync(matches12, sizeof(int32_t) * cap, S.m12, sizeof(int32_t) * m->K, sizeof(int32_t) * wcols, B, cudaMemcpyDeviceToHost, sd));
+    if (knn_idx) {
+        CKM(cudaMemcpy2DAsync(knn_idx, sizeof(int32_t) * 2 * cap, S.knn_idx, sizeof(int32_t) * 2 * m->K, sizeof(int32_t) * 2 * wcols, B, cudaMemcpyDeviceToHost, sd));
+        CKM(cudaMemcpy2DAsync(knn_dist, sizeof(int32_t) * 2 * cap, S.knn_dist, sizeof(int32_t) * 2 * m->K, sizeof(int32_t) * 2 * wcols, B, cudaMemcpyDeviceToHost, sd));
+    }
+    CKM(cudaEventRecord(S.ev_host, sd));
+    // (the staging set and the input buffer are reused by the batch after next, which cannot be submitted before this one was waited for)
+    S.busy = true; S.batch = batch;
+    *ticket = m->st_ticket++;
+    return ORBX_OK;
+}
+
+extern "C" int orbx_stream_wait(orbx_extractor* ex, orbx_matcher* m, long long ticket)
+{
+    if (!ex || !m || !m->st_init || ticket < 0 || ticket >= m->st_ticket) return ORBX_E_INVALID;
+    orbx_matcher::StreamSet& S = m->st[ticket & 1];
+    if (!S.busy || ticket + 2 < m->st_ticket) return ORBX_OK;             // already waited for
+    CKM(cudaSetDevice(m->p.device));
+    CKM(cudaEventSynchronize(S.ev_host));
+    S.busy = false;
+    if (S.h_err[0] || S.h_err[1]) {
+        char buf[48]; snprintf(buf, sizeof(buf), "extractor 0x%x matcher 0x%x", S.h_err[0], S.h_err[1]);
+        orbx_set_error("orbx_stream_wait: device capacity error flags %s%s", buf, " (raise max_candidates / capacities)");
+        cudaMemsetAsync(orbx_ex_err_device(ex), 0, sizeof(unsigned), orbx_ex_stream(ex));
+        cudaMemsetAsync(m->W.err, 0, sizeof(unsigned), orbx_ex_stream(ex));
+        return ORBX_E_CAPACITY;
+    }
     return ORBX_OK;
 }
 

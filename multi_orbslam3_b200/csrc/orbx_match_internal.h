@@ -143,6 +143,14 @@ struct orbx_matcher {
     int32_t* h_mono2; int mono2_cap;         // pinned monoIndex landing zone of the stereo pipeline (2 x batch)
     cudaStream_t s_h2d, s_d2h, s_match; cudaEvent_t ev[2 * ORBX_MAX_CHUNKS]; cudaEvent_t ev_ext[ORBX_MAX_CHUNKS]; cudaEvent_t ev_start;
     cudaEvent_t ev_r[2 * ORBX_MAX_CHUNKS];      // right camera of the stereo pipeline: [c] copy done, [MAX + c] extraction done
+    // streaming form (orbx_stream_submit / orbx_stream_wait): two result staging sets on the device, so that the results of batch k
+    // travel to the host while batch k+1 computes
+    struct StreamSet {
+        orbx_keypoint* kps; uint8_t* desc; int32_t* n; int32_t* mono; int32_t* m12; int32_t* nm; int32_t* knn_idx; int32_t* knn_dist;
+        cudaEvent_t ev_kernels, ev_host; unsigned* h_err;      // h_err: pinned {extractor flags, matcher flags}
+        bool busy; int batch;
+    } st[2];
+    size_t st_rows; int st_cap; long long st_ticket; bool st_init;
     std::vector<void*> allocs;
 };
 

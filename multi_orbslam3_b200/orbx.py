@@ -35,7 +35,7 @@ EXPORTS = [
     "orbx_level_keypoints_to_host",
     "orbx_matcher_create", "orbx_matcher_destroy", "orbx_matcher_sync", "orbx_hamming_pairs",
     "orbx_bf_knn2", "orbx_bf_knn2_device", "orbx_knn2_merge_device",
-    "orbx_search_for_initialization", "orbx_match_slots_device", "orbx_extract_match_batch", "orbx_extract_match_batch_prefetch", "orbx_extract_match_batch_device",
+    "orbx_search_for_initialization", "orbx_match_slots_device", "orbx_extract_match_batch", "orbx_extract_match_batch_prefetch", "orbx_stream_submit", "orbx_stream_wait", "orbx_extract_match_batch_device",
     "orbx_search_by_projection",
     "orbx_stereo_band_match", "orbx_stereo_matches", "orbx_stereo_matches_batch", "orbx_stereo_matches_batch_device",
     "orbx_extract_stereo_batch",
@@ -90,6 +90,8 @@ def lib():
         L.orbx_extractor_profile.argtypes = [vp, i32, vp, vp]
         L.orbx_extract_match_batch.argtypes = [vp, vp, vp, i32, i32, i32, i32, sz, i32, i32, vp, i32, f32, i32,
                                                vp, vp, i32, vp, vp, vp, vp, vp, vp]
+        L.orbx_stream_submit.argtypes = [vp, vp, vp, i32, i32, i32, i32, sz, i32, i32, vp, i32, f32, i32, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp]
+        L.orbx_stream_wait.argtypes = [vp, vp, C.c_longlong]
         L.orbx_extract_match_batch_prefetch.argtypes = [vp, vp, vp, i32, i32, i32, i32, sz]
         L.orbx_extract_match_batch_device.argtypes = [vp, vp, vp, i32, i32, i32, i32, sz, i32, i32, vp, i32, f32, i32,
                                                       vp, vp, vp, vp, vp]
@@ -699,6 +701,23 @@ def extract_match_batch(ex, m, imgs, lap, bounds, window, out):
                                           ex.cap, _p(out["n"]), _p(out["mono"]), _p(out["matches12"]), _p(out["nmatches"]),
                                           _p(out["knn_idx"]) if "knn_idx" in out else None,
                                           _p(out["knn_dist"]) if "knn_dist" in out else None))
+
+
+def stream_submit(ex, m, imgs, lap, bounds, window, out):
+    """orbx_stream_submit: queue one batch (pinned [B,H,W] frames, pinned result arrays as for extract_match_batch) -> ticket"""
+    B, H, W = imgs.shape
+    bb = np.array(bounds, np.float32)
+    t = C.c_longlong(-1)
+    _check(lib().orbx_stream_submit(ex._h, m._h, _p(imgs), B, W, H, imgs.strides[1], imgs.strides[0], int(lap[0]), int(lap[1]),
+                                    _p(bb), int(window), m.mfNNratio, int(m.mbCheckOrientation), _p(out["kps"]), _p(out["desc"]),
+                                    ex.cap, _p(out["n"]), _p(out["mono"]), _p(out["matches12"]), _p(out["nmatches"]),
+                                    _p(out["knn_idx"]) if "knn_idx" in out else None,
+                                    _p(out["knn_dist"]) if "knn_dist" in out else None, C.byref(t)))
+    return t.value
+
+
+def stream_wait(ex, m, ticket):
+    _check(lib().orbx_stream_wait(ex._h, m._h, int(ticket)))
 
 
 def extract_match_batch_prefetch(ex, m, imgs):

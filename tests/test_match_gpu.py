@@ -537,3 +537,61 @@ def test_projection_options_occupancy_origin_and_stereo_gate():
     assert n == rn and n > 40 and not np.array_equal(rbi, bi1)       # the stereo form changes the outcome on this input
     np.testing.assert_array_equal(bi, rbi); np.testing.assert_array_equal(bd, rbd)
     m.close()
+
+
+def test_stream_submit_wait_equals_plain_calls():
+    """orbx_stream_submit / orbx_stream_wait: two batches in flight (input copy, kernels and result copy of three consecutive
+    batches overlap); results and the predecessor carried from batch to batch must be those of the plain synchronous calls."""
+    import torch
+    B, W, H = 48, 640, 480
+    nb = 5
+    frames = synth.rects_stream(W, H, nb * B, seed=93)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    batches = [pin(frames[i * B:(i + 1) * B]) for i in range(nb)]
+
+    def buffers(cap, pinned):
+        mk = (lambda shape, dt: torch.zeros(shape, dtype=dt).pin_memory().numpy()) if pinned else (lambda shape, dt: torch.zeros(shape, dtype=dt).numpy())
+        return {"kps": mk((B, cap, 7), torch.float32).view(np.uint8).reshape(B, cap, 28).view(orbx.KP_DTYPE).reshape(B, cap),
+                "desc": mk((B, cap, 32), torch.uint8), "n": mk((B,), torch.int32), "mono": mk((B,), torch.int32),
+                "matches12": mk((B, cap), torch.int32), "nmatches": mk((B,), torch.int32),
+                "knn_idx": mk((B, cap, 2), torch.int32), "knn_dist": mk((B, cap, 2), torch.int32)}
+
+    ex = orbx.ORBextractor(800, 1.2, 8, 20, 7, max_width=W, max_height=H, max_batch=B)
+    m = orbx.ORBmatcher(0.9, True, max_keypoints=ex.cap, max_batch=B)
+    plain = []
+    for b in batches:
+        out = buffers(ex.cap, False)
+        orbx.extract_match_batch(ex, m, b, (0, 0), (0, W, 0, H), 100, out)
+        plain.append(out)
+    ex.close(); m.close()
+
+    ex = orbx.ORBextractor(800, 1.2, 8, 20, 7, max_width=W, max_height=H, max_batch=B)
+    m = orbx.ORBmatcher(0.9, True, max_keypoints=ex.cap, max_batch=B)
+    outs = [buffers(ex.cap, True) for _ in range(nb)]
+    tickets = [orbx.stream_submit(ex, m, batches[0], (0, 0), (0, W, 0, H), 100, outs[0])]
+    for k in range(1, nb):
+        tickets.append(orbx.stream_submit(ex, m, batches[k], (0, 0), (0, W, 0, H), 100, outs[k]))     # two in flight
+        if k == 2:
+            with pytest.raises(orbx.OrbxError) as e:      # a third one is refused
+                orbx.stream_submit(ex, m, batches[k], (0, 0), (0, W, 0, H), 100, outs[k])
+            assert e.value.code == orbx.ORBX_E_CAPACITY
+        orbx.stream_wait(ex, m, tickets[k - 1])
+    orbx.stream_wait(ex, m, tickets[-1])
+    orbx.stream_wait(ex, m, tickets[0])                   # waiting again is harmless
+    for ci, (a, b) in enumerate(zip(plain, outs)):
+        for k in ("n", "mono", "nmatches"):
+            np.testing.assert_array_equal(a[k], b[k], err_msg="%s batch %d" % (k, ci))
+        for f in range(B):
+            n = int(a["n"][f])
+            assert a["kps"][f, :n].tobytes() == b["kps"][f, :n].tobytes()
+            np.testing.assert_array_equal(a["desc"][f, :n], b["desc"][f, :n])
+            if f == 0 and ci == 0:
+                continue
+            npk = int(a["n"][f - 1]) if f else int(plain[ci - 1]["n"][B - 1])
+            for k in ("matches12", "knn_idx", "knn_dist"):
+                np.testing.assert_array_equal(a[k][f, :npk], b[k][f, :npk], err_msg="%s batch %d frame %d" % (k, ci, f))
+    # the plain call still works on the same handles afterwards (predecessor = last streamed frame)
+    out = buffers(ex.cap, False)
+    orbx.extract_match_batch(ex, m, batches[0], (0, 0), (0, W, 0, H), 100, out)
+    np.testing.assert_array_equal(out["n"], plain[0]["n"])
+    ex.close(); m.close()
