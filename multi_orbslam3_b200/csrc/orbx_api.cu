@@ -586,6 +586,7 @@ bool orbx_ex_take_prefetched(orbx_extractor* h, const uint8_t* imgs, int batch, 
 }
 int orbx_ex_pitch0(orbx_extractor* h) { return h->pitch0; }
 unsigned* orbx_ex_err_device(orbx_extractor* h) { return h->buf.err; }
+bool orbx_ex_profiling(orbx_extractor* h) { return h->profile; }
 bool orbx_host_pinned(const void* p) { return is_pinned(p); }
 long long orbx_ex_stride0(orbx_extractor* h) { return h->stride0; }
 

@@ -135,6 +135,7 @@ int orbx_ex_prefetch(orbx_extractor* h, const uint8_t* imgs, int batch, int widt
 bool orbx_ex_take_prefetched(orbx_extractor* h, const uint8_t* imgs, int batch, int width, int height, const uint8_t** d_frames, cudaEvent_t* ready);
 int orbx_ex_pitch0(orbx_extractor* h);
 unsigned* orbx_ex_err_device(orbx_extractor* h);
+bool orbx_ex_profiling(orbx_extractor* h);
 bool orbx_host_pinned(const void* p);
 long long orbx_ex_stride0(orbx_extractor* h);
 

@@ -800,6 +800,8 @@ extern "C" void orbx_matcher_destroy(orbx_matcher* m)
     if (m->s_h2d) {
         cudaStreamDestroy(m->s_h2d); cudaStreamDestroy(m->s_d2h); cudaStreamDestroy(m->s_match);
         if (m->st_init) for (int i = 0; i < 2; i++) { cudaEventDestroy(m->st[i].ev_kernels); cudaEventDestroy(m->st[i].ev_host); cudaFreeHost(m->st[i].h_err); }
+        if (m->lg.exec) cudaGraphExecDestroy(m->lg.exec);
+        if (m->lg.graph) cudaGraphDestroy(m->lg.graph);
         for (int i = 0; i < ORBX_MAX_CHUNKS; i++) cudaEventDestroy(m->ev_ext[i]);
         for (int i = 0; i < 2 * ORBX_MAX_CHUNKS; i++) { cudaEventDestroy(m->ev[i]); cudaEventDestroy(m->ev_r[i]); }
         cudaEventDestroy(m->ev_start);
@@ -1470,14 +1472,63 @@ static int extract_match_pipeline_impl(orbx_extractor* ex, orbx_matcher* m, bool
         // one synchronisation at the end that also brings back both handles' error flags.
         rc = orbx_ex_stage_input(ex, imgs, 0, batch, width, height, stride, frame_stride, s);
         if (rc) return rc;
-        rc = orbx_ex_run_staged(ex, 0, batch, lap0, lap1, 1, s);
-        if (rc) return rc;
-        if (m->cam_set) {
-            rc = orbx_undistort_slots_device(ex, 1, batch, m->cam_K, m->cam_dist, m->cam_ndist, m->cam_P, m->d_kps_un + (size_t)orbx_ex_out_cap(ex), s);
-            if (rc) return rc;
+        // The ~22 kernel launches of the step (pyramid x 8, FAST, octree, finalize, orient, describe, the matcher's 8) and the slot
+        // carry go through a CUDA graph: the first call with a set of arguments runs them directly (lazy allocations happen there),
+        // the second captures the same sequence, later calls replay it with one launch.  Copies in and out stay outside (their
+        // host pointers change from call to call).
+        auto issue_kernels = [&]() -> int {
+            int r = orbx_ex_run_staged(ex, 0, batch, lap0, lap1, 1, s);
+            if (r) return r;
+            if (m->cam_set) {
+                r = orbx_undistort_slots_device(ex, 1, batch, m->cam_K, m->cam_dist, m->cam_ndist, m->cam_P, m->d_kps_un + (size_t)orbx_ex_out_cap(ex), s);
+                if (r) return r;
+            }
+            return match_slots_impl(m, ex, m->d_pair_a, m->d_pair_b, batch, 0, bounds, window, nnratio, check_ori, dm12, dnm, d_knn_idx, d_knn_dist, s);
+        };
+        static const bool no_graph = getenv("ORBX_NO_GRAPH") != nullptr;
+        orbx_matcher::LatGraph& G = m->lg;
+        const bool same = G.seen > 0 && G.ex == ex && G.batch == batch && G.width == width && G.height == height && G.lap0 == lap0 && G.lap1 == lap1 &&
+                          G.window == window && G.check_ori == check_ori && G.knn == (d_knn_idx != nullptr) && G.cam == (int)m->cam_set &&
+                          G.nnratio == nnratio && memcmp(G.bounds, bounds, sizeof(G.bounds)) == 0 && G.d_knn == d_knn_idx;
+        if (no_graph || orbx_ex_profiling(ex)) {
+            if ((rc = issue_kernels())) return rc;
+        } else if (same && G.exec) {
+            CKM(cudaGraphLaunch(G.exec, s));
+            ORBX_COUNT_LAUNCH(G.nkernels);
+        } else if (same && G.seen == 1) {
+            if (G.exec) { cudaGraphExecDestroy(G.exec); G.exec = nullptr; }
+            if (G.graph) { cudaGraphDestroy(G.graph); G.graph = nullptr; }
+            const unsigned long long before = g_orbx_launches.load(std::memory_order_relaxed);
+            CKM(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+            rc = issue_kernels();
+            cudaGraph_t graph = nullptr;
+            const cudaError_t ce = cudaStreamEndCapture(s, &graph);
+            const int captured = (int)(g_orbx_launches.load(std::memory_order_relaxed) - before);
+            g_orbx_launches.fetch_sub(captured, std::memory_order_relaxed);            // nothing ran yet
+            if (rc || ce != cudaSuccess || !graph) {
+                cudaGetLastError();
+                if (graph) cudaGraphDestroy(graph);
+                G.seen = -1;                                                           // not capturable here: stay on direct launches
+                if (rc) return rc;
+                if ((rc = issue_kernels())) return rc;
+            } else {
+                if (cudaGraphInstantiate(&G.exec, graph, 0) != cudaSuccess) { cudaGetLastError(); cudaGraphDestroy(graph); G.exec = nullptr; G.seen = -1; if ((rc = issue_kernels())) return rc; }
+                else {
+                    G.graph = graph; G.nkernels = captured; G.seen = 2;
+                    CKM(cudaGraphLaunch(G.exec, s));
+                    ORBX_COUNT_LAUNCH(G.nkernels);
+                }
+            }
+        } else {
+            if (!same) {
+                if (G.exec) { cudaGraphExecDestroy(G.exec); G.exec = nullptr; }
+                if (G.graph) { cudaGraphDestroy(G.graph); G.graph = nullptr; }
+                G.ex = ex; G.batch = batch; G.width = width; G.height = height; G.lap0 = lap0; G.lap1 = lap1; G.window = window; G.check_ori = check_ori;
+                G.knn = d_knn_idx != nullptr; G.cam = (int)m->cam_set; G.nnratio = nnratio; memcpy(G.bounds, bounds, sizeof(G.bounds)); G.d_knn = d_knn_idx;
+                G.seen = 1;
+            }
+            if ((rc = issue_kernels())) return rc;
         }
-        rc = match_slots_impl(m, ex, m->d_pair_a, m->d_pair_b, batch, 0, bounds, window, nnratio, check_ori, dm12, dnm, d_knn_idx, d_knn_dist, s);
-        if (rc) return rc;
         rc = orbx_ex_fetch_async(ex, 1, batch, 0, kps, desc, cap, n, mono_index, s, direct);
         if (rc) return rc;
         if (matches12) CKM(cudaMemcpy2DAsync(matches12, sizeof(int32_t) * cap, dm12, sizeof(int32_t) * m->K, sizeof(int32_t) * (cap < m->K ? cap : m->K), batch,

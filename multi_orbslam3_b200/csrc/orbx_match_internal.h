@@ -151,6 +151,12 @@ struct orbx_matcher {
         bool busy; int batch;
     } st[2];
     size_t st_rows; int st_cap; long long st_ticket; bool st_init;
+    // CUDA graph of the kernels of the single-chunk host call (the batch-1 latency path): captured on the second call with the same
+    // arguments, replayed afterwards
+    struct LatGraph {
+        cudaGraphExec_t exec; cudaGraph_t graph; int nkernels; int seen;
+        const void* ex; int batch, width, height, lap0, lap1, window, check_ori, knn, cam; float bounds[4]; float nnratio; const void* d_knn;
+    } lg;
     std::vector<void*> allocs;
 };
 
