@@ -413,7 +413,8 @@ __global__ void __launch_bounds__(CAND_WARPS * 32, 6) k_window_candidates(WinBuf
 // mode 2 = SearchForInitialization, 0 / 1 = SearchByProjection overloads (see orbx.h)
 // out: mode 2 -> matches12 [P][K] (+ prev_xy update when prev != null); modes 0/1 -> assigned [P][K] (in/out)
 constexpr int INIT_UNRESOLVED = -1;       // nmatches[p] marker: the parallel resolve gave up on pair p, the sequential kernel takes it
-constexpr int INIT_NT = 256;
+constexpr int INIT_NT = 256;             // threads per pair in a batch; a launch over few pairs uses INIT_NT_FEW (one query per thread: latency)
+constexpr int INIT_NT_FEW = 1024;
 constexpr int INIT_CLAIMS = 4;            // claims kept per keypoint (more -> sequential fallback)
 constexpr int INIT_MAX_ROUNDS = 32;
 constexpr int INIT_MAX_K = 4096;          // shared memory of the parallel resolve: 6 ints per keypoint
@@ -430,14 +431,14 @@ constexpr int INIT_MAX_K = 4096;          // shared memory of the parallel resol
 // Steals (:760-764): the LAST claimer of a keypoint owns it; the rotation histogram counts every accepted claim, stolen or not,
 // as the reference's rotHist lists do (:772-779).  A keypoint with more than INIT_CLAIMS claimers, or no convergence within
 // INIT_MAX_ROUNDS, hands the pair to the sequential kernel (nmatches[p] = INIT_UNRESOLVED): still exact, never silently wrong.
-__global__ void __launch_bounds__(INIT_NT) k_init_resolve(WinBufs W, float nnratio, int check_ori, int32_t* out, int32_t* nmatches, float* prev_xy)
+__global__ void __launch_bounds__(INIT_NT_FEW) k_init_resolve(WinBufs W, float nnratio, int check_ori, int32_t* out, int32_t* nmatches, float* prev_xy)
 {
     extern __shared__ int s_mem[];
     __shared__ int hist[ORBX_HISTO_LENGTH];
     __shared__ int s_chg[2];                  // a decision changed in this round (indexed by round parity: reset two rounds later)
     __shared__ int s_over;                    // claim-list overflow
     __shared__ int s_count;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, NTH = blockDim.x;
     const int p = blockIdx.x;
     const PairDesc P = W.pairs[p];
     const int nq = min(P.nq, W.K), n2 = min(P.n2, W.K);
@@ -450,16 +451,16 @@ __global__ void __launch_bounds__(INIT_NT) k_init_resolve(WinBufs W, float nnrat
     const uint32_t* pool = W.pool + (long long)p * W.POOL;
     const int* q_off = W.q_off + (long long)p * W.K;
     const int* q_cnt = W.q_cnt + (long long)p * W.K;
-    for (int i = tid; i < nq; i += INIT_NT) dec[i] = NONE;
+    for (int i = tid; i < nq; i += NTH) dec[i] = NONE;
     if (tid < ORBX_HISTO_LENGTH) hist[tid] = 0;
     if (tid == 0) { s_over = 0; s_count = 0; }
     bool converged = false;
     for (int round = 0; round < INIT_MAX_ROUNDS; round++) {
-        for (int i = tid; i < n2; i += INIT_NT) cnt[i] = 0;
+        for (int i = tid; i < n2; i += NTH) cnt[i] = 0;
         if (tid == 0) s_chg[round & 1] = 0;
         __syncthreads();
         // claims of the current decisions, per keypoint
-        for (int i = tid; i < nq; i += INIT_NT) {
+        for (int i = tid; i < nq; i += NTH) {
             const uint32_t d = dec[i];
             if (d != NONE) {
                 const int i2 = d & 0xFFFF;
@@ -471,7 +472,7 @@ __global__ void __launch_bounds__(INIT_NT) k_init_resolve(WinBufs W, float nnrat
         __syncthreads();
         if (s_over) break;
         // every query decides again under the claims of the queries before it
-        for (int i = tid; i < nq; i += INIT_NT) {
+        for (int i = tid; i < nq; i += NTH) {
             const int c = q_cnt[i];
             if (c <= 0) continue;
             const int off = q_off[i];
@@ -499,7 +500,7 @@ __global__ void __launch_bounds__(INIT_NT) k_init_resolve(WinBufs W, float nnrat
     }
     if (!converged) { if (tid == 0) nmatches[p] = INIT_UNRESOLVED; return; }
     // the claim lists are those of the final decisions (the last round changed nothing)
-    for (int i = tid; i < nq; i += INIT_NT) {
+    for (int i = tid; i < nq; i += NTH) {
         const uint32_t d = dec[i];
         int r = -1; uint8_t bin = 0xFF;
         if (d != NONE) {
@@ -516,7 +517,7 @@ __global__ void __launch_bounds__(INIT_NT) k_init_resolve(WinBufs W, float nnrat
     int ind1 = -1, ind2 = -1, ind3 = -1;
     if (check_ori) three_maxima(hist, ind1, ind2, ind3);
     int mine = 0;
-    for (int i = tid; i < nq; i += INIT_NT) {
+    for (int i = tid; i < nq; i += NTH) {
         int m = res[i];
         if (check_ori) {
             const int b = bin_of[i];
@@ -1091,7 +1092,7 @@ static int run_window(orbx_matcher* m, const WinBufs& W, int npairs, int nq_max,
     if (mode == 2 && m->K <= INIT_MAX_K && !getenv("ORBX_SEQ_RESOLVE")) {
         // parallel fixed-point resolve; pairs it cannot finish are marked and fall through to the sequential kernel below
         CKM(ORBX_OPTIN_SMEM(k_init_resolve));
-        k_init_resolve<<<npairs, INIT_NT, (2 + INIT_CLAIMS) * m->K * sizeof(int), s>>>(W, nnratio, check_ori, d_out, d_nm, d_prev); ORBX_COUNT_LAUNCH(1);
+        k_init_resolve<<<npairs, npairs <= 32 ? INIT_NT_FEW : INIT_NT, (2 + INIT_CLAIMS) * m->K * sizeof(int), s>>>(W, nnratio, check_ori, d_out, d_nm, d_prev); ORBX_COUNT_LAUNCH(1);
         only_unresolved = 1;
     }
     k_window_resolve<<<npairs, 32, 2 * m->K * sizeof(int), s>>>(W, mode, nnratio, check_ori, max_dist, d_out, d_nm, d_prev, only_unresolved); ORBX_COUNT_LAUNCH(1);
