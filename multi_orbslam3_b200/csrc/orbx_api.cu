@@ -74,6 +74,8 @@ struct orbx_extractor {
     // input prefetch (orbx_extract_match_batch_prefetch): two extra staging buffers; entries are consumed first in, first out
     struct Prefetch { const uint8_t* src; int batch, width, height; uint8_t* buf; cudaEvent_t ev; };
     uint8_t* pf_buf[2]; size_t pf_bytes; cudaEvent_t pf_ev[2]; Prefetch pf[2]; int pf_count, pf_next;
+    cudaEvent_t pf_read[2]; bool pf_read_set[2];   // recorded on the kernel stream after the kernels that read pf_buf[i] were queued
+    int geom_gen;                                  // counts (re)configurations: cached launch graphs of other handles key on it
     orbx_keypoint* h_kps; uint8_t* h_desc; int* h_n; int* h_mono; unsigned* h_err;   // pinned
     // what the last batch used as level 0 (for pyramid_to_host)
     const uint8_t* last_level0; int last_pitch0; long long last_stride0; int last_batch;
@@ -136,6 +138,7 @@ static int configure_geometry_impl(orbx_extractor* h, int width, int height);
 static int configure_geometry(orbx_extractor* h, int width, int height)
 {
     if (h->geom.width == width && h->geom.height == height) return ORBX_OK;
+    h->geom_gen++;
     const int rc = configure_geometry_impl(h, width, height);
     if (rc != ORBX_OK) { h->geom.width = 0; h->geom.height = 0; }
     return rc;
@@ -316,6 +319,7 @@ extern "C" int orbx_extractor_create(const orbx_params* p, orbx_extractor** out)
     memset(&h->buf, 0, sizeof(h->buf));
     h->d_level0 = nullptr; h->last_level0 = nullptr; h->last_batch = 0;
     h->pf_buf[0] = h->pf_buf[1] = nullptr; h->pf_bytes = 0; h->pf_ev[0] = h->pf_ev[1] = nullptr; h->pf_count = 0; h->pf_next = 0;
+    h->pf_read[0] = h->pf_read[1] = nullptr; h->pf_read_set[0] = h->pf_read_set[1] = false; h->geom_gen = 0;
     h->d_raw = nullptr; h->raw_bytes = 0;
     h->profile = false; h->ev_head = 0; h->ev_count = 0; h->stage_batches = 0;
     for (int i = 0; i < 4; i++) h->stage_ms[i] = 0;
@@ -351,7 +355,7 @@ extern "C" void orbx_extractor_destroy(orbx_extractor* h)
     cudaStreamSynchronize(h->stream);
     for (void* p : h->allocs) cudaFree(p);
     if (h->d_raw) cudaFree(h->d_raw);
-    for (int i = 0; i < 2; i++) { if (h->pf_buf[i]) cudaFree(h->pf_buf[i]); if (h->pf_ev[i]) cudaEventDestroy(h->pf_ev[i]); }
+    for (int i = 0; i < 2; i++) { if (h->pf_buf[i]) cudaFree(h->pf_buf[i]); if (h->pf_ev[i]) cudaEventDestroy(h->pf_ev[i]); if (h->pf_read[i]) cudaEventDestroy(h->pf_read[i]); }
     cudaFreeHost(h->h_stage_in); cudaFreeHost(h->h_kps); cudaFreeHost(h->h_desc);
     cudaFreeHost(h->h_n); cudaFreeHost(h->h_mono); cudaFreeHost(h->h_err);
     for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
@@ -558,12 +562,19 @@ int orbx_ex_prefetch(orbx_extractor* h, const uint8_t* imgs, int batch, int widt
     if (need > h->pf_bytes) {
         if (h->pf_count) { orbx_set_error("%s%s", "orbx_extract_match_batch_prefetch: image size changed with a batch waiting", ""); return ORBX_E_INVALID; }
         for (int i = 0; i < 2; i++) { if (h->pf_buf[i]) { CK(cudaDeviceSynchronize()); cudaFree(h->pf_buf[i]); h->pf_buf[i] = nullptr; } }
-        for (int i = 0; i < 2; i++) { CK(cudaMalloc((void**)&h->pf_buf[i], need)); if (!h->pf_ev[i]) CK(cudaEventCreateWithFlags(&h->pf_ev[i], cudaEventDisableTiming)); }
+        for (int i = 0; i < 2; i++) {
+            CK(cudaMalloc((void**)&h->pf_buf[i], need));
+            if (!h->pf_ev[i]) CK(cudaEventCreateWithFlags(&h->pf_ev[i], cudaEventDisableTiming));
+            if (!h->pf_read[i]) CK(cudaEventCreateWithFlags(&h->pf_read[i], cudaEventDisableTiming));
+            h->pf_read_set[i] = false;
+        }
         h->pf_bytes = need;
     }
     const int slot = h->pf_next; h->pf_next ^= 1;
     orbx_extractor::Prefetch& e = h->pf[h->pf_count++];
     e.src = imgs; e.batch = batch; e.width = width; e.height = height; e.buf = h->pf_buf[slot]; e.ev = h->pf_ev[slot];
+    // the buffer may still be read by the kernels of the batch that used it last (streaming form: two batches in flight)
+    if (h->pf_read_set[slot]) CK(cudaStreamWaitEvent(s_copy, h->pf_read[slot], 0));
     CK(cudaMemcpyAsync(e.buf, imgs, (size_t)h->stride0 * batch, cudaMemcpyHostToDevice, s_copy));
     CK(cudaEventRecord(e.ev, s_copy));
     return ORBX_OK;
@@ -584,6 +595,14 @@ bool orbx_ex_take_prefetched(orbx_extractor* h, const uint8_t* imgs, int batch, 
     h->pf_count = 0;
     return false;
 }
+// to be called after the kernels that read a prefetched buffer were queued on `s`
+int orbx_ex_prefetch_mark_read(orbx_extractor* h, const uint8_t* d_frames, cudaStream_t s)
+{
+    for (int i = 0; i < 2; i++)
+        if (h->pf_buf[i] == d_frames && h->pf_read[i]) { CK(cudaEventRecord(h->pf_read[i], s)); h->pf_read_set[i] = true; }
+    return ORBX_OK;
+}
+int orbx_ex_geom_gen(orbx_extractor* h) { return h->geom_gen; }
 int orbx_ex_pitch0(orbx_extractor* h) { return h->pitch0; }
 unsigned* orbx_ex_err_device(orbx_extractor* h) { return h->buf.err; }
 bool orbx_ex_profiling(orbx_extractor* h) { return h->profile; }

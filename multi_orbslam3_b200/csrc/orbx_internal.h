@@ -134,6 +134,8 @@ int orbx_ex_fetch_err_async(orbx_extractor* h, cudaStream_t s);
 int orbx_ex_prefetch(orbx_extractor* h, const uint8_t* imgs, int batch, int width, int height, int stride, size_t frame_stride, cudaStream_t s_copy);
 bool orbx_ex_take_prefetched(orbx_extractor* h, const uint8_t* imgs, int batch, int width, int height, const uint8_t** d_frames, cudaEvent_t* ready);
 int orbx_ex_pitch0(orbx_extractor* h);
+int orbx_ex_prefetch_mark_read(orbx_extractor* h, const uint8_t* d_frames, cudaStream_t s);
+int orbx_ex_geom_gen(orbx_extractor* h);
 unsigned* orbx_ex_err_device(orbx_extractor* h);
 bool orbx_ex_profiling(orbx_extractor* h);
 bool orbx_host_pinned(const void* p);

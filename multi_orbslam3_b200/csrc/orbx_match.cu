@@ -1490,7 +1490,8 @@ static int extract_match_pipeline_impl(orbx_extractor* ex, orbx_matcher* m, bool
         orbx_matcher::LatGraph& G = m->lg;
         const bool same = G.seen > 0 && G.ex == ex && G.batch == batch && G.width == width && G.height == height && G.lap0 == lap0 && G.lap1 == lap1 &&
                           G.window == window && G.check_ori == check_ori && G.knn == (d_knn_idx != nullptr) && G.cam == (int)m->cam_set &&
-                          G.nnratio == nnratio && memcmp(G.bounds, bounds, sizeof(G.bounds)) == 0 && G.d_knn == d_knn_idx;
+                          G.nnratio == nnratio && memcmp(G.bounds, bounds, sizeof(G.bounds)) == 0 && G.d_knn == d_knn_idx &&
+                          G.geom_gen == orbx_ex_geom_gen(ex) && G.d_kps_un == m->d_kps_un;      // the extractor's / matcher's buffers are still the captured ones
         if (no_graph || orbx_ex_profiling(ex)) {
             if ((rc = issue_kernels())) return rc;
         } else if (same && G.exec) {
@@ -1526,6 +1527,7 @@ static int extract_match_pipeline_impl(orbx_extractor* ex, orbx_matcher* m, bool
                 if (G.graph) { cudaGraphDestroy(G.graph); G.graph = nullptr; }
                 G.ex = ex; G.batch = batch; G.width = width; G.height = height; G.lap0 = lap0; G.lap1 = lap1; G.window = window; G.check_ori = check_ori;
                 G.knn = d_knn_idx != nullptr; G.cam = (int)m->cam_set; G.nnratio = nnratio; memcpy(G.bounds, bounds, sizeof(G.bounds)); G.d_knn = d_knn_idx;
+                G.geom_gen = orbx_ex_geom_gen(ex); G.d_kps_un = m->d_kps_un;
                 G.seen = 1;
             }
             if ((rc = issue_kernels())) return rc;
@@ -1586,6 +1588,8 @@ static int extract_match_pipeline_impl(orbx_extractor* ex, orbx_matcher* m, bool
             if (rc) return rc;
         }
         CKM(cudaEventRecord(m->ev_ext[c], sc));
+        if (prefetched && c == nchunks - 1 && (rc = orbx_ex_prefetch_mark_read(ex, d_pref, s))) return rc;
+        if (!host && c == nchunks - 1 && (rc = orbx_ex_prefetch_mark_read(ex, imgs, sc))) return rc;      // streaming form: imgs IS a prefetch buffer
         // pairs (slot f0+i, slot f0+i+1) are matched on a second kernel stream, concurrently with the extraction of the
         // next chunk; each chunk owns its slice of the pair scratch
         CKM(cudaStreamWaitEvent(m->s_match, m->ev_ext[c], 0));

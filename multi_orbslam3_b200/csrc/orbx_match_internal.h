@@ -155,7 +155,7 @@ struct orbx_matcher {
     // arguments, replayed afterwards
     struct LatGraph {
         cudaGraphExec_t exec; cudaGraph_t graph; int nkernels; int seen;
-        const void* ex; int batch, width, height, lap0, lap1, window, check_ori, knn, cam; float bounds[4]; float nnratio; const void* d_knn;
+        const void* ex; int batch, width, height, lap0, lap1, window, check_ori, knn, cam, geom_gen; float bounds[4]; float nnratio; const void* d_knn; const void* d_kps_un;
     } lg;
     std::vector<void*> allocs;
 };

@@ -595,3 +595,45 @@ def test_stream_submit_wait_equals_plain_calls():
     orbx.extract_match_batch(ex, m, batches[0], (0, 0), (0, W, 0, H), 100, out)
     np.testing.assert_array_equal(out["n"], plain[0]["n"])
     ex.close(); m.close()
+
+
+def test_single_frame_call_graph_survives_reconfiguration():
+    """The batch-1 host call replays its kernels from a CUDA graph after two identical calls.  A reconfiguration of the extractor
+    through ANOTHER entry point (a different image size) re-allocates its buffers: the cached graph must not be replayed."""
+    W, H = 640, 480
+    frames = synth.rects_stream(W, H, 6, seed=94)
+    small = synth.rects_stream(320, 240, 1, seed=95)[0]
+    ex = orbx.ORBextractor(800, 1.2, 8, 20, 7, max_width=W, max_height=H, max_batch=1)
+    m = orbx.ORBmatcher(0.9, True, max_keypoints=ex.cap, max_batch=1)
+    ref = O.Extractor(800, 1.2, 8, 20, 7)
+    cap = ex.cap
+
+    def call(f):
+        out = {"kps": np.zeros((1, cap), orbx.KP_DTYPE), "desc": np.zeros((1, cap, 32), np.uint8), "n": np.zeros(1, np.int32),
+               "mono": np.zeros(1, np.int32), "matches12": np.zeros((1, cap), np.int32), "nmatches": np.zeros(1, np.int32),
+               "knn_idx": np.zeros((1, cap, 2), np.int32), "knn_dist": np.zeros((1, cap, 2), np.int32)}
+        orbx.extract_match_batch(ex, m, np.ascontiguousarray(frames[f:f + 1]), (0, 0), (0, W, 0, H), 100, out)
+        return out
+
+    def check(out, f, prev):
+        rmono, rk, rd = ref(frames[f], (0, 0))
+        n = int(out["n"][0])
+        assert n == len(rk) and np.array_equal(out["desc"][0, :n][out["kps"][0, :n]["angle"] == rk["angle"]], rd[out["kps"][0, :n]["angle"] == rk["angle"]])
+        if prev is not None:
+            pk, pd = prev
+            rn, rm12, _ = O.search_for_initialization(pk, pd, rk, rd, (0, W, 0, H), np.stack([pk["x"], pk["y"]], 1), 100, 0.9, True)
+            assert int(out["nmatches"][0]) == rn and np.array_equal(out["matches12"][0, :len(pk)], rm12)
+            ri, rdist = O.bf_knn2(pd, rd)
+            assert np.array_equal(out["knn_idx"][0, :len(pk)], ri) and np.array_equal(out["knn_dist"][0, :len(pk)], rdist)
+        return rk, rd
+
+    prev = None
+    for f in range(4):                                   # direct, captured, replayed, replayed
+        prev = check(call(f), f, prev)
+    _, sk, _ = ex(small, None, (0, 0))                   # reconfigures the extractor (320x240), then back
+    assert len(sk) > 0
+    prev = None                                          # slot 0 was rewritten by the plain call
+    out = call(4)
+    prev = check(out, 4, None)
+    check(call(5), 5, prev)
+    ex.close(); m.close()
