@@ -11,6 +11,7 @@
 #include "orbx_internal.h"
 
 std::atomic<unsigned long long> g_orbx_launches{0};
+bool orbx_pdl_enabled() { static const bool on = getenv("ORBX_NO_PDL") == nullptr; return on; }
 extern "C" unsigned long long orbx_launch_count(void) { return g_orbx_launches.load(std::memory_order_relaxed); }
 
 static thread_local std::string g_last_error;
@@ -83,6 +84,8 @@ struct orbx_extractor {
     // optional per-stage CUDA-event timing (bench.py): pyramid+blur | FAST | octree | finalize+orient+describe
     // a ring of event sets so that recording never makes the host wait inside a timed region; harvested on query
     bool profile; std::vector<cudaEvent_t> ev; int ev_head, ev_count; double stage_ms[4]; int stage_batches;
+    // level-parallel launch order of the few-frame path (run_batch_dag): one branch stream per level + one for the level-0 blur
+    cudaStream_t br[2 * ORBX_MAX_LEVELS]; cudaEvent_t ev_lvl[ORBX_MAX_LEVELS], ev_br[2 * ORBX_MAX_LEVELS]; bool dag_init;
 };
 #define ORBX_EV_SETS 512
 
@@ -359,6 +362,7 @@ extern "C" void orbx_extractor_destroy(orbx_extractor* h)
     cudaFreeHost(h->h_stage_in); cudaFreeHost(h->h_kps); cudaFreeHost(h->h_desc);
     cudaFreeHost(h->h_n); cudaFreeHost(h->h_mono); cudaFreeHost(h->h_err);
     for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
+    if (h->dag_init) for (int i = 0; i < 2 * ORBX_MAX_LEVELS; i++) { cudaStreamDestroy(h->br[i]); cudaEventDestroy(h->ev_br[i]); if (i < ORBX_MAX_LEVELS) cudaEventDestroy(h->ev_lvl[i]); }
     cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -417,6 +421,50 @@ static OrbxBuffers shifted(const orbx_extractor* h, int off)
     return b;
 }
 
+// The few-frame launch order.  With one or two frames every kernel is a handful of CTAs and the step is a CHAIN of latencies:
+// 8 pyramid levels, then FAST, then the octree whose level-0 CTA alone runs as long as the whole pyramid chain.  But level l's
+// FAST and octree need level l only, so they go to a branch stream of their own as soon as that level exists: FAST + octree of
+// level 0 run beside the resize chain 1 .. 7, and so on; the level-0 blur (needed by the descriptors only) leaves the chain too.
+// Everything joins before k_finalize.  Under stream capture the events become graph edges, so a replay costs one launch; issued
+// directly the ~60 API calls would cost more host time than the chain saves, which is why run_batch takes this path only when
+// the stream is being captured (the single-frame graph of orbx_extract_match_batch) or ORBX_DAG=1 forces it.
+static int ensure_dag(orbx_extractor* h)
+{
+    if (h->dag_init) return ORBX_OK;
+    for (int i = 0; i < 2 * ORBX_MAX_LEVELS; i++) {
+        CK(cudaStreamCreateWithFlags(&h->br[i], cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&h->ev_br[i], cudaEventDisableTiming));
+        if (i < ORBX_MAX_LEVELS) CK(cudaEventCreateWithFlags(&h->ev_lvl[i], cudaEventDisableTiming));
+    }
+    h->dag_init = true;
+    return ORBX_OK;
+}
+
+static int run_batch_dag(orbx_extractor* h, const OrbxBuffers& buf, const uint8_t* l0, int pitch0, long long stride0, int batch,
+                         int lap0, int lap1, int first_slot, cudaStream_t s)
+{
+    const OrbxGeom& g = h->geom;
+    const int nl = g.nlevels;
+    CK(cudaEventRecord(h->ev_lvl[0], s));                                   // level 0 = the input: whatever `s` carries so far
+    for (int l = 0; l < nl; l++) {
+        if (l >= 1) {
+            orbx_launch_pyramid(g, buf, l0, pitch0, stride0, batch, s, l, l + 1, ORBX_PYR_RESIZE);    // the chain: level l from level l - 1
+            CK(cudaEventRecord(h->ev_lvl[l], s));
+        }
+        cudaStream_t sf = h->br[l], sb = h->br[ORBX_MAX_LEVELS + l];
+        CK(cudaStreamWaitEvent(sf, h->ev_lvl[l], 0));
+        orbx_launch_fast(g, buf, l0, pitch0, stride0, batch, sf, l, l + 1);
+        orbx_launch_octree(g, buf, batch, sf, l, l + 1);
+        CK(cudaEventRecord(h->ev_br[l], sf));
+        CK(cudaStreamWaitEvent(sb, h->ev_lvl[l], 0));
+        orbx_launch_pyramid(g, buf, l0, pitch0, stride0, batch, sb, l, l + 1, ORBX_PYR_BLUR);         // needed by the descriptors only
+        CK(cudaEventRecord(h->ev_br[ORBX_MAX_LEVELS + l], sb));
+    }
+    for (int l = 0; l < nl; l++) { CK(cudaStreamWaitEvent(s, h->ev_br[l], 0)); CK(cudaStreamWaitEvent(s, h->ev_br[ORBX_MAX_LEVELS + l], 0)); }
+    orbx_launch_describe(g, buf, l0, pitch0, stride0, batch, lap0, lap1, first_slot, s);
+    return ORBX_OK;
+}
+
 static int run_batch(orbx_extractor* h, const uint8_t* d_level0, int pitch0, long long stride0, int batch,
                      int lap0, int lap1, int first_slot, cudaStream_t s, int frame_off = 0)
 {
@@ -424,6 +472,21 @@ static int run_batch(orbx_extractor* h, const uint8_t* d_level0, int pitch0, lon
     const OrbxBuffers buf = shifted(h, frame_off);
     const uint8_t* l0 = d_level0 + (long long)frame_off * stride0;
     const bool prof = h->profile;
+    static const int dag_env = getenv("ORBX_DAG") ? atoi(getenv("ORBX_DAG")) : -1;      // 0: never, 1: always for few frames, unset: under capture
+    if (!prof && batch <= 2 && g.nlevels > 1 && dag_env != 0) {
+        int rc = ensure_dag(h);                                             // (created on a direct call: not inside a capture)
+        if (rc) return rc;
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (dag_env != 1) CK(cudaStreamIsCapturing(s, &cs));
+        if (dag_env == 1 || cs == cudaStreamCaptureStatusActive) {
+            rc = run_batch_dag(h, buf, l0, pitch0, stride0, batch, lap0, lap1, first_slot, s);
+            if (rc) return rc;
+            h->last_level0 = d_level0; h->last_pitch0 = pitch0; h->last_stride0 = stride0;
+            if (frame_off + batch > h->last_batch || frame_off == 0) h->last_batch = frame_off + batch;
+            CK(cudaGetLastError());
+            return ORBX_OK;
+        }
+    }
     cudaEvent_t* e = nullptr;
     if (prof) {
         if (h->ev_count == ORBX_EV_SETS) harvest_stage_times(h, false);

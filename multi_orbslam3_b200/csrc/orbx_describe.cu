@@ -33,6 +33,7 @@ __global__ void __launch_bounds__(FIN_NT) k_finalize(OrbxGeom g, OrbxBuffers b, 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int f = blockIdx.x, slot_f = first_slot + f;
     const int* ln = b.lvl_n + (long long)f * g.nlevels;
+    orbx_pdl_prologue();
     if (tid == 0) {
         int run = 0;
         for (int l = 0; l < g.nlevels; l++) { s_base[l] = run; run += ln[l]; }
@@ -174,6 +175,7 @@ __global__ void __launch_bounds__(ORI_WARPS * 32, 5) k_orient(OrbxGeom g, OrbxBu
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int f = blockIdx.y;
     const int slot_f = first_slot + f;
+    orbx_pdl_prologue();
     const int total = b.n[slot_f];
     // a CTA walks groups blockIdx.x, blockIdx.x + gridDim.x, ...: the table copy is paid once per CTA, not once per 32 keypoints
     if (blockIdx.x * ORI_WARPS * G >= total) return;
@@ -268,6 +270,7 @@ __global__ void __launch_bounds__(DESC_WARPS * 32, 4) k_describe(OrbxGeom g, Orb
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int f = blockIdx.y;
     const int slot_f = first_slot + f;
+    orbx_pdl_prologue();
     const int total = b.n[slot_f];
     if (blockIdx.x * DESC_WARPS * G >= total) return;                     // whole CTA past the frame's keypoints
     for (int k = threadIdx.x; k < 8 * 32; k += DESC_WARPS * 32) s_pat[k] = d_pattern_f[k];
@@ -375,13 +378,13 @@ void orbx_upload_pattern()
 void orbx_launch_describe(const OrbxGeom& g, const OrbxBuffers& b, const uint8_t* level0, int pitch0,
                           long long stride0, int batch, int lap0, int lap1, int first_slot, cudaStream_t s)
 {
-    k_finalize<<<batch, FIN_NT, 0, s>>>(g, b, lap0, lap1, first_slot);
+    orbx_launch_pdl(k_finalize, dim3(batch), dim3(FIN_NT), 0, s, g, b, lap0, lap1, first_slot);
     // orientation: CTAs walk the keypoint groups of a frame in strides (the item table is copied once per CTA)
     {
         const int groups = (g.out_cap + ORI_WARPS * ORI_GROUP - 1) / (ORI_WARPS * ORI_GROUP);
         // big batches: 8 CTAs per frame amortise the table copy; a single frame spreads over the whole GPU instead
         dim3 grid(batch >= 32 && groups > 8 ? 8 : groups, batch);
-        k_orient<<<grid, ORI_WARPS * 32, 0, s>>>(g, b, level0, pitch0, stride0, first_slot);
+        orbx_launch_pdl(k_orient, grid, dim3(ORI_WARPS * 32), 0, s, g, b, level0, pitch0, stride0, first_slot);
     }
     dim3 grid((g.out_cap + DESC_WARPS * DESC_GROUP - 1) / (DESC_WARPS * DESC_GROUP), batch);
     // one 3-D tensor map (x, y, frame) per blurred level with a 64 x 37 box; the blurred levels are this library's own buffers
@@ -393,9 +396,9 @@ void orbx_launch_describe(const OrbxGeom& g, const OrbxBuffers& b, const uint8_t
         tma = orbx_make_tensor_map_3d(&maps.blur[l], b.blur[l], g.lv[l].w, g.lv[l].h, g.lv[l].pitch, g.lv[l].frame_stride, batch, PATCH_W, PATCH_H);
     if (tma) {
         ORBX_OPTIN_SMEM(k_describe<true>);
-        k_describe<true><<<grid, DESC_WARPS * 32, DESC_SMEM, s>>>(g, b, first_slot, maps);
+        orbx_launch_pdl(k_describe<true>, grid, dim3(DESC_WARPS * 32), (size_t)DESC_SMEM, s, g, b, first_slot, maps);
     } else {
-        k_describe<false><<<grid, DESC_WARPS * 32, 0, s>>>(g, b, first_slot, maps);
+        orbx_launch_pdl(k_describe<false>, grid, dim3(DESC_WARPS * 32), 0, s, g, b, first_slot, maps);
     }
     ORBX_COUNT_LAUNCH(3);
 }

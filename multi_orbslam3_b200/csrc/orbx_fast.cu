@@ -180,7 +180,7 @@ __host__ __device__ inline int tile_bytes(int nrow, int hs, int ng, int ncell)
 }
 
 __global__ void __launch_bounds__(NT, 5) k_fast_seg(OrbxGeom g, OrbxBuffers b, const uint8_t* level0, int pitch0,
-                                                    long long stride0, int smem_total)
+                                                    long long stride0, int smem_total, int unit0)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ FastSmem sh;
@@ -189,12 +189,14 @@ __global__ void __launch_bounds__(NT, 5) k_fast_seg(OrbxGeom g, OrbxBuffers b, c
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int f = blockIdx.y;
     // per-segment record precomputed by the host (orbx_fast_units)
-    const int4 u0 = __ldg(b.unit_tab + 4 * blockIdx.x), u1 = __ldg(b.unit_tab + 4 * blockIdx.x + 1), u2 = __ldg(b.unit_tab + 4 * blockIdx.x + 2);
+    const int unit = unit0 + blockIdx.x;                              // segment index inside the frame (a launch may cover one level only)
+    const int4 u0 = __ldg(b.unit_tab + 4 * unit), u1 = __ldg(b.unit_tab + 4 * unit + 1), u2 = __ldg(b.unit_tab + 4 * unit + 2);
     const int l = u0.x, iniY = u0.y, nrow = u0.z, hs = u0.w;          // level, first staged row, staged rows, scored rows (tile rows 3 .. nrow-4)
     const int xa0 = u1.x, sw = u1.y, X0 = u1.z, X1 = u1.w;            // staged columns [xa0, xa0+sw), scored tile columns [X0, X1)
     const int ncell = u2.x, tbytes = u2.y;
     const unsigned wrcp = (unsigned)u2.z, prcp = (unsigned)u2.w;      // (n * wrcp) >> 16 == n / wCell; (n * prcp) >> 20 == n / (pairs of groups per row)
-    int* row_count = b.row_count + (long long)f * g.total_rows + blockIdx.x;
+    orbx_pdl_prologue();                                              // (the segment table above is immutable after configure)
+    int* row_count = b.row_count + (long long)f * g.total_rows + unit;
     if (hs <= 0) { if (tid == 0) *row_count = 0; return; }
     const int wCell = g.lv[l].wCell, row_cap = g.lv[l].row_cap;
     const int g0 = X0 >> 2, g1 = (X1 - 1) >> 2, ng = g1 - g0 + 1;      // 4-pixel groups holding scored columns
@@ -419,7 +421,7 @@ __global__ void __launch_bounds__(NT, 5) k_fast_seg(OrbxGeom g, OrbxBuffers b, c
     __syncthreads();
 
     // ---- ordered emission: every survivor computes its own slot ----
-    uint32_t* out = b.row_cand + (long long)f * b.row_cand_stride + b.row_off[blockIdx.x];
+    uint32_t* out = b.row_cand + (long long)f * b.row_cand_stride + b.row_off[unit];
     const int yrel0 = iniY - ORBX_BORDER + 3;
     if (sh.cl_count <= CLCAP) {
         // one listed corner per thread: survivors of the NMS look up their own slot (dense lanes; the bitmap walk below
@@ -558,12 +560,16 @@ void orbx_fast_configure(const OrbxGeom& g)
 }
 
 void orbx_launch_fast(const OrbxGeom& g, const OrbxBuffers& b, const uint8_t* level0, int pitch0,
-                      long long stride0, int batch, cudaStream_t s)
+                      long long stride0, int batch, cudaStream_t s, int l_begin, int l_end)
 {
-    if (g.total_rows == 0) return;
-    dim3 grid(g.total_rows, batch);
+    if (l_end < 0 || l_end > g.nlevels) l_end = g.nlevels;
+    // the segments of a level are contiguous in the table: [row_base, row_base + nRows * nSeg)
+    const int unit0 = l_begin < g.nlevels ? g.lv[l_begin].row_base : g.total_rows;
+    const int unit1 = l_end < g.nlevels ? g.lv[l_end].row_base : g.total_rows;
+    if (unit1 <= unit0) return;
+    dim3 grid(unit1 - unit0, batch);
     const size_t smem = fast_smem_bytes(g);
     ORBX_OPTIN_SMEM(k_fast_seg);
-    k_fast_seg<<<grid, NT, smem, s>>>(g, b, level0, pitch0, stride0, (int)smem);
+    orbx_launch_pdl(k_fast_seg, grid, dim3(NT), smem, s, g, b, level0, pitch0, stride0, (int)smem, unit0);
     ORBX_COUNT_LAUNCH(1);
 }

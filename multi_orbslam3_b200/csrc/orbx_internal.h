@@ -86,12 +86,44 @@ __device__ __forceinline__ int orbx_reflect101(int p, int n)
 }
 #endif
 
+// ---- programmatic dependent launch (PDL) ----
+// The kernels of the per-frame chain (pyramid .. kNN merge) are launched with cudaLaunchAttributeProgrammaticStreamSerialization:
+// every CTA lets the NEXT kernel of the stream be scheduled as soon as it has started (griddepcontrol.launch_dependents) and
+// waits for the PREVIOUS kernel to have completed and flushed (griddepcontrol.wait) before it touches global memory, so the
+// launch latency and the CTA start-up of kernel k+1 hide behind the tail of kernel k.  On the single-frame path (15 short
+// kernels replayed from a CUDA graph) that is most of the gap between the kernels.  RULE: a kernel launched through
+// orbx_launch_pdl MUST call orbx_pdl_prologue() before its first global access (without the wait it would start early).
+// ORBX_NO_PDL=1 launches them as ordinary kernels (the prologue is then a no-op).
+#ifdef __CUDACC__
+__device__ __forceinline__ void orbx_pdl_prologue()
+{
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+#endif
+bool orbx_pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t orbx_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = orbx_pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // kernel launchers (defined in the .cu files)
+// (l_begin, l_end): the levels a launch covers, default all; the single-frame path launches level by level on branch streams
+// parts: the resize + store of a level and its blur can be launched apart (blur: from the stored level)
+#define ORBX_PYR_RESIZE 1
+#define ORBX_PYR_BLUR 2
 void orbx_launch_pyramid(const OrbxGeom& g, const OrbxBuffers& b, const uint8_t* level0, int pitch0,
-                         long long stride0, int batch, cudaStream_t s);
+                         long long stride0, int batch, cudaStream_t s, int l_begin = 0, int l_end = -1, int parts = ORBX_PYR_RESIZE | ORBX_PYR_BLUR);
 void orbx_launch_fast(const OrbxGeom& g, const OrbxBuffers& b, const uint8_t* level0, int pitch0,
-                      long long stride0, int batch, cudaStream_t s);
-void orbx_launch_octree(const OrbxGeom& g, const OrbxBuffers& b, int batch, cudaStream_t s);
+                      long long stride0, int batch, cudaStream_t s, int l_begin = 0, int l_end = -1);
+void orbx_launch_octree(const OrbxGeom& g, const OrbxBuffers& b, int batch, cudaStream_t s, int l_begin = 0, int l_end = -1);
 void orbx_launch_describe(const OrbxGeom& g, const OrbxBuffers& b, const uint8_t* level0, int pitch0,
                           long long stride0, int batch, int lap0, int lap1, int first_slot, cudaStream_t s);
 int  orbx_octree_smem_bytes(const OrbxGeom& g);

@@ -123,6 +123,7 @@ __global__ void __launch_bounds__(bftc::ws::NT, 1) k_bf_knn2_tcws(BfArgs A)
 {
     extern __shared__ __align__(128) uint8_t bf_smem[];
     const int p = blockIdx.z, split = blockIdx.y;
+    orbx_pdl_prologue();
     const uint8_t* q; const uint8_t* t; int nq; long long nt;
     if (A.q) { q = A.q; t = A.t; nq = A.nq; nt = A.nt; }
     else {
@@ -149,6 +150,7 @@ __global__ void k_knn2_merge(const int32_t* pidx, const int32_t* pdist, int npar
                              const int* n, const int* a, int32_t* idx, int32_t* dist)
 {
     const int p = blockIdx.y;
+    orbx_pdl_prologue();
     const int nq = n ? n[a[p]] : nq_fixed;
     const int qi = blockIdx.x * blockDim.x + threadIdx.x;
     if (qi >= nq) return;
@@ -176,6 +178,7 @@ __global__ void k_setup_slot_pairs(WinBufs W, const orbx_keypoint* kps, const ui
                                    const int* a, const int* b, int cap, float window)
 {
     const int p = blockIdx.x;
+    orbx_pdl_prologue();
     const int sa = a[p], sb = b[p];
     const orbx_keypoint* k1 = kps + (long long)sa * cap;
     if (threadIdx.x == 0) {
@@ -214,6 +217,8 @@ __global__ void __launch_bounds__(GRID_NT) k_grid_build(WinBufs W, int npad_max)
 {
     extern __shared__ uint32_t keys[];     // [npad]
     const int p = blockIdx.x;
+    orbx_pdl_prologue();
+    if (threadIdx.x == 0) W.pool_used[p] = 0;       // the candidate pool of the pair starts empty (k_window_candidates fills it)
     const PairDesc P = W.pairs[p];
     const int n = min(P.n2, W.K);
     int npad = 1; while (npad < n) npad <<= 1;
@@ -269,6 +274,7 @@ __global__ void __launch_bounds__(CAND_WARPS * 32, 6) k_window_candidates(WinBuf
 {
     const int lane = threadIdx.x & 31;
     const int p = blockIdx.y;
+    orbx_pdl_prologue();
     const PairDesc P = W.pairs[p];
     const int qi = blockIdx.x * CAND_WARPS + (threadIdx.x >> 5);
     if (qi >= P.nq || qi >= W.K) return;
@@ -440,6 +446,7 @@ __global__ void __launch_bounds__(INIT_NT_FEW) k_init_resolve(WinBufs W, float n
     __shared__ int s_count;
     const int tid = threadIdx.x, NTH = blockDim.x;
     const int p = blockIdx.x;
+    orbx_pdl_prologue();
     const PairDesc P = W.pairs[p];
     const int nq = min(P.nq, W.K), n2 = min(P.n2, W.K);
     uint32_t* dec = reinterpret_cast<uint32_t*>(s_mem);              // [K] by query: i2 | dist << 16, or NONE
@@ -539,6 +546,7 @@ __global__ void __launch_bounds__(32) k_window_resolve(WinBufs W, int mode, floa
     extern __shared__ int s_mem[];
     const int lane = threadIdx.x;
     const int p = blockIdx.x;
+    orbx_pdl_prologue();
     if (only_unresolved && nmatches[p] != INIT_UNRESOLVED) return;        // k_init_resolve finished this pair
     const PairDesc P = W.pairs[p];
     const int nq = min(P.nq, W.K), n2 = min(P.n2, W.K);
@@ -801,6 +809,7 @@ extern "C" void orbx_matcher_destroy(orbx_matcher* m)
     if (m->s_h2d) {
         cudaStreamDestroy(m->s_h2d); cudaStreamDestroy(m->s_d2h); cudaStreamDestroy(m->s_match);
         if (m->st_init) for (int i = 0; i < 2; i++) { cudaEventDestroy(m->st[i].ev_kernels); cudaEventDestroy(m->st[i].ev_host); cudaFreeHost(m->st[i].h_err); }
+        if (m->s_bf) { cudaStreamDestroy(m->s_bf); cudaEventDestroy(m->ev_bf_fork); cudaEventDestroy(m->ev_bf_join); }
         if (m->lg.exec) cudaGraphExecDestroy(m->lg.exec);
         if (m->lg.graph) cudaGraphDestroy(m->lg.graph);
         for (int i = 0; i < ORBX_MAX_CHUNKS; i++) cudaEventDestroy(m->ev_ext[i]);
@@ -899,7 +908,7 @@ static int bf_launch(orbx_matcher* m, BfArgs A, int npairs, int nq_max, long lon
     static const bool lockstep = getenv("ORBX_BF_LOCKSTEP") != nullptr;   // the first tensor-core kernel (all warps do everything), for comparison
     if (!use_popc && !lockstep) {
         CKM(ORBX_OPTIN_SMEM(k_bf_knn2_tcws));
-        k_bf_knn2_tcws<<<grid, bftc::ws::NT, bftc::ws::SMEM_BYTES, s>>>(A); ORBX_COUNT_LAUNCH(1);
+        orbx_launch_pdl(k_bf_knn2_tcws, grid, dim3(bftc::ws::NT), (size_t)bftc::ws::SMEM_BYTES, s, A); ORBX_COUNT_LAUNCH(1);
     } else if (!use_popc) {
         CKM(ORBX_OPTIN_SMEM(k_bf_knn2_tc));
         k_bf_knn2_tc<<<grid, bftc::NT, bftc::SMEM_BYTES, s>>>(A); ORBX_COUNT_LAUNCH(1);
@@ -908,7 +917,7 @@ static int bf_launch(orbx_matcher* m, BfArgs A, int npairs, int nq_max, long lon
     }
     if (nsplit > 1) {
         dim3 mg((nq_max + 127) / 128, npairs);
-        k_knn2_merge<<<mg, 128, 0, s>>>(A.part_idx, A.part_dist, nsplit, A.out_stride, A.nq, A.q ? nullptr : A.n, A.a, A.idx, A.dist); ORBX_COUNT_LAUNCH(1);
+        orbx_launch_pdl(k_knn2_merge, mg, dim3(128), 0, s, A.part_idx, A.part_dist, nsplit, A.out_stride, A.nq, A.q ? nullptr : A.n, A.a, A.idx, A.dist); ORBX_COUNT_LAUNCH(1);
     }
     CKM(cudaGetLastError());
     return ORBX_OK;
@@ -1081,21 +1090,20 @@ static int run_window(orbx_matcher* m, const WinBufs& W, int npairs, int nq_max,
                       int32_t* d_out, int32_t* d_nm, float* d_prev, cudaStream_t s, int max_dist = ORBX_TH_HIGH)
 {
     int npad = 1; while (npad < m->K) npad <<= 1;
-    CKM(cudaMemsetAsync(W.pool_used, 0, sizeof(int) * npairs, s));
     CKM(ORBX_OPTIN_SMEM(k_grid_build));
-    k_grid_build<<<npairs, GRID_NT, sizeof(uint32_t) * npad, s>>>(W, npad); ORBX_COUNT_LAUNCH(1);
+    orbx_launch_pdl(k_grid_build, dim3(npairs), dim3(GRID_NT), sizeof(uint32_t) * npad, s, W, npad); ORBX_COUNT_LAUNCH(1);      // also empties the pairs' candidate pools
     dim3 cg((nq_max + CAND_WARPS - 1) / CAND_WARPS, npairs);
-    if (nq_max > 0) { k_window_candidates<<<cg, CAND_WARPS * 32, 0, s>>>(W); ORBX_COUNT_LAUNCH(1); }
+    if (nq_max > 0) { orbx_launch_pdl(k_window_candidates, cg, dim3(CAND_WARPS * 32), 0, s, W); ORBX_COUNT_LAUNCH(1); }
     if (mode == 3) { CKM(cudaGetLastError()); return ORBX_OK; }
     CKM(ORBX_OPTIN_SMEM(k_window_resolve));
     int only_unresolved = 0;
     if (mode == 2 && m->K <= INIT_MAX_K && !getenv("ORBX_SEQ_RESOLVE")) {
         // parallel fixed-point resolve; pairs it cannot finish are marked and fall through to the sequential kernel below
         CKM(ORBX_OPTIN_SMEM(k_init_resolve));
-        k_init_resolve<<<npairs, npairs <= 32 ? INIT_NT_FEW : INIT_NT, (2 + INIT_CLAIMS) * m->K * sizeof(int), s>>>(W, nnratio, check_ori, d_out, d_nm, d_prev); ORBX_COUNT_LAUNCH(1);
+        orbx_launch_pdl(k_init_resolve, dim3(npairs), dim3(npairs <= 32 ? INIT_NT_FEW : INIT_NT), (2 + INIT_CLAIMS) * m->K * sizeof(int), s, W, nnratio, check_ori, d_out, d_nm, d_prev); ORBX_COUNT_LAUNCH(1);
         only_unresolved = 1;
     }
-    k_window_resolve<<<npairs, 32, 2 * m->K * sizeof(int), s>>>(W, mode, nnratio, check_ori, max_dist, d_out, d_nm, d_prev, only_unresolved); ORBX_COUNT_LAUNCH(1);
+    orbx_launch_pdl(k_window_resolve, dim3(npairs), dim3(32), 2 * m->K * sizeof(int), s, W, mode, nnratio, check_ori, max_dist, d_out, d_nm, d_prev, only_unresolved); ORBX_COUNT_LAUNCH(1);
     CKM(cudaGetLastError());
     return ORBX_OK;
 }
@@ -1296,13 +1304,37 @@ static int match_slots_impl(orbx_matcher* m, orbx_extractor* ex, const int32_t* 
     const WinBufs W = shifted_pairs(m, pair_base);
     // NOTE: outputs use row stride K (= matcher max_keypoints)
     // mvKeysUn when the caller supplied undistorted keypoints (same [slot][cap] layout), mvKeys otherwise
-    k_setup_slot_pairs<<<npairs, 256, 0, s>>>(W, m->d_kps_src ? m->d_kps_src : kps, desc, n, a, b, cap, (float)window); ORBX_COUNT_LAUNCH(1);
+    // The brute-force kNN-2 does not depend on the window search (both only read the slots).  With a few pairs each kernel is a
+    // few CTAs and the two chains run side by side (same policy as the extractor's run_batch_dag: under stream capture, where the
+    // fork / join are graph edges; ORBX_DAG=1 forces it, 0 disables it).  With a full batch either kernel fills the GPU and a
+    // fork gains nothing (measured: 3.424 vs 3.420 ms per 512 frames).
+    static const int dag_env = getenv("ORBX_DAG") ? atoi(getenv("ORBX_DAG")) : -1;
+    bool fork = false;
+    if (d_knn_idx && d_knn_dist && npairs <= 2 && dag_env != 0) {
+        if (!m->s_bf) {
+            CKM(cudaStreamCreateWithFlags(&m->s_bf, cudaStreamNonBlocking));
+            CKM(cudaEventCreateWithFlags(&m->ev_bf_fork, cudaEventDisableTiming));
+            CKM(cudaEventCreateWithFlags(&m->ev_bf_join, cudaEventDisableTiming));
+        }
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (dag_env != 1) CKM(cudaStreamIsCapturing(s, &cs));
+        fork = dag_env == 1 || cs == cudaStreamCaptureStatusActive;
+    }
+    BfArgs A{};
+    A.q = nullptr; A.desc = desc; A.n = n; A.a = a; A.b = b; A.cap = cap;
+    A.idx = d_knn_idx; A.dist = d_knn_dist; A.out_stride = m->K; A.idx_base = 0;
+    if (fork) {
+        CKM(cudaEventRecord(m->ev_bf_fork, s));
+        CKM(cudaStreamWaitEvent(m->s_bf, m->ev_bf_fork, 0));
+        rc = bf_launch(m, A, npairs, cap, cap, m->s_bf);
+        if (rc) return rc;
+        CKM(cudaEventRecord(m->ev_bf_join, m->s_bf));
+    }
+    orbx_launch_pdl(k_setup_slot_pairs, dim3(npairs), dim3(256), 0, s, W, m->d_kps_src ? m->d_kps_src : kps, desc, n, a, b, cap, (float)window); ORBX_COUNT_LAUNCH(1);
     rc = run_window(m, W, npairs, cap, 2, nnratio, check_ori, d_matches12, d_nmatches, nullptr, s);
     if (rc) return rc;
-    if (d_knn_idx && d_knn_dist) {
-        BfArgs A{};
-        A.q = nullptr; A.desc = desc; A.n = n; A.a = a; A.b = b; A.cap = cap;
-        A.idx = d_knn_idx; A.dist = d_knn_dist; A.out_stride = m->K; A.idx_base = 0;
+    if (fork) CKM(cudaStreamWaitEvent(s, m->ev_bf_join, 0));
+    else if (d_knn_idx && d_knn_dist) {
         rc = bf_launch(m, A, npairs, cap, cap, s);
         if (rc) return rc;
     }

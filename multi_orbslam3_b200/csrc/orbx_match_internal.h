@@ -141,6 +141,7 @@ struct orbx_matcher {
     uint8_t* d_gen; size_t gen_bytes;
     uint8_t* d_st; size_t st_bytes;          // stereo scratch
     int32_t* h_mono2; int mono2_cap;         // pinned monoIndex landing zone of the stereo pipeline (2 x batch)
+    cudaStream_t s_bf; cudaEvent_t ev_bf_fork, ev_bf_join;      // few-pair path: the brute-force search runs beside the window search
     cudaStream_t s_h2d, s_d2h, s_match; cudaEvent_t ev[2 * ORBX_MAX_CHUNKS]; cudaEvent_t ev_ext[ORBX_MAX_CHUNKS]; cudaEvent_t ev_start;
     cudaEvent_t ev_r[2 * ORBX_MAX_CHUNKS];      // right camera of the stereo pipeline: [c] copy done, [MAX + c] extraction done
     // streaming form (orbx_stream_submit / orbx_stream_wait): two result staging sets on the device, so that the results of batch k

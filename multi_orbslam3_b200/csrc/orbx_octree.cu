@@ -97,12 +97,12 @@ struct OctShared {
     int row_prefix[ORBX_MAX_UNITS + 1];
 };
 
-__global__ void __launch_bounds__(NT) k_octree(OrbxGeom g, OrbxBuffers b, int smem_pts, int ncap)
+__global__ void __launch_bounds__(NT) k_octree(OrbxGeom g, OrbxBuffers b, int smem_pts, int ncap, int level_base)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ OctShared sh;
     const int tid = threadIdx.x;
-    const int l = blockIdx.x, f = blockIdx.y;
+    const int l = level_base + blockIdx.x, f = blockIdx.y;
     const OrbxLevel L = g.lv[l];
     int* out_n = b.lvl_n + (long long)f * g.nlevels + l;
     uint32_t* out_kp = b.lvl_kp + (long long)f * g.kp_total_cap + L.kp_base;
@@ -117,6 +117,7 @@ __global__ void __launch_bounds__(NT) k_octree(OrbxGeom g, OrbxBuffers b, int sm
     unsigned* Vs = Vb + ncap;                                            // [pow2(ncap)] sort keys
     uint8_t* proc = reinterpret_cast<uint8_t*>(Vs + ncap * 2);           // [ncap]
 
+    orbx_pdl_prologue();
     // ---- gather the level's candidates in reference order (cell rows top to bottom) ----
     if (L.nRows <= 0 || L.nCols <= 0) { if (tid == 0) *out_n = 0; return; }
     const int* rc = b.row_count + (long long)f * g.total_rows + L.row_base;
@@ -409,12 +410,14 @@ OctCfg octree_cfg(const OrbxGeom& g)
 
 int orbx_octree_smem_bytes(const OrbxGeom& g) { return (int)octree_cfg(g).smem; }
 
-void orbx_launch_octree(const OrbxGeom& g, const OrbxBuffers& b, int batch, cudaStream_t s)
+void orbx_launch_octree(const OrbxGeom& g, const OrbxBuffers& b, int batch, cudaStream_t s, int l_begin, int l_end)
 {
     const OctCfg c = octree_cfg(g);
-    dim3 grid(g.nlevels, batch);
+    if (l_end < 0 || l_end > g.nlevels) l_end = g.nlevels;
+    if (l_end <= l_begin) return;
+    dim3 grid(l_end - l_begin, batch);
     ORBX_OPTIN_SMEM(k_octree);
-    k_octree<<<grid, NT, c.smem, s>>>(g, b, c.smem_pts, c.ncap);
+    orbx_launch_pdl(k_octree, grid, dim3(NT), (size_t)c.smem, s, g, b, c.smem_pts, c.ncap, l_begin);
     ORBX_COUNT_LAUNCH(1);
 }
 

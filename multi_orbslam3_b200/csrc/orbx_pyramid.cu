@@ -144,10 +144,12 @@ __global__ void __launch_bounds__(NT) k_pyr_level(PyrArgs a)
 }  // namespace generic
 
 static void launch_pyramid_generic(const OrbxGeom& g, const OrbxBuffers& b, const uint8_t* level0, int pitch0,
-                         long long stride0, int batch, cudaStream_t s)
+                         long long stride0, int batch, cudaStream_t s, int l_begin, int l_end, int parts)
 {
     using namespace generic;
-    for (int l = 0; l < g.nlevels; l++) {
+    for (int l = l_begin; l < l_end; l++) {
+        // (no split here: the resize part of a level runs the fused kernel, its blur part is then already done)
+        if ((parts == ORBX_PYR_BLUR && l >= 1) || (parts == ORBX_PYR_RESIZE && l == 0)) continue;
         const OrbxLevel& L = g.lv[l];
         PyrArgs a{};
         a.w = L.w; a.h = L.h;
@@ -203,6 +205,7 @@ struct Args {
     int sp;        // smem source pitch (multiple of 16) = TMA box width
     int sh_max;    // smem source rows = TMA box height
     int use_tma;   // source tile arrives by cp.async.bulk.tensor (3-D tiled map: x, y, frame)
+    int no_blur;   // resize and store the level only (the few-frame path runs the blur of the level on a branch stream)
 };
 
 // ---- TMA / mbarrier primitives (sm_90+ PTX; SASS: UTMALDG, SYNCS) ----
@@ -337,6 +340,7 @@ __global__ void __launch_bounds__(NT) k_pyr_fast(Args a, const __grid_constant__
     uint8_t* R = smem + s_bytes;                                   // [RH][RP]
     uint16_t* Hb = reinterpret_cast<uint16_t*>(R + RH * RP);       // [RH][TW]  (aliases Hs)
     const uint8_t* srcf = a.src + (long long)f * a.sstride;
+    orbx_pdl_prologue();
 
     if (RESIZE) {
         uint16_t* Hs = Hb;                                         // [sh_max][HP]
@@ -466,7 +470,7 @@ __global__ void __launch_bounds__(NT) k_pyr_fast(Args a, const __grid_constant__
                     *reinterpret_cast<const uint4*>(R + (3 + r) * RP + RO + c16 * 16);
         }
     }
-    blur_and_store(R, Hb, a.blur + (long long)f * a.bstride, a.bpitch, X0, Y0, tw, th);
+    if (!a.no_blur) blur_and_store(R, Hb, a.blur + (long long)f * a.bstride, a.bpitch, X0, Y0, tw, th);
 }
 
 }  // namespace fastp
@@ -510,28 +514,33 @@ bool orbx_make_tensor_map_3d(void* map128, const uint8_t* base, int w, int h, in
 }
 
 void orbx_launch_pyramid(const OrbxGeom& g, const OrbxBuffers& b, const uint8_t* level0, int pitch0,
-                         long long stride0, int batch, cudaStream_t s)
+                         long long stride0, int batch, cudaStream_t s, int l_begin, int l_end, int parts)
 {
     using namespace fastp;
+    if (l_end < 0 || l_end > g.nlevels) l_end = g.nlevels;
     // the fast kernels need a scale factor <= 1.5 (source tile extents) and a blur pitch that is a multiple of 16
     bool ok = true;
     for (int l = 1; l < g.nlevels; l++) {
         const double sx = (double)g.lv[l - 1].w / g.lv[l].w, sy = (double)g.lv[l - 1].h / g.lv[l].h;
         if (sx > 1.55 || sy > 1.55) ok = false;
     }
-    if (!ok) { launch_pyramid_generic(g, b, level0, pitch0, stride0, batch, s); return; }
-    for (int l = 0; l < g.nlevels; l++) {
+    if (!ok) { launch_pyramid_generic(g, b, level0, pitch0, stride0, batch, s, l_begin, l_end, parts); return; }
+    for (int l = l_begin; l < l_end; l++) {
+        if (l == 0 && !(parts & ORBX_PYR_BLUR)) continue;                 // level 0 has no resize part
         const OrbxLevel& L = g.lv[l];
         Args a{};
         a.w = L.w; a.h = L.h;
         a.blur = b.blur[l]; a.bpitch = L.pitch; a.bstride = L.frame_stride;
         dim3 grid((L.w + TW - 1) / TW, (L.h + TH - 1) / TH, batch);
-        if (l == 0) {
-            a.src = level0; a.spitch = pitch0; a.sstride = stride0; a.sw = L.w; a.sh = L.h;
+        if (l == 0 || parts == ORBX_PYR_BLUR) {
+            // blur only: of the caller's frame (level 0) or of a level the resize part has already stored
+            if (l == 0) { a.src = level0; a.spitch = pitch0; a.sstride = stride0; }
+            else { a.src = b.pyr[l]; a.spitch = L.pitch; a.sstride = L.frame_stride; }
+            a.sw = L.w; a.sh = L.h;
             const size_t smem = RH * RP + RH * TW * 2;
             ORBX_OPTIN_SMEM(k_pyr_fast<false>);
             CUtensorMap none; memset(&none, 0, sizeof(none));
-            k_pyr_fast<false><<<grid, NT, smem, s>>>(a, none);
+            orbx_launch_pdl(k_pyr_fast<false>, grid, dim3(NT), smem, s, a, none);
         } else {
             const OrbxLevel& P = g.lv[l - 1];
             a.src = (l == 1) ? level0 : b.pyr[l - 1];
@@ -543,12 +552,13 @@ void orbx_launch_pyramid(const OrbxGeom& g, const OrbxBuffers& b, const uint8_t*
             const double sx = (double)P.w / L.w, sy = (double)P.h / L.h;
             a.sp = (((int)(RW * sx) + 2 + 15 + 16) + 15) & ~15;     // span + alignment slack, multiple of 16
             a.sh_max = (int)(RH * sy) + 4;
+            a.no_blur = (parts & ORBX_PYR_BLUR) ? 0 : 1;
             const size_t hs_bytes = (size_t)a.sh_max * HP * 2 > (size_t)RH * TW * 2 ? (size_t)a.sh_max * HP * 2 : (size_t)RH * TW * 2;
             const size_t smem = (((size_t)a.sh_max * a.sp + 127) & ~(size_t)127) + RH * RP + hs_bytes + RH * sizeof(int4);
             ORBX_OPTIN_SMEM(k_pyr_fast<true>);
             CUtensorMap map; memset(&map, 0, sizeof(map));
             a.use_tma = make_map(&map, a.src, a.sw, a.sh, a.spitch, a.sstride, batch, a.sp, a.sh_max) ? 1 : 0;
-            k_pyr_fast<true><<<grid, NT, smem, s>>>(a, map);
+            orbx_launch_pdl(k_pyr_fast<true>, grid, dim3(NT), smem, s, a, map);
         }
         ORBX_COUNT_LAUNCH(1);
     }

@@ -598,8 +598,9 @@ def test_stream_submit_wait_equals_plain_calls():
 
 
 def test_single_frame_call_graph_survives_reconfiguration():
-    """The batch-1 host call replays its kernels from a CUDA graph after two identical calls.  A reconfiguration of the extractor
-    through ANOTHER entry point (a different image size) re-allocates its buffers: the cached graph must not be replayed."""
+    """The batch-1 host call replays its kernels from a CUDA graph after two identical calls (captured in the level-parallel order
+    of run_batch_dag: per-level FAST / octree / blur branches beside the resize chain, the brute-force search beside the window
+    search).  A reconfiguration of the extractor through ANOTHER entry point (a different image size) re-allocates its buffers: the cached graph must not be replayed."""
     W, H = 640, 480
     frames = synth.rects_stream(W, H, 6, seed=94)
     small = synth.rects_stream(320, 240, 1, seed=95)[0]
@@ -618,7 +619,10 @@ def test_single_frame_call_graph_survives_reconfiguration():
     def check(out, f, prev):
         rmono, rk, rd = ref(frames[f], (0, 0))
         n = int(out["n"][0])
-        assert n == len(rk) and np.array_equal(out["desc"][0, :n][out["kps"][0, :n]["angle"] == rk["angle"]], rd[out["kps"][0, :n]["angle"] == rk["angle"]])
+        assert n == len(rk) and int(out["mono"][0]) == rmono
+        for name in ("x", "y", "size", "response", "octave"):
+            np.testing.assert_array_equal(out["kps"][0, :n][name], rk[name])
+        assert np.array_equal(out["desc"][0, :n][out["kps"][0, :n]["angle"] == rk["angle"]], rd[out["kps"][0, :n]["angle"] == rk["angle"]])
         if prev is not None:
             pk, pd = prev
             rn, rm12, _ = O.search_for_initialization(pk, pd, rk, rd, (0, W, 0, H), np.stack([pk["x"], pk["y"]], 1), 100, 0.9, True)
