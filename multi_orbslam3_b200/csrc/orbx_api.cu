@@ -534,15 +534,28 @@ extern "C" int orbx_extractor_sync(orbx_extractor* h, void* stream)
     return deferred_error(h);
 }
 
+// one launch instead of four device-to-device copies: keypoints (7 words each), descriptors (8 words each), n, monoIndex
+__global__ void k_copy_slot(uint32_t* kps, uint32_t* desc, int* n, int* mono, int from, int to, int cap)
+{
+    static_assert(sizeof(orbx_keypoint) == 28, "keypoint record = 7 words");
+    const int wk = cap * 7, wd = cap * 8;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < wk + wd; i += gridDim.x * blockDim.x) {
+        if (i < wk) kps[(size_t)to * wk + i] = kps[(size_t)from * wk + i];
+        else desc[(size_t)to * wd + (i - wk)] = desc[(size_t)from * wd + (i - wk)];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { n[to] = n[from]; mono[to] = mono[from]; }
+}
+
 extern "C" int orbx_extractor_copy_slot(orbx_extractor* h, int from, int to, void* stream)
 {
     if (!h || from < 0 || to < 0 || from >= h->slots || to >= h->slots || !h->buf.kps) return ORBX_E_INVALID;
+    if (from == to) return ORBX_OK;
     cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
-    const size_t cap = h->geom.out_cap;
-    CK(cudaMemcpyAsync(h->buf.kps + to * cap, h->buf.kps + from * cap, sizeof(orbx_keypoint) * cap, cudaMemcpyDeviceToDevice, s));
-    CK(cudaMemcpyAsync(h->buf.desc + to * cap * 32, h->buf.desc + from * cap * 32, cap * 32, cudaMemcpyDeviceToDevice, s));
-    CK(cudaMemcpyAsync(h->buf.n + to, h->buf.n + from, sizeof(int), cudaMemcpyDeviceToDevice, s));
-    CK(cudaMemcpyAsync(h->buf.mono + to, h->buf.mono + from, sizeof(int), cudaMemcpyDeviceToDevice, s));
+    const int cap = h->geom.out_cap;
+    k_copy_slot<<<(cap * 15 + 1023) / 1024, 256, 0, s>>>(reinterpret_cast<uint32_t*>(h->buf.kps), reinterpret_cast<uint32_t*>(h->buf.desc),
+                                                         h->buf.n, h->buf.mono, from, to, cap);
+    ORBX_COUNT_LAUNCH(1);
+    CK(cudaGetLastError());
     return ORBX_OK;
 }
 
@@ -707,12 +720,14 @@ int orbx_ex_out_cap(orbx_extractor* h) { return h->geom.out_cap; }
 // direct into the caller's buffers when they are pinned and laid out with the handle's own capacity, else into the
 // handle's pinned staging (unpacked by _finish)
 int orbx_ex_fetch_async(orbx_extractor* h, int first_slot, int count, int host_off, orbx_keypoint* kps, uint8_t* desc, int cap,
-                        int32_t* n, int32_t* mono_index, cudaStream_t s, bool direct)
+                        int32_t* n, int32_t* mono_index, cudaStream_t s, bool direct, bool counts)
 {
     const size_t ocap = h->geom.out_cap;
     const size_t ho = (size_t)host_off;
-    CK(cudaMemcpyAsync(direct ? n + ho : h->h_n + ho, h->buf.n + first_slot, sizeof(int) * count, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(direct ? mono_index + ho : h->h_mono + ho, h->buf.mono + first_slot, sizeof(int) * count, cudaMemcpyDeviceToHost, s));
+    if (counts) {
+        CK(cudaMemcpyAsync(direct ? n + ho : h->h_n + ho, h->buf.n + first_slot, sizeof(int) * count, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(direct ? mono_index + ho : h->h_mono + ho, h->buf.mono + first_slot, sizeof(int) * count, cudaMemcpyDeviceToHost, s));
+    }
     CK(cudaMemcpyAsync(direct ? kps + ho * ocap : h->h_kps + ho * ocap, h->buf.kps + first_slot * ocap, sizeof(orbx_keypoint) * ocap * count, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(direct ? desc + ho * ocap * 32 : h->h_desc + ho * ocap * 32, h->buf.desc + first_slot * ocap * 32, ocap * 32 * count, cudaMemcpyDeviceToHost, s));
     return ORBX_OK;
@@ -725,6 +740,15 @@ bool orbx_ex_can_fetch_direct(orbx_extractor* h, orbx_keypoint* kps, uint8_t* de
 
 // after the stream(s) were synchronised: device error flags, then unpack the staging if the fetch was not direct
 // queues the D2H copy of the device error flags on `s` (the caller synchronises s, then calls orbx_ex_fetch_finish with err_fetched)
+// counts and error flags that reached the host another way (the matcher's mailbox): what the copies of orbx_ex_fetch_async /
+// orbx_ex_fetch_err_async would have delivered
+void orbx_ex_set_fetched(orbx_extractor* h, unsigned err, const int32_t* n, const int32_t* mono, int count, int32_t* user_n, int32_t* user_mono, bool direct)
+{
+    *h->h_err = err;
+    memcpy(direct ? user_n : h->h_n, n, sizeof(int32_t) * count);
+    memcpy(direct ? user_mono : h->h_mono, mono, sizeof(int32_t) * count);
+}
+
 int orbx_ex_fetch_err_async(orbx_extractor* h, cudaStream_t s)
 {
     CK(cudaMemcpyAsync(h->h_err, h->buf.err, sizeof(unsigned), cudaMemcpyDeviceToHost, s));

@@ -158,7 +158,8 @@ cudaStream_t orbx_ex_stream(orbx_extractor* h);
 int orbx_ex_out_cap(orbx_extractor* h);
 bool orbx_ex_can_fetch_direct(orbx_extractor* h, orbx_keypoint* kps, uint8_t* desc, int cap, int32_t* n, int32_t* mono_index);
 int orbx_ex_fetch_async(orbx_extractor* h, int first_slot, int count, int host_off, orbx_keypoint* kps, uint8_t* desc, int cap,
-                        int32_t* n, int32_t* mono_index, cudaStream_t s, bool direct);
+                        int32_t* n, int32_t* mono_index, cudaStream_t s, bool direct, bool counts = true);
+void orbx_ex_set_fetched(orbx_extractor* h, unsigned err, const int32_t* n, const int32_t* mono, int count, int32_t* user_n, int32_t* user_mono, bool direct);
 int orbx_ex_fetch_finish(orbx_extractor* h, int count, orbx_keypoint* kps, uint8_t* desc, int cap,
                          int32_t* n, int32_t* mono_index, bool direct, bool err_fetched = false);
 int orbx_ex_fetch_err_async(orbx_extractor* h, cudaStream_t s);

@@ -145,6 +145,16 @@ __global__ void __launch_bounds__(bftc::ws::NT, 1) k_bf_knn2_tcws(BfArgs A)
     bftc::ws::bf_tile_body(q, nq, blockIdx.x * bftc::MQ, t, t_begin, t_end, A.idx_base, oi, od, bf_smem);
 }
 
+// The small results of a single-chunk call in one place: mail = {extractor error word, matcher error word, n[batch], monoIndex[batch],
+// nmatches[batch]}; `mail` is mapped pinned host memory, so the stores ARE the transfer (complete when the kernel is).
+__global__ void k_mailbox(const int* ex_n, const int* ex_mono, const int* nm, const unsigned* ex_err, const unsigned* m_err, int batch, int* mail)
+{
+    orbx_pdl_prologue();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) { mail[0] = (int)*ex_err; mail[1] = (int)*m_err; }
+    if (i < batch) { mail[2 + i] = ex_n[i]; mail[2 + batch + i] = ex_mono[i]; mail[2 + 2 * batch + i] = nm ? nm[i] : 0; }
+}
+
 // merge partial top-2 tables: parts laid out [pair][part][stride][2]; lexicographic (dist, idx)
 __global__ void k_knn2_merge(const int32_t* pidx, const int32_t* pdist, int nparts, int stride, int nq_fixed,
                              const int* n, const int* a, int32_t* idx, int32_t* dist)
@@ -810,8 +820,8 @@ extern "C" void orbx_matcher_destroy(orbx_matcher* m)
         cudaStreamDestroy(m->s_h2d); cudaStreamDestroy(m->s_d2h); cudaStreamDestroy(m->s_match);
         if (m->st_init) for (int i = 0; i < 2; i++) { cudaEventDestroy(m->st[i].ev_kernels); cudaEventDestroy(m->st[i].ev_host); cudaFreeHost(m->st[i].h_err); }
         if (m->s_bf) { cudaStreamDestroy(m->s_bf); cudaEventDestroy(m->ev_bf_fork); cudaEventDestroy(m->ev_bf_join); }
-        if (m->lg.exec) cudaGraphExecDestroy(m->lg.exec);
-        if (m->lg.graph) cudaGraphDestroy(m->lg.graph);
+        for (int k = 0; k < 2; k++) { if (m->lg.exec[k]) cudaGraphExecDestroy(m->lg.exec[k]); if (m->lg.graph[k]) cudaGraphDestroy(m->lg.graph[k]); }
+        if (m->h_mail) { cudaFreeHost(m->h_mail); cudaEventDestroy(m->ev_ex); cudaEventDestroy(m->ev_done); cudaEventDestroy(m->ev_exd2h); cudaEventDestroy(m->ev_carry); }
         for (int i = 0; i < ORBX_MAX_CHUNKS; i++) cudaEventDestroy(m->ev_ext[i]);
         for (int i = 0; i < 2 * ORBX_MAX_CHUNKS; i++) { cudaEventDestroy(m->ev[i]); cudaEventDestroy(m->ev_r[i]); }
         cudaEventDestroy(m->ev_start);
@@ -1501,22 +1511,45 @@ static int extract_match_pipeline_impl(orbx_extractor* ex, orbx_matcher* m, bool
     int32_t* dm12 = host ? m->d_out : d_matches12;
     int32_t* dnm = host ? m->d_nm : d_nmatches;
     if (host && nchunks == 1 && !prefetched) {
-        // One chunk (small batches, the single-frame latency path): everything in order on ONE stream, no cross-stream events, and
-        // one synchronisation at the end that also brings back both handles' error flags.
+        // One chunk (small batches, the single-frame latency path).  Order of the call:
+        //   s     : H2D | extraction | ev_ex | matching + mailbox kernel | D2H matches12, kNN | ev_done | slot carry | ev_carry
+        //   s_d2h :                    ev_ex -> D2H keypoints, descriptors (beside the matcher) | ev_exd2h
+        // The host waits for ev_done and ev_exd2h: the carry of the last frame into slot 0 (needed by the NEXT call only) is off
+        // the latency path, and the five small results (n, monoIndex, nmatches, the two error words) arrive through ONE kernel
+        // that stores them into mapped pinned memory instead of five copies.
+        if (!m->h_mail) {
+            CKM(cudaHostAlloc((void**)&m->h_mail, sizeof(int32_t) * (2 + 3 * (size_t)m->P), cudaHostAllocMapped));
+            CKM(cudaHostGetDevicePointer((void**)&m->d_mail, m->h_mail, 0));
+            CKM(cudaEventCreateWithFlags(&m->ev_ex, cudaEventDisableTiming));
+            CKM(cudaEventCreateWithFlags(&m->ev_done, cudaEventDisableTiming));
+            CKM(cudaEventCreateWithFlags(&m->ev_exd2h, cudaEventDisableTiming));
+            CKM(cudaEventCreateWithFlags(&m->ev_carry, cudaEventDisableTiming));
+        }
         rc = orbx_ex_stage_input(ex, imgs, 0, batch, width, height, stride, frame_stride, s);
         if (rc) return rc;
-        // The ~22 kernel launches of the step (pyramid x 8, FAST, octree, finalize, orient, describe, the matcher's 8) and the slot
-        // carry go through a CUDA graph: the first call with a set of arguments runs them directly (lazy allocations happen there),
-        // the second captures the same sequence, later calls replay it with one launch.  Copies in and out stay outside (their
-        // host pointers change from call to call).
-        auto issue_kernels = [&]() -> int {
-            int r = orbx_ex_run_staged(ex, 0, batch, lap0, lap1, 1, s);
-            if (r) return r;
-            if (m->cam_set) {
-                r = orbx_undistort_slots_device(ex, 1, batch, m->cam_K, m->cam_dist, m->cam_ndist, m->cam_P, m->d_kps_un + (size_t)orbx_ex_out_cap(ex), s);
+        // The kernel launches of the step go through two CUDA graphs (extraction: in the level-parallel order of run_batch_dag;
+        // matching: window search beside the brute-force search, then the mailbox kernel): the first call with a set of arguments
+        // runs them directly (lazy allocations happen there), the second captures the same sequences, later calls replay them with
+        // one launch each.  Copies in and out stay outside (their host pointers change from call to call).
+        auto issue_part = [&](int part) -> int {
+            if (part == 0) {
+                int r = orbx_ex_run_staged(ex, 0, batch, lap0, lap1, 1, s);
                 if (r) return r;
+                if (m->cam_set) {
+                    r = orbx_undistort_slots_device(ex, 1, batch, m->cam_K, m->cam_dist, m->cam_ndist, m->cam_P, m->d_kps_un + (size_t)orbx_ex_out_cap(ex), s);
+                    if (r) return r;
+                }
+                return ORBX_OK;
             }
-            return match_slots_impl(m, ex, m->d_pair_a, m->d_pair_b, batch, 0, bounds, window, nnratio, check_ori, dm12, dnm, d_knn_idx, d_knn_dist, s);
+            int r = match_slots_impl(m, ex, m->d_pair_a, m->d_pair_b, batch, 0, bounds, window, nnratio, check_ori, dm12, dnm, d_knn_idx, d_knn_dist, s);
+            if (r) return r;
+            int32_t* dn = nullptr; int32_t* dmono = nullptr;
+            if ((r = orbx_extractor_results_device(ex, nullptr, nullptr, &dn, &dmono, nullptr, nullptr))) return r;
+            orbx_launch_pdl(k_mailbox, dim3((batch + 127) / 128), dim3(128), 0, s, (const int*)(dn + 1), (const int*)(dmono + 1), (const int*)dnm,
+                            (const unsigned*)orbx_ex_err_device(ex), (const unsigned*)m->W.err, batch, m->d_mail);
+            ORBX_COUNT_LAUNCH(1);
+            CKM(cudaGetLastError());
+            return ORBX_OK;
         };
         static const bool no_graph = getenv("ORBX_NO_GRAPH") != nullptr;
         orbx_matcher::LatGraph& G = m->lg;
@@ -1524,66 +1557,86 @@ static int extract_match_pipeline_impl(orbx_extractor* ex, orbx_matcher* m, bool
                           G.window == window && G.check_ori == check_ori && G.knn == (d_knn_idx != nullptr) && G.cam == (int)m->cam_set &&
                           G.nnratio == nnratio && memcmp(G.bounds, bounds, sizeof(G.bounds)) == 0 && G.d_knn == d_knn_idx &&
                           G.geom_gen == orbx_ex_geom_gen(ex) && G.d_kps_un == m->d_kps_un;      // the extractor's / matcher's buffers are still the captured ones
-        if (no_graph || orbx_ex_profiling(ex)) {
-            if ((rc = issue_kernels())) return rc;
-        } else if (same && G.exec) {
-            CKM(cudaGraphLaunch(G.exec, s));
-            ORBX_COUNT_LAUNCH(G.nkernels);
-        } else if (same && G.seen == 1) {
-            if (G.exec) { cudaGraphExecDestroy(G.exec); G.exec = nullptr; }
-            if (G.graph) { cudaGraphDestroy(G.graph); G.graph = nullptr; }
-            const unsigned long long before = g_orbx_launches.load(std::memory_order_relaxed);
-            CKM(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-            rc = issue_kernels();
-            cudaGraph_t graph = nullptr;
-            const cudaError_t ce = cudaStreamEndCapture(s, &graph);
-            const int captured = (int)(g_orbx_launches.load(std::memory_order_relaxed) - before);
-            g_orbx_launches.fetch_sub(captured, std::memory_order_relaxed);            // nothing ran yet
-            if (rc || ce != cudaSuccess || !graph) {
+        auto drop_graphs = [&]() {
+            for (int k = 0; k < 2; k++) {
+                if (G.exec[k]) { cudaGraphExecDestroy(G.exec[k]); G.exec[k] = nullptr; }
+                if (G.graph[k]) { cudaGraphDestroy(G.graph[k]); G.graph[k] = nullptr; }
+            }
+        };
+        int mode = 0;                                    // 0: direct launches, 1: capture now, 2: replay
+        if (no_graph || orbx_ex_profiling(ex)) mode = 0;
+        else if (same && G.seen == 2 && G.exec[0] && G.exec[1]) mode = 2;
+        else if (same && G.seen == 1) { drop_graphs(); mode = 1; }
+        else if (!same) {
+            drop_graphs();
+            G.ex = ex; G.batch = batch; G.width = width; G.height = height; G.lap0 = lap0; G.lap1 = lap1; G.window = window; G.check_ori = check_ori;
+            G.knn = d_knn_idx != nullptr; G.cam = (int)m->cam_set; G.nnratio = nnratio; memcpy(G.bounds, bounds, sizeof(G.bounds)); G.d_knn = d_knn_idx;
+            G.geom_gen = orbx_ex_geom_gen(ex); G.d_kps_un = m->d_kps_un;
+            G.seen = 1;
+        }
+        auto run_part = [&](int part) -> int {
+            if (mode == 2) { CKM(cudaGraphLaunch(G.exec[part], s)); ORBX_COUNT_LAUNCH(G.nkernels[part]); return ORBX_OK; }
+            if (mode == 1) {
+                const unsigned long long before = g_orbx_launches.load(std::memory_order_relaxed);
+                CKM(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+                int r = issue_part(part);
+                cudaGraph_t graph = nullptr;
+                const cudaError_t ce = cudaStreamEndCapture(s, &graph);
+                const int captured = (int)(g_orbx_launches.load(std::memory_order_relaxed) - before);
+                g_orbx_launches.fetch_sub(captured, std::memory_order_relaxed);        // nothing ran yet
+                if (!r && ce == cudaSuccess && graph && cudaGraphInstantiate(&G.exec[part], graph, 0) == cudaSuccess) {
+                    G.graph[part] = graph; G.nkernels[part] = captured;
+                    CKM(cudaGraphLaunch(G.exec[part], s)); ORBX_COUNT_LAUNCH(captured);
+                    if (part == 1) G.seen = 2;
+                    return ORBX_OK;
+                }
                 cudaGetLastError();
                 if (graph) cudaGraphDestroy(graph);
-                G.seen = -1;                                                           // not capturable here: stay on direct launches
-                if (rc) return rc;
-                if ((rc = issue_kernels())) return rc;
-            } else {
-                if (cudaGraphInstantiate(&G.exec, graph, 0) != cudaSuccess) { cudaGetLastError(); cudaGraphDestroy(graph); G.exec = nullptr; G.seen = -1; if ((rc = issue_kernels())) return rc; }
-                else {
-                    G.graph = graph; G.nkernels = captured; G.seen = 2;
-                    CKM(cudaGraphLaunch(G.exec, s));
-                    ORBX_COUNT_LAUNCH(G.nkernels);
-                }
+                G.exec[part] = nullptr;
+                G.seen = -1; mode = 0;                                                 // not capturable here: stay on direct launches
+                if (r) return r;
             }
-        } else {
-            if (!same) {
-                if (G.exec) { cudaGraphExecDestroy(G.exec); G.exec = nullptr; }
-                if (G.graph) { cudaGraphDestroy(G.graph); G.graph = nullptr; }
-                G.ex = ex; G.batch = batch; G.width = width; G.height = height; G.lap0 = lap0; G.lap1 = lap1; G.window = window; G.check_ori = check_ori;
-                G.knn = d_knn_idx != nullptr; G.cam = (int)m->cam_set; G.nnratio = nnratio; memcpy(G.bounds, bounds, sizeof(G.bounds)); G.d_knn = d_knn_idx;
-                G.geom_gen = orbx_ex_geom_gen(ex); G.d_kps_un = m->d_kps_un;
-                G.seen = 1;
-            }
-            if ((rc = issue_kernels())) return rc;
-        }
-        rc = orbx_ex_fetch_async(ex, 1, batch, 0, kps, desc, cap, n, mono_index, s, direct);
+            return issue_part(part);
+        };
+        if ((rc = run_part(0))) return rc;
+        CKM(cudaEventRecord(m->ev_ex, s));
+        CKM(cudaStreamWaitEvent(m->s_d2h, m->ev_ex, 0));
+        rc = orbx_ex_fetch_async(ex, 1, batch, 0, kps, desc, cap, n, mono_index, m->s_d2h, direct, false);
         if (rc) return rc;
+        CKM(cudaEventRecord(m->ev_exd2h, m->s_d2h));
+        if ((rc = run_part(1))) return rc;
         if (matches12) CKM(cudaMemcpy2DAsync(matches12, sizeof(int32_t) * cap, dm12, sizeof(int32_t) * m->K, sizeof(int32_t) * (cap < m->K ? cap : m->K), batch,
                                              cudaMemcpyDeviceToHost, s));
-        if (nmatches) CKM(cudaMemcpyAsync(nmatches, dnm, sizeof(int32_t) * batch, cudaMemcpyDeviceToHost, s));
         if (knn_idx && knn_dist) {
             const size_t wbytes = sizeof(int32_t) * 2 * (cap < m->K ? cap : m->K);
             CKM(cudaMemcpy2DAsync(knn_idx, sizeof(int32_t) * 2 * cap, d_knn_idx, sizeof(int32_t) * 2 * m->K, wbytes, batch, cudaMemcpyDeviceToHost, s));
             CKM(cudaMemcpy2DAsync(knn_dist, sizeof(int32_t) * 2 * cap, d_knn_dist, sizeof(int32_t) * 2 * m->K, wbytes, batch, cudaMemcpyDeviceToHost, s));
         }
+        CKM(cudaEventRecord(m->ev_done, s));
+        // the carry: after everything the caller waits for
         rc = orbx_extractor_copy_slot(ex, batch, 0, s);
         if (rc) return rc;
         if (m->cam_set) {
             const size_t capx = orbx_ex_out_cap(ex);
             CKM(cudaMemcpyAsync(m->d_kps_un, m->d_kps_un + (size_t)batch * capx, sizeof(orbx_keypoint) * capx, cudaMemcpyDeviceToDevice, s));
         }
-        if ((rc = orbx_ex_fetch_err_async(ex, s))) return rc;
-        rc = m_check_err(m, s);                          // the one synchronisation of the call
-        if (rc) return rc;
-        return orbx_ex_fetch_finish(ex, batch, kps, desc, cap, n, mono_index, direct, true);
+        CKM(cudaEventRecord(m->ev_carry, s));
+        CKM(cudaEventSynchronize(m->ev_done));
+        CKM(cudaEventSynchronize(m->ev_exd2h));
+        const int32_t* mail = m->h_mail;
+        orbx_ex_set_fetched(ex, (unsigned)mail[0], mail + 2, mail + 2 + batch, batch, n, mono_index, direct);
+        if (nmatches) memcpy(nmatches, mail + 2 + 2 * batch, sizeof(int32_t) * batch);
+        if (mail[1]) {
+            char buf[32]; snprintf(buf, sizeof(buf), "0x%x", (unsigned)mail[1]);
+            orbx_set_error("matcher device capacity error flags %s%s", buf, " (raise max_candidates)");
+            cudaMemsetAsync(m->W.err, 0, sizeof(unsigned), s);
+            return ORBX_E_CAPACITY;
+        }
+        rc = orbx_ex_fetch_finish(ex, batch, kps, desc, cap, n, mono_index, direct, true);
+        // the call still returns with nothing in flight (other entry points may read slot 0 on other streams): by now the carry,
+        // a few microseconds of device time, has run beside the host work above
+        CKM(cudaEventSynchronize(m->ev_carry));
+        return rc;
     }
     // the side streams must not run ahead of work already queued on the kernel stream (previous call's carry)
     CKM(cudaEventRecord(m->ev_start, s));

@@ -155,9 +155,13 @@ struct orbx_matcher {
     // CUDA graph of the kernels of the single-chunk host call (the batch-1 latency path): captured on the second call with the same
     // arguments, replayed afterwards
     struct LatGraph {
-        cudaGraphExec_t exec; cudaGraph_t graph; int nkernels; int seen;
+        cudaGraphExec_t exec[2]; cudaGraph_t graph[2]; int nkernels[2]; int seen;      // [0] extraction, [1] matching + mailbox
         const void* ex; int batch, width, height, lap0, lap1, window, check_ori, knn, cam, geom_gen; float bounds[4]; float nnratio; const void* d_knn; const void* d_kps_un;
     } lg;
+    // single-chunk host path: the small results (n, monoIndex, nmatches, both error words) reach the host through ONE kernel
+    // that stores them into mapped pinned memory; ev_ex: extraction done (the keypoint / descriptor copies start on s_d2h beside
+    // the matcher), ev_done / ev_exd2h: what the host waits for (the slot carry is queued after ev_done)
+    int32_t* h_mail; int32_t* d_mail; cudaEvent_t ev_ex, ev_done, ev_exd2h, ev_carry;
     std::vector<void*> allocs;
 };
 
