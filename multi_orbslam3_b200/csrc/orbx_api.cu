@@ -86,6 +86,10 @@ struct orbx_extractor {
     bool profile; std::vector<cudaEvent_t> ev; int ev_head, ev_count; double stage_ms[4]; int stage_batches;
     // level-parallel launch order of the few-frame path (run_batch_dag): one branch stream per level + one for the level-0 blur
     cudaStream_t br[2 * ORBX_MAX_LEVELS]; cudaEvent_t ev_lvl[ORBX_MAX_LEVELS], ev_br[2 * ORBX_MAX_LEVELS]; bool dag_init;
+    // launch graph of the one- / two-frame orbx_extract_batch call (the class API's operator()): seen 1 = ran directly once,
+    // 2 = captured, -1 = not capturable; keyed on the arguments and the configuration generation
+    struct SmallGraph { cudaGraphExec_t exec; cudaGraph_t graph; int seen, batch, lap0, lap1, gen, nkernels; } xg;
+    int32_t* h_mailx; int32_t* d_mailx;          // mapped pinned: {error word, n[2], monoIndex[2]} written by k_ex_mailbox
 };
 #define ORBX_EV_SETS 512
 
@@ -362,6 +366,9 @@ extern "C" void orbx_extractor_destroy(orbx_extractor* h)
     cudaFreeHost(h->h_stage_in); cudaFreeHost(h->h_kps); cudaFreeHost(h->h_desc);
     cudaFreeHost(h->h_n); cudaFreeHost(h->h_mono); cudaFreeHost(h->h_err);
     for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
+    if (h->xg.exec) cudaGraphExecDestroy(h->xg.exec);
+    if (h->xg.graph) cudaGraphDestroy(h->xg.graph);
+    if (h->h_mailx) cudaFreeHost(h->h_mailx);
     if (h->dag_init) for (int i = 0; i < 2 * ORBX_MAX_LEVELS; i++) { cudaStreamDestroy(h->br[i]); cudaEventDestroy(h->ev_br[i]); if (i < ORBX_MAX_LEVELS) cudaEventDestroy(h->ev_lvl[i]); }
     cudaStreamDestroy(h->stream);
     delete h;
@@ -787,6 +794,73 @@ extern "C" int orbx_extractor_download(orbx_extractor* h, int first_slot, int co
     return orbx_ex_fetch_finish(h, count, kps, desc, cap, n, mono_index, direct, false);
 }
 
+// n, monoIndex and the error word of slots 0 .. batch-1 into mapped pinned memory: one kernel instead of three copies
+__global__ void k_ex_mailbox(const int* n, const int* mono, const unsigned* err, int batch, int* mail)
+{
+    orbx_pdl_prologue();
+    const int i = threadIdx.x;
+    if (i == 0) mail[0] = (int)*err;
+    if (i < batch) { mail[1 + i] = n[i]; mail[1 + batch + i] = mono[i]; }
+}
+
+// One or two frames through the synchronous call (ORBextractor::operator() of the class API): the kernels replay from a launch
+// graph captured in the level-parallel order of run_batch_dag (the first call with a set of arguments runs directly, the second
+// captures), the counts come back through k_ex_mailbox: H2D | graph | 2 copies | one synchronisation.
+static int extract_small(orbx_extractor* h, int batch, int lap0, int lap1, orbx_keypoint* kps, uint8_t* desc, int cap, int32_t* n, int32_t* mono_index)
+{
+    cudaStream_t s = h->stream;
+    if (!h->h_mailx) {
+        CK(cudaHostAlloc((void**)&h->h_mailx, sizeof(int32_t) * 8, cudaHostAllocMapped));
+        CK(cudaHostGetDevicePointer((void**)&h->d_mailx, h->h_mailx, 0));
+    }
+    auto issue = [&]() -> int {
+        int r = run_batch(h, h->d_level0, h->pitch0, h->stride0, batch, lap0, lap1, 0, s, 0);
+        if (r) return r;
+        orbx_launch_pdl(k_ex_mailbox, dim3(1), dim3(32), 0, s, (const int*)h->buf.n, (const int*)h->buf.mono, (const unsigned*)h->buf.err, batch, h->d_mailx);
+        ORBX_COUNT_LAUNCH(1);
+        CK(cudaGetLastError());
+        return ORBX_OK;
+    };
+    static const bool no_graph = getenv("ORBX_NO_GRAPH") != nullptr;
+    orbx_extractor::SmallGraph& G = h->xg;
+    const bool same = G.seen > 0 && G.batch == batch && G.lap0 == lap0 && G.lap1 == lap1 && G.gen == h->geom_gen;
+    int rc = ORBX_OK;
+    if (no_graph || h->profile) rc = issue();
+    else if (same && G.seen == 2 && G.exec) { CK(cudaGraphLaunch(G.exec, s)); ORBX_COUNT_LAUNCH(G.nkernels); }
+    else if (same && G.seen == 1) {
+        const unsigned long long before = g_orbx_launches.load(std::memory_order_relaxed);
+        CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        rc = issue();
+        cudaGraph_t graph = nullptr;
+        const cudaError_t ce = cudaStreamEndCapture(s, &graph);
+        const int captured = (int)(g_orbx_launches.load(std::memory_order_relaxed) - before);
+        g_orbx_launches.fetch_sub(captured, std::memory_order_relaxed);                // nothing ran yet
+        if (!rc && ce == cudaSuccess && graph && cudaGraphInstantiate(&G.exec, graph, 0) == cudaSuccess) {
+            G.graph = graph; G.nkernels = captured; G.seen = 2;
+            CK(cudaGraphLaunch(G.exec, s)); ORBX_COUNT_LAUNCH(captured);
+        } else {
+            cudaGetLastError();
+            if (graph) cudaGraphDestroy(graph);
+            G.exec = nullptr; G.seen = -1;                                             // not capturable here: stay on direct launches
+            if (!rc) rc = issue();
+        }
+    } else {
+        if (!same) {
+            if (G.exec) { cudaGraphExecDestroy(G.exec); G.exec = nullptr; }
+            if (G.graph) { cudaGraphDestroy(G.graph); G.graph = nullptr; }
+            G.batch = batch; G.lap0 = lap0; G.lap1 = lap1; G.gen = h->geom_gen; G.seen = 1;
+        }
+        rc = issue();
+    }
+    if (rc) return rc;
+    const bool direct = orbx_ex_can_fetch_direct(h, kps, desc, cap, n, mono_index);
+    rc = orbx_ex_fetch_async(h, 0, batch, 0, kps, desc, cap, n, mono_index, s, direct, false);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(s));
+    orbx_ex_set_fetched(h, (unsigned)h->h_mailx[0], h->h_mailx + 1, h->h_mailx + 1 + batch, batch, n, mono_index, direct);
+    return orbx_ex_fetch_finish(h, batch, kps, desc, cap, n, mono_index, direct, true);
+}
+
 extern "C" int orbx_extract_batch(orbx_extractor* h, const uint8_t* imgs, int batch, int width, int height,
                                   int stride, size_t frame_stride, int lap0, int lap1,
                                   orbx_keypoint* kps, uint8_t* desc, int cap, int32_t* n, int32_t* mono_index)
@@ -798,6 +872,7 @@ extern "C" int orbx_extract_batch(orbx_extractor* h, const uint8_t* imgs, int ba
     if (rc) return rc;
     rc = orbx_ex_stage_input(h, imgs, 0, batch, width, height, stride, frame_stride, h->stream);
     if (rc) return rc;
+    if (batch <= 2) return extract_small(h, batch, lap0, lap1, kps, desc, cap, n, mono_index);
     rc = orbx_ex_run_staged(h, 0, batch, lap0, lap1, 0, h->stream);
     if (rc) return rc;
     return orbx_extractor_download(h, 0, batch, kps, desc, cap, n, mono_index, h->stream);

@@ -223,56 +223,87 @@ constexpr int GRID_NT = 512;
 
 // Frame::AssignFeaturesToGrid: keypoints sorted by (cell, index) == per-cell vectors in push_back order.
 // cell = ix*GR + iy so that the cells (ix, iy0..iy1) visited by GetFeaturesInArea are one contiguous range.
-__global__ void __launch_bounds__(GRID_NT) k_grid_build(WinBufs W, int npad_max)
+__global__ void __launch_bounds__(GRID_NT) k_grid_build(WinBufs W, int kmax)
 {
-    extern __shared__ uint32_t keys[];     // [npad]
-    const int p = blockIdx.x;
+    // The records of a pair sorted by (cell, keypoint index) = the reference's visit order inside a cell (insertion order).  A stable
+    // counting sort over the NCELL cells: histogram with shared-memory atomics, block-wide exclusive scan (also the cell_start table
+    // the candidate kernel reads), then ONE warp places the keypoints in index order, 32 per step: match.any groups the lanes of a
+    // cell, the lowest lane of a group advances the cell's cursor by the group size, a lane's place is cursor + its rank in the
+    // group.  (The first version sorted 32-bit keys with a 55-step bitonic network: 15 us for one pair.)
+    extern __shared__ int g_sm[];
+    int* cur = g_sm;                                                        // [NCELL + 2] counts -> exclusive starts -> cursors
+    unsigned short* cell_of = reinterpret_cast<unsigned short*>(cur + NCELL + 2);     // [kmax] cell of keypoint i (NCELL = outside the grid)
+    unsigned short* order = cell_of + kmax;                                 // [kmax] keypoint index at sorted position
+    __shared__ int s_wsum[GRID_NT / 32];
+    const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     orbx_pdl_prologue();
-    if (threadIdx.x == 0) W.pool_used[p] = 0;       // the candidate pool of the pair starts empty (k_window_candidates fills it)
+    if (tid == 0) W.pool_used[p] = 0;       // the candidate pool of the pair starts empty (k_window_candidates fills it)
     const PairDesc P = W.pairs[p];
-    const int n = min(P.n2, W.K);
-    int npad = 1; while (npad < n) npad <<= 1;
-    if (npad > npad_max) npad = npad_max;
-    for (int i = threadIdx.x; i < npad; i += GRID_NT) {
-        uint32_t key = 0xFFFFFFFFu;
-        if (i < n) {
-            const orbx_keypoint kp = P.k2[i];
-            const int px = (int)roundf(__fmul_rn(__fsub_rn(kp.x, W.minX), W.wInv));      // PosInGrid: round, not floor
-            const int py = (int)roundf(__fmul_rn(__fsub_rn(kp.y, W.minY), W.hInv));
-            if (px >= 0 && px < GC && py >= 0 && py < GR) key = ((uint32_t)(px * GR + py) << 16) | (uint32_t)i;
-        }
-        keys[i] = key;
+    const int n = min(min(P.n2, W.K), kmax);
+    for (int c = tid; c < NCELL + 2; c += GRID_NT) cur[c] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += GRID_NT) {
+        const orbx_keypoint kp = P.k2[i];
+        const int px = (int)roundf(__fmul_rn(__fsub_rn(kp.x, W.minX), W.wInv));      // PosInGrid: round, not floor
+        const int py = (int)roundf(__fmul_rn(__fsub_rn(kp.y, W.minY), W.hInv));
+        const int c = (px >= 0 && px < GC && py >= 0 && py < GR) ? px * GR + py : NCELL;
+        cell_of[i] = (unsigned short)c;
+        atomicAdd(&cur[c], 1);
     }
     __syncthreads();
-    for (int k = 2; k <= npad; k <<= 1)
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = threadIdx.x; t < (npad >> 1); t += GRID_NT) {
-                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                const int l = i | j;
-                const bool up = (i & k) == 0;
-                const uint32_t x = keys[i], y = keys[l];
-                if ((x > y) == up) { keys[i] = y; keys[l] = x; }
-            }
-            __syncthreads();
-        }
-    uint16_t* items = W.items + (long long)p * W.K;
-    float4* skp = W.skp + (long long)p * W.K;
-    for (int i = threadIdx.x; i < n; i += GRID_NT) {
-        const uint32_t key = keys[i];
-        const int idx = (int)(key & 0xFFFF);
-        items[i] = (uint16_t)idx;
-        if (key != 0xFFFFFFFFu) {
-            const orbx_keypoint kp = P.k2[idx];
-            skp[i] = make_float4(kp.x, kp.y, __int_as_float(kp.octave), __int_as_float(idx));
+    // exclusive scan of the NCELL + 1 counts: PER consecutive entries per thread, warp scan, block scan
+    constexpr int PER = (NCELL + 1 + GRID_NT - 1) / GRID_NT;
+    int v[PER], sum = 0;
+#pragma unroll
+    for (int k = 0; k < PER; k++) { const int c = tid * PER + k; v[k] = c <= NCELL ? cur[c] : 0; sum += v[k]; }
+    int inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) s_wsum[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int w = lane < GRID_NT / 32 ? s_wsum[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
+        if (lane < GRID_NT / 32) s_wsum[lane] = w;                          // inclusive over warps
+    }
+    __syncthreads();
+    int run = inc - sum + (warp ? s_wsum[warp - 1] : 0);
+    int* cs = W.cell_start + (long long)p * (NCELL + 1);
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+        const int c = tid * PER + k;
+        if (c <= NCELL) { cur[c] = run; cs[c] = run; }                      // cs[c] = first sorted position whose cell >= c; out-of-grid last
+        run += v[k];
+    }
+    __syncthreads();
+    if (warp == 0) {
+        for (int i0 = 0; i0 < n; i0 += 32) {
+            const int i = i0 + lane;
+            const bool act = i < n;
+            const int c = act ? (int)cell_of[i] : NCELL + 1;                // idle lanes form their own group on an unused cursor
+            const unsigned grp = __match_any_sync(0xffffffffu, c);
+            const int leader = __ffs(grp) - 1;
+            int base = 0;
+            if (lane == leader) { base = cur[c]; cur[c] = base + __popc(grp); }
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (act) order[base + __popc(grp & ((1u << lane) - 1u))] = (unsigned short)i;
+            __syncwarp();
         }
     }
-    int* cs = W.cell_start + (long long)p * (NCELL + 1);
-    for (int c = threadIdx.x; c <= NCELL; c += GRID_NT) {
-        // first sorted position whose cell >= c (out-of-grid keys sort last)
-        int lo = 0, hi = n;
-        const uint32_t kc = (uint32_t)c << 16;
-        while (lo < hi) { const int mid = (lo + hi) >> 1; if (keys[mid] < kc) lo = mid + 1; else hi = mid; }
-        cs[c] = lo;
+    __syncthreads();
+    const int n_in = cs[NCELL];                                             // (written above by this CTA; visible after the barrier)
+    uint16_t* items = W.items + (long long)p * W.K;
+    float4* skp = W.skp + (long long)p * W.K;
+    for (int i = tid; i < n; i += GRID_NT) {
+        if (i < n_in) {
+            const int idx = order[i];
+            items[i] = (uint16_t)idx;
+            const orbx_keypoint kp = P.k2[idx];
+            skp[i] = make_float4(kp.x, kp.y, __int_as_float(kp.octave), __int_as_float(idx));
+        } else {
+            items[i] = 0xFFFF;                                              // outside the grid: never visited
+        }
     }
 }
 
@@ -1101,7 +1132,7 @@ static int run_window(orbx_matcher* m, const WinBufs& W, int npairs, int nq_max,
 {
     int npad = 1; while (npad < m->K) npad <<= 1;
     CKM(ORBX_OPTIN_SMEM(k_grid_build));
-    orbx_launch_pdl(k_grid_build, dim3(npairs), dim3(GRID_NT), sizeof(uint32_t) * npad, s, W, npad); ORBX_COUNT_LAUNCH(1);      // also empties the pairs' candidate pools
+    orbx_launch_pdl(k_grid_build, dim3(npairs), dim3(GRID_NT), sizeof(int) * (NCELL + 2) + 2 * sizeof(unsigned short) * (size_t)m->K, s, W, m->K); ORBX_COUNT_LAUNCH(1);   // also empties the pairs' candidate pools
     dim3 cg((nq_max + CAND_WARPS - 1) / CAND_WARPS, npairs);
     if (nq_max > 0) { orbx_launch_pdl(k_window_candidates, cg, dim3(CAND_WARPS * 32), 0, s, W); ORBX_COUNT_LAUNCH(1); }
     if (mode == 3) { CKM(cudaGetLastError()); return ORBX_OK; }

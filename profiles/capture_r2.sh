@@ -7,7 +7,10 @@ python bench.py --impl reference --steps 3 --warmup 1 > $O/r2_bench_reference.js
 for w in c2 c3 c4; do python bench.py --workload $w --steps 20 > $O/r2_bench_${w}_1gpu.json 2>> $O/r2_bench_1gpu.err; done
 python bench.py --workload c5 --steps 5 > $O/r2_bench_c5_1gpu.json 2>> $O/r2_bench_1gpu.err
 python bench.py --workload bow --steps 20 > $O/r2_bench_bow_1gpu.json 2>> $O/r2_bench_1gpu.err
-PYTHONPATH=. python profiles/latency_probe.py 500 > $O/r2_latency.txt 2>&1
+PYTHONPATH=. python profiles/latency_probe.py 1000 > $O/r2_latency.txt 2>&1
+ORBX_DAG=0 PYTHONPATH=. python profiles/latency_probe.py 1000 | sed 's/^/serial launch order inside the graph (ORBX_DAG=0): /' >> $O/r2_latency.txt 2>&1
+ORBX_NO_GRAPH=1 PYTHONPATH=. python profiles/latency_probe.py 1000 | sed 's/^/direct launches (ORBX_NO_GRAPH=1): /' >> $O/r2_latency.txt 2>&1
+PYTHONPATH=. python profiles/latency_stages.py 500 >> $O/r2_latency.txt 2>&1
 python profiles/e2e_probe.py > $O/r2_e2e_probe.txt 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/r2_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/bench_under_ncu.log 2>&1
@@ -36,9 +39,12 @@ python profiles/summarize_launches.py $O/r2_launches.csv > $O/r2_launches_summar
 python profiles/summarize_launches.py $O/r2_latency_launches.csv > $O/r2_latency_launches_summary.txt 2>&1
 # memcheck over the kernels added this round (the tensor-core kNN, the rig searches, the keyframe DB) and the extraction suite
 timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_match_gpu.py tests/test_kfdb_gpu.py tests/test_extract_gpu.py tests/test_server_gpu.py -m gpu -x -q \
-    -k "knn or two_camera or kfdb or prefetch or projection or parity or pipeline or partial" > $O/r2_sanitizer.txt 2>&1; echo "memcheck exit code $?" >> $O/r2_sanitizer.txt
-timeout 600 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_match_gpu.py -m gpu -x -q -k "knn or two_camera or host_pipeline" > $O/r2_racecheck.txt 2>&1
+    -k "knn or two_camera or kfdb or prefetch or projection or parity or pipeline or partial or graph" > $O/r2_sanitizer.txt 2>&1; echo "memcheck exit code $?" >> $O/r2_sanitizer.txt
+timeout 600 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_match_gpu.py -m gpu -x -q -k "knn or two_camera or host_pipeline or graph" > $O/r2_racecheck.txt 2>&1
 echo "racecheck exit code $?" >> $O/r2_racecheck.txt
+# the level-parallel launch order forced onto direct launches (per-level FAST / octree / blur on branch streams), under memcheck
+ORBX_DAG=1 timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_extract_gpu.py tests/test_match_gpu.py -m gpu -x -q \
+    -k "graph or host_pipeline or single or parity" > $O/r2_sanitizer_dag.txt 2>&1; echo "memcheck (ORBX_DAG=1) exit code $?" >> $O/r2_sanitizer_dag.txt
 # the host pipeline's kNN tables against the oracle under the sanitizer's timing (the run that exposed the key-base race)
 timeout 300 compute-sanitizer --tool memcheck python profiles/pipeline_knn_check.py > $O/r2_pipeline_knn_check.txt 2>&1
 ls -la $O | tail -40

@@ -27,3 +27,25 @@ for i in range(n):
 ts = np.array(ts) * 1e3
 print("batch-1 latency over %d frames: p50 %.3f ms  p95 %.3f ms  min %.3f ms  (n=%d kp, %d matches)" %
       (n, np.percentile(ts, 50), np.percentile(ts, 95), ts.min(), int(out["n"][0]), int(out["nmatches"][0])))
+
+# ---- the extractor alone: ORBextractor::operator() of the class API = orbx_extract on one host image (pageable like a cv::Mat,
+# then pinned), keypoints + descriptors back in host arrays
+import ctypes as C
+L = orbx.lib()
+ex = orbx.ORBextractor(1000, 1.2, 8, 20, 7, max_width=W, max_height=H, max_batch=1)
+for tag, src in (("pageable image and results", np.ascontiguousarray(frames)), ("pinned image and results", hf)):
+    if tag.startswith("pinned"):
+        kps = out["kps"][0]; desc = out["desc"][0]
+    else:
+        kps = np.zeros(ex.cap, orbx.KP_DTYPE); desc = np.zeros((ex.cap, 32), np.uint8)
+    nn, mono = C.c_int(0), C.c_int(0)
+    ts = []
+    for i in range(n + 20):
+        img = src[i % 16]
+        t = time.perf_counter()
+        rc = L.orbx_extract(ex._h, img.ctypes.data_as(C.c_void_p), W, H, W, 0, 0, kps.ctypes.data_as(C.c_void_p), desc.ctypes.data_as(C.c_void_p), ex.cap,
+                            C.byref(nn), C.byref(mono))
+        ts.append(time.perf_counter() - t)
+        assert rc == 0
+    ts = np.array(ts[20:]) * 1e3
+    print("orbx_extract (operator()), one frame, %s: p50 %.3f ms  p95 %.3f ms  (n=%d kp)" % (tag, np.percentile(ts, 50), np.percentile(ts, 95), nn.value))

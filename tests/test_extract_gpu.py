@@ -114,6 +114,31 @@ def test_geometry_change_and_strided_input():
     ex.close()
 
 
+def test_single_image_call_replays_its_launch_graph():
+    """operator() on one image: the first call launches directly, the second captures the kernels (level-parallel order, counts through
+    the mailbox kernel) into a launch graph, later calls replay it.  Every call is checked against the oracle stage by stage, the
+    lapping area / the image size change in between (a new graph), and a two-frame batch goes through the same path."""
+    W, H = 640, 480
+    frames = synth.rects_stream(W, H, 8, seed=77)
+    ex = orbx.ORBextractor(900, 1.2, 8, 20, 7, max_width=W, max_height=H, max_batch=2)
+    ref = O.Extractor(900, 1.2, 8, 20, 7)
+    for f in range(4):                                   # direct, captured, replayed, replayed
+        check_frame(ex(frames[f], None, (0, 0)), ref(frames[f], (0, 0)))
+        stage_parity(ex, ref, slot=0)
+    for f in (4, 5, 6):                                  # other arguments: a new capture
+        check_frame(ex(frames[f], None, (100, 300)), ref(frames[f], (100, 300)))
+    small = np.ascontiguousarray(frames[7][:240, :320])
+    for _ in range(3):                                   # other geometry, then back
+        check_frame(ex(small, None, (0, 0)), ref(small, (0, 0)))
+    for f in (0, 1, 2):
+        check_frame(ex(frames[f], None, (0, 0)), ref(frames[f], (0, 0)))
+    for k in range(3):                                   # two frames per call
+        outs = ex.extract_batch(frames[2 * k:2 * k + 2], (0, 0))
+        for j in range(2):
+            check_frame(outs[j], ref(frames[2 * k + j], (0, 0)))
+    ex.close()
+
+
 def test_empty_image_returns_minus_one():
     ex = orbx.ORBextractor(500, 1.2, 8, 20, 7)
     mono, kps, desc = ex(np.empty((0, 0), np.uint8))
