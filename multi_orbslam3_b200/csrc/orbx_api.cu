@@ -11,7 +11,14 @@
 #include "orbx_internal.h"
 
 std::atomic<unsigned long long> g_orbx_launches{0};
-bool orbx_pdl_enabled() { static const bool on = getenv("ORBX_NO_PDL") == nullptr; return on; }
+// PDL policy: ORBX_PDL=1 always, ORBX_PDL=0 never, unset: only inside a few-frame step (OrbxPdlScope set by run_batch /
+// match_slots_impl for <= 2 frames / pairs), where the kernels are a handful of CTAs and early-resident dependents cost nothing
+thread_local int g_orbx_pdl_scope = 0;
+bool orbx_pdl_enabled()
+{
+    static const int env = getenv("ORBX_PDL") ? atoi(getenv("ORBX_PDL")) : -1;
+    return env == 1 || (env < 0 && g_orbx_pdl_scope > 0);
+}
 extern "C" unsigned long long orbx_launch_count(void) { return g_orbx_launches.load(std::memory_order_relaxed); }
 
 static thread_local std::string g_last_error;
@@ -479,6 +486,7 @@ static int run_batch(orbx_extractor* h, const uint8_t* d_level0, int pitch0, lon
     const OrbxBuffers buf = shifted(h, frame_off);
     const uint8_t* l0 = d_level0 + (long long)frame_off * stride0;
     const bool prof = h->profile;
+    OrbxPdlScope pdl_scope(batch <= 2);
     static const int dag_env = getenv("ORBX_DAG") ? atoi(getenv("ORBX_DAG")) : -1;      // 0: never, 1: always for few frames, unset: under capture
     if (!prof && batch <= 2 && g.nlevels > 1 && dag_env != 0) {
         int rc = ensure_dag(h);                                             // (created on a direct call: not inside a capture)

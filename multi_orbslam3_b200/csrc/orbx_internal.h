@@ -87,13 +87,15 @@ __device__ __forceinline__ int orbx_reflect101(int p, int n)
 #endif
 
 // ---- programmatic dependent launch (PDL) ----
-// The kernels of the per-frame chain (pyramid .. kNN merge) are launched with cudaLaunchAttributeProgrammaticStreamSerialization:
+// The kernels of the per-frame chain (pyramid .. kNN merge) can be launched with cudaLaunchAttributeProgrammaticStreamSerialization:
 // every CTA lets the NEXT kernel of the stream be scheduled as soon as it has started (griddepcontrol.launch_dependents) and
 // waits for the PREVIOUS kernel to have completed and flushed (griddepcontrol.wait) before it touches global memory, so the
-// launch latency and the CTA start-up of kernel k+1 hide behind the tail of kernel k.  On the single-frame path (15 short
-// kernels replayed from a CUDA graph) that is most of the gap between the kernels.  RULE: a kernel launched through
-// orbx_launch_pdl MUST call orbx_pdl_prologue() before its first global access (without the wait it would start early).
-// ORBX_NO_PDL=1 launches them as ordinary kernels (the prologue is then a no-op).
+// launch latency and the CTA start-up of kernel k+1 hide behind the tail of kernel k.  Measured on a B200: one frame per call
+// 0.303 -> 0.262 ms with direct launches (a few us with the launch graphs); C1 (512 mono frames) 3.415 -> 3.392 ms per step; but
+// C2 3.79 -> 3.86 ms and C3 (1241-wide stereo frames) 4.73 -> 5.35 ms: there the early-resident CTAs of the next kernel hold
+// shared memory and registers while they wait.  Policy (orbx_pdl_enabled): on inside a few-frame step only; ORBX_PDL=1 / 0
+// forces it on / off everywhere.  The prologue is a no-op in a kernel launched without the attribute.
+// RULE: a kernel launched through orbx_launch_pdl MUST call orbx_pdl_prologue() before its first global access.
 #ifdef __CUDACC__
 __device__ __forceinline__ void orbx_pdl_prologue()
 {
@@ -102,6 +104,12 @@ __device__ __forceinline__ void orbx_pdl_prologue()
 }
 #endif
 bool orbx_pdl_enabled();
+extern thread_local int g_orbx_pdl_scope;
+struct OrbxPdlScope {                       // marks the launches of a few-frame step (see orbx_pdl_enabled)
+    bool on;
+    explicit OrbxPdlScope(bool few) : on(few) { if (on) g_orbx_pdl_scope++; }
+    ~OrbxPdlScope() { if (on) g_orbx_pdl_scope--; }
+};
 template <typename... KArgs, typename... Args>
 inline cudaError_t orbx_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args)
 {

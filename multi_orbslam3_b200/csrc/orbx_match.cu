@@ -1350,6 +1350,7 @@ static int match_slots_impl(orbx_matcher* m, orbx_extractor* ex, const int32_t* 
     // fork / join are graph edges; ORBX_DAG=1 forces it, 0 disables it).  With a full batch either kernel fills the GPU and a
     // fork gains nothing (measured: 3.424 vs 3.420 ms per 512 frames).
     static const int dag_env = getenv("ORBX_DAG") ? atoi(getenv("ORBX_DAG")) : -1;
+    OrbxPdlScope pdl_scope(npairs <= 2);
     bool fork = false;
     if (d_knn_idx && d_knn_dist && npairs <= 2 && dag_env != 0) {
         if (!m->s_bf) {
