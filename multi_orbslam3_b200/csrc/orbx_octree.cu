@@ -61,6 +61,63 @@ __device__ void bitonic_sort(T* a, int npad)
     }
 }
 
+// Stable LSD radix sort of the indices 0 .. npad-1 by their 32-bit path key, 4 bits per pass, for npad a multiple of 512 (NT = 16
+// warps, warp w owns the npad / 16 consecutive positions w * C ..).  A pass: every warp walks its positions in order, 32 per step;
+// match.any groups the lanes of a digit, the lowest lane of a group advances the warp's private counter of that digit, a lane's
+// rank is counter + its place in the group (so equal digits keep their order); the 16 x 16 counters are scanned digit-major and
+// the indices scattered.  8 passes x 4 barriers against the 66 - 78 barriers (and ~2.5 x the instructions) of the bitonic network
+// on 64-bit keys.  keys[] is never moved: a pass reads the key through the index.  Result in ia.
+__device__ __noinline__ void radix_sort_indices(const uint32_t* keys, unsigned short* ia, unsigned short* ib, unsigned short* hist, int* s_part, int npad)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int C = npad / (NT / 32), IT = C >> 5;                          // IT <= 8 for npad <= 4096
+    unsigned short* in = ia; unsigned short* out = ib;
+    for (int pass = 0; pass < 8; pass++) {
+        const int shift = 4 * pass;
+        if (tid < 256) hist[tid] = 0;
+        __syncthreads();
+        int rk[8]; unsigned short id[8];
+#pragma unroll
+        for (int it = 0; it < 8; it++) {
+            if (it < IT) {
+                const int i = warp * C + it * 32 + lane;
+                const unsigned short x = pass == 0 ? (unsigned short)i : in[i];
+                const unsigned d = (keys[x] >> shift) & 15u;
+                const unsigned peers = __match_any_sync(0xffffffffu, d);
+                const int leader = __ffs(peers) - 1;
+                int old = 0;
+                if (lane == leader) { old = hist[warp * 16 + d]; hist[warp * 16 + d] = (unsigned short)(old + __popc(peers)); }
+                old = __shfl_sync(0xffffffffu, old, leader);
+                rk[it] = (old + __popc(peers & ((1u << lane) - 1u))) | (int)(d << 16);
+                id[it] = x;
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        // exclusive scan of the counters in (digit, warp) order by the first 256 threads
+        int cnt = 0, inc = 0;
+        if (tid < 256) {
+            cnt = hist[(tid & 15) * 16 + (tid >> 4)];
+            inc = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+            if (lane == 31) s_part[warp] = inc;
+        }
+        __syncthreads();
+        if (tid < 256) {
+            int base = inc - cnt;
+            for (int w2 = 0; w2 < warp; w2++) base += s_part[w2];
+            hist[(tid & 15) * 16 + (tid >> 4)] = (unsigned short)base;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int it = 0; it < 8; it++)
+            if (it < IT) out[hist[warp * 16 + (rk[it] >> 16)] + (rk[it] & 0xFFFF)] = id[it];
+        __syncthreads();
+        unsigned short* t = in; in = out; out = t;
+    }
+}
+
 __device__ __forceinline__ int lower_bound_key(const u64* buf, int lo, int hi, unsigned key)
 {
     while (lo < hi) {
@@ -94,10 +151,11 @@ struct OctShared {
     u64 warp_sums[NT / 32];
     int n_pts, n_nodes, n_vec, jstar, flag_overflow;
     int tot_c, tot_e;
+    int radix_part[8];
     int row_prefix[ORBX_MAX_UNITS + 1];
 };
 
-__global__ void __launch_bounds__(NT) k_octree(OrbxGeom g, OrbxBuffers b, int smem_pts, int ncap, int level_base)
+__global__ void __launch_bounds__(NT, 4) k_octree(OrbxGeom g, OrbxBuffers b, int smem_pts, int ncap, int level_base, int allow_radix)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ OctShared sh;
@@ -160,6 +218,10 @@ __global__ void __launch_bounds__(NT) k_octree(OrbxGeom g, OrbxBuffers b, int sm
 
     // ---- per-candidate root + path key (DivideNode geometry, :479-507; root assignment :553-567) ----
     const int Hbox = L.maxBY - ORBX_BORDER;
+    // shared-memory sort buffers of 1024 .. 4096 entries take the radix path: keys[npad] u32 | ia[npad] u16 | ib[npad] u16 = the
+    // 8 * npad bytes of buf; the 16 x 16 counters live in the (still unused) node list
+    const bool radix = allow_radix && buf == s_sort && npad >= 1024 && npad <= 4096;
+    uint32_t* rkeys = reinterpret_cast<uint32_t*>(buf);
     for (int i = tid; i < npad; i += NT) {
         u64 e = ~0ull;
         if (i < n) {
@@ -179,10 +241,29 @@ __global__ void __launch_bounds__(NT) k_octree(OrbxGeom g, OrbxBuffers b, int sm
             }
             e = ((u64)key << 32) | ((u64)(p >> 24) << 24) | (u64)(0xFFFFFF - i);
         }
-        buf[i] = e;
+        if (radix) rkeys[i] = (uint32_t)(e >> 32); else buf[i] = e;
     }
     __syncthreads();
-    bitonic_sort<u64, false>(buf, npad);
+    if (radix) {
+        unsigned short* ia = reinterpret_cast<unsigned short*>(rkeys + npad);
+        radix_sort_indices(rkeys, ia, ia + npad, reinterpret_cast<unsigned short*>(La), sh.radix_part, npad);
+        // the sorted records (key | score | 0xFFFFFF - index) replace keys and indices: read everything, then write
+        u64 ev[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int i = tid + k * NT;
+            if (i < npad) {
+                const int x = ia[i];
+                ev[k] = x < n ? ((u64)rkeys[x] << 32) | ((u64)(pts[x] >> 24) << 24) | (u64)(0xFFFFFF - x) : ~0ull;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 8; k++) { const int i = tid + k * NT; if (i < npad) buf[i] = ev[k]; }
+        __syncthreads();
+    } else {
+        bitonic_sort<u64, false>(buf, npad);
+    }
 
     // ---- initial list: non-empty roots in order (:550-583) ----
     if (tid == 0) {
@@ -417,7 +498,8 @@ void orbx_launch_octree(const OrbxGeom& g, const OrbxBuffers& b, int batch, cuda
     if (l_end <= l_begin) return;
     dim3 grid(l_end - l_begin, batch);
     ORBX_OPTIN_SMEM(k_octree);
-    orbx_launch_pdl(k_octree, grid, dim3(NT), (size_t)c.smem, s, g, b, c.smem_pts, c.ncap, l_begin);
+    static const int allow_radix = getenv("ORBX_OCTREE_BITONIC") ? 0 : 1;      // comparison runs: the bitonic network everywhere
+    orbx_launch_pdl(k_octree, grid, dim3(NT), (size_t)c.smem, s, g, b, c.smem_pts, c.ncap, l_begin, allow_radix);
     ORBX_COUNT_LAUNCH(1);
 }
 
