@@ -44,6 +44,44 @@ __device__ __forceinline__ u64 block_scan_excl(u64 v, u64* total, u64* s_warp)
     return base + inc - v;
 }
 
+// npad <= NT: one key per thread in a register.  Exchanges at distance < 32 are shuffles; only the distances >= 32 go through
+// shared memory, alternating between two halves of a scratch so that one barrier per such step is enough (npad = 512: 10 barriers
+// instead of 45).  The small pyramid levels and the largest-first rounds spend their time in these barriers, not in the compares.
+template <typename T, bool DESC>
+__device__ void bitonic_sort_small(T* a, T* scratch, int npad)
+{
+    const int t = threadIdx.x;
+    const bool act = t < npad;
+    T x = act ? a[t] : T(0);
+    int flip = 0;
+    for (int k = 2; k <= npad; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            T y;
+            if (j >= 32) {
+                T* sbuf = scratch + flip * NT; flip ^= 1;
+                if (act) sbuf[t] = x;
+                __syncthreads();
+                y = act ? sbuf[t ^ j] : T(0);
+            } else {
+                if (sizeof(T) == 8) {
+                    const unsigned lo = __shfl_xor_sync(0xffffffffu, (unsigned)((unsigned long long)x & 0xffffffffull), j);
+                    const unsigned hi = __shfl_xor_sync(0xffffffffu, (unsigned)((unsigned long long)x >> 32), j);
+                    y = (T)(((unsigned long long)hi << 32) | lo);
+                } else {
+                    y = (T)__shfl_xor_sync(0xffffffffu, (unsigned)x, j);
+                }
+            }
+            const bool up = ((t & k) == 0) != DESC;          // this block of k sorts ascending
+            const bool lower = (t & j) == 0;                 // this thread holds the lower position of the pair
+            const bool take_min = lower == up;
+            if ((y < x) == take_min && y != x) x = y;        // min or max of the pair
+        }
+    }
+    __syncthreads();                                          // (the scratch may alias `a`)
+    if (act) a[t] = x;
+    __syncthreads();
+}
+
 template <typename T, bool DESC>
 __device__ void bitonic_sort(T* a, int npad)
 {
@@ -262,7 +300,9 @@ __global__ void __launch_bounds__(NT, 4) k_octree(OrbxGeom g, OrbxBuffers b, int
         for (int k = 0; k < 8; k++) { const int i = tid + k * NT; if (i < npad) buf[i] = ev[k]; }
         __syncthreads();
     } else {
-        bitonic_sort<u64, false>(buf, npad);
+        // (buf holds smem_pts >= 4 * NT entries in shared memory, or the global scratch: entries npad .. are free)
+        if (npad <= NT && buf == s_sort) bitonic_sort_small<u64, false>(buf, buf + NT, npad);
+        else bitonic_sort<u64, false>(buf, npad);
     }
 
     // ---- initial list: non-empty roots in order (:550-583) ----
@@ -361,7 +401,12 @@ __global__ void __launch_bounds__(NT, 4) k_octree(OrbxGeom g, OrbxBuffers b, int
             for (int i = tid; i < nn; i += NT) proc[i] = 0;
             if (tid == 0) sh.jstar = nvec - 1;
             __syncthreads();
-            if (mpad > 1) bitonic_sort<unsigned, true>(Vs, mpad);
+            if (mpad > 1) {
+                // scratch: the segment-prefix table of the gather phase (ORBX_MAX_UNITS + 1 >= 2 * NT words), dead by now
+                static_assert(ORBX_MAX_UNITS + 1 >= 2 * NT, "row_prefix doubles as the small sort's scratch");
+                if (mpad <= NT) bitonic_sort_small<unsigned, true>(Vs, reinterpret_cast<unsigned*>(sh.row_prefix), mpad);
+                else bitonic_sort<unsigned, true>(Vs, mpad);
+            }
             int bd[MAX_IPT][5];
             int lpos[MAX_IPT];
             u64 mine = 0;                    // children | multi << 40   (growth = children - 1)
