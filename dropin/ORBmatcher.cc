@@ -28,6 +28,7 @@
 #include <stdexcept>
 #include <string>
 
+#include "BFMatcher.h"
 #include "ORBextractor.h"
 #include "orbx.h"
 
@@ -1236,6 +1237,36 @@ void ORBmatcher::ComputeStereoMatches(ORBextractor* pLeft, ORBextractor* pRight,
     if (orbx_stereo_matches(c.m, pLeft->handle(), pRight->handle(), 0, 0, 0, 0, mb, mbf, mvuRight.data(), mvDepth.data(), NULL, cap, &n) != ORBX_OK)
         fail("orbx_stereo_matches");
     mvuRight.resize(n); mvDepth.resize(n);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// Addition: the cv::BFMatcher member of Frame (R/include/Frame.h:288, R/src/Frame.cc:26) as a class over orbx_bf_knn2; it is
+// what Frame::ComputeStereoFishEyeMatches calls (R/src/Frame.cc:1130).  See dropin/BFMatcher.h.
+BFMatcherB200::BFMatcherB200(int normType, bool crossCheck) : norm_(normType)
+{
+    if (crossCheck) throw std::runtime_error("BFMatcherB200: crossCheck is not what the reference uses and is not implemented");
+}
+
+void BFMatcherB200::knnMatch(cv::InputArray queryDescriptors, cv::InputArray trainDescriptors, std::vector<std::vector<cv::DMatch> >& matches, int k) const
+{
+    const cv::Mat q = queryDescriptors.getMat(), t = trainDescriptors.getMat();
+    if (norm_ != cv::NORM_HAMMING || k != 2 || (q.rows > 0 && q.cols != 32) || (t.rows > 0 && t.cols != 32))
+        throw std::runtime_error("BFMatcherB200: only NORM_HAMMING, k = 2 and 32-byte descriptor rows (what Frame.cc:1130 asks for)");
+    matches.assign(q.rows, std::vector<cv::DMatch>());
+    if (q.rows == 0 || t.rows == 0) return;
+    std::vector<uint8_t> tq, tt;
+    const uint8_t* pq = rows32(q, tq);
+    const uint8_t* pt = rows32(t, tt);
+    std::vector<int32_t> idx((size_t)q.rows * 2), dist((size_t)q.rows * 2);
+    Context& c = context(1);
+    if (orbx_bf_knn2(c.m, pq, q.rows, pt, t.rows, idx.data(), dist.data()) != ORBX_OK) fail("orbx_bf_knn2");
+    for (int i = 0; i < q.rows; i++)
+        for (int j = 0; j < 2; j++)
+            if (idx[2 * i + j] >= 0) {
+                cv::DMatch dm(i, idx[2 * i + j], (float)dist[2 * i + j]);
+                dm.imgIdx = 0;                       // one train image, as cv::BFMatcher reports it
+                matches[i].push_back(dm);
+            }
 }
 
 } //namespace ORB_SLAM

@@ -79,6 +79,11 @@ extern "C" int orbx_hamming_pairs(orbx_matcher*, const uint8_t* a, const uint8_t
     return ORBX_OK;
 }
 
+extern "C" int orbx_bf_knn2(orbx_matcher*, const uint8_t* q, int nq, const uint8_t* t, int nt, int32_t* idx, int32_t* dist)
+{
+    orc_bf_knn2(q, nq, t, nt, idx, dist);
+    return ORBX_OK;
+}
 extern "C" int orbx_search_for_initialization(orbx_matcher* m, const orbx_keypoint* k1, const uint8_t* d1, int n1, const orbx_keypoint* k2,
                                               const uint8_t* d2, int n2, const float bounds[4], float* prev_xy, int32_t* matches12, int window,
                                               float nnratio, int check_ori, int* nmatches)

@@ -18,6 +18,9 @@
 #include <string>
 #include <vector>
 #include "orbslam_world.h"
+#ifdef SCENARIO_DROPIN
+#include "BFMatcher.h"
+#endif
 
 using namespace ORB_SLAM3;
 using std::vector;
@@ -531,6 +534,33 @@ int main(int argc, char** argv)
                 vector<int> bad, obs;
                 for (size_t i = 0; i < w.points.size(); i++) { bad.push_back(w.points[i]->isBad() ? 1 : 0); obs.push_back(w.points[i]->Observations()); }
                 dump_ints("  bad", bad); dump_ints("  observations", obs);
+            }
+        }
+
+        // ---- the brute-force matcher of Frame::ComputeStereoFishEyeMatches (R/src/Frame.cc:1112-1130): the descriptors of the lapping
+        //      areas of two frames, knnMatch(k = 2); cv::BFMatcher in the reference build, BFMatcherB200 in the drop-in builds.  Also a
+        //      train set of one row (one match per query) and an empty one ----
+        {
+#ifdef SCENARIO_DROPIN
+            const BFMatcherB200 bf(cv::NORM_HAMMING);
+#else
+            const cv::BFMatcher bf(cv::NORM_HAMMING);
+#endif
+            const int monoLeft = F[0]->N / 3, monoRight = F[1]->N / 4;
+            const cv::Mat dl = F[0]->mDescriptors.rowRange(monoLeft, F[0]->mDescriptors.rows);
+            const cv::Mat dr = F[1]->mDescriptors.rowRange(monoRight, F[1]->mDescriptors.rows);
+            const cv::Mat trains[3] = {dr, dr.rowRange(0, 1), dr.rowRange(0, 0)};
+            for (int c = 0; c < 3; c++) {
+                vector<vector<cv::DMatch> > mm;
+                bf.knnMatch(dl, trains[c], mm, 2);
+                vector<int> flat; int good = 0;
+                for (size_t i = 0; i < mm.size(); i++) {
+                    flat.push_back((int)mm[i].size());
+                    for (size_t j = 0; j < mm[i].size(); j++) { flat.push_back(mm[i][j].queryIdx); flat.push_back(mm[i][j].trainIdx); flat.push_back((int)mm[i][j].distance); }
+                    if (mm[i].size() >= 2 && mm[i][0].distance < mm[i][1].distance * 0.7) good++;      // Lowe's ratio of :1136
+                }
+                fprintf(g_out, "BFmatcher.knnMatch queries=%d train=%d ratio-accepted=%d\n", dl.rows, trains[c].rows, good);
+                dump_ints("  matches", flat);
             }
         }
 

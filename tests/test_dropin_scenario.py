@@ -74,6 +74,9 @@ def check_coverage(lines):
         assert hit, key
         n = int(hit[0].rsplit("n=", 1)[1].split()[0])
         assert n > 0, hit[0]
+    # the brute-force matcher of ComputeStereoFishEyeMatches: three train sets (full, one row, empty), ratio test passes somewhere
+    bf = [l for l in lines if l.startswith("BFmatcher.knnMatch")]
+    assert len(bf) == 3 and int(bf[0].rsplit("ratio-accepted=", 1)[1]) > 0 and " train=1 " in bf[1] and " train=0 " in bf[2], bf
 
 
 @pytest.mark.skipif(not binaries(), reason="tests/scenario/_build was not prebuilt and /root/reference is absent")
