@@ -118,9 +118,11 @@ constexpr int ORI_GROUP = 4;          // keypoints per warp in k_orient, process
 constexpr int DESC_WARPS = 8;
 constexpr int DESC_GROUP = 8;         // keypoints per warp in k_describe, one after the other through two staged boxes
 constexpr int PATCH_R = 18;           // |rotated pattern offset| <= round(18.385) = 18
-constexpr int PATCH_W = 64;           // box width in bytes.  The box must START on a 16-byte boundary of the image row (an unaligned
+constexpr int PATCH_W = 80;           // box width in bytes.  The box must START on a 16-byte boundary of the image row (an unaligned
                                       // inner coordinate faults with "illegal instruction": profiles/probes/tma_box_probe_b200.txt),
-                                      // so it begins at (cx - 18) & ~15 and needs 15 + 37 <= 64 columns
+                                      // so it begins at (cx - 18) & ~15 and needs 15 + 37 = 52 columns.  80 rather than 64: the row pitch
+                                      // in shared memory is the box width and the BRIEF samples cluster around the patch centre; with
+                                      // 16 words per row only two row phases exist, with 20 the rows cycle through 8 (0.440 -> 0.434 ms)
 constexpr int PATCH_H = 2 * PATCH_R + 1;
 constexpr int PATCH_BYTES = PATCH_W * PATCH_H;               // 2368
 constexpr int PATCH_SLOT = (PATCH_BYTES + 127) & ~127;       // 2432: every buffer starts 128-byte aligned
@@ -255,7 +257,7 @@ __global__ void __launch_bounds__(ORI_WARPS * 32, 5) k_orient(OrbxGeom g, OrbxBu
 
 // ---- k_describe: steered BRIEF from TMA-staged patches --------------------------------------------
 // One warp per group of DESC_GROUP keypoints.  The 37 x 37 window of the BLURRED level that the rotated pattern can reach is
-// staged in shared memory, one TMA box (64 x 37 bytes, cp.async.bulk.tensor on a per-level 3-D map) per keypoint, issued by one
+// staged in shared memory, one TMA box (80 x 37 bytes, cp.async.bulk.tensor on a per-level 3-D map) per keypoint, issued by one
 // lane, double-buffered per warp and completed on an mbarrier: the 512 scattered byte reads of a descriptor hit shared memory
 // instead of ~17 different L1 sectors per load instruction (with __ldg the kernel sat at 86 % of the L1TEX pipe, ncu r2_desc_v3).
 // Lane j produces descriptor byte j; the rotated sample offsets use separately rounded fp32 products (no FMA) and round-half-even,
@@ -387,7 +389,7 @@ void orbx_launch_describe(const OrbxGeom& g, const OrbxBuffers& b, const uint8_t
         orbx_launch_pdl(k_orient, grid, dim3(ORI_WARPS * 32), 0, s, g, b, level0, pitch0, stride0, first_slot);
     }
     dim3 grid((g.out_cap + DESC_WARPS * DESC_GROUP - 1) / (DESC_WARPS * DESC_GROUP), batch);
-    // one 3-D tensor map (x, y, frame) per blurred level with a 64 x 37 box; the blurred levels are this library's own buffers
+    // one 3-D tensor map (x, y, frame) per blurred level with an 80 x 37 box; the blurred levels are this library's own buffers
     // (64-byte pitches), so the layout is always TMA-legal; if the driver entry point is missing the plain-load kernel runs
     alignas(64) DescMaps maps;
     memset(&maps, 0, sizeof(maps));
