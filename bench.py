@@ -685,7 +685,22 @@ def main():
             ts.append(time.perf_counter() - t1)
         ts = np.array(ts[20:]) * 1e3
         latency = {"p50_ms": float(np.percentile(ts, 50)), "p95_ms": float(np.percentile(ts, 95)), "frames": nlat,
-                   "what": "one frame per call: orbx_extract_match_batch(batch=1) = H2D + extract + SearchForInitialization + BF kNN-2 vs previous frame + D2H"}
+                   "what": "one frame per call: orbx_extract_match_batch(batch=1) = H2D + extract + SearchForInitialization + BF kNN-2 vs previous frame + D2H; "
+                           "kernels replayed from two launch graphs (level-parallel order), DESIGN 5.1"}
+        # the extractor alone (ORBextractor::operator() of the class API = orbx_extract), pinned image and result arrays
+        import ctypes as C
+        L = orbx.lib()
+        nn, mono = C.c_int(0), C.c_int(0)
+        kp1, de1 = out1["kps"][0], out1["desc"][0]
+        ts = []
+        for i in range(nlat + 20):
+            f1 = h_np[i % B]
+            t1 = time.perf_counter()
+            rc = L.orbx_extract(ex1._h, f1.ctypes.data_as(C.c_void_p), W, H, W, 0, 0, kp1.ctypes.data_as(C.c_void_p), de1.ctypes.data_as(C.c_void_p), ex1.cap,
+                                C.byref(nn), C.byref(mono))
+            ts.append(time.perf_counter() - t1)
+            assert rc == 0
+        latency["extract_only_p50_ms"] = float(np.percentile(np.array(ts[20:]) * 1e3, 50))
         ex1.close(); m1.close()
 
     if rank != 0:
