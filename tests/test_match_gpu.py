@@ -597,6 +597,41 @@ def test_stream_submit_wait_equals_plain_calls():
     ex.close(); m.close()
 
 
+def test_full_c1_batch_matching_properties():
+    """BASELINE config C1 at the bench size through the host-buffer call (512 frames of 752x480, extract + SearchForInitialization +
+    BF kNN-2 against the previous frame).  The stream repeats with period 32, so pair (i-1, i) must give byte-identical matches and
+    kNN tables as pair (i-33, i-32) wherever it sits in the batch and in whichever chunk of the pipeline; pairs of one period are
+    compared with the oracle."""
+    W, H, B, PER = 752, 480, 512, 32
+    base = synth.rects_stream(W, H, PER, seed=321)
+    frames = np.ascontiguousarray(np.concatenate([base] * (B // PER)))
+    ex = orbx.ORBextractor(1000, 1.2, 8, 20, 7, max_width=W, max_height=H, max_batch=B)
+    m = orbx.ORBmatcher(0.9, True, max_keypoints=ex.cap, max_batch=B)
+    cap = ex.cap
+    out = {"kps": np.zeros((B, cap), orbx.KP_DTYPE), "desc": np.zeros((B, cap, 32), np.uint8), "n": np.zeros(B, np.int32),
+           "mono": np.zeros(B, np.int32), "matches12": np.zeros((B, cap), np.int32), "nmatches": np.zeros(B, np.int32),
+           "knn_idx": np.zeros((B, cap, 2), np.int32), "knn_dist": np.zeros((B, cap, 2), np.int32)}
+    orbx.extract_match_batch(ex, m, frames, (0, 0), (0, W, 0, H), 100, out)
+    n = out["n"]
+    assert n.min() >= 900
+    for i in range(PER + 1, B):
+        j = i - PER
+        npk = int(n[i - 1])                                  # rows of the pair's tables = keypoints of the predecessor
+        assert n[i] == n[j] and n[i - 1] == n[j - 1] and out["nmatches"][i] == out["nmatches"][j], i
+        assert np.array_equal(out["matches12"][i, :npk], out["matches12"][j, :npk]), i
+        assert np.array_equal(out["knn_idx"][i, :npk], out["knn_idx"][j, :npk]) and np.array_equal(out["knn_dist"][i, :npk], out["knn_dist"][j, :npk]), i
+    ref = O.Extractor(1000, 1.2, 8, 20, 7)
+    for i in (1, 17, PER):                                   # PER: frame 0 of the second period against frame 31 of the first
+        _, pk, pd = ref(frames[i - 1], (0, 0))
+        _, rk, rd = ref(frames[i], (0, 0))
+        rn, rm12, _ = O.search_for_initialization(pk, pd, rk, rd, (0, W, 0, H), np.stack([pk["x"], pk["y"]], 1), 100, 0.9, True)
+        assert int(out["nmatches"][i]) == rn and np.array_equal(out["matches12"][i, :len(pk)], rm12)
+        ri, rdist = O.bf_knn2(pd, rd)
+        assert np.array_equal(out["knn_idx"][i, :len(pk)], ri) and np.array_equal(out["knn_dist"][i, :len(pk)], rdist)
+    assert int(out["nmatches"][1:].min()) > 0
+    ex.close(); m.close()
+
+
 def test_single_frame_call_graph_survives_reconfiguration():
     """The batch-1 host call replays its kernels from a CUDA graph after two identical calls (captured in the level-parallel order
     of run_batch_dag: per-level FAST / octree / blur branches beside the resize chain, the brute-force search beside the window
