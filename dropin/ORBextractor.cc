@@ -83,7 +83,12 @@ int ORBextractor::operator()( cv::InputArray _image, cv::InputArray _mask, std::
         for (int i = 0; i < n; i++) std::memcpy(d.ptr(i), desc.data() + (size_t)i * 32, 32);
     }
     // mvImagePyramid as the reference leaves it (Frame::ComputeStereoMatches reads it), unless the integration keeps it on the GPU
-    if (g_pyramid_sync) SyncPyramidToHost();
+    if (g_pyramid_sync) {
+        // level 0 is the input itself (the reference keeps a bordered copy of it, :1165-1172): host copy; levels 1.. in one round trip
+        mvImagePyramid[0].create(image.rows, image.cols, CV_8UC1);
+        for (int y = 0; y < image.rows; y++) std::memcpy(mvImagePyramid[0].ptr(y), image.ptr(y), (size_t)image.cols);
+        DownloadLevels(1);
+    }
     else for (auto& m : mvImagePyramid) m.release();   // stale until SyncPyramidToHost()
     return mono;
 }
@@ -91,13 +96,24 @@ int ORBextractor::operator()( cv::InputArray _image, cv::InputArray _mask, std::
 // explicit download of mvImagePyramid (R/include/ORBextractor.h:88); only the stereo SAD refinement reads it
 void ORBextractor::SyncPyramidToHost()
 {
-    if (!mpHandle) return;
-    for (int l = 0; l < nlevels; l++) {
+    DownloadLevels(0);
+}
+
+// levels first .. nlevels-1 of the last frame into mvImagePyramid: one queue of copies into the handle's pinned staging, one
+// synchronisation, and cv::Mat HEADERS over that staging (no second copy).  The headers stay valid until the next frame of this
+// extractor, like the reference's own entries, which ComputePyramid re-creates every frame (R/src/ORBextractor.cc:1150-1177) and
+// which only Frame::ComputeStereoMatches reads, right after the extraction (R/src/Frame.cc:792, :882-901).
+void ORBextractor::DownloadLevels(int first)
+{
+    if (!mpHandle || first >= nlevels) return;
+    const int cnt = nlevels - first;
+    std::vector<const uint8_t*> ptr(cnt); std::vector<int> stride(cnt);
+    if (orbx_pyramid_levels_staged(mpHandle, 0, first, cnt, ptr.data(), stride.data()) != ORBX_OK)
+        throw std::runtime_error(std::string("ORBextractor (B200): ") + orbx_last_error());
+    for (int l = first; l < nlevels; l++) {
         int w = 0, h = 0;
         if (orbx_pyramid_level_size(mpHandle, l, &w, &h) != ORBX_OK) return;
-        mvImagePyramid[l].create(h, w, CV_8UC1);
-        if (orbx_pyramid_to_host(mpHandle, 0, l, mvImagePyramid[l].ptr(0), (int)mvImagePyramid[l].step) != ORBX_OK)
-            throw std::runtime_error(std::string("ORBextractor (B200): ") + orbx_last_error());
+        mvImagePyramid[l] = cv::Mat(h, w, CV_8UC1, const_cast<uint8_t*>(ptr[l - first]), (size_t)stride[l - first]);
     }
 }
 

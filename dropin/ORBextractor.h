@@ -73,10 +73,11 @@ public:
     // ---- additions of the B200 drop-in (not in the reference class) ----
     // The pyramid lives on the GPU.  By default operator() also downloads it into mvImagePyramid, exactly as the reference leaves
     // it (Frame::ComputeStereoMatches reads it, R/src/Frame.cc:792, :882-901).  A stereo integration that calls
-    // ORBmatcher::ComputeStereoMatches (device-side) turns the download off and saves 1.1 MB of D2H per 752x480 frame;
+    // ORBmatcher::ComputeStereoMatches (device-side) turns the download off and saves 0.8 MB of D2H per 752x480 frame (levels 1 .. 7; level 0 is copied from the input on the host);
     // SyncPyramidToHost() then fetches the levels of the last frame on demand.
     static void SetPyramidSync(bool on);
     void SyncPyramidToHost();
+    void DownloadLevels(int first);          // levels first .. nlevels-1 of the last frame into mvImagePyramid, one round trip
     // The GPU that extractors constructed from now on live on (multi-agent boxes: one agent per GPU); default 0
     static void SetDevice(int device);
     static int DefaultDevice();

@@ -122,6 +122,14 @@ int  orbx_fast_segment_plan(int level_width, int* n_cols, int* w_cell, int* seg_
  * stereo SAD refinement (R/src/Frame.cc:882-901) needs.  slot = frame within the last batch. */
 int  orbx_pyramid_level_size(const orbx_extractor* h, int level, int* width, int* height);
 int  orbx_pyramid_to_host(orbx_extractor* h, int slot, int level, uint8_t* dst, int dst_stride);
+/* Levels first_level .. first_level + n_levels - 1 of one frame in ONE round trip: the copies are queued into pinned staging,
+ * one synchronisation, then rows are unpacked into dst[k] (row stride dst_stride[k]) = what ORBextractor::operator() does
+ * after every frame to leave mvImagePyramid as the reference does (R/src/ORBextractor.cc:1150-1177). */
+int  orbx_pyramid_levels_to_host(orbx_extractor* h, int slot, int first_level, int n_levels, uint8_t* const* dst, const int* dst_stride);
+/* The same without the unpack: the levels land in pinned staging owned by the handle and ptr[k] / stride[k] point into it
+ * (valid until the next call of this function or of orbx_pyramid_levels_to_host on the handle, or its destruction): the class
+ * layer wraps them in cv::Mat headers, as short-lived as the reference's own mvImagePyramid entries (rewritten every frame). */
+int  orbx_pyramid_levels_staged(orbx_extractor* h, int slot, int first_level, int n_levels, const uint8_t** ptr, int* stride);
 /* test taps: blurred level (R/src/ORBextractor.cc:1114-1115) and the FAST candidates handed to
  * DistributeOctTree (R/src/ORBextractor.cc:845-851) as (x,y,response) float triples */
 int  orbx_blurred_to_host(orbx_extractor* h, int slot, int level, uint8_t* dst, int dst_stride);

@@ -97,6 +97,7 @@ struct orbx_extractor {
     // 2 = captured, -1 = not capturable; keyed on the arguments and the configuration generation
     struct SmallGraph { cudaGraphExec_t exec; cudaGraph_t graph; int seen, batch, lap0, lap1, gen, nkernels; } xg;
     int32_t* h_mailx; int32_t* d_mailx;          // mapped pinned: {error word, n[2], monoIndex[2]} written by k_ex_mailbox
+    uint8_t* h_pyr_stage; size_t pyr_stage_bytes;   // pinned staging of orbx_pyramid_levels_to_host
 };
 #define ORBX_EV_SETS 512
 
@@ -376,6 +377,7 @@ extern "C" void orbx_extractor_destroy(orbx_extractor* h)
     if (h->xg.exec) cudaGraphExecDestroy(h->xg.exec);
     if (h->xg.graph) cudaGraphDestroy(h->xg.graph);
     if (h->h_mailx) cudaFreeHost(h->h_mailx);
+    if (h->h_pyr_stage) cudaFreeHost(h->h_pyr_stage);
     if (h->dag_init) for (int i = 0; i < 2 * ORBX_MAX_LEVELS; i++) { cudaStreamDestroy(h->br[i]); cudaEventDestroy(h->ev_br[i]); if (i < ORBX_MAX_LEVELS) cudaEventDestroy(h->ev_lvl[i]); }
     cudaStreamDestroy(h->stream);
     delete h;
@@ -939,6 +941,64 @@ extern "C" int orbx_pyramid_to_host(orbx_extractor* h, int slot, int level, uint
     CK(cudaSetDevice(h->p.device));
     if (level == 0) return level_to_host(h, h->last_level0, h->last_pitch0, h->last_stride0, slot, 0, dst, dst_stride);
     return level_to_host(h, h->buf.pyr[level], h->geom.lv[level].pitch, h->geom.lv[level].frame_stride, slot, level, dst, dst_stride);
+}
+
+// levels [first_level, first_level + n_levels) of one frame into the handle's pinned staging (tight rows), one synchronisation
+static int stage_levels(orbx_extractor* h, int slot, int first_level, int n_levels)
+{
+    if (!h || h->geom.width == 0 || first_level < 0 || n_levels < 1 || first_level + n_levels > h->geom.nlevels || slot < 0 || slot >= h->last_batch)
+        return ORBX_E_INVALID;
+    CK(cudaSetDevice(h->p.device));
+    const OrbxGeom& g = h->geom;
+    size_t need = 0;
+    for (int l = first_level; l < first_level + n_levels; l++) need += ((size_t)g.lv[l].w * g.lv[l].h + 63) & ~(size_t)63;
+    if (need > h->pyr_stage_bytes) {
+        if (h->h_pyr_stage) { CK(cudaStreamSynchronize(h->stream)); cudaFreeHost(h->h_pyr_stage); h->h_pyr_stage = nullptr; h->pyr_stage_bytes = 0; }
+        CK(cudaMallocHost((void**)&h->h_pyr_stage, need));
+        h->pyr_stage_bytes = need;
+    }
+    size_t off = 0;
+    for (int l = first_level; l < first_level + n_levels; l++) {
+        const OrbxLevel& L = g.lv[l];
+        const uint8_t* src = l == 0 ? h->last_level0 + (long long)slot * h->last_stride0 : h->buf.pyr[l] + (long long)slot * L.frame_stride;
+        const int pitch = l == 0 ? h->last_pitch0 : L.pitch;
+        CK(cudaMemcpy2DAsync(h->h_pyr_stage + off, L.w, src, pitch, L.w, L.h, cudaMemcpyDeviceToHost, h->stream));
+        off += ((size_t)L.w * L.h + 63) & ~(size_t)63;
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    return ORBX_OK;
+}
+
+extern "C" int orbx_pyramid_levels_staged(orbx_extractor* h, int slot, int first_level, int n_levels, const uint8_t** ptr, int* stride)
+{
+    if (!ptr || !stride) return ORBX_E_INVALID;
+    const int rc = stage_levels(h, slot, first_level, n_levels);
+    if (rc) return rc;
+    size_t off = 0;
+    for (int l = first_level; l < first_level + n_levels; l++) {
+        const OrbxLevel& L = h->geom.lv[l];
+        ptr[l - first_level] = h->h_pyr_stage + off; stride[l - first_level] = L.w;
+        off += ((size_t)L.w * L.h + 63) & ~(size_t)63;
+    }
+    return ORBX_OK;
+}
+
+extern "C" int orbx_pyramid_levels_to_host(orbx_extractor* h, int slot, int first_level, int n_levels, uint8_t* const* dst, const int* dst_stride)
+{
+    if (!h || h->geom.width == 0 || !dst || !dst_stride || first_level < 0 || n_levels < 1 || first_level + n_levels > h->geom.nlevels) return ORBX_E_INVALID;
+    for (int l = first_level; l < first_level + n_levels; l++)
+        if (!dst[l - first_level] || dst_stride[l - first_level] < h->geom.lv[l].w) return ORBX_E_INVALID;
+    const int rc = stage_levels(h, slot, first_level, n_levels);
+    if (rc) return rc;
+    size_t off = 0;
+    for (int l = first_level; l < first_level + n_levels; l++) {
+        const OrbxLevel& L = h->geom.lv[l];
+        uint8_t* d = dst[l - first_level]; const int ds = dst_stride[l - first_level];
+        if (ds == L.w) memcpy(d, h->h_pyr_stage + off, (size_t)L.w * L.h);
+        else for (int y = 0; y < L.h; y++) memcpy(d + (size_t)y * ds, h->h_pyr_stage + off + (size_t)y * L.w, L.w);
+        off += ((size_t)L.w * L.h + 63) & ~(size_t)63;
+    }
+    return ORBX_OK;
 }
 
 extern "C" int orbx_blurred_to_host(orbx_extractor* h, int slot, int level, uint8_t* dst, int dst_stride)

@@ -31,7 +31,7 @@ EXPORTS = [
     "orbx_extractor_create", "orbx_extractor_destroy", "orbx_extractor_tables", "orbx_extractor_max_keypoints",
     "orbx_extract", "orbx_extract_batch", "orbx_extract_batch_device", "orbx_extractor_copy_slot",
     "orbx_extractor_results_device", "orbx_extractor_download", "orbx_extractor_sync", "orbx_extractor_profile",
-    "orbx_pyramid_level_size", "orbx_pyramid_to_host", "orbx_blurred_to_host", "orbx_candidates_to_host",
+    "orbx_pyramid_level_size", "orbx_pyramid_to_host", "orbx_pyramid_levels_to_host", "orbx_pyramid_levels_staged", "orbx_blurred_to_host", "orbx_candidates_to_host",
     "orbx_level_keypoints_to_host",
     "orbx_matcher_create", "orbx_matcher_destroy", "orbx_matcher_sync", "orbx_hamming_pairs",
     "orbx_bf_knn2", "orbx_bf_knn2_device", "orbx_knn2_merge_device",
@@ -109,6 +109,8 @@ def lib():
         L.orbx_extractor_sync.argtypes = [vp, vp]
         L.orbx_pyramid_level_size.argtypes = [vp, i32, vp, vp]
         L.orbx_pyramid_to_host.argtypes = [vp, i32, i32, vp, i32]
+        L.orbx_pyramid_levels_to_host.argtypes = [vp, i32, i32, i32, vp, vp]
+        L.orbx_pyramid_levels_staged.argtypes = [vp, i32, i32, i32, vp, vp]
         L.orbx_blurred_to_host.argtypes = [vp, i32, i32, vp, i32]
         L.orbx_candidates_to_host.argtypes = [vp, i32, i32, vp, i32, vp]
         L.orbx_level_keypoints_to_host.argtypes = [vp, i32, i32, vp, i32, vp]

@@ -16,7 +16,7 @@ extern "C" const char* orbx_last_error(void) { return g_err.c_str(); }
 extern "C" int orbx_device_count(void) { return 1; }
 extern "C" unsigned long long orbx_launch_count(void) { return 0; }
 
-struct orbx_extractor { OrcExtractor* e; orbx_params p; int w, h; };
+struct orbx_extractor { OrcExtractor* e; orbx_params p; int w, h; std::vector<std::vector<uint8_t> > staged; };
 struct orbx_matcher { orbx_matcher_params p; };
 struct orbx_vocab { OrcVocab* v; int words; };
 
@@ -59,6 +59,27 @@ extern "C" int orbx_extract(orbx_extractor* h, const uint8_t* img, int width, in
 extern "C" int orbx_pyramid_level_size(const orbx_extractor* h, int level, int* width, int* height)
 {
     return orc_level_size(h->e, level, width, height) == 0 ? ORBX_OK : ORBX_E_INVALID;
+}
+extern "C" int orbx_pyramid_to_host(orbx_extractor* h, int slot, int level, uint8_t* dst, int dst_stride);
+extern "C" int orbx_pyramid_level_size(const orbx_extractor* h, int level, int* width, int* height);
+extern "C" int orbx_pyramid_levels_staged(orbx_extractor* h, int slot, int first_level, int n_levels, const uint8_t** ptr, int* stride)
+{
+    std::vector<std::vector<uint8_t> >& keep = h->staged;                 // owned by the handle, like the pinned staging of the library
+    keep.assign(n_levels, std::vector<uint8_t>());
+    for (int k = 0; k < n_levels; k++) {
+        int w = 0, hh = 0;
+        if (orbx_pyramid_level_size(h, first_level + k, &w, &hh)) return ORBX_E_INVALID;
+        keep[k].resize((size_t)w * hh);
+        const int rc = orbx_pyramid_to_host(h, slot, first_level + k, keep[k].data(), w);
+        if (rc) return rc;
+        ptr[k] = keep[k].data(); stride[k] = w;
+    }
+    return ORBX_OK;
+}
+extern "C" int orbx_pyramid_levels_to_host(orbx_extractor* h, int slot, int first_level, int n_levels, uint8_t* const* dst, const int* dst_stride)
+{
+    for (int k = 0; k < n_levels; k++) { const int rc = orbx_pyramid_to_host(h, slot, first_level + k, dst[k], dst_stride[k]); if (rc) return rc; }
+    return ORBX_OK;
 }
 extern "C" int orbx_pyramid_to_host(orbx_extractor* h, int slot, int level, uint8_t* dst, int dst_stride)
 {

@@ -139,6 +139,41 @@ def test_single_image_call_replays_its_launch_graph():
     ex.close()
 
 
+def test_pyramid_levels_in_one_round_trip():
+    """orbx_pyramid_levels_to_host (what operator() uses to leave mvImagePyramid as the reference does) == the per-level download,
+    tight and strided destinations, any level range; bad arguments are rejected."""
+    import ctypes as C
+    W, H = 752, 480
+    img = synth.rects_frame(W, H, 11)
+    ex = orbx.ORBextractor(1000, 1.2, 8, 20, 7, max_width=W, max_height=H)
+    ex(img)
+    L = orbx.lib()
+    for first, cnt, pad in ((0, 8, 0), (1, 7, 0), (3, 2, 24)):
+        bufs = [np.full((ex.level_size(l)[1], ex.level_size(l)[0] + pad), 0xEE, np.uint8) for l in range(first, first + cnt)]
+        ptrs = (C.c_void_p * cnt)(*[b.ctypes.data for b in bufs])
+        strides = (C.c_int * cnt)(*[b.strides[0] for b in bufs])
+        assert L.orbx_pyramid_levels_to_host(ex._h, 0, first, cnt, ptrs, strides) == 0
+        for k, l in enumerate(range(first, first + cnt)):
+            w, h = ex.level_size(l)
+            np.testing.assert_array_equal(bufs[k][:, :w], ex.pyramid_level(l, 0), err_msg="level %d" % l)
+            assert (bufs[k][:, w:] == 0xEE).all()
+    # the staged form: pointers into the handle's pinned staging, no unpack
+    sp = (C.c_void_p * 7)(); ss = (C.c_int * 7)()
+    assert L.orbx_pyramid_levels_staged(ex._h, 0, 1, 7, sp, ss) == 0
+    for k, l in enumerate(range(1, 8)):
+        w, h = ex.level_size(l)
+        view = np.ctypeslib.as_array(C.cast(sp[k], C.POINTER(C.c_uint8)), shape=(h, ss[k]))[:, :w]
+        np.testing.assert_array_equal(view, ex.pyramid_level(l, 0), err_msg="staged level %d" % l)
+    assert L.orbx_pyramid_levels_staged(ex._h, 0, 6, 3, sp, ss) != 0
+    one = np.zeros((H, W), np.uint8)
+    ptrs = (C.c_void_p * 1)(one.ctypes.data); strides = (C.c_int * 1)(W - 1)
+    assert L.orbx_pyramid_levels_to_host(ex._h, 0, 0, 1, ptrs, strides) != 0        # stride smaller than the level
+    strides = (C.c_int * 1)(W)
+    assert L.orbx_pyramid_levels_to_host(ex._h, 0, 7, 2, ptrs, strides) != 0        # past the last level
+    assert L.orbx_pyramid_levels_to_host(ex._h, 3, 0, 1, ptrs, strides) != 0        # slot outside the last batch
+    ex.close()
+
+
 def test_empty_image_returns_minus_one():
     ex = orbx.ORBextractor(500, 1.2, 8, 20, 7)
     mono, kps, desc = ex(np.empty((0, 0), np.uint8))
