@@ -464,7 +464,8 @@ constexpr int INIT_NT = 256;             // threads per pair in a batch; a launc
 constexpr int INIT_NT_FEW = 1024;
 constexpr int INIT_CLAIMS = 4;            // claims kept per keypoint (more -> sequential fallback)
 constexpr int INIT_MAX_ROUNDS = 32;
-constexpr int INIT_MAX_K = 4096;          // shared memory of the parallel resolve: 6 ints per keypoint
+constexpr int INIT_MAX_K = 8192;          // shared memory of the parallel resolve: 6 ints per keypoint (192 KB at 8192)
+constexpr int PROJ_MAX_K = 16384;         // k_proj_resolve: 3 ints per keypoint
 
 // ---- k_init_resolve: SearchForInitialization's order-dependent part (R/src/ORBmatcher.cc:721-784), in parallel --------------
 // The reference visits the queries in order; query i skips a candidate i2 whose recorded match distance is <= its own
@@ -579,6 +580,111 @@ __global__ void __launch_bounds__(INIT_NT_FEW) k_init_resolve(WinBufs W, float n
     if (mine) atomicAdd(&s_count, mine);
     __syncthreads();
     if (tid == 0) nmatches[p] = s_count;
+}
+
+// ---- SearchByProjection modes 0 / 1 as a parallel fixed point ----
+// The sequential rule (:89-91 / :2045-2047): query i may not take a keypoint that is occupied, i.e. held by a MapPoint with
+// observations before the call (res[i2] >= 0) or claimed by an OCCUPYING query j < i (valid bit 1 clear); everything else about a
+// query's decision (best / second, thresholds, the level rule of mode 1) depends on its own candidate list only.  So the visit
+// order matters only through  minOcc[i2] = the smallest occupying query index that claims i2,  and the sequential result is the
+// unique fixed point of  X -> F(X),  F(X)[i] = decision of query i when i2 is barred iff minOcc_X[i2] < i  (induction on i, as for
+// k_init_resolve).  A round = one atomicMin per deciding query + one candidate-list scan per query, all queries in parallel; chains
+// are short (a query that loses its keypoint moves to another one), so a handful of rounds replaces one warp walking the queries in
+// order (0.55 ms for 1000 MapPoints against 1000 keypoints).  Final state: a keypoint belongs to the LAST query that claimed it
+// (non-occupying claimers are overwritten, :2063), every accepting query counts as a match and enters the rotation histogram.
+// No convergence within INIT_MAX_ROUNDS -> nmatches[p] = INIT_UNRESOLVED and the sequential kernel takes the pair (res untouched).
+__global__ void __launch_bounds__(INIT_NT_FEW) k_proj_resolve(WinBufs W, int mode, float nnratio, int check_ori, int max_dist, int32_t* out, int32_t* nmatches)
+{
+    extern __shared__ int s_mem[];
+    __shared__ int hist[ORBX_HISTO_LENGTH];
+    __shared__ int s_chg[2];
+    __shared__ int s_acc, s_cull;
+    const int tid = threadIdx.x, NTH = blockDim.x;
+    const int p = blockIdx.x;
+    orbx_pdl_prologue();
+    const PairDesc P = W.pairs[p];
+    const int nq = min(P.nq, W.K), n2 = min(P.n2, W.K);
+    uint32_t* dec = reinterpret_cast<uint32_t*>(s_mem);              // [K] by query: claimed keypoint, or NONE
+    int* base = s_mem + W.K;                                         // [K] by keypoint: -1 occupied before the call, else INT_MAX; later: owner
+    int* min_occ = s_mem + 2 * W.K;                                  // [K] by keypoint: smallest occupying claimer; later: claim_of by query
+    constexpr uint32_t NONE = 0xFFFFFFFFu;
+    int32_t* res = out + (long long)p * W.K;
+    uint8_t* bin_of = W.bin_of + (long long)p * W.K;
+    const uint32_t* pool = W.pool + (long long)p * W.POOL;
+    const int* q_off = W.q_off + (long long)p * W.K;
+    const int* q_cnt = W.q_cnt + (long long)p * W.K;
+    for (int i = tid; i < nq; i += NTH) dec[i] = NONE;
+    for (int i = tid; i < n2; i += NTH) base[i] = res[i] >= 0 ? -1 : 0x7fffffff;
+    if (tid < ORBX_HISTO_LENGTH) hist[tid] = 0;
+    if (tid == 0) { s_acc = 0; s_cull = 0; }
+    bool converged = false;
+    for (int round = 0; round < INIT_MAX_ROUNDS; round++) {
+        for (int i = tid; i < n2; i += NTH) min_occ[i] = base[i];
+        if (tid == 0) s_chg[round & 1] = 0;
+        __syncthreads();
+        for (int i = tid; i < nq; i += NTH) {
+            const uint32_t d = dec[i];
+            if (d != NONE && !(P.q[i].valid & 2)) atomicMin(&min_occ[d], i);
+        }
+        __syncthreads();
+        for (int i = tid; i < nq; i += NTH) {
+            const int c = q_cnt[i];
+            if (c <= 0) continue;
+            const int off = q_off[i];
+            int d0 = 0x7fffffff, d1 = 0x7fffffff; uint32_t e0 = 0, e1 = 0;
+            for (int k = 0; k < c; k++) {
+                const uint32_t e = __ldg(pool + off + k);
+                const int d = (e >> 16) & 0x1FF;
+                if (d >= d1) continue;                               // cannot change (best, second)
+                if (min_occ[e & 0xFFFF] < i) continue;               // occupied for this query
+                if (d < d0) { d1 = d0; e1 = e0; d0 = d; e0 = e; }
+                else { d1 = d; e1 = e; }
+            }
+            uint32_t nd = NONE;
+            if (mode == 0) {
+                if (d0 <= max_dist) nd = e0 & 0xFFFF;                // :2038, :2068 (or the caller's bound)
+            } else {
+                const int bd = d0 < 256 ? d0 : 256, bd2 = d1 < 256 ? d1 : 256;      // :78-141: best / second start at 256 with level -1
+                const int bl = d0 < 256 ? (int)(e0 >> 25) : -1, bl2 = d1 < 256 ? (int)(e1 >> 25) : -1;
+                if (bd <= ORBX_TH_HIGH && !(bl == bl2 && (float)bd > nnratio * (float)bd2)) nd = e0 & 0xFFFF;
+            }
+            if (nd != dec[i]) { dec[i] = nd; s_chg[round & 1] = 1; }
+        }
+        __syncthreads();
+        if (!s_chg[round & 1]) { converged = true; break; }
+    }
+    if (!converged) { if (tid == 0) nmatches[p] = INIT_UNRESOLVED; return; }
+    int* owner = base; int* claim_of = min_occ;
+    for (int i = tid; i < n2; i += NTH) owner[i] = -1;
+    __syncthreads();
+    int mine = 0;
+    for (int i = tid; i < nq; i += NTH) {
+        const uint32_t d = dec[i];
+        int c = -1; uint8_t bin = 0xFF;
+        if (d != NONE) {
+            c = (int)d; mine++;
+            atomicMax(&owner[c], i);
+            if (check_ori && mode != 1) { bin = (uint8_t)rot_bin(P.q[i].angle, P.k2[c].angle); atomicAdd(&hist[bin], 1); }
+        }
+        claim_of[i] = c; bin_of[i] = bin;
+    }
+    if (mine) atomicAdd(&s_acc, mine);
+    __syncthreads();
+    for (int i = tid; i < n2; i += NTH) if (owner[i] >= 0) res[i] = owner[i];
+    __syncthreads();
+    if (check_ori && mode != 1) {
+        // rotation consistency (:2163-2183): a keypoint claimed by a query of a rejected bin is cleared (-2: the caller NULLs the slot)
+        int ind1, ind2, ind3;
+        three_maxima(hist, ind1, ind2, ind3);
+        int culled = 0;
+        for (int i = tid; i < nq; i += NTH) {
+            const int b = bin_of[i];
+            if (b != 0xFF && b != ind1 && b != ind2 && b != ind3) { res[claim_of[i]] = -2; culled++; }
+        }
+        if (culled) atomicAdd(&s_cull, culled);
+        __syncthreads();
+    }
+    if (tid == 0) nmatches[p] = s_acc - s_cull;
 }
 
 __global__ void __launch_bounds__(32) k_window_resolve(WinBufs W, int mode, float nnratio, int check_ori, int max_dist,
@@ -1142,6 +1248,10 @@ static int run_window(orbx_matcher* m, const WinBufs& W, int npairs, int nq_max,
         // parallel fixed-point resolve; pairs it cannot finish are marked and fall through to the sequential kernel below
         CKM(ORBX_OPTIN_SMEM(k_init_resolve));
         orbx_launch_pdl(k_init_resolve, dim3(npairs), dim3(npairs <= 32 ? INIT_NT_FEW : INIT_NT), (2 + INIT_CLAIMS) * m->K * sizeof(int), s, W, nnratio, check_ori, d_out, d_nm, d_prev); ORBX_COUNT_LAUNCH(1);
+        only_unresolved = 1;
+    } else if ((mode == 0 || mode == 1) && m->K <= PROJ_MAX_K && !getenv("ORBX_SEQ_RESOLVE")) {
+        CKM(ORBX_OPTIN_SMEM(k_proj_resolve));
+        orbx_launch_pdl(k_proj_resolve, dim3(npairs), dim3(npairs <= 32 ? INIT_NT_FEW : INIT_NT), 3 * m->K * sizeof(int), s, W, mode, nnratio, check_ori, max_dist, d_out, d_nm); ORBX_COUNT_LAUNCH(1);
         only_unresolved = 1;
     }
     orbx_launch_pdl(k_window_resolve, dim3(npairs), dim3(32), 2 * m->K * sizeof(int), s, W, mode, nnratio, check_ori, max_dist, d_out, d_nm, d_prev, only_unresolved); ORBX_COUNT_LAUNCH(1);

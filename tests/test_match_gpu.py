@@ -124,6 +124,44 @@ def test_search_by_projection_parity(frames, mode):
 
 
 @pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("seed", [5, 6, 7])
+def test_search_by_projection_contention(mode, seed):
+    """Many queries compete for few keypoints (ORBmatcher.cc:89-91 / :2045-2047): long displacement chains for the parallel fixed-point
+    resolve (k_proj_resolve).  60 keypoints with near-identical descriptors (ties), 700 queries whose windows hold all of them,
+    occupying, non-occupying (0-observation owners, valid bit 1) and invalid queries mixed, some keypoints occupied before the call.
+    Also with ORBX-style tiny capacity headroom: max_keypoints just above the sizes."""
+    rng = np.random.default_rng(seed)
+    n2, nq = 60, 700
+    k2 = np.zeros(n2, O.KP_DTYPE)
+    k2["x"] = rng.uniform(300, 340, n2).astype(np.float32); k2["y"] = rng.uniform(200, 240, n2).astype(np.float32)
+    k2["angle"] = rng.uniform(0, 360, n2).astype(np.float32); k2["octave"] = rng.integers(0, 3, n2)
+    base = synth.random_descriptors(1, seed)[0]
+    d2 = np.tile(base, (n2, 1))
+    for i in range(n2):
+        for b in rng.integers(0, 256, int(rng.integers(0, 6))):
+            d2[i, b >> 3] ^= np.uint8(1 << (b & 7))
+    q = np.zeros(nq, O.PROJQ_DTYPE)
+    q["u"] = rng.uniform(310, 330, nq).astype(np.float32); q["v"] = rng.uniform(210, 230, nq).astype(np.float32)
+    q["r"] = 60.0; q["minl"] = 0; q["maxl"] = 7 if mode == 0 else rng.integers(0, 3, nq)
+    if mode == 1:
+        q["minl"] = np.maximum(q["maxl"] - 1, 0)
+    q["angle"] = rng.uniform(0, 360, nq).astype(np.float32); q["ur"] = q["u"] - 10
+    q["valid"] = rng.choice([0, 1, 1, 1, 3, 3], nq).astype(np.int32)
+    qd = np.tile(base, (nq, 1))
+    for i in range(nq):
+        for b in rng.integers(0, 256, int(rng.integers(0, 8))):
+            qd[i, b >> 3] ^= np.uint8(1 << (b & 7))
+    pre = np.full(n2, -1, np.int32); pre[::11] = 4242
+    for K in (1024, 768):
+        m = orbx.ORBmatcher(0.8, True, max_keypoints=K)
+        n, a = m.SearchByProjection(mode, q, qd, k2, d2, (0, 752, 0, 480), pre, None)
+        rn, ra = O.search_by_projection(mode, q, qd, k2, d2, (0, 752, 0, 480), pre, None, 0.8, True)
+        assert n == rn and n > 0
+        np.testing.assert_array_equal(a, ra)
+        m.close()
+
+
+@pytest.mark.parametrize("mode", [0, 1])
 def test_search_by_projection_two_camera_parity(mode):
     """Two-camera frame (Frame::Nleft != -1; R/src/ORBmatcher.cc:144-213, :2093-2160): left + right halves with their own grids, the
     queries of a point interleaved over one occupancy table, stereo partners (mode 1), 0-observation owners, one rotation histogram
