@@ -956,13 +956,14 @@ extern "C" void orbx_matcher_destroy(orbx_matcher* m)
     if (m->s_h2d) {
         cudaStreamDestroy(m->s_h2d); cudaStreamDestroy(m->s_d2h); cudaStreamDestroy(m->s_match);
         if (m->st_init) for (int i = 0; i < 2; i++) { cudaEventDestroy(m->st[i].ev_kernels); cudaEventDestroy(m->st[i].ev_host); cudaFreeHost(m->st[i].h_err); }
-        if (m->s_bf) { cudaStreamDestroy(m->s_bf); cudaEventDestroy(m->ev_bf_fork); cudaEventDestroy(m->ev_bf_join); }
         for (int k = 0; k < 2; k++) { if (m->lg.exec[k]) cudaGraphExecDestroy(m->lg.exec[k]); if (m->lg.graph[k]) cudaGraphDestroy(m->lg.graph[k]); }
         if (m->h_mail) { cudaFreeHost(m->h_mail); cudaEventDestroy(m->ev_ex); cudaEventDestroy(m->ev_done); cudaEventDestroy(m->ev_exd2h); cudaEventDestroy(m->ev_carry); }
         for (int i = 0; i < ORBX_MAX_CHUNKS; i++) cudaEventDestroy(m->ev_ext[i]);
         for (int i = 0; i < 2 * ORBX_MAX_CHUNKS; i++) { cudaEventDestroy(m->ev[i]); cudaEventDestroy(m->ev_r[i]); }
         cudaEventDestroy(m->ev_start);
     }
+    if (m->s_bf) { cudaStreamDestroy(m->s_bf); cudaEventDestroy(m->ev_bf_fork); cudaEventDestroy(m->ev_bf_join); }
+    if (m->d_pack) { cudaFree(m->d_pack); cudaFreeHost(m->h_pack); }
     if (m->h_err) cudaFreeHost(m->h_err);
     cudaStreamDestroy(m->stream);
     delete m;
@@ -1344,35 +1345,54 @@ extern "C" int orbx_search_by_projection_opts(orbx_matcher* m, int mode, const o
     m->W.gate_chi2 = chi2 > 0 ? chi2 : 0.0;
     m->W.gate_chi2_stereo = opt->chi2_stereo > 0 ? opt->chi2_stereo : 0.0;
     for (int l = 0; l < ORBX_MAX_LEVELS; l++) m->W.inv_sigma2[l] = (chi2 > 0 && l < nlevels) ? inv_level_sigma2[l] : 0.f;
-    CKM(cudaMemcpyAsync(m->W.q, q, sizeof(orbx_proj_query) * nq, cudaMemcpyHostToDevice, s));
-    CKM(cudaMemcpyAsync(m->d_qdesc, qdesc, (size_t)32 * nq, cudaMemcpyHostToDevice, s));
-    CKM(cudaMemcpyAsync(m->d_k2, k2, sizeof(orbx_keypoint) * n2, cudaMemcpyHostToDevice, s));
-    CKM(cudaMemcpyAsync(m->d_d2, d2, (size_t)32 * n2, cudaMemcpyHostToDevice, s));
-    if (uright2) CKM(cudaMemcpyAsync(m->d_uright, uright2, sizeof(float) * n2, cudaMemcpyHostToDevice, s));
-    if (!indep) {
-        CKM(cudaMemcpyAsync(m->d_out, assigned, sizeof(int32_t) * n2, cudaMemcpyHostToDevice, s));
+    // The caller's arrays are pageable (std::vector / cv::Mat in the class layer): seven separate copies cost ~8 us each.  They are
+    // packed into ONE pinned block (host memcpy: ~120 KB, a few us) that travels with one copy; the pair descriptor, the occupancy
+    // table (in / out) and the match count live in the same block, so the results come back with one copy too.
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t o_q = 0, o_qd = o_q + al(sizeof(orbx_proj_query) * nq), o_k2 = o_qd + al((size_t)32 * nq), o_d2 = o_k2 + al(sizeof(orbx_keypoint) * n2),
+                 o_ur = o_d2 + al((size_t)32 * n2), o_pd = o_ur + al(sizeof(float) * n2), o_as = o_pd + al(sizeof(PairDesc)),
+                 o_nm = o_as + al(sizeof(int32_t) * n2), total = o_nm + 256;
+    if (total > m->pack_bytes) {
+        if (m->d_pack) { CKM(cudaStreamSynchronize(s)); cudaFree(m->d_pack); cudaFreeHost(m->h_pack); m->d_pack = nullptr; m->h_pack = nullptr; m->pack_bytes = 0; }
+        const size_t cap_bytes = total + total / 2;
+        CKM(cudaMalloc((void**)&m->d_pack, cap_bytes));
+        if (cudaMallocHost((void**)&m->h_pack, cap_bytes) != cudaSuccess) { cudaFree(m->d_pack); m->d_pack = nullptr; orbx_set_error("%s%s", "cudaMallocHost failed", ""); return ORBX_E_NOMEM; }
+        m->pack_bytes = cap_bytes;
     }
+    uint8_t* hp = m->h_pack; uint8_t* dp = m->d_pack;
+    memcpy(hp + o_q, q, sizeof(orbx_proj_query) * nq);
+    memcpy(hp + o_qd, qdesc, (size_t)32 * nq);
+    memcpy(hp + o_k2, k2, sizeof(orbx_keypoint) * n2);
+    memcpy(hp + o_d2, d2, (size_t)32 * n2);
+    if (uright2) memcpy(hp + o_ur, uright2, sizeof(float) * n2);
+    if (!indep) memcpy(hp + o_as, assigned, sizeof(int32_t) * n2);
     PairDesc pd{};
-    pd.k1 = nullptr; pd.d1 = nullptr; pd.k2 = m->d_k2; pd.d2 = m->d_d2; pd.uright2 = uright2 ? m->d_uright : nullptr;
-    pd.q = m->W.q; pd.qdesc = m->d_qdesc; pd.n1 = nq; pd.n2 = n2; pd.nq = nq;
-    CKM(cudaMemcpyAsync(m->W.pairs, &pd, sizeof(pd), cudaMemcpyHostToDevice, s));
-    int rc = run_window(m, m->W, 1, nq, mode, nnratio, check_ori, m->d_out, m->d_nm, nullptr, s, max_dist);
+    pd.k1 = nullptr; pd.d1 = nullptr; pd.k2 = reinterpret_cast<const orbx_keypoint*>(dp + o_k2); pd.d2 = dp + o_d2;
+    pd.uright2 = uright2 ? reinterpret_cast<const float*>(dp + o_ur) : nullptr;
+    pd.q = reinterpret_cast<orbx_proj_query*>(dp + o_q); pd.qdesc = dp + o_qd; pd.n1 = nq; pd.n2 = n2; pd.nq = nq;
+    memcpy(hp + o_pd, &pd, sizeof(pd));
+    CKM(cudaMemcpyAsync(dp, hp, o_nm, cudaMemcpyHostToDevice, s));
+    WinBufs W = m->W;
+    W.pairs = reinterpret_cast<PairDesc*>(dp + o_pd);
+    int32_t* d_res = reinterpret_cast<int32_t*>(dp + o_as); int32_t* d_cnt = reinterpret_cast<int32_t*>(dp + o_nm);
+    int rc = run_window(m, W, 1, nq, mode, nnratio, check_ori, d_res, d_cnt, nullptr, s, max_dist);
     m->W.gate_chi2 = 0.0; m->W.gate_chi2_stereo = 0.0;
     m->W.qminX = m->W.minX; m->W.qminY = m->W.minY;
     if (rc) return rc;
     int nm = 0;
     if (indep) {
-        k_best_from_top2<<<(nq + 255) / 256, 256, 0, s>>>(m->W, nq, m->d_knn_idx, m->d_knn_dist); ORBX_COUNT_LAUNCH(1);
+        k_best_from_top2<<<(nq + 255) / 256, 256, 0, s>>>(W, nq, m->d_knn_idx, m->d_knn_dist); ORBX_COUNT_LAUNCH(1);
         CKM(cudaMemcpyAsync(best_idx, m->d_knn_idx, sizeof(int32_t) * nq, cudaMemcpyDeviceToHost, s));
         CKM(cudaMemcpyAsync(best_dist, m->d_knn_dist, sizeof(int32_t) * nq, cudaMemcpyDeviceToHost, s));
         rc = m_check_err(m, s);
         if (rc) return rc;
         for (int i = 0; i < nq; i++) nm += best_idx[i] >= 0;
     } else {
-        CKM(cudaMemcpyAsync(assigned, m->d_out, sizeof(int32_t) * n2, cudaMemcpyDeviceToHost, s));
-        CKM(cudaMemcpyAsync(&nm, m->d_nm, sizeof(int), cudaMemcpyDeviceToHost, s));
+        CKM(cudaMemcpyAsync(hp + o_as, dp + o_as, o_nm + sizeof(int32_t) - o_as, cudaMemcpyDeviceToHost, s));
         rc = m_check_err(m, s);
         if (rc) return rc;
+        memcpy(assigned, hp + o_as, sizeof(int32_t) * n2);
+        nm = *reinterpret_cast<const int32_t*>(hp + o_nm);
     }
     if (nmatches) *nmatches = nm;
     return ORBX_OK;

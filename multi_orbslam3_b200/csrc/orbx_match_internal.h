@@ -162,6 +162,7 @@ struct orbx_matcher {
     // that stores them into mapped pinned memory; ev_ex: extraction done (the keypoint / descriptor copies start on s_d2h beside
     // the matcher), ev_done / ev_exd2h: what the host waits for (the slot carry is queued after ev_done)
     int32_t* h_mail; int32_t* d_mail; cudaEvent_t ev_ex, ev_done, ev_exd2h, ev_carry;
+    uint8_t* h_pack; uint8_t* d_pack; size_t pack_bytes;      // one pinned + one device block for the arguments of a host-array search call
     std::vector<void*> allocs;
 };
 
