@@ -964,6 +964,7 @@ extern "C" void orbx_matcher_destroy(orbx_matcher* m)
     }
     if (m->s_bf) { cudaStreamDestroy(m->s_bf); cudaEventDestroy(m->ev_bf_fork); cudaEventDestroy(m->ev_bf_join); }
     if (m->d_pack) { cudaFree(m->d_pack); cudaFreeHost(m->h_pack); }
+    if (m->h_gen) cudaFreeHost(m->h_gen);
     if (m->h_err) cudaFreeHost(m->h_err);
     cudaStreamDestroy(m->stream);
     delete m;

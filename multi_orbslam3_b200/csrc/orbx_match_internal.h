@@ -139,6 +139,7 @@ struct orbx_matcher {
     bool cam_set; float cam_K[9], cam_P[9], cam_dist[12]; int cam_ndist;
     orbx_keypoint* d_kps_un; size_t kps_un_elems;
     uint8_t* d_gen; size_t gen_bytes;
+    uint8_t* h_gen; size_t h_gen_bytes;       // pinned mirror of d_gen for the host-array searches (one copy each way)
     uint8_t* d_st; size_t st_bytes;          // stereo scratch
     int32_t* h_mono2; int mono2_cap;         // pinned monoIndex landing zone of the stereo pipeline (2 x batch)
     cudaStream_t s_bf; cudaEvent_t ev_bf_fork, ev_bf_join;      // few-pair path: the brute-force search runs beside the window search

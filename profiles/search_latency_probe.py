@@ -34,3 +34,11 @@ print("SearchByProjection (mode 0, th 15)        p50 %.3f ms" % timeit(lambda: m
 print("SearchByProjection (mode 1)               p50 %.3f ms" % timeit(lambda: m.SearchByProjection(1, q, d1, k2, d2, bounds, pre.copy(), None)))
 print("SearchForInitialization (window 100)      p50 %.3f ms" % timeit(lambda: m.SearchForInitialization(k1, d1, k2, d2, bounds, prev.copy(), 100)))
 print("bf_knn2 (1000 x 1000)                     p50 %.3f ms" % timeit(lambda: m.knnMatch2(d1, d2)))
+# SearchByBoW(KeyFrame*, Frame&) (Tracking::TrackReferenceKeyFrame): feature vectors from an ORBvoc-shaped synthetic vocabulary
+vocab = synth.random_vocabulary(k=10, L=5, seed=13)
+V = orbx.ORBVocabulary(*vocab, L=5)
+fv1 = V.transform(d1, 4)[1]; fv2 = V.transform(d2, 4)[1]
+v1 = np.ones(len(k1), np.uint8)
+mb = orbx.ORBmatcher(0.7, True, max_keypoints=2048)
+print("SearchByBoW (KF, F)                       p50 %.3f ms" % timeit(lambda: mb.SearchByBoW(0, k1, d1, v1, fv1, k2, d2, None, fv2)))
+print("BoW transform of a frame (1000 desc)      p50 %.3f ms" % timeit(lambda: V.transform(d1, 4)))
