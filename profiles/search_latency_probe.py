@@ -42,3 +42,4 @@ v1 = np.ones(len(k1), np.uint8)
 mb = orbx.ORBmatcher(0.7, True, max_keypoints=2048)
 print("SearchByBoW (KF, F)                       p50 %.3f ms" % timeit(lambda: mb.SearchByBoW(0, k1, d1, v1, fv1, k2, d2, None, fv2)))
 print("BoW transform of a frame (1000 desc)      p50 %.3f ms" % timeit(lambda: V.transform(d1, 4)))
+print("orbx_bow_transform alone (C call)         p50 %.3f ms" % timeit(lambda: V.transform_features(d1, 4)))
