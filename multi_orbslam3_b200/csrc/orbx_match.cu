@@ -1373,6 +1373,7 @@ extern "C" int orbx_search_by_projection_opts(orbx_matcher* m, int mode, const o
     pd.q = reinterpret_cast<orbx_proj_query*>(dp + o_q); pd.qdesc = dp + o_qd; pd.n1 = nq; pd.n2 = n2; pd.nq = nq;
     memcpy(hp + o_pd, &pd, sizeof(pd));
     CKM(cudaMemcpyAsync(dp, hp, o_nm, cudaMemcpyHostToDevice, s));
+    OrbxPdlScope pdl_scope(true);                      // one pair: a chain of small kernels (programmatic dependent launch, orbx_internal.h)
     WinBufs W = m->W;
     W.pairs = reinterpret_cast<PairDesc*>(dp + o_pd);
     int32_t* d_res = reinterpret_cast<int32_t*>(dp + o_as); int32_t* d_cnt = reinterpret_cast<int32_t*>(dp + o_nm);
