@@ -223,7 +223,7 @@ constexpr int GRID_NT = 512;
 
 // Frame::AssignFeaturesToGrid: keypoints sorted by (cell, index) == per-cell vectors in push_back order.
 // cell = ix*GR + iy so that the cells (ix, iy0..iy1) visited by GetFeaturesInArea are one contiguous range.
-__global__ void __launch_bounds__(GRID_NT) k_grid_build(WinBufs W, int kmax)
+__global__ void __launch_bounds__(GRID_NT) k_grid_build(WinBufs W, int kmax, int only_level)
 {
     // The records of a pair sorted by (cell, keypoint index) = the reference's visit order inside a cell (insertion order).  A stable
     // counting sort over the NCELL cells: histogram with shared-memory atomics, block-wide exclusive scan (also the cell_start table
@@ -246,7 +246,9 @@ __global__ void __launch_bounds__(GRID_NT) k_grid_build(WinBufs W, int kmax)
         const orbx_keypoint kp = P.k2[i];
         const int px = (int)roundf(__fmul_rn(__fsub_rn(kp.x, W.minX), W.wInv));      // PosInGrid: round, not floor
         const int py = (int)roundf(__fmul_rn(__fsub_rn(kp.y, W.minY), W.hInv));
-        const int c = (px >= 0 && px < GC && py >= 0 && py < GR) ? px * GR + py : NCELL;
+        // only_level >= 0: every query of the search asks for that octave alone (SearchForInitialization: level1 == 0 on both sides,
+        // :714-718), so the other keypoints never enter the grid; dropping them keeps the visit order of the rest
+        const int c = (px >= 0 && px < GC && py >= 0 && py < GR && (only_level < 0 || kp.octave == only_level)) ? px * GR + py : NCELL;
         cell_of[i] = (unsigned short)c;
         atomicAdd(&cur[c], 1);
     }
@@ -1240,7 +1242,7 @@ static int run_window(orbx_matcher* m, const WinBufs& W, int npairs, int nq_max,
 {
     int npad = 1; while (npad < m->K) npad <<= 1;
     CKM(ORBX_OPTIN_SMEM(k_grid_build));
-    orbx_launch_pdl(k_grid_build, dim3(npairs), dim3(GRID_NT), sizeof(int) * (NCELL + 2) + 2 * sizeof(unsigned short) * (size_t)m->K, s, W, m->K); ORBX_COUNT_LAUNCH(1);   // also empties the pairs' candidate pools
+    orbx_launch_pdl(k_grid_build, dim3(npairs), dim3(GRID_NT), sizeof(int) * (NCELL + 2) + 2 * sizeof(unsigned short) * (size_t)m->K, s, W, m->K, mode == 2 ? 0 : -1); ORBX_COUNT_LAUNCH(1);   // also empties the pairs' candidate pools
     dim3 cg((nq_max + CAND_WARPS - 1) / CAND_WARPS, npairs);
     if (nq_max > 0) { orbx_launch_pdl(k_window_candidates, cg, dim3(CAND_WARPS * 32), 0, s, W); ORBX_COUNT_LAUNCH(1); }
     if (mode == 3) { CKM(cudaGetLastError()); return ORBX_OK; }
